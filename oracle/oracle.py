@@ -1,0 +1,262 @@
+"""ctypes binding of oracle/libhb_oracle.so (the C restatement in hb_oracle.c).
+
+TEST INFRASTRUCTURE ONLY — imported by tests/, __graft_entry__.smoke() and bench.py's CPU legs.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libhb_oracle.so")
+
+HBO_OK = 0
+HBO_ERR_UNDERFLOW = -3
+
+
+def build(force: bool = False) -> str:
+    src = os.path.join(_HERE, "hb_oracle.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_SO)
+        d, i32, i64, p = C.c_double, C.c_int, C.c_int64, C.c_void_p
+        L.hbo_dnorm_log.restype = d
+        L.hbo_dnorm_log.argtypes = [d, d, d]
+        L.hbo_dnorm.restype = d
+        L.hbo_dnorm.argtypes = [d, d, d]
+        L.hbo_stirlerr.restype = d
+        L.hbo_stirlerr.argtypes = [d]
+        L.hbo_bd0.restype = d
+        L.hbo_bd0.argtypes = [d, d]
+        L.hbo_dbinom.restype = d
+        L.hbo_dbinom.argtypes = [d, d, d, i32]
+        L.hbo_r_mean.restype = d
+        L.hbo_r_mean.argtypes = [p, i64]
+        L.hbo_r_sd.restype = d
+        L.hbo_r_sd.argtypes = [p, i64]
+        L.hbo_viterbi_logb.restype = i32
+        L.hbo_viterbi_logb.argtypes = [i32, i64, p, p, p, p, p]
+        L.hbo_viterbi_norm.restype = i32
+        L.hbo_viterbi_norm.argtypes = [i32, i64, p, p, p, p, p, p]
+        L.hbo_viterbi_binom.restype = i32
+        L.hbo_viterbi_binom.argtypes = [i32, i64, p, p, p, p, p, p]
+        L.hbo_forwardback_prob.restype = i32
+        L.hbo_forwardback_prob.argtypes = [i32, i64, p, p, p, p, p, p, p]
+        L.hbo_forwardback_norm.restype = i32
+        L.hbo_forwardback_norm.argtypes = [i32, i64, p, p, p, p, p, p, p]
+        L.hbo_forwardback_binom.restype = i32
+        L.hbo_forwardback_binom.argtypes = [i32, i64, p, p, p, p, p, p, p]
+        L.hbo_fbv_norm_batch.restype = i32
+        L.hbo_fbv_norm_batch.argtypes = [i64, i64, i64, p, p, i32, p, p, i32, p, p, p, p, p, i32]
+        L.hbo_fbv_binom_batch.restype = i32
+        L.hbo_fbv_binom_batch.argtypes = [i64, i64, i64, p, p, p, i32, p, p, p, p, p, p, i32]
+        L.hbo_pool_mean.restype = None
+        L.hbo_pool_mean.argtypes = [p, i64, p, i64, p]
+        L.hbo_pool_count_pos.restype = None
+        L.hbo_pool_count_pos.argtypes = [p, i64, p, i64, p]
+        L.hbo_num_threads.restype = i32
+        _lib = L
+    return _lib
+
+
+def _p(a: np.ndarray | None):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+# ---------------------------------------------------------------- scalar densities
+def dnorm_log(x, mu, sigma):
+    return lib().hbo_dnorm_log(float(x), float(mu), float(sigma))
+
+
+def dnorm(x, mu, sigma):
+    return lib().hbo_dnorm(float(x), float(mu), float(sigma))
+
+
+def dbinom(x, n, p, log=False):
+    return lib().hbo_dbinom(float(x), float(n), float(p), int(bool(log)))
+
+
+def stirlerr(n):
+    return lib().hbo_stirlerr(float(n))
+
+
+def bd0(x, np_):
+    return lib().hbo_bd0(float(x), float(np_))
+
+
+def r_mean(x):
+    x = _f64(x)
+    return lib().hbo_r_mean(_p(x), x.size)
+
+
+def r_sd(x):
+    x = _f64(x)
+    return lib().hbo_r_sd(_p(x), x.size)
+
+
+# ---------------------------------------------------------------- single chains
+def sym_Pi(S: int, t: float) -> np.ndarray:
+    """Transition matrix of R/HoneyBADGER.R:1150 (S=3: 1-2t / t) and :1409 (S=2: 1-t / t)."""
+    Pi = np.full((S, S), t, dtype=np.float64)
+    np.fill_diagonal(Pi, 1 - (S - 1) * t)
+    return Pi
+
+
+def viterbi_norm(x, mean, sd, Pi, delta):
+    """HiddenMarkov::Viterbi(dthmm(x, Pi, delta, "norm", list(mean, sd))) -> 1-based states."""
+    x = _f64(x)
+    mean, sd, Pi, delta = _f64(mean), _f64(sd), _f64(Pi), _f64(delta)
+    S = mean.size
+    y = np.zeros(x.size, dtype=np.int32)
+    rc = lib().hbo_viterbi_norm(S, x.size, _p(x), _p(mean), _p(sd), _p(Pi), _p(delta), _p(y))
+    if rc == HBO_ERR_UNDERFLOW:
+        raise FloatingPointError("Problems With Underflow")
+    if rc:
+        raise RuntimeError(f"oracle error {rc}")
+    return y
+
+
+def viterbi_binom(x, size, prob, Pi, delta):
+    x, size = _i32(x), _i32(size)
+    prob, Pi, delta = _f64(prob), _f64(Pi), _f64(delta)
+    S = prob.size
+    y = np.zeros(x.size, dtype=np.int32)
+    rc = lib().hbo_viterbi_binom(S, x.size, _p(x), _p(size), _p(prob), _p(Pi), _p(delta), _p(y))
+    if rc == HBO_ERR_UNDERFLOW:
+        raise FloatingPointError("Problems With Underflow")
+    if rc:
+        raise RuntimeError(f"oracle error {rc}")
+    return y
+
+
+def viterbi_logb(logb, Pi, delta, return_nu=False):
+    logb = _f64(logb)
+    T, S = logb.shape
+    Pi, delta = _f64(Pi), _f64(delta)
+    y = np.zeros(T, dtype=np.int32)
+    nu = np.zeros((T, S)) if return_nu else None
+    rc = lib().hbo_viterbi_logb(S, T, _p(logb), _p(Pi), _p(delta), _p(y), _p(nu))
+    if rc == HBO_ERR_UNDERFLOW:
+        raise FloatingPointError("Problems With Underflow")
+    if rc:
+        raise RuntimeError(f"oracle error {rc}")
+    return (y, nu) if return_nu else y
+
+
+def forwardback_norm(x, mean, sd, Pi, delta):
+    """(gamma[T,S], LL) with gamma = exp(logalpha + logbeta - LL) of HiddenMarkov::forwardback."""
+    x = _f64(x)
+    mean, sd, Pi, delta = _f64(mean), _f64(sd), _f64(Pi), _f64(delta)
+    S = mean.size
+    g = np.zeros((x.size, S))
+    ll = C.c_double(0)
+    rc = lib().hbo_forwardback_norm(S, x.size, _p(x), _p(mean), _p(sd), _p(Pi), _p(delta), _p(g),
+                                    C.addressof(ll))
+    if rc:
+        raise RuntimeError(f"oracle error {rc}")
+    return g, ll.value
+
+
+def forwardback_binom(x, size, prob, Pi, delta):
+    x, size = _i32(x), _i32(size)
+    prob, Pi, delta = _f64(prob), _f64(Pi), _f64(delta)
+    S = prob.size
+    g = np.zeros((x.size, S))
+    ll = C.c_double(0)
+    rc = lib().hbo_forwardback_binom(S, x.size, _p(x), _p(size), _p(prob), _p(Pi), _p(delta),
+                                     _p(g), C.addressof(ll))
+    if rc:
+        raise RuntimeError(f"oracle error {rc}")
+    return g, ll.value
+
+
+def forwardback_prob(prob, Pi, delta):
+    prob = _f64(prob)
+    T, S = prob.shape
+    Pi, delta = _f64(Pi), _f64(delta)
+    la, lb, g = np.zeros((T, S)), np.zeros((T, S)), np.zeros((T, S))
+    ll = C.c_double(0)
+    rc = lib().hbo_forwardback_prob(S, T, _p(prob), _p(Pi), _p(delta), _p(la), _p(lb), _p(g),
+                                    C.addressof(ll))
+    if rc:
+        raise RuntimeError(f"oracle error {rc}")
+    return la, lb, g, ll.value
+
+
+# ---------------------------------------------------------------- gene-major batches
+def fbv_norm_batch(x, seg_off, mean, sd, Pi, delta, want_gamma=True, nthreads=0):
+    """x[T,B] gene-major; one chain per (column, segment).  sd is [B] or [nseg,B].
+
+    Returns (y uint8 [T,B] 1-based (0 = chain hit underflow), gamma [3,T,B] | None, ll [nseg,B], rc).
+    """
+    x = _f64(x)
+    T, B = x.shape
+    seg_off = np.ascontiguousarray(seg_off, dtype=np.int64)
+    nseg = seg_off.size - 1
+    sd = _f64(sd)
+    per_seg = int(sd.ndim == 2)
+    mean, Pi, delta = _f64(mean), _f64(Pi), _f64(delta)
+    y = np.zeros((T, B), dtype=np.uint8)
+    g = np.zeros((3, T, B)) if want_gamma else None
+    ll = np.zeros((nseg, B))
+    nt = nthreads or lib().hbo_num_threads()
+    rc = lib().hbo_fbv_norm_batch(T, B, B, _p(x), _p(seg_off), nseg, _p(mean), _p(sd), per_seg,
+                                  _p(Pi), _p(delta), _p(y), _p(g), _p(ll), nt)
+    return y, g, ll, rc
+
+
+def fbv_binom_batch(x, n, seg_off, prob, Pi, delta, want_gamma=True, nthreads=0):
+    x, n = _i32(x), _i32(n)
+    T, B = x.shape
+    seg_off = np.ascontiguousarray(seg_off, dtype=np.int64)
+    nseg = seg_off.size - 1
+    prob, Pi, delta = _f64(prob), _f64(Pi), _f64(delta)
+    y = np.zeros((T, B), dtype=np.uint8)
+    g = np.zeros((2, T, B)) if want_gamma else None
+    ll = np.zeros((nseg, B))
+    nt = nthreads or lib().hbo_num_threads()
+    rc = lib().hbo_fbv_binom_batch(T, B, B, _p(x), _p(n), _p(seg_off), nseg, _p(prob), _p(Pi),
+                                   _p(delta), _p(y), _p(g), _p(ll), nt)
+    return y, g, ll, rc
+
+
+# ---------------------------------------------------------------- pooled statistics
+def pool_mean(mat_gn, cols):
+    """apply(M[, cols], 1, mean) for M given as a numpy [G, N] array (any memory order)."""
+    m = np.asfortranarray(mat_gn, dtype=np.float64)
+    G = m.shape[0]
+    cols = _i32(cols)
+    out = np.zeros(G)
+    lib().hbo_pool_mean(m.ctypes.data_as(C.c_void_p), G, _p(cols), cols.size, _p(out))
+    return out
+
+
+def pool_count_pos(mat_gn, cols):
+    """rowSums(M[, cols] > 0)."""
+    m = np.asfortranarray(mat_gn, dtype=np.float64)
+    G = m.shape[0]
+    cols = _i32(cols)
+    out = np.zeros(G, dtype=np.int32)
+    lib().hbo_pool_count_pos(m.ctypes.data_as(C.c_void_p), G, _p(cols), cols.size, _p(out))
+    return out
