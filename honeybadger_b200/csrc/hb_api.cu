@@ -1,0 +1,850 @@
+// hb_api.cu — the C ABI of libhb_b200.so (declared in include/hb_b200.h).
+//
+// Host side only: argument checks, host-libm parameter preparation (logs, emission table), the
+// per-device scratch cache, host<->device staging for the *_host entry points, kernel launches.
+// There is no CPU implementation of the path behind these functions.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "../../include/hb_b200.h"
+#include "hb_binom2.cuh"
+#include "hb_host_math.h"
+#include "hb_kernels.h"
+#include "hb_norm3.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(call)                                                                                  \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess)                                                                    \
+            return fail(e_ == cudaErrorMemoryAllocation ? HB_ERR_NOMEM : HB_ERR_CUDA,             \
+                        "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__,        \
+                        __LINE__);                                                                \
+    } while (0)
+
+#define HBTRY(call)                                                                               \
+    do {                                                                                          \
+        int rc_ = (call);                                                                         \
+        if (rc_ != HB_OK) return rc_;                                                             \
+    } while (0)
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes)
+    {
+        if (bytes <= cap) return HB_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            e = cudaMalloc(&p, bytes);
+            want = bytes;
+        }
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return fail(HB_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+        }
+        cap = want;
+        return HB_OK;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T> T *as() { return (T *)p; }
+};
+
+// Per-device scratch, grown on demand and reused across calls (no allocation in steady state).
+struct Workspace {
+    DevBuf psi, ckpt, sdaux, segtab, status, lut_lb, lut_rho, cellmask, gsize;
+    DevBuf st_in, st_in2, st_x, st_x2, st_y, st_g, st_out, st_sd, st_ll, st_member, st_pool, st_pool2;
+    std::vector<int64_t> seg_cached;
+    int64_t nchunks = 0;
+    double lut_key[3] = {-1, -1, -1};
+    int32_t lut_nmax = -1;
+    void release_all()
+    {
+        DevBuf *all[] = {&psi, &ckpt, &sdaux, &segtab, &status, &lut_lb, &lut_rho, &cellmask, &gsize,
+                         &st_in, &st_in2, &st_x, &st_x2, &st_y, &st_g, &st_out, &st_sd, &st_ll,
+                         &st_member, &st_pool, &st_pool2};
+        for (DevBuf *b : all) b->release();
+        seg_cached.clear();
+        lut_nmax = -1;
+        lut_key[0] = -1;
+    }
+};
+
+std::mutex g_mu;
+Workspace g_ws[16];
+int g_lut_nmax_cfg = 511;
+
+int cur_ws(Workspace **out)
+{
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(HB_ERR_NODEVICE, "no CUDA device: %s", cudaGetErrorString(e));
+    }
+    if (dev < 0 || dev >= 16) return fail(HB_ERR_ARG, "device index %d out of range", dev);
+    *out = &g_ws[dev];
+    return HB_OK;
+}
+
+// Segment tables on the device: seg_off[nseg+1] | chunk_off[nseg+1] | order[nseg] (int32).
+int prepare_segments(Workspace *ws, const int64_t *seg_off, int32_t nseg, int64_t T,
+                     cudaStream_t st, const int64_t **d_seg, const int64_t **d_chunk,
+                     const int32_t **d_order)
+{
+    if (nseg < 1 || !seg_off) return fail(HB_ERR_ARG, "need nseg >= 1 and seg_off");
+    if (seg_off[0] < 0 || seg_off[nseg] > T) return fail(HB_ERR_ARG, "seg_off outside [0, T]");
+    for (int32_t s = 0; s < nseg; s++)
+        if (seg_off[s + 1] < seg_off[s]) return fail(HB_ERR_ARG, "seg_off must be non-decreasing");
+    const size_t n64 = (size_t)(nseg + 1);
+    const size_t bytes = 2 * n64 * sizeof(int64_t) + (size_t)nseg * sizeof(int32_t);
+    const bool same = ws->seg_cached.size() == n64 &&
+                      memcmp(ws->seg_cached.data(), seg_off, n64 * sizeof(int64_t)) == 0 &&
+                      ws->segtab.cap >= bytes;
+    if (!same) {
+        HBTRY(ws->segtab.ensure(bytes));
+        std::vector<int64_t> host(2 * n64);
+        std::vector<int32_t> order(nseg);
+        int64_t acc = 0;
+        for (int32_t s = 0; s <= nseg; s++) {
+            host[s] = seg_off[s];
+            host[n64 + s] = acc;
+            if (s < nseg) acc += (seg_off[s + 1] - seg_off[s] + HB_CHUNK - 1) / HB_CHUNK;
+        }
+        std::iota(order.begin(), order.end(), 0);
+        std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
+            return (seg_off[a + 1] - seg_off[a]) > (seg_off[b + 1] - seg_off[b]);
+        });
+        // synchronous copies: the temporaries die at the end of this scope
+        CU(cudaStreamSynchronize(st));
+        CU(cudaMemcpy(ws->segtab.p, host.data(), 2 * n64 * sizeof(int64_t), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy((char *)ws->segtab.p + 2 * n64 * sizeof(int64_t), order.data(),
+                      (size_t)nseg * sizeof(int32_t), cudaMemcpyHostToDevice));
+        ws->seg_cached.assign(seg_off, seg_off + n64);
+        ws->nchunks = acc;
+    }
+    *d_seg = ws->segtab.as<int64_t>();
+    *d_chunk = ws->segtab.as<int64_t>() + n64;
+    *d_order = (const int32_t *)((char *)ws->segtab.p + 2 * n64 * sizeof(int64_t));
+    return HB_OK;
+}
+
+bool all_finite(const double *v, int n)
+{
+    for (int i = 0; i < n; i++)
+        if (!std::isfinite(v[i])) return false;
+    return true;
+}
+
+int fill_norm3_const(hb::Norm3Const &c, const double *mean, const double *Pi, const double *delta,
+                     bool *sym)
+{
+    if (!mean || !Pi || !delta) return fail(HB_ERR_ARG, "mean, Pi and delta are required");
+    if (!all_finite(mean, 3) || !all_finite(Pi, 9) || !all_finite(delta, 3))
+        return fail(HB_ERR_ARG, "non-finite HMM parameter");
+    for (int i = 0; i < 3; i++) {
+        c.mean[i] = mean[i];
+        c.delta[i] = delta[i];
+        c.logdelta[i] = log(delta[i]); // log(0) = -inf, as in R
+    }
+    for (int i = 0; i < 9; i++) {
+        if (Pi[i] < 0) return fail(HB_ERR_ARG, "negative transition probability");
+        c.Pi[i] = Pi[i];
+        c.logPi[i] = log(Pi[i]);
+    }
+    const bool sym_pi = Pi[0] == Pi[4] && Pi[0] == Pi[8] && Pi[1] == Pi[2] && Pi[1] == Pi[3] &&
+                        Pi[1] == Pi[5] && Pi[1] == Pi[6] && Pi[1] == Pi[7] && Pi[1] > 0;
+    const bool sym_mean = (mean[0] - mean[1]) == -(mean[2] - mean[1]);
+    *sym = sym_pi && sym_mean;
+    c.la = c.logPi[0];
+    c.lt = c.logPi[1];
+    c.amt = Pi[0] - Pi[1];
+    c.tt = Pi[1];
+    return HB_OK;
+}
+
+int check_flags(int32_t flags, const void *y, const void *gamma, const void *ll, bool *vit,
+                bool *fb)
+{
+    *vit = (flags & HB_WANT_VITERBI) != 0;
+    *fb = (flags & (HB_WANT_GAMMA | HB_WANT_LL)) != 0;
+    if (!*vit && !*fb) return fail(HB_ERR_ARG, "flags select nothing to compute");
+    if (*vit && !y) return fail(HB_ERR_ARG, "HB_WANT_VITERBI needs y");
+    if ((flags & HB_WANT_GAMMA) && !gamma) return fail(HB_ERR_ARG, "HB_WANT_GAMMA needs gamma");
+    if ((flags & HB_WANT_LL) && !ll) return fail(HB_ERR_ARG, "HB_WANT_LL needs ll");
+    return HB_OK;
+}
+
+// Core launch on device-resident gene-major data.  inv_sd/log_sd may be NULL (computed on device).
+int norm3_run(Workspace *ws, const double *x, int64_t ld, int64_t T, int64_t B,
+              const int64_t *seg_off, int32_t nseg, const double *mean, const double *sd,
+              const double *inv_sd, const double *log_sd, int32_t sd_per_seg, const double *Pi,
+              const double *delta, int32_t flags, uint8_t *y, int64_t ldy, double *gamma,
+              int64_t ldg, double *ll, cudaStream_t st)
+{
+    if (T < 1 || B < 1 || ld < B) return fail(HB_ERR_ARG, "bad shape T=%lld B=%lld ld=%lld",
+                                               (long long)T, (long long)B, (long long)ld);
+    if (!x || !sd) return fail(HB_ERR_ARG, "x and sd are required");
+    bool vit, fb, sym;
+    HBTRY(check_flags(flags, y, gamma, ll, &vit, &fb));
+    if (vit && ldy < B) return fail(HB_ERR_ARG, "ldy < B");
+    if ((flags & HB_WANT_GAMMA) && ldg < B) return fail(HB_ERR_ARG, "ldg < B");
+    hb::Norm3Args a;
+    memset(&a, 0, sizeof a);
+    HBTRY(fill_norm3_const(a.c, mean, Pi, delta, &sym));
+    HBTRY(prepare_segments(ws, seg_off, nseg, T, st, &a.seg_off, &a.chunk_off, &a.seg_order));
+    const int64_t nsd = sd_per_seg ? (int64_t)nseg * B : B;
+    if (!inv_sd || !log_sd) {
+        HBTRY(ws->sdaux.ensure((size_t)nsd * 2 * sizeof(double)));
+        double *aux = ws->sdaux.as<double>();
+        CU(hb::launch_sd_prep(sd, nsd, aux, aux + nsd, st));
+        inv_sd = aux;
+        log_sd = aux + nsd;
+    }
+    HBTRY(ws->status.ensure(sizeof(int32_t)));
+    if (vit) HBTRY(ws->psi.ensure((size_t)ws->nchunks * B * sizeof(uint64_t)));
+    if (fb) HBTRY(ws->ckpt.ensure((size_t)ws->nchunks * 3 * B * sizeof(double)));
+    CU(cudaMemsetAsync(ws->status.p, 0, sizeof(int32_t), st));
+    a.x = x;
+    a.ld = ld;
+    a.T = T;
+    a.B = B;
+    a.nseg = nseg;
+    a.nblk_per_seg = (int32_t)((B + HB_BLOCK - 1) / HB_BLOCK);
+    a.sd = sd;
+    a.inv_sd = inv_sd;
+    a.log_sd = log_sd;
+    a.sd_per_seg = sd_per_seg ? 1 : 0;
+    a.y = y;
+    a.ldy = ldy;
+    a.gamma = (flags & HB_WANT_GAMMA) ? gamma : nullptr;
+    a.ldg = ldg;
+    a.ll = (flags & HB_WANT_LL) ? ll : nullptr;
+    a.psi = ws->psi.as<uint64_t>();
+    a.ckpt = ws->ckpt.as<double>();
+    a.status = ws->status.as<int32_t>();
+    if (fb && !a.gamma) {
+        // LL only: the kernel still writes posteriors; give it scratch to write to
+        return fail(HB_ERR_ARG, "HB_WANT_LL currently requires HB_WANT_GAMMA");
+    }
+    CU(hb::launch_norm3(a, sym, vit, fb, st));
+    return HB_OK;
+}
+
+int read_status(Workspace *ws, cudaStream_t st)
+{
+    int32_t s = 0;
+    CU(cudaMemcpyAsync(&s, ws->status.p, sizeof s, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (s == 1) return fail(HB_ERR_UNDERFLOW, "Problems With Underflow");
+    if (s == 2) return fail(HB_ERR_ARG, "beta-binomial count above the emission table");
+    return HB_OK;
+}
+
+// Emission table for the binomial chains, cached per (p0, p1, rho, nmax).
+int prepare_lut(Workspace *ws, const double *prob, double rho, cudaStream_t st)
+{
+    const int32_t nmax = g_lut_nmax_cfg;
+    if (ws->lut_nmax == nmax && ws->lut_key[0] == prob[0] && ws->lut_key[1] == prob[1] &&
+        ws->lut_key[2] == rho)
+        return HB_OK;
+    const size_t cnt = (size_t)(nmax + 1) * (nmax + 2) / 2;
+    std::vector<double> lb(2 * cnt);
+    std::vector<hb::RhoME> rr(cnt);
+    for (int32_t n = 0; n <= nmax; n++)
+        for (int32_t x = 0; x <= n; x++) {
+            size_t ix = (size_t)n * (n + 1) / 2 + x;
+            double l0, l1;
+            if (rho > 0) {
+                l0 = hbhost::betabinom_logpmf(x, n, prob[0], rho);
+                l1 = hbhost::betabinom_logpmf(x, n, prob[1], rho);
+            } else {
+                l0 = hbhost::binom_logpmf(x, n, prob[0]);
+                l1 = hbhost::binom_logpmf(x, n, prob[1]);
+            }
+            lb[2 * ix] = l0;
+            lb[2 * ix + 1] = l1;
+            rr[ix] = hb::rho_from_logratio(l0 - l1);
+        }
+    HBTRY(ws->lut_lb.ensure(lb.size() * sizeof(double)));
+    HBTRY(ws->lut_rho.ensure(rr.size() * sizeof(hb::RhoME)));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaMemcpy(ws->lut_lb.p, lb.data(), lb.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(ws->lut_rho.p, rr.data(), rr.size() * sizeof(hb::RhoME), cudaMemcpyHostToDevice));
+    ws->lut_nmax = nmax;
+    ws->lut_key[0] = prob[0];
+    ws->lut_key[1] = prob[1];
+    ws->lut_key[2] = rho;
+    return HB_OK;
+}
+
+int binom2_run(Workspace *ws, const int32_t *x, const int32_t *n, int64_t ld, int64_t T, int64_t B,
+               const int64_t *seg_off, int32_t nseg, const double *prob, double rho,
+               const double *Pi, const double *delta, int32_t flags, uint8_t *y, int64_t ldy,
+               double *gamma, int64_t ldg, double *ll, cudaStream_t st)
+{
+    if (T < 1 || B < 1 || ld < B) return fail(HB_ERR_ARG, "bad shape T=%lld B=%lld ld=%lld",
+                                               (long long)T, (long long)B, (long long)ld);
+    if (!x || !n || !prob || !Pi || !delta) return fail(HB_ERR_ARG, "missing argument");
+    if (!all_finite(prob, 2) || !all_finite(Pi, 4) || !all_finite(delta, 2) || !(rho >= 0) ||
+        !(rho < 1))
+        return fail(HB_ERR_ARG, "bad HMM parameter");
+    for (int k = 0; k < 2; k++)
+        if (prob[k] < 0 || prob[k] > 1) return fail(HB_ERR_ARG, "prob outside [0,1]");
+    bool vit, fb;
+    HBTRY(check_flags(flags, y, gamma, ll, &vit, &fb));
+    if (vit && ldy < B) return fail(HB_ERR_ARG, "ldy < B");
+    if ((flags & HB_WANT_GAMMA) && ldg < B) return fail(HB_ERR_ARG, "ldg < B");
+    if (fb && !(flags & HB_WANT_GAMMA))
+        return fail(HB_ERR_ARG, "HB_WANT_LL currently requires HB_WANT_GAMMA");
+    hb::Binom2Args a;
+    memset(&a, 0, sizeof a);
+    for (int k = 0; k < 2; k++) {
+        a.c.prob[k] = prob[k];
+        a.c.q[k] = 1 - prob[k];
+        a.c.logp[k] = log(prob[k]);
+        a.c.logq[k] = log(1 - prob[k]);
+        a.c.delta[k] = delta[k];
+        a.c.logdelta[k] = log(delta[k]);
+    }
+    for (int i = 0; i < 4; i++) {
+        if (Pi[i] < 0) return fail(HB_ERR_ARG, "negative transition probability");
+        a.c.Pi[i] = Pi[i];
+        a.c.logPi[i] = log(Pi[i]);
+    }
+    a.c.bb = rho > 0 ? 1 : 0;
+    HBTRY(prepare_segments(ws, seg_off, nseg, T, st, &a.seg_off, &a.chunk_off, &a.seg_order));
+    HBTRY(prepare_lut(ws, prob, rho, st));
+    HBTRY(ws->status.ensure(sizeof(int32_t)));
+    if (vit) HBTRY(ws->psi.ensure((size_t)ws->nchunks * B * sizeof(uint64_t)));
+    if (fb) HBTRY(ws->ckpt.ensure((size_t)ws->nchunks * 3 * B * sizeof(double)));
+    CU(cudaMemsetAsync(ws->status.p, 0, sizeof(int32_t), st));
+    a.x = x;
+    a.n = n;
+    a.ld = ld;
+    a.T = T;
+    a.B = B;
+    a.nseg = nseg;
+    a.nblk_per_seg = (int32_t)((B + HB_BLOCK - 1) / HB_BLOCK);
+    a.lut_lb = ws->lut_lb.as<double2>();
+    a.lut_rho = ws->lut_rho.as<hb::RhoME>();
+    a.lut_nmax = ws->lut_nmax;
+    a.y = y;
+    a.ldy = ldy;
+    a.gamma = (flags & HB_WANT_GAMMA) ? gamma : nullptr;
+    a.ldg = ldg;
+    a.ll = (flags & HB_WANT_LL) ? ll : nullptr;
+    a.psi = ws->psi.as<uint64_t>();
+    a.ckpt = ws->ckpt.as<double>();
+    a.status = ws->status.as<int32_t>();
+    CU(hb::launch_binom2(a, vit, fb, st));
+    return HB_OK;
+}
+
+int64_t pad_ld(int64_t B) { return (B + 15) / 16 * 16; } // 128-byte rows for fp64
+
+// membership -> group sizes (host) ; returns HB_ERR_ARG on empty groups
+int group_sizes(const uint8_t *member, int32_t K, int64_t N, std::vector<int32_t> &sz)
+{
+    sz.assign(K, 0);
+    for (int32_t k = 0; k < K; k++) {
+        int32_t c = 0;
+        for (int64_t i = 0; i < N; i++) c += member[(int64_t)k * N + i] != 0;
+        if (c < 1) return fail(HB_ERR_ARG, "group %d has no cells", k);
+        sz[k] = c;
+    }
+    return HB_OK;
+}
+
+} // namespace
+
+// =====================================================================================
+extern "C" {
+
+int hb_version(void) { return 100; }
+
+const char *hb_last_error(void) { return g_err.c_str(); }
+
+int hb_device_count(int *count)
+{
+    if (!count) return fail(HB_ERR_ARG, "count is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        *count = 0;
+        return fail(HB_ERR_NODEVICE, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    }
+    *count = n;
+    return HB_OK;
+}
+
+int hb_set_device(int device)
+{
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(HB_ERR_NODEVICE, "cudaSetDevice(%d): %s", device, cudaGetErrorString(e));
+    }
+    return HB_OK;
+}
+
+int hb_release_workspace(void)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    Workspace *ws;
+    HBTRY(cur_ws(&ws));
+    cudaDeviceSynchronize();
+    ws->release_all();
+    return HB_OK;
+}
+
+int hb_set_binom_lut_max(int32_t nmax)
+{
+    if (nmax < 0 || nmax > 4095) return fail(HB_ERR_ARG, "nmax must be in [0, 4095]");
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_lut_nmax_cfg = nmax;
+    return HB_OK;
+}
+
+int hb_status_dev(void *stream)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    Workspace *ws;
+    HBTRY(cur_ws(&ws));
+    if (!ws->status.p) return HB_OK;
+    return read_status(ws, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------ Gaussian chains
+int hb_hmm_norm_dev(const double *x, int64_t ld, int64_t T, int64_t B, const int64_t *seg_off,
+                    int32_t nseg, const double *mean, const double *sd, int32_t sd_per_seg,
+                    const double *Pi, const double *delta, int32_t flags, uint8_t *y, int64_t ldy,
+                    double *gamma, int64_t ldg, double *ll, void *stream)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    Workspace *ws;
+    HBTRY(cur_ws(&ws));
+    return norm3_run(ws, x, ld, T, B, seg_off, nseg, mean, sd, nullptr, nullptr, sd_per_seg, Pi,
+                     delta, flags, y, ldy, gamma, ldg, ll, (cudaStream_t)stream);
+}
+
+int hb_hmm_norm_host(const double *x, int64_t T, int64_t B, const int64_t *seg_off, int32_t nseg,
+                     const double *mean, const double *sd, int32_t sd_per_seg, const double *Pi,
+                     const double *delta, int32_t flags, int32_t *y, double *gamma, double *ll)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    Workspace *ws;
+    HBTRY(cur_ws(&ws));
+    if (T < 1 || B < 1 || !x || !sd) return fail(HB_ERR_ARG, "bad arguments");
+    const int64_t one_seg[2] = {0, T};
+    if (!seg_off) {
+        seg_off = one_seg;
+        nseg = 1;
+    }
+    bool vit, fb;
+    HBTRY(check_flags(flags, y, gamma, ll, &vit, &fb));
+    cudaStream_t st = 0;
+    // Column batches sized to the free device memory (inputs + outputs + scratch ~ 60 B / step).
+    size_t free_b = 0, total_b = 0;
+    CU(cudaMemGetInfo(&free_b, &total_b));
+    int64_t Bc = std::max<int64_t>(1, std::min<int64_t>(B, (int64_t)(free_b * 0.6 / (80.0 * T))));
+    if (Bc >= 16) Bc = Bc / 16 * 16;
+    const int64_t nsd_seg = sd_per_seg ? nseg : 1;
+    std::vector<double> h_aux;
+    int rc_status = HB_OK;
+    for (int64_t b0 = 0; b0 < B; b0 += Bc) {
+        const int64_t bn = std::min(Bc, B - b0);
+        const int64_t ld = pad_ld(bn);
+        HBTRY(ws->st_in.ensure((size_t)T * bn * sizeof(double)));
+        HBTRY(ws->st_x.ensure((size_t)T * ld * sizeof(double)));
+        HBTRY(ws->st_sd.ensure((size_t)nsd_seg * bn * 3 * sizeof(double)));
+        CU(cudaMemcpyAsync(ws->st_in.p, x + b0 * T, (size_t)T * bn * sizeof(double),
+                           cudaMemcpyHostToDevice, st));
+        CU(hb::launch_transpose_f64(ws->st_in.as<double>(), T, bn, ws->st_x.as<double>(), ld, st));
+        // chain scales: sd, 1/sd (IEEE), log(sd) (host libm, as R)
+        h_aux.resize((size_t)nsd_seg * bn * 3);
+        for (int64_t s = 0; s < nsd_seg; s++)
+            for (int64_t b = 0; b < bn; b++) {
+                double v = sd[s * B + b0 + b];
+                h_aux[(0 * nsd_seg + s) * bn + b] = v;
+                h_aux[(1 * nsd_seg + s) * bn + b] = 1.0 / v;
+                h_aux[(2 * nsd_seg + s) * bn + b] = log(v);
+            }
+        CU(cudaMemcpyAsync(ws->st_sd.p, h_aux.data(), h_aux.size() * sizeof(double),
+                           cudaMemcpyHostToDevice, st));
+        CU(cudaStreamSynchronize(st)); // h_aux is reused by the next batch
+        const double *d_sd = ws->st_sd.as<double>();
+        uint8_t *d_y = nullptr;
+        double *d_g = nullptr, *d_ll = nullptr;
+        if (vit) {
+            HBTRY(ws->st_y.ensure((size_t)T * ld));
+            d_y = ws->st_y.as<uint8_t>();
+        }
+        if (flags & HB_WANT_GAMMA) {
+            HBTRY(ws->st_g.ensure((size_t)3 * T * ld * sizeof(double)));
+            d_g = ws->st_g.as<double>();
+        }
+        if (flags & HB_WANT_LL) {
+            HBTRY(ws->st_ll.ensure((size_t)nseg * bn * sizeof(double)));
+            d_ll = ws->st_ll.as<double>();
+        }
+        HBTRY(norm3_run(ws, ws->st_x.as<double>(), ld, T, bn, seg_off, nseg, mean, d_sd,
+                        d_sd + nsd_seg * bn, d_sd + 2 * nsd_seg * bn, sd_per_seg, Pi, delta, flags,
+                        d_y, ld, d_g, ld, d_ll, st));
+        if (vit) {
+            HBTRY(ws->st_out.ensure((size_t)T * bn * sizeof(int32_t)));
+            CU(hb::launch_transpose_u8_back(d_y, ld, T, bn, ws->st_out.as<int32_t>(), st));
+            CU(cudaMemcpyAsync(y + b0 * T, ws->st_out.p, (size_t)T * bn * sizeof(int32_t),
+                               cudaMemcpyDeviceToHost, st));
+        }
+        if (flags & HB_WANT_GAMMA) {
+            // st_in is free again: reuse it as the column-major staging of one state plane
+            for (int k = 0; k < 3; k++) {
+                CU(hb::launch_transpose_f64_back(d_g + (int64_t)k * T * ld, ld, T, bn,
+                                                 ws->st_in.as<double>(), st));
+                CU(cudaMemcpyAsync(gamma + ((int64_t)k * B + b0) * T, ws->st_in.p,
+                                   (size_t)T * bn * sizeof(double), cudaMemcpyDeviceToHost, st));
+            }
+        }
+        if (flags & HB_WANT_LL) {
+            for (int32_t s = 0; s < nseg; s++)
+                CU(cudaMemcpyAsync(ll + (int64_t)s * B + b0, d_ll + (int64_t)s * bn,
+                                   (size_t)bn * sizeof(double), cudaMemcpyDeviceToHost, st));
+        }
+        int rc = read_status(ws, st);
+        if (rc != HB_OK) rc_status = rc;
+    }
+    return rc_status;
+}
+
+// ------------------------------------------------------------------ binomial chains
+int hb_hmm_binom_dev(const int32_t *x, const int32_t *size, int64_t ld, int64_t T, int64_t B,
+                     const int64_t *seg_off, int32_t nseg, const double *prob, double rho,
+                     const double *Pi, const double *delta, int32_t flags, uint8_t *y,
+                     int64_t ldy, double *gamma, int64_t ldg, double *ll, void *stream)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    Workspace *ws;
+    HBTRY(cur_ws(&ws));
+    return binom2_run(ws, x, size, ld, T, B, seg_off, nseg, prob, rho, Pi, delta, flags, y, ldy,
+                      gamma, ldg, ll, (cudaStream_t)stream);
+}
+
+int hb_hmm_binom_host(const int32_t *x, const int32_t *size, int64_t T, int64_t B,
+                      const int64_t *seg_off, int32_t nseg, const double *prob, double rho,
+                      const double *Pi, const double *delta, int32_t flags, int32_t *y,
+                      double *gamma, double *ll)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    Workspace *ws;
+    HBTRY(cur_ws(&ws));
+    if (T < 1 || B < 1 || !x || !size) return fail(HB_ERR_ARG, "bad arguments");
+    const int64_t one_seg[2] = {0, T};
+    if (!seg_off) {
+        seg_off = one_seg;
+        nseg = 1;
+    }
+    bool vit, fb;
+    HBTRY(check_flags(flags, y, gamma, ll, &vit, &fb));
+    cudaStream_t st = 0;
+    size_t free_b = 0, total_b = 0;
+    CU(cudaMemGetInfo(&free_b, &total_b));
+    int64_t Bc = std::max<int64_t>(1, std::min<int64_t>(B, (int64_t)(free_b * 0.6 / (64.0 * T))));
+    if (Bc >= 32) Bc = Bc / 32 * 32;
+    int rc_status = HB_OK;
+    for (int64_t b0 = 0; b0 < B; b0 += Bc) {
+        const int64_t bn = std::min(Bc, B - b0);
+        const int64_t ld = (bn + 31) / 32 * 32;
+        HBTRY(ws->st_in.ensure((size_t)T * bn * sizeof(double))); // also the gamma staging
+        HBTRY(ws->st_x.ensure((size_t)T * ld * sizeof(int32_t)));
+        HBTRY(ws->st_x2.ensure((size_t)T * ld * sizeof(int32_t)));
+        CU(cudaMemcpyAsync(ws->st_in.p, x + b0 * T, (size_t)T * bn * sizeof(int32_t),
+                           cudaMemcpyHostToDevice, st));
+        CU(hb::launch_transpose_i32(ws->st_in.as<int32_t>(), T, bn, ws->st_x.as<int32_t>(), ld, st));
+        CU(cudaMemcpyAsync(ws->st_in.p, size + b0 * T, (size_t)T * bn * sizeof(int32_t),
+                           cudaMemcpyHostToDevice, st));
+        CU(hb::launch_transpose_i32(ws->st_in.as<int32_t>(), T, bn, ws->st_x2.as<int32_t>(), ld, st));
+        uint8_t *d_y = nullptr;
+        double *d_g = nullptr, *d_ll = nullptr;
+        if (vit) {
+            HBTRY(ws->st_y.ensure((size_t)T * ld));
+            d_y = ws->st_y.as<uint8_t>();
+        }
+        if (flags & HB_WANT_GAMMA) {
+            HBTRY(ws->st_g.ensure((size_t)2 * T * ld * sizeof(double)));
+            d_g = ws->st_g.as<double>();
+        }
+        if (flags & HB_WANT_LL) {
+            HBTRY(ws->st_ll.ensure((size_t)nseg * bn * sizeof(double)));
+            d_ll = ws->st_ll.as<double>();
+        }
+        HBTRY(binom2_run(ws, ws->st_x.as<int32_t>(), ws->st_x2.as<int32_t>(), ld, T, bn, seg_off,
+                         nseg, prob, rho, Pi, delta, flags, d_y, ld, d_g, ld, d_ll, st));
+        if (vit) {
+            HBTRY(ws->st_out.ensure((size_t)T * bn * sizeof(int32_t)));
+            CU(hb::launch_transpose_u8_back(d_y, ld, T, bn, ws->st_out.as<int32_t>(), st));
+            CU(cudaMemcpyAsync(y + b0 * T, ws->st_out.p, (size_t)T * bn * sizeof(int32_t),
+                               cudaMemcpyDeviceToHost, st));
+        }
+        if (flags & HB_WANT_GAMMA) {
+            for (int k = 0; k < 2; k++) {
+                CU(hb::launch_transpose_f64_back(d_g + (int64_t)k * T * ld, ld, T, bn,
+                                                 ws->st_in.as<double>(), st));
+                CU(cudaMemcpyAsync(gamma + ((int64_t)k * B + b0) * T, ws->st_in.p,
+                                   (size_t)T * bn * sizeof(double), cudaMemcpyDeviceToHost, st));
+            }
+        }
+        if (flags & HB_WANT_LL) {
+            for (int32_t s = 0; s < nseg; s++)
+                CU(cudaMemcpyAsync(ll + (int64_t)s * B + b0, d_ll + (int64_t)s * bn,
+                                   (size_t)bn * sizeof(double), cudaMemcpyDeviceToHost, st));
+        }
+        int rc = read_status(ws, st);
+        if (rc != HB_OK) rc_status = rc;
+    }
+    return rc_status;
+}
+
+// ------------------------------------------------------------------ layout
+int hb_transpose_f64_dev(const double *src, int64_t G, int64_t N, double *dst, int64_t ld,
+                         void *stream)
+{
+    if (!src || !dst || G < 1 || N < 1 || ld < N) return fail(HB_ERR_ARG, "bad arguments");
+    CU(hb::launch_transpose_f64(src, G, N, dst, ld, (cudaStream_t)stream));
+    return HB_OK;
+}
+
+int hb_transpose_f64_to_i32_dev(const double *src, int64_t G, int64_t N, int32_t *dst, int64_t ld,
+                                void *stream)
+{
+    if (!src || !dst || G < 1 || N < 1 || ld < N) return fail(HB_ERR_ARG, "bad arguments");
+    CU(hb::launch_transpose_f64_i32(src, G, N, dst, ld, (cudaStream_t)stream));
+    return HB_OK;
+}
+
+int hb_transpose_u8_back_dev(const uint8_t *src, int64_t ld, int64_t G, int64_t N, int32_t *dst,
+                             void *stream)
+{
+    if (!src || !dst || G < 1 || N < 1 || ld < N) return fail(HB_ERR_ARG, "bad arguments");
+    CU(hb::launch_transpose_u8_back(src, ld, G, N, dst, (cudaStream_t)stream));
+    return HB_OK;
+}
+
+int hb_transpose_f64_back_dev(const double *src, int64_t ld, int64_t G, int64_t N, double *dst,
+                              void *stream)
+{
+    if (!src || !dst || G < 1 || N < 1 || ld < N) return fail(HB_ERR_ARG, "bad arguments");
+    CU(hb::launch_transpose_f64_back(src, ld, G, N, dst, (cudaStream_t)stream));
+    return HB_OK;
+}
+
+// ------------------------------------------------------------------ statistics
+int hb_chain_sd_dev(const double *x, int64_t ld, int64_t T, int64_t B, const int64_t *seg_off,
+                    int32_t nseg, int32_t per_seg, double *sd, void *stream)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    Workspace *ws;
+    HBTRY(cur_ws(&ws));
+    if (!x || !sd || T < 2 || B < 1 || ld < B) return fail(HB_ERR_ARG, "bad arguments");
+    const int64_t one_seg[2] = {0, T};
+    if (!per_seg || !seg_off) {
+        seg_off = one_seg;
+        nseg = 1;
+    }
+    const int64_t *d_seg, *d_chunk;
+    const int32_t *d_order;
+    HBTRY(prepare_segments(ws, seg_off, nseg, T, (cudaStream_t)stream, &d_seg, &d_chunk, &d_order));
+    CU(hb::launch_chain_sd(x, ld, B, d_seg, nseg, sd, (cudaStream_t)stream));
+    return HB_OK;
+}
+
+int hb_pool_mean_dev(const double *x, int64_t ld, int64_t G, int64_t N, const uint8_t *member,
+                     int32_t K, double *out, void *stream)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    Workspace *ws;
+    HBTRY(cur_ws(&ws));
+    if (!x || !member || !out || G < 1 || N < 1 || K < 1 || ld < N)
+        return fail(HB_ERR_ARG, "bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    // group sizes: tiny D2H of the membership (K*N bytes)
+    std::vector<uint8_t> h_mem((size_t)K * N);
+    CU(cudaMemcpyAsync(h_mem.data(), member, h_mem.size(), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    std::vector<int32_t> sz;
+    HBTRY(group_sizes(h_mem.data(), K, N, sz));
+    HBTRY(ws->gsize.ensure((size_t)K * sizeof(int32_t)));
+    CU(cudaMemcpy(ws->gsize.p, sz.data(), (size_t)K * sizeof(int32_t), cudaMemcpyHostToDevice));
+    CU(hb::launch_pool_mean(x, ld, G, N, member, ws->gsize.as<int32_t>(), K, out, st));
+    return HB_OK;
+}
+
+int hb_pooled_sd_dev(const double *pooled, int64_t G, int32_t K, double *out_sd, void *stream)
+{
+    if (!pooled || !out_sd || G < 2 || K < 1) return fail(HB_ERR_ARG, "bad arguments");
+    CU(hb::launch_pooled_sd(pooled, G, K, out_sd, (cudaStream_t)stream));
+    return HB_OK;
+}
+
+int hb_pool_count_pos_dev(const int32_t *v, int64_t ld, int64_t G, int64_t N,
+                          const uint8_t *member, int32_t K, int32_t *out, void *stream)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    Workspace *ws;
+    HBTRY(cur_ws(&ws));
+    if (!v || !member || !out || G < 1 || N < 1 || K < 1 || ld < N)
+        return fail(HB_ERR_ARG, "bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    HBTRY(ws->cellmask.ensure((size_t)N * sizeof(uint32_t)));
+    for (int32_t k0 = 0; k0 < K; k0 += 32) {
+        const int32_t kn = std::min(32, K - k0);
+        CU(hb::launch_build_cellmask(member + (int64_t)k0 * N, N, kn, ws->cellmask.as<uint32_t>(), st));
+        CU(hb::launch_pool_count(v, ld, G, N, ws->cellmask.as<uint32_t>(), kn, out + (int64_t)k0 * G,
+                                 st));
+    }
+    return HB_OK;
+}
+
+// ------------------------------------------------------------------ the four reference call sites
+int hb_gexp_pooled_viterbi_host(const double *gexp_norm, int64_t G, int64_t N,
+                                const uint8_t *member, int32_t K, const double *mean,
+                                const double *Pi, const double *delta, int32_t *y,
+                                double *pooled_x, double *pooled_sd)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    Workspace *ws;
+    HBTRY(cur_ws(&ws));
+    if (!gexp_norm || !member || !y || G < 2 || N < 1 || K < 1)
+        return fail(HB_ERR_ARG, "bad arguments");
+    cudaStream_t st = 0;
+    std::vector<int32_t> sz;
+    HBTRY(group_sizes(member, K, N, sz));
+    const int64_t ld = pad_ld(N), ldk = pad_ld(K);
+    HBTRY(ws->st_in.ensure((size_t)G * N * sizeof(double)));
+    HBTRY(ws->st_x.ensure((size_t)G * ld * sizeof(double)));
+    HBTRY(ws->st_member.ensure((size_t)K * N));
+    HBTRY(ws->gsize.ensure((size_t)K * sizeof(int32_t)));
+    HBTRY(ws->st_pool.ensure((size_t)K * G * sizeof(double)));  // [K][G]
+    HBTRY(ws->st_pool2.ensure((size_t)G * ldk * sizeof(double))); // gene-major [G][ldk]
+    HBTRY(ws->st_sd.ensure((size_t)K * sizeof(double)));
+    HBTRY(ws->st_y.ensure((size_t)G * ldk));
+    HBTRY(ws->st_out.ensure((size_t)G * K * sizeof(int32_t)));
+    CU(cudaMemcpyAsync(ws->st_in.p, gexp_norm, (size_t)G * N * sizeof(double), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ws->st_member.p, member, (size_t)K * N, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ws->gsize.p, sz.data(), (size_t)K * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    CU(hb::launch_transpose_f64(ws->st_in.as<double>(), G, N, ws->st_x.as<double>(), ld, st));
+    CU(hb::launch_pool_mean(ws->st_x.as<double>(), ld, G, N, ws->st_member.as<uint8_t>(),
+                            ws->gsize.as<int32_t>(), K, ws->st_pool.as<double>(), st));
+    CU(hb::launch_pooled_sd(ws->st_pool.as<double>(), G, K, ws->st_sd.as<double>(), st));
+    // [K][G] row-major is column-major [G x K]: the same transpose as an R matrix upload
+    CU(hb::launch_transpose_f64(ws->st_pool.as<double>(), G, K, ws->st_pool2.as<double>(), ldk, st));
+    // log(sd) must be the host libm's: bring the K scales back, finish them here
+    std::vector<double> h_sd(K), h_aux(3 * (size_t)K);
+    CU(cudaMemcpyAsync(h_sd.data(), ws->st_sd.p, (size_t)K * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    for (int32_t k = 0; k < K; k++) {
+        h_aux[k] = h_sd[k];
+        h_aux[K + k] = 1.0 / h_sd[k];
+        h_aux[2 * K + k] = log(h_sd[k]);
+    }
+    HBTRY(ws->sdaux.ensure(h_aux.size() * sizeof(double)));
+    CU(cudaMemcpy(ws->sdaux.p, h_aux.data(), h_aux.size() * sizeof(double), cudaMemcpyHostToDevice));
+    const int64_t seg[2] = {0, G};
+    const double *aux = ws->sdaux.as<double>();
+    HBTRY(norm3_run(ws, ws->st_pool2.as<double>(), ldk, G, K, seg, 1, mean, aux, aux + K, aux + 2 * K,
+                    0, Pi, delta, HB_WANT_VITERBI, ws->st_y.as<uint8_t>(), ldk, nullptr, 0, nullptr,
+                    st));
+    CU(hb::launch_transpose_u8_back(ws->st_y.as<uint8_t>(), ldk, G, K, ws->st_out.as<int32_t>(), st));
+    CU(cudaMemcpyAsync(y, ws->st_out.p, (size_t)G * K * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    if (pooled_x)
+        CU(cudaMemcpyAsync(pooled_x, ws->st_pool.p, (size_t)K * G * sizeof(double),
+                           cudaMemcpyDeviceToHost, st));
+    if (pooled_sd) memcpy(pooled_sd, h_sd.data(), (size_t)K * sizeof(double));
+    return read_status(ws, st);
+}
+
+int hb_allele_pooled_viterbi_host(const double *r_maf, const double *n_sc, int64_t G, int64_t N,
+                                  const uint8_t *member, int32_t K, const double *prob,
+                                  const double *Pi, const double *delta, int32_t *y, int32_t *mafl,
+                                  int32_t *sizel)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    Workspace *ws;
+    HBTRY(cur_ws(&ws));
+    if (!r_maf || !n_sc || !member || !y || G < 2 || N < 1 || K < 1)
+        return fail(HB_ERR_ARG, "bad arguments");
+    cudaStream_t st = 0;
+    std::vector<int32_t> sz;
+    HBTRY(group_sizes(member, K, N, sz));
+    const int64_t ld = (N + 31) / 32 * 32, ldk = (K + 31) / 32 * 32;
+    HBTRY(ws->st_in.ensure((size_t)G * N * sizeof(double)));
+    HBTRY(ws->st_x.ensure((size_t)G * ld * sizeof(int32_t)));
+    HBTRY(ws->st_member.ensure((size_t)K * N));
+    HBTRY(ws->cellmask.ensure((size_t)N * sizeof(uint32_t)));
+    HBTRY(ws->st_pool.ensure((size_t)K * G * sizeof(int32_t) * 2));
+    HBTRY(ws->st_pool2.ensure((size_t)G * ldk * sizeof(int32_t) * 2));
+    HBTRY(ws->st_y.ensure((size_t)G * ldk));
+    HBTRY(ws->st_out.ensure((size_t)G * K * sizeof(int32_t)));
+    CU(cudaMemcpyAsync(ws->st_member.p, member, (size_t)K * N, cudaMemcpyHostToDevice, st));
+    int32_t *cnt[2] = {ws->st_pool.as<int32_t>(), ws->st_pool.as<int32_t>() + (int64_t)K * G};
+    int32_t *gm[2] = {ws->st_pool2.as<int32_t>(), ws->st_pool2.as<int32_t>() + G * ldk};
+    const double *src[2] = {r_maf, n_sc};
+    for (int i = 0; i < 2; i++) {
+        CU(cudaMemcpyAsync(ws->st_in.p, src[i], (size_t)G * N * sizeof(double), cudaMemcpyHostToDevice, st));
+        CU(hb::launch_transpose_f64_i32(ws->st_in.as<double>(), G, N, ws->st_x.as<int32_t>(), ld, st));
+        for (int32_t k0 = 0; k0 < K; k0 += 32) {
+            const int32_t kn = std::min(32, K - k0);
+            CU(hb::launch_build_cellmask(ws->st_member.as<uint8_t>() + (int64_t)k0 * N, N, kn,
+                                         ws->cellmask.as<uint32_t>(), st));
+            CU(hb::launch_pool_count(ws->st_x.as<int32_t>(), ld, G, N, ws->cellmask.as<uint32_t>(), kn,
+                                     cnt[i] + (int64_t)k0 * G, st));
+        }
+        CU(hb::launch_transpose_i32(cnt[i], G, K, gm[i], ldk, st));
+    }
+    const int64_t seg[2] = {0, G};
+    HBTRY(binom2_run(ws, gm[0], gm[1], ldk, G, K, seg, 1, prob, 0.0, Pi, delta, HB_WANT_VITERBI,
+                     ws->st_y.as<uint8_t>(), ldk, nullptr, 0, nullptr, st));
+    CU(hb::launch_transpose_u8_back(ws->st_y.as<uint8_t>(), ldk, G, K, ws->st_out.as<int32_t>(), st));
+    CU(cudaMemcpyAsync(y, ws->st_out.p, (size_t)G * K * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    if (mafl)
+        CU(cudaMemcpyAsync(mafl, cnt[0], (size_t)K * G * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    if (sizel)
+        CU(cudaMemcpyAsync(sizel, cnt[1], (size_t)K * G * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    return read_status(ws, st);
+}
+
+} // extern "C"

@@ -1,0 +1,142 @@
+// hb_device.cuh — small device helpers shared by the HMM kernels (sm_100a).
+//
+// Everything here is `HB_HD` so that tests/emul can compile the SAME chain bodies for the host and
+// step through them without a GPU (a debugging aid for the CPU test-suite; the package never
+// loads that build and has no CPU path).
+#pragma once
+#include <stdint.h>
+#include <math.h>
+#include <string.h>
+
+#if defined(__CUDACC__)
+#define HB_HD __host__ __device__ __forceinline__
+#define HB_HD_NOINLINE static __host__ __device__ __noinline__
+#else
+#define HB_HD inline
+#define HB_HD_NOINLINE inline
+struct double2 {
+    double x, y;
+};
+#endif
+
+namespace hb {
+
+// ---------------------------------------------------------------- bit access
+HB_HD int32_t hi32(double v)
+{
+#if defined(__CUDA_ARCH__)
+    return __double2hiint(v);
+#else
+    uint64_t u;
+    memcpy(&u, &v, 8);
+    return (int32_t)(u >> 32);
+#endif
+}
+HB_HD int32_t lo32(double v)
+{
+#if defined(__CUDA_ARCH__)
+    return __double2loint(v);
+#else
+    uint64_t u;
+    memcpy(&u, &v, 8);
+    return (int32_t)(u & 0xffffffffu);
+#endif
+}
+HB_HD double mk64(int32_t hi, int32_t lo)
+{
+#if defined(__CUDA_ARCH__)
+    return __hiloint2double(hi, lo);
+#else
+    uint64_t u = ((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo;
+    double v;
+    memcpy(&v, &u, 8);
+    return v;
+#endif
+}
+// Unbiased binary exponent of a positive normal double.
+HB_HD int32_t expo(double v) { return ((hi32(v) >> 20) & 0x7ff) - 1023; }
+// v * 2^k by integer add on the exponent field (v normal, result must stay normal).
+HB_HD double scale2(double v, int32_t k) { return mk64(hi32(v) + (k << 20), lo32(v)); }
+// 2^k as a double, k in [-1022, 1023].
+HB_HD double pow2i(int32_t k) { return mk64((1023 + k) << 20, 0); }
+
+HB_HD double dfma(double a, double b, double c)
+{
+#if defined(__CUDA_ARCH__)
+    return __fma_rn(a, b, c);
+#else
+    return fma(a, b, c);
+#endif
+}
+
+// ---------------------------------------------------------------- exact division by a chain constant
+// z = RN(d / b) given y = RN(1/b): Markstein's correction (q = d*y; r = d - b*q exactly by FMA;
+// q' = q + r*y) is correctly rounded for every d when y is the correctly rounded reciprocal
+// (tests/test_numerics.py checks the hardest cases).  3 fp64 instructions instead of ~12.
+HB_HD double div_by_const(double d, double b, double y)
+{
+    double q = d * y;
+    double r = dfma(-b, q, d);
+    return dfma(r, y, q);
+}
+
+// ---------------------------------------------------------------- reciprocal to ~1e-16 (posterior normalisation)
+HB_HD double rcp_fast(double a)
+{
+#if defined(__CUDA_ARCH__)
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
+#else
+    double r = (double)(1.0f / (float)a);
+#endif
+    double e = dfma(-a, r, 1.0);
+    r = dfma(r, e, r);
+    e = dfma(-a, r, 1.0);
+    r = dfma(r, e, r);
+    return r;
+}
+
+// ---------------------------------------------------------------- exp(u) and exp(-u) together
+// Returns Pp = e^r, Pm = e^-r with u = n ln2 + r, |r| <= ln2/2, and n clamped to +-NCLAMP so that
+// exponent arithmetic on the results can never leave the normal range (single-position evidence
+// saturates at e^+-346; Gaussian ratios on this path stay far below).  Relative error < 3e-16.
+// Shared range reduction, even/odd split of the degree-13 Taylor polynomial: 4 + 15 + 2 fp64 ops.
+#define HB_NCLAMP 500
+HB_HD void exp_pair(double u, double &Pp, double &Pm, int32_t &n)
+{
+    const double L2E = 1.4426950408889634074;
+    const double MAGIC = 6755399441055744.0; // 1.5 * 2^52
+    const double LN2_HI = 6.93147180369123816490e-01;
+    const double LN2_LO = 1.90821492927058770002e-10;
+    double t = dfma(u, L2E, MAGIC);
+    int32_t ni = lo32(t);
+    double nf = t - MAGIC;
+    double r = dfma(nf, -LN2_HI, u);
+    r = dfma(nf, -LN2_LO, r);
+    double q = r * r;
+    double ev = dfma(q, 1.0 / 479001600.0, 1.0 / 3628800.0); // q^6/12! ... 1
+    ev = dfma(q, ev, 1.0 / 40320.0);
+    ev = dfma(q, ev, 1.0 / 720.0);
+    ev = dfma(q, ev, 1.0 / 24.0);
+    ev = dfma(q, ev, 0.5);
+    ev = dfma(q, ev, 1.0);
+    double od = dfma(q, 1.0 / 6227020800.0, 1.0 / 39916800.0); // r*(q^6/13! ... 1)
+    od = dfma(q, od, 1.0 / 362880.0);
+    od = dfma(q, od, 1.0 / 5040.0);
+    od = dfma(q, od, 1.0 / 120.0);
+    od = dfma(q, od, 1.0 / 6.0);
+    od = dfma(q, od, 1.0);
+    od = od * r;
+    Pp = ev + od;
+    Pm = ev - od;
+    n = ni > HB_NCLAMP ? HB_NCLAMP : (ni < -HB_NCLAMP ? -HB_NCLAMP : ni);
+}
+
+// exp(u) alone (general, non-symmetric means): Pp * 2^n.
+HB_HD void exp_one(double u, double &Pp, int32_t &n)
+{
+    double Pm;
+    exp_pair(u, Pp, Pm, n);
+}
+
+} // namespace hb

@@ -1,0 +1,391 @@
+// hb_kernels.cu — __global__ entry points and launchers (sm_100a).
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false
+// (-fmad=false: the Viterbi path must keep one rounding per reference operation).
+#include <cuda_runtime.h>
+
+#include "hb_binom2.cuh"
+#include "hb_kernels.h"
+#include "hb_norm3.cuh"
+#include "hb_x87.cuh"
+
+namespace hb {
+
+// =====================================================================================
+// HMM chains: one thread per (cell column, segment); block = HB_BLOCK consecutive cells of
+// one segment, segments issued longest first.
+// =====================================================================================
+template <bool SYM, bool VIT, bool FB>
+__global__ void __launch_bounds__(HB_BLOCK)
+    norm3_kernel(const __grid_constant__ Norm3Args a)
+{
+    extern __shared__ double smem[];
+    const int32_t seg = a.seg_order[blockIdx.x / a.nblk_per_seg];
+    const int64_t b = (int64_t)(blockIdx.x % a.nblk_per_seg) * HB_BLOCK + threadIdx.x;
+    if (b >= a.B) return;
+    norm3_chain<SYM, VIT, FB>(a, seg, b, smem + threadIdx.x, HB_BLOCK);
+}
+
+template <bool VIT, bool FB>
+__global__ void __launch_bounds__(HB_BLOCK)
+    binom2_kernel(const __grid_constant__ Binom2Args a)
+{
+    extern __shared__ double smem[];
+    const int32_t seg = a.seg_order[blockIdx.x / a.nblk_per_seg];
+    const int64_t b = (int64_t)(blockIdx.x % a.nblk_per_seg) * HB_BLOCK + threadIdx.x;
+    if (b >= a.B) return;
+    binom2_chain<VIT, FB>(a, seg, b, smem + threadIdx.x, HB_BLOCK);
+}
+
+template <bool SYM>
+static cudaError_t launch_norm3_t(const Norm3Args &a, bool vit, bool fb, cudaStream_t st)
+{
+    const unsigned grid = (unsigned)((int64_t)a.nseg * a.nblk_per_seg);
+    const size_t sm_fb = (size_t)HB_CHUNK * HB_NORM3_SLOT * HB_BLOCK * sizeof(double);
+    if (vit && fb)
+        norm3_kernel<SYM, true, true><<<grid, HB_BLOCK, sm_fb, st>>>(a);
+    else if (fb)
+        norm3_kernel<SYM, false, true><<<grid, HB_BLOCK, sm_fb, st>>>(a);
+    else
+        norm3_kernel<SYM, true, false><<<grid, HB_BLOCK, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_norm3(const Norm3Args &a, bool sym, bool vit, bool fb, cudaStream_t st)
+{
+    return sym ? launch_norm3_t<true>(a, vit, fb, st) : launch_norm3_t<false>(a, vit, fb, st);
+}
+
+cudaError_t launch_binom2(const Binom2Args &a, bool vit, bool fb, cudaStream_t st)
+{
+    const unsigned grid = (unsigned)((int64_t)a.nseg * a.nblk_per_seg);
+    const size_t sm_fb = (size_t)HB_CHUNK * HB_BINOM2_SLOT * HB_BLOCK * sizeof(double);
+    if (vit && fb)
+        binom2_kernel<true, true><<<grid, HB_BLOCK, sm_fb, st>>>(a);
+    else if (fb)
+        binom2_kernel<false, true><<<grid, HB_BLOCK, sm_fb, st>>>(a);
+    else
+        binom2_kernel<true, false><<<grid, HB_BLOCK, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+// =====================================================================================
+// Per-chain emission scale helpers
+// =====================================================================================
+__global__ void sd_prep_kernel(const double *sd, int64_t n, double *inv_sd, double *log_sd)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        double s = sd[i];
+        inv_sd[i] = 1.0 / s; // IEEE division: the correctly rounded reciprocal div_by_const needs
+        log_sd[i] = log(s);
+    }
+}
+
+cudaError_t launch_sd_prep(const double *sd, int64_t n, double *inv_sd, double *log_sd,
+                           cudaStream_t st)
+{
+    sd_prep_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(sd, n, inv_sd, log_sd);
+    return cudaGetLastError();
+}
+
+// sd over positions of every (column, segment) chain: two passes, compensated sums (TwoSum).
+__device__ __forceinline__ void two_sum_acc(double &s, double &c, double v)
+{
+    double t = s + v;
+    double bp = t - s;
+    c += (s - (t - bp)) + (v - bp);
+    s = t;
+}
+
+__global__ void chain_sd_kernel(const double *x, int64_t ld, int64_t B, const int64_t *seg_off,
+                                int32_t nseg, double *sd)
+{
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int32_t seg = blockIdx.y;
+    if (b >= B || seg >= nseg) return;
+    const int64_t t0 = seg_off[seg], t1 = seg_off[seg + 1];
+    const int64_t L = t1 - t0;
+    if (L < 2) {
+        sd[(int64_t)seg * B + b] = NAN;
+        return;
+    }
+    double s = 0, c = 0;
+    for (int64_t t = t0; t < t1; t++) two_sum_acc(s, c, x[t * ld + b]);
+    const double mean = (s + c) / (double)L;
+    double q = 0, qc = 0;
+    for (int64_t t = t0; t < t1; t++) {
+        double d = x[t * ld + b] - mean;
+        double p = d * d;
+        double pe = __fma_rn(d, d, -p);
+        two_sum_acc(q, qc, p);
+        qc += pe;
+    }
+    sd[(int64_t)seg * B + b] = sqrt((q + qc) / (double)(L - 1));
+}
+
+cudaError_t launch_chain_sd(const double *x, int64_t ld, int64_t B, const int64_t *seg_off_dev,
+                            int32_t nseg, double *sd, cudaStream_t st)
+{
+    dim3 grid((unsigned)((B + 127) / 128), (unsigned)nseg);
+    chain_sd_kernel<<<grid, 128, 0, st>>>(x, ld, B, seg_off_dev, nseg, sd);
+    return cudaGetLastError();
+}
+
+// =====================================================================================
+// Layout: R column-major [G x N] (src[c*G + g]) <-> gene-major dst[g*ld + c]
+// =====================================================================================
+template <typename TI, typename TO, bool RINT>
+__global__ void transpose_in_kernel(const TI *src, int64_t G, int64_t N, TO *dst, int64_t ld)
+{
+    __shared__ TI tile[32][33];
+    const int64_t g0 = (int64_t)blockIdx.x * 32, c0 = (int64_t)blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        int64_t c = c0 + r, g = g0 + threadIdx.x;
+        if (c < N && g < G) tile[r][threadIdx.x] = src[c * G + g];
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        int64_t g = g0 + r, c = c0 + threadIdx.x;
+        if (g < G && c < N) {
+            TI v = tile[threadIdx.x][r];
+            dst[g * ld + c] = RINT ? (TO)rint((double)v) : (TO)v;
+        }
+    }
+}
+
+// gene-major src[g*ld + c] -> column-major dst[c*G + g]
+template <typename TI, typename TO>
+__global__ void transpose_out_kernel(const TI *src, int64_t ld, int64_t G, int64_t N, TO *dst)
+{
+    __shared__ TI tile[32][33];
+    const int64_t g0 = (int64_t)blockIdx.x * 32, c0 = (int64_t)blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        int64_t g = g0 + r, c = c0 + threadIdx.x;
+        if (g < G && c < N) tile[r][threadIdx.x] = src[g * ld + c];
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        int64_t c = c0 + r, g = g0 + threadIdx.x;
+        if (c < N && g < G) dst[c * G + g] = (TO)tile[threadIdx.x][r];
+    }
+}
+
+static dim3 tgrid(int64_t G, int64_t N) { return dim3((unsigned)((G + 31) / 32), (unsigned)((N + 31) / 32)); }
+
+cudaError_t launch_transpose_f64(const double *src, int64_t G, int64_t N, double *dst, int64_t ld,
+                                 cudaStream_t st)
+{
+    transpose_in_kernel<double, double, false><<<tgrid(G, N), dim3(32, 8), 0, st>>>(src, G, N, dst, ld);
+    return cudaGetLastError();
+}
+cudaError_t launch_transpose_f64_i32(const double *src, int64_t G, int64_t N, int32_t *dst,
+                                     int64_t ld, cudaStream_t st)
+{
+    transpose_in_kernel<double, int32_t, true><<<tgrid(G, N), dim3(32, 8), 0, st>>>(src, G, N, dst, ld);
+    return cudaGetLastError();
+}
+cudaError_t launch_transpose_i32(const int32_t *src, int64_t G, int64_t N, int32_t *dst,
+                                 int64_t ld, cudaStream_t st)
+{
+    transpose_in_kernel<int32_t, int32_t, false><<<tgrid(G, N), dim3(32, 8), 0, st>>>(src, G, N, dst, ld);
+    return cudaGetLastError();
+}
+cudaError_t launch_transpose_u8_back(const uint8_t *src, int64_t ld, int64_t G, int64_t N,
+                                     int32_t *dst, cudaStream_t st)
+{
+    transpose_out_kernel<uint8_t, int32_t><<<tgrid(G, N), dim3(32, 8), 0, st>>>(src, ld, G, N, dst);
+    return cudaGetLastError();
+}
+cudaError_t launch_transpose_f64_back(const double *src, int64_t ld, int64_t G, int64_t N,
+                                      double *dst, cudaStream_t st)
+{
+    transpose_out_kernel<double, double><<<tgrid(G, N), dim3(32, 8), 0, st>>>(src, ld, G, N, dst);
+    return cudaGetLastError();
+}
+
+// =====================================================================================
+// Pooled statistics of cell groups (R/HoneyBADGER.R:1141, :1149, :1404-1405)
+// =====================================================================================
+// out[k*G+g] = R mean() of {x[g*ld+c] : member[k*N+c]} in cell order, x87 semantics replayed in
+// integer arithmetic.  Block = 32 genes x PM_KB groups; the gene tile is staged through shared
+// memory in PM_TC-cell slabs so that global reads stay coalesced along the cell axis.
+#define PM_TC 64
+#define PM_KB 16
+__global__ void __launch_bounds__(32 * PM_KB)
+    pool_mean_kernel(const double *x, int64_t ld, int64_t G, int64_t N, const uint8_t *member,
+                     const int32_t *gsize, int32_t K, double *out)
+{
+    __shared__ double tile[32][PM_TC + 1];
+    const int64_t g0 = (int64_t)blockIdx.x * 32;
+    const int lane = threadIdx.x, ky = threadIdx.y;
+    const int tid = ky * 32 + lane;
+    for (int32_t kb = 0; kb < K; kb += PM_KB) {
+        const int32_t k = kb + ky;
+        const bool live = k < K && g0 + lane < G;
+        const uint8_t *mem = member + (int64_t)(live ? k : 0) * N;
+        const uint32_t n = live ? (uint32_t)gsize[k] : 1u;
+        x80 S = x80_zero(), T = x80_zero();
+        for (int pass = 0; pass < 2; pass++) {
+            for (int64_t c0 = 0; c0 < N; c0 += PM_TC) {
+                __syncthreads();
+                for (int i = tid; i < 32 * PM_TC; i += 32 * PM_KB) {
+                    int r = i / PM_TC, cc = i % PM_TC;
+                    int64_t g = g0 + r, c = c0 + cc;
+                    tile[r][cc] = (g < G && c < N) ? x[g * ld + c] : 0.0;
+                }
+                __syncthreads();
+                if (live) {
+                    const int lim = (int)((N - c0) < PM_TC ? (N - c0) : PM_TC);
+                    for (int cc = 0; cc < lim; cc++) {
+                        if (mem[c0 + cc]) {
+                            x80 v = x80_from_double(tile[lane][cc]);
+                            if (pass == 0)
+                                S = x80_add(S, v);
+                            else
+                                T = x80_add(T, x80_sub(v, S));
+                        }
+                    }
+                }
+            }
+            if (pass == 0)
+                S = x80_div_u32(S, n);
+            else
+                S = x80_add(S, x80_div_u32(T, n));
+        }
+        if (live) out[(int64_t)k * G + g0 + lane] = x80_to_double(S);
+    }
+}
+
+cudaError_t launch_pool_mean(const double *x, int64_t ld, int64_t G, int64_t N,
+                             const uint8_t *member, const int32_t *gsize, int32_t K, double *out,
+                             cudaStream_t st)
+{
+    pool_mean_kernel<<<(unsigned)((G + 31) / 32), dim3(32, PM_KB), 0, st>>>(x, ld, G, N, member,
+                                                                             gsize, K, out);
+    return cudaGetLastError();
+}
+
+// sd(x) of each pooled vector (cov.c cov_complete1 replayed): one warp per chain; the lanes form
+// the independent per-element terms in parallel, lane 0 does the order-dependent accumulation.
+__global__ void __launch_bounds__(32) pooled_sd_kernel(const double *pooled, int64_t G, double *sd)
+{
+    __shared__ uint64_t sm_m[32];
+    __shared__ int32_t sm_e[32];
+    __shared__ uint32_t sm_s[32];
+    __shared__ double sm_mean;
+    const double *xv = pooled + (int64_t)blockIdx.x * G;
+    const int lane = threadIdx.x;
+    x80 acc = x80_zero(), mean80 = x80_zero(), xm = x80_zero();
+    for (int pass = 0; pass < 3; pass++) {
+        acc = x80_zero();
+        for (int64_t i0 = 0; i0 < G; i0 += 32) {
+            const int64_t i = i0 + lane;
+            x80 term = x80_zero();
+            if (i < G) {
+                x80 v = x80_from_double(xv[i]);
+                if (pass == 0)
+                    term = v;
+                else if (pass == 1)
+                    term = x80_sub(v, mean80);
+                else {
+                    x80 d = x80_sub(v, xm);
+                    term = x80_mul(d, d);
+                }
+            }
+            sm_m[lane] = term.m;
+            sm_e[lane] = term.e;
+            sm_s[lane] = term.neg;
+            __syncwarp();
+            if (lane == 0) {
+                const int lim = (int)((G - i0) < 32 ? (G - i0) : 32);
+                for (int j = 0; j < lim; j++) {
+                    x80 t;
+                    t.m = sm_m[j];
+                    t.e = sm_e[j];
+                    t.neg = sm_s[j];
+                    acc = x80_add(acc, t);
+                }
+            }
+            __syncwarp();
+        }
+        // broadcast lane 0's running value
+        acc.m = __shfl_sync(0xffffffffu, acc.m, 0);
+        acc.e = __shfl_sync(0xffffffffu, acc.e, 0);
+        acc.neg = __shfl_sync(0xffffffffu, acc.neg, 0);
+        if (pass == 0) {
+            mean80 = x80_div_u32(acc, (uint32_t)G);
+        } else if (pass == 1) {
+            mean80 = x80_add(mean80, x80_div_u32(acc, (uint32_t)G));
+            if (lane == 0) sm_mean = x80_to_double(mean80); // xm[i] = (double)tmp
+            __syncwarp();
+            xm = x80_from_double(sm_mean);
+        } else if (lane == 0) {
+            double var = x80_to_double(x80_div_u32(acc, (uint32_t)(G - 1)));
+            sd[blockIdx.x] = sqrt(var);
+        }
+    }
+}
+
+cudaError_t launch_pooled_sd(const double *pooled, int64_t G, int32_t K, double *sd, cudaStream_t st)
+{
+    pooled_sd_kernel<<<(unsigned)K, 32, 0, st>>>(pooled, G, sd);
+    return cudaGetLastError();
+}
+
+// out[k*G+g] = #{c : member[k*N+c] && v[g*ld+c] > 0}; one block per gene, groups as a bitmask per
+// cell (K <= 32 per launch).  Integer, exact.
+__global__ void __launch_bounds__(256)
+    pool_count_kernel(const int32_t *v, int64_t ld, int64_t G, int64_t N, const uint32_t *cellmask,
+                      int32_t K, int32_t *out)
+{
+    __shared__ int32_t part[8][32];
+    const int64_t g = blockIdx.x;
+    int32_t cnt[32];
+#pragma unroll
+    for (int k = 0; k < 32; k++) cnt[k] = 0;
+    for (int64_t c = threadIdx.x; c < N; c += blockDim.x) {
+        uint32_t m = (v[g * ld + c] > 0) ? cellmask[c] : 0u;
+#pragma unroll
+        for (int k = 0; k < 32; k++) cnt[k] += (m >> k) & 1u;
+    }
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 32; k++) {
+        int32_t s = cnt[k];
+        for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) part[w][k] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < K) {
+        int32_t s = 0;
+        for (int i = 0; i < 8; i++) s += part[i][threadIdx.x];
+        out[(int64_t)threadIdx.x * G + g] = s;
+    }
+}
+
+cudaError_t launch_pool_count(const int32_t *v, int64_t ld, int64_t G, int64_t N,
+                              const uint32_t *cellmask, int32_t K, int32_t *out, cudaStream_t st)
+{
+    pool_count_kernel<<<(unsigned)G, 256, 0, st>>>(v, ld, G, N, cellmask, K, out);
+    return cudaGetLastError();
+}
+
+// cellmask[c] = OR_k (member[k*N+c] != 0) << k
+__global__ void build_cellmask_kernel(const uint8_t *member, int64_t N, int32_t K, uint32_t *mask)
+{
+    int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= N) return;
+    uint32_t m = 0;
+    for (int k = 0; k < K; k++) m |= (member[(int64_t)k * N + c] ? 1u : 0u) << k;
+    mask[c] = m;
+}
+
+cudaError_t launch_build_cellmask(const uint8_t *member, int64_t N, int32_t K, uint32_t *mask,
+                                  cudaStream_t st)
+{
+    build_cellmask_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(member, N, K, mask);
+    return cudaGetLastError();
+}
+
+} // namespace hb

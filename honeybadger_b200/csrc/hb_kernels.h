@@ -1,0 +1,39 @@
+// hb_kernels.h — launcher declarations shared by hb_kernels.cu and hb_api.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define HB_BLOCK 128
+
+namespace hb {
+
+struct Norm3Args;
+struct Binom2Args;
+
+cudaError_t launch_norm3(const Norm3Args &a, bool sym, bool vit, bool fb, cudaStream_t st);
+cudaError_t launch_binom2(const Binom2Args &a, bool vit, bool fb, cudaStream_t st);
+cudaError_t launch_sd_prep(const double *sd, int64_t n, double *inv_sd, double *log_sd,
+                           cudaStream_t st);
+cudaError_t launch_chain_sd(const double *x, int64_t ld, int64_t B, const int64_t *seg_off_dev,
+                            int32_t nseg, double *sd, cudaStream_t st);
+cudaError_t launch_transpose_f64(const double *src, int64_t G, int64_t N, double *dst, int64_t ld,
+                                 cudaStream_t st);
+cudaError_t launch_transpose_f64_i32(const double *src, int64_t G, int64_t N, int32_t *dst,
+                                     int64_t ld, cudaStream_t st);
+cudaError_t launch_transpose_i32(const int32_t *src, int64_t G, int64_t N, int32_t *dst,
+                                 int64_t ld, cudaStream_t st);
+cudaError_t launch_transpose_u8_back(const uint8_t *src, int64_t ld, int64_t G, int64_t N,
+                                     int32_t *dst, cudaStream_t st);
+cudaError_t launch_transpose_f64_back(const double *src, int64_t ld, int64_t G, int64_t N,
+                                      double *dst, cudaStream_t st);
+cudaError_t launch_pool_mean(const double *x, int64_t ld, int64_t G, int64_t N,
+                             const uint8_t *member, const int32_t *gsize, int32_t K, double *out,
+                             cudaStream_t st);
+cudaError_t launch_pooled_sd(const double *pooled, int64_t G, int32_t K, double *sd,
+                             cudaStream_t st);
+cudaError_t launch_pool_count(const int32_t *v, int64_t ld, int64_t G, int64_t N,
+                              const uint32_t *cellmask, int32_t K, int32_t *out, cudaStream_t st);
+cudaError_t launch_build_cellmask(const uint8_t *member, int64_t N, int32_t K, uint32_t *mask,
+                                  cudaStream_t st);
+
+} // namespace hb

@@ -1,0 +1,250 @@
+// hb_x87.cuh — exact integer emulation of x87 80-bit extended arithmetic (64-bit significand,
+// round-to-nearest-even), enough of it to reproduce base R's `mean()` and `var()`/`sd()` bit for
+// bit on a GPU.
+//
+// R accumulates in LDOUBLE (`long double`, x87 extended on x86-64 Linux): summary.c real_mean and
+// cov.c cov_complete1, reached from R/HoneyBADGER.R:1141 (`apply(.,1,mean)`)
+// and :1149 (`sd(mat.smooth)`).  Every add / subtract / multiply / divide there rounds to 64
+// significand bits, so the result depends on the summation order and cannot be reproduced by
+// "more accurate" arithmetic — it has to be replayed.  Values are finite and far from the
+// exponent limits on this path; infinities, NaNs and denormal extended results are not handled.
+#pragma once
+#include "hb_device.cuh"
+
+namespace hb {
+
+struct x80 {
+    uint64_t m;  // significand, msb set unless zero
+    int32_t e;   // value = (-1)^neg * m * 2^(e - 63)
+    uint32_t neg;
+};
+
+HB_HD int clz64(uint64_t v)
+{
+#if defined(__CUDA_ARCH__)
+    return __clzll((long long)v);
+#else
+    return v ? __builtin_clzll(v) : 64;
+#endif
+}
+
+HB_HD x80 x80_zero()
+{
+    x80 r;
+    r.m = 0;
+    r.e = 0;
+    r.neg = 0;
+    return r;
+}
+
+HB_HD x80 x80_from_double(double d)
+{
+    uint64_t u = ((uint64_t)(uint32_t)hi32(d) << 32) | (uint32_t)lo32(d);
+    x80 r;
+    r.neg = (uint32_t)(u >> 63);
+    int32_t ef = (int32_t)((u >> 52) & 0x7ff);
+    uint64_t fr = u & 0xfffffffffffffull;
+    if (ef == 0) {
+        if (fr == 0) {
+            r.m = 0;
+            r.e = 0;
+            return r;
+        }
+        int lz = clz64(fr);
+        r.m = fr << lz;
+        r.e = -1022 - 52 + (63 - lz);
+        return r;
+    }
+    r.m = (1ull << 63) | (fr << 11);
+    r.e = ef - 1023;
+    return r;
+}
+
+HB_HD x80 x80_from_u32(uint32_t n)
+{
+    x80 r;
+    r.neg = 0;
+    if (n == 0) {
+        r.m = 0;
+        r.e = 0;
+        return r;
+    }
+    int lz = clz64((uint64_t)n);
+    r.m = (uint64_t)n << lz;
+    r.e = 63 - lz;
+    return r;
+}
+
+// Round (hi:lo + sticky) to 64 bits, hi has its msb set.  Returns the significand and bumps e on carry.
+HB_HD uint64_t x80_round(uint64_t hi, uint64_t lo, bool sticky, int32_t &e)
+{
+    const uint64_t half = 1ull << 63;
+    bool up = (lo > half) || (lo == half && (sticky || (hi & 1ull)));
+    if (up) {
+        hi += 1;
+        if (hi == 0) {
+            hi = half;
+            e += 1;
+        }
+    }
+    return hi;
+}
+
+HB_HD x80 x80_add(x80 a, x80 b)
+{
+    if (a.m == 0) return b;
+    if (b.m == 0) return a;
+    if (a.e < b.e || (a.e == b.e && a.m < b.m)) {
+        x80 t = a;
+        a = b;
+        b = t;
+    }
+    // 128-bit significands with the msb at bit 126: A = a.m << 63
+    uint64_t ahi = a.m >> 1, alo = a.m << 63;
+    uint64_t bhi, blo;
+    bool sticky = false;
+    int32_t d = a.e - b.e;
+    {
+        uint64_t h = b.m >> 1, l = b.m << 63;
+        if (d == 0) {
+            bhi = h;
+            blo = l;
+        } else if (d < 64) {
+            sticky = (l << (64 - d)) != 0;
+            blo = (l >> d) | (h << (64 - d));
+            bhi = h >> d;
+        } else if (d < 128) {
+            int s = d - 64;
+            sticky = (l != 0) || (s ? ((h << (64 - s)) != 0) : false);
+            blo = s ? (h >> s) : h;
+            bhi = 0;
+        } else {
+            sticky = true;
+            blo = 0;
+            bhi = 0;
+        }
+    }
+    x80 r;
+    r.neg = a.neg;
+    r.e = a.e;
+    uint64_t rhi, rlo;
+    if (a.neg == b.neg) {
+        rlo = alo + blo;
+        rhi = ahi + bhi + (rlo < alo ? 1 : 0);
+        if (rhi >> 63) { // carry into bit 127
+            r.e += 1;
+        } else {
+            rhi = (rhi << 1) | (rlo >> 63);
+            rlo <<= 1;
+        }
+        r.m = x80_round(rhi, rlo, sticky, r.e);
+        return r;
+    }
+    // |a| >= |b|: A - B_trunc - sticky, remembering that the true value is a bit above
+    uint64_t bl2 = blo + (sticky ? 1 : 0);
+    uint64_t bh2 = bhi + ((sticky && bl2 == 0) ? 1 : 0);
+    rlo = alo - bl2;
+    rhi = ahi - bh2 - (alo < bl2 ? 1 : 0);
+    if (rhi == 0 && rlo == 0) {
+        if (!sticky) return x80_zero();
+    }
+    int lz;
+    if (rhi) {
+        lz = clz64(rhi);
+        if (lz) {
+            rhi = (rhi << lz) | (rlo >> (64 - lz));
+            rlo <<= lz;
+        }
+    } else {
+        lz = 64 + clz64(rlo);
+        int s = lz - 64;
+        rhi = s ? (rlo << s) : rlo;
+        rlo = 0;
+    }
+    r.e = a.e + 1 - lz; // msb was at bit 126 <=> lz == 1
+    r.m = x80_round(rhi, rlo, sticky, r.e);
+    return r;
+}
+
+HB_HD x80 x80_neg(x80 a)
+{
+    a.neg ^= 1u;
+    return a;
+}
+HB_HD x80 x80_sub(x80 a, x80 b) { return x80_add(a, x80_neg(b)); }
+
+HB_HD uint64_t umul64hi_(uint64_t a, uint64_t b)
+{
+#if defined(__CUDA_ARCH__)
+    return __umul64hi(a, b);
+#else
+    return (uint64_t)(((unsigned __int128)a * b) >> 64);
+#endif
+}
+
+HB_HD x80 x80_mul(x80 a, x80 b)
+{
+    if (a.m == 0 || b.m == 0) return x80_zero();
+    uint64_t hi = umul64hi_(a.m, b.m), lo = a.m * b.m;
+    x80 r;
+    r.neg = a.neg ^ b.neg;
+    if (hi >> 63) {
+        r.e = a.e + b.e + 1;
+    } else {
+        hi = (hi << 1) | (lo >> 63);
+        lo <<= 1;
+        r.e = a.e + b.e;
+    }
+    r.m = x80_round(hi, lo, false, r.e);
+    return r;
+}
+
+// a / n for an integer 1 <= n < 2^32 (exactly what `s /= n` does after the int -> LDOUBLE convert).
+HB_HD x80 x80_div_u32(x80 a, uint32_t n)
+{
+    if (a.m == 0) return a;
+    // Q = floor(a.m * 2^64 / n) by schoolbook division in 32-bit limbs
+    uint64_t q2 = a.m / n, r = a.m % n;
+    uint64_t t = r << 32;
+    uint64_t q1 = t / n;
+    r = t % n;
+    t = r << 32;
+    uint64_t q0 = t / n;
+    r = t % n;
+    uint64_t qhi = q2, qlo = (q1 << 32) | q0; // q1 < 2^32 because r < n <= 2^32
+    bool sticky = r != 0;
+    int lz = clz64(qhi); // qhi >= 2^31 since a.m >= 2^63 and n < 2^32
+    if (lz) {
+        qhi = (qhi << lz) | (qlo >> (64 - lz));
+        qlo <<= lz;
+    }
+    x80 res;
+    res.neg = a.neg;
+    res.e = a.e - lz;
+    res.m = x80_round(qhi, qlo, sticky, res.e);
+    return res;
+}
+
+// (double) of an extended value: one RNE rounding 64 -> 53 bits.
+HB_HD double x80_to_double(x80 a)
+{
+    if (a.m == 0) return a.neg ? -0.0 : 0.0;
+    uint64_t mant = a.m >> 11, rem = a.m & 0x7ffull;
+    int32_t e = a.e;
+    if (rem > 0x400ull || (rem == 0x400ull && (mant & 1ull))) {
+        mant += 1;
+        if (mant >> 53) {
+            mant >>= 1;
+            e += 1;
+        }
+    }
+    int32_t ef = e + 1023;
+    if (ef >= 1 && ef <= 2046) {
+        uint64_t u = ((uint64_t)a.neg << 63) | ((uint64_t)ef << 52) | (mant & 0xfffffffffffffull);
+        return mk64((int32_t)(u >> 32), (int32_t)(u & 0xffffffffu));
+    }
+    double v = ldexp((double)mant, e - 52); // out of the normal range (not reached on this path)
+    return a.neg ? -v : v;
+}
+
+} // namespace hb

@@ -1,0 +1,299 @@
+"""HiddenMarkov-shaped front end of the CUDA chains.
+
+Mirrors the three calls HoneyBADGER makes into (or, for forwardback, could make into) the CRAN
+package `HiddenMarkov` — same names, argument meaning and error behaviour:
+
+    z <- HiddenMarkov::dthmm(x, Pi, delta, "norm", list(mean=c(pd,pn,pa), sd=c(sd,sd,sd)))
+    y <- HiddenMarkov::Viterbi(z)                        # R/HoneyBADGER.R:1150-1151, _gexp.R:503-504
+    z <- HiddenMarkov::dthmm(mafl, Pi, delta, "binom", list(prob=c(pd,pn)), list(size=sizel), discrete=TRUE)
+    y <- HiddenMarkov::Viterbi(z)                        # R/HoneyBADGER.R:1409-1410, _allele.R:579-580
+
+plus the batched, device-resident entry points the segmentation driver and bench.py use
+(`hmm_norm_dev`, `hmm_binom_dev`: torch CUDA tensors in the gene-major layout, current stream).
+Everything runs in libhb_b200.so; there is no CPU implementation here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _lib
+
+__all__ = ["dthmm", "Viterbi", "forwardback", "hmm_norm_host", "hmm_binom_host", "hmm_norm_dev",
+           "hmm_binom_dev", "sym_Pi"]
+
+
+def sym_Pi(S: int, t: float) -> np.ndarray:
+    """matrix(c(1-2t,t,t, t,1-2t,t, t,t,1-2t), byrow=TRUE, nrow=3) / matrix(c(1-t,t,t,1-t), ...)."""
+    Pi = np.full((S, S), t, dtype=np.float64)
+    np.fill_diagonal(Pi, 1 - (S - 1) * t)
+    return Pi
+
+
+def _vp(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _seg(seg_off, T):
+    if seg_off is None:
+        seg_off = [0, T]
+    s = np.ascontiguousarray(seg_off, dtype=np.int64)
+    if s.ndim != 1 or s.size < 2:
+        raise ValueError("seg_off must hold nseg+1 offsets")
+    return s
+
+
+def _flags(viterbi, gamma, ll):
+    f = (_lib.WANT_VITERBI if viterbi else 0) | (_lib.WANT_GAMMA if gamma else 0)
+    if ll:
+        f |= _lib.WANT_LL | _lib.WANT_GAMMA
+    if not f:
+        raise ValueError("nothing requested")
+    return f
+
+
+# --------------------------------------------------------------------------- host buffers
+def hmm_norm_host(x, mean, sd, Pi, delta, seg_off=None, viterbi=True, gamma=False, ll=False):
+    """x: [T] or [T, B] (R matrix semantics: one chain per column).  sd: scalar, [B] or [nseg, B].
+
+    Returns dict(y=int32 [T,B] 1-based, gamma=[T,B,3], ll=[B,nseg]) with the requested keys.
+    """
+    lib = _lib.load()
+    x = np.asarray(x, dtype=np.float64)
+    vec = x.ndim == 1
+    xm = x.reshape(-1, 1) if vec else x
+    T, B = xm.shape
+    xf = np.asfortranarray(xm)
+    seg = _seg(seg_off, T)
+    nseg = seg.size - 1
+    sd = np.asarray(sd, dtype=np.float64)
+    if sd.ndim == 0:
+        sd = np.full(B, float(sd))
+    per_seg = int(sd.ndim == 2)
+    if sd.shape != ((nseg, B) if per_seg else (B,)):
+        raise ValueError(f"sd has shape {sd.shape}, expected ({B},) or ({nseg}, {B})")
+    sd = np.ascontiguousarray(sd)
+    mean, Pi, delta = _f64(mean), _f64(Pi), _f64(delta)
+    if mean.size != 3 or Pi.size != 9 or delta.size != 3:
+        raise ValueError("the Gaussian chain has 3 states: mean[3], Pi[3x3], delta[3]")
+    want_g = gamma or ll
+    y = np.zeros((T, B), dtype=np.int32, order="F") if viterbi else None
+    g = np.zeros((T, B, 3), dtype=np.float64, order="F") if want_g else None
+    l = np.zeros((B, nseg), dtype=np.float64, order="F") if ll else None
+    rc = lib.hb_hmm_norm_host(_vp(xf), T, B, _vp(seg), nseg, _vp(mean), _vp(sd), per_seg, _vp(Pi),
+                              _vp(delta), _flags(viterbi, gamma, ll), _vp(y), _vp(g), _vp(l))
+    _lib.check(rc)
+    out = {}
+    if viterbi:
+        out["y"] = y[:, 0] if vec else y
+    if gamma:
+        out["gamma"] = g[:, 0, :] if vec else g
+    if ll:
+        out["ll"] = l[0] if vec else l
+    return out
+
+
+def hmm_binom_host(x, size, prob, Pi, delta, seg_off=None, rho=0.0, viterbi=True, gamma=False,
+                   ll=False):
+    lib = _lib.load()
+    x = np.asarray(x)
+    size = np.asarray(size)
+    if x.shape != size.shape:
+        raise ValueError("x and size must have the same shape")
+    vec = x.ndim == 1
+    xm = (x.reshape(-1, 1) if vec else x)
+    sm = (size.reshape(-1, 1) if vec else size)
+    xr, sr = np.rint(xm), np.rint(sm)
+    xf = np.asfortranarray(xr, dtype=np.int32)
+    sf = np.asfortranarray(sr, dtype=np.int32)
+    T, B = xf.shape
+    seg = _seg(seg_off, T)
+    nseg = seg.size - 1
+    prob, Pi, delta = _f64(prob), _f64(Pi), _f64(delta)
+    if prob.size != 2 or Pi.size != 4 or delta.size != 2:
+        raise ValueError("the binomial chain has 2 states: prob[2], Pi[2x2], delta[2]")
+    want_g = gamma or ll
+    y = np.zeros((T, B), dtype=np.int32, order="F") if viterbi else None
+    g = np.zeros((T, B, 2), dtype=np.float64, order="F") if want_g else None
+    l = np.zeros((B, nseg), dtype=np.float64, order="F") if ll else None
+    rc = lib.hb_hmm_binom_host(_vp(xf), _vp(sf), T, B, _vp(seg), nseg, _vp(prob), float(rho),
+                               _vp(Pi), _vp(delta), _flags(viterbi, gamma, ll), _vp(y), _vp(g),
+                               _vp(l))
+    _lib.check(rc)
+    out = {}
+    if viterbi:
+        out["y"] = y[:, 0] if vec else y
+    if gamma:
+        out["gamma"] = g[:, 0, :] if vec else g
+    if ll:
+        out["ll"] = l[0] if vec else l
+    return out
+
+
+# --------------------------------------------------------------------------- HiddenMarkov mirror
+@dataclass
+class dthmm:
+    """HiddenMarkov::dthmm(x, Pi, delta, distn, pm, pn = NULL, discrete = NULL, nonstat = FALSE).
+
+    Supported on the device: distn "norm" with 3 states and a shared sd (pm = dict(mean=[3], sd=[3]
+    equal entries)), distn "binom" with 2 states (pm = dict(prob=[2]), pn = dict(size=[T])).
+    `x` may also be a [T, B] matrix: one chain per column (batch extension).
+    """
+    x: np.ndarray
+    Pi: np.ndarray
+    delta: np.ndarray
+    distn: str
+    pm: dict
+    pn: dict | None = None
+    discrete: bool | None = None
+    nonstat: bool = False
+    seg_off: np.ndarray | None = field(default=None)
+
+    def __post_init__(self):
+        self.Pi = np.asarray(self.Pi, dtype=np.float64)
+        self.delta = np.asarray(self.delta, dtype=np.float64)
+        m = self.Pi.shape[0]
+        if self.Pi.shape != (m, m) or self.delta.shape != (m,):
+            raise ValueError("Pi must be m x m and delta of length m")
+        if self.distn == "norm":
+            sd = np.asarray(self.pm["sd"], dtype=np.float64)
+            if m != 3 or np.asarray(self.pm["mean"]).size != 3:
+                raise NotImplementedError('distn "norm" is implemented for the 3-state chain')
+            if not (sd.ravel()[0] == sd).all():
+                raise NotImplementedError("the device chain shares one sd across the states")
+        elif self.distn == "binom":
+            if m != 2 or np.asarray(self.pm["prob"]).size != 2 or not self.pn or "size" not in self.pn:
+                raise NotImplementedError('distn "binom" needs 2 states, pm$prob[2] and pn$size')
+        else:
+            raise NotImplementedError(f'distn "{self.distn}" is not on the HoneyBADGER path')
+
+
+def _run(obj: dthmm, viterbi, gamma, ll):
+    if obj.distn == "norm":
+        sd = float(np.asarray(obj.pm["sd"], dtype=np.float64).ravel()[0])
+        return hmm_norm_host(obj.x, obj.pm["mean"], sd, obj.Pi, obj.delta, obj.seg_off,
+                             viterbi=viterbi, gamma=gamma, ll=ll)
+    return hmm_binom_host(obj.x, obj.pn["size"], obj.pm["prob"], obj.Pi, obj.delta, obj.seg_off,
+                          rho=float(obj.pm.get("rho", 0.0)), viterbi=viterbi, gamma=gamma, ll=ll)
+
+
+def Viterbi(obj: dthmm) -> np.ndarray:
+    """HiddenMarkov::Viterbi(object): most likely state path, 1-based integers.
+
+    Raises `_lib.UnderflowError` ("Problems With Underflow") exactly when the reference does: some
+    final nu equals -Inf.
+    """
+    return _run(obj, True, False, False)["y"]
+
+
+def forwardback(obj: dthmm) -> dict:
+    """State posteriors u = exp(logalpha + logbeta - LL) and LL of HiddenMarkov::forwardback/Estep."""
+    r = _run(obj, False, True, True)
+    return {"u": r["gamma"], "LL": r["ll"]}
+
+
+# --------------------------------------------------------------------------- device-resident (torch)
+def _stream():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _check_gm(t, dtype, name):
+    import torch
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == dtype and t.dim() == 2
+            and t.stride(1) == 1):
+        raise ValueError(f"{name} must be a 2-D CUDA {dtype} tensor with unit column stride")
+
+
+def hmm_norm_dev(x, sd, mean, Pi, delta, seg_off=None, viterbi=True, gamma=True, ll=False,
+                 out=None):
+    """Gene-major x[T, B] (fp64 CUDA tensor, row stride = ld), sd [B] or [nseg, B] on the device.
+
+    Enqueues on the current stream and returns dict(y=uint8 [T,B], gamma=[3,T,B], ll=[nseg,B])
+    of device tensors (reused from `out` when given).  Does not synchronise; call
+    `status_dev()` to surface HiddenMarkov's underflow error.
+    """
+    import torch
+    lib = _lib.load()
+    _check_gm(x, torch.float64, "x")
+    T, B = x.shape
+    seg = _seg(seg_off, T)
+    nseg = seg.size - 1
+    per_seg = int(sd.dim() == 2)
+    if not (sd.is_cuda and sd.dtype == torch.float64 and sd.is_contiguous()):
+        raise ValueError("sd must be a contiguous CUDA float64 tensor")
+    mean, Pi, delta = _f64(mean), _f64(Pi), _f64(delta)
+    out = dict(out or {})
+    want_g = gamma or ll
+    if viterbi and "y" not in out:
+        out["y"] = torch.empty((T, B), dtype=torch.uint8, device=x.device)
+    if want_g and "gamma" not in out:
+        out["gamma"] = torch.empty((3, T, B), dtype=torch.float64, device=x.device)
+    if ll and "ll" not in out:
+        out["ll"] = torch.empty((nseg, B), dtype=torch.float64, device=x.device)
+    y, g, l = out.get("y"), out.get("gamma"), out.get("ll")
+    rc = lib.hb_hmm_norm_dev(
+        x.data_ptr(), x.stride(0), T, B, _vp(seg), nseg, _vp(mean), sd.data_ptr(), per_seg,
+        _vp(Pi), _vp(delta), _flags(viterbi, gamma, ll),
+        y.data_ptr() if viterbi else None, y.stride(0) if viterbi else 0,
+        g.data_ptr() if want_g else None, g.stride(1) if want_g else 0,
+        l.data_ptr() if ll else None, _stream())
+    _lib.check(rc)
+    return out
+
+
+def hmm_binom_dev(x, size, prob, Pi, delta, seg_off=None, rho=0.0, viterbi=True, gamma=True,
+                  ll=False, out=None):
+    """Gene-major int32 x[T, B], size[T, B] CUDA tensors with the same row stride."""
+    import torch
+    lib = _lib.load()
+    _check_gm(x, torch.int32, "x")
+    _check_gm(size, torch.int32, "size")
+    if x.shape != size.shape or x.stride(0) != size.stride(0):
+        raise ValueError("x and size must share shape and row stride")
+    T, B = x.shape
+    seg = _seg(seg_off, T)
+    nseg = seg.size - 1
+    prob, Pi, delta = _f64(prob), _f64(Pi), _f64(delta)
+    out = dict(out or {})
+    want_g = gamma or ll
+    if viterbi and "y" not in out:
+        out["y"] = torch.empty((T, B), dtype=torch.uint8, device=x.device)
+    if want_g and "gamma" not in out:
+        out["gamma"] = torch.empty((2, T, B), dtype=torch.float64, device=x.device)
+    if ll and "ll" not in out:
+        out["ll"] = torch.empty((nseg, B), dtype=torch.float64, device=x.device)
+    y, g, l = out.get("y"), out.get("gamma"), out.get("ll")
+    rc = lib.hb_hmm_binom_dev(
+        x.data_ptr(), size.data_ptr(), x.stride(0), T, B, _vp(seg), nseg, _vp(prob), float(rho),
+        _vp(Pi), _vp(delta), _flags(viterbi, gamma, ll),
+        y.data_ptr() if viterbi else None, y.stride(0) if viterbi else 0,
+        g.data_ptr() if want_g else None, g.stride(1) if want_g else 0,
+        l.data_ptr() if ll else None, _stream())
+    _lib.check(rc)
+    return out
+
+
+def chain_sd_dev(x, seg_off=None, per_seg=False):
+    """sd() of every chain column (and segment) of a gene-major fp64 CUDA tensor."""
+    import torch
+    lib = _lib.load()
+    _check_gm(x, torch.float64, "x")
+    T, B = x.shape
+    seg = _seg(seg_off, T)
+    nseg = seg.size - 1 if per_seg else 1
+    sd = torch.empty((nseg, B) if per_seg else (B,), dtype=torch.float64, device=x.device)
+    _lib.check(lib.hb_chain_sd_dev(x.data_ptr(), x.stride(0), T, B, _vp(seg), seg.size - 1,
+                                   int(per_seg), sd.data_ptr(), _stream()))
+    return sd
+
+
+def status_dev():
+    """Wait for the current stream and raise UnderflowError if the last launch hit nu == -Inf."""
+    _lib.check(_lib.load().hb_status_dev(_stream()))

@@ -1,0 +1,146 @@
+/*
+ * hb_b200.h — C ABI of libhb_b200.so: B200 (sm_100a) HMM segmentation for HoneyBADGER.
+ *
+ * The reference (an R package) has no FFI for this path: the seam is the R-level pair
+ *     z <- HiddenMarkov::dthmm(x, Pi, delta, distn, pm[, pn, discrete=TRUE]);  y <- HiddenMarkov::Viterbi(z)
+ * at four call sites (R/HoneyBADGER.R:1150-1151, :1409-1410, R/HoneyBADGER_gexp.R:503-504,
+ * R/HoneyBADGER_allele.R:579-580), fed by the pooled statistics of R/HoneyBADGER.R:1141,1149
+ * (apply(.,1,mean), sd) and :1404-1405 (rowSums(.>0)).  The entry points below are what a `.Call`
+ * shim binds instead (see INTEGRATION.md and r/hb_shim.c).
+ *
+ * Conventions
+ *   - plain C, no C++ exceptions, no torch types; every function returns HB_OK (0) or a negative
+ *     code and hb_last_error() returns a thread-local message.
+ *   - *_host functions take HOST pointers in R's native layout (column-major, one chain per
+ *     column) and copy to/from the device internally.  The caller owns all buffers; inputs are
+ *     never written.
+ *   - *_dev functions take DEVICE pointers in the resident gene-major layout x[t*ld + b]
+ *     (t = gene/SNP position, b = chain column) and enqueue on `stream` (a cudaStream_t cast to
+ *     void*, NULL = legacy default stream) without synchronising.
+ *   - A chain is one (column b, segment s) pair; segments are [seg_off[s], seg_off[s+1]) on the
+ *     position axis (seg_off is a HOST array of nseg+1 offsets; nseg = 1 reproduces the
+ *     reference's single concatenated chain, R/HoneyBADGER.R:1117-1121).
+ *   - Viterbi states are 1-based like R's; state paths are bit-identical to the reference
+ *     recursion (operation order of HiddenMarkov::Viterbi.dthmm, first index wins ties).
+ *     Posteriors gamma = exp(logalpha + logbeta - LL) of HiddenMarkov::forwardback agree to 1e-9.
+ *   - There is no CPU fallback: without a CUDA device every compute entry point returns
+ *     HB_ERR_NODEVICE / HB_ERR_CUDA.
+ */
+#ifndef HB_B200_H
+#define HB_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HB_OK 0
+#define HB_ERR_ARG (-1)       /* bad argument */
+#define HB_ERR_CUDA (-2)      /* CUDA runtime / launch failure */
+#define HB_ERR_UNDERFLOW (-3) /* HiddenMarkov::Viterbi's stop("Problems With Underflow") */
+#define HB_ERR_NOMEM (-4)
+#define HB_ERR_NODEVICE (-5)
+
+#define HB_WANT_VITERBI 1 /* state path y */
+#define HB_WANT_GAMMA 2   /* forward-backward posteriors */
+#define HB_WANT_LL 4      /* log-likelihood per chain (needs the forward pass of HB_WANT_GAMMA) */
+
+/* ------------------------------------------------------------------ library / device */
+int hb_version(void);
+const char *hb_last_error(void);
+int hb_device_count(int *count);
+int hb_set_device(int device);
+/* Frees the per-device scratch cache (psi back-pointers, alpha checkpoints, staging). */
+int hb_release_workspace(void);
+/* *_dev entry points never synchronise; this waits for `stream` and returns HB_ERR_UNDERFLOW if a
+ * chain of the last launch ended with nu == -Inf (HiddenMarkov::Viterbi's error), else HB_OK. */
+int hb_status_dev(void *stream);
+/* Largest trial count served by the host-built binomial emission table (default 511, <= 4095). */
+int hb_set_binom_lut_max(int32_t nmax);
+
+/* ------------------------------------------------------------------ 3-state Gaussian chains
+ * Replaces dthmm(x, Pi, delta, "norm", list(mean=c(pd,pn,pa), sd=c(sd,sd,sd))) -> Viterbi
+ * (R/HoneyBADGER.R:1144-1151, R/HoneyBADGER_gexp.R:497-504) and adds forwardback posteriors.
+ * mean[3]; one sd per chain shared by the 3 states: sd[b] (sd_per_seg=0) or sd[s*B+b] (=1);
+ * Pi[9] row-major Pi[j*3+k] = P(j->k); delta[3].
+ */
+int hb_hmm_norm_host(const double *x /* [T x B] column-major */, int64_t T, int64_t B,
+                     const int64_t *seg_off, int32_t nseg, const double *mean, const double *sd,
+                     int32_t sd_per_seg, const double *Pi, const double *delta, int32_t flags,
+                     int32_t *y /* [T x B] column-major, 1-based, or NULL */,
+                     double *gamma /* [T x B x 3] column-major, or NULL */,
+                     double *ll /* [B x nseg] column-major, or NULL */);
+
+int hb_hmm_norm_dev(const double *x /* device, x[t*ld+b] */, int64_t ld, int64_t T, int64_t B,
+                    const int64_t *seg_off /* host */, int32_t nseg, const double *mean,
+                    const double *sd /* device */, int32_t sd_per_seg, const double *Pi,
+                    const double *delta, int32_t flags, uint8_t *y /* device y[t*ldy+b] */,
+                    int64_t ldy, double *gamma /* device gamma[(k*T+t)*ldg+b] */, int64_t ldg,
+                    double *ll /* device ll[s*B+b] */, void *stream);
+
+/* ------------------------------------------------------------------ 2-state binomial chains
+ * Replaces dthmm(mafl, Pi, delta, "binom", list(prob=c(pd,pn)), list(size=sizel), discrete=TRUE)
+ * -> Viterbi (R/HoneyBADGER.R:1408-1410, R/HoneyBADGER_allele.R:578-580).  prob[2], Pi[4], delta[2].
+ * rho >= 0 is the beta-binomial over-dispersion (extension, not in the reference); rho = 0 is the
+ * reference's binomial.
+ */
+int hb_hmm_binom_host(const int32_t *x /* [T x B] column-major */, const int32_t *size,
+                      int64_t T, int64_t B, const int64_t *seg_off, int32_t nseg,
+                      const double *prob, double rho, const double *Pi, const double *delta,
+                      int32_t flags, int32_t *y, double *gamma /* [T x B x 2] */, double *ll);
+
+int hb_hmm_binom_dev(const int32_t *x /* device x[t*ld+b] */, const int32_t *size, int64_t ld,
+                     int64_t T, int64_t B, const int64_t *seg_off /* host */, int32_t nseg,
+                     const double *prob, double rho, const double *Pi, const double *delta,
+                     int32_t flags, uint8_t *y, int64_t ldy, double *gamma, int64_t ldg,
+                     double *ll, void *stream);
+
+/* ------------------------------------------------------------------ layout + pooled statistics
+ * R matrices are column-major [G x N] (one cell's genes contiguous); the resident layout is
+ * gene-major [G][ld>=N].  hb_transpose_* convert on the device (both pointers device).
+ */
+int hb_transpose_f64_dev(const double *src_colmajor, int64_t G, int64_t N, double *dst,
+                         int64_t ld, void *stream);
+/* counts stored as R doubles -> int32 gene-major (values are rounded with rint). */
+int hb_transpose_f64_to_i32_dev(const double *src_colmajor, int64_t G, int64_t N, int32_t *dst,
+                                int64_t ld, void *stream);
+int hb_transpose_u8_back_dev(const uint8_t *src_gene_major, int64_t ld, int64_t G, int64_t N,
+                             int32_t *dst_colmajor, void *stream);
+int hb_transpose_f64_back_dev(const double *src_gene_major, int64_t ld, int64_t G, int64_t N,
+                              double *dst_colmajor, void *stream);
+
+/* Column sd over positions per chain (R's sd(): n-1 denominator), device -> device sd[b] or
+ * sd[s*B+b].  Double-double accumulation; rounds like R's long-double code to <= 1 ulp. */
+int hb_chain_sd_dev(const double *x, int64_t ld, int64_t T, int64_t B, const int64_t *seg_off,
+                    int32_t nseg, int32_t per_seg, double *sd, void *stream);
+
+/* Pooled expression observation of R/HoneyBADGER.R:1141 for K groups at once:
+ * out[k*G+g] = mean over cells c with member[k*N+c] != 0 of x[g*ld+c], R `mean` semantics
+ * (x87 long-double two-pass accumulation in cell order, emulated exactly on the device). */
+int hb_pool_mean_dev(const double *x, int64_t ld, int64_t G, int64_t N,
+                     const uint8_t *member /* device [K][N] */, int32_t K,
+                     double *out /* device [K][G] */, void *stream);
+/* sd(x) of each pooled vector, R semantics (long-double emulation): out_sd[k]. */
+int hb_pooled_sd_dev(const double *pooled /* device [K][G] */, int64_t G, int32_t K,
+                     double *out_sd /* device [K] */, void *stream);
+/* Pooled allele counts of R/HoneyBADGER.R:1404-1405: out[k*G+g] = #{c in group k: v[g*ld+c] > 0} */
+int hb_pool_count_pos_dev(const int32_t *v, int64_t ld, int64_t G, int64_t N,
+                          const uint8_t *member, int32_t K, int32_t *out, void *stream);
+
+/* Host-buffer convenience for the four reference call sites (K pooled chains of one round):
+ * gexp_norm column-major [G x N]; member[K][N] (0/1).  Outputs y[K][G] (1-based), pooled x and sd. */
+int hb_gexp_pooled_viterbi_host(const double *gexp_norm, int64_t G, int64_t N,
+                                const uint8_t *member, int32_t K, const double *mean,
+                                const double *Pi, const double *delta, int32_t *y /* [K][G] */,
+                                double *pooled_x /* [K][G] or NULL */, double *pooled_sd /* [K] */);
+int hb_allele_pooled_viterbi_host(const double *r_maf, const double *n_sc, int64_t G, int64_t N,
+                                  const uint8_t *member, int32_t K, const double *prob,
+                                  const double *Pi, const double *delta, int32_t *y /* [K][G] */,
+                                  int32_t *mafl /* [K][G] or NULL */,
+                                  int32_t *sizel /* [K][G] or NULL */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HB_B200_H */

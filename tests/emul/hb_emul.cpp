@@ -1,0 +1,197 @@
+// hb_emul.cpp — TEST-ONLY host build of the CUDA chain bodies.
+//
+// The per-thread bodies in honeybadger_b200/csrc/*.cuh are `__host__ __device__`; this file compiles
+// them with g++ and walks the (block, thread) space serially so the CPU test-suite can check the
+// kernels' LOGIC (packing, checkpoints, replay, scaling, tie handling) against the oracle without a
+// GPU.  It is built into tests/emul/libhb_emul.so by tests/conftest.py and is never loaded by the
+// honeybadger_b200 package: the product has no CPU path.
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <algorithm>
+#include <numeric>
+#include <vector>
+
+#include "hb_binom2.cuh"
+#include "hb_host_math.h"
+#include "hb_norm3.cuh"
+#include "hb_x87.cuh"
+
+using namespace hb;
+
+namespace {
+struct Seg {
+    std::vector<int64_t> off, chunk;
+    std::vector<int32_t> order;
+    int64_t nchunks;
+};
+Seg make_seg(const int64_t *seg_off, int nseg)
+{
+    Seg s;
+    s.off.assign(seg_off, seg_off + nseg + 1);
+    s.chunk.resize(nseg + 1);
+    int64_t acc = 0;
+    for (int i = 0; i <= nseg; i++) {
+        s.chunk[i] = acc;
+        if (i < nseg) acc += (seg_off[i + 1] - seg_off[i] + HB_CHUNK - 1) / HB_CHUNK;
+    }
+    s.nchunks = acc;
+    s.order.resize(nseg);
+    std::iota(s.order.begin(), s.order.end(), 0);
+    std::stable_sort(s.order.begin(), s.order.end(), [&](int a, int b) {
+        return (seg_off[a + 1] - seg_off[a]) > (seg_off[b + 1] - seg_off[b]);
+    });
+    return s;
+}
+} // namespace
+
+extern "C" {
+
+// flags: 1 = Viterbi, 2 = gamma, 4 = ll ; returns status flag (1 = underflow)
+int emul_norm3(const double *x, int64_t ld, int64_t T, int64_t B, const int64_t *seg_off, int nseg,
+               const double *mean, const double *sd, int sd_per_seg, const double *Pi,
+               const double *delta, int flags, int force_general, uint8_t *y, double *gamma,
+               double *ll)
+{
+    Seg sg = make_seg(seg_off, nseg);
+    Norm3Args a;
+    memset(&a, 0, sizeof a);
+    for (int i = 0; i < 3; i++) {
+        a.c.mean[i] = mean[i];
+        a.c.delta[i] = delta[i];
+        a.c.logdelta[i] = log(delta[i]);
+    }
+    for (int i = 0; i < 9; i++) {
+        a.c.Pi[i] = Pi[i];
+        a.c.logPi[i] = log(Pi[i]);
+    }
+    bool sym_pi = Pi[0] == Pi[4] && Pi[0] == Pi[8] && Pi[1] == Pi[2] && Pi[1] == Pi[3] &&
+                  Pi[1] == Pi[5] && Pi[1] == Pi[6] && Pi[1] == Pi[7] && Pi[1] > 0;
+    bool sym = sym_pi && (mean[0] - mean[1]) == -(mean[2] - mean[1]) && !force_general;
+    a.c.la = a.c.logPi[0];
+    a.c.lt = a.c.logPi[1];
+    a.c.amt = Pi[0] - Pi[1];
+    a.c.tt = Pi[1];
+    int64_t nsd = sd_per_seg ? (int64_t)nseg * B : B;
+    std::vector<double> inv(nsd), lg(nsd);
+    for (int64_t i = 0; i < nsd; i++) {
+        inv[i] = 1.0 / sd[i];
+        lg[i] = log(sd[i]);
+    }
+    std::vector<uint64_t> psi((size_t)sg.nchunks * B);
+    std::vector<double> ckpt((size_t)sg.nchunks * 3 * B);
+    std::vector<double> sm(HB_CHUNK * HB_NORM3_SLOT);
+    int32_t status = 0;
+    a.x = x; a.ld = ld; a.T = T; a.B = B;
+    a.seg_off = sg.off.data(); a.chunk_off = sg.chunk.data(); a.seg_order = sg.order.data();
+    a.nseg = nseg; a.nblk_per_seg = 1;
+    a.sd = sd; a.inv_sd = inv.data(); a.log_sd = lg.data(); a.sd_per_seg = sd_per_seg;
+    a.y = y; a.ldy = ld; a.gamma = gamma; a.ldg = ld; a.ll = (flags & 4) ? ll : nullptr;
+    a.psi = psi.data(); a.ckpt = ckpt.data(); a.status = &status;
+    const bool vit = flags & 1, fb = flags & 6;
+    for (int s = 0; s < nseg; s++)
+        for (int64_t b = 0; b < B; b++) {
+            int seg = sg.order[s];
+            if (sym) {
+                if (vit && fb) norm3_chain<true, true, true>(a, seg, b, sm.data(), 1);
+                else if (fb) norm3_chain<true, false, true>(a, seg, b, sm.data(), 1);
+                else norm3_chain<true, true, false>(a, seg, b, sm.data(), 1);
+            } else {
+                if (vit && fb) norm3_chain<false, true, true>(a, seg, b, sm.data(), 1);
+                else if (fb) norm3_chain<false, false, true>(a, seg, b, sm.data(), 1);
+                else norm3_chain<false, true, false>(a, seg, b, sm.data(), 1);
+            }
+        }
+    return status;
+}
+
+int emul_binom2(const int32_t *x, const int32_t *n, int64_t ld, int64_t T, int64_t B,
+                const int64_t *seg_off, int nseg, const double *prob, const double *Pi,
+                const double *delta, int flags, int lut_nmax, uint8_t *y, double *gamma, double *ll)
+{
+    Seg sg = make_seg(seg_off, nseg);
+    Binom2Args a;
+    memset(&a, 0, sizeof a);
+    for (int k = 0; k < 2; k++) {
+        a.c.prob[k] = prob[k];
+        a.c.q[k] = 1 - prob[k];
+        a.c.logp[k] = log(prob[k]);
+        a.c.logq[k] = log(1 - prob[k]);
+        a.c.delta[k] = delta[k];
+        a.c.logdelta[k] = log(delta[k]);
+    }
+    for (int i = 0; i < 4; i++) {
+        a.c.Pi[i] = Pi[i];
+        a.c.logPi[i] = log(Pi[i]);
+    }
+    size_t cnt = (size_t)(lut_nmax + 1) * (lut_nmax + 2) / 2;
+    std::vector<double2> lb(cnt);
+    std::vector<RhoME> rr(cnt);
+    for (int nn = 0; nn <= lut_nmax; nn++)
+        for (int xx = 0; xx <= nn; xx++) {
+            size_t ix = (size_t)nn * (nn + 1) / 2 + xx;
+            lb[ix].x = hbhost::binom_logpmf(xx, nn, prob[0]);
+            lb[ix].y = hbhost::binom_logpmf(xx, nn, prob[1]);
+            rr[ix] = rho_from_logratio(lb[ix].x - lb[ix].y);
+        }
+    std::vector<uint64_t> psi((size_t)sg.nchunks * B);
+    std::vector<double> ckpt((size_t)sg.nchunks * 3 * B);
+    std::vector<double> sm(HB_CHUNK * HB_BINOM2_SLOT);
+    int32_t status = 0;
+    a.x = x; a.n = n; a.ld = ld; a.T = T; a.B = B;
+    a.seg_off = sg.off.data(); a.chunk_off = sg.chunk.data(); a.seg_order = sg.order.data();
+    a.nseg = nseg; a.nblk_per_seg = 1;
+    a.lut_lb = lb.data(); a.lut_rho = rr.data(); a.lut_nmax = lut_nmax;
+    a.y = y; a.ldy = ld; a.gamma = gamma; a.ldg = ld; a.ll = (flags & 4) ? ll : nullptr;
+    a.psi = psi.data(); a.ckpt = ckpt.data(); a.status = &status;
+    const bool vit = flags & 1, fb = flags & 6;
+    for (int s = 0; s < nseg; s++)
+        for (int64_t b = 0; b < B; b++) {
+            int seg = sg.order[s];
+            if (vit && fb) binom2_chain<true, true>(a, seg, b, sm.data(), 1);
+            else if (fb) binom2_chain<false, true>(a, seg, b, sm.data(), 1);
+            else binom2_chain<true, false>(a, seg, b, sm.data(), 1);
+        }
+    return status;
+}
+
+// R mean() / sd() through the integer x87 emulation (the arithmetic of pool_mean_kernel / pooled_sd_kernel)
+double emul_x87_mean(const double *x, int64_t n)
+{
+    x80 S = x80_zero(), Tt = x80_zero();
+    for (int64_t i = 0; i < n; i++) S = x80_add(S, x80_from_double(x[i]));
+    S = x80_div_u32(S, (uint32_t)n);
+    for (int64_t i = 0; i < n; i++) Tt = x80_add(Tt, x80_sub(x80_from_double(x[i]), S));
+    S = x80_add(S, x80_div_u32(Tt, (uint32_t)n));
+    return x80_to_double(S);
+}
+
+double emul_x87_sd(const double *x, int64_t n)
+{
+    x80 xm = x80_from_double(emul_x87_mean(x, n)), SS = x80_zero();
+    for (int64_t i = 0; i < n; i++) {
+        x80 d = x80_sub(x80_from_double(x[i]), xm);
+        SS = x80_add(SS, x80_mul(d, d));
+    }
+    return sqrt(x80_to_double(x80_div_u32(SS, (uint32_t)(n - 1))));
+}
+
+double emul_div_by_const(double d, double b) { return div_by_const(d, b, 1.0 / b); }
+
+void emul_exp_pair(double u, double *ep, double *em)
+{
+    double Pp, Pm;
+    int32_t n;
+    exp_pair(u, Pp, Pm, n);
+    *ep = ldexp(Pp, n);
+    *em = ldexp(Pm, -n);
+}
+
+double emul_binom_logpmf_host(double x, double n, double p) { return hbhost::binom_logpmf(x, n, p); }
+double emul_binom_logpmf_dev(double x, double n, double p)
+{
+    return dev_dbinom_log(x, n, p, 1 - p, log(p), log(1 - p));
+}
+
+} // extern "C"

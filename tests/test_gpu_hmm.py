@@ -1,0 +1,108 @@
+"""GPU parity: CUDA chains (through the C ABI) vs the CPU oracle on seeded inputs."""
+from __future__ import annotations
+
+import numpy as np
+import pytest
+
+from honeybadger_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _sd_cols(O, x):
+    return np.array([O.r_sd(x[:, b]) for b in range(x.shape[1])])
+
+
+@pytest.mark.parametrize("nseg", [1, 22])
+def test_norm_host_vs_oracle(oracle, nseg):
+    from honeybadger_b200 import hmm
+    O = oracle
+    G, N = 3000, 300
+    x, seg22, _ = synth.expression(G, N, seed=2)
+    seg = seg22 if nseg == 22 else np.array([0, G], dtype=np.int64)
+    sd = _sd_cols(O, x)
+    Pi, delta, mean = O.sym_Pi(3, 1e-6), [0.0, 1.0, 0.0], [-synth.DEV, 0.0, synth.DEV]
+    r = hmm.hmm_norm_host(x, mean, sd, Pi, delta, seg_off=seg, viterbi=True, gamma=True, ll=True)
+    yo, go, llo, rc = O.fbv_norm_batch(x, seg, mean, sd, Pi, delta)
+    assert rc == 0
+    assert r["y"].dtype == np.int32 and r["y"].shape == (G, N)
+    assert (r["y"] == yo).all(), f"{(r['y'] != yo).sum()} Viterbi states differ"
+    assert np.abs(r["gamma"].transpose(2, 0, 1) - go).max() < 1e-9  # north_star tolerance
+    assert np.allclose(r["ll"].T, llo, rtol=1e-10, atol=0)
+    assert set(np.unique(r["y"])) <= {1, 2, 3} and (r["y"] != 2).any()
+
+
+def test_norm_general_path_vs_oracle(oracle):
+    """Asymmetric means + arbitrary Pi take the general kernel."""
+    from honeybadger_b200 import hmm
+    O = oracle
+    rng = np.random.default_rng(9)
+    G, N = 1500, 130
+    x = rng.standard_normal((G, N)) * 1.3
+    x[400:700, :60] += 0.9
+    x[900:1200, 40:] -= 1.4
+    sd = _sd_cols(O, x)
+    Pi = np.array([[0.98, 0.015, 0.005], [0.001, 0.998, 0.001], [0.02, 0.01, 0.97]])
+    delta, mean = [0.2, 0.5, 0.3], [-1.4, 0.1, 0.9]
+    seg = np.array([0, 700, G], dtype=np.int64)
+    r = hmm.hmm_norm_host(x, mean, sd, Pi, delta, seg_off=seg, viterbi=True, gamma=True, ll=True)
+    yo, go, llo, rc = O.fbv_norm_batch(x, seg, mean, sd, Pi, delta)
+    assert rc == 0 and (r["y"] == yo).all()
+    assert np.abs(r["gamma"].transpose(2, 0, 1) - go).max() < 1e-9
+    assert np.allclose(r["ll"].T, llo, rtol=1e-10, atol=0)
+
+
+@pytest.mark.parametrize("nseg", [1, 22])
+def test_binom_host_vs_oracle(oracle, nseg):
+    from honeybadger_b200 import hmm
+    O = oracle
+    G, N = 6000, 200
+    r_maf, n_sc, seg22, _ = synth.allele(G, N, seed=3)
+    seg = seg22 if nseg == 22 else np.array([0, G], dtype=np.int64)
+    Pi, delta, prob = O.sym_Pi(2, 1e-6), [0.0, 1.0], [0.1, 0.45]
+    r = hmm.hmm_binom_host(r_maf, n_sc, prob, Pi, delta, seg_off=seg, viterbi=True, gamma=True, ll=True)
+    yo, go, llo, rc = O.fbv_binom_batch(r_maf, n_sc, seg, prob, Pi, delta)
+    assert rc == 0
+    assert (r["y"] == yo).all(), f"{(r['y'] != yo).sum()} Viterbi states differ"
+    assert np.abs(r["gamma"].transpose(2, 0, 1) - go).max() < 1e-9
+    assert np.allclose(r["ll"].T, llo, rtol=1e-10, atol=0)
+    assert (r["y"] == 1).any()
+
+
+def test_vector_api_and_underflow(oracle):
+    """dthmm/Viterbi mirror on one chain; a length-1 chain reproduces R's underflow error."""
+    from honeybadger_b200 import _lib, hmm
+    O = oracle
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal(500)
+    x[100:200] += 1.5
+    sd = O.r_sd(x)
+    z = hmm.dthmm(x, O.sym_Pi(3, 1e-6), [0, 1, 0], "norm", dict(mean=[-1, 0, 1], sd=[sd] * 3))
+    y = hmm.Viterbi(z)
+    assert (y == O.viterbi_norm(x, [-1, 0, 1], [sd] * 3, O.sym_Pi(3, 1e-6), [0, 1, 0])).all()
+    fb = hmm.forwardback(z)
+    g, ll = O.forwardback_norm(x, [-1, 0, 1], [sd] * 3, O.sym_Pi(3, 1e-6), [0, 1, 0])
+    assert np.abs(fb["u"] - g).max() < 1e-9 and abs(fb["LL"][0] - ll) < 1e-9 * abs(ll)
+    with pytest.raises(_lib.UnderflowError, match="Problems With Underflow"):
+        hmm.Viterbi(hmm.dthmm(x[:1], O.sym_Pi(3, 1e-6), [0, 1, 0], "norm",
+                              dict(mean=[-1, 0, 1], sd=[1.0] * 3)))
+
+
+def test_dev_api_matches_host_api(oracle):
+    import torch
+    from honeybadger_b200 import hmm
+    O = oracle
+    G, N = 2000, 260
+    x, seg, _ = synth.expression(G, N, seed=5)
+    Pi, delta, mean = O.sym_Pi(3, 1e-6), [0.0, 1.0, 0.0], [-synth.DEV, 0.0, synth.DEV]
+    xd = torch.from_numpy(x).cuda()
+    sd = hmm.chain_sd_dev(xd)
+    sd_ref = _sd_cols(O, x)
+    assert np.allclose(sd.cpu().numpy(), sd_ref, rtol=1e-14, atol=0)
+    out = hmm.hmm_norm_dev(xd, sd, mean, Pi, delta, seg_off=seg, viterbi=True, gamma=True, ll=True)
+    hmm.status_dev()
+    sdh = sd.cpu().numpy()
+    yo, go, llo, rc = O.fbv_norm_batch(x, seg, mean, sdh, Pi, delta)
+    assert (out["y"].cpu().numpy() == yo).all()
+    assert np.abs(out["gamma"].cpu().numpy() - go).max() < 1e-9
+    assert np.allclose(out["ll"].cpu().numpy(), llo, rtol=1e-10, atol=0)
