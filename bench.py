@@ -225,7 +225,7 @@ def run_reference(args, wl, kind):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="expr", choices=list(WORKLOADS))
@@ -233,6 +233,7 @@ def main():
     ap.add_argument("--positions", type=int, default=0, help="override genes/SNPs (tests)")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
     args = ap.parse_args()
     kind = args.workload
     wl = dict(WORKLOADS[kind])
@@ -316,10 +317,11 @@ def main():
 
     # ---------------- end to end through the host-buffer C ABI (pinned host memory)
     e2e = None
-    try:
-        e2e = run_e2e(kind, wl, d, args, world, dev, hmm, dist if world > 1 else None)
-    except Exception as exc:  # report, never fake
-        e2e = {"value": None, "unit": UNIT, "error": repr(exc)[:200]}
+    if not args.no_e2e:
+        try:
+            e2e = run_e2e(kind, wl, d, args, world, dev, hmm, dist if world > 1 else None)
+        except Exception as exc:  # report, never fake
+            e2e = {"value": None, "unit": UNIT, "error": repr(exc)[:200]}
 
     peak, peak_src = measured_peak()
     mean_ms = float(np.mean(per_launch_ms))

@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libhb_b200.so")
+LIB_PATH = os.environ.get("HB_B200_LIB") or os.path.join(HERE, "libhb_b200.so")  # env: dev experiments
 
 HB_OK = 0
 HB_ERR_ARG = -1

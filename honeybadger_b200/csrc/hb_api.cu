@@ -193,6 +193,7 @@ int fill_norm3_const(hb::Norm3Const &c, const double *mean, const double *Pi, co
     c.lt = c.logPi[1];
     c.amt = Pi[0] - Pi[1];
     c.tt = Pi[1];
+    hb::norm3_fill_k(c);
     return HB_OK;
 }
 

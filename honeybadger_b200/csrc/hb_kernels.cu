@@ -15,15 +15,24 @@ namespace hb {
 // HMM chains: one thread per (cell column, segment); block = HB_BLOCK consecutive cells of
 // one segment, segments issued longest first.
 // =====================================================================================
-template <bool SYM, bool VIT, bool FB>
-__global__ void __launch_bounds__(HB_BLOCK)
+#ifndef HB_NORM3_MINB
+#define HB_NORM3_MINB 4
+#endif
+template <bool SYM, bool VIT, bool FB, bool LL>
+__global__ void __launch_bounds__(HB_BLOCK, HB_NORM3_MINB)
     norm3_kernel(const __grid_constant__ Norm3Args a)
 {
-    extern __shared__ double smem[];
+    extern __shared__ double2 smem2[];
     const int32_t seg = a.seg_order[blockIdx.x / a.nblk_per_seg];
     const int64_t b = (int64_t)(blockIdx.x % a.nblk_per_seg) * HB_BLOCK + threadIdx.x;
     if (b >= a.B) return;
-    norm3_chain<SYM, VIT, FB>(a, seg, b, smem + threadIdx.x, HB_BLOCK);
+    Norm3Smem m;
+    m.st = HB_BLOCK;
+    m.va = smem2 + threadIdx.x;
+    m.vb = m.va + HB_CHUNK * HB_BLOCK;
+    m.e2 = reinterpret_cast<double *>(smem2 + 2 * HB_CHUNK * HB_BLOCK) + threadIdx.x;
+    m.xs = FB ? m.e2 + HB_CHUNK * HB_BLOCK : reinterpret_cast<double *>(smem2) + threadIdx.x;
+    norm3_chain<SYM, VIT, FB, LL>(a, seg, b, m);
 }
 
 template <bool VIT, bool FB>
@@ -41,13 +50,22 @@ template <bool SYM>
 static cudaError_t launch_norm3_t(const Norm3Args &a, bool vit, bool fb, cudaStream_t st)
 {
     const unsigned grid = (unsigned)((int64_t)a.nseg * a.nblk_per_seg);
-    const size_t sm_fb = (size_t)HB_CHUNK * HB_NORM3_SLOT * HB_BLOCK * sizeof(double);
-    if (vit && fb)
-        norm3_kernel<SYM, true, true><<<grid, HB_BLOCK, sm_fb, st>>>(a);
-    else if (fb)
-        norm3_kernel<SYM, false, true><<<grid, HB_BLOCK, sm_fb, st>>>(a);
-    else
-        norm3_kernel<SYM, true, false><<<grid, HB_BLOCK, 0, st>>>(a);
+    const size_t sm_fb = (size_t)HB_NORM3_SMEM_BYTES_PER_THREAD * HB_BLOCK;
+    const bool ll = a.ll != nullptr;
+    if (vit && fb) {
+        if (ll)
+            norm3_kernel<SYM, true, true, true><<<grid, HB_BLOCK, sm_fb, st>>>(a);
+        else
+            norm3_kernel<SYM, true, true, false><<<grid, HB_BLOCK, sm_fb, st>>>(a);
+    } else if (fb) {
+        if (ll)
+            norm3_kernel<SYM, false, true, true><<<grid, HB_BLOCK, sm_fb, st>>>(a);
+        else
+            norm3_kernel<SYM, false, true, false><<<grid, HB_BLOCK, sm_fb, st>>>(a);
+    } else {
+        norm3_kernel<SYM, true, false, false>
+            <<<grid, HB_BLOCK, (size_t)HB_CHUNK * HB_BLOCK * sizeof(double), st>>>(a);
+    }
     return cudaGetLastError();
 }
 

@@ -23,13 +23,39 @@
 //   Forward-backward runs in the linear domain on emission RATIOS b_k/b_1 = exp(a_k x + c_k) (the
 //   posteriors are invariant to the common factor b_1), rescaled by an exact power of two every
 //   step; the log-likelihood adds the removed exponents and sum log b_1 back.
+//
+// Instruction economy (the kernel is fp64-issue bound, not HBM bound — see DESIGN.md): every
+// floating constant that is not a short immediate lives in the kernel-parameter block
+// (Norm3Const::k) so it is fetched from the constant bank instead of being rebuilt from two 32-bit
+// immediates per use; full 8-step chunks run without bounds checks; the next chunk's x is
+// prefetched into the register the current step just consumed.
 #pragma once
 #include "hb_device.cuh"
 
 namespace hb {
 
 #define HB_CHUNK 8
-#define HB_NORM3_SLOT 5 // doubles per step kept for the backward sweep: phi[3], E0, E2
+
+// indices into Norm3Const::k
+enum {
+    HBK_LNSQRT2PI = 0,
+    HBK_L2E,
+    HBK_LN2HI,
+    HBK_LN2LO,
+    HBK_E12,
+    HBK_E10,
+    HBK_E8,
+    HBK_E6,
+    HBK_E4,
+    HBK_O13,
+    HBK_O11,
+    HBK_O9,
+    HBK_O7,
+    HBK_O5,
+    HBK_O3,
+    HBK_LN2,
+    HBK_COUNT
+};
 
 struct Norm3Const {
     double mean[3];
@@ -39,7 +65,29 @@ struct Norm3Const {
     double delta[3];
     double la, lt;  // SYM: log(diag), log(off-diag)
     double amt, tt; // SYM: (diag - offdiag), offdiag
+    double k[HBK_COUNT];
 };
+
+// Fills the numeric constants (host side; the same values on every platform).
+inline void norm3_fill_k(Norm3Const &c)
+{
+    c.k[HBK_LNSQRT2PI] = 0.918938533204672741780329736406;
+    c.k[HBK_L2E] = 1.4426950408889634074;
+    c.k[HBK_LN2HI] = 0.69314670562744140625;     // 0x3FE62E4200000000: 21 significant bits
+    c.k[HBK_LN2LO] = 4.74932503903167232121458e-07; // ln2 - LN2HI, rounded once
+    c.k[HBK_E12] = 1.0 / 479001600.0;
+    c.k[HBK_E10] = 1.0 / 3628800.0;
+    c.k[HBK_E8] = 1.0 / 40320.0;
+    c.k[HBK_E6] = 1.0 / 720.0;
+    c.k[HBK_E4] = 1.0 / 24.0;
+    c.k[HBK_O13] = 1.0 / 6227020800.0;
+    c.k[HBK_O11] = 1.0 / 39916800.0;
+    c.k[HBK_O9] = 1.0 / 362880.0;
+    c.k[HBK_O7] = 1.0 / 5040.0;
+    c.k[HBK_O5] = 1.0 / 120.0;
+    c.k[HBK_O3] = 1.0 / 6.0;
+    c.k[HBK_LN2] = 0.693147180559945309417232121458;
+}
 
 struct Norm3Args {
     const double *x;
@@ -61,7 +109,34 @@ struct Norm3Args {
     Norm3Const c;
 };
 
-#define HB_LN_SQRT_2PI 0.918938533204672741780329736406
+// exp(u) and exp(-u): Pp = e^r, Pm = e^-r, u = n ln2 + r (see hb_device.cuh exp_pair; this variant
+// reads its constants from the parameter block).
+HB_HD void norm3_exp_pair(const Norm3Const &c, double u, double &Pp, double &Pm, int32_t &n)
+{
+    const double MAGIC = 6755399441055744.0; // 1.5 * 2^52 (short immediate)
+    double t = dfma(u, c.k[HBK_L2E], MAGIC);
+    int32_t ni = lo32(t);
+    double nf = t - MAGIC;
+    double r = dfma(nf, -c.k[HBK_LN2HI], u);
+    r = dfma(nf, -c.k[HBK_LN2LO], r);
+    double q = r * r;
+    double ev = dfma(q, c.k[HBK_E12], c.k[HBK_E10]);
+    double od = dfma(q, c.k[HBK_O13], c.k[HBK_O11]);
+    ev = dfma(q, ev, c.k[HBK_E8]);
+    od = dfma(q, od, c.k[HBK_O9]);
+    ev = dfma(q, ev, c.k[HBK_E6]);
+    od = dfma(q, od, c.k[HBK_O7]);
+    ev = dfma(q, ev, c.k[HBK_E4]);
+    od = dfma(q, od, c.k[HBK_O5]);
+    ev = dfma(q, ev, 0.5);
+    od = dfma(q, od, c.k[HBK_O3]);
+    ev = dfma(q, ev, 1.0);
+    od = dfma(q, od, 1.0);
+    od = od * r;
+    Pp = ev + od;
+    Pm = ev - od;
+    n = ni > HB_NCLAMP ? HB_NCLAMP : (ni < -HB_NCLAMP ? -HB_NCLAMP : ni);
+}
 
 // log dnorm(x, mean_k, sd) for the three states, R nmath operation order.
 HB_HD void norm3_logb(double xv, const Norm3Const &c, double sdv, double isd, double lsd,
@@ -73,9 +148,9 @@ HB_HD void norm3_logb(double xv, const Norm3Const &c, double sdv, double isd, do
     double h0 = (0.5 * z0) * z0;
     h1 = (0.5 * z1) * z1;
     double h2 = (0.5 * z2) * z2;
-    l0 = -((HB_LN_SQRT_2PI + h0) + lsd);
-    l1 = -((HB_LN_SQRT_2PI + h1) + lsd);
-    l2 = -((HB_LN_SQRT_2PI + h2) + lsd);
+    l0 = -((c.k[HBK_LNSQRT2PI] + h0) + lsd);
+    l1 = -((c.k[HBK_LNSQRT2PI] + h1) + lsd);
+    l2 = -((c.k[HBK_LNSQRT2PI] + h2) + lsd);
 }
 
 // One Viterbi step; returns the three back-pointers packed 2 bits each (k=0 in bits 0-1).
@@ -95,17 +170,19 @@ HB_HD uint32_t norm3_vit_step(const Norm3Const &c, double &n0, double &n1, doubl
         c01 = n0 + c.logPi[1]; c11 = n1 + c.logPi[4]; c21 = n2 + c.logPi[7];
         c02 = n0 + c.logPi[2]; c12 = n1 + c.logPi[5]; c22 = n2 + c.logPi[8];
     }
-    uint32_t p0 = 0, p1 = 0, p2 = 0;
-    double m0 = c00, m1 = c01, m2 = c02;
-    if (c10 > m0) { m0 = c10; p0 = 1; }
-    if (c20 > m0) { m0 = c20; p0 = 2; }
-    if (c11 > m1) { m1 = c11; p1 = 1; }
-    if (c21 > m1) { m1 = c21; p1 = 2; }
-    if (c12 > m2) { m2 = c12; p2 = 1; }
-    if (c22 > m2) { m2 = c22; p2 = 2; }
+    // first index wins ties: strict ">" when a later candidate replaces an earlier one
+    const bool a0 = c10 > c00, a1 = c11 > c01, a2 = c12 > c02;
+    double m0 = a0 ? c10 : c00, m1 = a1 ? c11 : c01, m2 = a2 ? c12 : c02;
+    const bool b0 = c20 > m0, b1 = c21 > m1, b2 = c22 > m2;
+    m0 = b0 ? c20 : m0;
+    m1 = b1 ? c21 : m1;
+    m2 = b2 ? c22 : m2;
     n0 = m0 + l0;
     n1 = m1 + l1;
     n2 = m2 + l2;
+    const uint32_t p0 = b0 ? 2u : (a0 ? 1u : 0u);
+    const uint32_t p1 = b1 ? 2u : (a1 ? 1u : 0u);
+    const uint32_t p2 = b2 ? 2u : (a2 ? 1u : 0u);
     return p0 | (p1 << 2) | (p2 << 4);
 }
 
@@ -145,30 +222,31 @@ HB_HD Norm3Fb norm3_fb_consts(const Norm3Const &c, double isd)
 
 // Emission ratios of one step, without the 2^n factors applied: E0 = r0 * 2^n0, E2 = r2 * 2^n2.
 template <bool SYM>
-HB_HD void norm3_ratios(const Norm3Fb &k, double xv, double &r0, int32_t &n0, double &r2,
-                        int32_t &n2)
+HB_HD void norm3_ratios(const Norm3Const &c, const Norm3Fb &k, double xv, double &r0, int32_t &n0,
+                        double &r2, int32_t &n2)
 {
     if (SYM) {
         double u = dfma(xv, k.A, k.Bc);
         int32_t n;
-        exp_pair(u, r2, r0, n);
+        norm3_exp_pair(c, u, r2, r0, n);
         n2 = n;
         n0 = -n;
     } else {
-        exp_one(dfma(xv, k.a0, k.c0), r0, n0);
-        exp_one(dfma(xv, k.a2, k.c2), r2, n2);
+        double dummy;
+        norm3_exp_pair(c, dfma(xv, k.a0, k.c0), r0, dummy, n0);
+        norm3_exp_pair(c, dfma(xv, k.a2, k.c2), r2, dummy, n2);
     }
 }
 
 // Forward filter step: phi <- ((phi Pi) . rho) * 2^-es with es = exponent of sum(phi_in).
-// FIRST: phi_in is delta and there is no transition.  Returns es (added to the chain's exponent sum).
-template <bool SYM, bool FIRST>
-HB_HD int32_t norm3_fwd_step(const Norm3Const &c, const Norm3Fb &k, double &f0, double &f1,
-                             double &f2, double r0, int32_t n0, double r2, int32_t n2)
+// `first`: phi_in is delta and there is no transition.  Returns es (added to the exponent sum).
+template <bool SYM>
+HB_HD int32_t norm3_fwd_step(const Norm3Const &c, const Norm3Fb &k, bool first, double &f0,
+                             double &f1, double &f2, double r0, int32_t n0, double r2, int32_t n2)
 {
     double p0, p1, p2;
     int32_t es;
-    if (FIRST) {
+    if (first) {
         p0 = c.delta[0] * k.K;
         p1 = c.delta[1];
         p2 = c.delta[2] * k.K;
@@ -217,167 +295,328 @@ HB_HD void norm3_bwd_step(const Norm3Const &c, const Norm3Fb &k, double &b0, dou
     }
 }
 
-// The whole chain.  `sm` points at this thread's first shared-memory word; consecutive slots of the
-// same thread are `sms` doubles apart (blockDim.x on the device: conflict-free columns).
+// Per-chain state carried through both sweeps (kept in registers).
+template <bool SYM>
+struct Norm3State {
+    double sdv, isd, lsd;
+    Norm3Fb k;
+    double n0, n1, n2; // Viterbi nu
+    double f0, f1, f2; // forward filter
+    double hsum;       // sum of (0.5 z_1) z_1 (log-likelihood)
+    int32_t esum;      // sum of removed binary exponents (|es| <= 502 per step: fine for L < 4e6)
+    double b0, b1, b2; // backward
+    int32_t eb, ycur;
+};
+
+// One forward step (Viterbi recursion + filter).  `first` is the chain's position 0.
+template <bool SYM, bool VIT, bool FB, bool LL>
+HB_HD uint32_t norm3_forward_one(const Norm3Const &c, Norm3State<SYM> &s, double xv, bool first)
+{
+    uint32_t ps = 0;
+    double h1 = 0;
+    if (VIT || (FB && LL)) {
+        double l0, l1, l2;
+        norm3_logb(xv, c, s.sdv, s.isd, s.lsd, l0, l1, l2, h1);
+        if (VIT) {
+            if (first) {
+                s.n0 = c.logdelta[0] + l0;
+                s.n1 = c.logdelta[1] + l1;
+                s.n2 = c.logdelta[2] + l2;
+            } else {
+                ps = norm3_vit_step<SYM>(c, s.n0, s.n1, s.n2, l0, l1, l2);
+            }
+        }
+    }
+    if (FB) {
+        double r0, r2;
+        int32_t e0, e2;
+        norm3_ratios<SYM>(c, s.k, xv, r0, e0, r2, e2);
+        s.esum += norm3_fwd_step<SYM>(c, s.k, first, s.f0, s.f1, s.f2, r0, e0, r2, e2);
+        if (LL) s.hsum += h1;
+    }
+    return ps;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Per-thread view of the block's shared memory.  All arrays are [step j][thread]; `st` is the
+// element stride between consecutive j for the same thread (blockDim.x on the device, 1 in the
+// host emulation), so a warp always touches consecutive addresses (no bank conflicts).
+//   va[j] = (phi0, phi1), vb[j] = (phi2, E0), e2[j] = E2 : parked by the replay for the backward pass
+//   xs[j]                                               : x staging ring filled by cp.async
+struct Norm3Smem {
+    double2 *va, *vb;
+    double *e2, *xs;
+    int32_t st;
+#if !defined(__CUDA_ARCH__)
+    // host emulation of cp.async groups: copies become visible only at wait (catches hazards)
+    double pend_v[64];
+    double *pend_p[64];
+    int pend_g[64];
+    int npend = 0, cur_group = 0;
+#endif
+};
+#define HB_NORM3_SMEM_BYTES_PER_THREAD (HB_CHUNK * (16 + 16 + 8 + 8))
+
+HB_HD void xs_refill(Norm3Smem &m, int j, const double *g)
+{
+#if defined(__CUDA_ARCH__)
+    unsigned sa = (unsigned)__cvta_generic_to_shared(m.xs + j * m.st);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(g) : "memory");
+#else
+    m.pend_v[m.npend] = *g;
+    m.pend_p[m.npend] = m.xs + j * m.st;
+    m.pend_g[m.npend] = m.cur_group;
+    m.npend++;
+#endif
+}
+HB_HD void xs_commit(Norm3Smem &m)
+{
+#if defined(__CUDA_ARCH__)
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#else
+    m.cur_group++;
+#endif
+}
+// Wait until at most N of the most recently committed groups are still in flight.
+template <int N>
+HB_HD void xs_wait(Norm3Smem &m)
+{
+#if defined(__CUDA_ARCH__)
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+#else
+    int keep = 0;
+    for (int i = 0; i < m.npend; i++) {
+        if (m.pend_g[i] < m.cur_group - N) {
+            *m.pend_p[i] = m.pend_v[i];
+        } else {
+            m.pend_v[keep] = m.pend_v[i];
+            m.pend_p[keep] = m.pend_p[i];
+            m.pend_g[keep] = m.pend_g[i];
+            keep++;
+        }
+    }
+    m.npend = keep;
+#endif
+}
+
+#ifndef HB_UNROLL_N
+#define HB_UNROLL_N 4
+#endif
+#define HB_STR_(x) #x
+#define HB_UNROLL_PRAGMA_(n) _Pragma(HB_STR_(unroll n))
+#define HB_UNROLL_STEPS HB_UNROLL_PRAGMA_(HB_UNROLL_N)
+#define HB_HALF (HB_CHUNK / 2)
+
+// Replay one filter step and park (phi, E0, E2) in slot j for the backward pass.
+template <bool SYM>
+HB_HD void norm3_replay_one(const Norm3Const &c, Norm3State<SYM> &s, double xv, bool first,
+                            Norm3Smem &m, int j)
+{
+    double r0, r2;
+    int32_t e0, e2;
+    norm3_ratios<SYM>(c, s.k, xv, r0, e0, r2, e2);
+    norm3_fwd_step<SYM>(c, s.k, first, s.f0, s.f1, s.f2, r0, e0, r2, e2);
+    double2 a, b;
+    a.x = s.f0;
+    a.y = s.f1;
+    b.x = s.f2;
+    b.y = scale2(r0, e0);
+    m.va[j * m.st] = a;
+    m.vb[j * m.st] = b;
+    m.e2[j * m.st] = scale2(r2, e2);
+}
+
+// One backward step at global row `row`: Viterbi state, posterior, beta update.
 template <bool SYM, bool VIT, bool FB>
-HB_HD void norm3_chain(const Norm3Args &a, int32_t seg, int64_t b, double *sm, int32_t sms)
+HB_HD void norm3_backward_one(const Norm3Args &a, Norm3State<SYM> &s, int64_t row, int64_t b,
+                              uint64_t pk, int j, const Norm3Smem &m)
+{
+    if (VIT) {
+        a.y[row * a.ldy + b] = (uint8_t)(s.ycur + 1);
+        s.ycur = (int32_t)((uint32_t)(pk >> (6 * j + 2 * s.ycur)) & 3u);
+    }
+    if (FB) {
+        const double2 va = m.va[j * m.st], vb = m.vb[j * m.st];
+        const double E2 = m.e2[j * m.st];
+        double g0 = va.x * s.b0, g1 = va.y * s.b1, g2 = vb.x * s.b2;
+        double rs = rcp_fast((g0 + g1) + g2);
+        double *gp = a.gamma + row * a.ldg + b;
+        const int64_t plane = a.T * a.ldg;
+        gp[0] = g0 * rs;
+        gp[plane] = g1 * rs;
+        gp[2 * plane] = g2 * rs;
+        norm3_bwd_step<SYM>(a.c, s.k, s.b0, s.b1, s.b2, s.eb, vb.y, E2);
+    }
+}
+
+// The whole chain.
+template <bool SYM, bool VIT, bool FB, bool LL>
+HB_HD void norm3_chain(const Norm3Args &a, int32_t seg, int64_t b, Norm3Smem &m)
 {
     const Norm3Const &c = a.c;
     const int64_t t0 = a.seg_off[seg];
-    const int64_t L = a.seg_off[seg + 1] - t0;
+    const int32_t L = (int32_t)(a.seg_off[seg + 1] - t0);
     if (L <= 0) return;
-    const int64_t nch = (L + HB_CHUNK - 1) / HB_CHUNK;
+    const int32_t nfull = L / HB_CHUNK;        // chunks with all 8 steps
+    const int32_t tail = L - nfull * HB_CHUNK; // steps in the last, partial chunk
     const int64_t cbase = a.chunk_off[seg];
     const int64_t pix = a.sd_per_seg ? (int64_t)seg * a.B + b : b;
-    const double sdv = a.sd[pix], isd = a.inv_sd[pix], lsd = a.log_sd[pix];
-    const double *xp = a.x + t0 * a.ld + b;
-    const Norm3Fb k = norm3_fb_consts<SYM>(c, isd);
+    const int64_t ld = a.ld;
+    const double *xp = a.x + t0 * ld + b;
+    uint64_t *psi = a.psi + cbase * a.B + b;
+    double *ckpt = a.ckpt + cbase * 3 * a.B + b;
 
-    double n0 = 0, n1 = 0, n2 = 0; // Viterbi nu
-    double f0 = 0, f1 = 0, f2 = 0; // forward filter
-    double hsum = 0;               // sum of (0.5 z_1) z_1 for the log-likelihood
-    int64_t esum = 0;              // sum of removed binary exponents
+    Norm3State<SYM> s;
+    s.sdv = a.sd[pix];
+    s.isd = a.inv_sd[pix];
+    s.lsd = a.log_sd[pix];
+    s.k = norm3_fb_consts<SYM>(c, s.isd);
+    s.n0 = s.n1 = s.n2 = 0;
+    s.f0 = s.f1 = s.f2 = 0;
+    s.hsum = 0;
+    s.esum = 0;
 
     // ------------------------------------------------------------ forward sweep
-    double xc[HB_CHUNK], xn[HB_CHUNK];
+    // x is staged through shared memory by cp.async in half-chunk groups: while a half-chunk is
+    // consumed, its slots are refilled with the same positions of the NEXT chunk (distance 8 steps).
+    if (nfull > 0) {
 #pragma unroll
-    for (int j = 0; j < HB_CHUNK; j++) xc[j] = (j < L) ? xp[(int64_t)j * a.ld] : 0.0;
-    for (int64_t ch = 0; ch < nch; ch++) {
-        const int64_t i0 = ch * HB_CHUNK;
-        {
-            const int64_t inext = i0 + HB_CHUNK;
+        for (int h = 0; h < 2; h++) {
 #pragma unroll
-            for (int j = 0; j < HB_CHUNK; j++)
-                xn[j] = (inext + j < L) ? xp[(inext + j) * a.ld] : 0.0;
+            for (int j = h * HB_HALF; j < (h + 1) * HB_HALF; j++) xs_refill(m, j, xp + (int64_t)j * ld);
+            xs_commit(m);
         }
+    }
+    for (int32_t ch = 0; ch < nfull; ch++) {
+        const double *xnext = xp + (int64_t)(ch + 1) * HB_CHUNK * ld;
+        const bool more = ch + 1 < nfull;
         uint64_t pk = 0;
 #pragma unroll
-        for (int j = 0; j < HB_CHUNK; j++) {
-            if (i0 + j < L) {
-                const double xv = xc[j];
-                double h1 = 0;
-                if (VIT || (FB && a.ll)) {
-                    double l0, l1, l2;
-                    norm3_logb(xv, c, sdv, isd, lsd, l0, l1, l2, h1);
-                    if (VIT) {
-                        if (i0 + j == 0) {
-                            n0 = c.logdelta[0] + l0;
-                            n1 = c.logdelta[1] + l1;
-                            n2 = c.logdelta[2] + l2;
-                        } else {
-                            uint32_t ps = norm3_vit_step<SYM>(c, n0, n1, n2, l0, l1, l2);
-                            pk |= (uint64_t)ps << (6 * j);
-                        }
-                    }
-                }
-                if (FB) {
-                    double r0, r2;
-                    int32_t e0, e2;
-                    norm3_ratios<SYM>(k, xv, r0, e0, r2, e2);
-                    if (i0 + j == 0)
-                        esum += norm3_fwd_step<SYM, true>(c, k, f0, f1, f2, r0, e0, r2, e2);
-                    else
-                        esum += norm3_fwd_step<SYM, false>(c, k, f0, f1, f2, r0, e0, r2, e2);
-                    hsum += h1;
-                }
+        for (int h = 0; h < 2; h++) {
+            xs_wait<1>(m);
+            HB_UNROLL_STEPS
+            for (int j = h * HB_HALF; j < (h + 1) * HB_HALF; j++) {
+                const double xv = m.xs[j * m.st];
+                if (more) xs_refill(m, j, xnext + (int64_t)j * ld);
+                uint32_t ps = norm3_forward_one<SYM, VIT, FB, LL>(c, s, xv, j == 0 && ch == 0);
+                pk |= (uint64_t)ps << (6 * j);
             }
+            xs_commit(m);
         }
-        if (VIT) a.psi[(cbase + ch) * a.B + b] = pk;
-        if (FB && ch + 1 < nch) {
-            double *ck = a.ckpt + (cbase + ch + 1) * 3 * a.B + b;
-            ck[0] = f0;
-            ck[a.B] = f1;
-            ck[2 * a.B] = f2;
+        if (VIT) psi[(int64_t)ch * a.B] = pk;
+        if (FB && (ch + 1 < nfull || tail > 0)) {
+            double *ck = ckpt + (int64_t)(ch + 1) * 3 * a.B;
+            ck[0] = s.f0;
+            ck[a.B] = s.f1;
+            ck[2 * a.B] = s.f2;
         }
-#pragma unroll
-        for (int j = 0; j < HB_CHUNK; j++) xc[j] = xn[j];
+    }
+    xs_wait<0>(m);
+    if (tail > 0) { // rolled: at most 7 steps per chain
+        uint64_t pk = 0;
+        for (int j = 0; j < tail; j++) {
+            const double xv = xp[(int64_t)(nfull * HB_CHUNK + j) * ld];
+            uint32_t ps = norm3_forward_one<SYM, VIT, FB, LL>(c, s, xv, nfull == 0 && j == 0);
+            pk |= (uint64_t)ps << (6 * j);
+        }
+        if (VIT) psi[(int64_t)nfull * a.B] = pk;
     }
 
-    if (FB && a.ll) {
+    if (FB && LL) {
         // LL = log sum(alpha_L) = log(sum phi) + ln2 * esum + sum_t log b_1(x_t)
-        const double LN2 = 0.693147180559945309417232121458;
-        a.ll[(int64_t)seg * a.B + b] =
-            ((log((f0 + f1) + f2) + LN2 * (double)esum) - hsum) - (double)L * (HB_LN_SQRT_2PI + lsd);
+        a.ll[(int64_t)seg * a.B + b] = ((log((s.f0 + s.f1) + s.f2) + c.k[HBK_LN2] * (double)s.esum) -
+                                        s.hsum) - (double)L * (c.k[HBK_LNSQRT2PI] + s.lsd);
     }
 
     // ------------------------------------------------------------ backward sweep
-    int32_t ycur = 0;
+    s.ycur = 0;
     if (VIT) {
-        if (n0 == -INFINITY || n1 == -INFINITY || n2 == -INFINITY) *a.status = 1;
-        double mv = n0;
-        if (n1 > mv) { mv = n1; ycur = 1; }
-        if (n2 > mv) { mv = n2; ycur = 2; }
+        if (s.n0 == -INFINITY || s.n1 == -INFINITY || s.n2 == -INFINITY) *a.status = 1;
+        double mv = s.n0;
+        if (s.n1 > mv) { mv = s.n1; s.ycur = 1; }
+        if (s.n2 > mv) { mv = s.n2; s.ycur = 2; }
     }
-    double b0 = 1.0, b1 = 1.0, b2 = 1.0;
-    int32_t eb = 0;
-    {
-        const int64_t i0 = (nch - 1) * HB_CHUNK;
+    s.b0 = s.b1 = s.b2 = 1.0;
+    s.eb = 0;
+    // stage the last full chunk while the tail (if any) is processed; second half first, because
+    // the replay walks j = 0..7 but the refill order only has to respect the group accounting
+    if (FB && nfull > 0) {
+        const double *xl = xp + (int64_t)(nfull - 1) * HB_CHUNK * ld;
 #pragma unroll
-        for (int j = 0; j < HB_CHUNK; j++) xc[j] = (i0 + j < L) ? xp[(i0 + j) * a.ld] : 0.0;
-    }
-    for (int64_t ch = nch - 1; ch >= 0; ch--) {
-        const int64_t i0 = ch * HB_CHUNK;
-        if (FB) {
-            const int64_t iprev = i0 - HB_CHUNK;
+        for (int h = 0; h < 2; h++) {
 #pragma unroll
-            for (int j = 0; j < HB_CHUNK; j++)
-                xn[j] = (iprev >= 0) ? xp[(iprev + j) * a.ld] : 0.0;
+            for (int j = h * HB_HALF; j < (h + 1) * HB_HALF; j++) xs_refill(m, j, xl + (int64_t)j * ld);
+            xs_commit(m);
         }
+    }
+    // The chunk's checkpoint and back-pointer word are fetched one chunk ahead (their latency
+    // would otherwise sit on the critical path at every chunk boundary).
+    uint64_t pk_nx = 0;
+    double c0_nx = 0, c1_nx = 0, c2_nx = 0;
+    if (nfull > 0) {
+        if (VIT) pk_nx = psi[(int64_t)(nfull - 1) * a.B];
+        if (FB && nfull > 1) {
+            const double *ck = ckpt + (int64_t)(nfull - 1) * 3 * a.B;
+            c0_nx = ck[0];
+            c1_nx = ck[a.B];
+            c2_nx = ck[2 * a.B];
+        }
+    }
+    if (tail > 0) {
         uint64_t pk = 0;
-        if (VIT) pk = a.psi[(cbase + ch) * a.B + b];
+        if (VIT) pk = psi[(int64_t)nfull * a.B];
         if (FB) {
-            // replay the filter through the chunk from its checkpoint, keeping phi and the ratios
-            if (ch > 0) {
-                const double *ck = a.ckpt + (cbase + ch) * 3 * a.B + b;
-                f0 = ck[0];
-                f1 = ck[a.B];
-                f2 = ck[2 * a.B];
+            if (nfull > 0) {
+                const double *ck = ckpt + (int64_t)nfull * 3 * a.B;
+                s.f0 = ck[0];
+                s.f1 = ck[a.B];
+                s.f2 = ck[2 * a.B];
             }
-#pragma unroll
-            for (int j = 0; j < HB_CHUNK; j++) {
-                if (i0 + j < L) {
-                    double r0, r2;
-                    int32_t e0, e2;
-                    norm3_ratios<SYM>(k, xc[j], r0, e0, r2, e2);
-                    if (i0 + j == 0)
-                        norm3_fwd_step<SYM, true>(c, k, f0, f1, f2, r0, e0, r2, e2);
-                    else
-                        norm3_fwd_step<SYM, false>(c, k, f0, f1, f2, r0, e0, r2, e2);
-                    double *s = sm + (int64_t)j * HB_NORM3_SLOT * sms;
-                    s[0] = f0;
-                    s[sms] = f1;
-                    s[2 * sms] = f2;
-                    s[3 * sms] = scale2(r0, e0);
-                    s[4 * sms] = scale2(r2, e2);
-                }
+            for (int j = 0; j < tail; j++) {
+                const double xv = xp[(int64_t)(nfull * HB_CHUNK + j) * ld];
+                norm3_replay_one<SYM>(c, s, xv, nfull == 0 && j == 0, m, j);
             }
         }
-#pragma unroll
-        for (int j = HB_CHUNK - 1; j >= 0; j--) {
-            const int64_t i = i0 + j;
-            if (i < L) {
-                if (VIT) {
-                    a.y[(t0 + i) * a.ldy + b] = (uint8_t)(ycur + 1);
-                    ycur = (int32_t)((pk >> (6 * j + 2 * ycur)) & 3u);
-                }
-                if (FB) {
-                    const double *s = sm + (int64_t)j * HB_NORM3_SLOT * sms;
-                    double g0 = s[0] * b0, g1 = s[sms] * b1, g2 = s[2 * sms] * b2;
-                    double rs = rcp_fast((g0 + g1) + g2);
-                    double *gp = a.gamma + (t0 + i) * a.ldg + b;
-                    const int64_t plane = a.T * a.ldg;
-                    gp[0] = g0 * rs;
-                    gp[plane] = g1 * rs;
-                    gp[2 * plane] = g2 * rs;
-                    norm3_bwd_step<SYM>(c, k, b0, b1, b2, eb, s[3 * sms], s[4 * sms]);
-                }
-            }
-        }
-        if (FB) {
-#pragma unroll
-            for (int j = 0; j < HB_CHUNK; j++) xc[j] = xn[j];
-        }
+        for (int j = tail - 1; j >= 0; j--)
+            norm3_backward_one<SYM, VIT, FB>(a, s, t0 + nfull * HB_CHUNK + j, b, pk, j, m);
     }
+    for (int32_t ch = nfull - 1; ch >= 0; ch--) {
+        const uint64_t pk = pk_nx;
+        if (FB && ch > 0) {
+            s.f0 = c0_nx;
+            s.f1 = c1_nx;
+            s.f2 = c2_nx;
+        }
+        if (ch > 0) {
+            if (VIT) pk_nx = psi[(int64_t)(ch - 1) * a.B];
+            if (FB && ch > 1) {
+                const double *ck = ckpt + (int64_t)(ch - 1) * 3 * a.B;
+                c0_nx = ck[0];
+                c1_nx = ck[a.B];
+                c2_nx = ck[2 * a.B];
+            }
+        }
+        if (FB) {
+            const double *xprev = xp + (int64_t)(ch - 1) * HB_CHUNK * ld;
+            const bool more = ch > 0;
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                xs_wait<1>(m);
+                HB_UNROLL_STEPS
+                for (int j = h * HB_HALF; j < (h + 1) * HB_HALF; j++) {
+                    const double xv = m.xs[j * m.st];
+                    if (more) xs_refill(m, j, xprev + (int64_t)j * ld);
+                    norm3_replay_one<SYM>(c, s, xv, j == 0 && ch == 0, m, j);
+                }
+                xs_commit(m);
+            }
+        }
+        const int64_t row0 = t0 + (int64_t)ch * HB_CHUNK;
+        HB_UNROLL_STEPS
+        for (int j = HB_CHUNK - 1; j >= 0; j--)
+            norm3_backward_one<SYM, VIT, FB>(a, s, row0 + j, b, pk, j, m);
+    }
+    xs_wait<0>(m);
 }
 
 } // namespace hb

@@ -73,6 +73,7 @@ int emul_norm3(const double *x, int64_t ld, int64_t T, int64_t B, const int64_t 
     a.c.lt = a.c.logPi[1];
     a.c.amt = Pi[0] - Pi[1];
     a.c.tt = Pi[1];
+    norm3_fill_k(a.c);
     int64_t nsd = sd_per_seg ? (int64_t)nseg * B : B;
     std::vector<double> inv(nsd), lg(nsd);
     for (int64_t i = 0; i < nsd; i++) {
@@ -81,7 +82,10 @@ int emul_norm3(const double *x, int64_t ld, int64_t T, int64_t B, const int64_t 
     }
     std::vector<uint64_t> psi((size_t)sg.nchunks * B);
     std::vector<double> ckpt((size_t)sg.nchunks * 3 * B);
-    std::vector<double> sm(HB_CHUNK * HB_NORM3_SLOT);
+    std::vector<double2> sva(HB_CHUNK), svb(HB_CHUNK);
+    std::vector<double> se2(HB_CHUNK), sxs(HB_CHUNK);
+    Norm3Smem sm;
+    sm.va = sva.data(); sm.vb = svb.data(); sm.e2 = se2.data(); sm.xs = sxs.data(); sm.st = 1;
     int32_t status = 0;
     a.x = x; a.ld = ld; a.T = T; a.B = B;
     a.seg_off = sg.off.data(); a.chunk_off = sg.chunk.data(); a.seg_order = sg.order.data();
@@ -93,14 +97,19 @@ int emul_norm3(const double *x, int64_t ld, int64_t T, int64_t B, const int64_t 
     for (int s = 0; s < nseg; s++)
         for (int64_t b = 0; b < B; b++) {
             int seg = sg.order[s];
+            const bool ll_on = a.ll != nullptr;
             if (sym) {
-                if (vit && fb) norm3_chain<true, true, true>(a, seg, b, sm.data(), 1);
-                else if (fb) norm3_chain<true, false, true>(a, seg, b, sm.data(), 1);
-                else norm3_chain<true, true, false>(a, seg, b, sm.data(), 1);
+                if (vit && fb && ll_on) norm3_chain<true, true, true, true>(a, seg, b, sm);
+                else if (vit && fb) norm3_chain<true, true, true, false>(a, seg, b, sm);
+                else if (fb && ll_on) norm3_chain<true, false, true, true>(a, seg, b, sm);
+                else if (fb) norm3_chain<true, false, true, false>(a, seg, b, sm);
+                else norm3_chain<true, true, false, false>(a, seg, b, sm);
             } else {
-                if (vit && fb) norm3_chain<false, true, true>(a, seg, b, sm.data(), 1);
-                else if (fb) norm3_chain<false, false, true>(a, seg, b, sm.data(), 1);
-                else norm3_chain<false, true, false>(a, seg, b, sm.data(), 1);
+                if (vit && fb && ll_on) norm3_chain<false, true, true, true>(a, seg, b, sm);
+                else if (vit && fb) norm3_chain<false, true, true, false>(a, seg, b, sm);
+                else if (fb && ll_on) norm3_chain<false, false, true, true>(a, seg, b, sm);
+                else if (fb) norm3_chain<false, false, true, false>(a, seg, b, sm);
+                else norm3_chain<false, true, false, false>(a, seg, b, sm);
             }
         }
     return status;

@@ -1,0 +1,31 @@
+"""norm3 V+FB timing for a list of library variants: python tools/probe_norm3.py lib1.so lib2.so ..."""
+import os, subprocess, sys
+if len(sys.argv) > 2 or (len(sys.argv) == 2 and not os.environ.get("HB_CHILD")):
+    for lib in sys.argv[1:]:
+        env = dict(os.environ, HB_B200_LIB=os.path.abspath(lib), HB_CHILD="1")
+        subprocess.run([sys.executable, __file__, lib], env=env)
+    sys.exit(0)
+import numpy as np, torch
+sys.path.insert(0, ".")
+from honeybadger_b200 import hmm, synth
+N, G = int(os.environ.get("HB_N", 10000)), int(os.environ.get("HB_G", 20000))
+dev = torch.device("cuda:0")
+g = torch.Generator(device=dev); g.manual_seed(2)
+x = torch.randn((G, N), dtype=torch.float64, device=dev, generator=g) * 2.5
+sd = hmm.chain_sd_dev(x)
+Pi, delta, mean = hmm.sym_Pi(3, 1e-6), [0., 1., 0.], [-synth.DEV, 0., synth.DEV]
+seg = synth.segments(G)
+out = hmm.hmm_norm_dev(x, sd, mean, Pi, delta, seg_off=seg, viterbi=True, gamma=True)
+res = []
+for mode, kw in (("V+FB", dict(viterbi=True, gamma=True)), ("FB", dict(viterbi=False, gamma=True)), ("V", dict(viterbi=True, gamma=False))):
+    fn = lambda: hmm.hmm_norm_dev(x, sd, mean, Pi, delta, seg_off=seg, out=out, **kw)
+    for _ in range(3): fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(7):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record(); torch.cuda.synchronize(); ts.append(a.elapsed_time(b))
+    ms = sorted(ts)[3]
+    res.append(f"{mode} {ms:.3f} ms {N*G/ms/1e6:.1f} G/s")
+hmm.status_dev()
+print(os.path.basename(sys.argv[1]), " | ".join(res), flush=True)
