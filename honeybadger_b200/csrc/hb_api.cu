@@ -741,42 +741,40 @@ int hb_pool_count_pos_dev(const int32_t *v, int64_t ld, int64_t G, int64_t N,
 }
 
 // ------------------------------------------------------------------ the four reference call sites
-int hb_gexp_pooled_viterbi_host(const double *gexp_norm, int64_t G, int64_t N,
-                                const uint8_t *member, int32_t K, const double *mean,
-                                const double *Pi, const double *delta, int32_t *y,
-                                double *pooled_x, double *pooled_sd)
+// One round of pooled chains on DEVICE-RESIDENT matrices: membership and the small results are
+// host buffers (K <= a few dozen chains), the [G x N] matrices never leave the GPU.
+int hb_gexp_pooled_viterbi_dev(const double *x, int64_t ld, int64_t G, int64_t N,
+                               const uint8_t *member, int32_t K, const double *mean,
+                               const double *Pi, const double *delta, int32_t *y, double *pooled_x,
+                               double *pooled_sd, void *stream)
 {
     std::lock_guard<std::mutex> lk(g_mu);
     Workspace *ws;
     HBTRY(cur_ws(&ws));
-    if (!gexp_norm || !member || !y || G < 2 || N < 1 || K < 1)
+    if (!x || !member || !y || G < 2 || N < 1 || K < 1 || ld < N)
         return fail(HB_ERR_ARG, "bad arguments");
-    cudaStream_t st = 0;
+    cudaStream_t st = (cudaStream_t)stream;
     std::vector<int32_t> sz;
     HBTRY(group_sizes(member, K, N, sz));
-    const int64_t ld = pad_ld(N), ldk = pad_ld(K);
-    HBTRY(ws->st_in.ensure((size_t)G * N * sizeof(double)));
-    HBTRY(ws->st_x.ensure((size_t)G * ld * sizeof(double)));
+    const int64_t ldk = pad_ld(K);
     HBTRY(ws->st_member.ensure((size_t)K * N));
     HBTRY(ws->gsize.ensure((size_t)K * sizeof(int32_t)));
-    HBTRY(ws->st_pool.ensure((size_t)K * G * sizeof(double)));  // [K][G]
+    HBTRY(ws->st_pool.ensure((size_t)K * G * sizeof(double)));    // [K][G]
     HBTRY(ws->st_pool2.ensure((size_t)G * ldk * sizeof(double))); // gene-major [G][ldk]
     HBTRY(ws->st_sd.ensure((size_t)K * sizeof(double)));
     HBTRY(ws->st_y.ensure((size_t)G * ldk));
     HBTRY(ws->st_out.ensure((size_t)G * K * sizeof(int32_t)));
-    CU(cudaMemcpyAsync(ws->st_in.p, gexp_norm, (size_t)G * N * sizeof(double), cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(ws->st_member.p, member, (size_t)K * N, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(ws->gsize.p, sz.data(), (size_t)K * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    CU(hb::launch_transpose_f64(ws->st_in.as<double>(), G, N, ws->st_x.as<double>(), ld, st));
-    CU(hb::launch_pool_mean(ws->st_x.as<double>(), ld, G, N, ws->st_member.as<uint8_t>(),
-                            ws->gsize.as<int32_t>(), K, ws->st_pool.as<double>(), st));
+    CU(hb::launch_pool_mean(x, ld, G, N, ws->st_member.as<uint8_t>(), ws->gsize.as<int32_t>(), K,
+                            ws->st_pool.as<double>(), st));
     CU(hb::launch_pooled_sd(ws->st_pool.as<double>(), G, K, ws->st_sd.as<double>(), st));
     // [K][G] row-major is column-major [G x K]: the same transpose as an R matrix upload
     CU(hb::launch_transpose_f64(ws->st_pool.as<double>(), G, K, ws->st_pool2.as<double>(), ldk, st));
-    // log(sd) must be the host libm's: bring the K scales back, finish them here
+    // log(sd) must be the host libm's (R evaluates it on the CPU): finish the K scales here
     std::vector<double> h_sd(K), h_aux(3 * (size_t)K);
     CU(cudaMemcpyAsync(h_sd.data(), ws->st_sd.p, (size_t)K * sizeof(double), cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
+    CU(cudaStreamSynchronize(st)); // also keeps `sz` alive until its copy is done
     for (int32_t k = 0; k < K; k++) {
         h_aux[k] = h_sd[k];
         h_aux[K + k] = 1.0 / h_sd[k];
@@ -798,22 +796,20 @@ int hb_gexp_pooled_viterbi_host(const double *gexp_norm, int64_t G, int64_t N,
     return read_status(ws, st);
 }
 
-int hb_allele_pooled_viterbi_host(const double *r_maf, const double *n_sc, int64_t G, int64_t N,
-                                  const uint8_t *member, int32_t K, const double *prob,
-                                  const double *Pi, const double *delta, int32_t *y, int32_t *mafl,
-                                  int32_t *sizel)
+int hb_allele_pooled_viterbi_dev(const int32_t *r_maf, const int32_t *n_sc, int64_t ld, int64_t G,
+                                 int64_t N, const uint8_t *member, int32_t K, const double *prob,
+                                 const double *Pi, const double *delta, int32_t *y, int32_t *mafl,
+                                 int32_t *sizel, void *stream)
 {
     std::lock_guard<std::mutex> lk(g_mu);
     Workspace *ws;
     HBTRY(cur_ws(&ws));
-    if (!r_maf || !n_sc || !member || !y || G < 2 || N < 1 || K < 1)
+    if (!r_maf || !n_sc || !member || !y || G < 2 || N < 1 || K < 1 || ld < N)
         return fail(HB_ERR_ARG, "bad arguments");
-    cudaStream_t st = 0;
+    cudaStream_t st = (cudaStream_t)stream;
     std::vector<int32_t> sz;
     HBTRY(group_sizes(member, K, N, sz));
-    const int64_t ld = (N + 31) / 32 * 32, ldk = (K + 31) / 32 * 32;
-    HBTRY(ws->st_in.ensure((size_t)G * N * sizeof(double)));
-    HBTRY(ws->st_x.ensure((size_t)G * ld * sizeof(int32_t)));
+    const int64_t ldk = (K + 31) / 32 * 32;
     HBTRY(ws->st_member.ensure((size_t)K * N));
     HBTRY(ws->cellmask.ensure((size_t)N * sizeof(uint32_t)));
     HBTRY(ws->st_pool.ensure((size_t)K * G * sizeof(int32_t) * 2));
@@ -823,15 +819,13 @@ int hb_allele_pooled_viterbi_host(const double *r_maf, const double *n_sc, int64
     CU(cudaMemcpyAsync(ws->st_member.p, member, (size_t)K * N, cudaMemcpyHostToDevice, st));
     int32_t *cnt[2] = {ws->st_pool.as<int32_t>(), ws->st_pool.as<int32_t>() + (int64_t)K * G};
     int32_t *gm[2] = {ws->st_pool2.as<int32_t>(), ws->st_pool2.as<int32_t>() + G * ldk};
-    const double *src[2] = {r_maf, n_sc};
+    const int32_t *src[2] = {r_maf, n_sc};
     for (int i = 0; i < 2; i++) {
-        CU(cudaMemcpyAsync(ws->st_in.p, src[i], (size_t)G * N * sizeof(double), cudaMemcpyHostToDevice, st));
-        CU(hb::launch_transpose_f64_i32(ws->st_in.as<double>(), G, N, ws->st_x.as<int32_t>(), ld, st));
         for (int32_t k0 = 0; k0 < K; k0 += 32) {
             const int32_t kn = std::min(32, K - k0);
             CU(hb::launch_build_cellmask(ws->st_member.as<uint8_t>() + (int64_t)k0 * N, N, kn,
                                          ws->cellmask.as<uint32_t>(), st));
-            CU(hb::launch_pool_count(ws->st_x.as<int32_t>(), ld, G, N, ws->cellmask.as<uint32_t>(), kn,
+            CU(hb::launch_pool_count(src[i], ld, G, N, ws->cellmask.as<uint32_t>(), kn,
                                      cnt[i] + (int64_t)k0 * G, st));
         }
         CU(hb::launch_transpose_i32(cnt[i], G, K, gm[i], ldk, st));
@@ -846,6 +840,56 @@ int hb_allele_pooled_viterbi_host(const double *r_maf, const double *n_sc, int64
     if (sizel)
         CU(cudaMemcpyAsync(sizel, cnt[1], (size_t)K * G * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     return read_status(ws, st);
+}
+
+// Host-buffer forms: upload the R matrices (column-major doubles), change layout, run the round.
+int hb_gexp_pooled_viterbi_host(const double *gexp_norm, int64_t G, int64_t N,
+                                const uint8_t *member, int32_t K, const double *mean,
+                                const double *Pi, const double *delta, int32_t *y,
+                                double *pooled_x, double *pooled_sd)
+{
+    if (!gexp_norm || G < 2 || N < 1) return fail(HB_ERR_ARG, "bad arguments");
+    const int64_t ld = pad_ld(N);
+    double *d_x = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        Workspace *ws;
+        HBTRY(cur_ws(&ws));
+        HBTRY(ws->st_in.ensure((size_t)G * N * sizeof(double)));
+        HBTRY(ws->st_x.ensure((size_t)G * ld * sizeof(double)));
+        CU(cudaMemcpyAsync(ws->st_in.p, gexp_norm, (size_t)G * N * sizeof(double),
+                           cudaMemcpyHostToDevice, 0));
+        CU(hb::launch_transpose_f64(ws->st_in.as<double>(), G, N, ws->st_x.as<double>(), ld, 0));
+        d_x = ws->st_x.as<double>();
+    }
+    return hb_gexp_pooled_viterbi_dev(d_x, ld, G, N, member, K, mean, Pi, delta, y, pooled_x,
+                                      pooled_sd, nullptr);
+}
+
+int hb_allele_pooled_viterbi_host(const double *r_maf, const double *n_sc, int64_t G, int64_t N,
+                                  const uint8_t *member, int32_t K, const double *prob,
+                                  const double *Pi, const double *delta, int32_t *y, int32_t *mafl,
+                                  int32_t *sizel)
+{
+    if (!r_maf || !n_sc || G < 2 || N < 1) return fail(HB_ERR_ARG, "bad arguments");
+    const int64_t ld = (N + 31) / 32 * 32;
+    int32_t *d_r = nullptr, *d_n = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        Workspace *ws;
+        HBTRY(cur_ws(&ws));
+        HBTRY(ws->st_in.ensure((size_t)G * N * sizeof(double)));
+        HBTRY(ws->st_x.ensure((size_t)G * ld * sizeof(int32_t)));
+        HBTRY(ws->st_x2.ensure((size_t)G * ld * sizeof(int32_t)));
+        CU(cudaMemcpyAsync(ws->st_in.p, r_maf, (size_t)G * N * sizeof(double), cudaMemcpyHostToDevice, 0));
+        CU(hb::launch_transpose_f64_i32(ws->st_in.as<double>(), G, N, ws->st_x.as<int32_t>(), ld, 0));
+        CU(cudaMemcpyAsync(ws->st_in.p, n_sc, (size_t)G * N * sizeof(double), cudaMemcpyHostToDevice, 0));
+        CU(hb::launch_transpose_f64_i32(ws->st_in.as<double>(), G, N, ws->st_x2.as<int32_t>(), ld, 0));
+        d_r = ws->st_x.as<int32_t>();
+        d_n = ws->st_x2.as<int32_t>();
+    }
+    return hb_allele_pooled_viterbi_dev(d_r, d_n, ld, G, N, member, K, prob, Pi, delta, y, mafl,
+                                        sizel, nullptr);
 }
 
 } // extern "C"

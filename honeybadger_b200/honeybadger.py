@@ -1,0 +1,611 @@
+"""Host-side mirror of HoneyBADGER's interface for the HMM segmentation path.
+
+Same names, argument meaning, defaults and quirks as the reference for
+
+    HoneyBADGER$calcGexpCnvBoundaries   R/HoneyBADGER.R:1091-1316   (recursive, stateful)
+    HoneyBADGER$calcAlleleCnvBoundaries R/HoneyBADGER.R:1336-1578
+    calcGexpCnvBoundaries               R/HoneyBADGER_gexp.R:462-584  (one round, stateless)
+    calcAlleleCnvBoundaries             R/HoneyBADGER_allele.R:543-651
+
+The matrices are uploaded once (gene-major, fp64 / int32) and stay on the GPU; each recursion
+level sends only the candidate cell sets (a [K x N] 0/1 membership) and gets back the K Viterbi
+paths.  Pooling (R `mean`/`sd`/`rowSums(.>0)` semantics), emissions and the Viterbi recursion run
+in libhb_b200.so; what stays in Python is the bookkeeping the reference does with names, votes and
+runs (vectorised here; the literal loops live in oracle/pyref.py for the tests).
+
+Outside the path (SURVEY.md §8f "next" rows), supplied as replaceable hooks:
+  * grouping — `dist` + `hclust(ward.D2)` + `cutree` on the windowed matrix (R/HoneyBADGER.R:1125-1136):
+    `ward_groups` below does it on the host with scipy; group labels are an INPUT of the path.
+  * retest   — the JAGS posteriors (`calcGexpCnvProb`, `calcAlleleCnvProb`): `retest_gexp_closed_form`
+    (exact marginal of inst/bug/expressionModel.bug) and a binomial likelihood-ratio
+    stand-in for the allele model; both on the device with torch ops, neither parity-pinned.
+R matrices with dimnames are pandas DataFrames here (index = gene / SNP names, columns = cells).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+import pandas as pd
+
+from . import _lib
+from .hmm import sym_Pi
+
+CHRS_DEFAULT = ["chr%d" % i for i in range(1, 23)]
+
+
+# --------------------------------------------------------------------------- GRanges stand-in
+@dataclass
+class GRanges:
+    """The slice of GenomicRanges::GRanges this path touches: names -> (seqnames, start, end)."""
+    seqnames: np.ndarray
+    start: np.ndarray
+    end: np.ndarray
+    names: list
+
+    def __post_init__(self):
+        self.seqnames = np.asarray(self.seqnames, dtype=object)
+        self.start = np.asarray(self.start, dtype=np.float64)
+        self.end = np.asarray(self.end, dtype=np.float64)
+        self.names = list(self.names)
+        self._ix = {n: i for i, n in enumerate(self.names)}
+
+    def __getitem__(self, names):
+        idx = [self._ix[n] for n in names]
+        return GRanges(self.seqnames[idx], self.start[idx], self.end[idx], [self.names[i] for i in idx])
+
+    def range(self):
+        """range(gr): one (seqname, min start, max end) per chromosome present, in first-seen order."""
+        out, seen = [], []
+        for s in self.seqnames:
+            if s not in seen:
+                seen.append(s)
+        for s in seen:
+            m = self.seqnames == s
+            out.append((s, float(self.start[m].min()), float(self.end[m].max())))
+        return out
+
+
+def snps_from_names(names) -> GRanges:
+    """R/HoneyBADGER.R:598-608: 'chr:pos' / 'chr:start-end' row names -> GRanges ('chr' prefixed)."""
+    chrom, st, en = [], [], []
+    for n in names:
+        parts = str(n).replace("-", ":").replace(" ", ":").split(":")
+        c = parts[0] if parts[0].startswith("chr") else "chr" + parts[0]
+        chrom.append(c)
+        st.append(float(parts[1]))
+        en.append(float(parts[2]) if len(parts) > 2 else float(parts[1]))
+    return GRanges(chrom, st, en, list(names))
+
+
+def _as_frame(m, prefix_r="g", prefix_c="cell") -> pd.DataFrame:
+    if isinstance(m, pd.DataFrame):
+        return m
+    a = np.asarray(m, dtype=np.float64)
+    return pd.DataFrame(a, index=[f"{prefix_r}{i + 1}" for i in range(a.shape[0])],
+                        columns=[f"{prefix_c}{i + 1}" for i in range(a.shape[1])])
+
+
+# --------------------------------------------------------------------------- hooks outside the path
+def runmean(mat: np.ndarray, k: int) -> np.ndarray:
+    """caTools::runmean(x, k) along rows of each column: centred window, shrinking at the ends,
+    non-finite values skipped (alg="C", endrule="mean")."""
+    G = mat.shape[0]
+    ok = np.isfinite(mat)
+    v = np.where(ok, mat, 0.0)
+    zero = np.zeros((1,) + mat.shape[1:])
+    cs = np.vstack([zero, np.cumsum(v, 0)])
+    cn = np.vstack([zero, np.cumsum(ok, 0)])
+    h = k // 2
+    lo = np.clip(np.arange(G) - h, 0, G)
+    hi = np.clip(np.arange(G) + h + 1, 0, G)
+    with np.errstate(all="ignore"):
+        return (cs[hi] - cs[lo]) / (cn[hi] - cn[lo])
+
+
+def ward_groups(mat_smooth: np.ndarray, heights) -> list:
+    """cutree(hclust(dist(t(mat.smooth)), "ward.D2"), k=h) for each h; clusters numbered by first
+    appearance in cell order (so group 1 always holds the first cell)."""
+    from scipy.cluster.hierarchy import cut_tree, linkage
+    X = np.nan_to_num(mat_smooth.T, nan=0.0, posinf=0.0, neginf=0.0)
+    N = X.shape[0]
+    if N == 1:
+        return [np.ones(1, dtype=np.int32) for _ in heights]
+    Z = linkage(X, method="ward")
+    out = []
+    for h in heights:
+        lab = cut_tree(Z, n_clusters=int(h))[:, 0]
+        remap, res = {}, np.zeros(N, dtype=np.int32)
+        for i, v in enumerate(lab):
+            res[i] = remap.setdefault(v, len(remap) + 1)
+        out.append(res)
+    return out
+
+
+def retest_gexp_closed_form(gexp_rows, mag0, sigma0=None):
+    """(P(amp), P(del)) per cell for one candidate region: the exact marginal posterior of
+    inst/bug/expressionModel.bug.  JAGS' dnorm takes a PRECISION and the reference
+    passes sigma0 there (expressionModel.bug:8) — kept.  torch ops on the device; statistical
+    stand-in for the MCMC of calcGexpCnvProb (R/HoneyBADGER.R:374-470), not parity-pinned."""
+    import torch
+    x = gexp_rows if torch.is_tensor(gexp_rows) else \
+        torch.as_tensor(np.asarray(gexp_rows, dtype=np.float64), device="cuda")
+    n = x.shape[1]
+    if sigma0 is None:
+        sigma0 = torch.ones(n, dtype=torch.float64, device=x.device)
+    prec = torch.as_tensor(sigma0, dtype=torch.float64, device=x.device)
+
+    def ll(mu):
+        return (0.5 * torch.log(prec / (2 * np.pi)) - 0.5 * prec * (x - mu) ** 2).sum(0)
+
+    l0, lp, lm = ll(0.0), ll(mag0), ll(-mag0)
+    lse = torch.logaddexp
+    Lamp, Ldel = lse(l0, lp) + np.log(0.5), lse(l0, lm) + np.log(0.5)
+    post_dd1 = torch.sigmoid(Lamp.sum() - Ldel.sum())
+    w_amp = torch.exp(lp + np.log(0.5) - Lamp)
+    w_del = torch.exp(lm + np.log(0.5) - Ldel)
+    return (post_dd1 * w_amp).cpu().numpy(), ((1 - post_dd1) * w_del).cpu().numpy()
+
+
+def retest_allele_lr(r_rows, n_rows, pd_=0.1, pn=0.45):
+    """P(deletion) per cell for one candidate region from the binomial likelihood ratio pooled over
+    the region's SNPs (equal priors).  Stand-in for calcAlleleCnvProb's JAGS snpModel
+    (R/HoneyBADGER.R:907-1042), not parity-pinned."""
+    import torch
+    r = (r_rows if torch.is_tensor(r_rows) else torch.as_tensor(np.asarray(r_rows), device="cuda")).double()
+    n = (n_rows if torch.is_tensor(n_rows) else torch.as_tensor(np.asarray(n_rows), device="cuda")).double()
+    ld = (r * np.log(pd_) + (n - r) * np.log(1 - pd_)).sum(0)
+    ln = (r * np.log(pn) + (n - r) * np.log(1 - pn)).sum(0)
+    return torch.sigmoid(ld - ln).cpu().numpy()
+
+
+# --------------------------------------------------------------------------- vote -> runs -> trim
+def _round_half_even(v: float) -> int:
+    return int(round(v))
+
+
+def runs_from_vote(vote, min_num: int, trim: float | None):
+    """R/HoneyBADGER.R:1178-1210 (+ trim :1476, _gexp.R:568, _allele.R:642), vectorised.
+
+    Returns a list of index arrays (one per surviving run, genomic order) or None.  The first
+    element of every run of voted positions is NOT part of the run (the reference's loop starts
+    labelling at the second element); runs are kept when the labelled count >= min_num; `trim`
+    keeps names[1:round(L - L*trim)] (half-even rounding, trailing end only).
+    """
+    vote = np.asarray(vote)
+    if vote.size == 0 or vote.max() == 0:
+        return None
+    v = vote > 0
+    lab = np.zeros(v.size, dtype=bool)
+    lab[1:] = v[1:] & v[:-1]
+    if not lab.any():
+        return None
+    d = np.diff(np.concatenate([[0], lab.view(np.int8), [0]]))
+    starts, ends = np.nonzero(d == 1)[0], np.nonzero(d == -1)[0]
+    out = []
+    for a, b in zip(starts, ends):
+        L = b - a
+        if L < min_num:
+            continue
+        idx = np.arange(a, b)
+        if trim is not None:
+            r = _round_half_even(L - L * trim)
+            if r < 0:
+                raise IndexError("only 0's may be mixed with negative subscripts")
+            idx = idx[:max(r, 1)]  # R: x[1:0] is x[c(1, 0)] = x[1]
+        out.append(idx)
+    return out or None
+
+
+def group_members(labels):
+    """[(group id, member index array)] in `unique(ct)` order (first appearance)."""
+    labels = np.asarray(labels)
+    _, first = np.unique(labels, return_index=True)
+    order = labels[np.sort(first)]
+    return [(g, np.nonzero(labels == g)[0]) for g in order]
+
+
+def _membership(labels_per_height, N):
+    """Stack the cell sets with > 1 member over (height, group) -> uint8 [K, N] + (h, g index)."""
+    rows, tags = [], []
+    for h, labels in enumerate(labels_per_height):
+        for gi, (_, cells) in enumerate(group_members(labels)):
+            if cells.size > 1:
+                m = np.zeros(N, dtype=np.uint8)
+                m[cells] = 1
+                rows.append(m)
+                tags.append((h, gi))
+    return (np.stack(rows) if rows else np.zeros((0, N), np.uint8)), tags
+
+
+# --------------------------------------------------------------------------- device rounds
+def _vp(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _stream():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def gexp_round_dev(x_dev, member, mean, t):
+    """K pooled 3-state chains on a resident gene-major fp64 tensor: (y int32 [K,G], x [K,G], sd [K])."""
+    lib = _lib.load()
+    G, N = x_dev.shape
+    member = np.ascontiguousarray(member, dtype=np.uint8)
+    K = member.shape[0]
+    y = np.zeros((K, G), dtype=np.int32)
+    px = np.zeros((K, G), dtype=np.float64)
+    psd = np.zeros(K, dtype=np.float64)
+    Pi, delta = sym_Pi(3, t), np.array([0.0, 1.0, 0.0])
+    mean = np.ascontiguousarray(mean, dtype=np.float64)
+    _lib.check(lib.hb_gexp_pooled_viterbi_dev(x_dev.data_ptr(), x_dev.stride(0), G, N, _vp(member), K,
+                                              _vp(mean), _vp(Pi), _vp(delta), _vp(y), _vp(px),
+                                              _vp(psd), _stream()))
+    return y, px, psd
+
+
+def allele_round_dev(r_dev, n_dev, member, pd_, pn, t):
+    """K pooled 2-state chains on resident gene-major int32 tensors: (y [K,G], mafl, sizel)."""
+    lib = _lib.load()
+    G, N = r_dev.shape
+    member = np.ascontiguousarray(member, dtype=np.uint8)
+    K = member.shape[0]
+    y = np.zeros((K, G), dtype=np.int32)
+    mafl = np.zeros((K, G), dtype=np.int32)
+    sizel = np.zeros((K, G), dtype=np.int32)
+    Pi, delta, prob = sym_Pi(2, t), np.array([0.0, 1.0]), np.array([pd_, pn], dtype=np.float64)
+    _lib.check(lib.hb_allele_pooled_viterbi_dev(r_dev.data_ptr(), n_dev.data_ptr(), r_dev.stride(0), G,
+                                                N, _vp(member), K, _vp(prob), _vp(Pi), _vp(delta),
+                                                _vp(y), _vp(mafl), _vp(sizel), _stream()))
+    return y, mafl, sizel
+
+
+def _to_dev_f64(a):
+    import torch
+    return torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64), device="cuda")
+
+
+def _to_dev_i32(a):
+    import torch
+    return torch.as_tensor(np.ascontiguousarray(np.rint(a), dtype=np.int32), device="cuda")
+
+
+# --------------------------------------------------------------------------- ordering (a1)
+def order_genes(rownames, genes: GRanges, chrs, has_na=None):
+    """R/HoneyBADGER.R:1114-1121: per chromosome (in `chrs` order) sort by (start+end)/2 (stable),
+    drop rows with NA, concatenate.  Returns positions into `rownames`."""
+    g = genes[rownames]
+    mid = (g.start + g.end) / 2
+    keep = np.ones(len(rownames), dtype=bool) if has_na is None else ~np.asarray(has_na)
+    out = []
+    for c in chrs:
+        ii = np.nonzero(g.seqnames == c)[0]
+        if ii.size == 0:
+            continue
+        ii = ii[np.argsort(mid[ii], kind="stable")]
+        out.append(ii[keep[ii]])
+    return np.concatenate(out) if out else np.zeros(0, dtype=np.int64)
+
+
+# --------------------------------------------------------------------------- stateless functions
+def calcGexpCnvBoundaries(gexp_norm, genes: GRanges, m=0.15, chrs=None, min_traverse=3, t=1e-6,
+                          min_num_genes=3, trim=0.1, verbose=False, grouping=None):
+    """R/HoneyBADGER_gexp.R:462-584.  Returns dict(amp=dict(info, regions) | None, del=...)."""
+    chrs = CHRS_DEFAULT if chrs is None else list(chrs)
+    df = _as_frame(gexp_norm)
+    ordr = order_genes(list(df.index), genes, chrs, has_na=df.isna().any(axis=1).values)
+    df = df.iloc[ordr]
+    mat = df.values
+    names = np.asarray(df.index, dtype=object)
+    G, N = mat.shape
+    heights = list(range(1, min(min_traverse, N) + 1))
+    labels = (grouping or (lambda M, hs: ward_groups(runmean(M, 101), hs)))(mat, heights)
+    member, _ = _membership(labels, N)
+    x_dev = _to_dev_f64(mat)
+    votes = {"amp": np.zeros(G, np.int64), "del": np.zeros(G, np.int64)}
+    if member.shape[0]:
+        y, _, _ = gexp_round_dev(x_dev, member, [-m, 0.0, m], t)
+        votes["amp"] = (y == 3).sum(0)
+        votes["del"] = (y == 1).sum(0)
+
+    def tbv(vote):
+        if verbose:
+            print(f"max vote:{vote.max()}")
+        runs = runs_from_vote(vote, min_num_genes, trim)
+        if runs is None:
+            return None
+        info = [list(names[i]) for i in runs]
+        regions = [r for bs in info for r in genes[bs].range()]
+        return {"info": info, "regions": regions}
+
+    return {"amp": tbv(votes["amp"]), "del": tbv(votes["del"])}
+
+
+def calcAlleleCnvBoundaries(r_maf, n_sc, l_maf=None, n_bulk=None, snps: GRanges | None = None,
+                            geneFactor=None, min_traverse=3, t=1e-6, pd=0.1, pn=0.45,
+                            min_num_snps=5, trim=0.1, verbose=False, grouping=None):
+    """R/HoneyBADGER_allele.R:543-651.  Only the first group of each height votes (:594-596)."""
+    rdf, ndf = _as_frame(r_maf, "snp"), _as_frame(n_sc, "snp")
+    names = np.asarray(rdf.index, dtype=object)
+    snps = snps if snps is not None else snps_from_names(names)
+    r, n = rdf.values, ndf.values
+    G, N = r.shape
+    heights = list(range(1, min(min_traverse, N) + 1))
+    if grouping is None:
+        with np.errstate(all="ignore"):
+            labels = ward_groups(runmean(r / n, 31), heights)
+    else:
+        labels = grouping(r, n, heights)
+    member, tags = _membership(labels, N)
+    vote = np.zeros(G, np.int64)
+    if member.shape[0]:
+        y, _, _ = allele_round_dev(_to_dev_i32(r), _to_dev_i32(n), member, pd, pn, t)
+        for k, (_, gi) in enumerate(tags):
+            if gi == 0:
+                vote += y[k] == 1
+    if verbose:
+        print(f"max vote:{vote.max()}")
+    runs = runs_from_vote(vote, min_num_snps, trim)
+    if runs is None:
+        return None
+    info = [list(names[i]) for i in runs]
+    return {"info": info, "regions": [rg for bs in info for rg in snps[bs].range()]}
+
+
+# --------------------------------------------------------------------------- RefClass mirror
+class HoneyBADGER:
+    """setRefClass("HoneyBADGER", ...) (R/HoneyBADGER.R:30-94): the fields and methods on the
+    segmentation path.  Matrices live on the GPU after set*Mats; recursion passes index sets."""
+
+    def __init__(self, name=None):
+        self.name = name
+        self.gexp_norm = None
+        self.genes = None
+        self.dev = None
+        self.mvFit = None
+        self.r_maf = self.n_sc = self.l_maf = self.n_bulk = self.snps = None
+        self.pred_genes_r = self.pred_snps_r = None
+        self.bound_genes_old = None
+        self.bound_genes_final = None
+        self.bound_snps_old = None
+        self.bound_snps_final = None
+        self.grouping_gexp = lambda M, hs: ward_groups(runmean(M, 101), hs)
+        self.grouping_allele = None
+        self.retest_gexp = retest_gexp_closed_form
+        self.retest_allele = retest_allele_lr
+        self._x_dev = self._r_dev = self._n_dev = None
+
+    # ---- inputs (kept as the reference defines them; R/HoneyBADGER.R:123-188, :485-614)
+    def setGexpMats(self, gexp_sc_init, gexp_ref_init, genes: GRanges, filter=True, minMeanBoth=0,
+                    minMeanTest=None, minMeanRef=None, scale=True, verbose=True):
+        """`genes` replaces the biomaRt lookup (mart.obj needs the network)."""
+        sc = _as_frame(gexp_sc_init)
+        ref = gexp_ref_init if isinstance(gexp_ref_init, pd.DataFrame) else \
+            pd.DataFrame(np.asarray(gexp_ref_init, dtype=np.float64).reshape(len(sc.index), -1),
+                         index=getattr(gexp_ref_init, "index", sc.index))
+        vi = [g for g in sc.index if g in set(ref.index)]
+        sc, ref = sc.loc[vi], ref.loc[vi]
+        if filter:
+            mt = sc.values[sc.values != 0].mean() if minMeanTest is None else minMeanTest
+            mr = ref.values[ref.values != 0].mean() if minMeanRef is None else minMeanRef
+            ms, mf = sc.mean(axis=1), ref.mean(axis=1)
+            keep = ((ms > minMeanBoth) & (mf > minMeanBoth)) | (ms > mt) | (mf > mr)
+            if verbose:
+                print(f"{int(keep.sum())} genes passed filtering ... ")
+            sc, ref = sc[keep], ref[keep]
+        if scale:
+            sc = (sc - sc.mean(axis=0)) / sc.std(axis=0, ddof=1)
+            ref = (ref - ref.mean(axis=0)) / ref.std(axis=0, ddof=1)
+        if verbose:
+            print(f"Normalizing gene expression for {sc.shape[0]} genes and {sc.shape[1]} cells ... ")
+        norm = sc.sub(ref.mean(axis=1), axis=0)
+        gvi = [g for g in norm.index if g in genes._ix]
+        self.genes = genes[gvi]
+        self.gexp_norm = norm.loc[gvi]
+        self._x_dev = None
+
+    def setGexpDev(self, dev=None, alpha=0.05, n=100, seed=0, verbose=False):
+        """R/HoneyBADGER.R:1054-1077 draws from R's RNG (ks.test of rnorm samples); the value is an
+        input here (the vignette's is 1.015658, docs/Getting_Started.md:108)."""
+        if dev is None:
+            raise NotImplementedError("setGexpDev needs R's RNG stream; pass dev= explicitly")
+        self.dev = float(dev)
+        if verbose:
+            print(f"Optimal deviance: {self.dev}")
+
+    def setAlleleMats(self, r_init, n_sc_init, l_init=None, n_bulk_init=None, filter=True,
+                      het_deviance_threshold=0.05, min_cell=3, verbose=True):
+        r, n = _as_frame(r_init, "snp"), _as_frame(n_sc_init, "snp")
+        if l_init is None or n_bulk_init is None:
+            l = (r.values > 0).sum(1).astype(np.float64)
+            nb = (n.values > 0).sum(1).astype(np.float64)
+        else:
+            l, nb = np.asarray(l_init, dtype=np.float64), np.asarray(n_bulk_init, dtype=np.float64)
+        if filter:
+            with np.errstate(all="ignore"):
+                E = l / nb
+            vi = (E > het_deviance_threshold) & (E < 1 - het_deviance_threshold)
+            r, n, l, nb = r[vi], n[vi], l[vi], nb[vi]
+            vi2 = (n.values > 0).sum(1) >= min_cell
+            print(f"{len(vi2)} heterozygous SNPs identified ")  # the reference prints length(vi)
+            r, n, l, nb = r[vi2], n[vi2], l[vi2], nb[vi2]
+        with np.errstate(all="ignore"):
+            E = l / nb
+        flip = E > 0.5
+        self.r_maf = pd.DataFrame(np.where(flip[:, None], n.values - r.values, r.values),
+                                  index=r.index, columns=r.columns)
+        self.n_sc = n
+        self.l_maf = np.where(flip, nb - l, l)
+        self.n_bulk = nb
+        self.snps = snps_from_names(r.index)
+        self._r_dev = self._n_dev = None
+
+    # ---- device residency: full matrices are uploaded once; every level gathers rows / columns there
+    def _resident(self, kind):
+        import torch
+        if kind == "gexp":
+            if self._x_dev is None:
+                self._x_dev = (_to_dev_f64(self.gexp_norm.values),
+                               {g: i for i, g in enumerate(self.gexp_norm.index)},
+                               {c: i for i, c in enumerate(self.gexp_norm.columns)})
+            return self._x_dev
+        if self._r_dev is None:
+            self._r_dev = (_to_dev_i32(self.r_maf.values), _to_dev_i32(self.n_sc.values),
+                           {g: i for i, g in enumerate(self.r_maf.index)},
+                           {c: i for i, c in enumerate(self.r_maf.columns)})
+        return self._r_dev
+
+    @staticmethod
+    def _gather(full, rix, cix, rows, cols):
+        """full[rows, cols] on the device, or None when a name is not resident (user sub-matrix)."""
+        import torch
+        try:
+            ri = torch.as_tensor([rix[r] for r in rows], device=full.device)
+            ci = torch.as_tensor([cix[c] for c in cols], device=full.device)
+        except KeyError:
+            return None
+        return full.index_select(0, ri).index_select(1, ci).contiguous()
+
+    # ---- expression boundaries (R/HoneyBADGER.R:1091-1316)
+    def calcGexpCnvBoundaries(self, gexp_norm_sub=None, chrs=None, min_traverse=5, min_num_genes=10,
+                              t=1e-6, init=False, verbose=False, **retest_kw):
+        chrs = CHRS_DEFAULT if chrs is None else list(chrs)
+        gexp = self.gexp_norm if gexp_norm_sub is None else gexp_norm_sub
+        if init:
+            self.pred_genes_r = pd.DataFrame(0.0, index=gexp.index, columns=gexp.columns)
+            self.bound_genes_old = []
+            self.bound_genes_final = []
+        if self.bound_genes_final is None:
+            print("ERROR! USE init=TRUE! ")
+            return None
+        old = set(self.bound_genes_old)
+        gexp = gexp[[g not in old for g in gexp.index]]
+        ordr = order_genes(list(gexp.index), self.genes, chrs, has_na=gexp.isna().any(axis=1).values)
+        gexp = gexp.iloc[ordr]
+        names = np.asarray(gexp.index, dtype=object)
+        mat = gexp.values
+        G, N = mat.shape
+        heights = list(range(1, min(min_traverse, N) + 1))
+        labels = self.grouping_gexp(mat, heights)
+        member, _ = _membership(labels, N)
+        x_dev = None
+        if self.gexp_norm is not None:
+            full, rix, cix = self._resident("gexp")
+            x_dev = self._gather(full, rix, cix, names, gexp.columns)
+        if x_dev is None:
+            x_dev = _to_dev_f64(mat)
+        amp_v, del_v = np.zeros(G, np.int64), np.zeros(G, np.int64)
+        if member.shape[0]:
+            y, _, _ = gexp_round_dev(x_dev, member, [-self.dev, 0.0, self.dev], t)
+            amp_v, del_v = (y == 3).sum(0), (y == 1).sum(0)
+
+        def tbv(vote, which):
+            # `vote[bound.genes.old] <- 0` only appends zero entries: the old rows are gone already
+            if verbose:
+                print(f"max vote:{vote.max()}")
+            runs = runs_from_vote(vote, min_num_genes, None)  # the method does not trim
+            if runs is None:
+                return []
+            out = []
+            for idx in runs:
+                ap, dp = self.retest_gexp(x_dev[idx], self.dev, **retest_kw)
+                out.append({"ap": ap, "dp": dp, "bs": list(names[idx])})
+            return out
+
+        amp_info, del_info = tbv(amp_v, "amp"), tbv(del_v, "del")
+        rows = [d["dp"] for d in del_info] + [a["ap"] for a in amp_info]
+        lists = [d["bs"] for d in del_info] + [a["bs"] for a in amp_info]
+        if not rows:
+            return None
+        prob = np.vstack(rows)
+        dps = (prob > 0.75).sum(1)  # rowSums(prob.bin, na.rm=TRUE): only the 1s count
+        dpsi = int(np.nonzero(dps == dps.max())[0][0])
+        prob_fin, bound_new = prob[dpsi], lists[dpsi]
+        cells = np.asarray(gexp.columns, dtype=object)
+        g1, g2 = list(cells[prob_fin > 0.75]), list(cells[prob_fin <= 0.25])
+        if g1:
+            self.pred_genes_r.loc[bound_new, g1] = 1
+            self.bound_genes_final.append([bound_new])
+        self.bound_genes_old = list(dict.fromkeys(bound_new + self.bound_genes_old))
+        for g in (g1, g2):  # the recursive calls use the DEFAULT arguments (R/HoneyBADGER.R:1304)
+            if len(g) >= 3:
+                try:
+                    self.calcGexpCnvBoundaries(gexp_norm_sub=gexp[g])
+                except Exception as e:  # tryCatch(..., error = function(e) cat(...))
+                    print(f"ERROR: {e}")
+        return None
+
+    # ---- allele boundaries (R/HoneyBADGER.R:1336-1578)
+    def calcAlleleCnvBoundaries(self, r_sub=None, n_sc_sub=None, l_sub=None, n_bulk_sub=None,
+                                min_traverse=3, t=1e-6, pd=0.1, pn=0.45, min_num_snps=5, trim=0.1,
+                                init=False, verbose=False, **retest_kw):
+        r_maf = self.r_maf if r_sub is None else r_sub
+        n_sc = self.n_sc if n_sc_sub is None else n_sc_sub
+        if init:
+            self.pred_snps_r = pandas_zeros_like(r_maf)
+            self.bound_snps_old = []
+            self.bound_snps_final = []
+        if self.bound_snps_final is None:
+            print("ERROR! USE init=TRUE! ")
+            return None
+        old = set(self.bound_snps_old)
+        vi = np.array([s not in old for s in r_maf.index])
+        r_maf, n_sc = r_maf[vi], n_sc[vi]
+        names = np.asarray(r_maf.index, dtype=object)
+        r, n = r_maf.values, n_sc.values
+        G, N = r.shape
+        heights = list(range(1, min(min_traverse, N) + 1))
+        if self.grouping_allele is None:
+            with np.errstate(all="ignore"):
+                labels = ward_groups(runmean(r / n, 31), heights)
+        else:
+            labels = self.grouping_allele(r, n, heights)
+        member, tags = _membership(labels, N)
+        r_dev = n_dev = None
+        if self.r_maf is not None:
+            rfull, nfull, rix, cix = self._resident("allele")
+            r_dev = self._gather(rfull, rix, cix, names, r_maf.columns)
+            n_dev = self._gather(nfull, rix, cix, names, r_maf.columns)
+        if r_dev is None:
+            r_dev, n_dev = _to_dev_i32(r), _to_dev_i32(n)
+        vote = np.zeros(G, np.int64)
+        if member.shape[0]:
+            y, _, _ = allele_round_dev(r_dev, n_dev, member, pd, pn, t)
+            for k, (_, gi) in enumerate(tags):
+                if gi == 0:  # vote[b[[1]]]: only the first group of each height (:1424-1426)
+                    vote += y[k] == 1
+        if verbose:
+            print(f"max vote:{vote.max()}")
+        runs = runs_from_vote(vote, min_num_snps, trim)
+        if runs is None:
+            return None
+        probs = [self.retest_allele(r_dev[idx], n_dev[idx], pd, pn, **retest_kw) for idx in runs]
+        lists = [list(names[idx]) for idx in runs]
+        prob = np.vstack(probs)
+        if len(runs) > 1:
+            dps = (prob > 0.75).sum(1)
+            dpsi = int(np.nonzero(dps == dps.max())[0][0])
+            prob_fin, bound_new = prob[dpsi], lists[dpsi]
+        else:
+            prob_fin, bound_new = prob[0], lists[0]
+        cells = np.asarray(r_maf.columns, dtype=object)
+        g1, g2 = list(cells[prob_fin > 0.75]), list(cells[prob_fin <= 0.25])
+        if g1:
+            self.pred_snps_r.loc[bound_new, g1] = 1
+            self.bound_snps_final.append([bound_new])
+        self.bound_snps_old = list(dict.fromkeys(bound_new + self.bound_snps_old))
+        for g in (g1, g2):
+            if len(g) >= 3:
+                try:
+                    self.calcAlleleCnvBoundaries(
+                        r_sub=r_maf[g], n_sc_sub=n_sc[g],
+                        l_sub=(r_maf[g].values > 0).sum(1), n_bulk_sub=(n_sc[g].values > 0).sum(1))
+                except Exception as e:
+                    print(f"ERROR: {e}")
+        return None
+
+
+def pandas_zeros_like(df: pd.DataFrame) -> pd.DataFrame:
+    return pd.DataFrame(0.0, index=df.index, columns=df.columns)

@@ -128,6 +128,22 @@ int hb_pooled_sd_dev(const double *pooled /* device [K][G] */, int64_t G, int32_
 int hb_pool_count_pos_dev(const int32_t *v, int64_t ld, int64_t G, int64_t N,
                           const uint8_t *member, int32_t K, int32_t *out, void *stream);
 
+/* One recursion round of the split-and-retest driver on DEVICE-RESIDENT matrices (gene-major,
+ * uploaded once): `member` [K][N] (0/1, host) names the K candidate cell sets of the round, the
+ * small results come back to host buffers: y [K][G] (1-based states), pooled vectors and their sd.
+ * The [G x N] matrices never leave the GPU between rounds.  Replaces the `lapply(heights, ...)`
+ * bodies at R/HoneyBADGER.R:1135-1161 and :1395-1417. */
+int hb_gexp_pooled_viterbi_dev(const double *x /* device x[g*ld+c] */, int64_t ld, int64_t G,
+                               int64_t N, const uint8_t *member /* host */, int32_t K,
+                               const double *mean, const double *Pi, const double *delta,
+                               int32_t *y /* host [K][G] */, double *pooled_x /* host or NULL */,
+                               double *pooled_sd /* host [K] or NULL */, void *stream);
+int hb_allele_pooled_viterbi_dev(const int32_t *r_maf /* device */, const int32_t *n_sc, int64_t ld,
+                                 int64_t G, int64_t N, const uint8_t *member /* host */, int32_t K,
+                                 const double *prob, const double *Pi, const double *delta,
+                                 int32_t *y /* host [K][G] */, int32_t *mafl /* host or NULL */,
+                                 int32_t *sizel /* host or NULL */, void *stream);
+
 /* Host-buffer convenience for the four reference call sites (K pooled chains of one round):
  * gexp_norm column-major [G x N]; member[K][N] (0/1).  Outputs y[K][G] (1-based), pooled x and sd. */
 int hb_gexp_pooled_viterbi_host(const double *gexp_norm, int64_t G, int64_t N,

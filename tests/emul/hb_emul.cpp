@@ -192,7 +192,9 @@ void emul_exp_pair(double u, double *ep, double *em)
 {
     double Pp, Pm;
     int32_t n;
-    exp_pair(u, Pp, Pm, n);
+    Norm3Const c;
+    norm3_fill_k(c);
+    norm3_exp_pair(c, u, Pp, Pm, n); // the kernel's exp(u), exp(-u)
     *ep = ldexp(Pp, n);
     *em = ldexp(Pm, -n);
 }

@@ -1,0 +1,163 @@
+"""GPU parity of the pooled (reference-shaped) rounds and of the driver, against goldens + oracle."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from honeybadger_b200 import synth
+from oracle import pyref as P
+
+pytestmark = pytest.mark.gpu
+
+
+def unrle(starts, vals, n):
+    y = np.zeros(n, dtype=np.int32)
+    for a, b, v in zip(starts, list(starts[1:]) + [n], vals):
+        y[a:b] = v
+    return y
+
+
+def test_gexp_pooled_round_on_bundled_data(golden_gexp, oracle):
+    """15 pooled chains of the MGH31 example (5 cut heights): pooled means and sd bit-identical to
+    R's long-double arithmetic, Viterbi paths identical."""
+    from honeybadger_b200 import honeybadger as hb
+    g = golden_gexp
+    x = g["gexp_norm_f32"].astype(np.float64)
+    member, _ = hb._membership(list(g["labels"]), x.shape[1])
+    assert member.shape[0] == 15
+    dev = float(g["dev"])
+    y, px, psd = hb.gexp_round_dev(hb._to_dev_f64(x), member, [-dev, 0.0, dev], 1e-6)
+    assert (px == g["pooled_x"]).all(), "pooled means differ from R mean() semantics"
+    assert (psd == g["pooled_sd"]).all(), "sd differs from R sd() semantics"
+    for k in range(15):
+        a, b = g["path_off"][k], g["path_off"][k + 1]
+        assert (y[k] == unrle(g["path_starts"][a:b], g["path_vals"][a:b], y.shape[1])).all()
+
+
+def test_allele_pooled_round_on_bundled_data(golden_allele):
+    from honeybadger_b200 import honeybadger as hb
+    g = golden_allele
+    r, n = g["r_maf"].astype(np.float64), g["n_sc"].astype(np.float64)
+    member, tags = hb._membership(list(g["labels"]), r.shape[1])
+    y, mafl, sizel = hb.allele_round_dev(hb._to_dev_i32(r), hb._to_dev_i32(n), member, 0.1, 0.45, 1e-6)
+    assert (mafl == g["mafl"]).all() and (sizel == g["sizel"]).all()
+    for k in range(member.shape[0]):
+        a, b = g["path_off"][k], g["path_off"][k + 1]
+        assert (y[k] == unrle(g["path_starts"][a:b], g["path_vals"][a:b], y.shape[1])).all()
+    # the vignette's call: all-cell chain, state 1 on chr1 (9 SNPs) and chr13..14 (54 SNPs)
+    s = np.nonzero(np.diff(np.concatenate([[0], (y[0] == 1).astype(int), [0]])))[0]
+    assert (s[1::2] - s[0::2]).tolist() == [9, 54]
+
+
+def test_host_wrappers_match_dev_rounds(golden_gexp, golden_allele):
+    from honeybadger_b200 import _lib, honeybadger as hb
+    from honeybadger_b200.hmm import sym_Pi
+    lib = _lib.load()
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    g = golden_gexp
+    x = np.asfortranarray(g["gexp_norm_f32"].astype(np.float64))
+    member, _ = hb._membership(list(g["labels"][:2]), x.shape[1])
+    K, (G, N) = member.shape[0], x.shape
+    y = np.zeros((K, G), np.int32)
+    px, psd = np.zeros((K, G)), np.zeros(K)
+    dev = float(g["dev"])
+    mean, Pi, delta = np.array([-dev, 0, dev]), sym_Pi(3, 1e-6), np.array([0., 1, 0])
+    _lib.check(lib.hb_gexp_pooled_viterbi_host(vp(x), G, N, vp(member), K, vp(mean), vp(Pi), vp(delta),
+                                               vp(y), vp(px), vp(psd)))
+    assert (px == g["pooled_x"][:K]).all() and (psd == g["pooled_sd"][:K]).all()
+    ga = golden_allele
+    r = np.asfortranarray(ga["r_maf"].astype(np.float64))
+    n = np.asfortranarray(ga["n_sc"].astype(np.float64))
+    member, _ = hb._membership(list(ga["labels"]), r.shape[1])
+    K, (G, N) = member.shape[0], r.shape
+    y = np.zeros((K, G), np.int32)
+    mafl, sizel = np.zeros((K, G), np.int32), np.zeros((K, G), np.int32)
+    prob, Pi2, d2 = np.array([0.1, 0.45]), sym_Pi(2, 1e-6), np.array([0., 1.])
+    _lib.check(lib.hb_allele_pooled_viterbi_host(vp(r), vp(n), G, N, vp(member), K, vp(prob), vp(Pi2),
+                                                 vp(d2), vp(y), vp(mafl), vp(sizel)))
+    assert (mafl == ga["mafl"]).all() and (sizel == ga["sizel"]).all()
+
+
+def test_pool_mean_random_groups_bit_exact(oracle):
+    """x87 replay on the device == R mean() for ragged random groups (incl. a 2-cell group)."""
+    import torch
+    from honeybadger_b200 import _lib, honeybadger as hb
+    rng = np.random.default_rng(12)
+    G, N = 777, 203
+    x = rng.normal(size=(G, N)) * 2.7 + rng.normal(size=(G, 1))
+    labels = rng.integers(1, 6, N)
+    labels[:2] = 9
+    member, _ = hb._membership([np.ones(N, int), labels], N)
+    xd = hb._to_dev_f64(x)
+    md = torch.as_tensor(member).cuda()
+    out = torch.empty((member.shape[0], G), dtype=torch.float64, device="cuda")
+    lib = _lib.load()
+    _lib.check(lib.hb_pool_mean_dev(xd.data_ptr(), xd.stride(0), G, N, md.data_ptr(), member.shape[0],
+                                    out.data_ptr(), None))
+    sd = torch.empty(member.shape[0], dtype=torch.float64, device="cuda")
+    _lib.check(lib.hb_pooled_sd_dev(out.data_ptr(), G, member.shape[0], sd.data_ptr(), None))
+    got, gsd = out.cpu().numpy(), sd.cpu().numpy()
+    for k in range(member.shape[0]):
+        ref = oracle.pool_mean(x, np.nonzero(member[k])[0])
+        assert (got[k] == ref).all()
+        assert gsd[k] == oracle.r_sd(ref)
+
+
+def test_function_variants_match_reference_restatement(golden_gexp, golden_allele):
+    """calcGexpCnvBoundaries / calcAlleleCnvBoundaries (stateless) == the literal R restatement."""
+    from honeybadger_b200 import honeybadger as hb
+    ga = golden_allele
+    names = [f"{c}:{p}" for c, p in zip(ga["chrom"], ga["pos"])]
+    cells = [f"c{i}" for i in range(ga["r_maf"].shape[1])]
+    r = pd.DataFrame(ga["r_maf"].astype(float), index=names, columns=cells)
+    n = pd.DataFrame(ga["n_sc"].astype(float), index=names, columns=cells)
+    labels = list(ga["labels"])
+    res = hb.calcAlleleCnvBoundaries(r, n, grouping=lambda R, Nn, hs: labels)
+    ref = P.calc_allele_cnv_boundaries_fn(ga["r_maf"].astype(float), ga["n_sc"].astype(float), labels)
+    assert [list(np.asarray(names, object)[i]) for i in ref["info"]] == res["info"]
+    assert all(rg[0] in ("chr1", "chr13", "chr14") for rg in res["regions"])
+    # expression: genes in stored order on 22 synthetic chromosomes
+    gg = golden_gexp
+    x = gg["gexp_norm_f32"].astype(np.float64)
+    G = x.shape[0]
+    seg = gg["seg_off"]
+    chrom = np.empty(G, dtype=object)
+    for s in range(22):
+        chrom[seg[s]:seg[s + 1]] = f"chr{s + 1}"
+    gnames = [f"g{i}" for i in range(G)]
+    genes = hb.GRanges(chrom, np.arange(G) * 10.0, np.arange(G) * 10.0 + 5, gnames)
+    xdf = pd.DataFrame(x, index=gnames, columns=[f"c{i}" for i in range(x.shape[1])])
+    labels3 = list(gg["labels"][:3])
+    res = hb.calcGexpCnvBoundaries(xdf, genes, m=float(gg["dev"]), grouping=lambda M, hs: labels3)
+    for key, idx, off in (("amp", gg["fn_amp_idx"], gg["fn_amp_off"]), ("del", gg["fn_del_idx"], gg["fn_del_off"])):
+        want = [[gnames[i] for i in idx[a:b]] for a, b in zip(off[:-1], off[1:])]
+        got = res[key]["info"] if res[key] else []
+        assert got == want
+
+
+def test_refclass_driver_finds_planted_clones():
+    """End-to-end recursion on synthetic clones (labels from the planted clone tree, retest hooks on
+    the device): the planted deletion/amplification segments come out and clones get split."""
+    from honeybadger_b200 import honeybadger as hb
+    G, N = 2200, 90
+    x, seg, clone = synth.expression(G, N, seed=11)
+    x = x / 2.5  # per-cell noise sd ~1 so the pooled chains see the signal at dev/2.5
+    chrom = np.empty(G, dtype=object)
+    for s in range(22):
+        chrom[seg[s]:seg[s + 1]] = f"chr{s + 1}"
+    gnames = [f"g{i}" for i in range(G)]
+    cells = [f"c{i}" for i in range(N)]
+    genes = hb.GRanges(chrom, np.arange(G) * 10.0, np.arange(G) * 10.0 + 5, gnames)
+    obj = hb.HoneyBADGER("synthetic")
+    obj.gexp_norm = pd.DataFrame(x, index=gnames, columns=cells)
+    obj.genes = genes
+    obj.setGexpDev(dev=synth.DEV / 2.5)
+    obj.calcGexpCnvBoundaries(init=True, min_num_genes=10)
+    assert obj.bound_genes_final, "no CNV found"
+    found = {g for lst in obj.bound_genes_final for g in lst[0]}
+    planted = set(gnames[seg[6]:seg[7]]) | set(gnames[seg[9]:seg[10]]) | set(gnames[seg[12]:seg[13]])
+    assert len(found & planted) > 0.5 * len(found)
+    assert obj.pred_genes_r.values.sum() > 0

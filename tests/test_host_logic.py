@@ -1,0 +1,116 @@
+"""CPU: host-side bookkeeping of the mirror (vote/runs/trim, ordering, ranges, sharding) and the ABI."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+from hypothesis import given, settings
+from hypothesis import strategies as st
+
+from honeybadger_b200 import _lib, dist, honeybadger as hb
+from oracle import pyref as P
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@settings(max_examples=300, deadline=None)
+@given(st.lists(st.integers(0, 3), min_size=2, max_size=120), st.integers(1, 6),
+       st.sampled_from([None, 0.1, 0.25, 0.5, 1.0]))
+def test_runs_from_vote_equals_literal_r_loop(vote, min_num, trim):
+    a = hb.runs_from_vote(np.array(vote), min_num, trim)
+    b = P.runs_filter_trim(np.array(vote), min_num, trim)
+    assert (a is None) == (b is None)
+    if a is not None:
+        assert len(a) == len(b) and all((x == y).all() for x, y in zip(a, b))
+
+
+def test_runs_quirks():
+    # the first element of a run is dropped; a run of L voted positions yields L-1 labelled ones
+    v = np.array([0, 1, 1, 1, 1, 0, 1, 1, 0])
+    runs = hb.runs_from_vote(v, 1, None)
+    assert [r.tolist() for r in runs] == [[2, 3, 4], [7]]
+    assert hb.runs_from_vote(v, 3, None)[0].tolist() == [2, 3, 4] and len(hb.runs_from_vote(v, 3, None)) == 1
+    assert hb.runs_from_vote(np.zeros(5), 1, 0.1) is None
+    # trim: names[1:round(L - L*trim)], half-even: L=5 -> round(4.5)=4 ; L=15 -> round(13.5)=14
+    v5 = np.array([0] + [1] * 6)
+    assert hb.runs_from_vote(v5, 1, 0.1)[0].size == 4
+    v15 = np.array([0] + [1] * 16)
+    assert hb.runs_from_vote(v15, 1, 0.1)[0].size == 14
+    # position 0 can never be labelled (the R loop starts at i = 2)
+    assert hb.runs_from_vote(np.array([1, 1, 1]), 1, None)[0].tolist() == [1, 2]
+
+
+def test_group_members_order_is_first_appearance():
+    lab = np.array([2, 2, 1, 3, 1, 2])
+    gm = hb.group_members(lab)
+    assert [g for g, _ in gm] == [2, 1, 3]
+    assert gm[0][1].tolist() == [0, 1, 5]
+    m, tags = hb._membership([np.array([1, 1, 1, 1, 1, 1]), lab], 6)
+    assert m.shape == (3, 6) and tags == [(0, 0), (1, 0), (1, 1)]  # the singleton group 3 is skipped
+
+
+def test_order_genes_and_range():
+    g = hb.GRanges(["chr2", "chr1", "chr1", "chrX", "chr2"], [50, 300, 100, 5, 10], [60, 400, 200, 9, 20],
+                   ["a", "b", "c", "d", "e"])
+    o = hb.order_genes(["a", "b", "c", "d", "e"], g, ["chr1", "chr2"])
+    assert o.tolist() == [2, 1, 4, 0]  # chr1 by midpoint, then chr2; chrX dropped
+    o = hb.order_genes(["a", "b", "c", "d", "e"], g, ["chr1", "chr2"], has_na=[False, True, False, False, False])
+    assert o.tolist() == [2, 4, 0]
+    assert g[["b", "c", "a"]].range() == [("chr1", 100.0, 400.0), ("chr2", 50.0, 60.0)]
+    s = hb.snps_from_names(["1:762273", "chr13:21949361", "14:5-9"])
+    assert list(s.seqnames) == ["chr1", "chr13", "chr14"] and s.end[2] == 9
+
+
+def test_ward_groups_numbering_and_runmean():
+    rng = np.random.default_rng(0)
+    a = rng.normal(size=(50, 6))
+    a[:, 3:] += 4
+    labs = hb.ward_groups(a, [1, 2, 3])
+    assert labs[0].tolist() == [1] * 6 and labs[1].tolist() == [1, 1, 1, 2, 2, 2] and labs[2][0] == 1
+    m = np.arange(10, dtype=float).reshape(-1, 1)
+    rm = hb.runmean(m, 3)[:, 0]
+    assert rm[0] == 0.5 and rm[1] == 1.0 and rm[-1] == 8.5
+    m[4] = np.nan
+    assert hb.runmean(m, 3)[4, 0] == 4.0
+
+
+def test_shard_ranges_cover_cells():
+    for n, w in [(10, 3), (200000, 8), (7, 8), (25000, 1)]:
+        r = [dist.shard_range(n, k, w) for k in range(w)]
+        assert r[0][0] == 0 and r[-1][1] == n and all(a[1] == b[0] for a, b in zip(r, r[1:]))
+        assert max(dist.shard_sizes(n, w)) - min(dist.shard_sizes(n, w)) <= 1
+
+
+def test_abi_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "hb_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(hb_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 20
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    lib = C.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} missing from libhb_b200.so"
+    assert _lib.load().hb_version() >= 100
+
+
+@pytest.mark.skipif(_lib.device_count() > 0, reason="checks the no-GPU behaviour")
+def test_no_cpu_fallback_without_a_device():
+    from honeybadger_b200 import hmm
+    with pytest.raises(_lib.HBError) as e:
+        hmm.hmm_norm_host(np.zeros(8), [-1, 0, 1], 1.0, hmm.sym_Pi(3, 1e-6), [0, 1, 0])
+    assert e.value.code in (_lib.HB_ERR_NODEVICE, _lib.HB_ERR_CUDA)
+    with pytest.raises(_lib.HBError):
+        hmm.hmm_binom_host(np.zeros(8), np.zeros(8), [0.1, 0.45], hmm.sym_Pi(2, 1e-6), [0, 1])
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "honeybadger_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dp, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
+                assert "hb_oracle" not in txt and "libhb_emul" not in txt, f

@@ -1,0 +1,72 @@
+"""CPU: numerics of the device helpers, through the host build of the same headers (tests/emul)."""
+from __future__ import annotations
+
+import ctypes as C
+import random
+from fractions import Fraction as F
+
+import numpy as np
+
+
+def test_div_by_const_is_correctly_rounded_on_hardest_cases(emul):
+    """Markstein's q' = q + (d - b q) y with y = RN(1/b): the quotients closest to rounding
+    midpoints (found with modular inverses) must still round correctly."""
+    rnd = random.Random(1)
+    n = fails = naive = 0
+    for trial in range(600):
+        B = rnd.randrange(2 ** 52, 2 ** 53) | 1
+        if trial % 10 == 0:
+            B = 2 ** 53 - 1 - 2 * rnd.randrange(0, 50)
+        b = B * 2.0 ** -52 * 2.0 ** rnd.randrange(-3, 3)
+        inv = pow(B, -1, 2 ** 53)
+        for delta in range(-9, 10, 2):
+            M = (delta * inv) % 2 ** 53 + 2 ** 53
+            num = B * M - delta
+            if num % 2 ** 53:
+                continue
+            A = num >> 53
+            if A >= 2 ** 53 and A % 2:
+                continue
+            a = float(A) * 2.0 ** -52 * (b / (B * 2.0 ** -52))
+            if F(a) != F(A, 2 ** 52) * F(b) / F(B, 2 ** 52):
+                continue
+            exact = float(F(a) / F(b))
+            n += 1
+            fails += emul.emul_div_by_const(a, b) != exact
+            naive += a * (1.0 / b) != exact
+    assert n > 2000 and fails == 0 and naive > n // 4
+    rng = np.random.default_rng(0)
+    for a, b in zip(rng.uniform(-20, 20, 20000), rng.uniform(0.2, 3.5, 20000)):
+        assert emul.emul_div_by_const(float(a), float(b)) == float(a) / float(b)
+
+
+def test_exp_pair_accuracy(emul):
+    import mpmath as mp
+    mp.mp.dps = 40
+    ep, em = C.c_double(), C.c_double()
+    worst = 0.0
+    for u in np.concatenate([np.linspace(-40, 40, 801), [1e-9, -1e-9, 0.0, 300.0, -300.0, 345.0]]):
+        emul.emul_exp_pair(float(u), C.byref(ep), C.byref(em))
+        for got, ref in ((ep.value, mp.e ** mp.mpf(float(u))), (em.value, mp.e ** mp.mpf(-float(u)))):
+            worst = max(worst, abs(float((mp.mpf(got) - ref) / ref)))
+    assert worst < 4e-16
+
+
+def test_x87_emulation_reproduces_r_mean_and_sd(emul, oracle):
+    rng = np.random.default_rng(4)
+    for n in (2, 3, 5, 64, 1001, 6082):
+        for shift in (0.0, 7.5):
+            x = np.ascontiguousarray(rng.normal(size=n) * 2.6 + shift)
+            p = x.ctypes.data_as(C.c_void_p)
+            assert emul.emul_x87_mean(p, n) == oracle.r_mean(x)
+            assert emul.emul_x87_sd(p, n) == oracle.r_sd(x)
+
+
+def test_binom_logpmf_host_and_device_restatements_match_oracle(emul, oracle):
+    for n in list(range(0, 70)) + [100, 255, 256, 511, 512, 1245, 5000]:
+        for x in sorted({0, 1, n // 3, n // 2, n - 1, n}):
+            if 0 <= x <= n:
+                for p in (0.1, 0.45):
+                    ref = oracle.dbinom(x, n, p, True)
+                    assert emul.emul_binom_logpmf_host(x, n, p) == ref
+                    assert emul.emul_binom_logpmf_dev(x, n, p) == ref  # same libm on the host build
