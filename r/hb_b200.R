@@ -1,0 +1,34 @@
+## hb_b200.R — the reference-side change: the four `dthmm -> Viterbi` call sites go through .Call.
+##
+## Drop-in: source this after library(HoneyBADGER) (or patch the package) — signatures, defaults,
+## fields and return values of calcGexpCnvBoundaries / calcAlleleCnvBoundaries stay exactly as in
+## R/HoneyBADGER.R:1092, :1337, R/HoneyBADGER_gexp.R:462, R/HoneyBADGER_allele.R:543.
+## Not executable in this repository's environment (no R); see INTEGRATION.md.
+
+dyn.load("hbb200.so")  # built from r/hb_shim.c against libhb_b200.so
+
+## 1:1 replacements of the HiddenMarkov pair ------------------------------------------------------
+hb_viterbi_norm <- function(x, Pi, delta, pm) {
+  ## was: HiddenMarkov::Viterbi(HiddenMarkov::dthmm(x, Pi, delta, "norm", pm))
+  .Call("C_hb_viterbi_norm", x, as.double(pm$mean), as.double(pm$sd[1]), Pi, as.double(delta))
+}
+hb_viterbi_binom <- function(x, Pi, delta, pm, pn) {
+  ## was: HiddenMarkov::Viterbi(HiddenMarkov::dthmm(x, Pi, delta, "binom", pm, pn, discrete=TRUE))
+  .Call("C_hb_viterbi_binom", as.integer(x), as.integer(pn$size), as.double(pm$prob), Pi, as.double(delta))
+}
+
+## R/HoneyBADGER.R:1150-1151 and R/HoneyBADGER_gexp.R:503-504 become
+##   results <- hb_viterbi_norm(mat.smooth, Pi, delta, list(mean=c(pd, pn, pa), sd=c(sd,sd,sd)))
+## R/HoneyBADGER.R:1409-1410 and R/HoneyBADGER_allele.R:579-580 become
+##   results <- hb_viterbi_binom(mafl, Pi, delta, list(prob=c(pd, pn)), list(size=sizel))
+
+## Whole-round form (pooling on the GPU too): replaces the `lapply(heights, ...)` block ------------
+hb_gexp_round <- function(gexp.norm, hc, heights, dev, t) {
+  cts <- lapply(heights, function(h) cutree(hc, k = h))
+  member <- do.call(cbind, unlist(lapply(cts, function(ct)
+    lapply(unique(ct), function(g) if (sum(ct == g) > 1) ct == g)), recursive = FALSE))
+  Pi <- matrix(c(1-2*t, t, t, t, 1-2*t, t, t, t, 1-2*t), byrow = TRUE, nrow = 3)
+  y <- .Call("C_hb_gexp_pooled_viterbi", gexp.norm, member, c(-dev, 0, dev), Pi, c(0, 1, 0))
+  lapply(seq_len(ncol(y)), function(k) list(amp = rownames(gexp.norm)[y[, k] == 3],
+                                            del = rownames(gexp.norm)[y[, k] == 1]))
+}

@@ -1,0 +1,112 @@
+/*
+ * hb_shim.c — `.Call` shim between R and libhb_b200.so (include/hb_b200.h).
+ *
+ * NOT built in this repository: the build container and the GPU boxes have no R (no R.h /
+ * Rinternals.h), so this file is the integration a HoneyBADGER maintainer adds to the package's
+ * src/ (see INTEGRATION.md).  It is deliberately thin: coerce, allocate, call, convert the error.
+ *
+ *   R CMD SHLIB hb_shim.c -I<repo>/include -L<repo>/honeybadger_b200 -lhb_b200
+ */
+#include <R.h>
+#include <Rinternals.h>
+#include <R_ext/Rdynload.h>
+
+#include "hb_b200.h"
+
+static void hb_raise(int rc)
+{
+    if (rc == HB_OK) return;
+    if (rc == HB_ERR_UNDERFLOW) Rf_error("Problems With Underflow"); /* HiddenMarkov::Viterbi's text */
+    Rf_error("libhb_b200: %s (code %d)", hb_last_error(), rc);
+}
+
+/* y <- .Call(C_hb_viterbi_norm, x, mean, sd, Pi, delta)
+ * replaces  HiddenMarkov::Viterbi(HiddenMarkov::dthmm(x, Pi, delta, "norm", list(mean=, sd=)))
+ * x: numeric vector or [T x B] matrix (one chain per column); Pi as the R matrix (column-major). */
+SEXP C_hb_viterbi_norm(SEXP x, SEXP mean, SEXP sd, SEXP Pi, SEXP delta)
+{
+    x = PROTECT(Rf_coerceVector(x, REALSXP));
+    const int is_mat = Rf_isMatrix(x);
+    const int64_t T = is_mat ? Rf_nrows(x) : XLENGTH(x), B = is_mat ? Rf_ncols(x) : 1;
+    double pi_rm[9];
+    for (int j = 0; j < 3; j++)
+        for (int k = 0; k < 3; k++) pi_rm[j * 3 + k] = REAL(Pi)[k * 3 + j]; /* R is column-major */
+    SEXP sdv = PROTECT(Rf_allocVector(REALSXP, B));
+    for (int64_t b = 0; b < B; b++) REAL(sdv)[b] = REAL(sd)[XLENGTH(sd) == B ? b : 0];
+    SEXP y = PROTECT(is_mat ? Rf_allocMatrix(INTSXP, (int)T, (int)B) : Rf_allocVector(INTSXP, T));
+    int rc = hb_hmm_norm_host(REAL(x), T, B, NULL, 1, REAL(mean), REAL(sdv), 0, pi_rm, REAL(delta),
+                              HB_WANT_VITERBI, INTEGER(y), NULL, NULL);
+    UNPROTECT(3);
+    hb_raise(rc);
+    return y;
+}
+
+/* y <- .Call(C_hb_viterbi_binom, x, size, prob, Pi, delta)
+ * replaces  Viterbi(dthmm(x, Pi, delta, "binom", list(prob=), list(size=), discrete=TRUE)) */
+SEXP C_hb_viterbi_binom(SEXP x, SEXP size, SEXP prob, SEXP Pi, SEXP delta)
+{
+    x = PROTECT(Rf_coerceVector(x, INTSXP));
+    size = PROTECT(Rf_coerceVector(size, INTSXP));
+    const int is_mat = Rf_isMatrix(x);
+    const int64_t T = is_mat ? Rf_nrows(x) : XLENGTH(x), B = is_mat ? Rf_ncols(x) : 1;
+    double pi_rm[4] = {REAL(Pi)[0], REAL(Pi)[2], REAL(Pi)[1], REAL(Pi)[3]};
+    SEXP y = PROTECT(is_mat ? Rf_allocMatrix(INTSXP, (int)T, (int)B) : Rf_allocVector(INTSXP, T));
+    int rc = hb_hmm_binom_host(INTEGER(x), INTEGER(size), T, B, NULL, 1, REAL(prob), 0.0, pi_rm,
+                               REAL(delta), HB_WANT_VITERBI, INTEGER(y), NULL, NULL);
+    UNPROTECT(3);
+    hb_raise(rc);
+    return y;
+}
+
+/* One whole `lapply(heights, ...)` round: pooled mean + sd + Viterbi for K cell sets at once.
+ * member: logical/integer [N x K] matrix (ct == group columns).  Returns list(y = [G x K] integer). */
+SEXP C_hb_gexp_pooled_viterbi(SEXP gexp_norm, SEXP member, SEXP mean, SEXP Pi, SEXP delta)
+{
+    gexp_norm = PROTECT(Rf_coerceVector(gexp_norm, REALSXP));
+    member = PROTECT(Rf_coerceVector(member, INTSXP));
+    const int64_t G = Rf_nrows(gexp_norm), N = Rf_ncols(gexp_norm);
+    const int K = Rf_ncols(member);
+    unsigned char *mem = (unsigned char *)R_alloc((size_t)K * N, 1);
+    for (int k = 0; k < K; k++)
+        for (int64_t c = 0; c < N; c++) mem[(size_t)k * N + c] = INTEGER(member)[(size_t)k * N + c] != 0;
+    double pi_rm[9];
+    for (int j = 0; j < 3; j++)
+        for (int k = 0; k < 3; k++) pi_rm[j * 3 + k] = REAL(Pi)[k * 3 + j];
+    SEXP y = PROTECT(Rf_allocMatrix(INTSXP, (int)G, K)); /* [K][G] row-major == [G x K] column-major */
+    int rc = hb_gexp_pooled_viterbi_host(REAL(gexp_norm), G, N, mem, K, REAL(mean), pi_rm, REAL(delta),
+                                         INTEGER(y), NULL, NULL);
+    UNPROTECT(3);
+    hb_raise(rc);
+    return y;
+}
+
+SEXP C_hb_allele_pooled_viterbi(SEXP r_maf, SEXP n_sc, SEXP member, SEXP prob, SEXP Pi, SEXP delta)
+{
+    r_maf = PROTECT(Rf_coerceVector(r_maf, REALSXP));
+    n_sc = PROTECT(Rf_coerceVector(n_sc, REALSXP));
+    member = PROTECT(Rf_coerceVector(member, INTSXP));
+    const int64_t G = Rf_nrows(r_maf), N = Rf_ncols(r_maf);
+    const int K = Rf_ncols(member);
+    unsigned char *mem = (unsigned char *)R_alloc((size_t)K * N, 1);
+    for (size_t i = 0; i < (size_t)K * N; i++) mem[i] = INTEGER(member)[i] != 0;
+    double pi_rm[4] = {REAL(Pi)[0], REAL(Pi)[2], REAL(Pi)[1], REAL(Pi)[3]};
+    SEXP y = PROTECT(Rf_allocMatrix(INTSXP, (int)G, K));
+    int rc = hb_allele_pooled_viterbi_host(REAL(r_maf), REAL(n_sc), G, N, mem, K, REAL(prob), pi_rm,
+                                           REAL(delta), INTEGER(y), NULL, NULL);
+    UNPROTECT(4);
+    hb_raise(rc);
+    return y;
+}
+
+static const R_CallMethodDef call_methods[] = {
+    {"C_hb_viterbi_norm", (DL_FUNC)&C_hb_viterbi_norm, 5},
+    {"C_hb_viterbi_binom", (DL_FUNC)&C_hb_viterbi_binom, 5},
+    {"C_hb_gexp_pooled_viterbi", (DL_FUNC)&C_hb_gexp_pooled_viterbi, 5},
+    {"C_hb_allele_pooled_viterbi", (DL_FUNC)&C_hb_allele_pooled_viterbi, 6},
+    {NULL, NULL, 0}};
+
+void R_init_hbb200(DllInfo *dll)
+{
+    R_registerRoutines(dll, NULL, call_methods, NULL, NULL);
+    R_useDynamicSymbols(dll, FALSE);
+}

@@ -118,7 +118,7 @@ def test_function_variants_match_reference_restatement(golden_gexp, golden_allel
     res = hb.calcAlleleCnvBoundaries(r, n, grouping=lambda R, Nn, hs: labels)
     ref = P.calc_allele_cnv_boundaries_fn(ga["r_maf"].astype(float), ga["n_sc"].astype(float), labels)
     assert [list(np.asarray(names, object)[i]) for i in ref["info"]] == res["info"]
-    assert all(rg[0] in ("chr1", "chr13", "chr14") for rg in res["regions"])
+    assert {rg[0] for rg in res["regions"]} >= {"chr13", "chr14"}  # the vignette's deletion calls
     # expression: genes in stored order on 22 synthetic chromosomes
     gg = golden_gexp
     x = gg["gexp_norm_f32"].astype(np.float64)
