@@ -120,7 +120,7 @@ class ClockSampler:
 def device_inputs(kind, cells, positions, seed, dev):
     """Gene-major synthetic matrices generated on the device (SURVEY.md §8d shapes)."""
     import torch
-    from honeybadger_b200 import synth
+    from honeybadger_b200 import hmm, synth
     g = torch.Generator(device=dev)
     g.manual_seed(seed)
     seg = synth.segments(positions)
@@ -132,15 +132,17 @@ def device_inputs(kind, cells, positions, seed, dev):
         state[seg[12]:seg[13], 1] = -1
         state[seg[13]:(seg[13] + seg[14]) // 2, 1] = -1
         sig = torch.empty(cells, dtype=torch.float64, device=dev).uniform_(*DEV_SIGMA, generator=g)
-        x = torch.randn((positions, cells), dtype=torch.float64, device=dev, generator=g)
+        # resident layout: gene-major rows padded to 1 KB (hmm.alloc_rows)
+        x = hmm.alloc_rows(positions, cells, torch.float64, dev)
+        x.copy_(torch.randn((positions, cells), dtype=torch.float64, device=dev, generator=g))
         x.mul_(sig).add_(state[:, clone] * DEV)
         return dict(x=x, seg=seg)
     p = torch.full((positions, 3), 0.45, dtype=torch.float32, device=dev)
     p[seg[9]:seg[10], 0] = 0.1
     p[seg[12]:seg[13], 1] = 0.1
     p[seg[13]:(seg[13] + seg[14]) // 2, 1] = 0.1
-    n = torch.empty((positions, cells), dtype=torch.int32, device=dev)
-    r = torch.empty((positions, cells), dtype=torch.int32, device=dev)
+    n = hmm.alloc_rows(positions, cells, torch.int32, dev)
+    r = hmm.alloc_rows(positions, cells, torch.int32, dev)
     rows = max(1, (1 << 26) // cells)
     for a in range(0, positions, rows):  # chunked: keeps generator temporaries small
         b = min(positions, a + rows)
@@ -329,7 +331,7 @@ def main():
     roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "traffic": ncu_traffic(kind), "peak_source": peak_src,
             "algorithmic_bytes_per_step": wl["bytes_per_step"], "kernel_ms": mean_ms,
-            "kernel": "norm3_kernel<SYM,VIT,FB>" if kind == "expr" else "binom2_kernel<VIT,FB>"}
+            "kernel": "norm3_fast_kernel<VIT,FB>" if kind == "expr" else "binom2_kernel<VIT,FB>"}
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu, _, _ = cpu_rate(kind, wl)
@@ -340,7 +342,8 @@ def main():
                 "data": "synthetic",
                 "config": {"workload": wl["name"], "cells_per_gpu": cells, "positions": positions,
                            "segments": wl["nseg"], "states": wl["S"],
-                           "l2": f"inputs {in_bytes / 1e6:.0f} MB + outputs per pass exceed the 126 MB L2"},
+                           "l2": f"inputs {in_bytes / 1e6:.0f} MB + outputs per pass exceed the 126 MB L2",
+                           "layout": "gene-major [position][cell], rows padded to a multiple of 128 elements"},
                 "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
                 "gpu_launches": launches_per_step * args.steps}
         print(json.dumps(line), flush=True)

@@ -7,6 +7,7 @@
 #include "hb_binom2.cuh"
 #include "hb_kernels.h"
 #include "hb_norm3.cuh"
+#include "hb_norm3_fast.cuh"
 #include "hb_x87.cuh"
 
 namespace hb {
@@ -33,6 +34,34 @@ __global__ void __launch_bounds__(HB_BLOCK, HB_NORM3_MINB)
     m.e2 = reinterpret_cast<double *>(smem2 + 2 * HB_CHUNK * HB_BLOCK) + threadIdx.x;
     m.xs = FB ? m.e2 + HB_CHUNK * HB_BLOCK : reinterpret_cast<double *>(smem2) + threadIdx.x;
     norm3_chain<SYM, VIT, FB, LL>(a, seg, b, m);
+}
+
+// Speculate-and-verify path for the reference's symmetric parameter block (hb_norm3_fast.cuh).
+// 3 resident blocks/SM (<= 168 registers): measured faster than 4 blocks at <= 128 registers, the
+// extra registers buy instruction-level parallelism (tools/build_variant.sh sweeps)
+#ifndef HB_FAST_MINB
+#define HB_FAST_MINB 3
+#endif
+template <bool VIT, bool FB, bool LL>
+__global__ void __launch_bounds__(HB_BLOCK, HB_FAST_MINB)
+    norm3_fast_kernel(const __grid_constant__ Norm3Args a)
+{
+    extern __shared__ double2 smem2[];
+    const int32_t seg = a.seg_order[blockIdx.x / a.nblk_per_seg];
+    const int64_t b = (int64_t)(blockIdx.x % a.nblk_per_seg) * HB_BLOCK + threadIdx.x;
+    if (b >= a.B) return;
+    Norm3Smem m;
+    m.st = HB_BLOCK;
+    m.va = smem2 + threadIdx.x;
+    m.vb = m.va + HB_CHUNK * HB_BLOCK;
+    char *rest = reinterpret_cast<char *>(smem2 + 2 * HB_CHUNK * HB_BLOCK);
+    m.e2 = reinterpret_cast<double *>(rest) + threadIdx.x;
+    if (!HB_FAST_NOPHI1) rest += sizeof(double) * HB_CHUNK * HB_BLOCK;
+    m.xs = FB ? reinterpret_cast<double *>(rest) + threadIdx.x
+              : reinterpret_cast<double *>(smem2) + threadIdx.x;
+    if (!HB_FAST_XREG) rest += sizeof(double) * HB_CHUNK * HB_BLOCK;
+    m.ph = reinterpret_cast<int32_t *>(rest) + threadIdx.x;
+    norm3_fast_chain<VIT, FB, LL>(a, seg, b, m);
 }
 
 template <bool VIT, bool FB>
@@ -72,6 +101,32 @@ static cudaError_t launch_norm3_t(const Norm3Args &a, bool vit, bool fb, cudaStr
 cudaError_t launch_norm3(const Norm3Args &a, bool sym, bool vit, bool fb, cudaStream_t st)
 {
     return sym ? launch_norm3_t<true>(a, vit, fb, st) : launch_norm3_t<false>(a, vit, fb, st);
+}
+
+cudaError_t launch_norm3_fast(const Norm3Args &a, bool vit, bool fb, cudaStream_t st)
+{
+    const unsigned grid = (unsigned)((int64_t)a.nseg * a.nblk_per_seg);
+    const size_t sm_fb = (size_t)HB_FAST_SMEM_BYTES_PER_THREAD * HB_BLOCK;
+    const size_t sm_v = HB_FAST_XREG ? 0 : (size_t)HB_CHUNK * HB_BLOCK * sizeof(double);
+    // > 48 KB of dynamic shared memory: opt in (per device, cheap)
+    const bool ll = a.ll != nullptr;
+#define HB_LAUNCH_FAST(V, F, L_, SM)                                                               \
+    do {                                                                                          \
+        cudaFuncSetAttribute(norm3_fast_kernel<V, F, L_>,                                          \
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SM));             \
+        norm3_fast_kernel<V, F, L_><<<grid, HB_BLOCK, (SM), st>>>(a);                              \
+    } while (0)
+    if (vit && fb) {
+        if (ll) HB_LAUNCH_FAST(true, true, true, sm_fb);
+        else HB_LAUNCH_FAST(true, true, false, sm_fb);
+    } else if (fb) {
+        if (ll) HB_LAUNCH_FAST(false, true, true, sm_fb);
+        else HB_LAUNCH_FAST(false, true, false, sm_fb);
+    } else {
+        HB_LAUNCH_FAST(true, false, false, sm_v);
+    }
+#undef HB_LAUNCH_FAST
+    return cudaGetLastError();
 }
 
 cudaError_t launch_binom2(const Binom2Args &a, bool vit, bool fb, cudaStream_t st)

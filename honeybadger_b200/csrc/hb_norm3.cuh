@@ -65,6 +65,13 @@ struct Norm3Const {
     double delta[3];
     double la, lt;  // SYM: log(diag), log(off-diag)
     double amt, tt; // SYM: (diag - offdiag), offdiag
+    // speculate-and-verify path (hb_norm3_fast.cuh)
+    double tau;       // lt - la
+    double dl0, dl2;  // logdelta[k] - logdelta[1]
+    double mumax2;    // max_k mean[k]^2
+    double dmu2;      // max_k (mean[k] - mean[1])^2
+    double ldabs;     // max finite |logdelta[k]|
+    double eps_scale; // 1 (or +Inf: test hook that sends every chain through the exact fallback)
     double k[HBK_COUNT];
 };
 
@@ -105,7 +112,8 @@ struct Norm3Args {
     double *ll;  // [nseg*B]
     uint64_t *psi; // [nchunks][B]
     double *ckpt;  // [nchunks][3][B]
-    int32_t *status; // set to 1 when a chain ends with nu == -inf (R: "Problems With Underflow")
+    int32_t *status; // [0] set to 1 when a chain ends with nu == -inf (R: "Problems With Underflow")
+                     // [1] chains of the speculative path that were re-run exactly
     Norm3Const c;
 };
 
@@ -346,6 +354,7 @@ HB_HD uint32_t norm3_forward_one(const Norm3Const &c, Norm3State<SYM> &s, double
 struct Norm3Smem {
     double2 *va, *vb;
     double *e2, *xs;
+    int32_t *ph; // hb_norm3_fast.cuh: high word of 2^-es per step
     int32_t st;
 #if !defined(__CUDA_ARCH__)
     // host emulation of cp.async groups: copies become visible only at wait (catches hazards)
@@ -440,7 +449,11 @@ HB_HD void norm3_backward_one(const Norm3Args &a, Norm3State<SYM> &s, int64_t ro
         const double E2 = m.e2[j * m.st];
         double g0 = va.x * s.b0, g1 = va.y * s.b1, g2 = vb.x * s.b2;
         double rs = rcp_fast((g0 + g1) + g2);
+#ifdef HB_DEBUG_NOGAMMA
+        double *gp = a.gamma + (row & 7) * a.ldg + b;
+#else
         double *gp = a.gamma + row * a.ldg + b;
+#endif
         const int64_t plane = a.T * a.ldg;
         gp[0] = g0 * rs;
         gp[plane] = g1 * rs;

@@ -1,0 +1,661 @@
+// hb_norm3_fast.cuh — 3-state Gaussian chain, symmetric parameters: speculate-and-verify Viterbi
+// fused with a normalisation-free forward-backward.  One thread per chain, same two-sweep layout
+// as hb_norm3.cuh (which stays the exact / general-parameter path and the fallback of this one).
+//
+// Replaces HiddenMarkov::dthmm(..., "norm", ...) -> HiddenMarkov::Viterbi at
+// R/HoneyBADGER.R:1150-1151 and R/HoneyBADGER_gexp.R:503-504 for the parameter block the reference
+// always builds (R/HoneyBADGER.R:1144-1150: Pi = [[1-2t,t,t],[t,1-2t,t],[t,t,1-2t]], means
+// (-dev, 0, +dev), one sd), and adds HiddenMarkov::forwardback's posteriors.
+//
+// Why a second formulation: hb_norm3.cuh replays the reference's arithmetic literally
+// (3 correctly rounded divisions + dnorm per step, nu in absolute log scale): 122 fp64
+// instructions per step, and the B200 fp64 pipe (2 warp-instructions/clk/SM) is what bounds the
+// kernel, not HBM.  This file cuts the step to ~81 fp64 instructions:
+//
+//  Viterbi (12 DADD/step instead of ~40 fp64).  Work on DIFFERENCES d_k = nu_k - nu_1, normalised by
+//  the "stay" cost: with tau = log t - log(1-2t) the three maxima become
+//        m0 = max(d0, tau, d2+tau)   m1 = max(d0+tau, 0, d2+tau)   m2 = max(d0+tau, tau, d2)
+//  (candidates in the reference's order j = 0,1,2; first index wins ties = strict ">" for a later j)
+//  and d_k' = (m_k - m1) + (log b_k - log b_1),  log b_{0,2} - log b_1 = lnK -+ u,  u = (m/sd^2)(x-mu_1).
+//  Every comparison is made on the SIGN of a rounded difference, whose magnitude is the decision
+//  margin; the chain tracks the minimum margin (integer min on the high words, ALU pipe).  The
+//  differences equal the reference's (computed with nu ~ 1e4 in absolute scale) up to an a-priori
+//  bound on its accumulated rounding, E <= 2 u L M (u = 2^-53, M >= max |nu|, bounded from sum x^2):
+//  if min margin > eps = 3 E every comparison provably has the reference's outcome, hence the same
+//  back-pointers, final state and path — bit-exact.  Otherwise (a few chains in 10^5 for
+//  per-chromosome chains) THE SAME THREAD re-runs the forward recursion with the
+//  literal reference arithmetic of hb_norm3.cuh before the backward sweep.  Exact ties have margin 0
+//  and always take that route, so "first index wins" is decided by the reference's own roundings.
+//
+//  Forward-backward (no per-step normalisation).  The filter phi_t is rescaled by 2^-es_t
+//  (es_t = exponent of sum phi_{t-1}); the backward vector uses THE SAME es_t, which makes
+//  sum_k phi_t(k) beta_t(k) independent of t.  Starting beta_T at 1/sum(phi_T) therefore yields
+//  gamma_t(k) = phi_t(k) * beta_t(k) directly: 3 multiplies, no sum, no reciprocal.
+//
+// Layout, staging (cp.async ring for x), checkpoints every HB_CHUNK steps, back-pointer words and
+// chunk-ahead prefetch are as in hb_norm3.cuh.  Build with -fmad=false (explicit dfma only).
+#pragma once
+#include "hb_norm3.cuh"
+
+namespace hb {
+
+// Longest chain the speculative path accepts: eps grows ~L^2, the flagged fraction ~L^3.
+#define HB_FAST_LMAX 4096
+
+// ---------------------------------------------------------------- small bit helpers
+// (code << 1) | signbit(q)
+HB_HD uint32_t push_sign(uint32_t code, double q)
+{
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_l((uint32_t)hi32(q), code, 1);
+#else
+    return (code << 1) | ((uint32_t)hi32(q) >> 31);
+#endif
+}
+// running minimum of |q| on the high word (monotone in |q|; NaN/Inf map above every finite value)
+HB_HD uint32_t absmin_hi(uint32_t mn, double q)
+{
+    const uint32_t h = (uint32_t)hi32(q) & 0x7fffffffu;
+    return h < mn ? h : mn;
+}
+// q < 0 (by sign bit) ? a : b
+HB_HD double sel_neg(double q, double a, double b) { return hi32(q) < 0 ? a : b; }
+
+// exp(u), exp(-u) as Pp * 2^n, Pm * 2^-n: one-FMA range reduction (|n| small on this path: the
+// reduction error is n * 2.3e-17), even/odd split of the degree-11 Taylor polynomial on
+// |r| <= ln2/2 (truncation 6e-15 at the interval ends, 5e-16 on average).  17 fp64 instructions.
+HB_HD void fast_exp_pair(const Norm3Const &c, double u, double &Pp, double &Pm, int32_t &n)
+{
+    const double MAGIC = 6755399441055744.0; // 1.5 * 2^52
+    const double t = dfma(u, c.k[HBK_L2E], MAGIC);
+    const int32_t ni = lo32(t);
+    const double nf = t - MAGIC;
+    const double r = dfma(nf, -c.k[HBK_LN2], u);
+    const double q = r * r;
+    double ev = dfma(q, c.k[HBK_E10], c.k[HBK_E8]);
+    double od = dfma(q, c.k[HBK_O11], c.k[HBK_O9]);
+    ev = dfma(q, ev, c.k[HBK_E6]);
+    od = dfma(q, od, c.k[HBK_O7]);
+    ev = dfma(q, ev, c.k[HBK_E4]);
+    od = dfma(q, od, c.k[HBK_O5]);
+    ev = dfma(q, ev, 0.5);
+    od = dfma(q, od, c.k[HBK_O3]);
+    ev = dfma(q, ev, 1.0);
+    od = dfma(q, od, 1.0);
+    od = od * r;
+    Pp = ev + od;
+    Pm = ev - od;
+    n = ni > HB_NCLAMP ? HB_NCLAMP : (ni < -HB_NCLAMP ? -HB_NCLAMP : ni);
+}
+
+// Per-chain state of both sweeps.
+struct Fast3State {
+    double A, Bc, lnK;    // u = A x + Bc ; log(b_{0,2}/b_1) = lnK -+ u
+    double K, aK, tK;     // filter: rho_{0,2} = K e^{-+u}; aK = K (a - t), tK = K t
+    double d0, d2;        // Viterbi differences
+    double sx2;           // sum x^2 (error bound), or sum (x - mu_1)^2 when the log-likelihood is wanted
+    int32_t esum;         // sum of removed binary exponents (log-likelihood)
+    uint32_t mn;          // min |decision difference|, high word
+    double f0, f1, f2;    // forward filter
+    double b0, b1, b2;    // backward vector (pre-divided by sum phi_T)
+    int32_t ycur;
+};
+
+// One Viterbi step on differences; returns the 6-bit code (state k's field at bit 4-2k holds
+// b_k<<1 | a_k: a_k = "j=1 beat j=0", b_k = "j=2 beat the winner"; back-pointer = min(field, 2)).
+HB_HD uint32_t fast_vit_step(const Norm3Const &c, Fast3State &s, double u, bool first)
+{
+    const double tau = c.tau;
+    const double e0 = s.lnK - u, e2 = s.lnK + u;
+    if (first) {
+        s.d0 = c.dl0 + e0;
+        s.d2 = c.dl2 + e2;
+        return 0;
+    }
+    const double d0 = s.d0, d2 = s.d2;
+    const double C0 = d0 + tau, C2 = d2 + tau;
+    uint32_t code = 0, mn = s.mn;
+    // state 0: d0 | tau | C2
+    const double qa0 = d0 - tau;
+    const double w0 = sel_neg(qa0, tau, d0);
+    const double qb0 = w0 - C2;
+    const double m0 = sel_neg(qb0, C2, w0);
+    code = push_sign(push_sign(code, qb0), qa0);
+    mn = absmin_hi(absmin_hi(mn, qa0), qb0);
+    // state 1: C0 | 0 | C2          (0 > C0  <=>  C0 < 0)
+    const double w1 = sel_neg(C0, 0.0, C0);
+    const double qb1 = w1 - C2;
+    const double m1 = sel_neg(qb1, C2, w1);
+    code = push_sign(push_sign(code, qb1), C0);
+    mn = absmin_hi(absmin_hi(mn, C0), qb1);
+    // state 2: C0 | tau | d2        (tau > C0  <=>  nu_1 > nu_0  <=>  d0 < 0)
+    const double w2 = sel_neg(d0, tau, C0);
+    const double qb2 = w2 - d2;
+    const double m2 = sel_neg(qb2, d2, w2);
+    code = push_sign(push_sign(code, qb2), d0);
+    mn = absmin_hi(absmin_hi(mn, d0), qb2);
+    s.mn = mn;
+    s.d0 = (m0 - m1) + e0;
+    s.d2 = (m2 - m1) + e2;
+    return code;
+}
+
+// Filter step phi <- ((phi Pi) . rho) 2^-es; returns the scaled ratios and the high word of 2^-es
+// (what the backward sweep needs).  `first`: phi = delta . rho, es = 0.
+HB_HD int32_t fast_fwd_step(const Norm3Const &c, Fast3State &s, double u, bool first, double &E0s,
+                            double &E2s, int32_t &ph)
+{
+    double Pp, Pm;
+    int32_t n;
+    fast_exp_pair(c, u, Pp, Pm, n);
+    double p0, p1, p2;
+    int32_t es;
+    if (first) {
+        p0 = c.delta[0] * s.K;
+        p1 = c.delta[1];
+        p2 = c.delta[2] * s.K;
+        es = 0;
+    } else {
+        const double sm = (s.f0 + s.f1) + s.f2;
+        es = expo(sm);
+        const double ts = c.tt * sm, tKs = s.tK * sm;
+        p1 = dfma(c.amt, s.f1, ts);
+        p0 = dfma(s.aK, s.f0, tKs);
+        p2 = dfma(s.aK, s.f2, tKs);
+    }
+    ph = (1023 - es) << 20;
+    E0s = scale2(Pm, -n - es);
+    E2s = scale2(Pp, n - es);
+    s.f1 = p1 * mk64(ph, 0);
+    s.f0 = p0 * E0s;
+    s.f2 = p2 * E2s;
+    return es;
+}
+
+// ---------------------------------------------------------------- shared-memory slots
+// Compile-time layout switches (tools/build_variant.sh explores them):
+//   HB_FAST_XREG   1: x is prefetched half a chunk ahead into registers (plain coalesced LDG);
+//                  0: cp.async ring in shared memory (as hb_norm3.cuh)
+//   HB_FAST_NOPHI1 1: phi_1 is not parked, gamma_1 = |1 - gamma_0 - gamma_2| (the posteriors of this
+//                  formulation sum to 1 within ~1e-13 by construction)
+#ifndef HB_FAST_XREG
+#define HB_FAST_XREG 0
+#endif
+#ifndef HB_FAST_NOPHI1
+#define HB_FAST_NOPHI1 1
+#endif
+// per step j and thread: va, vb (double2), [e2 (double)], ph = hi word of 2^-es, [xs = x ring]
+//   NOPHI1: va = (phi0, phi2), vb = (E0s, E2s);  else va = (phi0, phi1), vb = (phi2, E0s), e2 = E2s
+#define HB_FAST_PARK_BYTES (16 + 16 + (HB_FAST_NOPHI1 ? 0 : 8) + 4)
+#define HB_FAST_SMEM_BYTES_PER_THREAD (HB_CHUNK * (HB_FAST_PARK_BYTES + (HB_FAST_XREG ? 0 : 8)))
+
+HB_HD void fast_replay_one(const Norm3Const &c, Fast3State &s, double xv, bool first, Norm3Smem &m,
+                           int j)
+{
+    double E0s, E2s;
+    int32_t ph;
+    fast_fwd_step(c, s, dfma(xv, s.A, s.Bc), first, E0s, E2s, ph);
+    double2 a, b;
+#if HB_FAST_NOPHI1
+    a.x = s.f0;
+    a.y = s.f2;
+    b.x = E0s;
+    b.y = E2s;
+#else
+    a.x = s.f0;
+    a.y = s.f1;
+    b.x = s.f2;
+    b.y = E0s;
+    m.e2[j * m.st] = E2s;
+#endif
+    m.va[j * m.st] = a;
+    m.vb[j * m.st] = b;
+    m.ph[j * m.st] = ph;
+}
+
+// Backward step at one row: emit y and gamma, move beta one position back.  pw = the 32-bit word of
+// the chunk's back-pointer word that holds step j, sh = bit offset of step j's code inside it.
+// g0/g1/g2 point at this row in the three posterior planes.
+template <bool VIT, bool FB>
+HB_HD void fast_backward_one(const Norm3Const &c, Fast3State &s, uint8_t *yp, double *g0, double *g1,
+                             double *g2, uint32_t pw, int sh, int j, const Norm3Smem &m)
+{
+    if (VIT) {
+        *yp = (uint8_t)(s.ycur + 1);
+        const uint32_t f = (pw >> (sh + 4 - 2 * s.ycur)) & 3u;
+        s.ycur = (int32_t)(f < 2u ? f : 2u);
+    }
+    if (FB) {
+        const double2 va = m.va[j * m.st], vb = m.vb[j * m.st];
+        const double p2 = mk64(m.ph[j * m.st], 0);
+#if HB_FAST_NOPHI1
+        const double ga = va.x * s.b0, gc = va.y * s.b2;
+        *g0 = ga;
+        *g2 = gc;
+        *g1 = fabs(1.0 - (ga + gc));
+        const double v0 = vb.x * s.b0, v2 = vb.y * s.b2, v1 = p2 * s.b1;
+#else
+        const double E2s = m.e2[j * m.st];
+        *g0 = va.x * s.b0;
+        *g1 = va.y * s.b1;
+        *g2 = vb.x * s.b2;
+        const double v0 = vb.y * s.b0, v2 = E2s * s.b2, v1 = p2 * s.b1;
+#endif
+        const double sw = dfma(s.K, v0 + v2, v1);
+        const double tsw = c.tt * sw;
+        s.b1 = dfma(c.amt, v1, tsw);
+        s.b0 = dfma(s.aK, v0, tsw);
+        s.b2 = dfma(s.aK, v2, tsw);
+    }
+}
+
+// bit position of step j's 6-bit code: 5 steps per 32-bit word
+#define HB_PSI_WORD(j) ((j) / 5)
+#define HB_PSI_SHIFT(j) (6 * ((j) % 5))
+
+// ---------------------------------------------------------------- exact fallback (rare)
+// Recomputes the chain's back-pointer words with the literal reference arithmetic (hb_norm3.cuh),
+// reading x straight from global memory; returns the final state.  Same word format as the fast path.
+HB_HD_NOINLINE int32_t norm3_exact_forward(const Norm3Args &a, int32_t seg, int64_t b)
+{
+    const Norm3Const &c = a.c;
+    const int64_t t0 = a.seg_off[seg];
+    const int32_t L = (int32_t)(a.seg_off[seg + 1] - t0);
+    const int64_t pix = a.sd_per_seg ? (int64_t)seg * a.B + b : b;
+    const double sdv = a.sd[pix], isd = a.inv_sd[pix], lsd = a.log_sd[pix];
+    const double *xp = a.x + t0 * a.ld + b;
+    uint64_t *psi = a.psi + a.chunk_off[seg] * a.B + b;
+    const int32_t nch = (L + HB_CHUNK - 1) / HB_CHUNK;
+    double n0 = 0, n1 = 0, n2 = 0;
+    // Only this lane of the warp is active: keep one chunk of x in flight ahead of the recursion so
+    // the DRAM latency of the strided loads overlaps the (latency-bound) exact arithmetic.
+    double xc[HB_CHUNK], xn[HB_CHUNK];
+#pragma unroll
+    for (int j = 0; j < HB_CHUNK; j++) xc[j] = j < L ? xp[(int64_t)j * a.ld] : 0.0;
+    for (int32_t ch = 0; ch < nch; ch++) {
+        const int32_t i0 = ch * HB_CHUNK;
+#pragma unroll
+        for (int j = 0; j < HB_CHUNK; j++)
+            xn[j] = (i0 + HB_CHUNK + j < L) ? xp[(int64_t)(i0 + HB_CHUNK + j) * a.ld] : 0.0;
+        uint32_t w0 = 0u, w1 = 0u;
+#pragma unroll
+        for (int j = 0; j < HB_CHUNK; j++) {
+            if (i0 + j < L) {
+                double l0, l1, l2, h1;
+                norm3_logb(xc[j], c, sdv, isd, lsd, l0, l1, l2, h1);
+                if (i0 + j == 0) {
+                    n0 = c.logdelta[0] + l0;
+                    n1 = c.logdelta[1] + l1;
+                    n2 = c.logdelta[2] + l2;
+                } else {
+                    const uint32_t ps = norm3_vit_step<true>(c, n0, n1, n2, l0, l1, l2);
+                    const uint32_t code = ((ps & 3u) << 4) | (ps & 12u) | ((ps >> 4) & 3u);
+                    if (HB_PSI_WORD(j))
+                        w1 |= code << HB_PSI_SHIFT(j);
+                    else
+                        w0 |= code << HB_PSI_SHIFT(j);
+                }
+            }
+        }
+        psi[(int64_t)ch * a.B] = (uint64_t)w0 | ((uint64_t)w1 << 32);
+#pragma unroll
+        for (int j = 0; j < HB_CHUNK; j++) xc[j] = xn[j];
+    }
+    if (n0 == -INFINITY || n1 == -INFINITY || n2 == -INFINITY) *a.status = 1;
+    int32_t y = 0;
+    double mv = n0;
+    if (n1 > mv) { mv = n1; y = 1; }
+    if (n2 > mv) { mv = n2; y = 2; }
+    return y;
+}
+
+HB_HD void count_flagged(const Norm3Args &a)
+{
+#if defined(__CUDA_ARCH__)
+    atomicAdd(a.status + 1, 1);
+#else
+    a.status[1] += 1;
+#endif
+}
+
+// ---------------------------------------------------------------- the whole chain
+// sum x^2 (LL = false) or sum (x - mu_1)^2 (LL = true: also the quadratic part of sum log b_1)
+template <bool LL>
+HB_HD void fast_acc_sq(const Norm3Const &c, Fast3State &s, double xv)
+{
+    if (LL) {
+        const double dd = xv - c.mean[1];
+        s.sx2 = dfma(dd, dd, s.sx2);
+    } else {
+        s.sx2 = dfma(xv, xv, s.sx2);
+    }
+}
+
+template <bool VIT, bool FB, bool LL>
+HB_HD void norm3_fast_chain(const Norm3Args &a, int32_t seg, int64_t b, Norm3Smem &m)
+{
+    const Norm3Const &c = a.c;
+    const int64_t t0 = a.seg_off[seg];
+    const int32_t L = (int32_t)(a.seg_off[seg + 1] - t0);
+    if (L <= 0) return;
+    const int32_t nfull = L / HB_CHUNK;
+    const int32_t tail = L - nfull * HB_CHUNK;
+    const int64_t cbase = a.chunk_off[seg];
+    const int64_t pix = a.sd_per_seg ? (int64_t)seg * a.B + b : b;
+    const int64_t ld = a.ld;
+    const double *xp = a.x + t0 * ld + b;
+    uint64_t *psi = a.psi + cbase * a.B + b;
+    double *ckpt = a.ckpt + cbase * 3 * a.B + b;
+
+    Fast3State s;
+    const double isd = a.inv_sd[pix];
+    {
+        const double mm = c.mean[2] - c.mean[1];
+        const double mi = mm * isd;
+        s.A = mi * isd;
+        s.Bc = -s.A * c.mean[1];
+        s.lnK = -0.5 * mi * mi;
+        s.K = exp(s.lnK);
+        s.aK = s.K * c.amt;
+        s.tK = s.K * c.tt;
+    }
+    s.d0 = s.d2 = 0;
+    s.sx2 = 0;
+    s.esum = 0;
+    s.mn = 0x7fffffffu;
+    s.f0 = s.f1 = s.f2 = 0;
+
+    // ------------------------------------------------------------ forward sweep
+    // x reaches the arithmetic half a chunk (XREG) or a whole chunk (cp.async ring) ahead of its use.
+#if HB_FAST_XREG
+    double xa[HB_HALF], xb[HB_HALF];
+    if (nfull > 0) {
+#pragma unroll
+        for (int j = 0; j < HB_HALF; j++) xa[j] = xp[(int64_t)j * ld];
+    }
+#else
+    if (nfull > 0) {
+        const double *xr0 = xp;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+#pragma unroll
+            for (int j = h * HB_HALF; j < (h + 1) * HB_HALF; j++) {
+                xs_refill(m, j, xr0);
+                xr0 += ld;
+            }
+            xs_commit(m);
+        }
+    }
+#endif
+    {
+#if HB_FAST_XREG
+        const double *xr = xp + (int64_t)HB_HALF * ld; // next half-chunk to fetch
+#else
+        const double *xr = xp + (int64_t)HB_CHUNK * ld; // refill pointer: one chunk ahead
+#endif
+        uint64_t *pw = psi;
+        double *ck = ckpt;
+        for (int32_t ch = 0; ch < nfull; ch++) {
+            const bool more = ch + 1 < nfull;
+            uint32_t w[2] = {0u, 0u};
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+#if HB_FAST_XREG
+                // fetch the other half: second half of this chunk, or first half of the next one
+                if (h == 0 || more) {
+#pragma unroll
+                    for (int j = 0; j < HB_HALF; j++) (h == 0 ? xb : xa)[j] = xr[(int64_t)j * ld];
+                }
+                xr += (int64_t)HB_HALF * ld;
+#else
+                xs_wait<1>(m);
+#endif
+                HB_UNROLL_STEPS
+                for (int j = h * HB_HALF; j < (h + 1) * HB_HALF; j++) {
+#if HB_FAST_XREG
+                    const double xv = h == 0 ? xa[j] : xb[j - HB_HALF];
+#else
+                    const double xv = m.xs[j * m.st];
+                    if (more) xs_refill(m, j, xr);
+                    xr += ld;
+#endif
+                    const bool first = (j == 0) && (ch == 0);
+                    const double u = dfma(xv, s.A, s.Bc);
+                    if (VIT || LL) fast_acc_sq<LL>(c, s, xv);
+                    if (VIT) w[HB_PSI_WORD(j)] |= fast_vit_step(c, s, u, first) << HB_PSI_SHIFT(j);
+                    if (FB) {
+                        double E0s, E2s;
+                        int32_t ph;
+                        const int32_t es = fast_fwd_step(c, s, u, first, E0s, E2s, ph);
+                        if (LL) s.esum += es;
+                    }
+                }
+#if !HB_FAST_XREG
+                xs_commit(m);
+#endif
+            }
+            if (VIT) *pw = (uint64_t)w[0] | ((uint64_t)w[1] << 32);
+            pw += a.B;
+            ck += 3 * a.B;
+            if (FB && (more || tail > 0)) {
+                ck[0] = s.f0;
+                ck[a.B] = s.f1;
+                ck[2 * a.B] = s.f2;
+            }
+        }
+    }
+#if !HB_FAST_XREG
+    xs_wait<0>(m);
+#endif
+    if (tail > 0) { // rolled: at most HB_CHUNK-1 steps per chain
+        uint32_t w[2] = {0u, 0u};
+        for (int j = 0; j < tail; j++) {
+            const double xv = xp[(int64_t)(nfull * HB_CHUNK + j) * ld];
+            const bool first = nfull == 0 && j == 0;
+            const double u = dfma(xv, s.A, s.Bc);
+            if (VIT || LL) fast_acc_sq<LL>(c, s, xv);
+            if (VIT) {
+                const uint32_t code = fast_vit_step(c, s, u, first);
+                if (j < 5)
+                    w[0] |= code << (6 * j);
+                else
+                    w[1] |= code << (6 * (j - 5));
+            }
+            if (FB) {
+                double E0s, E2s;
+                int32_t ph;
+                const int32_t es = fast_fwd_step(c, s, u, first, E0s, E2s, ph);
+                if (LL) s.esum += es;
+            }
+        }
+        if (VIT) psi[(int64_t)nfull * a.B] = (uint64_t)w[0] | ((uint64_t)w[1] << 32);
+    }
+
+    if (FB && LL) {
+        // LL = log sum(alpha_L) = log(sum phi) + ln2 * esum + sum_t log b_1(x_t)
+        const double lsd = a.log_sd[pix];
+        a.ll[(int64_t)seg * a.B + b] =
+            ((log((s.f0 + s.f1) + s.f2) + c.k[HBK_LN2] * (double)s.esum) - 0.5 * (s.sx2 * (isd * isd))) -
+            (double)L * (c.k[HBK_LNSQRT2PI] + lsd);
+    }
+    // ------------------------------------------------------------ verify the speculation
+    s.ycur = 0;
+    if (VIT) {
+        // final state: nu_1 > nu_0 <=> d0 < 0 ; nu_2 > max <=> d2 > max(d0, 0)
+        const double wf = sel_neg(s.d0, 0.0, s.d0);
+        const double qf = wf - s.d2;
+        s.ycur = hi32(s.d0) < 0 ? 1 : 0;
+        if (hi32(qf) < 0) s.ycur = 2;
+        uint32_t mn = absmin_hi(absmin_hi(s.mn, s.d0), qf);
+        // a-priori bound on |reference difference - ours| (see the header): u (2 L M + 16 M + 16 L dmax)
+        const double U = 1.1102230246251565e-16;
+        const double Ld = (double)L;
+        const double lsd = a.log_sd[pix];
+        // |log b_k| <= C + |log sd| + ((x - r)^2 + (mu_k - r)^2) / sd^2 with r = 0 (sx2 = sum x^2) or
+        // r = mu_1 (LL); |u| <= |A| sqrt(sx2) + |A r - A mu_1|
+        const double M = Ld * ((c.k[HBK_LNSQRT2PI] + fabs(lsd)) + fabs(c.la)) +
+                         (s.sx2 + Ld * (LL ? c.dmu2 : c.mumax2)) * (isd * isd) + (fabs(c.lt) + c.ldabs);
+        const double dmax = ((fabs(c.tau) + fabs(s.lnK)) + fabs(s.A) * sqrt(s.sx2)) +
+                            ((LL ? 0.0 : fabs(s.Bc)) + 8.0);
+        const double eps = 3.0 * U * ((2.0 * Ld * M + 16.0 * M) + 16.0 * Ld * dmax) * c.eps_scale;
+        const double margin = mk64((int32_t)mn, 0); // <= the true minimum |difference|
+        if (!(margin > eps)) {
+            count_flagged(a);
+            s.ycur = norm3_exact_forward(a, seg, b);
+        } else if (s.d0 == -INFINITY || s.d2 == -INFINITY) {
+            *a.status = 1; // some nu_k(T) == -Inf (nu_1 is finite here): HiddenMarkov's underflow stop
+        }
+    }
+
+    // ------------------------------------------------------------ backward sweep
+    if (FB) {
+        const double q = 1.0 / ((s.f0 + s.f1) + s.f2);
+        s.b0 = s.b1 = s.b2 = q;
+    }
+    if (FB && nfull > 0) {
+        const double *xl = xp + (int64_t)(nfull - 1) * HB_CHUNK * ld;
+#if HB_FAST_XREG
+#pragma unroll
+        for (int j = 0; j < HB_HALF; j++) xa[j] = xl[(int64_t)j * ld];
+#else
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+#pragma unroll
+            for (int j = h * HB_HALF; j < (h + 1) * HB_HALF; j++) {
+                xs_refill(m, j, xl);
+                xl += ld;
+            }
+            xs_commit(m);
+        }
+#endif
+    }
+    uint64_t pk_nx = 0;
+    double c0_nx = 0, c1_nx = 0, c2_nx = 0;
+    if (nfull > 0) {
+        if (VIT) pk_nx = psi[(int64_t)(nfull - 1) * a.B];
+        if (FB && nfull > 1) {
+            const double *ck = ckpt + (int64_t)(nfull - 1) * 3 * a.B;
+            c0_nx = ck[0];
+            c1_nx = ck[a.B];
+            c2_nx = ck[2 * a.B];
+        }
+    }
+    const int64_t plane = a.T * a.ldg;
+    if (tail > 0) {
+        uint64_t pk = 0;
+        if (VIT) pk = psi[(int64_t)nfull * a.B];
+        if (FB) {
+            if (nfull > 0) {
+                const double *ck = ckpt + (int64_t)nfull * 3 * a.B;
+                s.f0 = ck[0];
+                s.f1 = ck[a.B];
+                s.f2 = ck[2 * a.B];
+            }
+            for (int j = 0; j < tail; j++) {
+                const double xv = xp[(int64_t)(nfull * HB_CHUNK + j) * ld];
+                fast_replay_one(c, s, xv, nfull == 0 && j == 0, m, j);
+            }
+        }
+        for (int j = tail - 1; j >= 0; j--) {
+            const int64_t row = t0 + nfull * HB_CHUNK + j;
+            const uint32_t pwd = j < 5 ? (uint32_t)pk : (uint32_t)(pk >> 32);
+            double *gr = FB ? a.gamma + row * a.ldg + b : nullptr;
+            fast_backward_one<VIT, FB>(c, s, VIT ? a.y + row * a.ldy + b : nullptr, gr, gr + plane,
+                                       gr + 2 * plane, pwd, j < 5 ? 6 * j : 6 * (j - 5), j, m);
+        }
+    }
+    {
+        // row pointers of the LAST row of the current chunk, stepped back one row per step
+        const int64_t rowl = t0 + (int64_t)nfull * HB_CHUNK - 1;
+        uint8_t *yp = VIT ? a.y + rowl * a.ldy + b : nullptr;
+        double *g0 = FB ? a.gamma + rowl * a.ldg + b : nullptr;
+        double *g1 = g0 + plane, *g2 = g1 + plane;
+#if HB_FAST_XREG
+        // next fetch: second half of the last full chunk (its first half is already in xa)
+        const double *xr = xp + ((int64_t)(nfull - 1) * HB_CHUNK + HB_HALF) * ld;
+#else
+        const double *xr = xp + (int64_t)(nfull - 2) * HB_CHUNK * ld; // refill: previous chunk
+#endif
+        const uint64_t *pr = psi + (int64_t)(nfull - 2) * a.B;
+        const double *cr = ckpt + (int64_t)(nfull - 2) * 3 * a.B;
+        for (int32_t ch = nfull - 1; ch >= 0; ch--) {
+            const uint64_t pk = pk_nx;
+            if (FB && ch > 0) {
+                s.f0 = c0_nx;
+                s.f1 = c1_nx;
+                s.f2 = c2_nx;
+            }
+            if (ch > 0) {
+                if (VIT) pk_nx = *pr;
+                if (FB && ch > 1) {
+                    c0_nx = cr[0];
+                    c1_nx = cr[a.B];
+                    c2_nx = cr[2 * a.B];
+                }
+            }
+            pr -= a.B;
+            cr -= 3 * a.B;
+            if (FB) {
+                const bool more = ch > 0;
+#if HB_FAST_XREG
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    // h = 0: fetch this chunk's second half; h = 1: the previous chunk's first half
+                    if (h == 0) {
+#pragma unroll
+                        for (int j = 0; j < HB_HALF; j++) xb[j] = xr[(int64_t)j * ld];
+                        xr -= (int64_t)(HB_CHUNK + HB_HALF) * ld;
+                    } else {
+                        if (more) {
+#pragma unroll
+                            for (int j = 0; j < HB_HALF; j++) xa[j] = xr[(int64_t)j * ld];
+                        }
+                        xr += (int64_t)HB_HALF * ld;
+                    }
+                    HB_UNROLL_STEPS
+                    for (int j = h * HB_HALF; j < (h + 1) * HB_HALF; j++)
+                        fast_replay_one(c, s, h == 0 ? xa[j] : xb[j - HB_HALF], j == 0 && ch == 0, m, j);
+                }
+#else
+                const double *xq = xr;
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    xs_wait<1>(m);
+                    HB_UNROLL_STEPS
+                    for (int j = h * HB_HALF; j < (h + 1) * HB_HALF; j++) {
+                        const double xv = m.xs[j * m.st];
+                        if (more) xs_refill(m, j, xq);
+                        xq += ld;
+                        fast_replay_one(c, s, xv, j == 0 && ch == 0, m, j);
+                    }
+                    xs_commit(m);
+                }
+                xr -= (int64_t)HB_CHUNK * ld;
+#endif
+            }
+            const uint32_t plo = (uint32_t)pk, phi = (uint32_t)(pk >> 32);
+#ifdef HB_FAST_BWD_UNROLL
+#pragma unroll HB_FAST_BWD_UNROLL
+#else
+#pragma unroll
+#endif
+            for (int j = HB_CHUNK - 1; j >= 0; j--) {
+                fast_backward_one<VIT, FB>(c, s, yp, g0, g1, g2, HB_PSI_WORD(j) ? phi : plo,
+                                           HB_PSI_SHIFT(j), j, m);
+                if (VIT) yp -= a.ldy;
+#ifndef HB_DEBUG_NOGAMMA // (debug variant: keep writing the same rows -> the stores stay in L2)
+                if (FB) {
+                    g0 -= a.ldg;
+                    g1 -= a.ldg;
+                    g2 -= a.ldg;
+                }
+#endif
+            }
+        }
+    }
+#if !HB_FAST_XREG
+    xs_wait<0>(m);
+#endif
+}
+
+} // namespace hb

@@ -211,6 +211,25 @@ def _check_gm(t, dtype, name):
         raise ValueError(f"{name} must be a 2-D CUDA {dtype} tensor with unit column stride")
 
 
+def alloc_rows(T, B, dtype, device, planes=None):
+    """[T, B] (or [planes, T, B]) view of a buffer whose rows are padded to a multiple of 128 elements:
+    the resident layout the chain kernels like best (every row starts on a 1 KB boundary for fp64)."""
+    import torch
+    ld = (B + 127) // 128 * 128
+    if planes is None:
+        return torch.empty((T, ld), dtype=dtype, device=device)[:, :B]
+    return torch.empty((planes, T, ld), dtype=dtype, device=device)[:, :, :B]
+
+
+def to_rows(t):
+    """Copy a [T, B] CUDA tensor into the padded resident layout (no-op if it already is)."""
+    if t.stride(0) % 128 == 0 and t.stride(1) == 1:
+        return t
+    out = alloc_rows(t.shape[0], t.shape[1], t.dtype, t.device)
+    out.copy_(t)
+    return out
+
+
 def hmm_norm_dev(x, sd, mean, Pi, delta, seg_off=None, viterbi=True, gamma=True, ll=False,
                  out=None):
     """Gene-major x[T, B] (fp64 CUDA tensor, row stride = ld), sd [B] or [nseg, B] on the device.
@@ -232,9 +251,9 @@ def hmm_norm_dev(x, sd, mean, Pi, delta, seg_off=None, viterbi=True, gamma=True,
     out = dict(out or {})
     want_g = gamma or ll
     if viterbi and "y" not in out:
-        out["y"] = torch.empty((T, B), dtype=torch.uint8, device=x.device)
+        out["y"] = alloc_rows(T, B, torch.uint8, x.device)
     if want_g and "gamma" not in out:
-        out["gamma"] = torch.empty((3, T, B), dtype=torch.float64, device=x.device)
+        out["gamma"] = alloc_rows(T, B, torch.float64, x.device, planes=3)
     if ll and "ll" not in out:
         out["ll"] = torch.empty((nseg, B), dtype=torch.float64, device=x.device)
     y, g, l = out.get("y"), out.get("gamma"), out.get("ll")
@@ -264,9 +283,9 @@ def hmm_binom_dev(x, size, prob, Pi, delta, seg_off=None, rho=0.0, viterbi=True,
     out = dict(out or {})
     want_g = gamma or ll
     if viterbi and "y" not in out:
-        out["y"] = torch.empty((T, B), dtype=torch.uint8, device=x.device)
+        out["y"] = alloc_rows(T, B, torch.uint8, x.device)
     if want_g and "gamma" not in out:
-        out["gamma"] = torch.empty((2, T, B), dtype=torch.float64, device=x.device)
+        out["gamma"] = alloc_rows(T, B, torch.float64, x.device, planes=2)
     if ll and "ll" not in out:
         out["ll"] = torch.empty((nseg, B), dtype=torch.float64, device=x.device)
     y, g, l = out.get("y"), out.get("gamma"), out.get("ll")
@@ -292,6 +311,14 @@ def chain_sd_dev(x, seg_off=None, per_seg=False):
     _lib.check(lib.hb_chain_sd_dev(x.data_ptr(), x.stride(0), T, B, _vp(seg), seg.size - 1,
                                    int(per_seg), sd.data_ptr(), _stream()))
     return sd
+
+
+def norm3_rerun_chains() -> int:
+    """Chains of the last Gaussian launch whose Viterbi recursion was re-run with the literal
+    reference arithmetic (speculate-and-verify kernel); waits for the current stream."""
+    n = C.c_int64(0)
+    _lib.check(_lib.load().hb_norm3_stats_dev(_stream(), C.byref(n)))
+    return int(n.value)
 
 
 def status_dev():

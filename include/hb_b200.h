@@ -56,6 +56,16 @@ int hb_release_workspace(void);
 /* *_dev entry points never synchronise; this waits for `stream` and returns HB_ERR_UNDERFLOW if a
  * chain of the last launch ended with nu == -Inf (HiddenMarkov::Viterbi's error), else HB_OK. */
 int hb_status_dev(void *stream);
+/* Gaussian chains, kernel choice.  Two kernels compute the same results (identical Viterbi paths,
+ * posteriors within 1e-11 of each other): the literal-arithmetic kernel, and the speculate-and-verify
+ * kernel (eligible when the parameter block is the reference's symmetric one, delta[1] > 0 and no
+ * chain is longer than 4096 positions).  mode 0 (default): speculative when eligible and the row
+ * strides are multiples of 128 elements, else literal; 1: literal always; 3: speculative whenever
+ * eligible; 2: speculative with EVERY chain re-run through its exact fallback (test hook). */
+int hb_set_norm3_mode(int32_t mode);
+/* Number of chains of the last Gaussian launch whose Viterbi recursion was re-run with the literal
+ * reference arithmetic because a decision margin fell below the rounding bound (waits for `stream`). */
+int hb_norm3_stats_dev(void *stream, int64_t *rerun_chains);
 /* Largest trial count served by the host-built binomial emission table (default 511, <= 4095). */
 int hb_set_binom_lut_max(int32_t nmax);
 

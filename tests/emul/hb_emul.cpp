@@ -16,6 +16,7 @@
 #include "hb_binom2.cuh"
 #include "hb_host_math.h"
 #include "hb_norm3.cuh"
+#include "hb_norm3_fast.cuh"
 #include "hb_x87.cuh"
 
 using namespace hb;
@@ -113,6 +114,75 @@ int emul_norm3(const double *x, int64_t ld, int64_t T, int64_t B, const int64_t 
             }
         }
     return status;
+}
+
+// The speculate-and-verify kernel body (hb_norm3_fast.cuh).  eps_scale: 1 = product setting,
+// +Inf = every chain takes the exact fallback, 0 = never verify (shows what speculation alone gives).
+// Returns status; *nflag receives the number of chains re-run exactly.
+int emul_norm3_fast(const double *x, int64_t ld, int64_t T, int64_t B, const int64_t *seg_off,
+                    int nseg, const double *mean, const double *sd, int sd_per_seg,
+                    const double *Pi, const double *delta, int flags, double eps_scale, uint8_t *y,
+                    double *gamma, double *ll, int32_t *nflag)
+{
+    Seg sg = make_seg(seg_off, nseg);
+    Norm3Args a;
+    memset(&a, 0, sizeof a);
+    for (int i = 0; i < 3; i++) {
+        a.c.mean[i] = mean[i];
+        a.c.delta[i] = delta[i];
+        a.c.logdelta[i] = log(delta[i]);
+    }
+    for (int i = 0; i < 9; i++) {
+        a.c.Pi[i] = Pi[i];
+        a.c.logPi[i] = log(Pi[i]);
+    }
+    a.c.la = a.c.logPi[0];
+    a.c.lt = a.c.logPi[1];
+    a.c.amt = Pi[0] - Pi[1];
+    a.c.tt = Pi[1];
+    a.c.tau = a.c.lt - a.c.la;
+    a.c.dl0 = a.c.logdelta[0] - a.c.logdelta[1];
+    a.c.dl2 = a.c.logdelta[2] - a.c.logdelta[1];
+    a.c.mumax2 = std::max(mean[0] * mean[0], std::max(mean[1] * mean[1], mean[2] * mean[2]));
+    a.c.dmu2 = std::max((mean[0] - mean[1]) * (mean[0] - mean[1]), (mean[2] - mean[1]) * (mean[2] - mean[1]));
+    a.c.ldabs = 0;
+    for (int i = 0; i < 3; i++)
+        if (std::isfinite(a.c.logdelta[i])) a.c.ldabs = std::max(a.c.ldabs, fabs(a.c.logdelta[i]));
+    a.c.eps_scale = eps_scale;
+    norm3_fill_k(a.c);
+    int64_t nsd = sd_per_seg ? (int64_t)nseg * B : B;
+    std::vector<double> inv(nsd), lg(nsd);
+    for (int64_t i = 0; i < nsd; i++) {
+        inv[i] = 1.0 / sd[i];
+        lg[i] = log(sd[i]);
+    }
+    std::vector<uint64_t> psi((size_t)sg.nchunks * B);
+    std::vector<double> ckpt((size_t)sg.nchunks * 3 * B);
+    std::vector<double2> sva(HB_CHUNK), svb(HB_CHUNK);
+    std::vector<double> se2(HB_CHUNK), sxs(HB_CHUNK);
+    std::vector<int32_t> sph(HB_CHUNK);
+    Norm3Smem sm;
+    sm.va = sva.data(); sm.vb = svb.data(); sm.e2 = se2.data(); sm.xs = sxs.data();
+    sm.ph = sph.data(); sm.st = 1;
+    int32_t status[4] = {0, 0, 0, 0};
+    a.x = x; a.ld = ld; a.T = T; a.B = B;
+    a.seg_off = sg.off.data(); a.chunk_off = sg.chunk.data(); a.seg_order = sg.order.data();
+    a.nseg = nseg; a.nblk_per_seg = 1;
+    a.sd = sd; a.inv_sd = inv.data(); a.log_sd = lg.data(); a.sd_per_seg = sd_per_seg;
+    a.y = y; a.ldy = ld; a.gamma = gamma; a.ldg = ld; a.ll = (flags & 4) ? ll : nullptr;
+    a.psi = psi.data(); a.ckpt = ckpt.data(); a.status = status;
+    const bool vit = flags & 1, fb = flags & 6, llon = flags & 4;
+    for (int s = 0; s < nseg; s++)
+        for (int64_t b = 0; b < B; b++) {
+            int seg = sg.order[s];
+            if (vit && fb && llon) norm3_fast_chain<true, true, true>(a, seg, b, sm);
+            else if (vit && fb) norm3_fast_chain<true, true, false>(a, seg, b, sm);
+            else if (fb && llon) norm3_fast_chain<false, true, true>(a, seg, b, sm);
+            else if (fb) norm3_fast_chain<false, true, false>(a, seg, b, sm);
+            else norm3_fast_chain<true, false, false>(a, seg, b, sm);
+        }
+    if (nflag) *nflag = status[1];
+    return status[0];
 }
 
 int emul_binom2(const int32_t *x, const int32_t *n, int64_t ld, int64_t T, int64_t B,

@@ -30,6 +30,20 @@ def run_norm3(L, x, seg, mean, sd, Pi, delta, flags, force_general=0):
     return st, y, g, ll
 
 
+def run_norm3_fast(L, x, seg, mean, sd, Pi, delta, flags, eps_scale=1.0):
+    T, B = x.shape
+    nseg = seg.size - 1
+    y = np.zeros((T, B), np.uint8)
+    g = np.zeros((3, T, B))
+    ll = np.zeros((nseg, B))
+    nflag = C.c_int32(0)
+    st = L.emul_norm3_fast(ptr(x), C.c_int64(B), C.c_int64(T), C.c_int64(B), ptr(seg), nseg, ptr(mean),
+                           ptr(sd), 0, ptr(Pi), ptr(delta), flags, C.c_double(eps_scale), ptr(y), ptr(g),
+                           ptr(ll), C.byref(nflag))
+    run_norm3_fast.ll = ll
+    return st, y, g, nflag.value
+
+
 def run_binom2(L, x, n, seg, prob, Pi, delta, flags, lut):
     T, B = x.shape
     nseg = seg.size - 1
@@ -61,6 +75,74 @@ def test_norm3_chain_vs_oracle(emul, oracle, force_general, segs):
             assert np.allclose(ll, llo, rtol=1e-12, atol=0)
 
 
+@pytest.mark.parametrize("eps_scale", [1.0, float("inf")])
+@pytest.mark.parametrize("segs", [[0, 1203], [0, 2, 9, 17, 500, 508, 1203], [0, 2, 4, 7, 1203]])
+def test_norm3_fast_chain_vs_oracle(emul, oracle, eps_scale, segs):
+    """Speculate-and-verify body: same paths as the oracle whether a chain is verified by its margin
+    (eps_scale 1) or re-run through the exact fallback (eps_scale inf); posteriors within 1e-9."""
+    x, _, _ = synth.expression(1203, 9, seed=4)
+    seg = np.array(segs, dtype=np.int64)
+    sd = np.array([oracle.r_sd(x[:, b]) for b in range(x.shape[1])])
+    mean, Pi, delta = np.array([-synth.DEV, 0, synth.DEV]), oracle.sym_Pi(3, 1e-6), np.array([0., 1, 0])
+    yo, go, llo, rc = oracle.fbv_norm_batch(x, seg, mean, sd, Pi, delta)
+    nchains = x.shape[1] * (seg.size - 1)
+    for flags in (7, 3, 1, 2, 6):
+        st, y, g, nflag = run_norm3_fast(emul, x, seg, mean, sd, Pi, delta, flags, eps_scale)
+        assert st == 0 and rc == 0
+        if flags & 1:
+            assert (y == yo).all()
+            assert nflag == (nchains if eps_scale > 1 else 0)
+        if flags & 2:
+            assert np.abs(g - go).max() < 1e-9
+            assert np.abs(g.sum(0) - 1).max() < 1e-11
+        if flags & 4:
+            assert np.allclose(run_norm3_fast.ll, llo, rtol=1e-12, atol=0)
+
+
+def test_norm3_fast_flags_ties_and_near_ties(emul, oracle):
+    """Adversarial chains: exact ties (x = 0 keeps both outer states level), decisions within a few
+    ulps, extreme outliers.  Every such chain must either be verified or take the exact fallback, and
+    the path must equal the oracle's."""
+    rng = np.random.default_rng(11)
+    T, B = 700, 24
+    x = rng.standard_normal((T, B)) * 2.3
+    x[:, 0] = 0.0                                   # symmetric: nu_0 == nu_2 exactly at every step
+    x[:, 1] = np.where(np.arange(T) % 2 == 0, 1.5, -1.5)
+    x[100:300, 2] += 3.0
+    x[350:500, 3] -= 3.0
+    x[:, 4] = np.round(x[:, 4], 1)                  # coarse grid: repeated values, structural ties
+    x[123, 5] = 400.0                               # absurd outlier: exponent clamps, huge margins
+    x[:, 6] = 1e-300
+    seg = np.array([0, 350, 700], dtype=np.int64)
+    sd = np.full(B, 2.3)
+    mean, Pi, delta = np.array([-1.0, 0, 1.0]), oracle.sym_Pi(3, 1e-6), np.array([0., 1, 0])
+    yo, go, _, rc = oracle.fbv_norm_batch(x, seg, mean, sd, Pi, delta)
+    st, y, g, nflag = run_norm3_fast(emul, x, seg, mean, sd, Pi, delta, 3)
+    assert rc == 0 and st == 0
+    assert (y == yo).all()
+    assert nflag >= 2          # the two all-zero chains tie at every step
+    # posteriors: the linear-domain reference underflows for the outlier column; compare the rest
+    keep = [b for b in range(B) if b != 5]
+    assert np.abs(g[:, :, keep] - go[:, :, keep]).max() < 1e-9
+    # with verification switched off the all-zero chain is NOT guaranteed: show the hook matters
+    st0, y0, _, nflag0 = run_norm3_fast(emul, x, seg, mean, sd, Pi, delta, 1, eps_scale=0.0)
+    assert nflag0 <= nflag
+
+
+def test_norm3_fast_other_priors(emul, oracle):
+    """delta with all states reachable, asymmetric in value (the differences start finite)."""
+    x, _, _ = synth.expression(900, 6, seed=9)
+    seg = np.array([0, 450, 900], dtype=np.int64)
+    sd = np.array([oracle.r_sd(x[:, b]) for b in range(x.shape[1])])
+    mean, Pi, delta = np.array([-0.8, 0.1, 1.0]), oracle.sym_Pi(3, 1e-4), np.array([0.2, 0.5, 0.3])
+    yo, go, _, rc = oracle.fbv_norm_batch(x, seg, mean, sd, Pi, delta)
+    yo, go, llo, rc = oracle.fbv_norm_batch(x, seg, mean, sd, Pi, delta)
+    st, y, g, _ = run_norm3_fast(emul, x, seg, mean, sd, Pi, delta, 7)
+    assert st == 0 and rc == 0 and (y == yo).all()
+    assert np.abs(g - go).max() < 1e-9
+    assert np.allclose(run_norm3_fast.ll, llo, rtol=1e-12, atol=0)
+
+
 def test_norm3_general_parameters(emul, oracle):
     rng = np.random.default_rng(2)
     x = rng.standard_normal((800, 5)) * 1.2
@@ -73,6 +155,14 @@ def test_norm3_general_parameters(emul, oracle):
     st, y, g, ll = run_norm3(emul, x, seg, mean, sd, Pi, delta, 7)
     assert st == 0 and rc == 0 and (y == yo).all()
     assert np.abs(g - go).max() < 1e-9 and np.allclose(ll, llo, rtol=1e-12, atol=0)
+
+
+def test_norm3_fast_length_one_chain_flags_underflow(emul, oracle):
+    x = np.array([[0.3], [0.1]])
+    for eps_scale in (1.0, float("inf")):
+        st, *_ = run_norm3_fast(emul, x, np.array([0, 1, 2], dtype=np.int64), np.array([-1., 0, 1]),
+                                np.array([1.0]), oracle.sym_Pi(3, 1e-6), np.array([0., 1, 0]), 1, eps_scale)
+        assert st == 1
 
 
 def test_norm3_length_one_chain_flags_underflow(emul, oracle):

@@ -106,3 +106,46 @@ def test_dev_api_matches_host_api(oracle):
     assert (out["y"].cpu().numpy() == yo).all()
     assert np.abs(out["gamma"].cpu().numpy() - go).max() < 1e-9
     assert np.allclose(out["ll"].cpu().numpy(), llo, rtol=1e-10, atol=0)
+
+
+@pytest.mark.parametrize("nseg", [1, 22])
+def test_norm_kernel_modes_agree(oracle, nseg):
+    """The speculate-and-verify kernel (mode 3), the literal-arithmetic kernel (mode 1) and the
+    speculative kernel with every chain re-run exactly (mode 2) give the same paths as the oracle;
+    posteriors within 1e-9 of it and within 1e-11 of each other."""
+    import torch
+    from honeybadger_b200 import _lib, hmm
+    O = oracle
+    G, N = 3500, 400
+    x, seg22, _ = synth.expression(G, N, seed=12)
+    x[:, 7] = 0.0
+    x[:, 8] = np.round(x[:, 8], 1)     # coarse values: repeated decisions
+    x[1000, 9] = 300.0                 # absurd outlier
+    seg = seg22 if nseg == 22 else np.array([0, G], dtype=np.int64)
+    sd = np.full(N, 2.5)
+    Pi, delta, mean = O.sym_Pi(3, 1e-6), [0.0, 1.0, 0.0], [-synth.DEV, 0.0, synth.DEV]
+    yo, go, llo, rc = O.fbv_norm_batch(x, seg, mean, sd, Pi, delta)
+    assert rc == 0
+    xd, sdd = torch.from_numpy(x).cuda(), torch.from_numpy(sd).cuda()
+    lib = _lib.load()
+    res = {}
+    try:
+        for mode in (3, 1, 2):
+            _lib.check(lib.hb_set_norm3_mode(mode))
+            out = hmm.hmm_norm_dev(xd, sdd, mean, Pi, delta, seg_off=seg, viterbi=True, gamma=True, ll=True)
+            hmm.status_dev()
+            res[mode] = (out["y"].cpu().numpy(), out["gamma"].cpu().numpy(), out["ll"].cpu().numpy(),
+                         hmm.norm3_rerun_chains())
+    finally:
+        lib.hb_set_norm3_mode(0)
+    keep = np.array([b for b in range(N) if b != 9])  # the linear-domain oracle underflows at the outlier
+    for mode, (y, g, ll, nre) in res.items():
+        assert (y == yo).all(), f"mode {mode}: {(y != yo).sum()} states differ"
+        assert np.abs(g[:, :, keep] - go[:, :, keep]).max() < 1e-9
+        assert np.allclose(ll[:, keep], llo[:, keep], rtol=1e-10, atol=0)
+    assert np.abs(res[3][1] - res[1][1]).max() < 1e-11
+    nchains = N * (seg.size - 1)
+    if nseg == 22:   # chains short enough for the speculative kernel
+        assert res[3][3] < nchains // 20           # almost nothing needs the exact re-run
+        assert res[2][3] == nchains
+    assert res[1][3] == 0

@@ -7,15 +7,21 @@ if len(sys.argv) > 2 or (len(sys.argv) == 2 and not os.environ.get("HB_CHILD")):
     sys.exit(0)
 import numpy as np, torch
 sys.path.insert(0, ".")
-from honeybadger_b200 import hmm, synth
+from honeybadger_b200 import _lib, hmm, synth
+_lib.check(_lib.load().hb_set_norm3_mode(int(os.environ.get("HB_MODE", "0"))))
 N, G = int(os.environ.get("HB_N", 10000)), int(os.environ.get("HB_G", 20000))
 dev = torch.device("cuda:0")
 g = torch.Generator(device=dev); g.manual_seed(2)
-x = torch.randn((G, N), dtype=torch.float64, device=dev, generator=g) * 2.5
+LD = int(os.environ.get("HB_LD", N))
+x = torch.empty((G, LD), dtype=torch.float64, device=dev)[:, :N]
+x.copy_(torch.randn((G, N), dtype=torch.float64, device=dev, generator=g))
+x.mul_(torch.empty(N, dtype=torch.float64, device=dev).uniform_(2.0, 3.1, generator=g))
 sd = hmm.chain_sd_dev(x)
 Pi, delta, mean = hmm.sym_Pi(3, 1e-6), [0., 1., 0.], [-synth.DEV, 0., synth.DEV]
 seg = synth.segments(G)
-out = hmm.hmm_norm_dev(x, sd, mean, Pi, delta, seg_off=seg, viterbi=True, gamma=True)
+out = dict(y=torch.empty((G, LD), dtype=torch.uint8, device=dev)[:, :N],
+           gamma=torch.empty((3, G, LD), dtype=torch.float64, device=dev)[:, :, :N])
+out = hmm.hmm_norm_dev(x, sd, mean, Pi, delta, seg_off=seg, viterbi=True, gamma=True, out=out)
 res = []
 for mode, kw in (("V+FB", dict(viterbi=True, gamma=True)), ("FB", dict(viterbi=False, gamma=True)), ("V", dict(viterbi=True, gamma=False))):
     fn = lambda: hmm.hmm_norm_dev(x, sd, mean, Pi, delta, seg_off=seg, out=out, **kw)
@@ -28,4 +34,6 @@ for mode, kw in (("V+FB", dict(viterbi=True, gamma=True)), ("FB", dict(viterbi=F
     ms = sorted(ts)[3]
     res.append(f"{mode} {ms:.3f} ms {N*G/ms/1e6:.1f} G/s")
 hmm.status_dev()
-print(os.path.basename(sys.argv[1]), " | ".join(res), flush=True)
+hmm.hmm_norm_dev(x, sd, mean, Pi, delta, seg_off=seg, out=out, viterbi=True, gamma=True)
+print(os.path.basename(sys.argv[1]), "ld", LD, "mode", os.environ.get("HB_MODE", "0"), " | ".join(res),
+      "| rerun chains", hmm.norm3_rerun_chains(), flush=True)
