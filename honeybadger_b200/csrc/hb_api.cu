@@ -17,6 +17,7 @@
 
 #include "../../include/hb_b200.h"
 #include "hb_binom2.cuh"
+#include "hb_binom2_fast.cuh"
 #include "hb_host_math.h"
 #include "hb_kernels.h"
 #include "hb_norm3.cuh"
@@ -86,7 +87,7 @@ struct DevBuf {
 
 // Per-device scratch, grown on demand and reused across calls (no allocation in steady state).
 struct Workspace {
-    DevBuf psi, ckpt, sdaux, segtab, status, lut_lb, lut_rho, cellmask, gsize;
+    DevBuf psi, ckpt, sdaux, segtab, status, lut_lb, lut_rho, lut_rho_d, cellmask, gsize;
     DevBuf st_in, st_in2, st_x, st_x2, st_y, st_g, st_out, st_sd, st_ll, st_member, st_pool, st_pool2;
     std::vector<int64_t> seg_cached;
     int64_t nchunks = 0;
@@ -94,7 +95,7 @@ struct Workspace {
     int32_t lut_nmax = -1;
     void release_all()
     {
-        DevBuf *all[] = {&psi, &ckpt, &sdaux, &segtab, &status, &lut_lb, &lut_rho, &cellmask, &gsize,
+        DevBuf *all[] = {&psi, &ckpt, &sdaux, &segtab, &status, &lut_lb, &lut_rho, &lut_rho_d, &cellmask, &gsize,
                          &st_in, &st_in2, &st_x, &st_x2, &st_y, &st_g, &st_out, &st_sd, &st_ll,
                          &st_member, &st_pool, &st_pool2};
         for (DevBuf *b : all) b->release();
@@ -107,6 +108,7 @@ struct Workspace {
 std::mutex g_mu;
 Workspace g_ws[16];
 int g_lut_nmax_cfg = 511;
+int g_binom2_mode = 0; // 0 auto (lean kernel, general kernel behind its gate), 1 general kernel only
 int g_norm3_mode = 0; // 0 auto, 1 literal kernel only, 2 speculative kernel with every chain re-run exactly, 3 speculative kernel whenever eligible
 
 int cur_ws(Workspace **out)
@@ -310,6 +312,7 @@ int prepare_lut(Workspace *ws, const double *prob, double rho, cudaStream_t st)
     const size_t cnt = (size_t)(nmax + 1) * (nmax + 2) / 2;
     std::vector<double> lb(2 * cnt);
     std::vector<hb::RhoME> rr(cnt);
+    std::vector<double> rd(cnt);
     for (int32_t n = 0; n <= nmax; n++)
         for (int32_t x = 0; x <= n; x++) {
             size_t ix = (size_t)n * (n + 1) / 2 + x;
@@ -324,12 +327,16 @@ int prepare_lut(Workspace *ws, const double *prob, double rho, cudaStream_t st)
             lb[2 * ix] = l0;
             lb[2 * ix + 1] = l1;
             rr[ix] = hb::rho_from_logratio(l0 - l1);
+            // impossible under both states: the general path uses rho = 1 (binom2_emit_slow)
+            rd[ix] = (l0 == -INFINITY && l1 == -INFINITY) ? 1.0 : hb::b2f_rho_double(rr[ix]);
         }
     HBTRY(ws->lut_lb.ensure(lb.size() * sizeof(double)));
     HBTRY(ws->lut_rho.ensure(rr.size() * sizeof(hb::RhoME)));
+    HBTRY(ws->lut_rho_d.ensure(rd.size() * sizeof(double)));
     CU(cudaStreamSynchronize(st));
     CU(cudaMemcpy(ws->lut_lb.p, lb.data(), lb.size() * sizeof(double), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(ws->lut_rho.p, rr.data(), rr.size() * sizeof(hb::RhoME), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(ws->lut_rho_d.p, rd.data(), rd.size() * sizeof(double), cudaMemcpyHostToDevice));
     ws->lut_nmax = nmax;
     ws->lut_key[0] = prob[0];
     ws->lut_key[1] = prob[1];
@@ -387,6 +394,7 @@ int binom2_run(Workspace *ws, const int32_t *x, const int32_t *n, int64_t ld, in
     a.nblk_per_seg = (int32_t)((B + HB_BLOCK - 1) / HB_BLOCK);
     a.lut_lb = ws->lut_lb.as<double2>();
     a.lut_rho = ws->lut_rho.as<hb::RhoME>();
+    a.lut_rho_d = ws->lut_rho_d.as<double>();
     a.lut_nmax = ws->lut_nmax;
     a.y = y;
     a.ldy = ldy;
@@ -396,6 +404,15 @@ int binom2_run(Workspace *ws, const int32_t *x, const int32_t *n, int64_t ld, in
     a.psi = ws->psi.as<uint64_t>();
     a.ckpt = ws->ckpt.as<double>();
     a.status = ws->status.as<int32_t>();
+    // Lean kernel first (plain-double filter, rows of Pi positive); it raises the gate when some
+    // position carries evidence beyond 2^+-900, and the general kernel then redoes the launch
+    // (otherwise its blocks exit at once).  Both are enqueued: no host synchronisation here.
+    const bool lean_ok = Pi[0] > 0 && Pi[1] > 0 && Pi[2] > 0 && Pi[3] > 0;
+    if (lean_ok && g_binom2_mode != 1) {
+        a.gate = ws->status.as<int32_t>() + 2;
+        CU(hb::launch_binom2_fast(a, vit, fb, st));
+        a.gate_in = a.gate;
+    }
     CU(hb::launch_binom2(a, vit, fb, st));
     return HB_OK;
 }
@@ -472,6 +489,29 @@ int hb_set_norm3_mode(int32_t mode)
         return fail(HB_ERR_ARG, "mode must be 0 (auto), 1 (literal), 2 (speculative, re-run all) or 3 (speculative)");
     std::lock_guard<std::mutex> lk(g_mu);
     g_norm3_mode = mode;
+    return HB_OK;
+}
+
+int hb_set_binom2_mode(int32_t mode)
+{
+    if (mode < 0 || mode > 1) return fail(HB_ERR_ARG, "mode must be 0 (auto) or 1 (general kernel only)");
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_binom2_mode = mode;
+    return HB_OK;
+}
+
+int hb_binom2_stats_dev(void *stream, int32_t *general_rerun)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    Workspace *ws;
+    HBTRY(cur_ws(&ws));
+    if (!general_rerun) return fail(HB_ERR_ARG, "general_rerun is NULL");
+    *general_rerun = 0;
+    if (!ws->status.p) return HB_OK;
+    int32_t s[3] = {0, 0, 0};
+    CU(cudaMemcpyAsync(s, ws->status.p, sizeof s, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CU(cudaStreamSynchronize((cudaStream_t)stream));
+    *general_rerun = s[2];
     return HB_OK;
 }
 

@@ -57,6 +57,7 @@ struct Binom2Args {
     int32_t nseg, nblk_per_seg;
     const double2 *lut_lb;  // [(n(n+1)/2 + x)] -> (logb_0, logb_1)
     const RhoME *lut_rho;   //                  -> b_0/b_1 = m * 2^e
+    const double *lut_rho_d; //                 -> b_0/b_1 as a double, < 0 = beyond 2^+-900 (hb_binom2_fast.cuh)
     int32_t lut_nmax;
     uint8_t *y;
     int64_t ldy;
@@ -66,6 +67,8 @@ struct Binom2Args {
     uint64_t *psi; // [nchunks][B]  (2 bits / step used)
     double *ckpt;  // [nchunks][2][B]
     int32_t *status;
+    int32_t *gate;          // lean kernel: set to 1 when the launch needs the general kernel
+    const int32_t *gate_in; // general kernel: run only if NULL or *gate_in != 0
     Binom2Const c;
 };
 

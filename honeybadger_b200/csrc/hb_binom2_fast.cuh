@@ -1,0 +1,355 @@
+// hb_binom2_fast.cuh — 2-state binomial chain, lean path: literal Viterbi + normalisation-free
+// forward-backward in plain doubles.  One thread per chain; hb_binom2.cuh stays the general path
+// (relative-exponent arithmetic for evidence beyond 2^+-900 per position) and re-runs the launch
+// when this kernel raises its gate.
+//
+// Replaces HiddenMarkov::dthmm(mafl, Pi, delta, "binom", list(prob=c(pd,pn)), list(size=sizel),
+// discrete=TRUE) -> HiddenMarkov::Viterbi at R/HoneyBADGER.R:1409-1410 and
+// R/HoneyBADGER_allele.R:579-580, plus HiddenMarkov::forwardback's posteriors.
+//
+// Viterbi: the reference's operation order on host-built log dbinom values (table lookup, see
+// hb_binom2.cuh) — per-cell allele chains tie EXACTLY at most zero-coverage positions
+// ((a + log t) + log(1-t) vs (a + log(1-t)) + log t), so only the literal arithmetic decides
+// "first index wins" the way R does; there is nothing to speculate on here.
+//
+// Forward-backward: phi_t = ((phi_{t-1} Pi) . (rho_t, 1)) 2^-es_t with es_t the exponent of the
+// un-normalised sum (phi stays in [1, 2)); the backward vector applies the SAME 2^-es_t, so
+// sum_k phi_t(k) beta_t(k) is constant and, with beta_T = 1 / sum(phi_T),
+//        gamma_t(0) = phi_t(0) beta_t(0),   gamma_t(1) = |1 - gamma_t(0)|.
+// rho = b_0 / b_1 comes from a table of doubles with the exponent limited to +-900 (entries beyond
+// that are marked and raise the gate).  Since rows of Pi are positive, beta's two components stay
+// within max Pi_jk / Pi_j'k of each other and beta <= const / max phi: nothing can overflow.
+//
+// 32 fp64 instructions per step (Viterbi 8, filter 8, replay 8, backward 8) against ~90 fp64 +
+// ~280 integer instructions of the general path.  HBM per step: x, n twice (16 B), gamma 16, y 1,
+// back-pointers 2 bits (0.5 B w+r), checkpoints 2 doubles / 8 steps (4 B w+r) = 37.5 B (25 B algorithmic).
+#pragma once
+#include "hb_binom2.cuh"
+
+namespace hb {
+
+#define HB_B2F_RHO_EXP_MAX 900
+
+// per step and thread: (phi0, rho 2^-es) as double2 + high word of 2^-es
+#define HB_B2F_SMEM_BYTES_PER_THREAD (HB_CHUNK * (16 + 4))
+
+struct B2fSmem {
+    double2 *pr;
+    int32_t *ph;
+    int32_t st;
+};
+
+// rho as a double for the table / the slow path: negative = "beyond the representable range"
+HB_HD double b2f_rho_double(const RhoME &r)
+{
+    if (r.e > HB_B2F_RHO_EXP_MAX || r.e < -HB_B2F_RHO_EXP_MAX) return -1.0;
+    return r.m * pow2i(r.e);
+}
+
+struct B2fState {
+    double n0, n1;   // Viterbi nu
+    double f0, f1;   // filter
+    double b0, b1;   // backward
+    double lsum;     // sum log b_1 (log-likelihood)
+    int32_t esum, ycur;
+};
+
+// Emission of one step: (l0, l1) literal log dbinom values, rho = b_0/b_1 as a double.
+template <bool WANT_LB, bool WANT_RHO>
+HB_HD void b2f_emit(const Binom2Args &a, int32_t xv, int32_t nv, double &l0, double &l1, double &rho)
+{
+    if ((uint32_t)nv <= (uint32_t)a.lut_nmax && (uint32_t)xv <= (uint32_t)nv) {
+        const int32_t ix = ((nv * (nv + 1)) >> 1) + xv;
+        if (WANT_LB) {
+            const double2 v = a.lut_lb[ix];
+            l0 = v.x;
+            l1 = v.y;
+        }
+        if (WANT_RHO) rho = a.lut_rho_d[ix];
+    } else {
+        if (a.c.bb) *a.status = 2;
+        RhoME r;
+        binom2_emit_slow(a.c, xv, nv, l0, l1, r);
+        rho = b2f_rho_double(r);
+    }
+    if (WANT_RHO && hi32(rho) < 0) { // marked entry: this launch needs the general kernel
+        *a.gate = 1;
+        rho = 1.0;
+    }
+}
+
+// phi <- ((phi Pi) . (rho, 1)) 2^-es, es = exponent of the un-normalised sum.  Returns es; rs = rho 2^-es.
+HB_HD int32_t b2f_fwd_step(const Binom2Const &c, B2fState &s, double rho, bool first, double &rs,
+                           int32_t &ph)
+{
+    double p0, p1;
+    if (first) {
+        p0 = c.delta[0];
+        p1 = c.delta[1];
+    } else {
+        p0 = dfma(s.f1, c.Pi[2], s.f0 * c.Pi[0]);
+        p1 = dfma(s.f1, c.Pi[3], s.f0 * c.Pi[1]);
+    }
+    const double q0 = p0 * rho;
+    const int32_t es = expo(q0 + p1);
+    ph = (1023 - es) << 20;
+    const double sc = mk64(ph, 0);
+    rs = rho * sc;
+    s.f0 = q0 * sc;
+    s.f1 = p1 * sc;
+    return es;
+}
+
+template <bool VIT, bool FB, bool LL>
+HB_HD void b2f_forward_one(const Binom2Args &a, B2fState &s, int32_t xv, int32_t nv, bool first,
+                           uint32_t &pk, int j)
+{
+    double l0 = 0, l1 = 0, rho = 1.0;
+    b2f_emit<VIT || LL, FB>(a, xv, nv, l0, l1, rho);
+    if (VIT) {
+        if (first) {
+            s.n0 = a.c.logdelta[0] + l0;
+            s.n1 = a.c.logdelta[1] + l1;
+        } else {
+            pk |= binom2_vit_step(a.c, s.n0, s.n1, l0, l1) << (2 * j);
+        }
+    }
+    if (FB) {
+        double rs;
+        int32_t ph;
+        const int32_t es = b2f_fwd_step(a.c, s, rho, first, rs, ph);
+        if (LL) {
+            s.esum += es;
+            s.lsum += l1;
+        }
+    }
+}
+
+HB_HD void b2f_replay_one(const Binom2Args &a, B2fState &s, int32_t xv, int32_t nv, bool first,
+                          const B2fSmem &m, int j)
+{
+    double l0, l1, rho = 1.0, rs;
+    int32_t ph;
+    b2f_emit<false, true>(a, xv, nv, l0, l1, rho);
+    b2f_fwd_step(a.c, s, rho, first, rs, ph);
+    double2 v;
+    v.x = s.f0;
+    v.y = rs;
+    m.pr[j * m.st] = v;
+    m.ph[j * m.st] = ph;
+}
+
+template <bool VIT, bool FB>
+HB_HD void b2f_backward_one(const Binom2Const &c, B2fState &s, uint8_t *yp, double *g0, double *g1,
+                            uint32_t pk, int j, const B2fSmem &m)
+{
+    if (VIT) {
+        *yp = (uint8_t)(s.ycur + 1);
+        s.ycur = (int32_t)((pk >> (2 * j + s.ycur)) & 1u);
+    }
+    if (FB) {
+        const double2 v = m.pr[j * m.st];
+        const double sc = mk64(m.ph[j * m.st], 0);
+        const double ga = v.x * s.b0;
+        *g0 = ga;
+        *g1 = fabs(1.0 - ga);
+        const double v0 = v.y * s.b0, v1 = sc * s.b1;
+        s.b0 = dfma(c.Pi[1], v1, c.Pi[0] * v0);
+        s.b1 = dfma(c.Pi[3], v1, c.Pi[2] * v0);
+    }
+}
+
+template <bool VIT, bool FB, bool LL>
+HB_HD void binom2_fast_chain(const Binom2Args &a, int32_t seg, int64_t b, const B2fSmem &m)
+{
+    const Binom2Const &c = a.c;
+    const int64_t t0 = a.seg_off[seg];
+    const int32_t L = (int32_t)(a.seg_off[seg + 1] - t0);
+    if (L <= 0) return;
+    const int32_t nfull = L / HB_CHUNK;
+    const int32_t tail = L - nfull * HB_CHUNK;
+    const int64_t cbase = a.chunk_off[seg];
+    const int64_t ld = a.ld;
+    const int32_t *xp = a.x + t0 * ld + b;
+    const int32_t *np = a.n + t0 * ld + b;
+    uint16_t *psi = reinterpret_cast<uint16_t *>(a.psi) + cbase * a.B + b; // 2 bits / step, 8 steps
+    double *ckpt = a.ckpt + cbase * 2 * a.B + b;
+
+    B2fState s;
+    s.n0 = s.n1 = 0;
+    s.f0 = s.f1 = 0;
+    s.lsum = 0;
+    s.esum = 0;
+
+    // ------------------------------------------------------------ forward sweep
+    // counts are prefetched half a chunk ahead into registers (two coalesced 128 B loads per step)
+    int32_t xa[HB_HALF], na[HB_HALF], xb[HB_HALF], nb[HB_HALF];
+    if (nfull > 0) {
+#pragma unroll
+        for (int j = 0; j < HB_HALF; j++) {
+            xa[j] = xp[(int64_t)j * ld];
+            na[j] = np[(int64_t)j * ld];
+        }
+    }
+    {
+        int64_t off = (int64_t)HB_HALF * ld; // next half-chunk to fetch
+        uint16_t *pw = psi;
+        double *ck = ckpt;
+        for (int32_t ch = 0; ch < nfull; ch++) {
+            const bool more = ch + 1 < nfull;
+            uint32_t pk = 0;
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                if (h == 0 || more) {
+#pragma unroll
+                    for (int j = 0; j < HB_HALF; j++) {
+                        (h == 0 ? xb : xa)[j] = xp[off + (int64_t)j * ld];
+                        (h == 0 ? nb : na)[j] = np[off + (int64_t)j * ld];
+                    }
+                }
+                off += (int64_t)HB_HALF * ld;
+#pragma unroll
+                for (int j = h * HB_HALF; j < (h + 1) * HB_HALF; j++)
+                    b2f_forward_one<VIT, FB, LL>(a, s, h == 0 ? xa[j] : xb[j - HB_HALF],
+                                                 h == 0 ? na[j] : nb[j - HB_HALF],
+                                                 j == 0 && ch == 0, pk, j);
+            }
+            if (VIT) *pw = (uint16_t)pk;
+            pw += a.B;
+            ck += 2 * a.B;
+            if (FB && (more || tail > 0)) {
+                ck[0] = s.f0;
+                ck[a.B] = s.f1;
+            }
+        }
+    }
+    if (tail > 0) {
+        uint32_t pk = 0;
+        for (int j = 0; j < tail; j++) {
+            const int64_t o = (int64_t)(nfull * HB_CHUNK + j) * ld;
+            b2f_forward_one<VIT, FB, LL>(a, s, xp[o], np[o], nfull == 0 && j == 0, pk, j);
+        }
+        if (VIT) psi[(int64_t)nfull * a.B] = (uint16_t)pk;
+    }
+
+    if (FB && LL) {
+        // LL = log(phi_0 + phi_1) + ln2 * esum + sum_t log b_1
+        const double LN2 = 0.693147180559945309417232121458;
+        a.ll[(int64_t)seg * a.B + b] = (log(s.f0 + s.f1) + LN2 * (double)s.esum) + s.lsum;
+    }
+    s.ycur = 0;
+    if (VIT) {
+        if (s.n0 == -INFINITY || s.n1 == -INFINITY) *a.status = 1;
+        if (s.n1 > s.n0) s.ycur = 1;
+    }
+
+    // ------------------------------------------------------------ backward sweep
+    if (FB) {
+        const double q = 1.0 / (s.f0 + s.f1);
+        s.b0 = s.b1 = q;
+    }
+    if (FB && nfull > 0) {
+        const int64_t o = (int64_t)(nfull - 1) * HB_CHUNK * ld;
+#pragma unroll
+        for (int j = 0; j < HB_HALF; j++) {
+            xa[j] = xp[o + (int64_t)j * ld];
+            na[j] = np[o + (int64_t)j * ld];
+        }
+    }
+    uint32_t pk_nx = 0;
+    double c0_nx = 0, c1_nx = 0;
+    if (nfull > 0) {
+        if (VIT) pk_nx = psi[(int64_t)(nfull - 1) * a.B];
+        if (FB && nfull > 1) {
+            const double *ck = ckpt + (int64_t)(nfull - 1) * 2 * a.B;
+            c0_nx = ck[0];
+            c1_nx = ck[a.B];
+        }
+    }
+    const int64_t plane = a.T * a.ldg;
+    if (tail > 0) {
+        uint32_t pk = 0;
+        if (VIT) pk = psi[(int64_t)nfull * a.B];
+        if (FB) {
+            if (nfull > 0) {
+                const double *ck = ckpt + (int64_t)nfull * 2 * a.B;
+                s.f0 = ck[0];
+                s.f1 = ck[a.B];
+            }
+            for (int j = 0; j < tail; j++) {
+                const int64_t o = (int64_t)(nfull * HB_CHUNK + j) * ld;
+                b2f_replay_one(a, s, xp[o], np[o], nfull == 0 && j == 0, m, j);
+            }
+        }
+        for (int j = tail - 1; j >= 0; j--) {
+            const int64_t row = t0 + nfull * HB_CHUNK + j;
+            double *gr = FB ? a.gamma + row * a.ldg + b : nullptr;
+            b2f_backward_one<VIT, FB>(c, s, VIT ? a.y + row * a.ldy + b : nullptr, gr, gr + plane, pk,
+                                      j, m);
+        }
+    }
+    {
+        const int64_t rowl = t0 + (int64_t)nfull * HB_CHUNK - 1;
+        uint8_t *yp = VIT ? a.y + rowl * a.ldy + b : nullptr;
+        double *g0 = FB ? a.gamma + rowl * a.ldg + b : nullptr;
+        double *g1 = g0 + plane;
+        // next fetch: second half of the last full chunk (its first half is already in xa/na)
+        int64_t off = ((int64_t)(nfull - 1) * HB_CHUNK + HB_HALF) * ld;
+        const uint16_t *pr = psi + (int64_t)(nfull - 2) * a.B;
+        const double *cr = ckpt + (int64_t)(nfull - 2) * 2 * a.B;
+        for (int32_t ch = nfull - 1; ch >= 0; ch--) {
+            const uint32_t pk = pk_nx;
+            if (FB && ch > 0) {
+                s.f0 = c0_nx;
+                s.f1 = c1_nx;
+            }
+            if (ch > 0) {
+                if (VIT) pk_nx = *pr;
+                if (FB && ch > 1) {
+                    c0_nx = cr[0];
+                    c1_nx = cr[a.B];
+                }
+            }
+            pr -= a.B;
+            cr -= 2 * a.B;
+            if (FB) {
+                const bool more = ch > 0;
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    if (h == 0) {
+#pragma unroll
+                        for (int j = 0; j < HB_HALF; j++) {
+                            xb[j] = xp[off + (int64_t)j * ld];
+                            nb[j] = np[off + (int64_t)j * ld];
+                        }
+                        off -= (int64_t)(HB_CHUNK + HB_HALF) * ld;
+                    } else {
+                        if (more) {
+#pragma unroll
+                            for (int j = 0; j < HB_HALF; j++) {
+                                xa[j] = xp[off + (int64_t)j * ld];
+                                na[j] = np[off + (int64_t)j * ld];
+                            }
+                        }
+                        off += (int64_t)HB_HALF * ld;
+                    }
+#pragma unroll
+                    for (int j = h * HB_HALF; j < (h + 1) * HB_HALF; j++)
+                        b2f_replay_one(a, s, h == 0 ? xa[j] : xb[j - HB_HALF],
+                                       h == 0 ? na[j] : nb[j - HB_HALF], j == 0 && ch == 0, m, j);
+                }
+            }
+#pragma unroll
+            for (int j = HB_CHUNK - 1; j >= 0; j--) {
+                b2f_backward_one<VIT, FB>(c, s, yp, g0, g1, pk, j, m);
+                if (VIT) yp -= a.ldy;
+                if (FB) {
+                    g0 -= a.ldg;
+                    g1 -= a.ldg;
+                }
+            }
+        }
+    }
+}
+
+} // namespace hb

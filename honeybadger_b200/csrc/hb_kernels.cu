@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include "hb_binom2.cuh"
+#include "hb_binom2_fast.cuh"
 #include "hb_kernels.h"
 #include "hb_norm3.cuh"
 #include "hb_norm3_fast.cuh"
@@ -72,7 +73,26 @@ __global__ void __launch_bounds__(HB_BLOCK)
     const int32_t seg = a.seg_order[blockIdx.x / a.nblk_per_seg];
     const int64_t b = (int64_t)(blockIdx.x % a.nblk_per_seg) * HB_BLOCK + threadIdx.x;
     if (b >= a.B) return;
+    if (a.gate_in && *a.gate_in == 0) return; // the lean kernel handled this launch
     binom2_chain<VIT, FB>(a, seg, b, smem + threadIdx.x, HB_BLOCK);
+}
+
+#ifndef HB_B2F_MINB
+#define HB_B2F_MINB 4
+#endif
+template <bool VIT, bool FB, bool LL>
+__global__ void __launch_bounds__(HB_BLOCK, HB_B2F_MINB)
+    binom2_fast_kernel(const __grid_constant__ Binom2Args a)
+{
+    extern __shared__ double2 smem2[];
+    const int32_t seg = a.seg_order[blockIdx.x / a.nblk_per_seg];
+    const int64_t b = (int64_t)(blockIdx.x % a.nblk_per_seg) * HB_BLOCK + threadIdx.x;
+    if (b >= a.B) return;
+    B2fSmem m;
+    m.st = HB_BLOCK;
+    m.pr = smem2 + threadIdx.x;
+    m.ph = reinterpret_cast<int32_t *>(smem2 + HB_CHUNK * HB_BLOCK) + threadIdx.x;
+    binom2_fast_chain<VIT, FB, LL>(a, seg, b, m);
 }
 
 template <bool SYM>
@@ -126,6 +146,27 @@ cudaError_t launch_norm3_fast(const Norm3Args &a, bool vit, bool fb, cudaStream_
         HB_LAUNCH_FAST(true, false, false, sm_v);
     }
 #undef HB_LAUNCH_FAST
+    return cudaGetLastError();
+}
+
+cudaError_t launch_binom2_fast(const Binom2Args &a, bool vit, bool fb, cudaStream_t st)
+{
+    const unsigned grid = (unsigned)((int64_t)a.nseg * a.nblk_per_seg);
+    const size_t sm_fb = (size_t)HB_B2F_SMEM_BYTES_PER_THREAD * HB_BLOCK;
+    const bool ll = a.ll != nullptr;
+    if (vit && fb) {
+        if (ll)
+            binom2_fast_kernel<true, true, true><<<grid, HB_BLOCK, sm_fb, st>>>(a);
+        else
+            binom2_fast_kernel<true, true, false><<<grid, HB_BLOCK, sm_fb, st>>>(a);
+    } else if (fb) {
+        if (ll)
+            binom2_fast_kernel<false, true, true><<<grid, HB_BLOCK, sm_fb, st>>>(a);
+        else
+            binom2_fast_kernel<false, true, false><<<grid, HB_BLOCK, sm_fb, st>>>(a);
+    } else {
+        binom2_fast_kernel<true, false, false><<<grid, HB_BLOCK, 0, st>>>(a);
+    }
     return cudaGetLastError();
 }
 

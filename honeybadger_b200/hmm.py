@@ -321,6 +321,13 @@ def norm3_rerun_chains() -> int:
     return int(n.value)
 
 
+def binom2_general_rerun() -> int:
+    """1 if the last binomial launch was redone by the general (relative-exponent) kernel."""
+    n = C.c_int32(0)
+    _lib.check(_lib.load().hb_binom2_stats_dev(_stream(), C.byref(n)))
+    return int(n.value)
+
+
 def status_dev():
     """Wait for the current stream and raise UnderflowError if the last launch hit nu == -Inf."""
     _lib.check(_lib.load().hb_status_dev(_stream()))

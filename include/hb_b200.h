@@ -66,6 +66,12 @@ int hb_set_norm3_mode(int32_t mode);
 /* Number of chains of the last Gaussian launch whose Viterbi recursion was re-run with the literal
  * reference arithmetic because a decision margin fell below the rounding bound (waits for `stream`). */
 int hb_norm3_stats_dev(void *stream, int64_t *rerun_chains);
+/* Binomial chains, kernel choice.  0 (default): the lean plain-double kernel, with the general
+ * relative-exponent kernel re-running the launch when some position carries evidence beyond 2^+-900
+ * (both enqueued, no synchronisation); 1: general kernel only.  Same results either way. */
+int hb_set_binom2_mode(int32_t mode);
+/* 1 if the last binomial launch had to be redone by the general kernel (waits for `stream`). */
+int hb_binom2_stats_dev(void *stream, int32_t *general_rerun);
 /* Largest trial count served by the host-built binomial emission table (default 511, <= 4095). */
 int hb_set_binom_lut_max(int32_t nmax);
 

@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "hb_binom2.cuh"
+#include "hb_binom2_fast.cuh"
 #include "hb_host_math.h"
 #include "hb_norm3.cuh"
 #include "hb_norm3_fast.cuh"
@@ -233,6 +234,77 @@ int emul_binom2(const int32_t *x, const int32_t *n, int64_t ld, int64_t T, int64
             else binom2_chain<true, false>(a, seg, b, sm.data(), 1);
         }
     return status;
+}
+
+// The lean binomial kernel body (hb_binom2_fast.cuh) followed, when it raises its gate, by the general
+// body — the sequence binom2_run() enqueues.  *gate_out tells whether the general body had to run.
+int emul_binom2_fast(const int32_t *x, const int32_t *n, int64_t ld, int64_t T, int64_t B,
+                     const int64_t *seg_off, int nseg, const double *prob, const double *Pi,
+                     const double *delta, int flags, int lut_nmax, uint8_t *y, double *gamma,
+                     double *ll, int32_t *gate_out)
+{
+    Seg sg = make_seg(seg_off, nseg);
+    Binom2Args a;
+    memset(&a, 0, sizeof a);
+    for (int k = 0; k < 2; k++) {
+        a.c.prob[k] = prob[k];
+        a.c.q[k] = 1 - prob[k];
+        a.c.logp[k] = log(prob[k]);
+        a.c.logq[k] = log(1 - prob[k]);
+        a.c.delta[k] = delta[k];
+        a.c.logdelta[k] = log(delta[k]);
+    }
+    for (int i = 0; i < 4; i++) {
+        a.c.Pi[i] = Pi[i];
+        a.c.logPi[i] = log(Pi[i]);
+    }
+    size_t cnt = (size_t)(lut_nmax + 1) * (lut_nmax + 2) / 2;
+    std::vector<double2> lb(cnt);
+    std::vector<RhoME> rr(cnt);
+    std::vector<double> rd(cnt);
+    for (int nn = 0; nn <= lut_nmax; nn++)
+        for (int xx = 0; xx <= nn; xx++) {
+            size_t ix = (size_t)nn * (nn + 1) / 2 + xx;
+            lb[ix].x = hbhost::binom_logpmf(xx, nn, prob[0]);
+            lb[ix].y = hbhost::binom_logpmf(xx, nn, prob[1]);
+            rr[ix] = rho_from_logratio(lb[ix].x - lb[ix].y);
+            rd[ix] = (lb[ix].x == -INFINITY && lb[ix].y == -INFINITY) ? 1.0 : b2f_rho_double(rr[ix]);
+        }
+    std::vector<uint64_t> psi((size_t)sg.nchunks * B);
+    std::vector<double> ckpt((size_t)sg.nchunks * 3 * B);
+    std::vector<double2> spr(HB_CHUNK);
+    std::vector<int32_t> sph(HB_CHUNK);
+    std::vector<double> sm(HB_CHUNK * HB_BINOM2_SLOT);
+    B2fSmem m;
+    m.pr = spr.data(); m.ph = sph.data(); m.st = 1;
+    int32_t status[4] = {0, 0, 0, 0};
+    a.x = x; a.n = n; a.ld = ld; a.T = T; a.B = B;
+    a.seg_off = sg.off.data(); a.chunk_off = sg.chunk.data(); a.seg_order = sg.order.data();
+    a.nseg = nseg; a.nblk_per_seg = 1;
+    a.lut_lb = lb.data(); a.lut_rho = rr.data(); a.lut_rho_d = rd.data(); a.lut_nmax = lut_nmax;
+    a.y = y; a.ldy = ld; a.gamma = gamma; a.ldg = ld; a.ll = (flags & 4) ? ll : nullptr;
+    a.psi = psi.data(); a.ckpt = ckpt.data(); a.status = status; a.gate = status + 2;
+    const bool vit = flags & 1, fb = flags & 6, llon = flags & 4;
+    for (int s = 0; s < nseg; s++)
+        for (int64_t b = 0; b < B; b++) {
+            int seg = sg.order[s];
+            if (vit && fb && llon) binom2_fast_chain<true, true, true>(a, seg, b, m);
+            else if (vit && fb) binom2_fast_chain<true, true, false>(a, seg, b, m);
+            else if (fb && llon) binom2_fast_chain<false, true, true>(a, seg, b, m);
+            else if (fb) binom2_fast_chain<false, true, false>(a, seg, b, m);
+            else binom2_fast_chain<true, false, false>(a, seg, b, m);
+        }
+    if (gate_out) *gate_out = status[2];
+    if (status[2]) {
+        for (int s = 0; s < nseg; s++)
+            for (int64_t b = 0; b < B; b++) {
+                int seg = sg.order[s];
+                if (vit && fb) binom2_chain<true, true>(a, seg, b, sm.data(), 1);
+                else if (fb) binom2_chain<false, true>(a, seg, b, sm.data(), 1);
+                else binom2_chain<true, false>(a, seg, b, sm.data(), 1);
+            }
+    }
+    return status[0];
 }
 
 // R mean() / sd() through the integer x87 emulation (the arithmetic of pool_mean_kernel / pooled_sd_kernel)

@@ -55,6 +55,19 @@ def run_binom2(L, x, n, seg, prob, Pi, delta, flags, lut):
     return st, y, g, ll
 
 
+def run_binom2_fast(L, x, n, seg, prob, Pi, delta, flags, lut):
+    T, B = x.shape
+    nseg = seg.size - 1
+    y = np.zeros((T, B), np.uint8)
+    g = np.zeros((2, T, B))
+    ll = np.zeros((nseg, B))
+    gate = C.c_int32(0)
+    st = L.emul_binom2_fast(ptr(x), ptr(n), C.c_int64(B), C.c_int64(T), C.c_int64(B), ptr(seg), nseg,
+                            ptr(prob), ptr(Pi), ptr(delta), flags, lut, ptr(y), ptr(g), ptr(ll),
+                            C.byref(gate))
+    return st, y, g, ll, gate.value
+
+
 @pytest.mark.parametrize("force_general", [0, 1])
 @pytest.mark.parametrize("segs", [[0, 1203], [0, 2, 9, 17, 500, 508, 1203]])
 def test_norm3_chain_vs_oracle(emul, oracle, force_general, segs):
@@ -202,3 +215,62 @@ def test_binom2_pooled_scale_counts_vs_exact_arithmetic(emul, oracle):
     logb = [[P.dbinom_log(float(a), float(c), q) for q in prob] for a, c in zip(x[:, 0], n[:, 0])]
     assert np.abs(g[:, :, 0].T - P.mp_posteriors(logb, Pi, delta, dps=80)).max() < 1e-12
     assert (y[:, 0] == oracle.viterbi_binom(x[:, 0], n[:, 0], prob, Pi, delta)).all()
+
+
+@pytest.mark.parametrize("lut", [511, 31, 0])
+@pytest.mark.parametrize("segs", [[0, 3001], [0, 700, 1301, 1305, 3001], [0, 2, 4, 3001]])
+def test_binom2_fast_chain_vs_oracle(emul, oracle, lut, segs):
+    """Lean binomial body: literal Viterbi (paths equal the oracle's, structural ties included),
+    normalisation-free posteriors within 1e-9, log-likelihood, for table and off-table counts."""
+    r, n, _, _ = synth.allele(3001, 10, seed=6, deep=0.002)
+    seg = np.array(segs, dtype=np.int64)
+    prob, Pi, delta = np.array([0.1, 0.45]), oracle.sym_Pi(2, 1e-6), np.array([0., 1.])
+    yo, go, llo, rc = oracle.fbv_binom_batch(r, n, seg, prob, Pi, delta)
+    assert rc == 0
+    for flags in (7, 3, 1, 2, 6):
+        st, y, g, ll, gate = run_binom2_fast(emul, r, n, seg, prob, Pi, delta, flags, lut)
+        assert st == 0 and gate == 0
+        if flags & 1:
+            assert (y == yo).all()
+        if flags & 2:
+            assert np.abs(g - go).max() < 1e-9
+            assert np.abs(g.sum(0) - 1).max() < 1e-12
+        if flags & 4:
+            assert np.allclose(ll, llo, rtol=1e-10, atol=1e-10)
+
+
+def test_binom2_fast_general_Pi_and_prior(emul, oracle):
+    r, n, _, _ = synth.allele(1500, 7, seed=8)
+    seg = np.array([0, 600, 1500], dtype=np.int64)
+    prob, delta = np.array([0.2, 0.5]), np.array([0.3, 0.7])
+    Pi = np.array([[0.98, 0.02], [0.001, 0.999]])
+    yo, go, llo, rc = oracle.fbv_binom_batch(r, n, seg, prob, Pi, delta)
+    st, y, g, ll, gate = run_binom2_fast(emul, r, n, seg, prob, Pi, delta, 7, 64)
+    assert st == 0 and rc == 0 and gate == 0
+    assert (y == yo).all() and np.abs(g - go).max() < 1e-9
+    assert np.allclose(ll, llo, rtol=1e-10, atol=1e-10)
+
+
+def test_binom2_fast_gate_on_extreme_evidence(emul, oracle):
+    """Pooled-scale counts (thousands of reads per position) exceed what a double ratio can hold: the
+    lean body must raise its gate, and the general body then produces the exact-arithmetic answer."""
+    rng = np.random.default_rng(7)
+    T = 300
+    n = rng.integers(2000, 6000, size=(T, 1)).astype(np.int32)
+    p = np.full((T, 1), 0.45)
+    p[80:160] = 0.1
+    x = rng.binomial(n, p).astype(np.int32)
+    prob, Pi, delta = np.array([0.1, 0.45]), oracle.sym_Pi(2, 1e-6), np.array([0., 1.])
+    st, y, g, _, gate = run_binom2_fast(emul, x, n, np.array([0, T], dtype=np.int64), prob, Pi, delta, 3, 511)
+    assert gate == 1 and st == 0
+    logb = [[P.dbinom_log(float(a), float(c), q) for q in prob] for a, c in zip(x[:, 0], n[:, 0])]
+    assert np.abs(g[:, :, 0].T - P.mp_posteriors(logb, Pi, delta, dps=80)).max() < 1e-12
+    assert (y[:, 0] == oracle.viterbi_binom(x[:, 0], n[:, 0], prob, Pi, delta)).all()
+    # moderate depth (hundreds of reads): within the plain-double range, no gate, same accuracy
+    n2 = rng.integers(100, 400, size=(T, 1)).astype(np.int32)
+    x2 = rng.binomial(n2, p).astype(np.int32)
+    st, y2, g2, _, gate2 = run_binom2_fast(emul, x2, n2, np.array([0, T], dtype=np.int64), prob, Pi, delta, 3, 511)
+    logb2 = [[P.dbinom_log(float(a), float(c), q) for q in prob] for a, c in zip(x2[:, 0], n2[:, 0])]
+    assert gate2 == 0 and st == 0
+    assert np.abs(g2[:, :, 0].T - P.mp_posteriors(logb2, Pi, delta, dps=80)).max() < 1e-11
+    assert (y2[:, 0] == oracle.viterbi_binom(x2[:, 0], n2[:, 0], prob, Pi, delta)).all()

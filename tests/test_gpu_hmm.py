@@ -149,3 +149,60 @@ def test_norm_kernel_modes_agree(oracle, nseg):
         assert res[3][3] < nchains // 20           # almost nothing needs the exact re-run
         assert res[2][3] == nchains
     assert res[1][3] == 0
+
+
+@pytest.mark.parametrize("nseg", [1, 22])
+def test_binom_kernel_modes_agree(oracle, nseg):
+    """Lean binomial kernel (auto mode) vs general kernel (mode 1) vs the oracle, with counts beyond
+    the emission table and a deep-coverage column; the gate stays closed for per-cell data."""
+    import torch
+    from honeybadger_b200 import _lib, hmm
+    O = oracle
+    G, N = 5000, 300
+    r_maf, n_sc, seg22, _ = synth.allele(G, N, seed=14, deep=0.002)
+    n_sc[:, 5] = np.minimum(n_sc[:, 5] * 40, 600)      # counts above the 511-entry table
+    r_maf[:, 5] = np.minimum(r_maf[:, 5] * 40, n_sc[:, 5])
+    seg = seg22 if nseg == 22 else np.array([0, G], dtype=np.int64)
+    Pi, delta, prob = O.sym_Pi(2, 1e-6), [0.0, 1.0], [0.1, 0.45]
+    yo, go, llo, rc = O.fbv_binom_batch(r_maf, n_sc, seg, prob, Pi, delta)
+    assert rc == 0
+    rd, nd = torch.from_numpy(r_maf).cuda(), torch.from_numpy(n_sc).cuda()
+    lib = _lib.load()
+    res = {}
+    try:
+        for mode in (0, 1):
+            _lib.check(lib.hb_set_binom2_mode(mode))
+            out = hmm.hmm_binom_dev(rd, nd, prob, Pi, delta, seg_off=seg, viterbi=True, gamma=True, ll=True)
+            hmm.status_dev()
+            res[mode] = (out["y"].cpu().numpy(), out["gamma"].cpu().numpy(), out["ll"].cpu().numpy(),
+                         hmm.binom2_general_rerun())
+    finally:
+        lib.hb_set_binom2_mode(0)
+    for mode, (y, g, ll, rerun) in res.items():
+        assert (y == yo).all(), f"mode {mode}: {(y != yo).sum()} states differ"
+        assert np.abs(g - go).max() < 1e-9
+        assert np.allclose(ll, llo, rtol=1e-10, atol=1e-9)
+    assert res[1][3] == 0   # (the general-only mode never reports a re-run; auto may, for the deep column)
+    assert np.abs(res[0][1] - res[1][1]).max() < 1e-11
+
+
+def test_binom_gate_reruns_general_kernel(oracle):
+    """Pooled-scale counts: the lean kernel raises its gate and the general kernel redoes the launch."""
+    import torch
+    from honeybadger_b200 import hmm
+    from oracle import pyref as P
+    rng = np.random.default_rng(7)
+    T = 300
+    n = rng.integers(2000, 6000, size=(T, 40)).astype(np.int32)
+    p = np.full((T, 1), 0.45)
+    p[80:160] = 0.1
+    x = rng.binomial(n, p).astype(np.int32)
+    prob, Pi, delta = [0.1, 0.45], hmm.sym_Pi(2, 1e-6), [0.0, 1.0]
+    out = hmm.hmm_binom_dev(torch.from_numpy(x).cuda(), torch.from_numpy(n).cuda(), prob, Pi, delta)
+    hmm.status_dev()
+    assert hmm.binom2_general_rerun() == 1
+    g = out["gamma"].cpu().numpy()
+    for b in (0, 39):
+        logb = [[P.dbinom_log(float(a), float(c), q) for q in prob] for a, c in zip(x[:, b], n[:, b])]
+        assert np.abs(g[:, :, b].T - P.mp_posteriors(logb, Pi, delta, dps=80)).max() < 1e-12
+        assert (out["y"][:, b].cpu().numpy() == oracle.viterbi_binom(x[:, b], n[:, b], prob, Pi, delta)).all()

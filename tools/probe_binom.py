@@ -9,7 +9,8 @@ import numpy as np, torch
 sys.path.insert(0, ".")
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench
-from honeybadger_b200 import hmm, synth
+from honeybadger_b200 import _lib, hmm, synth
+_lib.check(_lib.load().hb_set_binom2_mode(int(os.environ.get("HB_MODE", "0"))))
 N, G = int(os.environ.get("HB_N", 10000)), int(os.environ.get("HB_G", 50000))
 d = bench.device_inputs("allele", N, G, 3, torch.device("cuda:0"))
 r, n, seg = d["r"], d["n"], d["seg"]
@@ -27,4 +28,4 @@ for mode, kw in (("V+FB", dict(viterbi=True, gamma=True)), ("FB", dict(viterbi=F
     ms = sorted(ts)[2]
     res.append(f"{mode} {ms:.3f} ms {N*G/ms/1e6:.1f} G/s")
 hmm.status_dev()
-print(os.path.basename(sys.argv[1]), f"n>0 frac {(n>0).float().mean().item():.3f} max n {int(n.max())}", " | ".join(res), flush=True)
+print(os.path.basename(sys.argv[1]), "mode", os.environ.get("HB_MODE", "0"), "general rerun", hmm.binom2_general_rerun(), f"n>0 frac {(n>0).float().mean().item():.3f} max n {int(n.max())}", " | ".join(res), flush=True)
