@@ -29,14 +29,27 @@
 namespace hb {
 
 #define HB_B2F_RHO_EXP_MAX 900
+#ifndef HB_B2F_PF_CHUNKS
+#define HB_B2F_PF_CHUNKS 2 // L2 prefetch distance of the count planes, in chunks
+#endif
 
 // per step and thread: (phi0, rho 2^-es) as double2 + high word of 2^-es
 #define HB_B2F_SMEM_BYTES_PER_THREAD (HB_CHUNK * (16 + 4))
+
+// Emission table entries with n <= HB_B2F_SLUT_N live in shared memory (one copy per block): the
+// per-step lookup is then an LDS with a ~30-cycle latency instead of an L1/L2 gather that the
+// streaming traffic keeps evicting (ncu: 73 % of the stall samples were long-scoreboard waits).
+#define HB_B2F_SLUT_N 31
+#define HB_B2F_SLUT_ENTRIES ((HB_B2F_SLUT_N + 1) * (HB_B2F_SLUT_N + 2) / 2)
+#define HB_B2F_SLUT_BYTES (HB_B2F_SLUT_ENTRIES * 24)
 
 struct B2fSmem {
     double2 *pr;
     int32_t *ph;
     int32_t st;
+    const double2 *slb; // [HB_B2F_SLUT_ENTRIES] (l0, l1)
+    const double *srho; // [HB_B2F_SLUT_ENTRIES]
+    int32_t slut_n;     // min(HB_B2F_SLUT_N, lut_nmax)
 };
 
 // rho as a double for the table / the slow path: negative = "beyond the representable range"
@@ -56,9 +69,18 @@ struct B2fState {
 
 // Emission of one step: (l0, l1) literal log dbinom values, rho = b_0/b_1 as a double.
 template <bool WANT_LB, bool WANT_RHO>
-HB_HD void b2f_emit(const Binom2Args &a, int32_t xv, int32_t nv, double &l0, double &l1, double &rho)
+HB_HD void b2f_emit(const Binom2Args &a, const B2fSmem &m, int32_t xv, int32_t nv, double &l0,
+                    double &l1, double &rho)
 {
-    if ((uint32_t)nv <= (uint32_t)a.lut_nmax && (uint32_t)xv <= (uint32_t)nv) {
+    if ((uint32_t)nv <= (uint32_t)m.slut_n && (uint32_t)xv <= (uint32_t)nv) {
+        const int32_t ix = ((nv * (nv + 1)) >> 1) + xv;
+        if (WANT_LB) {
+            const double2 v = m.slb[ix];
+            l0 = v.x;
+            l1 = v.y;
+        }
+        if (WANT_RHO) rho = m.srho[ix];
+    } else if ((uint32_t)nv <= (uint32_t)a.lut_nmax && (uint32_t)xv <= (uint32_t)nv) {
         const int32_t ix = ((nv * (nv + 1)) >> 1) + xv;
         if (WANT_LB) {
             const double2 v = a.lut_lb[ix];
@@ -69,7 +91,10 @@ HB_HD void b2f_emit(const Binom2Args &a, int32_t xv, int32_t nv, double &l0, dou
     } else {
         if (a.c.bb) *a.status = 2;
         RhoME r;
-        binom2_emit_slow(a.c, xv, nv, l0, l1, r);
+        double sl0, sl1; // (address-taken by the out-of-line call: keep l0/l1 themselves in registers)
+        binom2_emit_slow(a.c, xv, nv, sl0, sl1, r);
+        l0 = sl0;
+        l1 = sl1;
         rho = b2f_rho_double(r);
     }
     if (WANT_RHO && hi32(rho) < 0) { // marked entry: this launch needs the general kernel
@@ -101,11 +126,11 @@ HB_HD int32_t b2f_fwd_step(const Binom2Const &c, B2fState &s, double rho, bool f
 }
 
 template <bool VIT, bool FB, bool LL>
-HB_HD void b2f_forward_one(const Binom2Args &a, B2fState &s, int32_t xv, int32_t nv, bool first,
-                           uint32_t &pk, int j)
+HB_HD void b2f_forward_one(const Binom2Args &a, const B2fSmem &m, B2fState &s, int32_t xv,
+                           int32_t nv, bool first, uint32_t &pk, int j)
 {
     double l0 = 0, l1 = 0, rho = 1.0;
-    b2f_emit<VIT || LL, FB>(a, xv, nv, l0, l1, rho);
+    b2f_emit<VIT || LL, FB>(a, m, xv, nv, l0, l1, rho);
     if (VIT) {
         if (first) {
             s.n0 = a.c.logdelta[0] + l0;
@@ -130,7 +155,7 @@ HB_HD void b2f_replay_one(const Binom2Args &a, B2fState &s, int32_t xv, int32_t 
 {
     double l0, l1, rho = 1.0, rs;
     int32_t ph;
-    b2f_emit<false, true>(a, xv, nv, l0, l1, rho);
+    b2f_emit<false, true>(a, m, xv, nv, l0, l1, rho);
     b2f_fwd_step(a.c, s, rho, first, rs, ph);
     double2 v;
     v.x = s.f0;
@@ -144,15 +169,15 @@ HB_HD void b2f_backward_one(const Binom2Const &c, B2fState &s, uint8_t *yp, doub
                             uint32_t pk, int j, const B2fSmem &m)
 {
     if (VIT) {
-        *yp = (uint8_t)(s.ycur + 1);
+        st_stream(yp, (uint8_t)(s.ycur + 1));
         s.ycur = (int32_t)((pk >> (2 * j + s.ycur)) & 1u);
     }
     if (FB) {
         const double2 v = m.pr[j * m.st];
         const double sc = mk64(m.ph[j * m.st], 0);
         const double ga = v.x * s.b0;
-        *g0 = ga;
-        *g1 = fabs(1.0 - ga);
+        st_stream(g0, ga);
+        st_stream(g1, fabs(1.0 - ga));
         const double v0 = v.y * s.b0, v1 = sc * s.b1;
         s.b0 = dfma(c.Pi[1], v1, c.Pi[0] * v0);
         s.b1 = dfma(c.Pi[3], v1, c.Pi[2] * v0);
@@ -187,8 +212,8 @@ HB_HD void binom2_fast_chain(const Binom2Args &a, int32_t seg, int64_t b, const 
     if (nfull > 0) {
 #pragma unroll
         for (int j = 0; j < HB_HALF; j++) {
-            xa[j] = xp[(int64_t)j * ld];
-            na[j] = np[(int64_t)j * ld];
+            xa[j] = ld_stream(xp + (int64_t)j * ld);
+            na[j] = ld_stream(np + (int64_t)j * ld);
         }
     }
     {
@@ -200,17 +225,29 @@ HB_HD void binom2_fast_chain(const Binom2Args &a, int32_t seg, int64_t b, const 
             uint32_t pk = 0;
 #pragma unroll
             for (int h = 0; h < 2; h++) {
+                if (ch + HB_B2F_PF_CHUNKS < nfull) { // L2 prefetch well ahead of the register prefetch
+#pragma unroll
+                    for (int j = 0; j < HB_HALF; j++) {
+                        prefetch_l2(xp + off + (int64_t)(HB_B2F_PF_CHUNKS * HB_CHUNK + j) * ld);
+                        prefetch_l2(np + off + (int64_t)(HB_B2F_PF_CHUNKS * HB_CHUNK + j) * ld);
+                    }
+                }
                 if (h == 0 || more) {
 #pragma unroll
                     for (int j = 0; j < HB_HALF; j++) {
-                        (h == 0 ? xb : xa)[j] = xp[off + (int64_t)j * ld];
-                        (h == 0 ? nb : na)[j] = np[off + (int64_t)j * ld];
+                        if (h == 0) {
+                            xb[j] = ld_stream(xp + off + (int64_t)j * ld);
+                            nb[j] = ld_stream(np + off + (int64_t)j * ld);
+                        } else {
+                            xa[j] = ld_stream(xp + off + (int64_t)j * ld);
+                            na[j] = ld_stream(np + off + (int64_t)j * ld);
+                        }
                     }
                 }
                 off += (int64_t)HB_HALF * ld;
 #pragma unroll
                 for (int j = h * HB_HALF; j < (h + 1) * HB_HALF; j++)
-                    b2f_forward_one<VIT, FB, LL>(a, s, h == 0 ? xa[j] : xb[j - HB_HALF],
+                    b2f_forward_one<VIT, FB, LL>(a, m, s, h == 0 ? xa[j] : xb[j - HB_HALF],
                                                  h == 0 ? na[j] : nb[j - HB_HALF],
                                                  j == 0 && ch == 0, pk, j);
             }
@@ -227,7 +264,7 @@ HB_HD void binom2_fast_chain(const Binom2Args &a, int32_t seg, int64_t b, const 
         uint32_t pk = 0;
         for (int j = 0; j < tail; j++) {
             const int64_t o = (int64_t)(nfull * HB_CHUNK + j) * ld;
-            b2f_forward_one<VIT, FB, LL>(a, s, xp[o], np[o], nfull == 0 && j == 0, pk, j);
+            b2f_forward_one<VIT, FB, LL>(a, m, s, xp[o], np[o], nfull == 0 && j == 0, pk, j);
         }
         if (VIT) psi[(int64_t)nfull * a.B] = (uint16_t)pk;
     }
@@ -252,8 +289,8 @@ HB_HD void binom2_fast_chain(const Binom2Args &a, int32_t seg, int64_t b, const 
         const int64_t o = (int64_t)(nfull - 1) * HB_CHUNK * ld;
 #pragma unroll
         for (int j = 0; j < HB_HALF; j++) {
-            xa[j] = xp[o + (int64_t)j * ld];
-            na[j] = np[o + (int64_t)j * ld];
+            xa[j] = ld_stream(xp + o + (int64_t)j * ld);
+            na[j] = ld_stream(np + o + (int64_t)j * ld);
         }
     }
     uint32_t pk_nx = 0;
@@ -316,19 +353,26 @@ HB_HD void binom2_fast_chain(const Binom2Args &a, int32_t seg, int64_t b, const 
                 const bool more = ch > 0;
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
+                    if (ch > HB_B2F_PF_CHUNKS) {
+#pragma unroll
+                        for (int j = 0; j < HB_HALF; j++) {
+                            prefetch_l2(xp + off + (int64_t)(j - HB_B2F_PF_CHUNKS * HB_CHUNK) * ld);
+                            prefetch_l2(np + off + (int64_t)(j - HB_B2F_PF_CHUNKS * HB_CHUNK) * ld);
+                        }
+                    }
                     if (h == 0) {
 #pragma unroll
                         for (int j = 0; j < HB_HALF; j++) {
-                            xb[j] = xp[off + (int64_t)j * ld];
-                            nb[j] = np[off + (int64_t)j * ld];
+                            xb[j] = ld_stream(xp + off + (int64_t)j * ld);
+                            nb[j] = ld_stream(np + off + (int64_t)j * ld);
                         }
                         off -= (int64_t)(HB_CHUNK + HB_HALF) * ld;
                     } else {
                         if (more) {
 #pragma unroll
                             for (int j = 0; j < HB_HALF; j++) {
-                                xa[j] = xp[off + (int64_t)j * ld];
-                                na[j] = np[off + (int64_t)j * ld];
+                                xa[j] = ld_stream(xp + off + (int64_t)j * ld);
+                                na[j] = ld_stream(np + off + (int64_t)j * ld);
                             }
                         }
                         off += (int64_t)HB_HALF * ld;

@@ -69,6 +69,38 @@ HB_HD double dfma(double a, double b, double c)
 #endif
 }
 
+// ---------------------------------------------------------------- streaming loads / stores
+// The chain kernels stream their inputs and outputs exactly once per sweep: keep them out of L1
+// (evict-first) so the emission table and the constant data stay resident there.
+template <typename T>
+HB_HD T ld_stream(const T *p)
+{
+#if defined(__CUDA_ARCH__)
+    return __ldcs(p);
+#else
+    return *p;
+#endif
+}
+template <typename T>
+HB_HD void st_stream(T *p, T v)
+{
+#if defined(__CUDA_ARCH__)
+    __stcs(p, v);
+#else
+    *p = v;
+#endif
+}
+
+// Hint: bring the line holding *p into L2 (no register, no dependency).
+HB_HD void prefetch_l2(const void *p)
+{
+#if defined(__CUDA_ARCH__)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+    (void)p;
+#endif
+}
+
 // ---------------------------------------------------------------- exact division by a chain constant
 // z = RN(d / b) given y = RN(1/b): Markstein's correction (q = d*y; r = d - b*q exactly by FMA;
 // q' = q + r*y) is correctly rounded for every d when y is the correctly rounded reciprocal

@@ -87,11 +87,25 @@ __global__ void __launch_bounds__(HB_BLOCK, HB_B2F_MINB)
     extern __shared__ double2 smem2[];
     const int32_t seg = a.seg_order[blockIdx.x / a.nblk_per_seg];
     const int64_t b = (int64_t)(blockIdx.x % a.nblk_per_seg) * HB_BLOCK + threadIdx.x;
+    // block-local copy of the emission table for small trial counts (before any thread may leave)
+    double2 *slb = smem2;
+    double *srho = reinterpret_cast<double *>(smem2 + HB_B2F_SLUT_ENTRIES);
+    const int32_t slut_n = a.lut_nmax < HB_B2F_SLUT_N ? a.lut_nmax : HB_B2F_SLUT_N;
+    const int32_t nent = (slut_n + 1) * (slut_n + 2) / 2;
+    for (int32_t i = threadIdx.x; i < nent; i += HB_BLOCK) {
+        slb[i] = a.lut_lb[i];
+        srho[i] = a.lut_rho_d[i];
+    }
+    __syncthreads();
     if (b >= a.B) return;
+    double2 *park = reinterpret_cast<double2 *>(reinterpret_cast<char *>(smem2) + HB_B2F_SLUT_BYTES);
     B2fSmem m;
     m.st = HB_BLOCK;
-    m.pr = smem2 + threadIdx.x;
-    m.ph = reinterpret_cast<int32_t *>(smem2 + HB_CHUNK * HB_BLOCK) + threadIdx.x;
+    m.pr = park + threadIdx.x;
+    m.ph = reinterpret_cast<int32_t *>(park + HB_CHUNK * HB_BLOCK) + threadIdx.x;
+    m.slb = slb;
+    m.srho = srho;
+    m.slut_n = slut_n;
     binom2_fast_chain<VIT, FB, LL>(a, seg, b, m);
 }
 
@@ -152,7 +166,7 @@ cudaError_t launch_norm3_fast(const Norm3Args &a, bool vit, bool fb, cudaStream_
 cudaError_t launch_binom2_fast(const Binom2Args &a, bool vit, bool fb, cudaStream_t st)
 {
     const unsigned grid = (unsigned)((int64_t)a.nseg * a.nblk_per_seg);
-    const size_t sm_fb = (size_t)HB_B2F_SMEM_BYTES_PER_THREAD * HB_BLOCK;
+    const size_t sm_fb = (size_t)HB_B2F_SLUT_BYTES + (size_t)HB_B2F_SMEM_BYTES_PER_THREAD * HB_BLOCK;
     const bool ll = a.ll != nullptr;
     if (vit && fb) {
         if (ll)
@@ -165,7 +179,7 @@ cudaError_t launch_binom2_fast(const Binom2Args &a, bool vit, bool fb, cudaStrea
         else
             binom2_fast_kernel<false, true, false><<<grid, HB_BLOCK, sm_fb, st>>>(a);
     } else {
-        binom2_fast_kernel<true, false, false><<<grid, HB_BLOCK, 0, st>>>(a);
+        binom2_fast_kernel<true, false, false><<<grid, HB_BLOCK, HB_B2F_SLUT_BYTES, st>>>(a);
     }
     return cudaGetLastError();
 }

@@ -277,6 +277,7 @@ int emul_binom2_fast(const int32_t *x, const int32_t *n, int64_t ld, int64_t T, 
     std::vector<double> sm(HB_CHUNK * HB_BINOM2_SLOT);
     B2fSmem m;
     m.pr = spr.data(); m.ph = sph.data(); m.st = 1;
+    m.slb = lb.data(); m.srho = rd.data(); m.slut_n = std::min(lut_nmax, HB_B2F_SLUT_N);
     int32_t status[4] = {0, 0, 0, 0};
     a.x = x; a.n = n; a.ld = ld; a.T = T; a.B = B;
     a.seg_off = sg.off.data(); a.chunk_off = sg.chunk.data(); a.seg_order = sg.order.data();
