@@ -89,6 +89,11 @@ struct DevBuf {
 struct Workspace {
     DevBuf psi, ckpt, sdaux, segtab, status, lut_lb, lut_rho, lut_rho_d, cellmask, gsize;
     DevBuf st_in, st_in2, st_x, st_x2, st_y, st_g, st_out, st_sd, st_ll, st_member, st_pool, st_pool2;
+    // host-buffer entry points: three-stream pipeline (upload | layout + chains | download), staging x2
+    DevBuf pin[2], pin2[2], pout_y[2], pout_g[2], pout_ll[2];
+    cudaStream_t s_in = nullptr, s_cmp = nullptr, s_out = nullptr;
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_free_in[2] = {nullptr, nullptr},
+                ev_out[2] = {nullptr, nullptr}, ev_free_out[2] = {nullptr, nullptr};
     std::vector<int64_t> seg_cached;
     int64_t nchunks = 0;
     double lut_key[3] = {-1, -1, -1};
@@ -97,7 +102,8 @@ struct Workspace {
     {
         DevBuf *all[] = {&psi, &ckpt, &sdaux, &segtab, &status, &lut_lb, &lut_rho, &lut_rho_d, &cellmask, &gsize,
                          &st_in, &st_in2, &st_x, &st_x2, &st_y, &st_g, &st_out, &st_sd, &st_ll,
-                         &st_member, &st_pool, &st_pool2};
+                         &st_member, &st_pool, &st_pool2, &pin[0], &pin[1], &pin2[0], &pin2[1],
+                         &pout_y[0], &pout_y[1], &pout_g[0], &pout_g[1], &pout_ll[0], &pout_ll[1]};
         for (DevBuf *b : all) b->release();
         seg_cached.clear();
         lut_nmax = -1;
@@ -227,7 +233,7 @@ int norm3_run(Workspace *ws, const double *x, int64_t ld, int64_t T, int64_t B,
               const int64_t *seg_off, int32_t nseg, const double *mean, const double *sd,
               const double *inv_sd, const double *log_sd, int32_t sd_per_seg, const double *Pi,
               const double *delta, int32_t flags, uint8_t *y, int64_t ldy, double *gamma,
-              int64_t ldg, double *ll, cudaStream_t st)
+              int64_t ldg, double *ll, cudaStream_t st, bool reset_status = true)
 {
     if (T < 1 || B < 1 || ld < B) return fail(HB_ERR_ARG, "bad shape T=%lld B=%lld ld=%lld",
                                                (long long)T, (long long)B, (long long)ld);
@@ -251,7 +257,7 @@ int norm3_run(Workspace *ws, const double *x, int64_t ld, int64_t T, int64_t B,
     HBTRY(ws->status.ensure(4 * sizeof(int32_t)));
     if (vit) HBTRY(ws->psi.ensure((size_t)ws->nchunks * B * sizeof(uint64_t)));
     if (fb) HBTRY(ws->ckpt.ensure((size_t)ws->nchunks * 3 * B * sizeof(double)));
-    CU(cudaMemsetAsync(ws->status.p, 0, 4 * sizeof(int32_t), st));
+    if (reset_status) CU(cudaMemsetAsync(ws->status.p, 0, 4 * sizeof(int32_t), st));
     a.x = x;
     a.ld = ld;
     a.T = T;
@@ -347,7 +353,7 @@ int prepare_lut(Workspace *ws, const double *prob, double rho, cudaStream_t st)
 int binom2_run(Workspace *ws, const int32_t *x, const int32_t *n, int64_t ld, int64_t T, int64_t B,
                const int64_t *seg_off, int32_t nseg, const double *prob, double rho,
                const double *Pi, const double *delta, int32_t flags, uint8_t *y, int64_t ldy,
-               double *gamma, int64_t ldg, double *ll, cudaStream_t st)
+               double *gamma, int64_t ldg, double *ll, cudaStream_t st, bool reset_status = true)
 {
     if (T < 1 || B < 1 || ld < B) return fail(HB_ERR_ARG, "bad shape T=%lld B=%lld ld=%lld",
                                                (long long)T, (long long)B, (long long)ld);
@@ -384,7 +390,7 @@ int binom2_run(Workspace *ws, const int32_t *x, const int32_t *n, int64_t ld, in
     HBTRY(ws->status.ensure(4 * sizeof(int32_t)));
     if (vit) HBTRY(ws->psi.ensure((size_t)ws->nchunks * B * sizeof(uint64_t)));
     if (fb) HBTRY(ws->ckpt.ensure((size_t)ws->nchunks * 3 * B * sizeof(double)));
-    CU(cudaMemsetAsync(ws->status.p, 0, 4 * sizeof(int32_t), st));
+    if (reset_status) CU(cudaMemsetAsync(ws->status.p, 0, 4 * sizeof(int32_t), st));
     a.x = x;
     a.n = n;
     a.ld = ld;
@@ -552,6 +558,44 @@ int hb_hmm_norm_dev(const double *x, int64_t ld, int64_t T, int64_t B, const int
                      delta, flags, y, ldy, gamma, ldg, ll, (cudaStream_t)stream);
 }
 
+// Pipeline of the host-buffer entry points.  Columns are cut into sub-batches; three streams work on
+// consecutive sub-batches at once: s_in uploads sub-batch i+1 (H2D), s_cmp changes the layout and
+// runs the chains of sub-batch i, s_out downloads sub-batch i-1 (D2H) — PCIe is full duplex, so the
+// call approaches max(H2D, D2H) instead of their sum.  Staging buffers are double-buffered and
+// handed over with events; with pageable host memory the copies degrade to the driver's staged
+// path (still correct, less overlap).
+static int pipe_init(Workspace *ws)
+{
+    if (ws->s_in) return HB_OK;
+    CU(cudaStreamCreateWithFlags(&ws->s_in, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&ws->s_cmp, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&ws->s_out, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; k++) {
+        CU(cudaEventCreateWithFlags(&ws->ev_in[k], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ws->ev_free_in[k], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ws->ev_out[k], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ws->ev_free_out[k], cudaEventDisableTiming));
+    }
+    return HB_OK;
+}
+
+// Sub-batch width: ~8+ sub-batches per call when B allows, a multiple of 128 columns, bounded by
+// the free device memory (`bytes_per_col` covers staging, resident copy, outputs and scratch).
+static int64_t pipe_batch(int64_t B, double bytes_per_col)
+{
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) {
+        cudaGetLastError();
+        free_b = (size_t)8 << 30;
+    }
+    int64_t cap = std::max<int64_t>(1, (int64_t)(free_b * 0.6 / bytes_per_col));
+    int64_t want = std::max<int64_t>(128, (B / 8 + 127) / 128 * 128);
+    want = std::min<int64_t>(want, 1024);
+    int64_t Bc = std::min(std::min(cap, want), B);
+    if (Bc >= 128) Bc = Bc / 128 * 128;
+    return std::max<int64_t>(1, Bc);
+}
+
 int hb_hmm_norm_host(const double *x, int64_t T, int64_t B, const int64_t *seg_off, int32_t nseg,
                      const double *mean, const double *sd, int32_t sd_per_seg, const double *Pi,
                      const double *delta, int32_t flags, int32_t *y, double *gamma, double *ll)
@@ -567,78 +611,93 @@ int hb_hmm_norm_host(const double *x, int64_t T, int64_t B, const int64_t *seg_o
     }
     bool vit, fb;
     HBTRY(check_flags(flags, y, gamma, ll, &vit, &fb));
-    cudaStream_t st = 0;
-    // Column batches sized to the free device memory (inputs + outputs + scratch ~ 60 B / step).
-    size_t free_b = 0, total_b = 0;
-    CU(cudaMemGetInfo(&free_b, &total_b));
-    int64_t Bc = std::max<int64_t>(1, std::min<int64_t>(B, (int64_t)(free_b * 0.6 / (80.0 * T))));
-    if (Bc >= 16) Bc = Bc / 16 * 16;
+    const bool want_g = (flags & HB_WANT_GAMMA) != 0, want_ll = (flags & HB_WANT_LL) != 0;
+    HBTRY(pipe_init(ws));
+    const int64_t Bc = pipe_batch(B, 130.0 * (double)T);
+    const int64_t nb = (B + Bc - 1) / Bc;
+    const int64_t ldc = (Bc + 127) / 128 * 128;
     const int64_t nsd_seg = sd_per_seg ? nseg : 1;
-    std::vector<double> h_aux;
-    int rc_status = HB_OK;
+    // every allocation before the first enqueue (cudaMalloc / cudaFree synchronise the device)
+    for (int k = 0; k < 2; k++) {
+        HBTRY(ws->pin[k].ensure((size_t)T * Bc * sizeof(double)));
+        if (vit) HBTRY(ws->pout_y[k].ensure((size_t)T * Bc * sizeof(int32_t)));
+        if (want_g) HBTRY(ws->pout_g[k].ensure((size_t)3 * T * Bc * sizeof(double)));
+        if (want_ll) HBTRY(ws->pout_ll[k].ensure((size_t)nseg * Bc * sizeof(double)));
+    }
+    HBTRY(ws->st_x.ensure((size_t)T * ldc * sizeof(double)));
+    if (vit) HBTRY(ws->st_y.ensure((size_t)T * ldc));
+    if (want_g) HBTRY(ws->st_g.ensure((size_t)3 * T * ldc * sizeof(double)));
+    HBTRY(ws->st_sd.ensure((size_t)nsd_seg * B * 3 * sizeof(double)));
+    // chain scales of all sub-batches in one upload: sd, 1/sd (IEEE), log(sd) (host libm, as R);
+    // sub-batch i occupies [3 * nsd_seg * b0, +3 * nsd_seg * bn) as three [nsd_seg][bn] blocks
+    std::vector<double> h_aux((size_t)nsd_seg * B * 3);
     for (int64_t b0 = 0; b0 < B; b0 += Bc) {
         const int64_t bn = std::min(Bc, B - b0);
-        const int64_t ld = pad_ld(bn);
-        HBTRY(ws->st_in.ensure((size_t)T * bn * sizeof(double)));
-        HBTRY(ws->st_x.ensure((size_t)T * ld * sizeof(double)));
-        HBTRY(ws->st_sd.ensure((size_t)nsd_seg * bn * 3 * sizeof(double)));
-        CU(cudaMemcpyAsync(ws->st_in.p, x + b0 * T, (size_t)T * bn * sizeof(double),
-                           cudaMemcpyHostToDevice, st));
-        CU(hb::launch_transpose_f64(ws->st_in.as<double>(), T, bn, ws->st_x.as<double>(), ld, st));
-        // chain scales: sd, 1/sd (IEEE), log(sd) (host libm, as R)
-        h_aux.resize((size_t)nsd_seg * bn * 3);
-        for (int64_t s = 0; s < nsd_seg; s++)
+        double *blk = h_aux.data() + (size_t)3 * nsd_seg * b0;
+        for (int64_t sg = 0; sg < nsd_seg; sg++)
             for (int64_t b = 0; b < bn; b++) {
-                double v = sd[s * B + b0 + b];
-                h_aux[(0 * nsd_seg + s) * bn + b] = v;
-                h_aux[(1 * nsd_seg + s) * bn + b] = 1.0 / v;
-                h_aux[(2 * nsd_seg + s) * bn + b] = log(v);
+                const double v = sd[sg * B + b0 + b];
+                blk[(0 * nsd_seg + sg) * bn + b] = v;
+                blk[(1 * nsd_seg + sg) * bn + b] = 1.0 / v;
+                blk[(2 * nsd_seg + sg) * bn + b] = log(v);
             }
-        CU(cudaMemcpyAsync(ws->st_sd.p, h_aux.data(), h_aux.size() * sizeof(double),
-                           cudaMemcpyHostToDevice, st));
-        CU(cudaStreamSynchronize(st)); // h_aux is reused by the next batch
-        const double *d_sd = ws->st_sd.as<double>();
-        uint8_t *d_y = nullptr;
-        double *d_g = nullptr, *d_ll = nullptr;
-        if (vit) {
-            HBTRY(ws->st_y.ensure((size_t)T * ld));
-            d_y = ws->st_y.as<uint8_t>();
-        }
-        if (flags & HB_WANT_GAMMA) {
-            HBTRY(ws->st_g.ensure((size_t)3 * T * ld * sizeof(double)));
-            d_g = ws->st_g.as<double>();
-        }
-        if (flags & HB_WANT_LL) {
-            HBTRY(ws->st_ll.ensure((size_t)nseg * bn * sizeof(double)));
-            d_ll = ws->st_ll.as<double>();
-        }
-        HBTRY(norm3_run(ws, ws->st_x.as<double>(), ld, T, bn, seg_off, nseg, mean, d_sd,
-                        d_sd + nsd_seg * bn, d_sd + 2 * nsd_seg * bn, sd_per_seg, Pi, delta, flags,
-                        d_y, ld, d_g, ld, d_ll, st));
-        if (vit) {
-            HBTRY(ws->st_out.ensure((size_t)T * bn * sizeof(int32_t)));
-            CU(hb::launch_transpose_u8_back(d_y, ld, T, bn, ws->st_out.as<int32_t>(), st));
-            CU(cudaMemcpyAsync(y + b0 * T, ws->st_out.p, (size_t)T * bn * sizeof(int32_t),
-                               cudaMemcpyDeviceToHost, st));
-        }
-        if (flags & HB_WANT_GAMMA) {
-            // st_in is free again: reuse it as the column-major staging of one state plane
-            for (int k = 0; k < 3; k++) {
-                CU(hb::launch_transpose_f64_back(d_g + (int64_t)k * T * ld, ld, T, bn,
-                                                 ws->st_in.as<double>(), st));
-                CU(cudaMemcpyAsync(gamma + ((int64_t)k * B + b0) * T, ws->st_in.p,
-                                   (size_t)T * bn * sizeof(double), cudaMemcpyDeviceToHost, st));
-            }
-        }
-        if (flags & HB_WANT_LL) {
-            for (int32_t s = 0; s < nseg; s++)
-                CU(cudaMemcpyAsync(ll + (int64_t)s * B + b0, d_ll + (int64_t)s * bn,
-                                   (size_t)bn * sizeof(double), cudaMemcpyDeviceToHost, st));
-        }
-        int rc = read_status(ws, st);
-        if (rc != HB_OK) rc_status = rc;
     }
-    return rc_status;
+    CU(cudaMemcpyAsync(ws->st_sd.p, h_aux.data(), h_aux.size() * sizeof(double), cudaMemcpyHostToDevice,
+                       ws->s_cmp));
+    int rc = HB_OK;
+    for (int64_t i = 0; i < nb && rc == HB_OK; i++) {
+        const int k = (int)(i & 1);
+        const int64_t b0 = i * Bc, bn = std::min(Bc, B - b0);
+        const int64_t ld = (bn + 127) / 128 * 128;
+        // upload
+        if (i >= 2) CU(cudaStreamWaitEvent(ws->s_in, ws->ev_free_in[k], 0));
+        CU(cudaMemcpyAsync(ws->pin[k].p, x + b0 * T, (size_t)T * bn * sizeof(double),
+                           cudaMemcpyHostToDevice, ws->s_in));
+        CU(cudaEventRecord(ws->ev_in[k], ws->s_in));
+        // layout + chains
+        CU(cudaStreamWaitEvent(ws->s_cmp, ws->ev_in[k], 0));
+        CU(hb::launch_transpose_f64(ws->pin[k].as<double>(), T, bn, ws->st_x.as<double>(), ld, ws->s_cmp));
+        CU(cudaEventRecord(ws->ev_free_in[k], ws->s_cmp));
+        const double *d_sd = ws->st_sd.as<double>() + (size_t)3 * nsd_seg * b0;
+        uint8_t *d_y = vit ? ws->st_y.as<uint8_t>() : nullptr;
+        double *d_g = want_g ? ws->st_g.as<double>() : nullptr;
+        double *d_ll = want_ll ? ws->pout_ll[k].as<double>() : nullptr;
+        if (i >= 2) CU(cudaStreamWaitEvent(ws->s_cmp, ws->ev_free_out[k], 0));
+        rc = norm3_run(ws, ws->st_x.as<double>(), ld, T, bn, seg_off, nseg, mean, d_sd,
+                       d_sd + nsd_seg * bn, d_sd + 2 * nsd_seg * bn, sd_per_seg, Pi, delta, flags, d_y,
+                       ld, d_g, ld, d_ll, ws->s_cmp, i == 0);
+        if (rc != HB_OK) break;
+        if (vit)
+            CU(hb::launch_transpose_u8_back(d_y, ld, T, bn, ws->pout_y[k].as<int32_t>(), ws->s_cmp));
+        if (want_g)
+            for (int pl = 0; pl < 3; pl++)
+                CU(hb::launch_transpose_f64_back(d_g + (int64_t)pl * T * ld, ld, T, bn,
+                                                 ws->pout_g[k].as<double>() + (int64_t)pl * T * bn,
+                                                 ws->s_cmp));
+        CU(cudaEventRecord(ws->ev_out[k], ws->s_cmp));
+        // download
+        CU(cudaStreamWaitEvent(ws->s_out, ws->ev_out[k], 0));
+        if (vit)
+            CU(cudaMemcpyAsync(y + b0 * T, ws->pout_y[k].p, (size_t)T * bn * sizeof(int32_t),
+                               cudaMemcpyDeviceToHost, ws->s_out));
+        if (want_g)
+            for (int pl = 0; pl < 3; pl++)
+                CU(cudaMemcpyAsync(gamma + ((int64_t)pl * B + b0) * T,
+                                   ws->pout_g[k].as<double>() + (int64_t)pl * T * bn,
+                                   (size_t)T * bn * sizeof(double), cudaMemcpyDeviceToHost, ws->s_out));
+        if (want_ll)
+            for (int32_t sg = 0; sg < nseg; sg++)
+                CU(cudaMemcpyAsync(ll + (int64_t)sg * B + b0, d_ll + (int64_t)sg * bn,
+                                   (size_t)bn * sizeof(double), cudaMemcpyDeviceToHost, ws->s_out));
+        CU(cudaEventRecord(ws->ev_free_out[k], ws->s_out));
+    }
+    // drain (also on the error path: host buffers must not be touched after we return)
+    cudaStreamSynchronize(ws->s_in);
+    cudaStreamSynchronize(ws->s_cmp);
+    cudaError_t e = cudaStreamSynchronize(ws->s_out);
+    if (rc != HB_OK) return rc;
+    if (e != cudaSuccess) return fail(HB_ERR_CUDA, "pipeline failed: %s", cudaGetErrorString(e));
+    return read_status(ws, ws->s_cmp);
 }
 
 // ------------------------------------------------------------------ binomial chains
@@ -670,63 +729,73 @@ int hb_hmm_binom_host(const int32_t *x, const int32_t *size, int64_t T, int64_t 
     }
     bool vit, fb;
     HBTRY(check_flags(flags, y, gamma, ll, &vit, &fb));
-    cudaStream_t st = 0;
-    size_t free_b = 0, total_b = 0;
-    CU(cudaMemGetInfo(&free_b, &total_b));
-    int64_t Bc = std::max<int64_t>(1, std::min<int64_t>(B, (int64_t)(free_b * 0.6 / (64.0 * T))));
-    if (Bc >= 32) Bc = Bc / 32 * 32;
-    int rc_status = HB_OK;
-    for (int64_t b0 = 0; b0 < B; b0 += Bc) {
-        const int64_t bn = std::min(Bc, B - b0);
-        const int64_t ld = (bn + 31) / 32 * 32;
-        HBTRY(ws->st_in.ensure((size_t)T * bn * sizeof(double))); // also the gamma staging
-        HBTRY(ws->st_x.ensure((size_t)T * ld * sizeof(int32_t)));
-        HBTRY(ws->st_x2.ensure((size_t)T * ld * sizeof(int32_t)));
-        CU(cudaMemcpyAsync(ws->st_in.p, x + b0 * T, (size_t)T * bn * sizeof(int32_t),
-                           cudaMemcpyHostToDevice, st));
-        CU(hb::launch_transpose_i32(ws->st_in.as<int32_t>(), T, bn, ws->st_x.as<int32_t>(), ld, st));
-        CU(cudaMemcpyAsync(ws->st_in.p, size + b0 * T, (size_t)T * bn * sizeof(int32_t),
-                           cudaMemcpyHostToDevice, st));
-        CU(hb::launch_transpose_i32(ws->st_in.as<int32_t>(), T, bn, ws->st_x2.as<int32_t>(), ld, st));
-        uint8_t *d_y = nullptr;
-        double *d_g = nullptr, *d_ll = nullptr;
-        if (vit) {
-            HBTRY(ws->st_y.ensure((size_t)T * ld));
-            d_y = ws->st_y.as<uint8_t>();
-        }
-        if (flags & HB_WANT_GAMMA) {
-            HBTRY(ws->st_g.ensure((size_t)2 * T * ld * sizeof(double)));
-            d_g = ws->st_g.as<double>();
-        }
-        if (flags & HB_WANT_LL) {
-            HBTRY(ws->st_ll.ensure((size_t)nseg * bn * sizeof(double)));
-            d_ll = ws->st_ll.as<double>();
-        }
-        HBTRY(binom2_run(ws, ws->st_x.as<int32_t>(), ws->st_x2.as<int32_t>(), ld, T, bn, seg_off,
-                         nseg, prob, rho, Pi, delta, flags, d_y, ld, d_g, ld, d_ll, st));
-        if (vit) {
-            HBTRY(ws->st_out.ensure((size_t)T * bn * sizeof(int32_t)));
-            CU(hb::launch_transpose_u8_back(d_y, ld, T, bn, ws->st_out.as<int32_t>(), st));
-            CU(cudaMemcpyAsync(y + b0 * T, ws->st_out.p, (size_t)T * bn * sizeof(int32_t),
-                               cudaMemcpyDeviceToHost, st));
-        }
-        if (flags & HB_WANT_GAMMA) {
-            for (int k = 0; k < 2; k++) {
-                CU(hb::launch_transpose_f64_back(d_g + (int64_t)k * T * ld, ld, T, bn,
-                                                 ws->st_in.as<double>(), st));
-                CU(cudaMemcpyAsync(gamma + ((int64_t)k * B + b0) * T, ws->st_in.p,
-                                   (size_t)T * bn * sizeof(double), cudaMemcpyDeviceToHost, st));
-            }
-        }
-        if (flags & HB_WANT_LL) {
-            for (int32_t s = 0; s < nseg; s++)
-                CU(cudaMemcpyAsync(ll + (int64_t)s * B + b0, d_ll + (int64_t)s * bn,
-                                   (size_t)bn * sizeof(double), cudaMemcpyDeviceToHost, st));
-        }
-        int rc = read_status(ws, st);
-        if (rc != HB_OK) rc_status = rc;
+    const bool want_g = (flags & HB_WANT_GAMMA) != 0, want_ll = (flags & HB_WANT_LL) != 0;
+    HBTRY(pipe_init(ws));
+    const int64_t Bc = pipe_batch(B, 100.0 * (double)T);
+    const int64_t nb = (B + Bc - 1) / Bc;
+    const int64_t ldc = (Bc + 127) / 128 * 128;
+    for (int k = 0; k < 2; k++) {
+        HBTRY(ws->pin[k].ensure((size_t)T * Bc * sizeof(int32_t)));
+        HBTRY(ws->pin2[k].ensure((size_t)T * Bc * sizeof(int32_t)));
+        if (vit) HBTRY(ws->pout_y[k].ensure((size_t)T * Bc * sizeof(int32_t)));
+        if (want_g) HBTRY(ws->pout_g[k].ensure((size_t)2 * T * Bc * sizeof(double)));
+        if (want_ll) HBTRY(ws->pout_ll[k].ensure((size_t)nseg * Bc * sizeof(double)));
     }
-    return rc_status;
+    HBTRY(ws->st_x.ensure((size_t)T * ldc * sizeof(int32_t)));
+    HBTRY(ws->st_x2.ensure((size_t)T * ldc * sizeof(int32_t)));
+    if (vit) HBTRY(ws->st_y.ensure((size_t)T * ldc));
+    if (want_g) HBTRY(ws->st_g.ensure((size_t)2 * T * ldc * sizeof(double)));
+    int rc = HB_OK;
+    for (int64_t i = 0; i < nb && rc == HB_OK; i++) {
+        const int k = (int)(i & 1);
+        const int64_t b0 = i * Bc, bn = std::min(Bc, B - b0);
+        const int64_t ld = (bn + 127) / 128 * 128;
+        if (i >= 2) CU(cudaStreamWaitEvent(ws->s_in, ws->ev_free_in[k], 0));
+        CU(cudaMemcpyAsync(ws->pin[k].p, x + b0 * T, (size_t)T * bn * sizeof(int32_t),
+                           cudaMemcpyHostToDevice, ws->s_in));
+        CU(cudaMemcpyAsync(ws->pin2[k].p, size + b0 * T, (size_t)T * bn * sizeof(int32_t),
+                           cudaMemcpyHostToDevice, ws->s_in));
+        CU(cudaEventRecord(ws->ev_in[k], ws->s_in));
+        CU(cudaStreamWaitEvent(ws->s_cmp, ws->ev_in[k], 0));
+        CU(hb::launch_transpose_i32(ws->pin[k].as<int32_t>(), T, bn, ws->st_x.as<int32_t>(), ld, ws->s_cmp));
+        CU(hb::launch_transpose_i32(ws->pin2[k].as<int32_t>(), T, bn, ws->st_x2.as<int32_t>(), ld, ws->s_cmp));
+        CU(cudaEventRecord(ws->ev_free_in[k], ws->s_cmp));
+        uint8_t *d_y = vit ? ws->st_y.as<uint8_t>() : nullptr;
+        double *d_g = want_g ? ws->st_g.as<double>() : nullptr;
+        double *d_ll = want_ll ? ws->pout_ll[k].as<double>() : nullptr;
+        if (i >= 2) CU(cudaStreamWaitEvent(ws->s_cmp, ws->ev_free_out[k], 0));
+        rc = binom2_run(ws, ws->st_x.as<int32_t>(), ws->st_x2.as<int32_t>(), ld, T, bn, seg_off, nseg,
+                        prob, rho, Pi, delta, flags, d_y, ld, d_g, ld, d_ll, ws->s_cmp, i == 0);
+        if (rc != HB_OK) break;
+        if (vit)
+            CU(hb::launch_transpose_u8_back(d_y, ld, T, bn, ws->pout_y[k].as<int32_t>(), ws->s_cmp));
+        if (want_g)
+            for (int pl = 0; pl < 2; pl++)
+                CU(hb::launch_transpose_f64_back(d_g + (int64_t)pl * T * ld, ld, T, bn,
+                                                 ws->pout_g[k].as<double>() + (int64_t)pl * T * bn,
+                                                 ws->s_cmp));
+        CU(cudaEventRecord(ws->ev_out[k], ws->s_cmp));
+        CU(cudaStreamWaitEvent(ws->s_out, ws->ev_out[k], 0));
+        if (vit)
+            CU(cudaMemcpyAsync(y + b0 * T, ws->pout_y[k].p, (size_t)T * bn * sizeof(int32_t),
+                               cudaMemcpyDeviceToHost, ws->s_out));
+        if (want_g)
+            for (int pl = 0; pl < 2; pl++)
+                CU(cudaMemcpyAsync(gamma + ((int64_t)pl * B + b0) * T,
+                                   ws->pout_g[k].as<double>() + (int64_t)pl * T * bn,
+                                   (size_t)T * bn * sizeof(double), cudaMemcpyDeviceToHost, ws->s_out));
+        if (want_ll)
+            for (int32_t sg = 0; sg < nseg; sg++)
+                CU(cudaMemcpyAsync(ll + (int64_t)sg * B + b0, d_ll + (int64_t)sg * bn,
+                                   (size_t)bn * sizeof(double), cudaMemcpyDeviceToHost, ws->s_out));
+        CU(cudaEventRecord(ws->ev_free_out[k], ws->s_out));
+    }
+    cudaStreamSynchronize(ws->s_in);
+    cudaStreamSynchronize(ws->s_cmp);
+    cudaError_t e = cudaStreamSynchronize(ws->s_out);
+    if (rc != HB_OK) return rc;
+    if (e != cudaSuccess) return fail(HB_ERR_CUDA, "pipeline failed: %s", cudaGetErrorString(e));
+    return read_status(ws, ws->s_cmp);
 }
 
 // ------------------------------------------------------------------ layout

@@ -347,6 +347,13 @@ HB_HD void binom2_fast_chain(const Binom2Args &a, int32_t seg, int64_t b, const 
                     c1_nx = cr[a.B];
                 }
             }
+            if (ch > 1 + HB_B2F_PF_CHUNKS) { // checkpoints / back-pointers further back
+                if (VIT) prefetch_l2(pr - (int64_t)HB_B2F_PF_CHUNKS * a.B);
+                if (FB) {
+                    prefetch_l2(cr - (int64_t)HB_B2F_PF_CHUNKS * 2 * a.B);
+                    prefetch_l2(cr - (int64_t)HB_B2F_PF_CHUNKS * 2 * a.B + a.B);
+                }
+            }
             pr -= a.B;
             cr -= 2 * a.B;
             if (FB) {

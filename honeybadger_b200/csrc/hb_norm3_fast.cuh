@@ -41,6 +41,9 @@ namespace hb {
 
 // Longest chain the speculative path accepts: eps grows ~L^2, the flagged fraction ~L^3.
 #define HB_FAST_LMAX 4096
+#ifndef HB_FAST_PF_CHUNKS
+#define HB_FAST_PF_CHUNKS 2 // L2 prefetch distance (chunks) ahead of the staging of x / checkpoints
+#endif
 
 // ---------------------------------------------------------------- small bit helpers
 // (code << 1) | signbit(q)
@@ -221,7 +224,7 @@ HB_HD void fast_backward_one(const Norm3Const &c, Fast3State &s, uint8_t *yp, do
                              double *g2, uint32_t pw, int sh, int j, const Norm3Smem &m)
 {
     if (VIT) {
-        *yp = (uint8_t)(s.ycur + 1);
+        st_stream(yp, (uint8_t)(s.ycur + 1));
         const uint32_t f = (pw >> (sh + 4 - 2 * s.ycur)) & 3u;
         s.ycur = (int32_t)(f < 2u ? f : 2u);
     }
@@ -230,9 +233,9 @@ HB_HD void fast_backward_one(const Norm3Const &c, Fast3State &s, uint8_t *yp, do
         const double p2 = mk64(m.ph[j * m.st], 0);
 #if HB_FAST_NOPHI1
         const double ga = va.x * s.b0, gc = va.y * s.b2;
-        *g0 = ga;
-        *g2 = gc;
-        *g1 = fabs(1.0 - (ga + gc));
+        st_stream(g0, ga);
+        st_stream(g2, gc);
+        st_stream(g1, fabs(1.0 - (ga + gc)));
         const double v0 = vb.x * s.b0, v2 = vb.y * s.b2, v1 = p2 * s.b1;
 #else
         const double E2s = m.e2[j * m.st];
@@ -397,6 +400,8 @@ HB_HD void norm3_fast_chain(const Norm3Args &a, int32_t seg, int64_t b, Norm3Sme
         double *ck = ckpt;
         for (int32_t ch = 0; ch < nfull; ch++) {
             const bool more = ch + 1 < nfull;
+            const bool pf = ch + 1 + HB_FAST_PF_CHUNKS < nfull;
+            (void)pf;
             uint32_t w[2] = {0u, 0u};
 #pragma unroll
             for (int h = 0; h < 2; h++) {
@@ -417,6 +422,7 @@ HB_HD void norm3_fast_chain(const Norm3Args &a, int32_t seg, int64_t b, Norm3Sme
 #else
                     const double xv = m.xs[j * m.st];
                     if (more) xs_refill(m, j, xr);
+                    if (pf) prefetch_l2(xr + (int64_t)HB_FAST_PF_CHUNKS * HB_CHUNK * ld);
                     xr += ld;
 #endif
                     const bool first = (j == 0) && (ch == 0);
@@ -593,6 +599,16 @@ HB_HD void norm3_fast_chain(const Norm3Args &a, int32_t seg, int64_t b, Norm3Sme
                     c2_nx = cr[2 * a.B];
                 }
             }
+            const bool pf = ch > 1 + HB_FAST_PF_CHUNKS;
+            if (pf) { // checkpoints / back-pointer words of the chunk HB_FAST_PF_CHUNKS further back
+                if (VIT) prefetch_l2(pr - (int64_t)HB_FAST_PF_CHUNKS * a.B);
+                if (FB) {
+                    const double *cf = cr - (int64_t)HB_FAST_PF_CHUNKS * 3 * a.B;
+                    prefetch_l2(cf);
+                    prefetch_l2(cf + a.B);
+                    prefetch_l2(cf + 2 * a.B);
+                }
+            }
             pr -= a.B;
             cr -= 3 * a.B;
             if (FB) {
@@ -625,6 +641,7 @@ HB_HD void norm3_fast_chain(const Norm3Args &a, int32_t seg, int64_t b, Norm3Sme
                     for (int j = h * HB_HALF; j < (h + 1) * HB_HALF; j++) {
                         const double xv = m.xs[j * m.st];
                         if (more) xs_refill(m, j, xq);
+                        if (pf) prefetch_l2(xq - (int64_t)HB_FAST_PF_CHUNKS * HB_CHUNK * ld);
                         xq += ld;
                         fast_replay_one(c, s, xv, j == 0 && ch == 0, m, j);
                     }

@@ -1,2 +1,4 @@
 cd $GRAFT_REPO_ROOT
-HB_MODE=0 python tools/probe_binom.py variants/lib_p2.so variants/lib_p4.so variants/lib_p2b5.so variants/lib_p2b3.so 2>&1 | grep "^lib" | tee gpurun_out/probe_binom3.log
+python -m pytest tests -m gpu -x -q 2>&1 | tail -8 | tee gpurun_out/pytest_gpu.log
+python bench.py --steps 30 --warmup 3 > gpurun_out/bench_expr.log 2>&1; tail -1 gpurun_out/bench_expr.log
+python bench.py --workload allele --steps 5 --warmup 3 --e2e-steps 1 > gpurun_out/bench_allele.log 2>&1; tail -1 gpurun_out/bench_allele.log
