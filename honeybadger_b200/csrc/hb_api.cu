@@ -88,7 +88,7 @@ struct DevBuf {
 // Per-device scratch, grown on demand and reused across calls (no allocation in steady state).
 struct Workspace {
     DevBuf psi, ckpt, sdaux, segtab, status, lut_lb, lut_rho, lut_rho_d, cellmask, gsize;
-    DevBuf st_in, st_in2, st_x, st_x2, st_y, st_g, st_out, st_sd, st_ll, st_member, st_pool, st_pool2;
+    DevBuf st_in, st_in2, st_x, st_x2, st_y, st_g, st_out, st_sd, st_ll, st_member, st_pool, st_pool2, st_pre;
     // host-buffer entry points: three-stream pipeline (upload | layout + chains | download), staging x2
     DevBuf pin[2], pin2[2], pout_y[2], pout_g[2], pout_ll[2];
     cudaStream_t s_in = nullptr, s_cmp = nullptr, s_out = nullptr;
@@ -102,7 +102,7 @@ struct Workspace {
     {
         DevBuf *all[] = {&psi, &ckpt, &sdaux, &segtab, &status, &lut_lb, &lut_rho, &lut_rho_d, &cellmask, &gsize,
                          &st_in, &st_in2, &st_x, &st_x2, &st_y, &st_g, &st_out, &st_sd, &st_ll,
-                         &st_member, &st_pool, &st_pool2, &pin[0], &pin[1], &pin2[0], &pin2[1],
+                         &st_member, &st_pool, &st_pool2, &st_pre, &pin[0], &pin[1], &pin2[0], &pin2[1],
                          &pout_y[0], &pout_y[1], &pout_g[0], &pout_g[1], &pout_ll[0], &pout_ll[1]};
         for (DevBuf *b : all) b->release();
         seg_cached.clear();
@@ -353,7 +353,8 @@ int prepare_lut(Workspace *ws, const double *prob, double rho, cudaStream_t st)
 int binom2_run(Workspace *ws, const int32_t *x, const int32_t *n, int64_t ld, int64_t T, int64_t B,
                const int64_t *seg_off, int32_t nseg, const double *prob, double rho,
                const double *Pi, const double *delta, int32_t flags, uint8_t *y, int64_t ldy,
-               double *gamma, int64_t ldg, double *ll, cudaStream_t st, bool reset_status = true)
+               double *gamma, int64_t ldg, double *ll, cudaStream_t st, bool reset_status = true,
+               bool pooled = false)
 {
     if (T < 1 || B < 1 || ld < B) return fail(HB_ERR_ARG, "bad shape T=%lld B=%lld ld=%lld",
                                                (long long)T, (long long)B, (long long)ld);
@@ -413,6 +414,15 @@ int binom2_run(Workspace *ws, const int32_t *x, const int32_t *n, int64_t ld, in
     // Lean kernel first (plain-double filter, rows of Pi positive); it raises the gate when some
     // position carries evidence beyond 2^+-900, and the general kernel then redoes the launch
     // (otherwise its blocks exit at once).  Both are enqueued: no host synchronisation here.
+    if (pooled && vit && !fb) {
+        // Pooled chains (a handful of long chains, deep counts at every position): evaluate all
+        // emissions in a parallel pre-pass, then run the literal Viterbi over the stored values.
+        HBTRY(ws->st_pre.ensure((size_t)T * ld * sizeof(double2)));
+        CU(hb::launch_binom2_emit(a, ws->st_pre.as<double2>(), st));
+        a.pre_lb = ws->st_pre.as<double2>();
+        CU(hb::launch_binom2(a, vit, fb, st));
+        return HB_OK;
+    }
     const bool lean_ok = Pi[0] > 0 && Pi[1] > 0 && Pi[2] > 0 && Pi[3] > 0;
     if (lean_ok && g_binom2_mode != 1) {
         a.gate = ws->status.as<int32_t>() + 2;
@@ -990,7 +1000,7 @@ int hb_allele_pooled_viterbi_dev(const int32_t *r_maf, const int32_t *n_sc, int6
     }
     const int64_t seg[2] = {0, G};
     HBTRY(binom2_run(ws, gm[0], gm[1], ldk, G, K, seg, 1, prob, 0.0, Pi, delta, HB_WANT_VITERBI,
-                     ws->st_y.as<uint8_t>(), ldk, nullptr, 0, nullptr, st));
+                     ws->st_y.as<uint8_t>(), ldk, nullptr, 0, nullptr, st, true, true));
     CU(hb::launch_transpose_u8_back(ws->st_y.as<uint8_t>(), ldk, G, K, ws->st_out.as<int32_t>(), st));
     CU(cudaMemcpyAsync(y, ws->st_out.p, (size_t)G * K * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     if (mafl)

@@ -59,6 +59,10 @@ struct Binom2Args {
     const RhoME *lut_rho;   //                  -> b_0/b_1 = m * 2^e
     const double *lut_rho_d; //                 -> b_0/b_1 as a double, < 0 = beyond 2^+-900 (hb_binom2_fast.cuh)
     int32_t lut_nmax;
+    // optional: (logb_0, logb_1) of every position evaluated beforehand by binom2_emit_kernel,
+    // pre_lb[t*ld+b] (pooled chains: deep counts at every position, the saddle-point evaluation is
+    // taken off the sequential chain).  Used by the Viterbi-only general kernel.
+    const double2 *pre_lb;
     uint8_t *y;
     int64_t ldy;
     double *gamma;
@@ -276,10 +280,21 @@ HB_HD void binom2_chain(const Binom2Args &a, int32_t seg, int64_t b, double *sm,
     const bool want_ll = FB && a.ll != nullptr;
 
     int32_t xc[HB_CHUNK], nc[HB_CHUNK], xn[HB_CHUNK], nn[HB_CHUNK];
+    // pooled chains: pre-evaluated emissions, fetched one chunk ahead (+ L2 prefetch further ahead):
+    // only a handful of threads run, so nothing else hides the latency of these loads
+    const bool pre = !FB && a.pre_lb != nullptr;
+    const double2 *plb = pre ? a.pre_lb + t0 * a.ld + b : nullptr;
+    double2 lbc[HB_CHUNK], lbn[HB_CHUNK];
 #pragma unroll
     for (int j = 0; j < HB_CHUNK; j++) {
-        xc[j] = (j < L) ? xp[(int64_t)j * a.ld] : 0;
-        nc[j] = (j < L) ? np[(int64_t)j * a.ld] : 0;
+        lbc[j].x = lbc[j].y = lbn[j].x = lbn[j].y = 0.0;
+        if (pre) {
+            if (j < L) lbc[j] = plb[(int64_t)j * a.ld];
+            xc[j] = nc[j] = 0;
+        } else {
+            xc[j] = (j < L) ? xp[(int64_t)j * a.ld] : 0;
+            nc[j] = (j < L) ? np[(int64_t)j * a.ld] : 0;
+        }
     }
     for (int64_t ch = 0; ch < nch; ch++) {
         const int64_t i0 = ch * HB_CHUNK;
@@ -287,8 +302,14 @@ HB_HD void binom2_chain(const Binom2Args &a, int32_t seg, int64_t b, double *sm,
             const int64_t inext = i0 + HB_CHUNK;
 #pragma unroll
             for (int j = 0; j < HB_CHUNK; j++) {
-                xn[j] = (inext + j < L) ? xp[(inext + j) * a.ld] : 0;
-                nn[j] = (inext + j < L) ? np[(inext + j) * a.ld] : 0;
+                if (pre) {
+                    if (inext + j < L) lbn[j] = plb[(inext + j) * a.ld];
+                    if (inext + 4 * HB_CHUNK + j < L) prefetch_l2(plb + (inext + 4 * HB_CHUNK + j) * a.ld);
+                    xn[j] = nn[j] = 0;
+                } else {
+                    xn[j] = (inext + j < L) ? xp[(inext + j) * a.ld] : 0;
+                    nn[j] = (inext + j < L) ? np[(inext + j) * a.ld] : 0;
+                }
             }
         }
         uint64_t pk = 0;
@@ -299,7 +320,12 @@ HB_HD void binom2_chain(const Binom2Args &a, int32_t seg, int64_t b, double *sm,
                 RhoME rho;
                 rho.m = 1.0;
                 rho.e = 0;
-                binom2_emit(a, xc[j], nc[j], l0, l1, rho, VIT || want_ll, FB);
+                if (pre) {
+                    l0 = lbc[j].x;
+                    l1 = lbc[j].y;
+                } else {
+                    binom2_emit(a, xc[j], nc[j], l0, l1, rho, VIT || want_ll, FB);
+                }
                 if (VIT) {
                     if (i0 + j == 0) {
                         n0 = c.logdelta[0] + l0;
@@ -329,6 +355,7 @@ HB_HD void binom2_chain(const Binom2Args &a, int32_t seg, int64_t b, double *sm,
         for (int j = 0; j < HB_CHUNK; j++) {
             xc[j] = xn[j];
             nc[j] = nn[j];
+            lbc[j] = lbn[j];
         }
     }
 
@@ -367,7 +394,10 @@ HB_HD void binom2_chain(const Binom2Args &a, int32_t seg, int64_t b, double *sm,
             }
         }
         uint64_t pk = 0;
-        if (VIT) pk = a.psi[(cbase + ch) * a.B + b];
+        if (VIT) {
+            pk = a.psi[(cbase + ch) * a.B + b];
+            if (ch >= 6) prefetch_l2(a.psi + (cbase + ch - 6) * a.B + b);
+        }
         if (FB) {
             if (ch > 0) {
                 const double *ck = a.ckpt + (cbase + ch) * 3 * a.B + b;

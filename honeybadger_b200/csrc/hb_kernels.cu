@@ -77,6 +77,25 @@ __global__ void __launch_bounds__(HB_BLOCK)
     binom2_chain<VIT, FB>(a, seg, b, smem + threadIdx.x, HB_BLOCK);
 }
 
+// Emission pre-pass for pooled chains: one thread per (position, chain).
+__global__ void __launch_bounds__(128)
+    binom2_emit_kernel(const __grid_constant__ Binom2Args a, double2 *pre_lb)
+{
+    const int64_t b = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
+    const int64_t t = blockIdx.x; // positions on grid.x (can exceed 65535)
+    if (b >= a.B || t >= a.T) return;
+    const int64_t o = t * a.ld + b;
+    double l0 = 0, l1 = 0;
+    RhoME rho;
+    rho.m = 1.0;
+    rho.e = 0;
+    binom2_emit(a, a.x[o], a.n[o], l0, l1, rho, true, false);
+    double2 v;
+    v.x = l0;
+    v.y = l1;
+    pre_lb[o] = v;
+}
+
 #ifndef HB_B2F_MINB
 #define HB_B2F_MINB 4
 #endif
@@ -160,6 +179,13 @@ cudaError_t launch_norm3_fast(const Norm3Args &a, bool vit, bool fb, cudaStream_
         HB_LAUNCH_FAST(true, false, false, sm_v);
     }
 #undef HB_LAUNCH_FAST
+    return cudaGetLastError();
+}
+
+cudaError_t launch_binom2_emit(const Binom2Args &a, double2 *pre_lb, cudaStream_t st)
+{
+    dim3 grid((unsigned)a.T, (unsigned)((a.B + 127) / 128));
+    binom2_emit_kernel<<<grid, 128, 0, st>>>(a, pre_lb);
     return cudaGetLastError();
 }
 
@@ -461,41 +487,37 @@ cudaError_t launch_pooled_sd(const double *pooled, int64_t G, int32_t K, double 
     return cudaGetLastError();
 }
 
-// out[k*G+g] = #{c : member[k*N+c] && v[g*ld+c] > 0}; one block per gene, groups as a bitmask per
-// cell (K <= 32 per launch).  Integer, exact.
-__global__ void __launch_bounds__(256)
+// out[k*G+g] = #{c : member[k*N+c] && v[g*ld+c] > 0}.  One warp per SNP row, lanes stride the cells
+// (coalesced 128 B rows of int32), groups as a bitmask per cell (K <= 32 per launch).  Each group's
+// count is a ballot + popc per 32 cells, so the kernel is a pure stream over the matrix:
+// 4 B / cell read once, K*4 B / row written.  Integer, exact.
+#define PC_WARPS 8
+__global__ void __launch_bounds__(32 * PC_WARPS)
     pool_count_kernel(const int32_t *v, int64_t ld, int64_t G, int64_t N, const uint32_t *cellmask,
                       int32_t K, int32_t *out)
 {
-    __shared__ int32_t part[8][32];
-    const int64_t g = blockIdx.x;
-    int32_t cnt[32];
-#pragma unroll
-    for (int k = 0; k < 32; k++) cnt[k] = 0;
-    for (int64_t c = threadIdx.x; c < N; c += blockDim.x) {
-        uint32_t m = (v[g * ld + c] > 0) ? cellmask[c] : 0u;
-#pragma unroll
-        for (int k = 0; k < 32; k++) cnt[k] += (m >> k) & 1u;
+    const int lane = threadIdx.x & 31;
+    const int64_t g = (int64_t)blockIdx.x * PC_WARPS + (threadIdx.x >> 5);
+    if (g >= G) return;
+    const int32_t *row = v + g * ld;
+    int32_t cnt = 0; // lane k accumulates group k
+    for (int64_t c0 = 0; c0 < N; c0 += 32) {
+        const int64_t c = c0 + lane;
+        uint32_t m = 0u;
+        if (c < N && ld_stream(row + c) > 0) m = cellmask[c];
+        for (int k = 0; k < K; k++) {
+            const uint32_t bal = __ballot_sync(0xffffffffu, (m >> k) & 1u);
+            if (lane == k) cnt += __popc(bal);
+        }
     }
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-#pragma unroll
-    for (int k = 0; k < 32; k++) {
-        int32_t s = cnt[k];
-        for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) part[w][k] = s;
-    }
-    __syncthreads();
-    if (threadIdx.x < K) {
-        int32_t s = 0;
-        for (int i = 0; i < 8; i++) s += part[i][threadIdx.x];
-        out[(int64_t)threadIdx.x * G + g] = s;
-    }
+    if (lane < K) out[(int64_t)lane * G + g] = cnt;
 }
 
 cudaError_t launch_pool_count(const int32_t *v, int64_t ld, int64_t G, int64_t N,
                               const uint32_t *cellmask, int32_t K, int32_t *out, cudaStream_t st)
 {
-    pool_count_kernel<<<(unsigned)G, 256, 0, st>>>(v, ld, G, N, cellmask, K, out);
+    pool_count_kernel<<<(unsigned)((G + PC_WARPS - 1) / PC_WARPS), 32 * PC_WARPS, 0, st>>>(v, ld, G, N,
+                                                                                          cellmask, K, out);
     return cudaGetLastError();
 }
 

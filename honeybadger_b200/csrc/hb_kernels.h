@@ -12,6 +12,7 @@ struct Binom2Args;
 
 cudaError_t launch_norm3(const Norm3Args &a, bool sym, bool vit, bool fb, cudaStream_t st);
 cudaError_t launch_norm3_fast(const Norm3Args &a, bool vit, bool fb, cudaStream_t st);
+cudaError_t launch_binom2_emit(const Binom2Args &a, double2 *pre_lb, cudaStream_t st);
 cudaError_t launch_binom2_fast(const Binom2Args &a, bool vit, bool fb, cudaStream_t st);
 cudaError_t launch_binom2(const Binom2Args &a, bool vit, bool fb, cudaStream_t st);
 cudaError_t launch_sd_prep(const double *sd, int64_t n, double *inv_sd, double *log_sd,

@@ -1,4 +1,3 @@
 cd $GRAFT_REPO_ROOT
-python -m pytest tests -m gpu -x -q 2>&1 | tail -8 | tee gpurun_out/pytest_gpu.log
-python bench.py --steps 30 --warmup 3 > gpurun_out/bench_expr.log 2>&1; tail -1 gpurun_out/bench_expr.log
-python bench.py --workload allele --steps 5 --warmup 3 --e2e-steps 1 > gpurun_out/bench_allele.log 2>&1; tail -1 gpurun_out/bench_allele.log
+python -m pytest tests/test_gpu_pooled.py tests/test_gpu_hmm.py -x -q 2>&1 | tail -4 | tee gpurun_out/pytest_gpu.log
+python tools/probe_pooled.py 2>&1 | tail -4 | tee gpurun_out/probe_pooled.log
