@@ -33,8 +33,8 @@ namespace hb {
 #define HB_B2F_PF_CHUNKS 2 // L2 prefetch distance of the count planes, in chunks
 #endif
 
-// per step and thread: (phi0, rho 2^-es) as double2 + high word of 2^-es
-#define HB_B2F_SMEM_BYTES_PER_THREAD (HB_CHUNK * (16 + 4))
+// per step and thread: (phi0, rho 2^-es) as double2 + high word of 2^-es + the two count rings
+#define HB_B2F_SMEM_BYTES_PER_THREAD (HB_CHUNK * (16 + 4 + 4 + 4))
 
 // Emission table entries with n <= HB_B2F_SLUT_N live in shared memory (one copy per block): the
 // per-step lookup is then an LDS with a ~30-cycle latency instead of an L1/L2 gather that the
@@ -46,6 +46,7 @@ namespace hb {
 struct B2fSmem {
     double2 *pr;
     int32_t *ph;
+    int32_t *xs, *ns; // cp.async rings of the count planes, one chunk deep
     int32_t st;
     const double2 *slb; // [HB_B2F_SLUT_ENTRIES] (l0, l1)
     const double *srho; // [HB_B2F_SLUT_ENTRIES]
@@ -207,49 +208,50 @@ HB_HD void binom2_fast_chain(const Binom2Args &a, int32_t seg, int64_t b, const 
     s.esum = 0;
 
     // ------------------------------------------------------------ forward sweep
-    // counts are prefetched half a chunk ahead into registers (two coalesced 128 B loads per step)
-    int32_t xa[HB_HALF], na[HB_HALF], xb[HB_HALF], nb[HB_HALF];
+    // counts are staged through shared memory with cp.async, one chunk ahead, in half-chunk groups
+    // (+ an L2 prefetch HB_B2F_PF_CHUNKS further ahead)
+    AsyncRing4 ring;
     if (nfull > 0) {
+        const int32_t *xr0 = xp, *nr0 = np;
 #pragma unroll
-        for (int j = 0; j < HB_HALF; j++) {
-            xa[j] = ld_stream(xp + (int64_t)j * ld);
-            na[j] = ld_stream(np + (int64_t)j * ld);
+        for (int h = 0; h < 2; h++) {
+#pragma unroll
+            for (int j = h * HB_HALF; j < (h + 1) * HB_HALF; j++) {
+                cpa4(ring, m.xs + j * m.st, xr0);
+                cpa4(ring, m.ns + j * m.st, nr0);
+                xr0 += ld;
+                nr0 += ld;
+            }
+            cpa_commit(ring);
         }
     }
     {
-        int64_t off = (int64_t)HB_HALF * ld; // next half-chunk to fetch
+        const int32_t *xr = xp + (int64_t)HB_CHUNK * ld, *nr = np + (int64_t)HB_CHUNK * ld;
         uint16_t *pw = psi;
         double *ck = ckpt;
         for (int32_t ch = 0; ch < nfull; ch++) {
             const bool more = ch + 1 < nfull;
+            const bool pf = ch + 1 + HB_B2F_PF_CHUNKS < nfull;
             uint32_t pk = 0;
 #pragma unroll
             for (int h = 0; h < 2; h++) {
-                if (ch + HB_B2F_PF_CHUNKS < nfull) { // L2 prefetch well ahead of the register prefetch
+                cpa_wait<1>(ring);
 #pragma unroll
-                    for (int j = 0; j < HB_HALF; j++) {
-                        prefetch_l2(xp + off + (int64_t)(HB_B2F_PF_CHUNKS * HB_CHUNK + j) * ld);
-                        prefetch_l2(np + off + (int64_t)(HB_B2F_PF_CHUNKS * HB_CHUNK + j) * ld);
+                for (int j = h * HB_HALF; j < (h + 1) * HB_HALF; j++) {
+                    const int32_t xv = m.xs[j * m.st], nv = m.ns[j * m.st];
+                    if (more) {
+                        cpa4(ring, m.xs + j * m.st, xr);
+                        cpa4(ring, m.ns + j * m.st, nr);
                     }
-                }
-                if (h == 0 || more) {
-#pragma unroll
-                    for (int j = 0; j < HB_HALF; j++) {
-                        if (h == 0) {
-                            xb[j] = ld_stream(xp + off + (int64_t)j * ld);
-                            nb[j] = ld_stream(np + off + (int64_t)j * ld);
-                        } else {
-                            xa[j] = ld_stream(xp + off + (int64_t)j * ld);
-                            na[j] = ld_stream(np + off + (int64_t)j * ld);
-                        }
+                    if (pf) {
+                        prefetch_l2(xr + (int64_t)HB_B2F_PF_CHUNKS * HB_CHUNK * ld);
+                        prefetch_l2(nr + (int64_t)HB_B2F_PF_CHUNKS * HB_CHUNK * ld);
                     }
+                    xr += ld;
+                    nr += ld;
+                    b2f_forward_one<VIT, FB, LL>(a, m, s, xv, nv, j == 0 && ch == 0, pk, j);
                 }
-                off += (int64_t)HB_HALF * ld;
-#pragma unroll
-                for (int j = h * HB_HALF; j < (h + 1) * HB_HALF; j++)
-                    b2f_forward_one<VIT, FB, LL>(a, m, s, h == 0 ? xa[j] : xb[j - HB_HALF],
-                                                 h == 0 ? na[j] : nb[j - HB_HALF],
-                                                 j == 0 && ch == 0, pk, j);
+                cpa_commit(ring);
             }
             if (VIT) *pw = (uint16_t)pk;
             pw += a.B;
@@ -260,6 +262,7 @@ HB_HD void binom2_fast_chain(const Binom2Args &a, int32_t seg, int64_t b, const 
             }
         }
     }
+    cpa_wait<0>(ring);
     if (tail > 0) {
         uint32_t pk = 0;
         for (int j = 0; j < tail; j++) {
@@ -286,11 +289,18 @@ HB_HD void binom2_fast_chain(const Binom2Args &a, int32_t seg, int64_t b, const 
         s.b0 = s.b1 = q;
     }
     if (FB && nfull > 0) {
-        const int64_t o = (int64_t)(nfull - 1) * HB_CHUNK * ld;
+        const int32_t *xl = xp + (int64_t)(nfull - 1) * HB_CHUNK * ld;
+        const int32_t *nl = np + (int64_t)(nfull - 1) * HB_CHUNK * ld;
 #pragma unroll
-        for (int j = 0; j < HB_HALF; j++) {
-            xa[j] = ld_stream(xp + o + (int64_t)j * ld);
-            na[j] = ld_stream(np + o + (int64_t)j * ld);
+        for (int h = 0; h < 2; h++) {
+#pragma unroll
+            for (int j = h * HB_HALF; j < (h + 1) * HB_HALF; j++) {
+                cpa4(ring, m.xs + j * m.st, xl);
+                cpa4(ring, m.ns + j * m.st, nl);
+                xl += ld;
+                nl += ld;
+            }
+            cpa_commit(ring);
         }
     }
     uint32_t pk_nx = 0;
@@ -330,8 +340,9 @@ HB_HD void binom2_fast_chain(const Binom2Args &a, int32_t seg, int64_t b, const 
         uint8_t *yp = VIT ? a.y + rowl * a.ldy + b : nullptr;
         double *g0 = FB ? a.gamma + rowl * a.ldg + b : nullptr;
         double *g1 = g0 + plane;
-        // next fetch: second half of the last full chunk (its first half is already in xa/na)
-        int64_t off = ((int64_t)(nfull - 1) * HB_CHUNK + HB_HALF) * ld;
+        // refill pointers: the chunk before the one being replayed
+        const int32_t *xr = xp + (int64_t)(nfull - 2) * HB_CHUNK * ld;
+        const int32_t *nr = np + (int64_t)(nfull - 2) * HB_CHUNK * ld;
         const uint16_t *pr = psi + (int64_t)(nfull - 2) * a.B;
         const double *cr = ckpt + (int64_t)(nfull - 2) * 2 * a.B;
         for (int32_t ch = nfull - 1; ch >= 0; ch--) {
@@ -358,37 +369,30 @@ HB_HD void binom2_fast_chain(const Binom2Args &a, int32_t seg, int64_t b, const 
             cr -= 2 * a.B;
             if (FB) {
                 const bool more = ch > 0;
+                const bool pf = ch > 1 + HB_B2F_PF_CHUNKS;
+                const int32_t *xq = xr, *nq = nr;
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
-                    if (ch > HB_B2F_PF_CHUNKS) {
+                    cpa_wait<1>(ring);
 #pragma unroll
-                        for (int j = 0; j < HB_HALF; j++) {
-                            prefetch_l2(xp + off + (int64_t)(j - HB_B2F_PF_CHUNKS * HB_CHUNK) * ld);
-                            prefetch_l2(np + off + (int64_t)(j - HB_B2F_PF_CHUNKS * HB_CHUNK) * ld);
-                        }
-                    }
-                    if (h == 0) {
-#pragma unroll
-                        for (int j = 0; j < HB_HALF; j++) {
-                            xb[j] = ld_stream(xp + off + (int64_t)j * ld);
-                            nb[j] = ld_stream(np + off + (int64_t)j * ld);
-                        }
-                        off -= (int64_t)(HB_CHUNK + HB_HALF) * ld;
-                    } else {
+                    for (int j = h * HB_HALF; j < (h + 1) * HB_HALF; j++) {
+                        const int32_t xv = m.xs[j * m.st], nv = m.ns[j * m.st];
                         if (more) {
-#pragma unroll
-                            for (int j = 0; j < HB_HALF; j++) {
-                                xa[j] = ld_stream(xp + off + (int64_t)j * ld);
-                                na[j] = ld_stream(np + off + (int64_t)j * ld);
-                            }
+                            cpa4(ring, m.xs + j * m.st, xq);
+                            cpa4(ring, m.ns + j * m.st, nq);
                         }
-                        off += (int64_t)HB_HALF * ld;
+                        if (pf) {
+                            prefetch_l2(xq - (int64_t)HB_B2F_PF_CHUNKS * HB_CHUNK * ld);
+                            prefetch_l2(nq - (int64_t)HB_B2F_PF_CHUNKS * HB_CHUNK * ld);
+                        }
+                        xq += ld;
+                        nq += ld;
+                        b2f_replay_one(a, s, xv, nv, j == 0 && ch == 0, m, j);
                     }
-#pragma unroll
-                    for (int j = h * HB_HALF; j < (h + 1) * HB_HALF; j++)
-                        b2f_replay_one(a, s, h == 0 ? xa[j] : xb[j - HB_HALF],
-                                       h == 0 ? na[j] : nb[j - HB_HALF], j == 0 && ch == 0, m, j);
+                    cpa_commit(ring);
                 }
+                xr -= (int64_t)HB_CHUNK * ld;
+                nr -= (int64_t)HB_CHUNK * ld;
             }
 #pragma unroll
             for (int j = HB_CHUNK - 1; j >= 0; j--) {
@@ -401,6 +405,7 @@ HB_HD void binom2_fast_chain(const Binom2Args &a, int32_t seg, int64_t b, const 
             }
         }
     }
+    cpa_wait<0>(ring);
 }
 
 } // namespace hb

@@ -101,6 +101,61 @@ HB_HD void prefetch_l2(const void *p)
 #endif
 }
 
+// ---------------------------------------------------------------- cp.async staging of 4-byte elements
+// Per-thread asynchronous copies global -> shared with explicit commit / wait groups.  Unlike a
+// register prefetch (whose first use can end up waiting on the scoreboard it shares with the NEXT
+// prefetch), a wait_group only waits for the groups it names.  The host build defers visibility
+// to the wait, so the CPU emulation catches group-accounting mistakes.
+struct AsyncRing4 {
+#if !defined(__CUDA_ARCH__)
+    int32_t pend_v[64];
+    int32_t *pend_p[64];
+    int pend_g[64];
+    int npend = 0, cur_group = 0;
+#endif
+};
+HB_HD void cpa4(AsyncRing4 &r, int32_t *dst_smem, const int32_t *g)
+{
+#if defined(__CUDA_ARCH__)
+    unsigned sa = (unsigned)__cvta_generic_to_shared(dst_smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(g) : "memory");
+#else
+    r.pend_v[r.npend] = *g;
+    r.pend_p[r.npend] = dst_smem;
+    r.pend_g[r.npend] = r.cur_group;
+    r.npend++;
+#endif
+}
+HB_HD void cpa_commit(AsyncRing4 &r)
+{
+#if defined(__CUDA_ARCH__)
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#else
+    r.cur_group++;
+#endif
+}
+// Wait until at most N of the most recently committed groups are still in flight.
+template <int N>
+HB_HD void cpa_wait(AsyncRing4 &r)
+{
+#if defined(__CUDA_ARCH__)
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+#else
+    int keep = 0;
+    for (int i = 0; i < r.npend; i++) {
+        if (r.pend_g[i] < r.cur_group - N) {
+            *r.pend_p[i] = r.pend_v[i];
+        } else {
+            r.pend_v[keep] = r.pend_v[i];
+            r.pend_p[keep] = r.pend_p[i];
+            r.pend_g[keep] = r.pend_g[i];
+            keep++;
+        }
+    }
+    r.npend = keep;
+#endif
+}
+
 // ---------------------------------------------------------------- exact division by a chain constant
 // z = RN(d / b) given y = RN(1/b): Markstein's correction (q = d*y; r = d - b*q exactly by FMA;
 // q' = q + r*y) is correctly rounded for every d when y is the correctly rounded reciprocal

@@ -122,6 +122,8 @@ __global__ void __launch_bounds__(HB_BLOCK, HB_B2F_MINB)
     m.st = HB_BLOCK;
     m.pr = park + threadIdx.x;
     m.ph = reinterpret_cast<int32_t *>(park + HB_CHUNK * HB_BLOCK) + threadIdx.x;
+    m.xs = m.ph + HB_CHUNK * HB_BLOCK;
+    m.ns = m.xs + HB_CHUNK * HB_BLOCK;
     m.slb = slb;
     m.srho = srho;
     m.slut_n = slut_n;
@@ -205,7 +207,7 @@ cudaError_t launch_binom2_fast(const Binom2Args &a, bool vit, bool fb, cudaStrea
         else
             binom2_fast_kernel<false, true, false><<<grid, HB_BLOCK, sm_fb, st>>>(a);
     } else {
-        binom2_fast_kernel<true, false, false><<<grid, HB_BLOCK, HB_B2F_SLUT_BYTES, st>>>(a);
+        binom2_fast_kernel<true, false, false><<<grid, HB_BLOCK, sm_fb, st>>>(a);
     }
     return cudaGetLastError();
 }

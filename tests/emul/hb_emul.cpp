@@ -273,10 +273,10 @@ int emul_binom2_fast(const int32_t *x, const int32_t *n, int64_t ld, int64_t T, 
     std::vector<uint64_t> psi((size_t)sg.nchunks * B);
     std::vector<double> ckpt((size_t)sg.nchunks * 3 * B);
     std::vector<double2> spr(HB_CHUNK);
-    std::vector<int32_t> sph(HB_CHUNK);
+    std::vector<int32_t> sph(HB_CHUNK), sxs(HB_CHUNK), sns(HB_CHUNK);
     std::vector<double> sm(HB_CHUNK * HB_BINOM2_SLOT);
     B2fSmem m;
-    m.pr = spr.data(); m.ph = sph.data(); m.st = 1;
+    m.pr = spr.data(); m.ph = sph.data(); m.xs = sxs.data(); m.ns = sns.data(); m.st = 1;
     m.slb = lb.data(); m.srho = rd.data(); m.slut_n = std::min(lut_nmax, HB_B2F_SLUT_N);
     int32_t status[4] = {0, 0, 0, 0};
     a.x = x; a.n = n; a.ld = ld; a.T = T; a.B = B;
