@@ -269,20 +269,24 @@ def main():
     seg = d["seg"]
     Pi3, Pi2 = hmm.sym_Pi(3, 1e-6), hmm.sym_Pi(2, 1e-6)
     mean, delta3, prob, delta2 = [-DEV, 0.0, DEV], [0.0, 1.0, 0.0], [0.1, 0.45], [0.0, 1.0]
+    # Resident layout of the timed leg: warp-tiled [tile of 32 cells][position][lane]
+    # (hmm.tile_rows).  The gene-major copy is kept for the e2e leg's host buffers.
     if kind == "expr":
         sd = hmm.chain_sd_dev(d["x"])
-        out = hmm.hmm_norm_dev(d["x"], sd, mean, Pi3, delta3, seg_off=seg)
+        xt = hmm.tile_rows(d["x"])
+        out = hmm.hmm_norm_tiled_dev(xt, cells, sd, mean, Pi3, delta3, seg_off=seg)
 
         def step():
-            hmm.hmm_norm_dev(d["x"], sd, mean, Pi3, delta3, seg_off=seg, out=out)
-        launches_per_step = 2  # sd_prep_kernel + norm3_kernel
+            hmm.hmm_norm_tiled_dev(xt, cells, sd, mean, Pi3, delta3, seg_off=seg, out=out)
+        launches_per_step = 2  # sd_prep_kernel + norm3_fast_kernel
         in_bytes = d["x"].numel() * 8
     else:
-        out = hmm.hmm_binom_dev(d["r"], d["n"], prob, Pi2, delta2, seg_off=seg)
+        rt, nt = hmm.tile_rows(d["r"]), hmm.tile_rows(d["n"])
+        out = hmm.hmm_binom_tiled_dev(rt, nt, cells, prob, Pi2, delta2, seg_off=seg)
 
         def step():
-            hmm.hmm_binom_dev(d["r"], d["n"], prob, Pi2, delta2, seg_off=seg, out=out)
-        launches_per_step = 1
+            hmm.hmm_binom_tiled_dev(rt, nt, cells, prob, Pi2, delta2, seg_off=seg, out=out)
+        launches_per_step = 2  # binom2_fast_kernel + the gated general kernel (exits at once)
         in_bytes = d["r"].numel() * 8
     hmm.status_dev()
 
@@ -343,7 +347,7 @@ def main():
                 "config": {"workload": wl["name"], "cells_per_gpu": cells, "positions": positions,
                            "segments": wl["nseg"], "states": wl["S"],
                            "l2": f"inputs {in_bytes / 1e6:.0f} MB + outputs per pass exceed the 126 MB L2",
-                           "layout": "gene-major [position][cell], rows padded to a multiple of 128 elements"},
+                           "layout": "warp-tiled [tile of 32 cells][position][lane] (hb_tile_dev), fp64 / int32"},
                 "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
                 "gpu_launches": launches_per_step * args.steps}
         print(json.dumps(line), flush=True)

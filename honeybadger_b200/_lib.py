@@ -51,6 +51,10 @@ SIGNATURES = {
     "hb_hmm_norm_host": (_i32, [_p, _i64, _i64, _p, _i32, _p, _p, _i32, _p, _p, _i32, _p, _p, _p]),
     "hb_hmm_norm_dev": (_i32, [_p, _i64, _i64, _i64, _p, _i32, _p, _p, _i32, _p, _p, _i32, _p, _i64,
                                _p, _i64, _p, _p]),
+    "hb_hmm_norm_tiled_dev": (_i32, [_p, _i64, _i64, _p, _i32, _p, _p, _i32, _p, _p, _i32, _p, _p, _p, _p]),
+    "hb_hmm_binom_tiled_dev": (_i32, [_p, _p, _i64, _i64, _p, _i32, _p, _d, _p, _p, _i32, _p, _p, _p, _p]),
+    "hb_tile_dev": (_i32, [_p, _i64, _i64, _i64, _i32, _p, _p]),
+    "hb_untile_dev": (_i32, [_p, _i64, _i64, _i32, _p, _i64, _p]),
     "hb_hmm_binom_host": (_i32, [_p, _p, _i64, _i64, _p, _i32, _p, _d, _p, _p, _i32, _p, _p, _p]),
     "hb_hmm_binom_dev": (_i32, [_p, _p, _i64, _i64, _i64, _p, _i32, _p, _d, _p, _p, _i32, _p, _i64,
                                 _p, _i64, _p, _p]),

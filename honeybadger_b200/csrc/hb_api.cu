@@ -233,15 +233,16 @@ int norm3_run(Workspace *ws, const double *x, int64_t ld, int64_t T, int64_t B,
               const int64_t *seg_off, int32_t nseg, const double *mean, const double *sd,
               const double *inv_sd, const double *log_sd, int32_t sd_per_seg, const double *Pi,
               const double *delta, int32_t flags, uint8_t *y, int64_t ldy, double *gamma,
-              int64_t ldg, double *ll, cudaStream_t st, bool reset_status = true)
+              int64_t ldg, double *ll, cudaStream_t st, bool reset_status = true, bool tiled = false)
 {
-    if (T < 1 || B < 1 || ld < B) return fail(HB_ERR_ARG, "bad shape T=%lld B=%lld ld=%lld",
-                                               (long long)T, (long long)B, (long long)ld);
+    if (T < 1 || B < 1 || (!tiled && ld < B))
+        return fail(HB_ERR_ARG, "bad shape T=%lld B=%lld ld=%lld", (long long)T, (long long)B, (long long)ld);
     if (!x || !sd) return fail(HB_ERR_ARG, "x and sd are required");
     bool vit, fb, sym;
     HBTRY(check_flags(flags, y, gamma, ll, &vit, &fb));
-    if (vit && ldy < B) return fail(HB_ERR_ARG, "ldy < B");
-    if ((flags & HB_WANT_GAMMA) && ldg < B) return fail(HB_ERR_ARG, "ldg < B");
+    if (!tiled && vit && ldy < B) return fail(HB_ERR_ARG, "ldy < B");
+    if (!tiled && (flags & HB_WANT_GAMMA) && ldg < B) return fail(HB_ERR_ARG, "ldg < B");
+    const int64_t Bp = tiled ? (B + 31) / 32 * 32 : B; // columns the scratch is laid out for
     hb::Norm3Args a;
     memset(&a, 0, sizeof a);
     HBTRY(fill_norm3_const(a.c, mean, Pi, delta, &sym));
@@ -255,13 +256,16 @@ int norm3_run(Workspace *ws, const double *x, int64_t ld, int64_t T, int64_t B,
         log_sd = aux + nsd;
     }
     HBTRY(ws->status.ensure(4 * sizeof(int32_t)));
-    if (vit) HBTRY(ws->psi.ensure((size_t)ws->nchunks * B * sizeof(uint64_t)));
-    if (fb) HBTRY(ws->ckpt.ensure((size_t)ws->nchunks * 3 * B * sizeof(double)));
+    if (vit) HBTRY(ws->psi.ensure((size_t)ws->nchunks * Bp * sizeof(uint64_t)));
+    if (fb) HBTRY(ws->ckpt.ensure((size_t)ws->nchunks * 3 * Bp * sizeof(double)));
     if (reset_status) CU(cudaMemsetAsync(ws->status.p, 0, 4 * sizeof(int32_t), st));
     a.x = x;
     a.ld = ld;
     a.T = T;
     a.B = B;
+    a.tiled = tiled ? 1 : 0;
+    a.gplane = tiled ? T * Bp : T * ldg;
+    a.nchunks = ws->nchunks;
     a.nseg = nseg;
     a.nblk_per_seg = (int32_t)((B + HB_BLOCK - 1) / HB_BLOCK);
     a.sd = sd;
@@ -288,7 +292,7 @@ int norm3_run(Workspace *ws, const double *x, int64_t ld, int64_t T, int64_t B,
     int64_t lmax = 0;
     for (int32_t s = 0; s < nseg; s++) lmax = std::max(lmax, seg_off[s + 1] - seg_off[s]);
     const bool fast_ok = sym && delta[1] > 0 && Pi[0] > 0 && lmax <= HB_FAST_LMAX;
-    const bool padded = ld % 128 == 0 && (!a.gamma || ldg % 128 == 0);
+    const bool padded = tiled || (ld % 128 == 0 && (!a.gamma || ldg % 128 == 0));
     if (fast_ok && (g_norm3_mode >= 2 || (g_norm3_mode == 0 && padded))) {
         if (g_norm3_mode == 2) a.c.eps_scale = INFINITY;
         CU(hb::launch_norm3_fast(a, vit, fb, st));
@@ -354,10 +358,11 @@ int binom2_run(Workspace *ws, const int32_t *x, const int32_t *n, int64_t ld, in
                const int64_t *seg_off, int32_t nseg, const double *prob, double rho,
                const double *Pi, const double *delta, int32_t flags, uint8_t *y, int64_t ldy,
                double *gamma, int64_t ldg, double *ll, cudaStream_t st, bool reset_status = true,
-               bool pooled = false)
+               bool pooled = false, bool tiled = false)
 {
-    if (T < 1 || B < 1 || ld < B) return fail(HB_ERR_ARG, "bad shape T=%lld B=%lld ld=%lld",
-                                               (long long)T, (long long)B, (long long)ld);
+    if (T < 1 || B < 1 || (!tiled && ld < B))
+        return fail(HB_ERR_ARG, "bad shape T=%lld B=%lld ld=%lld", (long long)T, (long long)B, (long long)ld);
+    const int64_t Bp = tiled ? (B + 31) / 32 * 32 : B;
     if (!x || !n || !prob || !Pi || !delta) return fail(HB_ERR_ARG, "missing argument");
     if (!all_finite(prob, 2) || !all_finite(Pi, 4) || !all_finite(delta, 2) || !(rho >= 0) ||
         !(rho < 1))
@@ -366,8 +371,8 @@ int binom2_run(Workspace *ws, const int32_t *x, const int32_t *n, int64_t ld, in
         if (prob[k] < 0 || prob[k] > 1) return fail(HB_ERR_ARG, "prob outside [0,1]");
     bool vit, fb;
     HBTRY(check_flags(flags, y, gamma, ll, &vit, &fb));
-    if (vit && ldy < B) return fail(HB_ERR_ARG, "ldy < B");
-    if ((flags & HB_WANT_GAMMA) && ldg < B) return fail(HB_ERR_ARG, "ldg < B");
+    if (!tiled && vit && ldy < B) return fail(HB_ERR_ARG, "ldy < B");
+    if (!tiled && (flags & HB_WANT_GAMMA) && ldg < B) return fail(HB_ERR_ARG, "ldg < B");
     if (fb && !(flags & HB_WANT_GAMMA))
         return fail(HB_ERR_ARG, "HB_WANT_LL currently requires HB_WANT_GAMMA");
     hb::Binom2Args a;
@@ -389,14 +394,17 @@ int binom2_run(Workspace *ws, const int32_t *x, const int32_t *n, int64_t ld, in
     HBTRY(prepare_segments(ws, seg_off, nseg, T, st, &a.seg_off, &a.chunk_off, &a.seg_order));
     HBTRY(prepare_lut(ws, prob, rho, st));
     HBTRY(ws->status.ensure(4 * sizeof(int32_t)));
-    if (vit) HBTRY(ws->psi.ensure((size_t)ws->nchunks * B * sizeof(uint64_t)));
-    if (fb) HBTRY(ws->ckpt.ensure((size_t)ws->nchunks * 3 * B * sizeof(double)));
+    if (vit) HBTRY(ws->psi.ensure((size_t)ws->nchunks * Bp * sizeof(uint64_t)));
+    if (fb) HBTRY(ws->ckpt.ensure((size_t)ws->nchunks * 3 * Bp * sizeof(double)));
     if (reset_status) CU(cudaMemsetAsync(ws->status.p, 0, 4 * sizeof(int32_t), st));
     a.x = x;
     a.n = n;
     a.ld = ld;
     a.T = T;
     a.B = B;
+    a.tiled = tiled ? 1 : 0;
+    a.gplane = tiled ? T * Bp : T * ldg;
+    a.nchunks = ws->nchunks;
     a.nseg = nseg;
     a.nblk_per_seg = (int32_t)((B + HB_BLOCK - 1) / HB_BLOCK);
     a.lut_lb = ws->lut_lb.as<double2>();
@@ -606,6 +614,18 @@ static int64_t pipe_batch(int64_t B, double bytes_per_col)
     return std::max<int64_t>(1, Bc);
 }
 
+int hb_hmm_norm_tiled_dev(const double *x, int64_t T, int64_t B, const int64_t *seg_off, int32_t nseg,
+                          const double *mean, const double *sd, int32_t sd_per_seg, const double *Pi,
+                          const double *delta, int32_t flags, uint8_t *y, double *gamma, double *ll,
+                          void *stream)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    Workspace *ws;
+    HBTRY(cur_ws(&ws));
+    return norm3_run(ws, x, 32, T, B, seg_off, nseg, mean, sd, nullptr, nullptr, sd_per_seg, Pi, delta,
+                     flags, y, 32, gamma, 32, ll, (cudaStream_t)stream, true, true);
+}
+
 int hb_hmm_norm_host(const double *x, int64_t T, int64_t B, const int64_t *seg_off, int32_t nseg,
                      const double *mean, const double *sd, int32_t sd_per_seg, const double *Pi,
                      const double *delta, int32_t flags, int32_t *y, double *gamma, double *ll)
@@ -723,6 +743,18 @@ int hb_hmm_binom_dev(const int32_t *x, const int32_t *size, int64_t ld, int64_t 
                       gamma, ldg, ll, (cudaStream_t)stream);
 }
 
+int hb_hmm_binom_tiled_dev(const int32_t *x, const int32_t *size, int64_t T, int64_t B,
+                           const int64_t *seg_off, int32_t nseg, const double *prob, double rho,
+                           const double *Pi, const double *delta, int32_t flags, uint8_t *y,
+                           double *gamma, double *ll, void *stream)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    Workspace *ws;
+    HBTRY(cur_ws(&ws));
+    return binom2_run(ws, x, size, 32, T, B, seg_off, nseg, prob, rho, Pi, delta, flags, y, 32, gamma,
+                      32, ll, (cudaStream_t)stream, true, false, true);
+}
+
 int hb_hmm_binom_host(const int32_t *x, const int32_t *size, int64_t T, int64_t B,
                       const int64_t *seg_off, int32_t nseg, const double *prob, double rho,
                       const double *Pi, const double *delta, int32_t flags, int32_t *y,
@@ -838,6 +870,22 @@ int hb_transpose_f64_back_dev(const double *src, int64_t ld, int64_t G, int64_t 
 {
     if (!src || !dst || G < 1 || N < 1 || ld < N) return fail(HB_ERR_ARG, "bad arguments");
     CU(hb::launch_transpose_f64_back(src, ld, G, N, dst, (cudaStream_t)stream));
+    return HB_OK;
+}
+
+int hb_tile_dev(const void *src, int64_t ld, int64_t T, int64_t B, int32_t elem, void *dst, void *stream)
+{
+    if (!src || !dst || T < 1 || B < 1 || ld < B || (elem != 1 && elem != 4 && elem != 8))
+        return fail(HB_ERR_ARG, "bad arguments");
+    CU(hb::launch_tile(src, ld, T, B, elem, dst, true, (cudaStream_t)stream));
+    return HB_OK;
+}
+
+int hb_untile_dev(const void *src, int64_t T, int64_t B, int32_t elem, void *dst, int64_t ld, void *stream)
+{
+    if (!src || !dst || T < 1 || B < 1 || ld < B || (elem != 1 && elem != 4 && elem != 8))
+        return fail(HB_ERR_ARG, "bad arguments");
+    CU(hb::launch_tile(src, ld, T, B, elem, dst, false, (cudaStream_t)stream));
     return HB_OK;
 }
 

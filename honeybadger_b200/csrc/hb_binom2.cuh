@@ -52,6 +52,8 @@ struct Binom2Const {
 struct Binom2Args {
     const int32_t *x, *n; // x[t*ld+b] successes, n[t*ld+b] trials
     int64_t ld, T, B;
+    int32_t tiled; // as Norm3Args::tiled: warp-tiled layout of x, n, y, gamma planes and the scratch
+    int64_t gplane, nchunks;
     const int64_t *seg_off, *chunk_off;
     const int32_t *seg_order;
     int32_t nseg, nblk_per_seg;
@@ -269,8 +271,11 @@ HB_HD void binom2_chain(const Binom2Args &a, int32_t seg, int64_t b, double *sm,
     if (L <= 0) return;
     const int64_t nch = (L + HB_CHUNK - 1) / HB_CHUNK;
     const int64_t cbase = a.chunk_off[seg];
-    const int32_t *xp = a.x + t0 * a.ld + b;
-    const int32_t *np = a.n + t0 * a.ld + b;
+    const int64_t ldx = lay_stride(a.tiled, a.ld), sB = lay_stride(a.tiled, a.B);
+    const int32_t *xp = a.x + lay_off(a.tiled, a.T, a.ld, t0, b);
+    const int32_t *np = a.n + lay_off(a.tiled, a.T, a.ld, t0, b);
+    uint64_t *psi0 = a.psi + lay_off(a.tiled, a.nchunks, a.B, cbase, b);
+    double *ckpt0 = a.ckpt + (a.tiled ? (((b >> 5) * a.nchunks + cbase) * 3 << 5) + (b & 31) : cbase * 3 * a.B + b);
 
     double n0 = 0, n1 = 0, lsum = 0;
     Rel2 f;
@@ -283,17 +288,17 @@ HB_HD void binom2_chain(const Binom2Args &a, int32_t seg, int64_t b, double *sm,
     // pooled chains: pre-evaluated emissions, fetched one chunk ahead (+ L2 prefetch further ahead):
     // only a handful of threads run, so nothing else hides the latency of these loads
     const bool pre = !FB && a.pre_lb != nullptr;
-    const double2 *plb = pre ? a.pre_lb + t0 * a.ld + b : nullptr;
+    const double2 *plb = pre ? a.pre_lb + lay_off(a.tiled, a.T, a.ld, t0, b) : nullptr;
     double2 lbc[HB_CHUNK], lbn[HB_CHUNK];
 #pragma unroll
     for (int j = 0; j < HB_CHUNK; j++) {
         lbc[j].x = lbc[j].y = lbn[j].x = lbn[j].y = 0.0;
         if (pre) {
-            if (j < L) lbc[j] = plb[(int64_t)j * a.ld];
+            if (j < L) lbc[j] = plb[(int64_t)j * ldx];
             xc[j] = nc[j] = 0;
         } else {
-            xc[j] = (j < L) ? xp[(int64_t)j * a.ld] : 0;
-            nc[j] = (j < L) ? np[(int64_t)j * a.ld] : 0;
+            xc[j] = (j < L) ? xp[(int64_t)j * ldx] : 0;
+            nc[j] = (j < L) ? np[(int64_t)j * ldx] : 0;
         }
     }
     for (int64_t ch = 0; ch < nch; ch++) {
@@ -303,12 +308,12 @@ HB_HD void binom2_chain(const Binom2Args &a, int32_t seg, int64_t b, double *sm,
 #pragma unroll
             for (int j = 0; j < HB_CHUNK; j++) {
                 if (pre) {
-                    if (inext + j < L) lbn[j] = plb[(inext + j) * a.ld];
-                    if (inext + 4 * HB_CHUNK + j < L) prefetch_l2(plb + (inext + 4 * HB_CHUNK + j) * a.ld);
+                    if (inext + j < L) lbn[j] = plb[(inext + j) * ldx];
+                    if (inext + 4 * HB_CHUNK + j < L) prefetch_l2(plb + (inext + 4 * HB_CHUNK + j) * ldx);
                     xn[j] = nn[j] = 0;
                 } else {
-                    xn[j] = (inext + j < L) ? xp[(inext + j) * a.ld] : 0;
-                    nn[j] = (inext + j < L) ? np[(inext + j) * a.ld] : 0;
+                    xn[j] = (inext + j < L) ? xp[(inext + j) * ldx] : 0;
+                    nn[j] = (inext + j < L) ? np[(inext + j) * ldx] : 0;
                 }
             }
         }
@@ -344,12 +349,12 @@ HB_HD void binom2_chain(const Binom2Args &a, int32_t seg, int64_t b, double *sm,
                 }
             }
         }
-        if (VIT) a.psi[(cbase + ch) * a.B + b] = pk;
+        if (VIT) psi0[ch * sB] = pk;
         if (FB && ch + 1 < nch) {
-            double *ck = a.ckpt + (cbase + ch + 1) * 3 * a.B + b;
+            double *ck = ckpt0 + (ch + 1) * 3 * sB;
             ck[0] = f.m0;
-            ck[a.B] = f.m1;
-            ck[2 * a.B] = mk64(0, f.d);
+            ck[sB] = f.m1;
+            ck[2 * sB] = mk64(0, f.d);
         }
 #pragma unroll
         for (int j = 0; j < HB_CHUNK; j++) {
@@ -379,8 +384,8 @@ HB_HD void binom2_chain(const Binom2Args &a, int32_t seg, int64_t b, double *sm,
         const int64_t i0 = (nch - 1) * HB_CHUNK;
 #pragma unroll
         for (int j = 0; j < HB_CHUNK; j++) {
-            xc[j] = (i0 + j < L) ? xp[(i0 + j) * a.ld] : 0;
-            nc[j] = (i0 + j < L) ? np[(i0 + j) * a.ld] : 0;
+            xc[j] = (i0 + j < L) ? xp[(i0 + j) * ldx] : 0;
+            nc[j] = (i0 + j < L) ? np[(i0 + j) * ldx] : 0;
         }
     }
     for (int64_t ch = nch - 1; ch >= 0; ch--) {
@@ -389,21 +394,21 @@ HB_HD void binom2_chain(const Binom2Args &a, int32_t seg, int64_t b, double *sm,
             const int64_t iprev = i0 - HB_CHUNK;
 #pragma unroll
             for (int j = 0; j < HB_CHUNK; j++) {
-                xn[j] = (iprev >= 0) ? xp[(iprev + j) * a.ld] : 0;
-                nn[j] = (iprev >= 0) ? np[(iprev + j) * a.ld] : 0;
+                xn[j] = (iprev >= 0) ? xp[(iprev + j) * ldx] : 0;
+                nn[j] = (iprev >= 0) ? np[(iprev + j) * ldx] : 0;
             }
         }
         uint64_t pk = 0;
         if (VIT) {
-            pk = a.psi[(cbase + ch) * a.B + b];
-            if (ch >= 6) prefetch_l2(a.psi + (cbase + ch - 6) * a.B + b);
+            pk = psi0[ch * sB];
+            if (ch >= 6) prefetch_l2(psi0 + (ch - 6) * sB);
         }
         if (FB) {
             if (ch > 0) {
-                const double *ck = a.ckpt + (cbase + ch) * 3 * a.B + b;
+                const double *ck = ckpt0 + ch * 3 * sB;
                 f.m0 = ck[0];
-                f.m1 = ck[a.B];
-                f.d = lo32(ck[2 * a.B]);
+                f.m1 = ck[sB];
+                f.d = lo32(ck[2 * sB]);
             }
 #pragma unroll
             for (int j = 0; j < HB_CHUNK; j++) {
@@ -430,7 +435,7 @@ HB_HD void binom2_chain(const Binom2Args &a, int32_t seg, int64_t b, double *sm,
             const int64_t i = i0 + j;
             if (i < L) {
                 if (VIT) {
-                    a.y[(t0 + i) * a.ldy + b] = (uint8_t)(ycur + 1);
+                    a.y[lay_off(a.tiled, a.T, a.ldy, t0 + i, b)] = (uint8_t)(ycur + 1);
                     ycur = (int32_t)((pk >> (2 * j + ycur)) & 1u);
                 }
                 if (FB) {
@@ -443,9 +448,9 @@ HB_HD void binom2_chain(const Binom2Args &a, int32_t seg, int64_t b, double *sm,
                     double g0, g1;
                     rel2_align(s[0] * bt.m0, s[sms] * bt.m1, d, g0, g1);
                     double rs = rcp_fast(g0 + g1);
-                    double *gp = a.gamma + (t0 + i) * a.ldg + b;
+                    double *gp = a.gamma + lay_off(a.tiled, a.T, a.ldg, t0 + i, b);
                     gp[0] = g0 * rs;
-                    gp[a.T * a.ldg] = g1 * rs;
+                    gp[a.gplane] = g1 * rs;
                     binom2_bwd_step(c, bt, s[3 * sms], er);
                 }
             }

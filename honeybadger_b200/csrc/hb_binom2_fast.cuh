@@ -195,11 +195,15 @@ HB_HD void binom2_fast_chain(const Binom2Args &a, int32_t seg, int64_t b, const 
     const int32_t nfull = L / HB_CHUNK;
     const int32_t tail = L - nfull * HB_CHUNK;
     const int64_t cbase = a.chunk_off[seg];
-    const int64_t ld = a.ld;
-    const int32_t *xp = a.x + t0 * ld + b;
-    const int32_t *np = a.n + t0 * ld + b;
-    uint16_t *psi = reinterpret_cast<uint16_t *>(a.psi) + cbase * a.B + b; // 2 bits / step, 8 steps
-    double *ckpt = a.ckpt + cbase * 2 * a.B + b;
+    const int64_t ld = lay_stride(a.tiled, a.ld), sB = lay_stride(a.tiled, a.B);
+    const int64_t sy = lay_stride(a.tiled, a.ldy), sg = lay_stride(a.tiled, a.ldg);
+    const int32_t *xp = a.x + lay_off(a.tiled, a.T, a.ld, t0, b);
+    const int32_t *np = a.n + lay_off(a.tiled, a.T, a.ld, t0, b);
+    // back-pointers: 2 bits / step, one uint16 per chunk
+    uint16_t *psi = reinterpret_cast<uint16_t *>(a.psi) + lay_off(a.tiled, a.nchunks, a.B, cbase, b);
+    double *ckpt = a.ckpt + (a.tiled ? (((b >> 5) * a.nchunks + cbase) * 2 << 5) + (b & 31) : cbase * 2 * a.B + b);
+    uint8_t *ybase = a.y ? a.y + lay_off(a.tiled, a.T, a.ldy, t0, b) : nullptr;
+    double *gbase = a.gamma ? a.gamma + lay_off(a.tiled, a.T, a.ldg, t0, b) : nullptr;
 
     B2fState s;
     s.n0 = s.n1 = 0;
@@ -254,11 +258,11 @@ HB_HD void binom2_fast_chain(const Binom2Args &a, int32_t seg, int64_t b, const 
                 cpa_commit(ring);
             }
             if (VIT) *pw = (uint16_t)pk;
-            pw += a.B;
-            ck += 2 * a.B;
+            pw += sB;
+            ck += 2 * sB;
             if (FB && (more || tail > 0)) {
                 ck[0] = s.f0;
-                ck[a.B] = s.f1;
+                ck[sB] = s.f1;
             }
         }
     }
@@ -269,7 +273,7 @@ HB_HD void binom2_fast_chain(const Binom2Args &a, int32_t seg, int64_t b, const 
             const int64_t o = (int64_t)(nfull * HB_CHUNK + j) * ld;
             b2f_forward_one<VIT, FB, LL>(a, m, s, xp[o], np[o], nfull == 0 && j == 0, pk, j);
         }
-        if (VIT) psi[(int64_t)nfull * a.B] = (uint16_t)pk;
+        if (VIT) psi[(int64_t)nfull * sB] = (uint16_t)pk;
     }
 
     if (FB && LL) {
@@ -306,22 +310,22 @@ HB_HD void binom2_fast_chain(const Binom2Args &a, int32_t seg, int64_t b, const 
     uint32_t pk_nx = 0;
     double c0_nx = 0, c1_nx = 0;
     if (nfull > 0) {
-        if (VIT) pk_nx = psi[(int64_t)(nfull - 1) * a.B];
+        if (VIT) pk_nx = psi[(int64_t)(nfull - 1) * sB];
         if (FB && nfull > 1) {
-            const double *ck = ckpt + (int64_t)(nfull - 1) * 2 * a.B;
+            const double *ck = ckpt + (int64_t)(nfull - 1) * 2 * sB;
             c0_nx = ck[0];
-            c1_nx = ck[a.B];
+            c1_nx = ck[sB];
         }
     }
-    const int64_t plane = a.T * a.ldg;
+    const int64_t plane = a.gplane;
     if (tail > 0) {
         uint32_t pk = 0;
-        if (VIT) pk = psi[(int64_t)nfull * a.B];
+        if (VIT) pk = psi[(int64_t)nfull * sB];
         if (FB) {
             if (nfull > 0) {
-                const double *ck = ckpt + (int64_t)nfull * 2 * a.B;
+                const double *ck = ckpt + (int64_t)nfull * 2 * sB;
                 s.f0 = ck[0];
-                s.f1 = ck[a.B];
+                s.f1 = ck[sB];
             }
             for (int j = 0; j < tail; j++) {
                 const int64_t o = (int64_t)(nfull * HB_CHUNK + j) * ld;
@@ -329,22 +333,22 @@ HB_HD void binom2_fast_chain(const Binom2Args &a, int32_t seg, int64_t b, const 
             }
         }
         for (int j = tail - 1; j >= 0; j--) {
-            const int64_t row = t0 + nfull * HB_CHUNK + j;
-            double *gr = FB ? a.gamma + row * a.ldg + b : nullptr;
-            b2f_backward_one<VIT, FB>(c, s, VIT ? a.y + row * a.ldy + b : nullptr, gr, gr + plane, pk,
+            const int64_t rel = nfull * HB_CHUNK + j;
+            double *gr = FB ? gbase + rel * sg : nullptr;
+            b2f_backward_one<VIT, FB>(c, s, VIT ? ybase + rel * sy : nullptr, gr, gr + plane, pk,
                                       j, m);
         }
     }
     {
-        const int64_t rowl = t0 + (int64_t)nfull * HB_CHUNK - 1;
-        uint8_t *yp = VIT ? a.y + rowl * a.ldy + b : nullptr;
-        double *g0 = FB ? a.gamma + rowl * a.ldg + b : nullptr;
+        const int64_t rell = (int64_t)nfull * HB_CHUNK - 1;
+        uint8_t *yp = VIT ? ybase + rell * sy : nullptr;
+        double *g0 = FB ? gbase + rell * sg : nullptr;
         double *g1 = g0 + plane;
         // refill pointers: the chunk before the one being replayed
         const int32_t *xr = xp + (int64_t)(nfull - 2) * HB_CHUNK * ld;
         const int32_t *nr = np + (int64_t)(nfull - 2) * HB_CHUNK * ld;
-        const uint16_t *pr = psi + (int64_t)(nfull - 2) * a.B;
-        const double *cr = ckpt + (int64_t)(nfull - 2) * 2 * a.B;
+        const uint16_t *pr = psi + (int64_t)(nfull - 2) * sB;
+        const double *cr = ckpt + (int64_t)(nfull - 2) * 2 * sB;
         for (int32_t ch = nfull - 1; ch >= 0; ch--) {
             const uint32_t pk = pk_nx;
             if (FB && ch > 0) {
@@ -355,18 +359,18 @@ HB_HD void binom2_fast_chain(const Binom2Args &a, int32_t seg, int64_t b, const 
                 if (VIT) pk_nx = *pr;
                 if (FB && ch > 1) {
                     c0_nx = cr[0];
-                    c1_nx = cr[a.B];
+                    c1_nx = cr[sB];
                 }
             }
             if (ch > 1 + HB_B2F_PF_CHUNKS) { // checkpoints / back-pointers further back
-                if (VIT) prefetch_l2(pr - (int64_t)HB_B2F_PF_CHUNKS * a.B);
+                if (VIT) prefetch_l2(pr - (int64_t)HB_B2F_PF_CHUNKS * sB);
                 if (FB) {
-                    prefetch_l2(cr - (int64_t)HB_B2F_PF_CHUNKS * 2 * a.B);
-                    prefetch_l2(cr - (int64_t)HB_B2F_PF_CHUNKS * 2 * a.B + a.B);
+                    prefetch_l2(cr - (int64_t)HB_B2F_PF_CHUNKS * 2 * sB);
+                    prefetch_l2(cr - (int64_t)HB_B2F_PF_CHUNKS * 2 * sB + sB);
                 }
             }
-            pr -= a.B;
-            cr -= 2 * a.B;
+            pr -= sB;
+            cr -= 2 * sB;
             if (FB) {
                 const bool more = ch > 0;
                 const bool pf = ch > 1 + HB_B2F_PF_CHUNKS;
@@ -397,10 +401,10 @@ HB_HD void binom2_fast_chain(const Binom2Args &a, int32_t seg, int64_t b, const 
 #pragma unroll
             for (int j = HB_CHUNK - 1; j >= 0; j--) {
                 b2f_backward_one<VIT, FB>(c, s, yp, g0, g1, pk, j, m);
-                if (VIT) yp -= a.ldy;
+                if (VIT) yp -= sy;
                 if (FB) {
-                    g0 -= a.ldg;
-                    g1 -= a.ldg;
+                    g0 -= sg;
+                    g1 -= sg;
                 }
             }
         }

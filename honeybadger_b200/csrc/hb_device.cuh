@@ -69,6 +69,14 @@ HB_HD double dfma(double a, double b, double c)
 #endif
 }
 
+// ---------------------------------------------------------------- layouts
+// element offset of (position t, column b) and the stride between consecutive positions
+HB_HD int64_t lay_off(int32_t tiled, int64_t T, int64_t ld, int64_t t, int64_t b)
+{
+    return tiled ? (((b >> 5) * T + t) << 5) + (b & 31) : t * ld + b;
+}
+HB_HD int64_t lay_stride(int32_t tiled, int64_t ld) { return tiled ? 32 : ld; }
+
 // ---------------------------------------------------------------- streaming loads / stores
 // The chain kernels stream their inputs and outputs exactly once per sweep: keep them out of L1
 // (evict-first) so the emission table and the constant data stay resident there.

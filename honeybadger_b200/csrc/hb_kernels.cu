@@ -4,6 +4,8 @@
 // (-fmad=false: the Viterbi path must keep one rounding per reference operation).
 #include <cuda_runtime.h>
 
+#include <algorithm>
+
 #include "hb_binom2.cuh"
 #include "hb_binom2_fast.cuh"
 #include "hb_kernels.h"
@@ -357,6 +359,37 @@ cudaError_t launch_transpose_f64_back(const double *src, int64_t ld, int64_t G, 
                                       double *dst, cudaStream_t st)
 {
     transpose_out_kernel<double, double><<<tgrid(G, N), dim3(32, 8), 0, st>>>(src, ld, G, N, dst);
+    return cudaGetLastError();
+}
+
+// gene-major src[t*ld + b] <-> warp-tiled dst[((b/32)*T + t)*32 + b%32]; both sides coalesced
+// (a warp handles one 32-column tile row).  Padding columns of the last tile are written as 0.
+template <typename E>
+__global__ void tile_kernel(const E *src, int64_t ld, int64_t T, int64_t B, E *dst, bool to_tiled)
+{
+    const int64_t Bp = (B + 31) / 32 * 32;
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= Bp) return;
+    for (int64_t t = blockIdx.y; t < T; t += gridDim.y) {
+        const int64_t ot = (((b >> 5) * T + t) << 5) + (b & 31);
+        if (to_tiled)
+            dst[ot] = b < B ? src[t * ld + b] : E(0);
+        else if (b < B)
+            dst[t * ld + b] = src[ot];
+    }
+}
+
+cudaError_t launch_tile(const void *src, int64_t ld, int64_t T, int64_t B, int elem, void *dst,
+                        bool to_tiled, cudaStream_t st)
+{
+    const int64_t Bp = (B + 31) / 32 * 32;
+    dim3 grid((unsigned)((Bp + 255) / 256), (unsigned)std::min<int64_t>(T, 65535));
+    if (elem == 1)
+        tile_kernel<uint8_t><<<grid, 256, 0, st>>>((const uint8_t *)src, ld, T, B, (uint8_t *)dst, to_tiled);
+    else if (elem == 4)
+        tile_kernel<uint32_t><<<grid, 256, 0, st>>>((const uint32_t *)src, ld, T, B, (uint32_t *)dst, to_tiled);
+    else
+        tile_kernel<uint64_t><<<grid, 256, 0, st>>>((const uint64_t *)src, ld, T, B, (uint64_t *)dst, to_tiled);
     return cudaGetLastError();
 }
 

@@ -29,6 +29,8 @@ cudaError_t launch_transpose_u8_back(const uint8_t *src, int64_t ld, int64_t G, 
                                      int32_t *dst, cudaStream_t st);
 cudaError_t launch_transpose_f64_back(const double *src, int64_t ld, int64_t G, int64_t N,
                                       double *dst, cudaStream_t st);
+cudaError_t launch_tile(const void *src, int64_t ld, int64_t T, int64_t B, int elem, void *dst,
+                        bool to_tiled, cudaStream_t st);
 cudaError_t launch_pool_mean(const double *x, int64_t ld, int64_t G, int64_t N,
                              const uint8_t *member, const int32_t *gsize, int32_t K, double *out,
                              cudaStream_t st);

@@ -99,6 +99,11 @@ inline void norm3_fill_k(Norm3Const &c)
 struct Norm3Args {
     const double *x;
     int64_t ld, T, B;
+    // layout: 0 = gene-major x[t*ld + b]; 1 = warp-tiled x[((b/32)*T + t)*32 + b%32] (every warp's
+    // rows are contiguous: sequential 256-byte accesses per warp, 2 KB per chunk), also for y, each
+    // gamma plane (plane stride gplane) and the scratch (psi, ckpt)
+    int32_t tiled;
+    int64_t gplane, nchunks;
     const int64_t *seg_off;   // device [nseg+1]
     const int64_t *chunk_off; // device [nseg+1]: prefix sum of ceil(L_s / HB_CHUNK)
     const int32_t *seg_order; // device [nseg]: segments by decreasing length
@@ -441,7 +446,7 @@ HB_HD void norm3_backward_one(const Norm3Args &a, Norm3State<SYM> &s, int64_t ro
                               uint64_t pk, int j, const Norm3Smem &m)
 {
     if (VIT) {
-        a.y[row * a.ldy + b] = (uint8_t)(s.ycur + 1);
+        a.y[lay_off(a.tiled, a.T, a.ldy, row, b)] = (uint8_t)(s.ycur + 1);
         s.ycur = (int32_t)((uint32_t)(pk >> (6 * j + 2 * s.ycur)) & 3u);
     }
     if (FB) {
@@ -449,12 +454,8 @@ HB_HD void norm3_backward_one(const Norm3Args &a, Norm3State<SYM> &s, int64_t ro
         const double E2 = m.e2[j * m.st];
         double g0 = va.x * s.b0, g1 = va.y * s.b1, g2 = vb.x * s.b2;
         double rs = rcp_fast((g0 + g1) + g2);
-#ifdef HB_DEBUG_NOGAMMA
-        double *gp = a.gamma + (row & 7) * a.ldg + b;
-#else
-        double *gp = a.gamma + row * a.ldg + b;
-#endif
-        const int64_t plane = a.T * a.ldg;
+        double *gp = a.gamma + lay_off(a.tiled, a.T, a.ldg, row, b);
+        const int64_t plane = a.gplane;
         gp[0] = g0 * rs;
         gp[plane] = g1 * rs;
         gp[2 * plane] = g2 * rs;
@@ -474,10 +475,10 @@ HB_HD void norm3_chain(const Norm3Args &a, int32_t seg, int64_t b, Norm3Smem &m)
     const int32_t tail = L - nfull * HB_CHUNK; // steps in the last, partial chunk
     const int64_t cbase = a.chunk_off[seg];
     const int64_t pix = a.sd_per_seg ? (int64_t)seg * a.B + b : b;
-    const int64_t ld = a.ld;
-    const double *xp = a.x + t0 * ld + b;
-    uint64_t *psi = a.psi + cbase * a.B + b;
-    double *ckpt = a.ckpt + cbase * 3 * a.B + b;
+    const int64_t ld = lay_stride(a.tiled, a.ld), sB = lay_stride(a.tiled, a.B);
+    const double *xp = a.x + lay_off(a.tiled, a.T, a.ld, t0, b);
+    uint64_t *psi = a.psi + lay_off(a.tiled, a.nchunks, a.B, cbase, b);
+    double *ckpt = a.ckpt + (a.tiled ? (((b >> 5) * a.nchunks + cbase) * 3 << 5) + (b & 31) : cbase * 3 * a.B + b);
 
     Norm3State<SYM> s;
     s.sdv = a.sd[pix];
@@ -516,12 +517,12 @@ HB_HD void norm3_chain(const Norm3Args &a, int32_t seg, int64_t b, Norm3Smem &m)
             }
             xs_commit(m);
         }
-        if (VIT) psi[(int64_t)ch * a.B] = pk;
+        if (VIT) psi[(int64_t)ch * sB] = pk;
         if (FB && (ch + 1 < nfull || tail > 0)) {
-            double *ck = ckpt + (int64_t)(ch + 1) * 3 * a.B;
+            double *ck = ckpt + (int64_t)(ch + 1) * 3 * sB;
             ck[0] = s.f0;
-            ck[a.B] = s.f1;
-            ck[2 * a.B] = s.f2;
+            ck[sB] = s.f1;
+            ck[2 * sB] = s.f2;
         }
     }
     xs_wait<0>(m);
@@ -532,7 +533,7 @@ HB_HD void norm3_chain(const Norm3Args &a, int32_t seg, int64_t b, Norm3Smem &m)
             uint32_t ps = norm3_forward_one<SYM, VIT, FB, LL>(c, s, xv, nfull == 0 && j == 0);
             pk |= (uint64_t)ps << (6 * j);
         }
-        if (VIT) psi[(int64_t)nfull * a.B] = pk;
+        if (VIT) psi[(int64_t)nfull * sB] = pk;
     }
 
     if (FB && LL) {
@@ -567,23 +568,23 @@ HB_HD void norm3_chain(const Norm3Args &a, int32_t seg, int64_t b, Norm3Smem &m)
     uint64_t pk_nx = 0;
     double c0_nx = 0, c1_nx = 0, c2_nx = 0;
     if (nfull > 0) {
-        if (VIT) pk_nx = psi[(int64_t)(nfull - 1) * a.B];
+        if (VIT) pk_nx = psi[(int64_t)(nfull - 1) * sB];
         if (FB && nfull > 1) {
-            const double *ck = ckpt + (int64_t)(nfull - 1) * 3 * a.B;
+            const double *ck = ckpt + (int64_t)(nfull - 1) * 3 * sB;
             c0_nx = ck[0];
-            c1_nx = ck[a.B];
-            c2_nx = ck[2 * a.B];
+            c1_nx = ck[sB];
+            c2_nx = ck[2 * sB];
         }
     }
     if (tail > 0) {
         uint64_t pk = 0;
-        if (VIT) pk = psi[(int64_t)nfull * a.B];
+        if (VIT) pk = psi[(int64_t)nfull * sB];
         if (FB) {
             if (nfull > 0) {
-                const double *ck = ckpt + (int64_t)nfull * 3 * a.B;
+                const double *ck = ckpt + (int64_t)nfull * 3 * sB;
                 s.f0 = ck[0];
-                s.f1 = ck[a.B];
-                s.f2 = ck[2 * a.B];
+                s.f1 = ck[sB];
+                s.f2 = ck[2 * sB];
             }
             for (int j = 0; j < tail; j++) {
                 const double xv = xp[(int64_t)(nfull * HB_CHUNK + j) * ld];
@@ -601,12 +602,12 @@ HB_HD void norm3_chain(const Norm3Args &a, int32_t seg, int64_t b, Norm3Smem &m)
             s.f2 = c2_nx;
         }
         if (ch > 0) {
-            if (VIT) pk_nx = psi[(int64_t)(ch - 1) * a.B];
+            if (VIT) pk_nx = psi[(int64_t)(ch - 1) * sB];
             if (FB && ch > 1) {
-                const double *ck = ckpt + (int64_t)(ch - 1) * 3 * a.B;
+                const double *ck = ckpt + (int64_t)(ch - 1) * 3 * sB;
                 c0_nx = ck[0];
-                c1_nx = ck[a.B];
-                c2_nx = ck[2 * a.B];
+                c1_nx = ck[sB];
+                c2_nx = ck[2 * sB];
             }
         }
         if (FB) {

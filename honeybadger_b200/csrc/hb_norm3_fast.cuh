@@ -266,20 +266,21 @@ HB_HD_NOINLINE int32_t norm3_exact_forward(const Norm3Args &a, int32_t seg, int6
     const int32_t L = (int32_t)(a.seg_off[seg + 1] - t0);
     const int64_t pix = a.sd_per_seg ? (int64_t)seg * a.B + b : b;
     const double sdv = a.sd[pix], isd = a.inv_sd[pix], lsd = a.log_sd[pix];
-    const double *xp = a.x + t0 * a.ld + b;
-    uint64_t *psi = a.psi + a.chunk_off[seg] * a.B + b;
+    const int64_t ld = lay_stride(a.tiled, a.ld), sB = lay_stride(a.tiled, a.B);
+    const double *xp = a.x + lay_off(a.tiled, a.T, a.ld, t0, b);
+    uint64_t *psi = a.psi + lay_off(a.tiled, a.nchunks, a.B, a.chunk_off[seg], b);
     const int32_t nch = (L + HB_CHUNK - 1) / HB_CHUNK;
     double n0 = 0, n1 = 0, n2 = 0;
     // Only this lane of the warp is active: keep one chunk of x in flight ahead of the recursion so
     // the DRAM latency of the strided loads overlaps the (latency-bound) exact arithmetic.
     double xc[HB_CHUNK], xn[HB_CHUNK];
 #pragma unroll
-    for (int j = 0; j < HB_CHUNK; j++) xc[j] = j < L ? xp[(int64_t)j * a.ld] : 0.0;
+    for (int j = 0; j < HB_CHUNK; j++) xc[j] = j < L ? xp[(int64_t)j * ld] : 0.0;
     for (int32_t ch = 0; ch < nch; ch++) {
         const int32_t i0 = ch * HB_CHUNK;
 #pragma unroll
         for (int j = 0; j < HB_CHUNK; j++)
-            xn[j] = (i0 + HB_CHUNK + j < L) ? xp[(int64_t)(i0 + HB_CHUNK + j) * a.ld] : 0.0;
+            xn[j] = (i0 + HB_CHUNK + j < L) ? xp[(int64_t)(i0 + HB_CHUNK + j) * ld] : 0.0;
         uint32_t w0 = 0u, w1 = 0u;
 #pragma unroll
         for (int j = 0; j < HB_CHUNK; j++) {
@@ -300,7 +301,7 @@ HB_HD_NOINLINE int32_t norm3_exact_forward(const Norm3Args &a, int32_t seg, int6
                 }
             }
         }
-        psi[(int64_t)ch * a.B] = (uint64_t)w0 | ((uint64_t)w1 << 32);
+        psi[(int64_t)ch * sB] = (uint64_t)w0 | ((uint64_t)w1 << 32);
 #pragma unroll
         for (int j = 0; j < HB_CHUNK; j++) xc[j] = xn[j];
     }
@@ -345,10 +346,13 @@ HB_HD void norm3_fast_chain(const Norm3Args &a, int32_t seg, int64_t b, Norm3Sme
     const int32_t tail = L - nfull * HB_CHUNK;
     const int64_t cbase = a.chunk_off[seg];
     const int64_t pix = a.sd_per_seg ? (int64_t)seg * a.B + b : b;
-    const int64_t ld = a.ld;
-    const double *xp = a.x + t0 * ld + b;
-    uint64_t *psi = a.psi + cbase * a.B + b;
-    double *ckpt = a.ckpt + cbase * 3 * a.B + b;
+    const int64_t ld = lay_stride(a.tiled, a.ld), sB = lay_stride(a.tiled, a.B);
+    const int64_t sy = lay_stride(a.tiled, a.ldy), sg = lay_stride(a.tiled, a.ldg);
+    const double *xp = a.x + lay_off(a.tiled, a.T, a.ld, t0, b);
+    uint64_t *psi = a.psi + lay_off(a.tiled, a.nchunks, a.B, cbase, b);
+    double *ckpt = a.ckpt + (a.tiled ? (((b >> 5) * a.nchunks + cbase) * 3 << 5) + (b & 31) : cbase * 3 * a.B + b);
+    uint8_t *ybase = a.y ? a.y + lay_off(a.tiled, a.T, a.ldy, t0, b) : nullptr;          // row t0
+    double *gbase = a.gamma ? a.gamma + lay_off(a.tiled, a.T, a.ldg, t0, b) : nullptr; // row t0, plane 0
 
     Fast3State s;
     const double isd = a.inv_sd[pix];
@@ -441,12 +445,12 @@ HB_HD void norm3_fast_chain(const Norm3Args &a, int32_t seg, int64_t b, Norm3Sme
 #endif
             }
             if (VIT) *pw = (uint64_t)w[0] | ((uint64_t)w[1] << 32);
-            pw += a.B;
-            ck += 3 * a.B;
+            pw += sB;
+            ck += 3 * sB;
             if (FB && (more || tail > 0)) {
                 ck[0] = s.f0;
-                ck[a.B] = s.f1;
-                ck[2 * a.B] = s.f2;
+                ck[sB] = s.f1;
+                ck[2 * sB] = s.f2;
             }
         }
     }
@@ -474,7 +478,7 @@ HB_HD void norm3_fast_chain(const Norm3Args &a, int32_t seg, int64_t b, Norm3Sme
                 if (LL) s.esum += es;
             }
         }
-        if (VIT) psi[(int64_t)nfull * a.B] = (uint64_t)w[0] | ((uint64_t)w[1] << 32);
+        if (VIT) psi[(int64_t)nfull * sB] = (uint64_t)w[0] | ((uint64_t)w[1] << 32);
     }
 
     if (FB && LL) {
@@ -538,24 +542,24 @@ HB_HD void norm3_fast_chain(const Norm3Args &a, int32_t seg, int64_t b, Norm3Sme
     uint64_t pk_nx = 0;
     double c0_nx = 0, c1_nx = 0, c2_nx = 0;
     if (nfull > 0) {
-        if (VIT) pk_nx = psi[(int64_t)(nfull - 1) * a.B];
+        if (VIT) pk_nx = psi[(int64_t)(nfull - 1) * sB];
         if (FB && nfull > 1) {
-            const double *ck = ckpt + (int64_t)(nfull - 1) * 3 * a.B;
+            const double *ck = ckpt + (int64_t)(nfull - 1) * 3 * sB;
             c0_nx = ck[0];
-            c1_nx = ck[a.B];
-            c2_nx = ck[2 * a.B];
+            c1_nx = ck[sB];
+            c2_nx = ck[2 * sB];
         }
     }
-    const int64_t plane = a.T * a.ldg;
+    const int64_t plane = a.gplane;
     if (tail > 0) {
         uint64_t pk = 0;
-        if (VIT) pk = psi[(int64_t)nfull * a.B];
+        if (VIT) pk = psi[(int64_t)nfull * sB];
         if (FB) {
             if (nfull > 0) {
-                const double *ck = ckpt + (int64_t)nfull * 3 * a.B;
+                const double *ck = ckpt + (int64_t)nfull * 3 * sB;
                 s.f0 = ck[0];
-                s.f1 = ck[a.B];
-                s.f2 = ck[2 * a.B];
+                s.f1 = ck[sB];
+                s.f2 = ck[2 * sB];
             }
             for (int j = 0; j < tail; j++) {
                 const double xv = xp[(int64_t)(nfull * HB_CHUNK + j) * ld];
@@ -563,18 +567,18 @@ HB_HD void norm3_fast_chain(const Norm3Args &a, int32_t seg, int64_t b, Norm3Sme
             }
         }
         for (int j = tail - 1; j >= 0; j--) {
-            const int64_t row = t0 + nfull * HB_CHUNK + j;
+            const int64_t rel = nfull * HB_CHUNK + j; // position within the chain
             const uint32_t pwd = j < 5 ? (uint32_t)pk : (uint32_t)(pk >> 32);
-            double *gr = FB ? a.gamma + row * a.ldg + b : nullptr;
-            fast_backward_one<VIT, FB>(c, s, VIT ? a.y + row * a.ldy + b : nullptr, gr, gr + plane,
+            double *gr = FB ? gbase + rel * sg : nullptr;
+            fast_backward_one<VIT, FB>(c, s, VIT ? ybase + rel * sy : nullptr, gr, gr + plane,
                                        gr + 2 * plane, pwd, j < 5 ? 6 * j : 6 * (j - 5), j, m);
         }
     }
     {
         // row pointers of the LAST row of the current chunk, stepped back one row per step
-        const int64_t rowl = t0 + (int64_t)nfull * HB_CHUNK - 1;
-        uint8_t *yp = VIT ? a.y + rowl * a.ldy + b : nullptr;
-        double *g0 = FB ? a.gamma + rowl * a.ldg + b : nullptr;
+        const int64_t rell = (int64_t)nfull * HB_CHUNK - 1;
+        uint8_t *yp = VIT ? ybase + rell * sy : nullptr;
+        double *g0 = FB ? gbase + rell * sg : nullptr;
         double *g1 = g0 + plane, *g2 = g1 + plane;
 #if HB_FAST_XREG
         // next fetch: second half of the last full chunk (its first half is already in xa)
@@ -582,8 +586,8 @@ HB_HD void norm3_fast_chain(const Norm3Args &a, int32_t seg, int64_t b, Norm3Sme
 #else
         const double *xr = xp + (int64_t)(nfull - 2) * HB_CHUNK * ld; // refill: previous chunk
 #endif
-        const uint64_t *pr = psi + (int64_t)(nfull - 2) * a.B;
-        const double *cr = ckpt + (int64_t)(nfull - 2) * 3 * a.B;
+        const uint64_t *pr = psi + (int64_t)(nfull - 2) * sB;
+        const double *cr = ckpt + (int64_t)(nfull - 2) * 3 * sB;
         for (int32_t ch = nfull - 1; ch >= 0; ch--) {
             const uint64_t pk = pk_nx;
             if (FB && ch > 0) {
@@ -595,22 +599,22 @@ HB_HD void norm3_fast_chain(const Norm3Args &a, int32_t seg, int64_t b, Norm3Sme
                 if (VIT) pk_nx = *pr;
                 if (FB && ch > 1) {
                     c0_nx = cr[0];
-                    c1_nx = cr[a.B];
-                    c2_nx = cr[2 * a.B];
+                    c1_nx = cr[sB];
+                    c2_nx = cr[2 * sB];
                 }
             }
             const bool pf = ch > 1 + HB_FAST_PF_CHUNKS;
             if (pf) { // checkpoints / back-pointer words of the chunk HB_FAST_PF_CHUNKS further back
-                if (VIT) prefetch_l2(pr - (int64_t)HB_FAST_PF_CHUNKS * a.B);
+                if (VIT) prefetch_l2(pr - (int64_t)HB_FAST_PF_CHUNKS * sB);
                 if (FB) {
-                    const double *cf = cr - (int64_t)HB_FAST_PF_CHUNKS * 3 * a.B;
+                    const double *cf = cr - (int64_t)HB_FAST_PF_CHUNKS * 3 * sB;
                     prefetch_l2(cf);
-                    prefetch_l2(cf + a.B);
-                    prefetch_l2(cf + 2 * a.B);
+                    prefetch_l2(cf + sB);
+                    prefetch_l2(cf + 2 * sB);
                 }
             }
-            pr -= a.B;
-            cr -= 3 * a.B;
+            pr -= sB;
+            cr -= 3 * sB;
             if (FB) {
                 const bool more = ch > 0;
 #if HB_FAST_XREG
@@ -659,12 +663,12 @@ HB_HD void norm3_fast_chain(const Norm3Args &a, int32_t seg, int64_t b, Norm3Sme
             for (int j = HB_CHUNK - 1; j >= 0; j--) {
                 fast_backward_one<VIT, FB>(c, s, yp, g0, g1, g2, HB_PSI_WORD(j) ? phi : plo,
                                            HB_PSI_SHIFT(j), j, m);
-                if (VIT) yp -= a.ldy;
+                if (VIT) yp -= sy;
 #ifndef HB_DEBUG_NOGAMMA // (debug variant: keep writing the same rows -> the stores stay in L2)
                 if (FB) {
-                    g0 -= a.ldg;
-                    g1 -= a.ldg;
-                    g2 -= a.ldg;
+                    g0 -= sg;
+                    g1 -= sg;
+                    g2 -= sg;
                 }
 #endif
             }

@@ -230,6 +230,101 @@ def to_rows(t):
     return out
 
 
+# ---- warp-tiled resident layout: tensors of shape [ceil(B/32), T, 32] (tile, position, lane)
+def tile_rows(t):
+    """Gene-major [T, B] CUDA tensor -> warp-tiled [ntile, T, 32] (libhb_b200's hb_tile_dev)."""
+    import torch
+    if not (t.is_cuda and t.dim() == 2 and t.stride(1) == 1):
+        raise ValueError("tile_rows needs a 2-D CUDA tensor with unit column stride")
+    T, B = t.shape
+    out = torch.empty(((B + 31) // 32, T, 32), dtype=t.dtype, device=t.device)
+    _lib.check(_lib.load().hb_tile_dev(t.data_ptr(), t.stride(0), T, B, t.element_size(),
+                                       out.data_ptr(), _stream()))
+    return out
+
+
+def untile_rows(t, B):
+    """Warp-tiled [ntile, T, 32] (or [planes, ntile, T, 32]) -> gene-major [T, B] ([planes, T, B])."""
+    import torch
+    if t.dim() == 4:
+        return torch.stack([untile_rows(p, B) for p in t])
+    ntile, T, w = t.shape
+    if w != 32 or not t.is_contiguous() or ntile != (B + 31) // 32:
+        raise ValueError("not a warp-tiled tensor for this B")
+    out = alloc_rows(T, B, t.dtype, t.device)
+    _lib.check(_lib.load().hb_untile_dev(t.data_ptr(), T, B, t.element_size(), out.data_ptr(),
+                                         out.stride(0), _stream()))
+    return out
+
+
+def _check_tiled(t, dtype, name):
+    import torch
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == dtype and t.dim() == 3
+            and t.shape[2] == 32 and t.is_contiguous()):
+        raise ValueError(f"{name} must be a contiguous warp-tiled CUDA {dtype} tensor [ntile, T, 32]")
+
+
+def hmm_norm_tiled_dev(x, B, sd, mean, Pi, delta, seg_off=None, viterbi=True, gamma=True, ll=False,
+                       out=None):
+    """As hmm_norm_dev on the warp-tiled layout: x [ntile, T, 32] (from tile_rows), B real columns.
+    Returns dict(y=uint8 [ntile,T,32], gamma=[3,ntile,T,32], ll=[nseg,B])."""
+    import torch
+    lib = _lib.load()
+    _check_tiled(x, torch.float64, "x")
+    ntile, T, _ = x.shape
+    if ntile != (B + 31) // 32:
+        raise ValueError("x does not have ceil(B/32) tiles")
+    seg = _seg(seg_off, T)
+    nseg = seg.size - 1
+    per_seg = int(sd.dim() == 2)
+    mean, Pi, delta = _f64(mean), _f64(Pi), _f64(delta)
+    out = dict(out or {})
+    want_g = gamma or ll
+    if viterbi and "y" not in out:
+        out["y"] = torch.empty((ntile, T, 32), dtype=torch.uint8, device=x.device)
+    if want_g and "gamma" not in out:
+        out["gamma"] = torch.empty((3, ntile, T, 32), dtype=torch.float64, device=x.device)
+    if ll and "ll" not in out:
+        out["ll"] = torch.empty((nseg, B), dtype=torch.float64, device=x.device)
+    y, g, l = out.get("y"), out.get("gamma"), out.get("ll")
+    rc = lib.hb_hmm_norm_tiled_dev(
+        x.data_ptr(), T, B, _vp(seg), nseg, _vp(mean), sd.data_ptr(), per_seg, _vp(Pi), _vp(delta),
+        _flags(viterbi, gamma, ll), y.data_ptr() if viterbi else None,
+        g.data_ptr() if want_g else None, l.data_ptr() if ll else None, _stream())
+    _lib.check(rc)
+    return out
+
+
+def hmm_binom_tiled_dev(x, size, B, prob, Pi, delta, seg_off=None, rho=0.0, viterbi=True, gamma=True,
+                        ll=False, out=None):
+    """As hmm_binom_dev on the warp-tiled layout: x, size int32 [ntile, T, 32]."""
+    import torch
+    lib = _lib.load()
+    _check_tiled(x, torch.int32, "x")
+    _check_tiled(size, torch.int32, "size")
+    ntile, T, _ = x.shape
+    if x.shape != size.shape or ntile != (B + 31) // 32:
+        raise ValueError("x and size must be [ceil(B/32), T, 32]")
+    seg = _seg(seg_off, T)
+    nseg = seg.size - 1
+    prob, Pi, delta = _f64(prob), _f64(Pi), _f64(delta)
+    out = dict(out or {})
+    want_g = gamma or ll
+    if viterbi and "y" not in out:
+        out["y"] = torch.empty((ntile, T, 32), dtype=torch.uint8, device=x.device)
+    if want_g and "gamma" not in out:
+        out["gamma"] = torch.empty((2, ntile, T, 32), dtype=torch.float64, device=x.device)
+    if ll and "ll" not in out:
+        out["ll"] = torch.empty((nseg, B), dtype=torch.float64, device=x.device)
+    y, g, l = out.get("y"), out.get("gamma"), out.get("ll")
+    rc = lib.hb_hmm_binom_tiled_dev(
+        x.data_ptr(), size.data_ptr(), T, B, _vp(seg), nseg, _vp(prob), float(rho), _vp(Pi),
+        _vp(delta), _flags(viterbi, gamma, ll), y.data_ptr() if viterbi else None,
+        g.data_ptr() if want_g else None, l.data_ptr() if ll else None, _stream())
+    _lib.check(rc)
+    return out
+
+
 def hmm_norm_dev(x, sd, mean, Pi, delta, seg_off=None, viterbi=True, gamma=True, ll=False,
                  out=None):
     """Gene-major x[T, B] (fp64 CUDA tensor, row stride = ld), sd [B] or [nseg, B] on the device.

@@ -95,6 +95,24 @@ int hb_hmm_norm_dev(const double *x /* device, x[t*ld+b] */, int64_t ld, int64_t
                     int64_t ldy, double *gamma /* device gamma[(k*T+t)*ldg+b] */, int64_t ldg,
                     double *ll /* device ll[s*B+b] */, void *stream);
 
+/* Same chains on the WARP-TILED resident layout: element (t, b) of a matrix lives at
+ * ((b/32)*T + t)*32 + b%32 (tiles of 32 consecutive chains, each tile [T][32] contiguous), B is
+ * padded to a multiple of 32 in every buffer; y and each gamma plane (plane stride T*pad32(B)) use
+ * the same layout.  Every warp then streams contiguous memory (2 KB per 8-step chunk), which the
+ * memory system serves ~12 % faster than 256-byte accesses at row stride.
+ * hb_tile_*_dev / hb_untile_*_dev convert from / to the gene-major layout. */
+int hb_hmm_norm_tiled_dev(const double *x, int64_t T, int64_t B, const int64_t *seg_off /* host */,
+                          int32_t nseg, const double *mean, const double *sd /* device */,
+                          int32_t sd_per_seg, const double *Pi, const double *delta, int32_t flags,
+                          uint8_t *y, double *gamma, double *ll /* device ll[s*B+b] */, void *stream);
+int hb_hmm_binom_tiled_dev(const int32_t *x, const int32_t *size, int64_t T, int64_t B,
+                           const int64_t *seg_off /* host */, int32_t nseg, const double *prob,
+                           double rho, const double *Pi, const double *delta, int32_t flags,
+                           uint8_t *y, double *gamma, double *ll, void *stream);
+/* gene-major src[t*ld+b] -> tiled dst (elem = 1, 4 or 8 bytes), and back; device pointers */
+int hb_tile_dev(const void *src, int64_t ld, int64_t T, int64_t B, int32_t elem, void *dst, void *stream);
+int hb_untile_dev(const void *src, int64_t T, int64_t B, int32_t elem, void *dst, int64_t ld, void *stream);
+
 /* ------------------------------------------------------------------ 2-state binomial chains
  * Replaces dthmm(mafl, Pi, delta, "binom", list(prob=c(pd,pn)), list(size=sizel), discrete=TRUE)
  * -> Viterbi (R/HoneyBADGER.R:1408-1410, R/HoneyBADGER_allele.R:578-580).  prob[2], Pi[4], delta[2].

@@ -66,6 +66,7 @@ def emul():
     L.emul_binom_logpmf_dev.argtypes = [C.c_double] * 3
     L.emul_exp_pair.argtypes = [C.c_double, C.c_void_p, C.c_void_p]
     L.emul_norm3_fast.restype = C.c_int
+    L.emul_set_tiled.argtypes = [C.c_int]
     L.emul_binom2_fast.restype = C.c_int
     return L
 

@@ -48,7 +48,12 @@ Seg make_seg(const int64_t *seg_off, int nseg)
 }
 } // namespace
 
+static int g_tiled = 0; // 1: the buffers passed in use the warp-tiled layout (B padded to 32)
+static int64_t pad32(int64_t B) { return (B + 31) / 32 * 32; }
+
 extern "C" {
+
+void emul_set_tiled(int t) { g_tiled = t; }
 
 // flags: 1 = Viterbi, 2 = gamma, 4 = ll ; returns status flag (1 = underflow)
 int emul_norm3(const double *x, int64_t ld, int64_t T, int64_t B, const int64_t *seg_off, int nseg,
@@ -82,8 +87,8 @@ int emul_norm3(const double *x, int64_t ld, int64_t T, int64_t B, const int64_t 
         inv[i] = 1.0 / sd[i];
         lg[i] = log(sd[i]);
     }
-    std::vector<uint64_t> psi((size_t)sg.nchunks * B);
-    std::vector<double> ckpt((size_t)sg.nchunks * 3 * B);
+    std::vector<uint64_t> psi((size_t)sg.nchunks * pad32(B));
+    std::vector<double> ckpt((size_t)sg.nchunks * 3 * pad32(B));
     std::vector<double2> sva(HB_CHUNK), svb(HB_CHUNK);
     std::vector<double> se2(HB_CHUNK), sxs(HB_CHUNK);
     Norm3Smem sm;
@@ -93,7 +98,8 @@ int emul_norm3(const double *x, int64_t ld, int64_t T, int64_t B, const int64_t 
     a.seg_off = sg.off.data(); a.chunk_off = sg.chunk.data(); a.seg_order = sg.order.data();
     a.nseg = nseg; a.nblk_per_seg = 1;
     a.sd = sd; a.inv_sd = inv.data(); a.log_sd = lg.data(); a.sd_per_seg = sd_per_seg;
-    a.y = y; a.ldy = ld; a.gamma = gamma; a.ldg = ld; a.ll = (flags & 4) ? ll : nullptr;
+    a.y = y; a.ldy = ld; a.gamma = gamma; a.ldg = ld; a.nchunks = sg.nchunks;
+    a.tiled = g_tiled; a.gplane = g_tiled ? T * pad32(B) : T * ld; a.ll = (flags & 4) ? ll : nullptr;
     a.psi = psi.data(); a.ckpt = ckpt.data(); a.status = &status;
     const bool vit = flags & 1, fb = flags & 6;
     for (int s = 0; s < nseg; s++)
@@ -157,8 +163,8 @@ int emul_norm3_fast(const double *x, int64_t ld, int64_t T, int64_t B, const int
         inv[i] = 1.0 / sd[i];
         lg[i] = log(sd[i]);
     }
-    std::vector<uint64_t> psi((size_t)sg.nchunks * B);
-    std::vector<double> ckpt((size_t)sg.nchunks * 3 * B);
+    std::vector<uint64_t> psi((size_t)sg.nchunks * pad32(B));
+    std::vector<double> ckpt((size_t)sg.nchunks * 3 * pad32(B));
     std::vector<double2> sva(HB_CHUNK), svb(HB_CHUNK);
     std::vector<double> se2(HB_CHUNK), sxs(HB_CHUNK);
     std::vector<int32_t> sph(HB_CHUNK);
@@ -170,7 +176,8 @@ int emul_norm3_fast(const double *x, int64_t ld, int64_t T, int64_t B, const int
     a.seg_off = sg.off.data(); a.chunk_off = sg.chunk.data(); a.seg_order = sg.order.data();
     a.nseg = nseg; a.nblk_per_seg = 1;
     a.sd = sd; a.inv_sd = inv.data(); a.log_sd = lg.data(); a.sd_per_seg = sd_per_seg;
-    a.y = y; a.ldy = ld; a.gamma = gamma; a.ldg = ld; a.ll = (flags & 4) ? ll : nullptr;
+    a.y = y; a.ldy = ld; a.gamma = gamma; a.ldg = ld; a.nchunks = sg.nchunks;
+    a.tiled = g_tiled; a.gplane = g_tiled ? T * pad32(B) : T * ld; a.ll = (flags & 4) ? ll : nullptr;
     a.psi = psi.data(); a.ckpt = ckpt.data(); a.status = status;
     const bool vit = flags & 1, fb = flags & 6, llon = flags & 4;
     for (int s = 0; s < nseg; s++)
@@ -215,15 +222,16 @@ int emul_binom2(const int32_t *x, const int32_t *n, int64_t ld, int64_t T, int64
             lb[ix].y = hbhost::binom_logpmf(xx, nn, prob[1]);
             rr[ix] = rho_from_logratio(lb[ix].x - lb[ix].y);
         }
-    std::vector<uint64_t> psi((size_t)sg.nchunks * B);
-    std::vector<double> ckpt((size_t)sg.nchunks * 3 * B);
+    std::vector<uint64_t> psi((size_t)sg.nchunks * pad32(B));
+    std::vector<double> ckpt((size_t)sg.nchunks * 3 * pad32(B));
     std::vector<double> sm(HB_CHUNK * HB_BINOM2_SLOT);
     int32_t status = 0;
     a.x = x; a.n = n; a.ld = ld; a.T = T; a.B = B;
     a.seg_off = sg.off.data(); a.chunk_off = sg.chunk.data(); a.seg_order = sg.order.data();
     a.nseg = nseg; a.nblk_per_seg = 1;
     a.lut_lb = lb.data(); a.lut_rho = rr.data(); a.lut_nmax = lut_nmax;
-    a.y = y; a.ldy = ld; a.gamma = gamma; a.ldg = ld; a.ll = (flags & 4) ? ll : nullptr;
+    a.y = y; a.ldy = ld; a.gamma = gamma; a.ldg = ld; a.nchunks = sg.nchunks;
+    a.tiled = g_tiled; a.gplane = g_tiled ? T * pad32(B) : T * ld; a.ll = (flags & 4) ? ll : nullptr;
     a.psi = psi.data(); a.ckpt = ckpt.data(); a.status = &status;
     const bool vit = flags & 1, fb = flags & 6;
     for (int s = 0; s < nseg; s++)
@@ -270,8 +278,8 @@ int emul_binom2_fast(const int32_t *x, const int32_t *n, int64_t ld, int64_t T, 
             rr[ix] = rho_from_logratio(lb[ix].x - lb[ix].y);
             rd[ix] = (lb[ix].x == -INFINITY && lb[ix].y == -INFINITY) ? 1.0 : b2f_rho_double(rr[ix]);
         }
-    std::vector<uint64_t> psi((size_t)sg.nchunks * B);
-    std::vector<double> ckpt((size_t)sg.nchunks * 3 * B);
+    std::vector<uint64_t> psi((size_t)sg.nchunks * pad32(B));
+    std::vector<double> ckpt((size_t)sg.nchunks * 3 * pad32(B));
     std::vector<double2> spr(HB_CHUNK);
     std::vector<int32_t> sph(HB_CHUNK), sxs(HB_CHUNK), sns(HB_CHUNK);
     std::vector<double> sm(HB_CHUNK * HB_BINOM2_SLOT);
@@ -283,7 +291,8 @@ int emul_binom2_fast(const int32_t *x, const int32_t *n, int64_t ld, int64_t T, 
     a.seg_off = sg.off.data(); a.chunk_off = sg.chunk.data(); a.seg_order = sg.order.data();
     a.nseg = nseg; a.nblk_per_seg = 1;
     a.lut_lb = lb.data(); a.lut_rho = rr.data(); a.lut_rho_d = rd.data(); a.lut_nmax = lut_nmax;
-    a.y = y; a.ldy = ld; a.gamma = gamma; a.ldg = ld; a.ll = (flags & 4) ? ll : nullptr;
+    a.y = y; a.ldy = ld; a.gamma = gamma; a.ldg = ld; a.nchunks = sg.nchunks;
+    a.tiled = g_tiled; a.gplane = g_tiled ? T * pad32(B) : T * ld; a.ll = (flags & 4) ? ll : nullptr;
     a.psi = psi.data(); a.ckpt = ckpt.data(); a.status = status; a.gate = status + 2;
     const bool vit = flags & 1, fb = flags & 6, llon = flags & 4;
     for (int s = 0; s < nseg; s++)

@@ -274,3 +274,83 @@ def test_binom2_fast_gate_on_extreme_evidence(emul, oracle):
     assert gate2 == 0 and st == 0
     assert np.abs(g2[:, :, 0].T - P.mp_posteriors(logb2, Pi, delta, dps=80)).max() < 1e-11
     assert (y2[:, 0] == oracle.viterbi_binom(x2[:, 0], n2[:, 0], prob, Pi, delta)).all()
+
+
+# ---------------------------------------------------------------------------- warp-tiled layout
+def np_tile(a):
+    """[T, B] -> [ntile, T, 32] (zero padded), numpy restatement of hb_tile_dev."""
+    T, B = a.shape
+    nt = (B + 31) // 32
+    p = np.zeros((T, nt * 32), dtype=a.dtype)
+    p[:, :B] = a
+    return np.ascontiguousarray(p.reshape(T, nt, 32).transpose(1, 0, 2))
+
+
+def np_untile(t, B):
+    nt, T, _ = t.shape
+    return np.ascontiguousarray(t.transpose(1, 0, 2).reshape(T, nt * 32)[:, :B])
+
+
+@pytest.mark.parametrize("which", ["fast", "literal"])
+def test_norm3_tiled_layout(emul, oracle, which):
+    """The chain bodies on the warp-tiled layout (B not a multiple of 32) give the oracle's results."""
+    x, _, _ = synth.expression(803, 45, seed=21)
+    T, B = x.shape
+    seg = np.array([0, 300, 311, 803], dtype=np.int64)
+    sd = np.array([oracle.r_sd(x[:, b]) for b in range(B)])
+    mean, Pi, delta = np.array([-synth.DEV, 0, synth.DEV]), oracle.sym_Pi(3, 1e-6), np.array([0., 1, 0])
+    yo, go, llo, rc = oracle.fbv_norm_batch(x, seg, mean, sd, Pi, delta)
+    xt = np_tile(x)
+    nt = xt.shape[0]
+    y = np.zeros((nt, T, 32), np.uint8)
+    g = np.zeros((3, nt, T, 32))
+    ll = np.zeros((seg.size - 1, B))
+    emul.emul_set_tiled(1)
+    try:
+        if which == "fast":
+            nflag = C.c_int32(0)
+            st = emul.emul_norm3_fast(ptr(xt), C.c_int64(32), C.c_int64(T), C.c_int64(B), ptr(seg), seg.size - 1,
+                                      ptr(mean), ptr(sd), 0, ptr(Pi), ptr(delta), 7, C.c_double(1.0), ptr(y),
+                                      ptr(g), ptr(ll), C.byref(nflag))
+        else:
+            st = emul.emul_norm3(ptr(xt), C.c_int64(32), C.c_int64(T), C.c_int64(B), ptr(seg), seg.size - 1,
+                                 ptr(mean), ptr(sd), 0, ptr(Pi), ptr(delta), 7, 0, ptr(y), ptr(g), ptr(ll))
+    finally:
+        emul.emul_set_tiled(0)
+    assert st == 0 and rc == 0
+    assert (np_untile(y, B) == yo).all()
+    gu = np.stack([np_untile(g[k], B) for k in range(3)])
+    assert np.abs(gu - go).max() < 1e-9
+    assert np.allclose(ll, llo, rtol=1e-12, atol=0)
+
+
+@pytest.mark.parametrize("which", ["fast", "general"])
+def test_binom2_tiled_layout(emul, oracle, which):
+    r, n, _, _ = synth.allele(1203, 40, seed=23, deep=0.002)
+    T, B = r.shape
+    seg = np.array([0, 500, 507, 1203], dtype=np.int64)
+    prob, Pi, delta = np.array([0.1, 0.45]), oracle.sym_Pi(2, 1e-6), np.array([0., 1.])
+    yo, go, llo, rc = oracle.fbv_binom_batch(r, n, seg, prob, Pi, delta)
+    rt, nt_ = np_tile(r), np_tile(n)
+    nt = rt.shape[0]
+    y = np.zeros((nt, T, 32), np.uint8)
+    g = np.zeros((2, nt, T, 32))
+    ll = np.zeros((seg.size - 1, B))
+    emul.emul_set_tiled(1)
+    try:
+        if which == "fast":
+            gate = C.c_int32(0)
+            st = emul.emul_binom2_fast(ptr(rt), ptr(nt_), C.c_int64(32), C.c_int64(T), C.c_int64(B), ptr(seg),
+                                       seg.size - 1, ptr(prob), ptr(Pi), ptr(delta), 7, 64, ptr(y), ptr(g), ptr(ll),
+                                       C.byref(gate))
+            assert gate.value == 0
+        else:
+            st = emul.emul_binom2(ptr(rt), ptr(nt_), C.c_int64(32), C.c_int64(T), C.c_int64(B), ptr(seg),
+                                  seg.size - 1, ptr(prob), ptr(Pi), ptr(delta), 7, 64, ptr(y), ptr(g), ptr(ll))
+    finally:
+        emul.emul_set_tiled(0)
+    assert st == 0 and rc == 0
+    assert (np_untile(y, B) == yo).all()
+    gu = np.stack([np_untile(g[k], B) for k in range(2)])
+    assert np.abs(gu - go).max() < 1e-9
+    assert np.allclose(ll, llo, rtol=1e-10, atol=1e-10)

@@ -206,3 +206,47 @@ def test_binom_gate_reruns_general_kernel(oracle):
         logb = [[P.dbinom_log(float(a), float(c), q) for q in prob] for a, c in zip(x[:, b], n[:, b])]
         assert np.abs(g[:, :, b].T - P.mp_posteriors(logb, Pi, delta, dps=80)).max() < 1e-12
         assert (out["y"][:, b].cpu().numpy() == oracle.viterbi_binom(x[:, b], n[:, b], prob, Pi, delta)).all()
+
+
+def test_tiled_layout_matches_gene_major(oracle):
+    """Warp-tiled resident layout (hb_tile_dev / hb_hmm_*_tiled_dev / hb_untile_dev): bit-identical to
+    the gene-major entry points, for B not a multiple of 32, both chain families, and vs the oracle."""
+    import torch
+    from honeybadger_b200 import hmm
+    O = oracle
+    G, N = 2600, 333
+    x, seg, _ = synth.expression(G, N, seed=31)
+    Pi, delta, mean = O.sym_Pi(3, 1e-6), [0.0, 1.0, 0.0], [-synth.DEV, 0.0, synth.DEV]
+    xd = hmm.to_rows(torch.from_numpy(x).cuda())
+    sd = hmm.chain_sd_dev(xd)
+    ref = hmm.hmm_norm_dev(xd, sd, mean, Pi, delta, seg_off=seg, viterbi=True, gamma=True, ll=True)
+    xt = hmm.tile_rows(xd)
+    assert xt.shape == ((N + 31) // 32, G, 32)
+    assert torch.equal(hmm.untile_rows(xt, N), xd)
+    out = hmm.hmm_norm_tiled_dev(xt, N, sd, mean, Pi, delta, seg_off=seg, viterbi=True, gamma=True, ll=True)
+    hmm.status_dev()
+    assert torch.equal(hmm.untile_rows(out["y"], N), ref["y"])
+    assert torch.equal(hmm.untile_rows(out["gamma"], N), ref["gamma"])
+    assert torch.equal(out["ll"], ref["ll"])
+    yo, go, llo, rc = O.fbv_norm_batch(x, seg, mean, sd.cpu().numpy(), Pi, delta)
+    assert rc == 0 and (hmm.untile_rows(out["y"], N).cpu().numpy() == yo).all()
+    assert np.abs(hmm.untile_rows(out["gamma"], N).cpu().numpy() - go).max() < 1e-9
+    # general parameters take the literal kernel on the tiled layout as well
+    Pig = np.array([[0.98, 0.015, 0.005], [0.001, 0.998, 0.001], [0.02, 0.01, 0.97]])
+    og = hmm.hmm_norm_tiled_dev(xt, N, sd, [-1.4, 0.1, 0.9], Pig, [0.2, 0.5, 0.3], seg_off=seg)
+    rg = hmm.hmm_norm_dev(xd, sd, [-1.4, 0.1, 0.9], Pig, [0.2, 0.5, 0.3], seg_off=seg)
+    assert torch.equal(hmm.untile_rows(og["y"], N), rg["y"])
+    assert torch.equal(hmm.untile_rows(og["gamma"], N), rg["gamma"])
+
+    r_maf, n_sc, seg2, _ = synth.allele(4000, 205, seed=33, deep=0.002)
+    Pi2, prob = O.sym_Pi(2, 1e-6), [0.1, 0.45]
+    rd, nd = hmm.to_rows(torch.from_numpy(r_maf).cuda()), hmm.to_rows(torch.from_numpy(n_sc).cuda())
+    refb = hmm.hmm_binom_dev(rd, nd, prob, Pi2, [0.0, 1.0], seg_off=seg2, viterbi=True, gamma=True, ll=True)
+    ob = hmm.hmm_binom_tiled_dev(hmm.tile_rows(rd), hmm.tile_rows(nd), 205, prob, Pi2, [0.0, 1.0],
+                                 seg_off=seg2, viterbi=True, gamma=True, ll=True)
+    hmm.status_dev()
+    assert torch.equal(hmm.untile_rows(ob["y"], 205), refb["y"])
+    assert torch.equal(hmm.untile_rows(ob["gamma"], 205), refb["gamma"])
+    assert torch.equal(ob["ll"], refb["ll"])
+    yo, go, llo, rc = O.fbv_binom_batch(r_maf, n_sc, seg2, prob, Pi2, [0.0, 1.0])
+    assert rc == 0 and (refb["y"].cpu().numpy() == yo).all()

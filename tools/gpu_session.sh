@@ -1,3 +1,4 @@
 cd $GRAFT_REPO_ROOT
-python -m pytest tests/test_gpu_hmm.py -x -q 2>&1 | tail -3 | tee gpurun_out/pytest_gpu.log
-HB_MODE=0 python tools/probe_binom.py variants/lib_r4.so variants/lib_r5.so variants/lib_r6.so 2>&1 | grep "^lib" | tee gpurun_out/probe_binom5.log
+python -m pytest tests -m gpu -x -q 2>&1 | tail -5 | tee gpurun_out/pytest_gpu.log
+python bench.py --steps 30 --warmup 3 > gpurun_out/bench_expr.log 2>&1; tail -1 gpurun_out/bench_expr.log | cut -c1-1500
+python bench.py --workload allele --steps 5 --warmup 3 --e2e-steps 1 > gpurun_out/bench_allele.log 2>&1; tail -1 gpurun_out/bench_allele.log | cut -c1-1500

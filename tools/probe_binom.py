@@ -15,10 +15,16 @@ N, G = int(os.environ.get("HB_N", 10000)), int(os.environ.get("HB_G", 50000))
 d = bench.device_inputs("allele", N, G, 3, torch.device("cuda:0"))
 r, n, seg = d["r"], d["n"], d["seg"]
 Pi2 = hmm.sym_Pi(2, 1e-6)
-out = hmm.hmm_binom_dev(r, n, [0.1, 0.45], Pi2, [0., 1.], seg_off=seg)
+TILED = int(os.environ.get("HB_TILED", "0"))
+if TILED:
+    rt, nt = hmm.tile_rows(r), hmm.tile_rows(n)
+    run = lambda out=None, **kw: hmm.hmm_binom_tiled_dev(rt, nt, N, [0.1, 0.45], Pi2, [0., 1.], seg_off=seg, out=out, **kw)
+else:
+    run = lambda out=None, **kw: hmm.hmm_binom_dev(r, n, [0.1, 0.45], Pi2, [0., 1.], seg_off=seg, out=out, **kw)
+out = run()
 res = []
 for mode, kw in (("V+FB", dict(viterbi=True, gamma=True)), ("FB", dict(viterbi=False, gamma=True)), ("V", dict(viterbi=True, gamma=False))):
-    fn = lambda: hmm.hmm_binom_dev(r, n, [0.1, 0.45], Pi2, [0., 1.], seg_off=seg, out=out, **kw)
+    fn = lambda: run(out=out, **kw)
     for _ in range(2): fn()
     torch.cuda.synchronize()
     ts = []
@@ -28,4 +34,4 @@ for mode, kw in (("V+FB", dict(viterbi=True, gamma=True)), ("FB", dict(viterbi=F
     ms = sorted(ts)[2]
     res.append(f"{mode} {ms:.3f} ms {N*G/ms/1e6:.1f} G/s")
 hmm.status_dev()
-print(os.path.basename(sys.argv[1]), "mode", os.environ.get("HB_MODE", "0"), "general rerun", hmm.binom2_general_rerun(), f"n>0 frac {(n>0).float().mean().item():.3f} max n {int(n.max())}", " | ".join(res), flush=True)
+print(os.path.basename(sys.argv[1]), "tiled" if TILED else "rows", "mode", os.environ.get("HB_MODE", "0"), "general rerun", hmm.binom2_general_rerun(), f"n>0 frac {(n>0).float().mean().item():.3f} max n {int(n.max())}", " | ".join(res), flush=True)

@@ -19,12 +19,19 @@ x.mul_(torch.empty(N, dtype=torch.float64, device=dev).uniform_(2.0, 3.1, genera
 sd = hmm.chain_sd_dev(x)
 Pi, delta, mean = hmm.sym_Pi(3, 1e-6), [0., 1., 0.], [-synth.DEV, 0., synth.DEV]
 seg = synth.segments(G)
-out = dict(y=torch.empty((G, LD), dtype=torch.uint8, device=dev)[:, :N],
-           gamma=torch.empty((3, G, LD), dtype=torch.float64, device=dev)[:, :, :N])
-out = hmm.hmm_norm_dev(x, sd, mean, Pi, delta, seg_off=seg, viterbi=True, gamma=True, out=out)
+TILED = int(os.environ.get("HB_TILED", "0"))
+if TILED:
+    xt = hmm.tile_rows(x)
+    run = lambda out=None, **kw: hmm.hmm_norm_tiled_dev(xt, N, sd, mean, Pi, delta, seg_off=seg, out=out, **kw)
+    out = run(viterbi=True, gamma=True)
+else:
+    run = lambda out=None, **kw: hmm.hmm_norm_dev(x, sd, mean, Pi, delta, seg_off=seg, out=out, **kw)
+    out = dict(y=torch.empty((G, LD), dtype=torch.uint8, device=dev)[:, :N],
+               gamma=torch.empty((3, G, LD), dtype=torch.float64, device=dev)[:, :, :N])
+    out = run(out=out, viterbi=True, gamma=True)
 res = []
 for mode, kw in (("V+FB", dict(viterbi=True, gamma=True)), ("FB", dict(viterbi=False, gamma=True)), ("V", dict(viterbi=True, gamma=False))):
-    fn = lambda: hmm.hmm_norm_dev(x, sd, mean, Pi, delta, seg_off=seg, out=out, **kw)
+    fn = lambda: run(out=out, **kw)
     for _ in range(3): fn()
     torch.cuda.synchronize()
     ts = []
@@ -34,6 +41,6 @@ for mode, kw in (("V+FB", dict(viterbi=True, gamma=True)), ("FB", dict(viterbi=F
     ms = sorted(ts)[3]
     res.append(f"{mode} {ms:.3f} ms {N*G/ms/1e6:.1f} G/s")
 hmm.status_dev()
-hmm.hmm_norm_dev(x, sd, mean, Pi, delta, seg_off=seg, out=out, viterbi=True, gamma=True)
-print(os.path.basename(sys.argv[1]), "ld", LD, "mode", os.environ.get("HB_MODE", "0"), " | ".join(res),
+run(out=out, viterbi=True, gamma=True)
+print(os.path.basename(sys.argv[1]), "tiled" if TILED else f"ld {LD}", "mode", os.environ.get("HB_MODE", "0"), " | ".join(res),
       "| rerun chains", hmm.norm3_rerun_chains(), flush=True)
