@@ -64,6 +64,7 @@ SIGNATURES = {
     "hb_transpose_f64_back_dev": (_i32, [_p, _i64, _i64, _i64, _p, _p]),
     "hb_chain_sd_dev": (_i32, [_p, _i64, _i64, _i64, _p, _i32, _i32, _p, _p]),
     "hb_pool_mean_dev": (_i32, [_p, _i64, _i64, _i64, _p, _i32, _p, _p]),
+    "hb_pool_mean_relay_dev": (_i32, [_p, _i64, _i64, _i64, _p, _i32, _p, _i32, _p, _p, _p, _p]),
     "hb_pooled_sd_dev": (_i32, [_p, _i64, _i32, _p, _p]),
     "hb_pool_count_pos_dev": (_i32, [_p, _i64, _i64, _i64, _p, _i32, _p, _p]),
     "hb_gexp_pooled_viterbi_dev": (_i32, [_p, _i64, _i64, _i64, _p, _i32, _p, _p, _p, _p, _p, _p, _p]),

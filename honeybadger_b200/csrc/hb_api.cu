@@ -88,7 +88,7 @@ struct DevBuf {
 // Per-device scratch, grown on demand and reused across calls (no allocation in steady state).
 struct Workspace {
     DevBuf psi, ckpt, sdaux, segtab, status, lut_lb, lut_rho, lut_rho_d, cellmask, gsize;
-    DevBuf st_in, st_in2, st_x, st_x2, st_y, st_g, st_out, st_sd, st_ll, st_member, st_pool, st_pool2, st_pre;
+    DevBuf st_in, st_in2, st_x, st_x2, st_y, st_g, st_out, st_sd, st_ll, st_member, st_pool, st_pool2, st_pre, st_x80;
     // host-buffer entry points: three-stream pipeline (upload | layout + chains | download), staging x2
     DevBuf pin[2], pin2[2], pout_y[2], pout_g[2], pout_ll[2];
     cudaStream_t s_in = nullptr, s_cmp = nullptr, s_out = nullptr;
@@ -102,7 +102,7 @@ struct Workspace {
     {
         DevBuf *all[] = {&psi, &ckpt, &sdaux, &segtab, &status, &lut_lb, &lut_rho, &lut_rho_d, &cellmask, &gsize,
                          &st_in, &st_in2, &st_x, &st_x2, &st_y, &st_g, &st_out, &st_sd, &st_ll,
-                         &st_member, &st_pool, &st_pool2, &st_pre, &pin[0], &pin[1], &pin2[0], &pin2[1],
+                         &st_member, &st_pool, &st_pool2, &st_pre, &st_x80, &pin[0], &pin[1], &pin2[0], &pin2[1],
                          &pout_y[0], &pout_y[1], &pout_g[0], &pout_g[1], &pout_ll[0], &pout_ll[1]};
         for (DevBuf *b : all) b->release();
         seg_cached.clear();
@@ -926,7 +926,31 @@ int hb_pool_mean_dev(const double *x, int64_t ld, int64_t G, int64_t N, const ui
     HBTRY(group_sizes(h_mem.data(), K, N, sz));
     HBTRY(ws->gsize.ensure((size_t)K * sizeof(int32_t)));
     CU(cudaMemcpy(ws->gsize.p, sz.data(), (size_t)K * sizeof(int32_t), cudaMemcpyHostToDevice));
-    CU(hb::launch_pool_mean(x, ld, G, N, member, ws->gsize.as<int32_t>(), K, out, st));
+    HBTRY(ws->st_x80.ensure((size_t)2 * K * G * 16));
+    CU(hb::launch_pool_mean(x, ld, G, N, member, ws->gsize.as<int32_t>(), K, out, ws->st_x80.p, st));
+    return HB_OK;
+}
+
+int hb_pool_mean_relay_dev(const double *x, int64_t ld, int64_t G, int64_t N, const uint8_t *member,
+                           int32_t K, const int32_t *n_total, int32_t phase, void *state,
+                           void *mean80, double *out, void *stream)
+{
+    if (G < 1 || K < 1 || !state || phase < 0 || phase > 3) return fail(HB_ERR_ARG, "bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (phase == 0 || phase == 2) {
+        if (N < 0 || (N > 0 && (!x || !member || ld < N))) return fail(HB_ERR_ARG, "bad arguments");
+        if (phase == 2 && !mean80) return fail(HB_ERR_ARG, "phase 2 needs mean80");
+        if (N > 0)
+            CU(hb::launch_pool_accum(x, ld, G, N, member, K, phase == 2 ? mean80 : nullptr, state, st));
+        return HB_OK;
+    }
+    if (!n_total || !mean80) return fail(HB_ERR_ARG, "phases 1 and 3 need n_total and mean80");
+    if (phase == 1) {
+        CU(hb::launch_pool_div(state, n_total, G, K, mean80, st));
+    } else {
+        if (!out) return fail(HB_ERR_ARG, "phase 3 needs out");
+        CU(hb::launch_pool_finish(mean80, state, n_total, G, K, out, st));
+    }
     return HB_OK;
 }
 
@@ -982,8 +1006,9 @@ int hb_gexp_pooled_viterbi_dev(const double *x, int64_t ld, int64_t G, int64_t N
     HBTRY(ws->st_out.ensure((size_t)G * K * sizeof(int32_t)));
     CU(cudaMemcpyAsync(ws->st_member.p, member, (size_t)K * N, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(ws->gsize.p, sz.data(), (size_t)K * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    HBTRY(ws->st_x80.ensure((size_t)2 * K * G * 16));
     CU(hb::launch_pool_mean(x, ld, G, N, ws->st_member.as<uint8_t>(), ws->gsize.as<int32_t>(), K,
-                            ws->st_pool.as<double>(), st));
+                            ws->st_pool.as<double>(), ws->st_x80.p, st));
     CU(hb::launch_pooled_sd(ws->st_pool.as<double>(), G, K, ws->st_sd.as<double>(), st));
     // [K][G] row-major is column-major [G x K]: the same transpose as an R matrix upload
     CU(hb::launch_transpose_f64(ws->st_pool.as<double>(), G, K, ws->st_pool2.as<double>(), ldk, st));

@@ -396,14 +396,20 @@ cudaError_t launch_tile(const void *src, int64_t ld, int64_t T, int64_t B, int e
 // =====================================================================================
 // Pooled statistics of cell groups (R/HoneyBADGER.R:1141, :1149, :1404-1405)
 // =====================================================================================
-// out[k*G+g] = R mean() of {x[g*ld+c] : member[k*N+c]} in cell order, x87 semantics replayed in
-// integer arithmetic.  Block = 32 genes x PM_KB groups; the gene tile is staged through shared
-// memory in PM_TC-cell slabs so that global reads stay coalesced along the cell axis.
+// Pooled expression observation, R `mean` semantics (summary.c real_mean: two passes in LDOUBLE, x87
+// arithmetic replayed in integer registers, hb_x87.cuh).  The accumulation is order-dependent, so it
+// is written as a RELAY over an 80-bit state per (group, gene): pool_accum_kernel continues `state`
+// with this matrix's member cells in cell order — pass 0 adds x, pass 1 adds (x - mean80) — and the
+// tiny kernels below close each pass.  One GPU runs accumulate / divide / accumulate / finish on
+// the whole matrix; several GPUs hand `state` from rank to rank (honeybadger_b200/dist.py), which
+// gives R's result bit for bit at any GPU count.
+// Block = 32 genes x PM_KB groups; the gene tile is staged through shared memory in PM_TC-cell
+// slabs so that global reads stay coalesced along the cell axis.
 #define PM_TC 64
 #define PM_KB 16
 __global__ void __launch_bounds__(32 * PM_KB)
-    pool_mean_kernel(const double *x, int64_t ld, int64_t G, int64_t N, const uint8_t *member,
-                     const int32_t *gsize, int32_t K, double *out)
+    pool_accum_kernel(const double *x, int64_t ld, int64_t G, int64_t N, const uint8_t *member,
+                      int32_t K, const x80 *mean80, x80 *state)
 {
     __shared__ double tile[32][PM_TC + 1];
     const int64_t g0 = (int64_t)blockIdx.x * 32;
@@ -413,46 +419,86 @@ __global__ void __launch_bounds__(32 * PM_KB)
         const int32_t k = kb + ky;
         const bool live = k < K && g0 + lane < G;
         const uint8_t *mem = member + (int64_t)(live ? k : 0) * N;
-        const uint32_t n = live ? (uint32_t)gsize[k] : 1u;
-        x80 S = x80_zero(), T = x80_zero();
-        for (int pass = 0; pass < 2; pass++) {
-            for (int64_t c0 = 0; c0 < N; c0 += PM_TC) {
-                __syncthreads();
-                for (int i = tid; i < 32 * PM_TC; i += 32 * PM_KB) {
-                    int r = i / PM_TC, cc = i % PM_TC;
-                    int64_t g = g0 + r, c = c0 + cc;
-                    tile[r][cc] = (g < G && c < N) ? x[g * ld + c] : 0.0;
-                }
-                __syncthreads();
-                if (live) {
-                    const int lim = (int)((N - c0) < PM_TC ? (N - c0) : PM_TC);
-                    for (int cc = 0; cc < lim; cc++) {
-                        if (mem[c0 + cc]) {
-                            x80 v = x80_from_double(tile[lane][cc]);
-                            if (pass == 0)
-                                S = x80_add(S, v);
-                            else
-                                T = x80_add(T, x80_sub(v, S));
-                        }
+        const int64_t si = (int64_t)(live ? k : 0) * G + (live ? g0 + lane : 0);
+        x80 S = live ? state[si] : x80_zero();
+        const bool centred = mean80 != nullptr;
+        const x80 M = (live && centred) ? mean80[si] : x80_zero();
+        for (int64_t c0 = 0; c0 < N; c0 += PM_TC) {
+            __syncthreads();
+            for (int i = tid; i < 32 * PM_TC; i += 32 * PM_KB) {
+                int r = i / PM_TC, cc = i % PM_TC;
+                int64_t g = g0 + r, c = c0 + cc;
+                tile[r][cc] = (g < G && c < N) ? x[g * ld + c] : 0.0;
+            }
+            __syncthreads();
+            if (live) {
+                const int lim = (int)((N - c0) < PM_TC ? (N - c0) : PM_TC);
+                for (int cc = 0; cc < lim; cc++) {
+                    if (mem[c0 + cc]) {
+                        x80 v = x80_from_double(tile[lane][cc]);
+                        S = x80_add(S, centred ? x80_sub(v, M) : v);
                     }
                 }
             }
-            if (pass == 0)
-                S = x80_div_u32(S, n);
-            else
-                S = x80_add(S, x80_div_u32(T, n));
         }
-        if (live) out[(int64_t)k * G + g0 + lane] = x80_to_double(S);
+        if (live) state[si] = S;
     }
 }
 
+// pass 0 closed: mean80 = state / n[k]
+__global__ void pool_div_kernel(const x80 *state, const int32_t *n, int64_t G, int32_t K, x80 *mean80)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)K * G) return;
+    mean80[i] = x80_div_u32(state[i], (uint32_t)n[i / G]);
+}
+
+// pass 1 closed: out = (double)(mean80 + state / n[k])
+__global__ void pool_finish_kernel(const x80 *mean80, const x80 *state, const int32_t *n, int64_t G,
+                                   int32_t K, double *out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)K * G) return;
+    out[i] = x80_to_double(x80_add(mean80[i], x80_div_u32(state[i], (uint32_t)n[i / G])));
+}
+
+cudaError_t launch_pool_accum(const double *x, int64_t ld, int64_t G, int64_t N, const uint8_t *member,
+                              int32_t K, const void *mean80, void *state, cudaStream_t st)
+{
+    pool_accum_kernel<<<(unsigned)((G + 31) / 32), dim3(32, PM_KB), 0, st>>>(
+        x, ld, G, N, member, K, (const x80 *)mean80, (x80 *)state);
+    return cudaGetLastError();
+}
+cudaError_t launch_pool_div(const void *state, const int32_t *n, int64_t G, int32_t K, void *mean80,
+                            cudaStream_t st)
+{
+    const int64_t tot = (int64_t)K * G;
+    pool_div_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>((const x80 *)state, n, G, K, (x80 *)mean80);
+    return cudaGetLastError();
+}
+cudaError_t launch_pool_finish(const void *mean80, const void *state, const int32_t *n, int64_t G,
+                               int32_t K, double *out, cudaStream_t st)
+{
+    const int64_t tot = (int64_t)K * G;
+    pool_finish_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>((const x80 *)mean80, (const x80 *)state,
+                                                                      n, G, K, out);
+    return cudaGetLastError();
+}
+
+// The whole mean on one GPU: `scratch` holds 2 * K * G 16-byte records.
 cudaError_t launch_pool_mean(const double *x, int64_t ld, int64_t G, int64_t N,
                              const uint8_t *member, const int32_t *gsize, int32_t K, double *out,
-                             cudaStream_t st)
+                             void *scratch, cudaStream_t st)
 {
-    pool_mean_kernel<<<(unsigned)((G + 31) / 32), dim3(32, PM_KB), 0, st>>>(x, ld, G, N, member,
-                                                                             gsize, K, out);
-    return cudaGetLastError();
+    const size_t rec = (size_t)K * G * sizeof(x80);
+    void *state = scratch, *mean80 = (char *)scratch + rec;
+    cudaError_t e = cudaMemsetAsync(state, 0, rec, st);
+    if (e != cudaSuccess) return e;
+    if ((e = launch_pool_accum(x, ld, G, N, member, K, nullptr, state, st)) != cudaSuccess) return e;
+    if ((e = launch_pool_div(state, gsize, G, K, mean80, st)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(state, 0, rec, st)) != cudaSuccess) return e;
+    if ((e = launch_pool_accum(x, ld, G, N, member, K, mean80, state, st)) != cudaSuccess) return e;
+    return launch_pool_finish(mean80, state, gsize, G, K, out, st);
 }
 
 // sd(x) of each pooled vector (cov.c cov_complete1 replayed): one warp per chain; the lanes form

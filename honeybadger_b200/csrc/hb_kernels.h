@@ -33,7 +33,13 @@ cudaError_t launch_tile(const void *src, int64_t ld, int64_t T, int64_t B, int e
                         bool to_tiled, cudaStream_t st);
 cudaError_t launch_pool_mean(const double *x, int64_t ld, int64_t G, int64_t N,
                              const uint8_t *member, const int32_t *gsize, int32_t K, double *out,
-                             cudaStream_t st);
+                             void *scratch /* 2*K*G 16-byte records */, cudaStream_t st);
+cudaError_t launch_pool_accum(const double *x, int64_t ld, int64_t G, int64_t N, const uint8_t *member,
+                              int32_t K, const void *mean80, void *state, cudaStream_t st);
+cudaError_t launch_pool_div(const void *state, const int32_t *n, int64_t G, int32_t K, void *mean80,
+                            cudaStream_t st);
+cudaError_t launch_pool_finish(const void *mean80, const void *state, const int32_t *n, int64_t G,
+                               int32_t K, double *out, cudaStream_t st);
 cudaError_t launch_pooled_sd(const double *pooled, int64_t G, int32_t K, double *sd,
                              cudaStream_t st);
 cudaError_t launch_pool_count(const int32_t *v, int64_t ld, int64_t G, int64_t N,

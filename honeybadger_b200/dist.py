@@ -73,3 +73,90 @@ def merge_votes(vote_local):
             t = t.cuda()
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return t
+
+
+# --------------------------------------------------------------------------- pooled expression mean
+# R's mean() (R/HoneyBADGER.R:1141) is an order-dependent 80-bit accumulation over the cells of a
+# group, so per-rank partial sums cannot be merged afterwards.  The exact multi-GPU form is a relay:
+# an 80-bit state per (group, gene) is continued by each rank with ITS cells and handed to the next
+# rank (cell order = rank order), twice (R's two passes).  hb_pool_mean_relay_dev does the per-rank
+# work; this module moves the state.
+def _relay_phase(lib, x, member_dev, K, n_total_dev, phase, state, mean80, out):
+    import ctypes as C
+    import torch
+    from . import _lib
+    G = state.numel() // (16 * K)
+    N = 0 if x is None else x.shape[1]
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    _lib.check(lib.hb_pool_mean_relay_dev(
+        None if x is None or N == 0 else x.data_ptr(), 0 if x is None else x.stride(0), G, N,
+        None if member_dev is None or N == 0 else member_dev.data_ptr(), K,
+        None if n_total_dev is None else n_total_dev.data_ptr(), phase, state.data_ptr(),
+        None if mean80 is None else mean80.data_ptr(), None if out is None else out.data_ptr(), stream))
+
+
+def pooled_mean_relay_shards(shards, members, group_sizes):
+    """Single-process form (tests, and a GPU that holds several shards): `shards` is a list of
+    gene-major CUDA tensors [G, N_i] in cell order, `members` the matching uint8 [K, N_i] arrays.
+    Returns the [K, G] pooled means — identical to hb_pool_mean_dev on the concatenated matrix."""
+    import torch
+    from . import _lib
+    lib = _lib.load()
+    K, G = int(members[0].shape[0]), int(shards[0].shape[0])
+    dev = shards[0].device
+    n_tot = torch.as_tensor(np.asarray(group_sizes, dtype=np.int32), device=dev)
+    state = torch.zeros(K * G * 16, dtype=torch.uint8, device=dev)
+    mean80 = torch.zeros(K * G * 16, dtype=torch.uint8, device=dev)
+    out = torch.empty((K, G), dtype=torch.float64, device=dev)
+    mems = [torch.as_tensor(np.ascontiguousarray(m, dtype=np.uint8), device=dev) for m in members]
+    for x, m in zip(shards, mems):
+        _relay_phase(lib, x, m, K, None, 0, state, None, None)
+    _relay_phase(lib, None, None, K, n_tot, 1, state, mean80, None)
+    state.zero_()
+    for x, m in zip(shards, mems):
+        _relay_phase(lib, x, m, K, None, 2, state, mean80, None)
+    _relay_phase(lib, None, None, K, n_tot, 3, state, mean80, out)
+    return out
+
+
+def pooled_mean_relay(x_local, member_local, group_sizes, accumulate=None):
+    """Multi-process form: every rank calls this with its gene-major shard [G, N_local] and its
+    uint8 [K, N_local] membership slice; `group_sizes` are the TOTAL group sizes.  The 16-byte
+    states travel rank -> rank+1 with send/recv, the last rank closes each pass and broadcasts.
+    Returns the [K, G] pooled means on every rank.  `accumulate(x, member, phase, state, mean80)` can
+    replace the device call (the gloo CPU test passes a long-double emulation)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    K, G = int(member_local.shape[0]), int(x_local.shape[0])
+    if accumulate is None:
+        from . import _lib
+        lib = _lib.load()
+        dev = x_local.device
+        mem = torch.as_tensor(np.ascontiguousarray(member_local, dtype=np.uint8), device=dev)
+        n_tot = torch.as_tensor(np.asarray(group_sizes, dtype=np.int32), device=dev)
+
+        def accumulate(x, member, phase, state, mean80, out=None):
+            if phase in (0, 2):
+                _relay_phase(lib, x, mem, K, None, phase, state, mean80 if phase == 2 else None, None)
+            else:
+                _relay_phase(lib, None, None, K, n_tot, phase, state, mean80, out)
+    else:
+        dev = torch.device("cpu")
+    state = torch.zeros(K * G * 16, dtype=torch.uint8, device=dev)
+    mean80 = torch.zeros(K * G * 16, dtype=torch.uint8, device=dev)
+    out = torch.empty((K, G), dtype=torch.float64, device=dev)
+    for phase in (0, 2):
+        if phase == 2:
+            state.zero_()
+        if rank > 0:
+            dist.recv(state, src=rank - 1)
+        accumulate(x_local, member_local, phase, state, mean80)
+        if rank < world - 1:
+            dist.send(state, dst=rank + 1)
+        else:
+            accumulate(None, None, phase + 1, state, mean80, out)  # close the pass on the last rank
+        if world > 1:
+            dist.broadcast(mean80 if phase == 0 else out, src=world - 1)
+    return out

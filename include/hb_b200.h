@@ -155,6 +155,19 @@ int hb_chain_sd_dev(const double *x, int64_t ld, int64_t T, int64_t B, const int
 int hb_pool_mean_dev(const double *x, int64_t ld, int64_t G, int64_t N,
                      const uint8_t *member /* device [K][N] */, int32_t K,
                      double *out /* device [K][G] */, void *stream);
+/* The same mean as a RELAY, for cells sharded over several GPUs.  R's mean is an order-dependent
+ * 80-bit accumulation, so partial sums cannot be merged afterwards; instead an 80-bit state per
+ * (group, gene) — `state`, K*G records of 16 bytes, device — is continued by each rank in turn
+ * with ITS cells (cell order = rank order) and handed to the next rank:
+ *   phase 0  state += x over this rank's members               (start from zeros on the first rank)
+ *   phase 1  mean80 = state / n_total[k]                        (last rank; then broadcast mean80, zero state)
+ *   phase 2  state += (x - mean80) over this rank's members
+ *   phase 3  out[k*G+g] = (double)(mean80 + state / n_total[k]) (last rank; R's result bit for bit)
+ * member is this rank's [K][N] slice (device), n_total (device int32[K]) the group sizes over all ranks.
+ * hb_pool_mean_dev is phases 0-3 on one GPU. */
+int hb_pool_mean_relay_dev(const double *x, int64_t ld, int64_t G, int64_t N, const uint8_t *member,
+                           int32_t K, const int32_t *n_total, int32_t phase, void *state,
+                           void *mean80, double *out, void *stream);
 /* sd(x) of each pooled vector, R semantics (long-double emulation): out_sd[k]. */
 int hb_pooled_sd_dev(const double *pooled /* device [K][G] */, int64_t G, int32_t K,
                      double *out_sd /* device [K] */, void *stream);

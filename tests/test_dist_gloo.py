@@ -44,6 +44,31 @@ def _worker(rank, world, port, q):
     post = torch.arange(3 * N, dtype=torch.float64).reshape(3, N)
     got = hd.allgather_region_posteriors(post[:, lo:hi].contiguous(), N)
     ok = ok and torch.equal(got, post)
+    # pooled expression mean: the 80-bit accumulator relay (device call replaced by np.longdouble,
+    # which is the x87 extended format on x86-64) reproduces R's mean over ALL cells on every rank
+    xg = rng.standard_normal((G, N)) * 2.5
+    memb = (rng.random((3, N)) < 0.5).astype(np.uint8)
+    memb[:, 0] = 1
+    sizes = memb.sum(1)
+
+    def accumulate(x, member, phase, state, mean80, out=None):
+        st = state.numpy().view(np.longdouble).reshape(3, G)
+        mn = mean80.numpy().view(np.longdouble).reshape(3, G)
+        x = x.numpy() if torch.is_tensor(x) else x
+        if phase in (0, 2):
+            for k in range(3):
+                for c in np.nonzero(member[k])[0]:
+                    st[k] += (x[:, c].astype(np.longdouble) - mn[k]) if phase == 2 else x[:, c].astype(np.longdouble)
+        elif phase == 1:
+            for k in range(3):
+                mn[k] = st[k] / np.longdouble(sizes[k])
+        else:
+            for k in range(3):
+                out[k] = torch.from_numpy((mn[k] + st[k] / np.longdouble(sizes[k])).astype(np.float64))
+
+    pm = hd.pooled_mean_relay(torch.from_numpy(xg[:, lo:hi]), memb[:, lo:hi], sizes, accumulate=accumulate)
+    for k in range(3):
+        ok = ok and (pm[k].numpy() == O.pool_mean(xg, np.nonzero(memb[k])[0])).all()
     v = hd.merge_votes(np.full(G, rank + 1))
     ok = ok and int(v[0]) == sum(range(1, world + 1))
     q.put((rank, bool(ok)))

@@ -161,3 +161,30 @@ def test_refclass_driver_finds_planted_clones():
     planted = set(gnames[seg[6]:seg[7]]) | set(gnames[seg[9]:seg[10]]) | set(gnames[seg[12]:seg[13]])
     assert len(found & planted) > 0.5 * len(found)
     assert obj.pred_genes_r.values.sum() > 0
+
+
+def test_pool_mean_relay_equals_single_pass(oracle):
+    """The accumulator relay (cells split into shards handed from 'rank' to 'rank') gives the same
+    bits as the one-GPU mean and as R's long-double mean, for uneven shards and an empty shard."""
+    import torch
+    from honeybadger_b200 import _lib, dist as hd, hmm
+    rng = np.random.default_rng(5)
+    G, N, K = 700, 211, 7
+    x = rng.standard_normal((G, N)) * 2.5
+    member = (rng.random((K, N)) < 0.4).astype(np.uint8)
+    member[0] = 1
+    member[:, 0] = 1            # no empty group
+    sizes = member.sum(1).astype(np.int32)
+    xd = hmm.to_rows(torch.from_numpy(x).cuda())
+    md = torch.from_numpy(member).cuda()
+    full = torch.empty((K, G), dtype=torch.float64, device="cuda")
+    lib = _lib.load()
+    _lib.check(lib.hb_pool_mean_dev(xd.data_ptr(), xd.stride(0), G, N, md.data_ptr(), K, full.data_ptr(), None))
+    cuts = [0, 50, 50, 131, N]   # includes an empty shard
+    shards = [hmm.to_rows(xd[:, a:b].contiguous()) if b > a else xd[:, a:a] for a, b in zip(cuts[:-1], cuts[1:])]
+    mems = [member[:, a:b] for a, b in zip(cuts[:-1], cuts[1:])]
+    keep = [i for i, (a, b) in enumerate(zip(cuts[:-1], cuts[1:])) if b > a]
+    relay = hd.pooled_mean_relay_shards([shards[i] for i in keep], [mems[i] for i in keep], sizes)
+    assert torch.equal(relay, full)
+    for k in (0, 3, 6):
+        assert (relay[k].cpu().numpy() == oracle.pool_mean(x, np.nonzero(member[k])[0])).all()
