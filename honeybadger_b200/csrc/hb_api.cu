@@ -88,7 +88,7 @@ struct DevBuf {
 // Per-device scratch, grown on demand and reused across calls (no allocation in steady state).
 struct Workspace {
     DevBuf psi, ckpt, sdaux, segtab, status, lut_lb, lut_rho, lut_rho_d, cellmask, gsize;
-    DevBuf st_in, st_in2, st_x, st_x2, st_y, st_g, st_out, st_sd, st_ll, st_member, st_pool, st_pool2, st_pre, st_x80;
+    DevBuf st_in, st_in2, st_x, st_x2, st_y, st_g, st_out, st_sd, st_ll, st_member, st_pool, st_pool2, st_pre, st_x80, st_part;
     // host-buffer entry points: three-stream pipeline (upload | layout + chains | download), staging x2
     DevBuf pin[2], pin2[2], pout_y[2], pout_g[2], pout_ll[2];
     cudaStream_t s_in = nullptr, s_cmp = nullptr, s_out = nullptr;
@@ -102,7 +102,7 @@ struct Workspace {
     {
         DevBuf *all[] = {&psi, &ckpt, &sdaux, &segtab, &status, &lut_lb, &lut_rho, &lut_rho_d, &cellmask, &gsize,
                          &st_in, &st_in2, &st_x, &st_x2, &st_y, &st_g, &st_out, &st_sd, &st_ll,
-                         &st_member, &st_pool, &st_pool2, &st_pre, &st_x80, &pin[0], &pin[1], &pin2[0], &pin2[1],
+                         &st_member, &st_pool, &st_pool2, &st_pre, &st_x80, &st_part, &pin[0], &pin[1], &pin2[0], &pin2[1],
                          &pout_y[0], &pout_y[1], &pout_g[0], &pout_g[1], &pout_ll[0], &pout_ll[1]};
         for (DevBuf *b : all) b->release();
         seg_cached.clear();
@@ -977,6 +977,38 @@ int hb_pool_count_pos_dev(const int32_t *v, int64_t ld, int64_t G, int64_t N,
         CU(hb::launch_pool_count(v, ld, G, N, ws->cellmask.as<uint32_t>(), kn, out + (int64_t)k0 * G,
                                  st));
     }
+    return HB_OK;
+}
+
+// ------------------------------------------------------------------ deterministic retest (8f-1)
+int hb_retest_gexp_dev(const double *x, int64_t ld, int64_t G, int64_t N, const int64_t *rows,
+                       int64_t nrows, double mag0, const double *sigma0, double *p_amp, double *p_del,
+                       double *mu0, double *D_local, const double *D_total, int32_t phase, void *stream)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    Workspace *ws;
+    HBTRY(cur_ws(&ws));
+    if (!x || !rows || !p_amp || !p_del || G < 1 || N < 1 || nrows < 1 || ld < N || phase < 0 || phase > 2)
+        return fail(HB_ERR_ARG, "bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t nb = (size_t)((N + 127) / 128);
+    HBTRY(ws->st_part.ensure(nb * sizeof(double)));
+    double *part = ws->st_part.as<double>();
+    if (phase == 0 || phase == 1)
+        CU(hb::launch_retest_gexp_a(x, ld, N, rows, nrows, mag0, sigma0, p_amp, p_del, mu0, part, D_local, st));
+    if (phase == 0 || phase == 2)
+        CU(hb::launch_retest_gexp_b(N, part, phase == 2 ? D_total : nullptr, p_amp, p_del, st));
+    return HB_OK;
+}
+
+int hb_retest_allele_lr_dev(const int32_t *r_maf, const int32_t *n_sc, int64_t ld, int64_t G, int64_t N,
+                            const int64_t *rows, int64_t nrows, double pd, double pn, double *p_del,
+                            void *stream)
+{
+    if (!r_maf || !n_sc || !rows || !p_del || G < 1 || N < 1 || nrows < 1 || ld < N || !(pd > 0 && pd < 1) ||
+        !(pn > 0 && pn < 1))
+        return fail(HB_ERR_ARG, "bad arguments");
+    CU(hb::launch_retest_allele(r_maf, n_sc, ld, N, rows, nrows, pd, pn, p_del, (cudaStream_t)stream));
     return HB_OK;
 }
 

@@ -394,6 +394,131 @@ cudaError_t launch_tile(const void *src, int64_t ld, int64_t T, int64_t B, int e
 }
 
 // =====================================================================================
+// Deterministic retest of a candidate region, expression model: the exact
+// marginal posterior of inst/bug/expressionModel.bug, which the reference samples with JAGS
+// (HoneyBADGER$calcGexpCnvProb, R/HoneyBADGER.R:374-470, called from :1220).  Priors integrate to
+// P(S_k = 1) = 1/2 per cell and P(dd = 1) = 1/2 shared; with l_k(mu) = sum_j log N(gexp[j,k]; mu,
+// precision sigma0_k):  L_k(d) = (exp l_k(0) + exp l_k(+-mag0)) / 2,  P(dd = 1 | data) =
+// sigmoid(sum_k log L_k(1) - log L_k(0)),  w_k(d) = exp l_k(+-mag0) / (2 L_k(d)),
+// P(amp_k) = P(dd=1) w_k(1),  P(del_k) = P(dd=0) w_k(0)  (= mean(S dd), mean(S (1-dd)), :460-461).
+// Phase A: one thread per cell streams the region's rows (coalesced along cells), writes w_k and
+// the block partials of D = sum_k log L_k(1) - log L_k(0).  Phase B: every block re-sums the
+// partials in a fixed order (deterministic), applies the sigmoid and scales.
+// Only differences against l_k(0) enter: dp = l_k(+mag0) - l_k(0) = prec (mag0 s1 - n mag0^2 / 2),
+// dm likewise with -mag0;  w_k(1) = sigmoid(dp), w_k(0) = sigmoid(dm),
+// log L_k(1) - log L_k(0) = softplus(dp) - softplus(dm)   (s1 = sum_j gexp[j,k]).
+__device__ __forceinline__ double softplus(double d) { return d > 0 ? d + log1p(exp(-d)) : log1p(exp(d)); }
+__device__ __forceinline__ double sigmoid(double d)
+{
+    return d >= 0 ? 1.0 / (1.0 + exp(-d)) : exp(d) / (1.0 + exp(d));
+}
+
+__global__ void __launch_bounds__(128)
+    retest_gexp_a_kernel(const double *x, int64_t ld, int64_t N, const int64_t *rows, int64_t nrows,
+                         double mag0, const double *sigma0, double *w_amp, double *w_del, double *mu0,
+                         double *partial)
+{
+    __shared__ double red[128];
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double dk = 0.0;
+    if (c < N) {
+        double s1 = 0.0;
+        for (int64_t j = 0; j < nrows; j++) s1 += ld_stream(x + rows[j] * ld + c);
+        const double n = (double)nrows, prec = sigma0 ? sigma0[c] : 1.0;
+        const double half = 0.5 * n * mag0 * mag0;
+        const double dp = prec * (mag0 * s1 - half), dm = prec * (-mag0 * s1 - half);
+        w_amp[c] = sigmoid(dp);
+        w_del[c] = sigmoid(dm);
+        if (mu0) mu0[c] = s1 / n;
+        dk = softplus(dp) - softplus(dm);
+    }
+    red[threadIdx.x] = dk;
+    __syncthreads();
+    for (int o = 64; o > 0; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[blockIdx.x] = red[0];
+}
+
+// D_total: sum of the partials of ALL ranks (device scalar), or NULL to sum this launch's partials
+__global__ void __launch_bounds__(128)
+    retest_gexp_b_kernel(int64_t N, const double *partial, int32_t npartial, const double *D_total,
+                         double *p_amp, double *p_del)
+{
+    __shared__ double Dsh;
+    if (threadIdx.x == 0) {
+        double D = 0.0;
+        if (D_total)
+            D = *D_total;
+        else
+            for (int32_t i = 0; i < npartial; i++) D += partial[i];
+        Dsh = D;
+    }
+    __syncthreads();
+    const double post1 = sigmoid(Dsh);
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < N) {
+        p_amp[c] *= post1;
+        p_del[c] *= (1.0 - post1);
+    }
+}
+
+__global__ void sum_partials_kernel(const double *partial, int32_t n, double *out)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double D = 0.0;
+        for (int32_t i = 0; i < n; i++) D += partial[i];
+        *out = D;
+    }
+}
+
+// Allele region retest, likelihood-ratio stand-in for calcAlleleCnvProb's JAGS snpModel
+// (R/HoneyBADGER.R:907-1042): P(deletion) per cell = sigmoid(sum over the region's SNPs of
+// log dbinom(r, n, pd) - log dbinom(r, n, pn)) with equal priors; the binomial coefficient cancels.
+__global__ void __launch_bounds__(128)
+    retest_allele_kernel(const int32_t *r, const int32_t *n, int64_t ld, int64_t N, const int64_t *rows,
+                         int64_t nrows, double lr_hit, double lr_miss, double *p_del)
+{
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= N) return;
+    int64_t sr = 0, sn = 0; // the log-ratio is linear in the counts: integer sums, exact
+    for (int64_t j = 0; j < nrows; j++) {
+        const int64_t o = rows[j] * ld + c;
+        sr += ld_stream(r + o);
+        sn += ld_stream(n + o);
+    }
+    p_del[c] = sigmoid((double)sr * lr_hit + (double)(sn - sr) * lr_miss);
+}
+
+cudaError_t launch_retest_allele(const int32_t *r, const int32_t *n, int64_t ld, int64_t N,
+                                 const int64_t *rows, int64_t nrows, double pd, double pn, double *p_del,
+                                 cudaStream_t st)
+{
+    retest_allele_kernel<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(
+        r, n, ld, N, rows, nrows, log(pd) - log(pn), log(1 - pd) - log(1 - pn), p_del);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_retest_gexp_a(const double *x, int64_t ld, int64_t N, const int64_t *rows,
+                                 int64_t nrows, double mag0, const double *sigma0, double *w_amp,
+                                 double *w_del, double *mu0, double *partial, double *D_local,
+                                 cudaStream_t st)
+{
+    const unsigned nb = (unsigned)((N + 127) / 128);
+    retest_gexp_a_kernel<<<nb, 128, 0, st>>>(x, ld, N, rows, nrows, mag0, sigma0, w_amp, w_del, mu0, partial);
+    if (D_local) sum_partials_kernel<<<1, 32, 0, st>>>(partial, (int32_t)nb, D_local);
+    return cudaGetLastError();
+}
+cudaError_t launch_retest_gexp_b(int64_t N, const double *partial, const double *D_total, double *p_amp,
+                                 double *p_del, cudaStream_t st)
+{
+    const unsigned nb = (unsigned)((N + 127) / 128);
+    retest_gexp_b_kernel<<<nb, 128, 0, st>>>(N, partial, (int32_t)nb, D_total, p_amp, p_del);
+    return cudaGetLastError();
+}
+
+// =====================================================================================
 // Pooled statistics of cell groups (R/HoneyBADGER.R:1141, :1149, :1404-1405)
 // =====================================================================================
 // Pooled expression observation, R `mean` semantics (summary.c real_mean: two passes in LDOUBLE, x87

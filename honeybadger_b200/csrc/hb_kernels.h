@@ -31,6 +31,15 @@ cudaError_t launch_transpose_f64_back(const double *src, int64_t ld, int64_t G, 
                                       double *dst, cudaStream_t st);
 cudaError_t launch_tile(const void *src, int64_t ld, int64_t T, int64_t B, int elem, void *dst,
                         bool to_tiled, cudaStream_t st);
+cudaError_t launch_retest_allele(const int32_t *r, const int32_t *n, int64_t ld, int64_t N,
+                                 const int64_t *rows, int64_t nrows, double pd, double pn, double *p_del,
+                                 cudaStream_t st);
+cudaError_t launch_retest_gexp_a(const double *x, int64_t ld, int64_t N, const int64_t *rows,
+                                 int64_t nrows, double mag0, const double *sigma0, double *w_amp,
+                                 double *w_del, double *mu0, double *partial, double *D_local,
+                                 cudaStream_t st);
+cudaError_t launch_retest_gexp_b(int64_t N, const double *partial, const double *D_total, double *p_amp,
+                                 double *p_del, cudaStream_t st);
 cudaError_t launch_pool_mean(const double *x, int64_t ld, int64_t G, int64_t N,
                              const uint8_t *member, const int32_t *gsize, int32_t K, double *out,
                              void *scratch /* 2*K*G 16-byte records */, cudaStream_t st);

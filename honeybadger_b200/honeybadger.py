@@ -125,39 +125,49 @@ def ward_groups(mat_smooth: np.ndarray, heights) -> list:
 
 def retest_gexp_closed_form(gexp_rows, mag0, sigma0=None):
     """(P(amp), P(del)) per cell for one candidate region: the exact marginal posterior of
-    inst/bug/expressionModel.bug.  JAGS' dnorm takes a PRECISION and the reference
-    passes sigma0 there (expressionModel.bug:8) — kept.  torch ops on the device; statistical
-    stand-in for the MCMC of calcGexpCnvProb (R/HoneyBADGER.R:374-470), not parity-pinned."""
+    inst/bug/expressionModel.bug, computed by libhb_b200's hb_retest_gexp_dev on the
+    device.  JAGS' dnorm takes a PRECISION and the reference passes sigma0 there
+    (expressionModel.bug:8) — kept.  Deterministic stand-in for the MCMC of calcGexpCnvProb
+    (R/HoneyBADGER.R:374-470); agrees with it statistically, not bit for bit.
+    gexp_rows: [genes of the region, cells] (CUDA fp64 tensor, or anything numpy can read)."""
     import torch
     x = gexp_rows if torch.is_tensor(gexp_rows) else \
-        torch.as_tensor(np.asarray(gexp_rows, dtype=np.float64), device="cuda")
-    n = x.shape[1]
-    if sigma0 is None:
-        sigma0 = torch.ones(n, dtype=torch.float64, device=x.device)
-    prec = torch.as_tensor(sigma0, dtype=torch.float64, device=x.device)
-
-    def ll(mu):
-        return (0.5 * torch.log(prec / (2 * np.pi)) - 0.5 * prec * (x - mu) ** 2).sum(0)
-
-    l0, lp, lm = ll(0.0), ll(mag0), ll(-mag0)
-    lse = torch.logaddexp
-    Lamp, Ldel = lse(l0, lp) + np.log(0.5), lse(l0, lm) + np.log(0.5)
-    post_dd1 = torch.sigmoid(Lamp.sum() - Ldel.sum())
-    w_amp = torch.exp(lp + np.log(0.5) - Lamp)
-    w_del = torch.exp(lm + np.log(0.5) - Ldel)
-    return (post_dd1 * w_amp).cpu().numpy(), ((1 - post_dd1) * w_del).cpu().numpy()
+        torch.as_tensor(np.ascontiguousarray(gexp_rows, dtype=np.float64), device="cuda")
+    if x.stride(1) != 1:
+        x = x.contiguous()
+    n, N = x.shape
+    rows = torch.arange(n, dtype=torch.int64, device=x.device)
+    prec = None if sigma0 is None else torch.as_tensor(sigma0, dtype=torch.float64, device=x.device).contiguous()
+    pa = torch.empty(N, dtype=torch.float64, device=x.device)
+    pd_ = torch.empty(N, dtype=torch.float64, device=x.device)
+    _lib.check(_lib.load().hb_retest_gexp_dev(
+        x.data_ptr(), x.stride(0), n, N, rows.data_ptr(), n, float(mag0),
+        None if prec is None else prec.data_ptr(), pa.data_ptr(), pd_.data_ptr(), None, None, None, 0,
+        _stream()))
+    return pa.cpu().numpy(), pd_.cpu().numpy()
 
 
 def retest_allele_lr(r_rows, n_rows, pd_=0.1, pn=0.45):
     """P(deletion) per cell for one candidate region from the binomial likelihood ratio pooled over
-    the region's SNPs (equal priors).  Stand-in for calcAlleleCnvProb's JAGS snpModel
-    (R/HoneyBADGER.R:907-1042), not parity-pinned."""
+    the region's SNPs (equal priors), libhb_b200's hb_retest_allele_lr_dev.  Stand-in for
+    calcAlleleCnvProb's JAGS snpModel (R/HoneyBADGER.R:907-1042), not parity-pinned."""
     import torch
-    r = (r_rows if torch.is_tensor(r_rows) else torch.as_tensor(np.asarray(r_rows), device="cuda")).double()
-    n = (n_rows if torch.is_tensor(n_rows) else torch.as_tensor(np.asarray(n_rows), device="cuda")).double()
-    ld = (r * np.log(pd_) + (n - r) * np.log(1 - pd_)).sum(0)
-    ln = (r * np.log(pn) + (n - r) * np.log(1 - pn)).sum(0)
-    return torch.sigmoid(ld - ln).cpu().numpy()
+
+    def dev_i32(a):
+        t = a if torch.is_tensor(a) else torch.as_tensor(np.ascontiguousarray(np.rint(a), dtype=np.int32),
+                                                          device="cuda")
+        return t if t.stride(1) == 1 else t.contiguous()
+
+    r, n = dev_i32(r_rows), dev_i32(n_rows)
+    if r.stride(0) != n.stride(0):
+        r, n = r.contiguous(), n.contiguous()
+    m, N = r.shape
+    rows = torch.arange(m, dtype=torch.int64, device=r.device)
+    out = torch.empty(N, dtype=torch.float64, device=r.device)
+    _lib.check(_lib.load().hb_retest_allele_lr_dev(r.data_ptr(), n.data_ptr(), r.stride(0), m, N,
+                                                   rows.data_ptr(), m, float(pd_), float(pn),
+                                                   out.data_ptr(), _stream()))
+    return out.cpu().numpy()
 
 
 # --------------------------------------------------------------------------- vote -> runs -> trim

@@ -175,6 +175,26 @@ int hb_pooled_sd_dev(const double *pooled /* device [K][G] */, int64_t G, int32_
 int hb_pool_count_pos_dev(const int32_t *v, int64_t ld, int64_t G, int64_t N,
                           const uint8_t *member, int32_t K, int32_t *out, void *stream);
 
+/* Deterministic retest of one candidate region for the expression model: the exact marginal posterior
+ * of inst/bug/expressionModel.bug that HoneyBADGER$calcGexpCnvProb
+ * (R/HoneyBADGER.R:374-470, called from :1220) estimates by JAGS sampling — statistical stand-in for
+ * the MCMC, not bit parity.  x is the resident gene-major matrix, rows[nrows] (device) the region's
+ * gene rows, sigma0[N] (device or NULL = 1) the per-cell dnorm PRECISION exactly as the reference
+ * passes it (expressionModel.bug:8), mag0 the deviation.  Outputs per cell (device): p_amp =
+ * mean(S dd), p_del = mean(S (1-dd)), mu0 = column mean of the region (or NULL).
+ * phase 0: everything on one GPU.  Cells sharded over ranks: phase 1 computes the per-cell weights
+ * and this rank's evidence D_local (device scalar); all-reduce D over the ranks; phase 2 applies
+ * the shared direction posterior from D_total (device scalar). */
+int hb_retest_gexp_dev(const double *x, int64_t ld, int64_t G, int64_t N, const int64_t *rows,
+                       int64_t nrows, double mag0, const double *sigma0, double *p_amp, double *p_del,
+                       double *mu0, double *D_local, const double *D_total, int32_t phase, void *stream);
+
+/* Allele counterpart (stand-in for the JAGS snpModel of calcAlleleCnvProb, R/HoneyBADGER.R:907-1042):
+ * P(deletion) per cell from the binomial likelihood ratio pd vs pn summed over the region's SNPs. */
+int hb_retest_allele_lr_dev(const int32_t *r_maf, const int32_t *n_sc, int64_t ld, int64_t G, int64_t N,
+                            const int64_t *rows, int64_t nrows, double pd, double pn, double *p_del,
+                            void *stream);
+
 /* One recursion round of the split-and-retest driver on DEVICE-RESIDENT matrices (gene-major,
  * uploaded once): `member` [K][N] (0/1, host) names the K candidate cell sets of the round, the
  * small results come back to host buffers: y [K][G] (1-based states), pooled vectors and their sd.

@@ -260,3 +260,22 @@ def pool_count_pos(mat_gn, cols):
     out = np.zeros(G, dtype=np.int32)
     lib().hbo_pool_count_pos(m.ctypes.data_as(C.c_void_p), G, _p(cols), cols.size, _p(out))
     return out
+
+
+def retest_gexp(x_rows, mag0, sigma0=None):
+    """Closed-form posterior of inst/bug/expressionModel.bug, plain numpy, written
+    from the likelihoods (not from the kernel's difference form): returns (P(amp), P(del)) per cell.
+    x_rows: [genes of the region, cells]; sigma0: per-cell dnorm PRECISION as the reference passes it."""
+    x = np.asarray(x_rows, dtype=np.float64)
+    n, N = x.shape
+    prec = np.ones(N) if sigma0 is None else np.asarray(sigma0, dtype=np.float64)
+
+    def ll(mu):
+        return (0.5 * np.log(prec / (2 * np.pi)) - 0.5 * prec * (x - mu) ** 2).sum(0)
+
+    l0, lp, lm = ll(0.0), ll(mag0), ll(-mag0)
+    La = np.logaddexp(l0, lp) + np.log(0.5)
+    Ld = np.logaddexp(l0, lm) + np.log(0.5)
+    D = La.sum() - Ld.sum()
+    post1 = 1.0 / (1.0 + np.exp(-D)) if D >= 0 else np.exp(D) / (1.0 + np.exp(D))
+    return post1 * np.exp(lp + np.log(0.5) - La), (1 - post1) * np.exp(lm + np.log(0.5) - Ld)

@@ -188,3 +188,39 @@ def test_pool_mean_relay_equals_single_pass(oracle):
     assert torch.equal(relay, full)
     for k in (0, 3, 6):
         assert (relay[k].cpu().numpy() == oracle.pool_mean(x, np.nonzero(member[k])[0])).all()
+
+
+def test_retest_gexp_closed_form_vs_oracle(oracle):
+    """hb_retest_gexp_dev (exact marginal of expressionModel.bug) vs the numpy restatement, with and
+    without per-cell precisions, on a region carried by a third of the cells."""
+    from honeybadger_b200 import honeybadger as hb
+    rng = np.random.default_rng(17)
+    n, N, m = 60, 500, 0.8
+    x = rng.standard_normal((n, N)) * 1.1
+    x[:, : N // 3] += m
+    for sigma0 in (None, rng.uniform(0.5, 1.5, N)):
+        pa, pd_ = hb.retest_gexp_closed_form(x, m, sigma0)
+        ra, rd = oracle.retest_gexp(x, m, sigma0)
+        assert np.abs(pa - ra).max() < 1e-12 and np.abs(pd_ - rd).max() < 1e-12
+        assert pa[: N // 3].mean() > 0.9 and pa[N // 3:].mean() < 0.1 and pd_.max() < 1e-6
+    # deletion direction, weak evidence: probabilities stay proper
+    y = rng.standard_normal((5, 40)) * 2.0
+    y[:, :10] -= 0.4
+    pa, pd_ = hb.retest_gexp_closed_form(y, 0.4)
+    ra, rd = oracle.retest_gexp(y, 0.4)
+    assert np.abs(pa - ra).max() < 1e-12 and np.abs(pd_ - rd).max() < 1e-12
+    assert ((pa + pd_) <= 1 + 1e-12).all() and (pa >= 0).all() and (pd_ >= 0).all()
+
+
+def test_retest_allele_lr_vs_numpy():
+    from honeybadger_b200 import honeybadger as hb
+    rng = np.random.default_rng(19)
+    n = np.where(rng.random((80, 300)) < 0.3, rng.integers(1, 9, (80, 300)), 0)
+    p = np.full(300, 0.45)
+    p[:90] = 0.1
+    r = rng.binomial(n, p)
+    got = hb.retest_allele_lr(r, n, 0.1, 0.45)
+    llr = (r * np.log(0.1 / 0.45) + (n - r) * np.log(0.9 / 0.55)).sum(0)
+    ref = 1 / (1 + np.exp(-llr))
+    assert np.abs(got - ref).max() < 1e-12
+    assert got[:90].mean() > 0.9 and got[90:].mean() < 0.1
