@@ -223,6 +223,19 @@ def run_reference(args, wl, kind):
     print(json.dumps(line), flush=True)
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this rank to the CPUs NVML reports as local to its GPU, so that the pinned host buffers of
+    the e2e leg are first-touched on the GPU's NUMA node (matters from 2 ranks up)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return None
+
+
 # ----------------------------------------------------------------------------- GPU arm
 def main():
     ap = argparse.ArgumentParser()
@@ -259,6 +272,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa_node(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     _lib.load()
@@ -338,6 +352,10 @@ def main():
             "kernel": "norm3_fast_kernel<VIT,FB>" if kind == "expr" else "binom2_fast_kernel<VIT,FB>"}
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
+        try:  # the CPU arm gets every host core again
+            os.sched_setaffinity(0, range(os.cpu_count() or 1))
+        except Exception:
+            pass
         cpu, _, _ = cpu_rate(kind, wl)
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -419,7 +437,7 @@ def run_e2e(kind, wl, d, args, world, dev, hmm, dist):
             "api": "hb_hmm_norm_host" if kind == "expr" else "hb_hmm_binom_host",
             "host_buffers": "pinned, R column-major layout; one call per window of %d cells, each call "
                             "pipelined internally (upload | layout+chains | download on three streams)" % batch,
-            "steps": args.e2e_steps}
+            "steps": args.e2e_steps, "cpus_bound_to_gpu_numa_node": len(os.sched_getaffinity(0))}
 
 
 if __name__ == "__main__":
