@@ -249,6 +249,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
+    ap.add_argument("--no-allele", action="store_true",
+                    help="skip the extra device-resident allele measurement reported under \"allele\"")
     args = ap.parse_args()
     kind = args.workload
     wl = dict(WORKLOADS[kind])
@@ -343,6 +345,18 @@ def main():
         except Exception as exc:  # report, never fake
             e2e = {"value": None, "unit": UNIT, "error": repr(exc)[:200]}
 
+    # ---------------- the other half of C4 (10k cells x 200k SNPs, 2-state binomial), device-resident
+    # only, a few steps: reported under "allele" beside the headline expression workload
+    allele = None
+    if kind == "expr" and not args.no_allele and not (args.cells or args.positions):
+        try:
+            del out, xt, step
+            d.pop("x", None)
+            torch.cuda.empty_cache()
+            allele = run_allele_extra(cells, rank, dev, hmm, world, dist if world > 1 else None)
+        except Exception as exc:
+            allele = {"value": None, "error": repr(exc)[:200]}
+
     peak, peak_src = measured_peak()
     mean_ms = float(np.mean(per_launch_ms))
     achieved = steps_per_pass * wl["bytes_per_step"] / (mean_ms * 1e-3) / 1e9
@@ -368,9 +382,48 @@ def main():
                            "layout": "warp-tiled [tile of 32 cells][position][lane] (hb_tile_dev), fp64 / int32"},
                 "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
                 "gpu_launches": launches_per_step * args.steps}
+        if allele is not None:
+            line["allele"] = allele
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_allele_extra(cells, rank, dev, hmm, world, dist, steps=5):
+    """Device-resident throughput of the allele half of C4 on the same GPU(s): max over ranks."""
+    import torch
+    wl = WORKLOADS["allele"]
+    positions = wl["positions"]
+    d = device_inputs("allele", cells, positions, seed=300 + rank, dev=dev)
+    Pi2 = hmm.sym_Pi(2, 1e-6)
+    rt, nt = hmm.tile_rows(d["r"]), hmm.tile_rows(d["n"])
+    del d["r"], d["n"]
+    torch.cuda.empty_cache()
+    out = hmm.hmm_binom_tiled_dev(rt, nt, cells, [0.1, 0.45], Pi2, [0.0, 1.0], seg_off=d["seg"])
+    for _ in range(3):
+        hmm.hmm_binom_tiled_dev(rt, nt, cells, [0.1, 0.45], Pi2, [0.0, 1.0], seg_off=d["seg"], out=out)
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        hmm.hmm_binom_tiled_dev(rt, nt, cells, [0.1, 0.45], Pi2, [0.0, 1.0], seg_off=d["seg"], out=out)
+    e1.record()
+    torch.cuda.synchronize()
+    hmm.status_dev()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / steps
+    val = world * cells * positions / (ms * 1e-3)
+    peak, _ = measured_peak()
+    ach = cells * positions * wl["bytes_per_step"] / (ms * 1e-3) / 1e9
+    return {"workload": wl["name"], "value": val, "unit": UNIT, "ms_per_step": ms, "steps": steps,
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                         "traffic": ncu_traffic("allele"), "algorithmic_bytes_per_step": wl["bytes_per_step"],
+                         "kernel": "binom2_fast_kernel<VIT,FB>"},
+            "general_kernel_rerun": hmm.binom2_general_rerun()}
 
 
 def run_e2e(kind, wl, d, args, world, dev, hmm, dist):
