@@ -43,9 +43,10 @@ WORKLOADS = {
                       "3-state Gaussian, fp64, Viterbi + posteriors",
                  cells=10000, positions=20000, nseg=22, S=3, bytes_per_step=33),
     # allele half: 10k cells x 200k het SNPs per GPU
+    # resident input: one packed word (n << 16) | x per position -> 4 + 1 + 16 algorithmic bytes / step
     "allele": dict(name="C4-allele: 10k cells x 200k SNPs per GPU, 22 chromosome segments, per-cell "
-                        "chains, 2-state binomial, Viterbi + posteriors",
-                   cells=10000, positions=200000, nseg=22, S=2, bytes_per_step=25),
+                        "chains, 2-state binomial, packed 16-bit counts, Viterbi + posteriors",
+                   cells=10000, positions=200000, nseg=22, S=2, bytes_per_step=21),
 }
 
 
@@ -297,13 +298,13 @@ def main():
         launches_per_step = 2  # sd_prep_kernel + norm3_fast_kernel
         in_bytes = d["x"].numel() * 8
     else:
-        rt, nt = hmm.tile_rows(d["r"]), hmm.tile_rows(d["n"])
-        out = hmm.hmm_binom_tiled_dev(rt, nt, cells, prob, Pi2, delta2, seg_off=seg)
+        xn = hmm.pack_counts(hmm.tile_rows(d["r"]), hmm.tile_rows(d["n"]))
+        out = hmm.hmm_binom_tiled_dev(xn, None, cells, prob, Pi2, delta2, seg_off=seg)
 
         def step():
-            hmm.hmm_binom_tiled_dev(rt, nt, cells, prob, Pi2, delta2, seg_off=seg, out=out)
+            hmm.hmm_binom_tiled_dev(xn, None, cells, prob, Pi2, delta2, seg_off=seg, out=out)
         launches_per_step = 2  # binom2_fast_kernel + the gated general kernel (exits at once)
-        in_bytes = d["r"].numel() * 8
+        in_bytes = d["r"].numel() * 4
     hmm.status_dev()
 
     def barrier():
@@ -396,19 +397,19 @@ def run_allele_extra(cells, rank, dev, hmm, world, dist, steps=5):
     positions = wl["positions"]
     d = device_inputs("allele", cells, positions, seed=300 + rank, dev=dev)
     Pi2 = hmm.sym_Pi(2, 1e-6)
-    rt, nt = hmm.tile_rows(d["r"]), hmm.tile_rows(d["n"])
+    xn = hmm.pack_counts(hmm.tile_rows(d["r"]), hmm.tile_rows(d["n"]))
     del d["r"], d["n"]
     torch.cuda.empty_cache()
-    out = hmm.hmm_binom_tiled_dev(rt, nt, cells, [0.1, 0.45], Pi2, [0.0, 1.0], seg_off=d["seg"])
+    out = hmm.hmm_binom_tiled_dev(xn, None, cells, [0.1, 0.45], Pi2, [0.0, 1.0], seg_off=d["seg"])
     for _ in range(3):
-        hmm.hmm_binom_tiled_dev(rt, nt, cells, [0.1, 0.45], Pi2, [0.0, 1.0], seg_off=d["seg"], out=out)
+        hmm.hmm_binom_tiled_dev(xn, None, cells, [0.1, 0.45], Pi2, [0.0, 1.0], seg_off=d["seg"], out=out)
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
-        hmm.hmm_binom_tiled_dev(rt, nt, cells, [0.1, 0.45], Pi2, [0.0, 1.0], seg_off=d["seg"], out=out)
+        hmm.hmm_binom_tiled_dev(xn, None, cells, [0.1, 0.45], Pi2, [0.0, 1.0], seg_off=d["seg"], out=out)
     e1.record()
     torch.cuda.synchronize()
     hmm.status_dev()

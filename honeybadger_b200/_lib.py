@@ -53,6 +53,8 @@ SIGNATURES = {
                                _p, _i64, _p, _p]),
     "hb_hmm_norm_tiled_dev": (_i32, [_p, _i64, _i64, _p, _i32, _p, _p, _i32, _p, _p, _i32, _p, _p, _p, _p]),
     "hb_hmm_binom_tiled_dev": (_i32, [_p, _p, _i64, _i64, _p, _i32, _p, _d, _p, _p, _i32, _p, _p, _p, _p]),
+    "hb_hmm_binom_packed_tiled_dev": (_i32, [_p, _i64, _i64, _p, _i32, _p, _d, _p, _p, _i32, _p, _p, _p, _p]),
+    "hb_pack_counts_dev": (_i32, [_p, _p, _i64, _p, _p]),
     "hb_tile_dev": (_i32, [_p, _i64, _i64, _i64, _i32, _p, _p]),
     "hb_untile_dev": (_i32, [_p, _i64, _i64, _i32, _p, _i64, _p]),
     "hb_hmm_binom_host": (_i32, [_p, _p, _i64, _i64, _p, _i32, _p, _d, _p, _p, _i32, _p, _p, _p]),

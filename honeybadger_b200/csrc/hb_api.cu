@@ -358,12 +358,12 @@ int binom2_run(Workspace *ws, const int32_t *x, const int32_t *n, int64_t ld, in
                const int64_t *seg_off, int32_t nseg, const double *prob, double rho,
                const double *Pi, const double *delta, int32_t flags, uint8_t *y, int64_t ldy,
                double *gamma, int64_t ldg, double *ll, cudaStream_t st, bool reset_status = true,
-               bool pooled = false, bool tiled = false)
+               bool pooled = false, bool tiled = false, bool packed = false)
 {
     if (T < 1 || B < 1 || (!tiled && ld < B))
         return fail(HB_ERR_ARG, "bad shape T=%lld B=%lld ld=%lld", (long long)T, (long long)B, (long long)ld);
     const int64_t Bp = tiled ? (B + 31) / 32 * 32 : B;
-    if (!x || !n || !prob || !Pi || !delta) return fail(HB_ERR_ARG, "missing argument");
+    if (!x || (!n && !packed) || !prob || !Pi || !delta) return fail(HB_ERR_ARG, "missing argument");
     if (!all_finite(prob, 2) || !all_finite(Pi, 4) || !all_finite(delta, 2) || !(rho >= 0) ||
         !(rho < 1))
         return fail(HB_ERR_ARG, "bad HMM parameter");
@@ -403,6 +403,7 @@ int binom2_run(Workspace *ws, const int32_t *x, const int32_t *n, int64_t ld, in
     a.T = T;
     a.B = B;
     a.tiled = tiled ? 1 : 0;
+    a.packed = packed ? 1 : 0;
     a.gplane = tiled ? T * Bp : T * ldg;
     a.nchunks = ws->nchunks;
     a.nseg = nseg;
@@ -753,6 +754,36 @@ int hb_hmm_binom_tiled_dev(const int32_t *x, const int32_t *size, int64_t T, int
     HBTRY(cur_ws(&ws));
     return binom2_run(ws, x, size, 32, T, B, seg_off, nseg, prob, rho, Pi, delta, flags, y, 32, gamma,
                       32, ll, (cudaStream_t)stream, true, false, true);
+}
+
+int hb_hmm_binom_packed_tiled_dev(const uint32_t *xn, int64_t T, int64_t B, const int64_t *seg_off,
+                                  int32_t nseg, const double *prob, double rho, const double *Pi,
+                                  const double *delta, int32_t flags, uint8_t *y, double *gamma,
+                                  double *ll, void *stream)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    Workspace *ws;
+    HBTRY(cur_ws(&ws));
+    return binom2_run(ws, (const int32_t *)xn, nullptr, 32, T, B, seg_off, nseg, prob, rho, Pi, delta, flags,
+                      y, 32, gamma, 32, ll, (cudaStream_t)stream, true, false, true, true);
+}
+
+int hb_pack_counts_dev(const int32_t *x, const int32_t *size, int64_t count, uint32_t *out, void *stream)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    Workspace *ws;
+    HBTRY(cur_ws(&ws));
+    if (!x || !size || !out || count < 1) return fail(HB_ERR_ARG, "bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    HBTRY(ws->status.ensure(4 * sizeof(int32_t)));
+    int32_t *flag = ws->status.as<int32_t>() + 3;
+    CU(cudaMemsetAsync(flag, 0, sizeof(int32_t), st));
+    CU(hb::launch_pack_counts(x, size, count, out, flag, st));
+    int32_t h = 0;
+    CU(cudaMemcpyAsync(&h, flag, sizeof h, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (h) return fail(HB_ERR_ARG, "a count does not fit 16 bits: use the two-plane entry points");
+    return HB_OK;
 }
 
 int hb_hmm_binom_host(const int32_t *x, const int32_t *size, int64_t T, int64_t B,

@@ -53,6 +53,7 @@ struct Binom2Args {
     const int32_t *x, *n; // x[t*ld+b] successes, n[t*ld+b] trials
     int64_t ld, T, B;
     int32_t tiled; // as Norm3Args::tiled: warp-tiled layout of x, n, y, gamma planes and the scratch
+    int32_t packed; // 1: x holds both counts per position, (n << 16) | x (each < 65536); n is unused
     int64_t gplane, nchunks;
     const int64_t *seg_off, *chunk_off;
     const int32_t *seg_order;
@@ -262,6 +263,20 @@ HB_HD void binom2_bwd_step(const Binom2Const &c, Rel2 &b, double mr, int32_t er)
     rel2_norm(q0, 0, q1, b);
 }
 
+// counts of one position: separate planes, or one packed word
+HB_HD void load_counts(const Binom2Args &a, const int32_t *xp, const int32_t *np, int64_t o, int32_t &xv,
+                       int32_t &nv)
+{
+    const int32_t w = xp[o];
+    if (a.packed) {
+        xv = w & 0xffff;
+        nv = (int32_t)((uint32_t)w >> 16);
+    } else {
+        xv = w;
+        nv = np[o];
+    }
+}
+
 template <bool VIT, bool FB>
 HB_HD void binom2_chain(const Binom2Args &a, int32_t seg, int64_t b, double *sm, int32_t sms)
 {
@@ -273,7 +288,7 @@ HB_HD void binom2_chain(const Binom2Args &a, int32_t seg, int64_t b, double *sm,
     const int64_t cbase = a.chunk_off[seg];
     const int64_t ldx = lay_stride(a.tiled, a.ld), sB = lay_stride(a.tiled, a.B);
     const int32_t *xp = a.x + lay_off(a.tiled, a.T, a.ld, t0, b);
-    const int32_t *np = a.n + lay_off(a.tiled, a.T, a.ld, t0, b);
+    const int32_t *np = a.packed ? nullptr : a.n + lay_off(a.tiled, a.T, a.ld, t0, b);
     uint64_t *psi0 = a.psi + lay_off(a.tiled, a.nchunks, a.B, cbase, b);
     double *ckpt0 = a.ckpt + (a.tiled ? (((b >> 5) * a.nchunks + cbase) * 3 << 5) + (b & 31) : cbase * 3 * a.B + b);
 
@@ -297,8 +312,8 @@ HB_HD void binom2_chain(const Binom2Args &a, int32_t seg, int64_t b, double *sm,
             if (j < L) lbc[j] = plb[(int64_t)j * ldx];
             xc[j] = nc[j] = 0;
         } else {
-            xc[j] = (j < L) ? xp[(int64_t)j * ldx] : 0;
-            nc[j] = (j < L) ? np[(int64_t)j * ldx] : 0;
+            xc[j] = nc[j] = 0;
+            if (j < L) load_counts(a, xp, np, (int64_t)j * ldx, xc[j], nc[j]);
         }
     }
     for (int64_t ch = 0; ch < nch; ch++) {
@@ -312,8 +327,8 @@ HB_HD void binom2_chain(const Binom2Args &a, int32_t seg, int64_t b, double *sm,
                     if (inext + 4 * HB_CHUNK + j < L) prefetch_l2(plb + (inext + 4 * HB_CHUNK + j) * ldx);
                     xn[j] = nn[j] = 0;
                 } else {
-                    xn[j] = (inext + j < L) ? xp[(inext + j) * ldx] : 0;
-                    nn[j] = (inext + j < L) ? np[(inext + j) * ldx] : 0;
+                    xn[j] = nn[j] = 0;
+                    if (inext + j < L) load_counts(a, xp, np, (inext + j) * ldx, xn[j], nn[j]);
                 }
             }
         }
@@ -384,8 +399,8 @@ HB_HD void binom2_chain(const Binom2Args &a, int32_t seg, int64_t b, double *sm,
         const int64_t i0 = (nch - 1) * HB_CHUNK;
 #pragma unroll
         for (int j = 0; j < HB_CHUNK; j++) {
-            xc[j] = (i0 + j < L) ? xp[(i0 + j) * ldx] : 0;
-            nc[j] = (i0 + j < L) ? np[(i0 + j) * ldx] : 0;
+            xc[j] = nc[j] = 0;
+            if (i0 + j < L) load_counts(a, xp, np, (i0 + j) * ldx, xc[j], nc[j]);
         }
     }
     for (int64_t ch = nch - 1; ch >= 0; ch--) {
@@ -394,8 +409,8 @@ HB_HD void binom2_chain(const Binom2Args &a, int32_t seg, int64_t b, double *sm,
             const int64_t iprev = i0 - HB_CHUNK;
 #pragma unroll
             for (int j = 0; j < HB_CHUNK; j++) {
-                xn[j] = (iprev >= 0) ? xp[(iprev + j) * ldx] : 0;
-                nn[j] = (iprev >= 0) ? np[(iprev + j) * ldx] : 0;
+                xn[j] = nn[j] = 0;
+                if (iprev >= 0) load_counts(a, xp, np, (iprev + j) * ldx, xn[j], nn[j]);
             }
         }
         uint64_t pk = 0;

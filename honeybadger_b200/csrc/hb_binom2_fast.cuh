@@ -185,7 +185,21 @@ HB_HD void b2f_backward_one(const Binom2Const &c, B2fState &s, uint8_t *yp, doub
     }
 }
 
-template <bool VIT, bool FB, bool LL>
+// PK: the counts come packed, one word (n << 16) | x per position in a.x (one ring, one 4-byte
+// load per step and sweep instead of two).
+template <bool PK>
+HB_HD void b2f_unpack(int32_t w, int32_t n_sep, int32_t &xv, int32_t &nv)
+{
+    if (PK) {
+        xv = w & 0xffff;
+        nv = (int32_t)((uint32_t)w >> 16);
+    } else {
+        xv = w;
+        nv = n_sep;
+    }
+}
+
+template <bool VIT, bool FB, bool LL, bool PK>
 HB_HD void binom2_fast_chain(const Binom2Args &a, int32_t seg, int64_t b, const B2fSmem &m)
 {
     const Binom2Const &c = a.c;
@@ -198,7 +212,7 @@ HB_HD void binom2_fast_chain(const Binom2Args &a, int32_t seg, int64_t b, const 
     const int64_t ld = lay_stride(a.tiled, a.ld), sB = lay_stride(a.tiled, a.B);
     const int64_t sy = lay_stride(a.tiled, a.ldy), sg = lay_stride(a.tiled, a.ldg);
     const int32_t *xp = a.x + lay_off(a.tiled, a.T, a.ld, t0, b);
-    const int32_t *np = a.n + lay_off(a.tiled, a.T, a.ld, t0, b);
+    const int32_t *np = PK ? nullptr : a.n + lay_off(a.tiled, a.T, a.ld, t0, b);
     // back-pointers: 2 bits / step, one uint16 per chunk
     uint16_t *psi = reinterpret_cast<uint16_t *>(a.psi) + lay_off(a.tiled, a.nchunks, a.B, cbase, b);
     double *ckpt = a.ckpt + (a.tiled ? (((b >> 5) * a.nchunks + cbase) * 2 << 5) + (b & 31) : cbase * 2 * a.B + b);
@@ -222,15 +236,15 @@ HB_HD void binom2_fast_chain(const Binom2Args &a, int32_t seg, int64_t b, const 
 #pragma unroll
             for (int j = h * HB_HALF; j < (h + 1) * HB_HALF; j++) {
                 cpa4(ring, m.xs + j * m.st, xr0);
-                cpa4(ring, m.ns + j * m.st, nr0);
+                if (!PK) cpa4(ring, m.ns + j * m.st, nr0);
                 xr0 += ld;
-                nr0 += ld;
+                if (!PK) nr0 += ld;
             }
             cpa_commit(ring);
         }
     }
     {
-        const int32_t *xr = xp + (int64_t)HB_CHUNK * ld, *nr = np + (int64_t)HB_CHUNK * ld;
+        const int32_t *xr = xp + (int64_t)HB_CHUNK * ld, *nr = PK ? nullptr : np + (int64_t)HB_CHUNK * ld;
         uint16_t *pw = psi;
         double *ck = ckpt;
         for (int32_t ch = 0; ch < nfull; ch++) {
@@ -242,17 +256,18 @@ HB_HD void binom2_fast_chain(const Binom2Args &a, int32_t seg, int64_t b, const 
                 cpa_wait<1>(ring);
 #pragma unroll
                 for (int j = h * HB_HALF; j < (h + 1) * HB_HALF; j++) {
-                    const int32_t xv = m.xs[j * m.st], nv = m.ns[j * m.st];
+                    int32_t xv, nv;
+                    b2f_unpack<PK>(m.xs[j * m.st], PK ? 0 : m.ns[j * m.st], xv, nv);
                     if (more) {
                         cpa4(ring, m.xs + j * m.st, xr);
-                        cpa4(ring, m.ns + j * m.st, nr);
+                        if (!PK) cpa4(ring, m.ns + j * m.st, nr);
                     }
                     if (pf) {
                         prefetch_l2(xr + (int64_t)HB_B2F_PF_CHUNKS * HB_CHUNK * ld);
-                        prefetch_l2(nr + (int64_t)HB_B2F_PF_CHUNKS * HB_CHUNK * ld);
+                        if (!PK) prefetch_l2(nr + (int64_t)HB_B2F_PF_CHUNKS * HB_CHUNK * ld);
                     }
                     xr += ld;
-                    nr += ld;
+                    if (!PK) nr += ld;
                     b2f_forward_one<VIT, FB, LL>(a, m, s, xv, nv, j == 0 && ch == 0, pk, j);
                 }
                 cpa_commit(ring);
@@ -271,7 +286,9 @@ HB_HD void binom2_fast_chain(const Binom2Args &a, int32_t seg, int64_t b, const 
         uint32_t pk = 0;
         for (int j = 0; j < tail; j++) {
             const int64_t o = (int64_t)(nfull * HB_CHUNK + j) * ld;
-            b2f_forward_one<VIT, FB, LL>(a, m, s, xp[o], np[o], nfull == 0 && j == 0, pk, j);
+            int32_t xv, nv;
+            b2f_unpack<PK>(xp[o], PK ? 0 : np[o], xv, nv);
+            b2f_forward_one<VIT, FB, LL>(a, m, s, xv, nv, nfull == 0 && j == 0, pk, j);
         }
         if (VIT) psi[(int64_t)nfull * sB] = (uint16_t)pk;
     }
@@ -294,15 +311,15 @@ HB_HD void binom2_fast_chain(const Binom2Args &a, int32_t seg, int64_t b, const 
     }
     if (FB && nfull > 0) {
         const int32_t *xl = xp + (int64_t)(nfull - 1) * HB_CHUNK * ld;
-        const int32_t *nl = np + (int64_t)(nfull - 1) * HB_CHUNK * ld;
+        const int32_t *nl = PK ? nullptr : np + (int64_t)(nfull - 1) * HB_CHUNK * ld;
 #pragma unroll
         for (int h = 0; h < 2; h++) {
 #pragma unroll
             for (int j = h * HB_HALF; j < (h + 1) * HB_HALF; j++) {
                 cpa4(ring, m.xs + j * m.st, xl);
-                cpa4(ring, m.ns + j * m.st, nl);
+                if (!PK) cpa4(ring, m.ns + j * m.st, nl);
                 xl += ld;
-                nl += ld;
+                if (!PK) nl += ld;
             }
             cpa_commit(ring);
         }
@@ -329,7 +346,9 @@ HB_HD void binom2_fast_chain(const Binom2Args &a, int32_t seg, int64_t b, const 
             }
             for (int j = 0; j < tail; j++) {
                 const int64_t o = (int64_t)(nfull * HB_CHUNK + j) * ld;
-                b2f_replay_one(a, s, xp[o], np[o], nfull == 0 && j == 0, m, j);
+                int32_t xv, nv;
+                b2f_unpack<PK>(xp[o], PK ? 0 : np[o], xv, nv);
+                b2f_replay_one(a, s, xv, nv, nfull == 0 && j == 0, m, j);
             }
         }
         for (int j = tail - 1; j >= 0; j--) {
@@ -346,7 +365,7 @@ HB_HD void binom2_fast_chain(const Binom2Args &a, int32_t seg, int64_t b, const 
         double *g1 = g0 + plane;
         // refill pointers: the chunk before the one being replayed
         const int32_t *xr = xp + (int64_t)(nfull - 2) * HB_CHUNK * ld;
-        const int32_t *nr = np + (int64_t)(nfull - 2) * HB_CHUNK * ld;
+        const int32_t *nr = PK ? nullptr : np + (int64_t)(nfull - 2) * HB_CHUNK * ld;
         const uint16_t *pr = psi + (int64_t)(nfull - 2) * sB;
         const double *cr = ckpt + (int64_t)(nfull - 2) * 2 * sB;
         for (int32_t ch = nfull - 1; ch >= 0; ch--) {
@@ -380,23 +399,24 @@ HB_HD void binom2_fast_chain(const Binom2Args &a, int32_t seg, int64_t b, const 
                     cpa_wait<1>(ring);
 #pragma unroll
                     for (int j = h * HB_HALF; j < (h + 1) * HB_HALF; j++) {
-                        const int32_t xv = m.xs[j * m.st], nv = m.ns[j * m.st];
+                        int32_t xv, nv;
+                        b2f_unpack<PK>(m.xs[j * m.st], PK ? 0 : m.ns[j * m.st], xv, nv);
                         if (more) {
                             cpa4(ring, m.xs + j * m.st, xq);
-                            cpa4(ring, m.ns + j * m.st, nq);
+                            if (!PK) cpa4(ring, m.ns + j * m.st, nq);
                         }
                         if (pf) {
                             prefetch_l2(xq - (int64_t)HB_B2F_PF_CHUNKS * HB_CHUNK * ld);
-                            prefetch_l2(nq - (int64_t)HB_B2F_PF_CHUNKS * HB_CHUNK * ld);
+                            if (!PK) prefetch_l2(nq - (int64_t)HB_B2F_PF_CHUNKS * HB_CHUNK * ld);
                         }
                         xq += ld;
-                        nq += ld;
+                        if (!PK) nq += ld;
                         b2f_replay_one(a, s, xv, nv, j == 0 && ch == 0, m, j);
                     }
                     cpa_commit(ring);
                 }
                 xr -= (int64_t)HB_CHUNK * ld;
-                nr -= (int64_t)HB_CHUNK * ld;
+                if (!PK) nr -= (int64_t)HB_CHUNK * ld;
             }
 #pragma unroll
             for (int j = HB_CHUNK - 1; j >= 0; j--) {

@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(128)
 #ifndef HB_B2F_MINB
 #define HB_B2F_MINB 4
 #endif
-template <bool VIT, bool FB, bool LL>
+template <bool VIT, bool FB, bool LL, bool PK>
 __global__ void __launch_bounds__(HB_BLOCK, HB_B2F_MINB)
     binom2_fast_kernel(const __grid_constant__ Binom2Args a)
 {
@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(HB_BLOCK, HB_B2F_MINB)
     m.slb = slb;
     m.srho = srho;
     m.slut_n = slut_n;
-    binom2_fast_chain<VIT, FB, LL>(a, seg, b, m);
+    binom2_fast_chain<VIT, FB, LL, PK>(a, seg, b, m);
 }
 
 template <bool SYM>
@@ -193,24 +193,48 @@ cudaError_t launch_binom2_emit(const Binom2Args &a, double2 *pre_lb, cudaStream_
     return cudaGetLastError();
 }
 
-cudaError_t launch_binom2_fast(const Binom2Args &a, bool vit, bool fb, cudaStream_t st)
+template <bool PK>
+static cudaError_t launch_binom2_fast_t(const Binom2Args &a, bool vit, bool fb, cudaStream_t st)
 {
     const unsigned grid = (unsigned)((int64_t)a.nseg * a.nblk_per_seg);
     const size_t sm_fb = (size_t)HB_B2F_SLUT_BYTES + (size_t)HB_B2F_SMEM_BYTES_PER_THREAD * HB_BLOCK;
     const bool ll = a.ll != nullptr;
     if (vit && fb) {
         if (ll)
-            binom2_fast_kernel<true, true, true><<<grid, HB_BLOCK, sm_fb, st>>>(a);
+            binom2_fast_kernel<true, true, true, PK><<<grid, HB_BLOCK, sm_fb, st>>>(a);
         else
-            binom2_fast_kernel<true, true, false><<<grid, HB_BLOCK, sm_fb, st>>>(a);
+            binom2_fast_kernel<true, true, false, PK><<<grid, HB_BLOCK, sm_fb, st>>>(a);
     } else if (fb) {
         if (ll)
-            binom2_fast_kernel<false, true, true><<<grid, HB_BLOCK, sm_fb, st>>>(a);
+            binom2_fast_kernel<false, true, true, PK><<<grid, HB_BLOCK, sm_fb, st>>>(a);
         else
-            binom2_fast_kernel<false, true, false><<<grid, HB_BLOCK, sm_fb, st>>>(a);
+            binom2_fast_kernel<false, true, false, PK><<<grid, HB_BLOCK, sm_fb, st>>>(a);
     } else {
-        binom2_fast_kernel<true, false, false><<<grid, HB_BLOCK, sm_fb, st>>>(a);
+        binom2_fast_kernel<true, false, false, PK><<<grid, HB_BLOCK, sm_fb, st>>>(a);
     }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_binom2_fast(const Binom2Args &a, bool vit, bool fb, cudaStream_t st)
+{
+    return a.packed ? launch_binom2_fast_t<true>(a, vit, fb, st) : launch_binom2_fast_t<false>(a, vit, fb, st);
+}
+
+// (n << 16) | x per element; *overflow is set when a count does not fit 16 bits
+__global__ void pack_counts_kernel(const int32_t *x, const int32_t *n, int64_t count, uint32_t *out,
+                                   int32_t *overflow)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const int32_t xv = x[i], nv = n[i];
+    if ((uint32_t)xv > 65535u || (uint32_t)nv > 65535u) *overflow = 1;
+    out[i] = ((uint32_t)nv << 16) | ((uint32_t)xv & 0xffffu);
+}
+
+cudaError_t launch_pack_counts(const int32_t *x, const int32_t *n, int64_t count, uint32_t *out,
+                               int32_t *overflow, cudaStream_t st)
+{
+    pack_counts_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(x, n, count, out, overflow);
     return cudaGetLastError();
 }
 

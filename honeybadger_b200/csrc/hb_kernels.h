@@ -12,6 +12,8 @@ struct Binom2Args;
 
 cudaError_t launch_norm3(const Norm3Args &a, bool sym, bool vit, bool fb, cudaStream_t st);
 cudaError_t launch_norm3_fast(const Norm3Args &a, bool vit, bool fb, cudaStream_t st);
+cudaError_t launch_pack_counts(const int32_t *x, const int32_t *n, int64_t count, uint32_t *out,
+                               int32_t *overflow, cudaStream_t st);
 cudaError_t launch_binom2_emit(const Binom2Args &a, double2 *pre_lb, cudaStream_t st);
 cudaError_t launch_binom2_fast(const Binom2Args &a, bool vit, bool fb, cudaStream_t st);
 cudaError_t launch_binom2(const Binom2Args &a, bool vit, bool fb, cudaStream_t st);

@@ -295,15 +295,31 @@ def hmm_norm_tiled_dev(x, B, sd, mean, Pi, delta, seg_off=None, viterbi=True, ga
     return out
 
 
+def pack_counts(x, size):
+    """(size << 16) | x per element as an int32 tensor of the same shape (hb_pack_counts_dev); raises
+    if a count does not fit 16 bits.  x, size: contiguous int32 CUDA tensors in any (same) layout."""
+    import torch
+    if not (x.is_cuda and x.dtype == torch.int32 and x.is_contiguous() and size.is_contiguous()
+            and x.shape == size.shape and size.dtype == torch.int32):
+        raise ValueError("pack_counts needs two contiguous int32 CUDA tensors of the same shape")
+    out = torch.empty_like(x)
+    _lib.check(_lib.load().hb_pack_counts_dev(x.data_ptr(), size.data_ptr(), x.numel(), out.data_ptr(),
+                                              _stream()))
+    return out
+
+
 def hmm_binom_tiled_dev(x, size, B, prob, Pi, delta, seg_off=None, rho=0.0, viterbi=True, gamma=True,
                         ll=False, out=None):
-    """As hmm_binom_dev on the warp-tiled layout: x, size int32 [ntile, T, 32]."""
+    """As hmm_binom_dev on the warp-tiled layout: x, size int32 [ntile, T, 32]; size=None means x
+    holds PACKED counts (pack_counts of the tiled planes): one 4-byte word per position."""
     import torch
     lib = _lib.load()
     _check_tiled(x, torch.int32, "x")
-    _check_tiled(size, torch.int32, "size")
+    packed = size is None
+    if not packed:
+        _check_tiled(size, torch.int32, "size")
     ntile, T, _ = x.shape
-    if x.shape != size.shape or ntile != (B + 31) // 32:
+    if (not packed and x.shape != size.shape) or ntile != (B + 31) // 32:
         raise ValueError("x and size must be [ceil(B/32), T, 32]")
     seg = _seg(seg_off, T)
     nseg = seg.size - 1
@@ -317,10 +333,13 @@ def hmm_binom_tiled_dev(x, size, B, prob, Pi, delta, seg_off=None, rho=0.0, vite
     if ll and "ll" not in out:
         out["ll"] = torch.empty((nseg, B), dtype=torch.float64, device=x.device)
     y, g, l = out.get("y"), out.get("gamma"), out.get("ll")
-    rc = lib.hb_hmm_binom_tiled_dev(
-        x.data_ptr(), size.data_ptr(), T, B, _vp(seg), nseg, _vp(prob), float(rho), _vp(Pi),
-        _vp(delta), _flags(viterbi, gamma, ll), y.data_ptr() if viterbi else None,
-        g.data_ptr() if want_g else None, l.data_ptr() if ll else None, _stream())
+    tail = (T, B, _vp(seg), nseg, _vp(prob), float(rho), _vp(Pi), _vp(delta), _flags(viterbi, gamma, ll),
+            y.data_ptr() if viterbi else None, g.data_ptr() if want_g else None,
+            l.data_ptr() if ll else None, _stream())
+    if packed:
+        rc = lib.hb_hmm_binom_packed_tiled_dev(x.data_ptr(), *tail)
+    else:
+        rc = lib.hb_hmm_binom_tiled_dev(x.data_ptr(), size.data_ptr(), *tail)
     _lib.check(rc)
     return out
 

@@ -109,6 +109,14 @@ int hb_hmm_binom_tiled_dev(const int32_t *x, const int32_t *size, int64_t T, int
                            const int64_t *seg_off /* host */, int32_t nseg, const double *prob,
                            double rho, const double *Pi, const double *delta, int32_t flags,
                            uint8_t *y, double *gamma, double *ll, void *stream);
+/* Binomial chains on PACKED counts: one uint32 per position, (size << 16) | x, both < 65536
+ * (hb_pack_counts_dev packs two int32 planes elementwise — any layout — and returns HB_ERR_ARG if
+ * a count does not fit).  Halves the input bytes of the allele path: 4 B / position instead of 8. */
+int hb_pack_counts_dev(const int32_t *x, const int32_t *size, int64_t count, uint32_t *out, void *stream);
+int hb_hmm_binom_packed_tiled_dev(const uint32_t *xn, int64_t T, int64_t B, const int64_t *seg_off,
+                                  int32_t nseg, const double *prob, double rho, const double *Pi,
+                                  const double *delta, int32_t flags, uint8_t *y, double *gamma,
+                                  double *ll, void *stream);
 /* gene-major src[t*ld+b] -> tiled dst (elem = 1, 4 or 8 bytes), and back; device pointers */
 int hb_tile_dev(const void *src, int64_t ld, int64_t T, int64_t B, int32_t elem, void *dst, void *stream);
 int hb_untile_dev(const void *src, int64_t T, int64_t B, int32_t elem, void *dst, int64_t ld, void *stream);

@@ -67,6 +67,7 @@ def emul():
     L.emul_exp_pair.argtypes = [C.c_double, C.c_void_p, C.c_void_p]
     L.emul_norm3_fast.restype = C.c_int
     L.emul_set_tiled.argtypes = [C.c_int]
+    L.emul_set_packed.argtypes = [C.c_int]
     L.emul_binom2_fast.restype = C.c_int
     return L
 

@@ -54,6 +54,8 @@ static int64_t pad32(int64_t B) { return (B + 31) / 32 * 32; }
 extern "C" {
 
 void emul_set_tiled(int t) { g_tiled = t; }
+static int g_packed = 0; // 1: `x` holds (n << 16) | x words, `n` is ignored
+void emul_set_packed(int p) { g_packed = p; }
 
 // flags: 1 = Viterbi, 2 = gamma, 4 = ll ; returns status flag (1 = underflow)
 int emul_norm3(const double *x, int64_t ld, int64_t T, int64_t B, const int64_t *seg_off, int nseg,
@@ -294,15 +296,24 @@ int emul_binom2_fast(const int32_t *x, const int32_t *n, int64_t ld, int64_t T, 
     a.y = y; a.ldy = ld; a.gamma = gamma; a.ldg = ld; a.nchunks = sg.nchunks;
     a.tiled = g_tiled; a.gplane = g_tiled ? T * pad32(B) : T * ld; a.ll = (flags & 4) ? ll : nullptr;
     a.psi = psi.data(); a.ckpt = ckpt.data(); a.status = status; a.gate = status + 2;
+    a.packed = g_packed;
     const bool vit = flags & 1, fb = flags & 6, llon = flags & 4;
     for (int s = 0; s < nseg; s++)
         for (int64_t b = 0; b < B; b++) {
             int seg = sg.order[s];
-            if (vit && fb && llon) binom2_fast_chain<true, true, true>(a, seg, b, m);
-            else if (vit && fb) binom2_fast_chain<true, true, false>(a, seg, b, m);
-            else if (fb && llon) binom2_fast_chain<false, true, true>(a, seg, b, m);
-            else if (fb) binom2_fast_chain<false, true, false>(a, seg, b, m);
-            else binom2_fast_chain<true, false, false>(a, seg, b, m);
+            if (g_packed) {
+                if (vit && fb && llon) binom2_fast_chain<true, true, true, true>(a, seg, b, m);
+                else if (vit && fb) binom2_fast_chain<true, true, false, true>(a, seg, b, m);
+                else if (fb && llon) binom2_fast_chain<false, true, true, true>(a, seg, b, m);
+                else if (fb) binom2_fast_chain<false, true, false, true>(a, seg, b, m);
+                else binom2_fast_chain<true, false, false, true>(a, seg, b, m);
+            } else {
+                if (vit && fb && llon) binom2_fast_chain<true, true, true, false>(a, seg, b, m);
+                else if (vit && fb) binom2_fast_chain<true, true, false, false>(a, seg, b, m);
+                else if (fb && llon) binom2_fast_chain<false, true, true, false>(a, seg, b, m);
+                else if (fb) binom2_fast_chain<false, true, false, false>(a, seg, b, m);
+                else binom2_fast_chain<true, false, false, false>(a, seg, b, m);
+            }
         }
     if (gate_out) *gate_out = status[2];
     if (status[2]) {

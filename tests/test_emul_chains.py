@@ -354,3 +354,31 @@ def test_binom2_tiled_layout(emul, oracle, which):
     gu = np.stack([np_untile(g[k], B) for k in range(2)])
     assert np.abs(gu - go).max() < 1e-9
     assert np.allclose(ll, llo, rtol=1e-10, atol=1e-10)
+
+
+def test_binom2_packed_counts(emul, oracle):
+    """One (n << 16) | x word per position: same results as the two-plane form, lean and general
+    bodies (the general one behind the gate for pooled-scale counts up to 65535)."""
+    r, n, _, _ = synth.allele(1503, 12, seed=29, deep=0.002)
+    n[:, 3] = np.minimum(n[:, 3] * 300, 60000)         # deep column: raises the gate
+    r[:, 3] = np.minimum(r[:, 3] * 300, n[:, 3])
+    seg = np.array([0, 700, 1503], dtype=np.int64)
+    prob, Pi, delta = np.array([0.1, 0.45]), oracle.sym_Pi(2, 1e-6), np.array([0., 1.])
+    yo, go, llo, rc = oracle.fbv_binom_batch(r, n, seg, prob, Pi, delta)
+    xn = ((n.astype(np.uint32) << 16) | r.astype(np.uint32)).view(np.int32)
+    emul.emul_set_packed(1)
+    try:
+        st, y, g, ll, gate = run_binom2_fast(emul, xn, np.zeros_like(xn), seg, prob, Pi, delta, 3, 64)
+    finally:
+        emul.emul_set_packed(0)
+    assert st == 0 and rc == 0 and gate == 1
+    assert (y == yo).all()
+    keep = [b for b in range(12) if b != 3]   # (the linear-domain oracle underflows on the deep column)
+    assert np.abs(g[:, :, keep] - go[:, :, keep]).max() < 1e-9
+    emul.emul_set_packed(1)
+    try:
+        st, y2, g2, _, gate2 = run_binom2_fast(emul, np.ascontiguousarray(xn[:, keep]), np.zeros((1503, 11), np.int32),
+                                               seg, prob, Pi, delta, 3, 64)
+    finally:
+        emul.emul_set_packed(0)
+    assert gate2 == 0 and (y2 == yo[:, keep]).all() and np.abs(g2 - go[:, :, keep]).max() < 1e-9

@@ -250,3 +250,15 @@ def test_tiled_layout_matches_gene_major(oracle):
     assert torch.equal(ob["ll"], refb["ll"])
     yo, go, llo, rc = O.fbv_binom_batch(r_maf, n_sc, seg2, prob, Pi2, [0.0, 1.0])
     assert rc == 0 and (refb["y"].cpu().numpy() == yo).all()
+    # packed counts: one (n << 16) | x word per position, same bits out
+    xn = hmm.pack_counts(hmm.tile_rows(rd), hmm.tile_rows(nd))
+    op = hmm.hmm_binom_tiled_dev(xn, None, 205, prob, Pi2, [0.0, 1.0], seg_off=seg2, viterbi=True, gamma=True,
+                                 ll=True)
+    hmm.status_dev()
+    assert torch.equal(hmm.untile_rows(op["y"], 205), refb["y"])          # (padding lanes are not written)
+    assert torch.equal(hmm.untile_rows(op["gamma"], 205), refb["gamma"])
+    assert torch.equal(op["ll"], ob["ll"])
+    big = nd.clone()
+    big[5, 7] = 70000
+    with pytest.raises(Exception, match="16 bits"):
+        hmm.pack_counts(rd.contiguous(), big.contiguous())
