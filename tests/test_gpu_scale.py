@@ -104,3 +104,21 @@ def test_ragged_and_tiny_shapes(oracle):
         yo, go, llo, rc = oracle.fbv_norm_batch(x, s, mean, sd, Pi, delta)
         assert rc == 0 and (r["y"] == yo).all()
         assert np.abs(r["gamma"].transpose(2, 0, 1) - go).max() < 1e-9
+
+
+@pytest.mark.parametrize("T", [4096, 4097, 9000])
+def test_norm_long_single_chains_cross_the_kernel_switch(oracle, T):
+    """One concatenated chain per cell (the reference's shape): up to 4096 positions the
+    speculate-and-verify kernel runs, beyond that the literal one; both equal the oracle."""
+    from honeybadger_b200 import hmm
+    x, _, _ = synth.expression(T, 40, seed=T)
+    sd = np.array([oracle.r_sd(x[:, b]) for b in range(x.shape[1])])
+    Pi, delta, mean = hmm.sym_Pi(3, 1e-6), [0.0, 1.0, 0.0], [-synth.DEV, 0.0, synth.DEV]
+    seg = np.array([0, T], dtype=np.int64)
+    r = hmm.hmm_norm_host(x, mean, sd, Pi, delta, seg_off=seg, viterbi=True, gamma=True, ll=True)
+    nre = hmm.norm3_rerun_chains()
+    yo, go, llo, rc = oracle.fbv_norm_batch(x, seg, mean, sd, Pi, delta)
+    assert rc == 0 and (r["y"] == yo).all()
+    assert np.abs(r["gamma"].transpose(2, 0, 1) - go).max() < 1e-9
+    assert np.allclose(r["ll"].T, llo, rtol=1e-10, atol=0)
+    assert nre <= 40 and (T <= 4096 or nre == 0)
