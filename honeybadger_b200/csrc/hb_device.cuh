@@ -164,6 +164,68 @@ HB_HD void cpa_wait(AsyncRing4 &r)
 #endif
 }
 
+// ---------------------------------------------------------------- bulk (TMA) staging on the tiled layout
+// On the warp-tiled layout the rows a warp needs for one chunk are ONE contiguous 2 KB block, so one
+// lane moves them with a single cp.async.bulk (the TMA engine's non-tensor form) instead of 32 lanes
+// x 8 cp.async, completion tracked by an mbarrier per stage.  Two stages per warp: while chunk c is
+// consumed, chunk c+1 is in flight; chunk c+2 is requested as soon as the warp is done with c.
+struct BulkRing {
+    double *buf;   // this lane's view of the warp's staging area: element (stage s, row j) at buf[(s*CH + j)*32]
+    uint32_t par[2];
+#if defined(__CUDACC__)
+    uint32_t mbar[2], sbuf; // shared-space addresses: mbarriers, staging area of the warp (lane 0)
+    uint32_t wmask;
+    bool leader;
+#else
+    double hbuf[64];        // host emulation (g++ build): one lane, copies are immediate
+#endif
+};
+
+template <int CH>
+HB_HD void bulk_issue(BulkRing &r, int s, const double *lane_src /* this lane's element of the chunk's first row */)
+{
+#if defined(__CUDA_ARCH__)
+    if (r.leader) {
+        const uint32_t bytes = CH * 32 * 8;
+        const double *src = lane_src - (threadIdx.x & 31);
+        const uint32_t dst = r.sbuf + (uint32_t)s * bytes;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(r.mbar[s]), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(dst), "l"(src), "r"(bytes), "r"(r.mbar[s]) : "memory");
+    }
+#elif !defined(__CUDACC__)
+    for (int j = 0; j < CH; j++) r.hbuf[s * CH + j] = lane_src[(int64_t)j * 32];
+#endif
+}
+HB_HD void bulk_wait(BulkRing &r, int s)
+{
+#if defined(__CUDA_ARCH__)
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok) : "r"(r.mbar[s]), "r"(r.par[s]) : "memory");
+    }
+#endif
+    r.par[s] ^= 1u;
+}
+template <int CH>
+HB_HD double bulk_read(const BulkRing &r, int s, int j)
+{
+#if defined(__CUDACC__)
+    return r.buf[(s * CH + j) * 32];
+#else
+    return r.hbuf[s * CH + j];
+#endif
+}
+// every lane is done reading stage s (before the leader overwrites it)
+HB_HD void bulk_release(BulkRing &r)
+{
+#if defined(__CUDA_ARCH__)
+    __syncwarp(r.wmask);
+#endif
+}
+
 // ---------------------------------------------------------------- exact division by a chain constant
 // z = RN(d / b) given y = RN(1/b): Markstein's correction (q = d*y; r = d - b*q exactly by FMA;
 // q' = q + r*y) is correctly rounded for every d when y is the correctly rounded reciprocal

@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(HB_BLOCK, HB_NORM3_MINB)
 #ifndef HB_FAST_MINB
 #define HB_FAST_MINB 3
 #endif
-template <bool VIT, bool FB, bool LL>
+template <bool VIT, bool FB, bool LL, bool BULK>
 __global__ void __launch_bounds__(HB_BLOCK, HB_FAST_MINB)
     norm3_fast_kernel(const __grid_constant__ Norm3Args a)
 {
@@ -60,11 +60,29 @@ __global__ void __launch_bounds__(HB_BLOCK, HB_FAST_MINB)
     char *rest = reinterpret_cast<char *>(smem2 + 2 * HB_CHUNK * HB_BLOCK);
     m.e2 = reinterpret_cast<double *>(rest) + threadIdx.x;
     if (!HB_FAST_NOPHI1) rest += sizeof(double) * HB_CHUNK * HB_BLOCK;
-    m.xs = FB ? reinterpret_cast<double *>(rest) + threadIdx.x
-              : reinterpret_cast<double *>(smem2) + threadIdx.x;
-    if (!HB_FAST_XREG) rest += sizeof(double) * HB_CHUNK * HB_BLOCK;
     m.ph = reinterpret_cast<int32_t *>(rest) + threadIdx.x;
-    norm3_fast_chain<VIT, FB, LL>(a, seg, b, m);
+    rest += sizeof(int32_t) * HB_CHUNK * HB_BLOCK;
+    m.xs = reinterpret_cast<double *>(rest) + threadIdx.x; // cp.async ring (one chunk) ...
+    BulkRing br;
+    br.par[0] = br.par[1] = 0u;
+    if (BULK) { // ... or, per warp, two chunks of bulk staging followed by the block's mbarriers
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        double *stage = reinterpret_cast<double *>(rest) + (size_t)warp * 2 * HB_CHUNK * 32;
+        uint64_t *bars = reinterpret_cast<uint64_t *>(rest + sizeof(double) * 2 * HB_CHUNK * HB_BLOCK) + 2 * warp;
+        br.buf = stage + lane;
+        br.sbuf = (uint32_t)__cvta_generic_to_shared(stage);
+        br.mbar[0] = (uint32_t)__cvta_generic_to_shared(bars);
+        br.mbar[1] = br.mbar[0] + 8;
+        br.wmask = __activemask();
+        br.leader = lane == 0;
+        if (br.leader) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(br.mbar[0]) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(br.mbar[1]) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp(br.wmask);
+    }
+    norm3_fast_chain<VIT, FB, LL, BULK>(a, seg, b, m, br);
 }
 
 template <bool VIT, bool FB>
@@ -160,18 +178,27 @@ cudaError_t launch_norm3(const Norm3Args &a, bool sym, bool vit, bool fb, cudaSt
     return sym ? launch_norm3_t<true>(a, vit, fb, st) : launch_norm3_t<false>(a, vit, fb, st);
 }
 
-cudaError_t launch_norm3_fast(const Norm3Args &a, bool vit, bool fb, cudaStream_t st)
+#ifndef HB_FAST_BULK
+// 1: on the tiled layout stage x with cp.async.bulk (TMA) + one mbarrier per stage and warp instead of
+// the per-thread cp.async ring.  Works (bit-identical results) and removes ~13 instructions per step,
+// but measured SLOWER on B200 (2.01 vs 1.95 ms on the probe workload): the kernel sits on the memory
+// system's ceiling, not on its issue slots, and the per-chunk mbarrier wait + warp sync cost more than
+// the ring's wait_group.  Kept as a build option (tools/build_variant.sh bulk -DHB_FAST_BULK=1).
+#define HB_FAST_BULK 0
+#endif
+template <bool BULK>
+static cudaError_t launch_norm3_fast_t(const Norm3Args &a, bool vit, bool fb, cudaStream_t st)
 {
     const unsigned grid = (unsigned)((int64_t)a.nseg * a.nblk_per_seg);
-    const size_t sm_fb = (size_t)HB_FAST_SMEM_BYTES_PER_THREAD * HB_BLOCK;
-    const size_t sm_v = HB_FAST_XREG ? 0 : (size_t)HB_CHUNK * HB_BLOCK * sizeof(double);
+    const size_t sm_fb = BULK ? HB_FAST_BULK_SMEM_BYTES(HB_BLOCK) : (size_t)HB_FAST_SMEM_BYTES_PER_THREAD * HB_BLOCK;
+    const size_t sm_v = sm_fb; // (the Viterbi-only form uses the same carve-up; the parking area stays idle)
     // > 48 KB of dynamic shared memory: opt in (per device, cheap)
     const bool ll = a.ll != nullptr;
 #define HB_LAUNCH_FAST(V, F, L_, SM)                                                               \
     do {                                                                                          \
-        cudaFuncSetAttribute(norm3_fast_kernel<V, F, L_>,                                          \
+        cudaFuncSetAttribute(norm3_fast_kernel<V, F, L_, BULK>,                                    \
                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SM));             \
-        norm3_fast_kernel<V, F, L_><<<grid, HB_BLOCK, (SM), st>>>(a);                              \
+        norm3_fast_kernel<V, F, L_, BULK><<<grid, HB_BLOCK, (SM), st>>>(a);                        \
     } while (0)
     if (vit && fb) {
         if (ll) HB_LAUNCH_FAST(true, true, true, sm_fb);
@@ -184,6 +211,12 @@ cudaError_t launch_norm3_fast(const Norm3Args &a, bool vit, bool fb, cudaStream_
     }
 #undef HB_LAUNCH_FAST
     return cudaGetLastError();
+}
+
+cudaError_t launch_norm3_fast(const Norm3Args &a, bool vit, bool fb, cudaStream_t st)
+{
+    if (HB_FAST_BULK && a.tiled) return launch_norm3_fast_t<true>(a, vit, fb, st);
+    return launch_norm3_fast_t<false>(a, vit, fb, st);
 }
 
 cudaError_t launch_binom2_emit(const Binom2Args &a, double2 *pre_lb, cudaStream_t st)

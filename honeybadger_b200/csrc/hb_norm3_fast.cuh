@@ -177,20 +177,18 @@ HB_HD int32_t fast_fwd_step(const Norm3Const &c, Fast3State &s, double u, bool f
 
 // ---------------------------------------------------------------- shared-memory slots
 // Compile-time layout switches (tools/build_variant.sh explores them):
-//   HB_FAST_XREG   1: x is prefetched half a chunk ahead into registers (plain coalesced LDG);
-//                  0: cp.async ring in shared memory (as hb_norm3.cuh)
 //   HB_FAST_NOPHI1 1: phi_1 is not parked, gamma_1 = |1 - gamma_0 - gamma_2| (the posteriors of this
 //                  formulation sum to 1 within ~1e-13 by construction)
-#ifndef HB_FAST_XREG
-#define HB_FAST_XREG 0
-#endif
 #ifndef HB_FAST_NOPHI1
 #define HB_FAST_NOPHI1 1
 #endif
 // per step j and thread: va, vb (double2), [e2 (double)], ph = hi word of 2^-es, [xs = x ring]
 //   NOPHI1: va = (phi0, phi2), vb = (E0s, E2s);  else va = (phi0, phi1), vb = (phi2, E0s), e2 = E2s
 #define HB_FAST_PARK_BYTES (16 + 16 + (HB_FAST_NOPHI1 ? 0 : 8) + 4)
-#define HB_FAST_SMEM_BYTES_PER_THREAD (HB_CHUNK * (HB_FAST_PARK_BYTES + (HB_FAST_XREG ? 0 : 8)))
+#define HB_FAST_SMEM_BYTES_PER_THREAD (HB_CHUNK * (HB_FAST_PARK_BYTES + 8))
+// bulk (TMA) staging on the tiled layout: two chunks of x per warp + two mbarriers per warp
+#define HB_FAST_BULK_SMEM_BYTES(nthreads) \
+    ((size_t)HB_CHUNK * HB_FAST_PARK_BYTES * (nthreads) + (size_t)2 * HB_CHUNK * 8 * (nthreads) + 16 * ((nthreads) / 32))
 
 HB_HD void fast_replay_one(const Norm3Const &c, Fast3State &s, double xv, bool first, Norm3Smem &m,
                            int j)
@@ -335,8 +333,9 @@ HB_HD void fast_acc_sq(const Norm3Const &c, Fast3State &s, double xv)
     }
 }
 
-template <bool VIT, bool FB, bool LL>
-HB_HD void norm3_fast_chain(const Norm3Args &a, int32_t seg, int64_t b, Norm3Smem &m)
+// BULK (tiled layout only): x is staged by cp.async.bulk, one 2 KB copy per warp and chunk (BulkRing)
+template <bool VIT, bool FB, bool LL, bool BULK>
+HB_HD void norm3_fast_chain(const Norm3Args &a, int32_t seg, int64_t b, Norm3Smem &m, BulkRing &br)
 {
     const Norm3Const &c = a.c;
     const int64_t t0 = a.seg_off[seg];
@@ -373,15 +372,11 @@ HB_HD void norm3_fast_chain(const Norm3Args &a, int32_t seg, int64_t b, Norm3Sme
     s.f0 = s.f1 = s.f2 = 0;
 
     // ------------------------------------------------------------ forward sweep
-    // x reaches the arithmetic half a chunk (XREG) or a whole chunk (cp.async ring) ahead of its use.
-#if HB_FAST_XREG
-    double xa[HB_HALF], xb[HB_HALF];
-    if (nfull > 0) {
-#pragma unroll
-        for (int j = 0; j < HB_HALF; j++) xa[j] = xp[(int64_t)j * ld];
-    }
-#else
-    if (nfull > 0) {
+    // x reaches the arithmetic one chunk ahead of its use: cp.async ring, or bulk copies (BULK)
+    if (BULK) {
+        if (nfull > 0) bulk_issue<HB_CHUNK>(br, 0, xp);
+        if (nfull > 1) bulk_issue<HB_CHUNK>(br, 1, xp + (int64_t)HB_CHUNK * ld);
+    } else if (nfull > 0) {
         const double *xr0 = xp;
 #pragma unroll
         for (int h = 0; h < 2; h++) {
@@ -393,13 +388,8 @@ HB_HD void norm3_fast_chain(const Norm3Args &a, int32_t seg, int64_t b, Norm3Sme
             xs_commit(m);
         }
     }
-#endif
     {
-#if HB_FAST_XREG
-        const double *xr = xp + (int64_t)HB_HALF * ld; // next half-chunk to fetch
-#else
         const double *xr = xp + (int64_t)HB_CHUNK * ld; // refill pointer: one chunk ahead
-#endif
         uint64_t *pw = psi;
         double *ck = ckpt;
         for (int32_t ch = 0; ch < nfull; ch++) {
@@ -407,28 +397,22 @@ HB_HD void norm3_fast_chain(const Norm3Args &a, int32_t seg, int64_t b, Norm3Sme
             const bool pf = ch + 1 + HB_FAST_PF_CHUNKS < nfull;
             (void)pf;
             uint32_t w[2] = {0u, 0u};
+            const int stg = ch & 1;
+            if (BULK) bulk_wait(br, stg);
 #pragma unroll
             for (int h = 0; h < 2; h++) {
-#if HB_FAST_XREG
-                // fetch the other half: second half of this chunk, or first half of the next one
-                if (h == 0 || more) {
-#pragma unroll
-                    for (int j = 0; j < HB_HALF; j++) (h == 0 ? xb : xa)[j] = xr[(int64_t)j * ld];
-                }
-                xr += (int64_t)HB_HALF * ld;
-#else
-                xs_wait<1>(m);
-#endif
+                if (!BULK) xs_wait<1>(m);
                 HB_UNROLL_STEPS
                 for (int j = h * HB_HALF; j < (h + 1) * HB_HALF; j++) {
-#if HB_FAST_XREG
-                    const double xv = h == 0 ? xa[j] : xb[j - HB_HALF];
-#else
-                    const double xv = m.xs[j * m.st];
-                    if (more) xs_refill(m, j, xr);
-                    if (pf) prefetch_l2(xr + (int64_t)HB_FAST_PF_CHUNKS * HB_CHUNK * ld);
-                    xr += ld;
-#endif
+                    double xv;
+                    if (BULK) {
+                        xv = bulk_read<HB_CHUNK>(br, stg, j);
+                    } else {
+                        xv = m.xs[j * m.st];
+                        if (more) xs_refill(m, j, xr);
+                        if (pf) prefetch_l2(xr + (int64_t)HB_FAST_PF_CHUNKS * HB_CHUNK * ld);
+                        xr += ld;
+                    }
                     const bool first = (j == 0) && (ch == 0);
                     const double u = dfma(xv, s.A, s.Bc);
                     if (VIT || LL) fast_acc_sq<LL>(c, s, xv);
@@ -440,9 +424,11 @@ HB_HD void norm3_fast_chain(const Norm3Args &a, int32_t seg, int64_t b, Norm3Sme
                         if (LL) s.esum += es;
                     }
                 }
-#if !HB_FAST_XREG
-                xs_commit(m);
-#endif
+                if (!BULK) xs_commit(m);
+            }
+            if (BULK) {
+                bulk_release(br);
+                if (ch + 2 < nfull) bulk_issue<HB_CHUNK>(br, stg, xp + (int64_t)(ch + 2) * HB_CHUNK * ld);
             }
             if (VIT) *pw = (uint64_t)w[0] | ((uint64_t)w[1] << 32);
             pw += sB;
@@ -454,9 +440,7 @@ HB_HD void norm3_fast_chain(const Norm3Args &a, int32_t seg, int64_t b, Norm3Sme
             }
         }
     }
-#if !HB_FAST_XREG
-    xs_wait<0>(m);
-#endif
+    if (!BULK) xs_wait<0>(m);
     if (tail > 0) { // rolled: at most HB_CHUNK-1 steps per chain
         uint32_t w[2] = {0u, 0u};
         for (int j = 0; j < tail; j++) {
@@ -522,12 +506,11 @@ HB_HD void norm3_fast_chain(const Norm3Args &a, int32_t seg, int64_t b, Norm3Sme
         const double q = 1.0 / ((s.f0 + s.f1) + s.f2);
         s.b0 = s.b1 = s.b2 = q;
     }
-    if (FB && nfull > 0) {
+    if (BULK) {
+        if (FB && nfull > 0) bulk_issue<HB_CHUNK>(br, 0, xp + (int64_t)(nfull - 1) * HB_CHUNK * ld);
+        if (FB && nfull > 1) bulk_issue<HB_CHUNK>(br, 1, xp + (int64_t)(nfull - 2) * HB_CHUNK * ld);
+    } else if (FB && nfull > 0) {
         const double *xl = xp + (int64_t)(nfull - 1) * HB_CHUNK * ld;
-#if HB_FAST_XREG
-#pragma unroll
-        for (int j = 0; j < HB_HALF; j++) xa[j] = xl[(int64_t)j * ld];
-#else
 #pragma unroll
         for (int h = 0; h < 2; h++) {
 #pragma unroll
@@ -537,7 +520,6 @@ HB_HD void norm3_fast_chain(const Norm3Args &a, int32_t seg, int64_t b, Norm3Sme
             }
             xs_commit(m);
         }
-#endif
     }
     uint64_t pk_nx = 0;
     double c0_nx = 0, c1_nx = 0, c2_nx = 0;
@@ -580,12 +562,7 @@ HB_HD void norm3_fast_chain(const Norm3Args &a, int32_t seg, int64_t b, Norm3Sme
         uint8_t *yp = VIT ? ybase + rell * sy : nullptr;
         double *g0 = FB ? gbase + rell * sg : nullptr;
         double *g1 = g0 + plane, *g2 = g1 + plane;
-#if HB_FAST_XREG
-        // next fetch: second half of the last full chunk (its first half is already in xa)
-        const double *xr = xp + ((int64_t)(nfull - 1) * HB_CHUNK + HB_HALF) * ld;
-#else
         const double *xr = xp + (int64_t)(nfull - 2) * HB_CHUNK * ld; // refill: previous chunk
-#endif
         const uint64_t *pr = psi + (int64_t)(nfull - 2) * sB;
         const double *cr = ckpt + (int64_t)(nfull - 2) * 3 * sB;
         for (int32_t ch = nfull - 1; ch >= 0; ch--) {
@@ -617,42 +594,32 @@ HB_HD void norm3_fast_chain(const Norm3Args &a, int32_t seg, int64_t b, Norm3Sme
             cr -= 3 * sB;
             if (FB) {
                 const bool more = ch > 0;
-#if HB_FAST_XREG
-#pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    // h = 0: fetch this chunk's second half; h = 1: the previous chunk's first half
-                    if (h == 0) {
-#pragma unroll
-                        for (int j = 0; j < HB_HALF; j++) xb[j] = xr[(int64_t)j * ld];
-                        xr -= (int64_t)(HB_CHUNK + HB_HALF) * ld;
-                    } else {
-                        if (more) {
-#pragma unroll
-                            for (int j = 0; j < HB_HALF; j++) xa[j] = xr[(int64_t)j * ld];
-                        }
-                        xr += (int64_t)HB_HALF * ld;
-                    }
-                    HB_UNROLL_STEPS
-                    for (int j = h * HB_HALF; j < (h + 1) * HB_HALF; j++)
-                        fast_replay_one(c, s, h == 0 ? xa[j] : xb[j - HB_HALF], j == 0 && ch == 0, m, j);
-                }
-#else
                 const double *xq = xr;
+                const int stg = (nfull - 1 - ch) & 1;
+                if (BULK) bulk_wait(br, stg);
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
-                    xs_wait<1>(m);
+                    if (!BULK) xs_wait<1>(m);
                     HB_UNROLL_STEPS
                     for (int j = h * HB_HALF; j < (h + 1) * HB_HALF; j++) {
-                        const double xv = m.xs[j * m.st];
-                        if (more) xs_refill(m, j, xq);
-                        if (pf) prefetch_l2(xq - (int64_t)HB_FAST_PF_CHUNKS * HB_CHUNK * ld);
-                        xq += ld;
+                        double xv;
+                        if (BULK) {
+                            xv = bulk_read<HB_CHUNK>(br, stg, j);
+                        } else {
+                            xv = m.xs[j * m.st];
+                            if (more) xs_refill(m, j, xq);
+                            if (pf) prefetch_l2(xq - (int64_t)HB_FAST_PF_CHUNKS * HB_CHUNK * ld);
+                            xq += ld;
+                        }
                         fast_replay_one(c, s, xv, j == 0 && ch == 0, m, j);
                     }
-                    xs_commit(m);
+                    if (!BULK) xs_commit(m);
+                }
+                if (BULK) {
+                    bulk_release(br);
+                    if (ch >= 2) bulk_issue<HB_CHUNK>(br, stg, xp + (int64_t)(ch - 2) * HB_CHUNK * ld);
                 }
                 xr -= (int64_t)HB_CHUNK * ld;
-#endif
             }
             const uint32_t plo = (uint32_t)pk, phi = (uint32_t)(pk >> 32);
 #ifdef HB_FAST_BWD_UNROLL
@@ -674,9 +641,7 @@ HB_HD void norm3_fast_chain(const Norm3Args &a, int32_t seg, int64_t b, Norm3Sme
             }
         }
     }
-#if !HB_FAST_XREG
-    xs_wait<0>(m);
-#endif
+    if (!BULK) xs_wait<0>(m);
 }
 
 } // namespace hb

@@ -185,11 +185,21 @@ int emul_norm3_fast(const double *x, int64_t ld, int64_t T, int64_t B, const int
     for (int s = 0; s < nseg; s++)
         for (int64_t b = 0; b < B; b++) {
             int seg = sg.order[s];
-            if (vit && fb && llon) norm3_fast_chain<true, true, true>(a, seg, b, sm);
-            else if (vit && fb) norm3_fast_chain<true, true, false>(a, seg, b, sm);
-            else if (fb && llon) norm3_fast_chain<false, true, true>(a, seg, b, sm);
-            else if (fb) norm3_fast_chain<false, true, false>(a, seg, b, sm);
-            else norm3_fast_chain<true, false, false>(a, seg, b, sm);
+            BulkRing br;
+            br.par[0] = br.par[1] = 0u;
+            if (g_tiled) { // the tiled layout takes the bulk-staging form of the body, as on the device
+                if (vit && fb && llon) norm3_fast_chain<true, true, true, true>(a, seg, b, sm, br);
+                else if (vit && fb) norm3_fast_chain<true, true, false, true>(a, seg, b, sm, br);
+                else if (fb && llon) norm3_fast_chain<false, true, true, true>(a, seg, b, sm, br);
+                else if (fb) norm3_fast_chain<false, true, false, true>(a, seg, b, sm, br);
+                else norm3_fast_chain<true, false, false, true>(a, seg, b, sm, br);
+            } else {
+                if (vit && fb && llon) norm3_fast_chain<true, true, true, false>(a, seg, b, sm, br);
+                else if (vit && fb) norm3_fast_chain<true, true, false, false>(a, seg, b, sm, br);
+                else if (fb && llon) norm3_fast_chain<false, true, true, false>(a, seg, b, sm, br);
+                else if (fb) norm3_fast_chain<false, true, false, false>(a, seg, b, sm, br);
+                else norm3_fast_chain<true, false, false, false>(a, seg, b, sm, br);
+            }
         }
     if (nflag) *nflag = status[1];
     return status[0];
