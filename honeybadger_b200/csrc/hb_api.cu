@@ -1011,6 +1011,47 @@ int hb_pool_count_pos_dev(const int32_t *v, int64_t ld, int64_t G, int64_t N,
     return HB_OK;
 }
 
+// ------------------------------------------------------------------ grouping of cells (8f-2)
+int hb_runmean_dev(const double *x, int64_t ld, int64_t G, int64_t N, int32_t k, double *out, int64_t ldo,
+                   void *stream)
+{
+    if (!x || !out || G < 1 || N < 1 || ld < N || ldo < N || k < 1 || (k & 1) == 0)
+        return fail(HB_ERR_ARG, "bad arguments (k must be odd)");
+    CU(hb::launch_runmean(x, nullptr, nullptr, ld, G, N, k, out, ldo, (cudaStream_t)stream));
+    return HB_OK;
+}
+
+int hb_runmean_ratio_dev(const int32_t *r, const int32_t *n, int64_t ld, int64_t G, int64_t N, int32_t k,
+                         double *out, int64_t ldo, void *stream)
+{
+    if (!r || !n || !out || G < 1 || N < 1 || ld < N || ldo < N || k < 1 || (k & 1) == 0)
+        return fail(HB_ERR_ARG, "bad arguments (k must be odd)");
+    CU(hb::launch_runmean(nullptr, r, n, ld, G, N, k, out, ldo, (cudaStream_t)stream));
+    return HB_OK;
+}
+
+int hb_dist_sq_dev(const double *s, int64_t ld, int64_t G, int64_t N, double *D, void *stream)
+{
+    if (!s || !D || G < 1 || N < 1 || ld < N) return fail(HB_ERR_ARG, "bad arguments");
+    CU(hb::launch_dist_sq(s, ld, G, N, D, (cudaStream_t)stream));
+    return HB_OK;
+}
+
+int hb_ward_linkage_dev(double *D, int64_t N, int32_t *merge_a, int32_t *merge_b, double *height,
+                        void *stream)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    Workspace *ws;
+    HBTRY(cur_ws(&ws));
+    if (!D || !merge_a || !merge_b || !height || N < 2) return fail(HB_ERR_ARG, "bad arguments");
+    HBTRY(ws->st_part.ensure((size_t)N * (sizeof(int32_t) * 2 + 1) + 64));
+    int32_t *size = ws->st_part.as<int32_t>();
+    int32_t *chain = size + N;
+    uint8_t *active = (uint8_t *)(chain + N);
+    CU(hb::launch_ward(D, N, size, active, chain, merge_a, merge_b, height, (cudaStream_t)stream));
+    return HB_OK;
+}
+
 // ------------------------------------------------------------------ deterministic retest (8f-1)
 int hb_retest_gexp_dev(const double *x, int64_t ld, int64_t G, int64_t N, const int64_t *rows,
                        int64_t nrows, double mag0, const double *sigma0, double *p_amp, double *p_del,

@@ -8,6 +8,7 @@
 
 #include "hb_binom2.cuh"
 #include "hb_binom2_fast.cuh"
+#include "hb_group.cuh"
 #include "hb_kernels.h"
 #include "hb_norm3.cuh"
 #include "hb_norm3_fast.cuh"
@@ -572,6 +573,31 @@ cudaError_t launch_retest_gexp_b(int64_t N, const double *partial, const double 
 {
     const unsigned nb = (unsigned)((N + 127) / 128);
     retest_gexp_b_kernel<<<nb, 128, 0, st>>>(N, partial, (int32_t)nb, D_total, p_amp, p_del);
+    return cudaGetLastError();
+}
+
+// =====================================================================================
+// Grouping of cells (hb_group.cuh)
+cudaError_t launch_runmean(const double *x, const int32_t *r, const int32_t *n, int64_t ld, int64_t G,
+                           int64_t N, int32_t k, double *out, int64_t ldo, cudaStream_t st)
+{
+    dim3 grid((unsigned)G, (unsigned)((N + 255) / 256));
+    if (x)
+        runmean_kernel<false><<<grid, 256, 0, st>>>(x, nullptr, nullptr, ld, G, N, k / 2, out, ldo);
+    else
+        runmean_kernel<true><<<grid, 256, 0, st>>>(nullptr, r, n, ld, G, N, k / 2, out, ldo);
+    return cudaGetLastError();
+}
+cudaError_t launch_dist_sq(const double *S, int64_t ld, int64_t G, int64_t N, double *D, cudaStream_t st)
+{
+    const unsigned nt = (unsigned)((N + GD_T - 1) / GD_T);
+    dist_sq_kernel<<<dim3(nt, nt), 256, 0, st>>>(S, ld, G, N, D);
+    return cudaGetLastError();
+}
+cudaError_t launch_ward(double *D, int64_t N, int32_t *size, uint8_t *active, int32_t *chain, int32_t *ma,
+                        int32_t *mb, double *height, cudaStream_t st)
+{
+    ward_nnchain_kernel<<<1, WL_THREADS, 0, st>>>(D, N, size, active, chain, ma, mb, height);
     return cudaGetLastError();
 }
 

@@ -15,7 +15,8 @@ runs (vectorised here; the literal loops live in oracle/pyref.py for the tests).
 
 Outside the path (SURVEY.md §8f "next" rows), supplied as replaceable hooks:
   * grouping — `dist` + `hclust(ward.D2)` + `cutree` on the windowed matrix (R/HoneyBADGER.R:1125-1136):
-    `ward_groups` below does it on the host with scipy; group labels are an INPUT of the path.
+    `ward_groups_dev` does it on the device (runmean, R dist with its NA rule, Ward.D2 by nearest-neighbour
+    chain); `ward_groups` is the scipy host form; any f(mat, heights) can be plugged in.
   * retest   — the JAGS posteriors (`calcGexpCnvProb`, `calcAlleleCnvProb`): `retest_gexp_closed_form`
     (exact marginal of inst/bug/expressionModel.bug) and a binomial likelihood-ratio
     stand-in for the allele model; both on the device with torch ops, neither parity-pinned.
@@ -121,6 +122,69 @@ def ward_groups(mat_smooth: np.ndarray, heights) -> list:
             res[i] = remap.setdefault(v, len(remap) + 1)
         out.append(res)
     return out
+
+
+def cut_merges(merge_a, merge_b, height, N, ks):
+    """cutree(hc, k) for each k in `ks` from a merge list (leaf representatives, any order in which
+    children precede parents): the N - k lowest merges are applied with union-find; clusters are
+    numbered by first appearance in cell order, as cutree does."""
+    order = np.argsort(np.asarray(height), kind="stable")
+    a, b = np.asarray(merge_a)[order], np.asarray(merge_b)[order]
+    out = []
+    for k in ks:
+        parent = np.arange(N)
+
+        def find(i):
+            while parent[i] != i:
+                parent[i] = parent[parent[i]]
+                i = parent[i]
+            return i
+
+        for m in range(max(0, N - int(k))):
+            ra, rb = find(int(a[m])), find(int(b[m]))
+            if ra != rb:
+                parent[ra] = rb
+        remap, lab = {}, np.zeros(N, dtype=np.int32)
+        for i in range(N):
+            lab[i] = remap.setdefault(find(i), len(remap) + 1)
+        out.append(lab)
+    return out
+
+
+def ward_groups_dev(x_dev, heights, k=101, counts=None):
+    """Grouping on the device (libhb_b200: hb_runmean_dev / hb_dist_sq_dev / hb_ward_linkage_dev):
+    cutree(hclust(dist(t(runmean(x, k))) with NA -> 0, "ward.D2"), h) for each h, as
+    R/HoneyBADGER.R:1122-1136.  x_dev: gene-major fp64 CUDA tensor [G, N]; or counts=(r_dev, n_dev)
+    int32 tensors for the allele form (r / n smoothed with k = 31, R/HoneyBADGER.R:1378-1385)."""
+    import torch
+    from .hmm import alloc_rows
+    lib = _lib.load()
+    if counts is not None:
+        r, n = counts
+        G, N = r.shape
+        dev = r.device
+    else:
+        G, N = x_dev.shape
+        dev = x_dev.device
+    if N == 1:
+        return [np.ones(1, dtype=np.int32) for _ in heights]
+    S = alloc_rows(G, N, torch.float64, dev)
+    if counts is not None:
+        if r.stride(0) != n.stride(0):
+            r, n = r.contiguous(), n.contiguous()
+        _lib.check(lib.hb_runmean_ratio_dev(r.data_ptr(), n.data_ptr(), r.stride(0), G, N, int(k),
+                                            S.data_ptr(), S.stride(0), _stream()))
+    else:
+        _lib.check(lib.hb_runmean_dev(x_dev.data_ptr(), x_dev.stride(0), G, N, int(k), S.data_ptr(),
+                                      S.stride(0), _stream()))
+    D = torch.empty((N, N), dtype=torch.float64, device=dev)
+    _lib.check(lib.hb_dist_sq_dev(S.data_ptr(), S.stride(0), G, N, D.data_ptr(), _stream()))
+    del S
+    ma = torch.empty(N - 1, dtype=torch.int32, device=dev)
+    mb = torch.empty(N - 1, dtype=torch.int32, device=dev)
+    hh = torch.empty(N - 1, dtype=torch.float64, device=dev)
+    _lib.check(lib.hb_ward_linkage_dev(D.data_ptr(), N, ma.data_ptr(), mb.data_ptr(), hh.data_ptr(), _stream()))
+    return cut_merges(ma.cpu().numpy(), mb.cpu().numpy(), hh.cpu().numpy(), N, heights)
 
 
 def retest_gexp_closed_form(gexp_rows, mag0, sigma0=None):
@@ -311,9 +375,9 @@ def calcGexpCnvBoundaries(gexp_norm, genes: GRanges, m=0.15, chrs=None, min_trav
     names = np.asarray(df.index, dtype=object)
     G, N = mat.shape
     heights = list(range(1, min(min_traverse, N) + 1))
-    labels = (grouping or (lambda M, hs: ward_groups(runmean(M, 101), hs)))(mat, heights)
-    member, _ = _membership(labels, N)
     x_dev = _to_dev_f64(mat)
+    labels = grouping(mat, heights) if grouping else ward_groups_dev(x_dev, heights, 101)
+    member, _ = _membership(labels, N)
     votes = {"amp": np.zeros(G, np.int64), "del": np.zeros(G, np.int64)}
     if member.shape[0]:
         y, _, _ = gexp_round_dev(x_dev, member, [-m, 0.0, m], t)
@@ -343,15 +407,15 @@ def calcAlleleCnvBoundaries(r_maf, n_sc, l_maf=None, n_bulk=None, snps: GRanges 
     r, n = rdf.values, ndf.values
     G, N = r.shape
     heights = list(range(1, min(min_traverse, N) + 1))
+    r_dev, n_dev = _to_dev_i32(r), _to_dev_i32(n)
     if grouping is None:
-        with np.errstate(all="ignore"):
-            labels = ward_groups(runmean(r / n, 31), heights)
+        labels = ward_groups_dev(None, heights, 31, counts=(r_dev, n_dev))
     else:
         labels = grouping(r, n, heights)
     member, tags = _membership(labels, N)
     vote = np.zeros(G, np.int64)
     if member.shape[0]:
-        y, _, _ = allele_round_dev(_to_dev_i32(r), _to_dev_i32(n), member, pd, pn, t)
+        y, _, _ = allele_round_dev(r_dev, n_dev, member, pd, pn, t)
         for k, (_, gi) in enumerate(tags):
             if gi == 0:
                 vote += y[k] == 1
@@ -381,7 +445,7 @@ class HoneyBADGER:
         self.bound_genes_final = None
         self.bound_snps_old = None
         self.bound_snps_final = None
-        self.grouping_gexp = lambda M, hs: ward_groups(runmean(M, 101), hs)
+        self.grouping_gexp = None   # None: ward_groups_dev on the resident matrix; or f(mat, heights)
         self.grouping_allele = None
         self.retest_gexp = retest_gexp_closed_form
         self.retest_allele = retest_allele_lr
@@ -498,14 +562,14 @@ class HoneyBADGER:
         mat = gexp.values
         G, N = mat.shape
         heights = list(range(1, min(min_traverse, N) + 1))
-        labels = self.grouping_gexp(mat, heights)
-        member, _ = _membership(labels, N)
         x_dev = None
         if self.gexp_norm is not None:
             full, rix, cix = self._resident("gexp")
             x_dev = self._gather(full, rix, cix, names, gexp.columns)
         if x_dev is None:
             x_dev = _to_dev_f64(mat)
+        labels = self.grouping_gexp(mat, heights) if self.grouping_gexp else ward_groups_dev(x_dev, heights, 101)
+        member, _ = _membership(labels, N)
         amp_v, del_v = np.zeros(G, np.int64), np.zeros(G, np.int64)
         if member.shape[0]:
             y, _, _ = gexp_round_dev(x_dev, member, [-self.dev, 0.0, self.dev], t)
@@ -567,12 +631,6 @@ class HoneyBADGER:
         r, n = r_maf.values, n_sc.values
         G, N = r.shape
         heights = list(range(1, min(min_traverse, N) + 1))
-        if self.grouping_allele is None:
-            with np.errstate(all="ignore"):
-                labels = ward_groups(runmean(r / n, 31), heights)
-        else:
-            labels = self.grouping_allele(r, n, heights)
-        member, tags = _membership(labels, N)
         r_dev = n_dev = None
         if self.r_maf is not None:
             rfull, nfull, rix, cix = self._resident("allele")
@@ -580,6 +638,11 @@ class HoneyBADGER:
             n_dev = self._gather(nfull, rix, cix, names, r_maf.columns)
         if r_dev is None:
             r_dev, n_dev = _to_dev_i32(r), _to_dev_i32(n)
+        if self.grouping_allele is None:
+            labels = ward_groups_dev(None, heights, 31, counts=(r_dev, n_dev))
+        else:
+            labels = self.grouping_allele(r, n, heights)
+        member, tags = _membership(labels, N)
         vote = np.zeros(G, np.int64)
         if member.shape[0]:
             y, _, _ = allele_round_dev(r_dev, n_dev, member, pd, pn, t)

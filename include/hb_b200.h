@@ -183,6 +183,25 @@ int hb_pooled_sd_dev(const double *pooled /* device [K][G] */, int64_t G, int32_
 int hb_pool_count_pos_dev(const int32_t *v, int64_t ld, int64_t G, int64_t N,
                           const uint8_t *member, int32_t K, int32_t *out, void *stream);
 
+/* ------------------------------------------------------------------ grouping of cells
+ * The step before the path: R/HoneyBADGER.R:1122-1136 and :1378-1397 smooth every cell with
+ * caTools::runmean, take stats::dist between cells (NA-aware, NA -> 0), build hclust(., "ward.D2")
+ * and cut it at k = 1..min.traverse groups.  All pointers are device pointers, gene-major layout.
+ * hb_runmean_dev: centred window of k (odd) positions, shrinking at the ends, non-finite values
+ *   skipped, NaN for an empty window; hb_runmean_ratio_dev smooths r / n of two count planes.
+ * hb_dist_sq_dev: SQUARED Euclidean distance between the N columns of s with R's NA rule (pairs with
+ *   a non-finite member are dropped and the sum scaled by G / pairs used; no pair -> 0), D is [N][N].
+ * hb_ward_linkage_dev: Ward.D2 by nearest-neighbour chain on D (destroyed).  Merge m joins the
+ *   clusters containing leaves merge_a[m] and merge_b[m] at height[m]; N-1 merges in chain order
+ *   (children before parents) — sort by height to cut the tree. */
+int hb_runmean_dev(const double *x, int64_t ld, int64_t G, int64_t N, int32_t k, double *out, int64_t ldo,
+                   void *stream);
+int hb_runmean_ratio_dev(const int32_t *r, const int32_t *n, int64_t ld, int64_t G, int64_t N, int32_t k,
+                         double *out, int64_t ldo, void *stream);
+int hb_dist_sq_dev(const double *s, int64_t ld, int64_t G, int64_t N, double *D, void *stream);
+int hb_ward_linkage_dev(double *D, int64_t N, int32_t *merge_a, int32_t *merge_b, double *height,
+                        void *stream);
+
 /* Deterministic retest of one candidate region for the expression model: the exact marginal posterior
  * of inst/bug/expressionModel.bug that HoneyBADGER$calcGexpCnvProb
  * (R/HoneyBADGER.R:374-470, called from :1220) estimates by JAGS sampling — statistical stand-in for

@@ -224,3 +224,57 @@ def test_retest_allele_lr_vs_numpy():
     ref = 1 / (1 + np.exp(-llr))
     assert np.abs(got - ref).max() < 1e-12
     assert got[:90].mean() > 0.9 and got[90:].mean() < 0.1
+
+
+def test_device_grouping_matches_scipy_ward():
+    """runmean + dist + Ward.D2 + cutree on the device vs the host form (numpy runmean, scipy ward):
+    identical memberships for k = 1..6 on clustered data; dist's NA rule vs a numpy restatement."""
+    import ctypes as C
+    import torch
+    from honeybadger_b200 import _lib, hmm
+    from honeybadger_b200 import honeybadger as hb
+    rng = np.random.default_rng(41)
+    G, N = 900, 157
+    clone = rng.choice(4, size=N, p=[0.4, 0.3, 0.2, 0.1])
+    x = rng.standard_normal((G, N)) * 1.5
+    for c, (a, b, s) in enumerate([(100, 300, 1.2), (400, 650, -1.0), (700, 850, 1.5), (0, 0, 0)]):
+        x[a:b, clone == c] += s
+    xd = hmm.to_rows(torch.from_numpy(x).cuda())
+    heights = [1, 2, 3, 4, 5, 6]
+    got = hb.ward_groups_dev(xd, heights, 101)
+    ref = hb.ward_groups(hb.runmean(x, 101), heights)
+    for g, r in zip(got, ref):
+        assert (g == r).all()
+    # the four planted clones are what k = 4 finds
+    lab4 = got[3]
+    assert len({(a, b) for a, b in zip(lab4, clone)}) == 4
+    # runmean on the device == the numpy restatement (NaN skipping, shrinking ends)
+    xn = x.copy()
+    xn[rng.random(x.shape) < 0.05] = np.nan
+    xnd = hmm.to_rows(torch.from_numpy(xn).cuda())
+    S = hmm.alloc_rows(G, N, torch.float64, xnd.device)
+    lib = _lib.load()
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    _lib.check(lib.hb_runmean_dev(xnd.data_ptr(), xnd.stride(0), G, N, 31, S.data_ptr(), S.stride(0), st))
+    assert np.allclose(S.cpu().numpy(), hb.runmean(xn, 31), rtol=1e-12, atol=1e-12, equal_nan=True)
+    # dist with R's NA rule: drop unusable pairs, scale by G / pairs used, nothing usable -> 0
+    Sn = S.cpu().numpy().copy()
+    Sn[:, 5] = np.nan
+    Sn[::2, 7] = np.nan
+    Sd = hmm.to_rows(torch.from_numpy(Sn).cuda())
+    D = torch.empty((N, N), dtype=torch.float64, device="cuda")
+    _lib.check(lib.hb_dist_sq_dev(Sd.data_ptr(), Sd.stride(0), G, N, D.data_ptr(), st))
+    Dh = D.cpu().numpy()
+    for i, j in [(0, 1), (3, 7), (7, 9), (5, 2), (5, 5), (7, 7)]:
+        d = Sn[:, i] - Sn[:, j]
+        ok = np.isfinite(d)
+        want = 0.0 if (i == j or not ok.any()) else (d[ok] ** 2).sum() * G / ok.sum()
+        assert abs(Dh[i, j] - want) <= 1e-10 * max(1.0, want) and Dh[i, j] == Dh[j, i]
+
+
+def test_device_grouping_allele_form():
+    import torch
+    from honeybadger_b200 import honeybadger as hb
+    r, n, _, clone = synth.allele(3000, 90, seed=43)
+    got = hb.ward_groups_dev(None, [1, 2, 3], 31, counts=(torch.from_numpy(r).cuda(), torch.from_numpy(n).cuda()))
+    assert [len(set(g)) for g in got] == [1, 2, 3] and all(g[0] == 1 for g in got)
