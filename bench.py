@@ -250,7 +250,7 @@ def main():
     ap.add_argument("--workload", default="expr", choices=list(WORKLOADS))
     ap.add_argument("--cells", type=int, default=0, help="override cells per GPU (tests)")
     ap.add_argument("--positions", type=int, default=0, help="override genes/SNPs (tests)")
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
     ap.add_argument("--no-allele", action="store_true",
@@ -438,7 +438,7 @@ def run_e2e(kind, wl, d, args, world, dev, hmm, dist):
     bounded pinned window so that host memory stays small at any N."""
     import torch
     cells, positions = wl["cells"], wl["positions"]
-    batch = min(cells, 5000 if kind == "expr" else 500)
+    batch = min(cells, 5000 if kind == "expr" else 1000)
     nb = (cells + batch - 1) // batch
     S = wl["S"]
     seg = d["seg"]

@@ -105,6 +105,18 @@ struct Workspace {
                          &st_member, &st_pool, &st_pool2, &st_pre, &st_x80, &st_part, &pin[0], &pin[1], &pin2[0], &pin2[1],
                          &pout_y[0], &pout_y[1], &pout_g[0], &pout_g[1], &pout_ll[0], &pout_ll[1]};
         for (DevBuf *b : all) b->release();
+        if (s_in) {
+            cudaStreamDestroy(s_in);
+            cudaStreamDestroy(s_cmp);
+            cudaStreamDestroy(s_out);
+            for (int k = 0; k < 2; k++) {
+                cudaEventDestroy(ev_in[k]);
+                cudaEventDestroy(ev_free_in[k]);
+                cudaEventDestroy(ev_out[k]);
+                cudaEventDestroy(ev_free_out[k]);
+            }
+            s_in = s_cmp = s_out = nullptr;
+        }
         seg_cached.clear();
         lut_nmax = -1;
         lut_key[0] = -1;
@@ -598,7 +610,7 @@ static int pipe_init(Workspace *ws)
     return HB_OK;
 }
 
-// Sub-batch width: ~8+ sub-batches per call when B allows, a multiple of 128 columns, bounded by
+// Sub-batch width: ~8+ sub-batches per call when B allows, a multiple of 32 columns, bounded by
 // the free device memory (`bytes_per_col` covers staging, resident copy, outputs and scratch).
 static int64_t pipe_batch(int64_t B, double bytes_per_col)
 {
@@ -608,10 +620,10 @@ static int64_t pipe_batch(int64_t B, double bytes_per_col)
         free_b = (size_t)8 << 30;
     }
     int64_t cap = std::max<int64_t>(1, (int64_t)(free_b * 0.6 / bytes_per_col));
-    int64_t want = std::max<int64_t>(128, (B / 8 + 127) / 128 * 128);
+    int64_t want = std::max<int64_t>(32, (B / 8 + 31) / 32 * 32);
     want = std::min<int64_t>(want, 1024);
     int64_t Bc = std::min(std::min(cap, want), B);
-    if (Bc >= 128) Bc = Bc / 128 * 128;
+    if (Bc >= 32) Bc = Bc / 32 * 32;
     return std::max<int64_t>(1, Bc);
 }
 
