@@ -18,6 +18,10 @@ EMUL_DIR = os.path.join(ROOT, "tests", "emul")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    # The C-ABI library is the product: build it in-tree if it is missing or older than its sources
+    # (nvcc cross-compiles sm_100a without a GPU; a minute on the first run, a no-op afterwards).
+    from honeybadger_b200 import build as hb_build
+    hb_build.build()
 
 
 def _has_gpu() -> bool:
