@@ -1064,6 +1064,104 @@ int hb_ward_linkage_dev(double *D, int64_t N, int32_t *merge_a, int32_t *merge_b
     return HB_OK;
 }
 
+// cutree(hc, k) for each k from the chain-ordered merge list: the N - k lowest merges (stable sort by
+// height keeps children before parents), union-find over leaves, clusters numbered by first appearance.
+static void cut_merges_host(const int32_t *ma, const int32_t *mb, const double *h, int64_t N,
+                            const int32_t *ks, int32_t nk, int32_t *labels)
+{
+    std::vector<int32_t> ord((size_t)(N - 1));
+    std::iota(ord.begin(), ord.end(), 0);
+    std::stable_sort(ord.begin(), ord.end(), [&](int32_t a, int32_t b) { return h[a] < h[b]; });
+    std::vector<int32_t> parent((size_t)N), remap((size_t)N);
+    for (int32_t q = 0; q < nk; q++) {
+        std::iota(parent.begin(), parent.end(), 0);
+        auto find = [&](int32_t i) {
+            while (parent[i] != i) {
+                parent[i] = parent[parent[i]];
+                i = parent[i];
+            }
+            return i;
+        };
+        const int64_t nm = std::max<int64_t>(0, N - std::max(1, ks[q]));
+        for (int64_t m = 0; m < nm; m++) {
+            const int32_t ra = find(ma[ord[m]]), rb = find(mb[ord[m]]);
+            if (ra != rb) parent[ra] = rb;
+        }
+        std::fill(remap.begin(), remap.end(), 0);
+        int32_t next = 0;
+        for (int64_t i = 0; i < N; i++) {
+            const int32_t r = find((int32_t)i);
+            if (!remap[r]) remap[r] = ++next;
+            labels[(int64_t)q * N + i] = remap[r];
+        }
+    }
+}
+
+// Host-buffer form of the grouping step: x (or r, n) column-major [G x N] as R holds them.
+static int group_host(const double *x, const double *r, const double *n, int64_t G, int64_t N,
+                      int32_t window, const int32_t *ks, int32_t nk, int32_t *labels)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    Workspace *ws;
+    HBTRY(cur_ws(&ws));
+    if (G < 1 || N < 1 || !ks || nk < 1 || !labels || window < 1 || (window & 1) == 0)
+        return fail(HB_ERR_ARG, "bad arguments");
+    if (N == 1) {
+        for (int32_t q = 0; q < nk; q++) labels[q] = 1;
+        return HB_OK;
+    }
+    cudaStream_t st = 0;
+    const int64_t ld = (N + 127) / 128 * 128;
+    HBTRY(ws->st_in.ensure((size_t)G * N * sizeof(double)));
+    HBTRY(ws->st_g.ensure((size_t)G * ld * sizeof(double))); // smoothed matrix
+    double *S = ws->st_g.as<double>();
+    if (x) {
+        HBTRY(ws->st_x.ensure((size_t)G * ld * sizeof(double)));
+        CU(cudaMemcpyAsync(ws->st_in.p, x, (size_t)G * N * sizeof(double), cudaMemcpyHostToDevice, st));
+        CU(hb::launch_transpose_f64(ws->st_in.as<double>(), G, N, ws->st_x.as<double>(), ld, st));
+        CU(hb::launch_runmean(ws->st_x.as<double>(), nullptr, nullptr, ld, G, N, window, S, ld, st));
+    } else {
+        HBTRY(ws->st_x.ensure((size_t)G * ld * sizeof(int32_t)));
+        HBTRY(ws->st_x2.ensure((size_t)G * ld * sizeof(int32_t)));
+        CU(cudaMemcpyAsync(ws->st_in.p, r, (size_t)G * N * sizeof(double), cudaMemcpyHostToDevice, st));
+        CU(hb::launch_transpose_f64_i32(ws->st_in.as<double>(), G, N, ws->st_x.as<int32_t>(), ld, st));
+        CU(cudaMemcpyAsync(ws->st_in.p, n, (size_t)G * N * sizeof(double), cudaMemcpyHostToDevice, st));
+        CU(hb::launch_transpose_f64_i32(ws->st_in.as<double>(), G, N, ws->st_x2.as<int32_t>(), ld, st));
+        CU(hb::launch_runmean(nullptr, ws->st_x.as<int32_t>(), ws->st_x2.as<int32_t>(), ld, G, N, window, S, ld, st));
+    }
+    HBTRY(ws->st_pool.ensure((size_t)N * N * sizeof(double)));
+    HBTRY(ws->st_pool2.ensure((size_t)N * 16 + 64));
+    HBTRY(ws->st_part.ensure((size_t)N * (sizeof(int32_t) * 2 + 1) + 64));
+    double *D = ws->st_pool.as<double>();
+    CU(hb::launch_dist_sq(S, ld, G, N, D, st));
+    int32_t *d_ma = ws->st_pool2.as<int32_t>(), *d_mb = d_ma + N;
+    double *d_h = reinterpret_cast<double *>(d_mb + N);
+    int32_t *size = ws->st_part.as<int32_t>(), *chain = size + N;
+    CU(hb::launch_ward(D, N, size, (uint8_t *)(chain + N), chain, d_ma, d_mb, d_h, st));
+    std::vector<int32_t> ma((size_t)N), mb((size_t)N);
+    std::vector<double> hh((size_t)N);
+    CU(cudaMemcpyAsync(ma.data(), d_ma, (size_t)(N - 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(mb.data(), d_mb, (size_t)(N - 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(hh.data(), d_h, (size_t)(N - 1) * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    cut_merges_host(ma.data(), mb.data(), hh.data(), N, ks, nk, labels);
+    return HB_OK;
+}
+
+int hb_group_gexp_host(const double *gexp_norm, int64_t G, int64_t N, int32_t window, const int32_t *ks,
+                       int32_t nk, int32_t *labels)
+{
+    if (!gexp_norm) return fail(HB_ERR_ARG, "bad arguments");
+    return group_host(gexp_norm, nullptr, nullptr, G, N, window, ks, nk, labels);
+}
+
+int hb_group_allele_host(const double *r_maf, const double *n_sc, int64_t G, int64_t N, int32_t window,
+                         const int32_t *ks, int32_t nk, int32_t *labels)
+{
+    if (!r_maf || !n_sc) return fail(HB_ERR_ARG, "bad arguments");
+    return group_host(nullptr, r_maf, n_sc, G, N, window, ks, nk, labels);
+}
+
 // ------------------------------------------------------------------ deterministic retest (8f-1)
 int hb_retest_gexp_dev(const double *x, int64_t ld, int64_t G, int64_t N, const int64_t *rows,
                        int64_t nrows, double mag0, const double *sigma0, double *p_amp, double *p_del,
@@ -1082,6 +1180,42 @@ int hb_retest_gexp_dev(const double *x, int64_t ld, int64_t G, int64_t N, const 
         CU(hb::launch_retest_gexp_a(x, ld, N, rows, nrows, mag0, sigma0, p_amp, p_del, mu0, part, D_local, st));
     if (phase == 0 || phase == 2)
         CU(hb::launch_retest_gexp_b(N, part, phase == 2 ? D_total : nullptr, p_amp, p_del, st));
+    return HB_OK;
+}
+
+int hb_retest_gexp_host(const double *gexp_rows, int64_t n, int64_t N, double mag0, const double *sigma0,
+                        double *p_amp, double *p_del, double *mu0)
+{
+    if (!gexp_rows || !p_amp || !p_del || n < 1 || N < 1) return fail(HB_ERR_ARG, "bad arguments");
+    const int64_t ld = (N + 127) / 128 * 128;
+    double *d_x, *d_out, *d_sig = nullptr;
+    int64_t *d_rows;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        Workspace *ws;
+        HBTRY(cur_ws(&ws));
+        HBTRY(ws->st_in.ensure((size_t)n * N * sizeof(double)));
+        HBTRY(ws->st_x.ensure((size_t)n * ld * sizeof(double)));
+        HBTRY(ws->st_out.ensure((size_t)4 * N * sizeof(double)));
+        HBTRY(ws->st_member.ensure((size_t)n * sizeof(int64_t)));
+        CU(cudaMemcpyAsync(ws->st_in.p, gexp_rows, (size_t)n * N * sizeof(double), cudaMemcpyHostToDevice, 0));
+        CU(hb::launch_transpose_f64(ws->st_in.as<double>(), n, N, ws->st_x.as<double>(), ld, 0));
+        std::vector<int64_t> rows((size_t)n);
+        std::iota(rows.begin(), rows.end(), (int64_t)0);
+        CU(cudaMemcpy(ws->st_member.p, rows.data(), (size_t)n * sizeof(int64_t), cudaMemcpyHostToDevice));
+        d_x = ws->st_x.as<double>();
+        d_out = ws->st_out.as<double>();
+        d_rows = ws->st_member.as<int64_t>();
+        if (sigma0) {
+            d_sig = d_out + 3 * N;
+            CU(cudaMemcpy(d_sig, sigma0, (size_t)N * sizeof(double), cudaMemcpyHostToDevice));
+        }
+    }
+    HBTRY(hb_retest_gexp_dev(d_x, ld, n, N, d_rows, n, mag0, d_sig, d_out, d_out + N, d_out + 2 * N, nullptr,
+                             nullptr, 0, nullptr));
+    CU(cudaMemcpy(p_amp, d_out, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(p_del, d_out + N, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost));
+    if (mu0) CU(cudaMemcpy(mu0, d_out + 2 * N, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost));
     return HB_OK;
 }
 

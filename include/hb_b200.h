@@ -202,6 +202,15 @@ int hb_dist_sq_dev(const double *s, int64_t ld, int64_t G, int64_t N, double *D,
 int hb_ward_linkage_dev(double *D, int64_t N, int32_t *merge_a, int32_t *merge_b, double *height,
                         void *stream);
 
+/* Host-buffer forms for the R side (matrices column-major [G x N] as R holds them): the whole
+ * `runmean -> dist -> hclust(ward.D2) -> cutree(k)` block of R/HoneyBADGER.R:1122-1136 (window 101) and
+ * :1378-1397 (window 31, r.maf / n.sc) in one call.  labels[q*N + c] = cutree(hc, k = ks[q])[c]
+ * (1-based, clusters numbered by first appearance as cutree does). */
+int hb_group_gexp_host(const double *gexp_norm, int64_t G, int64_t N, int32_t window, const int32_t *ks,
+                       int32_t nk, int32_t *labels);
+int hb_group_allele_host(const double *r_maf, const double *n_sc, int64_t G, int64_t N, int32_t window,
+                         const int32_t *ks, int32_t nk, int32_t *labels);
+
 /* Deterministic retest of one candidate region for the expression model: the exact marginal posterior
  * of inst/bug/expressionModel.bug that HoneyBADGER$calcGexpCnvProb
  * (R/HoneyBADGER.R:374-470, called from :1220) estimates by JAGS sampling — statistical stand-in for
@@ -215,6 +224,11 @@ int hb_ward_linkage_dev(double *D, int64_t N, int32_t *merge_a, int32_t *merge_b
 int hb_retest_gexp_dev(const double *x, int64_t ld, int64_t G, int64_t N, const int64_t *rows,
                        int64_t nrows, double mag0, const double *sigma0, double *p_amp, double *p_del,
                        double *mu0, double *D_local, const double *D_total, int32_t phase, void *stream);
+
+/* Host-buffer form: gexp_rows column-major [n x N] = gexp.norm[bound.genes.new, ] (R/HoneyBADGER.R:1220),
+ * outputs of length N; mu0 may be NULL. */
+int hb_retest_gexp_host(const double *gexp_rows, int64_t n, int64_t N, double mag0, const double *sigma0,
+                        double *p_amp, double *p_del, double *mu0);
 
 /* Allele counterpart (stand-in for the JAGS snpModel of calcAlleleCnvProb, R/HoneyBADGER.R:907-1042):
  * P(deletion) per cell from the binomial likelihood ratio pd vs pn summed over the region's SNPs. */

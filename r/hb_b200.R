@@ -32,3 +32,25 @@ hb_gexp_round <- function(gexp.norm, hc, heights, dev, t) {
   lapply(seq_len(ncol(y)), function(k) list(amp = rownames(gexp.norm)[y[, k] == 3],
                                             del = rownames(gexp.norm)[y[, k] == 1]))
 }
+
+## Grouping and retest on the GPU (optional; SURVEY.md 8f-1/8f-2) ----------------------------------
+## R/HoneyBADGER.R:1122-1136: runmean + dist + hclust("ward.D2") + cutree for every height at once
+hb_group_gexp <- function(gexp.norm, heights, k = 101L) {
+  ct <- .Call("C_hb_group_gexp", gexp.norm, as.integer(k), as.integer(heights))
+  rownames(ct) <- colnames(gexp.norm)
+  ct   # ct[, i] is cutree(hc, k = heights[i])
+}
+## R/HoneyBADGER.R:1378-1397
+hb_group_allele <- function(r.maf, n.sc, heights, k = 31L) {
+  ct <- .Call("C_hb_group_allele", r.maf, n.sc, as.integer(k), as.integer(heights))
+  rownames(ct) <- colnames(r.maf)
+  ct
+}
+## deterministic stand-in for calcGexpCnvProb's JAGS run (R/HoneyBADGER.R:374-470): same return shape
+hb_calcGexpCnvProb <- function(gexp.norm.sub, m, sigma0 = NULL) {
+  p <- .Call("C_hb_retest_gexp", gexp.norm.sub, as.double(m), sigma0)
+  for (i in 1:3) names(p[[i]]) <- colnames(gexp.norm.sub)
+  names(p) <- c("posterior probability of amplification", "posterior probability of deletion",
+                "estimated mean normalized expression deviation")
+  p
+}

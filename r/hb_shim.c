@@ -98,11 +98,64 @@ SEXP C_hb_allele_pooled_viterbi(SEXP r_maf, SEXP n_sc, SEXP member, SEXP prob, S
     return y;
 }
 
+/* ct <- .Call(C_hb_group_gexp, gexp.norm, 101L, heights): replaces, at R/HoneyBADGER.R:1122-1136,
+ *   mat.smooth <- apply(gexp.norm, 2, caTools::runmean, k); d <- dist(t(mat.smooth)); d[is.na(d)] <- 0
+ *   hc <- hclust(d, method = "ward.D2");  lapply(heights, function(h) cutree(hc, k = h))
+ * Returns an integer [N x length(heights)] matrix: column q is cutree(hc, k = heights[q]). */
+SEXP C_hb_group_gexp(SEXP gexp_norm, SEXP window, SEXP heights)
+{
+    gexp_norm = PROTECT(Rf_coerceVector(gexp_norm, REALSXP));
+    heights = PROTECT(Rf_coerceVector(heights, INTSXP));
+    const int64_t G = Rf_nrows(gexp_norm), N = Rf_ncols(gexp_norm);
+    const int nk = (int)XLENGTH(heights);
+    SEXP lab = PROTECT(Rf_allocMatrix(INTSXP, (int)N, nk)); /* [nk][N] row-major == [N x nk] column-major */
+    int rc = hb_group_gexp_host(REAL(gexp_norm), G, N, Rf_asInteger(window), INTEGER(heights), nk, INTEGER(lab));
+    UNPROTECT(3);
+    hb_raise(rc);
+    return lab;
+}
+
+/* The allele form (R/HoneyBADGER.R:1378-1397): r.maf / n.sc smoothed with k = 31. */
+SEXP C_hb_group_allele(SEXP r_maf, SEXP n_sc, SEXP window, SEXP heights)
+{
+    r_maf = PROTECT(Rf_coerceVector(r_maf, REALSXP));
+    n_sc = PROTECT(Rf_coerceVector(n_sc, REALSXP));
+    heights = PROTECT(Rf_coerceVector(heights, INTSXP));
+    const int64_t G = Rf_nrows(r_maf), N = Rf_ncols(r_maf);
+    const int nk = (int)XLENGTH(heights);
+    SEXP lab = PROTECT(Rf_allocMatrix(INTSXP, (int)N, nk));
+    int rc = hb_group_allele_host(REAL(r_maf), REAL(n_sc), G, N, Rf_asInteger(window), INTEGER(heights), nk,
+                                  INTEGER(lab));
+    UNPROTECT(4);
+    hb_raise(rc);
+    return lab;
+}
+
+/* prob <- .Call(C_hb_retest_gexp, gexp.norm[bound.genes.new, ], m, sigma0): the exact marginal of
+ * inst/bug/expressionModel.bug instead of the JAGS run of calcGexpCnvProb (R/HoneyBADGER.R:374-470).
+ * Returns list(amp, del, mu0), the three vectors calcGexpCnvProb returns. */
+SEXP C_hb_retest_gexp(SEXP gexp_rows, SEXP mag0, SEXP sigma0)
+{
+    gexp_rows = PROTECT(Rf_coerceVector(gexp_rows, REALSXP));
+    const int64_t n = Rf_nrows(gexp_rows), N = Rf_ncols(gexp_rows);
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, 3));
+    for (int i = 0; i < 3; i++) SET_VECTOR_ELT(out, i, Rf_allocVector(REALSXP, N));
+    int rc = hb_retest_gexp_host(REAL(gexp_rows), n, N, Rf_asReal(mag0),
+                                 Rf_isNull(sigma0) ? NULL : REAL(sigma0), REAL(VECTOR_ELT(out, 0)),
+                                 REAL(VECTOR_ELT(out, 1)), REAL(VECTOR_ELT(out, 2)));
+    UNPROTECT(2);
+    hb_raise(rc);
+    return out;
+}
+
 static const R_CallMethodDef call_methods[] = {
     {"C_hb_viterbi_norm", (DL_FUNC)&C_hb_viterbi_norm, 5},
     {"C_hb_viterbi_binom", (DL_FUNC)&C_hb_viterbi_binom, 5},
     {"C_hb_gexp_pooled_viterbi", (DL_FUNC)&C_hb_gexp_pooled_viterbi, 5},
     {"C_hb_allele_pooled_viterbi", (DL_FUNC)&C_hb_allele_pooled_viterbi, 6},
+    {"C_hb_group_gexp", (DL_FUNC)&C_hb_group_gexp, 3},
+    {"C_hb_group_allele", (DL_FUNC)&C_hb_group_allele, 4},
+    {"C_hb_retest_gexp", (DL_FUNC)&C_hb_retest_gexp, 3},
     {NULL, NULL, 0}};
 
 void R_init_hbb200(DllInfo *dll)

@@ -278,3 +278,41 @@ def test_device_grouping_allele_form():
     r, n, _, clone = synth.allele(3000, 90, seed=43)
     got = hb.ward_groups_dev(None, [1, 2, 3], 31, counts=(torch.from_numpy(r).cuda(), torch.from_numpy(n).cuda()))
     assert [len(set(g)) for g in got] == [1, 2, 3] and all(g[0] == 1 for g in got)
+
+
+def test_host_forms_of_grouping_and_retest(oracle):
+    """hb_group_*_host / hb_retest_gexp_host (what the .Call shim binds) vs the device forms."""
+    import ctypes as C
+    import torch
+    from honeybadger_b200 import _lib, hmm
+    from honeybadger_b200 import honeybadger as hb
+    lib = _lib.load()
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    rng = np.random.default_rng(47)
+    G, N = 700, 93
+    clone = rng.choice(3, size=N)
+    x = rng.standard_normal((G, N)) * 1.4
+    x[100:300, clone == 0] += 1.3
+    x[400:600, clone == 1] -= 1.1
+    ks = np.array([1, 2, 3, 4], dtype=np.int32)
+    lab = np.zeros((4, N), dtype=np.int32)
+    xf = np.asfortranarray(x)                         # R's layout
+    _lib.check(lib.hb_group_gexp_host(vp(xf), G, N, 101, vp(ks), 4, vp(lab)))
+    ref = hb.ward_groups_dev(hmm.to_rows(torch.from_numpy(x).cuda()), list(ks), 101)
+    for a, b in zip(lab, ref):
+        assert (a == b).all()
+    r, n, _, _ = synth.allele(2500, 60, seed=49)
+    lab2 = np.zeros((3, 60), dtype=np.int32)
+    k3 = np.array([1, 2, 3], dtype=np.int32)
+    _lib.check(lib.hb_group_allele_host(vp(np.asfortranarray(r, dtype=np.float64)),
+                                        vp(np.asfortranarray(n, dtype=np.float64)), 2500, 60, 31, vp(k3), 3, vp(lab2)))
+    ref2 = hb.ward_groups_dev(None, [1, 2, 3], 31, counts=(torch.from_numpy(r).cuda(), torch.from_numpy(n).cuda()))
+    for a, b in zip(lab2, ref2):
+        assert (a == b).all()
+    rows = np.asfortranarray(x[100:160])
+    sig = rng.uniform(0.5, 1.5, N)
+    pa, pd_, mu = np.zeros(N), np.zeros(N), np.zeros(N)
+    _lib.check(lib.hb_retest_gexp_host(vp(rows), 60, N, 1.3, vp(sig), vp(pa), vp(pd_), vp(mu)))
+    ra, rd = oracle.retest_gexp(x[100:160], 1.3, sig)
+    assert np.abs(pa - ra).max() < 1e-12 and np.abs(pd_ - rd).max() < 1e-12
+    assert np.allclose(mu, x[100:160].mean(0), rtol=1e-13, atol=1e-13)
