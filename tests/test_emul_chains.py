@@ -382,3 +382,105 @@ def test_binom2_packed_counts(emul, oracle):
     finally:
         emul.emul_set_packed(0)
     assert gate2 == 0 and (y2 == yo[:, keep]).all() and np.abs(g2 - go[:, :, keep]).max() < 1e-9
+
+
+# ---------------------------------------------------------------------------- randomised shapes / parameters
+from hypothesis import HealthCheck, given, settings, strategies as st_  # noqa: E402
+
+
+@st_.composite
+def _chain_case(draw):
+    T = draw(st_.integers(1, 90))
+    B = draw(st_.integers(1, 37))
+    ncut = draw(st_.integers(0, 4))
+    cuts = sorted(draw(st_.lists(st_.integers(0, T), min_size=ncut, max_size=ncut)))
+    seg = np.array([0] + cuts + [T], dtype=np.int64)
+    t = draw(st_.sampled_from([1e-8, 1e-6, 1e-3, 0.05, 0.2]))
+    seed = draw(st_.integers(0, 2 ** 31 - 1))
+    tiled = draw(st_.booleans())
+    return T, B, seg, t, seed, tiled
+
+
+@settings(max_examples=150, deadline=None, suppress_health_check=list(HealthCheck))
+@given(_chain_case(), st_.sampled_from([(0.0, 1.0, 0.0), (0.2, 0.5, 0.3), (0.0, 0.4, 0.6)]),
+       st_.floats(0.3, 2.0), st_.sampled_from([0.0, 1.0]))
+def test_norm3_fast_random_cases(emul, oracle, case, delta, m, coarse):
+    """Random lengths (incl. 1 and chunk boundaries), ragged / empty segments, transition rates, priors,
+    coarse-grid observations (many exact ties) and both layouts: paths equal the oracle's, always."""
+    T, B, seg, t, seed, tiled = case
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((T, B)) * 1.7
+    x[T // 3: 2 * T // 3, : B // 2] += m
+    if coarse:
+        x = np.round(x, 0)
+    sd = rng.uniform(0.7, 2.5, B)
+    mean, Pi, dl = np.array([-m, 0.0, m]), oracle.sym_Pi(3, t), np.array(delta)
+    yo, go, _, rc = oracle.fbv_norm_batch(x, seg, mean, sd, Pi, dl)
+    if rc != 0:                       # some chain ends with nu = -Inf (length-1 chain, zero prior)
+        return
+    if tiled:
+        xt = np_tile(x)
+        y = np.zeros((xt.shape[0], T, 32), np.uint8)
+        g = np.zeros((3, xt.shape[0], T, 32))
+        emul.emul_set_tiled(1)
+    else:
+        xt, y, g = x, np.zeros((T, B), np.uint8), np.zeros((3, T, B))
+    ll = np.zeros((seg.size - 1, B))
+    nflag = C.c_int32(0)
+    try:
+        st = emul.emul_norm3_fast(ptr(xt), C.c_int64(32 if tiled else B), C.c_int64(T), C.c_int64(B), ptr(seg),
+                                  seg.size - 1, ptr(mean), ptr(sd), 0, ptr(Pi), ptr(dl), 3, C.c_double(1.0),
+                                  ptr(y), ptr(g), ptr(ll), C.byref(nflag))
+    finally:
+        emul.emul_set_tiled(0)
+    assert st == 0
+    yy = np_untile(y, B) if tiled else y
+    gg = np.stack([np_untile(g[k], B) for k in range(3)]) if tiled else g
+    live = np.zeros(T, bool)          # positions covered by a segment
+    for a, b in zip(seg[:-1], seg[1:]):
+        live[a:b] = True
+    assert (yy[live] == yo[live]).all()
+    assert np.abs(gg[:, live] - go[:, live]).max() < 1e-9
+
+
+@settings(max_examples=150, deadline=None, suppress_health_check=list(HealthCheck))
+@given(_chain_case(), st_.sampled_from([(0.0, 1.0), (0.3, 0.7)]), st_.sampled_from([0, 5, 64]),
+       st_.booleans())
+def test_binom2_fast_random_cases(emul, oracle, case, delta, lut, packed):
+    T, B, seg, t, seed, tiled = case
+    rng = np.random.default_rng(seed)
+    n = np.where(rng.random((T, B)) < 0.3, rng.integers(1, 12, (T, B)), 0).astype(np.int32)
+    p = np.full((T, B), 0.45)
+    p[T // 4: T // 2, : B // 2] = 0.1
+    r = rng.binomial(n, p).astype(np.int32)
+    prob, Pi, dl = np.array([0.1, 0.45]), oracle.sym_Pi(2, t), np.array(delta)
+    yo, go, _, rc = oracle.fbv_binom_batch(r, n, seg, prob, Pi, dl)
+    if rc != 0:
+        return
+    xin = ((n.astype(np.uint32) << 16) | r.astype(np.uint32)).view(np.int32) if packed else r
+    nin = np.zeros_like(n) if packed else n
+    if tiled:
+        xin, nin = np_tile(xin), np_tile(nin)
+        y = np.zeros((xin.shape[0], T, 32), np.uint8)
+        g = np.zeros((2, xin.shape[0], T, 32))
+    else:
+        y, g = np.zeros((T, B), np.uint8), np.zeros((2, T, B))
+    ll = np.zeros((seg.size - 1, B))
+    gate = C.c_int32(0)
+    emul.emul_set_tiled(int(tiled))
+    emul.emul_set_packed(int(packed))
+    try:
+        st = emul.emul_binom2_fast(ptr(xin), ptr(nin), C.c_int64(32 if tiled else B), C.c_int64(T), C.c_int64(B),
+                                   ptr(seg), seg.size - 1, ptr(prob), ptr(Pi), ptr(dl), 3, lut, ptr(y), ptr(g),
+                                   ptr(ll), C.byref(gate))
+    finally:
+        emul.emul_set_tiled(0)
+        emul.emul_set_packed(0)
+    assert st == 0 and gate.value == 0
+    yy = np_untile(y, B) if tiled else y
+    gg = np.stack([np_untile(g[k], B) for k in range(2)]) if tiled else g
+    live = np.zeros(T, bool)
+    for a, b in zip(seg[:-1], seg[1:]):
+        live[a:b] = True
+    assert (yy[live] == yo[live]).all()
+    assert np.abs(gg[:, live] - go[:, live]).max() < 1e-9
