@@ -262,3 +262,73 @@ def test_tiled_layout_matches_gene_major(oracle):
     big[5, 7] = 70000
     with pytest.raises(Exception, match="16 bits"):
         hmm.pack_counts(rd.contiguous(), big.contiguous())
+
+
+def test_random_small_cases_on_the_device(oracle):
+    """60 random small problems per chain family through the device entry points (both layouts, packed
+    counts, every kernel mode): lengths 1..120 incl. chunk boundaries, ragged / empty segments, coarse
+    observations with exact ties.  Paths equal the oracle's; posteriors within 1e-9."""
+    import torch
+    from honeybadger_b200 import _lib, hmm
+    O = oracle
+    lib = _lib.load()
+    rng = np.random.default_rng(2024)
+    try:
+        for it in range(60):
+            T, B = int(rng.integers(1, 121)), int(rng.integers(1, 70))
+            cuts = sorted(rng.integers(0, T + 1, size=int(rng.integers(0, 4))).tolist())
+            seg = np.array([0] + cuts + [T], dtype=np.int64)
+            live = np.zeros(T, bool)
+            for a, b in zip(seg[:-1], seg[1:]):
+                live[a:b] = True
+            t = float(rng.choice([1e-8, 1e-6, 1e-3, 0.05]))
+            tiled = bool(rng.integers(0, 2))
+            # ---- Gaussian
+            m = float(rng.uniform(0.3, 2.0))
+            x = rng.standard_normal((T, B)) * 1.7
+            x[T // 3: 2 * T // 3, : B // 2] += m
+            if it % 3 == 0:
+                x = np.round(x, 0)
+            sd = rng.uniform(0.7, 2.5, B)
+            delta = [(0.0, 1.0, 0.0), (0.2, 0.5, 0.3)][it % 2]
+            mean, Pi = [-m, 0.0, m], O.sym_Pi(3, t)
+            yo, go, _, rc = O.fbv_norm_batch(x, seg, mean, sd, Pi, delta)
+            if rc == 0:
+                _lib.check(lib.hb_set_norm3_mode([3, 1, 2][it % 3]))
+                xd, sdd = hmm.to_rows(torch.from_numpy(x).cuda()), torch.from_numpy(sd).cuda()
+                if tiled:
+                    out = hmm.hmm_norm_tiled_dev(hmm.tile_rows(xd), B, sdd, mean, Pi, delta, seg_off=seg)
+                    y, g = hmm.untile_rows(out["y"], B), hmm.untile_rows(out["gamma"], B)
+                else:
+                    out = hmm.hmm_norm_dev(xd, sdd, mean, Pi, delta, seg_off=seg)
+                    y, g = out["y"], out["gamma"]
+                hmm.status_dev()
+                assert (y.cpu().numpy()[live] == yo[live]).all(), f"case {it}"
+                assert np.abs(g.cpu().numpy()[:, live] - go[:, live]).max() < 1e-9, f"case {it}"
+            # ---- binomial
+            n = np.where(rng.random((T, B)) < 0.3, rng.integers(1, 12, (T, B)), 0).astype(np.int32)
+            p = np.full((T, B), 0.45)
+            p[T // 4: T // 2, : B // 2] = 0.1
+            r = rng.binomial(n, p).astype(np.int32)
+            d2 = [(0.0, 1.0), (0.3, 0.7)][it % 2]
+            prob, Pi2 = [0.1, 0.45], O.sym_Pi(2, t)
+            yo, go, _, rc = O.fbv_binom_batch(r, n, seg, prob, Pi2, d2)
+            if rc == 0:
+                _lib.check(lib.hb_set_binom2_mode(it % 2))
+                rd, nd = hmm.to_rows(torch.from_numpy(r).cuda()), hmm.to_rows(torch.from_numpy(n).cuda())
+                if tiled:
+                    rt, nt = hmm.tile_rows(rd), hmm.tile_rows(nd)
+                    if it % 4 == 1:
+                        out = hmm.hmm_binom_tiled_dev(hmm.pack_counts(rt, nt), None, B, prob, Pi2, d2, seg_off=seg)
+                    else:
+                        out = hmm.hmm_binom_tiled_dev(rt, nt, B, prob, Pi2, d2, seg_off=seg)
+                    y, g = hmm.untile_rows(out["y"], B), hmm.untile_rows(out["gamma"], B)
+                else:
+                    out = hmm.hmm_binom_dev(rd, nd, prob, Pi2, d2, seg_off=seg)
+                    y, g = out["y"], out["gamma"]
+                hmm.status_dev()
+                assert (y.cpu().numpy()[live] == yo[live]).all(), f"case {it}"
+                assert np.abs(g.cpu().numpy()[:, live] - go[:, live]).max() < 1e-9, f"case {it}"
+    finally:
+        lib.hb_set_norm3_mode(0)
+        lib.hb_set_binom2_mode(0)
