@@ -43,6 +43,13 @@ namespace hb {
 #define HB_B2F_SLUT_ENTRIES ((HB_B2F_SLUT_N + 1) * (HB_B2F_SLUT_N + 2) / 2)
 #define HB_B2F_SLUT_BYTES (HB_B2F_SLUT_ENTRIES * 24)
 
+// back-pointer word of one chunk: 2 bits / step
+#if HB_CHUNK <= 8
+typedef uint16_t b2f_psi_t;
+#else
+typedef uint32_t b2f_psi_t;
+#endif
+
 struct B2fSmem {
     double2 *pr;
     int32_t *ph;
@@ -214,7 +221,7 @@ HB_HD void binom2_fast_chain(const Binom2Args &a, int32_t seg, int64_t b, const 
     const int32_t *xp = a.x + lay_off(a.tiled, a.T, a.ld, t0, b);
     const int32_t *np = PK ? nullptr : a.n + lay_off(a.tiled, a.T, a.ld, t0, b);
     // back-pointers: 2 bits / step, one uint16 per chunk
-    uint16_t *psi = reinterpret_cast<uint16_t *>(a.psi) + lay_off(a.tiled, a.nchunks, a.B, cbase, b);
+    b2f_psi_t *psi = reinterpret_cast<b2f_psi_t *>(a.psi) + lay_off(a.tiled, a.nchunks, a.B, cbase, b);
     double *ckpt = a.ckpt + (a.tiled ? (((b >> 5) * a.nchunks + cbase) * 2 << 5) + (b & 31) : cbase * 2 * a.B + b);
     uint8_t *ybase = a.y ? a.y + lay_off(a.tiled, a.T, a.ldy, t0, b) : nullptr;
     double *gbase = a.gamma ? a.gamma + lay_off(a.tiled, a.T, a.ldg, t0, b) : nullptr;
@@ -245,7 +252,7 @@ HB_HD void binom2_fast_chain(const Binom2Args &a, int32_t seg, int64_t b, const 
     }
     {
         const int32_t *xr = xp + (int64_t)HB_CHUNK * ld, *nr = PK ? nullptr : np + (int64_t)HB_CHUNK * ld;
-        uint16_t *pw = psi;
+        b2f_psi_t *pw = psi;
         double *ck = ckpt;
         for (int32_t ch = 0; ch < nfull; ch++) {
             const bool more = ch + 1 < nfull;
@@ -272,7 +279,7 @@ HB_HD void binom2_fast_chain(const Binom2Args &a, int32_t seg, int64_t b, const 
                 }
                 cpa_commit(ring);
             }
-            if (VIT) *pw = (uint16_t)pk;
+            if (VIT) *pw = (b2f_psi_t)pk;
             pw += sB;
             ck += 2 * sB;
             if (FB && (more || tail > 0)) {
@@ -290,7 +297,7 @@ HB_HD void binom2_fast_chain(const Binom2Args &a, int32_t seg, int64_t b, const 
             b2f_unpack<PK>(xp[o], PK ? 0 : np[o], xv, nv);
             b2f_forward_one<VIT, FB, LL>(a, m, s, xv, nv, nfull == 0 && j == 0, pk, j);
         }
-        if (VIT) psi[(int64_t)nfull * sB] = (uint16_t)pk;
+        if (VIT) psi[(int64_t)nfull * sB] = (b2f_psi_t)pk;
     }
 
     if (FB && LL) {
@@ -366,7 +373,7 @@ HB_HD void binom2_fast_chain(const Binom2Args &a, int32_t seg, int64_t b, const 
         // refill pointers: the chunk before the one being replayed
         const int32_t *xr = xp + (int64_t)(nfull - 2) * HB_CHUNK * ld;
         const int32_t *nr = PK ? nullptr : np + (int64_t)(nfull - 2) * HB_CHUNK * ld;
-        const uint16_t *pr = psi + (int64_t)(nfull - 2) * sB;
+        const b2f_psi_t *pr = psi + (int64_t)(nfull - 2) * sB;
         const double *cr = ckpt + (int64_t)(nfull - 2) * 2 * sB;
         for (int32_t ch = nfull - 1; ch >= 0; ch--) {
             const uint32_t pk = pk_nx;

@@ -34,6 +34,8 @@
 
 namespace hb {
 
+// steps per chunk: one back-pointer word and one checkpoint per chunk.  (10 was tried: 3 % less
+// scratch traffic, no gain in time on either chain family, so the kernels assume 8.)
 #define HB_CHUNK 8
 
 // indices into Norm3Const::k
