@@ -7,10 +7,13 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
+#include <future>
 #include <mutex>
+#include <thread>
 #include <numeric>
 #include <string>
 #include <vector>
@@ -91,6 +94,10 @@ struct Workspace {
     DevBuf st_in, st_in2, st_x, st_x2, st_y, st_g, st_out, st_sd, st_ll, st_member, st_pool, st_pool2, st_pre, st_x80, st_part;
     // host-buffer entry points: three-stream pipeline (upload | layout + chains | download), staging x2
     DevBuf pin[2], pin2[2], pout_y[2], pout_g[2], pout_ll[2];
+    // pinned bounce buffers for ordinary (pageable) host memory, e.g. R vectors: [slot]
+    void *bounce_in[2] = {nullptr, nullptr}, *bounce_out[2] = {nullptr, nullptr};
+    size_t bounce_in_cap = 0, bounce_out_cap = 0;
+    cudaEvent_t ev_bin[2] = {nullptr, nullptr}, ev_bout[2] = {nullptr, nullptr};
     cudaStream_t s_in = nullptr, s_cmp = nullptr, s_out = nullptr;
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_free_in[2] = {nullptr, nullptr},
                 ev_out[2] = {nullptr, nullptr}, ev_free_out[2] = {nullptr, nullptr};
@@ -117,6 +124,15 @@ struct Workspace {
             }
             s_in = s_cmp = s_out = nullptr;
         }
+        for (int k = 0; k < 2; k++) {
+            if (bounce_in[k]) cudaFreeHost(bounce_in[k]);
+            if (bounce_out[k]) cudaFreeHost(bounce_out[k]);
+            bounce_in[k] = bounce_out[k] = nullptr;
+            if (ev_bin[k]) cudaEventDestroy(ev_bin[k]);
+            if (ev_bout[k]) cudaEventDestroy(ev_bout[k]);
+            ev_bin[k] = ev_bout[k] = nullptr;
+        }
+        bounce_in_cap = bounce_out_cap = 0;
         seg_cached.clear();
         lut_nmax = -1;
         lut_key[0] = -1;
@@ -595,6 +611,146 @@ int hb_hmm_norm_dev(const double *x, int64_t ld, int64_t T, int64_t B, const int
 // call approaches max(H2D, D2H) instead of their sum.  Staging buffers are double-buffered and
 // handed over with events; with pageable host memory the copies degrade to the driver's staged
 // path (still correct, less overlap).
+// ---------------------------------------------------------------------------------------------
+// Host memory that is not page-locked (every R vector) cannot be the source or target of an
+// asynchronous copy: cudaMemcpyAsync silently degrades to a synchronous, staged transfer (measured:
+// 15 GB/s instead of 67 GB/s, no overlap).  HostStager routes such buffers through the library's own
+// pinned bounce buffers: the upload side copies user memory -> pinned with several host threads right
+// before the H2D of a sub-batch, the download side lands D2H in pinned memory and a background task
+// copies it out to the user's buffers while the GPU works on the next sub-batch.  Pinned user
+// buffers (bench.py) take the direct path.
+static bool host_is_pinned(const void *p)
+{
+    if (!p) return true;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged;
+}
+
+static void parallel_memcpy(void *dst, const void *src, size_t bytes, int nthreads)
+{
+    if (bytes < ((size_t)4 << 20) || nthreads <= 1) {
+        memcpy(dst, src, bytes);
+        return;
+    }
+    std::vector<std::thread> th;
+    const size_t per = (bytes / nthreads + 4095) & ~(size_t)4095;
+    for (int i = 0; i < nthreads; i++) {
+        const size_t a = (size_t)i * per;
+        if (a >= bytes) break;
+        const size_t n = std::min(per, bytes - a);
+        th.emplace_back([=] { memcpy((char *)dst + a, (const char *)src + a, n); });
+    }
+    for (auto &t : th) t.join();
+}
+
+struct HostStager {
+    Workspace *ws;
+    bool bounce_in, bounce_out;
+    int nthreads;
+    struct Copy {
+        const void *src;
+        void *dst;
+        size_t bytes;
+    };
+    std::vector<Copy> pend[2];
+    std::future<void> fut[2];
+    size_t off_out[2] = {0, 0}, off_in[2] = {0, 0};
+
+    int init(Workspace *w, bool b_in, bool b_out, size_t in_bytes, size_t out_bytes)
+    {
+        ws = w;
+        bounce_in = b_in;
+        bounce_out = b_out;
+        nthreads = (int)std::max(1u, std::min(8u, std::thread::hardware_concurrency() / 2));
+        if (const char *e = getenv("HB_STAGER_THREADS")) nthreads = std::max(1, atoi(e));
+        for (int k = 0; k < 2; k++) {
+            if (b_in && ws->bounce_in_cap < in_bytes) {
+                if (ws->bounce_in[k]) cudaFreeHost(ws->bounce_in[k]);
+                ws->bounce_in[k] = nullptr;
+                CU(cudaHostAlloc(&ws->bounce_in[k], in_bytes, cudaHostAllocDefault));
+            }
+            if (b_out && ws->bounce_out_cap < out_bytes) {
+                if (ws->bounce_out[k]) cudaFreeHost(ws->bounce_out[k]);
+                ws->bounce_out[k] = nullptr;
+                CU(cudaHostAlloc(&ws->bounce_out[k], out_bytes, cudaHostAllocDefault));
+            }
+            if (!ws->ev_bin[k]) CU(cudaEventCreateWithFlags(&ws->ev_bin[k], cudaEventDisableTiming));
+            if (!ws->ev_bout[k]) CU(cudaEventCreateWithFlags(&ws->ev_bout[k], cudaEventDisableTiming));
+        }
+        if (b_in) ws->bounce_in_cap = std::max(ws->bounce_in_cap, in_bytes);
+        if (b_out) ws->bounce_out_cap = std::max(ws->bounce_out_cap, out_bytes);
+        return HB_OK;
+    }
+    // slot k is about to be filled again: its previous H2D must have left the bounce buffer
+    int begin_in(int k, bool reused)
+    {
+        off_in[k] = 0;
+        if (bounce_in && reused) CU(cudaEventSynchronize(ws->ev_bin[k]));
+        return HB_OK;
+    }
+    int h2d(int k, void *dev, const void *host, size_t bytes, cudaStream_t st)
+    {
+        const void *src = host;
+        if (bounce_in) {
+            char *b = (char *)ws->bounce_in[k] + off_in[k];
+            parallel_memcpy(b, host, bytes, nthreads);
+            off_in[k] += (bytes + 255) & ~(size_t)255;
+            src = b;
+        }
+        CU(cudaMemcpyAsync(dev, src, bytes, cudaMemcpyHostToDevice, st));
+        return HB_OK;
+    }
+    int end_in(int k, cudaStream_t st)
+    {
+        if (bounce_in) CU(cudaEventRecord(ws->ev_bin[k], st));
+        return HB_OK;
+    }
+    // slot k's previous download must have been copied out to the user before D2H lands in it again
+    void begin_out(int k)
+    {
+        if (fut[k].valid()) fut[k].get();
+        pend[k].clear();
+        off_out[k] = 0;
+    }
+    int d2h(int k, void *host, const void *dev, size_t bytes, cudaStream_t st)
+    {
+        void *dst = host;
+        if (bounce_out) {
+            char *b = (char *)ws->bounce_out[k] + off_out[k];
+            off_out[k] += (bytes + 255) & ~(size_t)255;
+            pend[k].push_back({b, host, bytes});
+            dst = b;
+        }
+        CU(cudaMemcpyAsync(dst, dev, bytes, cudaMemcpyDeviceToHost, st));
+        return HB_OK;
+    }
+    int end_out(int k, cudaStream_t st)
+    {
+        if (!bounce_out) return HB_OK;
+        CU(cudaEventRecord(ws->ev_bout[k], st));
+        cudaEvent_t ev = ws->ev_bout[k];
+        std::vector<Copy> jobs = pend[k];
+        const int nt = nthreads;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        fut[k] = std::async(std::launch::async, [ev, jobs, nt, dev] {
+            cudaSetDevice(dev);
+            cudaEventSynchronize(ev);
+            for (const Copy &c : jobs) parallel_memcpy(c.dst, c.src, c.bytes, nt);
+        });
+        return HB_OK;
+    }
+    void finish()
+    {
+        for (int k = 0; k < 2; k++)
+            if (fut[k].valid()) fut[k].get();
+    }
+};
+
 static int pipe_init(Workspace *ws)
 {
     if (ws->s_in) return HB_OK;
@@ -671,6 +827,14 @@ int hb_hmm_norm_host(const double *x, int64_t T, int64_t B, const int64_t *seg_o
     if (vit) HBTRY(ws->st_y.ensure((size_t)T * ldc));
     if (want_g) HBTRY(ws->st_g.ensure((size_t)3 * T * ldc * sizeof(double)));
     HBTRY(ws->st_sd.ensure((size_t)nsd_seg * B * 3 * sizeof(double)));
+    HostStager hs;
+    HBTRY(hs.init(ws, !host_is_pinned(x),
+                  !(host_is_pinned(vit ? y : nullptr) && host_is_pinned(want_g ? gamma : nullptr) &&
+                    host_is_pinned(want_ll ? ll : nullptr)),
+                  (size_t)T * Bc * sizeof(double) + 256,
+                  (vit ? (size_t)T * Bc * sizeof(int32_t) + 256 : 0) +
+                      (want_g ? 3 * ((size_t)T * Bc * sizeof(double) + 256) : 0) +
+                      (want_ll ? (size_t)nseg * (Bc * sizeof(double) + 256) : 0)));
     // chain scales of all sub-batches in one upload: sd, 1/sd (IEEE), log(sd) (host libm, as R);
     // sub-batch i occupies [3 * nsd_seg * b0, +3 * nsd_seg * bn) as three [nsd_seg][bn] blocks
     std::vector<double> h_aux((size_t)nsd_seg * B * 3);
@@ -694,8 +858,9 @@ int hb_hmm_norm_host(const double *x, int64_t T, int64_t B, const int64_t *seg_o
         const int64_t ld = (bn + 127) / 128 * 128;
         // upload
         if (i >= 2) CU(cudaStreamWaitEvent(ws->s_in, ws->ev_free_in[k], 0));
-        CU(cudaMemcpyAsync(ws->pin[k].p, x + b0 * T, (size_t)T * bn * sizeof(double),
-                           cudaMemcpyHostToDevice, ws->s_in));
+        HBTRY(hs.begin_in(k, i >= 2));
+        HBTRY(hs.h2d(k, ws->pin[k].p, x + b0 * T, (size_t)T * bn * sizeof(double), ws->s_in));
+        HBTRY(hs.end_in(k, ws->s_in));
         CU(cudaEventRecord(ws->ev_in[k], ws->s_in));
         // layout + chains
         CU(cudaStreamWaitEvent(ws->s_cmp, ws->ev_in[k], 0));
@@ -720,24 +885,26 @@ int hb_hmm_norm_host(const double *x, int64_t T, int64_t B, const int64_t *seg_o
         CU(cudaEventRecord(ws->ev_out[k], ws->s_cmp));
         // download
         CU(cudaStreamWaitEvent(ws->s_out, ws->ev_out[k], 0));
+        hs.begin_out(k);
         if (vit)
-            CU(cudaMemcpyAsync(y + b0 * T, ws->pout_y[k].p, (size_t)T * bn * sizeof(int32_t),
-                               cudaMemcpyDeviceToHost, ws->s_out));
+            HBTRY(hs.d2h(k, y + b0 * T, ws->pout_y[k].p, (size_t)T * bn * sizeof(int32_t), ws->s_out));
         if (want_g)
             for (int pl = 0; pl < 3; pl++)
-                CU(cudaMemcpyAsync(gamma + ((int64_t)pl * B + b0) * T,
-                                   ws->pout_g[k].as<double>() + (int64_t)pl * T * bn,
-                                   (size_t)T * bn * sizeof(double), cudaMemcpyDeviceToHost, ws->s_out));
+                HBTRY(hs.d2h(k, gamma + ((int64_t)pl * B + b0) * T,
+                             ws->pout_g[k].as<double>() + (int64_t)pl * T * bn,
+                             (size_t)T * bn * sizeof(double), ws->s_out));
         if (want_ll)
             for (int32_t sg = 0; sg < nseg; sg++)
-                CU(cudaMemcpyAsync(ll + (int64_t)sg * B + b0, d_ll + (int64_t)sg * bn,
-                                   (size_t)bn * sizeof(double), cudaMemcpyDeviceToHost, ws->s_out));
+                HBTRY(hs.d2h(k, ll + (int64_t)sg * B + b0, d_ll + (int64_t)sg * bn,
+                             (size_t)bn * sizeof(double), ws->s_out));
         CU(cudaEventRecord(ws->ev_free_out[k], ws->s_out));
+        HBTRY(hs.end_out(k, ws->s_out));
     }
     // drain (also on the error path: host buffers must not be touched after we return)
     cudaStreamSynchronize(ws->s_in);
     cudaStreamSynchronize(ws->s_cmp);
     cudaError_t e = cudaStreamSynchronize(ws->s_out);
+    hs.finish();
     if (rc != HB_OK) return rc;
     if (e != cudaSuccess) return fail(HB_ERR_CUDA, "pipeline failed: %s", cudaGetErrorString(e));
     return read_status(ws, ws->s_cmp);
@@ -830,16 +997,24 @@ int hb_hmm_binom_host(const int32_t *x, const int32_t *size, int64_t T, int64_t 
     HBTRY(ws->st_x2.ensure((size_t)T * ldc * sizeof(int32_t)));
     if (vit) HBTRY(ws->st_y.ensure((size_t)T * ldc));
     if (want_g) HBTRY(ws->st_g.ensure((size_t)2 * T * ldc * sizeof(double)));
+    HostStager hs;
+    HBTRY(hs.init(ws, !(host_is_pinned(x) && host_is_pinned(size)),
+                  !(host_is_pinned(vit ? y : nullptr) && host_is_pinned(want_g ? gamma : nullptr) &&
+                    host_is_pinned(want_ll ? ll : nullptr)),
+                  2 * ((size_t)T * Bc * sizeof(int32_t) + 256),
+                  (vit ? (size_t)T * Bc * sizeof(int32_t) + 256 : 0) +
+                      (want_g ? 2 * ((size_t)T * Bc * sizeof(double) + 256) : 0) +
+                      (want_ll ? (size_t)nseg * (Bc * sizeof(double) + 256) : 0)));
     int rc = HB_OK;
     for (int64_t i = 0; i < nb && rc == HB_OK; i++) {
         const int k = (int)(i & 1);
         const int64_t b0 = i * Bc, bn = std::min(Bc, B - b0);
         const int64_t ld = (bn + 127) / 128 * 128;
         if (i >= 2) CU(cudaStreamWaitEvent(ws->s_in, ws->ev_free_in[k], 0));
-        CU(cudaMemcpyAsync(ws->pin[k].p, x + b0 * T, (size_t)T * bn * sizeof(int32_t),
-                           cudaMemcpyHostToDevice, ws->s_in));
-        CU(cudaMemcpyAsync(ws->pin2[k].p, size + b0 * T, (size_t)T * bn * sizeof(int32_t),
-                           cudaMemcpyHostToDevice, ws->s_in));
+        HBTRY(hs.begin_in(k, i >= 2));
+        HBTRY(hs.h2d(k, ws->pin[k].p, x + b0 * T, (size_t)T * bn * sizeof(int32_t), ws->s_in));
+        HBTRY(hs.h2d(k, ws->pin2[k].p, size + b0 * T, (size_t)T * bn * sizeof(int32_t), ws->s_in));
+        HBTRY(hs.end_in(k, ws->s_in));
         CU(cudaEventRecord(ws->ev_in[k], ws->s_in));
         CU(cudaStreamWaitEvent(ws->s_cmp, ws->ev_in[k], 0));
         CU(hb::launch_transpose_i32(ws->pin[k].as<int32_t>(), T, bn, ws->st_x.as<int32_t>(), ld, ws->s_cmp));
@@ -861,23 +1036,25 @@ int hb_hmm_binom_host(const int32_t *x, const int32_t *size, int64_t T, int64_t 
                                                  ws->s_cmp));
         CU(cudaEventRecord(ws->ev_out[k], ws->s_cmp));
         CU(cudaStreamWaitEvent(ws->s_out, ws->ev_out[k], 0));
+        hs.begin_out(k);
         if (vit)
-            CU(cudaMemcpyAsync(y + b0 * T, ws->pout_y[k].p, (size_t)T * bn * sizeof(int32_t),
-                               cudaMemcpyDeviceToHost, ws->s_out));
+            HBTRY(hs.d2h(k, y + b0 * T, ws->pout_y[k].p, (size_t)T * bn * sizeof(int32_t), ws->s_out));
         if (want_g)
             for (int pl = 0; pl < 2; pl++)
-                CU(cudaMemcpyAsync(gamma + ((int64_t)pl * B + b0) * T,
-                                   ws->pout_g[k].as<double>() + (int64_t)pl * T * bn,
-                                   (size_t)T * bn * sizeof(double), cudaMemcpyDeviceToHost, ws->s_out));
+                HBTRY(hs.d2h(k, gamma + ((int64_t)pl * B + b0) * T,
+                             ws->pout_g[k].as<double>() + (int64_t)pl * T * bn,
+                             (size_t)T * bn * sizeof(double), ws->s_out));
         if (want_ll)
             for (int32_t sg = 0; sg < nseg; sg++)
-                CU(cudaMemcpyAsync(ll + (int64_t)sg * B + b0, d_ll + (int64_t)sg * bn,
-                                   (size_t)bn * sizeof(double), cudaMemcpyDeviceToHost, ws->s_out));
+                HBTRY(hs.d2h(k, ll + (int64_t)sg * B + b0, d_ll + (int64_t)sg * bn,
+                             (size_t)bn * sizeof(double), ws->s_out));
         CU(cudaEventRecord(ws->ev_free_out[k], ws->s_out));
+        HBTRY(hs.end_out(k, ws->s_out));
     }
     cudaStreamSynchronize(ws->s_in);
     cudaStreamSynchronize(ws->s_cmp);
     cudaError_t e = cudaStreamSynchronize(ws->s_out);
+    hs.finish();
     if (rc != HB_OK) return rc;
     if (e != cudaSuccess) return fail(HB_ERR_CUDA, "pipeline failed: %s", cudaGetErrorString(e));
     return read_status(ws, ws->s_cmp);

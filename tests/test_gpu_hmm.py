@@ -332,3 +332,73 @@ def test_random_small_cases_on_the_device(oracle):
     finally:
         lib.hb_set_norm3_mode(0)
         lib.hb_set_binom2_mode(0)
+
+
+def test_host_entry_pinned_and_pageable_buffers_agree():
+    """hb_hmm_*_host stages ordinary host memory (R vectors, numpy) through its own pinned bounce
+    buffers and copies page-locked buffers directly; both must give the same bytes, over several
+    sub-batches and a ragged last one."""
+    import ctypes as C
+
+    import torch
+
+    from honeybadger_b200 import _lib, hmm
+
+    lib = _lib.load()
+    T, B = 700, 333
+    rng = np.random.default_rng(5)
+    seg = np.array([0, 250, 253, 700], dtype=np.int64)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    tp = lambda t: C.c_void_p(t.data_ptr())
+
+    def pinned(a):
+        t = torch.from_numpy(a.copy()).pin_memory()
+        assert t.is_pinned()
+        return t
+
+    # Gaussian
+    x = rng.standard_normal((B, T))
+    x[:40, 300:500] += 1.0
+    sd = np.full(B, 0.7)
+    Pi, mean, delta = hmm.sym_Pi(3, 1e-6), np.array([-1.0, 0.0, 1.0]), np.array([0.0, 1.0, 0.0])
+    outs = []
+    for pin in (False, True):
+        y = np.full((B, T), -1, np.int32)
+        g = np.full((3, B, T), np.nan)
+        l = np.full((3, B), np.nan)
+        if pin:
+            xb, yb, gb, lb = pinned(x), pinned(y), pinned(g), pinned(l)
+            rc = lib.hb_hmm_norm_host(tp(xb), T, B, vp(seg), 3, vp(mean), vp(sd), 0, vp(Pi), vp(delta), 7,
+                                      tp(yb), tp(gb), tp(lb))
+            outs.append((yb.numpy().copy(), gb.numpy().copy(), lb.numpy().copy()))
+        else:
+            rc = lib.hb_hmm_norm_host(vp(x), T, B, vp(seg), 3, vp(mean), vp(sd), 0, vp(Pi), vp(delta), 7,
+                                      vp(y), vp(g), vp(l))
+            outs.append((y, g, l))
+        _lib.check(rc)
+    for a, b in zip(*outs):
+        assert np.array_equal(a, b)
+    assert outs[0][0].min() >= 1 and np.isfinite(outs[0][1]).all()
+
+    # binomial
+    n = rng.integers(0, 40, (B, T)).astype(np.int32)
+    k = rng.binomial(n, 0.3).astype(np.int32)
+    P2, prob, d2 = hmm.sym_Pi(2, 1e-5), np.array([0.5, 0.1]), np.array([0.5, 0.5])
+    outs = []
+    for pin in (False, True):
+        y = np.full((B, T), -1, np.int32)
+        g = np.full((2, B, T), np.nan)
+        l = np.full((3, B), np.nan)
+        if pin:
+            kb, nb, yb, gb, lb = pinned(k), pinned(n), pinned(y), pinned(g), pinned(l)
+            rc = lib.hb_hmm_binom_host(tp(kb), tp(nb), T, B, vp(seg), 3, vp(prob), 0.0, vp(P2), vp(d2), 7,
+                                       tp(yb), tp(gb), tp(lb))
+            outs.append((yb.numpy().copy(), gb.numpy().copy(), lb.numpy().copy()))
+        else:
+            rc = lib.hb_hmm_binom_host(vp(k), vp(n), T, B, vp(seg), 3, vp(prob), 0.0, vp(P2), vp(d2), 7,
+                                       vp(y), vp(g), vp(l))
+            outs.append((y, g, l))
+        _lib.check(rc)
+    for a, b in zip(*outs):
+        assert np.array_equal(a, b)
+    assert outs[0][0].min() >= 1 and np.isfinite(outs[0][1]).all()
