@@ -75,6 +75,17 @@ SIGNATURES = {
     "hb_ward_linkage_dev": (_i32, [_p, _i64, _p, _p, _p, _p]),
     "hb_group_gexp_host": (_i32, [_p, _i64, _i64, _i32, _p, _i32, _p]),
     "hb_group_allele_host": (_i32, [_p, _p, _i64, _i64, _i32, _p, _i32, _p]),
+    "hb_set_gexp_mats_dev": (_i32, [_p, _i64, _i64, _i64, _p, _i64, _i64, _i32, _d, _p, _p, _i32, _p, _i64,
+                                    _p, _p, _p, _p]),
+    "hb_set_gexp_mats_host": (_i32, [_p, _i64, _i64, _p, _i64, _i32, _d, _p, _p, _i32, _p, _p, _p, _p]),
+    "hb_row_means_dev": (_i32, [_p, _i64, _i64, _i64, _p, _p]),
+    "hb_col_scale_stats_dev": (_i32, [_p, _i64, _i64, _i64, _p, _p, _p, _p]),
+    "hb_gexp_apply_dev": (_i32, [_p, _i64, _i64, _p, _i64, _p, _p, _p, _p, _i64, _p]),
+    "hb_mean_nonzero_dev": (_i32, [_p, _i64, _i64, _i64, _i32, _p, _p, _p]),
+    "hb_set_allele_mats_dev": (_i32, [_p, _p, _i64, _i64, _i64, _p, _p, _i32, _d, _i32, _p, _p, _i64, _p, _p,
+                                      _p, _p, _p, _p, _p]),
+    "hb_set_allele_mats_host": (_i32, [_p, _p, _i64, _i64, _p, _p, _i32, _d, _i32, _p, _p, _p, _p, _p, _p,
+                                       _p, _p]),
     "hb_retest_gexp_host": (_i32, [_p, _i64, _i64, _d, _p, _p, _p, _p]),
     "hb_retest_gexp_dev": (_i32, [_p, _i64, _i64, _i64, _p, _i64, _d, _p, _p, _p, _p, _p, _p, _i32, _p]),
     "hb_retest_allele_lr_dev": (_i32, [_p, _p, _i64, _i64, _i64, _p, _i64, _d, _d, _p, _p]),

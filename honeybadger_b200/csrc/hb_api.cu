@@ -91,7 +91,7 @@ struct DevBuf {
 // Per-device scratch, grown on demand and reused across calls (no allocation in steady state).
 struct Workspace {
     DevBuf psi, ckpt, sdaux, segtab, status, lut_lb, lut_rho, lut_rho_d, cellmask, gsize;
-    DevBuf st_in, st_in2, st_x, st_x2, st_y, st_g, st_out, st_sd, st_ll, st_member, st_pool, st_pool2, st_pre, st_x80, st_part;
+    DevBuf st_in, st_in2, st_x, st_x2, st_y, st_g, st_out, st_sd, st_ll, st_member, st_pool, st_pool2, st_pre, st_x80, st_part, st_inp, st_inp2;
     // host-buffer entry points: three-stream pipeline (upload | layout + chains | download), staging x2
     DevBuf pin[2], pin2[2], pout_y[2], pout_g[2], pout_ll[2];
     // pinned bounce buffers for ordinary (pageable) host memory, e.g. R vectors: [slot]
@@ -109,7 +109,7 @@ struct Workspace {
     {
         DevBuf *all[] = {&psi, &ckpt, &sdaux, &segtab, &status, &lut_lb, &lut_rho, &lut_rho_d, &cellmask, &gsize,
                          &st_in, &st_in2, &st_x, &st_x2, &st_y, &st_g, &st_out, &st_sd, &st_ll,
-                         &st_member, &st_pool, &st_pool2, &st_pre, &st_x80, &st_part, &pin[0], &pin[1], &pin2[0], &pin2[1],
+                         &st_member, &st_pool, &st_pool2, &st_pre, &st_x80, &st_part, &st_inp, &st_inp2, &pin[0], &pin[1], &pin2[0], &pin2[1],
                          &pout_y[0], &pout_y[1], &pout_g[0], &pout_g[1], &pout_ll[0], &pout_ll[1]};
         for (DevBuf *b : all) b->release();
         if (s_in) {
@@ -1337,6 +1337,319 @@ int hb_group_allele_host(const double *r_maf, const double *n_sc, int64_t G, int
 {
     if (!r_maf || !n_sc) return fail(HB_ERR_ARG, "bad arguments");
     return group_host(nullptr, r_maf, n_sc, G, N, window, ks, nk, labels);
+}
+
+// ------------------------------------------------------------------ input construction (8f-3)
+int hb_row_means_dev(const double *x, int64_t ld, int64_t G, int64_t N, double *out, void *stream)
+{
+    if (!x || !out || G < 1 || N < 1 || ld < N || N >= ((int64_t)1 << 32)) return fail(HB_ERR_ARG, "bad arguments");
+    CU(hb::launch_row_means(x, ld, G, N, out, (cudaStream_t)stream));
+    return HB_OK;
+}
+
+int hb_col_scale_stats_dev(const double *x, int64_t ld, int64_t G, int64_t N, const uint8_t *keep,
+                           double *center, double *scl, void *stream)
+{
+    if (!x || !center || G < 1 || N < 1 || ld < N || G >= ((int64_t)1 << 32)) return fail(HB_ERR_ARG, "bad arguments");
+    CU(hb::launch_col_stats(x, ld, G, N, keep, center, scl, (cudaStream_t)stream));
+    return HB_OK;
+}
+
+int hb_gexp_apply_dev(const double *x, int64_t ld, int64_t N, const int32_t *rows, int64_t Gk,
+                      const double *center, const double *scl, const double *refmean, double *out,
+                      int64_t ldo, void *stream)
+{
+    if (!x || !out || N < 1 || Gk < 0 || ld < N || ldo < N) return fail(HB_ERR_ARG, "bad arguments");
+    if (Gk == 0) return HB_OK;
+    CU(hb::launch_gexp_apply(x, ld, N, rows, Gk, center, scl, refmean, out, ldo, (cudaStream_t)stream));
+    return HB_OK;
+}
+
+// mean(x[x != 0]).  exact = 0: parallel double-double sum; *margin bounds |result - R's value| (R's
+// serial evaluation can differ from the true mean by n * 2^-62 * max|x|).  exact = 1: R's loop replayed.
+static int mean_nonzero(Workspace *ws, const double *x, int64_t ld, int64_t G, int64_t N, int32_t exact,
+                        double *mean, double *margin, cudaStream_t st)
+{
+    const int nblk = 148 * 4;
+    HBTRY(ws->st_part.ensure((size_t)nblk * 4 * sizeof(double) + 64));
+    double *ph = ws->st_part.as<double>(), *pl = ph + nblk, *pm = pl + nblk;
+    unsigned long long *pn = (unsigned long long *)(pm + nblk);
+    CU(hb::launch_nz_sum(x, ld, G, N, nblk, ph, pl, pn, pm, st));
+    std::vector<double> h((size_t)nblk * 4);
+    CU(cudaMemcpyAsync(h.data(), ph, h.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    // combine the block partials in double-double (error-free additions, libm-free)
+    double H = 0.0, L = 0.0, mx = 0.0;
+    unsigned long long n = 0;
+    auto dd = [&](double v) {
+        volatile double s = H + v;
+        volatile double bb = s - H;
+        volatile double e1 = H - (s - bb), e2 = v - bb;
+        H = s;
+        L += e1 + e2;
+    };
+    for (int i = 0; i < nblk; i++) {
+        dd(h[i]);
+        dd(h[nblk + i]);
+        mx = std::max(mx, h[2 * nblk + i]);
+        unsigned long long c;
+        memcpy(&c, &h[3 * nblk + i], sizeof c);
+        n += c;
+    }
+    if (n == 0) { // mean(numeric(0)) is NaN in R
+        *mean = NAN;
+        if (margin) *margin = 0.0;
+        return HB_OK;
+    }
+    if (n >= (1ull << 32)) return fail(HB_ERR_ARG, "more than 2^32 non-zero entries");
+    if (!exact) {
+        const long double m = ((long double)H + (long double)L) / (long double)n;
+        *mean = (double)m;
+        if (margin) *margin = (double)n * ldexp(mx, -62) + ldexp(fabs(*mean), -50);
+        return HB_OK;
+    }
+    double *d_out = ws->st_part.as<double>();
+    CU(hb::launch_nz_mean_seq(x, ld, G, N, n, d_out, st));
+    CU(cudaMemcpyAsync(mean, d_out, sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (margin) *margin = 0.0;
+    return HB_OK;
+}
+
+int hb_mean_nonzero_dev(const double *x, int64_t ld, int64_t G, int64_t N, int32_t exact, double *mean,
+                        double *margin, void *stream)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    Workspace *ws;
+    HBTRY(cur_ws(&ws));
+    if (!x || !mean || G < 1 || N < 1 || ld < N) return fail(HB_ERR_ARG, "bad arguments");
+    return mean_nonzero(ws, x, ld, G, N, exact, mean, margin, (cudaStream_t)stream);
+}
+
+// setGexpMats (R/HoneyBADGER.R:124-188) on device-resident gene-major matrices; caller holds g_mu.
+static int set_gexp_mats(Workspace *ws, const double *sc, int64_t ld, int64_t G, int64_t N, const double *ref,
+                         int64_t ldr, int64_t R, int32_t filter, double min_both, const double *min_test,
+                         const double *min_ref, int32_t scale, double *norm, int64_t ldo, int32_t *keep_rows,
+                         int64_t *Gk_out, int32_t *info, cudaStream_t st)
+{
+    if (info) *info = 0;
+    // scratch: rm_s[G] rm_r[G] refmean[G] | center_s[N] scl_s[N] | center_r[R] scl_r[R] | rows[G] | keep[G]
+    const size_t nd = (size_t)3 * G + 2 * N + 2 * R;
+    HBTRY(ws->st_inp.ensure(nd * sizeof(double) + (size_t)G * sizeof(int32_t) + (size_t)G + 64));
+    double *rm_s = ws->st_inp.as<double>(), *rm_r = rm_s + G, *refmean = rm_r + G;
+    double *cen_s = refmean + G, *scl_s = cen_s + N, *cen_r = scl_s + N, *scl_r = cen_r + R;
+    int32_t *d_rows = (int32_t *)(scl_r + R);
+    uint8_t *d_keep = (uint8_t *)(d_rows + G);
+    CU(hb::launch_row_means(ref, ldr, G, R, rm_r, st));
+    std::vector<int32_t> rows;
+    rows.reserve((size_t)G);
+    if (filter) {
+        CU(hb::launch_row_means(sc, ld, G, N, rm_s, st));
+        std::vector<double> h((size_t)2 * G);
+        CU(cudaMemcpyAsync(h.data(), rm_s, h.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+        double mt = 0, mr = 0, mgt = 0, mgr = 0;
+        if (min_test) mt = *min_test;
+        else HBTRY(mean_nonzero(ws, sc, ld, G, N, 0, &mt, &mgt, st));
+        if (min_ref) mr = *min_ref;
+        else HBTRY(mean_nonzero(ws, ref, ldr, G, R, 0, &mr, &mgr, st));
+        CU(cudaStreamSynchronize(st));
+        // a row mean inside the safety margin of a default threshold: only R's serial evaluation decides
+        bool near_t = false, near_r = false;
+        for (int64_t g = 0; g < G; g++) {
+            if (!min_test && fabs(h[g] - mt) <= mgt) near_t = true;
+            if (!min_ref && fabs(h[G + g] - mr) <= mgr) near_r = true;
+        }
+        if (near_t) HBTRY(mean_nonzero(ws, sc, ld, G, N, 1, &mt, nullptr, st));
+        if (near_r) HBTRY(mean_nonzero(ws, ref, ldr, G, R, 1, &mr, nullptr, st));
+        if (info) *info = (near_t ? 1 : 0) | (near_r ? 2 : 0);
+        for (int64_t g = 0; g < G; g++) {
+            const double a = h[g], b = h[G + g];
+            if ((a > min_both && b > min_both) || a > mt || b > mr) rows.push_back((int32_t)g);
+        }
+    } else {
+        rows.resize((size_t)G);
+        std::iota(rows.begin(), rows.end(), 0);
+    }
+    const int64_t Gk = (int64_t)rows.size();
+    *Gk_out = Gk;
+    if (keep_rows) memcpy(keep_rows, rows.data(), (size_t)Gk * sizeof(int32_t));
+    if (Gk == 0) return HB_OK;
+    std::vector<uint8_t> keep((size_t)G, 0);
+    for (int32_t g : rows) keep[(size_t)g] = 1;
+    CU(cudaMemcpyAsync(d_rows, rows.data(), (size_t)Gk * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_keep, keep.data(), (size_t)G, cudaMemcpyHostToDevice, st));
+    if (scale) {
+        // scale(gexp.ref): centre / scale the kept rows of every reference column, then rowMeans
+        const int64_t ldr2 = (R + 31) / 32 * 32;
+        HBTRY(ws->st_inp2.ensure((size_t)Gk * ldr2 * sizeof(double)));
+        double *ref2 = ws->st_inp2.as<double>();
+        CU(hb::launch_col_stats(ref, ldr, G, R, d_keep, cen_r, scl_r, st));
+        CU(hb::launch_gexp_apply(ref, ldr, R, d_rows, Gk, cen_r, scl_r, nullptr, ref2, ldr2, st));
+        CU(hb::launch_row_means(ref2, ldr2, Gk, R, refmean, st));
+        CU(hb::launch_col_stats(sc, ld, G, N, d_keep, cen_s, scl_s, st));
+        CU(hb::launch_gexp_apply(sc, ld, N, d_rows, Gk, cen_s, scl_s, refmean, norm, ldo, st));
+    } else {
+        // rowMeans of a row subset is the subset of the rowMeans: gather rm_r (N = 1 "matrix")
+        CU(hb::launch_gexp_apply(rm_r, 1, 1, d_rows, Gk, nullptr, nullptr, nullptr, refmean, 1, st));
+        CU(hb::launch_gexp_apply(sc, ld, N, d_rows, Gk, nullptr, nullptr, refmean, norm, ldo, st));
+    }
+    CU(cudaStreamSynchronize(st)); // `rows` / `keep` are host temporaries of this call
+    return HB_OK;
+}
+
+int hb_set_gexp_mats_dev(const double *sc, int64_t ld, int64_t G, int64_t N, const double *ref, int64_t ldr,
+                         int64_t R, int32_t filter, double min_mean_both, const double *min_mean_test,
+                         const double *min_mean_ref, int32_t scale, double *norm, int64_t ldo,
+                         int32_t *keep_rows, int64_t *Gk, int32_t *info, void *stream)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    Workspace *ws;
+    HBTRY(cur_ws(&ws));
+    if (!sc || !ref || !norm || !Gk || G < 1 || N < 1 || R < 1 || ld < N || ldr < R || ldo < N ||
+        G >= ((int64_t)1 << 31) || N >= ((int64_t)1 << 32))
+        return fail(HB_ERR_ARG, "bad arguments");
+    return set_gexp_mats(ws, sc, ld, G, N, ref, ldr, R, filter, min_mean_both, min_mean_test, min_mean_ref,
+                         scale, norm, ldo, keep_rows, Gk, info, (cudaStream_t)stream);
+}
+
+int hb_set_gexp_mats_host(const double *sc, int64_t G, int64_t N, const double *ref, int64_t R, int32_t filter,
+                          double min_mean_both, const double *min_mean_test, const double *min_mean_ref,
+                          int32_t scale, double *norm, int32_t *keep_rows, int64_t *Gk, int32_t *info)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    Workspace *ws;
+    HBTRY(cur_ws(&ws));
+    if (!sc || !ref || !norm || !Gk || G < 1 || N < 1 || R < 1 || G >= ((int64_t)1 << 31) ||
+        N >= ((int64_t)1 << 32))
+        return fail(HB_ERR_ARG, "bad arguments");
+    const int64_t ld = (N + 127) / 128 * 128, ldr = (R + 31) / 32 * 32;
+    // R's column-major G x N is [cell][gene] in memory: upload, turn gene-major, build, turn back
+    HBTRY(ws->st_in.ensure((size_t)G * N * sizeof(double)));
+    HBTRY(ws->st_in2.ensure((size_t)G * R * sizeof(double)));
+    HBTRY(ws->st_x.ensure((size_t)G * ld * sizeof(double)));
+    HBTRY(ws->st_x2.ensure((size_t)G * ldr * sizeof(double)));
+    HBTRY(ws->st_g.ensure((size_t)G * ld * sizeof(double)));
+    cudaStream_t st = 0;
+    CU(cudaMemcpyAsync(ws->st_in.p, sc, (size_t)G * N * sizeof(double), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ws->st_in2.p, ref, (size_t)G * R * sizeof(double), cudaMemcpyHostToDevice, st));
+    CU(hb::launch_transpose_f64(ws->st_in.as<double>(), G, N, ws->st_x.as<double>(), ld, st));
+    CU(hb::launch_transpose_f64(ws->st_in2.as<double>(), G, R, ws->st_x2.as<double>(), ldr, st));
+    HBTRY(set_gexp_mats(ws, ws->st_x.as<double>(), ld, G, N, ws->st_x2.as<double>(), ldr, R, filter,
+                        min_mean_both, min_mean_test, min_mean_ref, scale, ws->st_g.as<double>(), ld,
+                        keep_rows, Gk, info, st));
+    if (*Gk == 0) return HB_OK;
+    CU(hb::launch_transpose_f64_back(ws->st_g.as<double>(), ld, *Gk, N, ws->st_in.as<double>(), st));
+    CU(cudaMemcpyAsync(norm, ws->st_in.p, (size_t)*Gk * N * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return HB_OK;
+}
+
+// setAlleleMats (R/HoneyBADGER.R:486-614) on gene-major int32 count matrices; caller holds g_mu.
+static int set_allele_mats(Workspace *ws, const int32_t *r, const int32_t *n, int64_t ld, int64_t G, int64_t N,
+                           const double *l_init, const double *n_bulk_init, int32_t filter, double thr,
+                           int32_t min_cell, int32_t *r_maf, int32_t *n_sc, int64_t ldo, double *l_out,
+                           double *n_bulk_out, double *l_maf, int32_t *keep_rows, int64_t *Gk_out,
+                           int64_t *n_het, cudaStream_t st)
+{
+    // rowSums(r.init > 0), rowSums(n.sc.init > 0): the pooled-count kernel with one all-cells group
+    HBTRY(ws->cellmask.ensure((size_t)N * sizeof(uint32_t)));
+    HBTRY(ws->st_inp.ensure((size_t)2 * G * sizeof(int32_t) + (size_t)G * sizeof(int32_t) + (size_t)G + 64));
+    int32_t *d_cnt = ws->st_inp.as<int32_t>(), *d_rows = d_cnt + 2 * G;
+    uint8_t *d_code = (uint8_t *)(d_rows + G);
+    CU(cudaMemsetAsync(ws->cellmask.p, 0x01, (size_t)N * sizeof(uint32_t), st));
+    CU(hb::launch_pool_count(r, ld, G, N, ws->cellmask.as<uint32_t>(), 1, d_cnt, st));
+    CU(hb::launch_pool_count(n, ld, G, N, ws->cellmask.as<uint32_t>(), 1, d_cnt + G, st));
+    std::vector<int32_t> cnt((size_t)2 * G);
+    CU(cudaMemcpyAsync(cnt.data(), d_cnt, cnt.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    const bool silico = !l_init || !n_bulk_init;
+    std::vector<int32_t> rows;
+    std::vector<uint8_t> code;
+    rows.reserve((size_t)G);
+    code.reserve((size_t)G);
+    const double hi = 1 - thr;
+    int64_t het = 0;
+    for (int64_t g = 0; g < G; g++) {
+        const double l = silico ? (double)cnt[g] : l_init[g];
+        const double nb = silico ? (double)cnt[G + g] : n_bulk_init[g];
+        const double E = l / nb; // NaN for 0/0: dropped by which(), coded "NA" without the filter
+        if (filter) {
+            if (!(E > thr && E < hi)) continue;
+            het++;                               // what "heterozygous SNPs identified" reports (:527)
+            if (cnt[G + g] < min_cell) continue; // rowSums(n.sc > 0) >= min.cell
+        }
+        const int64_t k = (int64_t)rows.size();
+        rows.push_back((int32_t)g);
+        const uint8_t cd = (E != E) ? 2 : (E <= 0.5 ? 0 : 1);
+        code.push_back(cd);
+        if (l_out) l_out[k] = l;
+        if (n_bulk_out) n_bulk_out[k] = nb;
+        if (l_maf) l_maf[k] = cd == 2 ? 0.0 : (cd == 0 ? l : nb - l);
+    }
+    const int64_t Gk = (int64_t)rows.size();
+    *Gk_out = Gk;
+    if (n_het) *n_het = filter ? het : Gk;
+    if (keep_rows) memcpy(keep_rows, rows.data(), (size_t)Gk * sizeof(int32_t));
+    if (Gk == 0) return HB_OK;
+    CU(cudaMemcpyAsync(d_rows, rows.data(), (size_t)Gk * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_code, code.data(), (size_t)Gk, cudaMemcpyHostToDevice, st));
+    CU(hb::launch_allele_flip(r, n, ld, N, d_rows, Gk, d_code, r_maf, n_sc, ldo, st));
+    CU(cudaStreamSynchronize(st));
+    return HB_OK;
+}
+
+int hb_set_allele_mats_dev(const int32_t *r, const int32_t *n_sc_init, int64_t ld, int64_t G, int64_t N,
+                           const double *l_init, const double *n_bulk_init, int32_t filter,
+                           double het_deviance_threshold, int32_t min_cell, int32_t *r_maf, int32_t *n_sc,
+                           int64_t ldo, double *l, double *n_bulk, double *l_maf, int32_t *keep_rows,
+                           int64_t *Gk, int64_t *n_het, void *stream)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    Workspace *ws;
+    HBTRY(cur_ws(&ws));
+    if (!r || !n_sc_init || !r_maf || !Gk || G < 1 || N < 1 || ld < N || ldo < N || G >= ((int64_t)1 << 31))
+        return fail(HB_ERR_ARG, "bad arguments");
+    return set_allele_mats(ws, r, n_sc_init, ld, G, N, l_init, n_bulk_init, filter, het_deviance_threshold,
+                           min_cell, r_maf, n_sc, ldo, l, n_bulk, l_maf, keep_rows, Gk, n_het,
+                           (cudaStream_t)stream);
+}
+
+int hb_set_allele_mats_host(const int32_t *r, const int32_t *n_sc_init, int64_t G, int64_t N,
+                            const double *l_init, const double *n_bulk_init, int32_t filter,
+                            double het_deviance_threshold, int32_t min_cell, int32_t *r_maf, int32_t *n_sc,
+                            double *l, double *n_bulk, double *l_maf, int32_t *keep_rows, int64_t *Gk,
+                            int64_t *n_het)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    Workspace *ws;
+    HBTRY(cur_ws(&ws));
+    if (!r || !n_sc_init || !r_maf || !Gk || G < 1 || N < 1 || G >= ((int64_t)1 << 31))
+        return fail(HB_ERR_ARG, "bad arguments");
+    const int64_t ld = (N + 127) / 128 * 128;
+    const size_t mat = (size_t)G * ld * sizeof(int32_t);
+    HBTRY(ws->st_in.ensure((size_t)G * N * sizeof(int32_t)));
+    HBTRY(ws->st_in2.ensure((size_t)G * N * sizeof(int32_t)));
+    HBTRY(ws->st_x.ensure(mat));
+    HBTRY(ws->st_x2.ensure(mat));
+    HBTRY(ws->st_g.ensure(2 * mat));
+    cudaStream_t st = 0;
+    CU(cudaMemcpyAsync(ws->st_in.p, r, (size_t)G * N * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ws->st_in2.p, n_sc_init, (size_t)G * N * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    CU(hb::launch_transpose_i32(ws->st_in.as<int32_t>(), G, N, ws->st_x.as<int32_t>(), ld, st));
+    CU(hb::launch_transpose_i32(ws->st_in2.as<int32_t>(), G, N, ws->st_x2.as<int32_t>(), ld, st));
+    int32_t *o_r = ws->st_g.as<int32_t>(), *o_n = o_r + (size_t)G * ld;
+    HBTRY(set_allele_mats(ws, ws->st_x.as<int32_t>(), ws->st_x2.as<int32_t>(), ld, G, N, l_init, n_bulk_init,
+                          filter, het_deviance_threshold, min_cell, o_r, n_sc ? o_n : nullptr, ld, l, n_bulk,
+                          l_maf, keep_rows, Gk, n_het, st));
+    if (*Gk == 0) return HB_OK;
+    CU(hb::launch_transpose_i32_back(o_r, ld, *Gk, N, ws->st_in.as<int32_t>(), st));
+    CU(cudaMemcpyAsync(r_maf, ws->st_in.p, (size_t)*Gk * N * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    if (n_sc) {
+        CU(hb::launch_transpose_i32_back(o_n, ld, *Gk, N, ws->st_in2.as<int32_t>(), st));
+        CU(cudaMemcpyAsync(n_sc, ws->st_in2.p, (size_t)*Gk * N * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    }
+    CU(cudaStreamSynchronize(st));
+    return HB_OK;
 }
 
 // ------------------------------------------------------------------ deterministic retest (8f-1)

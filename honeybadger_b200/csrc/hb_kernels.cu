@@ -9,6 +9,7 @@
 #include "hb_binom2.cuh"
 #include "hb_binom2_fast.cuh"
 #include "hb_group.cuh"
+#include "hb_inputs.cuh"
 #include "hb_kernels.h"
 #include "hb_norm3.cuh"
 #include "hb_norm3_fast.cuh"
@@ -420,6 +421,13 @@ cudaError_t launch_transpose_f64_back(const double *src, int64_t ld, int64_t G, 
     return cudaGetLastError();
 }
 
+cudaError_t launch_transpose_i32_back(const int32_t *src, int64_t ld, int64_t G, int64_t N,
+                                      int32_t *dst, cudaStream_t st)
+{
+    transpose_out_kernel<int32_t, int32_t><<<tgrid(G, N), dim3(32, 8), 0, st>>>(src, ld, G, N, dst);
+    return cudaGetLastError();
+}
+
 // gene-major src[t*ld + b] <-> warp-tiled dst[((b/32)*T + t)*32 + b%32]; both sides coalesced
 // (a warp handles one 32-column tile row).  Padding columns of the last tile are written as 0.
 template <typename E>
@@ -824,6 +832,48 @@ cudaError_t launch_build_cellmask(const uint8_t *member, int64_t N, int32_t K, u
                                   cudaStream_t st)
 {
     build_cellmask_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(member, N, K, mask);
+    return cudaGetLastError();
+}
+
+// =====================================================================================
+// Input construction (hb_inputs.cuh)
+cudaError_t launch_row_means(const double *x, int64_t ld, int64_t G, int64_t N, double *out, cudaStream_t st)
+{
+    row_means_kernel<<<(unsigned)((G + 31) / 32), 128, 0, st>>>(x, ld, G, N, out);
+    return cudaGetLastError();
+}
+cudaError_t launch_col_stats(const double *x, int64_t ld, int64_t G, int64_t N, const uint8_t *keep,
+                             double *center, double *scl, cudaStream_t st)
+{
+    col_stats_kernel<<<(unsigned)((N + 31) / 32), 32, 0, st>>>(x, ld, G, N, keep, center, scl);
+    return cudaGetLastError();
+}
+cudaError_t launch_gexp_apply(const double *x, int64_t ld, int64_t N, const int32_t *rows, int64_t Gk,
+                              const double *center, const double *scl, const double *refmean, double *out,
+                              int64_t ldo, cudaStream_t st)
+{
+    const unsigned gy = (unsigned)std::min<int64_t>((N + 255) / 256, 64);
+    gexp_apply_kernel<<<dim3((unsigned)Gk, gy), 256, 0, st>>>(x, ld, N, rows, Gk, center, scl, refmean, out, ldo);
+    return cudaGetLastError();
+}
+cudaError_t launch_nz_sum(const double *x, int64_t ld, int64_t G, int64_t N, int nblocks, double *part_hi,
+                          double *part_lo, unsigned long long *part_n, double *part_max, cudaStream_t st)
+{
+    nz_sum_kernel<<<nblocks, 256, 0, st>>>(x, ld, G, N, part_hi, part_lo, part_n, part_max);
+    return cudaGetLastError();
+}
+cudaError_t launch_nz_mean_seq(const double *x, int64_t ld, int64_t G, int64_t N, unsigned long long n,
+                               double *out, cudaStream_t st)
+{
+    nz_mean_seq_kernel<<<1, 32, 0, st>>>(x, ld, G, N, n, out);
+    return cudaGetLastError();
+}
+cudaError_t launch_allele_flip(const int32_t *r, const int32_t *n, int64_t ld, int64_t N, const int32_t *rows,
+                               int64_t Gk, const uint8_t *code, int32_t *out_r, int32_t *out_n, int64_t ldo,
+                               cudaStream_t st)
+{
+    const unsigned gy = (unsigned)std::min<int64_t>((N + 255) / 256, 64);
+    allele_flip_kernel<<<dim3((unsigned)Gk, gy), 256, 0, st>>>(r, n, ld, N, rows, code, out_r, out_n, ldo);
     return cudaGetLastError();
 }
 

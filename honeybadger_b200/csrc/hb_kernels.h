@@ -31,6 +31,8 @@ cudaError_t launch_transpose_u8_back(const uint8_t *src, int64_t ld, int64_t G, 
                                      int32_t *dst, cudaStream_t st);
 cudaError_t launch_transpose_f64_back(const double *src, int64_t ld, int64_t G, int64_t N,
                                       double *dst, cudaStream_t st);
+cudaError_t launch_transpose_i32_back(const int32_t *src, int64_t ld, int64_t G, int64_t N,
+                                      int32_t *dst, cudaStream_t st);
 cudaError_t launch_tile(const void *src, int64_t ld, int64_t T, int64_t B, int elem, void *dst,
                         bool to_tiled, cudaStream_t st);
 cudaError_t launch_retest_allele(const int32_t *r, const int32_t *n, int64_t ld, int64_t N,
@@ -62,5 +64,19 @@ cudaError_t launch_pool_count(const int32_t *v, int64_t ld, int64_t G, int64_t N
                               const uint32_t *cellmask, int32_t K, int32_t *out, cudaStream_t st);
 cudaError_t launch_build_cellmask(const uint8_t *member, int64_t N, int32_t K, uint32_t *mask,
                                   cudaStream_t st);
+
+cudaError_t launch_row_means(const double *x, int64_t ld, int64_t G, int64_t N, double *out, cudaStream_t st);
+cudaError_t launch_col_stats(const double *x, int64_t ld, int64_t G, int64_t N, const uint8_t *keep,
+                             double *center, double *scl, cudaStream_t st);
+cudaError_t launch_gexp_apply(const double *x, int64_t ld, int64_t N, const int32_t *rows, int64_t Gk,
+                              const double *center, const double *scl, const double *refmean, double *out,
+                              int64_t ldo, cudaStream_t st);
+cudaError_t launch_nz_sum(const double *x, int64_t ld, int64_t G, int64_t N, int nblocks, double *part_hi,
+                          double *part_lo, unsigned long long *part_n, double *part_max, cudaStream_t st);
+cudaError_t launch_nz_mean_seq(const double *x, int64_t ld, int64_t G, int64_t N, unsigned long long n,
+                               double *out, cudaStream_t st);
+cudaError_t launch_allele_flip(const int32_t *r, const int32_t *n, int64_t ld, int64_t N, const int32_t *rows,
+                               int64_t Gk, const uint8_t *code, int32_t *out_r, int32_t *out_n, int64_t ldo,
+                               cudaStream_t st);
 
 } // namespace hb

@@ -346,6 +346,56 @@ def _to_dev_i32(a):
     return torch.as_tensor(np.ascontiguousarray(np.rint(a), dtype=np.int32), device="cuda")
 
 
+# --------------------------------------------------------------------------- input construction (8f-3)
+def set_gexp_mats_dev(sc, ref, filter=True, minMeanBoth=0.0, minMeanTest=None, minMeanRef=None, scale=True):
+    """Arithmetic of setGexpMats (R/HoneyBADGER.R:139-161) on the device: rowMeans filter, scale(),
+    gexp.sc - rowMeans(gexp.ref), with R's 80-bit accumulators replayed.  sc [G, N], ref [G, R] are
+    row-aligned numpy arrays or resident cuda fp64 tensors.  Returns (gexp.norm as a resident gene-major
+    tensor [Gk, N], kept row indices, info bits)."""
+    import torch
+    lib = _lib.load()
+    sc_d = sc if isinstance(sc, torch.Tensor) else _to_dev_f64(sc)
+    ref_d = ref if isinstance(ref, torch.Tensor) else _to_dev_f64(np.asarray(ref, dtype=np.float64).reshape(sc_d.shape[0], -1))
+    G, N = sc_d.shape
+    R = ref_d.shape[1]
+    norm = torch.empty((G, N), dtype=torch.float64, device="cuda")
+    keep = np.zeros(G, dtype=np.int32)
+    gk, info = C.c_int64(0), C.c_int32(0)
+    mt = None if minMeanTest is None else C.byref(C.c_double(float(minMeanTest)))
+    mr = None if minMeanRef is None else C.byref(C.c_double(float(minMeanRef)))
+    _lib.check(lib.hb_set_gexp_mats_dev(sc_d.data_ptr(), sc_d.stride(0), G, N, ref_d.data_ptr(), ref_d.stride(0),
+                                        R, int(bool(filter)), float(minMeanBoth), mt, mr, int(bool(scale)),
+                                        norm.data_ptr(), norm.stride(0), _vp(keep), C.byref(gk), C.byref(info),
+                                        _stream()))
+    return norm[:gk.value], keep[:gk.value].copy(), info.value
+
+
+def set_allele_mats_dev(r, n_sc, l_init=None, n_bulk_init=None, filter=True, het_deviance_threshold=0.05,
+                        min_cell=3):
+    """Arithmetic of setAlleleMats (R/HoneyBADGER.R:493-595) on the device: in-silico bulk, heterozygosity
+    and coverage filters, lesser-allele flip.  r, n_sc [G, N]: numpy or resident cuda int32 tensors.
+    Returns dict(r_maf, n_sc (resident [Gk, N]), l, n_bulk, l_maf (numpy [Gk]), keep, n_het)."""
+    import torch
+    lib = _lib.load()
+    r_d = r if isinstance(r, torch.Tensor) else _to_dev_i32(r)
+    n_d = n_sc if isinstance(n_sc, torch.Tensor) else _to_dev_i32(n_sc)
+    G, N = r_d.shape
+    o_r = torch.empty((G, N), dtype=torch.int32, device="cuda")
+    o_n = torch.empty((G, N), dtype=torch.int32, device="cuda")
+    l, nb, lm = np.zeros(G), np.zeros(G), np.zeros(G)
+    keep = np.zeros(G, dtype=np.int32)
+    gk, nhet = C.c_int64(0), C.c_int64(0)
+    li = None if l_init is None or n_bulk_init is None else np.ascontiguousarray(l_init, dtype=np.float64)
+    ni = None if li is None else np.ascontiguousarray(n_bulk_init, dtype=np.float64)
+    _lib.check(lib.hb_set_allele_mats_dev(r_d.data_ptr(), n_d.data_ptr(), r_d.stride(0), G, N, _vp(li), _vp(ni),
+                                          int(bool(filter)), float(het_deviance_threshold), int(min_cell),
+                                          o_r.data_ptr(), o_n.data_ptr(), o_r.stride(0), _vp(l), _vp(nb),
+                                          _vp(lm), _vp(keep), C.byref(gk), C.byref(nhet), _stream()))
+    k = gk.value
+    return dict(r_maf=o_r[:k], n_sc=o_n[:k], l=l[:k].copy(), n_bulk=nb[:k].copy(), l_maf=lm[:k].copy(),
+                keep=keep[:k].copy(), n_het=nhet.value)
+
+
 # --------------------------------------------------------------------------- ordering (a1)
 def order_genes(rownames, genes: GRanges, chrs, has_na=None):
     """R/HoneyBADGER.R:1114-1121: per chromosome (in `chrs` order) sort by (start+end)/2 (stable),
@@ -454,31 +504,56 @@ class HoneyBADGER:
     # ---- inputs (kept as the reference defines them; R/HoneyBADGER.R:123-188, :485-614)
     def setGexpMats(self, gexp_sc_init, gexp_ref_init, genes: GRanges, filter=True, minMeanBoth=0,
                     minMeanTest=None, minMeanRef=None, scale=True, verbose=True):
-        """`genes` replaces the biomaRt lookup (mart.obj needs the network)."""
+        """R/HoneyBADGER.R:124-188.  `genes` replaces the biomaRt lookup (mart.obj needs the network);
+        minMeanTest / minMeanRef None = the reference's defaults mean(m[m != 0]) of the init matrices.
+        The arithmetic runs on the device (`set_gexp_mats_dev`); the result stays resident."""
+        import torch
+        if verbose:
+            print("Initializing expression matrices ... ")
         sc = _as_frame(gexp_sc_init)
         ref = gexp_ref_init if isinstance(gexp_ref_init, pd.DataFrame) else \
             pd.DataFrame(np.asarray(gexp_ref_init, dtype=np.float64).reshape(len(sc.index), -1),
                          index=getattr(gexp_ref_init, "index", sc.index))
-        vi = [g for g in sc.index if g in set(ref.index)]
+        inref = set(ref.index)
+        vi = [g for g in sc.index if g in inref]
+        if len(vi) < 10:
+            print("WARNING! GENE NAMES IN EXPRESSION MATRICES DO NOT SEEM TO MATCH! ")
+        if filter and (len(vi) != len(sc.index) or len(vi) != len(ref.index)):
+            # the default thresholds are promises on the *init* matrices: when the name intersection
+            # drops rows they are not the library's defaults (taken on the matrices it is handed), so
+            # evaluate them here with R's serial mean replayed exactly
+            lib = _lib.load()
+            for which, m in (("t", sc), ("r", ref)):
+                if (minMeanTest if which == "t" else minMeanRef) is not None:
+                    continue
+                d = _to_dev_f64(m.values)
+                mean = C.c_double(0)
+                _lib.check(lib.hb_mean_nonzero_dev(d.data_ptr(), d.stride(0), d.shape[0], d.shape[1], 1,
+                                                   C.byref(mean), None, _stream()))
+                if which == "t":
+                    minMeanTest = mean.value
+                else:
+                    minMeanRef = mean.value
         sc, ref = sc.loc[vi], ref.loc[vi]
-        if filter:
-            mt = sc.values[sc.values != 0].mean() if minMeanTest is None else minMeanTest
-            mr = ref.values[ref.values != 0].mean() if minMeanRef is None else minMeanRef
-            ms, mf = sc.mean(axis=1), ref.mean(axis=1)
-            keep = ((ms > minMeanBoth) & (mf > minMeanBoth)) | (ms > mt) | (mf > mr)
-            if verbose:
-                print(f"{int(keep.sum())} genes passed filtering ... ")
-            sc, ref = sc[keep], ref[keep]
-        if scale:
-            sc = (sc - sc.mean(axis=0)) / sc.std(axis=0, ddof=1)
-            ref = (ref - ref.mean(axis=0)) / ref.std(axis=0, ddof=1)
+        norm_dev, keep, _ = set_gexp_mats_dev(sc.values, ref.values, filter, minMeanBoth, minMeanTest,
+                                              minMeanRef, scale)
+        if filter and verbose:
+            print(f"{keep.size} genes passed filtering ... ")
+        if scale and verbose:
+            print("Scaling coverage ... ")
         if verbose:
-            print(f"Normalizing gene expression for {sc.shape[0]} genes and {sc.shape[1]} cells ... ")
-        norm = sc.sub(ref.mean(axis=1), axis=0)
-        gvi = [g for g in norm.index if g in genes._ix]
+            print(f"Normalizing gene expression for {keep.size} genes and {sc.shape[1]} cells ... ")
+        names = np.asarray(sc.index, dtype=object)[keep]
+        has_pos = np.array([g in genes._ix for g in names], dtype=bool)
+        gvi = list(names[has_pos])
         self.genes = genes[gvi]
-        self.gexp_norm = norm.loc[gvi]
-        self._x_dev = None
+        if not has_pos.all():
+            norm_dev = norm_dev.index_select(0, torch.as_tensor(np.nonzero(has_pos)[0], device=norm_dev.device))
+        norm_dev = norm_dev.contiguous()
+        self.gexp_norm = pd.DataFrame(norm_dev.cpu().numpy(), index=gvi, columns=sc.columns)
+        self._x_dev = (norm_dev, {g: i for i, g in enumerate(gvi)}, {c: i for i, c in enumerate(sc.columns)})
+        if verbose:
+            print("Done setting initial expression matrices! ")
 
     def setGexpDev(self, dev=None, alpha=0.05, n=100, seed=0, verbose=False):
         """R/HoneyBADGER.R:1054-1077 draws from R's RNG (ks.test of rnorm samples); the value is an
@@ -491,30 +566,34 @@ class HoneyBADGER:
 
     def setAlleleMats(self, r_init, n_sc_init, l_init=None, n_bulk_init=None, filter=True,
                       het_deviance_threshold=0.05, min_cell=3, verbose=True):
+        """R/HoneyBADGER.R:486-614; counting, filtering and the lesser-allele flip run on the device
+        (`set_allele_mats_dev`) and the matrices stay resident."""
+        if verbose:
+            print("Initializing allele matrices ... ")
         r, n = _as_frame(r_init, "snp"), _as_frame(n_sc_init, "snp")
-        if l_init is None or n_bulk_init is None:
-            l = (r.values > 0).sum(1).astype(np.float64)
-            nb = (n.values > 0).sum(1).astype(np.float64)
-        else:
-            l, nb = np.asarray(l_init, dtype=np.float64), np.asarray(n_bulk_init, dtype=np.float64)
+        if verbose and (l_init is None or n_bulk_init is None):
+            print("Creating in-silico bulk ... ")
+            print(f"using {r.shape[1]} cells ... ")
+        out = set_allele_mats_dev(r.values, n.values, l_init, n_bulk_init, filter, het_deviance_threshold,
+                                  min_cell)
+        keep = out["keep"]
         if filter:
-            with np.errstate(all="ignore"):
-                E = l / nb
-            vi = (E > het_deviance_threshold) & (E < 1 - het_deviance_threshold)
-            r, n, l, nb = r[vi], n[vi], l[vi], nb[vi]
-            vi2 = (n.values > 0).sum(1) >= min_cell
-            print(f"{len(vi2)} heterozygous SNPs identified ")  # the reference prints length(vi)
-            r, n, l, nb = r[vi2], n[vi2], l[vi2], nb[vi2]
-        with np.errstate(all="ignore"):
-            E = l / nb
-        flip = E > 0.5
-        self.r_maf = pd.DataFrame(np.where(flip[:, None], n.values - r.values, r.values),
-                                  index=r.index, columns=r.columns)
-        self.n_sc = n
-        self.l_maf = np.where(flip, nb - l, l)
-        self.n_bulk = nb
-        self.snps = snps_from_names(r.index)
-        self._r_dev = self._n_dev = None
+            if verbose:
+                print("Filtering for putative heterozygous snps ... ")
+                print(f"allowing for a {het_deviance_threshold} deviation from the expected 0.5 heterozygous allele fraction ... ")
+                print(f"must have coverage in at least {min_cell} cells ... ")
+            # the reference prints length(vi) of the coverage filter = SNPs that passed the first one
+            print(f"{out['n_het']} heterozygous SNPs identified ")
+        names = list(np.asarray(r.index, dtype=object)[keep])
+        self.r_maf = pd.DataFrame(out["r_maf"].cpu().numpy(), index=names, columns=r.columns)
+        self.n_sc = pd.DataFrame(out["n_sc"].cpu().numpy(), index=names, columns=r.columns)
+        self.l_maf = out["l_maf"]
+        self.n_bulk = out["n_bulk"]
+        self.snps = snps_from_names(names)
+        self._r_dev = (out["r_maf"].contiguous(), out["n_sc"].contiguous(), {g: i for i, g in enumerate(names)},
+                       {c: i for i, c in enumerate(r.columns)})
+        if verbose:
+            print("Done setting initial allele matrices! ")
 
     # ---- device residency: full matrices are uploaded once; every level gathers rows / columns there
     def _resident(self, kind):

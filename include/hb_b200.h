@@ -211,6 +211,59 @@ int hb_group_gexp_host(const double *gexp_norm, int64_t G, int64_t N, int32_t wi
 int hb_group_allele_host(const double *r_maf, const double *n_sc, int64_t G, int64_t N, int32_t window,
                          const int32_t *ks, int32_t nk, int32_t *labels);
 
+/* ---- Input construction: the matrices the path consumes, built on the device.
+ *
+ * setGexpMats (R/HoneyBADGER.R:124-188; function form R/HoneyBADGER_gexp.R:28-90), the arithmetic
+ * part: rowMeans filter, scale() of both matrices, gexp.norm = gexp.sc - rowMeans(gexp.ref).  Gene
+ * positions (biomaRt) and name intersections stay with the caller; rows of `sc` and `ref` are aligned.
+ * R semantics reproduced bit for bit (80-bit LDOUBLE accumulators of rowMeans / colMeans / sum
+ * replayed, no FMA contraction); inputs must be finite (no NA).
+ *   filter != 0:  keep = (rowMeans(sc) > both & rowMeans(ref) > both) | rowMeans(sc) > test |
+ *                 rowMeans(ref) > refthr;  min_mean_test / min_mean_ref NULL = R's defaults
+ *                 mean(m[m != 0]) of the respective matrix.
+ *   scale != 0:   scale(sc), scale(ref) on the kept rows (centre = colMeans, scale =
+ *                 sqrt(sum(v^2) / max(1, n - 1))).
+ * Outputs: *Gk kept rows, keep_rows[0..Gk) their 0-based indices (host, capacity G, may be NULL),
+ * norm = the Gk x N result.  info (may be NULL): bit 0 / bit 1 set when a row mean fell inside the
+ * safety margin of the default test / ref threshold and R's serial mean was replayed exactly. */
+int hb_set_gexp_mats_dev(const double *sc, int64_t ld, int64_t G, int64_t N, const double *ref, int64_t ldr,
+                         int64_t R, int32_t filter, double min_mean_both, const double *min_mean_test,
+                         const double *min_mean_ref, int32_t scale, double *norm /* dev [G][ldo] */,
+                         int64_t ldo, int32_t *keep_rows, int64_t *Gk, int32_t *info, void *stream);
+/* Host form: sc, ref, norm column-major as R holds them ([G x N], [G x R], [Gk x N]; norm capacity G*N). */
+int hb_set_gexp_mats_host(const double *sc, int64_t G, int64_t N, const double *ref, int64_t R, int32_t filter,
+                          double min_mean_both, const double *min_mean_test, const double *min_mean_ref,
+                          int32_t scale, double *norm, int32_t *keep_rows, int64_t *Gk, int32_t *info);
+/* Building blocks (device, gene-major x[g*ld + c]). */
+int hb_row_means_dev(const double *x, int64_t ld, int64_t G, int64_t N, double *out /* [G] */, void *stream);
+int hb_col_scale_stats_dev(const double *x, int64_t ld, int64_t G, int64_t N, const uint8_t *keep /* [G] or NULL */,
+                           double *center /* [N] */, double *scl /* [N] or NULL */, void *stream);
+int hb_gexp_apply_dev(const double *x, int64_t ld, int64_t N, const int32_t *rows /* [Gk] or NULL */, int64_t Gk,
+                      const double *center, const double *scl, const double *refmean /* [Gk] */, double *out,
+                      int64_t ldo, void *stream);
+/* R's mean(x[x != 0]) into *mean (host).  exact = 0: parallel double-double sum, *margin (host, may be
+ * NULL) bounds the distance to R's serially rounded value; exact = 1: R's two-pass loop replayed. */
+int hb_mean_nonzero_dev(const double *x, int64_t ld, int64_t G, int64_t N, int32_t exact, double *mean,
+                        double *margin, void *stream);
+
+/* setAlleleMats (R/HoneyBADGER.R:486-614; function form R/HoneyBADGER_allele.R:23-120): in-silico bulk
+ * l = rowSums(r > 0), n.bulk = rowSums(n.sc > 0) unless both are given (host [G]); filter: E = l / n.bulk
+ * in (thr, 1 - thr) and coverage in >= min_cell cells; lesser-allele flip r.maf = E <= 0.5 ? r : n.sc - r
+ * (0 where E is NA), l.maf likewise.  Integer, exact.  Outputs: r_maf, n_sc ([Gk] rows; n_sc may be
+ * NULL), l, n_bulk, l_maf (host [Gk], capacity G, may be NULL), keep_rows, *Gk, and *n_het (may be
+ * NULL) = SNPs that passed the heterozygosity filter, the number the reference prints (:527). */
+int hb_set_allele_mats_dev(const int32_t *r, const int32_t *n_sc_init, int64_t ld, int64_t G, int64_t N,
+                           const double *l_init, const double *n_bulk_init, int32_t filter,
+                           double het_deviance_threshold, int32_t min_cell, int32_t *r_maf /* dev [G][ldo] */,
+                           int32_t *n_sc /* dev [G][ldo] or NULL */, int64_t ldo, double *l, double *n_bulk,
+                           double *l_maf, int32_t *keep_rows, int64_t *Gk, int64_t *n_het, void *stream);
+/* Host form: r, n_sc_init, r_maf, n_sc column-major int32 as R holds integer matrices. */
+int hb_set_allele_mats_host(const int32_t *r, const int32_t *n_sc_init, int64_t G, int64_t N,
+                            const double *l_init, const double *n_bulk_init, int32_t filter,
+                            double het_deviance_threshold, int32_t min_cell, int32_t *r_maf, int32_t *n_sc,
+                            double *l, double *n_bulk, double *l_maf, int32_t *keep_rows, int64_t *Gk,
+                            int64_t *n_het);
+
 /* Deterministic retest of one candidate region for the expression model: the exact marginal posterior
  * of inst/bug/expressionModel.bug that HoneyBADGER$calcGexpCnvProb
  * (R/HoneyBADGER.R:374-470, called from :1220) estimates by JAGS sampling — statistical stand-in for

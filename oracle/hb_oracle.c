@@ -528,6 +528,129 @@ void hbo_pool_count_pos(const double *m, int64_t G, const int32_t *cols, int64_t
     }
 }
 
+/* ------------------------------------------------------------ input construction
+ * setGexpMats (R/HoneyBADGER.R:124-188) and setAlleleMats (R/HoneyBADGER.R:486-614), arithmetic part,
+ * on COLUMN-MAJOR matrices exactly as R evaluates them. */
+
+/* rowMeans(m) (array.c do_colsum, OP 3): one LDOUBLE accumulator per row, columns in order, / p. */
+void hbo_row_means(const double *m, int64_t G, int64_t N, double *out)
+{
+    for (int64_t g = 0; g < G; g++) {
+        long double s = 0.0L;
+        for (int64_t c = 0; c < N; c++) s += m[c * G + g];
+        s /= N;
+        out[g] = (double)s;
+    }
+}
+
+/* scale(m) in place (scale.default): center <- colMeans(m, na.rm=TRUE); m <- sweep(m, 2, center);
+ * f(v) = sqrt(sum(v^2) / max(1, length(v) - 1)); m <- sweep(m, 2, apply(m, 2, f), "/"). */
+void hbo_scale(double *m, int64_t G, int64_t N)
+{
+    for (int64_t c = 0; c < N; c++) {
+        double *v = m + c * G;
+        long double s = 0.0L;
+        for (int64_t g = 0; g < G; g++) s += v[g];
+        s /= G;
+        const double center = (double)s;
+        for (int64_t g = 0; g < G; g++) v[g] = v[g] - center;
+        long double ss = 0.0L; /* sum(): rsum accumulates the double vector v^2 in LDOUBLE */
+        for (int64_t g = 0; g < G; g++) {
+            const double sq = v[g] * v[g]; /* R_pow(x, 2.0) = x * x */
+            ss += sq;
+        }
+        const double den = (double)(G - 1 > 1 ? G - 1 : 1);
+        const double scl = sqrt((double)ss / den);
+        for (int64_t g = 0; g < G; g++) v[g] = v[g] / scl;
+    }
+}
+
+/* mean(m[m != 0]): the subset vector in column-major order, then real_mean. */
+double hbo_mean_nonzero(const double *m, int64_t count)
+{
+    double *nz = (double *)malloc((size_t)(count > 0 ? count : 1) * sizeof(double));
+    int64_t n = 0;
+    for (int64_t i = 0; i < count; i++)
+        if (m[i] != 0.0) nz[n++] = m[i];
+    double r = n ? hbo_r_mean(nz, n) : NAN;
+    free(nz);
+    return r;
+}
+
+/* Returns the number of kept rows Gk; norm is the Gk x N column-major result, keep_rows their indices. */
+int64_t hbo_set_gexp_mats(const double *sc, int64_t G, int64_t N, const double *ref, int64_t R, int filter,
+                          double min_both, const double *min_test, const double *min_ref, int scale,
+                          double *norm, int32_t *keep_rows)
+{
+    int64_t Gk = 0;
+    if (filter) {
+        const double mt = min_test ? *min_test : hbo_mean_nonzero(sc, G * N);
+        const double mr = min_ref ? *min_ref : hbo_mean_nonzero(ref, G * R);
+        double *rs = (double *)malloc((size_t)G * 2 * sizeof(double)), *rr = rs + G;
+        hbo_row_means(sc, G, N, rs);
+        hbo_row_means(ref, G, R, rr);
+        for (int64_t g = 0; g < G; g++)
+            if ((rs[g] > min_both && rr[g] > min_both) || rs[g] > mt || rr[g] > mr) keep_rows[Gk++] = (int32_t)g;
+        free(rs);
+    } else {
+        for (int64_t g = 0; g < G; g++) keep_rows[Gk++] = (int32_t)g;
+    }
+    if (Gk == 0) return 0;
+    double *r2 = (double *)malloc((size_t)Gk * R * sizeof(double));
+    double *rm = (double *)malloc((size_t)Gk * sizeof(double));
+    for (int64_t c = 0; c < N; c++)
+        for (int64_t k = 0; k < Gk; k++) norm[c * Gk + k] = sc[c * G + keep_rows[k]];
+    for (int64_t c = 0; c < R; c++)
+        for (int64_t k = 0; k < Gk; k++) r2[c * Gk + k] = ref[c * G + keep_rows[k]];
+    if (scale) {
+        hbo_scale(norm, Gk, N);
+        hbo_scale(r2, Gk, R);
+    }
+    hbo_row_means(r2, Gk, R, rm);
+    for (int64_t c = 0; c < N; c++)
+        for (int64_t k = 0; k < Gk; k++) norm[c * Gk + k] = norm[c * Gk + k] - rm[k];
+    free(r2);
+    free(rm);
+    return Gk;
+}
+
+/* setAlleleMats on column-major integer-valued matrices.  l_init / n_bulk_init NULL = in-silico bulk. */
+int64_t hbo_set_allele_mats(const int32_t *r, const int32_t *n, int64_t G, int64_t N, const double *l_init,
+                            const double *n_bulk_init, int filter, double thr, int min_cell, int32_t *r_maf,
+                            int32_t *n_sc, double *l_out, double *n_bulk_out, double *l_maf,
+                            int32_t *keep_rows)
+{
+    int64_t Gk = 0;
+    const int silico = !l_init || !n_bulk_init;
+    for (int64_t g = 0; g < G; g++) {
+        int64_t cr = 0, cn = 0;
+        for (int64_t c = 0; c < N; c++) {
+            cr += r[c * G + g] > 0;
+            cn += n[c * G + g] > 0;
+        }
+        const double l = silico ? (double)cr : l_init[g], nb = silico ? (double)cn : n_bulk_init[g];
+        const double E = l / nb;
+        if (filter) {
+            if (!(E > thr && E < 1 - thr)) continue; /* which() drops NA */
+            if (cn < min_cell) continue;
+        }
+        keep_rows[Gk] = (int32_t)g;
+        l_out[Gk] = l;
+        n_bulk_out[Gk] = nb;
+        l_maf[Gk] = isnan(E) ? 0.0 : (E <= 0.5 ? l : nb - l);
+        Gk++;
+    }
+    for (int64_t c = 0; c < N; c++)
+        for (int64_t k = 0; k < Gk; k++) {
+            const int64_t g = keep_rows[k];
+            const double E = l_out[k] / n_bulk_out[k];
+            const int32_t rv = r[c * G + g], nv = n[c * G + g];
+            r_maf[c * Gk + k] = isnan(E) ? 0 : (E <= 0.5 ? rv : nv - rv);
+            n_sc[c * Gk + k] = nv;
+        }
+    return Gk;
+}
+
 int hbo_num_threads(void)
 {
 #ifdef _OPENMP

@@ -67,6 +67,16 @@ def lib():
         L.hbo_pool_mean.argtypes = [p, i64, p, i64, p]
         L.hbo_pool_count_pos.restype = None
         L.hbo_pool_count_pos.argtypes = [p, i64, p, i64, p]
+        L.hbo_row_means.restype = None
+        L.hbo_row_means.argtypes = [p, i64, i64, p]
+        L.hbo_scale.restype = None
+        L.hbo_scale.argtypes = [p, i64, i64]
+        L.hbo_mean_nonzero.restype = d
+        L.hbo_mean_nonzero.argtypes = [p, i64]
+        L.hbo_set_gexp_mats.restype = i64
+        L.hbo_set_gexp_mats.argtypes = [p, i64, i64, p, i64, i32, d, p, p, i32, p, p]
+        L.hbo_set_allele_mats.restype = i64
+        L.hbo_set_allele_mats.argtypes = [p, p, i64, i64, p, p, i32, d, i32, p, p, p, p, p, p]
         L.hbo_num_threads.restype = i32
         _lib = L
     return _lib
@@ -260,6 +270,61 @@ def pool_count_pos(mat_gn, cols):
     out = np.zeros(G, dtype=np.int32)
     lib().hbo_pool_count_pos(m.ctypes.data_as(C.c_void_p), G, _p(cols), cols.size, _p(out))
     return out
+
+
+# ---------------------------------------------------------------- input construction (8f-3)
+def row_means(mat_gn):
+    """rowMeans(M)."""
+    m = np.asfortranarray(mat_gn, dtype=np.float64)
+    out = np.zeros(m.shape[0])
+    lib().hbo_row_means(_p(m), m.shape[0], m.shape[1], _p(out))
+    return out
+
+
+def scale(mat_gn):
+    """scale(M) (centre and scale every column)."""
+    m = np.array(mat_gn, dtype=np.float64, order="F", copy=True)
+    lib().hbo_scale(_p(m), m.shape[0], m.shape[1])
+    return m
+
+
+def mean_nonzero(mat_gn):
+    """mean(M[M != 0])."""
+    m = np.asfortranarray(mat_gn, dtype=np.float64)
+    return float(lib().hbo_mean_nonzero(_p(m), m.size))
+
+
+def set_gexp_mats(sc, ref, filter=True, min_mean_both=0.0, min_mean_test=None, min_mean_ref=None, scale=True):
+    """Arithmetic of setGexpMats (R/HoneyBADGER.R:124-161) for row-aligned sc [G, N], ref [G, R].
+    Returns (gexp.norm [Gk, N], kept row indices)."""
+    sc = np.asfortranarray(sc, dtype=np.float64)
+    ref = np.asfortranarray(np.asarray(ref, dtype=np.float64).reshape(sc.shape[0], -1))
+    G, N = sc.shape
+    norm = np.zeros(G * N)
+    keep = np.zeros(G, dtype=np.int32)
+    mt = None if min_mean_test is None else C.c_double(min_mean_test)
+    mr = None if min_mean_ref is None else C.c_double(min_mean_ref)
+    Gk = lib().hbo_set_gexp_mats(_p(sc), G, N, _p(ref), ref.shape[1], int(filter), float(min_mean_both),
+                                 None if mt is None else C.byref(mt), None if mr is None else C.byref(mr),
+                                 int(scale), _p(norm), _p(keep))
+    return norm[:Gk * N].reshape(N, Gk).T, keep[:Gk]
+
+
+def set_allele_mats(r, n, l_init=None, n_bulk_init=None, filter=True, het_deviance_threshold=0.05, min_cell=3):
+    """Arithmetic of setAlleleMats (R/HoneyBADGER.R:486-595) for integer matrices r, n [G, N].
+    Returns dict(r_maf, n_sc, l, n_bulk, l_maf, keep)."""
+    r = np.asfortranarray(r, dtype=np.int32)
+    n = np.asfortranarray(n, dtype=np.int32)
+    G, N = r.shape
+    rm, ns = np.zeros(G * N, np.int32), np.zeros(G * N, np.int32)
+    l, nb, lm = np.zeros(G), np.zeros(G), np.zeros(G)
+    keep = np.zeros(G, dtype=np.int32)
+    li = None if l_init is None else _f64(l_init)
+    ni = None if n_bulk_init is None else _f64(n_bulk_init)
+    Gk = lib().hbo_set_allele_mats(_p(r), _p(n), G, N, _p(li), _p(ni), int(filter), float(het_deviance_threshold),
+                                   int(min_cell), _p(rm), _p(ns), _p(l), _p(nb), _p(lm), _p(keep))
+    return dict(r_maf=rm[:Gk * N].reshape(N, Gk).T, n_sc=ns[:Gk * N].reshape(N, Gk).T, l=l[:Gk],
+                n_bulk=nb[:Gk], l_maf=lm[:Gk], keep=keep[:Gk])
 
 
 def retest_gexp(x_rows, mag0, sigma0=None):

@@ -84,3 +84,8 @@ def golden_allele():
 @pytest.fixture(scope="session")
 def golden_gexp():
     return np.load(os.path.join(GOLDEN, "gexp_mgh31.npz"))
+
+
+@pytest.fixture(scope="session")
+def golden_inputs():
+    return np.load(os.path.join(GOLDEN, "inputs_raw_mgh31.npz"))

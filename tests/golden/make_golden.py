@@ -19,6 +19,8 @@ What is pinned, and by what:
                           sd, Viterbi paths, sampled posteriors with dev = 1.015658
                           (docs/Getting_Started.md:108).  Gene coordinates are not bundled (biomaRt),
                           so genes stay in stored order, split into 22 synthetic segments.
+  * inputs_raw_mgh31.npz — raw r / cov.sc (uint16) and gexp[:800] / ref[:800] for the input
+                          construction (`python tests/golden/make_golden.py inputs` writes only this).
 State paths / posteriors are produced by oracle/hb_oracle.c and REQUIRED to equal the independent
 pure-Python restatement (oracle/pyref.py) before they are written.  Group labels come from scipy's
 Ward linkage on a simplified smoothing — they are inputs of the path, not a claim about R's hclust.
@@ -221,7 +223,25 @@ def make_gexp():
           "del runs:", len(res["del"] or []))
 
 
+def make_inputs_raw():
+    """Raw inputs of setAlleleMats / setGexpMats: the bundled r / cov.sc count matrices in
+    full and the first 800 genes of gexp / ref, so that the device construction can be checked against
+    the reference's printed known answers (5359/4357 at 0.1, 5552/4550 at 0.05) on the GPU box."""
+    r, rn, cn = as_matrix(read_rda(f"{REF}/r.rda")["r"])
+    cov, _, _ = as_matrix(read_rda(f"{REF}/cov.sc.rda")["cov.sc"])
+    assert (r == np.rint(r)).all() and (cov == np.rint(cov)).all() and cov.max() < 65536
+    gexp, gn, _ = as_matrix(read_rda(f"{REF}/gexp.rda")["gexp"])
+    ref = np.asarray(read_rda(f"{REF}/ref.rda")["ref"]["value"])
+    np.savez_compressed(os.path.join(HERE, "inputs_raw_mgh31.npz"), r=r.astype(np.uint16),
+                        cov=cov.astype(np.uint16), gexp=gexp[:800], ref=ref[:800],
+                        known_counts=np.array([[5552, 4550], [5359, 4357]], dtype=np.int32))
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "inputs":
+        make_inputs_raw()
+        sys.exit(0)
+    make_inputs_raw()
     make_densities()
     runs = make_allele()
     make_gexp()

@@ -1,0 +1,89 @@
+"""Oracle restatement of the input construction (setGexpMats / setAlleleMats arithmetic)
+against independent numpy evaluations and the reference's printed known answers.  CPU only."""
+from __future__ import annotations
+
+import numpy as np
+
+
+def _ld_seq_sum(a, axis):
+    """sequential (index-order) accumulation in x87 extended precision: cumsum never re-associates"""
+    return np.cumsum(a.astype(np.longdouble), axis=axis).take(-1, axis=axis)
+
+
+def test_long_double_is_x87():
+    assert np.finfo(np.longdouble).nmant == 63  # the independent check below needs 80-bit long double
+
+
+def test_row_means_and_scale_match_numpy_longdouble(oracle):
+    rng = np.random.default_rng(3)
+    m = rng.gamma(2.0, 1.5, (257, 91)) * (rng.random((257, 91)) > 0.3)
+    want = (_ld_seq_sum(m, 1) / np.longdouble(91)).astype(np.float64)
+    assert np.array_equal(oracle.row_means(m), want)
+    # scale(): colMeans, centre, sqrt(sum(v^2) / (n - 1)), divide — every double op rounded separately
+    center = (_ld_seq_sum(m, 0) / np.longdouble(257)).astype(np.float64)
+    v = m - center
+    ss = _ld_seq_sum(v * v, 0).astype(np.float64)
+    want = v / np.sqrt(ss / 256.0)
+    assert np.array_equal(oracle.scale(m), want)
+    # and they are what they claim to be, to rounding
+    assert np.allclose(oracle.row_means(m), m.mean(1), rtol=1e-14)
+    assert np.allclose(oracle.scale(m).std(0, ddof=1), 1.0, rtol=1e-12)
+
+
+def test_mean_nonzero_is_r_mean_of_the_subset(oracle):
+    rng = np.random.default_rng(4)
+    m = rng.gamma(2.0, 1.5, (300, 40)) * (rng.random((300, 40)) > 0.5)
+    nz = np.asfortranarray(m).ravel(order="F")
+    nz = nz[nz != 0]
+    assert oracle.mean_nonzero(m) == oracle.r_mean(nz)
+    assert abs(oracle.mean_nonzero(m) - nz.mean()) < 1e-13
+
+
+def test_set_gexp_mats_vignette_form_is_gexp_minus_ref(oracle, golden_inputs, golden_gexp):
+    gexp, ref = golden_inputs["gexp"], golden_inputs["ref"]
+    norm, keep = oracle.set_gexp_mats(gexp, ref, filter=False, scale=False)  # Getting_Started.Rmd:52
+    assert np.array_equal(keep, np.arange(gexp.shape[0]))
+    assert np.array_equal(norm, gexp - ref[:, None])
+    # the committed expression fixture was made from the same matrices
+    g32 = golden_gexp["gexp_norm_f32"]
+    assert np.array_equal(norm[:, :40].astype(np.float32), g32[:800])
+
+
+def test_set_gexp_mats_filter_and_scale_match_numpy(oracle, golden_inputs):
+    gexp, ref = golden_inputs["gexp"], golden_inputs["ref"][:, None]
+    norm, keep = oracle.set_gexp_mats(gexp, ref, filter=True, scale=True)
+    rs, rr = oracle.row_means(gexp), oracle.row_means(ref)
+    mt, mr = oracle.mean_nonzero(gexp), oracle.mean_nonzero(ref)
+    want_keep = np.nonzero(((rs > 0) & (rr > 0)) | (rs > mt) | (rr > mr))[0]
+    assert np.array_equal(keep, want_keep) and 0 < keep.size < gexp.shape[0]
+    want = oracle.scale(gexp[keep]) - oracle.row_means(oracle.scale(ref[keep]))[:, None]
+    assert np.array_equal(norm, want)
+
+
+def test_set_allele_mats_reproduces_the_reference_printouts(oracle, golden_inputs, golden_allele):
+    r, cov = golden_inputs["r"].astype(np.int32), golden_inputs["cov"].astype(np.int32)
+    for thr, (printed, final) in zip((0.05, 0.1), golden_inputs["known_counts"]):
+        out = oracle.set_allele_mats(r, cov, het_deviance_threshold=thr)
+        l, nb = (r > 0).sum(1), (cov > 0).sum(1)
+        with np.errstate(all="ignore"):
+            E = l / nb
+        assert int(((E > thr) & (E < 1 - thr)).sum()) == printed  # docs/Integrating.md:27, Getting_Started.md:230
+        assert out["keep"].size == final
+    # threshold 0.1 is what the committed allele fixture holds
+    assert np.array_equal(out["r_maf"], golden_allele["r_maf"].astype(np.int32))
+    assert np.array_equal(out["n_sc"], golden_allele["n_sc"].astype(np.int32))
+    assert np.array_equal(out["l_maf"], golden_allele["l_maf"])
+    assert np.array_equal(out["n_bulk"], golden_allele["n_bulk"])
+
+
+def test_set_allele_mats_without_filter_codes_na_rows_as_zero(oracle):
+    rng = np.random.default_rng(6)
+    n = rng.integers(0, 4, (50, 12)).astype(np.int32)
+    n[7] = 0  # no coverage at all: E = 0/0 = NA -> r.maf row of zeros, l.maf 0
+    r = rng.binomial(n, 0.6).astype(np.int32)
+    out = oracle.set_allele_mats(r, n, filter=False)
+    assert out["keep"].size == 50 and (out["r_maf"][7] == 0).all() and out["l_maf"][7] == 0
+    l, nb = (r > 0).sum(1), (n > 0).sum(1)
+    flip = np.divide(l, nb, out=np.zeros(50), where=nb > 0) > 0.5
+    assert np.array_equal(out["r_maf"], np.where(flip[:, None], n - r, r))
+    assert np.array_equal(out["l_maf"], np.where(flip, nb - l, l))
