@@ -54,3 +54,28 @@ hb_calcGexpCnvProb <- function(gexp.norm.sub, m, sigma0 = NULL) {
                 "estimated mean normalized expression deviation")
   p
 }
+
+## Input construction on the GPU (optional; SURVEY.md 8f-3) ----------------------------------------
+## R/HoneyBADGER.R:139-161 inside setGexpMats: everything between the name intersection and the biomaRt
+## lookup.  Bit-identical to rowMeans / scale / `-` of base R; returns gexp.norm with dimnames.
+hb_setGexpMats_core <- function(gexp.sc, gexp.ref, filter = TRUE, minMeanBoth = 0, minMeanTest = NULL,
+                                minMeanRef = NULL, scale = TRUE) {
+  gexp.ref <- as.matrix(gexp.ref)
+  res <- .Call("C_hb_set_gexp_mats", gexp.sc, gexp.ref, filter, as.double(minMeanBoth), minMeanTest,
+               minMeanRef, scale)
+  gexp.norm <- res[[1]]
+  dimnames(gexp.norm) <- list(rownames(gexp.sc)[res[[2]]], colnames(gexp.sc))
+  gexp.norm
+}
+## R/HoneyBADGER.R:493-595 inside setAlleleMats (the nested lapply of :538-565 is the reference's slowest
+## input step): list(r.maf, n.sc, l, n.bulk, l.maf) with names, plus n.het for the cat() of :527.
+hb_setAlleleMats_core <- function(r.init, n.sc.init, l.init = NULL, n.bulk.init = NULL, filter = TRUE,
+                                  het.deviance.threshold = 0.05, min.cell = 3) {
+  res <- .Call("C_hb_set_allele_mats", r.init, n.sc.init, l.init, n.bulk.init, filter,
+               as.double(het.deviance.threshold), as.integer(min.cell))
+  names(res) <- c("r.maf", "n.sc", "l", "n.bulk", "l.maf", "keep", "n.het")
+  nm <- rownames(r.init)[res$keep]
+  dimnames(res$r.maf) <- dimnames(res$n.sc) <- list(nm, colnames(r.init))
+  names(res$l) <- names(res$n.bulk) <- names(res$l.maf) <- nm
+  res
+}

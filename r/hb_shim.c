@@ -10,6 +10,7 @@
 #include <R.h>
 #include <Rinternals.h>
 #include <R_ext/Rdynload.h>
+#include <string.h>
 
 #include "hb_b200.h"
 
@@ -148,6 +149,76 @@ SEXP C_hb_retest_gexp(SEXP gexp_rows, SEXP mag0, SEXP sigma0)
     return out;
 }
 
+/* res <- .Call(C_hb_set_gexp_mats, gexp.sc, gexp.ref, filter, minMeanBoth, minMeanTest, minMeanRef, scale)
+ * replaces the arithmetic of setGexpMats, R/HoneyBADGER.R:139-161 (rowMeans filter, scale(), gexp.sc -
+ * rowMeans(gexp.ref)); rows of the two matrices already intersected (:135-137).  minMeanTest / minMeanRef
+ * NULL = the defaults mean(m[m != 0]).  Returns list(gexp.norm [Gk x N], keep = 1-based kept rows). */
+SEXP C_hb_set_gexp_mats(SEXP sc, SEXP ref, SEXP filter, SEXP min_both, SEXP min_test, SEXP min_ref, SEXP scale)
+{
+    sc = PROTECT(Rf_coerceVector(sc, REALSXP));
+    ref = PROTECT(Rf_coerceVector(ref, REALSXP));
+    const int64_t G = Rf_nrows(sc), N = Rf_ncols(sc), R = Rf_isMatrix(ref) ? Rf_ncols(ref) : 1;
+    double mt = Rf_isNull(min_test) ? 0 : Rf_asReal(min_test), mr = Rf_isNull(min_ref) ? 0 : Rf_asReal(min_ref);
+    SEXP full = PROTECT(Rf_allocVector(REALSXP, (R_xlen_t)G * N));
+    SEXP keep = PROTECT(Rf_allocVector(INTSXP, (R_xlen_t)G));
+    int64_t Gk = 0;
+    int rc = hb_set_gexp_mats_host(REAL(sc), G, N, REAL(ref), R, Rf_asLogical(filter), Rf_asReal(min_both),
+                                   Rf_isNull(min_test) ? NULL : &mt, Rf_isNull(min_ref) ? NULL : &mr,
+                                   Rf_asLogical(scale), REAL(full), INTEGER(keep), &Gk, NULL);
+    if (rc != 0) {
+        UNPROTECT(4);
+        hb_raise(rc);
+    }
+    SEXP norm = PROTECT(Rf_allocMatrix(REALSXP, (int)Gk, (int)N)); /* the library wrote Gk x N contiguously */
+    memcpy(REAL(norm), REAL(full), (size_t)Gk * N * sizeof(double));
+    SEXP keep1 = PROTECT(Rf_allocVector(INTSXP, (R_xlen_t)Gk));
+    for (int64_t k = 0; k < Gk; k++) INTEGER(keep1)[k] = INTEGER(keep)[k] + 1;
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, 2));
+    SET_VECTOR_ELT(out, 0, norm);
+    SET_VECTOR_ELT(out, 1, keep1);
+    UNPROTECT(7);
+    return out;
+}
+
+/* res <- .Call(C_hb_set_allele_mats, r.init, n.sc.init, l.init, n.bulk.init, filter, het.deviance.threshold,
+ * min.cell) replaces R/HoneyBADGER.R:493-595 (in-silico bulk, both filters, the nested lapply of the
+ * lesser-allele flip).  Returns list(r.maf, n.sc, l, n.bulk, l.maf, keep (1-based), n.het). */
+SEXP C_hb_set_allele_mats(SEXP r, SEXP n_sc, SEXP l_init, SEXP n_bulk_init, SEXP filter, SEXP thr, SEXP min_cell)
+{
+    r = PROTECT(Rf_coerceVector(r, INTSXP));
+    n_sc = PROTECT(Rf_coerceVector(n_sc, INTSXP));
+    const int64_t G = Rf_nrows(r), N = Rf_ncols(r);
+    const int given = !Rf_isNull(l_init) && !Rf_isNull(n_bulk_init);
+    SEXP li = PROTECT(given ? Rf_coerceVector(l_init, REALSXP) : R_NilValue);
+    SEXP ni = PROTECT(given ? Rf_coerceVector(n_bulk_init, REALSXP) : R_NilValue);
+    int32_t *o_r = (int32_t *)R_alloc((size_t)G * N, sizeof(int32_t));
+    int32_t *o_n = (int32_t *)R_alloc((size_t)G * N, sizeof(int32_t));
+    double *l = (double *)R_alloc((size_t)G * 3, sizeof(double)), *nb = l + G, *lm = nb + G;
+    int32_t *keep = (int32_t *)R_alloc((size_t)G, sizeof(int32_t));
+    int64_t Gk = 0, nhet = 0;
+    int rc = hb_set_allele_mats_host(INTEGER(r), INTEGER(n_sc), G, N, given ? REAL(li) : NULL,
+                                     given ? REAL(ni) : NULL, Rf_asLogical(filter), Rf_asReal(thr),
+                                     Rf_asInteger(min_cell), o_r, o_n, l, nb, lm, keep, &Gk, &nhet);
+    if (rc != 0) {
+        UNPROTECT(4);
+        hb_raise(rc);
+    }
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, 7));
+    SET_VECTOR_ELT(out, 0, Rf_allocMatrix(INTSXP, (int)Gk, (int)N));
+    SET_VECTOR_ELT(out, 1, Rf_allocMatrix(INTSXP, (int)Gk, (int)N));
+    memcpy(INTEGER(VECTOR_ELT(out, 0)), o_r, (size_t)Gk * N * sizeof(int32_t));
+    memcpy(INTEGER(VECTOR_ELT(out, 1)), o_n, (size_t)Gk * N * sizeof(int32_t));
+    for (int i = 2; i < 5; i++) SET_VECTOR_ELT(out, i, Rf_allocVector(REALSXP, (R_xlen_t)Gk));
+    memcpy(REAL(VECTOR_ELT(out, 2)), l, (size_t)Gk * sizeof(double));
+    memcpy(REAL(VECTOR_ELT(out, 3)), nb, (size_t)Gk * sizeof(double));
+    memcpy(REAL(VECTOR_ELT(out, 4)), lm, (size_t)Gk * sizeof(double));
+    SET_VECTOR_ELT(out, 5, Rf_allocVector(INTSXP, (R_xlen_t)Gk));
+    for (int64_t k = 0; k < Gk; k++) INTEGER(VECTOR_ELT(out, 5))[k] = keep[k] + 1;
+    SET_VECTOR_ELT(out, 6, Rf_ScalarInteger((int)nhet));
+    UNPROTECT(5);
+    return out;
+}
+
 static const R_CallMethodDef call_methods[] = {
     {"C_hb_viterbi_norm", (DL_FUNC)&C_hb_viterbi_norm, 5},
     {"C_hb_viterbi_binom", (DL_FUNC)&C_hb_viterbi_binom, 5},
@@ -156,6 +227,8 @@ static const R_CallMethodDef call_methods[] = {
     {"C_hb_group_gexp", (DL_FUNC)&C_hb_group_gexp, 3},
     {"C_hb_group_allele", (DL_FUNC)&C_hb_group_allele, 4},
     {"C_hb_retest_gexp", (DL_FUNC)&C_hb_retest_gexp, 3},
+    {"C_hb_set_gexp_mats", (DL_FUNC)&C_hb_set_gexp_mats, 7},
+    {"C_hb_set_allele_mats", (DL_FUNC)&C_hb_set_allele_mats, 7},
     {NULL, NULL, 0}};
 
 void R_init_hbb200(DllInfo *dll)
