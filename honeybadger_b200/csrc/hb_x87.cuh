@@ -90,7 +90,58 @@ HB_HD uint64_t x80_round(uint64_t hi, uint64_t lo, bool sticky, int32_t &e)
     return hi;
 }
 
+// General case of a + b (any magnitudes, cancellation, far-apart exponents).
+HB_HD x80 x80_add_general(x80 a, x80 b);
+
+// a + b.  The accumulations this file exists for add a term to a much larger running sum, so the
+// common case is handled first and in 64-bit registers: a's exponent exceeds b's by d in [0, 63]
+// (d >= 2 when the signs differ, so at most one leading bit cancels).  b's significand is cut at the
+// 2^-d point into an integer part (added to / subtracted from a.m) and a 64-bit remainder that holds
+// every shifted-out bit, i.e. the result is still the exactly rounded one.
 HB_HD x80 x80_add(x80 a, x80 b)
+{
+    const int32_t d = a.e - b.e;
+    const bool same = a.neg == b.neg;
+    if (a.m != 0 && b.m != 0 && d < 64 && d >= (same ? 0 : 2)) {
+        const uint64_t half = 1ull << 63;
+        const uint64_t bhi = b.m >> d, blo = d ? (b.m << (64 - d)) : 0ull;
+        x80 r;
+        r.neg = a.neg;
+        r.e = a.e;
+        uint64_t m, lo;
+        bool sticky = false;
+        if (same) {
+            m = a.m + bhi;
+            lo = blo;
+            if (m < a.m) { // carry out of bit 63: renormalise by one bit
+                sticky = (lo & 1ull) != 0;
+                lo = (lo >> 1) | (m << 63);
+                m = half | (m >> 1);
+                r.e += 1;
+            }
+        } else {
+            lo = 0ull - blo;
+            m = a.m - bhi - (blo != 0 ? 1ull : 0ull);
+            if (!(m >> 63)) { // one leading bit cancelled
+                m = (m << 1) | (lo >> 63);
+                lo <<= 1;
+                r.e -= 1;
+            }
+        }
+        if (lo > half || (lo == half && (sticky || (m & 1ull)))) {
+            m += 1;
+            if (m == 0) {
+                m = half;
+                r.e += 1;
+            }
+        }
+        r.m = m;
+        return r;
+    }
+    return x80_add_general(a, b);
+}
+
+HB_HD x80 x80_add_general(x80 a, x80 b)
 {
     if (a.m == 0) return b;
     if (b.m == 0) return a;

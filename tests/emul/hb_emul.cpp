@@ -349,6 +349,32 @@ double emul_x87_mean(const double *x, int64_t n)
     return x80_to_double(S);
 }
 
+// Every step of a running sum through x80_add against the host's own x87 unit (long double):
+// returns the number of steps whose 80-bit result differs.  mode 0: s += x[i]; mode 1: s += x[i] - c
+// (the second pass of mean); mode 2: s += x[i] * x[i+1] style products are not needed on this path.
+int64_t emul_x87_addcheck(const double *x, int64_t n, double c, int mode)
+{
+    x80 S = x80_zero();
+    const x80 C80 = x80_from_double(c);
+    volatile long double s = 0.0L;
+    const long double cl = c;
+    int64_t bad = 0;
+    for (int64_t i = 0; i < n; i++) {
+        if (mode == 0) {
+            S = x80_add(S, x80_from_double(x[i]));
+            s = s + (long double)x[i];
+        } else {
+            S = x80_add(S, x80_sub(x80_from_double(x[i]), C80));
+            volatile long double t = (long double)x[i] - cl;
+            s = s + t;
+        }
+        long double mine = S.m ? ldexpl((long double)S.m, S.e - 63) : 0.0L;
+        if (S.neg) mine = -mine;
+        if (mine != s) bad++;
+    }
+    return bad;
+}
+
 double emul_x87_sd(const double *x, int64_t n)
 {
     x80 xm = x80_from_double(emul_x87_mean(x, n)), SS = x80_zero();

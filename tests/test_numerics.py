@@ -62,6 +62,26 @@ def test_x87_emulation_reproduces_r_mean_and_sd(emul, oracle):
             assert emul.emul_x87_sd(p, n) == oracle.r_sd(x)
 
 
+def test_x87_add_matches_the_hardware_step_by_step(emul):
+    """x80_add (fast path and general path) against the host's x87 unit after every single addition:
+    same-sign growth, mixed signs, cancellation, exact ties, terms far below / above the accumulator."""
+    rng = np.random.default_rng(17)
+    cases = []
+    cases.append(rng.gamma(2.0, 1.5, 20000))                                  # all positive (rowMeans)
+    cases.append(rng.normal(size=20000) * 2.6)                                # mixed signs
+    cases.append(rng.normal(size=5000) * 10.0 ** rng.integers(-12, 12, 5000))  # wide exponent range
+    cases.append(np.ldexp(rng.integers(1, 1 << 20, 5000).astype(float), rng.integers(-70, 70, 5000)))
+    cases.append(np.array([1.0, 2.0 ** -64, 2.0 ** -64, -1.0, 2.0 ** -63, 1.0, -(1.0 - 2.0 ** -53), 3.0, -3.0]))
+    t = np.ldexp(rng.integers(1, 1 << 30, 4000).astype(float), -40)            # few significant bits: many ties
+    cases.append(np.concatenate([[float(1 << 23)], t, -t]))
+    cases.append(np.concatenate([np.full(3000, 0.1), np.full(3000, -0.1), [1e300, -1e300, 1e-300]]))
+    for x in cases:
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        p = x.ctypes.data_as(C.c_void_p)
+        assert emul.emul_x87_addcheck(p, x.size, 0.0, 0) == 0
+        assert emul.emul_x87_addcheck(p, x.size, float(x.mean()), 1) == 0
+
+
 def test_binom_logpmf_host_and_device_restatements_match_oracle(emul, oracle):
     for n in list(range(0, 70)) + [100, 255, 256, 511, 512, 1245, 5000]:
         for x in sorted({0, 1, n // 3, n // 2, n - 1, n}):
