@@ -64,32 +64,58 @@ __global__ void __launch_bounds__(256)
     for (int a = 0; a < 4; a++)
 #pragma unroll
         for (int b = 0; b < 4; b++) acc[a][b] = cnt[a][b] = 0.0;
+    double nfast = 0.0; // positions of slabs without a single non-finite value: counted once, not per pair
     for (int64_t g0 = 0; g0 < G; g0 += GD_K) {
+        int bad = 0;
         for (int e = threadIdx.x; e < GD_K * GD_T; e += 256) {
             const int k = e / GD_T, cc = e % GD_T;
             const int64_t g = g0 + k;
-            sa[k][cc] = (g < G && i0 + cc < N) ? S[g * ld + i0 + cc] : NAN;
-            sb[k][cc] = (g < G && j0 + cc < N) ? S[g * ld + j0 + cc] : NAN;
+            const double a = (g < G && i0 + cc < N) ? S[g * ld + i0 + cc] : NAN;
+            const double b = (g < G && j0 + cc < N) ? S[g * ld + j0 + cc] : NAN;
+            bad |= !isfinite(a) || !isfinite(b);
+            sa[k][cc] = a;
+            sb[k][cc] = b;
         }
-        __syncthreads();
+        // R_euclidean (distance.c): dev = x_i - x_j; if (!ISNAN(dev)) { dist += dev * dev; count++; } —
+        // a product and an addition, each rounded (no FMA), positions in order
+        if (!__syncthreads_or(bad)) {
 #pragma unroll 4
-        for (int k = 0; k < GD_K; k++) {
-            double va[4], vb[4];
+            for (int k = 0; k < GD_K; k++) {
+                double va[4], vb[4];
 #pragma unroll
-            for (int a = 0; a < 4; a++) {
-                va[a] = sa[k][ty * 4 + a];
-                vb[a] = sb[k][tx * 4 + a];
-            }
-#pragma unroll
-            for (int a = 0; a < 4; a++)
-#pragma unroll
-                for (int b = 0; b < 4; b++) {
-                    const double d = va[a] - vb[b]; // NaN or Inf-Inf when a member is unusable
-                    if (isfinite(d)) {
-                        acc[a][b] = fma(d, d, acc[a][b]);
-                        cnt[a][b] += 1.0;
-                    }
+                for (int a = 0; a < 4; a++) {
+                    va[a] = sa[k][ty * 4 + a];
+                    vb[a] = sb[k][tx * 4 + a];
                 }
+#pragma unroll
+                for (int a = 0; a < 4; a++)
+#pragma unroll
+                    for (int b = 0; b < 4; b++) {
+                        const double d = va[a] - vb[b];
+                        acc[a][b] = __dadd_rn(acc[a][b], __dmul_rn(d, d));
+                    }
+            }
+            nfast += (double)GD_K;
+        } else {
+#pragma unroll 4
+            for (int k = 0; k < GD_K; k++) {
+                double va[4], vb[4];
+#pragma unroll
+                for (int a = 0; a < 4; a++) {
+                    va[a] = sa[k][ty * 4 + a];
+                    vb[a] = sb[k][tx * 4 + a];
+                }
+#pragma unroll
+                for (int a = 0; a < 4; a++)
+#pragma unroll
+                    for (int b = 0; b < 4; b++) {
+                        const double d = va[a] - vb[b]; // NaN or Inf-Inf when a member is unusable
+                        if (isfinite(d)) {
+                            acc[a][b] = __dadd_rn(acc[a][b], __dmul_rn(d, d));
+                            cnt[a][b] += 1.0;
+                        }
+                    }
+            }
         }
         __syncthreads();
     }
@@ -99,7 +125,14 @@ __global__ void __launch_bounds__(256)
         for (int b = 0; b < 4; b++) {
             const int64_t i = i0 + ty * 4 + a, j = j0 + tx * 4 + b;
             if (i < N && j < N) {
-                const double v = cnt[a][b] > 0 ? acc[a][b] * ((double)G / cnt[a][b]) : 0.0;
+                // if (count != nc) dist /= ((double)count / nc); return sqrt(dist); hclust squares it again
+                const double c = cnt[a][b] + nfast;
+                double v = 0.0;
+                if (c > 0) {
+                    v = c != (double)G ? acc[a][b] / (c / (double)G) : acc[a][b];
+                    const double r = sqrt(v);
+                    v = __dmul_rn(r, r);
+                }
                 const double w = (i == j) ? 0.0 : v;
                 D[i * N + j] = w;
                 D[j * N + i] = w;

@@ -500,6 +500,7 @@ class HoneyBADGER:
         self.retest_gexp = retest_gexp_closed_form
         self.retest_allele = retest_allele_lr
         self._x_dev = self._r_dev = self._n_dev = None
+        self._x_any_nan = None
 
     # ---- inputs (kept as the reference defines them; R/HoneyBADGER.R:123-188, :485-614)
     def setGexpMats(self, gexp_sc_init, gexp_ref_init, genes: GRanges, filter=True, minMeanBoth=0,
@@ -552,6 +553,7 @@ class HoneyBADGER:
         norm_dev = norm_dev.contiguous()
         self.gexp_norm = pd.DataFrame(norm_dev.cpu().numpy(), index=gvi, columns=sc.columns)
         self._x_dev = (norm_dev, {g: i for i, g in enumerate(gvi)}, {c: i for i, c in enumerate(sc.columns)})
+        self._x_any_nan = None
         if verbose:
             print("Done setting initial expression matrices! ")
 
@@ -595,6 +597,15 @@ class HoneyBADGER:
         if verbose:
             print("Done setting initial allele matrices! ")
 
+    # ---- sub-matrices of the recursion: names only, the values stay on the device
+    class _View:
+        """`m[rows, cols]` of a resident matrix by name — what the recursive calls hand down instead
+        of a host copy (R/HoneyBADGER.R:1304-1309 passes `gexp.norm[, g1]`)."""
+
+        def __init__(self, index, columns):
+            self.index = np.asarray(index, dtype=object)
+            self.columns = np.asarray(columns, dtype=object)
+
     # ---- device residency: full matrices are uploaded once; every level gathers rows / columns there
     def _resident(self, kind):
         import torch
@@ -624,30 +635,49 @@ class HoneyBADGER:
     # ---- expression boundaries (R/HoneyBADGER.R:1091-1316)
     def calcGexpCnvBoundaries(self, gexp_norm_sub=None, chrs=None, min_traverse=5, min_num_genes=10,
                               t=1e-6, init=False, verbose=False, **retest_kw):
+        import torch
         chrs = CHRS_DEFAULT if chrs is None else list(chrs)
-        gexp = self.gexp_norm if gexp_norm_sub is None else gexp_norm_sub
+        sub = self.gexp_norm if gexp_norm_sub is None else gexp_norm_sub
+        rows_all = np.asarray(sub.index, dtype=object)
+        cols = np.asarray(sub.columns, dtype=object)
         if init:
-            self.pred_genes_r = pd.DataFrame(0.0, index=gexp.index, columns=gexp.columns)
+            self.pred_genes_r = pd.DataFrame(np.zeros((rows_all.size, cols.size)), index=rows_all, columns=cols,
+                                             copy=False)
             self.bound_genes_old = []
             self.bound_genes_final = []
         if self.bound_genes_final is None:
             print("ERROR! USE init=TRUE! ")
             return None
         old = set(self.bound_genes_old)
-        gexp = gexp[[g not in old for g in gexp.index]]
-        ordr = order_genes(list(gexp.index), self.genes, chrs, has_na=gexp.isna().any(axis=1).values)
-        gexp = gexp.iloc[ordr]
-        names = np.asarray(gexp.index, dtype=object)
-        mat = gexp.values
-        G, N = mat.shape
-        heights = list(range(1, min(min_traverse, N) + 1))
+        keep = np.fromiter((g not in old for g in rows_all), dtype=bool, count=rows_all.size)
+        rows = rows_all[keep]
+        # the values never leave the device: rows / columns are gathered by name from the resident
+        # matrix; only a sub-matrix with names that are not resident is uploaded
         x_dev = None
-        if self.gexp_norm is not None:
+        resident = self.gexp_norm is not None
+        if resident:
             full, rix, cix = self._resident("gexp")
-            x_dev = self._gather(full, rix, cix, names, gexp.columns)
-        if x_dev is None:
-            x_dev = _to_dev_f64(mat)
-        labels = self.grouping_gexp(mat, heights) if self.grouping_gexp else ward_groups_dev(x_dev, heights, 101)
+            if self._x_any_nan is None:
+                self._x_any_nan = bool(torch.isnan(full).any().item())
+            if not self._x_any_nan:  # na.omit has nothing to drop: order by name, gather once
+                ordr = order_genes(list(rows), self.genes, chrs)
+                x_dev = self._gather(full, rix, cix, rows[ordr], cols)
+            else:
+                x_dev = self._gather(full, rix, cix, rows, cols)
+        fresh = x_dev is None
+        if fresh:
+            if isinstance(sub, HoneyBADGER._View):
+                raise KeyError("sub-matrix names are not resident")
+            x_dev = _to_dev_f64(sub.values[keep])
+        if fresh or self._x_any_nan:
+            has_na = torch.isnan(x_dev).any(dim=1).cpu().numpy()
+            ordr = order_genes(list(rows), self.genes, chrs, has_na=has_na)
+            x_dev = x_dev.index_select(0, torch.as_tensor(ordr, device=x_dev.device))
+        names = rows[ordr]
+        G, N = x_dev.shape
+        heights = list(range(1, min(min_traverse, N) + 1))
+        labels = self.grouping_gexp(x_dev.cpu().numpy(), heights) if self.grouping_gexp else \
+            ward_groups_dev(x_dev, heights, 101)
         member, _ = _membership(labels, N)
         amp_v, del_v = np.zeros(G, np.int64), np.zeros(G, np.int64)
         if member.shape[0]:
@@ -676,7 +706,7 @@ class HoneyBADGER:
         dps = (prob > 0.75).sum(1)  # rowSums(prob.bin, na.rm=TRUE): only the 1s count
         dpsi = int(np.nonzero(dps == dps.max())[0][0])
         prob_fin, bound_new = prob[dpsi], lists[dpsi]
-        cells = np.asarray(gexp.columns, dtype=object)
+        cells = cols
         g1, g2 = list(cells[prob_fin > 0.75]), list(cells[prob_fin <= 0.25])
         if g1:
             self.pred_genes_r.loc[bound_new, g1] = 1
@@ -685,7 +715,8 @@ class HoneyBADGER:
         for g in (g1, g2):  # the recursive calls use the DEFAULT arguments (R/HoneyBADGER.R:1304)
             if len(g) >= 3:
                 try:
-                    self.calcGexpCnvBoundaries(gexp_norm_sub=gexp[g])
+                    self.calcGexpCnvBoundaries(gexp_norm_sub=HoneyBADGER._View(names, g) if resident and not fresh
+                                               else sub.loc[list(names), g])
                 except Exception as e:  # tryCatch(..., error = function(e) cat(...))
                     print(f"ERROR: {e}")
         return None
@@ -696,31 +727,36 @@ class HoneyBADGER:
                                 init=False, verbose=False, **retest_kw):
         r_maf = self.r_maf if r_sub is None else r_sub
         n_sc = self.n_sc if n_sc_sub is None else n_sc_sub
+        rows_all = np.asarray(r_maf.index, dtype=object)
+        cols = np.asarray(r_maf.columns, dtype=object)
         if init:
-            self.pred_snps_r = pandas_zeros_like(r_maf)
+            self.pred_snps_r = pd.DataFrame(np.zeros((rows_all.size, cols.size)), index=rows_all, columns=cols,
+                                            copy=False)
             self.bound_snps_old = []
             self.bound_snps_final = []
         if self.bound_snps_final is None:
             print("ERROR! USE init=TRUE! ")
             return None
         old = set(self.bound_snps_old)
-        vi = np.array([s not in old for s in r_maf.index])
-        r_maf, n_sc = r_maf[vi], n_sc[vi]
-        names = np.asarray(r_maf.index, dtype=object)
-        r, n = r_maf.values, n_sc.values
-        G, N = r.shape
-        heights = list(range(1, min(min_traverse, N) + 1))
+        vi = np.fromiter((s not in old for s in rows_all), dtype=bool, count=rows_all.size)
+        names = rows_all[vi]
         r_dev = n_dev = None
-        if self.r_maf is not None:
+        resident = self.r_maf is not None
+        if resident:  # gather by name on the device; the recursion hands down names, not copies
             rfull, nfull, rix, cix = self._resident("allele")
-            r_dev = self._gather(rfull, rix, cix, names, r_maf.columns)
-            n_dev = self._gather(nfull, rix, cix, names, r_maf.columns)
-        if r_dev is None:
-            r_dev, n_dev = _to_dev_i32(r), _to_dev_i32(n)
+            r_dev = self._gather(rfull, rix, cix, names, cols)
+            n_dev = self._gather(nfull, rix, cix, names, cols)
+        fresh = r_dev is None
+        if fresh:
+            if isinstance(r_maf, HoneyBADGER._View):
+                raise KeyError("sub-matrix names are not resident")
+            r_dev, n_dev = _to_dev_i32(r_maf.values[vi]), _to_dev_i32(n_sc.values[vi])
+        G, N = r_dev.shape
+        heights = list(range(1, min(min_traverse, N) + 1))
         if self.grouping_allele is None:
             labels = ward_groups_dev(None, heights, 31, counts=(r_dev, n_dev))
         else:
-            labels = self.grouping_allele(r, n, heights)
+            labels = self.grouping_allele(r_dev.cpu().numpy(), n_dev.cpu().numpy(), heights)
         member, tags = _membership(labels, N)
         vote = np.zeros(G, np.int64)
         if member.shape[0]:
@@ -742,7 +778,7 @@ class HoneyBADGER:
             prob_fin, bound_new = prob[dpsi], lists[dpsi]
         else:
             prob_fin, bound_new = prob[0], lists[0]
-        cells = np.asarray(r_maf.columns, dtype=object)
+        cells = cols
         g1, g2 = list(cells[prob_fin > 0.75]), list(cells[prob_fin <= 0.25])
         if g1:
             self.pred_snps_r.loc[bound_new, g1] = 1
@@ -751,9 +787,13 @@ class HoneyBADGER:
         for g in (g1, g2):
             if len(g) >= 3:
                 try:
-                    self.calcAlleleCnvBoundaries(
-                        r_sub=r_maf[g], n_sc_sub=n_sc[g],
-                        l_sub=(r_maf[g].values > 0).sum(1), n_bulk_sub=(n_sc[g].values > 0).sum(1))
+                    # l.sub / n.bulk.sub (R/HoneyBADGER.R:1563-1566) feed only the bulk term of the JAGS retest
+                    # (:1486), which the retest hook used here does not have
+                    if resident and not fresh:
+                        v = HoneyBADGER._View(names, g)
+                        self.calcAlleleCnvBoundaries(r_sub=v, n_sc_sub=v)
+                    else:
+                        self.calcAlleleCnvBoundaries(r_sub=r_maf.loc[list(names), g], n_sc_sub=n_sc.loc[list(names), g])
                 except Exception as e:
                     print(f"ERROR: {e}")
         return None
