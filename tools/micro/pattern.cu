@@ -42,9 +42,17 @@ __global__ void __launch_bounds__(128) pat(const double *x, long ld, long T, lon
             for (int j = 7; j >= 0; j--) {
                 if (t + j < t1) {
                     acc = acc * 0.999 + v[j];
+                    if (tiled == 2) {
+                        // one record per (tile, chunk): 3 planes x 8 steps x 32 lanes doubles, then 8 x 32 bytes
+                        const long rec = ((b >> 5) * (T / 8 + 24) + c + s) * (3 * 8 * 32 + 32); // in doubles (y: 256 B = 32 doubles)
+                        double *gr = g + rec;
+                        gr[(0 * 8 + j) * 32 + (b & 31)] = acc; gr[(1 * 8 + j) * 32 + (b & 31)] = acc + 1; gr[(2 * 8 + j) * 32 + (b & 31)] = acc + 2;
+                        ((unsigned char *)(gr + 3 * 8 * 32))[j * 32 + (b & 31)] = (unsigned char)(int)acc;
+                    } else {
                     long o = XI(t + j);
                     g[o] = acc; g[o + plane] = acc + 1; g[o + 2 * plane] = acc + 2;
                     y[o] = (unsigned char)(int)acc;
+                    }
                 }
             }
         }
@@ -60,13 +68,13 @@ int main(int argc, char **argv)
     std::vector<int> order(22); std::iota(order.begin(), order.end(), 0);
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return seg[a + 1] - seg[a] > seg[b + 1] - seg[b]; });
     double *x, *g, *ck; unsigned char *y; long *dseg; int *dord;
-    cudaMalloc(&x, T * ld * 8); cudaMalloc(&g, 3 * T * ld * 8); cudaMalloc(&y, T * ld); cudaMalloc(&ck, (T / 8 + 64) * 4 * B * 8);
+    cudaMalloc(&x, T * ld * 8); cudaMalloc(&g, 3 * T * ld * 8 + T * ld * 2 + (1 << 24)); cudaMalloc(&y, T * ld); cudaMalloc(&ck, (T / 8 + 64) * 4 * B * 8);
     cudaMemset(x, 0, T * ld * 8);
     cudaMalloc(&dseg, 23 * 8); cudaMalloc(&dord, 22 * 4);
     cudaMemcpy(dseg, seg.data(), 23 * 8, cudaMemcpyHostToDevice); cudaMemcpy(dord, order.data(), 22 * 4, cudaMemcpyHostToDevice);
     int nblk = (B + 127) / 128;
     B = 9984; ld = B; nblk = (B + 127) / 128; // multiple of 32 for the tiled variant
-    for (int tiled : {0, 1}) {
+    for (int tiled : {0, 1, 2}) {
         size_t smem = 53248;
         cudaFuncSetAttribute(pat, cudaFuncAttributeMaxDynamicSharedMemorySize, 60000);
         for (int mode : {1, 2, 3}) {
