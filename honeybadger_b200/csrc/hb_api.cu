@@ -1720,6 +1720,141 @@ int hb_retest_allele_lr_dev(const int32_t *r_maf, const int32_t *n_sc, int64_t l
     return HB_OK;
 }
 
+// Gauss-Legendre nodes / weights on [-1, 1] (Newton on P_n; n small).
+static void gauss_legendre(int n, std::vector<double> &x, std::vector<double> &w)
+{
+    x.assign(n, 0.0);
+    w.assign(n, 0.0);
+    for (int i = 0; i < (n + 1) / 2; i++) {
+        double z = cos(M_PI * (i + 0.75) / (n + 0.5)), pp = 1.0;
+        for (int it = 0; it < 100; it++) {
+            double p1 = 1.0, p2 = 0.0;
+            for (int j = 0; j < n; j++) {
+                const double p3 = p2;
+                p2 = p1;
+                p1 = ((2.0 * j + 1.0) * z * p2 - j * p3) / (j + 1.0);
+            }
+            pp = n * (z * p1 - p2) / (z * z - 1.0);
+            const double z1 = z;
+            z = z1 - p1 / pp;
+            if (fabs(z - z1) < 1e-15) break;
+        }
+        x[i] = -z;
+        x[n - 1 - i] = z;
+        w[i] = w[n - 1 - i] = 2.0 / ((1.0 - z * z) * pp * pp);
+    }
+}
+
+// Exact marginal of inst/bug/snpModel.bug per cell (see retest_allele_model_kernel).
+int hb_retest_allele_model_dev(const int32_t *r_maf, const int32_t *n_sc, int64_t ld, int64_t G, int64_t N,
+                               const int64_t *rows, int64_t nrows, const uint8_t *gene_end,
+                               const double *l_maf, const double *n_bulk, double pseudo, double mono,
+                               double *p_del, void *stream)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    Workspace *ws;
+    HBTRY(cur_ws(&ws));
+    if (!r_maf || !n_sc || !rows || !l_maf || !n_bulk || !p_del || G < 1 || N < 1 || nrows < 1 || ld < N ||
+        !(pseudo > 0 && pseudo < 0.5) || !(mono > 0 && mono < 1))
+        return fail(HB_ERR_ARG, "bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    // h ~ dnorm(0.5, 0.1)T(pseudo, 1 - pseudo): JAGS' second argument is a precision (sd = 1/sqrt(0.1))
+    const int panels = 16, gl = 16, nq = panels * gl;
+    const double sd = 1.0 / sqrt(0.1), lo = pseudo, hi = 1.0 - pseudo;
+    const double Z = sd * sqrt(2.0 * M_PI) * 0.5 * (erf((hi - 0.5) / (sd * M_SQRT2)) - erf((lo - 0.5) / (sd * M_SQRT2)));
+    std::vector<double> gx, gw, tab((size_t)3 * nq);
+    gauss_legendre(gl, gx, gw);
+    const double pw = (hi - lo) / panels;
+    for (int p = 0; p < panels; p++)
+        for (int i = 0; i < gl; i++) {
+            const double h = lo + pw * (p + 0.5 * (gx[i] + 1.0));
+            const double dens = exp(-0.5 * (h - 0.5) * (h - 0.5) / (sd * sd)) / Z;
+            const int q = p * gl + i;
+            tab[q] = log(h);
+            tab[nq + q] = log1p(-h);
+            tab[2 * nq + q] = log(0.5 * pw * gw[i] * dens);
+        }
+    // bulk posterior of the allele indicator: l ~ Bin(n.bulk, fma), fma = pseudo (ma = 1) | 1 - pseudo (ma = 0)
+    std::vector<double> lq((size_t)2 * nrows);
+    const double lr = log((1.0 - pseudo) / pseudo);
+    std::vector<uint8_t> ge((size_t)nrows, 1); // no gene factor: every SNP is its own gene
+    if (gene_end) memcpy(ge.data(), gene_end, (size_t)nrows);
+    ge[(size_t)nrows - 1] = 1;
+    for (int64_t j = 0; j < nrows; j++) {
+        const double d = (n_bulk[j] - 2.0 * l_maf[j]) * lr; // log odds of ma = 1
+        lq[j] = d >= 0 ? -log1p(exp(-d)) : d - log1p(exp(d));
+        lq[nrows + j] = d >= 0 ? -d - log1p(exp(-d)) : -log1p(exp(d));
+    }
+    const size_t bytes = ((size_t)3 * nq + 2 * nrows) * sizeof(double) + (size_t)nrows;
+    HBTRY(ws->st_part.ensure(bytes + 64));
+    double *d_tab = ws->st_part.as<double>(), *d_lq = d_tab + 3 * nq;
+    uint8_t *d_ge = (uint8_t *)(d_lq + 2 * nrows);
+    CU(cudaMemcpyAsync(d_tab, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_lq, lq.data(), lq.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_ge, ge.data(), ge.size(), cudaMemcpyHostToDevice, st));
+    CU(hb::launch_retest_allele_model(r_maf, n_sc, ld, N, rows, nrows, d_ge, d_lq, d_lq + nrows, d_tab, nq, pseudo,
+                                      mono, p_del, st));
+    CU(cudaStreamSynchronize(st)); // tab / lq / ge are host temporaries
+    return HB_OK;
+}
+
+// Host form for the R side: r_rows, n_rows are the region's [n x N] column-major integer sub-matrices
+// (`r.maf[bound.snps.new, ]`), gene[n] the gene factor codes (any integers; NULL = one gene per SNP).
+int hb_retest_allele_model_host(const int32_t *r_rows, const int32_t *n_rows, int64_t n, int64_t N,
+                                const double *l_maf, const double *n_bulk, const int32_t *gene, double pseudo,
+                                double mono, double *p_del)
+{
+    if (!r_rows || !n_rows || !l_maf || !n_bulk || !p_del || n < 1 || N < 1) return fail(HB_ERR_ARG, "bad arguments");
+    // group the SNPs by gene in order of first appearance (unique(geneFactor), R/HoneyBADGER.R:963)
+    std::vector<int64_t> order((size_t)n);
+    std::iota(order.begin(), order.end(), (int64_t)0);
+    std::vector<uint8_t> ge((size_t)n, 1);
+    if (gene) {
+        std::vector<int32_t> seen;
+        std::vector<int64_t> rank((size_t)n);
+        for (int64_t j = 0; j < n; j++) {
+            auto it = std::find(seen.begin(), seen.end(), gene[j]);
+            rank[j] = it - seen.begin();
+            if (it == seen.end()) seen.push_back(gene[j]);
+        }
+        std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return rank[a] < rank[b]; });
+        for (int64_t j = 0; j < n; j++) ge[j] = (j + 1 == n) || rank[order[j + 1]] != rank[order[j]];
+    }
+    std::vector<double> l2((size_t)n), nb2((size_t)n);
+    for (int64_t j = 0; j < n; j++) {
+        l2[j] = l_maf[order[j]];
+        nb2[j] = n_bulk[order[j]];
+    }
+    const int64_t ld = (N + 127) / 128 * 128;
+    int32_t *d_r, *d_n;
+    int64_t *d_rows;
+    double *d_out;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        Workspace *ws;
+        HBTRY(cur_ws(&ws));
+        HBTRY(ws->st_in.ensure((size_t)n * N * sizeof(int32_t)));
+        HBTRY(ws->st_in2.ensure((size_t)n * N * sizeof(int32_t)));
+        HBTRY(ws->st_x.ensure((size_t)n * ld * sizeof(int32_t)));
+        HBTRY(ws->st_x2.ensure((size_t)n * ld * sizeof(int32_t)));
+        HBTRY(ws->st_out.ensure((size_t)N * sizeof(double)));
+        HBTRY(ws->st_member.ensure((size_t)n * sizeof(int64_t)));
+        CU(cudaMemcpyAsync(ws->st_in.p, r_rows, (size_t)n * N * sizeof(int32_t), cudaMemcpyHostToDevice, 0));
+        CU(cudaMemcpyAsync(ws->st_in2.p, n_rows, (size_t)n * N * sizeof(int32_t), cudaMemcpyHostToDevice, 0));
+        CU(hb::launch_transpose_i32(ws->st_in.as<int32_t>(), n, N, ws->st_x.as<int32_t>(), ld, 0));
+        CU(hb::launch_transpose_i32(ws->st_in2.as<int32_t>(), n, N, ws->st_x2.as<int32_t>(), ld, 0));
+        CU(cudaMemcpy(ws->st_member.p, order.data(), (size_t)n * sizeof(int64_t), cudaMemcpyHostToDevice));
+        d_r = ws->st_x.as<int32_t>();
+        d_n = ws->st_x2.as<int32_t>();
+        d_rows = ws->st_member.as<int64_t>();
+        d_out = ws->st_out.as<double>();
+    }
+    HBTRY(hb_retest_allele_model_dev(d_r, d_n, ld, n, N, d_rows, n, ge.data(), l2.data(), nb2.data(), pseudo, mono,
+                                     d_out, nullptr));
+    CU(cudaMemcpy(p_del, d_out, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost));
+    return HB_OK;
+}
+
 // ------------------------------------------------------------------ the four reference call sites
 // One round of pooled chains on DEVICE-RESIDENT matrices: membership and the small results are
 // host buffers (K <= a few dozen chains), the [G x N] matrices never leave the GPU.

@@ -566,6 +566,74 @@ cudaError_t launch_retest_allele(const int32_t *r, const int32_t *n, int64_t ld,
     return cudaGetLastError();
 }
 
+// Allele region retest, the model itself: exact marginal posterior P(S_k = 1 | data) of
+// inst/bug/snpModel.bug (sampled with JAGS by calcAlleleCnvProb, R/HoneyBADGER.R:907-1042) with every
+// per-cell latent variable integrated out —
+//   S_k ~ Bern(alpha_k), alpha_k ~ U(0,1)                      => prior odds 1
+//   S_k = 1:  r ~ Bin(n, fma),  fma = pseudo (ma = 1) | 1 - pseudo (ma = 0)
+//   S_k = 0:  per gene j: b ~ Bern(mono), d ~ Bern(1/2);  b = 1: every SNP of the gene has p = pseudo (d = 1)
+//             or 1 - pseudo (d = 0);  b = 0: p = h, h ~ N(0.5, precision 0.1) truncated to [pseudo, 1-pseudo],
+//             independent per SNP: the integral over h is a 256-node composite Gauss-Legendre rule
+// — and the per-SNP allele indicator ma, which the cells share through the bulk, replaced by its bulk
+// posterior q = P(ma = 1 | l, n.bulk) (the one approximation; the bulk counts dominate it).
+// One thread per cell; the binomial coefficients are common to both hypotheses and dropped.
+// tab = [lh | l1h | lw][nq]: log h_q, log(1 - h_q), log(weight_q * density(h_q)); rows are gene-grouped,
+// gene_end[j] marks the last SNP of a gene; lq1 / lq0 = log q, log(1 - q) per SNP.
+#define RA_THREADS 128
+__device__ __forceinline__ double lse2(double a, double b)
+{
+    const double m = fmax(a, b);
+    if (m == -INFINITY) return m;
+    return m + log(exp(a - m) + exp(b - m));
+}
+__global__ void __launch_bounds__(RA_THREADS)
+    retest_allele_model_kernel(const int32_t *r, const int32_t *n, int64_t ld, int64_t N, const int64_t *rows,
+                               int64_t nrows, const uint8_t *gene_end, const double *lq1, const double *lq0,
+                               const double *tab, int32_t nq, double lps, double l1ps, double lmono_half,
+                               double l1mono, double *p_del)
+{
+    extern __shared__ double sh[];
+    for (int i = threadIdx.x; i < 3 * nq; i += RA_THREADS) sh[i] = tab[i];
+    __syncthreads();
+    const double *lh = sh, *l1h = sh + nq, *lw = sh + 2 * nq;
+    const int64_t c = (int64_t)blockIdx.x * RA_THREADS + threadIdx.x;
+    if (c >= N) return;
+    double L1 = 0.0, L0 = 0.0, A = 0.0, B1 = 0.0, B0 = 0.0;
+    for (int64_t j = 0; j < nrows; j++) {
+        const int64_t o = rows[j] * ld + c;
+        const int32_t nv = ld_stream(n + o);
+        if (nv > 0) {
+            const double rv = (double)ld_stream(r + o), mv = (double)nv - rv;
+            const double a = rv * lps + mv * l1ps, b = rv * l1ps + mv * lps;
+            L1 += lse2(lq1[j] + a, lq0[j] + b);
+            B1 += a;
+            B0 += b;
+            double mx = -INFINITY;
+            for (int q = 0; q < nq; q++) mx = fmax(mx, lw[q] + rv * lh[q] + mv * l1h[q]);
+            double sum = 0.0;
+            for (int q = 0; q < nq; q++) sum += exp(lw[q] + rv * lh[q] + mv * l1h[q] - mx);
+            A += mx + log(sum);
+        }
+        if (gene_end[j]) {
+            L0 += lse2(l1mono + A, lmono_half + lse2(B1, B0));
+            A = B1 = B0 = 0.0;
+        }
+    }
+    p_del[c] = sigmoid(L1 - L0);
+}
+
+cudaError_t launch_retest_allele_model(const int32_t *r, const int32_t *n, int64_t ld, int64_t N,
+                                       const int64_t *rows, int64_t nrows, const uint8_t *gene_end,
+                                       const double *lq1, const double *lq0, const double *tab, int32_t nq,
+                                       double pseudo, double mono, double *p_del, cudaStream_t st)
+{
+    retest_allele_model_kernel<<<(unsigned)((N + RA_THREADS - 1) / RA_THREADS), RA_THREADS,
+                                 (size_t)3 * nq * sizeof(double), st>>>(
+        r, n, ld, N, rows, nrows, gene_end, lq1, lq0, tab, nq, log(pseudo), log(1 - pseudo), log(mono / 2),
+        log(1 - mono), p_del);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_retest_gexp_a(const double *x, int64_t ld, int64_t N, const int64_t *rows,
                                  int64_t nrows, double mag0, const double *sigma0, double *w_amp,
                                  double *w_del, double *mu0, double *partial, double *D_local,

@@ -18,8 +18,10 @@ Outside the path (SURVEY.md §8f "next" rows), supplied as replaceable hooks:
     `ward_groups_dev` does it on the device (runmean, R dist with its NA rule, Ward.D2 by nearest-neighbour
     chain); `ward_groups` is the scipy host form; any f(mat, heights) can be plugged in.
   * retest   — the JAGS posteriors (`calcGexpCnvProb`, `calcAlleleCnvProb`): `retest_gexp_closed_form`
-    (exact marginal of inst/bug/expressionModel.bug) and a binomial likelihood-ratio
-    stand-in for the allele model; both on the device with torch ops, neither parity-pinned.
+    (exact marginal of inst/bug/expressionModel.bug) and `retest_allele_model` (per-cell
+    marginal of inst/bug/snpModel.bug with the shared allele indicators at their bulk posterior), both
+    CUDA kernels behind the C ABI; `retest_allele_lr` is a plain likelihood-ratio alternative.  None of
+    them is parity-pinned: the reference samples these posteriors by MCMC.
 R matrices with dimnames are pandas DataFrames here (index = gene / SNP names, columns = cells).
 """
 from __future__ import annotations
@@ -231,6 +233,39 @@ def retest_allele_lr(r_rows, n_rows, pd_=0.1, pn=0.45):
     _lib.check(_lib.load().hb_retest_allele_lr_dev(r.data_ptr(), n.data_ptr(), r.stride(0), m, N,
                                                    rows.data_ptr(), m, float(pd_), float(pn),
                                                    out.data_ptr(), _stream()))
+    return out.cpu().numpy()
+
+
+def retest_allele_model(r_rows, n_rows, l_maf, n_bulk, gene=None, pe=0.1, mono=0.7):
+    """P(deletion) per cell for one candidate region: the exact per-cell marginal of
+    inst/bug/snpModel.bug (calcAlleleCnvProb, R/HoneyBADGER.R:907-1042, samples it with JAGS; the caller
+    at :1486 passes pe = pd), libhb_b200's hb_retest_allele_model_dev.  `gene`: the geneFactor codes of
+    the region's SNPs (None = one gene per SNP).  Statistical stand-in for the MCMC, not parity-pinned."""
+    import torch
+
+    def dev_i32(a):
+        t = a if torch.is_tensor(a) else torch.as_tensor(np.ascontiguousarray(np.rint(a), dtype=np.int32),
+                                                          device="cuda")
+        return t if t.stride(1) == 1 else t.contiguous()
+
+    r, n = dev_i32(r_rows), dev_i32(n_rows)
+    if r.stride(0) != n.stride(0):
+        r, n = r.contiguous(), n.contiguous()
+    m, N = r.shape
+    order = np.arange(m)
+    gene_end = None
+    if gene is not None:  # group by first appearance, like unique(geneFactor) (R/HoneyBADGER.R:963)
+        codes = pd.factorize(np.asarray(gene, dtype=object))[0]
+        order = np.argsort(codes, kind="stable")
+        sc = codes[order]
+        gene_end = np.ascontiguousarray(np.r_[sc[1:] != sc[:-1], True], dtype=np.uint8)
+    rows = torch.as_tensor(order, dtype=torch.int64, device=r.device)
+    l2 = np.ascontiguousarray(np.asarray(l_maf, dtype=np.float64)[order])
+    nb2 = np.ascontiguousarray(np.asarray(n_bulk, dtype=np.float64)[order])
+    out = torch.empty(N, dtype=torch.float64, device=r.device)
+    _lib.check(_lib.load().hb_retest_allele_model_dev(r.data_ptr(), n.data_ptr(), r.stride(0), m, N,
+                                                      rows.data_ptr(), m, _vp(gene_end), _vp(l2), _vp(nb2),
+                                                      float(pe), float(mono), out.data_ptr(), _stream()))
     return out.cpu().numpy()
 
 
@@ -498,7 +533,8 @@ class HoneyBADGER:
         self.grouping_gexp = None   # None: ward_groups_dev on the resident matrix; or f(mat, heights)
         self.grouping_allele = None
         self.retest_gexp = retest_gexp_closed_form
-        self.retest_allele = retest_allele_lr
+        self.retest_allele = None   # None: retest_allele_model (snpModel.bug marginal); or f(r, n, pd, pn)
+        self.geneFactor = None      # SNP name -> gene (setGeneFactors needs TxDb; pass a dict); None: 1 SNP = 1 gene
         self._x_dev = self._r_dev = self._n_dev = None
         self._x_any_nan = None
 
@@ -641,8 +677,7 @@ class HoneyBADGER:
         rows_all = np.asarray(sub.index, dtype=object)
         cols = np.asarray(sub.columns, dtype=object)
         if init:
-            self.pred_genes_r = pd.DataFrame(np.zeros((rows_all.size, cols.size)), index=rows_all, columns=cols,
-                                             copy=False)
+            self.pred_genes_r = _zeros_frame(rows_all, cols)
             self.bound_genes_old = []
             self.bound_genes_final = []
         if self.bound_genes_final is None:
@@ -730,8 +765,7 @@ class HoneyBADGER:
         rows_all = np.asarray(r_maf.index, dtype=object)
         cols = np.asarray(r_maf.columns, dtype=object)
         if init:
-            self.pred_snps_r = pd.DataFrame(np.zeros((rows_all.size, cols.size)), index=rows_all, columns=cols,
-                                            copy=False)
+            self.pred_snps_r = _zeros_frame(rows_all, cols)  # (`pd` is the deletion probability in here)
             self.bound_snps_old = []
             self.bound_snps_final = []
         if self.bound_snps_final is None:
@@ -769,7 +803,26 @@ class HoneyBADGER:
         runs = runs_from_vote(vote, min_num_snps, trim)
         if runs is None:
             return None
-        probs = [self.retest_allele(r_dev[idx], n_dev[idx], pd, pn, **retest_kw) for idx in runs]
+        def bulk_for(idx):
+            # l.maf / n.bulk of the region (R/HoneyBADGER.R:1486): the object's fields at the top level,
+            # l.sub / n.bulk.sub when given, else what the recursion passes down (:1563-1566):
+            # rowSums(r.maf[, g] > 0), rowSums(n.sc[, g] > 0) — counted on the device
+            if r_sub is None and self.l_maf is not None:
+                ii = [self._r_dev[2][s] for s in names[idx]]
+                return np.asarray(self.l_maf, dtype=np.float64)[ii], np.asarray(self.n_bulk, dtype=np.float64)[ii]
+            if l_sub is not None and n_bulk_sub is not None:
+                return (np.asarray(l_sub, dtype=np.float64)[vi][idx],
+                        np.asarray(n_bulk_sub, dtype=np.float64)[vi][idx])
+            return ((r_dev[idx] > 0).sum(1).double().cpu().numpy(), (n_dev[idx] > 0).sum(1).double().cpu().numpy())
+
+        def retest(idx):
+            if self.retest_allele is not None:  # user hook f(r_rows, n_rows, pd, pn, ...)
+                return self.retest_allele(r_dev[idx], n_dev[idx], pd, pn, **retest_kw)
+            lb, nbk = bulk_for(idx)
+            gf = None if self.geneFactor is None else [self.geneFactor.get(s, s) for s in names[idx]]
+            return retest_allele_model(r_dev[idx], n_dev[idx], lb, nbk, gene=gf, pe=pd, **retest_kw)
+
+        probs = [retest(idx) for idx in runs]
         lists = [list(names[idx]) for idx in runs]
         prob = np.vstack(probs)
         if len(runs) > 1:
@@ -787,8 +840,8 @@ class HoneyBADGER:
         for g in (g1, g2):
             if len(g) >= 3:
                 try:
-                    # l.sub / n.bulk.sub (R/HoneyBADGER.R:1563-1566) feed only the bulk term of the JAGS retest
-                    # (:1486), which the retest hook used here does not have
+                    # l.sub / n.bulk.sub (R/HoneyBADGER.R:1563-1566) feed only the bulk term of the retest (:1486):
+                    # the next level counts them on the device from the same sub-matrices (bulk_for)
                     if resident and not fresh:
                         v = HoneyBADGER._View(names, g)
                         self.calcAlleleCnvBoundaries(r_sub=v, n_sc_sub=v)
@@ -799,5 +852,6 @@ class HoneyBADGER:
         return None
 
 
-def pandas_zeros_like(df: pd.DataFrame) -> pd.DataFrame:
-    return pd.DataFrame(0.0, index=df.index, columns=df.columns)
+def _zeros_frame(index, columns) -> pd.DataFrame:
+    """matrix(0, nrow, ncol) with dimnames; calloc-backed, not copied."""
+    return pd.DataFrame(np.zeros((len(index), len(columns))), index=index, columns=columns, copy=False)

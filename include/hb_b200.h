@@ -289,6 +289,24 @@ int hb_retest_allele_lr_dev(const int32_t *r_maf, const int32_t *n_sc, int64_t l
                             const int64_t *rows, int64_t nrows, double pd, double pn, double *p_del,
                             void *stream);
 
+/* The allele model itself: exact marginal posterior P(S_k = 1 | data) of inst/bug/snpModel.bug, which
+ * HoneyBADGER$calcAlleleCnvProb (R/HoneyBADGER.R:907-1042, caller :1486 with pe = pd, mono = 0.7) samples
+ * with JAGS.  Per cell every latent variable (S, alpha, per-gene b and d, per-SNP h) is integrated out —
+ * h by a 256-node composite Gauss-Legendre rule over the truncated normal — and the per-SNP allele
+ * indicator ma is replaced by its bulk posterior P(ma = 1 | l.maf, n.bulk) (the single approximation).
+ * Statistical stand-in for the MCMC, not bit parity.  rows[nrows] (device) are the region's SNP rows
+ * grouped by gene, gene_end[nrows] (host, NULL = one gene per SNP) marks each gene's last SNP, l_maf /
+ * n_bulk (host [nrows]) the bulk counts in the same order.  p_del[N] on the device. */
+int hb_retest_allele_model_dev(const int32_t *r_maf, const int32_t *n_sc, int64_t ld, int64_t G, int64_t N,
+                               const int64_t *rows, int64_t nrows, const uint8_t *gene_end,
+                               const double *l_maf, const double *n_bulk, double pseudo, double mono,
+                               double *p_del, void *stream);
+/* Host form: the region's [n x N] column-major integer sub-matrices, gene[n] factor codes (NULL = one gene
+ * per SNP; grouped by first appearance like unique(geneFactor), R/HoneyBADGER.R:963). */
+int hb_retest_allele_model_host(const int32_t *r_rows, const int32_t *n_rows, int64_t n, int64_t N,
+                                const double *l_maf, const double *n_bulk, const int32_t *gene, double pseudo,
+                                double mono, double *p_del);
+
 /* One recursion round of the split-and-retest driver on DEVICE-RESIDENT matrices (gene-major,
  * uploaded once): `member` [K][N] (0/1, host) names the K candidate cell sets of the round, the
  * small results come back to host buffers: y [K][G] (1-based states), pooled vectors and their sd.

@@ -344,3 +344,52 @@ def retest_gexp(x_rows, mag0, sigma0=None):
     D = La.sum() - Ld.sum()
     post1 = 1.0 / (1.0 + np.exp(-D)) if D >= 0 else np.exp(D) / (1.0 + np.exp(D))
     return post1 * np.exp(lp + np.log(0.5) - La), (1 - post1) * np.exp(lm + np.log(0.5) - Ld)
+
+
+def retest_allele_model(r_rows, n_rows, l_maf, n_bulk, gene=None, pseudo=0.1, mono=0.7):
+    """Exact per-cell marginal P(S_k = 1 | data) of inst/bug/snpModel.bug (sampled with JAGS by
+    calcAlleleCnvProb, R/HoneyBADGER.R:907-1042) with the shared allele indicators ma at their bulk
+    posterior — the quantity libhb_b200's hb_retest_allele_model_dev computes.  Plain numpy; the integral
+    over h ~ dnorm(0.5, 0.1)T(pseudo, 1 - pseudo) by adaptive quadrature (scipy.integrate.quad)."""
+    from scipy import integrate, special
+    r = np.asarray(r_rows, dtype=np.float64)
+    n = np.asarray(n_rows, dtype=np.float64)
+    m, N = r.shape
+    gene = np.arange(m) if gene is None else np.asarray(gene)
+    sd = 1.0 / np.sqrt(0.1)
+    lo, hi = pseudo, 1.0 - pseudo
+    Z = integrate.quad(lambda h: np.exp(-0.5 * ((h - 0.5) / sd) ** 2), lo, hi, epsabs=0, epsrel=1e-13)[0]
+    lq_odds = (np.asarray(n_bulk, float) - 2.0 * np.asarray(l_maf, float)) * np.log((1 - pseudo) / pseudo)
+    lq1, lq0 = -np.logaddexp(0.0, -lq_odds), -np.logaddexp(0.0, lq_odds)
+    lp, l1p = np.log(pseudo), np.log1p(-pseudo)
+    cache = {}
+
+    def log_int(rv, nv):
+        key = (rv, nv)
+        if key not in cache:
+            pk = rv / nv  # integrand peak: scale it out so quad sees O(1) values
+            pk = min(max(pk, lo), hi)
+            ref = rv * np.log(pk) + (nv - rv) * np.log1p(-pk)
+            f = lambda h: np.exp(rv * np.log(h) + (nv - rv) * np.log1p(-h) - ref - 0.5 * ((h - 0.5) / sd) ** 2)
+            val = integrate.quad(f, lo, hi, points=[pk] if lo < pk < hi else None, epsabs=0, epsrel=1e-12,
+                                 limit=400)[0]
+            cache[key] = ref + np.log(val / Z)
+        return cache[key]
+
+    out = np.zeros(N)
+    uniq = list(dict.fromkeys(gene.tolist()))
+    for c in range(N):
+        L1 = L0 = 0.0
+        for g in uniq:
+            A = B1 = B0 = 0.0
+            for j in np.nonzero(gene == g)[0]:
+                if n[j, c] > 0:
+                    a = r[j, c] * lp + (n[j, c] - r[j, c]) * l1p
+                    b = r[j, c] * l1p + (n[j, c] - r[j, c]) * lp
+                    L1 += np.logaddexp(lq1[j] + a, lq0[j] + b)
+                    B1 += a
+                    B0 += b
+                    A += log_int(r[j, c], n[j, c])
+            L0 += np.logaddexp(np.log1p(-mono) + A, np.log(mono / 2) + np.logaddexp(B1, B0))
+        out[c] = special.expit(L1 - L0)
+    return out

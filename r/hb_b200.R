@@ -105,6 +105,16 @@ hb_calcGexpCnvProb <- function(gexp.norm.sub, m, sigma0 = NULL) {
   p
 }
 
+## deterministic stand-in for calcAlleleCnvProb's JAGS run (R/HoneyBADGER.R:907-1042): same 1 x K matrix
+hb_calcAlleleCnvProb <- function(r.sub, n.sc.sub, l.sub, n.bulk.sub, geneFactor = NULL, pe = 0.1, mono = 0.7) {
+  gf <- if (is.null(geneFactor)) NULL else as.integer(factor(geneFactor[rownames(r.sub)],
+                                                            levels = unique(geneFactor[rownames(r.sub)])))
+  pm <- .Call("C_hb_retest_allele", r.sub, n.sc.sub, as.double(l.sub), as.double(n.bulk.sub), gf,
+              as.double(pe), as.double(mono))
+  colnames(pm) <- colnames(r.sub)
+  pm
+}
+
 ## Input construction on the GPU (optional; SURVEY.md 8f-3) ----------------------------------------
 ## R/HoneyBADGER.R:139-161 inside setGexpMats: everything between the name intersection and the biomaRt
 ## lookup.  Bit-identical to rowMeans / scale / `-` of base R; returns gexp.norm with dimnames.

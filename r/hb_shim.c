@@ -219,6 +219,26 @@ SEXP C_hb_set_allele_mats(SEXP r, SEXP n_sc, SEXP l_init, SEXP n_bulk_init, SEXP
     return out;
 }
 
+/* pm <- .Call(C_hb_retest_allele, r.maf[snps, ], n.sc[snps, ], l.maf[snps], n.bulk[snps], geneFactor, pe, mono):
+ * the per-cell marginal of inst/bug/snpModel.bug instead of the JAGS run of calcAlleleCnvProb
+ * (R/HoneyBADGER.R:907-1042).  geneFactor: integer codes per SNP (as.integer(factor(...))) or NULL. */
+SEXP C_hb_retest_allele(SEXP r_rows, SEXP n_rows, SEXP l_maf, SEXP n_bulk, SEXP gene, SEXP pe, SEXP mono)
+{
+    r_rows = PROTECT(Rf_coerceVector(r_rows, INTSXP));
+    n_rows = PROTECT(Rf_coerceVector(n_rows, INTSXP));
+    l_maf = PROTECT(Rf_coerceVector(l_maf, REALSXP));
+    n_bulk = PROTECT(Rf_coerceVector(n_bulk, REALSXP));
+    SEXP gf = PROTECT(Rf_isNull(gene) ? R_NilValue : Rf_coerceVector(gene, INTSXP));
+    const int64_t n = Rf_nrows(r_rows), N = Rf_ncols(r_rows);
+    SEXP out = PROTECT(Rf_allocMatrix(REALSXP, 1, (int)N)); /* calcAlleleCnvProb returns a 1 x K matrix */
+    int rc = hb_retest_allele_model_host(INTEGER(r_rows), INTEGER(n_rows), n, N, REAL(l_maf), REAL(n_bulk),
+                                         Rf_isNull(gene) ? NULL : INTEGER(gf), Rf_asReal(pe), Rf_asReal(mono),
+                                         REAL(out));
+    UNPROTECT(6);
+    hb_raise(rc);
+    return out;
+}
+
 static const R_CallMethodDef call_methods[] = {
     {"C_hb_viterbi_norm", (DL_FUNC)&C_hb_viterbi_norm, 5},
     {"C_hb_viterbi_binom", (DL_FUNC)&C_hb_viterbi_binom, 5},
@@ -227,6 +247,7 @@ static const R_CallMethodDef call_methods[] = {
     {"C_hb_group_gexp", (DL_FUNC)&C_hb_group_gexp, 3},
     {"C_hb_group_allele", (DL_FUNC)&C_hb_group_allele, 4},
     {"C_hb_retest_gexp", (DL_FUNC)&C_hb_retest_gexp, 3},
+    {"C_hb_retest_allele", (DL_FUNC)&C_hb_retest_allele, 7},
     {"C_hb_set_gexp_mats", (DL_FUNC)&C_hb_set_gexp_mats, 7},
     {"C_hb_set_allele_mats", (DL_FUNC)&C_hb_set_allele_mats, 7},
     {NULL, NULL, 0}};

@@ -316,3 +316,64 @@ def test_host_forms_of_grouping_and_retest(oracle):
     ra, rd = oracle.retest_gexp(x[100:160], 1.3, sig)
     assert np.abs(pa - ra).max() < 1e-12 and np.abs(pd_ - rd).max() < 1e-12
     assert np.allclose(mu, x[100:160].mean(0), rtol=1e-13, atol=1e-13)
+
+
+def test_retest_allele_model_vs_oracle(oracle):
+    """hb_retest_allele_model_dev (per-cell marginal of inst/bug/snpModel.bug) vs the numpy / scipy.quad
+    restatement: with and without a gene factor, small and large coverage, decisive and ambiguous bulk."""
+    from honeybadger_b200 import honeybadger as hb
+    rng = np.random.default_rng(23)
+    m, N = 40, 64
+    n = (rng.random((m, N)) < 0.35) * rng.integers(1, 30, (m, N))
+    n[3, 5], n[7, 9] = 400, 1245  # sharply peaked integrands (bundled maximum coverage)
+    p = np.where(np.arange(N) < N // 3, 0.1, 0.45)
+    r = rng.binomial(n, p[None, :])
+    l, nb = (r > 0).sum(1).astype(float), (n > 0).sum(1).astype(float)
+    nb[::5] = 2 * l[::5]          # bulk exactly balanced: q = 1/2
+    for gene in (None, np.arange(m) // 4, rng.integers(0, 6, m)):
+        for pe, mono in ((0.1, 0.7), (0.01, 0.3)):
+            got = hb.retest_allele_model(r, n, l, nb, gene=gene, pe=pe, mono=mono)
+            want = oracle.retest_allele_model(r, n, l, nb, gene=gene, pseudo=pe, mono=mono)
+            assert np.abs(got - want).max() < 1e-9
+    # lesser-allele counts as setAlleleMats leaves them (l.maf well below n.bulk / 2): the planted cells,
+    # whose r / n sits at pseudo, come out as deleted
+    got = hb.retest_allele_model(r, n, np.floor(0.2 * nb), nb, pe=0.1)
+    assert got[: N // 3].mean() > 0.9 and got[N // 3:].mean() < 0.1
+    # host form in R's layout, gene codes in arbitrary order
+    import ctypes as C
+    from honeybadger_b200 import _lib
+    gene = rng.integers(0, 6, m).astype(np.int32)
+    rf, nf = np.asfortranarray(r.astype(np.int32)), np.asfortranarray(n.astype(np.int32))
+    out = np.zeros(N)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    _lib.check(_lib.load().hb_retest_allele_model_host(vp(rf), vp(nf), m, N, vp(l), vp(nb), vp(gene), 0.1, 0.7, vp(out)))
+    assert np.abs(out - oracle.retest_allele_model(r, n, l, nb, gene=gene)).max() < 1e-9
+
+
+def test_refclass_allele_recursion_uses_the_model_retest():
+    """calcAlleleCnvBoundaries(init=TRUE) end to end with the default (snpModel marginal) retest on planted
+    deletions: the deleted clone's cells are split off and the region is recorded."""
+    import pandas as pd
+    from honeybadger_b200 import honeybadger as hb
+    rng = np.random.default_rng(31)
+    G, N = 3000, 120
+    chrom = np.repeat(np.arange(1, 11), G // 10)
+    names = [f"{c}:{1000 + 50 * i}" for i, c in enumerate(chrom)]
+    cells = [f"c{i}" for i in range(N)]
+    # the pooled chain sees presence / absence (rowSums(r.maf > 0) of rowSums(n.sc > 0)): shallow coverage,
+    # lesser allele seen in ~half of the covered cells when neutral, almost never in the deleted clone
+    n = (rng.random((G, N)) < 0.3) * rng.integers(1, 3, (G, N))
+    p = np.full((G, N), 0.45)
+    dele = slice(900, 1200)          # chromosome 4
+    p[dele, :50] = 0.02              # clone of 50 cells
+    r = rng.binomial(n, p)
+    obj = hb.HoneyBADGER("allele")
+    obj.setAlleleMats(pd.DataFrame(r, index=names, columns=cells), pd.DataFrame(n, index=names, columns=cells),
+                      filter=False, verbose=False)
+    obj.calcAlleleCnvBoundaries(init=True)
+    assert obj.bound_snps_final, "no deletion found"
+    found = [s for lst in obj.bound_snps_final for s in lst[0]]
+    inside = [s for s in found if s in set(names[dele])]
+    assert len(inside) > 0.8 * len(found) and len(inside) > 100
+    hit = obj.pred_snps_r.loc[inside[0]].values > 0
+    assert hit[:50].mean() > 0.9 and hit[50:].mean() < 0.05
