@@ -88,7 +88,8 @@ SIGNATURES = {
                                        _p, _p]),
     "hb_retest_gexp_host": (_i32, [_p, _i64, _i64, _d, _p, _p, _p, _p]),
     "hb_retest_gexp_dev": (_i32, [_p, _i64, _i64, _i64, _p, _i64, _d, _p, _p, _p, _p, _p, _p, _i32, _p]),
-    "hb_retest_allele_model_dev": (_i32, [_p, _p, _i64, _i64, _i64, _p, _i64, _p, _p, _p, _d, _d, _p, _p]),
+    "hb_retest_allele_model_dev": (_i32, [_p, _p, _i64, _i64, _i64, _p, _i64, _p, _p, _p, _d, _d, _i32, _p, _p]),
+    "hb_retest_comb_dev": (_i32, [_p, _i64, _i64, _i64, _p, _i64, _d, _p, _p, _p, _p, _p, _p, _p, _i32, _p]),
     "hb_retest_allele_model_host": (_i32, [_p, _p, _i64, _i64, _p, _p, _p, _d, _d, _p]),
     "hb_retest_allele_lr_dev": (_i32, [_p, _p, _i64, _i64, _i64, _p, _i64, _d, _d, _p, _p]),
     "hb_gexp_pooled_viterbi_dev": (_i32, [_p, _i64, _i64, _i64, _p, _i32, _p, _p, _p, _p, _p, _p, _p]),

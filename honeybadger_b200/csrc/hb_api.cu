@@ -91,7 +91,7 @@ struct DevBuf {
 // Per-device scratch, grown on demand and reused across calls (no allocation in steady state).
 struct Workspace {
     DevBuf psi, ckpt, sdaux, segtab, status, lut_lb, lut_rho, lut_rho_d, cellmask, gsize;
-    DevBuf st_in, st_in2, st_x, st_x2, st_y, st_g, st_out, st_sd, st_ll, st_member, st_pool, st_pool2, st_pre, st_x80, st_part, st_inp, st_inp2;
+    DevBuf st_in, st_in2, st_x, st_x2, st_y, st_g, st_out, st_sd, st_ll, st_member, st_pool, st_pool2, st_pre, st_x80, st_part, st_inp, st_inp2, st_tab;
     // host-buffer entry points: three-stream pipeline (upload | layout + chains | download), staging x2
     DevBuf pin[2], pin2[2], pout_y[2], pout_g[2], pout_ll[2];
     // pinned bounce buffers for ordinary (pageable) host memory, e.g. R vectors: [slot]
@@ -109,7 +109,7 @@ struct Workspace {
     {
         DevBuf *all[] = {&psi, &ckpt, &sdaux, &segtab, &status, &lut_lb, &lut_rho, &lut_rho_d, &cellmask, &gsize,
                          &st_in, &st_in2, &st_x, &st_x2, &st_y, &st_g, &st_out, &st_sd, &st_ll,
-                         &st_member, &st_pool, &st_pool2, &st_pre, &st_x80, &st_part, &st_inp, &st_inp2, &pin[0], &pin[1], &pin2[0], &pin2[1],
+                         &st_member, &st_pool, &st_pool2, &st_pre, &st_x80, &st_part, &st_inp, &st_inp2, &st_tab, &pin[0], &pin[1], &pin2[0], &pin2[1],
                          &pout_y[0], &pout_y[1], &pout_g[0], &pout_g[1], &pout_ll[0], &pout_ll[1]};
         for (DevBuf *b : all) b->release();
         if (s_in) {
@@ -1653,9 +1653,10 @@ int hb_set_allele_mats_host(const int32_t *r, const int32_t *n_sc_init, int64_t 
 }
 
 // ------------------------------------------------------------------ deterministic retest (8f-1)
-int hb_retest_gexp_dev(const double *x, int64_t ld, int64_t G, int64_t N, const int64_t *rows,
-                       int64_t nrows, double mag0, const double *sigma0, double *p_amp, double *p_del,
-                       double *mu0, double *D_local, const double *D_total, int32_t phase, void *stream)
+int hb_retest_comb_dev(const double *x, int64_t ld, int64_t G, int64_t N, const int64_t *rows,
+                       int64_t nrows, double mag0, const double *sigma0, const double *del_logodds,
+                       double *p_amp, double *p_del, double *mu0, double *D_local, const double *D_total,
+                       int32_t phase, void *stream)
 {
     std::lock_guard<std::mutex> lk(g_mu);
     Workspace *ws;
@@ -1667,10 +1668,19 @@ int hb_retest_gexp_dev(const double *x, int64_t ld, int64_t G, int64_t N, const 
     HBTRY(ws->st_part.ensure(nb * sizeof(double)));
     double *part = ws->st_part.as<double>();
     if (phase == 0 || phase == 1)
-        CU(hb::launch_retest_gexp_a(x, ld, N, rows, nrows, mag0, sigma0, p_amp, p_del, mu0, part, D_local, st));
+        CU(hb::launch_retest_gexp_a(x, ld, N, rows, nrows, mag0, sigma0, del_logodds, p_amp, p_del, mu0, part,
+                                    D_local, st));
     if (phase == 0 || phase == 2)
         CU(hb::launch_retest_gexp_b(N, part, phase == 2 ? D_total : nullptr, p_amp, p_del, st));
     return HB_OK;
+}
+
+int hb_retest_gexp_dev(const double *x, int64_t ld, int64_t G, int64_t N, const int64_t *rows,
+                       int64_t nrows, double mag0, const double *sigma0, double *p_amp, double *p_del,
+                       double *mu0, double *D_local, const double *D_total, int32_t phase, void *stream)
+{
+    return hb_retest_comb_dev(x, ld, G, N, rows, nrows, mag0, sigma0, nullptr, p_amp, p_del, mu0, D_local,
+                              D_total, phase, stream);
 }
 
 int hb_retest_gexp_host(const double *gexp_rows, int64_t n, int64_t N, double mag0, const double *sigma0,
@@ -1749,7 +1759,7 @@ static void gauss_legendre(int n, std::vector<double> &x, std::vector<double> &w
 int hb_retest_allele_model_dev(const int32_t *r_maf, const int32_t *n_sc, int64_t ld, int64_t G, int64_t N,
                                const int64_t *rows, int64_t nrows, const uint8_t *gene_end,
                                const double *l_maf, const double *n_bulk, double pseudo, double mono,
-                               double *p_del, void *stream)
+                               int32_t logodds, double *p_del, void *stream)
 {
     std::lock_guard<std::mutex> lk(g_mu);
     Workspace *ws;
@@ -1786,14 +1796,14 @@ int hb_retest_allele_model_dev(const int32_t *r_maf, const int32_t *n_sc, int64_
         lq[nrows + j] = d >= 0 ? -d - log1p(exp(-d)) : -log1p(exp(d));
     }
     const size_t bytes = ((size_t)3 * nq + 2 * nrows) * sizeof(double) + (size_t)nrows;
-    HBTRY(ws->st_part.ensure(bytes + 64));
-    double *d_tab = ws->st_part.as<double>(), *d_lq = d_tab + 3 * nq;
+    HBTRY(ws->st_tab.ensure(bytes + 64));
+    double *d_tab = ws->st_tab.as<double>(), *d_lq = d_tab + 3 * nq;
     uint8_t *d_ge = (uint8_t *)(d_lq + 2 * nrows);
     CU(cudaMemcpyAsync(d_tab, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(d_lq, lq.data(), lq.size() * sizeof(double), cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(d_ge, ge.data(), ge.size(), cudaMemcpyHostToDevice, st));
     CU(hb::launch_retest_allele_model(r_maf, n_sc, ld, N, rows, nrows, d_ge, d_lq, d_lq + nrows, d_tab, nq, pseudo,
-                                      mono, p_del, st));
+                                      mono, logodds, p_del, st));
     CU(cudaStreamSynchronize(st)); // tab / lq / ge are host temporaries
     return HB_OK;
 }
@@ -1850,7 +1860,7 @@ int hb_retest_allele_model_host(const int32_t *r_rows, const int32_t *n_rows, in
         d_out = ws->st_out.as<double>();
     }
     HBTRY(hb_retest_allele_model_dev(d_r, d_n, ld, n, N, d_rows, n, ge.data(), l2.data(), nb2.data(), pseudo, mono,
-                                     d_out, nullptr));
+                                     0, d_out, nullptr));
     CU(cudaMemcpy(p_del, d_out, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost));
     return HB_OK;
 }

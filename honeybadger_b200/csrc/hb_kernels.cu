@@ -481,8 +481,8 @@ __device__ __forceinline__ double sigmoid(double d)
 
 __global__ void __launch_bounds__(128)
     retest_gexp_a_kernel(const double *x, int64_t ld, int64_t N, const int64_t *rows, int64_t nrows,
-                         double mag0, const double *sigma0, double *w_amp, double *w_del, double *mu0,
-                         double *partial)
+                         double mag0, const double *sigma0, const double *del_off, double *w_amp,
+                         double *w_del, double *mu0, double *partial)
 {
     __shared__ double red[128];
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -492,7 +492,9 @@ __global__ void __launch_bounds__(128)
         for (int64_t j = 0; j < nrows; j++) s1 += ld_stream(x + rows[j] * ld + c);
         const double n = (double)nrows, prec = sigma0 ? sigma0[c] : 1.0;
         const double half = 0.5 * n * mag0 * mag0;
-        const double dp = prec * (mag0 * s1 - half), dm = prec * (-mag0 * s1 - half);
+        // combined model (inst/bug/combinedModel.bug): the deletion hypothesis also switches the cell's
+        // allele likelihood from the neutral to the deleted form — a per-cell log-odds added to dm
+        const double dp = prec * (mag0 * s1 - half), dm = prec * (-mag0 * s1 - half) + (del_off ? del_off[c] : 0.0);
         w_amp[c] = sigmoid(dp);
         w_del[c] = sigmoid(dm);
         if (mu0) mu0[c] = s1 / n;
@@ -590,7 +592,7 @@ __global__ void __launch_bounds__(RA_THREADS)
     retest_allele_model_kernel(const int32_t *r, const int32_t *n, int64_t ld, int64_t N, const int64_t *rows,
                                int64_t nrows, const uint8_t *gene_end, const double *lq1, const double *lq0,
                                const double *tab, int32_t nq, double lps, double l1ps, double lmono_half,
-                               double l1mono, double *p_del)
+                               double l1mono, int32_t logodds, double *p_del)
 {
     extern __shared__ double sh[];
     for (int i = threadIdx.x; i < 3 * nq; i += RA_THREADS) sh[i] = tab[i];
@@ -619,28 +621,30 @@ __global__ void __launch_bounds__(RA_THREADS)
             A = B1 = B0 = 0.0;
         }
     }
-    p_del[c] = sigmoid(L1 - L0);
+    p_del[c] = logodds ? L1 - L0 : sigmoid(L1 - L0);
 }
 
 cudaError_t launch_retest_allele_model(const int32_t *r, const int32_t *n, int64_t ld, int64_t N,
                                        const int64_t *rows, int64_t nrows, const uint8_t *gene_end,
                                        const double *lq1, const double *lq0, const double *tab, int32_t nq,
-                                       double pseudo, double mono, double *p_del, cudaStream_t st)
+                                       double pseudo, double mono, int32_t logodds, double *p_del,
+                                       cudaStream_t st)
 {
     retest_allele_model_kernel<<<(unsigned)((N + RA_THREADS - 1) / RA_THREADS), RA_THREADS,
                                  (size_t)3 * nq * sizeof(double), st>>>(
         r, n, ld, N, rows, nrows, gene_end, lq1, lq0, tab, nq, log(pseudo), log(1 - pseudo), log(mono / 2),
-        log(1 - mono), p_del);
+        log(1 - mono), logodds, p_del);
     return cudaGetLastError();
 }
 
 cudaError_t launch_retest_gexp_a(const double *x, int64_t ld, int64_t N, const int64_t *rows,
-                                 int64_t nrows, double mag0, const double *sigma0, double *w_amp,
-                                 double *w_del, double *mu0, double *partial, double *D_local,
+                                 int64_t nrows, double mag0, const double *sigma0, const double *del_off,
+                                 double *w_amp, double *w_del, double *mu0, double *partial, double *D_local,
                                  cudaStream_t st)
 {
     const unsigned nb = (unsigned)((N + 127) / 128);
-    retest_gexp_a_kernel<<<nb, 128, 0, st>>>(x, ld, N, rows, nrows, mag0, sigma0, w_amp, w_del, mu0, partial);
+    retest_gexp_a_kernel<<<nb, 128, 0, st>>>(x, ld, N, rows, nrows, mag0, sigma0, del_off, w_amp, w_del, mu0,
+                                             partial);
     if (D_local) sum_partials_kernel<<<1, 32, 0, st>>>(partial, (int32_t)nb, D_local);
     return cudaGetLastError();
 }

@@ -41,10 +41,11 @@ cudaError_t launch_retest_allele(const int32_t *r, const int32_t *n, int64_t ld,
 cudaError_t launch_retest_allele_model(const int32_t *r, const int32_t *n, int64_t ld, int64_t N,
                                        const int64_t *rows, int64_t nrows, const uint8_t *gene_end,
                                        const double *lq1, const double *lq0, const double *tab, int32_t nq,
-                                       double pseudo, double mono, double *p_del, cudaStream_t st);
+                                       double pseudo, double mono, int32_t logodds, double *p_del,
+                                       cudaStream_t st);
 cudaError_t launch_retest_gexp_a(const double *x, int64_t ld, int64_t N, const int64_t *rows,
-                                 int64_t nrows, double mag0, const double *sigma0, double *w_amp,
-                                 double *w_del, double *mu0, double *partial, double *D_local,
+                                 int64_t nrows, double mag0, const double *sigma0, const double *del_off,
+                                 double *w_amp, double *w_del, double *mu0, double *partial, double *D_local,
                                  cudaStream_t st);
 cudaError_t launch_retest_gexp_b(int64_t N, const double *partial, const double *D_total, double *p_amp,
                                  double *p_del, cudaStream_t st);

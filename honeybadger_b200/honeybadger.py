@@ -236,7 +236,8 @@ def retest_allele_lr(r_rows, n_rows, pd_=0.1, pn=0.45):
     return out.cpu().numpy()
 
 
-def retest_allele_model(r_rows, n_rows, l_maf, n_bulk, gene=None, pe=0.1, mono=0.7):
+def retest_allele_model(r_rows, n_rows, l_maf, n_bulk, gene=None, pe=0.1, mono=0.7, logodds=False,
+                        keep_on_device=False):
     """P(deletion) per cell for one candidate region: the exact per-cell marginal of
     inst/bug/snpModel.bug (calcAlleleCnvProb, R/HoneyBADGER.R:907-1042, samples it with JAGS; the caller
     at :1486 passes pe = pd), libhb_b200's hb_retest_allele_model_dev.  `gene`: the geneFactor codes of
@@ -265,8 +266,34 @@ def retest_allele_model(r_rows, n_rows, l_maf, n_bulk, gene=None, pe=0.1, mono=0
     out = torch.empty(N, dtype=torch.float64, device=r.device)
     _lib.check(_lib.load().hb_retest_allele_model_dev(r.data_ptr(), n.data_ptr(), r.stride(0), m, N,
                                                       rows.data_ptr(), m, _vp(gene_end), _vp(l2), _vp(nb2),
-                                                      float(pe), float(mono), out.data_ptr(), _stream()))
-    return out.cpu().numpy()
+                                                      float(pe), float(mono), int(bool(logodds)), out.data_ptr(),
+                                                      _stream()))
+    return out if keep_on_device else out.cpu().numpy()
+
+
+def retest_comb_closed_form(gexp_rows, mag0, r_rows, n_rows, l_maf, n_bulk, sigma0=None, gene=None, pe=0.1,
+                            mono=0.7):
+    """(P(amp), P(del)) per cell for one region from expression AND allele data: the marginal posterior of
+    inst/bug/combinedModel.bug (calcCombCnvProb, R/HoneyBADGER.R:1620-1782, samples it with JAGS).  The
+    two data types share S_k and the direction dd, so it is the expression retest with every cell's
+    deletion hypothesis shifted by that cell's allele log-odds (hb_retest_comb_dev)."""
+    import torch
+    off = retest_allele_model(r_rows, n_rows, l_maf, n_bulk, gene=gene, pe=pe, mono=mono, logodds=True,
+                              keep_on_device=True)
+    x = gexp_rows if torch.is_tensor(gexp_rows) else \
+        torch.as_tensor(np.ascontiguousarray(gexp_rows, dtype=np.float64), device="cuda")
+    if x.stride(1) != 1:
+        x = x.contiguous()
+    n, N = x.shape
+    rows = torch.arange(n, dtype=torch.int64, device=x.device)
+    prec = None if sigma0 is None else torch.as_tensor(sigma0, dtype=torch.float64, device=x.device).contiguous()
+    pa = torch.empty(N, dtype=torch.float64, device=x.device)
+    pd_ = torch.empty(N, dtype=torch.float64, device=x.device)
+    _lib.check(_lib.load().hb_retest_comb_dev(
+        x.data_ptr(), x.stride(0), n, N, rows.data_ptr(), n, float(mag0),
+        None if prec is None else prec.data_ptr(), off.data_ptr(), pa.data_ptr(), pd_.data_ptr(), None, None,
+        None, 0, _stream()))
+    return pa.cpu().numpy(), pd_.cpu().numpy()
 
 
 # --------------------------------------------------------------------------- vote -> runs -> trim

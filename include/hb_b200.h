@@ -296,11 +296,21 @@ int hb_retest_allele_lr_dev(const int32_t *r_maf, const int32_t *n_sc, int64_t l
  * indicator ma is replaced by its bulk posterior P(ma = 1 | l.maf, n.bulk) (the single approximation).
  * Statistical stand-in for the MCMC, not bit parity.  rows[nrows] (device) are the region's SNP rows
  * grouped by gene, gene_end[nrows] (host, NULL = one gene per SNP) marks each gene's last SNP, l_maf /
- * n_bulk (host [nrows]) the bulk counts in the same order.  p_del[N] on the device. */
+ * n_bulk (host [nrows]) the bulk counts in the same order.  p_del[N] on the device; logodds != 0 stores
+ * log P(data | S = 1) - log P(data | S = 0) instead of the probability. */
 int hb_retest_allele_model_dev(const int32_t *r_maf, const int32_t *n_sc, int64_t ld, int64_t G, int64_t N,
                                const int64_t *rows, int64_t nrows, const uint8_t *gene_end,
                                const double *l_maf, const double *n_bulk, double pseudo, double mono,
-                               double *p_del, void *stream);
+                               int32_t logodds, double *p_del, void *stream);
+/* The combined model (inst/bug/combinedModel.bug; HoneyBADGER$calcCombCnvProb, R/HoneyBADGER.R:1620-1782,
+ * caller :1866): expression and allele evidence share S_k and the direction dd.  Its exact marginal is the
+ * expression retest with the deletion hypothesis of every cell shifted by that cell's allele log-odds
+ * log P(alleles | deleted) - log P(alleles | neutral) = hb_retest_allele_model_dev(..., logodds = 1, ...):
+ * pass that vector as del_logodds (device [N]; NULL = hb_retest_gexp_dev).  Phases as hb_retest_gexp_dev. */
+int hb_retest_comb_dev(const double *x, int64_t ld, int64_t G, int64_t N, const int64_t *rows,
+                       int64_t nrows, double mag0, const double *sigma0, const double *del_logodds,
+                       double *p_amp, double *p_del, double *mu0, double *D_local, const double *D_total,
+                       int32_t phase, void *stream);
 /* Host form: the region's [n x N] column-major integer sub-matrices, gene[n] factor codes (NULL = one gene
  * per SNP; grouped by first appearance like unique(geneFactor), R/HoneyBADGER.R:963). */
 int hb_retest_allele_model_host(const int32_t *r_rows, const int32_t *n_rows, int64_t n, int64_t N,

@@ -327,10 +327,12 @@ def set_allele_mats(r, n, l_init=None, n_bulk_init=None, filter=True, het_devian
                 n_bulk=nb[:Gk], l_maf=lm[:Gk], keep=keep[:Gk])
 
 
-def retest_gexp(x_rows, mag0, sigma0=None):
+def retest_gexp(x_rows, mag0, sigma0=None, del_loglik=None):
     """Closed-form posterior of inst/bug/expressionModel.bug, plain numpy, written
     from the likelihoods (not from the kernel's difference form): returns (P(amp), P(del)) per cell.
-    x_rows: [genes of the region, cells]; sigma0: per-cell dnorm PRECISION as the reference passes it."""
+    x_rows: [genes of the region, cells]; sigma0: per-cell dnorm PRECISION as the reference passes it.
+    del_loglik: per-cell log-likelihood of further data under "deleted" minus under "not deleted"
+    (inst/bug/combinedModel.bug: the allele counts), multiplying the deletion branch only."""
     x = np.asarray(x_rows, dtype=np.float64)
     n, N = x.shape
     prec = np.ones(N) if sigma0 is None else np.asarray(sigma0, dtype=np.float64)
@@ -339,6 +341,8 @@ def retest_gexp(x_rows, mag0, sigma0=None):
         return (0.5 * np.log(prec / (2 * np.pi)) - 0.5 * prec * (x - mu) ** 2).sum(0)
 
     l0, lp, lm = ll(0.0), ll(mag0), ll(-mag0)
+    if del_loglik is not None:
+        lm = lm + np.asarray(del_loglik, dtype=np.float64)
     La = np.logaddexp(l0, lp) + np.log(0.5)
     Ld = np.logaddexp(l0, lm) + np.log(0.5)
     D = La.sum() - Ld.sum()
@@ -346,7 +350,7 @@ def retest_gexp(x_rows, mag0, sigma0=None):
     return post1 * np.exp(lp + np.log(0.5) - La), (1 - post1) * np.exp(lm + np.log(0.5) - Ld)
 
 
-def retest_allele_model(r_rows, n_rows, l_maf, n_bulk, gene=None, pseudo=0.1, mono=0.7):
+def retest_allele_model(r_rows, n_rows, l_maf, n_bulk, gene=None, pseudo=0.1, mono=0.7, logodds=False):
     """Exact per-cell marginal P(S_k = 1 | data) of inst/bug/snpModel.bug (sampled with JAGS by
     calcAlleleCnvProb, R/HoneyBADGER.R:907-1042) with the shared allele indicators ma at their bulk
     posterior — the quantity libhb_b200's hb_retest_allele_model_dev computes.  Plain numpy; the integral
@@ -391,5 +395,11 @@ def retest_allele_model(r_rows, n_rows, l_maf, n_bulk, gene=None, pseudo=0.1, mo
                     B0 += b
                     A += log_int(r[j, c], n[j, c])
             L0 += np.logaddexp(np.log1p(-mono) + A, np.log(mono / 2) + np.logaddexp(B1, B0))
-        out[c] = special.expit(L1 - L0)
+        out[c] = (L1 - L0) if logodds else special.expit(L1 - L0)
     return out
+
+
+def retest_comb(x_rows, mag0, r_rows, n_rows, l_maf, n_bulk, sigma0=None, gene=None, pseudo=0.1, mono=0.7):
+    """Marginal posterior of inst/bug/combinedModel.bug: (P(amp), P(del)) per cell."""
+    off = retest_allele_model(r_rows, n_rows, l_maf, n_bulk, gene=gene, pseudo=pseudo, mono=mono, logodds=True)
+    return retest_gexp(x_rows, mag0, sigma0, del_loglik=off)

@@ -377,3 +377,26 @@ def test_refclass_allele_recursion_uses_the_model_retest():
     assert len(inside) > 0.8 * len(found) and len(inside) > 100
     hit = obj.pred_snps_r.loc[inside[0]].values > 0
     assert hit[:50].mean() > 0.9 and hit[50:].mean() < 0.05
+
+
+def test_retest_comb_vs_oracle(oracle):
+    """hb_retest_comb_dev (marginal of inst/bug/combinedModel.bug: expression retest with the allele model's
+    per-cell log-odds on the deletion branch) vs the numpy restatement; alleles rescue a deletion that the
+    expression data alone leave undecided."""
+    from honeybadger_b200 import honeybadger as hb
+    rng = np.random.default_rng(41)
+    J, m, N, mag = 25, 30, 96, 0.5
+    x = rng.standard_normal((J, N)) * 1.5
+    x[:, :32] -= mag
+    n = (rng.random((m, N)) < 0.4) * rng.integers(1, 6, (m, N))
+    p = np.where(np.arange(N) < 32, 0.1, 0.45)
+    r = rng.binomial(n, p[None, :])
+    nb = (n > 0).sum(1).astype(float)
+    l = np.floor(0.2 * nb)
+    gene = np.arange(m) // 3
+    for sigma0 in (None, rng.uniform(0.3, 0.8, N)):
+        pa, pd_ = hb.retest_comb_closed_form(x, mag, r, n, l, nb, sigma0=sigma0, gene=gene)
+        ra, rd = oracle.retest_comb(x, mag, r, n, l, nb, sigma0=sigma0, gene=gene)
+        assert np.abs(pa - ra).max() < 1e-9 and np.abs(pd_ - rd).max() < 1e-9
+    ea, ed = hb.retest_gexp_closed_form(x, mag, sigma0)
+    assert pd_[:32].mean() > 0.9 and pd_[32:].mean() < 0.05 and pd_[:32].mean() > ed[:32].mean()

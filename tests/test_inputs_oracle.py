@@ -87,3 +87,33 @@ def test_set_allele_mats_without_filter_codes_na_rows_as_zero(oracle):
     flip = np.divide(l, nb, out=np.zeros(50), where=nb > 0) > 0.5
     assert np.array_equal(out["r_maf"], np.where(flip[:, None], n - r, r))
     assert np.array_equal(out["l_maf"], np.where(flip, nb - l, l))
+
+
+def test_retest_closed_forms_equal_brute_force_enumeration(oracle):
+    """oracle.retest_gexp / retest_comb (the closed forms the kernels are checked against) vs summing the
+    joint of inst/bug/expressionModel.bug / combinedModel.bug over every (S_1..S_K, dd) for K = 5 cells;
+    alpha_k, beta ~ U(0,1) integrate to prior 1/2 on each S_k and on dd."""
+    import itertools
+    rng = np.random.default_rng(9)
+    J, K, mag = 7, 5, 0.9
+    x = rng.standard_normal((J, K))
+    x[:, :2] -= mag
+    prec = rng.uniform(0.5, 1.5, K)
+    off = rng.normal(0, 3, K)  # per-cell allele log-odds of the combined model
+
+    def ll(mu):
+        return (0.5 * np.log(prec / (2 * np.pi)) - 0.5 * prec * (x - mu) ** 2).sum(0)
+
+    l0, lp, lm = ll(0.0), ll(mag), ll(-mag)
+    for extra in (None, off):
+        amp, dele, Z = np.zeros(K), np.zeros(K), 0.0
+        for dd in (0, 1):
+            for S in itertools.product((0, 1), repeat=K):
+                S = np.array(S)
+                l1 = lp if dd else (lm + (0 if extra is None else extra))
+                w = np.exp(np.where(S == 1, l1, l0).sum() - l0.sum())
+                Z += w
+                amp += w * S * dd
+                dele += w * S * (1 - dd)
+        pa, pd_ = oracle.retest_gexp(x, mag, prec, del_loglik=extra)
+        assert np.abs(pa - amp / Z).max() < 1e-12 and np.abs(pd_ - dele / Z).max() < 1e-12
