@@ -43,7 +43,11 @@ __global__ void __launch_bounds__(HB_BLOCK, HB_NORM3_MINB)
 
 // Speculate-and-verify path for the reference's symmetric parameter block (hb_norm3_fast.cuh).
 // 3 resident blocks/SM (<= 168 registers): measured faster than 4 blocks at <= 128 registers, the
-// extra registers buy instruction-level parallelism (tools/build_variant.sh sweeps)
+// extra registers buy instruction-level parallelism (tools/build_variant.sh sweeps).
+// Also measured: the two sweeps as two kernels (forward + verification, backward; 124-128 registers each
+// without spills, 4 blocks/SM, per-chain hand-off of 1 / sum phi_T and the final state): 2.24 ms against
+// 1.95 ms fused — blocks in different sweeps overlap read-heavy and write-heavy phases, two uniform
+// kernels do not.
 #ifndef HB_FAST_MINB
 #define HB_FAST_MINB 3
 #endif
