@@ -15,6 +15,10 @@
  * no FMA contraction (build with -O2 -ffp-contract=off -mno-fma) and x87 `long double` where R
  * accumulates in LDOUBLE.  They are cross-checked against mpmath and an independent pure-Python
  * restatement (oracle/pyref.py) and against the bundled-data known answers (tests/golden).
+ * What the reference's own rendered outputs do pin (tests/test_inputs_oracle.py): the setAlleleMats SNP
+ * counts printed in docs/Getting_Started.md:230 and docs/Integrating.md:27, and the chromosomes of the
+ * regions the stateless calcAlleleCnvBoundaries finds on the bundled data
+ * (docs/figure/Integrating/unnamed-chunk-6-1.png) — end-to-end answers, not per-step arithmetic.
  */
 #include <float.h>
 #include <math.h>

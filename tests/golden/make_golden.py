@@ -232,9 +232,16 @@ def make_inputs_raw():
     assert (r == np.rint(r)).all() and (cov == np.rint(cov)).all() and cov.max() < 65536
     gexp, gn, _ = as_matrix(read_rda(f"{REF}/gexp.rda")["gexp"])
     ref = np.asarray(read_rda(f"{REF}/ref.rda")["ref"]["value"])
+    chrom = np.array([int(s.split(":")[0]) for s in rn], dtype=np.uint8)
+    pos = np.array([int(s.split(":")[1]) for s in rn], dtype=np.int32)
+    # docs/figure/Integrating/unnamed-chunk-6-1.png: the panels plotAlleleProfile draws for
+    # region = calcAlleleCnvBoundaries(...)$region on this data (setAlleleMats defaults, i.e. threshold
+    # 0.05) are region@seqnames@values (R/HoneyBADGER_allele.R:248) = chr1 chr3 chr9 chr10 chr12 chr13
+    # chr14 chr15 chr19 — the reference's own rendered answer for the stateless allele path
     np.savez_compressed(os.path.join(HERE, "inputs_raw_mgh31.npz"), r=r.astype(np.uint16),
-                        cov=cov.astype(np.uint16), gexp=gexp[:800], ref=ref[:800],
-                        known_counts=np.array([[5552, 4550], [5359, 4357]], dtype=np.int32))
+                        cov=cov.astype(np.uint16), chrom=chrom, pos=pos, gexp=gexp[:800], ref=ref[:800],
+                        known_counts=np.array([[5552, 4550], [5359, 4357]], dtype=np.int32),
+                        figure_region_chroms=np.array([1, 3, 9, 10, 12, 13, 14, 15, 19], dtype=np.uint8))
 
 
 if __name__ == "__main__":

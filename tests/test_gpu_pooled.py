@@ -400,3 +400,26 @@ def test_retest_comb_vs_oracle(oracle):
         assert np.abs(pa - ra).max() < 1e-9 and np.abs(pd_ - rd).max() < 1e-9
     ea, ed = hb.retest_gexp_closed_form(x, mag, sigma0)
     assert pd_[:32].mean() > 0.9 and pd_[32:].mean() < 0.05 and pd_[:32].mean() > ed[:32].mean()
+
+
+def test_stateless_allele_function_reproduces_the_vignette_figure(golden_inputs):
+    """The whole deterministic allele path on the device — setAlleleMats, runmean / dist / Ward.D2 / cutree,
+    pooled counts, binomial Viterbi, vote, runs, trim, range() — against the reference's own rendered answer:
+    the panels of docs/figure/Integrating/unnamed-chunk-6-1.png are chr1 chr3 chr9 chr10 chr12 chr13 chr14
+    chr15 chr19 (region@seqnames@values, R/HoneyBADGER_allele.R:248)."""
+    import pandas as pd
+    from honeybadger_b200 import honeybadger as hb
+    r, cov = golden_inputs["r"].astype(np.int32), golden_inputs["cov"].astype(np.int32)
+    names = [f"{c}:{p}" for c, p in zip(golden_inputs["chrom"], golden_inputs["pos"])]
+    cells = [f"c{i}" for i in range(r.shape[1])]
+    am = hb.set_allele_mats_dev(r, cov, het_deviance_threshold=0.05)
+    assert am["keep"].size == 4550 and am["n_het"] == 5552  # docs/Integrating.md:27
+    kept = [names[i] for i in am["keep"]]
+    res = hb.calcAlleleCnvBoundaries(pd.DataFrame(am["r_maf"].cpu().numpy(), index=kept, columns=cells),
+                                     pd.DataFrame(am["n_sc"].cpu().numpy(), index=kept, columns=cells))
+    chroms = []
+    for seqname, _, _ in res["regions"]:
+        c = int(str(seqname).replace("chr", ""))
+        if not chroms or chroms[-1] != c:
+            chroms.append(c)
+    assert chroms == list(golden_inputs["figure_region_chroms"])

@@ -117,3 +117,31 @@ def test_retest_closed_forms_equal_brute_force_enumeration(oracle):
                 dele += w * S * (1 - dd)
         pa, pd_ = oracle.retest_gexp(x, mag, prec, del_loglik=extra)
         assert np.abs(pa - amp / Z).max() < 1e-12 and np.abs(pd_ - dele / Z).max() < 1e-12
+
+
+def _rle_values(seq):
+    out = []
+    for v in seq:
+        if not out or out[-1] != v:
+            out.append(int(v))
+    return out
+
+
+def test_stateless_allele_path_reproduces_the_vignette_figure(oracle, golden_inputs):
+    """docs/figure/Integrating/unnamed-chunk-6-1.png: plotAlleleProfile(region = calcAlleleCnvBoundaries(...)
+    $region) on the bundled data draws one panel per run of region@seqnames (R/HoneyBADGER_allele.R:248):
+    chr1 chr3 chr9 chr10 chr12 chr13 chr14 chr15 chr19.  The restated path — setAlleleMats at the default
+    threshold, runmean(k=31) -> Ward.D2 -> cutree(1..3), pooled counts, 2-state binomial Viterbi, vote,
+    runs, trim, range() per chromosome — must land on the same chromosomes in the same order."""
+    from oracle import pyref as P
+    from honeybadger_b200.honeybadger import runmean, ward_groups
+    r, cov = golden_inputs["r"].astype(np.int32), golden_inputs["cov"].astype(np.int32)
+    out = oracle.set_allele_mats(r, cov, het_deviance_threshold=0.05)
+    assert out["keep"].size == 4550
+    chrom = golden_inputs["chrom"][out["keep"]]
+    r_maf, n_sc = out["r_maf"].astype(float), out["n_sc"].astype(float)
+    with np.errstate(all="ignore"):
+        labels = ward_groups(runmean(r_maf / n_sc, 31), [1, 2, 3])
+    res = P.calc_allele_cnv_boundaries_fn(r_maf, n_sc, labels)
+    region_chroms = [c for idx in res["info"] for c in _rle_values(chrom[idx])]
+    assert _rle_values(region_chroms) == list(golden_inputs["figure_region_chroms"])
