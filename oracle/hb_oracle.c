@@ -18,7 +18,9 @@
  * What the reference's own rendered outputs do pin (tests/test_inputs_oracle.py): the setAlleleMats SNP
  * counts printed in docs/Getting_Started.md:230 and docs/Integrating.md:27, and the chromosomes of the
  * regions the stateless calcAlleleCnvBoundaries finds on the bundled data
- * (docs/figure/Integrating/unnamed-chunk-6-1.png) — end-to-end answers, not per-step arithmetic.
+ * (docs/figure/Integrating/unnamed-chunk-6-1.png), and — through the GPU suite — the regions printed
+ * after the RefClass allele run (docs/Getting_Started.md:287-293; three of four to the base pair) —
+ * end-to-end answers, not per-step arithmetic.
  */
 #include <float.h>
 #include <math.h>

@@ -252,7 +252,14 @@ if __name__ == "__main__":
     make_densities()
     runs = make_allele()
     make_gexp()
-    json.dump({"allele_all_cell_state1_runs": runs},
+    json.dump({"allele_all_cell_state1_runs": runs,
+               # docs/Getting_Started.md:287-293, printed by the reference after the RefClass allele run
+               "getting_started_allele_regions": [["chr10", 3180316, 126670356], ["chr13", 21949267, 114175032],
+                                                  ["chr14", 20216560, 73465003], ["chr19", 20727463, 48598823]],
+               "getting_started_allele_regions_source":
+                   "docs/Getting_Started.md:287-293: print(range(snps[unlist(bound.snps.final)])) after "
+                   "hb$calcAlleleCnvBoundaries(init=TRUE) on the bundled data (het.deviance.threshold=0.1); "
+                   "the recursion's splits come from JAGS, so cell sets are stochastic, the HMM boundaries are not"},
               open(os.path.join(HERE, "known_answers.json"), "w"), indent=1)
     for f in sorted(os.listdir(HERE)):
         print(f, os.path.getsize(os.path.join(HERE, f)))

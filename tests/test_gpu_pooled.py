@@ -423,3 +423,31 @@ def test_stateless_allele_function_reproduces_the_vignette_figure(golden_inputs)
         if not chroms or chroms[-1] != c:
             chroms.append(c)
     assert chroms == list(golden_inputs["figure_region_chroms"])
+
+
+def test_refclass_allele_run_reproduces_the_vignette_regions(golden_inputs):
+    """docs/Getting_Started.md:287-293 prints the regions the reference's RefClass run finds on the bundled
+    data: chr10 [3180316, 126670356], chr13 [21949267, 114175032], chr14 [20216560, 73465003],
+    chr19 [20727463, 48598823].  The mirror's whole device flow (setAlleleMats 0.1 -> Ward grouping -> pooled
+    binomial Viterbi -> vote / runs / trim -> snpModel-marginal retest -> split -> recursion) finds the same
+    four; chr10 / chr13 / chr14 to the base pair.  The chr19 run is found in a sub-population whose cell set
+    the reference draws by MCMC, so its far end may sit a SNP or two away."""
+    import json
+    import os
+    import pandas as pd
+    from honeybadger_b200 import honeybadger as hb
+    want = {c: (a, b) for c, a, b in json.load(open(os.path.join(
+        os.path.dirname(__file__), "golden", "known_answers.json")))["getting_started_allele_regions"]}
+    r, cov = golden_inputs["r"].astype(np.int32), golden_inputs["cov"].astype(np.int32)
+    names = [f"{c}:{p}" for c, p in zip(golden_inputs["chrom"], golden_inputs["pos"])]
+    cells = [f"c{i}" for i in range(r.shape[1])]
+    obj = hb.HoneyBADGER("MGH31")
+    obj.setAlleleMats(pd.DataFrame(r, index=names, columns=cells), pd.DataFrame(cov, index=names, columns=cells),
+                      het_deviance_threshold=0.1, verbose=False)
+    obj.calcAlleleCnvBoundaries(init=True)
+    found = [s for lst in obj.bound_snps_final for s in lst[0]]
+    got = {c: (int(a), int(b)) for c, a, b in obj.snps[found].range()}
+    assert set(got) == set(want)
+    for c in ("chr10", "chr13", "chr14"):
+        assert got[c] == tuple(want[c])
+    assert got["chr19"][0] == want["chr19"][0] and abs(got["chr19"][1] - want["chr19"][1]) < 100_000
