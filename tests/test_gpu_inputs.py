@@ -188,3 +188,32 @@ def test_refclass_set_mats_stay_resident(oracle, golden_inputs):
     wa = oracle.set_allele_mats(r, cov, het_deviance_threshold=0.1)
     assert np.array_equal(hb.r_maf.values, wa["r_maf"]) and np.array_equal(hb.n_sc.values, wa["n_sc"])
     assert np.array_equal(hb.l_maf, wa["l_maf"]) and hb._r_dev is not None
+
+
+def test_set_gexp_mats_edge_shapes_and_values(oracle):
+    """Ragged and degenerate inputs: one gene, one cell, constant columns (scale() divides 0 by 0 -> NaN in R
+    too), negative and large-magnitude values, every row filtered out."""
+    from honeybadger_b200.honeybadger import set_gexp_mats_dev
+    rng = np.random.default_rng(77)
+    cases = []
+    for G, N, R in ((1, 1, 1), (1, 9, 2), (5, 1, 1), (33, 2, 3), (130, 67, 1), (64, 300, 5)):
+        sc = rng.normal(0, 3, (G, N)) * (rng.random((G, N)) > 0.2)
+        ref = rng.normal(0, 2, (G, R))
+        cases.append((sc, ref))
+    big = rng.normal(0, 1, (40, 17)) * 1e12
+    cases.append((big, rng.normal(0, 1, (40, 2)) * 1e-9))
+    const = rng.normal(0, 1, (20, 6))
+    const[:, 2] = 3.25  # a constant cell: centred to 0, scale 0
+    cases.append((const, rng.normal(0, 1, (20, 1))))
+    for sc, ref in cases:
+        for filt, scale in ((False, False), (False, True), (True, True)):
+            want, keep = oracle.set_gexp_mats(sc, ref, filter=filt, scale=scale)
+            with np.errstate(all="ignore"):
+                norm, k, _ = set_gexp_mats_dev(sc, ref, filter=filt, scale=scale)
+            assert np.array_equal(k, keep)
+            assert np.array_equal(norm.cpu().numpy(), want, equal_nan=True)
+    # nothing passes the filter
+    sc = -np.abs(rng.normal(0, 1, (12, 5))) - 1.0
+    norm, k, _ = set_gexp_mats_dev(sc, sc[:, :1], filter=True, minMeanBoth=0.0, minMeanTest=0.0, minMeanRef=0.0,
+                                   scale=False)
+    assert k.size == 0 and norm.shape[0] == 0
