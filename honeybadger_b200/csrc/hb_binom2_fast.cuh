@@ -206,9 +206,11 @@ HB_HD void b2f_unpack(int32_t w, int32_t n_sep, int32_t &xv, int32_t &nv)
     }
 }
 
-template <bool VIT, bool FB, bool LL, bool PK>
+// TL: warp-tiled layout known at compile time (strides fold into immediates, as in norm3_fast_chain)
+template <bool VIT, bool FB, bool LL, bool PK, bool TL = false>
 HB_HD void binom2_fast_chain(const Binom2Args &a, int32_t seg, int64_t b, const B2fSmem &m)
 {
+    const int32_t tiled = TL ? 1 : a.tiled;
     const Binom2Const &c = a.c;
     const int64_t t0 = a.seg_off[seg];
     const int32_t L = (int32_t)(a.seg_off[seg + 1] - t0);
@@ -216,15 +218,15 @@ HB_HD void binom2_fast_chain(const Binom2Args &a, int32_t seg, int64_t b, const 
     const int32_t nfull = L / HB_CHUNK;
     const int32_t tail = L - nfull * HB_CHUNK;
     const int64_t cbase = a.chunk_off[seg];
-    const int64_t ld = lay_stride(a.tiled, a.ld), sB = lay_stride(a.tiled, a.B);
-    const int64_t sy = lay_stride(a.tiled, a.ldy), sg = lay_stride(a.tiled, a.ldg);
-    const int32_t *xp = a.x + lay_off(a.tiled, a.T, a.ld, t0, b);
-    const int32_t *np = PK ? nullptr : a.n + lay_off(a.tiled, a.T, a.ld, t0, b);
+    const int64_t ld = lay_stride(tiled, a.ld), sB = lay_stride(tiled, a.B);
+    const int64_t sy = lay_stride(tiled, a.ldy), sg = lay_stride(tiled, a.ldg);
+    const int32_t *xp = a.x + lay_off(tiled, a.T, a.ld, t0, b);
+    const int32_t *np = PK ? nullptr : a.n + lay_off(tiled, a.T, a.ld, t0, b);
     // back-pointers: 2 bits / step, one uint16 per chunk
-    b2f_psi_t *psi = reinterpret_cast<b2f_psi_t *>(a.psi) + lay_off(a.tiled, a.nchunks, a.B, cbase, b);
-    double *ckpt = a.ckpt + (a.tiled ? (((b >> 5) * a.nchunks + cbase) * 2 << 5) + (b & 31) : cbase * 2 * a.B + b);
-    uint8_t *ybase = a.y ? a.y + lay_off(a.tiled, a.T, a.ldy, t0, b) : nullptr;
-    double *gbase = a.gamma ? a.gamma + lay_off(a.tiled, a.T, a.ldg, t0, b) : nullptr;
+    b2f_psi_t *psi = reinterpret_cast<b2f_psi_t *>(a.psi) + lay_off(tiled, a.nchunks, a.B, cbase, b);
+    double *ckpt = a.ckpt + (tiled ? (((b >> 5) * a.nchunks + cbase) * 2 << 5) + (b & 31) : cbase * 2 * a.B + b);
+    uint8_t *ybase = a.y ? a.y + lay_off(tiled, a.T, a.ldy, t0, b) : nullptr;
+    double *gbase = a.gamma ? a.gamma + lay_off(tiled, a.T, a.ldg, t0, b) : nullptr;
 
     B2fState s;
     s.n0 = s.n1 = 0;

@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(HB_BLOCK, HB_NORM3_MINB)
 #ifndef HB_FAST_MINB
 #define HB_FAST_MINB 3
 #endif
-template <bool VIT, bool FB, bool LL, bool BULK>
+template <bool VIT, bool FB, bool LL, bool BULK, bool TL>
 __global__ void __launch_bounds__(HB_BLOCK, HB_FAST_MINB)
     norm3_fast_kernel(const __grid_constant__ Norm3Args a)
 {
@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(HB_BLOCK, HB_FAST_MINB)
         }
         __syncwarp(br.wmask);
     }
-    norm3_fast_chain<VIT, FB, LL, BULK>(a, seg, b, m, br);
+    norm3_fast_chain<VIT, FB, LL, BULK, TL>(a, seg, b, m, br);
 }
 
 template <bool VIT, bool FB>
@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(128)
 #ifndef HB_B2F_MINB
 #define HB_B2F_MINB 4
 #endif
-template <bool VIT, bool FB, bool LL, bool PK>
+template <bool VIT, bool FB, bool LL, bool PK, bool TL>
 __global__ void __launch_bounds__(HB_BLOCK, HB_B2F_MINB)
     binom2_fast_kernel(const __grid_constant__ Binom2Args a)
 {
@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(HB_BLOCK, HB_B2F_MINB)
     m.slb = slb;
     m.srho = srho;
     m.slut_n = slut_n;
-    binom2_fast_chain<VIT, FB, LL, PK>(a, seg, b, m);
+    binom2_fast_chain<VIT, FB, LL, PK, TL>(a, seg, b, m);
 }
 
 template <bool SYM>
@@ -192,7 +192,7 @@ cudaError_t launch_norm3(const Norm3Args &a, bool sym, bool vit, bool fb, cudaSt
 // the ring's wait_group.  Kept as a build option (tools/build_variant.sh bulk -DHB_FAST_BULK=1).
 #define HB_FAST_BULK 0
 #endif
-template <bool BULK>
+template <bool BULK, bool TL>
 static cudaError_t launch_norm3_fast_t(const Norm3Args &a, bool vit, bool fb, cudaStream_t st)
 {
     const unsigned grid = (unsigned)((int64_t)a.nseg * a.nblk_per_seg);
@@ -202,9 +202,9 @@ static cudaError_t launch_norm3_fast_t(const Norm3Args &a, bool vit, bool fb, cu
     const bool ll = a.ll != nullptr;
 #define HB_LAUNCH_FAST(V, F, L_, SM)                                                               \
     do {                                                                                          \
-        cudaFuncSetAttribute(norm3_fast_kernel<V, F, L_, BULK>,                                    \
+        cudaFuncSetAttribute(norm3_fast_kernel<V, F, L_, BULK, TL>,                                \
                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SM));             \
-        norm3_fast_kernel<V, F, L_, BULK><<<grid, HB_BLOCK, (SM), st>>>(a);                        \
+        norm3_fast_kernel<V, F, L_, BULK, TL><<<grid, HB_BLOCK, (SM), st>>>(a);                    \
     } while (0)
     if (vit && fb) {
         if (ll) HB_LAUNCH_FAST(true, true, true, sm_fb);
@@ -221,8 +221,11 @@ static cudaError_t launch_norm3_fast_t(const Norm3Args &a, bool vit, bool fb, cu
 
 cudaError_t launch_norm3_fast(const Norm3Args &a, bool vit, bool fb, cudaStream_t st)
 {
-    if (HB_FAST_BULK && a.tiled) return launch_norm3_fast_t<true>(a, vit, fb, st);
-    return launch_norm3_fast_t<false>(a, vit, fb, st);
+#if HB_FAST_BULK
+    if (a.tiled) return launch_norm3_fast_t<true, true>(a, vit, fb, st);
+#endif
+    if (a.tiled) return launch_norm3_fast_t<false, true>(a, vit, fb, st);
+    return launch_norm3_fast_t<false, false>(a, vit, fb, st);
 }
 
 cudaError_t launch_binom2_emit(const Binom2Args &a, double2 *pre_lb, cudaStream_t st)
@@ -232,7 +235,7 @@ cudaError_t launch_binom2_emit(const Binom2Args &a, double2 *pre_lb, cudaStream_
     return cudaGetLastError();
 }
 
-template <bool PK>
+template <bool PK, bool TL>
 static cudaError_t launch_binom2_fast_t(const Binom2Args &a, bool vit, bool fb, cudaStream_t st)
 {
     const unsigned grid = (unsigned)((int64_t)a.nseg * a.nblk_per_seg);
@@ -240,23 +243,27 @@ static cudaError_t launch_binom2_fast_t(const Binom2Args &a, bool vit, bool fb, 
     const bool ll = a.ll != nullptr;
     if (vit && fb) {
         if (ll)
-            binom2_fast_kernel<true, true, true, PK><<<grid, HB_BLOCK, sm_fb, st>>>(a);
+            binom2_fast_kernel<true, true, true, PK, TL><<<grid, HB_BLOCK, sm_fb, st>>>(a);
         else
-            binom2_fast_kernel<true, true, false, PK><<<grid, HB_BLOCK, sm_fb, st>>>(a);
+            binom2_fast_kernel<true, true, false, PK, TL><<<grid, HB_BLOCK, sm_fb, st>>>(a);
     } else if (fb) {
         if (ll)
-            binom2_fast_kernel<false, true, true, PK><<<grid, HB_BLOCK, sm_fb, st>>>(a);
+            binom2_fast_kernel<false, true, true, PK, TL><<<grid, HB_BLOCK, sm_fb, st>>>(a);
         else
-            binom2_fast_kernel<false, true, false, PK><<<grid, HB_BLOCK, sm_fb, st>>>(a);
+            binom2_fast_kernel<false, true, false, PK, TL><<<grid, HB_BLOCK, sm_fb, st>>>(a);
     } else {
-        binom2_fast_kernel<true, false, false, PK><<<grid, HB_BLOCK, sm_fb, st>>>(a);
+        binom2_fast_kernel<true, false, false, PK, TL><<<grid, HB_BLOCK, sm_fb, st>>>(a);
     }
     return cudaGetLastError();
 }
 
 cudaError_t launch_binom2_fast(const Binom2Args &a, bool vit, bool fb, cudaStream_t st)
 {
-    return a.packed ? launch_binom2_fast_t<true>(a, vit, fb, st) : launch_binom2_fast_t<false>(a, vit, fb, st);
+    if (a.tiled)
+        return a.packed ? launch_binom2_fast_t<true, true>(a, vit, fb, st)
+                        : launch_binom2_fast_t<false, true>(a, vit, fb, st);
+    return a.packed ? launch_binom2_fast_t<true, false>(a, vit, fb, st)
+                    : launch_binom2_fast_t<false, false>(a, vit, fb, st);
 }
 
 // (n << 16) | x per element; *overflow is set when a count does not fit 16 bits

@@ -338,9 +338,13 @@ HB_HD void fast_acc_sq(const Norm3Const &c, Fast3State &s, double xv)
 }
 
 // BULK (tiled layout only): x is staged by cp.async.bulk, one 2 KB copy per warp and chunk (BulkRing)
-template <bool VIT, bool FB, bool LL, bool BULK>
+// TL: the layout is the warp-tiled one at compile time — every stride is the constant 32, so the
+// row-to-row pointer updates of x, y, the three posterior planes and the scratch fold into immediate
+// offsets (the gene-major form keeps run-time strides).
+template <bool VIT, bool FB, bool LL, bool BULK, bool TL = false>
 HB_HD void norm3_fast_chain(const Norm3Args &a, int32_t seg, int64_t b, Norm3Smem &m, BulkRing &br)
 {
+    const int32_t tiled = TL ? 1 : a.tiled;
     const Norm3Const &c = a.c;
     const int64_t t0 = a.seg_off[seg];
     const int32_t L = (int32_t)(a.seg_off[seg + 1] - t0);
@@ -349,13 +353,13 @@ HB_HD void norm3_fast_chain(const Norm3Args &a, int32_t seg, int64_t b, Norm3Sme
     const int32_t tail = L - nfull * HB_CHUNK;
     const int64_t cbase = a.chunk_off[seg];
     const int64_t pix = a.sd_per_seg ? (int64_t)seg * a.B + b : b;
-    const int64_t ld = lay_stride(a.tiled, a.ld), sB = lay_stride(a.tiled, a.B);
-    const int64_t sy = lay_stride(a.tiled, a.ldy), sg = lay_stride(a.tiled, a.ldg);
-    const double *xp = a.x + lay_off(a.tiled, a.T, a.ld, t0, b);
-    uint64_t *psi = a.psi + lay_off(a.tiled, a.nchunks, a.B, cbase, b);
-    double *ckpt = a.ckpt + (a.tiled ? (((b >> 5) * a.nchunks + cbase) * 3 << 5) + (b & 31) : cbase * 3 * a.B + b);
-    uint8_t *ybase = a.y ? a.y + lay_off(a.tiled, a.T, a.ldy, t0, b) : nullptr;          // row t0
-    double *gbase = a.gamma ? a.gamma + lay_off(a.tiled, a.T, a.ldg, t0, b) : nullptr; // row t0, plane 0
+    const int64_t ld = lay_stride(tiled, a.ld), sB = lay_stride(tiled, a.B);
+    const int64_t sy = lay_stride(tiled, a.ldy), sg = lay_stride(tiled, a.ldg);
+    const double *xp = a.x + lay_off(tiled, a.T, a.ld, t0, b);
+    uint64_t *psi = a.psi + lay_off(tiled, a.nchunks, a.B, cbase, b);
+    double *ckpt = a.ckpt + (tiled ? (((b >> 5) * a.nchunks + cbase) * 3 << 5) + (b & 31) : cbase * 3 * a.B + b);
+    uint8_t *ybase = a.y ? a.y + lay_off(tiled, a.T, a.ldy, t0, b) : nullptr;          // row t0
+    double *gbase = a.gamma ? a.gamma + lay_off(tiled, a.T, a.ldg, t0, b) : nullptr; // row t0, plane 0
 
     Fast3State s;
     const double isd = a.inv_sd[pix];
