@@ -271,7 +271,14 @@ HB_HD void binom2_fast_chain(const Binom2Args &a, int32_t seg, int64_t b, const 
                         cpa4(ring, m.xs + j * m.st, xr);
                         if (!PK) cpa4(ring, m.ns + j * m.st, nr);
                     }
-                    if (pf) {
+                    if (TL) {
+                        if (j == 0 && pf) {
+                            prefetch_l2_chunk(xr + (int64_t)HB_B2F_PF_CHUNKS * HB_CHUNK * 32, (int)(b & 31), HB_CHUNK);
+                            if (!PK)
+                                prefetch_l2_chunk(nr + (int64_t)HB_B2F_PF_CHUNKS * HB_CHUNK * 32, (int)(b & 31),
+                                                  HB_CHUNK);
+                        }
+                    } else if (pf) {
                         prefetch_l2(xr + (int64_t)HB_B2F_PF_CHUNKS * HB_CHUNK * ld);
                         if (!PK) prefetch_l2(nr + (int64_t)HB_B2F_PF_CHUNKS * HB_CHUNK * ld);
                     }
@@ -414,7 +421,15 @@ HB_HD void binom2_fast_chain(const Binom2Args &a, int32_t seg, int64_t b, const 
                             cpa4(ring, m.xs + j * m.st, xq);
                             if (!PK) cpa4(ring, m.ns + j * m.st, nq);
                         }
-                        if (pf) {
+                        if (TL) {
+                            if (j == 0 && pf) {
+                                prefetch_l2_chunk(xq - (int64_t)HB_B2F_PF_CHUNKS * HB_CHUNK * 32, (int)(b & 31),
+                                                  HB_CHUNK);
+                                if (!PK)
+                                    prefetch_l2_chunk(nq - (int64_t)HB_B2F_PF_CHUNKS * HB_CHUNK * 32, (int)(b & 31),
+                                                      HB_CHUNK);
+                            }
+                        } else if (pf) {
                             prefetch_l2(xq - (int64_t)HB_B2F_PF_CHUNKS * HB_CHUNK * ld);
                             if (!PK) prefetch_l2(nq - (int64_t)HB_B2F_PF_CHUNKS * HB_CHUNK * ld);
                         }

@@ -99,6 +99,20 @@ HB_HD void st_stream(T *p, T v)
 #endif
 }
 
+// Warp-tiled layout: one instruction prefetches a whole chunk.  `p` is this lane's element of the
+// chunk's first row; the chunk is `lines` consecutive 128-byte lines starting at the warp's row, and
+// lane l touches line l % lines (instead of every lane touching its own row's two lines at every step).
+template <typename T>
+HB_HD void prefetch_l2_chunk(const T *p, int lane, int lines)
+{
+#if defined(__CUDA_ARCH__)
+    const char *base = reinterpret_cast<const char *>(p - lane) + 128 * (lane % lines);
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(base));
+#else
+    (void)p, (void)lane, (void)lines;
+#endif
+}
+
 // Hint: bring the line holding *p into L2 (no register, no dependency).
 HB_HD void prefetch_l2(const void *p)
 {

@@ -418,7 +418,13 @@ HB_HD void norm3_fast_chain(const Norm3Args &a, int32_t seg, int64_t b, Norm3Sme
                     } else {
                         xv = m.xs[j * m.st];
                         if (more) xs_refill(m, j, xr);
-                        if (pf) prefetch_l2(xr + (int64_t)HB_FAST_PF_CHUNKS * HB_CHUNK * ld);
+                        if (TL) {
+                            if (j == 0 && pf)
+                                prefetch_l2_chunk(xr + (int64_t)HB_FAST_PF_CHUNKS * HB_CHUNK * 32, (int)(b & 31),
+                                                  HB_CHUNK * 2);
+                        } else if (pf) {
+                            prefetch_l2(xr + (int64_t)HB_FAST_PF_CHUNKS * HB_CHUNK * ld);
+                        }
                         xr += ld;
                     }
                     const bool first = (j == 0) && (ch == 0);
@@ -616,7 +622,13 @@ HB_HD void norm3_fast_chain(const Norm3Args &a, int32_t seg, int64_t b, Norm3Sme
                         } else {
                             xv = m.xs[j * m.st];
                             if (more) xs_refill(m, j, xq);
-                            if (pf) prefetch_l2(xq - (int64_t)HB_FAST_PF_CHUNKS * HB_CHUNK * ld);
+                            if (TL) {
+                                if (j == 0 && pf)
+                                    prefetch_l2_chunk(xq - (int64_t)HB_FAST_PF_CHUNKS * HB_CHUNK * 32,
+                                                      (int)(b & 31), HB_CHUNK * 2);
+                            } else if (pf) {
+                                prefetch_l2(xq - (int64_t)HB_FAST_PF_CHUNKS * HB_CHUNK * ld);
+                            }
                             xq += ld;
                         }
                         fast_replay_one(c, s, xv, j == 0 && ch == 0, m, j);
