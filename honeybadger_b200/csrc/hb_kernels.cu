@@ -57,18 +57,31 @@ __global__ void __launch_bounds__(HB_BLOCK, HB_FAST_MINB)
 {
     extern __shared__ double2 smem2[];
     const int32_t seg = a.seg_order[blockIdx.x / a.nblk_per_seg];
-    const int64_t b = (int64_t)(blockIdx.x % a.nblk_per_seg) * HB_BLOCK + threadIdx.x;
-    if (b >= a.B) return;
+    int64_t b = (int64_t)(blockIdx.x % a.nblk_per_seg) * HB_BLOCK + threadIdx.x;
+    int tix = (int)threadIdx.x;
+    bool live = true;
+    if (TL && !BULK) {
+        // cooperative staging needs complete warps: in a partially filled tile the lanes past the last
+        // chain repeat that chain (same slots, same addresses, same values)
+        if ((b & ~(int64_t)31) >= a.B) return;
+        if (b >= a.B) {
+            tix -= (int)(b - (a.B - 1));
+            b = a.B - 1;
+            live = false;
+        }
+    } else if (b >= a.B) {
+        return;
+    }
     Norm3Smem m;
     m.st = HB_BLOCK;
-    m.va = smem2 + threadIdx.x;
+    m.va = smem2 + tix;
     m.vb = m.va + HB_CHUNK * HB_BLOCK;
     char *rest = reinterpret_cast<char *>(smem2 + 2 * HB_CHUNK * HB_BLOCK);
-    m.e2 = reinterpret_cast<double *>(rest) + threadIdx.x;
+    m.e2 = reinterpret_cast<double *>(rest) + tix;
     if (!HB_FAST_NOPHI1) rest += sizeof(double) * HB_CHUNK * HB_BLOCK;
-    m.ph = reinterpret_cast<int32_t *>(rest) + threadIdx.x;
+    m.ph = reinterpret_cast<int32_t *>(rest) + tix;
     rest += sizeof(int32_t) * HB_CHUNK * HB_BLOCK;
-    m.xs = reinterpret_cast<double *>(rest) + threadIdx.x; // cp.async ring (one chunk) ...
+    m.xs = reinterpret_cast<double *>(rest) + tix; // cp.async ring (one chunk) ...
     BulkRing br;
     br.par[0] = br.par[1] = 0u;
     if (BULK) { // ... or, per warp, two chunks of bulk staging followed by the block's mbarriers
@@ -88,7 +101,7 @@ __global__ void __launch_bounds__(HB_BLOCK, HB_FAST_MINB)
         }
         __syncwarp(br.wmask);
     }
-    norm3_fast_chain<VIT, FB, LL, BULK, TL>(a, seg, b, m, br);
+    norm3_fast_chain<VIT, FB, LL, BULK, TL>(a, seg, b, m, br, live);
 }
 
 template <bool VIT, bool FB>

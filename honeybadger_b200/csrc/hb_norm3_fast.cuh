@@ -254,6 +254,33 @@ HB_HD void fast_backward_one(const Norm3Const &c, Fast3State &s, uint8_t *yp, do
     }
 }
 
+// Warp-cooperative staging on the tiled layout: a half chunk of a warp's x is HB_HALF rows of 256
+// contiguous bytes, copied as 16-byte pieces — two cp.async per lane and half instead of one 8-byte
+// cp.async per lane and row.  g = this chain's element of the half's first row, lane_c = this chain's
+// column inside its tile (pointer bases), lane = the executing lane (which pieces it moves).  Lanes
+// read slots that other lanes filled: a __syncwarp follows every wait and precedes every refill.
+HB_HD void xs_refill_half_coop(Norm3Smem &m, int h, const double *g, int lane_c, int lane)
+{
+#if defined(__CUDA_ARCH__)
+    const double *gb = g - lane_c;
+    double *sb = m.xs - lane_c + h * HB_HALF * m.st;
+#pragma unroll
+    for (int q = 0; q < HB_HALF / 2; q++) {
+        const int p = lane + 32 * q, r = p >> 4, e = (p & 15) * 2;
+        unsigned sa = (unsigned)__cvta_generic_to_shared(sb + r * m.st + e);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gb + r * 32 + e) : "memory");
+    }
+#else
+    (void)m, (void)h, (void)g, (void)lane_c, (void)lane;
+#endif
+}
+HB_HD void warp_sync()
+{
+#if defined(__CUDA_ARCH__)
+    __syncwarp();
+#endif
+}
+
 // bit position of step j's 6-bit code: 5 steps per 32-bit word
 #define HB_PSI_WORD(j) ((j) / 5)
 #define HB_PSI_SHIFT(j) (6 * ((j) % 5))
@@ -341,10 +368,22 @@ HB_HD void fast_acc_sq(const Norm3Const &c, Fast3State &s, double xv)
 // TL: the layout is the warp-tiled one at compile time — every stride is the constant 32, so the
 // row-to-row pointer updates of x, y, the three posterior planes and the scratch fold into immediate
 // offsets (the gene-major form keeps run-time strides).
+// live = false: this thread is a stand-in that repeats the last real chain of a partially filled tile
+// so that the warp stays complete for the cooperative staging; it writes the same values to the same
+// places and must only stay out of the counters.
 template <bool VIT, bool FB, bool LL, bool BULK, bool TL = false>
-HB_HD void norm3_fast_chain(const Norm3Args &a, int32_t seg, int64_t b, Norm3Smem &m, BulkRing &br)
+HB_HD void norm3_fast_chain(const Norm3Args &a, int32_t seg, int64_t b, Norm3Smem &m, BulkRing &br,
+                            bool live = true)
 {
     const int32_t tiled = TL ? 1 : a.tiled;
+#if defined(__CUDA_ARCH__)
+    constexpr bool COOP = TL && !BULK;
+    const int lane = (int)(threadIdx.x & 31u);
+#else
+    constexpr bool COOP = false;
+    const int lane = 0;
+#endif
+    const int lane_c = (int)(b & 31);
     const Norm3Const &c = a.c;
     const int64_t t0 = a.seg_off[seg];
     const int32_t L = (int32_t)(a.seg_off[seg + 1] - t0);
@@ -388,10 +427,15 @@ HB_HD void norm3_fast_chain(const Norm3Args &a, int32_t seg, int64_t b, Norm3Sme
         const double *xr0 = xp;
 #pragma unroll
         for (int h = 0; h < 2; h++) {
+            if (COOP) {
+                xs_refill_half_coop(m, h, xr0, lane_c, lane);
+                xr0 += HB_HALF * ld;
+            } else {
 #pragma unroll
-            for (int j = h * HB_HALF; j < (h + 1) * HB_HALF; j++) {
-                xs_refill(m, j, xr0);
-                xr0 += ld;
+                for (int j = h * HB_HALF; j < (h + 1) * HB_HALF; j++) {
+                    xs_refill(m, j, xr0);
+                    xr0 += ld;
+                }
             }
             xs_commit(m);
         }
@@ -410,6 +454,8 @@ HB_HD void norm3_fast_chain(const Norm3Args &a, int32_t seg, int64_t b, Norm3Sme
 #pragma unroll
             for (int h = 0; h < 2; h++) {
                 if (!BULK) xs_wait<1>(m);
+                if (COOP) warp_sync();
+                const double *xh = xr; // this chain's element of the next chunk's row h * HB_HALF
                 HB_UNROLL_STEPS
                 for (int j = h * HB_HALF; j < (h + 1) * HB_HALF; j++) {
                     double xv;
@@ -417,7 +463,7 @@ HB_HD void norm3_fast_chain(const Norm3Args &a, int32_t seg, int64_t b, Norm3Sme
                         xv = bulk_read<HB_CHUNK>(br, stg, j);
                     } else {
                         xv = m.xs[j * m.st];
-                        if (more) xs_refill(m, j, xr);
+                        if (!COOP && more) xs_refill(m, j, xr);
                         if (TL) {
                             if (j == 0 && pf)
                                 prefetch_l2_chunk(xr + (int64_t)HB_FAST_PF_CHUNKS * HB_CHUNK * 32, (int)(b & 31),
@@ -437,6 +483,10 @@ HB_HD void norm3_fast_chain(const Norm3Args &a, int32_t seg, int64_t b, Norm3Sme
                         const int32_t es = fast_fwd_step(c, s, u, first, E0s, E2s, ph);
                         if (LL) s.esum += es;
                     }
+                }
+                if (COOP) {
+                    warp_sync(); // every lane has read this half's rows
+                    if (more) xs_refill_half_coop(m, h, xh, lane_c, lane);
                 }
                 if (!BULK) xs_commit(m);
             }
@@ -508,7 +558,7 @@ HB_HD void norm3_fast_chain(const Norm3Args &a, int32_t seg, int64_t b, Norm3Sme
         const double eps = 3.0 * U * ((2.0 * Ld * M + 16.0 * M) + 16.0 * Ld * dmax) * c.eps_scale;
         const double margin = mk64((int32_t)mn, 0); // <= the true minimum |difference|
         if (!(margin > eps)) {
-            count_flagged(a);
+            if (live) count_flagged(a);
             s.ycur = norm3_exact_forward(a, seg, b);
         } else if (s.d0 == -INFINITY || s.d2 == -INFINITY) {
             *a.status = 1; // some nu_k(T) == -Inf (nu_1 is finite here): HiddenMarkov's underflow stop
@@ -527,10 +577,15 @@ HB_HD void norm3_fast_chain(const Norm3Args &a, int32_t seg, int64_t b, Norm3Sme
         const double *xl = xp + (int64_t)(nfull - 1) * HB_CHUNK * ld;
 #pragma unroll
         for (int h = 0; h < 2; h++) {
+            if (COOP) {
+                xs_refill_half_coop(m, h, xl, lane_c, lane);
+                xl += HB_HALF * ld;
+            } else {
 #pragma unroll
-            for (int j = h * HB_HALF; j < (h + 1) * HB_HALF; j++) {
-                xs_refill(m, j, xl);
-                xl += ld;
+                for (int j = h * HB_HALF; j < (h + 1) * HB_HALF; j++) {
+                    xs_refill(m, j, xl);
+                    xl += ld;
+                }
             }
             xs_commit(m);
         }
@@ -614,6 +669,8 @@ HB_HD void norm3_fast_chain(const Norm3Args &a, int32_t seg, int64_t b, Norm3Sme
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
                     if (!BULK) xs_wait<1>(m);
+                    if (COOP) warp_sync();
+                    const double *xh = xq;
                     HB_UNROLL_STEPS
                     for (int j = h * HB_HALF; j < (h + 1) * HB_HALF; j++) {
                         double xv;
@@ -621,7 +678,7 @@ HB_HD void norm3_fast_chain(const Norm3Args &a, int32_t seg, int64_t b, Norm3Sme
                             xv = bulk_read<HB_CHUNK>(br, stg, j);
                         } else {
                             xv = m.xs[j * m.st];
-                            if (more) xs_refill(m, j, xq);
+                            if (!COOP && more) xs_refill(m, j, xq);
                             if (TL) {
                                 if (j == 0 && pf)
                                     prefetch_l2_chunk(xq - (int64_t)HB_FAST_PF_CHUNKS * HB_CHUNK * 32,
@@ -632,6 +689,10 @@ HB_HD void norm3_fast_chain(const Norm3Args &a, int32_t seg, int64_t b, Norm3Sme
                             xq += ld;
                         }
                         fast_replay_one(c, s, xv, j == 0 && ch == 0, m, j);
+                    }
+                    if (COOP) {
+                        warp_sync();
+                        if (more) xs_refill_half_coop(m, h, xh, lane_c, lane);
                     }
                     if (!BULK) xs_commit(m);
                 }
