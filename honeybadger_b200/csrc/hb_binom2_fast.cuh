@@ -206,11 +206,40 @@ HB_HD void b2f_unpack(int32_t w, int32_t n_sep, int32_t &xv, int32_t &nv)
     }
 }
 
+// Warp-cooperative staging on the tiled layout (see xs_refill_half_coop in hb_norm3_fast.cuh): a half
+// chunk of a warp's counts is HB_HALF rows of 128 contiguous bytes = 32 pieces of 16 bytes, one
+// cp.async per lane.  slots = this chain's slot of the ring's row 0, g = this chain's element of the
+// half's first row.
+HB_HD void b2f_refill_half_coop(int32_t *slots, int st, int h, const int32_t *g, int lane_c, int lane)
+{
+#if defined(__CUDA_ARCH__)
+    const int r = lane >> 3, e = (lane & 7) * 4;
+    unsigned sa = (unsigned)__cvta_generic_to_shared(slots - lane_c + (h * HB_HALF + r) * st + e);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(g - lane_c + r * 32 + e) : "memory");
+#else
+    (void)slots, (void)st, (void)h, (void)g, (void)lane_c, (void)lane;
+#endif
+}
+HB_HD void b2f_warp_sync()
+{
+#if defined(__CUDA_ARCH__)
+    __syncwarp();
+#endif
+}
+
 // TL: warp-tiled layout known at compile time (strides fold into immediates, as in norm3_fast_chain)
 template <bool VIT, bool FB, bool LL, bool PK, bool TL = false>
 HB_HD void binom2_fast_chain(const Binom2Args &a, int32_t seg, int64_t b, const B2fSmem &m)
 {
     const int32_t tiled = TL ? 1 : a.tiled;
+#if defined(__CUDA_ARCH__)
+    constexpr bool COOP = TL;
+    const int lane = (int)(threadIdx.x & 31u);
+#else
+    constexpr bool COOP = false;
+    const int lane = 0;
+#endif
+    const int lane_c = (int)(b & 31);
     const Binom2Const &c = a.c;
     const int64_t t0 = a.seg_off[seg];
     const int32_t L = (int32_t)(a.seg_off[seg + 1] - t0);
@@ -242,12 +271,19 @@ HB_HD void binom2_fast_chain(const Binom2Args &a, int32_t seg, int64_t b, const 
         const int32_t *xr0 = xp, *nr0 = np;
 #pragma unroll
         for (int h = 0; h < 2; h++) {
+            if (COOP) {
+                b2f_refill_half_coop(m.xs, m.st, h, xr0, lane_c, lane);
+                if (!PK) b2f_refill_half_coop(m.ns, m.st, h, nr0, lane_c, lane);
+                xr0 += HB_HALF * ld;
+                if (!PK) nr0 += HB_HALF * ld;
+            } else {
 #pragma unroll
-            for (int j = h * HB_HALF; j < (h + 1) * HB_HALF; j++) {
-                cpa4(ring, m.xs + j * m.st, xr0);
-                if (!PK) cpa4(ring, m.ns + j * m.st, nr0);
-                xr0 += ld;
-                if (!PK) nr0 += ld;
+                for (int j = h * HB_HALF; j < (h + 1) * HB_HALF; j++) {
+                    cpa4(ring, m.xs + j * m.st, xr0);
+                    if (!PK) cpa4(ring, m.ns + j * m.st, nr0);
+                    xr0 += ld;
+                    if (!PK) nr0 += ld;
+                }
             }
             cpa_commit(ring);
         }
@@ -263,11 +299,13 @@ HB_HD void binom2_fast_chain(const Binom2Args &a, int32_t seg, int64_t b, const 
 #pragma unroll
             for (int h = 0; h < 2; h++) {
                 cpa_wait<1>(ring);
+                if (COOP) b2f_warp_sync();
+                const int32_t *xh = xr, *nh = nr;
 #pragma unroll
                 for (int j = h * HB_HALF; j < (h + 1) * HB_HALF; j++) {
                     int32_t xv, nv;
                     b2f_unpack<PK>(m.xs[j * m.st], PK ? 0 : m.ns[j * m.st], xv, nv);
-                    if (more) {
+                    if (!COOP && more) {
                         cpa4(ring, m.xs + j * m.st, xr);
                         if (!PK) cpa4(ring, m.ns + j * m.st, nr);
                     }
@@ -285,6 +323,13 @@ HB_HD void binom2_fast_chain(const Binom2Args &a, int32_t seg, int64_t b, const 
                     xr += ld;
                     if (!PK) nr += ld;
                     b2f_forward_one<VIT, FB, LL>(a, m, s, xv, nv, j == 0 && ch == 0, pk, j);
+                }
+                if (COOP) {
+                    b2f_warp_sync(); // every lane has read this half's rows
+                    if (more) {
+                        b2f_refill_half_coop(m.xs, m.st, h, xh, lane_c, lane);
+                        if (!PK) b2f_refill_half_coop(m.ns, m.st, h, nh, lane_c, lane);
+                    }
                 }
                 cpa_commit(ring);
             }
@@ -330,12 +375,19 @@ HB_HD void binom2_fast_chain(const Binom2Args &a, int32_t seg, int64_t b, const 
         const int32_t *nl = PK ? nullptr : np + (int64_t)(nfull - 1) * HB_CHUNK * ld;
 #pragma unroll
         for (int h = 0; h < 2; h++) {
+            if (COOP) {
+                b2f_refill_half_coop(m.xs, m.st, h, xl, lane_c, lane);
+                if (!PK) b2f_refill_half_coop(m.ns, m.st, h, nl, lane_c, lane);
+                xl += HB_HALF * ld;
+                if (!PK) nl += HB_HALF * ld;
+            } else {
 #pragma unroll
-            for (int j = h * HB_HALF; j < (h + 1) * HB_HALF; j++) {
-                cpa4(ring, m.xs + j * m.st, xl);
-                if (!PK) cpa4(ring, m.ns + j * m.st, nl);
-                xl += ld;
-                if (!PK) nl += ld;
+                for (int j = h * HB_HALF; j < (h + 1) * HB_HALF; j++) {
+                    cpa4(ring, m.xs + j * m.st, xl);
+                    if (!PK) cpa4(ring, m.ns + j * m.st, nl);
+                    xl += ld;
+                    if (!PK) nl += ld;
+                }
             }
             cpa_commit(ring);
         }
@@ -413,11 +465,13 @@ HB_HD void binom2_fast_chain(const Binom2Args &a, int32_t seg, int64_t b, const 
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
                     cpa_wait<1>(ring);
+                    if (COOP) b2f_warp_sync();
+                    const int32_t *xh = xq, *nh = nq;
 #pragma unroll
                     for (int j = h * HB_HALF; j < (h + 1) * HB_HALF; j++) {
                         int32_t xv, nv;
                         b2f_unpack<PK>(m.xs[j * m.st], PK ? 0 : m.ns[j * m.st], xv, nv);
-                        if (more) {
+                        if (!COOP && more) {
                             cpa4(ring, m.xs + j * m.st, xq);
                             if (!PK) cpa4(ring, m.ns + j * m.st, nq);
                         }
@@ -436,6 +490,13 @@ HB_HD void binom2_fast_chain(const Binom2Args &a, int32_t seg, int64_t b, const 
                         xq += ld;
                         if (!PK) nq += ld;
                         b2f_replay_one(a, s, xv, nv, j == 0 && ch == 0, m, j);
+                    }
+                    if (COOP) {
+                        b2f_warp_sync();
+                        if (more) {
+                            b2f_refill_half_coop(m.xs, m.st, h, xh, lane_c, lane);
+                            if (!PK) b2f_refill_half_coop(m.ns, m.st, h, nh, lane_c, lane);
+                        }
                     }
                     cpa_commit(ring);
                 }

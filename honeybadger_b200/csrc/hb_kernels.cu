@@ -155,18 +155,28 @@ __global__ void __launch_bounds__(HB_BLOCK, HB_B2F_MINB)
         srho[i] = a.lut_rho_d[i];
     }
     __syncthreads();
-    if (b >= a.B) return;
+    int tix = (int)threadIdx.x;
+    int64_t bb = b;
+    if (TL) { // complete warps for the cooperative staging: lanes past the last chain repeat it
+        if ((b & ~(int64_t)31) >= a.B) return;
+        if (b >= a.B) {
+            tix -= (int)(b - (a.B - 1));
+            bb = a.B - 1;
+        }
+    } else if (b >= a.B) {
+        return;
+    }
     double2 *park = reinterpret_cast<double2 *>(reinterpret_cast<char *>(smem2) + HB_B2F_SLUT_BYTES);
     B2fSmem m;
     m.st = HB_BLOCK;
-    m.pr = park + threadIdx.x;
-    m.ph = reinterpret_cast<int32_t *>(park + HB_CHUNK * HB_BLOCK) + threadIdx.x;
+    m.pr = park + tix;
+    m.ph = reinterpret_cast<int32_t *>(park + HB_CHUNK * HB_BLOCK) + tix;
     m.xs = m.ph + HB_CHUNK * HB_BLOCK;
     m.ns = m.xs + HB_CHUNK * HB_BLOCK;
     m.slb = slb;
     m.srho = srho;
     m.slut_n = slut_n;
-    binom2_fast_chain<VIT, FB, LL, PK, TL>(a, seg, b, m);
+    binom2_fast_chain<VIT, FB, LL, PK, TL>(a, seg, bb, m);
 }
 
 template <bool SYM>
