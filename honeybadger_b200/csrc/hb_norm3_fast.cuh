@@ -46,7 +46,8 @@ namespace hb {
 // (Tried and rejected: 2-double checkpoints — state divided by its largest component, position of that
 // component in the free sign bits, beta renormalised at every chunk entry.  8 B less scratch per chunk
 // each way (48.4 -> 46.4 B/step) but one more division per chunk and sweep and 6 more registers:
-// FB-only 1.549 -> 1.521 ms, Viterbi + FB 1.940 -> 1.954 ms.  Not kept.)
+// FB-only 1.549 -> 1.521 ms, Viterbi + FB 1.940 -> 1.954 ms; again after the instruction-count work
+// (cooperative staging etc.): FB-only 1.55 -> 1.51 ms, Viterbi + FB 1.85 -> 1.88 ms.  Not kept.)
 #endif
 
 // ---------------------------------------------------------------- small bit helpers
