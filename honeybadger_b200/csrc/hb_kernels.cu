@@ -82,6 +82,8 @@ __global__ void __launch_bounds__(HB_BLOCK, HB_FAST_MINB)
     m.ph = reinterpret_cast<int32_t *>(rest) + tix;
     rest += sizeof(int32_t) * HB_CHUNK * HB_BLOCK;
     m.xs = reinterpret_cast<double *>(rest) + tix; // cp.async ring (one chunk) ...
+    m.ys = reinterpret_cast<uint8_t *>(rest + sizeof(double) * HB_CHUNK * HB_BLOCK) + (tix >> 5) * (HB_CHUNK * 32) +
+           (tix & 31); // ... then the warps' [HB_CHUNK][32] state tiles
     BulkRing br;
     br.par[0] = br.par[1] = 0u;
     if (BULK) { // ... or, per warp, two chunks of bulk staging followed by the block's mbarriers

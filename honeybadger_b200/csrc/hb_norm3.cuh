@@ -362,6 +362,7 @@ struct Norm3Smem {
     double2 *va, *vb;
     double *e2, *xs;
     int32_t *ph; // hb_norm3_fast.cuh: high word of 2^-es per step
+    uint8_t *ys; // hb_norm3_fast.cuh, tiled layout: this chain's column of the warp's [HB_CHUNK][32] state tile
     int32_t st;
 #if !defined(__CUDA_ARCH__)
     // host emulation of cp.async groups: copies become visible only at wait (catches hazards)

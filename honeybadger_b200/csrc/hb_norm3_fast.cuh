@@ -190,7 +190,7 @@ HB_HD int32_t fast_fwd_step(const Norm3Const &c, Fast3State &s, double u, bool f
 // per step j and thread: va, vb (double2), [e2 (double)], ph = hi word of 2^-es, [xs = x ring]
 //   NOPHI1: va = (phi0, phi2), vb = (E0s, E2s);  else va = (phi0, phi1), vb = (phi2, E0s), e2 = E2s
 #define HB_FAST_PARK_BYTES (16 + 16 + (HB_FAST_NOPHI1 ? 0 : 8) + 4)
-#define HB_FAST_SMEM_BYTES_PER_THREAD (HB_CHUNK * (HB_FAST_PARK_BYTES + 8))
+#define HB_FAST_SMEM_BYTES_PER_THREAD (HB_CHUNK * (HB_FAST_PARK_BYTES + 8 + 1))
 // bulk (TMA) staging on the tiled layout: two chunks of x per warp + two mbarriers per warp
 #define HB_FAST_BULK_SMEM_BYTES(nthreads) \
     ((size_t)HB_CHUNK * HB_FAST_PARK_BYTES * (nthreads) + (size_t)2 * HB_CHUNK * 8 * (nthreads) + 16 * ((nthreads) / 32))
@@ -222,12 +222,17 @@ HB_HD void fast_replay_one(const Norm3Const &c, Fast3State &s, double xv, bool f
 // Backward step at one row: emit y and gamma, move beta one position back.  pw = the 32-bit word of
 // the chunk's back-pointer word that holds step j, sh = bit offset of step j's code inside it.
 // g0/g1/g2 point at this row in the three posterior planes.
-template <bool VIT, bool FB>
+// YS: the state goes to the warp's shared-memory tile (m.ys) instead of global memory; the caller
+// writes the tile out once per chunk.
+template <bool VIT, bool FB, bool YS = false>
 HB_HD void fast_backward_one(const Norm3Const &c, Fast3State &s, uint8_t *yp, double *g0, double *g1,
                              double *g2, uint32_t pw, int sh, int j, const Norm3Smem &m)
 {
     if (VIT) {
-        st_stream(yp, (uint8_t)(s.ycur + 1));
+        if (YS)
+            m.ys[j * 32] = (uint8_t)(s.ycur + 1);
+        else
+            st_stream(yp, (uint8_t)(s.ycur + 1));
         const uint32_t f = (pw >> (sh + 4 - 2 * s.ycur)) & 3u;
         s.ycur = (int32_t)(f < 2u ? f : 2u);
     }
@@ -710,9 +715,9 @@ HB_HD void norm3_fast_chain(const Norm3Args &a, int32_t seg, int64_t b, Norm3Sme
 #pragma unroll
 #endif
             for (int j = HB_CHUNK - 1; j >= 0; j--) {
-                fast_backward_one<VIT, FB>(c, s, yp, g0, g1, g2, HB_PSI_WORD(j) ? phi : plo,
-                                           HB_PSI_SHIFT(j), j, m);
-                if (VIT) yp -= sy;
+                fast_backward_one<VIT, FB, COOP>(c, s, yp, g0, g1, g2, HB_PSI_WORD(j) ? phi : plo,
+                                                 HB_PSI_SHIFT(j), j, m);
+                if (VIT && !COOP) yp -= sy;
 #ifndef HB_DEBUG_NOGAMMA // (debug variant: keep writing the same rows -> the stores stay in L2)
                 if (FB) {
                     g0 -= sg;
@@ -720,6 +725,13 @@ HB_HD void norm3_fast_chain(const Norm3Args &a, int32_t seg, int64_t b, Norm3Sme
                     g2 -= sg;
                 }
 #endif
+            }
+            if (COOP && VIT) {
+                // the chunk's states: 8 rows x 32 bytes of the warp = 256 contiguous bytes, 8 per lane
+                warp_sync();
+                const uint64_t v = *reinterpret_cast<const uint64_t *>(m.ys - lane_c + lane * 8);
+                st_stream(reinterpret_cast<uint64_t *>(ybase + (int64_t)ch * HB_CHUNK * sy - lane_c + lane * 8), v);
+                if (!FB) warp_sync(); // (with FB the next chunk's staging syncs order the tile's reuse)
             }
         }
     }
