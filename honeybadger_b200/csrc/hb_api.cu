@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdarg.h>
+#include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -791,6 +792,8 @@ int hb_hmm_norm_tiled_dev(const double *x, int64_t T, int64_t B, const int64_t *
     std::lock_guard<std::mutex> lk(g_mu);
     Workspace *ws;
     HBTRY(cur_ws(&ws));
+    // tiles are moved in 16-byte pieces and the states of a chunk as one 8-byte store per lane
+    if (((uintptr_t)x & 15) || ((uintptr_t)y & 7)) return fail(HB_ERR_ARG, "tiled buffers must be 16-byte aligned");
     return norm3_run(ws, x, 32, T, B, seg_off, nseg, mean, sd, nullptr, nullptr, sd_per_seg, Pi, delta,
                      flags, y, 32, gamma, 32, ll, (cudaStream_t)stream, true, true);
 }
@@ -931,6 +934,7 @@ int hb_hmm_binom_tiled_dev(const int32_t *x, const int32_t *size, int64_t T, int
     std::lock_guard<std::mutex> lk(g_mu);
     Workspace *ws;
     HBTRY(cur_ws(&ws));
+    if (((uintptr_t)x & 15) || ((uintptr_t)size & 15)) return fail(HB_ERR_ARG, "tiled buffers must be 16-byte aligned");
     return binom2_run(ws, x, size, 32, T, B, seg_off, nseg, prob, rho, Pi, delta, flags, y, 32, gamma,
                       32, ll, (cudaStream_t)stream, true, false, true);
 }
@@ -943,6 +947,7 @@ int hb_hmm_binom_packed_tiled_dev(const uint32_t *xn, int64_t T, int64_t B, cons
     std::lock_guard<std::mutex> lk(g_mu);
     Workspace *ws;
     HBTRY(cur_ws(&ws));
+    if ((uintptr_t)xn & 15) return fail(HB_ERR_ARG, "tiled buffers must be 16-byte aligned");
     return binom2_run(ws, (const int32_t *)xn, nullptr, 32, T, B, seg_off, nseg, prob, rho, Pi, delta, flags,
                       y, 32, gamma, 32, ll, (cudaStream_t)stream, true, false, true, true);
 }

@@ -100,7 +100,9 @@ int hb_hmm_norm_dev(const double *x /* device, x[t*ld+b] */, int64_t ld, int64_t
  * padded to a multiple of 32 in every buffer; y and each gamma plane (plane stride T*pad32(B)) use
  * the same layout.  Every warp then streams contiguous memory (2 KB per 8-step chunk), which the
  * memory system serves ~12 % faster than 256-byte accesses at row stride.
- * hb_tile_*_dev / hb_untile_*_dev convert from / to the gene-major layout. */
+ * hb_tile_*_dev / hb_untile_*_dev convert from / to the gene-major layout. 
+ * The tiled buffers (x / counts, y) must be 16-byte aligned (cudaMalloc'd buffers are): tiles are staged in
+ * 16-byte pieces. */
 int hb_hmm_norm_tiled_dev(const double *x, int64_t T, int64_t B, const int64_t *seg_off /* host */,
                           int32_t nseg, const double *mean, const double *sd /* device */,
                           int32_t sd_per_seg, const double *Pi, const double *delta, int32_t flags,
