@@ -24,6 +24,7 @@
 #include "hb_binom2_fast.cuh"
 #include "hb_host_math.h"
 #include "hb_kernels.h"
+#include "hb_longchain.cuh"
 #include "hb_norm3.cuh"
 #include "hb_norm3_fast.cuh"
 
@@ -92,6 +93,10 @@ struct DevBuf {
 // Per-device scratch, grown on demand and reused across calls (no allocation in steady state).
 struct Workspace {
     DevBuf psi, ckpt, sdaux, segtab, status, lut_lb, lut_rho, lut_rho_d, cellmask, gsize;
+    DevBuf lc, lc_lb, lc_y;
+    int32_t lc_K = 0;
+    int64_t lc_nb = 0;
+    int32_t *lc_cstate = nullptr;
     DevBuf st_in, st_in2, st_x, st_x2, st_y, st_g, st_out, st_sd, st_ll, st_member, st_pool, st_pool2, st_pre, st_x80, st_part, st_inp, st_inp2, st_tab;
     // host-buffer entry points: three-stream pipeline (upload | layout + chains | download), staging x2
     DevBuf pin[2], pin2[2], pout_y[2], pout_g[2], pout_ll[2];
@@ -108,7 +113,7 @@ struct Workspace {
     int32_t lut_nmax = -1;
     void release_all()
     {
-        DevBuf *all[] = {&psi, &ckpt, &sdaux, &segtab, &status, &lut_lb, &lut_rho, &lut_rho_d, &cellmask, &gsize,
+        DevBuf *all[] = {&lc, &lc_lb, &lc_y, &psi, &ckpt, &sdaux, &segtab, &status, &lut_lb, &lut_rho, &lut_rho_d, &cellmask, &gsize,
                          &st_in, &st_in2, &st_x, &st_x2, &st_y, &st_g, &st_out, &st_sd, &st_ll,
                          &st_member, &st_pool, &st_pool2, &st_pre, &st_x80, &st_part, &st_inp, &st_inp2, &st_tab, &pin[0], &pin[1], &pin2[0], &pin2[1],
                          &pout_y[0], &pout_y[1], &pout_g[0], &pout_g[1], &pout_ll[0], &pout_ll[1]};
@@ -144,6 +149,7 @@ std::mutex g_mu;
 Workspace g_ws[16];
 int g_lut_nmax_cfg = 511;
 int g_binom2_mode = 0; // 0 auto (lean kernel, general kernel behind its gate), 1 general kernel only
+int g_longchain_mode = 0; // 0 auto (pooled allele rounds), 1 never, 2 also the pooled expression rounds
 int g_norm3_mode = 0; // 0 auto, 1 literal kernel only, 2 speculative kernel with every chain re-run exactly, 3 speculative kernel whenever eligible
 
 int cur_ws(Workspace **out)
@@ -331,6 +337,64 @@ int norm3_run(Workspace *ws, const double *x, int64_t ld, int64_t T, int64_t B,
     return HB_OK;
 }
 
+// Few long chains, Viterbi parallel along the gene axis (hb_longchain.cuh).  lb: device [K][T][S]
+// literal log-emissions; y: device [K][T] int32, 1-based.  Enqueues ~12 small kernels, no sync.
+int longchain_run(Workspace *ws, int32_t S, const double *lb, int64_t T, int32_t K, const double *Pi,
+                  const double *delta, int32_t *y, cudaStream_t st, bool reset_status = true, int32_t L = 0)
+{
+    if ((S != 2 && S != 3) || T < 1 || K < 1 || !lb || !y || !Pi || !delta)
+        return fail(HB_ERR_ARG, "bad arguments");
+    if (!all_finite(Pi, S * S) || !all_finite(delta, S)) return fail(HB_ERR_ARG, "bad HMM parameter");
+    hb::LcArgs a;
+    memset(&a, 0, sizeof a);
+    a.lb = lb;
+    a.T = T;
+    a.K = K;
+    a.S = S;
+    a.L = L > 0 ? L : hb::lc_block_len(T);
+    a.nb = T > 1 ? (T - 1 + a.L - 1) / a.L : 0;
+    for (int i = 0; i < S * S; i++) {
+        if (Pi[i] < 0) return fail(HB_ERR_ARG, "negative transition probability");
+        a.lp[i] = log(Pi[i]);
+    }
+    for (int i = 0; i < S; i++) a.ld[i] = log(delta[i]);
+    const size_t nkb = (size_t)K * a.nb + 1, al = 256;
+    auto up = [&](size_t v) { return (v + al - 1) / al * al; };
+    size_t off = 0;
+    const size_t o_f = off; off += up(nkb * S * S * sizeof(double));
+    const size_t o_im = off; off += up(nkb * 2 * S * S * sizeof(int64_t));
+    const size_t o_en = off; off += up(nkb * S * sizeof(double));
+    const size_t o_le = off; off += up(nkb * S * sizeof(double));
+    const size_t o_be = off; off += up(nkb * sizeof(int32_t));
+    const size_t o_cs = off; off += up((size_t)K * HB_LC_CS * sizeof(int32_t));
+    const size_t o_io = off; off += up(nkb);
+    const size_t o_bm = off; off += up(nkb);
+    const size_t o_yb = off; off += up(nkb);
+    const size_t o_ps = off; off += up((size_t)K * T);
+    HBTRY(ws->lc.ensure(off));
+    HBTRY(ws->status.ensure(4 * sizeof(int32_t)));
+    char *base = ws->lc.as<char>();
+    a.fmat = (double *)(base + o_f);
+    a.imat = (int64_t *)(base + o_im);
+    a.entry = (double *)(base + o_en);
+    a.lexit = (double *)(base + o_le);
+    a.bexp = (int32_t *)(base + o_be);
+    a.cstate = (int32_t *)(base + o_cs);
+    a.iok = (uint8_t *)(base + o_io);
+    a.bmap = (uint8_t *)(base + o_bm);
+    a.ybound = (uint8_t *)(base + o_yb);
+    a.psi = (uint8_t *)(base + o_ps);
+    a.y = y;
+    a.status = ws->status.as<int32_t>();
+    if (reset_status) CU(cudaMemsetAsync(ws->status.p, 0, 4 * sizeof(int32_t), st));
+    CU(cudaMemsetAsync(a.cstate, 0, (size_t)K * HB_LC_CS * sizeof(int32_t), st));
+    ws->lc_K = K;
+    ws->lc_nb = a.nb;
+    ws->lc_cstate = a.cstate;
+    CU(hb::launch_longchain(a, st));
+    return HB_OK;
+}
+
 int read_status(Workspace *ws, cudaStream_t st)
 {
     int32_t s = 0;
@@ -469,6 +533,34 @@ int binom2_run(Workspace *ws, const int32_t *x, const int32_t *n, int64_t ld, in
     }
     CU(hb::launch_binom2(a, vit, fb, st));
     return HB_OK;
+}
+
+// Pooled allele round on the long-chain path: literal emissions of all (chain, position) pairs in
+// parallel, then the gene-axis parallel Viterbi.  x, n: device [K][G] pooled counts; y: device [K][G].
+int binom2_longchain(Workspace *ws, const int32_t *x, const int32_t *n, int64_t G, int32_t K,
+                     const double *prob, const double *Pi, const double *delta, int32_t *y, cudaStream_t st)
+{
+    if (!all_finite(prob, 2) || prob[0] < 0 || prob[0] > 1 || prob[1] < 0 || prob[1] > 1)
+        return fail(HB_ERR_ARG, "prob outside [0,1]");
+    hb::Binom2Args a;
+    memset(&a, 0, sizeof a);
+    for (int k = 0; k < 2; k++) {
+        a.c.prob[k] = prob[k];
+        a.c.q[k] = 1 - prob[k];
+        a.c.logp[k] = log(prob[k]);
+        a.c.logq[k] = log(1 - prob[k]);
+    }
+    HBTRY(prepare_lut(ws, prob, 0.0, st));
+    HBTRY(ws->status.ensure(4 * sizeof(int32_t)));
+    CU(cudaMemsetAsync(ws->status.p, 0, 4 * sizeof(int32_t), st));
+    a.lut_lb = ws->lut_lb.as<double2>();
+    a.lut_rho = ws->lut_rho.as<hb::RhoME>();
+    a.lut_rho_d = ws->lut_rho_d.as<double>();
+    a.lut_nmax = ws->lut_nmax;
+    a.status = ws->status.as<int32_t>();
+    HBTRY(ws->lc_lb.ensure((size_t)K * G * sizeof(double2)));
+    CU(hb::launch_binom2_emit_cm(a, x, n, (int64_t)K * G, ws->lc_lb.as<double2>(), st));
+    return longchain_run(ws, 2, ws->lc_lb.as<double>(), G, K, Pi, delta, y, st, false);
 }
 
 int64_t pad_ld(int64_t B) { return (B + 15) / 16 * 16; } // 128-byte rows for fp64
@@ -1870,6 +1962,46 @@ int hb_retest_allele_model_host(const int32_t *r_rows, const int32_t *n_rows, in
     return HB_OK;
 }
 
+// ------------------------------------------------------------------ few long chains
+int hb_set_longchain_mode(int32_t mode)
+{
+    if (mode < 0 || mode > 2) return fail(HB_ERR_ARG, "mode must be 0, 1 or 2");
+    g_longchain_mode = mode;
+    return HB_OK;
+}
+
+int hb_viterbi_long_logb_dev(const double *logb, int32_t S, int64_t T, int32_t K, const double *Pi,
+                             const double *delta, int32_t block_len, int32_t *y, void *stream)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    Workspace *ws;
+    HBTRY(cur_ws(&ws));
+    if (block_len < 0 || block_len > 4096) return fail(HB_ERR_ARG, "block_len out of range");
+    return longchain_run(ws, S, logb, T, K, Pi, delta, y, (cudaStream_t)stream, true, block_len);
+}
+
+int hb_longchain_stats_dev(void *stream, int64_t *out)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    Workspace *ws;
+    HBTRY(cur_ws(&ws));
+    if (!out) return fail(HB_ERR_ARG, "out is NULL");
+    for (int i = 0; i < 5; i++) out[i] = 0;
+    if (!ws->lc_cstate || ws->lc_K < 1) return HB_OK;
+    std::vector<int32_t> cs((size_t)ws->lc_K * HB_LC_CS);
+    CU(cudaMemcpyAsync(cs.data(), ws->lc_cstate, cs.size() * sizeof(int32_t), cudaMemcpyDeviceToHost,
+                       (cudaStream_t)stream));
+    CU(cudaStreamSynchronize((cudaStream_t)stream));
+    out[0] = ws->lc_K;
+    out[1] = ws->lc_nb;
+    for (int32_t c = 0; c < ws->lc_K; c++) {
+        out[2] += cs[(size_t)c * HB_LC_CS + 1] == 2;             // chains finished on the sequential path
+        out[3] = std::max<int64_t>(out[3], cs[(size_t)c * HB_LC_CS + 2]); // repair rounds used (max over chains)
+        out[4] += cs[(size_t)c * HB_LC_CS + 3];                  // blocks run literally by the sequential walkers
+    }
+    return HB_OK;
+}
+
 // ------------------------------------------------------------------ the four reference call sites
 // One round of pooled chains on DEVICE-RESIDENT matrices: membership and the small results are
 // host buffers (K <= a few dozen chains), the [G x N] matrices never leave the GPU.
@@ -1915,10 +2047,21 @@ int hb_gexp_pooled_viterbi_dev(const double *x, int64_t ld, int64_t G, int64_t N
     CU(cudaMemcpy(ws->sdaux.p, h_aux.data(), h_aux.size() * sizeof(double), cudaMemcpyHostToDevice));
     const int64_t seg[2] = {0, G};
     const double *aux = ws->sdaux.as<double>();
-    HBTRY(norm3_run(ws, ws->st_pool2.as<double>(), ldk, G, K, seg, 1, mean, aux, aux + K, aux + 2 * K,
-                    0, Pi, delta, HB_WANT_VITERBI, ws->st_y.as<uint8_t>(), ldk, nullptr, 0, nullptr,
-                    st));
-    CU(hb::launch_transpose_u8_back(ws->st_y.as<uint8_t>(), ldk, G, K, ws->st_out.as<int32_t>(), st));
+    if (g_longchain_mode == 2) {
+        hb::Norm3Const nc;
+        bool sym;
+        memset(&nc, 0, sizeof nc);
+        HBTRY(fill_norm3_const(nc, mean, Pi, delta, &sym));
+        HBTRY(ws->lc_lb.ensure((size_t)K * G * 3 * sizeof(double)));
+        CU(hb::launch_norm3_emit_cm(nc, ws->st_pool.as<double>(), G, K, aux, aux + K, aux + 2 * K,
+                                    ws->lc_lb.as<double>(), st));
+        HBTRY(longchain_run(ws, 3, ws->lc_lb.as<double>(), G, K, Pi, delta, ws->st_out.as<int32_t>(), st));
+    } else {
+        HBTRY(norm3_run(ws, ws->st_pool2.as<double>(), ldk, G, K, seg, 1, mean, aux, aux + K, aux + 2 * K,
+                        0, Pi, delta, HB_WANT_VITERBI, ws->st_y.as<uint8_t>(), ldk, nullptr, 0, nullptr,
+                        st));
+        CU(hb::launch_transpose_u8_back(ws->st_y.as<uint8_t>(), ldk, G, K, ws->st_out.as<int32_t>(), st));
+    }
     CU(cudaMemcpyAsync(y, ws->st_out.p, (size_t)G * K * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     if (pooled_x)
         CU(cudaMemcpyAsync(pooled_x, ws->st_pool.p, (size_t)K * G * sizeof(double),
@@ -1959,12 +2102,18 @@ int hb_allele_pooled_viterbi_dev(const int32_t *r_maf, const int32_t *n_sc, int6
             CU(hb::launch_pool_count(src[i], ld, G, N, ws->cellmask.as<uint32_t>(), kn,
                                      cnt[i] + (int64_t)k0 * G, st));
         }
-        CU(hb::launch_transpose_i32(cnt[i], G, K, gm[i], ldk, st));
     }
-    const int64_t seg[2] = {0, G};
-    HBTRY(binom2_run(ws, gm[0], gm[1], ldk, G, K, seg, 1, prob, 0.0, Pi, delta, HB_WANT_VITERBI,
-                     ws->st_y.as<uint8_t>(), ldk, nullptr, 0, nullptr, st, true, true));
-    CU(hb::launch_transpose_u8_back(ws->st_y.as<uint8_t>(), ldk, G, K, ws->st_out.as<int32_t>(), st));
+    if (g_longchain_mode != 1) {
+        // a handful of chains of G positions: parallel along the gene axis (hb_longchain.cuh), straight
+        // from the chain-major pooled counts into the [G x K] result
+        HBTRY(binom2_longchain(ws, cnt[0], cnt[1], G, K, prob, Pi, delta, ws->st_out.as<int32_t>(), st));
+    } else {
+        for (int i = 0; i < 2; i++) CU(hb::launch_transpose_i32(cnt[i], G, K, gm[i], ldk, st));
+        const int64_t seg[2] = {0, G};
+        HBTRY(binom2_run(ws, gm[0], gm[1], ldk, G, K, seg, 1, prob, 0.0, Pi, delta, HB_WANT_VITERBI,
+                         ws->st_y.as<uint8_t>(), ldk, nullptr, 0, nullptr, st, true, true));
+        CU(hb::launch_transpose_u8_back(ws->st_y.as<uint8_t>(), ldk, G, K, ws->st_out.as<int32_t>(), st));
+    }
     CU(cudaMemcpyAsync(y, ws->st_out.p, (size_t)G * K * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     if (mafl)
         CU(cudaMemcpyAsync(mafl, cnt[0], (size_t)K * G * sizeof(int32_t), cudaMemcpyDeviceToHost, st));

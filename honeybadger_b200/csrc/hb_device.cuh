@@ -123,6 +123,16 @@ HB_HD void prefetch_l2(const void *p)
 #endif
 }
 
+// Hint: bring the line holding *p into L1 (few-thread sequential walkers: nothing else hides L2 latency).
+HB_HD void prefetch_l1(const void *p)
+{
+#if defined(__CUDA_ARCH__)
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#else
+    (void)p;
+#endif
+}
+
 // ---------------------------------------------------------------- cp.async staging of 4-byte elements
 // Per-thread asynchronous copies global -> shared with explicit commit / wait groups.  Unlike a
 // register prefetch (whose first use can end up waiting on the scoreboard it shares with the NEXT

@@ -11,6 +11,7 @@
 #include "hb_group.cuh"
 #include "hb_inputs.cuh"
 #include "hb_kernels.h"
+#include "hb_longchain.cuh"
 #include "hb_norm3.cuh"
 #include "hb_norm3_fast.cuh"
 #include "hb_x87.cuh"
@@ -319,6 +320,165 @@ cudaError_t launch_binom2(const Binom2Args &a, bool vit, bool fb, cudaStream_t s
         binom2_kernel<false, true><<<grid, HB_BLOCK, sm_fb, st>>>(a);
     else
         binom2_kernel<true, false><<<grid, HB_BLOCK, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+// =====================================================================================
+// Few long chains: Viterbi parallel along the gene axis (hb_longchain.cuh)
+// =====================================================================================
+#define LC_TPB 32 // threads per block of the parallel phases: spread the few thousand walkers over all SMs
+template <int S, int PH>
+__global__ void __launch_bounds__(LC_TPB) lc_par_kernel(const __grid_constant__ LcArgs a)
+{
+    const int64_t i = (int64_t)blockIdx.x * LC_TPB + threadIdx.x;
+    if (i >= (int64_t)a.K * a.nb) return;
+    const int32_t c = (int32_t)(i / a.nb);
+    const int64_t b = i % a.nb;
+    if (PH == 0) lc_fmat<S>(a, c, b);
+    if (PH == 2) lc_imat<S>(a, c, b);
+    if (PH == 4) lc_literal<S>(a, c, b);
+    if (PH == 6) lc_write_y<S>(a, c, b);
+}
+// Sequential walkers: one warp per chain.  The warp stages the per-block tables of HB_LC_WIN blocks in
+// shared memory (coalesced), lane 0 walks them (a dependent recursion over the blocks).
+template <typename T>
+__device__ __forceinline__ void lc_stage(T *dst, const T *src, int64_t count, int lane)
+{
+    for (int64_t i = lane; i < count; i += 32) dst[i] = src[i];
+}
+
+template <int S>
+__global__ void __launch_bounds__(32) lc_p1_kernel(const __grid_constant__ LcArgs a)
+{
+    __shared__ double s_f[HB_LC_WIN * S * S];
+    __shared__ int32_t s_be[HB_LC_WIN];
+    const int32_t c = blockIdx.x;
+    const int lane = threadIdx.x;
+    double v[S];
+    if (lane == 0) lc_prefix_approx_begin<S>(a, c, v);
+    for (int64_t w0 = 0; w0 < a.nb; w0 += HB_LC_WIN) {
+        const int64_t n = a.nb - w0 < HB_LC_WIN ? a.nb - w0 : HB_LC_WIN;
+        lc_stage(s_f, a.fmat + ((int64_t)c * a.nb + w0) * S * S, n * S * S, lane);
+        __syncwarp();
+        if (lane == 0) {
+            LcArgs w = a;
+            w.win_b0 = w0;
+            w.wf = s_f;
+            lc_prefix_approx_range<S>(w, c, w0, w0 + n, v, s_be);
+        }
+        __syncwarp();
+        lc_stage(a.bexp + (int64_t)c * a.nb + w0, (const int32_t *)s_be, n, lane);
+        __syncwarp();
+    }
+}
+
+template <int S>
+__global__ void __launch_bounds__(32) lc_p3_kernel(const __grid_constant__ LcArgs a, int32_t round)
+{
+    __shared__ int64_t s_i[HB_LC_WIN * 2 * S * S];
+    __shared__ int32_t s_be[HB_LC_WIN];
+    __shared__ uint8_t s_io[HB_LC_WIN];
+    const int32_t c = blockIdx.x;
+    const int lane = threadIdx.x;
+    double nu[S];
+    int64_t b0 = 0, forced_end = 0;
+    int32_t nlit = 0;
+    bool active = false;
+    if (lane == 0) active = lc_prefix_exact_begin<S>(a, c, round, nu, b0, forced_end);
+    active = __shfl_sync(0xffffffffu, active ? 1 : 0, 0) != 0;
+    if (!active) return;
+    b0 = __shfl_sync(0xffffffffu, b0, 0);
+    for (int64_t w0 = b0; w0 < a.nb; w0 += HB_LC_WIN) {
+        const int64_t n = a.nb - w0 < HB_LC_WIN ? a.nb - w0 : HB_LC_WIN;
+        const int64_t o = (int64_t)c * a.nb + w0;
+        lc_stage(s_i, (const int64_t *)a.imat + o * 2 * S * S, n * 2 * S * S, lane);
+        lc_stage(s_be, (const int32_t *)a.bexp + o, n, lane);
+        lc_stage(s_io, (const uint8_t *)a.iok + o, n, lane);
+        __syncwarp();
+        if (lane == 0) {
+            LcArgs w = a;
+            w.win_b0 = w0;
+            w.wi = s_i;
+            w.wbe = s_be;
+            w.wio = s_io;
+            lc_prefix_exact_range<S>(w, c, w0, w0 + n, nu, forced_end, nlit);
+        }
+        __syncwarp();
+    }
+    if (lane == 0) a.cstate[c * HB_LC_CS + 3] += nlit;
+}
+
+template <int S>
+__global__ void __launch_bounds__(32) lc_p5_kernel(const __grid_constant__ LcArgs a)
+{
+    if (threadIdx.x == 0) lc_resolve<S>(a, blockIdx.x);
+}
+
+template <int S>
+static cudaError_t launch_longchain_t(const LcArgs &a, cudaStream_t st)
+{
+    const int64_t nw = (int64_t)a.K * a.nb;
+    const unsigned gp = (unsigned)((nw + LC_TPB - 1) / LC_TPB);
+    if (nw > 0) {
+        lc_par_kernel<S, 0><<<gp, LC_TPB, 0, st>>>(a);
+        lc_p1_kernel<S><<<a.K, 32, 0, st>>>(a);
+        lc_par_kernel<S, 2><<<gp, LC_TPB, 0, st>>>(a);
+        for (int r = 0; r < HB_LC_ROUNDS; r++) {
+            lc_p3_kernel<S><<<a.K, 32, 0, st>>>(a, r);
+            lc_par_kernel<S, 4><<<gp, LC_TPB, 0, st>>>(a);
+        }
+    }
+    lc_p5_kernel<S><<<a.K, 32, 0, st>>>(a);
+    if (nw > 0) lc_par_kernel<S, 6><<<gp, LC_TPB, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_longchain(const LcArgs &a, cudaStream_t st)
+{
+    return a.S == 2 ? launch_longchain_t<2>(a, st) : launch_longchain_t<3>(a, st);
+}
+
+// Literal log-emissions of pooled chains, chain-major [K][G][S]: one thread per (chain, position).
+__global__ void __launch_bounds__(128)
+    binom2_emit_cm_kernel(const __grid_constant__ Binom2Args a, const int32_t *x, const int32_t *n,
+                          int64_t count, double2 *out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    double l0 = 0, l1 = 0;
+    RhoME rho;
+    rho.m = 1.0;
+    rho.e = 0;
+    binom2_emit(a, x[i], n[i], l0, l1, rho, true, false);
+    double2 v;
+    v.x = l0;
+    v.y = l1;
+    out[i] = v;
+}
+cudaError_t launch_binom2_emit_cm(const Binom2Args &a, const int32_t *x, const int32_t *n, int64_t count,
+                                  double2 *out, cudaStream_t st)
+{
+    binom2_emit_cm_kernel<<<(unsigned)((count + 127) / 128), 128, 0, st>>>(a, x, n, count, out);
+    return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(128)
+    norm3_emit_cm_kernel(const __grid_constant__ Norm3Const c, const double *x, int64_t G, int32_t K,
+                         const double *sd, const double *inv_sd, const double *log_sd, double *out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= G * K) return;
+    const int64_t k = i / G;
+    double l0, l1, l2, h1;
+    norm3_logb(x[i], c, sd[k], inv_sd[k], log_sd[k], l0, l1, l2, h1);
+    out[3 * i] = l0;
+    out[3 * i + 1] = l1;
+    out[3 * i + 2] = l2;
+}
+cudaError_t launch_norm3_emit_cm(const Norm3Const &c, const double *x, int64_t G, int32_t K, const double *sd,
+                                 const double *inv_sd, const double *log_sd, double *out, cudaStream_t st)
+{
+    norm3_emit_cm_kernel<<<(unsigned)((G * K + 127) / 128), 128, 0, st>>>(c, x, G, K, sd, inv_sd, log_sd, out);
     return cudaGetLastError();
 }
 
@@ -918,9 +1078,76 @@ __global__ void __launch_bounds__(32 * PC_WARPS)
     if (lane < K) out[(int64_t)lane * G + g] = cnt;
 }
 
+// Same result, 16-byte loads: lane l takes cells 128 s + 4 l .. + 3 of slab s, four ballots give the
+// positive cells of the slab as four 32-bit words, and lane k counts group k with one AND + POPC per word
+// against the group's membership words in the same bit order (built once per block in shared memory).
+// ~6 instructions per 128 bytes instead of ~35: the kernel becomes a plain HBM stream.
+__global__ void __launch_bounds__(256)
+    pool_count_v4_kernel(const int32_t *v, int64_t ld, int64_t G, int64_t N, const uint32_t *cellmask,
+                         int32_t K, int32_t *out)
+{
+    extern __shared__ uint4 pc_w[]; // [nslab][K]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int64_t nslab = (N + 127) / 128;
+    for (int64_t s = warp; s < nslab; s += nw) {
+        uint32_t m[4], w[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int64_t c = 128 * s + 4 * lane + i;
+            m[i] = c < N ? cellmask[c] : 0u;
+        }
+        for (int k = 0; k < K; k++)
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const uint32_t bal = __ballot_sync(0xffffffffu, (m[i] >> k) & 1u);
+                if (lane == k) w[i] = bal;
+            }
+        if (lane < K) pc_w[s * K + lane] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    __syncthreads();
+    for (int64_t g = (int64_t)blockIdx.x * nw + warp; g < G; g += (int64_t)gridDim.x * nw) {
+        const int32_t *row = v + g * ld;
+        int32_t cnt = 0;
+#pragma unroll 2
+        for (int64_t s = 0; s < nslab; s++) {
+            const int64_t c = 128 * s + 4 * lane;
+            int4 x = make_int4(0, 0, 0, 0);
+            if (c + 3 < ld) {
+                x = __ldcs(reinterpret_cast<const int4 *>(row + c));
+            } else {
+                if (c < ld) x.x = row[c];
+                if (c + 1 < ld) x.y = row[c + 1];
+                if (c + 2 < ld) x.z = row[c + 2];
+            }
+            const uint32_t b0 = __ballot_sync(0xffffffffu, x.x > 0), b1 = __ballot_sync(0xffffffffu, x.y > 0),
+                           b2 = __ballot_sync(0xffffffffu, x.z > 0), b3 = __ballot_sync(0xffffffffu, x.w > 0);
+            if (lane < K) {
+                const uint4 w = pc_w[s * K + lane];
+                cnt += __popc(b0 & w.x) + __popc(b1 & w.y) + __popc(b2 & w.z) + __popc(b3 & w.w);
+            }
+        }
+        if (lane < K) out[(int64_t)lane * G + g] = cnt;
+    }
+}
+
 cudaError_t launch_pool_count(const int32_t *v, int64_t ld, int64_t G, int64_t N,
                               const uint32_t *cellmask, int32_t K, int32_t *out, cudaStream_t st)
 {
+    const size_t smem = (size_t)((N + 127) / 128) * K * sizeof(uint4);
+    if (((uintptr_t)v & 15) == 0 && ld % 4 == 0 && smem <= 200 * 1024) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaFuncSetAttribute(pool_count_v4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            attr_set = true;
+        }
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const int per_sm = smem > 48 * 1024 ? 1 : (smem > 24 * 1024 ? 4 : 8);
+        const unsigned grid = (unsigned)std::min<int64_t>((G + 7) / 8, (int64_t)sms * per_sm);
+        pool_count_v4_kernel<<<grid, 256, smem, st>>>(v, ld, G, N, cellmask, K, out);
+        return cudaGetLastError();
+    }
     pool_count_kernel<<<(unsigned)((G + PC_WARPS - 1) / PC_WARPS), 32 * PC_WARPS, 0, st>>>(v, ld, G, N,
                                                                                           cellmask, K, out);
     return cudaGetLastError();

@@ -442,6 +442,35 @@ def binom2_general_rerun() -> int:
     return int(n.value)
 
 
+def viterbi_long_logb_dev(logb, Pi, delta, block_len=0):
+    """HiddenMarkov::Viterbi for a few LONG chains on precomputed log-emissions, parallel along the
+    chain and bit-exact (csrc/hb_longchain.cuh).  logb: CUDA float64 [K, T, S] (S = 2 or 3), the
+    reference's own log-densities; returns CUDA int32 [K, T], 1-based states.  No synchronisation."""
+    import torch
+    if logb.dtype != torch.float64 or not logb.is_cuda or logb.dim() != 3 or not logb.is_contiguous():
+        raise ValueError("logb must be a contiguous CUDA float64 tensor [K, T, S]")
+    K, T, S = logb.shape
+    Pi = _f64(Pi).reshape(S * S)
+    delta = _f64(delta).reshape(S)
+    y = torch.empty((K, T), dtype=torch.int32, device=logb.device)
+    _lib.check(_lib.load().hb_viterbi_long_logb_dev(logb.data_ptr(), S, T, K, _vp(Pi), _vp(delta),
+                                                    int(block_len), y.data_ptr(), _stream()))
+    return y
+
+
+def longchain_stats() -> dict:
+    """Counters of the last long-chain launch; waits for the current stream."""
+    out = (C.c_int64 * 5)()
+    _lib.check(_lib.load().hb_longchain_stats_dev(_stream(), out))
+    return {"chains": out[0], "blocks": out[1], "sequential_chains": out[2], "repair_rounds": out[3],
+            "literal_blocks": out[4]}
+
+
+def set_longchain_mode(mode: int):
+    """Pooled rounds: 0 allele round on the long-chain path (default), 1 neither, 2 both."""
+    _lib.check(_lib.load().hb_set_longchain_mode(int(mode)))
+
+
 def status_dev():
     """Wait for the current stream and raise UnderflowError if the last launch hit nu == -Inf."""
     _lib.check(_lib.load().hb_status_dev(_stream()))

@@ -319,6 +319,27 @@ int hb_retest_allele_model_host(const int32_t *r_rows, const int32_t *n_rows, in
                                 const double *l_maf, const double *n_bulk, const int32_t *gene, double pseudo,
                                 double mono, double *p_del);
 
+/* ------------------------------------------------------------------ a few LONG chains
+ * HiddenMarkov::Viterbi on precomputed log-emissions, parallel ALONG the chain (the pooled rounds of
+ * R/HoneyBADGER.R:1150-1151 and :1409-1410 run K <= a few dozen chains of G positions; one thread per
+ * chain would leave the GPU idle).  Blocks of positions get exact integer max-plus transfer matrices
+ * (inside one binade the rounded recursion is an integer recursion), block entries are predicted from
+ * them, and every block is then run with the literal fp64 recursion from its entry; a chain's result is
+ * accepted only when every block's literal exit is bit-identical to the next block's entry, otherwise
+ * the rest of the chain is finished sequentially — the states are the sequential recursion's in all cases.
+ * logb: device [K][T][S] (chain-major; the reference's own dnorm / dbinom values), S = 2 or 3,
+ * Pi [S*S] row-major, delta [S], block_len 0 = chosen from T, y: device [K][T] 1-based.
+ * No synchronisation; hb_status_dev reports HiddenMarkov's underflow error. */
+int hb_viterbi_long_logb_dev(const double *logb, int32_t S, int64_t T, int32_t K, const double *Pi,
+                             const double *delta, int32_t block_len, int32_t *y, void *stream);
+/* Counters of the last long-chain launch (waits for `stream`): out[0] chains, out[1] blocks per chain,
+ * out[2] chains finished on the sequential path, out[3] repair rounds used (max over chains), out[4]
+ * blocks the sequential walkers ran literally (entry outside the predicted binade, first blocks). */
+int hb_longchain_stats_dev(void *stream, int64_t *out /* [5] */);
+/* Pooled rounds: 0 (default) the allele round uses the long-chain path, 1 neither round does (one
+ * thread per chain), 2 the expression round uses it too.  Same states in every mode. */
+int hb_set_longchain_mode(int32_t mode);
+
 /* One recursion round of the split-and-retest driver on DEVICE-RESIDENT matrices (gene-major,
  * uploaded once): `member` [K][N] (0/1, host) names the K candidate cell sets of the round, the
  * small results come back to host buffers: y [K][G] (1-based states), pooled vectors and their sd.

@@ -16,6 +16,7 @@
 #include "hb_binom2.cuh"
 #include "hb_binom2_fast.cuh"
 #include "hb_host_math.h"
+#include "hb_longchain.cuh"
 #include "hb_norm3.cuh"
 #include "hb_norm3_fast.cuh"
 #include "hb_x87.cuh"
@@ -405,3 +406,80 @@ double emul_binom_logpmf_dev(double x, double n, double p)
 }
 
 } // extern "C"
+
+// Gene-axis parallel Viterbi for long chains (hb_longchain.cuh), phases walked serially; the
+// sequential walkers go through staging windows (copies of the per-block tables) like the device's.
+// lb [K][T][S]; y [K][T]; stats [K][4] (first four cstate words).  L <= 0: the library's block length.
+template <int S>
+static int emul_longchain_t(int64_t T, int K, const double *lb, const double *Pi, const double *delta,
+                            int L, int32_t *y, int32_t *stats)
+{
+    LcArgs a;
+    memset(&a, 0, sizeof a);
+    a.lb = lb; a.T = T; a.K = K; a.S = S; a.L = L > 0 ? L : lc_block_len(T);
+    a.nb = T > 1 ? (T - 1 + a.L - 1) / a.L : 0;
+    for (int i = 0; i < S * S; i++) a.lp[i] = log(Pi[i]);
+    for (int i = 0; i < S; i++) a.ld[i] = log(delta[i]);
+    const size_t nkb = (size_t)K * a.nb + 1;
+    std::vector<double> fmat(nkb * S * S), entry(nkb * S), lexit(nkb * S);
+    std::vector<int32_t> bexp(nkb), cstate((size_t)K * HB_LC_CS, 0);
+    std::vector<int64_t> imat(nkb * 2 * S * S);
+    std::vector<uint8_t> iok(nkb), psi((size_t)K * T), bmap(nkb), ybound(nkb);
+    int32_t status = 0;
+    a.fmat = fmat.data(); a.bexp = bexp.data(); a.imat = imat.data(); a.iok = iok.data();
+    a.entry = entry.data(); a.lexit = lexit.data(); a.psi = psi.data(); a.bmap = bmap.data();
+    a.cstate = cstate.data(); a.ybound = ybound.data(); a.y = y; a.status = &status;
+    for (int c = 0; c < K; c++)
+        for (int64_t b = 0; b < a.nb; b++) lc_fmat<S>(a, c, b);
+    for (int c = 0; c < K && a.nb; c++) {
+        double v[S];
+        lc_prefix_approx_begin<S>(a, c, v);
+        for (int64_t w0 = 0; w0 < a.nb; w0 += HB_LC_WIN) {
+            const int64_t n = std::min<int64_t>(HB_LC_WIN, a.nb - w0);
+            std::vector<double> wf(fmat.begin() + ((size_t)c * a.nb + w0) * S * S,
+                                   fmat.begin() + ((size_t)c * a.nb + w0 + n) * S * S);
+            int32_t be[HB_LC_WIN];
+            LcArgs w = a;
+            w.win_b0 = w0; w.wf = wf.data();
+            lc_prefix_approx_range<S>(w, c, w0, w0 + n, v, be);
+            for (int64_t i = 0; i < n; i++) bexp[(size_t)c * a.nb + w0 + i] = be[i];
+        }
+    }
+    for (int c = 0; c < K; c++)
+        for (int64_t b = 0; b < a.nb; b++) lc_imat<S>(a, c, b);
+    for (int r = 0; r < HB_LC_ROUNDS && a.nb; r++) {
+        for (int c = 0; c < K; c++) {
+            double nu[S];
+            int64_t b0, forced_end;
+            if (!lc_prefix_exact_begin<S>(a, c, r, nu, b0, forced_end)) continue;
+            int32_t nlit = 0;
+            for (int64_t w0 = b0; w0 < a.nb; w0 += HB_LC_WIN) {
+                const int64_t n = std::min<int64_t>(HB_LC_WIN, a.nb - w0);
+                const size_t o = (size_t)c * a.nb + w0;
+                std::vector<int64_t> wi(imat.begin() + o * 2 * S * S, imat.begin() + (o + n) * 2 * S * S);
+                std::vector<int32_t> wbe(bexp.begin() + o, bexp.begin() + o + n);
+                std::vector<uint8_t> wio(iok.begin() + o, iok.begin() + o + n);
+                LcArgs w = a;
+                w.win_b0 = w0; w.wi = wi.data(); w.wbe = wbe.data(); w.wio = wio.data();
+                lc_prefix_exact_range<S>(w, c, w0, w0 + n, nu, forced_end, nlit);
+            }
+            cstate[(size_t)c * HB_LC_CS + 3] += nlit;
+        }
+        for (int c = 0; c < K; c++)
+            for (int64_t b = 0; b < a.nb; b++) lc_literal<S>(a, c, b);
+    }
+    for (int c = 0; c < K; c++) lc_resolve<S>(a, c);
+    for (int c = 0; c < K; c++)
+        for (int64_t b = 0; b < a.nb; b++) lc_write_y<S>(a, c, b);
+    if (stats)
+        for (int c = 0; c < K; c++) memcpy(stats + 4 * c, cstate.data() + (size_t)c * HB_LC_CS, 4 * sizeof(int32_t));
+    return status;
+}
+
+extern "C" int emul_longchain(int S, int64_t T, int K, const double *lb, const double *Pi,
+                              const double *delta, int L, int32_t *y, int32_t *stats)
+{
+    if (S == 2) return emul_longchain_t<2>(T, K, lb, Pi, delta, L, y, stats);
+    if (S == 3) return emul_longchain_t<3>(T, K, lb, Pi, delta, L, y, stats);
+    return -1;
+}
