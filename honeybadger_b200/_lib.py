@@ -93,6 +93,7 @@ SIGNATURES = {
     "hb_retest_allele_model_host": (_i32, [_p, _p, _i64, _i64, _p, _p, _p, _d, _d, _p]),
     "hb_retest_allele_lr_dev": (_i32, [_p, _p, _i64, _i64, _i64, _p, _i64, _d, _d, _p, _p]),
     "hb_viterbi_long_logb_dev": (_i32, [_p, _i32, _i64, _i32, _p, _p, _i32, _p, _p]),
+    "hb_forwardback_long_logb_dev": (_i32, [_p, _i32, _i64, _i32, _p, _p, _i32, _p, _p, _p]),
     "hb_longchain_stats_dev": (_i32, [_p, _p]),
     "hb_set_longchain_mode": (_i32, [_i32]),
     "hb_gexp_pooled_viterbi_dev": (_i32, [_p, _i64, _i64, _i64, _p, _i32, _p, _p, _p, _p, _p, _p, _p]),

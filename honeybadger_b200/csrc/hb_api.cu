@@ -93,7 +93,7 @@ struct DevBuf {
 // Per-device scratch, grown on demand and reused across calls (no allocation in steady state).
 struct Workspace {
     DevBuf psi, ckpt, sdaux, segtab, status, lut_lb, lut_rho, lut_rho_d, cellmask, gsize;
-    DevBuf lc, lc_lb, lc_y;
+    DevBuf lc, lc_fb, lc_lb, lc_y;
     int32_t lc_K = 0;
     int64_t lc_nb = 0;
     int32_t *lc_cstate = nullptr;
@@ -113,7 +113,7 @@ struct Workspace {
     int32_t lut_nmax = -1;
     void release_all()
     {
-        DevBuf *all[] = {&lc, &lc_lb, &lc_y, &psi, &ckpt, &sdaux, &segtab, &status, &lut_lb, &lut_rho, &lut_rho_d, &cellmask, &gsize,
+        DevBuf *all[] = {&lc, &lc_fb, &lc_lb, &lc_y, &psi, &ckpt, &sdaux, &segtab, &status, &lut_lb, &lut_rho, &lut_rho_d, &cellmask, &gsize,
                          &st_in, &st_in2, &st_x, &st_x2, &st_y, &st_g, &st_out, &st_sd, &st_ll,
                          &st_member, &st_pool, &st_pool2, &st_pre, &st_x80, &st_part, &st_inp, &st_inp2, &st_tab, &pin[0], &pin[1], &pin2[0], &pin2[1],
                          &pout_y[0], &pout_y[1], &pout_g[0], &pout_g[1], &pout_ll[0], &pout_ll[1]};
@@ -392,6 +392,47 @@ int longchain_run(Workspace *ws, int32_t S, const double *lb, int64_t T, int32_t
     ws->lc_nb = a.nb;
     ws->lc_cstate = a.cstate;
     CU(hb::launch_longchain(a, st));
+    return HB_OK;
+}
+
+// Posteriors of a few long chains (lc_fb_* in hb_longchain.cuh).  gamma: device [K][T][S]; ll: device [K] or NULL.
+int longchain_fb_run(Workspace *ws, int32_t S, const double *lb, int64_t T, int32_t K, const double *Pi,
+                     const double *delta, double *gamma, double *ll, cudaStream_t st, int32_t L = 0)
+{
+    if ((S != 2 && S != 3) || T < 1 || K < 1 || !lb || !gamma || !Pi || !delta)
+        return fail(HB_ERR_ARG, "bad arguments");
+    if (!all_finite(Pi, S * S) || !all_finite(delta, S)) return fail(HB_ERR_ARG, "bad HMM parameter");
+    hb::LcArgs a;
+    memset(&a, 0, sizeof a);
+    a.lb = lb;
+    a.T = T;
+    a.K = K;
+    a.S = S;
+    a.L = L > 0 ? L : hb::lc_block_len(T);
+    a.nb = T > 1 ? (T - 1 + a.L - 1) / a.L : 0;
+    for (int i = 0; i < S * S; i++) {
+        if (Pi[i] < 0) return fail(HB_ERR_ARG, "negative transition probability");
+        a.pi[i] = Pi[i];
+    }
+    for (int i = 0; i < S; i++) a.dl[i] = delta[i];
+    const size_t nkb = (size_t)K * a.nb + 1, al = 256;
+    auto up = [&](size_t v) { return (v + al - 1) / al * al; };
+    size_t off = 0;
+    const size_t o_f = off; off += up(nkb * S * S * sizeof(double));
+    const size_t o_ae = off; off += up(nkb * S * sizeof(double));
+    const size_t o_be = off; off += up(nkb * S * sizeof(double));
+    const size_t o_ls = off; off += up(nkb * sizeof(double));
+    const size_t o_e = off; off += up(nkb * S * sizeof(int32_t));
+    HBTRY(ws->lc_fb.ensure(off));
+    char *base = ws->lc_fb.as<char>();
+    a.ffm = (double *)(base + o_f);
+    a.fae = (double *)(base + o_ae);
+    a.fbe = (double *)(base + o_be);
+    a.fls = (double *)(base + o_ls);
+    a.ffe = (int32_t *)(base + o_e);
+    a.gamma = gamma;
+    a.ll = ll;
+    CU(hb::launch_longchain_fb(a, st));
     return HB_OK;
 }
 
@@ -1978,6 +2019,17 @@ int hb_viterbi_long_logb_dev(const double *logb, int32_t S, int64_t T, int32_t K
     HBTRY(cur_ws(&ws));
     if (block_len < 0 || block_len > 4096) return fail(HB_ERR_ARG, "block_len out of range");
     return longchain_run(ws, S, logb, T, K, Pi, delta, y, (cudaStream_t)stream, true, block_len);
+}
+
+int hb_forwardback_long_logb_dev(const double *logb, int32_t S, int64_t T, int32_t K, const double *Pi,
+                                 const double *delta, int32_t block_len, double *gamma, double *ll,
+                                 void *stream)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    Workspace *ws;
+    HBTRY(cur_ws(&ws));
+    if (block_len < 0 || block_len > 4096) return fail(HB_ERR_ARG, "block_len out of range");
+    return longchain_fb_run(ws, S, logb, T, K, Pi, delta, gamma, ll, (cudaStream_t)stream, block_len);
 }
 
 int hb_longchain_stats_dev(void *stream, int64_t *out)

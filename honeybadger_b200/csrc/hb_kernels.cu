@@ -433,6 +433,77 @@ static cudaError_t launch_longchain_t(const LcArgs &a, cudaStream_t st)
     return cudaGetLastError();
 }
 
+// ---- posteriors of the same chains (lc_fb_*)
+template <int S, int PH>
+__global__ void __launch_bounds__(LC_TPB) lc_fb_par_kernel(const __grid_constant__ LcArgs a)
+{
+    const int64_t i = (int64_t)blockIdx.x * LC_TPB + threadIdx.x;
+    if (i >= (int64_t)a.K * a.nb) return;
+    const int32_t c = (int32_t)(i / a.nb);
+    const int64_t b = i % a.nb;
+    if (PH == 0) lc_fb_mat<S>(a, c, b);
+    if (PH == 2) lc_fb_block<S>(a, c, b);
+}
+template <int S>
+__global__ void __launch_bounds__(32) lc_fb_p1_kernel(const __grid_constant__ LcArgs a)
+{
+    __shared__ double s_f[HB_LC_WIN * S * S];
+    __shared__ int32_t s_e[HB_LC_WIN * S];
+    const int32_t c = blockIdx.x;
+    const int lane = threadIdx.x;
+    double al[S], bt[S];
+    if (lane == 0) {
+        lc_fb_begin<S>(a, c, al);
+#pragma unroll
+        for (int k = 0; k < S; k++) bt[k] = 1.0 / S;
+    }
+    for (int dir = 0; dir < 2; dir++) {
+        const int64_t nwin = (a.nb + HB_LC_WIN - 1) / HB_LC_WIN;
+        for (int64_t wi = 0; wi < nwin; wi++) {
+            // forward: windows from the front; backward: from the back, aligned to the same cuts
+            const int64_t w0 = (dir == 0 ? wi : nwin - 1 - wi) * HB_LC_WIN;
+            const int64_t n = a.nb - w0 < HB_LC_WIN ? a.nb - w0 : HB_LC_WIN;
+            const int64_t o = (int64_t)c * a.nb + w0;
+            lc_stage(s_f, (const double *)a.ffm + o * S * S, n * S * S, lane);
+            lc_stage(s_e, (const int32_t *)a.ffe + o * S, n * S, lane);
+            __syncwarp();
+            if (lane == 0) {
+                LcArgs w = a;
+                w.win_b0 = w0;
+                w.wff = s_f;
+                w.wfe = s_e;
+                if (dir == 0)
+                    lc_fb_fwd_range<S>(w, c, w0, w0 + n, al);
+                else
+                    lc_fb_bwd_range<S>(w, c, w0, w0 + n, bt);
+            }
+            __syncwarp();
+        }
+    }
+}
+template <int S>
+__global__ void __launch_bounds__(32) lc_fb_p3_kernel(const __grid_constant__ LcArgs a)
+{
+    if (threadIdx.x == 0) lc_fb_ll<S>(a, blockIdx.x);
+}
+template <int S>
+static cudaError_t launch_longchain_fb_t(const LcArgs &a, cudaStream_t st)
+{
+    const int64_t nw = (int64_t)a.K * a.nb;
+    const unsigned gp = (unsigned)((nw + LC_TPB - 1) / LC_TPB);
+    if (nw > 0) {
+        lc_fb_par_kernel<S, 0><<<gp, LC_TPB, 0, st>>>(a);
+        lc_fb_p1_kernel<S><<<a.K, 32, 0, st>>>(a);
+        lc_fb_par_kernel<S, 2><<<gp, LC_TPB, 0, st>>>(a);
+    }
+    lc_fb_p3_kernel<S><<<a.K, 32, 0, st>>>(a);
+    return cudaGetLastError();
+}
+cudaError_t launch_longchain_fb(const LcArgs &a, cudaStream_t st)
+{
+    return a.S == 2 ? launch_longchain_fb_t<2>(a, st) : launch_longchain_fb_t<3>(a, st);
+}
+
 cudaError_t launch_longchain(const LcArgs &a, cudaStream_t st)
 {
     return a.S == 2 ? launch_longchain_t<2>(a, st) : launch_longchain_t<3>(a, st);

@@ -13,6 +13,7 @@ struct Binom2Args;
 struct LcArgs;
 
 cudaError_t launch_longchain(const LcArgs &a, cudaStream_t st);
+cudaError_t launch_longchain_fb(const LcArgs &a, cudaStream_t st);
 cudaError_t launch_binom2_emit_cm(const Binom2Args &a, const int32_t *x, const int32_t *n, int64_t count,
                                   double2 *out, cudaStream_t st);
 cudaError_t launch_norm3_emit_cm(const Norm3Const &c, const double *x, int64_t G, int32_t K, const double *sd,

@@ -74,6 +74,17 @@ struct LcArgs {
     const int64_t *wi;
     const int32_t *wbe;
     const uint8_t *wio;
+    // forward-backward posteriors of the same chains (lc_fb_*): linear-domain block products
+    double pi[9], dl[3]; // Pi, delta
+    double *ffm;         // [K][nb][S*S] row j0: e_j0 (prod_t Pi diag(b_t)), each row scaled by 2^-ffe
+    int32_t *ffe;        // [K][nb][S]
+    double *fae;         // [K][nb][S]  filter at the position before the block (sums to 1)
+    double *fbe;         // [K][nb][S]  beta at the block's last position (sums to 1)
+    double *fls;         // [K][nb]     sum over the block of log c_t + max_k logb_t
+    double *gamma;       // [K][T][S]   out
+    double *ll;          // [K]         out (or NULL)
+    const double *wff;
+    const int32_t *wfe;
 };
 #define HB_LC_CS 8
 #define HB_LC_NOFAIL 0x7fffffff
@@ -549,6 +560,293 @@ HB_HD void lc_write_y(const LcArgs &a, int32_t c, int64_t b)
             }
     }
     if (b == 0) y[0] = (int32_t)st + 1;
+}
+
+
+// =====================================================================================================
+// Forward-backward posteriors for the same few long chains (semantics of HiddenMarkov::forwardback,
+// gamma_t = exp(logalpha_t + logbeta_t - LL); not bit-level: 1e-9, north_star).  Linear domain:
+// alpha_t = (alpha_{t-1} Pi) o b_t, beta_{t-1} = Pi (b_t o beta_t), b_t = exp(logb_t - max_k logb_t).
+// With A_t = Pi diag(b_t) one block product F_b = prod_t A_t serves both sweeps (alpha_exit = alpha_entry F_b,
+// beta_entry = F_b beta_exit); it is associative up to rounding, all terms non-negative (no cancellation).
+//   F0 parallel    F_b, one row per entry state, each row with its own binary exponent      lc_fb_mat
+//   F1 sequential  filter before every block (forward), beta at every block end (backward)  lc_fb_fwd/bwd
+//   F2 parallel    inside the block: filter forward (parked in gamma), beta backward, gamma  lc_fb_block
+//   F3 sequential  LL = sum of the blocks' log normalisers                                   lc_fb_ll
+template <int S>
+HB_HD void lc_emis(const double *l, double *b, double &m)
+{
+    m = l[0];
+#pragma unroll
+    for (int k = 1; k < S; k++) m = l[k] > m ? l[k] : m;
+#pragma unroll
+    for (int k = 0; k < S; k++) b[k] = m == -INFINITY ? 0.0 : exp(l[k] - m);
+}
+// w <- (w Pi) o b
+template <int S>
+HB_HD void lc_fwd_vec(const double *pi, double *w, const double *b)
+{
+    double n[S];
+#pragma unroll
+    for (int k = 0; k < S; k++) {
+        double acc = w[0] * pi[k];
+#pragma unroll
+        for (int j = 1; j < S; j++) acc += w[j] * pi[j * S + k];
+        n[k] = acc * b[k];
+    }
+#pragma unroll
+    for (int k = 0; k < S; k++) w[k] = n[k];
+}
+// w <- Pi (b o w)
+template <int S>
+HB_HD void lc_bwd_vec(const double *pi, double *w, const double *b)
+{
+    double u[S], n[S];
+#pragma unroll
+    for (int k = 0; k < S; k++) u[k] = b[k] * w[k];
+#pragma unroll
+    for (int j = 0; j < S; j++) {
+        double acc = pi[j * S] * u[0];
+#pragma unroll
+        for (int k = 1; k < S; k++) acc += pi[j * S + k] * u[k];
+        n[j] = acc;
+    }
+#pragma unroll
+    for (int k = 0; k < S; k++) w[k] = n[k];
+}
+template <int S>
+HB_HD double lc_normalise(double *w)
+{
+    double s = w[0];
+#pragma unroll
+    for (int k = 1; k < S; k++) s += w[k];
+    const double r = 1.0 / s;
+#pragma unroll
+    for (int k = 0; k < S; k++) w[k] *= r;
+    return s;
+}
+// power-of-two rescale of a non-negative vector to max ~ 1; returns the exponent taken out
+template <int S>
+HB_HD int32_t lc_rescale(double *w)
+{
+    double m = w[0];
+#pragma unroll
+    for (int k = 1; k < S; k++) m = w[k] > m ? w[k] : m;
+    if (!(m > 0.0) || !(m < INFINITY)) return 0;
+    const int32_t e = ((hi32(m) >> 20) & 0x7ff) - 1023;
+    if (e == 0 || e < -1000) return 0; // already ~1, or denormal (leave)
+    const double f = pow2i(-e);
+#pragma unroll
+    for (int k = 0; k < S; k++) w[k] *= f;
+    return e;
+}
+
+// ---- F0
+template <int S>
+HB_HD void lc_fb_mat(const LcArgs &a, int32_t c, int64_t b)
+{
+    constexpr int C = LcChunk<S>::C;
+    const int64_t t0 = lc_t0(a, b), n = lc_t1(a, b) - t0;
+    const double *HB_RESTRICT l = a.lb + ((int64_t)c * a.T + t0) * S;
+    double w[S][S];
+    int32_t e[S];
+#pragma unroll
+    for (int j = 0; j < S; j++) {
+        e[j] = 0;
+#pragma unroll
+        for (int k = 0; k < S; k++) w[j][k] = j == k ? 1.0 : 0.0;
+    }
+    LcChunk<S> cur, nxt;
+    lc_fetch<S>(cur, l, n);
+    for (int64_t i0 = 0; i0 < n; i0 += C) {
+        lc_fetch<S>(nxt, l + (i0 + C) * S, n - i0 - C);
+#pragma unroll
+        for (int j = 0; j < C; j++)
+            if (i0 + j < n) {
+                double bv[S], m;
+                lc_emis<S>(cur.v + j * S, bv, m);
+#pragma unroll
+                for (int j0 = 0; j0 < S; j0++) lc_fwd_vec<S>(a.pi, w[j0], bv);
+            }
+#pragma unroll
+        for (int j0 = 0; j0 < S; j0++) e[j0] += lc_rescale<S>(w[j0]);
+        cur = nxt;
+    }
+    const int64_t ib = (int64_t)c * a.nb + b;
+#pragma unroll
+    for (int j = 0; j < S; j++) {
+        a.ffe[ib * S + j] = e[j];
+#pragma unroll
+        for (int k = 0; k < S; k++) a.ffm[ib * S * S + j * S + k] = w[j][k];
+    }
+}
+template <int S> HB_HD const double *lc_ff(const LcArgs &a, int32_t c, int64_t b)
+{
+    return a.wff ? a.wff + (b - a.win_b0) * S * S : a.ffm + ((int64_t)c * a.nb + b) * S * S;
+}
+template <int S> HB_HD const int32_t *lc_fe(const LcArgs &a, int32_t c, int64_t b)
+{
+    return a.wfe ? a.wfe + (b - a.win_b0) * S : a.ffe + ((int64_t)c * a.nb + b) * S;
+}
+HB_HD double lc_pow2_clamped(int32_t k) { return k < -1020 ? 0.0 : pow2i(k > 1000 ? 1000 : k); }
+
+// ---- F1 forward: filter at the position before each block of [bb, be_); `al` carried (sums to 1)
+template <int S>
+HB_HD void lc_fb_begin(const LcArgs &a, int32_t c, double *al)
+{
+    const double *l0 = a.lb + (int64_t)c * a.T * S;
+    double bv[S], m;
+    lc_emis<S>(l0, bv, m);
+#pragma unroll
+    for (int k = 0; k < S; k++) al[k] = a.dl[k] * bv[k];
+    lc_normalise<S>(al);
+}
+template <int S>
+HB_HD void lc_fb_fwd_range(const LcArgs &a, int32_t c, int64_t bb, int64_t be_, double *al)
+{
+    for (int64_t b = bb; b < be_; b++) {
+        double *o = a.fae + ((int64_t)c * a.nb + b) * S;
+#pragma unroll
+        for (int k = 0; k < S; k++) o[k] = al[k];
+        const double *f = lc_ff<S>(a, c, b);
+        const int32_t *e = lc_fe<S>(a, c, b);
+        int32_t em = -100000;
+#pragma unroll
+        for (int j = 0; j < S; j++) em = (al[j] > 0.0 && e[j] > em) ? e[j] : em;
+        double n[S];
+#pragma unroll
+        for (int k = 0; k < S; k++) n[k] = 0.0;
+#pragma unroll
+        for (int j = 0; j < S; j++) {
+            const double wgt = al[j] > 0.0 ? al[j] * lc_pow2_clamped(e[j] - em) : 0.0;
+#pragma unroll
+            for (int k = 0; k < S; k++) n[k] += wgt * f[j * S + k];
+        }
+        lc_normalise<S>(n);
+#pragma unroll
+        for (int k = 0; k < S; k++) al[k] = n[k];
+    }
+}
+// ---- F1 backward: beta at the last position of each block, blocks be_-1 down to bb; `be` carried
+template <int S>
+HB_HD void lc_fb_bwd_range(const LcArgs &a, int32_t c, int64_t bb, int64_t be_, double *bt)
+{
+    for (int64_t b = be_ - 1; b >= bb; b--) {
+        double *o = a.fbe + ((int64_t)c * a.nb + b) * S;
+#pragma unroll
+        for (int k = 0; k < S; k++) o[k] = bt[k];
+        const double *f = lc_ff<S>(a, c, b);
+        const int32_t *e = lc_fe<S>(a, c, b);
+        double n[S];
+        int32_t em = -100000;
+#pragma unroll
+        for (int j = 0; j < S; j++) {
+            double acc = 0.0;
+#pragma unroll
+            for (int k = 0; k < S; k++) acc += f[j * S + k] * bt[k];
+            n[j] = acc;
+            em = (acc > 0.0 && e[j] > em) ? e[j] : em;
+        }
+#pragma unroll
+        for (int j = 0; j < S; j++) n[j] = n[j] > 0.0 ? n[j] * lc_pow2_clamped(e[j] - em) : 0.0;
+        lc_normalise<S>(n);
+#pragma unroll
+        for (int k = 0; k < S; k++) bt[k] = n[k];
+    }
+}
+
+// ---- F2: posteriors inside a block
+template <int S>
+HB_HD void lc_fb_block(const LcArgs &a, int32_t c, int64_t b)
+{
+    constexpr int C = LcChunk<S>::C;
+    const int64_t t0 = lc_t0(a, b), n = lc_t1(a, b) - t0;
+    const int64_t ib = (int64_t)c * a.nb + b;
+    const double *HB_RESTRICT l = a.lb + ((int64_t)c * a.T + t0) * S;
+    double *HB_RESTRICT g = a.gamma + ((int64_t)c * a.T + t0) * S;
+    double al[S], bt[S], ls = 0.0;
+#pragma unroll
+    for (int k = 0; k < S; k++) al[k] = a.fae[ib * S + k];
+    LcChunk<S> cur, nxt;
+    lc_fetch<S>(cur, l, n);
+    for (int64_t i0 = 0; i0 < n; i0 += C) { // filter forward, parked in gamma
+        lc_fetch<S>(nxt, l + (i0 + C) * S, n - i0 - C);
+#pragma unroll
+        for (int j = 0; j < C; j++)
+            if (i0 + j < n) {
+                double bv[S], m;
+                lc_emis<S>(cur.v + j * S, bv, m);
+                lc_fwd_vec<S>(a.pi, al, bv);
+                ls += log(lc_normalise<S>(al)) + m;
+#pragma unroll
+                for (int k = 0; k < S; k++) g[(i0 + j) * S + k] = al[k];
+            }
+        cur = nxt;
+    }
+    a.fls[ib] = ls;
+#pragma unroll
+    for (int k = 0; k < S; k++) bt[k] = a.fbe[ib * S + k];
+    // beta backward, gamma = alpha o beta / sum; emissions and parked filter fetched a chunk ahead
+    constexpr int CB = S == 2 ? 8 : 4;
+    double ec[CB * S], en[CB * S], gc[CB * S], gn[CB * S];
+    int64_t i0 = n > 0 ? (n - 1) / CB * CB : 0;
+#pragma unroll
+    for (int i = 0; i < CB * S; i++) {
+        ec[i] = i < (n - i0) * S ? l[i0 * S + i] : 0.0;
+        gc[i] = i < (n - i0) * S ? g[i0 * S + i] : 0.0;
+    }
+    for (; i0 >= 0 && n > 0; i0 -= CB) {
+#pragma unroll
+        for (int i = 0; i < CB * S; i++) {
+            en[i] = i0 >= CB ? l[(i0 - CB) * S + i] : 0.0;
+            gn[i] = i0 >= CB ? g[(i0 - CB) * S + i] : 0.0;
+        }
+#pragma unroll
+        for (int j = CB - 1; j >= 0; j--)
+            if (i0 + j < n) {
+                double gv[S], bv[S], m;
+#pragma unroll
+                for (int k = 0; k < S; k++) gv[k] = gc[j * S + k] * bt[k];
+                lc_normalise<S>(gv);
+#pragma unroll
+                for (int k = 0; k < S; k++) g[(i0 + j) * S + k] = gv[k];
+                lc_emis<S>(ec + j * S, bv, m);
+                lc_bwd_vec<S>(a.pi, bt, bv);
+                lc_normalise<S>(bt);
+            }
+#pragma unroll
+        for (int i = 0; i < CB * S; i++) {
+            ec[i] = en[i];
+            gc[i] = gn[i];
+        }
+    }
+    if (b == 0) { // position 0 belongs to no block: bt is now beta_0
+        double gv[S];
+        lc_fb_begin<S>(a, c, gv);
+#pragma unroll
+        for (int k = 0; k < S; k++) gv[k] *= bt[k];
+        lc_normalise<S>(gv);
+#pragma unroll
+        for (int k = 0; k < S; k++) a.gamma[(int64_t)c * a.T * S + k] = gv[k];
+    }
+}
+
+// ---- F3: log-likelihood; chains of one position
+template <int S>
+HB_HD void lc_fb_ll(const LcArgs &a, int32_t c)
+{
+    const double *l0 = a.lb + (int64_t)c * a.T * S;
+    double bv[S], m, al[S];
+    lc_emis<S>(l0, bv, m);
+#pragma unroll
+    for (int k = 0; k < S; k++) al[k] = a.dl[k] * bv[k];
+    double ll = log(lc_normalise<S>(al)) + m;
+    if (a.nb == 0) {
+#pragma unroll
+        for (int k = 0; k < S; k++) a.gamma[(int64_t)c * a.T * S + k] = al[k];
+    }
+    for (int64_t b = 0; b < a.nb; b++) ll += a.fls[(int64_t)c * a.nb + b];
+    if (a.ll) a.ll[c] = ll;
 }
 
 // Block length: the sequential passes cost ~ T / L, the parallel ones ~ L.

@@ -458,6 +458,23 @@ def viterbi_long_logb_dev(logb, Pi, delta, block_len=0):
     return y
 
 
+def forwardback_long_logb_dev(logb, Pi, delta, block_len=0, ll=True):
+    """State posteriors (HiddenMarkov::forwardback semantics) of a few LONG chains, parallel along the
+    chain.  logb: CUDA float64 [K, T, S]; returns (gamma [K, T, S], ll [K] or None) on the device."""
+    import torch
+    if logb.dtype != torch.float64 or not logb.is_cuda or logb.dim() != 3 or not logb.is_contiguous():
+        raise ValueError("logb must be a contiguous CUDA float64 tensor [K, T, S]")
+    K, T, S = logb.shape
+    Pi = _f64(Pi).reshape(S * S)
+    delta = _f64(delta).reshape(S)
+    gamma = torch.empty((K, T, S), dtype=torch.float64, device=logb.device)
+    llv = torch.empty(K, dtype=torch.float64, device=logb.device) if ll else None
+    _lib.check(_lib.load().hb_forwardback_long_logb_dev(logb.data_ptr(), S, T, K, _vp(Pi), _vp(delta),
+                                                        int(block_len), gamma.data_ptr(),
+                                                        llv.data_ptr() if ll else None, _stream()))
+    return gamma, llv
+
+
 def longchain_stats() -> dict:
     """Counters of the last long-chain launch; waits for the current stream."""
     out = (C.c_int64 * 5)()

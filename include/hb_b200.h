@@ -332,6 +332,15 @@ int hb_retest_allele_model_host(const int32_t *r_rows, const int32_t *n_rows, in
  * No synchronisation; hb_status_dev reports HiddenMarkov's underflow error. */
 int hb_viterbi_long_logb_dev(const double *logb, int32_t S, int64_t T, int32_t K, const double *Pi,
                              const double *delta, int32_t block_len, int32_t *y, void *stream);
+/* State posteriors of the same chains, parallel along the chain: gamma_t(k) = P(state_t = k | all x), the
+ * semantics of HiddenMarkov::forwardback followed by exp(logalpha + logbeta - LL) (the reference
+ * never runs it on the pooled chains — north_star capability).  Linear domain with per-position
+ * normalisation on emissions exp(logb_t - max_k logb_t), one S x S product per block of positions serving
+ * both sweeps; agreement with the oracle 1e-9 (the oracle's own log-space rounding grows with T).
+ * gamma: device [K][T][S]; ll: device [K] log-likelihoods or NULL.  No synchronisation. */
+int hb_forwardback_long_logb_dev(const double *logb, int32_t S, int64_t T, int32_t K, const double *Pi,
+                                 const double *delta, int32_t block_len, double *gamma, double *ll,
+                                 void *stream);
 /* Counters of the last long-chain launch (waits for `stream`): out[0] chains, out[1] blocks per chain,
  * out[2] chains finished on the sequential path, out[3] repair rounds used (max over chains), out[4]
  * blocks the sequential walkers ran literally (entry outside the predicted binade, first blocks). */

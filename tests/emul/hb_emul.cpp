@@ -483,3 +483,53 @@ extern "C" int emul_longchain(int S, int64_t T, int K, const double *lb, const d
     if (S == 3) return emul_longchain_t<3>(T, K, lb, Pi, delta, L, y, stats);
     return -1;
 }
+
+// Posteriors of long chains (lc_fb_*), phases walked serially.  gamma [K][T][S], ll [K].
+template <int S>
+static void emul_longchain_fb_t(int64_t T, int K, const double *lb, const double *Pi, const double *delta,
+                                int L, double *gamma, double *ll)
+{
+    LcArgs a;
+    memset(&a, 0, sizeof a);
+    a.lb = lb; a.T = T; a.K = K; a.S = S; a.L = L > 0 ? L : lc_block_len(T);
+    a.nb = T > 1 ? (T - 1 + a.L - 1) / a.L : 0;
+    for (int i = 0; i < S * S; i++) a.pi[i] = Pi[i];
+    for (int i = 0; i < S; i++) a.dl[i] = delta[i];
+    const size_t nkb = (size_t)K * a.nb + 1;
+    std::vector<double> ffm(nkb * S * S), fae(nkb * S), fbe(nkb * S), fls(nkb);
+    std::vector<int32_t> ffe(nkb * S);
+    a.ffm = ffm.data(); a.ffe = ffe.data(); a.fae = fae.data(); a.fbe = fbe.data(); a.fls = fls.data();
+    a.gamma = gamma; a.ll = ll;
+    for (int c = 0; c < K; c++)
+        for (int64_t b = 0; b < a.nb; b++) lc_fb_mat<S>(a, c, b);
+    for (int c = 0; c < K && a.nb; c++) {
+        double al[S], bt[S];
+        lc_fb_begin<S>(a, c, al);
+        for (int64_t w0 = 0; w0 < a.nb; w0 += HB_LC_WIN) {
+            const int64_t n = std::min<int64_t>(HB_LC_WIN, a.nb - w0);
+            const size_t o = (size_t)c * a.nb + w0;
+            std::vector<double> wf(ffm.begin() + o * S * S, ffm.begin() + (o + n) * S * S);
+            std::vector<int32_t> we(ffe.begin() + o * S, ffe.begin() + (o + n) * S);
+            LcArgs w = a;
+            w.win_b0 = w0; w.wff = wf.data(); w.wfe = we.data();
+            lc_fb_fwd_range<S>(w, c, w0, w0 + n, al);
+        }
+        for (int k = 0; k < S; k++) bt[k] = 1.0 / S;
+        for (int64_t w1 = a.nb; w1 > 0; w1 -= HB_LC_WIN) {
+            const int64_t w0 = std::max<int64_t>(0, w1 - HB_LC_WIN);
+            lc_fb_bwd_range<S>(a, c, w0, w1, bt);
+        }
+    }
+    for (int c = 0; c < K; c++)
+        for (int64_t b = 0; b < a.nb; b++) lc_fb_block<S>(a, c, b);
+    for (int c = 0; c < K; c++) lc_fb_ll<S>(a, c);
+}
+
+extern "C" int emul_longchain_fb(int S, int64_t T, int K, const double *lb, const double *Pi,
+                                 const double *delta, int L, double *gamma, double *ll)
+{
+    if (S == 2) emul_longchain_fb_t<2>(T, K, lb, Pi, delta, L, gamma, ll);
+    else if (S == 3) emul_longchain_fb_t<3>(T, K, lb, Pi, delta, L, gamma, ll);
+    else return -1;
+    return 0;
+}

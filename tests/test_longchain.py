@@ -174,6 +174,74 @@ def test_random_chains(emul, oracle, S, T, K, L, t, scale, grid, seed):
     assert rc == 0 and np.array_equal(y, yr)
 
 
+# ------------------------------------------------------------------------------ posteriors (lc_fb_*)
+def ref_posteriors(oracle, lb, Pi, delta):
+    """HiddenMarkov::forwardback + exp(logalpha + logbeta - LL) on the linear densities exp(logb)."""
+    O = oracle.lib()
+    K, T, S = lb.shape
+    g, ll = np.zeros((K, T, S)), np.zeros(K)
+    for c in range(K):
+        prob, gc, L = np.ascontiguousarray(np.exp(lb[c])), np.zeros((T, S)), C.c_double(0)
+        assert O.hbo_forwardback_prob(S, C.c_int64(T), ptr(prob), ptr(Pi), ptr(delta), None, None, ptr(gc),
+                                      C.byref(L)) == 0
+        g[c], ll[c] = gc, L.value
+    return g, ll
+
+
+def longdouble_posteriors(lb, Pi, delta):
+    """Scaled forward-backward in 80-bit arithmetic (independent of the oracle's log-space roundings)."""
+    T, S = lb.shape
+    ld = np.longdouble
+    P, b = Pi.astype(ld), np.exp((lb - lb.max(1, keepdims=True)).astype(ld))
+    al = np.zeros((T, S), ld)
+    a = delta.astype(ld) * b[0]
+    al[0] = a / a.sum()
+    for t in range(1, T):
+        a = (al[t - 1] @ P) * b[t]
+        al[t] = a / a.sum()
+    g = np.zeros((T, S), ld)
+    bt = np.ones(S, ld)
+    for t in range(T - 1, -1, -1):
+        v = al[t] * bt
+        g[t] = v / v.sum()
+        bt = P @ (b[t] * bt)
+        bt = bt / bt.sum()
+    return g.astype(np.float64)
+
+
+def run_emul_fb(emul, lb, Pi, delta, L=0):
+    K, T, S = lb.shape
+    g, ll = np.zeros((K, T, S)), np.zeros(K)
+    emul.emul_longchain_fb.restype = C.c_int
+    assert emul.emul_longchain_fb(S, C.c_int64(T), K, ptr(lb), ptr(np.ascontiguousarray(Pi, dtype=np.float64)),
+                                  ptr(np.ascontiguousarray(delta, dtype=np.float64)), L, ptr(g), ptr(ll)) == 0
+    return g, ll
+
+
+@pytest.mark.parametrize("S,T,K,L", [(2, 5000, 2, 0), (3, 5000, 2, 0), (3, 1, 2, 0), (2, 2, 2, 0), (3, 700, 2, 16),
+                                     (2, 129, 1, 128), (2, 1000, 2, 1), (3, 6082, 3, 0)])
+def test_posteriors_match_the_oracle(emul, oracle, S, T, K, L):
+    """north_star: forward-backward posteriors within 1e-9 absolute in fp64."""
+    rng = np.random.default_rng(S * 31 + T)
+    lb = binom_lb(rng, K, T, depth=60) if S == 2 else norm_lb(rng, K, T, sd=1.0)
+    Pi, delta = sym_Pi(S, 1e-6), np.array([0.3, 0.7] if S == 2 else [0., 1., 0.])
+    g, ll = run_emul_fb(emul, lb, Pi, delta, L)
+    gr, llr = ref_posteriors(oracle, lb, Pi, delta)
+    assert np.abs(g - gr).max() < 1e-9
+    assert np.abs(g.sum(-1) - 1).max() < 1e-14
+    assert np.allclose(ll, llr, rtol=1e-12, atol=1e-9)
+
+
+def test_posteriors_of_a_long_deep_chain(emul):
+    """40 000 positions with pooled-scale evidence (hundreds of nats per position: exp(logb) underflows,
+    the reference's linear-density forwardback returns NaN there) against 80-bit arithmetic."""
+    rng = np.random.default_rng(2)
+    lb = binom_lb(rng, 1, 40000)
+    Pi, delta = sym_Pi(2, 1e-6), np.array([0., 1.])
+    g, _ = run_emul_fb(emul, lb, Pi, delta)
+    assert np.abs(g[0] - longdouble_posteriors(lb[0], Pi, delta)).max() < 1e-10
+
+
 # ------------------------------------------------------------------------------------------------ GPU
 @pytest.mark.gpu
 @pytest.mark.parametrize("S,T,K,L", [(2, 200000, 6, 0), (3, 20000, 15, 0), (2, 4550, 6, 0), (3, 6082, 15, 16),
@@ -237,3 +305,35 @@ def test_pooled_rounds_same_states_in_every_mode(golden_gexp, golden_allele):
         hmm.set_longchain_mode(0)
     for mode in (1, 2):
         assert np.array_equal(out[0][0], out[mode][0]) and np.array_equal(out[0][1], out[mode][1])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("S,T,K,L", [(2, 6000, 6, 0), (3, 6082, 15, 0), (3, 1, 2, 0), (2, 3000, 3, 16)])
+def test_gpu_posteriors_match_the_oracle(oracle, S, T, K, L):
+    import torch
+    from honeybadger_b200 import hmm
+    rng = np.random.default_rng(S * 5 + T)
+    lb = binom_lb(rng, K, T, depth=60) if S == 2 else norm_lb(rng, K, T, sd=1.0)
+    Pi, delta = sym_Pi(S, 1e-6), np.array([0.3, 0.7] if S == 2 else [0., 1., 0.])
+    g, ll = hmm.forwardback_long_logb_dev(torch.from_numpy(lb).cuda(), Pi, delta, L)
+    gr, llr = ref_posteriors(oracle, lb, Pi, delta)
+    assert np.abs(g.cpu().numpy() - gr).max() < 1e-9
+    assert np.allclose(ll.cpu().numpy(), llr, rtol=1e-12, atol=1e-9)
+
+
+@pytest.mark.gpu
+def test_gpu_posteriors_long_deep_chains():
+    import torch
+    from honeybadger_b200 import hmm
+    rng = np.random.default_rng(4)
+    lb = binom_lb(rng, 6, 200000)
+    Pi, delta = sym_Pi(2, 1e-6), np.array([0., 1.])
+    g, ll = hmm.forwardback_long_logb_dev(torch.from_numpy(lb).cuda(), Pi, delta)
+    g = g.cpu().numpy()
+    assert np.isfinite(g).all() and np.abs(g.sum(-1) - 1).max() < 1e-14 and np.isfinite(ll.cpu().numpy()).all()
+    ref = longdouble_posteriors(lb[2], Pi, delta)
+    assert np.abs(g[2] - ref).max() < 1e-10
+    # posteriors and Viterbi states agree where the posterior is decisive
+    y = hmm.viterbi_long_logb_dev(torch.from_numpy(lb).cuda(), Pi, delta).cpu().numpy()
+    sure = g.max(-1) > 0.999
+    assert (g.argmax(-1)[sure] + 1 == y[sure]).mean() > 0.999
