@@ -402,6 +402,12 @@ def run_allele_extra(cells, rank, dev, hmm, world, dist, steps=5):
     positions = wl["positions"]
     d = device_inputs("allele", cells, positions, seed=300 + rank, dev=dev)
     Pi2 = hmm.sym_Pi(2, 1e-6)
+    pooled = None
+    if world == 1:
+        try:
+            pooled = run_pooled_round(d, cells, hmm)
+        except Exception as exc:
+            pooled = {"error": repr(exc)[:200]}
     xn = hmm.pack_counts(hmm.tile_rows(d["r"]), hmm.tile_rows(d["n"]))
     del d["r"], d["n"]
     torch.cuda.empty_cache()
@@ -429,7 +435,41 @@ def run_allele_extra(cells, rank, dev, hmm, world, dist, steps=5):
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                          "traffic": ncu_traffic("allele"), "algorithmic_bytes_per_step": wl["bytes_per_step"],
                          "kernel": "binom2_fast_kernel<VIT,FB>"},
-            "general_kernel_rerun": hmm.binom2_general_rerun()}
+            "general_kernel_rerun": hmm.binom2_general_rerun(), "pooled_round": pooled}
+
+
+def run_pooled_round(d, cells, hmm):
+    """The reference's own call shape on the same resident matrices: one `lapply(heights, ...)` round of
+    calcAlleleCnvBoundaries (R/HoneyBADGER.R:1395-1417) — pooled counts of K = 6 cell sets, K binomial chains
+    of all 200k SNPs — through hb_allele_pooled_viterbi_dev, host results included.  The chains run parallel
+    along the gene axis (csrc/hb_longchain.cuh); `ms_thread_per_chain` is the same round with one thread per
+    chain (hb_set_longchain_mode(1)), same states."""
+    import time
+    import torch
+    from honeybadger_b200 import honeybadger as hb
+    idx = np.arange(cells)
+    member = np.stack([np.ones(cells, bool)] + [idx % 2 == k for k in range(2)] + [idx % 3 == k for k in range(3)])
+    res = {}
+    ys = {}
+    for mode, key in ((0, "ms"), (1, "ms_thread_per_chain")):
+        hmm.set_longchain_mode(mode)
+        try:
+            ts = []
+            for _ in range(4):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                y, _, _ = hb.allele_round_dev(d["r"], d["n"], member, 0.1, 0.45, 1e-6)
+                ts.append((time.perf_counter() - t0) * 1e3)
+            res[key] = float(np.median(ts[1:]))
+            ys[mode] = y
+            if mode == 0:
+                res["longchain"] = hmm.longchain_stats()
+        finally:
+            hmm.set_longchain_mode(0)
+    res.update({"chains": int(member.shape[0]), "positions": int(d["r"].shape[0]), "cells": int(cells),
+                "same_states": bool(np.array_equal(ys[0], ys[1])),
+                "api": "hb_allele_pooled_viterbi_dev (pooled counts + emissions + K long chains + download)"})
+    return res
 
 
 def run_e2e(kind, wl, d, args, world, dev, hmm, dist):
