@@ -451,3 +451,19 @@ def test_refclass_allele_run_reproduces_the_vignette_regions(golden_inputs):
     for c in ("chr10", "chr13", "chr14"):
         assert got[c] == tuple(want[c])
     assert got["chr19"][0] == want["chr19"][0] and abs(got["chr19"][1] - want["chr19"][1]) < 100_000
+
+
+def test_large_count_uploads_convert_on_the_device():
+    """_to_dev_i32 on matrices past the slab threshold: C / Fortran order (a DataFrame's .values), integer and
+    double inputs, half-even rounding — identical to the small-matrix host path."""
+    from honeybadger_b200 import honeybadger as hb
+    rng = np.random.default_rng(8)
+    a = rng.integers(0, 40, size=(4200, 4100)).astype(np.int16)
+    want = a.astype(np.int32)
+    for arr in (a, np.asfortranarray(a), a.astype(np.float64), np.asfortranarray(a.astype(np.float64))):
+        assert arr.size >= 1 << 24
+        assert np.array_equal(hb._to_dev_i32(arr).cpu().numpy(), want)
+    f = a.astype(np.float64) + 0.5                       # ties: R's rint / numpy rint round half to even
+    assert np.array_equal(hb._to_dev_i32(np.asfortranarray(f)).cpu().numpy(), np.rint(f).astype(np.int32))
+    df = pd.DataFrame(a)
+    assert np.array_equal(hb._to_dev_i32(df.values).cpu().numpy(), want)
