@@ -604,6 +604,12 @@ int binom2_longchain(Workspace *ws, const int32_t *x, const int32_t *n, int64_t 
     return longchain_run(ws, 2, ws->lc_lb.as<double>(), G, K, Pi, delta, y, st, false);
 }
 
+// Host calls shaped like the reference's own: a few chains, each long, one segment, Viterbi only.
+bool long_chain_shape(int64_t T, int64_t B, int32_t nseg, int32_t flags)
+{
+    return g_longchain_mode != 1 && nseg == 1 && B <= 32 && T >= 1024 && flags == HB_WANT_VITERBI;
+}
+
 int64_t pad_ld(int64_t B) { return (B + 15) / 16 * 16; } // 128-byte rows for fp64
 
 // membership -> group sizes (host) ; returns HB_ERR_ARG on empty groups
@@ -947,6 +953,32 @@ int hb_hmm_norm_host(const double *x, int64_t T, int64_t B, const int64_t *seg_o
     bool vit, fb;
     HBTRY(check_flags(flags, y, gamma, ll, &vit, &fb));
     const bool want_g = (flags & HB_WANT_GAMMA) != 0, want_ll = (flags & HB_WANT_LL) != 0;
+    if (long_chain_shape(T, B, nseg, flags)) {
+        // the drop-in seam itself: Viterbi(dthmm(x, ...)) on one (or a few) long pooled vectors.  R's
+        // column-major [T x B] is already chain-major: emissions in parallel, chains along the gene axis.
+        hb::Norm3Const nc;
+        bool sym;
+        memset(&nc, 0, sizeof nc);
+        HBTRY(fill_norm3_const(nc, mean, Pi, delta, &sym));
+        std::vector<double> h_aux(3 * (size_t)B);
+        for (int64_t b = 0; b < B; b++) {
+            h_aux[b] = sd[b];
+            h_aux[B + b] = 1.0 / sd[b];
+            h_aux[2 * B + b] = log(sd[b]);
+        }
+        HBTRY(ws->st_in.ensure((size_t)T * B * sizeof(double)));
+        HBTRY(ws->st_out.ensure((size_t)T * B * sizeof(int32_t)));
+        HBTRY(ws->sdaux.ensure(h_aux.size() * sizeof(double)));
+        HBTRY(ws->lc_lb.ensure((size_t)T * B * 3 * sizeof(double)));
+        CU(cudaMemcpyAsync(ws->st_in.p, x, (size_t)T * B * sizeof(double), cudaMemcpyHostToDevice, 0));
+        CU(cudaMemcpyAsync(ws->sdaux.p, h_aux.data(), h_aux.size() * sizeof(double), cudaMemcpyHostToDevice, 0));
+        const double *aux = ws->sdaux.as<double>();
+        CU(hb::launch_norm3_emit_cm(nc, ws->st_in.as<double>(), T, (int32_t)B, aux, aux + B, aux + 2 * B,
+                                    ws->lc_lb.as<double>(), 0));
+        HBTRY(longchain_run(ws, 3, ws->lc_lb.as<double>(), T, (int32_t)B, Pi, delta, ws->st_out.as<int32_t>(), 0));
+        CU(cudaMemcpyAsync(y, ws->st_out.p, (size_t)T * B * sizeof(int32_t), cudaMemcpyDeviceToHost, 0));
+        return read_status(ws, 0);
+    }
     HBTRY(pipe_init(ws));
     const int64_t Bc = pipe_batch(B, 130.0 * (double)T);
     const int64_t nb = (B + Bc - 1) / Bc;
@@ -1120,6 +1152,18 @@ int hb_hmm_binom_host(const int32_t *x, const int32_t *size, int64_t T, int64_t 
     bool vit, fb;
     HBTRY(check_flags(flags, y, gamma, ll, &vit, &fb));
     const bool want_g = (flags & HB_WANT_GAMMA) != 0, want_ll = (flags & HB_WANT_LL) != 0;
+    if (rho == 0.0 && long_chain_shape(T, B, nseg, flags)) {
+        // Viterbi(dthmm(mafl, ..., "binom", ...)) on one (or a few) pooled count vectors: see hb_hmm_norm_host
+        HBTRY(ws->st_in.ensure((size_t)T * B * sizeof(int32_t)));
+        HBTRY(ws->st_in2.ensure((size_t)T * B * sizeof(int32_t)));
+        HBTRY(ws->st_out.ensure((size_t)T * B * sizeof(int32_t)));
+        CU(cudaMemcpyAsync(ws->st_in.p, x, (size_t)T * B * sizeof(int32_t), cudaMemcpyHostToDevice, 0));
+        CU(cudaMemcpyAsync(ws->st_in2.p, size, (size_t)T * B * sizeof(int32_t), cudaMemcpyHostToDevice, 0));
+        HBTRY(binom2_longchain(ws, ws->st_in.as<int32_t>(), ws->st_in2.as<int32_t>(), T, (int32_t)B, prob, Pi,
+                               delta, ws->st_out.as<int32_t>(), 0));
+        CU(cudaMemcpyAsync(y, ws->st_out.p, (size_t)T * B * sizeof(int32_t), cudaMemcpyDeviceToHost, 0));
+        return read_status(ws, 0);
+    }
     HBTRY(pipe_init(ws));
     const int64_t Bc = pipe_batch(B, 100.0 * (double)T);
     const int64_t nb = (B + Bc - 1) / Bc;

@@ -337,3 +337,52 @@ def test_gpu_posteriors_long_deep_chains():
     y = hmm.viterbi_long_logb_dev(torch.from_numpy(lb).cuda(), Pi, delta).cpu().numpy()
     sure = g.max(-1) > 0.999
     assert (g.argmax(-1)[sure] + 1 == y[sure]).mean() > 0.999
+
+
+@pytest.mark.gpu
+def test_gpu_dropin_seam_uses_the_long_chain_path(oracle, golden_gexp, golden_allele):
+    """Viterbi(dthmm(x, ...)) on ONE pooled vector — the reference's literal call (R/HoneyBADGER.R:1150-1151,
+    :1409-1410) through hb_hmm_*_host — runs along the gene axis; states equal the oracle's and the
+    one-thread-per-chain kernels' (mode 1)."""
+    import time
+    from honeybadger_b200 import hmm
+    g = golden_gexp
+    x, sd, dev = g["pooled_x"], g["pooled_sd"], float(g["dev"])
+    Pi3, d3, mean = sym_Pi(3, 1e-6), np.array([0., 1., 0.]), np.array([-dev, 0.0, dev])
+    O = oracle.lib()
+    for k in (0, 7):
+        y = hmm.hmm_norm_host(x[k], mean, float(sd[k]), Pi3, d3)["y"]
+        assert hmm.longchain_stats()["chains"] == 1
+        yo = np.zeros(x.shape[1], np.int32)
+        assert O.hbo_viterbi_norm(3, C.c_int64(x.shape[1]), ptr(np.ascontiguousarray(x[k])), ptr(mean),
+                                  ptr(np.full(3, float(sd[k]))), ptr(Pi3), ptr(d3), ptr(yo)) == 0
+        assert np.array_equal(y, yo)
+    a = golden_allele
+    Pi2, d2, prob = sym_Pi(2, 1e-6), np.array([0., 1.]), np.array([0.1, 0.45])
+    mafl, sizel = a["mafl"].astype(np.int32), a["sizel"].astype(np.int32)
+    y0 = hmm.hmm_binom_host(mafl[0], sizel[0], prob, Pi2, d2)["y"]
+    yo = np.zeros(mafl.shape[1], np.int32)
+    assert O.hbo_viterbi_binom(2, C.c_int64(mafl.shape[1]), ptr(np.ascontiguousarray(mafl[0])),
+                               ptr(np.ascontiguousarray(sizel[0])), ptr(prob), ptr(Pi2), ptr(d2), ptr(yo)) == 0
+    assert np.array_equal(y0, yo)
+    # a 200 000-SNP pooled vector: same states either way, and the seam is no longer latency-bound
+    rng = np.random.default_rng(21)
+    n = rng.binomial(5000, 0.108, size=200000).astype(np.int32)
+    dele = np.zeros(200000, bool)
+    dele[50000:58000] = True
+    xx = rng.binomial(n, np.where(dele, 0.1, 0.45)).astype(np.int32)
+    res = {}
+    try:
+        for mode in (0, 1):
+            hmm.set_longchain_mode(mode)
+            hmm.hmm_binom_host(xx, n, prob, Pi2, d2)
+            t0 = time.perf_counter()
+            res[mode] = hmm.hmm_binom_host(xx, n, prob, Pi2, d2)["y"]
+            res[mode, "ms"] = (time.perf_counter() - t0) * 1e3
+    finally:
+        hmm.set_longchain_mode(0)
+    assert np.array_equal(res[0], res[1])
+    assert (res[0][52000:57000] == 1).all() and (res[0][:40000] == 2).all()
+    print(f"one 200k-SNP chain through hb_hmm_binom_host: {res[0, 'ms']:.2f} ms along the gene axis, "
+          f"{res[1, 'ms']:.2f} ms one thread")
+    assert res[0, "ms"] < res[1, "ms"]
