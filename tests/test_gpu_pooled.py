@@ -467,3 +467,6 @@ def test_large_count_uploads_convert_on_the_device():
     assert np.array_equal(hb._to_dev_i32(np.asfortranarray(f)).cpu().numpy(), np.rint(f).astype(np.int32))
     df = pd.DataFrame(a)
     assert np.array_equal(hb._to_dev_i32(df.values).cpu().numpy(), want)
+    x = rng.standard_normal((4200, 4100))
+    for arr in (x, np.asfortranarray(x), np.asfortranarray(x.astype(np.float32))):
+        assert np.array_equal(hb._to_dev_f64(arr).cpu().numpy(), arr.astype(np.float64))

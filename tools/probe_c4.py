@@ -23,14 +23,24 @@ for c in range(22):
     chrom[seg[c]:seg[c + 1]] = f"chr{c + 1}"
 pos = np.concatenate([np.arange(seg[c + 1] - seg[c]) * 1000.0 for c in range(22)])
 genes = hb.GRanges(chrom, pos, pos + 500, genes_names)
+torch.zeros(1, device="cuda").sum().item()   # CUDA context + torch lazy init outside the timed region
 t0 = time.perf_counter()
 h = hb.HoneyBADGER("c4")
 h.genes = genes
 h.gexp_norm = pd.DataFrame(x, index=genes_names, columns=[f"c{i}" for i in range(N)])
 h.setGexpDev(dev=dev)
 t1 = time.perf_counter()
-h.calcGexpCnvBoundaries(init=True)
-torch.cuda.synchronize()
+if len(sys.argv) > 3 and sys.argv[3] == "profile":
+    import cProfile, pstats
+    pr = cProfile.Profile()
+    pr.enable()
+    h.calcGexpCnvBoundaries(init=True)
+    torch.cuda.synchronize()
+    pr.disable()
+    pstats.Stats(pr).sort_stats("cumulative").print_stats(30)
+else:
+    h.calcGexpCnvBoundaries(init=True)
+    torch.cuda.synchronize()
 t2 = time.perf_counter()
 print(f"N={N} G={G}: setup {t1-t0:.1f} s, calcGexpCnvBoundaries(init=TRUE) {t2-t1:.1f} s, "
       f"{len(h.bound_genes_final)} regions recorded")
