@@ -131,26 +131,29 @@ def cut_merges(merge_a, merge_b, height, N, ks):
     children precede parents): the N - k lowest merges are applied with union-find; clusters are
     numbered by first appearance in cell order, as cutree does."""
     order = np.argsort(np.asarray(height), kind="stable")
-    a, b = np.asarray(merge_a)[order], np.asarray(merge_b)[order]
-    out = []
-    for k in ks:
-        parent = np.arange(N)
+    a, b = np.asarray(merge_a)[order].tolist(), np.asarray(merge_b)[order].tolist()
+    parent = list(range(N))
 
-        def find(i):
-            while parent[i] != i:
-                parent[i] = parent[parent[i]]
-                i = parent[i]
-            return i
+    def find(i):
+        while parent[i] != i:
+            parent[i] = parent[parent[i]]
+            i = parent[i]
+        return i
 
-        for m in range(max(0, N - int(k))):
-            ra, rb = find(int(a[m])), find(int(b[m]))
+    # one pass over the merges: the cuts with more clusters are prefixes of those with fewer
+    res, done = {}, 0
+    for k in sorted({int(k) for k in ks}, reverse=True):
+        upto = max(0, N - k)
+        for m in range(done, upto):
+            ra, rb = find(a[m]), find(b[m])
             if ra != rb:
                 parent[ra] = rb
+        done = max(done, upto)
         remap, lab = {}, np.zeros(N, dtype=np.int32)
         for i in range(N):
             lab[i] = remap.setdefault(find(i), len(remap) + 1)
-        out.append(lab)
-    return out
+        res[k] = lab
+    return [res[int(k)].copy() for k in ks]
 
 
 def ward_groups_dev(x_dev, heights, k=101, counts=None):

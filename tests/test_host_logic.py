@@ -114,3 +114,26 @@ def test_product_never_imports_the_oracle():
                 txt = open(os.path.join(dp, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
                 assert "hb_oracle" not in txt and "libhb_emul" not in txt, f
+
+
+def test_cut_merges_matches_scipy_cut_tree():
+    """cutree from a merge list of leaf representatives: same partitions as scipy for every k, numbered by
+    first appearance in cell order (R's cutree), for any order of the requested cuts."""
+    from scipy.cluster.hierarchy import cut_tree, linkage
+    rng = np.random.default_rng(12)
+    N = 300
+    Z = linkage(rng.standard_normal((N, 5)), "ward")
+    rep = list(range(N)) + [0] * (N - 1)
+    ma, mb = [], []
+    for i, (a, b, _, _) in enumerate(Z):
+        ma.append(rep[int(a)])
+        mb.append(rep[int(b)])
+        rep[N + i] = rep[int(a)]
+    ks = [3, 1, 5, 2, 4, 300, 299]
+    labs = hb.cut_merges(ma, mb, Z[:, 2], N, ks)
+    for k, lab in zip(ks, labs):
+        ref = cut_tree(Z, n_clusters=k)[:, 0]
+        assert len(set(lab)) == k
+        assert np.array_equal(lab[:, None] == lab[None, :], ref[:, None] == ref[None, :])
+        first = [int(np.nonzero(lab == g)[0][0]) for g in range(1, k + 1)]
+        assert first == sorted(first)          # clusters numbered in order of first appearance
