@@ -49,7 +49,8 @@ __global__ void __launch_bounds__(256)
 // stats::dist(t(S)) squared, Euclidean, with R's NA rule: pairs with a non-finite member are left
 // out and the sum is scaled up by G / (pairs used); no usable pair -> NA, which the reference then
 // sets to 0 (R/HoneyBADGER.R:1126-1128).  Direct differences (as R's C code), 64 x 64 tile of cell
-// pairs per block, 4 x 4 per thread, positions streamed through shared memory 16 at a time.
+// pairs per block, 4 x 4 per thread (rows ty + 16 a, columns tx + 16 b: the 16 lanes of a half warp read 16
+// consecutive doubles, no bank conflicts), positions streamed through shared memory 16 at a time.
 #define GD_T 64
 #define GD_K 16
 __global__ void __launch_bounds__(256)
@@ -84,8 +85,8 @@ __global__ void __launch_bounds__(256)
                 double va[4], vb[4];
 #pragma unroll
                 for (int a = 0; a < 4; a++) {
-                    va[a] = sa[k][ty * 4 + a];
-                    vb[a] = sb[k][tx * 4 + a];
+                    va[a] = sa[k][ty + 16 * a];
+                    vb[a] = sb[k][tx + 16 * a];
                 }
 #pragma unroll
                 for (int a = 0; a < 4; a++)
@@ -102,8 +103,8 @@ __global__ void __launch_bounds__(256)
                 double va[4], vb[4];
 #pragma unroll
                 for (int a = 0; a < 4; a++) {
-                    va[a] = sa[k][ty * 4 + a];
-                    vb[a] = sb[k][tx * 4 + a];
+                    va[a] = sa[k][ty + 16 * a];
+                    vb[a] = sb[k][tx + 16 * a];
                 }
 #pragma unroll
                 for (int a = 0; a < 4; a++)
@@ -123,7 +124,7 @@ __global__ void __launch_bounds__(256)
     for (int a = 0; a < 4; a++)
 #pragma unroll
         for (int b = 0; b < 4; b++) {
-            const int64_t i = i0 + ty * 4 + a, j = j0 + tx * 4 + b;
+            const int64_t i = i0 + ty + 16 * a, j = j0 + tx + 16 * b;
             if (i < N && j < N) {
                 // if (count != nc) dist /= ((double)count / nc); return sqrt(dist); hclust squares it again
                 const double c = cnt[a][b] + nfast;

@@ -1206,11 +1206,8 @@ cudaError_t launch_pool_count(const int32_t *v, int64_t ld, int64_t G, int64_t N
 {
     const size_t smem = (size_t)((N + 127) / 128) * K * sizeof(uint4);
     if (((uintptr_t)v & 15) == 0 && ld % 4 == 0 && smem <= 200 * 1024) {
-        static bool attr_set = false;
-        if (!attr_set) {
+        if (smem > 48 * 1024) // per device: set whenever it is needed
             cudaFuncSetAttribute(pool_count_v4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-            attr_set = true;
-        }
         int dev = 0, sms = 148;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
