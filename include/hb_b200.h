@@ -181,7 +181,8 @@ int hb_pool_mean_relay_dev(const double *x, int64_t ld, int64_t G, int64_t N, co
 /* sd(x) of each pooled vector, R semantics (long-double emulation): out_sd[k]. */
 int hb_pooled_sd_dev(const double *pooled /* device [K][G] */, int64_t G, int32_t K,
                      double *out_sd /* device [K] */, void *stream);
-/* Pooled allele counts of R/HoneyBADGER.R:1404-1405: out[k*G+g] = #{c in group k: v[g*ld+c] > 0} */
+/* Pooled allele counts of R/HoneyBADGER.R:1404-1405: out[k*G+g] = #{c in group k: v[g*ld+c] > 0};
+ * v, member [K][N] (0/1) and out are DEVICE pointers. */
 int hb_pool_count_pos_dev(const int32_t *v, int64_t ld, int64_t G, int64_t N,
                           const uint8_t *member, int32_t K, int32_t *out, void *stream);
 

@@ -470,3 +470,29 @@ def test_large_count_uploads_convert_on_the_device():
     x = rng.standard_normal((4200, 4100))
     for arr in (x, np.asfortranarray(x), np.asfortranarray(x.astype(np.float32))):
         assert np.array_equal(hb._to_dev_f64(arr).cpu().numpy(), arr.astype(np.float64))
+
+
+@pytest.mark.parametrize("N,K,ld_extra", [(75, 6, 0), (20037, 32, 0), (20037, 40, 0), (1000, 3, 1), (333, 33, 3),
+                                          (60000, 32, 0)])
+def test_pool_count_kernels_against_numpy(N, K, ld_extra):
+    """rowSums(m[, grp] > 0) for K groups (R/HoneyBADGER.R:1404-1405): the 16-byte-load stream (aligned rows,
+    membership words in shared memory, > 48 KB of them for many groups x cells), its ragged last slab, the
+    passes of 32 groups, and the per-group ballot kernel that serves unaligned rows and oversized tables —
+    exact integers either way."""
+    import torch
+    from honeybadger_b200 import _lib
+    rng = np.random.default_rng(N + K)
+    G = 97
+    ld = (N + 3) // 4 * 4 + ld_extra
+    v = np.full((G, ld), 7, np.int32)                 # padding holds positives: must not be counted
+    v[:, :N] = rng.integers(-1, 3, size=(G, N))
+    member = (rng.random((K, N)) < 0.4).astype(np.uint8)
+    member[:, 0] = 1
+    vd = torch.from_numpy(v).cuda()
+    out = torch.zeros((K, G), dtype=torch.int32, device="cuda")
+    lib = _lib.load()
+    md = torch.from_numpy(member).cuda()
+    _lib.check(lib.hb_pool_count_pos_dev(vd.data_ptr(), ld, G, N, md.data_ptr(), K, out.data_ptr(), None))
+    torch.cuda.synchronize()
+    want = (member.astype(np.int64) @ (v[:, :N] > 0).T.astype(np.int64)).astype(np.int32)
+    assert np.array_equal(out.cpu().numpy(), want)
