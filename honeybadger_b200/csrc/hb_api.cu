@@ -397,7 +397,8 @@ int longchain_run(Workspace *ws, int32_t S, const double *lb, int64_t T, int32_t
 
 // Posteriors of a few long chains (lc_fb_* in hb_longchain.cuh).  gamma: device [K][T][S]; ll: device [K] or NULL.
 int longchain_fb_run(Workspace *ws, int32_t S, const double *lb, int64_t T, int32_t K, const double *Pi,
-                     const double *delta, double *gamma, double *ll, cudaStream_t st, int32_t L = 0)
+                     const double *delta, double *gamma, double *ll, cudaStream_t st, int32_t L = 0,
+                     bool planes = false)
 {
     if ((S != 2 && S != 3) || T < 1 || K < 1 || !lb || !gamma || !Pi || !delta)
         return fail(HB_ERR_ARG, "bad arguments");
@@ -432,6 +433,9 @@ int longchain_fb_run(Workspace *ws, int32_t S, const double *lb, int64_t T, int3
     a.ffe = (int32_t *)(base + o_e);
     a.gamma = gamma;
     a.ll = ll;
+    a.g_sc = planes ? T : T * S; // planes: R's [T x K x S] column-major, one plane per state
+    a.g_st = planes ? 1 : S;
+    a.g_sk = planes ? (int64_t)K * T : 1;
     CU(hb::launch_longchain_fb(a, st));
     return HB_OK;
 }
@@ -578,8 +582,10 @@ int binom2_run(Workspace *ws, const int32_t *x, const int32_t *n, int64_t ld, in
 
 // Pooled allele round on the long-chain path: literal emissions of all (chain, position) pairs in
 // parallel, then the gene-axis parallel Viterbi.  x, n: device [K][G] pooled counts; y: device [K][G].
-int binom2_longchain(Workspace *ws, const int32_t *x, const int32_t *n, int64_t G, int32_t K,
-                     const double *prob, const double *Pi, const double *delta, int32_t *y, cudaStream_t st)
+// Literal dbinom log-emissions of pooled count vectors x, n (device [K][G]) into ws->lc_lb ([K][G][2]);
+// resets the status words.
+int binom2_emissions_cm(Workspace *ws, const int32_t *x, const int32_t *n, int64_t G, int32_t K,
+                        const double *prob, cudaStream_t st)
 {
     if (!all_finite(prob, 2) || prob[0] < 0 || prob[0] > 1 || prob[1] < 0 || prob[1] > 1)
         return fail(HB_ERR_ARG, "prob outside [0,1]");
@@ -601,13 +607,48 @@ int binom2_longchain(Workspace *ws, const int32_t *x, const int32_t *n, int64_t 
     a.status = ws->status.as<int32_t>();
     HBTRY(ws->lc_lb.ensure((size_t)K * G * sizeof(double2)));
     CU(hb::launch_binom2_emit_cm(a, x, n, (int64_t)K * G, ws->lc_lb.as<double2>(), st));
+    return HB_OK;
+}
+
+// Pooled allele round on the long-chain path: literal emissions of all (chain, position) pairs in
+// parallel, then the gene-axis parallel Viterbi.  x, n: device [K][G] pooled counts; y: device [K][G].
+int binom2_longchain(Workspace *ws, const int32_t *x, const int32_t *n, int64_t G, int32_t K,
+                     const double *prob, const double *Pi, const double *delta, int32_t *y, cudaStream_t st)
+{
+    HBTRY(binom2_emissions_cm(ws, x, n, G, K, prob, st));
     return longchain_run(ws, 2, ws->lc_lb.as<double>(), G, K, Pi, delta, y, st, false);
 }
 
 // Host calls shaped like the reference's own: a few chains, each long, one segment, Viterbi only.
 bool long_chain_shape(int64_t T, int64_t B, int32_t nseg, int32_t flags)
 {
-    return g_longchain_mode != 1 && nseg == 1 && B <= 32 && T >= 1024 && flags == HB_WANT_VITERBI;
+    (void)flags; // Viterbi, posteriors and LL all have a long-chain form
+    return g_longchain_mode != 1 && nseg == 1 && B <= 32 && T >= 1024;
+}
+
+// Shared tail of the long-chain host routes: lb = ws->lc_lb holds the literal log-emissions [B][T][S].
+int longchain_host_outputs(Workspace *ws, int32_t S, int64_t T, int64_t B, const double *Pi, const double *delta,
+                           int32_t flags, int32_t *y, double *gamma, double *ll, bool status_reset)
+{
+    const bool vit = (flags & HB_WANT_VITERBI) != 0, want_g = (flags & HB_WANT_GAMMA) != 0,
+               want_ll = (flags & HB_WANT_LL) != 0;
+    if (want_ll && !want_g) return fail(HB_ERR_ARG, "HB_WANT_LL currently requires HB_WANT_GAMMA");
+    if (vit) {
+        HBTRY(ws->st_out.ensure((size_t)T * B * sizeof(int32_t)));
+        HBTRY(longchain_run(ws, S, ws->lc_lb.as<double>(), T, (int32_t)B, Pi, delta, ws->st_out.as<int32_t>(), 0,
+                            status_reset));
+        CU(cudaMemcpyAsync(y, ws->st_out.p, (size_t)T * B * sizeof(int32_t), cudaMemcpyDeviceToHost, 0));
+    }
+    if (want_g) {
+        HBTRY(ws->st_g.ensure((size_t)T * B * S * sizeof(double)));
+        HBTRY(ws->st_ll.ensure((size_t)B * sizeof(double)));
+        HBTRY(longchain_fb_run(ws, S, ws->lc_lb.as<double>(), T, (int32_t)B, Pi, delta, ws->st_g.as<double>(),
+                               want_ll ? ws->st_ll.as<double>() : nullptr, 0, 0, true));
+        CU(cudaMemcpyAsync(gamma, ws->st_g.p, (size_t)T * B * S * sizeof(double), cudaMemcpyDeviceToHost, 0));
+        if (want_ll)
+            CU(cudaMemcpyAsync(ll, ws->st_ll.p, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, 0));
+    }
+    return read_status(ws, 0);
 }
 
 int64_t pad_ld(int64_t B) { return (B + 15) / 16 * 16; } // 128-byte rows for fp64
@@ -967,17 +1008,16 @@ int hb_hmm_norm_host(const double *x, int64_t T, int64_t B, const int64_t *seg_o
             h_aux[2 * B + b] = log(sd[b]);
         }
         HBTRY(ws->st_in.ensure((size_t)T * B * sizeof(double)));
-        HBTRY(ws->st_out.ensure((size_t)T * B * sizeof(int32_t)));
         HBTRY(ws->sdaux.ensure(h_aux.size() * sizeof(double)));
+        HBTRY(ws->status.ensure(4 * sizeof(int32_t)));
+        CU(cudaMemsetAsync(ws->status.p, 0, 4 * sizeof(int32_t), 0));
         HBTRY(ws->lc_lb.ensure((size_t)T * B * 3 * sizeof(double)));
         CU(cudaMemcpyAsync(ws->st_in.p, x, (size_t)T * B * sizeof(double), cudaMemcpyHostToDevice, 0));
         CU(cudaMemcpyAsync(ws->sdaux.p, h_aux.data(), h_aux.size() * sizeof(double), cudaMemcpyHostToDevice, 0));
         const double *aux = ws->sdaux.as<double>();
         CU(hb::launch_norm3_emit_cm(nc, ws->st_in.as<double>(), T, (int32_t)B, aux, aux + B, aux + 2 * B,
                                     ws->lc_lb.as<double>(), 0));
-        HBTRY(longchain_run(ws, 3, ws->lc_lb.as<double>(), T, (int32_t)B, Pi, delta, ws->st_out.as<int32_t>(), 0));
-        CU(cudaMemcpyAsync(y, ws->st_out.p, (size_t)T * B * sizeof(int32_t), cudaMemcpyDeviceToHost, 0));
-        return read_status(ws, 0);
+        return longchain_host_outputs(ws, 3, T, B, Pi, delta, flags, y, gamma, ll, false);
     }
     HBTRY(pipe_init(ws));
     const int64_t Bc = pipe_batch(B, 130.0 * (double)T);
@@ -1156,13 +1196,10 @@ int hb_hmm_binom_host(const int32_t *x, const int32_t *size, int64_t T, int64_t 
         // Viterbi(dthmm(mafl, ..., "binom", ...)) on one (or a few) pooled count vectors: see hb_hmm_norm_host
         HBTRY(ws->st_in.ensure((size_t)T * B * sizeof(int32_t)));
         HBTRY(ws->st_in2.ensure((size_t)T * B * sizeof(int32_t)));
-        HBTRY(ws->st_out.ensure((size_t)T * B * sizeof(int32_t)));
         CU(cudaMemcpyAsync(ws->st_in.p, x, (size_t)T * B * sizeof(int32_t), cudaMemcpyHostToDevice, 0));
         CU(cudaMemcpyAsync(ws->st_in2.p, size, (size_t)T * B * sizeof(int32_t), cudaMemcpyHostToDevice, 0));
-        HBTRY(binom2_longchain(ws, ws->st_in.as<int32_t>(), ws->st_in2.as<int32_t>(), T, (int32_t)B, prob, Pi,
-                               delta, ws->st_out.as<int32_t>(), 0));
-        CU(cudaMemcpyAsync(y, ws->st_out.p, (size_t)T * B * sizeof(int32_t), cudaMemcpyDeviceToHost, 0));
-        return read_status(ws, 0);
+        HBTRY(binom2_emissions_cm(ws, ws->st_in.as<int32_t>(), ws->st_in2.as<int32_t>(), T, (int32_t)B, prob, 0));
+        return longchain_host_outputs(ws, 2, T, B, Pi, delta, flags, y, gamma, ll, false);
     }
     HBTRY(pipe_init(ws));
     const int64_t Bc = pipe_batch(B, 100.0 * (double)T);

@@ -81,7 +81,8 @@ struct LcArgs {
     double *fae;         // [K][nb][S]  filter at the position before the block (sums to 1)
     double *fbe;         // [K][nb][S]  beta at the block's last position (sums to 1)
     double *fls;         // [K][nb]     sum over the block of log c_t + max_k logb_t
-    double *gamma;       // [K][T][S]   out
+    double *gamma;       // out: gamma_t(k) of chain c at gamma[c * g_sc + t * g_st + k * g_sk]
+    int64_t g_sc, g_st, g_sk; // chain-major [K][T][S]: T*S, S, 1; R's [T x K x S] column-major: T, 1, K*T
     double *ll;          // [K]         out (or NULL)
     const double *wff;
     const int32_t *wfe;
@@ -763,7 +764,8 @@ HB_HD void lc_fb_block(const LcArgs &a, int32_t c, int64_t b)
     const int64_t t0 = lc_t0(a, b), n = lc_t1(a, b) - t0;
     const int64_t ib = (int64_t)c * a.nb + b;
     const double *HB_RESTRICT l = a.lb + ((int64_t)c * a.T + t0) * S;
-    double *HB_RESTRICT g = a.gamma + ((int64_t)c * a.T + t0) * S;
+    double *HB_RESTRICT g = a.gamma + (int64_t)c * a.g_sc + t0 * a.g_st;
+    const int64_t gt = a.g_st, gk = a.g_sk;
     double al[S], bt[S], ls = 0.0;
 #pragma unroll
     for (int k = 0; k < S; k++) al[k] = a.fae[ib * S + k];
@@ -779,7 +781,7 @@ HB_HD void lc_fb_block(const LcArgs &a, int32_t c, int64_t b)
                 lc_fwd_vec<S>(a.pi, al, bv);
                 ls += log(lc_normalise<S>(al)) + m;
 #pragma unroll
-                for (int k = 0; k < S; k++) g[(i0 + j) * S + k] = al[k];
+                for (int k = 0; k < S; k++) g[(i0 + j) * gt + k * gk] = al[k];
             }
         cur = nxt;
     }
@@ -793,13 +795,13 @@ HB_HD void lc_fb_block(const LcArgs &a, int32_t c, int64_t b)
 #pragma unroll
     for (int i = 0; i < CB * S; i++) {
         ec[i] = i < (n - i0) * S ? l[i0 * S + i] : 0.0;
-        gc[i] = i < (n - i0) * S ? g[i0 * S + i] : 0.0;
+        gc[i] = i < (n - i0) * S ? g[(i0 + i / S) * gt + (i % S) * gk] : 0.0;
     }
     for (; i0 >= 0 && n > 0; i0 -= CB) {
 #pragma unroll
         for (int i = 0; i < CB * S; i++) {
             en[i] = i0 >= CB ? l[(i0 - CB) * S + i] : 0.0;
-            gn[i] = i0 >= CB ? g[(i0 - CB) * S + i] : 0.0;
+            gn[i] = i0 >= CB ? g[(i0 - CB + i / S) * gt + (i % S) * gk] : 0.0;
         }
 #pragma unroll
         for (int j = CB - 1; j >= 0; j--)
@@ -809,7 +811,7 @@ HB_HD void lc_fb_block(const LcArgs &a, int32_t c, int64_t b)
                 for (int k = 0; k < S; k++) gv[k] = gc[j * S + k] * bt[k];
                 lc_normalise<S>(gv);
 #pragma unroll
-                for (int k = 0; k < S; k++) g[(i0 + j) * S + k] = gv[k];
+                for (int k = 0; k < S; k++) g[(i0 + j) * gt + k * gk] = gv[k];
                 lc_emis<S>(ec + j * S, bv, m);
                 lc_bwd_vec<S>(a.pi, bt, bv);
                 lc_normalise<S>(bt);
@@ -827,7 +829,7 @@ HB_HD void lc_fb_block(const LcArgs &a, int32_t c, int64_t b)
         for (int k = 0; k < S; k++) gv[k] *= bt[k];
         lc_normalise<S>(gv);
 #pragma unroll
-        for (int k = 0; k < S; k++) a.gamma[(int64_t)c * a.T * S + k] = gv[k];
+        for (int k = 0; k < S; k++) a.gamma[(int64_t)c * a.g_sc + k * gk] = gv[k];
     }
 }
 
@@ -843,7 +845,7 @@ HB_HD void lc_fb_ll(const LcArgs &a, int32_t c)
     double ll = log(lc_normalise<S>(al)) + m;
     if (a.nb == 0) {
 #pragma unroll
-        for (int k = 0; k < S; k++) a.gamma[(int64_t)c * a.T * S + k] = al[k];
+        for (int k = 0; k < S; k++) a.gamma[(int64_t)c * a.g_sc + k * a.g_sk] = al[k];
     }
     for (int64_t b = 0; b < a.nb; b++) ll += a.fls[(int64_t)c * a.nb + b];
     if (a.ll) a.ll[c] = ll;

@@ -484,7 +484,10 @@ extern "C" int emul_longchain(int S, int64_t T, int K, const double *lb, const d
     return -1;
 }
 
-// Posteriors of long chains (lc_fb_*), phases walked serially.  gamma [K][T][S], ll [K].
+// Posteriors of long chains (lc_fb_*), phases walked serially.  gamma [K][T][S] (or, after
+// emul_set_fb_planes(1), R's [T x K x S] column-major), ll [K].
+static int g_fb_planes = 0;
+extern "C" void emul_set_fb_planes(int v) { g_fb_planes = v; }
 template <int S>
 static void emul_longchain_fb_t(int64_t T, int K, const double *lb, const double *Pi, const double *delta,
                                 int L, double *gamma, double *ll)
@@ -500,6 +503,8 @@ static void emul_longchain_fb_t(int64_t T, int K, const double *lb, const double
     std::vector<int32_t> ffe(nkb * S);
     a.ffm = ffm.data(); a.ffe = ffe.data(); a.fae = fae.data(); a.fbe = fbe.data(); a.fls = fls.data();
     a.gamma = gamma; a.ll = ll;
+    if (g_fb_planes) { a.g_sc = T; a.g_st = 1; a.g_sk = (int64_t)K * T; }   // R's [T x K x S] column-major
+    else { a.g_sc = T * S; a.g_st = S; a.g_sk = 1; }
     for (int c = 0; c < K; c++)
         for (int64_t b = 0; b < a.nb; b++) lc_fb_mat<S>(a, c, b);
     for (int c = 0; c < K && a.nb; c++) {

@@ -232,6 +232,21 @@ def test_posteriors_match_the_oracle(emul, oracle, S, T, K, L):
     assert np.allclose(ll, llr, rtol=1e-12, atol=1e-9)
 
 
+def test_posteriors_in_r_plane_layout(emul, oracle):
+    """gamma written straight into R's [T x K x S] column-major array (what hb_hmm_*_host hands back)."""
+    rng = np.random.default_rng(9)
+    lb = norm_lb(rng, 3, 2500, sd=1.0)
+    Pi, delta = sym_Pi(3, 1e-6), np.array([0., 1., 0.])
+    g0, ll0 = run_emul_fb(emul, lb, Pi, delta)
+    emul.emul_set_fb_planes(1)
+    try:
+        g1, ll1 = run_emul_fb(emul, lb, Pi, delta)
+    finally:
+        emul.emul_set_fb_planes(0)
+    planes = g1.reshape(-1).reshape(3, 3, 2500)            # [S][K][T]
+    assert np.array_equal(planes.transpose(1, 2, 0), g0) and np.array_equal(ll0, ll1)
+
+
 def test_posteriors_of_a_long_deep_chain(emul):
     """40 000 positions with pooled-scale evidence (hundreds of nats per position: exp(logb) underflows,
     the reference's linear-density forwardback returns NaN there) against 80-bit arithmetic."""
@@ -386,3 +401,40 @@ def test_gpu_dropin_seam_uses_the_long_chain_path(oracle, golden_gexp, golden_al
     print(f"one 200k-SNP chain through hb_hmm_binom_host: {res[0, 'ms']:.2f} ms along the gene axis, "
           f"{res[1, 'ms']:.2f} ms one thread")
     assert res[0, "ms"] < res[1, "ms"]
+
+
+@pytest.mark.gpu
+def test_gpu_seam_posteriors(oracle, golden_gexp):
+    """forwardback(dthmm(x, ...)) on pooled vectors through hb_hmm_*_host: long-chain posteriors in R's layout,
+    equal to the thread-per-chain kernels' (mode 1) and the oracle's within 1e-9; LL too."""
+    from honeybadger_b200 import hmm
+    g = golden_gexp
+    x, sd, dev = g["pooled_x"][:4].T.copy(), g["pooled_sd"][:4], float(g["dev"])      # [T, B]
+    Pi3, d3, mean = sym_Pi(3, 1e-6), np.array([0., 1., 0.]), np.array([-dev, 0.0, dev])
+    res = {}
+    try:
+        for mode in (0, 1):
+            hmm.set_longchain_mode(mode)
+            res[mode] = hmm.hmm_norm_host(x, mean, sd, Pi3, d3, viterbi=True, gamma=True, ll=True)
+    finally:
+        hmm.set_longchain_mode(0)
+    assert np.array_equal(res[0]["y"], res[1]["y"])
+    assert np.abs(res[0]["gamma"] - res[1]["gamma"]).max() < 1e-9
+    assert np.allclose(res[0]["ll"], res[1]["ll"], rtol=1e-12)
+    yo, go, llo, rc = oracle.fbv_norm_batch(x, np.array([0, x.shape[0]], dtype=np.int64), mean, sd, Pi3, d3)
+    assert rc == 0 and np.array_equal(res[0]["y"], yo)
+    assert np.abs(res[0]["gamma"].transpose(2, 0, 1) - go).max() < 1e-9
+    rng = np.random.default_rng(6)
+    n = rng.binomial(60, 0.3, size=(5000, 2)).astype(np.int32)
+    r = rng.binomial(n, 0.45).astype(np.int32)
+    r[2000:2600, 0] = rng.binomial(n[2000:2600, 0], 0.1)
+    Pi2, d2 = sym_Pi(2, 1e-6), np.array([0., 1.])
+    try:
+        for mode in (0, 1):
+            hmm.set_longchain_mode(mode)
+            res[mode] = hmm.hmm_binom_host(r, n, [0.1, 0.45], Pi2, d2, viterbi=True, gamma=True, ll=True)
+    finally:
+        hmm.set_longchain_mode(0)
+    assert np.array_equal(res[0]["y"], res[1]["y"]) and (res[0]["y"][2100:2500, 0] == 1).all()
+    assert np.abs(res[0]["gamma"] - res[1]["gamma"]).max() < 1e-9
+    assert np.allclose(res[0]["ll"], res[1]["ll"], rtol=1e-12)
