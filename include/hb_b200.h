@@ -346,8 +346,10 @@ int hb_forwardback_long_logb_dev(const double *logb, int32_t S, int64_t T, int32
  * out[2] chains finished on the sequential path, out[3] repair rounds used (max over chains), out[4]
  * blocks the sequential walkers ran literally (entry outside the predicted binade, first blocks). */
 int hb_longchain_stats_dev(void *stream, int64_t *out /* [5] */);
-/* Pooled rounds: 0 (default) the allele round uses the long-chain path, 1 neither round does (one
- * thread per chain), 2 the expression round uses it too.  Same states in every mode. */
+/* Where the long-chain path is used.  0 (default): the pooled allele round, and hb_hmm_norm_host /
+ * hb_hmm_binom_host calls of the reference's own shape (<= 32 chains, >= 1024 positions, one segment —
+ * Viterbi(dthmm(x, ...)) on a pooled vector; states, posteriors and LL); 1: nowhere (one thread per chain);
+ * 2: as 0 plus the pooled expression round.  Same states in every mode, posteriors within 1e-9. */
 int hb_set_longchain_mode(int32_t mode);
 
 /* One recursion round of the split-and-retest driver on DEVICE-RESIDENT matrices (gene-major,
