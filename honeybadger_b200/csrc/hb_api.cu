@@ -994,7 +994,7 @@ int hb_hmm_norm_host(const double *x, int64_t T, int64_t B, const int64_t *seg_o
     bool vit, fb;
     HBTRY(check_flags(flags, y, gamma, ll, &vit, &fb));
     const bool want_g = (flags & HB_WANT_GAMMA) != 0, want_ll = (flags & HB_WANT_LL) != 0;
-    if (long_chain_shape(T, B, nseg, flags)) {
+    if (long_chain_shape(T, B, nseg, flags) && seg_off[0] == 0 && seg_off[1] == T) {
         // the drop-in seam itself: Viterbi(dthmm(x, ...)) on one (or a few) long pooled vectors.  R's
         // column-major [T x B] is already chain-major: emissions in parallel, chains along the gene axis.
         hb::Norm3Const nc;
@@ -1192,7 +1192,7 @@ int hb_hmm_binom_host(const int32_t *x, const int32_t *size, int64_t T, int64_t 
     bool vit, fb;
     HBTRY(check_flags(flags, y, gamma, ll, &vit, &fb));
     const bool want_g = (flags & HB_WANT_GAMMA) != 0, want_ll = (flags & HB_WANT_LL) != 0;
-    if (rho == 0.0 && long_chain_shape(T, B, nseg, flags)) {
+    if (rho == 0.0 && long_chain_shape(T, B, nseg, flags) && seg_off[0] == 0 && seg_off[1] == T) {
         // Viterbi(dthmm(mafl, ..., "binom", ...)) on one (or a few) pooled count vectors: see hb_hmm_norm_host
         HBTRY(ws->st_in.ensure((size_t)T * B * sizeof(int32_t)));
         HBTRY(ws->st_in2.ensure((size_t)T * B * sizeof(int32_t)));
