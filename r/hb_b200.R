@@ -17,6 +17,18 @@ hb_viterbi_binom <- function(x, Pi, delta, pm, pn) {
   .Call("C_hb_viterbi_binom", as.integer(x), as.integer(pn$size), as.double(pm$prob), Pi, as.double(delta))
 }
 
+## States + posteriors (gamma[t, chain, state] = P(state_t | all x), HiddenMarkov::forwardback semantics) + LL
+hb_posteriors_norm <- function(x, Pi, delta, pm) {
+  r <- .Call("C_hb_posteriors_norm", x, as.double(pm$mean), as.double(pm$sd[1]), Pi, as.double(delta))
+  list(y = r[[1]], gamma = array(r[[2]], dim = c(NROW(x), NCOL(x), 3L)), LL = r[[3]])
+}
+hb_posteriors_binom <- function(x, Pi, delta, pm, pn) {
+  size <- pn$size
+  storage.mode(x) <- "integer"; storage.mode(size) <- "integer"   # keeps a matrix a matrix (as.integer would not)
+  r <- .Call("C_hb_posteriors_binom", x, size, as.double(pm$prob), Pi, as.double(delta))
+  list(y = r[[1]], gamma = array(r[[2]], dim = c(NROW(x), NCOL(x), 2L)), LL = r[[3]])
+}
+
 ## R/HoneyBADGER.R:1150-1151 and R/HoneyBADGER_gexp.R:503-504 become
 ##   results <- hb_viterbi_norm(mat.smooth, Pi, delta, list(mean=c(pd, pn, pa), sd=c(sd,sd,sd)))
 ## R/HoneyBADGER.R:1409-1410 and R/HoneyBADGER_allele.R:579-580 become

@@ -239,9 +239,61 @@ SEXP C_hb_retest_allele(SEXP r_rows, SEXP n_rows, SEXP l_maf, SEXP n_bulk, SEXP 
     return out;
 }
 
+/* list(y, gamma, LL) <- .Call(C_hb_posteriors_norm, x, mean, sd, Pi, delta)
+ * Viterbi states plus the state posteriors gamma [T x B x 3] = exp(logalpha + logbeta - LL) of
+ * HiddenMarkov::forwardback and the log-likelihoods (north_star's posterior output; the reference never
+ * computes it).  A pooled vector (one long chain) runs parallel along the gene axis. */
+SEXP C_hb_posteriors_norm(SEXP x, SEXP mean, SEXP sd, SEXP Pi, SEXP delta)
+{
+    x = PROTECT(Rf_coerceVector(x, REALSXP));
+    const int is_mat = Rf_isMatrix(x);
+    const int64_t T = is_mat ? Rf_nrows(x) : XLENGTH(x), B = is_mat ? Rf_ncols(x) : 1;
+    double pi_rm[9];
+    for (int j = 0; j < 3; j++)
+        for (int k = 0; k < 3; k++) pi_rm[j * 3 + k] = REAL(Pi)[k * 3 + j];
+    SEXP sdv = PROTECT(Rf_allocVector(REALSXP, B));
+    for (int64_t b = 0; b < B; b++) REAL(sdv)[b] = REAL(sd)[XLENGTH(sd) == B ? b : 0];
+    SEXP y = PROTECT(Rf_allocMatrix(INTSXP, (int)T, (int)B));
+    SEXP g = PROTECT(Rf_allocVector(REALSXP, (R_xlen_t)T * B * 3)); /* [T x B x 3], dim set by the R wrapper */
+    SEXP ll = PROTECT(Rf_allocVector(REALSXP, B));
+    int rc = hb_hmm_norm_host(REAL(x), T, B, NULL, 1, REAL(mean), REAL(sdv), 0, pi_rm, REAL(delta),
+                              HB_WANT_VITERBI | HB_WANT_GAMMA | HB_WANT_LL, INTEGER(y), REAL(g), REAL(ll));
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, 3));
+    SET_VECTOR_ELT(out, 0, y);
+    SET_VECTOR_ELT(out, 1, g);
+    SET_VECTOR_ELT(out, 2, ll);
+    UNPROTECT(6);
+    hb_raise(rc);
+    return out;
+}
+
+/* list(y, gamma, LL) <- .Call(C_hb_posteriors_binom, x, size, prob, Pi, delta): gamma [T x B x 2] */
+SEXP C_hb_posteriors_binom(SEXP x, SEXP size, SEXP prob, SEXP Pi, SEXP delta)
+{
+    x = PROTECT(Rf_coerceVector(x, INTSXP));
+    size = PROTECT(Rf_coerceVector(size, INTSXP));
+    const int is_mat = Rf_isMatrix(x);
+    const int64_t T = is_mat ? Rf_nrows(x) : XLENGTH(x), B = is_mat ? Rf_ncols(x) : 1;
+    double pi_rm[4] = {REAL(Pi)[0], REAL(Pi)[2], REAL(Pi)[1], REAL(Pi)[3]};
+    SEXP y = PROTECT(Rf_allocMatrix(INTSXP, (int)T, (int)B));
+    SEXP g = PROTECT(Rf_allocVector(REALSXP, (R_xlen_t)T * B * 2));
+    SEXP ll = PROTECT(Rf_allocVector(REALSXP, B));
+    int rc = hb_hmm_binom_host(INTEGER(x), INTEGER(size), T, B, NULL, 1, REAL(prob), 0.0, pi_rm, REAL(delta),
+                               HB_WANT_VITERBI | HB_WANT_GAMMA | HB_WANT_LL, INTEGER(y), REAL(g), REAL(ll));
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, 3));
+    SET_VECTOR_ELT(out, 0, y);
+    SET_VECTOR_ELT(out, 1, g);
+    SET_VECTOR_ELT(out, 2, ll);
+    UNPROTECT(6);
+    hb_raise(rc);
+    return out;
+}
+
 static const R_CallMethodDef call_methods[] = {
     {"C_hb_viterbi_norm", (DL_FUNC)&C_hb_viterbi_norm, 5},
     {"C_hb_viterbi_binom", (DL_FUNC)&C_hb_viterbi_binom, 5},
+    {"C_hb_posteriors_norm", (DL_FUNC)&C_hb_posteriors_norm, 5},
+    {"C_hb_posteriors_binom", (DL_FUNC)&C_hb_posteriors_binom, 5},
     {"C_hb_gexp_pooled_viterbi", (DL_FUNC)&C_hb_gexp_pooled_viterbi, 5},
     {"C_hb_allele_pooled_viterbi", (DL_FUNC)&C_hb_allele_pooled_viterbi, 6},
     {"C_hb_group_gexp", (DL_FUNC)&C_hb_group_gexp, 3},

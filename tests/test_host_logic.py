@@ -137,3 +137,31 @@ def test_cut_merges_matches_scipy_cut_tree():
         assert np.array_equal(lab[:, None] == lab[None, :], ref[:, None] == ref[None, :])
         first = [int(np.nonzero(lab == g)[0][0]) for g in range(1, k + 1)]
         assert first == sorted(first)          # clusters numbered in order of first appearance
+
+
+def test_r_shim_is_well_formed_against_the_c_abi():
+    """R is not in this image, so nobody links r/hb_shim.c here; at least it must be valid C against
+    include/hb_b200.h (argument counts and pointer types of every hb_* call) with a stand-in for the R API
+    (tests/r_stub), its registration table must carry each entry point's real arity, and every .Call in
+    r/hb_b200.R must name a registered routine."""
+    import subprocess
+    shim = os.path.join(ROOT, "r", "hb_shim.c")
+    cmd = ["/usr/bin/gcc", "-std=c11", "-fsyntax-only", "-Wall", "-Wextra", "-Werror", "-Wno-cast-function-type",
+           "-I" + os.path.join(ROOT, "tests", "r_stub"), "-I" + os.path.join(ROOT, "include"), shim]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    src = open(shim).read()
+    defs = {m.group(1): m.group(2).count("SEXP") for m in re.finditer(r"^SEXP (C_hb_\w+)\(([^)]*)\)", src, flags=re.M)}
+    table = {m.group(1): int(m.group(2)) for m in re.finditer(r'\{"(C_hb_\w+)", \(DL_FUNC\)&\1, (\d+)\}', src)}
+    assert defs and defs == table, (defs, table)
+    rsrc = open(os.path.join(ROOT, "r", "hb_b200.R")).read()
+    called = set(re.findall(r'\.Call\("(C_hb_\w+)"', rsrc))
+    assert called and called <= set(table), called - set(table)
+    for name in called:                              # argument count of each .Call == registered arity
+        for m in re.finditer(r'\.Call\("%s"((?:[^()]|\([^()]*(?:\([^()]*\)[^()]*)*\))*)\)' % name, rsrc):
+            depth, nargs = 0, 0
+            for ch in m.group(1):
+                depth += ch in "([" 
+                depth -= ch in ")]"
+                nargs += ch == "," and depth == 0
+            assert nargs == table[name], (name, nargs, table[name])
