@@ -118,6 +118,9 @@ struct Workspace {
                          &st_member, &st_pool, &st_pool2, &st_pre, &st_x80, &st_part, &st_inp, &st_inp2, &st_tab, &pin[0], &pin[1], &pin2[0], &pin2[1],
                          &pout_y[0], &pout_y[1], &pout_g[0], &pout_g[1], &pout_ll[0], &pout_ll[1]};
         for (DevBuf *b : all) b->release();
+        lc_cstate = nullptr; // pointed into `lc`
+        lc_K = 0;
+        lc_nb = 0;
         if (s_in) {
             cudaStreamDestroy(s_in);
             cudaStreamDestroy(s_cmp);
