@@ -497,7 +497,7 @@ def run_e2e(kind, wl, d, args, world, dev, hmm, dist):
         h2d = positions * cells * 8
     yout = torch.empty((batch, positions), dtype=torch.int32).pin_memory()
     gout = torch.empty((S, batch, positions), dtype=torch.float64).pin_memory()
-    d2h = positions * cells * (4 + 8 * S)
+    d2h = positions * cells * (1 + 8 * S)   # states cross PCIe as bytes (widened to R integers on the host)
     from honeybadger_b200 import _lib
     import ctypes as C
     lib = _lib.load()

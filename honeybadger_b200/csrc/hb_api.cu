@@ -103,6 +103,8 @@ struct Workspace {
     // pinned bounce buffers for ordinary (pageable) host memory, e.g. R vectors: [slot]
     void *bounce_in[2] = {nullptr, nullptr}, *bounce_out[2] = {nullptr, nullptr};
     size_t bounce_in_cap = 0, bounce_out_cap = 0;
+    void *bounce_y[2] = {nullptr, nullptr}; // states cross PCIe as bytes and are widened to R integers here
+    size_t bounce_y_cap = 0;
     cudaEvent_t ev_bin[2] = {nullptr, nullptr}, ev_bout[2] = {nullptr, nullptr};
     cudaStream_t s_in = nullptr, s_cmp = nullptr, s_out = nullptr;
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_free_in[2] = {nullptr, nullptr},
@@ -136,12 +138,13 @@ struct Workspace {
         for (int k = 0; k < 2; k++) {
             if (bounce_in[k]) cudaFreeHost(bounce_in[k]);
             if (bounce_out[k]) cudaFreeHost(bounce_out[k]);
-            bounce_in[k] = bounce_out[k] = nullptr;
+            if (bounce_y[k]) cudaFreeHost(bounce_y[k]);
+            bounce_in[k] = bounce_out[k] = bounce_y[k] = nullptr;
             if (ev_bin[k]) cudaEventDestroy(ev_bin[k]);
             if (ev_bout[k]) cudaEventDestroy(ev_bout[k]);
             ev_bin[k] = ev_bout[k] = nullptr;
         }
-        bounce_in_cap = bounce_out_cap = 0;
+        bounce_in_cap = bounce_out_cap = bounce_y_cap = 0;
         seg_cached.clear();
         lut_nmax = -1;
         lut_key[0] = -1;
@@ -831,6 +834,25 @@ static void parallel_memcpy(void *dst, const void *src, size_t bytes, int nthrea
     for (auto &t : th) t.join();
 }
 
+static void parallel_widen(int32_t *dst, const uint8_t *src, size_t count, int nthreads)
+{
+    auto body = [=](size_t a, size_t b) {
+        for (size_t i = a; i < b; i++) dst[i] = src[i];
+    };
+    if (count < ((size_t)1 << 20) || nthreads <= 1) {
+        body(0, count);
+        return;
+    }
+    std::vector<std::thread> th;
+    const size_t per = (count / nthreads + 4095) & ~(size_t)4095;
+    for (int i = 0; i < nthreads; i++) {
+        const size_t a = (size_t)i * per;
+        if (a >= count) break;
+        th.emplace_back(body, a, std::min(count, a + per));
+    }
+    for (auto &t : th) t.join();
+}
+
 struct HostStager {
     Workspace *ws;
     bool bounce_in, bounce_out;
@@ -840,13 +862,27 @@ struct HostStager {
         void *dst;
         size_t bytes;
     };
+    struct Widen {
+        const uint8_t *src;
+        int32_t *dst;
+        size_t count;
+    };
     std::vector<Copy> pend[2];
+    std::vector<Widen> pend_w[2];
     std::future<void> fut[2];
     size_t off_out[2] = {0, 0}, off_in[2] = {0, 0};
 
-    int init(Workspace *w, bool b_in, bool b_out, size_t in_bytes, size_t out_bytes)
+    int init(Workspace *w, bool b_in, bool b_out, size_t in_bytes, size_t out_bytes, size_t y_count = 0)
     {
         ws = w;
+        if (y_count && w->bounce_y_cap < y_count) {
+            for (int k = 0; k < 2; k++) {
+                if (w->bounce_y[k]) cudaFreeHost(w->bounce_y[k]);
+                w->bounce_y[k] = nullptr;
+                CU(cudaHostAlloc(&w->bounce_y[k], y_count, cudaHostAllocDefault));
+            }
+            w->bounce_y_cap = y_count;
+        }
         bounce_in = b_in;
         bounce_out = b_out;
         nthreads = (int)std::max(1u, std::min(8u, std::thread::hardware_concurrency() / 2));
@@ -898,7 +934,16 @@ struct HostStager {
     {
         if (fut[k].valid()) fut[k].get();
         pend[k].clear();
+        pend_w[k].clear();
         off_out[k] = 0;
+    }
+    // Viterbi states: one byte per position over PCIe (a quarter of R's integers), landed in pinned memory
+    // and widened into the caller's int32 array by the background task while the GPU works on
+    int d2h_widen(int k, int32_t *host, const uint8_t *dev, size_t count, cudaStream_t st)
+    {
+        CU(cudaMemcpyAsync(ws->bounce_y[k], dev, count, cudaMemcpyDeviceToHost, st));
+        pend_w[k].push_back({(const uint8_t *)ws->bounce_y[k], host, count});
+        return HB_OK;
     }
     int d2h(int k, void *host, const void *dev, size_t bytes, cudaStream_t st)
     {
@@ -914,17 +959,19 @@ struct HostStager {
     }
     int end_out(int k, cudaStream_t st)
     {
-        if (!bounce_out) return HB_OK;
+        if (pend[k].empty() && pend_w[k].empty()) return HB_OK;
         CU(cudaEventRecord(ws->ev_bout[k], st));
         cudaEvent_t ev = ws->ev_bout[k];
         std::vector<Copy> jobs = pend[k];
+        std::vector<Widen> wjobs = pend_w[k];
         const int nt = nthreads;
         int dev = 0;
         cudaGetDevice(&dev);
-        fut[k] = std::async(std::launch::async, [ev, jobs, nt, dev] {
+        fut[k] = std::async(std::launch::async, [ev, jobs, wjobs, nt, dev] {
             cudaSetDevice(dev);
             cudaEventSynchronize(ev);
             for (const Copy &c : jobs) parallel_memcpy(c.dst, c.src, c.bytes, nt);
+            for (const Widen &w : wjobs) parallel_widen(w.dst, w.src, w.count, nt);
         });
         return HB_OK;
     }
@@ -1030,7 +1077,7 @@ int hb_hmm_norm_host(const double *x, int64_t T, int64_t B, const int64_t *seg_o
     // every allocation before the first enqueue (cudaMalloc / cudaFree synchronise the device)
     for (int k = 0; k < 2; k++) {
         HBTRY(ws->pin[k].ensure((size_t)T * Bc * sizeof(double)));
-        if (vit) HBTRY(ws->pout_y[k].ensure((size_t)T * Bc * sizeof(int32_t)));
+        if (vit) HBTRY(ws->pout_y[k].ensure((size_t)T * Bc));
         if (want_g) HBTRY(ws->pout_g[k].ensure((size_t)3 * T * Bc * sizeof(double)));
         if (want_ll) HBTRY(ws->pout_ll[k].ensure((size_t)nseg * Bc * sizeof(double)));
     }
@@ -1040,12 +1087,11 @@ int hb_hmm_norm_host(const double *x, int64_t T, int64_t B, const int64_t *seg_o
     HBTRY(ws->st_sd.ensure((size_t)nsd_seg * B * 3 * sizeof(double)));
     HostStager hs;
     HBTRY(hs.init(ws, !host_is_pinned(x),
-                  !(host_is_pinned(vit ? y : nullptr) && host_is_pinned(want_g ? gamma : nullptr) &&
-                    host_is_pinned(want_ll ? ll : nullptr)),
+                  !(host_is_pinned(want_g ? gamma : nullptr) && host_is_pinned(want_ll ? ll : nullptr)),
                   (size_t)T * Bc * sizeof(double) + 256,
-                  (vit ? (size_t)T * Bc * sizeof(int32_t) + 256 : 0) +
-                      (want_g ? 3 * ((size_t)T * Bc * sizeof(double) + 256) : 0) +
-                      (want_ll ? (size_t)nseg * (Bc * sizeof(double) + 256) : 0)));
+                  (want_g ? 3 * ((size_t)T * Bc * sizeof(double) + 256) : 0) +
+                      (want_ll ? (size_t)nseg * (Bc * sizeof(double) + 256) : 0) + 256,
+                  vit ? (size_t)T * Bc : 0));
     // chain scales of all sub-batches in one upload: sd, 1/sd (IEEE), log(sd) (host libm, as R);
     // sub-batch i occupies [3 * nsd_seg * b0, +3 * nsd_seg * bn) as three [nsd_seg][bn] blocks
     std::vector<double> h_aux((size_t)nsd_seg * B * 3);
@@ -1087,7 +1133,7 @@ int hb_hmm_norm_host(const double *x, int64_t T, int64_t B, const int64_t *seg_o
                        ld, d_g, ld, d_ll, ws->s_cmp, i == 0);
         if (rc != HB_OK) break;
         if (vit)
-            CU(hb::launch_transpose_u8_back(d_y, ld, T, bn, ws->pout_y[k].as<int32_t>(), ws->s_cmp));
+            CU(hb::launch_transpose_u8_back_u8(d_y, ld, T, bn, ws->pout_y[k].as<uint8_t>(), ws->s_cmp));
         if (want_g)
             for (int pl = 0; pl < 3; pl++)
                 CU(hb::launch_transpose_f64_back(d_g + (int64_t)pl * T * ld, ld, T, bn,
@@ -1098,7 +1144,7 @@ int hb_hmm_norm_host(const double *x, int64_t T, int64_t B, const int64_t *seg_o
         CU(cudaStreamWaitEvent(ws->s_out, ws->ev_out[k], 0));
         hs.begin_out(k);
         if (vit)
-            HBTRY(hs.d2h(k, y + b0 * T, ws->pout_y[k].p, (size_t)T * bn * sizeof(int32_t), ws->s_out));
+            HBTRY(hs.d2h_widen(k, y + b0 * T, ws->pout_y[k].as<uint8_t>(), (size_t)T * bn, ws->s_out));
         if (want_g)
             for (int pl = 0; pl < 3; pl++)
                 HBTRY(hs.d2h(k, gamma + ((int64_t)pl * B + b0) * T,
@@ -1211,7 +1257,7 @@ int hb_hmm_binom_host(const int32_t *x, const int32_t *size, int64_t T, int64_t 
     for (int k = 0; k < 2; k++) {
         HBTRY(ws->pin[k].ensure((size_t)T * Bc * sizeof(int32_t)));
         HBTRY(ws->pin2[k].ensure((size_t)T * Bc * sizeof(int32_t)));
-        if (vit) HBTRY(ws->pout_y[k].ensure((size_t)T * Bc * sizeof(int32_t)));
+        if (vit) HBTRY(ws->pout_y[k].ensure((size_t)T * Bc));
         if (want_g) HBTRY(ws->pout_g[k].ensure((size_t)2 * T * Bc * sizeof(double)));
         if (want_ll) HBTRY(ws->pout_ll[k].ensure((size_t)nseg * Bc * sizeof(double)));
     }
@@ -1221,12 +1267,11 @@ int hb_hmm_binom_host(const int32_t *x, const int32_t *size, int64_t T, int64_t 
     if (want_g) HBTRY(ws->st_g.ensure((size_t)2 * T * ldc * sizeof(double)));
     HostStager hs;
     HBTRY(hs.init(ws, !(host_is_pinned(x) && host_is_pinned(size)),
-                  !(host_is_pinned(vit ? y : nullptr) && host_is_pinned(want_g ? gamma : nullptr) &&
-                    host_is_pinned(want_ll ? ll : nullptr)),
+                  !(host_is_pinned(want_g ? gamma : nullptr) && host_is_pinned(want_ll ? ll : nullptr)),
                   2 * ((size_t)T * Bc * sizeof(int32_t) + 256),
-                  (vit ? (size_t)T * Bc * sizeof(int32_t) + 256 : 0) +
-                      (want_g ? 2 * ((size_t)T * Bc * sizeof(double) + 256) : 0) +
-                      (want_ll ? (size_t)nseg * (Bc * sizeof(double) + 256) : 0)));
+                  (want_g ? 2 * ((size_t)T * Bc * sizeof(double) + 256) : 0) +
+                      (want_ll ? (size_t)nseg * (Bc * sizeof(double) + 256) : 0) + 256,
+                  vit ? (size_t)T * Bc : 0));
     int rc = HB_OK;
     for (int64_t i = 0; i < nb && rc == HB_OK; i++) {
         const int k = (int)(i & 1);
@@ -1250,7 +1295,7 @@ int hb_hmm_binom_host(const int32_t *x, const int32_t *size, int64_t T, int64_t 
                         prob, rho, Pi, delta, flags, d_y, ld, d_g, ld, d_ll, ws->s_cmp, i == 0);
         if (rc != HB_OK) break;
         if (vit)
-            CU(hb::launch_transpose_u8_back(d_y, ld, T, bn, ws->pout_y[k].as<int32_t>(), ws->s_cmp));
+            CU(hb::launch_transpose_u8_back_u8(d_y, ld, T, bn, ws->pout_y[k].as<uint8_t>(), ws->s_cmp));
         if (want_g)
             for (int pl = 0; pl < 2; pl++)
                 CU(hb::launch_transpose_f64_back(d_g + (int64_t)pl * T * ld, ld, T, bn,
@@ -1260,7 +1305,7 @@ int hb_hmm_binom_host(const int32_t *x, const int32_t *size, int64_t T, int64_t 
         CU(cudaStreamWaitEvent(ws->s_out, ws->ev_out[k], 0));
         hs.begin_out(k);
         if (vit)
-            HBTRY(hs.d2h(k, y + b0 * T, ws->pout_y[k].p, (size_t)T * bn * sizeof(int32_t), ws->s_out));
+            HBTRY(hs.d2h_widen(k, y + b0 * T, ws->pout_y[k].as<uint8_t>(), (size_t)T * bn, ws->s_out));
         if (want_g)
             for (int pl = 0; pl < 2; pl++)
                 HBTRY(hs.d2h(k, gamma + ((int64_t)pl * B + b0) * T,

@@ -681,6 +681,12 @@ cudaError_t launch_transpose_u8_back(const uint8_t *src, int64_t ld, int64_t G, 
     transpose_out_kernel<uint8_t, int32_t><<<tgrid(G, N), dim3(32, 8), 0, st>>>(src, ld, G, N, dst);
     return cudaGetLastError();
 }
+cudaError_t launch_transpose_u8_back_u8(const uint8_t *src, int64_t ld, int64_t G, int64_t N,
+                                        uint8_t *dst, cudaStream_t st)
+{
+    transpose_out_kernel<uint8_t, uint8_t><<<tgrid(G, N), dim3(32, 8), 0, st>>>(src, ld, G, N, dst);
+    return cudaGetLastError();
+}
 cudaError_t launch_transpose_f64_back(const double *src, int64_t ld, int64_t G, int64_t N,
                                       double *dst, cudaStream_t st)
 {

@@ -38,6 +38,8 @@ cudaError_t launch_transpose_i32(const int32_t *src, int64_t G, int64_t N, int32
                                  int64_t ld, cudaStream_t st);
 cudaError_t launch_transpose_u8_back(const uint8_t *src, int64_t ld, int64_t G, int64_t N,
                                      int32_t *dst, cudaStream_t st);
+cudaError_t launch_transpose_u8_back_u8(const uint8_t *src, int64_t ld, int64_t G, int64_t N,
+                                        uint8_t *dst, cudaStream_t st);
 cudaError_t launch_transpose_f64_back(const double *src, int64_t ld, int64_t G, int64_t N,
                                       double *dst, cudaStream_t st);
 cudaError_t launch_transpose_i32_back(const int32_t *src, int64_t ld, int64_t G, int64_t N,
