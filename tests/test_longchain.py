@@ -438,3 +438,36 @@ def test_gpu_seam_posteriors(oracle, golden_gexp):
     assert np.array_equal(res[0]["y"], res[1]["y"]) and (res[0]["y"][2100:2500, 0] == 1).all()
     assert np.abs(res[0]["gamma"] - res[1]["gamma"]).max() < 1e-9
     assert np.allclose(res[0]["ll"], res[1]["ll"], rtol=1e-12)
+
+
+@pytest.mark.gpu
+def test_gpu_random_shapes(oracle):
+    """Odd chain counts and lengths around the staging-window and block sizes (nb = 1, 63, 64, 65, 129 ...),
+    forced block lengths, coarse emission grids: device states equal the oracle's; posteriors 1e-9."""
+    import torch
+    from honeybadger_b200 import hmm
+    rng = np.random.default_rng(77)
+    cases = [(2, 1 + 64 * 16, 3, 16), (3, 2 + 64 * 16, 2, 16), (2, 65 * 16, 5, 16), (3, 129 * 32 + 7, 1, 32),
+             (2, 63 * 16 + 1, 33, 16), (3, 4097, 40, 0), (2, 2, 1, 0), (3, 3, 7, 1)]
+    for _ in range(24):
+        cases.append((int(rng.choice([2, 3])), int(rng.integers(1, 6000)), int(rng.integers(1, 9)),
+                      int(rng.choice([0, 1, 3, 16, 64, 512]))))
+    for S, T, K, L in cases:
+        scale = float(rng.choice([0.01, 1.0, 50.0]))
+        lb = -rng.gamma(1.5, scale, size=(K, T, S))
+        if rng.random() < 0.5:
+            grid = 2.0 ** -int(rng.integers(20, 46))
+            lb = np.round(lb / grid) * grid - grid / 2
+        lb = np.ascontiguousarray(lb)
+        Pi = sym_Pi(S, float(rng.choice([1e-8, 1e-6, 1e-2])))
+        delta = rng.dirichlet(np.ones(S))
+        dl = torch.from_numpy(lb).cuda()
+        y = hmm.viterbi_long_logb_dev(dl, Pi, delta, L)
+        hmm.status_dev()
+        rcs, yr = ref_paths(oracle, lb, Pi, delta)
+        assert not any(rcs) and np.array_equal(y.cpu().numpy(), yr), (S, T, K, L)
+        if scale <= 1.0:
+            g, ll = hmm.forwardback_long_logb_dev(dl, Pi, delta, L)
+            gr, llr = ref_posteriors(oracle, lb, Pi, delta)
+            assert np.abs(g.cpu().numpy() - gr).max() < 1e-9, (S, T, K, L)
+            assert np.allclose(ll.cpu().numpy(), llr, rtol=1e-11, atol=1e-9)
