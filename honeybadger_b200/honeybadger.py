@@ -391,9 +391,9 @@ def allele_round_dev(r_dev, n_dev, member, pd_, pn, t):
     G, N = r_dev.shape
     member = np.ascontiguousarray(member, dtype=np.uint8)
     K = member.shape[0]
-    y = np.zeros((K, G), dtype=np.int32)
-    mafl = np.zeros((K, G), dtype=np.int32)
-    sizel = np.zeros((K, G), dtype=np.int32)
+    y = np.empty((K, G), dtype=np.int32)      # filled by the call (an error raises before they are used)
+    mafl = np.empty((K, G), dtype=np.int32)
+    sizel = np.empty((K, G), dtype=np.int32)
     Pi, delta, prob = sym_Pi(2, t), np.array([0.0, 1.0]), np.array([pd_, pn], dtype=np.float64)
     _lib.check(lib.hb_allele_pooled_viterbi_dev(r_dev.data_ptr(), n_dev.data_ptr(), r_dev.stride(0), G,
                                                 N, _vp(member), K, _vp(prob), _vp(Pi), _vp(delta),
