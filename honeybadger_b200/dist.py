@@ -35,6 +35,35 @@ def allreduce_pooled_counts(mafl_local, sizel_local):
     return t[0], t[1]
 
 
+def pooled_allele_round(r_local, n_local, member_local, pd_=0.1, pn=0.45, t=1e-6):
+    """One pooled round of calcAlleleCnvBoundaries (R/HoneyBADGER.R:1395-1417) on cells sharded over the ranks.
+
+    r_local, n_local: this rank's columns of the resident count matrices (gene-major int32 CUDA tensors);
+    member_local [K, cells of this rank].  Every rank counts its own cells (`hb_pool_count_pos_dev`), the
+    integer partials are all-reduced — exact and invariant to the GPU count — and the K pooled chains then
+    run on every rank through the reference-shaped host entry point, i.e. parallel along the gene axis
+    (csrc/hb_longchain.cuh; 0.75 ms for 6 x 200 000), which is cheaper than shipping states around.
+    Returns (y int32 [K, G] 1-based, mafl, sizel) — identical on all ranks and to a single-GPU round."""
+    import ctypes as C
+    import torch
+    from . import _lib, hmm
+    lib = _lib.load()
+    G = r_local.shape[0]
+    member_local = np.ascontiguousarray(member_local, dtype=np.uint8)
+    K, n_loc = member_local.shape
+    md = torch.from_numpy(member_local).to(r_local.device)
+    cnt = torch.zeros((2, K, G), dtype=torch.int32, device=r_local.device)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    if n_loc > 0:
+        for i, m in enumerate((r_local, n_local)):
+            _lib.check(lib.hb_pool_count_pos_dev(m.data_ptr(), m.stride(0), G, n_loc, md.data_ptr(), K,
+                                                 cnt[i].data_ptr(), st))
+    mafl, sizel = allreduce_pooled_counts(cnt[0], cnt[1])
+    mafl, sizel = mafl.cpu().numpy(), sizel.cpu().numpy()
+    out = hmm.hmm_binom_host(mafl.T, sizel.T, [pd_, pn], hmm.sym_Pi(2, t), [0.0, 1.0])
+    return np.ascontiguousarray(out["y"].T), mafl, sizel
+
+
 def allgather_region_posteriors(local, n_cells: int):
     """local: [regions, cells_of_this_rank] -> [regions, n_cells] on every rank (cells in global order).
 

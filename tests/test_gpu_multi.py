@@ -61,6 +61,19 @@ def _worker(rank, world, port, q):
     _, mafl_f, sizel_f = hb.allele_round_dev(torch.from_numpy(r).cuda(), torch.from_numpy(n).cuda(), memb,
                                              0.1, 0.45, 1e-6)
     ok = ok and (mafl.cpu().numpy() == mafl_f[0]).all() and (sizel.cpu().numpy() == sizel_f[0]).all()
+    # the whole pooled round on sharded cells == the single-GPU round (states, counts), on every rank
+    memb3 = np.stack([np.ones(N, bool), np.arange(N) % 2 == 0, np.arange(N) % 2 == 1]).astype(np.uint8)
+    nn = np.where(rng.random((2600, N)) < 0.3, rng.integers(1, 4, (2600, N)), 0).astype(np.int32)
+    pp = np.full((2600, 1), 0.45)
+    pp[700:1100] = 0.02
+    rr = rng.binomial(nn, pp).astype(np.int32)
+    y_s, mafl_s, sizel_s = hd.pooled_allele_round(torch.from_numpy(np.ascontiguousarray(rr[:, lo:hi])).cuda(),
+                                                  torch.from_numpy(np.ascontiguousarray(nn[:, lo:hi])).cuda(),
+                                                  memb3[:, lo:hi])
+    y_1, mafl_1, sizel_1 = hb.allele_round_dev(torch.from_numpy(rr).cuda(), torch.from_numpy(nn).cuda(), memb3,
+                                               0.1, 0.45, 1e-6)
+    ok = ok and np.array_equal(y_s, y_1) and np.array_equal(mafl_s, mafl_1) and np.array_equal(sizel_s, sizel_1)
+    ok = ok and bool((y_1[0, 750:1050] == 1).all())
     post = torch.arange(4 * N, dtype=torch.float64, device="cuda").reshape(4, N)
     got = hd.allgather_region_posteriors(post[:, lo:hi].contiguous(), N)
     ok = ok and bool(torch.equal(got, post))
