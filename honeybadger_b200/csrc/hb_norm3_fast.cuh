@@ -265,15 +265,30 @@ HB_HD void fast_backward_one(const Norm3Const &c, Fast3State &s, uint8_t *yp, do
 // cp.async per lane and row.  g = this chain's element of the half's first row, lane_c = this chain's
 // column inside its tile (pointer bases), lane = the executing lane (which pieces it moves).  Lanes
 // read slots that other lanes filled: a __syncwarp follows every wait and precedes every refill.
+// LAST: the backward sweep's reads are the last use of x — with -DHB_BWD_EVICT_FIRST they carry an L2
+// evict-first policy so that the forward sweeps' freshly read tails survive longer (experiment).
+template <bool LAST = false>
 HB_HD void xs_refill_half_coop(Norm3Smem &m, int h, const double *g, int lane_c, int lane)
 {
 #if defined(__CUDA_ARCH__)
     const double *gb = g - lane_c;
     double *sb = m.xs - lane_c + h * HB_HALF * m.st;
+#if defined(HB_BWD_EVICT_FIRST)
+    uint64_t pol = 0;
+    if (LAST) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+#endif
 #pragma unroll
     for (int q = 0; q < HB_HALF / 2; q++) {
         const int p = lane + 32 * q, r = p >> 4, e = (p & 15) * 2;
         unsigned sa = (unsigned)__cvta_generic_to_shared(sb + r * m.st + e);
+#if defined(HB_BWD_EVICT_FIRST)
+        if (LAST) {
+            asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(sa),
+                         "l"(gb + r * 32 + e), "l"(pol)
+                         : "memory");
+            continue;
+        }
+#endif
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gb + r * 32 + e) : "memory");
     }
 #else
@@ -584,7 +599,7 @@ HB_HD void norm3_fast_chain(const Norm3Args &a, int32_t seg, int64_t b, Norm3Sme
 #pragma unroll
         for (int h = 0; h < 2; h++) {
             if (COOP) {
-                xs_refill_half_coop(m, h, xl, lane_c, lane);
+                xs_refill_half_coop<true>(m, h, xl, lane_c, lane);
                 xl += HB_HALF * ld;
             } else {
 #pragma unroll
@@ -698,7 +713,7 @@ HB_HD void norm3_fast_chain(const Norm3Args &a, int32_t seg, int64_t b, Norm3Sme
                     }
                     if (COOP) {
                         warp_sync();
-                        if (more) xs_refill_half_coop(m, h, xh, lane_c, lane);
+                        if (more) xs_refill_half_coop<true>(m, h, xh, lane_c, lane);
                     }
                     if (!BULK) xs_commit(m);
                 }
