@@ -111,6 +111,19 @@ struct Workspace {
                 ev_out[2] = {nullptr, nullptr}, ev_free_out[2] = {nullptr, nullptr};
     std::vector<int64_t> seg_cached;
     int64_t nchunks = 0;
+    int32_t last_norm3_fast = -1, last_binom2_lean = -1; // kernels of the last launches (hb_last_kernels)
+    // Stream hand-over: the scratch above is shared by every call on this device.  Each entry point records
+    // ev_use on its stream when it has enqueued its work; a call on a DIFFERENT stream first makes its stream
+    // wait for that event, so two streams never overlap on the same scratch (WsUse below).
+    cudaEvent_t ev_use = nullptr;
+    cudaStream_t last_st = nullptr;
+    bool used = false;
+    // Pinned staging for small host tables (segment offsets, emission tables): uploaded with
+    // cudaMemcpyAsync on the caller's stream, no device-wide or stream-wide synchronisation.
+    void *stage = nullptr;
+    size_t stage_cap = 0, stage_off = 0;
+    cudaEvent_t ev_stage = nullptr;
+    bool stage_pending = false;
     double lut_key[3] = {-1, -1, -1};
     int32_t lut_nmax = -1;
     void release_all()
@@ -145,6 +158,14 @@ struct Workspace {
             ev_bin[k] = ev_bout[k] = nullptr;
         }
         bounce_in_cap = bounce_out_cap = bounce_y_cap = 0;
+        if (stage) cudaFreeHost(stage);
+        stage = nullptr;
+        stage_cap = stage_off = 0;
+        stage_pending = false;
+        if (ev_stage) cudaEventDestroy(ev_stage);
+        if (ev_use) cudaEventDestroy(ev_use);
+        ev_stage = ev_use = nullptr;
+        used = false;
         seg_cached.clear();
         lut_nmax = -1;
         lut_key[0] = -1;
@@ -154,9 +175,11 @@ struct Workspace {
 std::mutex g_mu;
 Workspace g_ws[16];
 int g_lut_nmax_cfg = 511;
-int g_binom2_mode = 0; // 0 auto (lean kernel, general kernel behind its gate), 1 general kernel only
-int g_longchain_mode = 0; // 0 auto (pooled allele rounds), 1 never, 2 also the pooled expression rounds
-int g_norm3_mode = 0; // 0 auto, 1 literal kernel only, 2 speculative kernel with every chain re-run exactly, 3 speculative kernel whenever eligible
+// Kernel-choice switches are per calling thread (test / experiment hooks; two callers with different
+// settings do not interfere).
+thread_local int g_binom2_mode = 0; // 0 auto (lean kernel, general kernel behind its gate), 1 general kernel only
+thread_local int g_longchain_mode = 0; // 0 auto (pooled allele rounds), 1 never, 2 also the pooled expression rounds
+thread_local int g_norm3_mode = 0; // 0 auto, 1 literal kernel only, 2 speculative kernel with every chain re-run exactly, 3 speculative kernel whenever eligible
 
 int cur_ws(Workspace **out)
 {
@@ -170,6 +193,72 @@ int cur_ws(Workspace **out)
     *out = &g_ws[dev];
     return HB_OK;
 }
+
+// Host table -> device on `st` without synchronising the stream: the bytes are parked in a pinned arena
+// that lives until the copy has run.  The arena is recycled per API call (stage_begin, from WsUse::enter); the only host wait
+// is for an EARLIER call's table copy that has not executed yet, and only when tables change (they are
+// cached per workspace), never in steady state.
+int stage_begin(Workspace *ws)
+{
+    if (ws->stage_pending) {
+        CU(cudaEventSynchronize(ws->ev_stage));
+        ws->stage_pending = false;
+    }
+    ws->stage_off = 0;
+    return HB_OK;
+}
+int upload_async(Workspace *ws, void *dst, const void *src, size_t bytes, cudaStream_t st)
+{
+    if (!bytes) return HB_OK;
+    const size_t need = ws->stage_off + ((bytes + 255) & ~(size_t)255);
+    if (need > ws->stage_cap) {
+        // earlier copies of this call may still read the old arena: let them finish before it goes
+        if (ws->stage_off) CU(cudaStreamSynchronize(st));
+        void *np_ = nullptr;
+        const size_t cap = std::max(need + need / 2, (size_t)1 << 20);
+        CU(cudaHostAlloc(&np_, cap, cudaHostAllocDefault));
+        if (ws->stage) cudaFreeHost(ws->stage);
+        ws->stage = np_;
+        ws->stage_cap = cap;
+        ws->stage_off = 0;
+    }
+    if (!ws->ev_stage) CU(cudaEventCreateWithFlags(&ws->ev_stage, cudaEventDisableTiming));
+    char *b = (char *)ws->stage + ws->stage_off;
+    memcpy(b, src, bytes);
+    ws->stage_off += (bytes + 255) & ~(size_t)255;
+    CU(cudaMemcpyAsync(dst, b, bytes, cudaMemcpyHostToDevice, st));
+    CU(cudaEventRecord(ws->ev_stage, st));
+    ws->stage_pending = true;
+    return HB_OK;
+}
+
+// RAII: orders this call's use of the per-device scratch after the previous user's (other stream).
+struct WsUse {
+    Workspace *ws = nullptr;
+    cudaStream_t st = nullptr;
+    int enter(Workspace *w, cudaStream_t s)
+    {
+        if (!w->ev_use) CU(cudaEventCreateWithFlags(&w->ev_use, cudaEventDisableTiming));
+        if (w->used && w->last_st != s) CU(cudaStreamWaitEvent(s, w->ev_use, 0));
+        HBTRY(stage_begin(w));
+        ws = w;
+        st = s;
+        return HB_OK;
+    }
+    ~WsUse()
+    {
+        if (!ws) return;
+        if (cudaEventRecord(ws->ev_use, st) == cudaSuccess) {
+            ws->last_st = st;
+            ws->used = true;
+        } else {
+            cudaGetLastError();
+        }
+    }
+};
+#define WS_USE(stream_)                                                                           \
+    WsUse ws_use_;                                                                                \
+    HBTRY(ws_use_.enter(ws, (cudaStream_t)(stream_)))
 
 // Segment tables on the device: seg_off[nseg+1] | chunk_off[nseg+1] | order[nseg] (int32).
 int prepare_segments(Workspace *ws, const int64_t *seg_off, int32_t nseg, int64_t T,
@@ -199,11 +288,10 @@ int prepare_segments(Workspace *ws, const int64_t *seg_off, int32_t nseg, int64_
         std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
             return (seg_off[a + 1] - seg_off[a]) > (seg_off[b + 1] - seg_off[b]);
         });
-        // synchronous copies: the temporaries die at the end of this scope
-        CU(cudaStreamSynchronize(st));
-        CU(cudaMemcpy(ws->segtab.p, host.data(), 2 * n64 * sizeof(int64_t), cudaMemcpyHostToDevice));
-        CU(cudaMemcpy((char *)ws->segtab.p + 2 * n64 * sizeof(int64_t), order.data(),
-                      (size_t)nseg * sizeof(int32_t), cudaMemcpyHostToDevice));
+        // through the pinned arena: the temporaries die at the end of this scope, the stream is not waited for
+        HBTRY(upload_async(ws, ws->segtab.p, host.data(), 2 * n64 * sizeof(int64_t), st));
+        HBTRY(upload_async(ws, (char *)ws->segtab.p + 2 * n64 * sizeof(int64_t), order.data(),
+                           (size_t)nseg * sizeof(int32_t), st));
         ws->seg_cached.assign(seg_off, seg_off + n64);
         ws->nchunks = acc;
     }
@@ -321,10 +409,9 @@ int norm3_run(Workspace *ws, const double *x, int64_t ld, int64_t T, int64_t B,
     a.psi = ws->psi.as<uint64_t>();
     a.ckpt = ws->ckpt.as<double>();
     a.status = ws->status.as<int32_t>();
-    if (fb && !a.gamma) {
-        // LL only: the kernel still writes posteriors; give it scratch to write to
-        return fail(HB_ERR_ARG, "HB_WANT_LL currently requires HB_WANT_GAMMA");
-    }
+    // HB_WANT_LL without HB_WANT_GAMMA: the forward sweep alone (the kernels return after storing LL when
+    // no posterior buffer is given); with Viterbi as well, the Viterbi-only launch precedes it.
+    const bool ll_only = fb && !a.gamma;
     // Speculate-and-verify kernel: the reference's symmetric parameter block, state 1 reachable at
     // t = 0 (the differences are taken against nu_1), chains short enough for a useful error bound.
     // Auto mode uses it when every row starts on a 1 KB boundary (ld, ldy/8... multiples of 128
@@ -334,11 +421,17 @@ int norm3_run(Workspace *ws, const double *x, int64_t ld, int64_t T, int64_t B,
     for (int32_t s = 0; s < nseg; s++) lmax = std::max(lmax, seg_off[s + 1] - seg_off[s]);
     const bool fast_ok = sym && delta[1] > 0 && Pi[0] > 0 && lmax <= HB_FAST_LMAX;
     const bool padded = tiled || (ld % 128 == 0 && (!a.gamma || ldg % 128 == 0));
-    if (fast_ok && (g_norm3_mode >= 2 || (g_norm3_mode == 0 && padded))) {
-        if (g_norm3_mode == 2) a.c.eps_scale = INFINITY;
-        CU(hb::launch_norm3_fast(a, vit, fb, st));
+    const bool fast = fast_ok && (g_norm3_mode >= 2 || (g_norm3_mode == 0 && padded));
+    if (fast && g_norm3_mode == 2) a.c.eps_scale = INFINITY;
+    ws->last_norm3_fast = fast ? 1 : 0;
+    auto launch = [&](bool v, bool f) {
+        return fast ? hb::launch_norm3_fast(a, v, f, st) : hb::launch_norm3(a, sym, v, f, st);
+    };
+    if (ll_only) {
+        if (vit) CU(launch(true, false));
+        CU(launch(false, true));
     } else {
-        CU(hb::launch_norm3(a, sym, vit, fb, st));
+        CU(launch(vit, fb));
     }
     return HB_OK;
 }
@@ -487,10 +580,9 @@ int prepare_lut(Workspace *ws, const double *prob, double rho, cudaStream_t st)
     HBTRY(ws->lut_lb.ensure(lb.size() * sizeof(double)));
     HBTRY(ws->lut_rho.ensure(rr.size() * sizeof(hb::RhoME)));
     HBTRY(ws->lut_rho_d.ensure(rd.size() * sizeof(double)));
-    CU(cudaStreamSynchronize(st));
-    CU(cudaMemcpy(ws->lut_lb.p, lb.data(), lb.size() * sizeof(double), cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(ws->lut_rho.p, rr.data(), rr.size() * sizeof(hb::RhoME), cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(ws->lut_rho_d.p, rd.data(), rd.size() * sizeof(double), cudaMemcpyHostToDevice));
+    HBTRY(upload_async(ws, ws->lut_lb.p, lb.data(), lb.size() * sizeof(double), st));
+    HBTRY(upload_async(ws, ws->lut_rho.p, rr.data(), rr.size() * sizeof(hb::RhoME), st));
+    HBTRY(upload_async(ws, ws->lut_rho_d.p, rd.data(), rd.size() * sizeof(double), st));
     ws->lut_nmax = nmax;
     ws->lut_key[0] = prob[0];
     ws->lut_key[1] = prob[1];
@@ -517,8 +609,7 @@ int binom2_run(Workspace *ws, const int32_t *x, const int32_t *n, int64_t ld, in
     HBTRY(check_flags(flags, y, gamma, ll, &vit, &fb));
     if (!tiled && vit && ldy < B) return fail(HB_ERR_ARG, "ldy < B");
     if (!tiled && (flags & HB_WANT_GAMMA) && ldg < B) return fail(HB_ERR_ARG, "ldg < B");
-    if (fb && !(flags & HB_WANT_GAMMA))
-        return fail(HB_ERR_ARG, "HB_WANT_LL currently requires HB_WANT_GAMMA");
+    const bool ll_only = fb && !(flags & HB_WANT_GAMMA);
     hb::Binom2Args a;
     memset(&a, 0, sizeof a);
     for (int k = 0; k < 2; k++) {
@@ -577,12 +668,25 @@ int binom2_run(Workspace *ws, const int32_t *x, const int32_t *n, int64_t ld, in
         return HB_OK;
     }
     const bool lean_ok = Pi[0] > 0 && Pi[1] > 0 && Pi[2] > 0 && Pi[3] > 0;
-    if (lean_ok && g_binom2_mode != 1) {
-        a.gate = ws->status.as<int32_t>() + 2;
-        CU(hb::launch_binom2_fast(a, vit, fb, st));
-        a.gate_in = a.gate;
+    const bool lean = lean_ok && g_binom2_mode != 1;
+    ws->last_binom2_lean = lean ? 1 : 0;
+    if (lean) a.gate = ws->status.as<int32_t>() + 2;
+    auto launch = [&](bool v, bool f) -> cudaError_t {
+        hb::Binom2Args c = a;
+        if (lean) {
+            cudaError_t e = hb::launch_binom2_fast(c, v, f, st);
+            if (e != cudaSuccess) return e;
+            c.gate_in = c.gate;
+        }
+        return hb::launch_binom2(c, v, f, st);
+    };
+    // HB_WANT_LL without HB_WANT_GAMMA: Viterbi-only launch (if wanted), then the forward sweep alone
+    if (ll_only) {
+        if (vit) CU(launch(true, false));
+        CU(launch(false, true));
+    } else {
+        CU(launch(vit, fb));
     }
-    CU(hb::launch_binom2(a, vit, fb, st));
     return HB_OK;
 }
 
@@ -638,19 +742,19 @@ int longchain_host_outputs(Workspace *ws, int32_t S, int64_t T, int64_t B, const
 {
     const bool vit = (flags & HB_WANT_VITERBI) != 0, want_g = (flags & HB_WANT_GAMMA) != 0,
                want_ll = (flags & HB_WANT_LL) != 0;
-    if (want_ll && !want_g) return fail(HB_ERR_ARG, "HB_WANT_LL currently requires HB_WANT_GAMMA");
     if (vit) {
         HBTRY(ws->st_out.ensure((size_t)T * B * sizeof(int32_t)));
         HBTRY(longchain_run(ws, S, ws->lc_lb.as<double>(), T, (int32_t)B, Pi, delta, ws->st_out.as<int32_t>(), 0,
                             status_reset));
         CU(cudaMemcpyAsync(y, ws->st_out.p, (size_t)T * B * sizeof(int32_t), cudaMemcpyDeviceToHost, 0));
     }
-    if (want_g) {
+    if (want_g || want_ll) { // (LL alone: the posteriors land in scratch and stay on the device)
         HBTRY(ws->st_g.ensure((size_t)T * B * S * sizeof(double)));
         HBTRY(ws->st_ll.ensure((size_t)B * sizeof(double)));
         HBTRY(longchain_fb_run(ws, S, ws->lc_lb.as<double>(), T, (int32_t)B, Pi, delta, ws->st_g.as<double>(),
                                want_ll ? ws->st_ll.as<double>() : nullptr, 0, 0, true));
-        CU(cudaMemcpyAsync(gamma, ws->st_g.p, (size_t)T * B * S * sizeof(double), cudaMemcpyDeviceToHost, 0));
+        if (want_g)
+            CU(cudaMemcpyAsync(gamma, ws->st_g.p, (size_t)T * B * S * sizeof(double), cudaMemcpyDeviceToHost, 0));
         if (want_ll)
             CU(cudaMemcpyAsync(ll, ws->st_ll.p, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, 0));
     }
@@ -727,16 +831,14 @@ int hb_set_norm3_mode(int32_t mode)
 {
     if (mode < 0 || mode > 3)
         return fail(HB_ERR_ARG, "mode must be 0 (auto), 1 (literal), 2 (speculative, re-run all) or 3 (speculative)");
-    std::lock_guard<std::mutex> lk(g_mu);
-    g_norm3_mode = mode;
+    g_norm3_mode = mode; // thread-local
     return HB_OK;
 }
 
 int hb_set_binom2_mode(int32_t mode)
 {
     if (mode < 0 || mode > 1) return fail(HB_ERR_ARG, "mode must be 0 (auto) or 1 (general kernel only)");
-    std::lock_guard<std::mutex> lk(g_mu);
-    g_binom2_mode = mode;
+    g_binom2_mode = mode; // thread-local
     return HB_OK;
 }
 
@@ -745,6 +847,7 @@ int hb_binom2_stats_dev(void *stream, int32_t *general_rerun)
     std::lock_guard<std::mutex> lk(g_mu);
     Workspace *ws;
     HBTRY(cur_ws(&ws));
+    WS_USE(stream);
     if (!general_rerun) return fail(HB_ERR_ARG, "general_rerun is NULL");
     *general_rerun = 0;
     if (!ws->status.p) return HB_OK;
@@ -760,6 +863,7 @@ int hb_norm3_stats_dev(void *stream, int64_t *rerun_chains)
     std::lock_guard<std::mutex> lk(g_mu);
     Workspace *ws;
     HBTRY(cur_ws(&ws));
+    WS_USE(stream);
     if (!rerun_chains) return fail(HB_ERR_ARG, "rerun_chains is NULL");
     *rerun_chains = 0;
     if (!ws->status.p) return HB_OK;
@@ -770,11 +874,22 @@ int hb_norm3_stats_dev(void *stream, int64_t *rerun_chains)
     return HB_OK;
 }
 
+int hb_last_kernels(int32_t *norm3_fast, int32_t *binom2_lean)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    Workspace *ws;
+    HBTRY(cur_ws(&ws));
+    if (norm3_fast) *norm3_fast = ws->last_norm3_fast;
+    if (binom2_lean) *binom2_lean = ws->last_binom2_lean;
+    return HB_OK;
+}
+
 int hb_status_dev(void *stream)
 {
     std::lock_guard<std::mutex> lk(g_mu);
     Workspace *ws;
     HBTRY(cur_ws(&ws));
+    WS_USE(stream);
     if (!ws->status.p) return HB_OK;
     return read_status(ws, (cudaStream_t)stream);
 }
@@ -788,6 +903,7 @@ int hb_hmm_norm_dev(const double *x, int64_t ld, int64_t T, int64_t B, const int
     std::lock_guard<std::mutex> lk(g_mu);
     Workspace *ws;
     HBTRY(cur_ws(&ws));
+    WS_USE(stream);
     return norm3_run(ws, x, ld, T, B, seg_off, nseg, mean, sd, nullptr, nullptr, sd_per_seg, Pi,
                      delta, flags, y, ldy, gamma, ldg, ll, (cudaStream_t)stream);
 }
@@ -1022,6 +1138,7 @@ int hb_hmm_norm_tiled_dev(const double *x, int64_t T, int64_t B, const int64_t *
     std::lock_guard<std::mutex> lk(g_mu);
     Workspace *ws;
     HBTRY(cur_ws(&ws));
+    WS_USE(stream);
     // tiles are moved in 16-byte pieces and the states of a chunk as one 8-byte store per lane
     if (((uintptr_t)x & 15) || ((uintptr_t)y & 7)) return fail(HB_ERR_ARG, "tiled buffers must be 16-byte aligned");
     return norm3_run(ws, x, 32, T, B, seg_off, nseg, mean, sd, nullptr, nullptr, sd_per_seg, Pi, delta,
@@ -1044,7 +1161,9 @@ int hb_hmm_norm_host(const double *x, int64_t T, int64_t B, const int64_t *seg_o
     bool vit, fb;
     HBTRY(check_flags(flags, y, gamma, ll, &vit, &fb));
     const bool want_g = (flags & HB_WANT_GAMMA) != 0, want_ll = (flags & HB_WANT_LL) != 0;
+    WsUse ws_use_;
     if (long_chain_shape(T, B, nseg, flags) && seg_off[0] == 0 && seg_off[1] == T) {
+        HBTRY(ws_use_.enter(ws, 0));
         // the drop-in seam itself: Viterbi(dthmm(x, ...)) on one (or a few) long pooled vectors.  R's
         // column-major [T x B] is already chain-major: emissions in parallel, chains along the gene axis.
         hb::Norm3Const nc;
@@ -1070,6 +1189,7 @@ int hb_hmm_norm_host(const double *x, int64_t T, int64_t B, const int64_t *seg_o
         return longchain_host_outputs(ws, 3, T, B, Pi, delta, flags, y, gamma, ll, false);
     }
     HBTRY(pipe_init(ws));
+    HBTRY(ws_use_.enter(ws, ws->s_cmp));
     const int64_t Bc = pipe_batch(B, 130.0 * (double)T);
     const int64_t nb = (B + Bc - 1) / Bc;
     const int64_t ldc = (Bc + 127) / 128 * 128;
@@ -1176,6 +1296,7 @@ int hb_hmm_binom_dev(const int32_t *x, const int32_t *size, int64_t ld, int64_t 
     std::lock_guard<std::mutex> lk(g_mu);
     Workspace *ws;
     HBTRY(cur_ws(&ws));
+    WS_USE(stream);
     return binom2_run(ws, x, size, ld, T, B, seg_off, nseg, prob, rho, Pi, delta, flags, y, ldy,
                       gamma, ldg, ll, (cudaStream_t)stream);
 }
@@ -1188,6 +1309,7 @@ int hb_hmm_binom_tiled_dev(const int32_t *x, const int32_t *size, int64_t T, int
     std::lock_guard<std::mutex> lk(g_mu);
     Workspace *ws;
     HBTRY(cur_ws(&ws));
+    WS_USE(stream);
     if (((uintptr_t)x & 15) || ((uintptr_t)size & 15)) return fail(HB_ERR_ARG, "tiled buffers must be 16-byte aligned");
     return binom2_run(ws, x, size, 32, T, B, seg_off, nseg, prob, rho, Pi, delta, flags, y, 32, gamma,
                       32, ll, (cudaStream_t)stream, true, false, true);
@@ -1201,6 +1323,7 @@ int hb_hmm_binom_packed_tiled_dev(const uint32_t *xn, int64_t T, int64_t B, cons
     std::lock_guard<std::mutex> lk(g_mu);
     Workspace *ws;
     HBTRY(cur_ws(&ws));
+    WS_USE(stream);
     if ((uintptr_t)xn & 15) return fail(HB_ERR_ARG, "tiled buffers must be 16-byte aligned");
     return binom2_run(ws, (const int32_t *)xn, nullptr, 32, T, B, seg_off, nseg, prob, rho, Pi, delta, flags,
                       y, 32, gamma, 32, ll, (cudaStream_t)stream, true, false, true, true);
@@ -1211,6 +1334,7 @@ int hb_pack_counts_dev(const int32_t *x, const int32_t *size, int64_t count, uin
     std::lock_guard<std::mutex> lk(g_mu);
     Workspace *ws;
     HBTRY(cur_ws(&ws));
+    WS_USE(stream);
     if (!x || !size || !out || count < 1) return fail(HB_ERR_ARG, "bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
     HBTRY(ws->status.ensure(4 * sizeof(int32_t)));
@@ -1241,7 +1365,9 @@ int hb_hmm_binom_host(const int32_t *x, const int32_t *size, int64_t T, int64_t 
     bool vit, fb;
     HBTRY(check_flags(flags, y, gamma, ll, &vit, &fb));
     const bool want_g = (flags & HB_WANT_GAMMA) != 0, want_ll = (flags & HB_WANT_LL) != 0;
+    WsUse ws_use_;
     if (rho == 0.0 && long_chain_shape(T, B, nseg, flags) && seg_off[0] == 0 && seg_off[1] == T) {
+        HBTRY(ws_use_.enter(ws, 0));
         // Viterbi(dthmm(mafl, ..., "binom", ...)) on one (or a few) pooled count vectors: see hb_hmm_norm_host
         HBTRY(ws->st_in.ensure((size_t)T * B * sizeof(int32_t)));
         HBTRY(ws->st_in2.ensure((size_t)T * B * sizeof(int32_t)));
@@ -1251,6 +1377,7 @@ int hb_hmm_binom_host(const int32_t *x, const int32_t *size, int64_t T, int64_t 
         return longchain_host_outputs(ws, 2, T, B, Pi, delta, flags, y, gamma, ll, false);
     }
     HBTRY(pipe_init(ws));
+    HBTRY(ws_use_.enter(ws, ws->s_cmp));
     const int64_t Bc = pipe_batch(B, 100.0 * (double)T);
     const int64_t nb = (B + Bc - 1) / Bc;
     const int64_t ldc = (Bc + 127) / 128 * 128;
@@ -1383,6 +1510,7 @@ int hb_chain_sd_dev(const double *x, int64_t ld, int64_t T, int64_t B, const int
     std::lock_guard<std::mutex> lk(g_mu);
     Workspace *ws;
     HBTRY(cur_ws(&ws));
+    WS_USE(stream);
     if (!x || !sd || T < 2 || B < 1 || ld < B) return fail(HB_ERR_ARG, "bad arguments");
     const int64_t one_seg[2] = {0, T};
     if (!per_seg || !seg_off) {
@@ -1402,6 +1530,7 @@ int hb_pool_mean_dev(const double *x, int64_t ld, int64_t G, int64_t N, const ui
     std::lock_guard<std::mutex> lk(g_mu);
     Workspace *ws;
     HBTRY(cur_ws(&ws));
+    WS_USE(stream);
     if (!x || !member || !out || G < 1 || N < 1 || K < 1 || ld < N)
         return fail(HB_ERR_ARG, "bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
@@ -1454,6 +1583,7 @@ int hb_pool_count_pos_dev(const int32_t *v, int64_t ld, int64_t G, int64_t N,
     std::lock_guard<std::mutex> lk(g_mu);
     Workspace *ws;
     HBTRY(cur_ws(&ws));
+    WS_USE(stream);
     if (!v || !member || !out || G < 1 || N < 1 || K < 1 || ld < N)
         return fail(HB_ERR_ARG, "bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
@@ -1499,6 +1629,7 @@ int hb_ward_linkage_dev(double *D, int64_t N, int32_t *merge_a, int32_t *merge_b
     std::lock_guard<std::mutex> lk(g_mu);
     Workspace *ws;
     HBTRY(cur_ws(&ws));
+    WS_USE(stream);
     if (!D || !merge_a || !merge_b || !height || N < 2) return fail(HB_ERR_ARG, "bad arguments");
     HBTRY(ws->st_part.ensure((size_t)N * (sizeof(int32_t) * 2 + 1) + 64));
     int32_t *size = ws->st_part.as<int32_t>();
@@ -1548,6 +1679,7 @@ static int group_host(const double *x, const double *r, const double *n, int64_t
     std::lock_guard<std::mutex> lk(g_mu);
     Workspace *ws;
     HBTRY(cur_ws(&ws));
+    WS_USE(0);
     if (G < 1 || N < 1 || !ks || nk < 1 || !labels || window < 1 || (window & 1) == 0)
         return fail(HB_ERR_ARG, "bad arguments");
     if (N == 1) {
@@ -1689,6 +1821,7 @@ int hb_mean_nonzero_dev(const double *x, int64_t ld, int64_t G, int64_t N, int32
     std::lock_guard<std::mutex> lk(g_mu);
     Workspace *ws;
     HBTRY(cur_ws(&ws));
+    WS_USE(stream);
     if (!x || !mean || G < 1 || N < 1 || ld < N) return fail(HB_ERR_ARG, "bad arguments");
     return mean_nonzero(ws, x, ld, G, N, exact, mean, margin, (cudaStream_t)stream);
 }
@@ -1772,6 +1905,7 @@ int hb_set_gexp_mats_dev(const double *sc, int64_t ld, int64_t G, int64_t N, con
     std::lock_guard<std::mutex> lk(g_mu);
     Workspace *ws;
     HBTRY(cur_ws(&ws));
+    WS_USE(stream);
     if (!sc || !ref || !norm || !Gk || G < 1 || N < 1 || R < 1 || ld < N || ldr < R || ldo < N ||
         G >= ((int64_t)1 << 31) || N >= ((int64_t)1 << 32))
         return fail(HB_ERR_ARG, "bad arguments");
@@ -1786,6 +1920,7 @@ int hb_set_gexp_mats_host(const double *sc, int64_t G, int64_t N, const double *
     std::lock_guard<std::mutex> lk(g_mu);
     Workspace *ws;
     HBTRY(cur_ws(&ws));
+    WS_USE(0);
     if (!sc || !ref || !norm || !Gk || G < 1 || N < 1 || R < 1 || G >= ((int64_t)1 << 31) ||
         N >= ((int64_t)1 << 32))
         return fail(HB_ERR_ARG, "bad arguments");
@@ -1874,6 +2009,7 @@ int hb_set_allele_mats_dev(const int32_t *r, const int32_t *n_sc_init, int64_t l
     std::lock_guard<std::mutex> lk(g_mu);
     Workspace *ws;
     HBTRY(cur_ws(&ws));
+    WS_USE(stream);
     if (!r || !n_sc_init || !r_maf || !Gk || G < 1 || N < 1 || ld < N || ldo < N || G >= ((int64_t)1 << 31))
         return fail(HB_ERR_ARG, "bad arguments");
     return set_allele_mats(ws, r, n_sc_init, ld, G, N, l_init, n_bulk_init, filter, het_deviance_threshold,
@@ -1890,6 +2026,7 @@ int hb_set_allele_mats_host(const int32_t *r, const int32_t *n_sc_init, int64_t 
     std::lock_guard<std::mutex> lk(g_mu);
     Workspace *ws;
     HBTRY(cur_ws(&ws));
+    WS_USE(0);
     if (!r || !n_sc_init || !r_maf || !Gk || G < 1 || N < 1 || G >= ((int64_t)1 << 31))
         return fail(HB_ERR_ARG, "bad arguments");
     const int64_t ld = (N + 127) / 128 * 128;
@@ -1928,6 +2065,7 @@ int hb_retest_comb_dev(const double *x, int64_t ld, int64_t G, int64_t N, const 
     std::lock_guard<std::mutex> lk(g_mu);
     Workspace *ws;
     HBTRY(cur_ws(&ws));
+    WS_USE(stream);
     if (!x || !rows || !p_amp || !p_del || G < 1 || N < 1 || nrows < 1 || ld < N || phase < 0 || phase > 2)
         return fail(HB_ERR_ARG, "bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
@@ -1961,6 +2099,7 @@ int hb_retest_gexp_host(const double *gexp_rows, int64_t n, int64_t N, double ma
         std::lock_guard<std::mutex> lk(g_mu);
         Workspace *ws;
         HBTRY(cur_ws(&ws));
+        WS_USE(0);
         HBTRY(ws->st_in.ensure((size_t)n * N * sizeof(double)));
         HBTRY(ws->st_x.ensure((size_t)n * ld * sizeof(double)));
         HBTRY(ws->st_out.ensure((size_t)4 * N * sizeof(double)));
@@ -2031,6 +2170,7 @@ int hb_retest_allele_model_dev(const int32_t *r_maf, const int32_t *n_sc, int64_
     std::lock_guard<std::mutex> lk(g_mu);
     Workspace *ws;
     HBTRY(cur_ws(&ws));
+    WS_USE(stream);
     if (!r_maf || !n_sc || !rows || !l_maf || !n_bulk || !p_del || G < 1 || N < 1 || nrows < 1 || ld < N ||
         !(pseudo > 0 && pseudo < 0.5) || !(mono > 0 && mono < 1))
         return fail(HB_ERR_ARG, "bad arguments");
@@ -2110,6 +2250,7 @@ int hb_retest_allele_model_host(const int32_t *r_rows, const int32_t *n_rows, in
         std::lock_guard<std::mutex> lk(g_mu);
         Workspace *ws;
         HBTRY(cur_ws(&ws));
+        WS_USE(0);
         HBTRY(ws->st_in.ensure((size_t)n * N * sizeof(int32_t)));
         HBTRY(ws->st_in2.ensure((size_t)n * N * sizeof(int32_t)));
         HBTRY(ws->st_x.ensure((size_t)n * ld * sizeof(int32_t)));
@@ -2146,6 +2287,7 @@ int hb_viterbi_long_logb_dev(const double *logb, int32_t S, int64_t T, int32_t K
     std::lock_guard<std::mutex> lk(g_mu);
     Workspace *ws;
     HBTRY(cur_ws(&ws));
+    WS_USE(stream);
     if (block_len < 0 || block_len > 4096) return fail(HB_ERR_ARG, "block_len out of range");
     return longchain_run(ws, S, logb, T, K, Pi, delta, y, (cudaStream_t)stream, true, block_len);
 }
@@ -2157,6 +2299,7 @@ int hb_forwardback_long_logb_dev(const double *logb, int32_t S, int64_t T, int32
     std::lock_guard<std::mutex> lk(g_mu);
     Workspace *ws;
     HBTRY(cur_ws(&ws));
+    WS_USE(stream);
     if (block_len < 0 || block_len > 4096) return fail(HB_ERR_ARG, "block_len out of range");
     return longchain_fb_run(ws, S, logb, T, K, Pi, delta, gamma, ll, (cudaStream_t)stream, block_len);
 }
@@ -2166,6 +2309,7 @@ int hb_longchain_stats_dev(void *stream, int64_t *out)
     std::lock_guard<std::mutex> lk(g_mu);
     Workspace *ws;
     HBTRY(cur_ws(&ws));
+    WS_USE(stream);
     if (!out) return fail(HB_ERR_ARG, "out is NULL");
     for (int i = 0; i < 5; i++) out[i] = 0;
     if (!ws->lc_cstate || ws->lc_K < 1) return HB_OK;
@@ -2194,6 +2338,7 @@ int hb_gexp_pooled_viterbi_dev(const double *x, int64_t ld, int64_t G, int64_t N
     std::lock_guard<std::mutex> lk(g_mu);
     Workspace *ws;
     HBTRY(cur_ws(&ws));
+    WS_USE(stream);
     if (!x || !member || !y || G < 2 || N < 1 || K < 1 || ld < N)
         return fail(HB_ERR_ARG, "bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
@@ -2259,6 +2404,7 @@ int hb_allele_pooled_viterbi_dev(const int32_t *r_maf, const int32_t *n_sc, int6
     std::lock_guard<std::mutex> lk(g_mu);
     Workspace *ws;
     HBTRY(cur_ws(&ws));
+    WS_USE(stream);
     if (!r_maf || !n_sc || !member || !y || G < 2 || N < 1 || K < 1 || ld < N)
         return fail(HB_ERR_ARG, "bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
@@ -2316,6 +2462,7 @@ int hb_gexp_pooled_viterbi_host(const double *gexp_norm, int64_t G, int64_t N,
         std::lock_guard<std::mutex> lk(g_mu);
         Workspace *ws;
         HBTRY(cur_ws(&ws));
+        WS_USE(0);
         HBTRY(ws->st_in.ensure((size_t)G * N * sizeof(double)));
         HBTRY(ws->st_x.ensure((size_t)G * ld * sizeof(double)));
         CU(cudaMemcpyAsync(ws->st_in.p, gexp_norm, (size_t)G * N * sizeof(double),
@@ -2339,6 +2486,7 @@ int hb_allele_pooled_viterbi_host(const double *r_maf, const double *n_sc, int64
         std::lock_guard<std::mutex> lk(g_mu);
         Workspace *ws;
         HBTRY(cur_ws(&ws));
+        WS_USE(0);
         HBTRY(ws->st_in.ensure((size_t)G * N * sizeof(double)));
         HBTRY(ws->st_x.ensure((size_t)G * ld * sizeof(int32_t)));
         HBTRY(ws->st_x2.ensure((size_t)G * ld * sizeof(int32_t)));

@@ -385,6 +385,7 @@ HB_HD void binom2_chain(const Binom2Args &a, int32_t seg, int64_t b, double *sm,
         double a0, a1;
         int32_t C = rel2_align(f.m0, f.m1, f.d, a0, a1);
         a.ll[(int64_t)seg * a.B + b] = (log(a0 + a1) + LN2 * (double)(esum + C)) + lsum;
+        if (!VIT && !a.gamma) return; // HB_WANT_LL alone: the forward sweep is the whole job
     }
 
     int32_t ycur = 0;

@@ -358,6 +358,7 @@ HB_HD void binom2_fast_chain(const Binom2Args &a, int32_t seg, int64_t b, const 
         // LL = log(phi_0 + phi_1) + ln2 * esum + sum_t log b_1
         const double LN2 = 0.693147180559945309417232121458;
         a.ll[(int64_t)seg * a.B + b] = (log(s.f0 + s.f1) + LN2 * (double)s.esum) + s.lsum;
+        if (!VIT && !a.gamma) return; // HB_WANT_LL alone: the forward sweep is the whole job
     }
     s.ycur = 0;
     if (VIT) {

@@ -1189,12 +1189,14 @@ __global__ void __launch_bounds__(256)
         for (int64_t s = 0; s < nslab; s++) {
             const int64_t c = 128 * s + 4 * lane;
             int4 x = make_int4(0, 0, 0, 0);
-            if (c + 3 < ld) {
+            // bounded by N, not ld: for a column-slice view (ld = the parent's stride) the tail of the
+            // last row beyond N lies outside the allocation
+            if (c + 3 < N) {
                 x = __ldcs(reinterpret_cast<const int4 *>(row + c));
             } else {
-                if (c < ld) x.x = row[c];
-                if (c + 1 < ld) x.y = row[c + 1];
-                if (c + 2 < ld) x.z = row[c + 2];
+                if (c < N) x.x = row[c];
+                if (c + 1 < N) x.y = row[c + 1];
+                if (c + 2 < N) x.z = row[c + 2];
             }
             const uint32_t b0 = __ballot_sync(0xffffffffu, x.x > 0), b1 = __ballot_sync(0xffffffffu, x.y > 0),
                            b2 = __ballot_sync(0xffffffffu, x.z > 0), b3 = __ballot_sync(0xffffffffu, x.w > 0);

@@ -543,6 +543,7 @@ HB_HD void norm3_chain(const Norm3Args &a, int32_t seg, int64_t b, Norm3Smem &m)
         // LL = log sum(alpha_L) = log(sum phi) + ln2 * esum + sum_t log b_1(x_t)
         a.ll[(int64_t)seg * a.B + b] = ((log((s.f0 + s.f1) + s.f2) + c.k[HBK_LN2] * (double)s.esum) -
                                         s.hsum) - (double)L * (c.k[HBK_LNSQRT2PI] + s.lsd);
+        if (!VIT && !a.gamma) return; // HB_WANT_LL alone: the forward sweep is the whole job
     }
 
     // ------------------------------------------------------------ backward sweep

@@ -556,6 +556,7 @@ HB_HD void norm3_fast_chain(const Norm3Args &a, int32_t seg, int64_t b, Norm3Sme
         a.ll[(int64_t)seg * a.B + b] =
             ((log((s.f0 + s.f1) + s.f2) + c.k[HBK_LN2] * (double)s.esum) - 0.5 * (s.sx2 * (isd * isd))) -
             (double)L * (c.k[HBK_LNSQRT2PI] + lsd);
+        if (!VIT && !a.gamma) return; // HB_WANT_LL alone: the forward sweep is the whole job
     }
     // ------------------------------------------------------------ verify the speculation
     s.ycur = 0;

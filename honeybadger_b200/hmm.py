@@ -52,7 +52,7 @@ def _seg(seg_off, T):
 def _flags(viterbi, gamma, ll):
     f = (_lib.WANT_VITERBI if viterbi else 0) | (_lib.WANT_GAMMA if gamma else 0)
     if ll:
-        f |= _lib.WANT_LL | _lib.WANT_GAMMA
+        f |= _lib.WANT_LL  # alone: the forward sweep only
     if not f:
         raise ValueError("nothing requested")
     return f
@@ -82,7 +82,7 @@ def hmm_norm_host(x, mean, sd, Pi, delta, seg_off=None, viterbi=True, gamma=Fals
     mean, Pi, delta = _f64(mean), _f64(Pi), _f64(delta)
     if mean.size != 3 or Pi.size != 9 or delta.size != 3:
         raise ValueError("the Gaussian chain has 3 states: mean[3], Pi[3x3], delta[3]")
-    want_g = gamma or ll
+    want_g = gamma
     y = np.zeros((T, B), dtype=np.int32, order="F") if viterbi else None
     g = np.zeros((T, B, 3), dtype=np.float64, order="F") if want_g else None
     l = np.zeros((B, nseg), dtype=np.float64, order="F") if ll else None
@@ -118,7 +118,7 @@ def hmm_binom_host(x, size, prob, Pi, delta, seg_off=None, rho=0.0, viterbi=True
     prob, Pi, delta = _f64(prob), _f64(Pi), _f64(delta)
     if prob.size != 2 or Pi.size != 4 or delta.size != 2:
         raise ValueError("the binomial chain has 2 states: prob[2], Pi[2x2], delta[2]")
-    want_g = gamma or ll
+    want_g = gamma
     y = np.zeros((T, B), dtype=np.int32, order="F") if viterbi else None
     g = np.zeros((T, B, 2), dtype=np.float64, order="F") if want_g else None
     l = np.zeros((B, nseg), dtype=np.float64, order="F") if ll else None
@@ -279,7 +279,7 @@ def hmm_norm_tiled_dev(x, B, sd, mean, Pi, delta, seg_off=None, viterbi=True, ga
     per_seg = int(sd.dim() == 2)
     mean, Pi, delta = _f64(mean), _f64(Pi), _f64(delta)
     out = dict(out or {})
-    want_g = gamma or ll
+    want_g = gamma
     if viterbi and "y" not in out:
         out["y"] = torch.empty((ntile, T, 32), dtype=torch.uint8, device=x.device)
     if want_g and "gamma" not in out:
@@ -325,7 +325,7 @@ def hmm_binom_tiled_dev(x, size, B, prob, Pi, delta, seg_off=None, rho=0.0, vite
     nseg = seg.size - 1
     prob, Pi, delta = _f64(prob), _f64(Pi), _f64(delta)
     out = dict(out or {})
-    want_g = gamma or ll
+    want_g = gamma
     if viterbi and "y" not in out:
         out["y"] = torch.empty((ntile, T, 32), dtype=torch.uint8, device=x.device)
     if want_g and "gamma" not in out:
@@ -363,7 +363,7 @@ def hmm_norm_dev(x, sd, mean, Pi, delta, seg_off=None, viterbi=True, gamma=True,
         raise ValueError("sd must be a contiguous CUDA float64 tensor")
     mean, Pi, delta = _f64(mean), _f64(Pi), _f64(delta)
     out = dict(out or {})
-    want_g = gamma or ll
+    want_g = gamma
     if viterbi and "y" not in out:
         out["y"] = alloc_rows(T, B, torch.uint8, x.device)
     if want_g and "gamma" not in out:
@@ -395,7 +395,7 @@ def hmm_binom_dev(x, size, prob, Pi, delta, seg_off=None, rho=0.0, viterbi=True,
     nseg = seg.size - 1
     prob, Pi, delta = _f64(prob), _f64(Pi), _f64(delta)
     out = dict(out or {})
-    want_g = gamma or ll
+    want_g = gamma
     if viterbi and "y" not in out:
         out["y"] = alloc_rows(T, B, torch.uint8, x.device)
     if want_g and "gamma" not in out:
@@ -433,6 +433,14 @@ def norm3_rerun_chains() -> int:
     n = C.c_int64(0)
     _lib.check(_lib.load().hb_norm3_stats_dev(_stream(), C.byref(n)))
     return int(n.value)
+
+
+def last_kernels() -> dict:
+    """Which kernels the last chain launches used: norm3_fast (1 speculate-and-verify, 0 literal),
+    binom2_lean (1 lean kernel + gated general kernel, 0 general only); -1 = none yet."""
+    a, b = C.c_int32(-1), C.c_int32(-1)
+    _lib.check(_lib.load().hb_last_kernels(C.byref(a), C.byref(b)))
+    return {"norm3_fast": int(a.value), "binom2_lean": int(b.value)}
 
 
 def binom2_general_rerun() -> int:

@@ -16,7 +16,8 @@ runs (vectorised here; the literal loops live in oracle/pyref.py for the tests).
 Outside the path (SURVEY.md §8f "next" rows), supplied as replaceable hooks:
   * grouping — `dist` + `hclust(ward.D2)` + `cutree` on the windowed matrix (R/HoneyBADGER.R:1125-1136):
     `ward_groups_dev` does it on the device (runmean, R dist with its NA rule, Ward.D2 by nearest-neighbour
-    chain); `ward_groups` is the scipy host form; any f(mat, heights) can be plugged in.
+    chain); any f(mat, heights) can be plugged in (the numpy / scipy restatement the tests
+    check it against lives in oracle/oracle.py — the package itself has no CPU compute).
   * retest   — the JAGS posteriors (`calcGexpCnvProb`, `calcAlleleCnvProb`): `retest_gexp_closed_form`
     (exact marginal of inst/bug/expressionModel.bug) and `retest_allele_model` (per-cell
     marginal of inst/bug/snpModel.bug with the shared allele indicators at their bulk posterior), both
@@ -91,41 +92,6 @@ def _as_frame(m, prefix_r="g", prefix_c="cell") -> pd.DataFrame:
 
 
 # --------------------------------------------------------------------------- hooks outside the path
-def runmean(mat: np.ndarray, k: int) -> np.ndarray:
-    """caTools::runmean(x, k) along rows of each column: centred window, shrinking at the ends,
-    non-finite values skipped (alg="C", endrule="mean")."""
-    G = mat.shape[0]
-    ok = np.isfinite(mat)
-    v = np.where(ok, mat, 0.0)
-    zero = np.zeros((1,) + mat.shape[1:])
-    cs = np.vstack([zero, np.cumsum(v, 0)])
-    cn = np.vstack([zero, np.cumsum(ok, 0)])
-    h = k // 2
-    lo = np.clip(np.arange(G) - h, 0, G)
-    hi = np.clip(np.arange(G) + h + 1, 0, G)
-    with np.errstate(all="ignore"):
-        return (cs[hi] - cs[lo]) / (cn[hi] - cn[lo])
-
-
-def ward_groups(mat_smooth: np.ndarray, heights) -> list:
-    """cutree(hclust(dist(t(mat.smooth)), "ward.D2"), k=h) for each h; clusters numbered by first
-    appearance in cell order (so group 1 always holds the first cell)."""
-    from scipy.cluster.hierarchy import cut_tree, linkage
-    X = np.nan_to_num(mat_smooth.T, nan=0.0, posinf=0.0, neginf=0.0)
-    N = X.shape[0]
-    if N == 1:
-        return [np.ones(1, dtype=np.int32) for _ in heights]
-    Z = linkage(X, method="ward")
-    out = []
-    for h in heights:
-        lab = cut_tree(Z, n_clusters=int(h))[:, 0]
-        remap, res = {}, np.zeros(N, dtype=np.int32)
-        for i, v in enumerate(lab):
-            res[i] = remap.setdefault(v, len(remap) + 1)
-        out.append(res)
-    return out
-
-
 def cut_merges(merge_a, merge_b, height, N, ks):
     """cutree(hc, k) for each k in `ks` from a merge list (leaf representatives, any order in which
     children precede parents): the N - k lowest merges are applied with union-find; clusters are

@@ -16,7 +16,18 @@
  *     never written.
  *   - *_dev functions take DEVICE pointers in the resident gene-major layout x[t*ld + b]
  *     (t = gene/SNP position, b = chain column) and enqueue on `stream` (a cudaStream_t cast to
- *     void*, NULL = legacy default stream) without synchronising.
+ *     void*, NULL = legacy default stream).  The chain entry points (hb_hmm_*_dev, *_tiled_dev, the
+ *     long-chain and retest *_dev calls, transposes / tiling, pooled counts) never wait for the stream:
+ *     host tables (segment offsets, emission table) go up with cudaMemcpyAsync from a pinned arena and are
+ *     cached per device.  Entry points that RETURN host results (hb_pack_counts_dev's overflow check,
+ *     hb_pool_mean_dev's group sizes, hb_set_*_mats_dev, hb_mean_nonzero_dev, the pooled-round calls,
+ *     *_stats_dev, hb_status_dev) wait for `stream` — each says so.
+ *   - Streams: the library keeps ONE scratch workspace per device (back-pointers, checkpoints, tables).
+ *     Calls may come from any stream; a call on a different stream than the previous one first makes its
+ *     stream wait (cudaStreamWaitEvent) for the previous call's work, so two streams never overlap on the
+ *     scratch — calls are serialised per device, not per stream.  The status word reports the LAST launch
+ *     (hb_status_dev before the next launch if every launch's underflow flag matters).
+ *   - Kernel-choice switches (hb_set_*_mode) are per calling thread.
  *   - A chain is one (column b, segment s) pair; segments are [seg_off[s], seg_off[s+1]) on the
  *     position axis (seg_off is a HOST array of nseg+1 offsets; nseg = 1 reproduces the
  *     reference's single concatenated chain, R/HoneyBADGER.R:1117-1121).
@@ -44,7 +55,7 @@ extern "C" {
 
 #define HB_WANT_VITERBI 1 /* state path y */
 #define HB_WANT_GAMMA 2   /* forward-backward posteriors */
-#define HB_WANT_LL 4      /* log-likelihood per chain (needs the forward pass of HB_WANT_GAMMA) */
+#define HB_WANT_LL 4      /* log-likelihood per chain (alone: the forward sweep only) */
 
 /* ------------------------------------------------------------------ library / device */
 int hb_version(void);
@@ -66,6 +77,11 @@ int hb_set_norm3_mode(int32_t mode);
 /* Number of chains of the last Gaussian launch whose Viterbi recursion was re-run with the literal
  * reference arithmetic because a decision margin fell below the rounding bound (waits for `stream`). */
 int hb_norm3_stats_dev(void *stream, int64_t *rerun_chains);
+/* Which kernels the last chain launches on the current device went to (no synchronisation; host-side
+ * bookkeeping): *norm3_fast = 1 speculate-and-verify kernel, 0 literal kernel, -1 none yet;
+ * *binom2_lean = 1 lean plain-double kernel (general kernel behind its gate), 0 general kernel only.
+ * Either pointer may be NULL.  Lets a caller (and the parity tests) assert which code path produced a result. */
+int hb_last_kernels(int32_t *norm3_fast, int32_t *binom2_lean);
 /* Binomial chains, kernel choice.  0 (default): the lean plain-double kernel, with the general
  * relative-exponent kernel re-running the launch when some position carries evidence beyond 2^+-900
  * (both enqueued, no synchronisation); 1: general kernel only.  Same results either way. */

@@ -403,3 +403,41 @@ def retest_comb(x_rows, mag0, r_rows, n_rows, l_maf, n_bulk, sigma0=None, gene=N
     """Marginal posterior of inst/bug/combinedModel.bug: (P(amp), P(del)) per cell."""
     off = retest_allele_model(r_rows, n_rows, l_maf, n_bulk, gene=gene, pseudo=pseudo, mono=mono, logodds=True)
     return retest_gexp(x_rows, mag0, sigma0, del_loglik=off)
+
+
+# --------------------------------------------------------------------------- grouping (checker for hb_group.cuh)
+# numpy / scipy restatements of caTools::runmean and cutree(hclust(dist(.), "ward.D2")) — test infrastructure
+# for the device grouping kernels (SURVEY.md 8f-2); they lived in the package until round 2.
+def runmean(mat: np.ndarray, k: int) -> np.ndarray:
+    """caTools::runmean(x, k) along rows of each column: centred window, shrinking at the ends,
+    non-finite values skipped (alg="C", endrule="mean")."""
+    G = mat.shape[0]
+    ok = np.isfinite(mat)
+    v = np.where(ok, mat, 0.0)
+    zero = np.zeros((1,) + mat.shape[1:])
+    cs = np.vstack([zero, np.cumsum(v, 0)])
+    cn = np.vstack([zero, np.cumsum(ok, 0)])
+    h = k // 2
+    lo = np.clip(np.arange(G) - h, 0, G)
+    hi = np.clip(np.arange(G) + h + 1, 0, G)
+    with np.errstate(all="ignore"):
+        return (cs[hi] - cs[lo]) / (cn[hi] - cn[lo])
+
+
+def ward_groups(mat_smooth: np.ndarray, heights) -> list:
+    """cutree(hclust(dist(t(mat.smooth)), "ward.D2"), k=h) for each h; clusters numbered by first
+    appearance in cell order (so group 1 always holds the first cell)."""
+    from scipy.cluster.hierarchy import cut_tree, linkage
+    X = np.nan_to_num(mat_smooth.T, nan=0.0, posinf=0.0, neginf=0.0)
+    N = X.shape[0]
+    if N == 1:
+        return [np.ones(1, dtype=np.int32) for _ in heights]
+    Z = linkage(X, method="ward")
+    out = []
+    for h in heights:
+        lab = cut_tree(Z, n_clusters=int(h))[:, 0]
+        remap, res = {}, np.zeros(N, dtype=np.int32)
+        for i, v in enumerate(lab):
+            res[i] = remap.setdefault(v, len(remap) + 1)
+        out.append(res)
+    return out

@@ -134,7 +134,7 @@ def test_stateless_allele_path_reproduces_the_vignette_figure(oracle, golden_inp
     threshold, runmean(k=31) -> Ward.D2 -> cutree(1..3), pooled counts, 2-state binomial Viterbi, vote,
     runs, trim, range() per chromosome — must land on the same chromosomes in the same order."""
     from oracle import pyref as P
-    from honeybadger_b200.honeybadger import runmean, ward_groups
+    from oracle.oracle import runmean, ward_groups
     r, cov = golden_inputs["r"].astype(np.int32), golden_inputs["cov"].astype(np.int32)
     out = oracle.set_allele_mats(r, cov, het_deviance_threshold=0.05)
     assert out["keep"].size == 4550
