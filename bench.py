@@ -60,12 +60,31 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def kernel_source_hash():
+    """sha256 (16 hex) over the CUDA sources the chain kernels are built from: profiles/traffic.json records
+    the hash of the build its ncu capture was taken on, so a stale traffic figure cannot be printed beside a
+    changed kernel."""
+    import hashlib
+    h = hashlib.sha256()
+    csrc = os.path.join(ROOT, "honeybadger_b200", "csrc")
+    for f in sorted(os.listdir(csrc)):
+        if f.endswith((".cu", ".cuh", ".h")):
+            h.update(f.encode())
+            h.update(open(os.path.join(csrc, f), "rb").read())
+    return h.hexdigest()[:16]
+
+
 def ncu_traffic(workload):
+    """dram bytes per launch from the committed ncu capture — only if it was taken on THIS kernel source
+    (profiles/traffic.json: {workload: {"bytes": .., "src": hash}}); otherwise null (stale capture)."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     try:
-        return json.load(open(p)).get(workload)
+        e = json.load(open(p)).get(workload)
+        if isinstance(e, dict) and e.get("src") == kernel_source_hash():
+            return e.get("bytes")
     except Exception:
-        return None
+        pass
+    return None
 
 
 class ClockSampler:
@@ -253,6 +272,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
+    ap.add_argument("--no-modes", action="store_true",
+                    help="skip the viterbi_only / fb_only / sustained legs reported under \"modes\"")
     ap.add_argument("--no-allele", action="store_true",
                     help="skip the extra device-resident allele measurement reported under \"allele\"")
     args = ap.parse_args()
@@ -340,6 +361,50 @@ def main():
     total_ms = float(t.item())
     steps_per_pass = cells * positions
     value = world * steps_per_pass * args.steps / (total_ms * 1e-3)
+    peak, peak_src = measured_peak()
+
+    # ---------------- parity of the timed buffers against the oracle (rank 0; part of the CPU leg)
+    parity = None
+    if rank == 0 and not args.no_cpu:
+        try:
+            parity = parity_block(kind, d, out, cells, seg, sd if kind == "expr" else None, hmm)
+        except Exception as exc:
+            parity = {"error": repr(exc)[:200]}
+
+    # ---------------- the same kernel in its other modes, each against its own roofline, and a sustained run
+    modes = None
+    if not args.no_modes:
+        try:
+            modes = {}
+            nl = max(5, args.steps // 3)
+            for name, kw, bps in (("viterbi_only", dict(viterbi=True, gamma=False), 8 + 1 if kind == "expr" else 4 + 1),
+                                  ("fb_only", dict(viterbi=False, gamma=True),
+                                   8 + 24 if kind == "expr" else 4 + 16)):
+                if kind == "expr":
+                    o_m = hmm.hmm_norm_tiled_dev(xt, cells, sd, mean, Pi3, delta3, seg_off=seg, **kw)
+                    fn = lambda: hmm.hmm_norm_tiled_dev(xt, cells, sd, mean, Pi3, delta3, seg_off=seg, out=o_m, **kw)  # noqa: E731
+                else:
+                    o_m = hmm.hmm_binom_tiled_dev(xn, None, cells, prob, Pi2, delta2, seg_off=seg, **kw)
+                    fn = lambda: hmm.hmm_binom_tiled_dev(xn, None, cells, prob, Pi2, delta2, seg_off=seg, out=o_m, **kw)  # noqa: E731
+                ms = time_launches(fn, nl, torch)
+                ach = steps_per_pass * bps / (ms * 1e-3) / 1e9
+                modes[name] = {"ms": ms, "value": steps_per_pass / (ms * 1e-3), "algorithmic_bytes_per_step": bps,
+                               "roofline_frac": ach / peak, "launches": nl}
+                del o_m
+            # sustained: >= 2 s of back-to-back launches of the headline kernel, clocks sampled throughout
+            ns = max(args.steps, int(2000.0 / (total_ms / args.steps)) + 1)
+            smp = ClockSampler(local)
+            smp.start()
+            time.sleep(0.2)
+            tw0 = time.time()
+            ms = time_launches(step, ns, torch)
+            tw1 = time.time()
+            ach = steps_per_pass * wl["bytes_per_step"] / (ms * 1e-3) / 1e9
+            modes["sustained"] = {"ms": ms, "launches": ns, "value": steps_per_pass / (ms * 1e-3),
+                                  "roofline_frac": ach / peak, "clocks": smp.stop(tw0, tw1)}
+            hmm.status_dev()
+        except Exception as exc:
+            modes = {"error": repr(exc)[:200]}
 
     # ---------------- end to end through the host-buffer C ABI (pinned host memory)
     e2e = None
@@ -361,7 +426,6 @@ def main():
         except Exception as exc:
             allele = {"value": None, "error": repr(exc)[:200]}
 
-    peak, peak_src = measured_peak()
     mean_ms = float(np.mean(per_launch_ms))
     achieved = steps_per_pass * wl["bytes_per_step"] / (mean_ms * 1e-3) / 1e9
     q = np.percentile(per_launch_ms, [0, 25, 50, 75, 100])
@@ -387,12 +451,67 @@ def main():
                            "l2": f"inputs {in_bytes / 1e6:.0f} MB + outputs per pass exceed the 126 MB L2",
                            "layout": "warp-tiled [tile of 32 cells][position][lane] (hb_tile_dev), fp64 / int32"},
                 "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
-                "gpu_launches": launches_per_step * args.steps}
+                "gpu_launches": launches_per_step * args.steps, "parity": parity, "modes": modes,
+                "kernel_source_hash": kernel_source_hash()}
         if allele is not None:
             line["allele"] = allele
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def tiled_cols(t, cols):
+    """columns of a warp-tiled [ntile, T, 32] / [planes, ntile, T, 32] tensor as numpy [T, n] / [planes, T, n]"""
+    import torch
+    if t.dim() == 4:
+        return np.stack([tiled_cols(p, cols) for p in t])
+    c = torch.as_tensor(np.asarray(cols), device=t.device)
+    return t[c // 32, :, c % 32].t().cpu().numpy()
+
+
+def parity_block(kind, d, out, cells, seg, sd, hmm, ncols=96):
+    """Chains sampled from the TIMED buffers (plus, for the Gaussian kernel, every chain it re-ran exactly)
+    against the CPU oracle: states must be identical, posteriors within 1e-9.  Part of the cpu_baseline leg —
+    the oracle is the checker, never the thing measured."""
+    import torch
+    from oracle import oracle as O
+    O.build()
+    rng = np.random.default_rng(11)
+    cols = rng.choice(cells, size=min(ncols, cells), replace=False)
+    info = {}
+    if kind == "expr":
+        fl = hmm.norm3_flagged_chains(cells)
+        info["flagged_chains"] = int(hmm.norm3_rerun_chains())
+        cols = np.unique(np.concatenate([cols, fl[:64, 1]])).astype(np.int64)
+        ct = torch.as_tensor(cols, device=d["x"].device)
+        yo, go, _, rc = O.fbv_norm_batch(d["x"][:, ct].cpu().numpy(), seg, [-DEV, 0.0, DEV], sd[ct].cpu().numpy(),
+                                         O.sym_Pi(3, 1e-6), [0.0, 1.0, 0.0])
+        info["kernel"] = "norm3_fast_kernel" if hmm.last_kernels()["norm3_fast"] == 1 else "norm3_kernel"
+    else:
+        cols = np.unique(cols).astype(np.int64)
+        ct = torch.as_tensor(cols, device=d["r"].device)
+        yo, go, _, rc = O.fbv_binom_batch(d["r"][:, ct].cpu().numpy(), d["n"][:, ct].cpu().numpy(), seg,
+                                          [0.1, 0.45], O.sym_Pi(2, 1e-6), [0.0, 1.0])
+        info["kernel"] = "binom2_fast_kernel" if hmm.last_kernels()["binom2_lean"] == 1 else "binom2_kernel"
+    y = tiled_cols(out["y"], cols)
+    g = tiled_cols(out["gamma"], cols)
+    info.update({"chains_checked": int(len(cols) * (len(seg) - 1)), "cells_checked": int(len(cols)),
+                 "state_mismatches": int((y != yo).sum()), "max_gamma_err": float(np.abs(g - go).max()),
+                 "oracle_rc": int(rc), "against": "oracle/hb_oracle.c on the same resident inputs"})
+    return info
+
+
+def time_launches(fn, n, torch):
+    for _ in range(2):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
 
 
 def run_allele_extra(cells, rank, dev, hmm, world, dist, steps=5):
@@ -497,7 +616,10 @@ def run_e2e(kind, wl, d, args, world, dev, hmm, dist):
         h2d = positions * cells * 8
     yout = torch.empty((batch, positions), dtype=torch.int32).pin_memory()
     gout = torch.empty((S, batch, positions), dtype=torch.float64).pin_memory()
-    d2h = positions * cells * (1 + 8 * S)   # states cross PCIe as bytes (widened to R integers on the host)
+    # states cross PCIe as bytes (widened to R integers on the host); the neutral-state posterior plane is
+    # rebuilt on the host from the S - 1 planes that do cross (HB_E2E_FULL_PLANES=1 downloads all S)
+    full = os.environ.get("HB_E2E_FULL_PLANES", "0") not in ("", "0")
+    d2h = positions * cells * (1 + 8 * (S if full else S - 1))
     from honeybadger_b200 import _lib
     import ctypes as C
     lib = _lib.load()

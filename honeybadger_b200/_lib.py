@@ -49,6 +49,7 @@ SIGNATURES = {
     "hb_set_binom2_mode": (_i32, [_i32]),
     "hb_binom2_stats_dev": (_i32, [_p, C.POINTER(C.c_int32)]),
     "hb_norm3_stats_dev": (_i32, [_p, C.POINTER(C.c_int64)]),
+    "hb_norm3_flagged_dev": (_i32, [_p, _p, _i64, C.POINTER(C.c_int64)]),
     "hb_hmm_norm_host": (_i32, [_p, _i64, _i64, _p, _i32, _p, _p, _i32, _p, _p, _i32, _p, _p, _p]),
     "hb_hmm_norm_dev": (_i32, [_p, _i64, _i64, _i64, _p, _i32, _p, _p, _i32, _p, _p, _i32, _p, _i64,
                                _p, _i64, _p, _p]),

@@ -4,6 +4,7 @@
 // per-device scratch cache, host<->device staging for the *_host entry points, kernel launches.
 // There is no CPU implementation of the path behind these functions.
 #include <cuda_runtime.h>
+#include <emmintrin.h>
 #include <math.h>
 #include <stdarg.h>
 #include <stdint.h>
@@ -92,7 +93,7 @@ struct DevBuf {
 
 // Per-device scratch, grown on demand and reused across calls (no allocation in steady state).
 struct Workspace {
-    DevBuf psi, ckpt, sdaux, segtab, status, lut_lb, lut_rho, lut_rho_d, cellmask, gsize;
+    DevBuf psi, ckpt, sdaux, segtab, status, flagged, lut_lb, lut_rho, lut_rho_d, cellmask, gsize;
     DevBuf lc, lc_fb, lc_lb, lc_y;
     int32_t lc_K = 0;
     int64_t lc_nb = 0;
@@ -128,7 +129,7 @@ struct Workspace {
     int32_t lut_nmax = -1;
     void release_all()
     {
-        DevBuf *all[] = {&lc, &lc_fb, &lc_lb, &lc_y, &psi, &ckpt, &sdaux, &segtab, &status, &lut_lb, &lut_rho, &lut_rho_d, &cellmask, &gsize,
+        DevBuf *all[] = {&flagged, &lc, &lc_fb, &lc_lb, &lc_y, &psi, &ckpt, &sdaux, &segtab, &status, &lut_lb, &lut_rho, &lut_rho_d, &cellmask, &gsize,
                          &st_in, &st_in2, &st_x, &st_x2, &st_y, &st_g, &st_out, &st_sd, &st_ll,
                          &st_member, &st_pool, &st_pool2, &st_pre, &st_x80, &st_part, &st_inp, &st_inp2, &st_tab, &pin[0], &pin[1], &pin2[0], &pin2[1],
                          &pout_y[0], &pout_y[1], &pout_g[0], &pout_g[1], &pout_ll[0], &pout_ll[1]};
@@ -172,6 +173,7 @@ struct Workspace {
     }
 };
 
+#define HB_FLAGGED_CAP 16384 // re-run chains recorded per Gaussian launch (hb_norm3_flagged_dev)
 std::mutex g_mu;
 Workspace g_ws[16];
 int g_lut_nmax_cfg = 511;
@@ -409,6 +411,9 @@ int norm3_run(Workspace *ws, const double *x, int64_t ld, int64_t T, int64_t B,
     a.psi = ws->psi.as<uint64_t>();
     a.ckpt = ws->ckpt.as<double>();
     a.status = ws->status.as<int32_t>();
+    HBTRY(ws->flagged.ensure((size_t)HB_FLAGGED_CAP * sizeof(int64_t)));
+    a.flagged = ws->flagged.as<int64_t>();
+    a.flagged_cap = HB_FLAGGED_CAP;
     // HB_WANT_LL without HB_WANT_GAMMA: the forward sweep alone (the kernels return after storing LL when
     // no posterior buffer is given); with Viterbi as well, the Viterbi-only launch precedes it.
     const bool ll_only = fb && !a.gamma;
@@ -884,6 +889,28 @@ int hb_last_kernels(int32_t *norm3_fast, int32_t *binom2_lean)
     return HB_OK;
 }
 
+int hb_norm3_flagged_dev(void *stream, int64_t *chains, int64_t cap, int64_t *n)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    Workspace *ws;
+    HBTRY(cur_ws(&ws));
+    WS_USE(stream);
+    if (!n || cap < 0 || (cap > 0 && !chains)) return fail(HB_ERR_ARG, "bad arguments");
+    *n = 0;
+    if (!ws->status.p || !ws->flagged.p) return HB_OK;
+    int32_t s[2] = {0, 0};
+    CU(cudaMemcpyAsync(s, ws->status.p, sizeof s, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CU(cudaStreamSynchronize((cudaStream_t)stream));
+    const int64_t have = std::min<int64_t>(s[1], HB_FLAGGED_CAP);
+    *n = std::min(have, cap);
+    if (*n > 0) {
+        CU(cudaMemcpyAsync(chains, ws->flagged.p, (size_t)*n * sizeof(int64_t), cudaMemcpyDeviceToHost,
+                           (cudaStream_t)stream));
+        CU(cudaStreamSynchronize((cudaStream_t)stream));
+    }
+    return HB_OK;
+}
+
 int hb_status_dev(void *stream)
 {
     std::lock_guard<std::mutex> lk(g_mu);
@@ -969,6 +996,49 @@ static void parallel_widen(int32_t *dst, const uint8_t *src, size_t count, int n
     for (auto &t : th) t.join();
 }
 
+// The neutral-state posterior plane does not cross PCIe: the chain kernels define it as
+// gamma_1 = |1 - (gamma_0 + gamma_2)| (3 states) / gamma_1 = |1 - gamma_0| (2 states) — the host rebuilds it
+// with the same two IEEE operations from the planes that did come down (streaming stores: the plane is
+// write-only here).  a, c: the downloaded planes (c may be NULL), out: the rebuilt one.
+static void recon_range(const double *a, const double *c, double *out, size_t n)
+{
+    size_t i = 0;
+    auto one = [&](size_t k) { out[k] = fabs(1.0 - (c ? a[k] + c[k] : a[k])); };
+    while (i < n && ((uintptr_t)(out + i) & 15)) one(i++);
+    const __m128d ones = _mm_set1_pd(1.0), sign = _mm_set1_pd(-0.0);
+    for (; i + 2 <= n; i += 2) {
+        __m128d s = _mm_loadu_pd(a + i);
+        if (c) s = _mm_add_pd(s, _mm_loadu_pd(c + i));
+        _mm_stream_pd(out + i, _mm_andnot_pd(sign, _mm_sub_pd(ones, s)));
+    }
+    for (; i < n; i++) one(i);
+    _mm_sfence();
+}
+
+static void parallel_recon(const double *a, const double *c, double *out, size_t count, int nthreads)
+{
+    if (count < ((size_t)1 << 18) || nthreads <= 1) {
+        recon_range(a, c, out, count);
+        return;
+    }
+    std::vector<std::thread> th;
+    const size_t per = (count / nthreads + 511) & ~(size_t)511;
+    for (int i = 0; i < nthreads; i++) {
+        const size_t lo = (size_t)i * per;
+        if (lo >= count) break;
+        const size_t n = std::min(per, count - lo);
+        th.emplace_back([=] { recon_range(a + lo, c ? c + lo : nullptr, out + lo, n); });
+    }
+    for (auto &t : th) t.join();
+}
+
+// HB_E2E_FULL_PLANES=1: download every posterior plane instead (A/B measurements)
+static bool recon_enabled()
+{
+    const char *e = getenv("HB_E2E_FULL_PLANES");
+    return !(e && atoi(e) != 0);
+}
+
 struct HostStager {
     Workspace *ws;
     bool bounce_in, bounce_out;
@@ -983,8 +1053,14 @@ struct HostStager {
         int32_t *dst;
         size_t count;
     };
+    struct Recon {
+        const double *a, *c;
+        double *out;
+        size_t count;
+    };
     std::vector<Copy> pend[2];
     std::vector<Widen> pend_w[2];
+    std::vector<Recon> pend_r[2];
     std::future<void> fut[2];
     size_t off_out[2] = {0, 0}, off_in[2] = {0, 0};
 
@@ -1051,6 +1127,7 @@ struct HostStager {
         if (fut[k].valid()) fut[k].get();
         pend[k].clear();
         pend_w[k].clear();
+        pend_r[k].clear();
         off_out[k] = 0;
     }
     // Viterbi states: one byte per position over PCIe (a quarter of R's integers), landed in pinned memory
@@ -1073,21 +1150,28 @@ struct HostStager {
         CU(cudaMemcpyAsync(dst, dev, bytes, cudaMemcpyDeviceToHost, st));
         return HB_OK;
     }
+    // after this slot's downloads (and copy-outs): out = |1 - (a + c)| on the caller's arrays
+    void recon(int k, const double *a, const double *c, double *out, size_t count)
+    {
+        pend_r[k].push_back({a, c, out, count});
+    }
     int end_out(int k, cudaStream_t st)
     {
-        if (pend[k].empty() && pend_w[k].empty()) return HB_OK;
+        if (pend[k].empty() && pend_w[k].empty() && pend_r[k].empty()) return HB_OK;
         CU(cudaEventRecord(ws->ev_bout[k], st));
         cudaEvent_t ev = ws->ev_bout[k];
         std::vector<Copy> jobs = pend[k];
         std::vector<Widen> wjobs = pend_w[k];
+        std::vector<Recon> rjobs = pend_r[k];
         const int nt = nthreads;
         int dev = 0;
         cudaGetDevice(&dev);
-        fut[k] = std::async(std::launch::async, [ev, jobs, wjobs, nt, dev] {
+        fut[k] = std::async(std::launch::async, [ev, jobs, wjobs, rjobs, nt, dev] {
             cudaSetDevice(dev);
             cudaEventSynchronize(ev);
             for (const Copy &c : jobs) parallel_memcpy(c.dst, c.src, c.bytes, nt);
             for (const Widen &w : wjobs) parallel_widen(w.dst, w.src, w.count, nt);
+            for (const Recon &r : rjobs) parallel_recon(r.a, r.c, r.out, r.count, nt);
         });
         return HB_OK;
     }
@@ -1190,6 +1274,7 @@ int hb_hmm_norm_host(const double *x, int64_t T, int64_t B, const int64_t *seg_o
     }
     HBTRY(pipe_init(ws));
     HBTRY(ws_use_.enter(ws, ws->s_cmp));
+    const bool recon = want_g && recon_enabled();
     const int64_t Bc = pipe_batch(B, 130.0 * (double)T);
     const int64_t nb = (B + Bc - 1) / Bc;
     const int64_t ldc = (Bc + 127) / 128 * 128;
@@ -1255,21 +1340,28 @@ int hb_hmm_norm_host(const double *x, int64_t T, int64_t B, const int64_t *seg_o
         if (vit)
             CU(hb::launch_transpose_u8_back_u8(d_y, ld, T, bn, ws->pout_y[k].as<uint8_t>(), ws->s_cmp));
         if (want_g)
-            for (int pl = 0; pl < 3; pl++)
+            for (int pl = 0; pl < 3; pl++) {
+                if (recon && pl == 1) continue; // the neutral-state plane is rebuilt on the host
                 CU(hb::launch_transpose_f64_back(d_g + (int64_t)pl * T * ld, ld, T, bn,
                                                  ws->pout_g[k].as<double>() + (int64_t)pl * T * bn,
                                                  ws->s_cmp));
+            }
         CU(cudaEventRecord(ws->ev_out[k], ws->s_cmp));
         // download
         CU(cudaStreamWaitEvent(ws->s_out, ws->ev_out[k], 0));
         hs.begin_out(k);
         if (vit)
             HBTRY(hs.d2h_widen(k, y + b0 * T, ws->pout_y[k].as<uint8_t>(), (size_t)T * bn, ws->s_out));
-        if (want_g)
-            for (int pl = 0; pl < 3; pl++)
+        if (want_g) {
+            for (int pl = 0; pl < 3; pl++) {
+                if (recon && pl == 1) continue;
                 HBTRY(hs.d2h(k, gamma + ((int64_t)pl * B + b0) * T,
                              ws->pout_g[k].as<double>() + (int64_t)pl * T * bn,
                              (size_t)T * bn * sizeof(double), ws->s_out));
+            }
+            if (recon)
+                hs.recon(k, gamma + b0 * T, gamma + (2 * B + b0) * T, gamma + (B + b0) * T, (size_t)T * bn);
+        }
         if (want_ll)
             for (int32_t sg = 0; sg < nseg; sg++)
                 HBTRY(hs.d2h(k, ll + (int64_t)sg * B + b0, d_ll + (int64_t)sg * bn,
@@ -1378,6 +1470,7 @@ int hb_hmm_binom_host(const int32_t *x, const int32_t *size, int64_t T, int64_t 
     }
     HBTRY(pipe_init(ws));
     HBTRY(ws_use_.enter(ws, ws->s_cmp));
+    const bool recon = want_g && recon_enabled();
     const int64_t Bc = pipe_batch(B, 100.0 * (double)T);
     const int64_t nb = (B + Bc - 1) / Bc;
     const int64_t ldc = (Bc + 127) / 128 * 128;
@@ -1424,7 +1517,7 @@ int hb_hmm_binom_host(const int32_t *x, const int32_t *size, int64_t T, int64_t 
         if (vit)
             CU(hb::launch_transpose_u8_back_u8(d_y, ld, T, bn, ws->pout_y[k].as<uint8_t>(), ws->s_cmp));
         if (want_g)
-            for (int pl = 0; pl < 2; pl++)
+            for (int pl = 0; pl < (recon ? 1 : 2); pl++)
                 CU(hb::launch_transpose_f64_back(d_g + (int64_t)pl * T * ld, ld, T, bn,
                                                  ws->pout_g[k].as<double>() + (int64_t)pl * T * bn,
                                                  ws->s_cmp));
@@ -1433,11 +1526,13 @@ int hb_hmm_binom_host(const int32_t *x, const int32_t *size, int64_t T, int64_t 
         hs.begin_out(k);
         if (vit)
             HBTRY(hs.d2h_widen(k, y + b0 * T, ws->pout_y[k].as<uint8_t>(), (size_t)T * bn, ws->s_out));
-        if (want_g)
-            for (int pl = 0; pl < 2; pl++)
+        if (want_g) {
+            for (int pl = 0; pl < (recon ? 1 : 2); pl++)
                 HBTRY(hs.d2h(k, gamma + ((int64_t)pl * B + b0) * T,
                              ws->pout_g[k].as<double>() + (int64_t)pl * T * bn,
                              (size_t)T * bn * sizeof(double), ws->s_out));
+            if (recon) hs.recon(k, gamma + b0 * T, nullptr, gamma + (B + b0) * T, (size_t)T * bn);
+        }
         if (want_ll)
             for (int32_t sg = 0; sg < nseg; sg++)
                 HBTRY(hs.d2h(k, ll + (int64_t)sg * B + b0, d_ll + (int64_t)sg * bn,

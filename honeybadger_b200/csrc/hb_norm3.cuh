@@ -121,6 +121,8 @@ struct Norm3Args {
     double *ckpt;  // [nchunks][3][B]
     int32_t *status; // [0] set to 1 when a chain ends with nu == -inf (R: "Problems With Underflow")
                      // [1] chains of the speculative path that were re-run exactly
+    int64_t *flagged;     // [flagged_cap] seg * B + b of the first re-run chains (diagnostics / parity tests)
+    int32_t flagged_cap;
     Norm3Const c;
 };
 

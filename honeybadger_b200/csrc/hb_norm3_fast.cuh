@@ -363,13 +363,14 @@ HB_HD_NOINLINE int32_t norm3_exact_forward(const Norm3Args &a, int32_t seg, int6
     return y;
 }
 
-HB_HD void count_flagged(const Norm3Args &a)
+HB_HD void count_flagged(const Norm3Args &a, int32_t seg, int64_t b)
 {
 #if defined(__CUDA_ARCH__)
-    atomicAdd(a.status + 1, 1);
+    const int32_t i = atomicAdd(a.status + 1, 1);
 #else
-    a.status[1] += 1;
+    const int32_t i = a.status[1]++;
 #endif
+    if (a.flagged && i < a.flagged_cap) a.flagged[i] = (int64_t)seg * a.B + b;
 }
 
 // ---------------------------------------------------------------- the whole chain
@@ -580,7 +581,7 @@ HB_HD void norm3_fast_chain(const Norm3Args &a, int32_t seg, int64_t b, Norm3Sme
         const double eps = 3.0 * U * ((2.0 * Ld * M + 16.0 * M) + 16.0 * Ld * dmax) * c.eps_scale;
         const double margin = mk64((int32_t)mn, 0); // <= the true minimum |difference|
         if (!(margin > eps)) {
-            if (live) count_flagged(a);
+            if (live) count_flagged(a, seg, b);
             s.ycur = norm3_exact_forward(a, seg, b);
         } else if (s.d0 == -INFINITY || s.d2 == -INFINITY) {
             *a.status = 1; // some nu_k(T) == -Inf (nu_1 is finite here): HiddenMarkov's underflow stop

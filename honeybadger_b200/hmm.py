@@ -435,6 +435,16 @@ def norm3_rerun_chains() -> int:
     return int(n.value)
 
 
+def norm3_flagged_chains(B: int, cap: int = 16384):
+    """(segment, column) pairs of the chains the last Gaussian launch re-ran with the literal arithmetic
+    (first `cap` of them); waits for the current stream."""
+    buf = np.zeros(cap, dtype=np.int64)
+    n = C.c_int64(0)
+    _lib.check(_lib.load().hb_norm3_flagged_dev(_stream(), _vp(buf), cap, C.byref(n)))
+    ids = buf[: n.value]
+    return np.stack([ids // B, ids % B], axis=1)
+
+
 def last_kernels() -> dict:
     """Which kernels the last chain launches used: norm3_fast (1 speculate-and-verify, 0 literal),
     binom2_lean (1 lean kernel + gated general kernel, 0 general only); -1 = none yet."""

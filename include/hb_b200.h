@@ -31,6 +31,9 @@
  *   - A chain is one (column b, segment s) pair; segments are [seg_off[s], seg_off[s+1]) on the
  *     position axis (seg_off is a HOST array of nseg+1 offsets; nseg = 1 reproduces the
  *     reference's single concatenated chain, R/HoneyBADGER.R:1117-1121).
+ *   - *_host posteriors: the S - 1 non-neutral planes cross PCIe; the neutral-state plane (state 2 of 3, state 2
+ *     of 2) is rebuilt on the host as |1 - sum of the others| — the definition the speculate-and-verify /
+ *     lean kernels use on the device — by the copy-out threads that also widen the states to R integers.
  *   - Viterbi states are 1-based like R's; state paths are bit-identical to the reference
  *     recursion (operation order of HiddenMarkov::Viterbi.dthmm, first index wins ties).
  *     Posteriors gamma = exp(logalpha + logbeta - LL) of HiddenMarkov::forwardback agree to 1e-9.
@@ -77,6 +80,9 @@ int hb_set_norm3_mode(int32_t mode);
 /* Number of chains of the last Gaussian launch whose Viterbi recursion was re-run with the literal
  * reference arithmetic because a decision margin fell below the rounding bound (waits for `stream`). */
 int hb_norm3_stats_dev(void *stream, int64_t *rerun_chains);
+/* Which chains those were: up to `cap` entries seg * B + b (chain column b of segment seg) of the last
+ * Gaussian launch, *n of them written (at most the first 16384 are recorded; waits for `stream`). */
+int hb_norm3_flagged_dev(void *stream, int64_t *chains, int64_t cap, int64_t *n);
 /* Which kernels the last chain launches on the current device went to (no synchronisation; host-side
  * bookkeeping): *norm3_fast = 1 speculate-and-verify kernel, 0 literal kernel, -1 none yet;
  * *binom2_lean = 1 lean plain-double kernel (general kernel behind its gate), 0 general kernel only.

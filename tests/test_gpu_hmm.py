@@ -402,3 +402,79 @@ def test_host_entry_pinned_and_pageable_buffers_agree():
     for a, b in zip(*outs):
         assert np.array_equal(a, b)
     assert outs[0][0].min() >= 1 and np.isfinite(outs[0][1]).all()
+
+
+def test_ll_alone_runs_the_forward_sweep_only(oracle):
+    """HB_WANT_LL without HB_WANT_GAMMA (header: 'alone: the forward sweep only'): same LL as the full run on
+    every kernel family, with and without Viterbi; no posterior buffer is needed or touched."""
+    import torch
+    from honeybadger_b200 import _lib, hmm
+    lib = _lib.load()
+    x, seg, _ = synth.expression(2600, 150, seed=5)
+    xd = hmm.to_rows(torch.from_numpy(x).cuda())
+    sd = hmm.chain_sd_dev(xd)
+    mean, Pi, delta = [-synth.DEV, 0.0, synth.DEV], hmm.sym_Pi(3, 1e-6), [0.0, 1.0, 0.0]
+    full = hmm.hmm_norm_dev(xd, sd, mean, Pi, delta, seg_off=seg, viterbi=True, gamma=True, ll=True)
+    _, _, llo, _ = oracle.fbv_norm_batch(x, seg, mean, sd.cpu().numpy(), Pi, delta)
+    for mode in (0, 1):          # speculate-and-verify kernel (padded rows), literal kernel
+        lib.hb_set_norm3_mode(mode)
+        try:
+            for vit in (False, True):
+                o = hmm.hmm_norm_dev(xd, sd, mean, Pi, delta, seg_off=seg, viterbi=vit, gamma=False, ll=True)
+                hmm.status_dev()
+                assert "gamma" not in o
+                assert np.allclose(o["ll"].cpu().numpy(), llo, rtol=1e-10, atol=0)
+                if vit:
+                    assert torch.equal(o["y"], full["y"])
+        finally:
+            lib.hb_set_norm3_mode(0)
+    xt = hmm.tile_rows(xd)
+    o = hmm.hmm_norm_tiled_dev(xt, 150, sd, mean, Pi, delta, seg_off=seg, viterbi=False, gamma=False, ll=True)
+    assert torch.equal(o["ll"], full["ll"])
+    # binomial: lean kernel and general kernel, host entry point (pipeline) as well
+    r, n, seg2, _ = synth.allele(5000, 100, seed=6)
+    Pi2, prob = hmm.sym_Pi(2, 1e-6), [0.1, 0.45]
+    yo, _, llo2, _ = oracle.fbv_binom_batch(r, n, seg2, prob, Pi2, [0.0, 1.0])
+    for mode in (0, 1):
+        lib.hb_set_binom2_mode(mode)
+        try:
+            res = hmm.hmm_binom_host(r, n, prob, Pi2, [0.0, 1.0], seg_off=seg2, viterbi=True, gamma=False, ll=True)
+            assert (res["y"] == yo).all() and np.allclose(res["ll"].T, llo2, rtol=1e-10, atol=0)
+            res = hmm.hmm_binom_host(r, n, prob, Pi2, [0.0, 1.0], seg_off=seg2, viterbi=False, gamma=False, ll=True)
+            assert np.allclose(res["ll"].T, llo2, rtol=1e-10, atol=0)
+        finally:
+            lib.hb_set_binom2_mode(0)
+    # a pooled-shaped single chain (long-chain route): LL alone
+    one = hmm.hmm_norm_host(x[:, 0], mean, float(sd[0]), Pi, delta, viterbi=False, gamma=False, ll=True)
+    _, _, ll1, _ = oracle.fbv_norm_batch(x[:, :1], np.array([0, x.shape[0]]), mean, sd[:1].cpu().numpy(), Pi, delta)
+    assert np.allclose(one["ll"], ll1.ravel(), rtol=1e-9, atol=0)
+
+
+def test_two_streams_share_the_workspace_safely(oracle):
+    """Calls alternating between two non-blocking streams (different inputs, different segment tables) must
+    each produce the single-stream result: the per-device scratch is handed over with an event."""
+    import torch
+    from honeybadger_b200 import hmm
+    mean, Pi, delta = [-synth.DEV, 0.0, synth.DEV], hmm.sym_Pi(3, 1e-6), [0.0, 1.0, 0.0]
+    xa, sega, _ = synth.expression(4000, 700, seed=11)
+    xb, _, _ = synth.expression(3000, 900, seed=12)
+    segb = np.array([0, 1000, 3000], dtype=np.int64)
+    xa_d, xb_d = hmm.to_rows(torch.from_numpy(xa).cuda()), hmm.to_rows(torch.from_numpy(xb).cuda())
+    sda, sdb = hmm.chain_sd_dev(xa_d), hmm.chain_sd_dev(xb_d)
+    ra = hmm.hmm_norm_dev(xa_d, sda, mean, Pi, delta, seg_off=sega)
+    ra = {k: v.clone() for k, v in ra.items()}
+    rb = hmm.hmm_norm_dev(xb_d, sdb, mean, Pi, delta, seg_off=segb)
+    rb = {k: v.clone() for k, v in rb.items()}
+    torch.cuda.synchronize()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    outs = []
+    for i in range(6):
+        with torch.cuda.stream(s1 if i % 2 == 0 else s2):
+            if i % 2 == 0:
+                outs.append(("a", hmm.hmm_norm_dev(xa_d, sda, mean, Pi, delta, seg_off=sega)))
+            else:
+                outs.append(("b", hmm.hmm_norm_dev(xb_d, sdb, mean, Pi, delta, seg_off=segb)))
+    torch.cuda.synchronize()
+    for tag, o in outs:
+        ref = ra if tag == "a" else rb
+        assert torch.equal(o["y"], ref["y"]) and torch.equal(o["gamma"], ref["gamma"])

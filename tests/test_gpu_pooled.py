@@ -497,3 +497,28 @@ def test_pool_count_kernels_against_numpy(N, K, ld_extra):
     torch.cuda.synchronize()
     want = (member.astype(np.int64) @ (v[:, :N] > 0).T.astype(np.int64)).astype(np.int32)
     assert np.array_equal(out.cpu().numpy(), want)
+
+
+def test_pool_count_on_column_slice_views():
+    """A rank's shard is a column slice r[:, lo:hi] of the parent matrix: ld is the parent's stride and the
+    tail of the last row beyond N is NOT part of the allocation — the 16-byte stream must stay inside N
+    (run under compute-sanitizer memcheck in profiles/r2_sanitizer.txt)."""
+    import torch
+    from honeybadger_b200 import _lib
+    rng = np.random.default_rng(8)
+    G, Nfull, K = 61, 1024, 5
+    v = rng.integers(-1, 3, size=(G, Nfull)).astype(np.int32)
+    vd = torch.from_numpy(v).cuda()
+    lib = _lib.load()
+    for lo, hi in [(0, 1024), (512, 1024), (768, 1021), (4, 1024), (1000, 1024)]:
+        N = hi - lo
+        member = (rng.random((K, N)) < 0.5).astype(np.uint8)
+        member[:, 0] = 1
+        md = torch.from_numpy(member).cuda()
+        out = torch.zeros((K, G), dtype=torch.int32, device="cuda")
+        view = vd[:, lo:hi]
+        _lib.check(lib.hb_pool_count_pos_dev(view.data_ptr(), vd.stride(0), G, N, md.data_ptr(), K,
+                                             out.data_ptr(), None))
+        torch.cuda.synchronize()
+        want = (member.astype(np.int64) @ (v[:, lo:hi] > 0).T.astype(np.int64)).astype(np.int32)
+        assert np.array_equal(out.cpu().numpy(), want), (lo, hi)

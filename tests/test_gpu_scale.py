@@ -22,72 +22,134 @@ def _expr_device(G, N, seed):
     return x, seg
 
 
-def test_c4_expression_full_size_properties(oracle):
-    """10k cells x 20k genes: posteriors are distributions, states valid, re-running is idempotent,
-    sampled chains equal the oracle, segment results do not depend on the batch around them."""
+def _tiled_cols(t, cols):
+    """Columns `cols` of a warp-tiled [ntile, T, 32] (or [planes, ntile, T, 32]) tensor -> numpy [T, n] / [planes, T, n]."""
     import torch
+    c = torch.as_tensor(np.asarray(cols), device=t.device)
+    if t.dim() == 4:
+        return np.stack([_tiled_cols(p, cols) for p in t])
+    return t[c // 32, :, c % 32].t().cpu().numpy()  # advanced indices around a slice: [n, T]
+
+
+def test_c4_expression_full_size_on_the_timed_path(oracle):
+    """BASELINE config 4, expression half, exactly as bench.py runs it: 10k cells x 20k genes x 22 segments
+    from bench.device_inputs, warp-tiled resident layout, hb_hmm_norm_tiled_dev in auto mode.  Asserts that the
+    speculate-and-verify kernel is the one that ran, then compares 512 sampled cells (11 264 chains) PLUS every
+    chain the kernel re-ran exactly with the oracle: states exact, posteriors 1e-9.  Size-independent
+    properties on the whole output."""
+    import torch
+    import bench
     from honeybadger_b200 import hmm
     G, N = 20000, 10000
-    x, seg = _expr_device(G, N, 21)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    d = bench.device_inputs("expr", N, G, seed=100, dev=dev)
+    x, seg = d["x"], d["seg"]
     sd = hmm.chain_sd_dev(x)
     mean, Pi, delta = [-synth.DEV, 0.0, synth.DEV], hmm.sym_Pi(3, 1e-6), [0.0, 1.0, 0.0]
-    out = hmm.hmm_norm_dev(x, sd, mean, Pi, delta, seg_off=seg, viterbi=True, gamma=True, ll=True)
+    xt = hmm.tile_rows(x)
+    out = hmm.hmm_norm_tiled_dev(xt, N, sd, mean, Pi, delta, seg_off=seg, viterbi=True, gamma=True, ll=True)
     hmm.status_dev()
+    assert hmm.last_kernels()["norm3_fast"] == 1, "auto mode did not pick the speculate-and-verify kernel"
+    nre = hmm.norm3_rerun_chains()
+    flagged = hmm.norm3_flagged_chains(N)
+    assert nre == len(flagged) and nre < 220000 // 500, f"{nre} of 220000 chains needed the exact fallback"
     y, g = out["y"], out["gamma"]
     assert int(y.min()) >= 1 and int(y.max()) <= 3
-    assert float((g.sum(0) - 1).abs().max()) < 1e-12
-    assert float(g.min()) >= 0.0
-    chk = (int(y.to(torch.int64).sum()), float(g[0].sum()), float(g[2].sum()))
-    out2 = hmm.hmm_norm_dev(x, sd, mean, Pi, delta, seg_off=seg, viterbi=True, gamma=True, ll=True)
+    assert float((g.sum(0) - 1).abs().max()) < 1e-12 and float(g.min()) >= 0.0
+    out2 = hmm.hmm_norm_tiled_dev(xt, N, sd, mean, Pi, delta, seg_off=seg, viterbi=True, gamma=True, ll=True)
     assert torch.equal(out2["y"], y) and torch.equal(out2["gamma"], g)  # deterministic
-    nre = hmm.norm3_rerun_chains()
-    assert nre < 220000 // 500, f"{nre} of 220000 chains needed the exact fallback"
-    assert chk == (int(out2["y"].to(torch.int64).sum()), float(out2["gamma"][0].sum()), float(out2["gamma"][2].sum()))
-    cols = np.array([0, 1, 4999, 5000, 9998, 9999, 1234, 7777])
-    xs = x[:, cols].cpu().numpy()
-    sds = sd[cols].cpu().numpy()
+    # forcing EVERY chain through the literal re-run gives the same states (mode 2), and so does the literal kernel
+    lib = __import__("honeybadger_b200._lib", fromlist=["load"]).load()
+    try:
+        lib.hb_set_norm3_mode(2)
+        o2 = hmm.hmm_norm_tiled_dev(xt, N, sd, mean, Pi, delta, seg_off=seg, viterbi=True, gamma=False)
+        assert hmm.norm3_rerun_chains() == 220000
+        assert torch.equal(o2["y"], y)
+        lib.hb_set_norm3_mode(1)
+        o1 = hmm.hmm_norm_tiled_dev(xt, N, sd, mean, Pi, delta, seg_off=seg, viterbi=True, gamma=True)
+        assert hmm.last_kernels()["norm3_fast"] == 0
+        assert torch.equal(o1["y"], y)
+        assert float((o1["gamma"] - g).abs().max()) < 1e-10
+    finally:
+        lib.hb_set_norm3_mode(0)
+    rng = np.random.default_rng(4)
+    cols = np.unique(np.concatenate([rng.choice(N, 512, replace=False), [0, 31, 32, N - 1], flagged[:, 1]]))
+    xs = x[:, torch.as_tensor(cols, device=dev)].cpu().numpy()
+    sds = sd[torch.as_tensor(cols, device=dev)].cpu().numpy()
     yo, go, llo, rc = oracle.fbv_norm_batch(xs, seg, mean, sds, Pi, delta)
-    assert rc == 0 and (y[:, cols].cpu().numpy() == yo).all()
-    assert np.abs(g[:, :, cols].cpu().numpy() - go).max() < 1e-9
-    assert np.allclose(out["ll"][:, cols].cpu().numpy(), llo, rtol=1e-10, atol=1e-9)
-    # a sub-batch gives the same chains (no cross-chain coupling, any B / alignment)
-    sub = x[:, 100:357].contiguous()
-    o3 = hmm.hmm_norm_dev(sub, sd[100:357].contiguous(), mean, Pi, delta, seg_off=seg)
-    assert torch.equal(o3["y"], y[:, 100:357]) and torch.equal(o3["gamma"], g[:, :, 100:357])
-    # amplified / deleted segments are called in the carrier cells
-    assert float((y[seg[6]:seg[7], : N // 2] == 3).double().mean()) > 0.5
-    assert float((y[seg[9]:seg[10], : N // 2] == 1).double().mean()) > 0.5
+    assert rc == 0
+    ys = _tiled_cols(y, cols)
+    assert (ys == yo).all(), f"{(ys != yo).sum()} states differ on {len(cols)} sampled cells"
+    assert np.abs(_tiled_cols(g, cols) - go).max() < 1e-9
+    assert np.allclose(out["ll"][:, torch.as_tensor(cols, device=dev)].cpu().numpy(), llo, rtol=1e-10, atol=1e-9)
+    # amplified / deleted segments are called in the carrier cells (clone labels are inside device_inputs:
+    # at least a third of all cells carry them)
+    yg = hmm.untile_rows(y, N)
+    assert float((yg[seg[6]:seg[7]] == 3).double().mean()) > 0.3
+    assert float((yg[seg[9]:seg[10]] == 1).double().mean()) > 0.3
 
 
-def test_c3_allele_large_properties(oracle):
-    """2000 cells x 200k SNPs (C3's chain length): same properties for the binomial chains."""
+def test_c2_expression_at_its_stated_size(oracle):
+    """BASELINE config 2: 2k cells x 10k genes, fp64, Viterbi parity — ALL 2000 chains against the oracle, in
+    the reference's own shape (nseg = 1: one 10k-position chain per cell, R/HoneyBADGER.R:1117-1121; longer
+    than the speculative kernel accepts, so the literal kernel) and per chromosome (nseg = 22, speculative
+    kernel on the tiled layout)."""
     import torch
     from honeybadger_b200 import hmm
-    G, N = 200000, 2000
-    r_np, n_np, seg, _ = synth.allele(G, 64, seed=31)
-    g = torch.Generator(device="cuda")
-    g.manual_seed(5)
-    n = ((torch.rand((G, N), device="cuda", generator=g) < 0.108).to(torch.int32)
-         * torch.randint(1, 9, (G, N), device="cuda", generator=g, dtype=torch.int32))
-    r = (torch.rand((G, N), device="cuda", generator=g) * (n + 1)).floor().to(torch.int32).clamp(max=n)
-    r[:, :64] = torch.from_numpy(r_np).cuda()
-    n[:, :64] = torch.from_numpy(n_np).cuda()
+    G, N = 10000, 2000
+    x, seg22, _ = synth.expression(G, N, seed=2)
+    xd = hmm.to_rows(torch.from_numpy(x).cuda())
+    sd = hmm.chain_sd_dev(xd)
+    sdh = sd.cpu().numpy()
+    mean, Pi, delta = [-synth.DEV, 0.0, synth.DEV], hmm.sym_Pi(3, 1e-6), [0.0, 1.0, 0.0]
+    xt = hmm.tile_rows(xd)
+    for seg, fast in ((np.array([0, G], dtype=np.int64), 0), (seg22, 1)):
+        out = hmm.hmm_norm_tiled_dev(xt, N, sd, mean, Pi, delta, seg_off=seg, viterbi=True, gamma=True)
+        hmm.status_dev()
+        assert hmm.last_kernels()["norm3_fast"] == fast
+        yo, go, _, rc = oracle.fbv_norm_batch(x, seg, mean, sdh, Pi, delta)
+        assert rc == 0
+        y = hmm.untile_rows(out["y"], N).cpu().numpy()
+        assert (y == yo).all(), f"nseg={len(seg) - 1}: {(y != yo).sum()} of {y.size} states differ"
+        g = hmm.untile_rows(out["gamma"], N).cpu().numpy()
+        assert np.abs(g - go).max() < 1e-9
+        # gene-major padded rows give the same answer as the tiled layout
+        o2 = hmm.hmm_norm_dev(xd, sd, mean, Pi, delta, seg_off=seg, viterbi=True, gamma=False)
+        assert (o2["y"].cpu().numpy() == yo).all()
+
+
+def test_c3_allele_full_size_on_the_timed_path(oracle):
+    """BASELINE config 3 as bench.py runs its allele half: 10k cells x 200k SNPs from bench.device_inputs,
+    PACKED 16-bit counts on the warp-tiled layout, hb_hmm_binom_packed_tiled_dev (lean kernel + gated general
+    kernel).  512 sampled cells (11 264 chains, 1e8 steps) against the oracle: states exact, posteriors 1e-9."""
+    import torch
+    import bench
+    from honeybadger_b200 import hmm
+    G, N = 200000, 10000
+    dev = torch.device("cuda", torch.cuda.current_device())
+    d = bench.device_inputs("allele", N, G, seed=300, dev=dev)
+    seg = d["seg"]
+    rng = np.random.default_rng(5)
+    cols = np.unique(np.concatenate([rng.choice(N, 512, replace=False), [0, 31, 32, N - 1]]))
+    ct = torch.as_tensor(cols, device=dev)
+    r_np, n_np = d["r"][:, ct].cpu().numpy(), d["n"][:, ct].cpu().numpy()
+    xn = hmm.pack_counts(hmm.tile_rows(d["r"]), hmm.tile_rows(d["n"]))
+    del d
+    torch.cuda.empty_cache()
     Pi, delta, prob = hmm.sym_Pi(2, 1e-6), [0.0, 1.0], [0.1, 0.45]
-    out = hmm.hmm_binom_dev(r, n, prob, Pi, delta, seg_off=seg, viterbi=True, gamma=True, ll=True)
+    out = hmm.hmm_binom_tiled_dev(xn, None, N, prob, Pi, delta, seg_off=seg, viterbi=True, gamma=True, ll=True)
     hmm.status_dev()
+    assert hmm.last_kernels()["binom2_lean"] == 1 and hmm.binom2_general_rerun() == 0
     y, gm = out["y"], out["gamma"]
     assert int(y.min()) >= 1 and int(y.max()) <= 2
-    assert float((gm.sum(0) - 1).abs().max()) < 1e-12
+    assert float((gm[0] + gm[1] - 1).abs().max()) < 1e-12 and float(gm.min()) >= 0.0
     yo, go, llo, rc = oracle.fbv_binom_batch(r_np, n_np, seg, prob, Pi, delta)
-    assert rc == 0 and (y[:, :64].cpu().numpy() == yo).all()
-    assert np.abs(gm[:, :, :64].cpu().numpy() - go).max() < 1e-9
-    assert np.allclose(out["ll"][:, :64].cpu().numpy(), llo, rtol=1e-10, atol=1e-9)
-    # single concatenated chain (the reference's shape, nseg = 1) on a few cells
-    one = np.array([0, G], dtype=np.int64)
-    o1 = hmm.hmm_binom_dev(r[:, :32].contiguous(), n[:, :32].contiguous(), prob, Pi, delta, seg_off=one)
-    y1, g1, _, rc = oracle.fbv_binom_batch(r_np[:, :32], n_np[:, :32], one, prob, Pi, delta)
-    assert rc == 0 and (o1["y"].cpu().numpy() == y1).all()
-    assert np.abs(o1["gamma"].cpu().numpy() - g1).max() < 1e-9
+    assert rc == 0
+    ys = _tiled_cols(y, cols)
+    assert (ys == yo).all(), f"{(ys != yo).sum()} states differ on {len(cols)} sampled cells"
+    assert np.abs(_tiled_cols(gm, cols) - go).max() < 1e-9
+    assert np.allclose(out["ll"][:, ct].cpu().numpy(), llo, rtol=1e-10, atol=1e-9)
+    assert float((y == 1).double().mean()) > 0.005  # deleted segments are called
 
 
 def test_ragged_and_tiny_shapes(oracle):
