@@ -550,11 +550,49 @@ def run_allele_extra(cells, rank, dev, hmm, world, dist, steps=5):
     val = world * cells * positions / (ms * 1e-3)
     peak, _ = measured_peak()
     ach = cells * positions * wl["bytes_per_step"] / (ms * 1e-3) / 1e9
+    rerun = hmm.binom2_general_rerun()
+    bb = None
+    if world == 1:
+        try:
+            bb = run_betabinom(xn, cells, positions, d["seg"], hmm, wl, peak, steps)
+        except Exception as exc:
+            bb = {"error": repr(exc)[:200]}
     return {"workload": wl["name"], "value": val, "unit": UNIT, "ms_per_step": ms, "steps": steps,
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                          "traffic": ncu_traffic("allele"), "algorithmic_bytes_per_step": wl["bytes_per_step"],
                          "kernel": "binom2_fast_kernel<VIT,FB>"},
-            "general_kernel_rerun": hmm.binom2_general_rerun(), "pooled_round": pooled}
+            "general_kernel_rerun": rerun, "pooled_round": pooled, "betabinom": bb}
+
+
+def run_betabinom(xn, cells, positions, seg, hmm, wl, peak, steps, rho=0.02):
+    """BASELINE config 3 with north_star's beta-binomial emissions (rho > 0; an extension — the reference is
+    binomial): the same resident packed counts and kernel, emission table built for the over-dispersed model
+    up to the workload's maximum count; sampled chains against the oracle at the same rho."""
+    import torch
+    from honeybadger_b200 import _lib
+    from oracle import oracle as O
+    lib = _lib.load()
+    Pi2, prob, delta = hmm.sym_Pi(2, 1e-6), [0.1, 0.45], [0.0, 1.0]
+    _lib.check(lib.hb_set_binom_lut_max(1245))
+    try:
+        out = hmm.hmm_binom_tiled_dev(xn, None, cells, prob, Pi2, delta, seg_off=seg, rho=rho)
+        hmm.status_dev()
+        fn = lambda: hmm.hmm_binom_tiled_dev(xn, None, cells, prob, Pi2, delta, seg_off=seg, rho=rho, out=out)  # noqa: E731
+        ms = time_launches(fn, steps, torch)
+        hmm.status_dev()
+        cols = np.random.default_rng(13).choice(cells, size=32, replace=False)
+        w = tiled_cols(xn, cols)
+        r_np, n_np = (w & 0xFFFF).astype(np.int32), ((w >> 16) & 0xFFFF).astype(np.int32)
+        yo, go, _, rc = O.fbv_binom_batch(r_np, n_np, seg, prob, O.sym_Pi(2, 1e-6), delta, rho=rho)
+        y, g = tiled_cols(out["y"], cols), tiled_cols(out["gamma"], cols)
+        par = {"chains_checked": int(len(cols) * (len(seg) - 1)), "state_mismatches": int((y != yo).sum()),
+               "max_gamma_err": float(np.abs(g - go).max()), "oracle_rc": int(rc)}
+    finally:
+        _lib.check(lib.hb_set_binom_lut_max(511))
+    ach = cells * positions * wl["bytes_per_step"] / (ms * 1e-3) / 1e9
+    return {"rho": rho, "ms_per_step": ms, "value": cells * positions / (ms * 1e-3), "roofline_frac": ach / peak,
+            "general_kernel_rerun": hmm.binom2_general_rerun(), "parity": par,
+            "note": "beta-binomial emissions (mean p, intra-class correlation rho) — extension, reference is binomial"}
 
 
 def run_pooled_round(d, cells, hmm):

@@ -565,13 +565,14 @@ int prepare_lut(Workspace *ws, const double *prob, double rho, cudaStream_t st)
     std::vector<double> lb(2 * cnt);
     std::vector<hb::RhoME> rr(cnt);
     std::vector<double> rd(cnt);
+    const hbhost::BetaBinomCorr bb0(prob[0], rho, nmax), bb1(prob[1], rho, nmax);
     for (int32_t n = 0; n <= nmax; n++)
         for (int32_t x = 0; x <= n; x++) {
             size_t ix = (size_t)n * (n + 1) / 2 + x;
             double l0, l1;
             if (rho > 0) {
-                l0 = hbhost::betabinom_logpmf(x, n, prob[0], rho);
-                l1 = hbhost::betabinom_logpmf(x, n, prob[1], rho);
+                l0 = hbhost::betabinom_logpmf(bb0, x, n, prob[0]);
+                l1 = hbhost::betabinom_logpmf(bb1, x, n, prob[1]);
             } else {
                 l0 = hbhost::binom_logpmf(x, n, prob[0]);
                 l1 = hbhost::binom_logpmf(x, n, prob[1]);

@@ -9,6 +9,8 @@
 #include <float.h>
 #include <math.h>
 
+#include <vector>
+
 namespace hbhost {
 
 static const double kSferrHalves[31] = {
@@ -77,15 +79,47 @@ inline double binom_logpmf(double x, double n, double p)
     return lc - 0.5 * lf;
 }
 
-// Beta-binomial log-pmf with mean p and intra-class correlation rho in (0, 1):
-// alpha = p (1-rho)/rho, beta = (1-p)(1-rho)/rho.  Extension over the reference;
-// tends to binom_logpmf as rho -> 0.
-inline double betabinom_logpmf(double x, double n, double p, double rho)
+// Beta-binomial log-pmf with mean p and intra-class correlation rho in [0, 1): alpha = p (1-rho)/rho,
+// beta = (1-p)(1-rho)/rho.  An EXTENSION over the reference, which is binomial (R/HoneyBADGER.R:1409,
+// R/HoneyBADGER_allele.R:579); it reduces to binom_logpmf EXACTLY at rho = 0 and smoothly
+// as rho -> 0, because it is evaluated as the binomial value plus a correction:
+//     BB(x; n, p, rho) = C(n,x) prod_{i<x}(p + i th) prod_{i<n-x}(q + i th) / prod_{i<n}(1 + i th),  th = rho/(1-rho)
+//     log BB = log dbinom(x; n, p) + [ sum_{i<x} log1p(i th / p) + sum_{i<n-x} log1p(i th / q) - sum_{i<n} log1p(i th) ]
+// (no lgamma of arguments ~ p/rho, whose cancellation destroys the limit).  The three sums are accumulated
+// in long double in increasing i; BetaBinomCorr keeps them as prefix arrays so that a whole emission table
+// costs O(nmax) log1p evaluations.  oracle/hb_oracle.c: hbo_dbetabinom_log follows the same definition with
+// direct loops and must agree bit for bit; oracle/pyref.py checks both against mpmath's exact value.
+struct BetaBinomCorr {
+    std::vector<long double> la, lb, ld; // la[k] = sum_{i<k} log1pl(i th / p), lb: / q, ld: / 1
+    bool degenerate = true;
+    BetaBinomCorr(double p, double rho, int nmax)
+    {
+        const double q = 1 - p;
+        if (!(rho > 0) || p == 0 || q == 0) return;
+        degenerate = false;
+        const long double th = (long double)rho / (1.0L - (long double)rho);
+        la.assign((size_t)nmax + 2, 0.0L);
+        lb.assign((size_t)nmax + 2, 0.0L);
+        ld.assign((size_t)nmax + 2, 0.0L);
+        for (int k = 0; k <= nmax; k++) {
+            const long double it = (long double)k * th;
+            la[(size_t)k + 1] = la[k] + log1pl(it / (long double)p);
+            lb[(size_t)k + 1] = lb[k] + log1pl(it / (long double)q);
+            ld[(size_t)k + 1] = ld[k] + log1pl(it);
+        }
+    }
+    double corr(int x, int n) const
+    {
+        if (degenerate) return 0.0;
+        return (double)((la[x] + lb[n - x]) - ld[n]);
+    }
+};
+
+inline double betabinom_logpmf(const BetaBinomCorr &c, int x, int n, double p)
 {
     if (x < 0 || x > n) return -INFINITY;
-    const double th = (1 - rho) / rho, al = p * th, be = (1 - p) * th;
-    return lgamma(n + 1) - lgamma(x + 1) - lgamma(n - x + 1) + lgamma(x + al) + lgamma(n - x + be) -
-           lgamma(n + al + be) + lgamma(al + be) - lgamma(al) - lgamma(be);
+    const double b = binom_logpmf((double)x, (double)n, p);
+    return c.degenerate ? b : b + c.corr(x, n);
 }
 
 } // namespace hbhost

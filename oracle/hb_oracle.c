@@ -313,19 +313,57 @@ int hbo_viterbi_norm(int S, int64_t T, const double *x, const double *mean, cons
     return rc;
 }
 
-/* dthmm(x, Pi, delta, "binom", list(prob=), list(size=), discrete=TRUE) -> Viterbi */
-int hbo_viterbi_binom(int S, int64_t T, const int32_t *x, const int32_t *size, const double *prob,
-                      const double *Pi, const double *delta, int32_t *y)
+/* Beta-binomial log-pmf, mean p, intra-class correlation rho in [0, 1) (alpha = p(1-rho)/rho,
+ * beta = (1-p)(1-rho)/rho).  NOT in the reference — HoneyBADGER's allele chain is binomial
+ * (R/HoneyBADGER.R:1409, R/HoneyBADGER_allele.R:579); north_star names it as an extension, so there is no
+ * reference arithmetic to restate and THIS is the definition the product's emission table follows
+ * (honeybadger_b200/csrc/hb_host_math.h builds the same sums as prefix arrays):
+ *     th   = rho / (1 - rho)                                              (long double)
+ *     corr = [ sum_{i=0}^{x-1} log1pl(i th / p) + sum_{i=0}^{n-x-1} log1pl(i th / q) ] - sum_{i=0}^{n-1} log1pl(i th)
+ *            each sum accumulated from 0 in increasing i, long double, q = 1 - p rounded to double first
+ *     log BB(x; n, p, rho) = dbinom(x, n, p, log = TRUE) + (double) corr
+ * i.e. the identity BB = C(n,x) prod(p + i th) prod(q + i th) / prod(1 + i th) written relative to the binomial,
+ * so that rho = 0 IS the reference's binomial and rho -> 0 converges without cancellation.
+ * tests/test_oracle.py pins it on mpmath's exact log-pmf (oracle/pyref.py: betabinom_logpmf_exact). */
+double hbo_dbetabinom_log(double x, double n, double p, double rho)
+{
+    if (x < 0 || x > n) return -INFINITY;
+    const double base = hbo_dbinom(x, n, p, 1);
+    const double q = 1 - p;
+    if (!(rho > 0) || p == 0 || q == 0) return base;
+    const long double th = (long double)rho / (1.0L - (long double)rho);
+    long double sa = 0.0L, sb = 0.0L, sd = 0.0L;
+    const int64_t xi = (int64_t)x, ni = (int64_t)n;
+    for (int64_t i = 0; i < xi; i++) sa += log1pl((long double)i * th / (long double)p);
+    for (int64_t i = 0; i < ni - xi; i++) sb += log1pl((long double)i * th / (long double)q);
+    for (int64_t i = 0; i < ni; i++) sd += log1pl((long double)i * th);
+    return base + (double)((sa + sb) - sd);
+}
+
+static double binom_like_log(double x, double n, double p, double rho)
+{
+    return rho > 0 ? hbo_dbetabinom_log(x, n, p, rho) : hbo_dbinom(x, n, p, 1);
+}
+
+/* dthmm(x, Pi, delta, "binom", list(prob=), list(size=), discrete=TRUE) -> Viterbi; rho > 0: beta-binomial */
+int hbo_viterbi_binom_rho(int S, int64_t T, const int32_t *x, const int32_t *size, const double *prob,
+                          double rho, const double *Pi, const double *delta, int32_t *y)
 {
     if (S < 1 || S > HBO_MAX_S || T < 1) return HBO_ERR_ARG;
     double *logb = (double *)malloc(sizeof(double) * (size_t)T * S);
     if (!logb) return HBO_ERR_NOMEM;
     for (int64_t i = 0; i < T; i++)
         for (int k = 0; k < S; k++)
-            logb[i * S + k] = hbo_dbinom((double)x[i], (double)size[i], prob[k], 1);
+            logb[i * S + k] = binom_like_log((double)x[i], (double)size[i], prob[k], rho);
     int rc = hbo_viterbi_logb(S, T, logb, Pi, delta, y, NULL);
     free(logb);
     return rc;
+}
+
+int hbo_viterbi_binom(int S, int64_t T, const int32_t *x, const int32_t *size, const double *prob,
+                      const double *Pi, const double *delta, int32_t *y)
+{
+    return hbo_viterbi_binom_rho(S, T, x, size, prob, 0.0, Pi, delta, y);
 }
 
 /* ---------------------------------- HiddenMarkov::forwardback.dthmm + Estep u */
@@ -399,18 +437,26 @@ int hbo_forwardback_norm(int S, int64_t T, const double *x, const double *mean, 
     return rc;
 }
 
-int hbo_forwardback_binom(int S, int64_t T, const int32_t *x, const int32_t *size,
-                          const double *prob_k, const double *Pi, const double *delta,
-                          double *gamma, double *LL)
+int hbo_forwardback_binom_rho(int S, int64_t T, const int32_t *x, const int32_t *size,
+                              const double *prob_k, double rho, const double *Pi, const double *delta,
+                              double *gamma, double *LL)
 {
     double *prob = (double *)malloc(sizeof(double) * (size_t)T * S);
     if (!prob) return HBO_ERR_NOMEM;
     for (int64_t i = 0; i < T; i++)
         for (int k = 0; k < S; k++)
-            prob[i * S + k] = hbo_dbinom((double)x[i], (double)size[i], prob_k[k], 0);
+            prob[i * S + k] = rho > 0 ? exp(hbo_dbetabinom_log((double)x[i], (double)size[i], prob_k[k], rho))
+                                      : hbo_dbinom((double)x[i], (double)size[i], prob_k[k], 0);
     int rc = hbo_forwardback_prob(S, T, prob, Pi, delta, NULL, NULL, gamma, LL);
     free(prob);
     return rc;
+}
+
+int hbo_forwardback_binom(int S, int64_t T, const int32_t *x, const int32_t *size,
+                          const double *prob_k, const double *Pi, const double *delta,
+                          double *gamma, double *LL)
+{
+    return hbo_forwardback_binom_rho(S, T, x, size, prob_k, 0.0, Pi, delta, gamma, LL);
 }
 
 /* ------------------------------------------------------------------ batched drivers
@@ -467,10 +513,23 @@ int hbo_fbv_norm_batch(int64_t T, int64_t B, int64_t ld, const double *x, const 
     return rc_all;
 }
 
+int hbo_fbv_binom_batch_rho(int64_t T, int64_t B, int64_t ld, const int32_t *x, const int32_t *n,
+                            const int64_t *seg_off, int nseg, const double *prob /*[2]*/, double rho,
+                            const double *Pi, const double *delta, uint8_t *y, double *gamma,
+                            double *ll, int nthreads);
+
 int hbo_fbv_binom_batch(int64_t T, int64_t B, int64_t ld, const int32_t *x, const int32_t *n,
                         const int64_t *seg_off, int nseg, const double *prob /*[2]*/,
                         const double *Pi, const double *delta, uint8_t *y, double *gamma,
                         double *ll, int nthreads)
+{
+    return hbo_fbv_binom_batch_rho(T, B, ld, x, n, seg_off, nseg, prob, 0.0, Pi, delta, y, gamma, ll, nthreads);
+}
+
+int hbo_fbv_binom_batch_rho(int64_t T, int64_t B, int64_t ld, const int32_t *x, const int32_t *n,
+                            const int64_t *seg_off, int nseg, const double *prob /*[2]*/, double rho,
+                            const double *Pi, const double *delta, uint8_t *y, double *gamma,
+                            double *ll, int nthreads)
 {
     const int S = 2;
     int rc_all = HBO_OK;
@@ -492,11 +551,11 @@ int hbo_fbv_binom_batch(int64_t T, int64_t B, int64_t ld, const int32_t *x, cons
             xs[i] = x[(t0 + i) * ld + b];
             ns[i] = n[(t0 + i) * ld + b];
         }
-        int rc = hbo_viterbi_binom(S, L, xs, ns, prob, Pi, delta, ys);
+        int rc = hbo_viterbi_binom_rho(S, L, xs, ns, prob, rho, Pi, delta, ys);
         for (int64_t i = 0; i < L; i++) y[(t0 + i) * ld + b] = rc == HBO_OK ? (uint8_t)ys[i] : 0;
         if (gamma || ll) {
             double llv = 0;
-            hbo_forwardback_binom(S, L, xs, ns, prob, Pi, delta, gs, &llv);
+            hbo_forwardback_binom_rho(S, L, xs, ns, prob, rho, Pi, delta, gs, &llv);
             if (ll) ll[s * B + b] = llv;
             if (gamma)
                 for (int64_t i = 0; i < L; i++)

@@ -63,6 +63,10 @@ def lib():
         L.hbo_fbv_norm_batch.argtypes = [i64, i64, i64, p, p, i32, p, p, i32, p, p, p, p, p, i32]
         L.hbo_fbv_binom_batch.restype = i32
         L.hbo_fbv_binom_batch.argtypes = [i64, i64, i64, p, p, p, i32, p, p, p, p, p, p, i32]
+        L.hbo_fbv_binom_batch_rho.restype = i32
+        L.hbo_fbv_binom_batch_rho.argtypes = [i64, i64, i64, p, p, p, i32, p, d, p, p, p, p, p, i32]
+        L.hbo_dbetabinom_log.restype = d
+        L.hbo_dbetabinom_log.argtypes = [d, d, d, d]
         L.hbo_pool_mean.restype = None
         L.hbo_pool_mean.argtypes = [p, i64, p, i64, p]
         L.hbo_pool_count_pos.restype = None
@@ -236,7 +240,12 @@ def fbv_norm_batch(x, seg_off, mean, sd, Pi, delta, want_gamma=True, nthreads=0)
     return y, g, ll, rc
 
 
-def fbv_binom_batch(x, n, seg_off, prob, Pi, delta, want_gamma=True, nthreads=0):
+def dbetabinom_log(x, n, p, rho):
+    """log beta-binomial pmf (mean p, intra-class correlation rho): binomial + correction, see hb_oracle.c"""
+    return lib().hbo_dbetabinom_log(float(x), float(n), float(p), float(rho))
+
+
+def fbv_binom_batch(x, n, seg_off, prob, Pi, delta, want_gamma=True, nthreads=0, rho=0.0):
     x, n = _i32(x), _i32(n)
     T, B = x.shape
     seg_off = np.ascontiguousarray(seg_off, dtype=np.int64)
@@ -246,8 +255,8 @@ def fbv_binom_batch(x, n, seg_off, prob, Pi, delta, want_gamma=True, nthreads=0)
     g = np.zeros((2, T, B)) if want_gamma else None
     ll = np.zeros((nseg, B))
     nt = nthreads or lib().hbo_num_threads()
-    rc = lib().hbo_fbv_binom_batch(T, B, B, _p(x), _p(n), _p(seg_off), nseg, _p(prob), _p(Pi),
-                                   _p(delta), _p(y), _p(g), _p(ll), nt)
+    rc = lib().hbo_fbv_binom_batch_rho(T, B, B, _p(x), _p(n), _p(seg_off), nseg, _p(prob), float(rho), _p(Pi),
+                                       _p(delta), _p(y), _p(g), _p(ll), nt)
     return y, g, ll, rc
 
 

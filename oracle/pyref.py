@@ -116,6 +116,25 @@ def mp_dbinom_log(x, n, p, dps=50):
                 + ((n - x) * mp.log(1 - P) if n - x else 0))
 
 
+def betabinom_logpmf_exact(x, n, p, rho, dps=60):
+    """Exact (mpmath) log beta-binomial pmf with mean p and intra-class correlation rho:
+    log C(n,x) + log B(x + a, n - x + b) - log B(a, b), a = p(1-rho)/rho, b = (1-p)(1-rho)/rho — an independent
+    formulation (log-gamma at high precision) of what hb_oracle.c's hbo_dbetabinom_log evaluates as
+    binomial + correction."""
+    import mpmath as mp
+    with mp.workdps(dps):
+        x, n = int(x), int(n)
+        if x < 0 or x > n:
+            return -mp.inf
+        P, R = mp.mpf(p), mp.mpf(rho)
+        if R == 0:
+            return mp_dbinom_log(x, n, p, dps)
+        s = (1 - R) / R
+        a, b = P * s, (1 - P) * s
+        lbeta = lambda u, v: mp.loggamma(u) + mp.loggamma(v) - mp.loggamma(u + v)  # noqa: E731
+        return mp.log(mp.binomial(n, x)) + lbeta(x + a, n - x + b) - lbeta(a, b)
+
+
 # --------------------------------------------------------------------------- base-R reductions
 def r_mean(x) -> float:
     """summary.c real_mean: x87 LDOUBLE, two passes, sequential order."""

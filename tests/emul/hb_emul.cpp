@@ -400,6 +400,19 @@ void emul_exp_pair(double u, double *ep, double *em)
 }
 
 double emul_binom_logpmf_host(double x, double n, double p) { return hbhost::binom_logpmf(x, n, p); }
+// the product's beta-binomial table entry (prefix-sum builder, as prepare_lut uses it)
+double emul_betabinom_logpmf(int x, int n, double p, double rho, int nmax)
+{
+    static hbhost::BetaBinomCorr *c = nullptr;
+    static double cp = -1, cr = -1;
+    static int cn = -1;
+    if (!c || cp != p || cr != rho || cn != nmax) {
+        delete c;
+        c = new hbhost::BetaBinomCorr(p, rho, nmax);
+        cp = p, cr = rho, cn = nmax;
+    }
+    return hbhost::betabinom_logpmf(*c, x, n, p);
+}
 double emul_binom_logpmf_dev(double x, double n, double p)
 {
     return dev_dbinom_log(x, n, p, 1 - p, log(p), log(1 - p));

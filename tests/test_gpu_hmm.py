@@ -439,9 +439,9 @@ def test_ll_alone_runs_the_forward_sweep_only(oracle):
         lib.hb_set_binom2_mode(mode)
         try:
             res = hmm.hmm_binom_host(r, n, prob, Pi2, [0.0, 1.0], seg_off=seg2, viterbi=True, gamma=False, ll=True)
-            assert (res["y"] == yo).all() and np.allclose(res["ll"].T, llo2, rtol=1e-10, atol=0)
+            assert (res["y"] == yo).all() and np.allclose(res["ll"].T, llo2, rtol=1e-10, atol=1e-12)
             res = hmm.hmm_binom_host(r, n, prob, Pi2, [0.0, 1.0], seg_off=seg2, viterbi=False, gamma=False, ll=True)
-            assert np.allclose(res["ll"].T, llo2, rtol=1e-10, atol=0)
+            assert np.allclose(res["ll"].T, llo2, rtol=1e-10, atol=1e-12)
         finally:
             lib.hb_set_binom2_mode(0)
     # a pooled-shaped single chain (long-chain route): LL alone
@@ -478,3 +478,57 @@ def test_two_streams_share_the_workspace_safely(oracle):
     for tag, o in outs:
         ref = ra if tag == "a" else rb
         assert torch.equal(o["y"], ref["y"]) and torch.equal(o["gamma"], ref["gamma"])
+
+
+def test_betabinom_emissions_reduce_to_the_binomial_and_match_the_oracle(oracle):
+    """north_star's beta-binomial allele emissions (an extension: the reference is binomial,
+    R/HoneyBADGER.R:1409).  rho = 1e-12: the binomial's exact states, posteriors within 1e-9 of the binomial's;
+    rho = 1e-6 and 0.05: states exactly the oracle's at the same rho, posteriors within 1e-9; both kernels
+    (lean + general), tiled packed layout as well; counts beyond the emission table are an error, not a
+    silent binomial."""
+    import torch
+    from honeybadger_b200 import _lib, hmm
+    lib = _lib.load()
+    r, n, seg, _ = synth.allele(6000, 96, seed=3)
+    Pi, delta, prob = hmm.sym_Pi(2, 1e-6), [0.0, 1.0], [0.1, 0.45]
+    y0, g0, ll0, rc = oracle.fbv_binom_batch(r, n, seg, prob, Pi, delta)
+    assert rc == 0
+    assert int(n.max()) <= 511
+    for rho in (1e-12, 1e-6, 0.05):
+        yo, go, llo, rc = oracle.fbv_binom_batch(r, n, seg, prob, Pi, delta, rho=rho)
+        assert rc == 0
+        for mode in (0, 1):
+            lib.hb_set_binom2_mode(mode)
+            try:
+                res = hmm.hmm_binom_host(r, n, prob, Pi, delta, seg_off=seg, rho=rho, viterbi=True, gamma=True,
+                                         ll=True)
+            finally:
+                lib.hb_set_binom2_mode(0)
+            assert (res["y"] == yo).all(), f"rho={rho} mode={mode}: {(res['y'] != yo).sum()} states differ"
+            assert np.abs(res["gamma"].transpose(2, 0, 1) - go).max() < 1e-9
+            assert np.allclose(res["ll"].T, llo, rtol=1e-10, atol=1e-12)
+            if rho == 1e-12:
+                assert (res["y"] == y0).all()
+                assert np.abs(res["gamma"].transpose(2, 0, 1) - g0).max() < 1e-9
+        if rho == 0.05:
+            assert np.abs(go - g0).max() > 1e-3  # the dispersion changes the posteriors
+    # the resident form bench.py uses: packed counts, warp-tiled
+    rd, nd = torch.from_numpy(r).cuda(), torch.from_numpy(n).cuda()
+    xn = hmm.pack_counts(hmm.tile_rows(rd), hmm.tile_rows(nd))
+    yo, go, _, _ = oracle.fbv_binom_batch(r, n, seg, prob, Pi, delta, rho=0.05)
+    o = hmm.hmm_binom_tiled_dev(xn, None, r.shape[1], prob, Pi, delta, seg_off=seg, rho=0.05)
+    hmm.status_dev()
+    assert (hmm.untile_rows(o["y"], r.shape[1]).cpu().numpy() == yo).all()
+    assert np.abs(hmm.untile_rows(o["gamma"], r.shape[1]).cpu().numpy() - go).max() < 1e-9
+    # counts above the table: error under rho > 0; fine once the table is enlarged
+    r2, n2 = r.copy(), n.copy()
+    n2[100, 3], r2[100, 3] = 900, 130
+    with pytest.raises(_lib.HBError):
+        hmm.hmm_binom_host(r2, n2, prob, Pi, delta, seg_off=seg, rho=0.05)
+    _lib.check(lib.hb_set_binom_lut_max(1245))
+    try:
+        res = hmm.hmm_binom_host(r2, n2, prob, Pi, delta, seg_off=seg, rho=0.05, viterbi=True, gamma=True)
+        yo, go, _, _ = oracle.fbv_binom_batch(r2, n2, seg, prob, Pi, delta, rho=0.05)
+        assert (res["y"] == yo).all() and np.abs(res["gamma"].transpose(2, 0, 1) - go).max() < 1e-9
+    finally:
+        _lib.check(lib.hb_set_binom_lut_max(511))

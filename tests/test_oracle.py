@@ -132,3 +132,66 @@ def test_forwardback_matches_exact_arithmetic(oracle):
 def test_underflow_error_like_hiddenmarkov(oracle):
     with pytest.raises(FloatingPointError, match="Problems With Underflow"):
         oracle.viterbi_norm([0.3], [-1, 0, 1], [1.0] * 3, oracle.sym_Pi(3, 1e-6), [0, 1, 0])
+
+
+def test_betabinom_logpmf_against_mpmath_and_its_binomial_limit(oracle):
+    """hbo_dbetabinom_log (binomial + correction; an extension — the reference is binomial,
+    R/HoneyBADGER.R:1409) against the exact log-gamma formulation in mpmath, over dispersion from 1e-14 to
+    0.3 and counts up to the bundled maximum 1245; rho = 0 IS dbinom, and rho -> 0 converges to it without the
+    cancellation a lgamma-of-(p/rho) form suffers (error stays ~1e-15 relative at rho = 1e-12)."""
+    from oracle import pyref
+    rng = np.random.default_rng(0)
+    cases = [(0, 0), (0, 5), (5, 5), (1, 2), (3, 17), (40, 100), (12, 511), (600, 1245), (0, 1245), (1245, 1245)]
+    cases += [(int(rng.integers(0, n + 1)), int(n)) for n in rng.integers(1, 400, size=40)]
+    worst = 0.0
+    for rho in (1e-14, 1e-12, 1e-9, 1e-6, 1e-3, 0.05, 0.3):
+        for p in (0.1, 0.45):
+            for x, n in cases:
+                got = oracle.dbetabinom_log(x, n, p, rho)
+                want = float(pyref.betabinom_logpmf_exact(x, n, p, rho))
+                # the value is binomial + correction: both can be hundreds of nats apart and cancel, so the
+                # error scales with the binomial term, not with the (possibly small) result
+                scale = max(1.0, abs(want), abs(oracle.dbinom(x, n, p, log=True)))
+                err = abs(got - want) / scale
+                worst = max(worst, err)
+                assert err < 2e-14, (x, n, p, rho, got, want)
+    # exact reduction at rho = 0, and a correction that vanishes linearly
+    for x, n in cases:
+        b = oracle.dbinom(x, n, 0.1, log=True)
+        assert oracle.dbetabinom_log(x, n, 0.1, 0.0) == b
+        d12, d6 = oracle.dbetabinom_log(x, n, 0.1, 1e-12) - b, oracle.dbetabinom_log(x, n, 0.1, 1e-6) - b
+        assert abs(d12) <= 1e-12 * (n * n + 1) * 6 and abs(d6) <= 1e-6 * (n * n + 1) * 6
+    # zero coverage carries no information under any dispersion (the structural ties of SURVEY 7.2-1 survive)
+    assert oracle.dbetabinom_log(0, 0, 0.1, 0.05) == 0.0 and oracle.dbetabinom_log(0, 0, 0.45, 0.05) == 0.0
+
+
+def test_betabinom_table_of_the_product_equals_the_oracle_bit_for_bit(oracle, emul):
+    """The product's emission table builder (hb_host_math.h: BetaBinomCorr prefix sums) against the oracle's
+    direct loops: the same long-double sums in the same order, so identical doubles for every (x, n)."""
+    import ctypes as C
+    emul.emul_betabinom_logpmf.restype = C.c_double
+    emul.emul_betabinom_logpmf.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double, C.c_int]
+    for rho in (1e-12, 1e-6, 0.05, 0.3):
+        for p in (0.1, 0.45):
+            for n in list(range(0, 40)) + [97, 200, 511, 1245]:
+                for x in sorted({0, 1, n // 3, n // 2, max(0, n - 1), n}):
+                    a = emul.emul_betabinom_logpmf(x, n, p, rho, 1245)
+                    b = oracle.dbetabinom_log(x, n, p, rho)
+                    assert a == b, (x, n, p, rho, a, b)
+
+
+def test_betabinom_chains_reduce_to_binomial_chains(oracle):
+    """Oracle level: Viterbi paths and posteriors of beta-binomial chains at rho = 1e-14 / 1e-12 against the
+    binomial chains on the same counts (zero-coverage ties included): states identical, posteriors within 1e-9;
+    rho = 0.05 gives different posteriors (the extension does something)."""
+    from honeybadger_b200 import synth
+    r, n, seg, _ = synth.allele(6000, 48, seed=3)
+    Pi, delta, prob = oracle.sym_Pi(2, 1e-6), [0.0, 1.0], [0.1, 0.45]
+    y0, g0, _, rc0 = oracle.fbv_binom_batch(r, n, seg, prob, Pi, delta)
+    assert rc0 == 0
+    for rho in (1e-14, 1e-12):
+        y, g, _, rc = oracle.fbv_binom_batch(r, n, seg, prob, Pi, delta, rho=rho)
+        assert rc == 0 and (y == y0).all(), f"rho={rho}: {(y != y0).sum()} states differ"
+        assert np.abs(g - g0).max() < 1e-9
+    y5, g5, _, rc = oracle.fbv_binom_batch(r, n, seg, prob, Pi, delta, rho=0.05)
+    assert rc == 0 and np.abs(g5 - g0).max() > 1e-3
