@@ -87,8 +87,8 @@ inline double binom_logpmf(double x, double n, double p)
 //     log BB = log dbinom(x; n, p) + [ sum_{i<x} log1p(i th / p) + sum_{i<n-x} log1p(i th / q) - sum_{i<n} log1p(i th) ]
 // (no lgamma of arguments ~ p/rho, whose cancellation destroys the limit).  The three sums are accumulated
 // in long double in increasing i; BetaBinomCorr keeps them as prefix arrays so that a whole emission table
-// costs O(nmax) log1p evaluations.  oracle/hb_oracle.c: hbo_dbetabinom_log follows the same definition with
-// direct loops and must agree bit for bit; oracle/pyref.py checks both against mpmath's exact value.
+// costs O(nmax) log1p evaluations.  The CPU checker's hbo_dbetabinom_log (under oracle/) follows the same
+// definition with direct loops and must agree bit for bit; oracle/pyref.py checks both against mpmath's exact value.
 struct BetaBinomCorr {
     std::vector<long double> la, lb, ld; // la[k] = sum_{i<k} log1pl(i th / p), lb: / q, ld: / 1
     bool degenerate = true;
