@@ -31,6 +31,15 @@ def _tiled_cols(t, cols):
     return t[c // 32, :, c % 32].t().cpu().numpy()  # advanced indices around a slice: [n, T]
 
 
+def _valid_parts(t, N):
+    """The real chains of a warp-tiled tensor ([.., ntile, T, 32]): all full tiles, and the filled lanes of
+    the last one (lanes past B in the last tile are padding the kernels never write)."""
+    rem = N % 32
+    if rem == 0:
+        return [t]
+    return [t[..., :-1, :, :], t[..., -1:, :, :rem]]
+
+
 def test_c4_expression_full_size_on_the_timed_path(oracle):
     """BASELINE config 4, expression half, exactly as bench.py runs it: 10k cells x 20k genes x 22 segments
     from bench.device_inputs, warp-tiled resident layout, hb_hmm_norm_tiled_dev in auto mode.  Asserts that the
@@ -54,22 +63,24 @@ def test_c4_expression_full_size_on_the_timed_path(oracle):
     flagged = hmm.norm3_flagged_chains(N)
     assert nre == len(flagged) and nre < 220000 // 500, f"{nre} of 220000 chains needed the exact fallback"
     y, g = out["y"], out["gamma"]
-    assert int(y.min()) >= 1 and int(y.max()) <= 3
-    assert float((g.sum(0) - 1).abs().max()) < 1e-12 and float(g.min()) >= 0.0
+    for yp, gp in zip(_valid_parts(y, N), _valid_parts(g, N)):
+        assert int(yp.min()) >= 1 and int(yp.max()) <= 3
+        assert float((gp.sum(0) - 1).abs().max()) < 1e-12 and float(gp.min()) >= 0.0
     out2 = hmm.hmm_norm_tiled_dev(xt, N, sd, mean, Pi, delta, seg_off=seg, viterbi=True, gamma=True, ll=True)
-    assert torch.equal(out2["y"], y) and torch.equal(out2["gamma"], g)  # deterministic
+    for a, b in zip(_valid_parts(out2["y"], N) + _valid_parts(out2["gamma"], N), _valid_parts(y, N) + _valid_parts(g, N)):
+        assert torch.equal(a, b)  # deterministic
     # forcing EVERY chain through the literal re-run gives the same states (mode 2), and so does the literal kernel
     lib = __import__("honeybadger_b200._lib", fromlist=["load"]).load()
     try:
         lib.hb_set_norm3_mode(2)
         o2 = hmm.hmm_norm_tiled_dev(xt, N, sd, mean, Pi, delta, seg_off=seg, viterbi=True, gamma=False)
         assert hmm.norm3_rerun_chains() == 220000
-        assert torch.equal(o2["y"], y)
+        assert all(torch.equal(a, b) for a, b in zip(_valid_parts(o2["y"], N), _valid_parts(y, N)))
         lib.hb_set_norm3_mode(1)
         o1 = hmm.hmm_norm_tiled_dev(xt, N, sd, mean, Pi, delta, seg_off=seg, viterbi=True, gamma=True)
         assert hmm.last_kernels()["norm3_fast"] == 0
-        assert torch.equal(o1["y"], y)
-        assert float((o1["gamma"] - g).abs().max()) < 1e-10
+        assert all(torch.equal(a, b) for a, b in zip(_valid_parts(o1["y"], N), _valid_parts(y, N)))
+        assert all(float((a - b).abs().max()) < 1e-10 for a, b in zip(_valid_parts(o1["gamma"], N), _valid_parts(g, N)))
     finally:
         lib.hb_set_norm3_mode(0)
     rng = np.random.default_rng(4)
@@ -141,8 +152,9 @@ def test_c3_allele_full_size_on_the_timed_path(oracle):
     hmm.status_dev()
     assert hmm.last_kernels()["binom2_lean"] == 1 and hmm.binom2_general_rerun() == 0
     y, gm = out["y"], out["gamma"]
-    assert int(y.min()) >= 1 and int(y.max()) <= 2
-    assert float((gm[0] + gm[1] - 1).abs().max()) < 1e-12 and float(gm.min()) >= 0.0
+    for yp, gp in zip(_valid_parts(y, N), _valid_parts(gm, N)):
+        assert int(yp.min()) >= 1 and int(yp.max()) <= 2
+        assert float((gp[0] + gp[1] - 1).abs().max()) < 1e-12 and float(gp.min()) >= 0.0
     yo, go, llo, rc = oracle.fbv_binom_batch(r_np, n_np, seg, prob, Pi, delta)
     assert rc == 0
     ys = _tiled_cols(y, cols)
