@@ -90,3 +90,43 @@ def test_binom_logpmf_host_and_device_restatements_match_oracle(emul, oracle):
                     ref = oracle.dbinom(x, n, p, True)
                     assert emul.emul_binom_logpmf_host(x, n, p) == ref
                     assert emul.emul_binom_logpmf_dev(x, n, p) == ref  # same libm on the host build
+
+
+def test_emission_table_against_exact_arithmetic_for_every_pair(emul):
+    """The product's emission table (hb_host_math.h: binom_logpmf, what prepare_lut uploads) for EVERY
+    (x, n <= 511) pair and both states against the exact log-pmf from mpmath — an arithmetic-independent anchor
+    that a shared mis-recollection of nmath (the oracle restates the same published algorithm) could not pass.
+    Loader's saddle point is not correctly rounded: the error is measured in ulps of the exact value, its
+    distribution printed, and bounded (a wrong Stirling constant or bd0 branch shows up as >= 1e-10)."""
+    import mpmath as mp
+    NMAX = 511
+    worst = {}
+    hist = np.zeros(6, dtype=np.int64)  # <=0.5, <=1, <=2, <=4, <=16, >16 ulp
+    with mp.workdps(40):
+        lfact = [mp.mpf(0)]
+        for i in range(1, NMAX + 1):
+            lfact.append(lfact[-1] + mp.log(i))
+        for p in (0.1, 0.45):
+            lp, lq = mp.log(mp.mpf(p)), mp.log(1 - mp.mpf(p))
+            for n in range(NMAX + 1):
+                for x in range(n + 1):
+                    exact = lfact[n] - lfact[x] - lfact[n - x] + x * lp + (n - x) * lq
+                    got = emul.emul_binom_logpmf_host(float(x), float(n), p)
+                    ex = float(exact)
+                    if ex == 0.0:
+                        assert got == 0.0
+                        hist[0] += 1
+                        continue
+                    ulps = abs(float((mp.mpf(got) - exact) / mp.mpf(np.spacing(abs(ex)))))
+                    b = 0 if ulps <= 0.5 else 1 if ulps <= 1 else 2 if ulps <= 2 else 3 if ulps <= 4 else 4 if ulps <= 16 else 5
+                    hist[b] += 1
+                    if ulps > worst.get(p, (0,))[0]:
+                        worst[p] = (ulps, x, n)
+    total = int(hist.sum())
+    print(f"\nemission table vs exact: {total} entries; <=0.5 ulp {hist[0]}, <=1 {hist[1]}, <=2 {hist[2]}, "
+          f"<=4 {hist[3]}, <=16 {hist[4]}, >16 {hist[5]}; worst {worst}")
+    assert total == 2 * (NMAX + 1) * (NMAX + 2) // 2
+    # measured: worst 38 ulp (8e-15 relative, at the mode of deep counts where stirlerr / bd0 terms cancel);
+    # a wrong constant or branch would be off by >= 1e5 ulp
+    assert all(w[0] <= 64 for w in worst.values()), worst
+    assert hist[5] < 0.01 * total and hist[0] + hist[1] + hist[2] > 0.6 * total, hist
