@@ -391,6 +391,50 @@ def main():
                 modes[name] = {"ms": ms, "value": steps_per_pass / (ms * 1e-3), "algorithmic_bytes_per_step": bps,
                                "roofline_frac": ach / peak, "launches": nl}
                 del o_m
+            if kind == "expr":
+                # The chain-resident design (csrc/hb_norm3_resident.cuh): posteriors with x read once and no
+                # checkpoints (32 B / step of traffic), on a chain-major copy of the same matrix; and the
+                # two-kernel form of the whole step — Viterbi-only (thread per chain, tiled copy) on one stream
+                # BESIDE the resident posteriors on another: 43 B / step of traffic instead of 49.
+                x_cm = d["x"].t().contiguous()
+                g_cm = torch.empty((3, cells, positions), dtype=torch.float64, device=dev)
+                fr = lambda: hmm.forwardback_norm_cm_dev(x_cm, sd, mean, Pi3, delta3, seg_off=seg, out=g_cm)  # noqa: E731
+                fr()
+                gate = hmm.fbr_gate()
+                ms = time_launches(fr, nl, torch)
+                chk = rng_cols = np.random.default_rng(3).choice(cells, 64, replace=False)
+                a_ = g_cm[:, torch.as_tensor(chk, device=dev), :].permute(0, 2, 1).cpu().numpy()
+                b_ = tiled_cols(out["gamma"], chk)
+                modes["fb_only_resident"] = {
+                    "ms": ms, "value": steps_per_pass / (ms * 1e-3), "algorithmic_bytes_per_step": 32,
+                    "roofline_frac": steps_per_pass * 32 / (ms * 1e-3) / 1e9 / peak, "launches": nl, "gate": gate,
+                    "max_abs_diff_vs_thread_per_chain": float(np.abs(a_ - b_).max()),
+                    "layout": "chain-major x[cell][gene] (R's column-major), one block of 1-4 warps per chain"}
+                o_v = hmm.hmm_norm_tiled_dev(xt, cells, sd, mean, Pi3, delta3, seg_off=seg, viterbi=True, gamma=False)
+                s_a, s_b = torch.cuda.Stream(), torch.cuda.Stream()
+
+                def both():
+                    cur = torch.cuda.current_stream()
+                    s_a.wait_stream(cur)
+                    s_b.wait_stream(cur)
+                    with torch.cuda.stream(s_a):
+                        hmm.hmm_norm_tiled_dev(xt, cells, sd, mean, Pi3, delta3, seg_off=seg, viterbi=True,
+                                               gamma=False, out=o_v)
+                    with torch.cuda.stream(s_b):
+                        hmm.forwardback_norm_cm_dev(x_cm, sd, mean, Pi3, delta3, seg_off=seg, out=g_cm)
+                    cur.wait_stream(s_a)
+                    cur.wait_stream(s_b)
+                ms = time_launches(both, nl, torch)
+                same_y = bool(all(torch.equal(p, q) for p, q in zip(
+                    [o_v["y"][:-1], o_v["y"][-1:, :, :cells % 32 or 32]],
+                    [out["y"][:-1], out["y"][-1:, :, :cells % 32 or 32]])))
+                modes["viterbi_beside_resident_fb"] = {
+                    "ms": ms, "value": steps_per_pass / (ms * 1e-3), "algorithmic_bytes_per_step": 33,
+                    "roofline_frac": steps_per_pass * 33 / (ms * 1e-3) / 1e9 / peak, "launches": nl,
+                    "same_states_as_fused_kernel": same_y,
+                    "note": "two streams: norm3_fast_kernel<VIT> (tiled copy) || norm3_resident_kernel (chain-major "
+                            "copy); needs the matrix resident in both layouts"}
+                del x_cm, g_cm, o_v
             # sustained: >= 2 s of back-to-back launches of the headline kernel, clocks sampled throughout
             ns = max(args.steps, int(2000.0 / (total_ms / args.steps)) + 1)
             smp = ClockSampler(local)

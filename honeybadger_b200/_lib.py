@@ -57,6 +57,8 @@ SIGNATURES = {
     "hb_hmm_binom_tiled_dev": (_i32, [_p, _p, _i64, _i64, _p, _i32, _p, _d, _p, _p, _i32, _p, _p, _p, _p]),
     "hb_hmm_binom_packed_tiled_dev": (_i32, [_p, _i64, _i64, _p, _i32, _p, _d, _p, _p, _i32, _p, _p, _p, _p]),
     "hb_pack_counts_dev": (_i32, [_p, _p, _i64, _p, _p]),
+    "hb_fbr_stats_dev": (_i32, [_p, C.POINTER(C.c_int32)]),
+    "hb_forwardback_norm_cm_dev": (_i32, [_p, _i64, _i64, _p, _i32, _p, _p, _i32, _p, _p, _p, _p]),
     "hb_tile_dev": (_i32, [_p, _i64, _i64, _i64, _i32, _p, _p]),
     "hb_untile_dev": (_i32, [_p, _i64, _i64, _i32, _p, _i64, _p]),
     "hb_hmm_binom_host": (_i32, [_p, _p, _i64, _i64, _p, _i32, _p, _d, _p, _p, _i32, _p, _p, _p]),

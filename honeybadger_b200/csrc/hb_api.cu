@@ -28,6 +28,7 @@
 #include "hb_longchain.cuh"
 #include "hb_norm3.cuh"
 #include "hb_norm3_fast.cuh"
+#include "hb_norm3_resident.cuh"
 
 namespace {
 
@@ -93,7 +94,7 @@ struct DevBuf {
 
 // Per-device scratch, grown on demand and reused across calls (no allocation in steady state).
 struct Workspace {
-    DevBuf psi, ckpt, sdaux, segtab, status, flagged, lut_lb, lut_rho, lut_rho_d, cellmask, gsize;
+    DevBuf psi, ckpt, sdaux, segtab, status, flagged, fbr_gate, lut_lb, lut_rho, lut_rho_d, cellmask, gsize;
     DevBuf lc, lc_fb, lc_lb, lc_y;
     int32_t lc_K = 0;
     int64_t lc_nb = 0;
@@ -129,7 +130,7 @@ struct Workspace {
     int32_t lut_nmax = -1;
     void release_all()
     {
-        DevBuf *all[] = {&flagged, &lc, &lc_fb, &lc_lb, &lc_y, &psi, &ckpt, &sdaux, &segtab, &status, &lut_lb, &lut_rho, &lut_rho_d, &cellmask, &gsize,
+        DevBuf *all[] = {&fbr_gate, &flagged, &lc, &lc_fb, &lc_lb, &lc_y, &psi, &ckpt, &sdaux, &segtab, &status, &lut_lb, &lut_rho, &lut_rho_d, &cellmask, &gsize,
                          &st_in, &st_in2, &st_x, &st_x2, &st_y, &st_g, &st_out, &st_sd, &st_ll,
                          &st_member, &st_pool, &st_pool2, &st_pre, &st_x80, &st_part, &st_inp, &st_inp2, &st_tab, &pin[0], &pin[1], &pin2[0], &pin2[1],
                          &pout_y[0], &pout_y[1], &pout_g[0], &pout_g[1], &pout_ll[0], &pout_ll[1]};
@@ -934,6 +935,77 @@ int hb_hmm_norm_dev(const double *x, int64_t ld, int64_t T, int64_t B, const int
     WS_USE(stream);
     return norm3_run(ws, x, ld, T, B, seg_off, nseg, mean, sd, nullptr, nullptr, sd_per_seg, Pi,
                      delta, flags, y, ldy, gamma, ldg, ll, (cudaStream_t)stream);
+}
+
+// Chain-resident posteriors on CHAIN-MAJOR data (hb_norm3_resident.cuh): x[b*T + t] (R's column-major
+// [T x B]), gamma[(k*B + b)*T + t] (R's [T x B x 3]).  One launch per segment, longest first.
+int hb_forwardback_norm_cm_dev(const double *x, int64_t T, int64_t B, const int64_t *seg_off, int32_t nseg,
+                               const double *mean, const double *sd, int32_t sd_per_seg, const double *Pi,
+                               const double *delta, double *gamma, void *stream)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    Workspace *ws;
+    HBTRY(cur_ws(&ws));
+    // no WS_USE: this path touches none of the shared scratch (its only device state is its own gate
+    // word), so it may run on another stream BESIDE a chain launch — e.g. next to the Viterbi-only kernel
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!x || !sd || !gamma || T < 1 || B < 1) return fail(HB_ERR_ARG, "bad arguments");
+    const int64_t one_seg[2] = {0, T};
+    if (!seg_off) {
+        seg_off = one_seg;
+        nseg = 1;
+    }
+    if (nseg < 1 || seg_off[0] < 0 || seg_off[nseg] > T) return fail(HB_ERR_ARG, "seg_off outside [0, T]");
+    hb::FbrArgs a;
+    memset(&a, 0, sizeof a);
+    bool sym;
+    HBTRY(fill_norm3_const(a.c, mean, Pi, delta, &sym));
+    if (!sym || !(Pi[1] > 0)) return fail(HB_ERR_ARG, "the chain-resident kernel serves the symmetric parameter block only");
+    HBTRY(ws->fbr_gate.ensure(sizeof(int32_t)));
+    CU(cudaMemsetAsync(ws->fbr_gate.p, 0, sizeof(int32_t), st));
+    a.x = x;
+    a.T = T;
+    a.B = B;
+    a.sd = sd;
+    a.sd_per_seg = sd_per_seg ? 1 : 0;
+    a.gamma = gamma;
+    a.gate = ws->fbr_gate.as<int32_t>();
+    std::vector<int32_t> order(nseg);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int32_t p, int32_t q) {
+        return (seg_off[p + 1] - seg_off[p]) > (seg_off[q + 1] - seg_off[q]);
+    });
+    for (int32_t s : order) {
+        const int64_t L = seg_off[s + 1] - seg_off[s];
+        if (L < 0) return fail(HB_ERR_ARG, "seg_off must be non-decreasing");
+        if (L == 0) continue;
+        // lanes per chain: pieces of <= ~32 positions while a block (<= 4 warps) can hold the chain
+        const int nw = L <= 1024 ? 1 : (L <= 2048 ? 2 : 4);
+        int m = 0;
+        const size_t smem = hb::fbr_smem_bytes((int)L, nw, &m);
+        if (smem > 220 * 1024)
+            return fail(HB_ERR_ARG, "segment of %lld positions does not fit the chain-resident kernel (<= %d)",
+                        (long long)L, 220 * 1024 / 36);
+        a.t0 = seg_off[s];
+        a.L = (int32_t)L;
+        a.m = m;
+        a.seg = s;
+        CU(hb::launch_norm3_resident(a, nw, smem, st));
+    }
+    return HB_OK;
+}
+
+int hb_fbr_stats_dev(void *stream, int32_t *gate)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    Workspace *ws;
+    HBTRY(cur_ws(&ws));
+    if (!gate) return fail(HB_ERR_ARG, "gate is NULL");
+    *gate = 0;
+    if (!ws->fbr_gate.p) return HB_OK;
+    CU(cudaMemcpyAsync(gate, ws->fbr_gate.p, sizeof(int32_t), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CU(cudaStreamSynchronize((cudaStream_t)stream));
+    return HB_OK;
 }
 
 // Pipeline of the host-buffer entry points.  Columns are cut into sub-batches; three streams work on

@@ -14,6 +14,7 @@
 #include "hb_longchain.cuh"
 #include "hb_norm3.cuh"
 #include "hb_norm3_fast.cuh"
+#include "hb_norm3_resident.cuh"
 #include "hb_x87.cuh"
 
 namespace hb {
@@ -77,11 +78,13 @@ __global__ void __launch_bounds__(HB_BLOCK, HB_FAST_MINB)
     m.st = HB_BLOCK;
     m.va = smem2 + tix;
     m.vb = m.va + HB_CHUNK * HB_BLOCK;
-    char *rest = reinterpret_cast<char *>(smem2 + 2 * HB_CHUNK * HB_BLOCK);
+    // (Viterbi only: no parking area — the block needs just the x ring and the state tiles, 9 KB instead of
+    // 45, which leaves the SM's shared memory to whatever runs beside it)
+    char *rest = reinterpret_cast<char *>(smem2 + (FB ? 2 * HB_CHUNK * HB_BLOCK : 0));
     m.e2 = reinterpret_cast<double *>(rest) + tix;
-    if (!HB_FAST_NOPHI1) rest += sizeof(double) * HB_CHUNK * HB_BLOCK;
+    if (FB && !HB_FAST_NOPHI1) rest += sizeof(double) * HB_CHUNK * HB_BLOCK;
     m.ph = reinterpret_cast<int32_t *>(rest) + tix;
-    rest += sizeof(int32_t) * HB_CHUNK * HB_BLOCK;
+    if (FB) rest += sizeof(int32_t) * HB_CHUNK * HB_BLOCK;
     m.xs = reinterpret_cast<double *>(rest) + tix; // cp.async ring (one chunk) ...
     m.ys = reinterpret_cast<uint8_t *>(rest + sizeof(double) * HB_CHUNK * HB_BLOCK) + (tix >> 5) * (HB_CHUNK * 32) +
            (tix & 31); // ... then the warps' [HB_CHUNK][32] state tiles
@@ -223,7 +226,8 @@ static cudaError_t launch_norm3_fast_t(const Norm3Args &a, bool vit, bool fb, cu
 {
     const unsigned grid = (unsigned)((int64_t)a.nseg * a.nblk_per_seg);
     const size_t sm_fb = BULK ? HB_FAST_BULK_SMEM_BYTES(HB_BLOCK) : (size_t)HB_FAST_SMEM_BYTES_PER_THREAD * HB_BLOCK;
-    const size_t sm_v = sm_fb; // (the Viterbi-only form uses the same carve-up; the parking area stays idle)
+    // Viterbi only: x ring (one chunk) + the warps' state tiles; the bulk form keeps the full carve-up
+    const size_t sm_v = BULK ? sm_fb : (size_t)HB_CHUNK * HB_BLOCK * (sizeof(double) + 1);
     // > 48 KB of dynamic shared memory: opt in (per device, cheap)
     const bool ll = a.ll != nullptr;
 #define HB_LAUNCH_FAST(V, F, L_, SM)                                                               \
@@ -252,6 +256,29 @@ cudaError_t launch_norm3_fast(const Norm3Args &a, bool vit, bool fb, cudaStream_
 #endif
     if (a.tiled) return launch_norm3_fast_t<false, true>(a, vit, fb, st);
     return launch_norm3_fast_t<false, false>(a, vit, fb, st);
+}
+
+// Chain-resident posteriors (hb_norm3_resident.cuh): one chain per block of NW warps, one launch per segment.
+template <int NW>
+__global__ void __launch_bounds__(32 * NW) norm3_resident_kernel(const __grid_constant__ FbrArgs a)
+{
+    extern __shared__ double fbr_smem[];
+    fbr_chain<NW>(a, (int64_t)blockIdx.x, fbr_smem);
+}
+
+cudaError_t launch_norm3_resident(const FbrArgs &a, int nw, size_t smem, cudaStream_t st)
+{
+    const unsigned grid = (unsigned)a.B;
+#define HB_LAUNCH_FBR(NW_)                                                                                    \
+    do {                                                                                                      \
+        cudaFuncSetAttribute(norm3_resident_kernel<NW_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); \
+        norm3_resident_kernel<NW_><<<grid, 32 * NW_, smem, st>>>(a);                                          \
+    } while (0)
+    if (nw == 1) HB_LAUNCH_FBR(1);
+    else if (nw == 2) HB_LAUNCH_FBR(2);
+    else HB_LAUNCH_FBR(4);
+#undef HB_LAUNCH_FBR
+    return cudaGetLastError();
 }
 
 cudaError_t launch_binom2_emit(const Binom2Args &a, double2 *pre_lb, cudaStream_t st)

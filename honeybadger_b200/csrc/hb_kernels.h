@@ -11,6 +11,7 @@ struct Norm3Args;
 struct Norm3Const;
 struct Binom2Args;
 struct LcArgs;
+struct FbrArgs;
 
 cudaError_t launch_longchain(const LcArgs &a, cudaStream_t st);
 cudaError_t launch_longchain_fb(const LcArgs &a, cudaStream_t st);
@@ -20,6 +21,7 @@ cudaError_t launch_norm3_emit_cm(const Norm3Const &c, const double *x, int64_t G
                                  const double *inv_sd, const double *log_sd, double *out, cudaStream_t st);
 
 cudaError_t launch_norm3(const Norm3Args &a, bool sym, bool vit, bool fb, cudaStream_t st);
+cudaError_t launch_norm3_resident(const FbrArgs &a, int nw, size_t smem, cudaStream_t st);
 cudaError_t launch_norm3_fast(const Norm3Args &a, bool vit, bool fb, cudaStream_t st);
 cudaError_t launch_pack_counts(const int32_t *x, const int32_t *n, int64_t count, uint32_t *out,
                                int32_t *overflow, cudaStream_t st);

@@ -295,6 +295,31 @@ def hmm_norm_tiled_dev(x, B, sd, mean, Pi, delta, seg_off=None, viterbi=True, ga
     return out
 
 
+def forwardback_norm_cm_dev(x_cm, sd, mean, Pi, delta, seg_off=None, out=None):
+    """Posteriors by the chain-resident kernel on CHAIN-MAJOR data: x_cm [B, T] contiguous fp64 CUDA tensor
+    (R's column-major [T x B]); returns gamma [3, B, T] (R's [T x B x 3]).  `fbr_gate()` != 0 afterwards
+    means a transfer matrix degenerated (extreme emission ratios): use hmm_norm_dev for that input."""
+    import torch
+    if not (x_cm.is_cuda and x_cm.dtype == torch.float64 and x_cm.dim() == 2 and x_cm.is_contiguous()):
+        raise ValueError("x_cm must be a contiguous CUDA float64 tensor [B, T]")
+    B, T = x_cm.shape
+    seg = _seg(seg_off, T)
+    per_seg = int(sd.dim() == 2)
+    mean, Pi, delta = _f64(mean), _f64(Pi), _f64(delta)
+    g = out if out is not None else torch.empty((3, B, T), dtype=torch.float64, device=x_cm.device)
+    _lib.check(_lib.load().hb_forwardback_norm_cm_dev(x_cm.data_ptr(), T, B, _vp(seg), seg.size - 1, _vp(mean),
+                                                      sd.data_ptr(), per_seg, _vp(Pi), _vp(delta), g.data_ptr(),
+                                                      _stream()))
+    return g
+
+
+def fbr_gate() -> int:
+    """1 if the last chain-resident launch met a degenerate transfer matrix; waits for the current stream."""
+    g = C.c_int32(0)
+    _lib.check(_lib.load().hb_fbr_stats_dev(_stream(), C.byref(g)))
+    return int(g.value)
+
+
 def pack_counts(x, size):
     """(size << 16) | x per element as an int32 tensor of the same shape (hb_pack_counts_dev); raises
     if a count does not fit 16 bits.  x, size: contiguous int32 CUDA tensors in any (same) layout."""

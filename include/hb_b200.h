@@ -133,6 +133,21 @@ int hb_hmm_binom_tiled_dev(const int32_t *x, const int32_t *size, int64_t T, int
                            const int64_t *seg_off /* host */, int32_t nseg, const double *prob,
                            double rho, const double *Pi, const double *delta, int32_t flags,
                            uint8_t *y, double *gamma, double *ll, void *stream);
+/* Posteriors only, CHAIN-RESIDENT and parallel along the gene axis (csrc/hb_norm3_resident.cuh): every chain
+ * is held in shared memory by one block of 1-4 warps, x is read once and the posteriors written once (32 B
+ * of HBM traffic per step against 46 for the two-sweep kernel).  Layout: CHAIN-MAJOR, x[b*T + t] — R's own
+ * column-major [T x B], no transpose — and gamma[(k*B + b)*T + t] = R's [T x B x 3].  Symmetric parameter
+ * block only (R/HoneyBADGER.R:1144-1150), segments of at most 6 200 positions; same posteriors as
+ * hb_hmm_norm_dev(HB_WANT_GAMMA) within 1e-9.  A degenerate transfer matrix (emission ratios beyond the
+ * double range inside one piece of a chain) raises the gate word hb_fbr_stats_dev reports; the caller then
+ * falls back to hb_hmm_norm_dev.  No synchronisation, and none of the shared per-device scratch: the call may
+ * run on a second stream beside a chain launch (e.g. the Viterbi-only kernel on the warp-tiled copy). */
+int hb_forwardback_norm_cm_dev(const double *x, int64_t T, int64_t B, const int64_t *seg_off /* host */,
+                               int32_t nseg, const double *mean, const double *sd /* device */,
+                               int32_t sd_per_seg, const double *Pi, const double *delta, double *gamma,
+                               void *stream);
+/* *gate = 1 if the last chain-resident launch met a degenerate transfer matrix (waits for `stream`). */
+int hb_fbr_stats_dev(void *stream, int32_t *gate);
 /* Binomial chains on PACKED counts: one uint32 per position, (size << 16) | x, both < 65536
  * (hb_pack_counts_dev packs two int32 planes elementwise — any layout — and returns HB_ERR_ARG if
  * a count does not fit).  Halves the input bytes of the allele path: 4 B / position instead of 8. */
