@@ -105,6 +105,16 @@ SIGNATURES = {
                                             _p, _p]),
     "hb_gexp_pooled_viterbi_host": (_i32, [_p, _i64, _i64, _p, _i32, _p, _p, _p, _p, _p, _p]),
     "hb_allele_pooled_viterbi_host": (_i32, [_p, _p, _i64, _i64, _p, _i32, _p, _p, _p, _p, _p, _p]),
+    "hb_upload_gexp_host": (_i32, [_p, _i64, _i64, C.POINTER(_p)]),
+    "hb_upload_counts_host": (_i32, [_p, _p, _i64, _i64, C.POINTER(_p)]),
+    "hb_free_handle": (_i32, [_p]),
+    "hb_handle_info": (_i32, [_p, C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_int64),
+                              C.POINTER(C.c_int64)]),
+    "hb_gexp_round_handle": (_i32, [_p, _p, _i64, _p, _i64, _p, _i32, _p, _p, _p, _p, _p, _p]),
+    "hb_allele_round_handle": (_i32, [_p, _p, _i64, _p, _i64, _p, _i32, _p, _p, _p, _p, _p, _p]),
+    "hb_group_handle": (_i32, [_p, _p, _i64, _p, _i64, _i32, _p, _i32, _p]),
+    "hb_retest_gexp_handle": (_i32, [_p, _p, _i64, _p, _i64, _d, _p, _p, _p, _p]),
+    "hb_retest_allele_handle": (_i32, [_p, _p, _i64, _p, _i64, _p, _p, _p, _d, _d, _p]),
 }
 
 _lib = None

@@ -1840,44 +1840,24 @@ static void cut_merges_host(const int32_t *ma, const int32_t *mb, const double *
     }
 }
 
-// Host-buffer form of the grouping step: x (or r, n) column-major [G x N] as R holds them.
-static int group_host(const double *x, const double *r, const double *n, int64_t G, int64_t N,
-                      int32_t window, const int32_t *ks, int32_t nk, int32_t *labels)
+// Grouping core on device-resident gene-major data (caller holds g_mu and a WsUse): runmean -> dist ->
+// Ward.D2 -> cutree for each k.  Either xg (fp64) or rg / ng (int32 counts) is given.
+static int group_core(Workspace *ws, const double *xg, const int32_t *rg, const int32_t *ng, int64_t ld, int64_t G,
+                      int64_t N, int32_t window, const int32_t *ks, int32_t nk, int32_t *labels, cudaStream_t st)
 {
-    std::lock_guard<std::mutex> lk(g_mu);
-    Workspace *ws;
-    HBTRY(cur_ws(&ws));
-    WS_USE(0);
-    if (G < 1 || N < 1 || !ks || nk < 1 || !labels || window < 1 || (window & 1) == 0)
-        return fail(HB_ERR_ARG, "bad arguments");
     if (N == 1) {
         for (int32_t q = 0; q < nk; q++) labels[q] = 1;
         return HB_OK;
     }
-    cudaStream_t st = 0;
-    const int64_t ld = (N + 127) / 128 * 128;
-    HBTRY(ws->st_in.ensure((size_t)G * N * sizeof(double)));
-    HBTRY(ws->st_g.ensure((size_t)G * ld * sizeof(double))); // smoothed matrix
+    const int64_t lds = (N + 127) / 128 * 128;
+    HBTRY(ws->st_g.ensure((size_t)G * lds * sizeof(double))); // smoothed matrix
     double *S = ws->st_g.as<double>();
-    if (x) {
-        HBTRY(ws->st_x.ensure((size_t)G * ld * sizeof(double)));
-        CU(cudaMemcpyAsync(ws->st_in.p, x, (size_t)G * N * sizeof(double), cudaMemcpyHostToDevice, st));
-        CU(hb::launch_transpose_f64(ws->st_in.as<double>(), G, N, ws->st_x.as<double>(), ld, st));
-        CU(hb::launch_runmean(ws->st_x.as<double>(), nullptr, nullptr, ld, G, N, window, S, ld, st));
-    } else {
-        HBTRY(ws->st_x.ensure((size_t)G * ld * sizeof(int32_t)));
-        HBTRY(ws->st_x2.ensure((size_t)G * ld * sizeof(int32_t)));
-        CU(cudaMemcpyAsync(ws->st_in.p, r, (size_t)G * N * sizeof(double), cudaMemcpyHostToDevice, st));
-        CU(hb::launch_transpose_f64_i32(ws->st_in.as<double>(), G, N, ws->st_x.as<int32_t>(), ld, st));
-        CU(cudaMemcpyAsync(ws->st_in.p, n, (size_t)G * N * sizeof(double), cudaMemcpyHostToDevice, st));
-        CU(hb::launch_transpose_f64_i32(ws->st_in.as<double>(), G, N, ws->st_x2.as<int32_t>(), ld, st));
-        CU(hb::launch_runmean(nullptr, ws->st_x.as<int32_t>(), ws->st_x2.as<int32_t>(), ld, G, N, window, S, ld, st));
-    }
+    CU(hb::launch_runmean(xg, rg, ng, ld, G, N, window, S, lds, st));
     HBTRY(ws->st_pool.ensure((size_t)N * N * sizeof(double)));
     HBTRY(ws->st_pool2.ensure((size_t)N * 16 + 64));
     HBTRY(ws->st_part.ensure((size_t)N * (sizeof(int32_t) * 2 + 1) + 64));
     double *D = ws->st_pool.as<double>();
-    CU(hb::launch_dist_sq(S, ld, G, N, D, st));
+    CU(hb::launch_dist_sq(S, lds, G, N, D, st));
     int32_t *d_ma = ws->st_pool2.as<int32_t>(), *d_mb = d_ma + N;
     double *d_h = reinterpret_cast<double *>(d_mb + N);
     int32_t *size = ws->st_part.as<int32_t>(), *chain = size + N;
@@ -1890,6 +1870,35 @@ static int group_host(const double *x, const double *r, const double *n, int64_t
     CU(cudaStreamSynchronize(st));
     cut_merges_host(ma.data(), mb.data(), hh.data(), N, ks, nk, labels);
     return HB_OK;
+}
+
+// Host-buffer form of the grouping step: x (or r, n) column-major [G x N] as R holds them.
+static int group_host(const double *x, const double *r, const double *n, int64_t G, int64_t N,
+                      int32_t window, const int32_t *ks, int32_t nk, int32_t *labels)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    Workspace *ws;
+    HBTRY(cur_ws(&ws));
+    WS_USE(0);
+    if (G < 1 || N < 1 || !ks || nk < 1 || !labels || window < 1 || (window & 1) == 0)
+        return fail(HB_ERR_ARG, "bad arguments");
+    cudaStream_t st = 0;
+    const int64_t ld = (N + 127) / 128 * 128;
+    HBTRY(ws->st_in.ensure((size_t)G * N * sizeof(double)));
+    if (x) {
+        HBTRY(ws->st_x.ensure((size_t)G * ld * sizeof(double)));
+        CU(cudaMemcpyAsync(ws->st_in.p, x, (size_t)G * N * sizeof(double), cudaMemcpyHostToDevice, st));
+        CU(hb::launch_transpose_f64(ws->st_in.as<double>(), G, N, ws->st_x.as<double>(), ld, st));
+        return group_core(ws, ws->st_x.as<double>(), nullptr, nullptr, ld, G, N, window, ks, nk, labels, st);
+    }
+    HBTRY(ws->st_x.ensure((size_t)G * ld * sizeof(int32_t)));
+    HBTRY(ws->st_x2.ensure((size_t)G * ld * sizeof(int32_t)));
+    CU(cudaMemcpyAsync(ws->st_in.p, r, (size_t)G * N * sizeof(double), cudaMemcpyHostToDevice, st));
+    CU(hb::launch_transpose_f64_i32(ws->st_in.as<double>(), G, N, ws->st_x.as<int32_t>(), ld, st));
+    CU(cudaMemcpyAsync(ws->st_in.p, n, (size_t)G * N * sizeof(double), cudaMemcpyHostToDevice, st));
+    CU(hb::launch_transpose_f64_i32(ws->st_in.as<double>(), G, N, ws->st_x2.as<int32_t>(), ld, st));
+    return group_core(ws, nullptr, ws->st_x.as<int32_t>(), ws->st_x2.as<int32_t>(), ld, G, N, window, ks, nk, labels,
+                      st);
 }
 
 int hb_group_gexp_host(const double *gexp_norm, int64_t G, int64_t N, int32_t window, const int32_t *ks,
@@ -2667,6 +2676,269 @@ int hb_allele_pooled_viterbi_host(const double *r_maf, const double *n_sc, int64
     }
     return hb_allele_pooled_viterbi_dev(d_r, d_n, ld, G, N, member, K, prob, Pi, delta, y, mafl,
                                         sizel, nullptr);
+}
+
+
+// ------------------------------------------------------------------ device-resident handle
+// The state the reference keeps across its recursive calls is the matrices themselves
+// (R/HoneyBADGER.R:1098-1102; sub-matrices handed down at :1304-1309).  Here they are uploaded ONCE and stay
+// on the device behind an opaque handle; every later call names rows / cells by index sets.
+} // extern "C"
+
+struct hb_handle {
+    int32_t kind = 0; // 1 expression (fp64), 2 allele counts (two int32 planes)
+    int dev = 0;
+    int64_t G = 0, N = 0, ld = 0, h2d_bytes = 0;
+    DevBuf a, b;         // resident gene-major matrices
+    DevBuf sa, sb, idx;  // gathered sub-matrix of the current call, index sets
+    int64_t sub_ld = 0;
+};
+
+static int handle_check(const hb_handle *h, int kind)
+{
+    if (!h || h->kind != kind) return fail(HB_ERR_ARG, "not a %s handle", kind == 1 ? "gexp" : "counts");
+    int dev = -1;
+    cudaGetDevice(&dev);
+    if (dev != h->dev) return fail(HB_ERR_ARG, "handle lives on device %d, current device is %d", h->dev, dev);
+    return HB_OK;
+}
+
+// column slabs: upload [G x n] column-major pieces and transpose them into the resident rows
+template <typename T>
+static int upload_slabs(Workspace *ws, const double *src, int64_t G, int64_t N, T *dst, int64_t ld, int64_t *bytes)
+{
+    const int64_t slab = std::max<int64_t>(1, std::min<int64_t>(N, ((int64_t)256 << 20) / (G * (int64_t)sizeof(double))));
+    HBTRY(ws->st_in.ensure((size_t)G * slab * sizeof(double)));
+    for (int64_t c0 = 0; c0 < N; c0 += slab) {
+        const int64_t n = std::min(slab, N - c0);
+        CU(cudaMemcpyAsync(ws->st_in.p, src + c0 * G, (size_t)G * n * sizeof(double), cudaMemcpyHostToDevice, 0));
+        if (sizeof(T) == 8)
+            CU(hb::launch_transpose_f64(ws->st_in.as<double>(), G, n, (double *)dst + c0, ld, 0));
+        else
+            CU(hb::launch_transpose_f64_i32(ws->st_in.as<double>(), G, n, (int32_t *)dst + c0, ld, 0));
+        *bytes += G * n * (int64_t)sizeof(double);
+    }
+    CU(cudaStreamSynchronize(0));
+    return HB_OK;
+}
+
+extern "C" {
+
+int hb_upload_gexp_host(const double *gexp_norm, int64_t G, int64_t N, hb_handle **out)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    Workspace *ws;
+    HBTRY(cur_ws(&ws));
+    WS_USE(0);
+    if (!gexp_norm || !out || G < 1 || N < 1) return fail(HB_ERR_ARG, "bad arguments");
+    hb_handle *h = new hb_handle;
+    h->kind = 1;
+    cudaGetDevice(&h->dev);
+    h->G = G;
+    h->N = N;
+    h->ld = (N + 127) / 128 * 128;
+    int rc = h->a.ensure((size_t)G * h->ld * sizeof(double));
+    if (rc == HB_OK) rc = upload_slabs<double>(ws, gexp_norm, G, N, h->a.as<double>(), h->ld, &h->h2d_bytes);
+    if (rc != HB_OK) {
+        h->a.release();
+        delete h;
+        return rc;
+    }
+    *out = h;
+    return HB_OK;
+}
+
+int hb_upload_counts_host(const double *r_maf, const double *n_sc, int64_t G, int64_t N, hb_handle **out)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    Workspace *ws;
+    HBTRY(cur_ws(&ws));
+    WS_USE(0);
+    if (!r_maf || !n_sc || !out || G < 1 || N < 1) return fail(HB_ERR_ARG, "bad arguments");
+    hb_handle *h = new hb_handle;
+    h->kind = 2;
+    cudaGetDevice(&h->dev);
+    h->G = G;
+    h->N = N;
+    h->ld = (N + 127) / 128 * 128;
+    int rc = h->a.ensure((size_t)G * h->ld * sizeof(int32_t));
+    if (rc == HB_OK) rc = h->b.ensure((size_t)G * h->ld * sizeof(int32_t));
+    if (rc == HB_OK) rc = upload_slabs<int32_t>(ws, r_maf, G, N, h->a.as<int32_t>(), h->ld, &h->h2d_bytes);
+    if (rc == HB_OK) rc = upload_slabs<int32_t>(ws, n_sc, G, N, h->b.as<int32_t>(), h->ld, &h->h2d_bytes);
+    if (rc != HB_OK) {
+        h->a.release();
+        h->b.release();
+        delete h;
+        return rc;
+    }
+    *out = h;
+    return HB_OK;
+}
+
+int hb_free_handle(hb_handle *h)
+{
+    if (!h) return HB_OK;
+    std::lock_guard<std::mutex> lk(g_mu);
+    int cur = -1;
+    cudaGetDevice(&cur);
+    if (cur != h->dev) cudaSetDevice(h->dev);
+    cudaDeviceSynchronize();
+    DevBuf *all[] = {&h->a, &h->b, &h->sa, &h->sb, &h->idx};
+    for (DevBuf *b : all) b->release();
+    if (cur != h->dev && cur >= 0) cudaSetDevice(cur);
+    delete h;
+    return HB_OK;
+}
+
+int hb_handle_info(const hb_handle *h, int32_t *kind, int64_t *G, int64_t *N, int64_t *h2d_bytes)
+{
+    if (!h) return fail(HB_ERR_ARG, "handle is NULL");
+    if (kind) *kind = h->kind;
+    if (G) *G = h->G;
+    if (N) *N = h->N;
+    if (h2d_bytes) *h2d_bytes = h->h2d_bytes;
+    return HB_OK;
+}
+
+// rows / cols (host, 0-based, NULL = all) -> gathered sub-matrix in the handle's own buffers; the index sets
+// are the only bytes that cross PCIe.  Caller holds g_mu.
+static int handle_gather(Workspace *ws, hb_handle *h, const int32_t *rows, int64_t nrows, const int32_t *cols,
+                         int64_t ncols, int64_t *G2, int64_t *N2, cudaStream_t st)
+{
+    *G2 = rows ? nrows : h->G;
+    *N2 = cols ? ncols : h->N;
+    if (*G2 < 1 || *N2 < 1) return fail(HB_ERR_ARG, "empty row or cell set");
+    for (int64_t i = 0; rows && i < nrows; i++)
+        if (rows[i] < 0 || rows[i] >= h->G) return fail(HB_ERR_ARG, "row index %d outside [0, %lld)", rows[i], (long long)h->G);
+    for (int64_t j = 0; cols && j < ncols; j++)
+        if (cols[j] < 0 || cols[j] >= h->N) return fail(HB_ERR_ARG, "cell index %d outside [0, %lld)", cols[j], (long long)h->N);
+    h->sub_ld = (*N2 + 127) / 128 * 128;
+    const size_t el = h->kind == 1 ? sizeof(double) : sizeof(int32_t);
+    HBTRY(h->sa.ensure((size_t)*G2 * h->sub_ld * el));
+    if (h->kind == 2) HBTRY(h->sb.ensure((size_t)*G2 * h->sub_ld * el));
+    HBTRY(h->idx.ensure((size_t)(*G2 + *N2) * sizeof(int32_t)));
+    int32_t *d_rows = rows ? h->idx.as<int32_t>() : nullptr, *d_cols = cols ? h->idx.as<int32_t>() + *G2 : nullptr;
+    if (rows) HBTRY(upload_async(ws, d_rows, rows, (size_t)nrows * sizeof(int32_t), st));
+    if (cols) HBTRY(upload_async(ws, d_cols, cols, (size_t)ncols * sizeof(int32_t), st));
+    CU(hb::launch_gather_rc(h->a.p, (int32_t)el, h->ld, d_rows, *G2, d_cols, *N2, h->sa.p, h->sub_ld, st));
+    if (h->kind == 2)
+        CU(hb::launch_gather_rc(h->b.p, (int32_t)el, h->ld, d_rows, *G2, d_cols, *N2, h->sb.p, h->sub_ld, st));
+    return HB_OK;
+}
+
+int hb_gexp_round_handle(hb_handle *h, const int32_t *rows, int64_t nrows, const int32_t *cols, int64_t ncols,
+                         const uint8_t *member, int32_t K, const double *mean, const double *Pi,
+                         const double *delta, int32_t *y, double *pooled_x, double *pooled_sd)
+{
+    int64_t G2, N2;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        Workspace *ws;
+        HBTRY(cur_ws(&ws));
+        HBTRY(handle_check(h, 1));
+        WS_USE(0);
+        HBTRY(handle_gather(ws, h, rows, nrows, cols, ncols, &G2, &N2, 0));
+    }
+    return hb_gexp_pooled_viterbi_dev(h->sa.as<double>(), h->sub_ld, G2, N2, member, K, mean, Pi, delta, y, pooled_x,
+                                      pooled_sd, nullptr);
+}
+
+int hb_allele_round_handle(hb_handle *h, const int32_t *rows, int64_t nrows, const int32_t *cols, int64_t ncols,
+                           const uint8_t *member, int32_t K, const double *prob, const double *Pi,
+                           const double *delta, int32_t *y, int32_t *mafl, int32_t *sizel)
+{
+    int64_t G2, N2;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        Workspace *ws;
+        HBTRY(cur_ws(&ws));
+        HBTRY(handle_check(h, 2));
+        WS_USE(0);
+        HBTRY(handle_gather(ws, h, rows, nrows, cols, ncols, &G2, &N2, 0));
+    }
+    return hb_allele_pooled_viterbi_dev(h->sa.as<int32_t>(), h->sb.as<int32_t>(), h->sub_ld, G2, N2, member, K, prob,
+                                        Pi, delta, y, mafl, sizel, nullptr);
+}
+
+int hb_group_handle(hb_handle *h, const int32_t *rows, int64_t nrows, const int32_t *cols, int64_t ncols,
+                    int32_t window, const int32_t *ks, int32_t nk, int32_t *labels)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    Workspace *ws;
+    HBTRY(cur_ws(&ws));
+    if (!h || (h->kind != 1 && h->kind != 2)) return fail(HB_ERR_ARG, "bad handle");
+    HBTRY(handle_check(h, h->kind));
+    if (!ks || nk < 1 || !labels || window < 1 || (window & 1) == 0) return fail(HB_ERR_ARG, "bad arguments");
+    WS_USE(0);
+    int64_t G2, N2;
+    HBTRY(handle_gather(ws, h, rows, nrows, cols, ncols, &G2, &N2, 0));
+    if (h->kind == 1)
+        return group_core(ws, h->sa.as<double>(), nullptr, nullptr, h->sub_ld, G2, N2, window, ks, nk, labels, 0);
+    return group_core(ws, nullptr, h->sa.as<int32_t>(), h->sb.as<int32_t>(), h->sub_ld, G2, N2, window, ks, nk, labels, 0);
+}
+
+int hb_retest_gexp_handle(hb_handle *h, const int32_t *rows, int64_t nrows, const int32_t *cols, int64_t ncols,
+                          double mag0, const double *sigma0, double *p_amp, double *p_del, double *mu0)
+{
+    int64_t G2, N2;
+    double *d_out;
+    int64_t *d_rows;
+    double *d_sig = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        Workspace *ws;
+        HBTRY(cur_ws(&ws));
+        HBTRY(handle_check(h, 1));
+        if (!p_amp || !p_del) return fail(HB_ERR_ARG, "bad arguments");
+        WS_USE(0);
+        HBTRY(handle_gather(ws, h, rows, nrows, cols, ncols, &G2, &N2, 0));
+        HBTRY(ws->st_out.ensure((size_t)4 * N2 * sizeof(double)));
+        HBTRY(ws->st_member.ensure((size_t)G2 * sizeof(int64_t)));
+        std::vector<int64_t> iota_rows((size_t)G2);
+        std::iota(iota_rows.begin(), iota_rows.end(), (int64_t)0);
+        HBTRY(upload_async(ws, ws->st_member.p, iota_rows.data(), (size_t)G2 * sizeof(int64_t), 0));
+        d_out = ws->st_out.as<double>();
+        d_rows = ws->st_member.as<int64_t>();
+        if (sigma0) {
+            d_sig = d_out + 3 * N2;
+            HBTRY(upload_async(ws, d_sig, sigma0, (size_t)N2 * sizeof(double), 0));
+        }
+    }
+    HBTRY(hb_retest_gexp_dev(h->sa.as<double>(), h->sub_ld, G2, N2, d_rows, G2, mag0, d_sig, d_out, d_out + N2,
+                             d_out + 2 * N2, nullptr, nullptr, 0, nullptr));
+    CU(cudaMemcpy(p_amp, d_out, (size_t)N2 * sizeof(double), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(p_del, d_out + N2, (size_t)N2 * sizeof(double), cudaMemcpyDeviceToHost));
+    if (mu0) CU(cudaMemcpy(mu0, d_out + 2 * N2, (size_t)N2 * sizeof(double), cudaMemcpyDeviceToHost));
+    return HB_OK;
+}
+
+int hb_retest_allele_handle(hb_handle *h, const int32_t *rows, int64_t nrows, const int32_t *cols, int64_t ncols,
+                            const double *l_maf, const double *n_bulk, const uint8_t *gene_end, double pseudo,
+                            double mono, double *p_del)
+{
+    int64_t G2, N2;
+    double *d_out;
+    int64_t *d_rows;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        Workspace *ws;
+        HBTRY(cur_ws(&ws));
+        HBTRY(handle_check(h, 2));
+        if (!l_maf || !n_bulk || !p_del) return fail(HB_ERR_ARG, "bad arguments");
+        WS_USE(0);
+        HBTRY(handle_gather(ws, h, rows, nrows, cols, ncols, &G2, &N2, 0));
+        HBTRY(ws->st_out.ensure((size_t)N2 * sizeof(double)));
+        HBTRY(ws->st_member.ensure((size_t)G2 * sizeof(int64_t)));
+        std::vector<int64_t> iota_rows((size_t)G2);
+        std::iota(iota_rows.begin(), iota_rows.end(), (int64_t)0);
+        HBTRY(upload_async(ws, ws->st_member.p, iota_rows.data(), (size_t)G2 * sizeof(int64_t), 0));
+        d_out = ws->st_out.as<double>();
+        d_rows = ws->st_member.as<int64_t>();
+    }
+    HBTRY(hb_retest_allele_model_dev(h->sa.as<int32_t>(), h->sb.as<int32_t>(), h->sub_ld, G2, N2, d_rows, G2, gene_end,
+                                     l_maf, n_bulk, pseudo, mono, 0, d_out, nullptr));
+    CU(cudaMemcpy(p_del, d_out, (size_t)N2 * sizeof(double), cudaMemcpyDeviceToHost));
+    return HB_OK;
 }
 
 } // extern "C"

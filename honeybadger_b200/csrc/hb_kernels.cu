@@ -1256,6 +1256,32 @@ cudaError_t launch_pool_count(const int32_t *v, int64_t ld, int64_t G, int64_t N
     return cudaGetLastError();
 }
 
+// Sub-matrix of a resident gene-major matrix: out[i*ldo + j] = x[rows[i]*ld + cols[j]] (NULL = identity).
+// What a recursion level of the split-and-retest driver needs instead of `gexp.norm[rows, g1]` on the host
+// (R/HoneyBADGER.R:1304-1309): index sets go down, the matrix stays on the device.
+template <typename T>
+__global__ void gather_rc_kernel(const T *x, int64_t ld, const int32_t *rows, int64_t nrows, const int32_t *cols,
+                                 int64_t ncols, T *out, int64_t ldo)
+{
+    const int64_t i = blockIdx.x;
+    const int64_t r = rows ? rows[i] : i;
+    const T *src = x + r * ld;
+    T *dst = out + i * ldo;
+    for (int64_t j = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; j < ncols; j += (int64_t)gridDim.y * blockDim.x)
+        dst[j] = src[cols ? cols[j] : j];
+}
+
+cudaError_t launch_gather_rc(const void *x, int32_t elem, int64_t ld, const int32_t *rows, int64_t nrows,
+                             const int32_t *cols, int64_t ncols, void *out, int64_t ldo, cudaStream_t st)
+{
+    const dim3 grid((unsigned)nrows, (unsigned)std::min<int64_t>((ncols + 255) / 256, 64));
+    if (elem == 8)
+        gather_rc_kernel<double><<<grid, 256, 0, st>>>((const double *)x, ld, rows, nrows, cols, ncols, (double *)out, ldo);
+    else
+        gather_rc_kernel<int32_t><<<grid, 256, 0, st>>>((const int32_t *)x, ld, rows, nrows, cols, ncols, (int32_t *)out, ldo);
+    return cudaGetLastError();
+}
+
 // cellmask[c] = OR_k (member[k*N+c] != 0) << k
 __global__ void build_cellmask_kernel(const uint8_t *member, int64_t N, int32_t K, uint32_t *mask)
 {

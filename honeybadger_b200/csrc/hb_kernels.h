@@ -21,6 +21,8 @@ cudaError_t launch_norm3_emit_cm(const Norm3Const &c, const double *x, int64_t G
                                  const double *inv_sd, const double *log_sd, double *out, cudaStream_t st);
 
 cudaError_t launch_norm3(const Norm3Args &a, bool sym, bool vit, bool fb, cudaStream_t st);
+cudaError_t launch_gather_rc(const void *x, int32_t elem, int64_t ld, const int32_t *rows, int64_t nrows,
+                             const int32_t *cols, int64_t ncols, void *out, int64_t ldo, cudaStream_t st);
 cudaError_t launch_norm3_resident(const FbrArgs &a, int nw, size_t smem, cudaStream_t st);
 cudaError_t launch_norm3_fast(const Norm3Args &a, bool vit, bool fb, cudaStream_t st);
 cudaError_t launch_pack_counts(const int32_t *x, const int32_t *n, int64_t count, uint32_t *out,

@@ -417,6 +417,46 @@ int hb_allele_pooled_viterbi_host(const double *r_maf, const double *n_sc, int64
                                   int32_t *mafl /* [K][G] or NULL */,
                                   int32_t *sizel /* [K][G] or NULL */);
 
+/* ------------------------------------------------------------------ device-resident handle
+ * The state the reference keeps across its recursive calls is the matrices themselves (RefClass fields,
+ * R/HoneyBADGER.R:1098-1102), and every recursion level copies sub-matrices `gexp.norm[, g1]`
+ * (:1304-1309, allele :1559-1575).  With a handle the matrices cross PCIe ONCE: hb_upload_* turns R's
+ * column-major doubles into the resident gene-major layout and returns an opaque pointer (the .Call shim wraps
+ * it in an EXTPTRSXP whose finalizer is hb_free_handle and keeps it in a RefClass field, r/hb_shim.c,
+ * r/hb_b200.R); each later call names the candidate genes / cells of the level by 0-based index sets (host
+ * int32 arrays, NULL = all) and only those indices, the [K x ncols] membership and the small results move.
+ * Row / cell order of the results is the order of the index sets.  All calls run on the legacy stream and
+ * return finished host results. */
+typedef struct hb_handle hb_handle;
+int hb_upload_gexp_host(const double *gexp_norm /* [G x N] column-major */, int64_t G, int64_t N, hb_handle **out);
+int hb_upload_counts_host(const double *r_maf, const double *n_sc /* [G x N] column-major, R doubles */,
+                          int64_t G, int64_t N, hb_handle **out);
+int hb_free_handle(hb_handle *h);
+/* kind 1 = expression, 2 = allele counts; h2d_bytes = bytes the uploads moved host -> device (the later calls
+ * add only index sets and memberships).  Any output pointer may be NULL. */
+int hb_handle_info(const hb_handle *h, int32_t *kind, int64_t *G, int64_t *N, int64_t *h2d_bytes);
+/* One `lapply(heights, ...)` round (R/HoneyBADGER.R:1135-1161 / :1395-1417) on the sub-matrix
+ * [rows x cols] of the resident data: member [K][ncols] (0/1) over the SELECTED cells, outputs as
+ * hb_gexp_pooled_viterbi_host / hb_allele_pooled_viterbi_host with G = nrows. */
+int hb_gexp_round_handle(hb_handle *h, const int32_t *rows, int64_t nrows, const int32_t *cols, int64_t ncols,
+                         const uint8_t *member, int32_t K, const double *mean, const double *Pi,
+                         const double *delta, int32_t *y /* [K][nrows] */, double *pooled_x, double *pooled_sd);
+int hb_allele_round_handle(hb_handle *h, const int32_t *rows, int64_t nrows, const int32_t *cols, int64_t ncols,
+                           const uint8_t *member, int32_t K, const double *prob, const double *Pi,
+                           const double *delta, int32_t *y /* [K][nrows] */, int32_t *mafl, int32_t *sizel);
+/* runmean -> dist -> hclust(ward.D2) -> cutree(k = ks[q]) on the same sub-matrix (R/HoneyBADGER.R:1122-1136 with
+ * window 101; :1378-1397 with window 31 on r.maf / n.sc): labels[q * ncols + c], 1-based. */
+int hb_group_handle(hb_handle *h, const int32_t *rows, int64_t nrows, const int32_t *cols, int64_t ncols,
+                    int32_t window, const int32_t *ks, int32_t nk, int32_t *labels);
+/* The retests of one candidate region (rows) over the level's cells (cols): hb_retest_gexp_host /
+ * hb_retest_allele_model_host on the resident data.  sigma0 (host [ncols] or NULL), l_maf / n_bulk (host
+ * [nrows]), gene_end (host [nrows] or NULL = one gene per SNP; rows must already be grouped by gene). */
+int hb_retest_gexp_handle(hb_handle *h, const int32_t *rows, int64_t nrows, const int32_t *cols, int64_t ncols,
+                          double mag0, const double *sigma0, double *p_amp, double *p_del, double *mu0);
+int hb_retest_allele_handle(hb_handle *h, const int32_t *rows, int64_t nrows, const int32_t *cols, int64_t ncols,
+                            const double *l_maf, const double *n_bulk, const uint8_t *gene_end, double pseudo,
+                            double mono, double *p_del);
+
 #ifdef __cplusplus
 }
 #endif

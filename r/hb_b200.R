@@ -151,3 +151,49 @@ hb_setAlleleMats_core <- function(r.init, n.sc.init, l.init = NULL, n.bulk.init 
   names(res$l) <- names(res$n.bulk) <- names(res$l.maf) <- nm
   res
 }
+
+## Device-resident recursion (SURVEY.md 8b-3) -------------------------------------------------------
+## The reference keeps gexp.norm / r.maf / n.sc in RefClass fields and hands sub-matrices down its recursion
+## (`gexp.norm[, g1]`, R/HoneyBADGER.R:1304-1309; `r.maf[, g1]`, :1559-1575).  With a device handle the
+## matrices cross PCIe ONCE; the handle lives in a new field `.dev` (an external pointer whose finalizer
+## frees the device memory) and every level names its genes / cells by index:
+##
+##   HoneyBADGER$fields(.dev = "list")                       # list(gexp = <externalptr>, allele = <externalptr>)
+##   setGexpMats(...)   : .dev$gexp   <<- hb_dev_gexp(gexp.norm)
+##   setAlleleMats(...) : .dev$allele <<- hb_dev_counts(r.maf, n.sc)
+##
+## calcGexpCnvBoundaries keeps its signature (R/HoneyBADGER.R:1092); where it read `gexp.norm.sub` it now
+## carries `cells` (column indices into the resident matrix) and `genes` (row indices, minus bound.genes.old),
+## and its body uses the four calls below instead of runmean / dist / hclust / apply(mean) / dthmm / Viterbi.
+hb_dev_gexp <- function(gexp.norm) .Call("C_hb_upload_gexp", gexp.norm)
+hb_dev_counts <- function(r.maf, n.sc) .Call("C_hb_upload_counts", r.maf, n.sc)
+hb_dev_free <- function(dev) invisible(.Call("C_hb_free_handle", dev))
+hb_dev_bytes <- function(dev) .Call("C_hb_handle_bytes", dev)
+
+## R/HoneyBADGER.R:1122-1136 (window 101) / :1378-1397 (window 31): ct[, i] == cutree(hc, k = heights[i])
+hb_dev_group <- function(dev, genes, cells, heights, k) {
+  .Call("C_hb_group_dev", dev, genes, cells, as.integer(k), as.integer(heights))
+}
+## R/HoneyBADGER.R:1135-1161: all (height, group) chains of one level in one call
+hb_dev_gexp_round <- function(dev, genes, cells, ct, dev.mag, t) {
+  member <- do.call(cbind, unlist(lapply(seq_len(ncol(ct)), function(i)
+    lapply(unique(ct[, i]), function(g) if (sum(ct[, i] == g) > 1) ct[, i] == g)), recursive = FALSE))
+  Pi <- matrix(c(1-2*t, t, t, t, 1-2*t, t, t, t, 1-2*t), byrow = TRUE, nrow = 3)
+  .Call("C_hb_gexp_round_dev", dev, genes, cells, member, c(-dev.mag, 0, dev.mag), Pi, c(0, 1, 0))
+}
+## R/HoneyBADGER.R:1395-1417
+hb_dev_allele_round <- function(dev, snps, cells, ct, pd, pn, t) {
+  member <- do.call(cbind, unlist(lapply(seq_len(ncol(ct)), function(i)
+    lapply(unique(ct[, i]), function(g) if (sum(ct[, i] == g) > 1) ct[, i] == g)), recursive = FALSE))
+  Pi <- matrix(c(1-t, t, t, 1-t), byrow = TRUE, nrow = 2)
+  res <- .Call("C_hb_allele_round_dev", dev, snps, cells, member, c(pd, pn), Pi, c(0, 1))
+  names(res) <- c("y", "mafl", "sizel")
+  res
+}
+## R/HoneyBADGER.R:1220 (calcGexpCnvProb on gexp.norm[bound.genes.new, cells]) without the sub-matrix copy
+hb_dev_retest_gexp <- function(dev, genes, cells, m, sigma0 = NULL) {
+  p <- .Call("C_hb_retest_gexp_dev", dev, genes, cells, as.double(m), sigma0)
+  names(p) <- c("posterior probability of amplification", "posterior probability of deletion",
+                "estimated mean normalized expression deviation")
+  p
+}

@@ -289,6 +289,188 @@ SEXP C_hb_posteriors_binom(SEXP x, SEXP size, SEXP prob, SEXP Pi, SEXP delta)
     return out;
 }
 
+/* ------------------------------------------------------------------ device-resident handle
+ * The matrices cross PCIe once; the RefClass keeps the external pointer in a field (`.dev`) for the whole
+ * recursion (R/HoneyBADGER.R:1098-1102 keeps the matrices themselves there), and every level passes 0-based
+ * index sets instead of copying `gexp.norm[, g1]` (:1304-1309).  The finalizer frees the device memory when
+ * the R object is collected (or at exit). */
+static void hb_handle_finalizer(SEXP ptr)
+{
+    hb_handle *h = (hb_handle *)R_ExternalPtrAddr(ptr);
+    if (h) {
+        hb_free_handle(h);
+        R_ClearExternalPtr(ptr);
+    }
+}
+
+static hb_handle *hb_handle_of(SEXP ptr)
+{
+    hb_handle *h = TYPEOF(ptr) == EXTPTRSXP ? (hb_handle *)R_ExternalPtrAddr(ptr) : NULL;
+    if (!h) Rf_error("libhb_b200: invalid or released device handle");
+    return h;
+}
+
+static SEXP hb_wrap_handle(hb_handle *h)
+{
+    SEXP ptr = PROTECT(R_MakeExternalPtr(h, Rf_install("hb_handle"), R_NilValue));
+    R_RegisterCFinalizerEx(ptr, hb_handle_finalizer, 1);
+    UNPROTECT(1);
+    return ptr;
+}
+
+/* idx: NULL (all) or a 1-based integer vector -> 0-based copy in R-managed memory */
+static const int *hb_index0(SEXP idx, SEXP *keep, int64_t *n)
+{
+    if (Rf_isNull(idx)) {
+        *keep = R_NilValue;
+        *n = 0;
+        return NULL;
+    }
+    SEXP src = PROTECT(Rf_coerceVector(idx, INTSXP));
+    *n = XLENGTH(src);
+    *keep = PROTECT(Rf_allocVector(INTSXP, (R_xlen_t)*n));
+    for (int64_t i = 0; i < *n; i++) INTEGER(*keep)[i] = INTEGER(src)[i] - 1;
+    UNPROTECT(2); /* callers PROTECT *keep again */
+    return INTEGER(*keep);
+}
+
+/* dev <- .Call(C_hb_upload_gexp, gexp.norm)   (once, in setGexpMats / at init = TRUE) */
+SEXP C_hb_upload_gexp(SEXP gexp_norm)
+{
+    gexp_norm = PROTECT(Rf_coerceVector(gexp_norm, REALSXP));
+    hb_handle *h = NULL;
+    int rc = hb_upload_gexp_host(REAL(gexp_norm), Rf_nrows(gexp_norm), Rf_ncols(gexp_norm), &h);
+    UNPROTECT(1);
+    hb_raise(rc);
+    return hb_wrap_handle(h);
+}
+
+/* dev <- .Call(C_hb_upload_counts, r.maf, n.sc) */
+SEXP C_hb_upload_counts(SEXP r_maf, SEXP n_sc)
+{
+    r_maf = PROTECT(Rf_coerceVector(r_maf, REALSXP));
+    n_sc = PROTECT(Rf_coerceVector(n_sc, REALSXP));
+    hb_handle *h = NULL;
+    int rc = hb_upload_counts_host(REAL(r_maf), REAL(n_sc), Rf_nrows(r_maf), Rf_ncols(r_maf), &h);
+    UNPROTECT(2);
+    hb_raise(rc);
+    return hb_wrap_handle(h);
+}
+
+/* .Call(C_hb_free_handle, dev): release now instead of waiting for the garbage collector */
+SEXP C_hb_free_handle(SEXP ptr)
+{
+    hb_handle_finalizer(ptr);
+    return R_NilValue;
+}
+
+/* bytes <- .Call(C_hb_handle_bytes, dev): what the upload moved host -> device */
+SEXP C_hb_handle_bytes(SEXP ptr)
+{
+    int64_t b = 0;
+    hb_raise(hb_handle_info(hb_handle_of(ptr), NULL, NULL, NULL, &b));
+    return Rf_ScalarReal((double)b);
+}
+
+/* y <- .Call(C_hb_gexp_round_dev, dev, rows, cols, member, mean, Pi, delta): one lapply(heights, ...) round of
+ * R/HoneyBADGER.R:1135-1161 on the resident matrix restricted to `rows` (genes) x `cols` (cells), 1-based or
+ * NULL; member: logical / integer [length(cols) x K]; returns the [length(rows) x K] state matrix. */
+SEXP C_hb_gexp_round_dev(SEXP ptr, SEXP rows, SEXP cols, SEXP member, SEXP mean, SEXP Pi, SEXP delta)
+{
+    hb_handle *h = hb_handle_of(ptr);
+    int64_t G = 0, N = 0, nr = 0, nc = 0;
+    hb_raise(hb_handle_info(h, NULL, &G, &N, NULL));
+    SEXP kr, kc;
+    const int *r0 = hb_index0(rows, &kr, &nr);
+    PROTECT(kr);
+    const int *c0 = hb_index0(cols, &kc, &nc);
+    PROTECT(kc);
+    const int64_t G2 = r0 ? nr : G, N2 = c0 ? nc : N;
+    member = PROTECT(Rf_coerceVector(member, INTSXP));
+    const int K = Rf_ncols(member);
+    SEXP mem8 = PROTECT(Rf_allocVector(LGLSXP, (R_xlen_t)((K * N2 + 3) / 4 + 1))); /* scratch bytes */
+    unsigned char *m8 = (unsigned char *)LOGICAL(mem8);
+    for (int64_t i = 0; i < (int64_t)K * N2; i++) m8[i] = INTEGER(member)[i] != 0; /* [N2 x K] column-major == [K][N2] */
+    double pi_rm[9];
+    for (int j = 0; j < 3; j++)
+        for (int k = 0; k < 3; k++) pi_rm[j * 3 + k] = REAL(Pi)[k * 3 + j];
+    SEXP y = PROTECT(Rf_allocMatrix(INTSXP, (int)G2, K)); /* [K][G2] row-major == [G2 x K] column-major */
+    int rc = hb_gexp_round_handle(h, r0, nr, c0, nc, m8, K, REAL(mean), pi_rm, REAL(delta), INTEGER(y), NULL, NULL);
+    UNPROTECT(5);
+    hb_raise(rc);
+    return y;
+}
+
+/* res <- .Call(C_hb_allele_round_dev, dev, rows, cols, member, prob, Pi, delta): R/HoneyBADGER.R:1395-1417;
+ * list(y, mafl, sizel), each [length(rows) x K]. */
+SEXP C_hb_allele_round_dev(SEXP ptr, SEXP rows, SEXP cols, SEXP member, SEXP prob, SEXP Pi, SEXP delta)
+{
+    hb_handle *h = hb_handle_of(ptr);
+    int64_t G = 0, N = 0, nr = 0, nc = 0;
+    hb_raise(hb_handle_info(h, NULL, &G, &N, NULL));
+    SEXP kr, kc;
+    const int *r0 = hb_index0(rows, &kr, &nr);
+    PROTECT(kr);
+    const int *c0 = hb_index0(cols, &kc, &nc);
+    PROTECT(kc);
+    const int64_t G2 = r0 ? nr : G, N2 = c0 ? nc : N;
+    member = PROTECT(Rf_coerceVector(member, INTSXP));
+    const int K = Rf_ncols(member);
+    SEXP mem8 = PROTECT(Rf_allocVector(LGLSXP, (R_xlen_t)((K * N2 + 3) / 4 + 1)));
+    unsigned char *m8 = (unsigned char *)LOGICAL(mem8);
+    for (int64_t i = 0; i < (int64_t)K * N2; i++) m8[i] = INTEGER(member)[i] != 0;
+    double pi_rm[4] = {REAL(Pi)[0], REAL(Pi)[2], REAL(Pi)[1], REAL(Pi)[3]};
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, 3));
+    for (int i = 0; i < 3; i++) SET_VECTOR_ELT(out, i, Rf_allocMatrix(INTSXP, (int)G2, K));
+    int rc = hb_allele_round_handle(h, r0, nr, c0, nc, m8, K, REAL(prob), pi_rm, REAL(delta),
+                                    INTEGER(VECTOR_ELT(out, 0)), INTEGER(VECTOR_ELT(out, 1)),
+                                    INTEGER(VECTOR_ELT(out, 2)));
+    UNPROTECT(5);
+    hb_raise(rc);
+    return out;
+}
+
+/* ct <- .Call(C_hb_group_dev, dev, rows, cols, window, heights): cutree labels [length(cols) x length(heights)] */
+SEXP C_hb_group_dev(SEXP ptr, SEXP rows, SEXP cols, SEXP window, SEXP heights)
+{
+    hb_handle *h = hb_handle_of(ptr);
+    int64_t N = 0, nr = 0, nc = 0;
+    hb_raise(hb_handle_info(h, NULL, NULL, &N, NULL));
+    SEXP kr, kc;
+    const int *r0 = hb_index0(rows, &kr, &nr);
+    PROTECT(kr);
+    const int *c0 = hb_index0(cols, &kc, &nc);
+    PROTECT(kc);
+    heights = PROTECT(Rf_coerceVector(heights, INTSXP));
+    const int nk = (int)XLENGTH(heights);
+    SEXP lab = PROTECT(Rf_allocMatrix(INTSXP, (int)(c0 ? nc : N), nk));
+    int rc = hb_group_handle(h, r0, nr, c0, nc, Rf_asInteger(window), INTEGER(heights), nk, INTEGER(lab));
+    UNPROTECT(4);
+    hb_raise(rc);
+    return lab;
+}
+
+/* p <- .Call(C_hb_retest_gexp_dev, dev, rows, cols, m, sigma0): list(amp, del, mu0) over `cols` for region `rows` */
+SEXP C_hb_retest_gexp_dev(SEXP ptr, SEXP rows, SEXP cols, SEXP mag0, SEXP sigma0)
+{
+    hb_handle *h = hb_handle_of(ptr);
+    int64_t N = 0, nr = 0, nc = 0;
+    hb_raise(hb_handle_info(h, NULL, NULL, &N, NULL));
+    SEXP kr, kc;
+    const int *r0 = hb_index0(rows, &kr, &nr);
+    PROTECT(kr);
+    const int *c0 = hb_index0(cols, &kc, &nc);
+    PROTECT(kc);
+    const int64_t N2 = c0 ? nc : N;
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, 3));
+    for (int i = 0; i < 3; i++) SET_VECTOR_ELT(out, i, Rf_allocVector(REALSXP, (R_xlen_t)N2));
+    int rc = hb_retest_gexp_handle(h, r0, nr, c0, nc, Rf_asReal(mag0), Rf_isNull(sigma0) ? NULL : REAL(sigma0),
+                                   REAL(VECTOR_ELT(out, 0)), REAL(VECTOR_ELT(out, 1)), REAL(VECTOR_ELT(out, 2)));
+    UNPROTECT(3);
+    hb_raise(rc);
+    return out;
+}
+
 static const R_CallMethodDef call_methods[] = {
     {"C_hb_viterbi_norm", (DL_FUNC)&C_hb_viterbi_norm, 5},
     {"C_hb_viterbi_binom", (DL_FUNC)&C_hb_viterbi_binom, 5},
@@ -302,6 +484,14 @@ static const R_CallMethodDef call_methods[] = {
     {"C_hb_retest_allele", (DL_FUNC)&C_hb_retest_allele, 7},
     {"C_hb_set_gexp_mats", (DL_FUNC)&C_hb_set_gexp_mats, 7},
     {"C_hb_set_allele_mats", (DL_FUNC)&C_hb_set_allele_mats, 7},
+    {"C_hb_upload_gexp", (DL_FUNC)&C_hb_upload_gexp, 1},
+    {"C_hb_upload_counts", (DL_FUNC)&C_hb_upload_counts, 2},
+    {"C_hb_free_handle", (DL_FUNC)&C_hb_free_handle, 1},
+    {"C_hb_handle_bytes", (DL_FUNC)&C_hb_handle_bytes, 1},
+    {"C_hb_gexp_round_dev", (DL_FUNC)&C_hb_gexp_round_dev, 7},
+    {"C_hb_allele_round_dev", (DL_FUNC)&C_hb_allele_round_dev, 7},
+    {"C_hb_group_dev", (DL_FUNC)&C_hb_group_dev, 5},
+    {"C_hb_retest_gexp_dev", (DL_FUNC)&C_hb_retest_gexp_dev, 5},
     {NULL, NULL, 0}};
 
 void R_init_hbb200(DllInfo *dll)

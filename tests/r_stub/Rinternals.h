@@ -32,4 +32,14 @@ double Rf_asReal(SEXP);
 int Rf_asLogical(SEXP);
 int Rf_asInteger(SEXP);
 SEXP Rf_ScalarInteger(int);
+SEXP Rf_ScalarReal(double);
+#define EXTPTRSXP 22
+typedef void (*R_CFinalizer_t)(SEXP);
+typedef enum { FALSE_ = 0, TRUE_ } Rboolean_stub;
+SEXP R_MakeExternalPtr(void *p, SEXP tag, SEXP prot);
+void *R_ExternalPtrAddr(SEXP s);
+void R_ClearExternalPtr(SEXP s);
+void R_RegisterCFinalizerEx(SEXP s, R_CFinalizer_t fun, int onexit);
+SEXP Rf_install(const char *);
+int TYPEOF(SEXP);
 #endif

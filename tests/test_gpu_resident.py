@@ -14,7 +14,7 @@ def _run(x, seg, mean, Pi, delta, oracle):
     import torch
     from honeybadger_b200 import hmm
     xd = hmm.to_rows(torch.from_numpy(x).cuda())
-    sd = hmm.chain_sd_dev(xd)
+    sd = hmm.chain_sd_dev(xd) if x.shape[0] > 1 else torch.full((x.shape[1],), 1.7, dtype=torch.float64, device="cuda")
     x_cm = torch.from_numpy(np.ascontiguousarray(x.T)).cuda()
     g = hmm.forwardback_norm_cm_dev(x_cm, sd, mean, Pi, delta, seg_off=seg)
     assert hmm.fbr_gate() == 0

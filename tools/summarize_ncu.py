@@ -44,6 +44,7 @@ if len(rows) > 2:
     ops, stalls, tot = defaultdict(float), defaultdict(float), 0.0
     for r in rows[2:]:
         if len(r) <= ei: continue
+        if r[ei] == "Instructions Executed": break  # a second kernel's section: the summary is of the first
         m = re.match(r"\s*(@!?U?P\w+\s+)?([A-Z0-9_]+)", r[si])
         if not m: continue
         n = float(r[ei] or 0); ops[m.group(2)] += n; tot += n
