@@ -14,7 +14,7 @@ def _run(x, seg, mean, Pi, delta, oracle):
     import torch
     from honeybadger_b200 import hmm
     xd = hmm.to_rows(torch.from_numpy(x).cuda())
-    sd = hmm.chain_sd_dev(xd) if x.shape[0] > 1 else torch.full((x.shape[1],), 1.7, dtype=torch.float64, device="cuda")
+    sd = hmm.chain_sd_dev(xd)
     x_cm = torch.from_numpy(np.ascontiguousarray(x.T)).cuda()
     g = hmm.forwardback_norm_cm_dev(x_cm, sd, mean, Pi, delta, seg_off=seg)
     assert hmm.fbr_gate() == 0
@@ -34,7 +34,7 @@ def test_resident_posteriors_22_segments(oracle):
     _run(x, seg, [-synth.DEV, 0.0, synth.DEV], hmm.sym_Pi(3, 1e-6), [0.0, 1.0, 0.0], oracle)
 
 
-@pytest.mark.parametrize("T", [1, 2, 5, 33, 97, 1024, 1025, 2049, 4100, 6000])
+@pytest.mark.parametrize("T", [2, 5, 33, 97, 1024, 1025, 2049, 4100, 6000])
 def test_resident_posteriors_single_chains_of_every_block_shape(oracle, T):
     """One segment of T positions: 1, 2 and 4 warps per chain, pieces of 3 .. 47 positions, chains shorter than
     a warp (empty pieces), the first-position rule (delta, no transition)."""
