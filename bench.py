@@ -274,6 +274,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
     ap.add_argument("--no-modes", action="store_true",
                     help="skip the viterbi_only / fb_only / sustained legs reported under \"modes\"")
+    ap.add_argument("--no-sharded", action="store_true", help="skip the sharded recursion-level leg")
+    ap.add_argument("--flow", action="store_true",
+                    help="add the device-resident end-to-end leg (upload once, calcGexpCnvBoundaries(init=TRUE))")
     ap.add_argument("--no-allele", action="store_true",
                     help="skip the extra device-resident allele measurement reported under \"allele\"")
     args = ap.parse_args()
@@ -450,6 +453,24 @@ def main():
         except Exception as exc:
             modes = {"error": repr(exc)[:200]}
 
+    # ---------------- one recursion level of the split-and-retest driver on the SHARDED resident matrix: the
+    # exchanges of SURVEY.md 8e (group sizes, 80-bit relay of the pooled means, retest all-reduce, posterior
+    # all-gather) run here, on NCCL when N > 1, and the result is compared with one rank holding every cell
+    sharded = None
+    if kind == "expr" and not args.no_sharded:
+        try:
+            sharded = run_sharded_level(d["x"], cells, rank, world, dev, dist if world > 1 else None)
+        except Exception as exc:
+            sharded = {"error": repr(exc)[:300]}
+
+    # ---------------- device-resident end to end (upload once -> boundaries out), rank 0 of a 1-GPU run
+    flow = None
+    if kind == "expr" and world == 1 and args.flow and not (args.cells or args.positions):
+        try:
+            flow = run_resident_flow(cells, positions)
+        except Exception as exc:
+            flow = {"error": repr(exc)[:300]}
+
     # ---------------- end to end through the host-buffer C ABI (pinned host memory)
     e2e = None
     if not args.no_e2e:
@@ -496,12 +517,137 @@ def main():
                            "layout": "warp-tiled [tile of 32 cells][position][lane] (hb_tile_dev), fp64 / int32"},
                 "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
                 "gpu_launches": launches_per_step * args.steps, "parity": parity, "modes": modes,
+                "sharded_level": sharded, "resident_flow": flow,
                 "kernel_source_hash": kernel_source_hash()}
         if allele is not None:
             line["allele"] = allele
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def level_labels(cells, rank, world, dev, seed):
+    """Group labels of a 5-height cut for this rank's cells (GLOBAL ids), the way the benchmark sizes get them
+    (supplied by the generator — nested cuts of the clone tree, the clones of device_inputs)."""
+    import torch
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    clone = torch.multinomial(torch.tensor([0.5, 0.3, 0.2], device=dev), cells, True, generator=g).cpu().numpy()
+    idx = np.arange(cells) + rank * cells
+    return [np.zeros(cells, np.int64), (clone == 0).astype(np.int64), clone.astype(np.int64),
+            clone * 2 + (idx % 2) * (clone == 0), clone * 3 + (idx % 3) * (clone == 0)]
+
+
+def run_sharded_level(x, cells, rank, world, dev, dist, check_cells=1024, check_genes=4000):
+    """(1) timed: one level (labels given) on every rank's full shard — pooled means by the exact relay, K
+    pooled chains, vote / runs, retest with its all-reduce, posterior all-gather.  (2) checked: the same level
+    on a reduced slice (first `check_cells` cells of every rank x first `check_genes` genes) against rank 0
+    running it alone on the gathered slice — pooled means / states / runs / cell sets must be identical."""
+    import torch
+    from honeybadger_b200 import dist as hd
+    n_total = cells * world
+    labels = level_labels(cells, rank, world, dev, seed=100 + rank)  # the clones device_inputs planted
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    t0 = time.perf_counter()
+    lvl = hd.sharded_gexp_level(x, labels, n_total, DEV)
+    torch.cuda.synchronize()
+    t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    res = {"ms": float(t.item()) * 1e3, "cells_total": n_total, "groups": lvl["K"],
+           "runs": len(lvl.get("runs", [])), "g1_cells": int(lvl["g1"].size) if "g1" in lvl else 0,
+           "collectives": lvl["collectives"], "backend": "nccl" if dist is not None else "none (1 rank)"}
+    # ---- equality with a single rank on a reduced slice
+    cc, gg = min(check_cells, cells), min(check_genes, x.shape[0])
+    xs = x[:gg, :cc].contiguous()
+    ls = [l[:cc] for l in labels]
+    got = hd.sharded_gexp_level(xs, ls, cc * world, DEV)
+    if dist is not None:
+        parts = [torch.empty_like(xs) for _ in range(world)]
+        dist.all_gather(parts, xs)
+        lab_t = torch.as_tensor(np.stack(ls), device=dev)
+        labs = [torch.empty_like(lab_t) for _ in range(world)]
+        dist.all_gather(labs, lab_t)
+        same = True
+        if rank == 0:
+            import torch.distributed as tdist
+            full = torch.cat(parts, dim=1).contiguous()
+            lab_full = torch.cat(labs, dim=1).cpu().numpy()
+            # rank 0 alone: temporarily outside the group's collectives (world-1 code path of the same function)
+            ref = _single_rank_level(hd, full, [lab_full[h] for h in range(lab_full.shape[0])], cc * world)
+            same = bool(np.array_equal(got["pooled"], ref["pooled"]) and np.array_equal(got["y"], ref["y"])
+                        and len(got["runs"]) == len(ref["runs"])
+                        and all(np.array_equal(p, q) for p, q in zip(got["runs"], ref["runs"]))
+                        and ("g1" not in ref or (np.array_equal(got["g1"], ref["g1"])
+                                                 and np.array_equal(got["g2"], ref["g2"])
+                                                 and float(np.abs(got["prob"] - ref["prob"]).max()) < 1e-12)))
+        flag = torch.tensor([1 if same else 0], device=dev)
+        dist.broadcast(flag, src=0)
+        res["equals_single_gpu"] = bool(flag.item())
+        res["checked_on"] = f"{cc * world} cells x {gg} genes (first {cc} cells of every rank)"
+    return res
+
+
+def _single_rank_level(hd, x_full, labels_full, n_cells):
+    """sharded_gexp_level's world = 1 path while a process group exists: patch the world size it sees."""
+    import torch.distributed as tdist
+    real_ws, real_init = tdist.get_world_size, tdist.is_initialized
+    tdist.get_world_size, tdist.is_initialized = (lambda *a, **k: 1), (lambda: False)
+    try:
+        return hd.sharded_gexp_level(x_full, labels_full, n_cells, DEV)
+    finally:
+        tdist.get_world_size, tdist.is_initialized = real_ws, real_init
+
+
+def run_resident_flow(cells, positions):
+    """Device-resident end to end: BASELINE config 4's expression half the way the product is meant to be
+    used — the host matrix (R layout) is uploaded ONCE, then HoneyBADGER$calcGexpCnvBoundaries(init=TRUE)
+    (R/HoneyBADGER.R:1091-1316: grouping, pooled rounds, vote / runs, retest, split, recursion) runs on the
+    resident matrix through the RefClass mirror; only index sets, memberships, K state paths per level and the
+    per-region posteriors cross PCIe afterwards.  Wall time includes the upload."""
+    import pandas as pd
+    import torch
+    from honeybadger_b200 import honeybadger as hb, synth
+    rng = np.random.default_rng(4)
+    G, N = positions, cells
+    seg = synth.segments(G)
+    clone = rng.choice(3, size=N, p=[0.5, 0.3, 0.2])
+    x = rng.standard_normal((G, N))
+    x *= rng.uniform(*DEV_SIGMA, size=N)
+    x[seg[6]:seg[7], clone == 0] += DEV
+    x[seg[9]:seg[10], clone == 0] -= DEV
+    x[seg[12]:seg[13], clone == 1] -= DEV
+    names = [f"g{i}" for i in range(G)]
+    chrom = np.empty(G, dtype=object)
+    for c in range(22):
+        chrom[seg[c]:seg[c + 1]] = f"chr{c + 1}"
+    pos = np.concatenate([np.arange(seg[c + 1] - seg[c]) * 1000.0 for c in range(22)])
+    genes = hb.GRanges(chrom, pos, pos + 500, names)
+    frame = pd.DataFrame(np.asfortranarray(x), index=names, columns=[f"c{i}" for i in range(N)])
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    h = hb.HoneyBADGER("c4")
+    h.genes = genes
+    h.gexp_norm = frame
+    h.setGexpDev(dev=DEV)
+    h._resident("gexp")                      # the one upload
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    h.calcGexpCnvBoundaries(init=True)
+    torch.cuda.synchronize()
+    t2 = time.perf_counter()
+    regs = []
+    for reg in h.bound_genes_final:
+        nm = reg[0]
+        cells_in = (h.pred_genes_r.loc[nm[0]] > 0).values
+        regs.append({"chr": int(np.searchsorted(seg, int(nm[0][1:]), side="right")), "genes": len(nm),
+                     "cells": int(cells_in.sum()), "clone_mix": np.bincount(clone[cells_in], minlength=3).tolist()})
+    return {"api": "HoneyBADGER.calcGexpCnvBoundaries(init=True) on the resident matrix (RefClass mirror)",
+            "cells": N, "genes": G, "upload_s": t1 - t0, "flow_s": t2 - t1, "total_s": t2 - t0,
+            "h2d_bytes": int(G) * int(N) * 8, "regions": regs,
+            "steps_per_s_pooled_equivalent": float(G) * N / (t2 - t0)}
 
 
 def tiled_cols(t, cols):

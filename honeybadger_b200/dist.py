@@ -22,6 +22,49 @@ def shard_sizes(n_cells: int, world: int) -> list[int]:
     return [shard_range(n_cells, r, world)[1] - shard_range(n_cells, r, world)[0] for r in range(world)]
 
 
+# ---- collectives that also work on the gloo backend with CUDA tensors (the single-GPU CI path runs two
+# ranks on one device over gloo): there the payload is staged through the host; NCCL moves it directly.
+def _staged(t):
+    import torch.distributed as dist
+    return t.is_cuda and dist.get_backend() == "gloo"
+
+
+def _all_reduce(t, op=None):
+    import torch.distributed as dist
+    op = dist.ReduceOp.SUM if op is None else op
+    if _staged(t):
+        c = t.cpu()
+        dist.all_reduce(c, op=op)
+        t.copy_(c)
+    else:
+        dist.all_reduce(t, op=op)
+
+
+def _broadcast(t, src):
+    import torch.distributed as dist
+    if _staged(t):
+        c = t.cpu()
+        dist.broadcast(c, src=src)
+        t.copy_(c)
+    else:
+        dist.broadcast(t, src=src)
+
+
+def _send(t, dst):
+    import torch.distributed as dist
+    dist.send(t.cpu() if _staged(t) else t, dst=dst)
+
+
+def _recv(t, src):
+    import torch.distributed as dist
+    if _staged(t):
+        c = t.cpu()
+        dist.recv(c, src=src)
+        t.copy_(c)
+    else:
+        dist.recv(t, src=src)
+
+
 def allreduce_pooled_counts(mafl_local, sizel_local):
     """Sum the per-rank partial counts of R/HoneyBADGER.R:1404-1405 (`rowSums(. > 0)` over the
     rank's cells): int32 all-reduce — exact, so pooled allele chains are identical at any GPU count."""
@@ -79,9 +122,10 @@ def allgather_region_posteriors(local, n_cells: int):
     mx = max(sizes)
     pad = torch.zeros((local.shape[0], mx), dtype=local.dtype, device=local.device)
     pad[:, :local.shape[1]] = local
-    out = [torch.empty_like(pad) for _ in range(world)]
-    dist.all_gather(out, pad)
-    return torch.cat([o[:, :s] for o, s in zip(out, sizes)], dim=1)
+    src = pad.cpu() if _staged(pad) else pad
+    out = [torch.empty_like(src) for _ in range(world)]
+    dist.all_gather(out, src)
+    return torch.cat([o[:, :s] for o, s in zip(out, sizes)], dim=1).to(local.device)
 
 
 def allgather_states(y_local, n_cells: int):
@@ -180,12 +224,129 @@ def pooled_mean_relay(x_local, member_local, group_sizes, accumulate=None):
         if phase == 2:
             state.zero_()
         if rank > 0:
-            dist.recv(state, src=rank - 1)
+            _recv(state, rank - 1)
         accumulate(x_local, member_local, phase, state, mean80)
         if rank < world - 1:
-            dist.send(state, dst=rank + 1)
+            _send(state, rank + 1)
         else:
             accumulate(None, None, phase + 1, state, mean80, out)  # close the pass on the last rank
         if world > 1:
-            dist.broadcast(mean80 if phase == 0 else out, src=world - 1)
+            _broadcast(mean80 if phase == 0 else out, world - 1)
     return out
+
+
+# --------------------------------------------------------------------------- one sharded recursion level
+def sharded_gexp_level(x_local, labels_local, n_cells, dev_mag, t=1e-6, min_num_genes=10, sigma0_local=None,
+                       mean_local=None):
+    """One level of HoneyBADGER$calcGexpCnvBoundaries (R/HoneyBADGER.R:1135-1298) with the CELLS SHARDED over the
+    ranks of the default process group (one process per GPU; world = 1 runs the same code without exchanges).
+
+    x_local [G, N_local]: this rank's columns of the resident gene-major matrix (genes already ordered);
+    labels_local: one int array [N_local] per cut height with GLOBAL group ids (the benchmark sizes take the
+    labels as input — dist + hclust over 200 k cells is 160 GB).  Exchanges, all inside this call:
+
+      group sizes            int64 all-reduce
+      pooled means           80-bit accumulator relay rank -> rank+1, twice (`pooled_mean_relay`): R's `mean` bit
+                             for bit at any GPU count
+      K pooled chains        no exchange: every rank runs them on the identical pooled vectors (hmm_norm_host on
+                             [G, K]: the reference-shaped call)
+      retest of every run    per-cell weights locally (hb_retest_gexp_dev phase 1), ONE fp64 all-reduce of the
+                             shared direction evidence per run, phase 2 locally
+      per-region posteriors  all-gather [runs, N_local] -> [runs, n_cells]  (`allgather_region_posteriors`)
+
+    Returns a dict identical on every rank: y [K, G] states, pooled [K, G], sd [K], runs (index arrays), lists
+    of amp / del runs, prob [runs, n_cells], chosen region index, g1 / g2 global cell indices, and the names of
+    the collectives that ran."""
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    from . import _lib, hmm
+    from .honeybadger import _vp, runs_from_vote
+    lib = _lib.load()
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    G, n_loc = x_local.shape
+    device = x_local.device
+    used = []
+    # ---- groups with more than one cell (globally), in (height, first id) order — the same on every rank
+    ids = [np.asarray(l, dtype=np.int64) for l in labels_local]
+    nid = int(max((int(l.max()) if l.size else 0) for l in ids)) + 1
+    if world > 1:
+        mx = torch.tensor([nid], dtype=torch.int64, device=device)
+        _all_reduce(mx, dist.ReduceOp.MAX)
+        nid = int(mx.item())
+    counts = torch.zeros((len(ids), nid), dtype=torch.int64, device=device)
+    for h, l in enumerate(ids):
+        if l.size:
+            counts[h] += torch.bincount(torch.as_tensor(l, device=device), minlength=nid)
+    if world > 1:
+        _all_reduce(counts)
+        used.append("all_reduce(int64 group sizes)")
+    counts = counts.cpu().numpy()
+    groups = [(h, g) for h in range(len(ids)) for g in range(nid) if counts[h, g] > 1]
+    K = len(groups)
+    out = {"collectives": used, "K": K}
+    if K == 0:
+        return out
+    member = np.stack([(ids[h] == g) for h, g in groups]).astype(np.uint8).reshape(K, n_loc)
+    sizes = np.array([counts[h, g] for h, g in groups], dtype=np.int32)
+    # ---- pooled observation of every group (R/HoneyBADGER.R:1141): exact at any GPU count
+    if world > 1:
+        pooled = pooled_mean_relay(x_local, member, sizes)
+        used.append("send/recv relay of 80-bit accumulators (x2) + broadcast")
+    else:
+        pooled = torch.empty((K, G), dtype=torch.float64, device=device)
+        md = torch.from_numpy(member).to(device)
+        _lib.check(lib.hb_pool_mean_dev(x_local.data_ptr(), x_local.stride(0), G, n_loc, md.data_ptr(), K,
+                                        pooled.data_ptr(), _cur_stream()))
+    sd = torch.empty(K, dtype=torch.float64, device=device)
+    _lib.check(lib.hb_pooled_sd_dev(pooled.data_ptr(), G, K, sd.data_ptr(), _cur_stream()))
+    pooled_h, sd_h = pooled.cpu().numpy(), sd.cpu().numpy()
+    # ---- the K chains (R/HoneyBADGER.R:1144-1151), redundantly on every rank: identical inputs, identical paths
+    res = hmm.hmm_norm_host(np.ascontiguousarray(pooled_h.T), [-dev_mag, 0.0, dev_mag], sd_h, hmm.sym_Pi(3, t),
+                            [0.0, 1.0, 0.0])
+    y = np.ascontiguousarray(res["y"].T)
+    out.update({"y": y, "pooled": pooled_h, "sd": sd_h})
+    amp_v, del_v = (y == 3).sum(0), (y == 1).sum(0)
+    runs, kinds = [], []
+    for vote, kind in ((del_v, "del"), (amp_v, "amp")):        # deletion rows first (R/HoneyBADGER.R:1245-1246)
+        for idx in runs_from_vote(vote, min_num_genes, None) or []:
+            runs.append(idx)
+            kinds.append(kind)
+    out.update({"runs": runs, "kinds": kinds})
+    if not runs:
+        return out
+    # ---- retest of every run on the sharded cells: phase 1, one scalar all-reduce, phase 2
+    st = _cur_stream()
+    pa = torch.empty(n_loc, dtype=torch.float64, device=device)
+    pdl = torch.empty(n_loc, dtype=torch.float64, device=device)
+    d_loc = torch.zeros(1, dtype=torch.float64, device=device)
+    sig = None if sigma0_local is None else torch.as_tensor(sigma0_local, dtype=torch.float64, device=device)
+    rows_local = []
+    for idx, kind in zip(runs, kinds):
+        rows = torch.as_tensor(np.asarray(idx, dtype=np.int64), device=device)
+        args = (x_local.data_ptr(), x_local.stride(0), G, n_loc, rows.data_ptr(), rows.numel(), float(dev_mag),
+                None if sig is None else sig.data_ptr(), pa.data_ptr(), pdl.data_ptr(), None)
+        if world > 1:
+            _lib.check(lib.hb_retest_gexp_dev(*args, d_loc.data_ptr(), None, 1, st))
+            _all_reduce(d_loc)
+            _lib.check(lib.hb_retest_gexp_dev(*args, None, d_loc.data_ptr(), 2, st))
+        else:
+            _lib.check(lib.hb_retest_gexp_dev(*args, None, None, 0, st))
+        rows_local.append((pdl if kind == "del" else pa).clone())
+    if world > 1:
+        used.append("all_reduce(fp64 direction evidence) per run")
+    prob = allgather_region_posteriors(torch.stack(rows_local), n_cells)
+    if world > 1:
+        used.append("all_gather(per-region posteriors)")
+    prob = prob.cpu().numpy()
+    dps = (prob > 0.75).sum(1)
+    dpsi = int(np.nonzero(dps == dps.max())[0][0])
+    out.update({"prob": prob, "chosen": dpsi, "g1": np.nonzero(prob[dpsi] > 0.75)[0],
+                "g2": np.nonzero(prob[dpsi] <= 0.25)[0]})
+    return out
+
+
+def _cur_stream():
+    import ctypes as C
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
