@@ -547,6 +547,7 @@ def run_sharded_level(x, cells, rank, world, dev, dist, check_cells=1024, check_
     from honeybadger_b200 import dist as hd
     n_total = cells * world
     labels = level_labels(cells, rank, world, dev, seed=100 + rank)  # the clones device_inputs planted
+    hd.sharded_gexp_level(x, labels, n_total, DEV)                   # warm-up (workspace growth, first launches)
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
