@@ -826,7 +826,7 @@ def run_e2e(kind, wl, d, args, world, dev, hmm, dist):
     bounded pinned window so that host memory stays small at any N."""
     import torch
     cells, positions = wl["cells"], wl["positions"]
-    batch = min(cells, 5000 if kind == "expr" else 1000)
+    batch = min(cells, 10000 if kind == "expr" else 1000)
     nb = (cells + batch - 1) // batch
     S = wl["S"]
     seg = d["seg"]

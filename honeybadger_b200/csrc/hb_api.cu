@@ -1272,7 +1272,7 @@ static int pipe_init(Workspace *ws)
 
 // Sub-batch width: ~8+ sub-batches per call when B allows, a multiple of 32 columns, bounded by
 // the free device memory (`bytes_per_col` covers staging, resident copy, outputs and scratch).
-static int64_t pipe_batch(int64_t B, double bytes_per_col)
+static int64_t pipe_batch(int64_t B, double bytes_per_col, int64_t want_cap = 1024)
 {
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) {
@@ -1281,7 +1281,7 @@ static int64_t pipe_batch(int64_t B, double bytes_per_col)
     }
     int64_t cap = std::max<int64_t>(1, (int64_t)(free_b * 0.6 / bytes_per_col));
     int64_t want = std::max<int64_t>(32, (B / 8 + 31) / 32 * 32);
-    want = std::min<int64_t>(want, 1024);
+    want = std::min<int64_t>(want, want_cap);
     int64_t Bc = std::min(std::min(cap, want), B);
     if (Bc >= 32) Bc = Bc / 32 * 32;
     return std::max<int64_t>(1, Bc);
@@ -1348,7 +1348,9 @@ int hb_hmm_norm_host(const double *x, int64_t T, int64_t B, const int64_t *seg_o
     HBTRY(pipe_init(ws));
     HBTRY(ws_use_.enter(ws, ws->s_cmp));
     const bool recon = want_g && recon_enabled();
-    const int64_t Bc = pipe_batch(B, 130.0 * (double)T);
+    // <= 512 columns per sub-batch: the pipeline's fill (first upload) and drain (last download + copy-out) are
+    // one sub-batch each and are not overlapped with anything
+    const int64_t Bc = pipe_batch(B, 130.0 * (double)T, T >= 4096 ? 512 : 1024);
     const int64_t nb = (B + Bc - 1) / Bc;
     const int64_t ldc = (Bc + 127) / 128 * 128;
     const int64_t nsd_seg = sd_per_seg ? nseg : 1;
