@@ -94,7 +94,7 @@ struct DevBuf {
 
 // Per-device scratch, grown on demand and reused across calls (no allocation in steady state).
 struct Workspace {
-    DevBuf psi, ckpt, sdaux, segtab, status, flagged, fbr_gate, lut_lb, lut_rho, lut_rho_d, cellmask, gsize;
+    DevBuf psi, ckpt, sdaux, segtab, status, flagged, fbr_gate, pool_fast, lut_lb, lut_rho, lut_rho_d, cellmask, gsize;
     DevBuf lc, lc_fb, lc_lb, lc_y;
     int32_t lc_K = 0;
     int64_t lc_nb = 0;
@@ -130,7 +130,7 @@ struct Workspace {
     int32_t lut_nmax = -1;
     void release_all()
     {
-        DevBuf *all[] = {&fbr_gate, &flagged, &lc, &lc_fb, &lc_lb, &lc_y, &psi, &ckpt, &sdaux, &segtab, &status, &lut_lb, &lut_rho, &lut_rho_d, &cellmask, &gsize,
+        DevBuf *all[] = {&pool_fast, &fbr_gate, &flagged, &lc, &lc_fb, &lc_lb, &lc_y, &psi, &ckpt, &sdaux, &segtab, &status, &lut_lb, &lut_rho, &lut_rho_d, &cellmask, &gsize,
                          &st_in, &st_in2, &st_x, &st_x2, &st_y, &st_g, &st_out, &st_sd, &st_ll,
                          &st_member, &st_pool, &st_pool2, &st_pre, &st_x80, &st_part, &st_inp, &st_inp2, &st_tab, &pin[0], &pin[1], &pin2[0], &pin2[1],
                          &pout_y[0], &pout_y[1], &pout_g[0], &pout_g[1], &pout_ll[0], &pout_ll[1]};
@@ -1694,6 +1694,29 @@ int hb_chain_sd_dev(const double *x, int64_t ld, int64_t T, int64_t B, const int
     return HB_OK;
 }
 
+// group sizes + launch order (largest group first) -> device, scratch of the throughput form (falls back to the
+// block-per-gene-tile kernel when the cell-major copy does not fit), then the two passes.  Caller holds g_mu.
+static int pool_mean_launch(Workspace *ws, const double *x, int64_t ld, int64_t G, int64_t N, const uint8_t *member_dev,
+                            const std::vector<int32_t> &sz, int32_t K, double *out, cudaStream_t st)
+{
+    std::vector<int32_t> tab(2 * (size_t)K);
+    std::vector<int32_t> order(K);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int32_t p, int32_t q) { return sz[p] > sz[q]; });
+    for (int32_t k = 0; k < K; k++) {
+        tab[k] = sz[k];
+        tab[K + k] = order[k];
+    }
+    HBTRY(ws->gsize.ensure(tab.size() * sizeof(int32_t)));
+    HBTRY(upload_async(ws, ws->gsize.p, tab.data(), tab.size() * sizeof(int32_t), st));
+    HBTRY(ws->st_x80.ensure((size_t)2 * K * G * 16));
+    void *fast = nullptr;
+    if (ws->pool_fast.ensure(hb::pool_accum_scratch_bytes(G, N, K)) == HB_OK) fast = ws->pool_fast.p;
+    CU(hb::launch_pool_mean(x, ld, G, N, member_dev, ws->gsize.as<int32_t>(), K, out, ws->st_x80.p, fast,
+                            ws->gsize.as<int32_t>() + K, st));
+    return HB_OK;
+}
+
 int hb_pool_mean_dev(const double *x, int64_t ld, int64_t G, int64_t N, const uint8_t *member,
                      int32_t K, double *out, void *stream)
 {
@@ -1710,10 +1733,7 @@ int hb_pool_mean_dev(const double *x, int64_t ld, int64_t G, int64_t N, const ui
     CU(cudaStreamSynchronize(st));
     std::vector<int32_t> sz;
     HBTRY(group_sizes(h_mem.data(), K, N, sz));
-    HBTRY(ws->gsize.ensure((size_t)K * sizeof(int32_t)));
-    CU(cudaMemcpy(ws->gsize.p, sz.data(), (size_t)K * sizeof(int32_t), cudaMemcpyHostToDevice));
-    HBTRY(ws->st_x80.ensure((size_t)2 * K * G * 16));
-    CU(hb::launch_pool_mean(x, ld, G, N, member, ws->gsize.as<int32_t>(), K, out, ws->st_x80.p, st));
+    HBTRY(pool_mean_launch(ws, x, ld, G, N, member, sz, K, out, st));
     return HB_OK;
 }
 
@@ -1726,8 +1746,19 @@ int hb_pool_mean_relay_dev(const double *x, int64_t ld, int64_t G, int64_t N, co
     if (phase == 0 || phase == 2) {
         if (N < 0 || (N > 0 && (!x || !member || ld < N))) return fail(HB_ERR_ARG, "bad arguments");
         if (phase == 2 && !mean80) return fail(HB_ERR_ARG, "phase 2 needs mean80");
-        if (N > 0)
-            CU(hb::launch_pool_accum(x, ld, G, N, member, K, phase == 2 ? mean80 : nullptr, state, st));
+        if (N > 0) {
+            std::lock_guard<std::mutex> lk(g_mu);
+            Workspace *ws;
+            HBTRY(cur_ws(&ws));
+            WS_USE(stream);
+            if (ws->pool_fast.ensure(hb::pool_accum_scratch_bytes(G, N, K)) == HB_OK) {
+                CU(hb::launch_pool_accum_prepare(x, ld, G, N, member, K, ws->pool_fast.p, st));
+                CU(hb::launch_pool_accum_fast(G, N, K, nullptr, phase == 2 ? mean80 : nullptr, state,
+                                              ws->pool_fast.p, st));
+            } else {
+                CU(hb::launch_pool_accum(x, ld, G, N, member, K, phase == 2 ? mean80 : nullptr, state, st));
+            }
+        }
         return HB_OK;
     }
     if (!n_total || !mean80) return fail(HB_ERR_ARG, "phases 1 and 3 need n_total and mean80");
@@ -2525,17 +2556,13 @@ int hb_gexp_pooled_viterbi_dev(const double *x, int64_t ld, int64_t G, int64_t N
     HBTRY(group_sizes(member, K, N, sz));
     const int64_t ldk = pad_ld(K);
     HBTRY(ws->st_member.ensure((size_t)K * N));
-    HBTRY(ws->gsize.ensure((size_t)K * sizeof(int32_t)));
     HBTRY(ws->st_pool.ensure((size_t)K * G * sizeof(double)));    // [K][G]
     HBTRY(ws->st_pool2.ensure((size_t)G * ldk * sizeof(double))); // gene-major [G][ldk]
     HBTRY(ws->st_sd.ensure((size_t)K * sizeof(double)));
     HBTRY(ws->st_y.ensure((size_t)G * ldk));
     HBTRY(ws->st_out.ensure((size_t)G * K * sizeof(int32_t)));
     CU(cudaMemcpyAsync(ws->st_member.p, member, (size_t)K * N, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(ws->gsize.p, sz.data(), (size_t)K * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    HBTRY(ws->st_x80.ensure((size_t)2 * K * G * 16));
-    CU(hb::launch_pool_mean(x, ld, G, N, ws->st_member.as<uint8_t>(), ws->gsize.as<int32_t>(), K,
-                            ws->st_pool.as<double>(), ws->st_x80.p, st));
+    HBTRY(pool_mean_launch(ws, x, ld, G, N, ws->st_member.as<uint8_t>(), sz, K, ws->st_pool.as<double>(), st));
     CU(hb::launch_pooled_sd(ws->st_pool.as<double>(), G, K, ws->st_sd.as<double>(), st));
     // [K][G] row-major is column-major [G x K]: the same transpose as an R matrix upload
     CU(hb::launch_transpose_f64(ws->st_pool.as<double>(), G, K, ws->st_pool2.as<double>(), ldk, st));

@@ -1033,6 +1033,74 @@ __global__ void __launch_bounds__(32 * PM_KB)
     }
 }
 
+// ---- the same accumulation, organised for throughput (what launch_pool_accum uses when it is given scratch):
+//   * member cells of every group as an index list (pool_cells_kernel: ballot compaction, cell order kept),
+//     so a thread visits only its group's cells instead of testing all N;
+//   * x transposed once per call into a CELL-MAJOR scratch xc[c * G + g]: the 32 lanes of a warp (32
+//     consecutive genes) read one 256-byte line per cell, no shared-memory staging, no block barriers;
+//   * one WARP per (tile of 32 genes, group): 9 375 independent warps at K = 15, G = 20 000 instead of 625
+//     blocks whose duration is set by their largest group and whose last 33 form a second wave;
+//   * the loads do not depend on the 80-bit recursion: PA_U cells are in flight ahead of the additions.
+// Same operations in the same (cell) order on every accumulator: bit-identical states.
+#define PA_U 8
+__global__ void __launch_bounds__(32) pool_cells_kernel(const uint8_t *member, int64_t N, int32_t *cells, int32_t *count)
+{
+    const int k = blockIdx.x, lane = threadIdx.x;
+    const uint8_t *mem = member + (int64_t)k * N;
+    int32_t *out = cells + (int64_t)k * N;
+    int32_t n = 0;
+    for (int64_t c0 = 0; c0 < N; c0 += 32) {
+        const int64_t c = c0 + lane;
+        const bool in = c < N && mem[c] != 0;
+        const unsigned bal = __ballot_sync(0xffffffffu, in);
+        if (in) out[n + __popc(bal & ((1u << lane) - 1u))] = (int32_t)c;
+        n += __popc(bal);
+    }
+    if (lane == 0) count[k] = n;
+}
+
+__global__ void __launch_bounds__(128)
+    pool_accum_cm_kernel(const double *xc, int64_t G, int64_t N, const int32_t *cells, const int32_t *count,
+                         const int32_t *order, int32_t K, const x80 *mean80, x80 *state)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t tile = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int32_t k = order ? order[blockIdx.y] : (int32_t)blockIdx.y;
+    const int64_t g = tile * 32 + lane;
+    if (tile * 32 >= G) return;
+    const bool live = g < G;
+    const int64_t gi = live ? g : G - 1; // lanes past the last gene repeat it (uniform loop, result dropped)
+    const int64_t si = (int64_t)k * G + gi;
+    const bool centred = mean80 != nullptr;
+    x80 S = state[si];
+    const x80 M = centred ? x80_neg(mean80[si]) : x80_zero();
+    const int32_t *cl = cells + (int64_t)k * N;
+    const int32_t n = count[k];
+    const double *col = xc + gi;
+    double v[PA_U], w[PA_U];
+    int32_t i = 0;
+#pragma unroll
+    for (int u = 0; u < PA_U; u++) v[u] = u < n ? __ldcs(col + (int64_t)cl[u] * G) : 0.0;
+    for (; i + PA_U <= n; i += PA_U) {
+#pragma unroll
+        for (int u = 0; u < PA_U; u++) {
+            const int32_t j = i + PA_U + u;
+            w[u] = j < n ? __ldcs(col + (int64_t)cl[j] * G) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < PA_U; u++) {
+            const x80 t = x80_from_double(v[u]);
+            S = x80_add(S, centred ? x80_add(t, M) : t);
+            v[u] = w[u];
+        }
+    }
+    for (int u = 0; i + u < n; u++) {
+        const x80 t = x80_from_double(v[u]);
+        S = x80_add(S, centred ? x80_add(t, M) : t);
+    }
+    if (live) state[si] = S;
+}
+
 // pass 0 closed: mean80 = state / n[k]
 __global__ void pool_div_kernel(const x80 *state, const int32_t *n, int64_t G, int32_t K, x80 *mean80)
 {
@@ -1057,6 +1125,36 @@ cudaError_t launch_pool_accum(const double *x, int64_t ld, int64_t G, int64_t N,
         x, ld, G, N, member, K, (const x80 *)mean80, (x80 *)state);
     return cudaGetLastError();
 }
+
+// bytes of scratch launch_pool_accum_fast needs: cell-major copy of x + cell lists + counts
+size_t pool_accum_scratch_bytes(int64_t G, int64_t N, int32_t K)
+{
+    return (size_t)G * N * sizeof(double) + (size_t)K * N * sizeof(int32_t) + (size_t)K * sizeof(int32_t) + 512;
+}
+
+// prepare: transposes x and builds the cell lists (once per matrix / membership; both passes reuse them)
+cudaError_t launch_pool_accum_prepare(const double *x, int64_t ld, int64_t G, int64_t N, const uint8_t *member,
+                                      int32_t K, void *scratch, cudaStream_t st)
+{
+    double *xc = (double *)scratch;
+    int32_t *cells = (int32_t *)((char *)scratch + (((size_t)G * N * sizeof(double) + 255) & ~(size_t)255));
+    int32_t *count = cells + (size_t)K * N;
+    cudaError_t e = launch_transpose_f64_back(x, ld, G, N, xc, st);
+    if (e != cudaSuccess) return e;
+    pool_cells_kernel<<<(unsigned)K, 32, 0, st>>>(member, N, cells, count);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pool_accum_fast(int64_t G, int64_t N, int32_t K, const int32_t *order, const void *mean80,
+                                   void *state, const void *scratch, cudaStream_t st)
+{
+    const double *xc = (const double *)scratch;
+    const int32_t *cells = (const int32_t *)((const char *)scratch + (((size_t)G * N * sizeof(double) + 255) & ~(size_t)255));
+    const int32_t *count = cells + (size_t)K * N;
+    const dim3 grid((unsigned)((G + 127) / 128), (unsigned)K);
+    pool_accum_cm_kernel<<<grid, 128, 0, st>>>(xc, G, N, cells, count, order, K, (const x80 *)mean80, (x80 *)state);
+    return cudaGetLastError();
+}
 cudaError_t launch_pool_div(const void *state, const int32_t *n, int64_t G, int32_t K, void *mean80,
                             cudaStream_t st)
 {
@@ -1073,19 +1171,26 @@ cudaError_t launch_pool_finish(const void *mean80, const void *state, const int3
     return cudaGetLastError();
 }
 
-// The whole mean on one GPU: `scratch` holds 2 * K * G 16-byte records.
+// The whole mean on one GPU: `scratch` holds 2 * K * G 16-byte records; `fast` (pool_accum_scratch_bytes, or
+// NULL) the cell-major copy and cell lists of the throughput form; `order` (device [K] or NULL): groups by
+// decreasing size, so that the longest accumulations start first.
 cudaError_t launch_pool_mean(const double *x, int64_t ld, int64_t G, int64_t N,
                              const uint8_t *member, const int32_t *gsize, int32_t K, double *out,
-                             void *scratch, cudaStream_t st)
+                             void *scratch, void *fast, const int32_t *order, cudaStream_t st)
 {
     const size_t rec = (size_t)K * G * sizeof(x80);
     void *state = scratch, *mean80 = (char *)scratch + rec;
     cudaError_t e = cudaMemsetAsync(state, 0, rec, st);
     if (e != cudaSuccess) return e;
-    if ((e = launch_pool_accum(x, ld, G, N, member, K, nullptr, state, st)) != cudaSuccess) return e;
+    if (fast && (e = launch_pool_accum_prepare(x, ld, G, N, member, K, fast, st)) != cudaSuccess) return e;
+    auto accum = [&](const void *m80) {
+        return fast ? launch_pool_accum_fast(G, N, K, order, m80, state, fast, st)
+                    : launch_pool_accum(x, ld, G, N, member, K, m80, state, st);
+    };
+    if ((e = accum(nullptr)) != cudaSuccess) return e;
     if ((e = launch_pool_div(state, gsize, G, K, mean80, st)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(state, 0, rec, st)) != cudaSuccess) return e;
-    if ((e = launch_pool_accum(x, ld, G, N, member, K, mean80, state, st)) != cudaSuccess) return e;
+    if ((e = accum(mean80)) != cudaSuccess) return e;
     return launch_pool_finish(mean80, state, gsize, G, K, out, st);
 }
 

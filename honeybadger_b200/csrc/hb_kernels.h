@@ -69,9 +69,14 @@ cudaError_t launch_runmean(const double *x, const int32_t *r, const int32_t *n, 
 cudaError_t launch_dist_sq(const double *S, int64_t ld, int64_t G, int64_t N, double *D, cudaStream_t st);
 cudaError_t launch_ward(double *D, int64_t N, int32_t *size, uint8_t *active, int32_t *chain, int32_t *ma,
                         int32_t *mb, double *height, cudaStream_t st);
-cudaError_t launch_pool_mean(const double *x, int64_t ld, int64_t G, int64_t N,
-                             const uint8_t *member, const int32_t *gsize, int32_t K, double *out,
-                             void *scratch /* 2*K*G 16-byte records */, cudaStream_t st);
+cudaError_t launch_pool_mean(const double *x, int64_t ld, int64_t G, int64_t N, const uint8_t *member,
+                             const int32_t *gsize, int32_t K, double *out, void *scratch, void *fast,
+                             const int32_t *order, cudaStream_t st);
+size_t pool_accum_scratch_bytes(int64_t G, int64_t N, int32_t K);
+cudaError_t launch_pool_accum_prepare(const double *x, int64_t ld, int64_t G, int64_t N, const uint8_t *member,
+                                      int32_t K, void *scratch, cudaStream_t st);
+cudaError_t launch_pool_accum_fast(int64_t G, int64_t N, int32_t K, const int32_t *order, const void *mean80,
+                                   void *state, const void *scratch, cudaStream_t st);
 cudaError_t launch_pool_accum(const double *x, int64_t ld, int64_t G, int64_t N, const uint8_t *member,
                               int32_t K, const void *mean80, void *state, cudaStream_t st);
 cudaError_t launch_pool_div(const void *state, const int32_t *n, int64_t G, int32_t K, void *mean80,
