@@ -99,6 +99,57 @@ HB_HD void st_stream(T *p, T v)
 #endif
 }
 
+// Experiment (off by default, -DHB_SCRATCH_L2_HINTS=1): the scratch written in the forward sweep and read back
+// once in the backward sweep (back-pointer words, filter checkpoints) with an L2 evict-LAST policy on the stores
+// and evict-first on the one re-read, so that the ~100 MB of live scratch might survive in the 126 MB L2 between
+// the sweeps.  Measured A/B in one session (round 2, tools/build_variant.sh): SLOWER — Viterbi + posteriors
+// 1.800 vs 1.771 ms (median), posteriors only 1.589 vs 1.521 ms: pinning the scratch takes L2 away from the
+// read-ahead of x and from write combining of the posterior stores.
+#ifndef HB_SCRATCH_L2_HINTS
+#define HB_SCRATCH_L2_HINTS 0
+#endif
+struct L2Pol {
+    uint64_t keep, drop;
+};
+HB_HD L2Pol l2pol_make()
+{
+    L2Pol p;
+    p.keep = p.drop = 0;
+#if defined(__CUDA_ARCH__) && HB_SCRATCH_L2_HINTS
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p.keep));
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p.drop));
+#endif
+    return p;
+}
+template <typename T>
+HB_HD void st_keep(const L2Pol &p, T *ptr, T v)
+{
+#if defined(__CUDA_ARCH__) && HB_SCRATCH_L2_HINTS
+    static_assert(sizeof(T) == 8, "8-byte scratch words");
+    uint64_t u;
+    memcpy(&u, &v, 8);
+    asm volatile("st.global.L2::cache_hint.b64 [%0], %1, %2;" ::"l"(ptr), "l"(u), "l"(p.keep) : "memory");
+#else
+    (void)p;
+    *ptr = v;
+#endif
+}
+template <typename T>
+HB_HD T ld_drop(const L2Pol &p, const T *ptr)
+{
+#if defined(__CUDA_ARCH__) && HB_SCRATCH_L2_HINTS
+    static_assert(sizeof(T) == 8, "8-byte scratch words");
+    uint64_t u;
+    asm volatile("ld.global.L2::cache_hint.b64 %0, [%1], %2;" : "=l"(u) : "l"(ptr), "l"(p.drop) : "memory");
+    T v;
+    memcpy(&v, &u, 8);
+    return v;
+#else
+    (void)p;
+    return *ptr;
+#endif
+}
+
 // Warp-tiled layout: one instruction prefetches a whole chunk.  `p` is this lane's element of the
 // chunk's first row; the chunk is `lines` consecutive 128-byte lines starting at the warp's row, and
 // lane l touches line l % lines (instead of every lane touching its own row's two lines at every step).

@@ -439,6 +439,7 @@ HB_HD void norm3_fast_chain(const Norm3Args &a, int32_t seg, int64_t b, Norm3Sme
     s.esum = 0;
     s.mn = 0x7fffffffu;
     s.f0 = s.f1 = s.f2 = 0;
+    const L2Pol pol = l2pol_make();
 
     // ------------------------------------------------------------ forward sweep
     // x reaches the arithmetic one chunk ahead of its use: cp.async ring, or bulk copies (BULK)
@@ -516,13 +517,13 @@ HB_HD void norm3_fast_chain(const Norm3Args &a, int32_t seg, int64_t b, Norm3Sme
                 bulk_release(br);
                 if (ch + 2 < nfull) bulk_issue<HB_CHUNK>(br, stg, xp + (int64_t)(ch + 2) * HB_CHUNK * ld);
             }
-            if (VIT) *pw = (uint64_t)w[0] | ((uint64_t)w[1] << 32);
+            if (VIT) st_keep(pol, pw, (uint64_t)w[0] | ((uint64_t)w[1] << 32));
             pw += sB;
             ck += 3 * sB;
             if (FB && (more || tail > 0)) {
-                ck[0] = s.f0;
-                ck[sB] = s.f1;
-                ck[2 * sB] = s.f2;
+                st_keep(pol, ck, s.f0);
+                st_keep(pol, ck + sB, s.f1);
+                st_keep(pol, ck + 2 * sB, s.f2);
             }
         }
     }
@@ -616,12 +617,12 @@ HB_HD void norm3_fast_chain(const Norm3Args &a, int32_t seg, int64_t b, Norm3Sme
     uint64_t pk_nx = 0;
     double c0_nx = 0, c1_nx = 0, c2_nx = 0;
     if (nfull > 0) {
-        if (VIT) pk_nx = psi[(int64_t)(nfull - 1) * sB];
+        if (VIT) pk_nx = ld_drop(pol, psi + (int64_t)(nfull - 1) * sB);
         if (FB && nfull > 1) {
             const double *ck = ckpt + (int64_t)(nfull - 1) * 3 * sB;
-            c0_nx = ck[0];
-            c1_nx = ck[sB];
-            c2_nx = ck[2 * sB];
+            c0_nx = ld_drop(pol, ck);
+            c1_nx = ld_drop(pol, ck + sB);
+            c2_nx = ld_drop(pol, ck + 2 * sB);
         }
     }
     const int64_t plane = a.gplane;
@@ -665,11 +666,11 @@ HB_HD void norm3_fast_chain(const Norm3Args &a, int32_t seg, int64_t b, Norm3Sme
                 s.f2 = c2_nx;
             }
             if (ch > 0) {
-                if (VIT) pk_nx = *pr;
+                if (VIT) pk_nx = ld_drop(pol, pr);
                 if (FB && ch > 1) {
-                    c0_nx = cr[0];
-                    c1_nx = cr[sB];
-                    c2_nx = cr[2 * sB];
+                    c0_nx = ld_drop(pol, cr);
+                    c1_nx = ld_drop(pol, cr + sB);
+                    c2_nx = ld_drop(pol, cr + 2 * sB);
                 }
             }
             const bool pf = ch > 1 + HB_FAST_PF_CHUNKS;
