@@ -192,12 +192,16 @@ def pooled_mean_relay_shards(shards, members, group_sizes):
     return out
 
 
-def pooled_mean_relay(x_local, member_local, group_sizes, accumulate=None):
+def pooled_mean_relay(x_local, member_local, group_sizes, accumulate=None, chunks=None):
     """Multi-process form: every rank calls this with its gene-major shard [G, N_local] and its
     uint8 [K, N_local] membership slice; `group_sizes` are the TOTAL group sizes.  The 16-byte
     states travel rank -> rank+1 with send/recv, the last rank closes each pass and broadcasts.
     Returns the [K, G] pooled means on every rank.  `accumulate(x, member, phase, state, mean80)` can
-    replace the device call (the gloo CPU test passes a long-double emulation)."""
+    replace the device call (the gloo CPU test passes a long-double emulation).
+
+    The relay is PIPELINED over blocks of genes (accumulators of different genes are independent; only the
+    cell order inside one accumulator is fixed): rank r works on block j while rank r+1 works on block j-1, so a
+    pass over W ranks costs (W + J - 1) / J rank-times instead of W.  `chunks` = J (default 16 from 2 ranks up)."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size() if dist.is_initialized() else 1
@@ -217,22 +221,32 @@ def pooled_mean_relay(x_local, member_local, group_sizes, accumulate=None):
                 _relay_phase(lib, None, None, K, n_tot, phase, state, mean80, out)
     else:
         dev = torch.device("cpu")
-    state = torch.zeros(K * G * 16, dtype=torch.uint8, device=dev)
-    mean80 = torch.zeros(K * G * 16, dtype=torch.uint8, device=dev)
-    out = torch.empty((K, G), dtype=torch.float64, device=dev)
+    J = int(chunks) if chunks else (16 if world > 1 else 1)
+    J = max(1, min(J, G // 32 if G >= 32 else 1))
+    bounds = [int(round(j * G / J)) for j in range(J + 1)]
+    sizes = [bounds[j + 1] - bounds[j] for j in range(J)]
+    offs = np.concatenate([[0], np.cumsum([K * g * 16 for g in sizes])]).astype(np.int64)
+    state_all = torch.zeros(int(offs[-1]), dtype=torch.uint8, device=dev)
+    mean_all = torch.zeros(int(offs[-1]), dtype=torch.uint8, device=dev)
+    out_all = torch.empty(K * G, dtype=torch.float64, device=dev)
+    ooffs = np.concatenate([[0], np.cumsum([K * g for g in sizes])]).astype(np.int64)
+    st = [state_all[int(offs[j]):int(offs[j + 1])] for j in range(J)]
+    mn = [mean_all[int(offs[j]):int(offs[j + 1])] for j in range(J)]
+    ou = [out_all[int(ooffs[j]):int(ooffs[j + 1])].view(K, sizes[j]) for j in range(J)]
     for phase in (0, 2):
         if phase == 2:
-            state.zero_()
-        if rank > 0:
-            _recv(state, rank - 1)
-        accumulate(x_local, member_local, phase, state, mean80)
-        if rank < world - 1:
-            _send(state, rank + 1)
-        else:
-            accumulate(None, None, phase + 1, state, mean80, out)  # close the pass on the last rank
+            state_all.zero_()
+        for j in range(J):
+            if rank > 0:
+                _recv(st[j], rank - 1)
+            accumulate(x_local[bounds[j]:bounds[j + 1]], member_local, phase, st[j], mn[j])
+            if rank < world - 1:
+                _send(st[j], rank + 1)
+            else:
+                accumulate(None, None, phase + 1, st[j], mn[j], ou[j])  # close the pass on the last rank
         if world > 1:
-            _broadcast(mean80 if phase == 0 else out, world - 1)
-    return out
+            _broadcast(mean_all if phase == 0 else out_all, world - 1)
+    return torch.cat(ou, dim=1) if J > 1 else ou[0]
 
 
 # --------------------------------------------------------------------------- one sharded recursion level

@@ -52,8 +52,8 @@ def _worker(rank, world, port, q):
     sizes = memb.sum(1)
 
     def accumulate(x, member, phase, state, mean80, out=None):
-        st = state.numpy().view(np.longdouble).reshape(3, G)
-        mn = mean80.numpy().view(np.longdouble).reshape(3, G)
+        st = state.numpy().view(np.longdouble).reshape(3, -1)     # one block of genes of the pipelined relay
+        mn = mean80.numpy().view(np.longdouble).reshape(3, -1)
         x = x.numpy() if torch.is_tensor(x) else x
         if phase in (0, 2):
             for k in range(3):
@@ -66,7 +66,7 @@ def _worker(rank, world, port, q):
             for k in range(3):
                 out[k] = torch.from_numpy((mn[k] + st[k] / np.longdouble(sizes[k])).astype(np.float64))
 
-    pm = hd.pooled_mean_relay(torch.from_numpy(xg[:, lo:hi]), memb[:, lo:hi], sizes, accumulate=accumulate)
+    pm = hd.pooled_mean_relay(torch.from_numpy(xg[:, lo:hi]), memb[:, lo:hi], sizes, accumulate=accumulate, chunks=5)
     for k in range(3):
         ok = ok and (pm[k].numpy() == O.pool_mean(xg, np.nonzero(memb[k])[0])).all()
     v = hd.merge_votes(np.full(G, rank + 1))
