@@ -201,10 +201,11 @@ def pooled_mean_relay(x_local, member_local, group_sizes, accumulate=None, chunk
 
     The relay is PIPELINED over blocks of genes (accumulators of different genes are independent; only the
     cell order inside one accumulator is fixed): rank r works on block j while rank r+1 works on block j-1, so a
-    pass over W ranks costs (W + J - 1) / J rank-times instead of W.  `chunks` = J, default min(W, 8): a block must
-    keep the GPU busy — the longest accumulation of a block (the largest group's cells, ~600 cycles per 80-bit
-    addition) is a latency floor that does not shrink with the block, so 16 blocks of 1 250 genes measured 3x
-    SLOWER than no pipelining at 2 ranks."""
+    pass over W ranks costs (W + J - 1) / J rank-times instead of W in the ideal case.  The longest accumulation
+    of a block (the largest group's cells, hundreds of cycles per emulated 80-bit addition) is a latency floor that
+    does not shrink with the block, so small blocks lose: measured (10 k cells per rank, 15 groups, whole sharded
+    level) 2 ranks: no pipelining 97 ms, J = 2 112 ms, J = 16 295 ms; 8 ranks: no pipelining 428 ms, J = 8 295 ms.
+    `chunks` = J; default W (at most 8) from 3 ranks up, 1 below; env HB_RELAY_CHUNKS overrides."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size() if dist.is_initialized() else 1
@@ -224,7 +225,9 @@ def pooled_mean_relay(x_local, member_local, group_sizes, accumulate=None, chunk
                 _relay_phase(lib, None, None, K, n_tot, phase, state, mean80, out)
     else:
         dev = torch.device("cpu")
-    J = int(chunks) if chunks else (min(world, 8) if world > 1 else 1)
+    import os
+    env = int(os.environ.get("HB_RELAY_CHUNKS", "0") or 0)
+    J = int(chunks) if chunks else (env if env > 0 else (min(world, 8) if world > 2 else 1))
     J = max(1, min(J, G // 32 if G >= 32 else 1))
     bounds = [int(round(j * G / J)) for j in range(J + 1)]
     sizes = [bounds[j + 1] - bounds[j] for j in range(J)]
