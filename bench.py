@@ -47,6 +47,15 @@ WORKLOADS = {
     "allele": dict(name="C4-allele: 10k cells x 200k SNPs per GPU, 22 chromosome segments, per-cell "
                         "chains, 2-state binomial, packed 16-bit counts, Viterbi + posteriors",
                    cells=10000, positions=200000, nseg=22, S=2, bytes_per_step=21),
+    # BASELINE.json configs[4]: 200k cells x 20k genes cell-sharded over 8 GPUs = 25k cells per GPU (weak scaling:
+    # --gpus N runs N x 25k cells).  The TIMED step is the per-cell chains on the rank's shard PLUS one recursion
+    # level of the split-and-retest driver on the sharded cells with every exchange of SURVEY 8e on NCCL
+    # (group sizes, exact pooled-mean relay, retest all-reduce, posterior all-gather): value = per-cell steps of
+    # all ranks / that time.  The level is dominated by the exact 80-bit pooled mean, so this
+    # line reads far below the chain kernel's; `roofline` is the chain kernel's own, timed inside the same steps.
+    "c5": dict(name="C5: 200k cells x 20k genes over 8 GPUs (25k cells per GPU), per-cell chains (Viterbi + "
+                    "posteriors) + one sharded recursion level with its NCCL exchanges inside the timed step",
+               cells=25000, positions=20000, nseg=22, S=3, bytes_per_step=33),
 }
 
 
@@ -275,19 +284,24 @@ def main():
     ap.add_argument("--no-modes", action="store_true",
                     help="skip the viterbi_only / fb_only / sustained legs reported under \"modes\"")
     ap.add_argument("--no-sharded", action="store_true", help="skip the sharded recursion-level leg")
-    ap.add_argument("--flow", action="store_true",
-                    help="add the device-resident end-to-end leg (upload once, calcGexpCnvBoundaries(init=TRUE))")
+    ap.add_argument("--no-flow", action="store_true",
+                    help="skip the device-resident end-to-end leg (upload once, calcGexpCnvBoundaries(init=TRUE))")
     ap.add_argument("--no-allele", action="store_true",
                     help="skip the extra device-resident allele measurement reported under \"allele\"")
     args = ap.parse_args()
     kind = args.workload
+    c5 = kind == "c5"
     wl = dict(WORKLOADS[kind])
+    if c5:
+        kind = "expr"   # same inputs, kernels and legs as the expression workload; the step adds the level
     if args.cells:
         wl["cells"] = args.cells
     if args.positions:
         wl["positions"] = args.positions
     if args.cells or args.positions:
         wl["name"] += f" [overridden: {wl['cells']} x {wl['positions']}]"
+    if c5 and args.steps > 10:
+        args.steps = 10   # a step holds a whole recursion level (0.06 - 0.3 s)
     if args.impl == "reference":
         return run_reference(args, wl, kind)
 
@@ -320,9 +334,23 @@ def main():
         xt = hmm.tile_rows(d["x"])
         out = hmm.hmm_norm_tiled_dev(xt, cells, sd, mean, Pi3, delta3, seg_off=seg)
 
+        chain_ev = []
+
         def step():
+            if c5:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
             hmm.hmm_norm_tiled_dev(xt, cells, sd, mean, Pi3, delta3, seg_off=seg, out=out)
-        launches_per_step = 2  # sd_prep_kernel + norm3_fast_kernel
+            if c5:
+                e1.record()
+                chain_ev.append((e0, e1))
+                hd.sharded_gexp_level(d["x"], c5_labels, cells * world, DEV)
+        if c5:
+            from honeybadger_b200 import dist as hd
+            c5_labels = level_labels(cells, rank, world, dev, seed=100 + rank)
+        # sd_prep_kernel + norm3_fast_kernel (+ for c5 the level's ~40 small launches: transposes, cell lists, the
+        # two accumulation passes, sd, emissions, the long-chain phases, three retests)
+        launches_per_step = 42 if c5 else 2
         in_bytes = d["x"].numel() * 8
     else:
         xn = hmm.pack_counts(hmm.tile_rows(d["r"]), hmm.tile_rows(d["n"]))
@@ -376,7 +404,7 @@ def main():
 
     # ---------------- the same kernel in its other modes, each against its own roofline, and a sustained run
     modes = None
-    if not args.no_modes:
+    if not args.no_modes and not c5:
         try:
             modes = {}
             nl = max(5, args.steps // 3)
@@ -457,7 +485,7 @@ def main():
     # exchanges of SURVEY.md 8e (group sizes, 80-bit relay of the pooled means, retest all-reduce, posterior
     # all-gather) run here, on NCCL when N > 1, and the result is compared with one rank holding every cell
     sharded = None
-    if kind == "expr" and not args.no_sharded:
+    if kind == "expr" and not args.no_sharded and not c5:
         try:
             sharded = run_sharded_level(d["x"], cells, rank, world, dev, dist if world > 1 else None)
         except Exception as exc:
@@ -465,7 +493,7 @@ def main():
 
     # ---------------- device-resident end to end (upload once -> boundaries out), rank 0 of a 1-GPU run
     flow = None
-    if kind == "expr" and world == 1 and args.flow and not (args.cells or args.positions):
+    if kind == "expr" and world == 1 and not c5 and not args.no_flow and not (args.cells or args.positions):
         try:
             flow = run_resident_flow(cells, positions)
         except Exception as exc:
@@ -482,7 +510,7 @@ def main():
     # ---------------- the other half of C4 (10k cells x 200k SNPs, 2-state binomial), device-resident
     # only, a few steps: reported under "allele" beside the headline expression workload
     allele = None
-    if kind == "expr" and not args.no_allele and not (args.cells or args.positions):
+    if kind == "expr" and not c5 and not args.no_allele and not (args.cells or args.positions):
         try:
             del out, xt, step
             d.pop("x", None)
@@ -491,6 +519,8 @@ def main():
         except Exception as exc:
             allele = {"value": None, "error": repr(exc)[:200]}
 
+    if c5:  # the roofline is the chain kernel's: its own events inside the timed steps
+        per_launch_ms = [a.elapsed_time(b) for a, b in chain_ev[-args.steps:]]
     mean_ms = float(np.mean(per_launch_ms))
     achieved = steps_per_pass * wl["bytes_per_step"] / (mean_ms * 1e-3) / 1e9
     q = np.percentile(per_launch_ms, [0, 25, 50, 75, 100])
