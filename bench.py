@@ -77,7 +77,8 @@ def kernel_source_hash():
     h = hashlib.sha256()
     csrc = os.path.join(ROOT, "honeybadger_b200", "csrc")
     for f in sorted(os.listdir(csrc)):
-        if f.endswith((".cu", ".cuh", ".h")):
+        # device code only: the kernels (*.cuh, hb_kernels.*); hb_api.cu / hb_host_math.h are host-side
+        if f.endswith(".cuh") or f in ("hb_kernels.cu", "hb_kernels.h"):
             h.update(f.encode())
             h.update(open(os.path.join(csrc, f), "rb").read())
     return h.hexdigest()[:16]
