@@ -901,8 +901,14 @@ def run_e2e(kind, wl, d, args, world, dev, hmm, dist):
                                            bn, vp(segp), segp.size - 1, vp(prob), 0.0, vp(Pi2), vp(delta2),
                                            3, yout.data_ptr(), gout.data_ptr(), None)
             _lib.check(rc)
+            lib.hb_last_host_io(C.byref(io[0]), C.byref(io[1]), C.byref(io[2]))
+            for q in range(3):
+                tot[q] += io[q].value
 
+    io = [C.c_int64(0) for _ in range(3)]
+    tot = [0, 0, 0]
     one_pass()  # warm-up (workspace allocation, LUT)
+    tot = [0, 0, 0]
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize()
@@ -914,7 +920,10 @@ def run_e2e(kind, wl, d, args, world, dev, hmm, dist):
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     val = world * cells * positions * args.e2e_steps / float(t.item())
+    # bytes counted by the library itself (hb_last_host_io)
+    h2d, d2h = tot[0] // args.e2e_steps, tot[1] // args.e2e_steps
     return {"value": val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            "posterior_bytes_rebuilt_on_host_per_step": tot[2] // args.e2e_steps,
             "api": "hb_hmm_norm_host" if kind == "expr" else "hb_hmm_binom_host",
             "host_buffers": "pinned, R column-major layout; one call per window of %d cells, each call "
                             "pipelined internally (upload | layout+chains | download on three streams)" % batch,

@@ -43,6 +43,7 @@ SIGNATURES = {
     "hb_set_device": (_i32, [C.c_int]),
     "hb_release_workspace": (_i32, []),
     "hb_status_dev": (_i32, [_p]),
+    "hb_last_host_io": (_i32, [C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "hb_last_kernels": (_i32, [C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "hb_set_binom_lut_max": (_i32, [_i32]),
     "hb_set_norm3_mode": (_i32, [_i32]),

@@ -114,6 +114,7 @@ struct Workspace {
     std::vector<int64_t> seg_cached;
     int64_t nchunks = 0;
     int32_t last_norm3_fast = -1, last_binom2_lean = -1; // kernels of the last launches (hb_last_kernels)
+    int64_t io_h2d = 0, io_d2h = 0, io_rebuilt = 0;      // bytes of the last *_host pipeline call (hb_last_host_io)
     // Stream hand-over: the scratch above is shared by every call on this device.  Each entry point records
     // ev_use on its stream when it has enqueued its work; a call on a DIFFERENT stream first makes its stream
     // wait for that event, so two streams never overlap on the same scratch (WsUse below).
@@ -913,6 +914,17 @@ int hb_norm3_flagged_dev(void *stream, int64_t *chains, int64_t cap, int64_t *n)
     return HB_OK;
 }
 
+int hb_last_host_io(int64_t *h2d_bytes, int64_t *d2h_bytes, int64_t *rebuilt_bytes)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    Workspace *ws;
+    HBTRY(cur_ws(&ws));
+    if (h2d_bytes) *h2d_bytes = ws->io_h2d;
+    if (d2h_bytes) *d2h_bytes = ws->io_d2h;
+    if (rebuilt_bytes) *rebuilt_bytes = ws->io_rebuilt;
+    return HB_OK;
+}
+
 int hb_status_dev(void *stream)
 {
     std::lock_guard<std::mutex> lk(g_mu);
@@ -1105,11 +1117,20 @@ static void parallel_recon(const double *a, const double *c, double *out, size_t
     for (auto &t : th) t.join();
 }
 
-// HB_E2E_FULL_PLANES=1: download every posterior plane instead (A/B measurements)
+// HB_E2E_FULL_PLANES=1: download every posterior plane instead (A/B measurements);
+// HB_E2E_ADAPTIVE=1 (experiment, off): download the plane after all for a sub-batch whose slot's previous copy-out
+// job is still running.  Measured worse (1.71-1.74 vs 2.09-2.19 G steps/s, allele 2.22 vs 2.56): the enqueueing
+// thread runs sub-batches ahead of the GPU, so "job still running" is nearly always true and says nothing about
+// which side is the bottleneck.
 static bool recon_enabled()
 {
     const char *e = getenv("HB_E2E_FULL_PLANES");
     return !(e && atoi(e) != 0);
+}
+static bool recon_adaptive()
+{
+    const char *e = getenv("HB_E2E_ADAPTIVE");
+    return e && atoi(e) != 0;
 }
 
 struct HostStager {
@@ -1140,6 +1161,7 @@ struct HostStager {
     int init(Workspace *w, bool b_in, bool b_out, size_t in_bytes, size_t out_bytes, size_t y_count = 0)
     {
         ws = w;
+        w->io_h2d = w->io_d2h = w->io_rebuilt = 0;
         if (y_count && w->bounce_y_cap < y_count) {
             for (int k = 0; k < 2; k++) {
                 if (w->bounce_y[k]) cudaFreeHost(w->bounce_y[k]);
@@ -1184,6 +1206,7 @@ struct HostStager {
     }
     int h2d(int k, void *dev, const void *host, size_t bytes, cudaStream_t st)
     {
+        ws->io_h2d += (int64_t)bytes;
         const void *src = host;
         if (bounce_in) {
             char *b = (char *)ws->bounce_in[k] + off_in[k];
@@ -1212,12 +1235,14 @@ struct HostStager {
     // and widened into the caller's int32 array by the background task while the GPU works on
     int d2h_widen(int k, int32_t *host, const uint8_t *dev, size_t count, cudaStream_t st)
     {
+        ws->io_d2h += (int64_t)count;
         CU(cudaMemcpyAsync(ws->bounce_y[k], dev, count, cudaMemcpyDeviceToHost, st));
         pend_w[k].push_back({(const uint8_t *)ws->bounce_y[k], host, count});
         return HB_OK;
     }
     int d2h(int k, void *host, const void *dev, size_t bytes, cudaStream_t st)
     {
+        ws->io_d2h += (int64_t)bytes;
         void *dst = host;
         if (bounce_out) {
             char *b = (char *)ws->bounce_out[k] + off_out[k];
@@ -1227,6 +1252,11 @@ struct HostStager {
         }
         CU(cudaMemcpyAsync(dst, dev, bytes, cudaMemcpyDeviceToHost, st));
         return HB_OK;
+    }
+    // true while the copy-out job that last used slot k is still running: the host side is the bottleneck
+    bool host_busy(int k)
+    {
+        return fut[k].valid() && fut[k].wait_for(std::chrono::seconds(0)) != std::future_status::ready;
     }
     // after this slot's downloads (and copy-outs): out = |1 - (a + c)| on the caller's arrays
     void recon(int k, const double *a, const double *c, double *out, size_t count)
@@ -1354,7 +1384,7 @@ int hb_hmm_norm_host(const double *x, int64_t T, int64_t B, const int64_t *seg_o
     }
     HBTRY(pipe_init(ws));
     HBTRY(ws_use_.enter(ws, ws->s_cmp));
-    const bool recon = want_g && recon_enabled();
+    const bool recon_all = want_g && recon_enabled(), adaptive = recon_adaptive();
     // <= 512 columns per sub-batch: the pipeline's fill (first upload) and drain (last download + copy-out) are
     // one sub-batch each and are not overlapped with anything
     const int64_t Bc = pipe_batch(B, 130.0 * (double)T, T >= 4096 ? 512 : 1024);
@@ -1400,6 +1430,9 @@ int hb_hmm_norm_host(const double *x, int64_t T, int64_t B, const int64_t *seg_o
         const int k = (int)(i & 1);
         const int64_t b0 = i * Bc, bn = std::min(Bc, B - b0);
         const int64_t ld = (bn + 127) / 128 * 128;
+        // The neutral plane is rebuilt on the host unless the host is the bottleneck: if the copy-out job that
+        // last used this slot is still running, PCIe has slack and this sub-batch downloads all planes instead.
+        const bool recon = recon_all && !(adaptive && i >= 2 && hs.host_busy(k));
         // upload
         if (i >= 2) CU(cudaStreamWaitEvent(ws->s_in, ws->ev_free_in[k], 0));
         HBTRY(hs.begin_in(k, i >= 2));
@@ -1441,8 +1474,10 @@ int hb_hmm_norm_host(const double *x, int64_t T, int64_t B, const int64_t *seg_o
                              ws->pout_g[k].as<double>() + (int64_t)pl * T * bn,
                              (size_t)T * bn * sizeof(double), ws->s_out));
             }
-            if (recon)
+            if (recon) {
                 hs.recon(k, gamma + b0 * T, gamma + (2 * B + b0) * T, gamma + (B + b0) * T, (size_t)T * bn);
+                ws->io_rebuilt += (int64_t)T * bn * (int64_t)sizeof(double);
+            }
         }
         if (want_ll)
             for (int32_t sg = 0; sg < nseg; sg++)
@@ -1552,7 +1587,7 @@ int hb_hmm_binom_host(const int32_t *x, const int32_t *size, int64_t T, int64_t 
     }
     HBTRY(pipe_init(ws));
     HBTRY(ws_use_.enter(ws, ws->s_cmp));
-    const bool recon = want_g && recon_enabled();
+    const bool recon_all = want_g && recon_enabled(), adaptive = recon_adaptive();
     const int64_t Bc = pipe_batch(B, 100.0 * (double)T);
     const int64_t nb = (B + Bc - 1) / Bc;
     const int64_t ldc = (Bc + 127) / 128 * 128;
@@ -1579,6 +1614,7 @@ int hb_hmm_binom_host(const int32_t *x, const int32_t *size, int64_t T, int64_t 
         const int k = (int)(i & 1);
         const int64_t b0 = i * Bc, bn = std::min(Bc, B - b0);
         const int64_t ld = (bn + 127) / 128 * 128;
+        const bool recon = recon_all && !(adaptive && i >= 2 && hs.host_busy(k)); // see hb_hmm_norm_host
         if (i >= 2) CU(cudaStreamWaitEvent(ws->s_in, ws->ev_free_in[k], 0));
         HBTRY(hs.begin_in(k, i >= 2));
         HBTRY(hs.h2d(k, ws->pin[k].p, x + b0 * T, (size_t)T * bn * sizeof(int32_t), ws->s_in));
@@ -1613,7 +1649,10 @@ int hb_hmm_binom_host(const int32_t *x, const int32_t *size, int64_t T, int64_t 
                 HBTRY(hs.d2h(k, gamma + ((int64_t)pl * B + b0) * T,
                              ws->pout_g[k].as<double>() + (int64_t)pl * T * bn,
                              (size_t)T * bn * sizeof(double), ws->s_out));
-            if (recon) hs.recon(k, gamma + b0 * T, nullptr, gamma + (B + b0) * T, (size_t)T * bn);
+            if (recon) {
+                hs.recon(k, gamma + b0 * T, nullptr, gamma + (B + b0) * T, (size_t)T * bn);
+                ws->io_rebuilt += (int64_t)T * bn * (int64_t)sizeof(double);
+            }
         }
         if (want_ll)
             for (int32_t sg = 0; sg < nseg; sg++)

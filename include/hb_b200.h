@@ -88,6 +88,9 @@ int hb_norm3_flagged_dev(void *stream, int64_t *chains, int64_t cap, int64_t *n)
  * *binom2_lean = 1 lean plain-double kernel (general kernel behind its gate), 0 general kernel only.
  * Either pointer may be NULL.  Lets a caller (and the parity tests) assert which code path produced a result. */
 int hb_last_kernels(int32_t *norm3_fast, int32_t *binom2_lean);
+/* Bytes the last pipelined hb_hmm_*_host call moved host -> device and device -> host, and bytes of posterior
+ * planes it rebuilt on the host instead of downloading (the neutral-state plane).  Any pointer may be NULL. */
+int hb_last_host_io(int64_t *h2d_bytes, int64_t *d2h_bytes, int64_t *rebuilt_bytes);
 /* Binomial chains, kernel choice.  0 (default): the lean plain-double kernel, with the general
  * relative-exponent kernel re-running the launch when some position carries evidence beyond 2^+-900
  * (both enqueued, no synchronisation); 1: general kernel only.  Same results either way. */
