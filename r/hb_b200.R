@@ -197,3 +197,9 @@ hb_dev_retest_gexp <- function(dev, genes, cells, m, sigma0 = NULL) {
                 "estimated mean normalized expression deviation")
   p
 }
+## R/HoneyBADGER.R:1486 (calcAlleleCnvProb on r.maf[bound.snps.new, cells]) on the resident counts
+hb_dev_retest_allele <- function(dev, snps, cells, l.maf, n.bulk, geneFactor = NULL, pe = 0.1, mono = 0.7) {
+  gf <- if (is.null(geneFactor)) NULL else as.integer(factor(geneFactor, levels = unique(geneFactor)))
+  .Call("C_hb_retest_allele_dev", dev, snps, cells, as.double(l.maf), as.double(n.bulk), gf, as.double(pe),
+        as.double(mono))
+}

@@ -471,6 +471,36 @@ SEXP C_hb_retest_gexp_dev(SEXP ptr, SEXP rows, SEXP cols, SEXP mag0, SEXP sigma0
     return out;
 }
 
+/* pm <- .Call(C_hb_retest_allele_dev, dev, rows, cols, l.maf, n.bulk, gene, pe, mono): the snpModel marginal of
+ * R/HoneyBADGER.R:1486 on the resident counts; rows already grouped by gene, `gene` = integer factor codes of the
+ * rows (NULL: one gene per SNP).  Returns the 1 x length(cols) matrix calcAlleleCnvProb returns. */
+SEXP C_hb_retest_allele_dev(SEXP ptr, SEXP rows, SEXP cols, SEXP l_maf, SEXP n_bulk, SEXP gene, SEXP pe, SEXP mono)
+{
+    hb_handle *h = hb_handle_of(ptr);
+    int64_t G = 0, N = 0, nr = 0, nc = 0;
+    hb_raise(hb_handle_info(h, NULL, &G, &N, NULL));
+    SEXP kr, kc;
+    const int *r0 = hb_index0(rows, &kr, &nr);
+    PROTECT(kr);
+    const int *c0 = hb_index0(cols, &kc, &nc);
+    PROTECT(kc);
+    const int64_t G2 = r0 ? nr : G, N2 = c0 ? nc : N;
+    l_maf = PROTECT(Rf_coerceVector(l_maf, REALSXP));
+    n_bulk = PROTECT(Rf_coerceVector(n_bulk, REALSXP));
+    unsigned char *ge = NULL;
+    if (!Rf_isNull(gene)) { /* last SNP of every run of equal codes */
+        gene = Rf_coerceVector(gene, INTSXP);
+        ge = (unsigned char *)R_alloc((size_t)G2, 1);
+        for (int64_t j = 0; j < G2; j++) ge[j] = (j + 1 == G2) || INTEGER(gene)[j + 1] != INTEGER(gene)[j];
+    }
+    SEXP out = PROTECT(Rf_allocMatrix(REALSXP, 1, (int)N2));
+    int rc = hb_retest_allele_handle(h, r0, nr, c0, nc, REAL(l_maf), REAL(n_bulk), ge, Rf_asReal(pe), Rf_asReal(mono),
+                                     REAL(out));
+    UNPROTECT(5);
+    hb_raise(rc);
+    return out;
+}
+
 static const R_CallMethodDef call_methods[] = {
     {"C_hb_viterbi_norm", (DL_FUNC)&C_hb_viterbi_norm, 5},
     {"C_hb_viterbi_binom", (DL_FUNC)&C_hb_viterbi_binom, 5},
@@ -492,6 +522,7 @@ static const R_CallMethodDef call_methods[] = {
     {"C_hb_allele_round_dev", (DL_FUNC)&C_hb_allele_round_dev, 7},
     {"C_hb_group_dev", (DL_FUNC)&C_hb_group_dev, 5},
     {"C_hb_retest_gexp_dev", (DL_FUNC)&C_hb_retest_gexp_dev, 5},
+    {"C_hb_retest_allele_dev", (DL_FUNC)&C_hb_retest_allele_dev, 8},
     {NULL, NULL, 0}};
 
 void R_init_hbb200(DllInfo *dll)
