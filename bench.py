@@ -322,6 +322,9 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     _lib.load()
     _lib.check(_lib.load().hb_set_device(local))
+    # the ranks of one box share its cores: divide them for the host pipeline's copy-out threads
+    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 4)
+    _lib.check(_lib.load().hb_set_host_threads(max(2, min(16, (ncpu - 2) // max(1, world)))))
 
     cells, positions = wl["cells"], wl["positions"]
     d = device_inputs(kind, cells, positions, seed=100 + rank, dev=dev)

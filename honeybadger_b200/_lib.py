@@ -46,6 +46,7 @@ SIGNATURES = {
     "hb_last_host_io": (_i32, [C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "hb_last_kernels": (_i32, [C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "hb_set_binom_lut_max": (_i32, [_i32]),
+    "hb_set_host_threads": (_i32, [_i32]),
     "hb_set_norm3_mode": (_i32, [_i32]),
     "hb_set_binom2_mode": (_i32, [_i32]),
     "hb_binom2_stats_dev": (_i32, [_p, C.POINTER(C.c_int32)]),

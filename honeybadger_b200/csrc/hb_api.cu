@@ -179,6 +179,7 @@ struct Workspace {
 std::mutex g_mu;
 Workspace g_ws[16];
 int g_lut_nmax_cfg = 511;
+int g_host_threads = 0; // copy-out threads of the host pipeline; 0 = all but two of this process's CPUs (<= 16)
 // Kernel-choice switches are per calling thread (test / experiment hooks; two callers with different
 // settings do not interfere).
 thread_local int g_binom2_mode = 0; // 0 auto (lean kernel, general kernel behind its gate), 1 general kernel only
@@ -835,6 +836,14 @@ int hb_set_binom_lut_max(int32_t nmax)
     return HB_OK;
 }
 
+int hb_set_host_threads(int32_t n)
+{
+    if (n < 0 || n > 256) return fail(HB_ERR_ARG, "n must be in [0, 256]");
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_host_threads = n;
+    return HB_OK;
+}
+
 int hb_set_norm3_mode(int32_t mode)
 {
     if (mode < 0 || mode > 3)
@@ -1176,7 +1185,8 @@ struct HostStager {
         // fast PCIe (measured 16 threads 2.22 vs 8 threads 2.05 G steps/s on a 16-vCPU box): all but two cores
         {
             const unsigned hw = std::thread::hardware_concurrency();
-            nthreads = (int)std::max(1u, std::min(16u, hw > 4 ? hw - 2 : hw / 2));
+            nthreads = g_host_threads > 0 ? g_host_threads
+                                          : (int)std::max(1u, std::min(16u, hw > 4 ? hw - 2 : hw / 2));
         }
         if (const char *e = getenv("HB_STAGER_THREADS")) nthreads = std::max(1, atoi(e));
         for (int k = 0; k < 2; k++) {

@@ -70,6 +70,10 @@ int hb_release_workspace(void);
 /* *_dev entry points never synchronise; this waits for `stream` and returns HB_ERR_UNDERFLOW if a
  * chain of the last launch ended with nu == -Inf (HiddenMarkov::Viterbi's error), else HB_OK. */
 int hb_status_dev(void *stream);
+/* Host threads the pipelined hb_hmm_*_host calls use to copy results out of the pinned landing buffers, widen
+ * the states to R integers and rebuild the neutral posterior plane.  0 (default): all but two of the machine's
+ * cores, at most 16.  Several processes sharing one host (one per GPU) should divide the cores between them. */
+int hb_set_host_threads(int32_t n);
 /* Gaussian chains, kernel choice.  Two kernels compute the same results (identical Viterbi paths,
  * posteriors within 1e-11 of each other): the literal-arithmetic kernel, and the speculate-and-verify
  * kernel (eligible when the parameter block is the reference's symmetric one, delta[1] > 0 and no
