@@ -60,6 +60,12 @@ int fail(int code, const char *fmt, ...)
         if (rc_ != HB_OK) return rc_;                                                             \
     } while (0)
 
+// Slots of the host-buffer pipeline (staging buffers, events, copy-out jobs).  Two are enough to overlap upload |
+// compute | download, but the enqueueing thread waits for the copy-out job that last used a slot before it reuses
+// it, and with two slots that wait sat on the critical path (a 2.6 ms bubble on the link per 4 ms download at the
+// bench sizes, traced with HB_PIPE_TRACE): four let it run two sub-batches further ahead.
+#define HB_PIPE_SLOTS 4
+
 struct DevBuf {
     void *p = nullptr;
     size_t cap = 0;
@@ -101,16 +107,16 @@ struct Workspace {
     int32_t *lc_cstate = nullptr;
     DevBuf st_in, st_in2, st_x, st_x2, st_y, st_g, st_out, st_sd, st_ll, st_member, st_pool, st_pool2, st_pre, st_x80, st_part, st_inp, st_inp2, st_tab;
     // host-buffer entry points: three-stream pipeline (upload | layout + chains | download), staging x2
-    DevBuf pin[2], pin2[2], pout_y[2], pout_g[2], pout_ll[2];
+    DevBuf pin[HB_PIPE_SLOTS], pin2[HB_PIPE_SLOTS], pout_y[HB_PIPE_SLOTS], pout_g[HB_PIPE_SLOTS], pout_ll[HB_PIPE_SLOTS];
     // pinned bounce buffers for ordinary (pageable) host memory, e.g. R vectors: [slot]
-    void *bounce_in[2] = {nullptr, nullptr}, *bounce_out[2] = {nullptr, nullptr};
+    void *bounce_in[HB_PIPE_SLOTS] = {}, *bounce_out[HB_PIPE_SLOTS] = {};
     size_t bounce_in_cap = 0, bounce_out_cap = 0;
-    void *bounce_y[2] = {nullptr, nullptr}; // states cross PCIe as bytes and are widened to R integers here
+    void *bounce_y[HB_PIPE_SLOTS] = {}; // states cross PCIe as bytes and are widened to R integers here
     size_t bounce_y_cap = 0;
-    cudaEvent_t ev_bin[2] = {nullptr, nullptr}, ev_bout[2] = {nullptr, nullptr};
+    cudaEvent_t ev_bin[HB_PIPE_SLOTS] = {}, ev_bout[HB_PIPE_SLOTS] = {};
     cudaStream_t s_in = nullptr, s_cmp = nullptr, s_out = nullptr;
-    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_free_in[2] = {nullptr, nullptr},
-                ev_out[2] = {nullptr, nullptr}, ev_free_out[2] = {nullptr, nullptr};
+    cudaEvent_t ev_in[HB_PIPE_SLOTS] = {}, ev_free_in[HB_PIPE_SLOTS] = {},
+                ev_out[HB_PIPE_SLOTS] = {}, ev_free_out[HB_PIPE_SLOTS] = {};
     std::vector<int64_t> seg_cached;
     int64_t nchunks = 0;
     int32_t last_norm3_fast = -1, last_binom2_lean = -1; // kernels of the last launches (hb_last_kernels)
@@ -133,9 +139,12 @@ struct Workspace {
     {
         DevBuf *all[] = {&pool_fast, &fbr_gate, &flagged, &lc, &lc_fb, &lc_lb, &lc_y, &psi, &ckpt, &sdaux, &segtab, &status, &lut_lb, &lut_rho, &lut_rho_d, &cellmask, &gsize,
                          &st_in, &st_in2, &st_x, &st_x2, &st_y, &st_g, &st_out, &st_sd, &st_ll,
-                         &st_member, &st_pool, &st_pool2, &st_pre, &st_x80, &st_part, &st_inp, &st_inp2, &st_tab, &pin[0], &pin[1], &pin2[0], &pin2[1],
-                         &pout_y[0], &pout_y[1], &pout_g[0], &pout_g[1], &pout_ll[0], &pout_ll[1]};
+                         &st_member, &st_pool, &st_pool2, &st_pre, &st_x80, &st_part, &st_inp, &st_inp2, &st_tab};
         for (DevBuf *b : all) b->release();
+        for (int k = 0; k < HB_PIPE_SLOTS; k++) {
+            DevBuf *slot[] = {&pin[k], &pin2[k], &pout_y[k], &pout_g[k], &pout_ll[k]};
+            for (DevBuf *b : slot) b->release();
+        }
         lc_cstate = nullptr; // pointed into `lc`
         lc_K = 0;
         lc_nb = 0;
@@ -143,7 +152,7 @@ struct Workspace {
             cudaStreamDestroy(s_in);
             cudaStreamDestroy(s_cmp);
             cudaStreamDestroy(s_out);
-            for (int k = 0; k < 2; k++) {
+            for (int k = 0; k < HB_PIPE_SLOTS; k++) {
                 cudaEventDestroy(ev_in[k]);
                 cudaEventDestroy(ev_free_in[k]);
                 cudaEventDestroy(ev_out[k]);
@@ -151,7 +160,7 @@ struct Workspace {
             }
             s_in = s_cmp = s_out = nullptr;
         }
-        for (int k = 0; k < 2; k++) {
+        for (int k = 0; k < HB_PIPE_SLOTS; k++) {
             if (bounce_in[k]) cudaFreeHost(bounce_in[k]);
             if (bounce_out[k]) cudaFreeHost(bounce_out[k]);
             if (bounce_y[k]) cudaFreeHost(bounce_y[k]);
@@ -1127,10 +1136,14 @@ static void parallel_recon(const double *a, const double *c, double *out, size_t
 }
 
 // HB_E2E_FULL_PLANES=1: download every posterior plane instead (A/B measurements);
-// HB_E2E_ADAPTIVE=1 (experiment, off): download the plane after all for a sub-batch whose slot's previous copy-out
-// job is still running.  Measured worse (1.71-1.74 vs 2.09-2.19 G steps/s, allele 2.22 vs 2.56): the enqueueing
-// thread runs sub-batches ahead of the GPU, so "job still running" is nearly always true and says nothing about
-// which side is the bottleneck.
+// HB_E2E_ADAPTIVE=1 switches HostStager::plan()'s balancing on (off by default: every sub-batch rebuilds the
+// plane).  Measured with HB_PIPE_TRACE on a 55 GB/s box, 10 k x 20 k: the copy-out threads need 58 ms per pass
+// (0.07 + 0.22 ns per element), the downloads 79-87 ms at the 39-44 GB/s the link delivers while uploads and the
+// host threads run beside it — the call is link-bound with the plane rebuilt, so there is nothing to balance,
+// and with four slots in flight the per-job timings plan() relies on are inflated by the jobs overlapping
+// (100.9 ms with balancing vs 90.1 ms without).  A first heuristic ("download the plane when the slot's previous
+// copy-out job is still running") was worse still: the enqueueing thread runs ahead of the GPU, so that test is
+// nearly always true.
 static bool recon_enabled()
 {
     const char *e = getenv("HB_E2E_FULL_PLANES");
@@ -1161,18 +1174,102 @@ struct HostStager {
         double *out;
         size_t count;
     };
-    std::vector<Copy> pend[2];
-    std::vector<Widen> pend_w[2];
-    std::vector<Recon> pend_r[2];
-    std::future<void> fut[2];
-    size_t off_out[2] = {0, 0}, off_in[2] = {0, 0};
+    std::vector<Copy> pend[HB_PIPE_SLOTS];
+    std::vector<Widen> pend_w[HB_PIPE_SLOTS];
+    std::vector<Recon> pend_r[HB_PIPE_SLOTS];
+    std::future<void> fut[HB_PIPE_SLOTS];
+    size_t off_out[HB_PIPE_SLOTS] = {}, off_in[HB_PIPE_SLOTS] = {};
+    // ---- balance between the download link and the copy-out threads (plan()): per sub-batch the neutral
+    // posterior plane is either rebuilt by the host threads (less PCIe, more host work) or downloaded (the
+    // reverse); both sides are timed — CUDA events around the sub-batch's D2H copies, a clock inside the
+    // copy-out job — and each sub-batch takes the option that keeps the two cumulative loads level.
+    cudaEvent_t ev_t0[HB_PIPE_SLOTS] = {}, ev_t1[HB_PIPE_SLOTS] = {};
+    double job_other_s[HB_PIPE_SLOTS] = {}, job_recon_s[HB_PIPE_SLOTS] = {};
+    size_t slot_bytes[HB_PIPE_SLOTS] = {}, slot_elems[HB_PIPE_SLOTS] = {};
+    bool slot_recon[HB_PIPE_SLOTS] = {}, slot_used[HB_PIPE_SLOTS] = {};
+    double s_per_byte = 0, other_per_elem = 0, recon_per_elem = 0, cumD = 0, cumH = 0;
+    int n_link = 0, n_other = 0, n_recon = 0;
+    bool balance = false;
+
+    // Decide for sub-batch i (slot k, `elems` = positions x chains, S states): true = rebuild on the host.
+    bool plan(int k, size_t elems, int S, bool recon_allowed)
+    {
+        if (slot_used[k]) { // harvest the measurements of this slot's previous sub-batch
+            if (fut[k].valid()) fut[k].get();
+            float ms = 0;
+            if (ev_t0[k] && cudaEventElapsedTime(&ms, ev_t0[k], ev_t1[k]) == cudaSuccess && ms > 0 && slot_bytes[k]) {
+                const double v = ms * 1e-3 / (double)slot_bytes[k];
+                s_per_byte = n_link ? 0.7 * s_per_byte + 0.3 * v : v;
+                n_link++;
+            } else {
+                cudaGetLastError();
+            }
+            if (slot_elems[k]) {
+                const double o = job_other_s[k] / (double)slot_elems[k];
+                other_per_elem = n_other ? 0.7 * other_per_elem + 0.3 * o : o;
+                n_other++;
+                if (slot_recon[k]) {
+                    const double r = job_recon_s[k] / (double)slot_elems[k];
+                    recon_per_elem = n_recon ? 0.7 * recon_per_elem + 0.3 * r : r;
+                    n_recon++;
+                }
+            }
+        }
+        bool recon = recon_allowed;
+        if (recon_allowed && balance && n_link >= 1 && n_recon >= 1) {
+            const double b_r = (double)elems * (1 + 8.0 * (S - 1)), b_f = (double)elems * (1 + 8.0 * S);
+            const double Dr = b_r * s_per_byte, Df = b_f * s_per_byte;
+            const double Hr = (double)elems * (other_per_elem + recon_per_elem), Hf = (double)elems * other_per_elem;
+            recon = std::max(cumD + Dr, cumH + Hr) <= std::max(cumD + Df, cumH + Hf);
+            cumD += recon ? Dr : Df;
+            cumH += recon ? Hr : Hf;
+            const double base = std::min(cumD, cumH); // only the difference matters
+            cumD -= base;
+            cumH -= base;
+        }
+        slot_used[k] = true;
+        slot_recon[k] = recon;
+        slot_elems[k] = elems;
+        slot_bytes[k] = 0;
+        return recon;
+    }
+    int link_begin(int k, cudaStream_t st)
+    {
+        if (!ev_t0[k]) {
+            CU(cudaEventCreate(&ev_t0[k]));
+            CU(cudaEventCreate(&ev_t1[k]));
+        }
+        CU(cudaEventRecord(ev_t0[k], st));
+        return HB_OK;
+    }
+    int link_end(int k, cudaStream_t st)
+    {
+        CU(cudaEventRecord(ev_t1[k], st));
+        return HB_OK;
+    }
+    void trace(const char *what, int64_t T, int64_t B, double wall_s)
+    {
+        if (!getenv("HB_PIPE_TRACE")) return;
+        fprintf(stderr, "[hb pipe] %s T=%lld B=%lld wall %.1f ms | link %.1f GB/s (%d obs) | copy-out other %.2f ns/elem, "
+                        "rebuild %.2f ns/elem (%d threads) | d2h %.0f MB rebuilt %.0f MB\n",
+                what, (long long)T, (long long)B, wall_s * 1e3, s_per_byte > 0 ? 1e-9 / s_per_byte : 0.0, n_link,
+                other_per_elem * 1e9, recon_per_elem * 1e9, nthreads, ws->io_d2h / 1e6, ws->io_rebuilt / 1e6);
+    }
+    ~HostStager()
+    {
+        for (int k = 0; k < HB_PIPE_SLOTS; k++) {
+            if (fut[k].valid()) fut[k].get();
+            if (ev_t0[k]) cudaEventDestroy(ev_t0[k]);
+            if (ev_t1[k]) cudaEventDestroy(ev_t1[k]);
+        }
+    }
 
     int init(Workspace *w, bool b_in, bool b_out, size_t in_bytes, size_t out_bytes, size_t y_count = 0)
     {
         ws = w;
         w->io_h2d = w->io_d2h = w->io_rebuilt = 0;
         if (y_count && w->bounce_y_cap < y_count) {
-            for (int k = 0; k < 2; k++) {
+            for (int k = 0; k < HB_PIPE_SLOTS; k++) {
                 if (w->bounce_y[k]) cudaFreeHost(w->bounce_y[k]);
                 w->bounce_y[k] = nullptr;
                 CU(cudaHostAlloc(&w->bounce_y[k], y_count, cudaHostAllocDefault));
@@ -1189,7 +1286,7 @@ struct HostStager {
                                           : (int)std::max(1u, std::min(16u, hw > 4 ? hw - 2 : hw / 2));
         }
         if (const char *e = getenv("HB_STAGER_THREADS")) nthreads = std::max(1, atoi(e));
-        for (int k = 0; k < 2; k++) {
+        for (int k = 0; k < HB_PIPE_SLOTS; k++) {
             if (b_in && ws->bounce_in_cap < in_bytes) {
                 if (ws->bounce_in[k]) cudaFreeHost(ws->bounce_in[k]);
                 ws->bounce_in[k] = nullptr;
@@ -1246,6 +1343,7 @@ struct HostStager {
     int d2h_widen(int k, int32_t *host, const uint8_t *dev, size_t count, cudaStream_t st)
     {
         ws->io_d2h += (int64_t)count;
+        slot_bytes[k] += count;
         CU(cudaMemcpyAsync(ws->bounce_y[k], dev, count, cudaMemcpyDeviceToHost, st));
         pend_w[k].push_back({(const uint8_t *)ws->bounce_y[k], host, count});
         return HB_OK;
@@ -1253,6 +1351,7 @@ struct HostStager {
     int d2h(int k, void *host, const void *dev, size_t bytes, cudaStream_t st)
     {
         ws->io_d2h += (int64_t)bytes;
+        slot_bytes[k] += bytes;
         void *dst = host;
         if (bounce_out) {
             char *b = (char *)ws->bounce_out[k] + off_out[k];
@@ -1284,18 +1383,24 @@ struct HostStager {
         const int nt = nthreads;
         int dev = 0;
         cudaGetDevice(&dev);
-        fut[k] = std::async(std::launch::async, [ev, jobs, wjobs, rjobs, nt, dev] {
+        double *t_other = &job_other_s[k], *t_recon = &job_recon_s[k];
+        fut[k] = std::async(std::launch::async, [ev, jobs, wjobs, rjobs, nt, dev, t_other, t_recon] {
             cudaSetDevice(dev);
             cudaEventSynchronize(ev);
+            const auto c0 = std::chrono::steady_clock::now();
             for (const Copy &c : jobs) parallel_memcpy(c.dst, c.src, c.bytes, nt);
             for (const Widen &w : wjobs) parallel_widen(w.dst, w.src, w.count, nt);
+            const auto c1 = std::chrono::steady_clock::now();
             for (const Recon &r : rjobs) parallel_recon(r.a, r.c, r.out, r.count, nt);
+            const auto c2 = std::chrono::steady_clock::now();
+            *t_other = std::chrono::duration<double>(c1 - c0).count();
+            *t_recon = std::chrono::duration<double>(c2 - c1).count();
         });
         return HB_OK;
     }
     void finish()
     {
-        for (int k = 0; k < 2; k++)
+        for (int k = 0; k < HB_PIPE_SLOTS; k++)
             if (fut[k].valid()) fut[k].get();
     }
 };
@@ -1306,7 +1411,7 @@ static int pipe_init(Workspace *ws)
     CU(cudaStreamCreateWithFlags(&ws->s_in, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&ws->s_cmp, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&ws->s_out, cudaStreamNonBlocking));
-    for (int k = 0; k < 2; k++) {
+    for (int k = 0; k < HB_PIPE_SLOTS; k++) {
         CU(cudaEventCreateWithFlags(&ws->ev_in[k], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&ws->ev_free_in[k], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&ws->ev_out[k], cudaEventDisableTiming));
@@ -1394,15 +1499,15 @@ int hb_hmm_norm_host(const double *x, int64_t T, int64_t B, const int64_t *seg_o
     }
     HBTRY(pipe_init(ws));
     HBTRY(ws_use_.enter(ws, ws->s_cmp));
-    const bool recon_all = want_g && recon_enabled(), adaptive = recon_adaptive();
+    const bool recon_all = want_g && recon_enabled();
     // <= 512 columns per sub-batch: the pipeline's fill (first upload) and drain (last download + copy-out) are
     // one sub-batch each and are not overlapped with anything
-    const int64_t Bc = pipe_batch(B, 130.0 * (double)T, T >= 4096 ? 512 : 1024);
+    const int64_t Bc = pipe_batch(B, 200.0 * (double)T, T >= 4096 ? 512 : 1024);
     const int64_t nb = (B + Bc - 1) / Bc;
     const int64_t ldc = (Bc + 127) / 128 * 128;
     const int64_t nsd_seg = sd_per_seg ? nseg : 1;
     // every allocation before the first enqueue (cudaMalloc / cudaFree synchronise the device)
-    for (int k = 0; k < 2; k++) {
+    for (int k = 0; k < HB_PIPE_SLOTS; k++) {
         HBTRY(ws->pin[k].ensure((size_t)T * Bc * sizeof(double)));
         if (vit) HBTRY(ws->pout_y[k].ensure((size_t)T * Bc));
         if (want_g) HBTRY(ws->pout_g[k].ensure((size_t)3 * T * Bc * sizeof(double)));
@@ -1413,6 +1518,8 @@ int hb_hmm_norm_host(const double *x, int64_t T, int64_t B, const int64_t *seg_o
     if (want_g) HBTRY(ws->st_g.ensure((size_t)3 * T * ldc * sizeof(double)));
     HBTRY(ws->st_sd.ensure((size_t)nsd_seg * B * 3 * sizeof(double)));
     HostStager hs;
+    hs.balance = recon_adaptive();
+    const auto wall0 = std::chrono::steady_clock::now();
     HBTRY(hs.init(ws, !host_is_pinned(x),
                   !(host_is_pinned(want_g ? gamma : nullptr) && host_is_pinned(want_ll ? ll : nullptr)),
                   (size_t)T * Bc * sizeof(double) + 256,
@@ -1437,15 +1544,14 @@ int hb_hmm_norm_host(const double *x, int64_t T, int64_t B, const int64_t *seg_o
                        ws->s_cmp));
     int rc = HB_OK;
     for (int64_t i = 0; i < nb && rc == HB_OK; i++) {
-        const int k = (int)(i & 1);
+        const int k = (int)(i % HB_PIPE_SLOTS);
         const int64_t b0 = i * Bc, bn = std::min(Bc, B - b0);
         const int64_t ld = (bn + 127) / 128 * 128;
-        // The neutral plane is rebuilt on the host unless the host is the bottleneck: if the copy-out job that
-        // last used this slot is still running, PCIe has slack and this sub-batch downloads all planes instead.
-        const bool recon = recon_all && !(adaptive && i >= 2 && hs.host_busy(k));
+        // neutral plane: rebuilt on the host or downloaded, whichever keeps link and host threads level (plan())
+        const bool recon = want_g ? hs.plan(k, (size_t)T * bn, 3, recon_all) : false;
         // upload
-        if (i >= 2) CU(cudaStreamWaitEvent(ws->s_in, ws->ev_free_in[k], 0));
-        HBTRY(hs.begin_in(k, i >= 2));
+        if (i >= HB_PIPE_SLOTS) CU(cudaStreamWaitEvent(ws->s_in, ws->ev_free_in[k], 0));
+        HBTRY(hs.begin_in(k, i >= HB_PIPE_SLOTS));
         HBTRY(hs.h2d(k, ws->pin[k].p, x + b0 * T, (size_t)T * bn * sizeof(double), ws->s_in));
         HBTRY(hs.end_in(k, ws->s_in));
         CU(cudaEventRecord(ws->ev_in[k], ws->s_in));
@@ -1457,7 +1563,7 @@ int hb_hmm_norm_host(const double *x, int64_t T, int64_t B, const int64_t *seg_o
         uint8_t *d_y = vit ? ws->st_y.as<uint8_t>() : nullptr;
         double *d_g = want_g ? ws->st_g.as<double>() : nullptr;
         double *d_ll = want_ll ? ws->pout_ll[k].as<double>() : nullptr;
-        if (i >= 2) CU(cudaStreamWaitEvent(ws->s_cmp, ws->ev_free_out[k], 0));
+        if (i >= HB_PIPE_SLOTS) CU(cudaStreamWaitEvent(ws->s_cmp, ws->ev_free_out[k], 0));
         rc = norm3_run(ws, ws->st_x.as<double>(), ld, T, bn, seg_off, nseg, mean, d_sd,
                        d_sd + nsd_seg * bn, d_sd + 2 * nsd_seg * bn, sd_per_seg, Pi, delta, flags, d_y,
                        ld, d_g, ld, d_ll, ws->s_cmp, i == 0);
@@ -1475,6 +1581,7 @@ int hb_hmm_norm_host(const double *x, int64_t T, int64_t B, const int64_t *seg_o
         // download
         CU(cudaStreamWaitEvent(ws->s_out, ws->ev_out[k], 0));
         hs.begin_out(k);
+        HBTRY(hs.link_begin(k, ws->s_out));
         if (vit)
             HBTRY(hs.d2h_widen(k, y + b0 * T, ws->pout_y[k].as<uint8_t>(), (size_t)T * bn, ws->s_out));
         if (want_g) {
@@ -1493,6 +1600,7 @@ int hb_hmm_norm_host(const double *x, int64_t T, int64_t B, const int64_t *seg_o
             for (int32_t sg = 0; sg < nseg; sg++)
                 HBTRY(hs.d2h(k, ll + (int64_t)sg * B + b0, d_ll + (int64_t)sg * bn,
                              (size_t)bn * sizeof(double), ws->s_out));
+        HBTRY(hs.link_end(k, ws->s_out));
         CU(cudaEventRecord(ws->ev_free_out[k], ws->s_out));
         HBTRY(hs.end_out(k, ws->s_out));
     }
@@ -1501,6 +1609,7 @@ int hb_hmm_norm_host(const double *x, int64_t T, int64_t B, const int64_t *seg_o
     cudaStreamSynchronize(ws->s_cmp);
     cudaError_t e = cudaStreamSynchronize(ws->s_out);
     hs.finish();
+    hs.trace("host pipeline", T, B, std::chrono::duration<double>(std::chrono::steady_clock::now() - wall0).count());
     if (rc != HB_OK) return rc;
     if (e != cudaSuccess) return fail(HB_ERR_CUDA, "pipeline failed: %s", cudaGetErrorString(e));
     return read_status(ws, ws->s_cmp);
@@ -1597,11 +1706,11 @@ int hb_hmm_binom_host(const int32_t *x, const int32_t *size, int64_t T, int64_t 
     }
     HBTRY(pipe_init(ws));
     HBTRY(ws_use_.enter(ws, ws->s_cmp));
-    const bool recon_all = want_g && recon_enabled(), adaptive = recon_adaptive();
-    const int64_t Bc = pipe_batch(B, 100.0 * (double)T);
+    const bool recon_all = want_g && recon_enabled();
+    const int64_t Bc = pipe_batch(B, 160.0 * (double)T);
     const int64_t nb = (B + Bc - 1) / Bc;
     const int64_t ldc = (Bc + 127) / 128 * 128;
-    for (int k = 0; k < 2; k++) {
+    for (int k = 0; k < HB_PIPE_SLOTS; k++) {
         HBTRY(ws->pin[k].ensure((size_t)T * Bc * sizeof(int32_t)));
         HBTRY(ws->pin2[k].ensure((size_t)T * Bc * sizeof(int32_t)));
         if (vit) HBTRY(ws->pout_y[k].ensure((size_t)T * Bc));
@@ -1613,6 +1722,8 @@ int hb_hmm_binom_host(const int32_t *x, const int32_t *size, int64_t T, int64_t 
     if (vit) HBTRY(ws->st_y.ensure((size_t)T * ldc));
     if (want_g) HBTRY(ws->st_g.ensure((size_t)2 * T * ldc * sizeof(double)));
     HostStager hs;
+    hs.balance = recon_adaptive();
+    const auto wall0 = std::chrono::steady_clock::now();
     HBTRY(hs.init(ws, !(host_is_pinned(x) && host_is_pinned(size)),
                   !(host_is_pinned(want_g ? gamma : nullptr) && host_is_pinned(want_ll ? ll : nullptr)),
                   2 * ((size_t)T * Bc * sizeof(int32_t) + 256),
@@ -1621,12 +1732,12 @@ int hb_hmm_binom_host(const int32_t *x, const int32_t *size, int64_t T, int64_t 
                   vit ? (size_t)T * Bc : 0));
     int rc = HB_OK;
     for (int64_t i = 0; i < nb && rc == HB_OK; i++) {
-        const int k = (int)(i & 1);
+        const int k = (int)(i % HB_PIPE_SLOTS);
         const int64_t b0 = i * Bc, bn = std::min(Bc, B - b0);
         const int64_t ld = (bn + 127) / 128 * 128;
-        const bool recon = recon_all && !(adaptive && i >= 2 && hs.host_busy(k)); // see hb_hmm_norm_host
-        if (i >= 2) CU(cudaStreamWaitEvent(ws->s_in, ws->ev_free_in[k], 0));
-        HBTRY(hs.begin_in(k, i >= 2));
+        const bool recon = want_g ? hs.plan(k, (size_t)T * bn, 2, recon_all) : false; // see hb_hmm_norm_host
+        if (i >= HB_PIPE_SLOTS) CU(cudaStreamWaitEvent(ws->s_in, ws->ev_free_in[k], 0));
+        HBTRY(hs.begin_in(k, i >= HB_PIPE_SLOTS));
         HBTRY(hs.h2d(k, ws->pin[k].p, x + b0 * T, (size_t)T * bn * sizeof(int32_t), ws->s_in));
         HBTRY(hs.h2d(k, ws->pin2[k].p, size + b0 * T, (size_t)T * bn * sizeof(int32_t), ws->s_in));
         HBTRY(hs.end_in(k, ws->s_in));
@@ -1638,7 +1749,7 @@ int hb_hmm_binom_host(const int32_t *x, const int32_t *size, int64_t T, int64_t 
         uint8_t *d_y = vit ? ws->st_y.as<uint8_t>() : nullptr;
         double *d_g = want_g ? ws->st_g.as<double>() : nullptr;
         double *d_ll = want_ll ? ws->pout_ll[k].as<double>() : nullptr;
-        if (i >= 2) CU(cudaStreamWaitEvent(ws->s_cmp, ws->ev_free_out[k], 0));
+        if (i >= HB_PIPE_SLOTS) CU(cudaStreamWaitEvent(ws->s_cmp, ws->ev_free_out[k], 0));
         rc = binom2_run(ws, ws->st_x.as<int32_t>(), ws->st_x2.as<int32_t>(), ld, T, bn, seg_off, nseg,
                         prob, rho, Pi, delta, flags, d_y, ld, d_g, ld, d_ll, ws->s_cmp, i == 0);
         if (rc != HB_OK) break;
@@ -1652,6 +1763,7 @@ int hb_hmm_binom_host(const int32_t *x, const int32_t *size, int64_t T, int64_t 
         CU(cudaEventRecord(ws->ev_out[k], ws->s_cmp));
         CU(cudaStreamWaitEvent(ws->s_out, ws->ev_out[k], 0));
         hs.begin_out(k);
+        HBTRY(hs.link_begin(k, ws->s_out));
         if (vit)
             HBTRY(hs.d2h_widen(k, y + b0 * T, ws->pout_y[k].as<uint8_t>(), (size_t)T * bn, ws->s_out));
         if (want_g) {
@@ -1668,6 +1780,7 @@ int hb_hmm_binom_host(const int32_t *x, const int32_t *size, int64_t T, int64_t 
             for (int32_t sg = 0; sg < nseg; sg++)
                 HBTRY(hs.d2h(k, ll + (int64_t)sg * B + b0, d_ll + (int64_t)sg * bn,
                              (size_t)bn * sizeof(double), ws->s_out));
+        HBTRY(hs.link_end(k, ws->s_out));
         CU(cudaEventRecord(ws->ev_free_out[k], ws->s_out));
         HBTRY(hs.end_out(k, ws->s_out));
     }
@@ -1675,6 +1788,7 @@ int hb_hmm_binom_host(const int32_t *x, const int32_t *size, int64_t T, int64_t 
     cudaStreamSynchronize(ws->s_cmp);
     cudaError_t e = cudaStreamSynchronize(ws->s_out);
     hs.finish();
+    hs.trace("host pipeline", T, B, std::chrono::duration<double>(std::chrono::steady_clock::now() - wall0).count());
     if (rc != HB_OK) return rc;
     if (e != cudaSuccess) return fail(HB_ERR_CUDA, "pipeline failed: %s", cudaGetErrorString(e));
     return read_status(ws, ws->s_cmp);
