@@ -1362,11 +1362,6 @@ struct HostStager {
         CU(cudaMemcpyAsync(dst, dev, bytes, cudaMemcpyDeviceToHost, st));
         return HB_OK;
     }
-    // true while the copy-out job that last used slot k is still running: the host side is the bottleneck
-    bool host_busy(int k)
-    {
-        return fut[k].valid() && fut[k].wait_for(std::chrono::seconds(0)) != std::future_status::ready;
-    }
     // after this slot's downloads (and copy-outs): out = |1 - (a + c)| on the caller's arrays
     void recon(int k, const double *a, const double *c, double *out, size_t count)
     {
