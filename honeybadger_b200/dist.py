@@ -370,3 +370,102 @@ def _cur_stream():
     import ctypes as C
     import torch
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def sharded_allele_level(r_local, n_local, labels_local, n_cells, l_maf=None, n_bulk=None, pd_=0.1, pn=0.45, t=1e-6,
+                         min_num_snps=5, trim=0.1, pe=0.1, mono=0.7):
+    """One level of HoneyBADGER$calcAlleleCnvBoundaries (R/HoneyBADGER.R:1395-1551) with the CELLS SHARDED over the
+    ranks of the default process group.  r_local, n_local: this rank's columns of the resident lesser-allele /
+    coverage count matrices (gene-major int32 CUDA tensors); labels_local: one int array per cut height with
+    GLOBAL group ids.  Exchanges:
+
+      group sizes            int64 all-reduce
+      pooled counts          mafl / sizel of every group: per-rank `rowSums(. > 0)` + ONE int32 all-reduce — integers,
+                             so the K pooled chains are identical at any GPU count (R/HoneyBADGER.R:1404-1405)
+      bulk counts            l.maf / n.bulk of the level (rowSums over ALL its cells, :1563-1566) ride in the same
+                             all-reduce as an extra "all cells" group when the caller does not pass them
+      K pooled chains        none (every rank runs them, parallel along the gene axis, hb_longchain.cuh)
+      retest of every run    none: the snpModel marginal is per cell given the bulk counts (hb_retest_allele_model_dev)
+      per-region posteriors  all-gather [runs, N_local] -> [runs, n_cells]
+
+    Returns a dict identical on every rank (y, mafl, sizel, runs, prob, chosen, g1, g2, collectives)."""
+    import torch
+    import torch.distributed as dist
+    from . import _lib, hmm
+    from .honeybadger import retest_allele_model, runs_from_vote
+    lib = _lib.load()
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    G, n_loc = r_local.shape
+    device = r_local.device
+    used = []
+    ids = [np.asarray(l, dtype=np.int64) for l in labels_local]
+    nid = int(max((int(l.max()) if l.size else 0) for l in ids)) + 1
+    if world > 1:
+        mx = torch.tensor([nid], dtype=torch.int64, device=device)
+        _all_reduce(mx, dist.ReduceOp.MAX)
+        nid = int(mx.item())
+    counts = torch.zeros((len(ids), nid), dtype=torch.int64, device=device)
+    for h, l in enumerate(ids):
+        if l.size:
+            counts[h] += torch.bincount(torch.as_tensor(l, device=device), minlength=nid)
+    if world > 1:
+        _all_reduce(counts)
+        used.append("all_reduce(int64 group sizes)")
+    counts = counts.cpu().numpy()
+    groups = [(h, g) for h in range(len(ids)) for g in range(nid) if counts[h, g] > 1]
+    first = {}                     # vote counts only b[[1]]: the first group of each height (:1424-1426) — the
+    for h in range(len(ids)):      # group of the level's FIRST cell, which lives on rank 0
+        f0 = torch.tensor([int(ids[h][0]) if (n_loc and (not dist.is_initialized() or dist.get_rank() == 0)) else 0],
+                          dtype=torch.int64, device=device)
+        if world > 1:
+            _broadcast(f0, 0)
+        first[h] = int(f0.item())
+    K = len(groups)
+    out = {"collectives": used, "K": K}
+    if K == 0:
+        return out
+    want_bulk = l_maf is None or n_bulk is None
+    member = np.stack([(ids[h] == g) for h, g in groups] + ([np.ones(n_loc, bool)] if want_bulk else []))
+    member = np.ascontiguousarray(member.astype(np.uint8).reshape(-1, n_loc))
+    Kx = member.shape[0]
+    md = torch.from_numpy(member).to(device)
+    cnt = torch.zeros((2, Kx, G), dtype=torch.int32, device=device)
+    if n_loc > 0:
+        for i, m in enumerate((r_local, n_local)):
+            _lib.check(lib.hb_pool_count_pos_dev(m.data_ptr(), m.stride(0), G, n_loc, md.data_ptr(), Kx,
+                                                 cnt[i].data_ptr(), _cur_stream()))
+    if world > 1:
+        _all_reduce(cnt)
+        used.append("all_reduce(int32 pooled counts)")
+    cnt_h = cnt.cpu().numpy()
+    mafl, sizel = cnt_h[0, :K], cnt_h[1, :K]
+    if want_bulk:
+        l_maf, n_bulk = cnt_h[0, K].astype(np.float64), cnt_h[1, K].astype(np.float64)
+    res = hmm.hmm_binom_host(np.ascontiguousarray(mafl.T), np.ascontiguousarray(sizel.T), [pd_, pn], hmm.sym_Pi(2, t),
+                             [0.0, 1.0])
+    y = np.ascontiguousarray(res["y"].T)
+    out.update({"y": y, "mafl": mafl, "sizel": sizel})
+    vote = np.zeros(G, np.int64)
+    for k, (h, g) in enumerate(groups):
+        if g == first[h]:
+            vote += y[k] == 1
+    runs = runs_from_vote(vote, min_num_snps, trim) or []
+    out["runs"] = runs
+    if not runs:
+        return out
+    rows_local = []
+    for idx in runs:
+        it = torch.as_tensor(np.asarray(idx, dtype=np.int64), device=device)
+        rows_local.append(retest_allele_model(r_local.index_select(0, it), n_local.index_select(0, it),
+                                              np.asarray(l_maf)[idx], np.asarray(n_bulk)[idx], pe=pe, mono=mono,
+                                              keep_on_device=True) if n_loc > 0 else
+                          torch.zeros(0, dtype=torch.float64, device=device))
+    prob = allgather_region_posteriors(torch.stack(rows_local), n_cells)
+    if world > 1:
+        used.append("all_gather(per-region posteriors)")
+    prob = prob.cpu().numpy()
+    dps = (prob > 0.75).sum(1)
+    dpsi = int(np.nonzero(dps == dps.max())[0][0]) if len(runs) > 1 else 0
+    out.update({"prob": prob, "chosen": dpsi, "g1": np.nonzero(prob[dpsi] > 0.75)[0],
+                "g2": np.nonzero(prob[dpsi] <= 0.25)[0]})
+    return out

@@ -57,6 +57,10 @@ def _worker(rank, world, port, q):
         x, labels = make_case()
         G, N = x.shape
         ref = hd.sharded_gexp_level(hmm.to_rows(torch.from_numpy(x).cuda()), labels, N, synth.DEV)
+        ra, na, _, clone_a = synth.allele(4000, 150, seed=5)
+        labs_a = [np.zeros(150, np.int64), (clone_a != clone_a[0]).astype(np.int64), clone_a.astype(np.int64)]
+        ref_a = hd.sharded_allele_level(hmm.to_rows(torch.from_numpy(ra).cuda()), hmm.to_rows(torch.from_numpy(na).cuda()),
+                                        labs_a, 150)
         os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
         dist.init_process_group("gloo", rank=rank, world_size=world)
         lo, hi = hd.shard_range(N, rank, world)
@@ -64,6 +68,20 @@ def _worker(rank, world, port, q):
         got = hd.sharded_gexp_level(xl, [l[lo:hi] for l in labels], N, synth.DEV)
         ok = compare_levels(got, ref) and len(got["runs"]) > 0 and len(got["collectives"]) == 4
         ok = ok and got["g1"].size > 10
+        # the allele level: integer exchanges only, so EVERYTHING is exact at any rank count
+        r, n, _, clone = synth.allele(4000, 150, seed=5)
+        idx = np.arange(150)
+        labs = [np.zeros(150, np.int64), (clone != clone[0]).astype(np.int64), clone.astype(np.int64)]
+        lo, hi = hd.shard_range(150, rank, world)
+        rd = hmm.to_rows(torch.from_numpy(np.ascontiguousarray(r[:, lo:hi])).cuda())
+        nd = hmm.to_rows(torch.from_numpy(np.ascontiguousarray(n[:, lo:hi])).cuda())
+        ga = hd.sharded_allele_level(rd, nd, [l[lo:hi] for l in labs], 150)
+        dist.barrier()
+        ok = ok and len(ga["collectives"]) == 3 and np.array_equal(ga["y"], ref_a["y"]) \
+            and np.array_equal(ga["mafl"], ref_a["mafl"]) and np.array_equal(ga["sizel"], ref_a["sizel"]) \
+            and len(ga["runs"]) == len(ref_a["runs"]) and len(ga["runs"]) > 0 \
+            and all(np.array_equal(p, q) for p, q in zip(ga["runs"], ref_a["runs"])) \
+            and np.array_equal(ga["prob"], ref_a["prob"]) and np.array_equal(ga["g1"], ref_a["g1"])
         dist.destroy_process_group()
         q.put((rank, bool(ok), ""))
     except Exception as e:  # noqa: BLE001
