@@ -1010,7 +1010,9 @@ int hb_forwardback_norm_cm_dev(const double *x, int64_t T, int64_t B, const int6
         if (L < 0) return fail(HB_ERR_ARG, "seg_off must be non-decreasing");
         if (L == 0) continue;
         // lanes per chain: pieces of <= ~32 positions while a block (<= 4 warps) can hold the chain
-        const int nw = L <= 1024 ? 1 : (L <= 2048 ? 2 : 4);
+        int nw = L <= 1024 ? 1 : (L <= 2048 ? 2 : 4);
+        if (const char *e = getenv("HB_FBR_NW")) // experiment knob: warps per chain (1, 2, 4)
+            if (atoi(e) == 1 || atoi(e) == 2 || atoi(e) == 4) nw = atoi(e);
         int m = 0;
         const size_t smem = hb::fbr_smem_bytes((int)L, nw, &m);
         if (smem > 220 * 1024)
