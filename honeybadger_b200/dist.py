@@ -107,10 +107,11 @@ def pooled_allele_round(r_local, n_local, member_local, pd_=0.1, pn=0.45, t=1e-6
     return np.ascontiguousarray(out["y"].T), mafl, sizel
 
 
-def allgather_region_posteriors(local, n_cells: int):
+def allgather_region_posteriors(local, n_cells: int, sizes=None):
     """local: [regions, cells_of_this_rank] -> [regions, n_cells] on every rank (cells in global order).
 
-    Shards may differ by one cell, so blocks are padded to the largest shard for the fixed-size
+    Shards may differ in size (by one cell for the contiguous sharding; arbitrarily for the sub-populations of a
+    recursion, `sizes` = cells of every rank), so blocks are padded to the largest shard for the fixed-size
     all-gather and trimmed afterwards."""
     import torch
     import torch.distributed as dist
@@ -118,7 +119,7 @@ def allgather_region_posteriors(local, n_cells: int):
     if not (dist.is_initialized() and dist.get_world_size() > 1):
         return local
     world = dist.get_world_size()
-    sizes = shard_sizes(n_cells, world)
+    sizes = shard_sizes(n_cells, world) if sizes is None else [int(v) for v in sizes]
     mx = max(sizes)
     pad = torch.zeros((local.shape[0], mx), dtype=local.dtype, device=local.device)
     pad[:, :local.shape[1]] = local
@@ -257,7 +258,7 @@ def pooled_mean_relay(x_local, member_local, group_sizes, accumulate=None, chunk
 
 # --------------------------------------------------------------------------- one sharded recursion level
 def sharded_gexp_level(x_local, labels_local, n_cells, dev_mag, t=1e-6, min_num_genes=10, sigma0_local=None,
-                       mean_local=None):
+                       mean_local=None, local_sizes=None):
     """One level of HoneyBADGER$calcGexpCnvBoundaries (R/HoneyBADGER.R:1135-1298) with the CELLS SHARDED over the
     ranks of the default process group (one process per GPU; world = 1 runs the same code without exchanges).
 
@@ -347,15 +348,18 @@ def sharded_gexp_level(x_local, labels_local, n_cells, dev_mag, t=1e-6, min_num_
         args = (x_local.data_ptr(), x_local.stride(0), G, n_loc, rows.data_ptr(), rows.numel(), float(dev_mag),
                 None if sig is None else sig.data_ptr(), pa.data_ptr(), pdl.data_ptr(), None)
         if world > 1:
-            _lib.check(lib.hb_retest_gexp_dev(*args, d_loc.data_ptr(), None, 1, st))
+            d_loc.zero_()
+            if n_loc > 0:
+                _lib.check(lib.hb_retest_gexp_dev(*args, d_loc.data_ptr(), None, 1, st))
             _all_reduce(d_loc)
-            _lib.check(lib.hb_retest_gexp_dev(*args, None, d_loc.data_ptr(), 2, st))
+            if n_loc > 0:
+                _lib.check(lib.hb_retest_gexp_dev(*args, None, d_loc.data_ptr(), 2, st))
         else:
             _lib.check(lib.hb_retest_gexp_dev(*args, None, None, 0, st))
         rows_local.append((pdl if kind == "del" else pa).clone())
     if world > 1:
         used.append("all_reduce(fp64 direction evidence) per run")
-    prob = allgather_region_posteriors(torch.stack(rows_local), n_cells)
+    prob = allgather_region_posteriors(torch.stack(rows_local), n_cells, sizes=local_sizes)
     if world > 1:
         used.append("all_gather(per-region posteriors)")
     prob = prob.cpu().numpy()
@@ -469,3 +473,67 @@ def sharded_allele_level(r_local, n_local, labels_local, n_cells, l_maf=None, n_
     out.update({"prob": prob, "chosen": dpsi, "g1": np.nonzero(prob[dpsi] > 0.75)[0],
                 "g2": np.nonzero(prob[dpsi] <= 0.25)[0]})
     return out
+
+
+class ShardedGexpDriver:
+    """HoneyBADGER$calcGexpCnvBoundaries(init = TRUE) with its recursion (R/HoneyBADGER.R:1091-1316) on cells SHARDED
+    over the ranks: every level is `sharded_gexp_level` on the level's cells (each rank gathers ITS members of the
+    sub-population on the device, ranks may hold none), the split sets g1 / g2 come back as global cell ids and the
+    recursion continues on them with the found genes removed (`vi <- !(rownames %in% bound.genes.old)`, :1110).
+    Group labels come from `labels_fn(cell_ids, heights)` -> one int array per height over those cells (GLOBAL ids;
+    dist + hclust over the cells of all ranks is an input at these sizes).  Results — identical on
+    every rank and to a single rank holding every cell (tests/test_gpu_sharded.py): `bound_genes_final` (list of gene
+    index arrays, the reference's bound.genes.final), `regions` (genes, g1 cells), `bound_genes_old`."""
+
+    def __init__(self, x_local, n_cells, dev_mag, labels_fn, t=1e-6, min_traverse=5, min_num_genes=10, max_depth=32):
+        import torch.distributed as dist
+        self.x, self.n_cells, self.dev = x_local, int(n_cells), float(dev_mag)
+        self.labels_fn, self.t, self.H, self.min_genes, self.max_depth = labels_fn, t, min_traverse, min_num_genes, max_depth
+        world = dist.get_world_size() if dist.is_initialized() else 1
+        rank = dist.get_rank() if dist.is_initialized() else 0
+        self.world = world
+        self.lo, self.hi = shard_range(self.n_cells, rank, world)
+        assert x_local.shape[1] == self.hi - self.lo, "x_local must hold this rank's contiguous block of cells"
+        self.bound_genes_old = np.zeros(0, dtype=np.int64)
+        self.bound_genes_final, self.regions, self.levels = [], [], 0
+
+    def run(self):
+        self._level(np.arange(self.n_cells, dtype=np.int64), 0)
+        return self
+
+    def _level(self, cells, depth):
+        import torch
+        import torch.distributed as dist
+        from .hmm import to_rows
+        self.levels += 1
+        G = self.x.shape[0]
+        genes = np.setdiff1d(np.arange(G, dtype=np.int64), self.bound_genes_old)   # keeps genomic order
+        mine = cells[(cells >= self.lo) & (cells < self.hi)]
+        dev = self.x.device
+        xs = self.x.index_select(0, torch.as_tensor(genes, device=dev))
+        xs = to_rows(xs.index_select(1, torch.as_tensor(mine - self.lo, device=dev)).contiguous()) if mine.size else \
+            torch.zeros((genes.size, 0), dtype=torch.float64, device=dev)
+        heights = list(range(1, min(self.H, cells.size) + 1))
+        labels = self.labels_fn(cells, heights)
+        sel = (cells >= self.lo) & (cells < self.hi)
+        sizes = None
+        if self.world > 1:
+            cnt = torch.zeros(self.world, dtype=torch.int64, device=dev)
+            cnt[dist.get_rank()] = int(mine.size)
+            _all_reduce(cnt)
+            sizes = cnt.cpu().numpy().tolist()
+        lvl = sharded_gexp_level(xs, [np.asarray(l)[sel] for l in labels], cells.size, self.dev, t=self.t,
+                                 min_num_genes=self.min_genes, local_sizes=sizes)
+        if not lvl.get("runs"):
+            return
+        bound_new = genes[lvl["runs"][lvl["chosen"]]]
+        g1, g2 = cells[lvl["g1"]], cells[lvl["g2"]]
+        if g1.size:
+            self.bound_genes_final.append(bound_new)
+            self.regions.append({"genes": bound_new, "cells": g1, "kind": lvl["kinds"][lvl["chosen"]], "depth": depth})
+        self.bound_genes_old = np.union1d(self.bound_genes_old, bound_new)
+        if depth + 1 >= self.max_depth:
+            return
+        for g in (g1, g2):
+            if g.size >= 3:
+                self._level(g, depth + 1)

@@ -51,6 +51,23 @@ def allele_case(G=16000, N=220, seed=5):
     return r, n, labels
 
 
+def labels_fn_for(labels):
+    """labels_fn of ShardedGexpDriver from full-population label arrays (nested cuts of the clone tree)"""
+    def fn(cells, heights):
+        return [np.asarray(labels[h - 1])[cells] for h in heights]
+    return fn
+
+
+def compare_drivers(a, b):
+    assert a.levels == b.levels and len(a.bound_genes_final) == len(b.bound_genes_final) >= 2
+    for p, q in zip(a.bound_genes_final, b.bound_genes_final):
+        assert np.array_equal(p, q)
+    for p, q in zip(a.regions, b.regions):
+        assert np.array_equal(p["cells"], q["cells"]) and p["kind"] == q["kind"] and p["depth"] == q["depth"]
+    assert np.array_equal(a.bound_genes_old, b.bound_genes_old)
+    return True
+
+
 def compare_levels(a, b, tol=1e-12):
     """sharded result `a` vs single-rank result `b`: exact except the retest posteriors (one fp64 all-reduce)."""
     assert a["K"] == b["K"]
@@ -76,6 +93,7 @@ def _worker(rank, world, port, q):
         x, labels = make_case()
         G, N = x.shape
         ref = hd.sharded_gexp_level(hmm.to_rows(torch.from_numpy(x).cuda()), labels, N, synth.DEV)
+        ref_drv = hd.ShardedGexpDriver(hmm.to_rows(torch.from_numpy(x).cuda()), N, synth.DEV, labels_fn_for(labels)).run()
         ra, na, labs_a = allele_case()
         ref_a = hd.sharded_allele_level(hmm.to_rows(torch.from_numpy(ra).cuda()), hmm.to_rows(torch.from_numpy(na).cuda()),
                                         labs_a, ra.shape[1])
@@ -86,6 +104,9 @@ def _worker(rank, world, port, q):
         got = hd.sharded_gexp_level(xl, [l[lo:hi] for l in labels], N, synth.DEV)
         ok = compare_levels(got, ref) and len(got["runs"]) > 0 and len(got["collectives"]) == 4
         ok = ok and got["g1"].size > 10
+        # the whole recursion on sharded cells (sub-populations unevenly spread over the ranks) == one rank
+        drv = hd.ShardedGexpDriver(xl, N, synth.DEV, labels_fn_for(labels)).run()
+        ok = ok and compare_drivers(drv, ref_drv)
         # the allele level: integer exchanges only, so EVERYTHING is exact at any rank count
         r, n, labs = allele_case()
         lo, hi = hd.shard_range(r.shape[1], rank, world)
