@@ -81,15 +81,16 @@ def compare_levels(a, b, tol=1e-12):
     return True
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, backend="gloo"):
     try:
         import torch
         import torch.distributed as dist
         sys.path.insert(0, ROOT)
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         from honeybadger_b200 import _lib, dist as hd, hmm, synth
-        torch.cuda.set_device(0)
-        _lib.check(_lib.load().hb_set_device(0))
+        devno = rank if backend == "nccl" else 0    # gloo: the ranks share cuda:0 (single-GPU boxes)
+        torch.cuda.set_device(devno)
+        _lib.check(_lib.load().hb_set_device(devno))
         x, labels = make_case()
         G, N = x.shape
         ref = hd.sharded_gexp_level(hmm.to_rows(torch.from_numpy(x).cuda()), labels, N, synth.DEV)
@@ -98,7 +99,10 @@ def _worker(rank, world, port, q):
         ref_a = hd.sharded_allele_level(hmm.to_rows(torch.from_numpy(ra).cuda()), hmm.to_rows(torch.from_numpy(na).cuda()),
                                         labs_a, ra.shape[1])
         os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
-        dist.init_process_group("gloo", rank=rank, world_size=world)
+        if backend == "nccl":
+            dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", devno))
+        else:
+            dist.init_process_group("gloo", rank=rank, world_size=world)
         lo, hi = hd.shard_range(N, rank, world)
         xl = hmm.to_rows(torch.from_numpy(np.ascontiguousarray(x[:, lo:hi])).cuda())
         got = hd.sharded_gexp_level(xl, [l[lo:hi] for l in labels], N, synth.DEV)
@@ -132,12 +136,18 @@ def _worker(rank, world, port, q):
         q.put((rank, False, traceback.format_exc()[-1500:]))
 
 
-def test_sharded_level_equals_single_rank_level():
+@pytest.mark.parametrize("backend", ["gloo", "nccl"])
+def test_sharded_level_equals_single_rank_level(backend):
+    """levels (expression + allele) and the whole expression recursion, sharded over two ranks vs one rank;
+    gloo: both ranks on cuda:0; nccl: one GPU per rank (skipped on a single-GPU box)"""
+    import torch
     import torch.multiprocessing as mp
+    if backend == "nccl" and torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    ps = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    ps = [ctx.Process(target=_worker, args=(r, 2, port, q, backend)) for r in range(2)]
     for p in ps:
         p.start()
     res = [q.get(timeout=300) for _ in ps]
