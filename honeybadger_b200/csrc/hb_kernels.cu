@@ -16,6 +16,7 @@
 #include "hb_norm3_fast.cuh"
 #include "hb_norm3_resident.cuh"
 #include "hb_x87.cuh"
+#include "hb_x87_pair.cuh"
 
 namespace hb {
 
@@ -995,6 +996,12 @@ cudaError_t launch_ward(double *D, int64_t N, int32_t *size, uint8_t *active, in
 // slabs so that global reads stay coalesced along the cell axis.
 #define PM_TC 64
 #define PM_KB 16
+// One step of either pass on the double-pair form of the 80-bit state (hb_x87_pair.cuh): pass 0 adds v,
+// pass 1 adds RN64(v - mean) with `negmean` = -mean.  Two roundings in pass 1, as R's loop has them.
+__device__ __forceinline__ x80p pool_step(x80p S, x80p negmean, double v, bool centred)
+{
+    return centred ? x80p_add(S, x80p_add_double(negmean, v)) : x80p_add_double(S, v);
+}
 __global__ void __launch_bounds__(32 * PM_KB)
     pool_accum_kernel(const double *x, int64_t ld, int64_t G, int64_t N, const uint8_t *member,
                       int32_t K, const x80 *mean80, x80 *state)
@@ -1008,9 +1015,9 @@ __global__ void __launch_bounds__(32 * PM_KB)
         const bool live = k < K && g0 + lane < G;
         const uint8_t *mem = member + (int64_t)(live ? k : 0) * N;
         const int64_t si = (int64_t)(live ? k : 0) * G + (live ? g0 + lane : 0);
-        x80 S = live ? state[si] : x80_zero();
+        x80p S = x80p_from_x80(live ? state[si] : x80_zero());
         const bool centred = mean80 != nullptr;
-        const x80 M = (live && centred) ? mean80[si] : x80_zero();
+        const x80p M = x80p_from_x80((live && centred) ? x80_neg(mean80[si]) : x80_zero());
         for (int64_t c0 = 0; c0 < N; c0 += PM_TC) {
             __syncthreads();
             for (int i = tid; i < 32 * PM_TC; i += 32 * PM_KB) {
@@ -1022,14 +1029,11 @@ __global__ void __launch_bounds__(32 * PM_KB)
             if (live) {
                 const int lim = (int)((N - c0) < PM_TC ? (N - c0) : PM_TC);
                 for (int cc = 0; cc < lim; cc++) {
-                    if (mem[c0 + cc]) {
-                        x80 v = x80_from_double(tile[lane][cc]);
-                        S = x80_add(S, centred ? x80_sub(v, M) : v);
-                    }
+                    if (mem[c0 + cc]) S = pool_step(S, M, tile[lane][cc], centred);
                 }
             }
         }
-        if (live) state[si] = S;
+        if (live) state[si] = x80_from_x80p(S);
     }
 }
 
@@ -1059,6 +1063,7 @@ __global__ void __launch_bounds__(32) pool_cells_kernel(const uint8_t *member, i
     if (lane == 0) count[k] = n;
 }
 
+template <bool CENTRED>
 __global__ void __launch_bounds__(128)
     pool_accum_cm_kernel(const double *xc, int64_t G, int64_t N, const int32_t *cells, const int32_t *count,
                          const int32_t *order, int32_t K, const x80 *mean80, x80 *state)
@@ -1071,9 +1076,9 @@ __global__ void __launch_bounds__(128)
     const bool live = g < G;
     const int64_t gi = live ? g : G - 1; // lanes past the last gene repeat it (uniform loop, result dropped)
     const int64_t si = (int64_t)k * G + gi;
-    const bool centred = mean80 != nullptr;
-    x80 S = state[si];
-    const x80 M = centred ? x80_neg(mean80[si]) : x80_zero();
+    constexpr bool centred = CENTRED;
+    x80p S = x80p_from_x80(state[si]);
+    const x80p M = x80p_from_x80(centred ? x80_neg(mean80[si]) : x80_zero());
     const int32_t *cl = cells + (int64_t)k * N;
     const int32_t n = count[k];
     const double *col = xc + gi;
@@ -1089,16 +1094,12 @@ __global__ void __launch_bounds__(128)
         }
 #pragma unroll
         for (int u = 0; u < PA_U; u++) {
-            const x80 t = x80_from_double(v[u]);
-            S = x80_add(S, centred ? x80_add(t, M) : t);
+            S = pool_step(S, M, v[u], centred);
             v[u] = w[u];
         }
     }
-    for (int u = 0; i + u < n; u++) {
-        const x80 t = x80_from_double(v[u]);
-        S = x80_add(S, centred ? x80_add(t, M) : t);
-    }
-    if (live) state[si] = S;
+    for (int u = 0; i + u < n; u++) S = pool_step(S, M, v[u], centred);
+    if (live) state[si] = x80_from_x80p(S);
 }
 
 // pass 0 closed: mean80 = state / n[k]
@@ -1152,7 +1153,10 @@ cudaError_t launch_pool_accum_fast(int64_t G, int64_t N, int32_t K, const int32_
     const int32_t *cells = (const int32_t *)((const char *)scratch + (((size_t)G * N * sizeof(double) + 255) & ~(size_t)255));
     const int32_t *count = cells + (size_t)K * N;
     const dim3 grid((unsigned)((G + 127) / 128), (unsigned)K);
-    pool_accum_cm_kernel<<<grid, 128, 0, st>>>(xc, G, N, cells, count, order, K, (const x80 *)mean80, (x80 *)state);
+    if (mean80)
+        pool_accum_cm_kernel<true><<<grid, 128, 0, st>>>(xc, G, N, cells, count, order, K, (const x80 *)mean80, (x80 *)state);
+    else
+        pool_accum_cm_kernel<false><<<grid, 128, 0, st>>>(xc, G, N, cells, count, order, K, nullptr, (x80 *)state);
     return cudaGetLastError();
 }
 cudaError_t launch_pool_div(const void *state, const int32_t *n, int64_t G, int32_t K, void *mean80,

@@ -67,6 +67,11 @@ def emul():
     L.emul_x87_sd.argtypes = [C.c_void_p, C.c_int64]
     L.emul_x87_addcheck.restype = C.c_int64
     L.emul_x87_addcheck.argtypes = [C.c_void_p, C.c_int64, C.c_double, C.c_int]
+    L.emul_x87_paircheck.restype = C.c_int64
+    L.emul_x87_paircheck.argtypes = [C.c_void_p, C.c_int64, C.c_double, C.c_double, C.c_int, C.c_void_p]
+    L.emul_x87_pair_add80.restype = C.c_int64
+    L.emul_x87_pair_add80.argtypes = [C.c_void_p] * 6 + [C.c_int64, C.c_int]
+    L.emul_x87_pair_cover.argtypes = [C.c_void_p, C.c_int]
     L.emul_div_by_const.argtypes = [C.c_double, C.c_double]
     L.emul_binom_logpmf_host.argtypes = [C.c_double] * 3
     L.emul_binom_logpmf_dev.argtypes = [C.c_double] * 3

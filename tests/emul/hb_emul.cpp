@@ -20,6 +20,9 @@
 #include "hb_norm3.cuh"
 #include "hb_norm3_fast.cuh"
 #include "hb_x87.cuh"
+static int64_t g_x80p_cover[8];
+#define HB_X80P_COVER(i) (g_x80p_cover[(i)]++)
+#include "hb_x87_pair.cuh"
 
 using namespace hb;
 
@@ -374,6 +377,73 @@ int64_t emul_x87_addcheck(const double *x, int64_t n, double c, int mode)
         if (mine != s) bad++;
     }
     return bad;
+}
+
+// The same check for the double-pair form (hb_x87_pair.cuh).  mode 0: s += x[i]; mode 1: s += (x[i] - c80)
+// with c80 = c + c2 (an 80-bit centre).  Returns the number of differing steps (emul_x87_pair_cover tells
+// which cases of the rounding step and how many integer fall-backs were taken).
+int64_t emul_x87_paircheck(const double *x, int64_t n, double c, double c2, int mode, int64_t *fallbacks)
+{
+    x80p S = {0.0, 0.0};
+    volatile long double cl = (long double)c + (long double)c2;
+    const x80p Mneg = x80p_from_x80(x80_neg(x80_add(x80_from_double(c), x80_from_double(c2))));
+    volatile long double s = 0.0L;
+    int64_t bad = 0;
+    for (int64_t i = 0; i < n; i++) {
+        if (mode == 0) {
+            S = x80p_add_double(S, x[i]);
+            s = s + (long double)x[i];
+        } else {
+            const x80p D = x80p_add_double(Mneg, x[i]);
+            volatile long double t = (long double)x[i] - cl;
+            if ((long double)D.h + (long double)D.l != t) bad++;
+            S = x80p_add(S, D);
+            s = s + t;
+        }
+        if ((long double)S.h + (long double)S.l != s) bad++;
+        if (S.h != (double)s) bad++;
+    }
+    (void)fallbacks;
+    return bad;
+}
+
+// x80p_add / x80p_add_double on explicit 64-bit operands (significand, exponent, sign as hb::x80 holds them)
+// against the host's x87 unit; returns the number of mismatches.  dbl != 0: the second operand is first
+// rounded to double and added with x80p_add_double.
+int64_t emul_x87_pair_add80(const uint64_t *ms, const int32_t *es, const uint8_t *ns, const uint64_t *md,
+                            const int32_t *ed, const uint8_t *nd, int64_t n, int dbl)
+{
+    int64_t bad = 0;
+    for (int64_t i = 0; i < n; i++) {
+        x80 A, B;
+        A.m = ms[i], A.e = es[i], A.neg = ns[i];
+        B.m = md[i], B.e = ed[i], B.neg = nd[i];
+        if (A.m) A.m |= 1ull << 63;
+        if (B.m) B.m |= 1ull << 63;
+        const x80p a = x80p_from_x80(A);
+        volatile long double la = (long double)a.h + (long double)a.l, want;
+        x80p r;
+        if (dbl) {
+            const double v = x80_to_double(B);
+            r = x80p_add_double(a, v);
+            want = la + (long double)v;
+        } else {
+            const x80p b = x80p_from_x80(B);
+            volatile long double lb = (long double)b.h + (long double)b.l;
+            r = x80p_add(a, b);
+            want = la + lb;
+        }
+        if ((long double)r.h + (long double)r.l != want || r.h != (double)want) bad++;
+    }
+    return bad;
+}
+
+void emul_x87_pair_cover(int64_t *out, int reset)
+{
+    for (int i = 0; i < 8; i++) {
+        out[i] = g_x80p_cover[i];
+        if (reset) g_x80p_cover[i] = 0;
+    }
 }
 
 double emul_x87_sd(const double *x, int64_t n)

@@ -82,6 +82,98 @@ def test_x87_add_matches_the_hardware_step_by_step(emul):
         assert emul.emul_x87_addcheck(p, x.size, float(x.mean()), 1) == 0
 
 
+def _pair_cover(emul, reset=True):
+    cov = (C.c_int64 * 8)()
+    emul.emul_x87_pair_cover(cov, 1 if reset else 0)
+    return list(cov)
+
+
+def test_x87_pair_accumulation_matches_the_hardware_step_by_step(emul):
+    """The double-pair form of the 80-bit running sums (hb_x87_pair.cuh, what pool_accum_*_kernel runs)
+    against the host's x87 unit after every addition, both passes of R's mean: s += x and s += (x - c80)
+    with an 80-bit centre.  Same cases as the integer form above plus tie-heavy and cancelling ones."""
+    rng = np.random.default_rng(23)
+    cases = [(rng.gamma(2.0, 1.5, 100000), 1.3, 1e-18),
+             (rng.normal(size=100000) * 2.6, 0.01, 3e-20),
+             (rng.normal(size=30000) * 10.0 ** rng.integers(-12, 12, 30000), 1.0, 1e-17),
+             (np.ldexp(rng.integers(1, 1 << 20, 30000).astype(float), rng.integers(-70, 70, 30000)), 3.0, 2.0 ** -62),
+             (np.array([1.0, 2.0 ** -64, 2.0 ** -64, -1.0, 2.0 ** -63, 1.0, -(1.0 - 2.0 ** -53), 3.0, -3.0]), 1.0, 2.0 ** -60),
+             (rng.integers(0, 50, 50000).astype(float), 3.0, 0.0),
+             (np.log2(rng.gamma(2, 2, 50000) + 1) - 2.0, 0.3, 1e-19),
+             (np.concatenate([np.full(3000, 0.1), np.full(3000, -0.1), [1e300, -1e300, 1e-300]]), 0.1, 0.0)]
+    t = np.ldexp(rng.integers(1, 1 << 30, 20000).astype(float), -40)
+    cases.append((np.concatenate([[float(1 << 23)], t, -t]), 0.5, 2.0 ** -64))
+    for k in (0, 5, 11, 30):  # accumulator near 2^k, terms with bits right at half a unit of the result
+        adds = np.ldexp(rng.integers(-(1 << 14), 1 << 14, 30000).astype(float), k - 64 - rng.integers(0, 4, 30000))
+        cases.append((np.concatenate([[2.0 ** k], adds]), 2.0 ** k, 2.0 ** (k - 63)))
+    pw = []
+    for _ in range(10000):  # powers of two pulled just below themselves (the exponent of the sum drops)
+        k = int(rng.integers(-20, 20))
+        pw += [2.0 ** k, -2.0 ** (k - int(rng.integers(50, 70))), -2.0 ** k * (1 - 2.0 ** -int(rng.integers(1, 53)))]
+    cases.append((np.array(pw), 1.0, -2.0 ** -64))
+    y = rng.normal(size=20000)
+    z = np.empty(40000)
+    z[0::2] = y
+    z[1::2] = -y + np.ldexp(rng.integers(-8, 8, 20000).astype(float), -70)  # sums that cancel to (almost) nothing
+    cases.append((z, 0.0, 2.0 ** -70))
+    for x, c, c2 in cases:
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        for mode in (0, 1):
+            assert emul.emul_x87_paircheck(x.ctypes.data_as(C.c_void_p), x.size, c, c2, mode, None) == 0
+
+
+def test_x87_pair_add_on_explicit_64_bit_operands(emul):
+    """x80p_add / x80p_add_double on operands given as 64-bit significands: sparse bit patterns (exact sums,
+    ties, long carries), full ones, exponents from equal to 130 apart, both signs."""
+    rng = np.random.default_rng(29)
+    N = 60000
+    _pair_cover(emul)
+
+    def sparse(keep):
+        m = np.zeros(N, dtype=np.uint64)
+        for _ in range(keep):
+            m |= np.uint64(1) << rng.integers(0, 64, N).astype(np.uint64)
+        return m
+
+    def full():
+        return rng.integers(0, 1 << 63, N, dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, N).astype(np.uint64)
+
+    def go(ms, es, md, ed):
+        ns = rng.integers(0, 2, N).astype(np.uint8)
+        nd = rng.integers(0, 2, N).astype(np.uint8)
+        ms, md = np.ascontiguousarray(ms, np.uint64), np.ascontiguousarray(md, np.uint64)
+        es, ed = np.ascontiguousarray(es, np.int32), np.ascontiguousarray(ed, np.int32)
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        for dbl in (0, 1):
+            assert emul.emul_x87_pair_add80(p(ms), p(es), p(ns), p(md), p(ed), p(nd), N, dbl) == 0
+
+    for spread in (2, 12, 40, 64, 70, 130):
+        for k in (1, 2, 3, 5):
+            go(sparse(k), rng.integers(-3, 3, N), sparse(k), rng.integers(-spread, 1, N))
+        go(full(), rng.integers(-3, 3, N), full(), rng.integers(-spread, spread // 8 + 1, N))
+        go(full(), rng.integers(-3, 3, N), sparse(3), rng.integers(-spread, 1, N))
+        go(sparse(2), rng.integers(-3, 3, N), full(), rng.integers(-spread, 1, N))
+    low = (np.uint64(1) << np.uint64(63)) | rng.integers(0, 4096, N).astype(np.uint64)
+    dm = rng.integers(0, 1 << 16, N).astype(np.uint64) << rng.integers(0, 48, N).astype(np.uint64)
+    go(low, np.zeros(N), dm, rng.integers(-70, -40, N))
+    cov = _pair_cover(emul)
+    assert all(v > 0 for v in cov), cov  # every case of the rounding step and both integer fall-backs were taken
+
+
+def test_x87_pair_fast_path_covers_expression_like_data(emul):
+    """On data shaped like the pooled-mean inputs no step leaves the branch-free path (a fall-back is
+    correct but serialises a warp, so this is the performance contract of the kernel)."""
+    rng = np.random.default_rng(31)
+    for x in (rng.normal(size=200000) * 2.6, rng.gamma(2.0, 1.5, 200000), np.log2(rng.gamma(2, 2, 200000) + 1) - 2):
+        x = np.ascontiguousarray(x)
+        m = float(np.mean(x))
+        for mode in (0, 1):
+            _pair_cover(emul)
+            assert emul.emul_x87_paircheck(x.ctypes.data_as(C.c_void_p), x.size, m, m * 2.0 ** -55, mode, None) == 0
+            cov = _pair_cover(emul)
+            assert cov[6] == 0 and cov[7] == 0, cov
+
+
 def test_binom_logpmf_host_and_device_restatements_match_oracle(emul, oracle):
     for n in list(range(0, 70)) + [100, 255, 256, 511, 512, 1245, 5000]:
         for x in sorted({0, 1, n // 3, n // 2, n - 1, n}):
