@@ -192,6 +192,7 @@ int g_host_threads = 0; // copy-out threads of the host pipeline; 0 = all but tw
 // Kernel-choice switches are per calling thread (test / experiment hooks; two callers with different
 // settings do not interfere).
 thread_local int g_binom2_mode = 0; // 0 auto (lean kernel, general kernel behind its gate), 1 general kernel only
+thread_local int g_ward_mode = 0;      // 0 auto (cluster kernel from 1 024 cells up), 1 single block, 2 cluster
 thread_local int g_longchain_mode = 0; // 0 auto (pooled allele rounds), 1 never, 2 also the pooled expression rounds
 thread_local int g_norm3_mode = 0; // 0 auto, 1 literal kernel only, 2 speculative kernel with every chain re-run exactly, 3 speculative kernel whenever eligible
 
@@ -1999,11 +2000,8 @@ int hb_ward_linkage_dev(double *D, int64_t N, int32_t *merge_a, int32_t *merge_b
     HBTRY(cur_ws(&ws));
     WS_USE(stream);
     if (!D || !merge_a || !merge_b || !height || N < 2) return fail(HB_ERR_ARG, "bad arguments");
-    HBTRY(ws->st_part.ensure((size_t)N * (sizeof(int32_t) * 2 + 1) + 64));
-    int32_t *size = ws->st_part.as<int32_t>();
-    int32_t *chain = size + N;
-    uint8_t *active = (uint8_t *)(chain + N);
-    CU(hb::launch_ward(D, N, size, active, chain, merge_a, merge_b, height, (cudaStream_t)stream));
+    HBTRY(ws->st_part.ensure(hb::ward_scratch_bytes(N)));
+    CU(hb::launch_ward(D, N, ws->st_part.p, merge_a, merge_b, height, g_ward_mode, (cudaStream_t)stream));
     return HB_OK;
 }
 
@@ -2055,13 +2053,12 @@ static int group_core(Workspace *ws, const double *xg, const int32_t *rg, const 
     CU(hb::launch_runmean(xg, rg, ng, ld, G, N, window, S, lds, st));
     HBTRY(ws->st_pool.ensure((size_t)N * N * sizeof(double)));
     HBTRY(ws->st_pool2.ensure((size_t)N * 16 + 64));
-    HBTRY(ws->st_part.ensure((size_t)N * (sizeof(int32_t) * 2 + 1) + 64));
+    HBTRY(ws->st_part.ensure(hb::ward_scratch_bytes(N)));
     double *D = ws->st_pool.as<double>();
     CU(hb::launch_dist_sq(S, lds, G, N, D, st));
     int32_t *d_ma = ws->st_pool2.as<int32_t>(), *d_mb = d_ma + N;
     double *d_h = reinterpret_cast<double *>(d_mb + N);
-    int32_t *size = ws->st_part.as<int32_t>(), *chain = size + N;
-    CU(hb::launch_ward(D, N, size, (uint8_t *)(chain + N), chain, d_ma, d_mb, d_h, st));
+    CU(hb::launch_ward(D, N, ws->st_part.p, d_ma, d_mb, d_h, g_ward_mode, st));
     std::vector<int32_t> ma((size_t)N), mb((size_t)N);
     std::vector<double> hh((size_t)N);
     CU(cudaMemcpyAsync(ma.data(), d_ma, (size_t)(N - 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
@@ -2651,6 +2648,13 @@ int hb_retest_allele_model_host(const int32_t *r_rows, const int32_t *n_rows, in
 }
 
 // ------------------------------------------------------------------ few long chains
+int hb_set_ward_mode(int32_t mode)
+{
+    if (mode < 0 || mode > 2) return fail(HB_ERR_ARG, "mode must be 0, 1 or 2");
+    g_ward_mode = mode;
+    return HB_OK;
+}
+
 int hb_set_longchain_mode(int32_t mode)
 {
     if (mode < 0 || mode > 2) return fail(HB_ERR_ARG, "mode must be 0, 1 or 2");

@@ -6,6 +6,7 @@
 // is O(N^2 G) on one core and stops scaling near 10^4 cells; here it is three kernels.
 // Group MEMBERSHIP is what the path consumes; distances are not compared bit for bit.
 #pragma once
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -260,6 +261,175 @@ __global__ void __launch_bounds__(WL_THREADS)
         nmerge++;
         __syncthreads();
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// The same linkage on a thread-block CLUSTER (up to 16 SMs).  The merges stay sequential, but every
+// step of the single-block kernel is bounded by one SM's load latency and issue rate over a row of
+// N distances; here each CTA owns a contiguous slice of the columns and
+//   * a thread keeps its (at most WC_OWN) columns' liveness in a register bit mask, so a row scan is
+//     one round of independent L2 loads (no dependent `active[k]` load in front of each);
+//   * the per-CTA winners are exchanged through distributed shared memory — every CTA stores its
+//     (value, index) into all peers' slot tables, one hardware cluster barrier, every CTA reduces the
+//     same table — so all CTAs take the same decision without a broadcast step;
+//   * control state (chain, cluster sizes) is replicated per CTA (size_rep / chain_rep: [R][N]),
+//     only the distance matrix is shared, read with ld.global.cg after a fence + cluster barrier.
+// Same comparison order (wl_better is a total order, so the winner does not depend on how the
+// reduction is split), same Lance-Williams expression: merges, order and heights are bit-identical
+// to ward_nnchain_kernel's (tests/test_gpu_group.py).  One barrier per chain extension, two per
+// merge.
+#define WC_THREADS 256
+#define WC_WARPS (WC_THREADS / 32)
+#define WC_OWN 16
+#define WC_MAXR 16
+// distance -> unsigned key with the order of the doubles (-0 counted as +0, as `v1 != v2` does; no NaN here)
+__device__ __forceinline__ uint64_t wc_key(double v)
+{
+    const uint64_t u = (uint64_t)__double_as_longlong(v + 0.0);
+    return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+// index -> key of the tie rule: the preferred cluster first, then the lowest index
+__device__ __forceinline__ uint32_t wc_ikey(int32_t k, int32_t prefer) { return k == prefer ? 0u : (uint32_t)k + 1u; }
+// lexicographic minimum of (key, ik) over the warp, result in every lane
+__device__ __forceinline__ void wc_warp_min(uint64_t &key, uint32_t &ik)
+{
+    const uint32_t hi = (uint32_t)(key >> 32), lo = (uint32_t)key;
+    const uint32_t mh = __reduce_min_sync(0xffffffffu, hi);
+    const uint32_t ml = __reduce_min_sync(0xffffffffu, hi == mh ? lo : 0xffffffffu);
+    const uint32_t mi = __reduce_min_sync(0xffffffffu, (hi == mh && lo == ml) ? ik : 0xffffffffu);
+    key = ((uint64_t)mh << 32) | ml;
+    ik = mi;
+}
+__global__ void __launch_bounds__(WC_THREADS)
+    ward_cluster_kernel(double *D, int64_t N, int32_t *size_rep, int32_t *chain_rep, int32_t *ma, int32_t *mb,
+                        double *height)
+{
+    namespace cg = cooperative_groups;
+    cg::cluster_group cl = cg::this_cluster();
+    const int R = (int)cl.num_blocks(), rk = (int)cl.block_rank();
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // winners of every warp of every CTA, two tables used alternately
+    __shared__ uint64_t pkey[2][WC_MAXR * WC_WARPS];
+    __shared__ uint32_t pidx[2][WC_MAXR * WC_WARPS];
+    int32_t *size = size_rep + (int64_t)rk * N, *chain = chain_rep + (int64_t)rk * N;
+    const int64_t chunk = ((N + R - 1) / R + 31) & ~(int64_t)31;
+    const int64_t lo = (int64_t)rk * chunk, hi = lo + chunk < N ? lo + chunk : N;
+    uint32_t alive = 0;
+#pragma unroll
+    for (int i = 0; i < WC_OWN; i++)
+        if (lo + tid + (int64_t)i * WC_THREADS < hi) alive |= 1u << i;
+    for (int64_t k = tid; k < N; k += WC_THREADS) size[k] = 1;
+    __syncthreads();
+    cl.sync(); // every CTA of the cluster is running: its shared memory may be written from now on
+    int par = 0;
+    const int nent = R * WC_WARPS;
+
+    const int nown = (int)((chunk + WC_THREADS - 1) / WC_THREADS); // columns per thread in use (uniform)
+
+    // nearest active neighbour of cluster a (ties: `prefer`, then lowest index), known to every thread on return.
+    // Candidates are compared as (wc_key(distance), wc_ikey(index)) pairs of unsigned integers — the same
+    // total order as wl_better — so that a warp finds its winner with three redux.sync.min instead of five
+    // rounds of 64-bit shuffles and fp64 compares.
+    auto argmin = [&](int32_t a, int32_t prefer) -> int32_t {
+        const double *row = D + (int64_t)a * N + lo + tid;
+        double v[WC_OWN];
+#pragma unroll
+        for (int i = 0; i < WC_OWN; i++)
+            if (i < nown && ((alive >> i) & 1u)) v[i] = __ldcg(row + (int64_t)i * WC_THREADS);
+        uint64_t bk = ~0ull;
+        uint32_t bi = 0xffffffffu;
+#pragma unroll
+        for (int i = 0; i < WC_OWN; i++) {
+            if (i < nown) {
+                const int32_t k = (int32_t)(lo + tid + (int64_t)i * WC_THREADS);
+                if (((alive >> i) & 1u) && k != a) {
+                    const uint64_t key = wc_key(v[i]);
+                    const uint32_t ik = wc_ikey(k, prefer);
+                    if (key < bk || (key == bk && ik < bi)) {
+                        bk = key;
+                        bi = ik;
+                    }
+                }
+            }
+        }
+        wc_warp_min(bk, bi);
+        if (lane < R) { // lane t hands this warp's winner to CTA t
+            *cl.map_shared_rank(&pkey[par][rk * WC_WARPS + warp], lane) = bk;
+            *cl.map_shared_rank(&pidx[par][rk * WC_WARPS + warp], lane) = bi;
+        }
+        cl.sync();
+        bk = ~0ull;
+        bi = 0xffffffffu;
+        for (int e = lane; e < nent; e += 32) {
+            const uint64_t key = pkey[par][e];
+            const uint32_t ik = pidx[par][e];
+            if (key < bk || (key == bk && ik < bi)) {
+                bk = key;
+                bi = ik;
+            }
+        }
+        wc_warp_min(bk, bi);
+        par ^= 1; // the next exchange uses the other table: a fast CTA cannot overwrite what a slow one still reads
+        return bi == 0xffffffffu ? -1 : bi == 0 ? prefer : (int32_t)bi - 1;
+    };
+
+    int32_t clen = 0, nmerge = 0, first_active = 0;
+    while (nmerge < N - 1) {
+        if (clen == 0) {
+            while (size[first_active] == 0) first_active++;
+            if (tid == 0) chain[0] = first_active;
+            clen = 1;
+            __syncthreads();
+        }
+        int32_t a = chain[clen - 1], prev = clen >= 2 ? chain[clen - 2] : -1;
+        for (;;) {
+            const int32_t b = argmin(a, prev);
+            if (b == prev) break;
+            if (tid == 0) chain[clen] = b;
+            clen++;
+            prev = a;
+            a = b;
+        }
+        const int32_t b = prev; // a and b are reciprocal nearest neighbours
+        clen -= 2;
+        const double dab = __ldcg(D + (int64_t)a * N + b);
+        const int32_t na = size[a], nb = size[b];
+        // the union lives in slot b; slot a dies
+        {
+            const double *ra = D + (int64_t)a * N + lo + tid, *rb = D + (int64_t)b * N + lo + tid;
+            double va[WC_OWN], vb[WC_OWN];
+#pragma unroll
+            for (int i = 0; i < WC_OWN; i++)
+                if (i < nown && ((alive >> i) & 1u)) {
+                    va[i] = __ldcg(ra + (int64_t)i * WC_THREADS);
+                    vb[i] = __ldcg(rb + (int64_t)i * WC_THREADS);
+                }
+#pragma unroll
+            for (int i = 0; i < WC_OWN; i++) {
+                const int64_t k = lo + tid + (int64_t)i * WC_THREADS;
+                if (i < nown && ((alive >> i) & 1u) && k != a && k != b) {
+                    const double nk = (double)size[k];
+                    const double v = ((na + nk) * va[i] + (nb + nk) * vb[i] - nk * dab) / (na + nb + nk);
+                    D[(int64_t)b * N + k] = v;
+                    D[k * N + b] = v;
+                }
+                if (k == a) alive &= ~(1u << i);
+            }
+        }
+        __syncthreads(); // size[a], size[b] have been read by everybody
+        if (tid == 0) {
+            if (rk == 0) {
+                ma[nmerge] = a;
+                mb[nmerge] = b;
+                height[nmerge] = sqrt(dab > 0 ? dab : 0.0);
+            }
+            size[b] = na + nb;
+            size[a] = 0;
+        }
+        nmerge++;
+        cl.sync(); // release / acquire at cluster scope: the updated row and column of b are visible to their readers
+    }
+    cl.sync(); // nobody leaves while a peer may still store into its shared memory
 }
 
 } // namespace hb

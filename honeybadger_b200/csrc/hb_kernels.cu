@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 
 #include "hb_binom2.cuh"
 #include "hb_binom2_fast.cuh"
@@ -975,9 +977,54 @@ cudaError_t launch_dist_sq(const double *S, int64_t ld, int64_t G, int64_t N, do
     dist_sq_kernel<<<dim3(nt, nt), 256, 0, st>>>(S, ld, G, N, D);
     return cudaGetLastError();
 }
-cudaError_t launch_ward(double *D, int64_t N, int32_t *size, uint8_t *active, int32_t *chain, int32_t *ma,
-                        int32_t *mb, double *height, cudaStream_t st)
+// Scratch of the linkage: the cluster form keeps one copy of the chain and the cluster sizes per CTA.
+size_t ward_scratch_bytes(int64_t N) { return (size_t)N * sizeof(int32_t) * 2 * WC_MAXR + (size_t)N + 256; }
+
+// mode 0: cluster kernel from WARD_CLUSTER_MIN clusters up, single block below; 1: single block; 2: cluster
+#define WARD_CLUSTER_MIN 1024
+cudaError_t launch_ward(double *D, int64_t N, void *work, int32_t *ma, int32_t *mb, double *height, int mode,
+                        cudaStream_t st)
 {
+    int32_t *size = (int32_t *)work, *chain = size + (int64_t)N * WC_MAXR;
+    const bool fits = N <= (int64_t)WC_MAXR * WC_THREADS * WC_OWN / 2 - 64; // also at cluster size 8
+    if (mode != 1 && fits && (mode == 2 || N >= WARD_CLUSTER_MIN)) {
+        static int cluster_max = -1; // 16 (non-portable size, opt-in), else 8, else none
+        if (cluster_max < 0) {
+            cluster_max = 0;
+            for (int r : {16, 8}) {
+                if (r > 8 && cudaFuncSetAttribute(ward_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed,
+                                                  1) != cudaSuccess) {
+                    cudaGetLastError();
+                    continue;
+                }
+                cudaLaunchConfig_t cfg = {};
+                cudaLaunchAttribute at[1];
+                at[0].id = cudaLaunchAttributeClusterDimension;
+                at[0].val.clusterDim.x = r, at[0].val.clusterDim.y = 1, at[0].val.clusterDim.z = 1;
+                cfg.gridDim = dim3(r), cfg.blockDim = dim3(WC_THREADS), cfg.attrs = at, cfg.numAttrs = 1;
+                int ncl = 0;
+                if (cudaOccupancyMaxActiveClusters(&ncl, ward_cluster_kernel, &cfg) == cudaSuccess && ncl >= 1) {
+                    cluster_max = r;
+                    break;
+                }
+                cudaGetLastError();
+            }
+        }
+        if (cluster_max) {
+            // measured (tools/probe_ward.py): 8 CTAs are best up to ~8 k cells, 16 beyond; a step costs ~2 us at
+            // any size (L2 latency + cluster barrier), so small problems stay on one block
+            int r = std::min(cluster_max, N >= 8192 ? 16 : 8);
+            if (const char *e = getenv("HB_WARD_R")) r = std::max(1, std::min(cluster_max, atoi(e))); // experiments
+            if ((N + r - 1) / r + 32 > (int64_t)WC_THREADS * WC_OWN) r = cluster_max;
+            cudaLaunchConfig_t cfg = {};
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = r, at[0].val.clusterDim.y = 1, at[0].val.clusterDim.z = 1;
+            cfg.gridDim = dim3(r), cfg.blockDim = dim3(WC_THREADS), cfg.stream = st, cfg.attrs = at, cfg.numAttrs = 1;
+            return cudaLaunchKernelEx(&cfg, ward_cluster_kernel, D, N, size, chain, ma, mb, height);
+        }
+    }
+    uint8_t *active = (uint8_t *)(chain + (int64_t)N * WC_MAXR);
     ward_nnchain_kernel<<<1, WL_THREADS, 0, st>>>(D, N, size, active, chain, ma, mb, height);
     return cudaGetLastError();
 }

@@ -67,8 +67,9 @@ cudaError_t launch_retest_gexp_b(int64_t N, const double *partial, const double 
 cudaError_t launch_runmean(const double *x, const int32_t *r, const int32_t *n, int64_t ld, int64_t G,
                            int64_t N, int32_t k, double *out, int64_t ldo, cudaStream_t st);
 cudaError_t launch_dist_sq(const double *S, int64_t ld, int64_t G, int64_t N, double *D, cudaStream_t st);
-cudaError_t launch_ward(double *D, int64_t N, int32_t *size, uint8_t *active, int32_t *chain, int32_t *ma,
-                        int32_t *mb, double *height, cudaStream_t st);
+size_t ward_scratch_bytes(int64_t N);
+cudaError_t launch_ward(double *D, int64_t N, void *work, int32_t *ma, int32_t *mb, double *height, int mode,
+                        cudaStream_t st);
 cudaError_t launch_pool_mean(const double *x, int64_t ld, int64_t G, int64_t N, const uint8_t *member,
                              const int32_t *gsize, int32_t K, double *out, void *scratch, void *fast,
                              const int32_t *order, cudaStream_t st);

@@ -531,6 +531,11 @@ def set_longchain_mode(mode: int):
     _lib.check(_lib.load().hb_set_longchain_mode(int(mode)))
 
 
+def set_ward_mode(mode: int):
+    """Ward linkage kernel: 0 cluster of CTAs from 1 024 cells up (default), 1 one block, 2 always the cluster."""
+    _lib.check(_lib.load().hb_set_ward_mode(int(mode)))
+
+
 def status_dev():
     """Wait for the current stream and raise UnderflowError if the last launch hit nu == -Inf."""
     _lib.check(_lib.load().hb_status_dev(_stream()))

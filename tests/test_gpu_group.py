@@ -1,0 +1,85 @@
+"""GPU: the Ward linkage on a thread-block cluster (csrc/hb_group.cuh, ward_cluster_kernel) against the
+single-block kernel — merges, their order and heights must be bit-identical — and against scipy."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _linkage(D, mode):
+    import torch
+    from honeybadger_b200 import _lib, hmm
+    lib = _lib.load()
+    N = D.shape[0]
+    d = torch.from_numpy(np.ascontiguousarray(D)).cuda()
+    ma = torch.empty(N - 1, dtype=torch.int32, device="cuda")
+    mb = torch.empty(N - 1, dtype=torch.int32, device="cuda")
+    hh = torch.empty(N - 1, dtype=torch.float64, device="cuda")
+    hmm.set_ward_mode(mode)
+    try:
+        _lib.check(lib.hb_ward_linkage_dev(d.data_ptr(), N, ma.data_ptr(), mb.data_ptr(), hh.data_ptr(), None))
+        torch.cuda.synchronize()
+    finally:
+        hmm.set_ward_mode(0)
+    return ma.cpu().numpy(), mb.cpu().numpy(), hh.cpu().numpy()
+
+
+def _sqdist(x):
+    g = x @ x.T
+    n = np.diag(g)
+    d = n[:, None] + n[None, :] - 2 * g
+    d = np.maximum((d + d.T) / 2, 0.0)
+    np.fill_diagonal(d, 0.0)
+    return d
+
+
+@pytest.mark.parametrize("N", [2, 3, 33, 64, 511, 512, 513, 1000, 2049, 4100])
+def test_cluster_linkage_is_bit_identical_to_the_single_block_kernel(N):
+    rng = np.random.default_rng(N)
+    x = rng.normal(size=(N, 12))
+    x[: N // 3] += 3.0
+    D = _sqdist(x)
+    a1, b1, h1 = _linkage(D, 1)
+    a2, b2, h2 = _linkage(D, 2)
+    assert np.array_equal(a1, a2) and np.array_equal(b1, b2)
+    assert np.array_equal(h1.view(np.int64), h2.view(np.int64))
+
+
+def test_cluster_linkage_with_ties():
+    """Integer coordinates: many equal distances, the tie rules (previous chain element, then lowest index)
+    decide — the two kernels must still agree merge for merge."""
+    rng = np.random.default_rng(5)
+    for N in (130, 777, 1500):
+        x = rng.integers(0, 3, size=(N, 4)).astype(np.float64)
+        D = _sqdist(x)
+        a1, b1, h1 = _linkage(D, 1)
+        a2, b2, h2 = _linkage(D, 2)
+        assert np.array_equal(a1, a2) and np.array_equal(b1, b2)
+        assert np.array_equal(h1.view(np.int64), h2.view(np.int64))
+
+
+def test_cluster_linkage_matches_scipy_ward_heights():
+    from scipy.cluster.hierarchy import linkage
+    from scipy.spatial.distance import squareform
+    rng = np.random.default_rng(9)
+    N = 1200
+    x = rng.normal(size=(N, 20))
+    x[:400] += 2.0
+    D = _sqdist(x)
+    _, _, h = _linkage(D, 2)
+    Z = linkage(squareform(np.sqrt(D), checks=False), method="ward")
+    np.testing.assert_allclose(np.sort(h), Z[:, 2], rtol=1e-9, atol=1e-9)
+
+
+def test_default_mode_uses_the_cluster_from_1024_cells(monkeypatch):
+    """mode 0 must give the same answer on both sides of the switch-over (and run at all)."""
+    rng = np.random.default_rng(11)
+    for N in (1023, 1024):
+        D = _sqdist(rng.normal(size=(N, 8)))
+        a0, b0, h0 = _linkage(D, 0)
+        a1, b1, h1 = _linkage(D, 1)
+        assert np.array_equal(a0, a1) and np.array_equal(b0, b1) and np.array_equal(h0, h1)
