@@ -103,6 +103,7 @@ SIGNATURES = {
     "hb_longchain_stats_dev": (_i32, [_p, _p]),
     "hb_set_longchain_mode": (_i32, [_i32]),
     "hb_set_ward_mode": (_i32, [_i32]),
+    "hb_set_dist_mode": (_i32, [_i32]),
     "hb_gexp_pooled_viterbi_dev": (_i32, [_p, _i64, _i64, _i64, _p, _i32, _p, _p, _p, _p, _p, _p, _p]),
     "hb_allele_pooled_viterbi_dev": (_i32, [_p, _p, _i64, _i64, _i64, _p, _i32, _p, _p, _p, _p, _p,
                                             _p, _p]),

@@ -192,6 +192,7 @@ int g_host_threads = 0; // copy-out threads of the host pipeline; 0 = all but tw
 // Kernel-choice switches are per calling thread (test / experiment hooks; two callers with different
 // settings do not interfere).
 thread_local int g_binom2_mode = 0; // 0 auto (lean kernel, general kernel behind its gate), 1 general kernel only
+thread_local int g_dist_mode = 0;      // 0 pipelined dist kernel (cp.async ring, flag pre-pass), 1 the plain one
 thread_local int g_ward_mode = 0;      // 0 auto (cluster kernel from 1 024 cells up), 1 single block, 2 cluster
 thread_local int g_longchain_mode = 0; // 0 auto (pooled allele rounds), 1 never, 2 also the pooled expression rounds
 thread_local int g_norm3_mode = 0; // 0 auto, 1 literal kernel only, 2 speculative kernel with every chain re-run exactly, 3 speculative kernel whenever eligible
@@ -1987,8 +1988,17 @@ int hb_runmean_ratio_dev(const int32_t *r, const int32_t *n, int64_t ld, int64_t
 
 int hb_dist_sq_dev(const double *s, int64_t ld, int64_t G, int64_t N, double *D, void *stream)
 {
+    std::lock_guard<std::mutex> lk(g_mu);
+    Workspace *ws;
+    HBTRY(cur_ws(&ws));
+    WS_USE(stream);
     if (!s || !D || G < 1 || N < 1 || ld < N) return fail(HB_ERR_ARG, "bad arguments");
-    CU(hb::launch_dist_sq(s, ld, G, N, D, (cudaStream_t)stream));
+    void *flags = nullptr;
+    if (g_dist_mode != 1) {
+        HBTRY(ws->st_part.ensure(hb::dist_flag_bytes(G, N)));
+        flags = ws->st_part.p;
+    }
+    CU(hb::launch_dist_sq(s, ld, G, N, D, flags, (cudaStream_t)stream));
     return HB_OK;
 }
 
@@ -2053,9 +2063,9 @@ static int group_core(Workspace *ws, const double *xg, const int32_t *rg, const 
     CU(hb::launch_runmean(xg, rg, ng, ld, G, N, window, S, lds, st));
     HBTRY(ws->st_pool.ensure((size_t)N * N * sizeof(double)));
     HBTRY(ws->st_pool2.ensure((size_t)N * 16 + 64));
-    HBTRY(ws->st_part.ensure(hb::ward_scratch_bytes(N)));
+    HBTRY(ws->st_part.ensure(std::max(hb::ward_scratch_bytes(N), hb::dist_flag_bytes(G, N))));
     double *D = ws->st_pool.as<double>();
-    CU(hb::launch_dist_sq(S, lds, G, N, D, st));
+    CU(hb::launch_dist_sq(S, lds, G, N, D, g_dist_mode != 1 ? ws->st_part.p : nullptr, st));
     int32_t *d_ma = ws->st_pool2.as<int32_t>(), *d_mb = d_ma + N;
     double *d_h = reinterpret_cast<double *>(d_mb + N);
     CU(hb::launch_ward(D, N, ws->st_part.p, d_ma, d_mb, d_h, g_ward_mode, st));
@@ -2652,6 +2662,13 @@ int hb_set_ward_mode(int32_t mode)
 {
     if (mode < 0 || mode > 2) return fail(HB_ERR_ARG, "mode must be 0, 1 or 2");
     g_ward_mode = mode;
+    return HB_OK;
+}
+
+int hb_set_dist_mode(int32_t mode)
+{
+    if (mode < 0 || mode > 1) return fail(HB_ERR_ARG, "mode must be 0 or 1");
+    g_dist_mode = mode;
     return HB_OK;
 }
 

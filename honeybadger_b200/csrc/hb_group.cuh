@@ -143,6 +143,129 @@ __global__ void __launch_bounds__(256)
 }
 
 // ---------------------------------------------------------------------------------------------
+// The same distances with the loads taken off the critical path.  dist_sq_kernel stages a slab of 16
+// positions through shared memory with ordinary loads between two block barriers: while a block
+// waits for its slab nothing of it computes, and the test for non-finite values re-reads every
+// staged element.  Here
+//   * a pre-pass (dist_flag_kernel) marks every (slab of 16 positions, tile of 64 cells) that holds a
+//     non-finite value, once per matrix — the main kernel reads two bytes per slab instead;
+//   * slabs move with 16-byte cp.async into a three-stage ring, two slabs ahead of the arithmetic,
+//     one block barrier per slab;
+//   * columns past N are clamped (their pairs are never stored), so edge tiles stay on the fast path.
+// Per pair the same operations in the same order as dist_sq_kernel — results are bit-identical
+// (tests/test_gpu_group.py).  Needs ld even and S 16-byte aligned (the launcher checks).
+#define GP_STAGES 3
+__global__ void __launch_bounds__(256)
+    dist_flag_kernel(const double *S, int64_t ld, int64_t G, int64_t N, uint8_t *flags, int ntile)
+{
+    const int64_t g0 = (int64_t)blockIdx.x * GD_K, c0 = (int64_t)blockIdx.y * GD_T;
+    int bad = 0;
+    for (int e = threadIdx.x; e < GD_K * GD_T; e += 256) {
+        const int64_t g = g0 + e / GD_T, c = c0 + e % GD_T;
+        if (g < G && c < N) bad |= !isfinite(S[g * ld + c]);
+    }
+    bad = __syncthreads_or(bad);
+    if (threadIdx.x == 0) flags[(int64_t)blockIdx.x * ntile + blockIdx.y] = bad ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(256)
+    dist_sq_pipe_kernel(const double *S, int64_t ld, int64_t G, int64_t N, const uint8_t *flags, int ntile, double *D)
+{
+    extern __shared__ __align__(16) double gp_sm[]; // [GP_STAGES][2][GD_K][GD_T]
+    const int64_t i0 = (int64_t)blockIdx.y * GD_T, j0 = (int64_t)blockIdx.x * GD_T;
+    if (j0 + GD_T <= i0) return; // lower triangle: mirrored from the upper one
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int64_t nslab = (G + GD_K - 1) / GD_K;
+    const int64_t cclamp = (N - 1) & ~(int64_t)1;
+    auto issue = [&](int64_t s) {
+        if (s < nslab) {
+            double *base = gp_sm + (s % GP_STAGES) * (2 * GD_K * GD_T);
+            for (int e = threadIdx.x; e < 2 * GD_K * GD_T / 2; e += 256) {
+                const int which = e >> 9, k = (e >> 5) & (GD_K - 1), ch = e & 31;
+                int64_t g = s * GD_K + k, c = (which ? j0 : i0) + 2 * ch;
+                g = g < G ? g : G - 1;
+                c = c < cclamp ? c : cclamp;
+                const unsigned dst = (unsigned)__cvta_generic_to_shared(base + which * (GD_K * GD_T) + k * GD_T + 2 * ch);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(S + g * ld + c) : "memory");
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    double acc[4][4], cnt[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) acc[a][b] = cnt[a][b] = 0.0;
+    double nfast = 0.0;
+    issue(0);
+    issue(1);
+    for (int64_t s = 0; s < nslab; s++) {
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        __syncthreads(); // slab s has landed for everybody, and everybody is done with slab s - 1
+        issue(s + 2);    // into the stage slab s - 1 used
+        const double *sa = gp_sm + (s % GP_STAGES) * (2 * GD_K * GD_T), *sb = sa + GD_K * GD_T;
+        const int kmax = (int)(G - s * GD_K < GD_K ? G - s * GD_K : GD_K);
+        const bool bad = flags[s * ntile + blockIdx.y] | flags[s * ntile + blockIdx.x];
+        if (!bad && kmax == GD_K) {
+#pragma unroll 4
+            for (int k = 0; k < GD_K; k++) {
+                double va[4], vb[4];
+#pragma unroll
+                for (int a = 0; a < 4; a++) {
+                    va[a] = sa[k * GD_T + ty + 16 * a];
+                    vb[a] = sb[k * GD_T + tx + 16 * a];
+                }
+#pragma unroll
+                for (int a = 0; a < 4; a++)
+#pragma unroll
+                    for (int b = 0; b < 4; b++) {
+                        const double d = va[a] - vb[b];
+                        acc[a][b] = __dadd_rn(acc[a][b], __dmul_rn(d, d));
+                    }
+            }
+            nfast += (double)GD_K;
+        } else {
+            for (int k = 0; k < kmax; k++) {
+                double va[4], vb[4];
+#pragma unroll
+                for (int a = 0; a < 4; a++) {
+                    va[a] = sa[k * GD_T + ty + 16 * a];
+                    vb[a] = sb[k * GD_T + tx + 16 * a];
+                }
+#pragma unroll
+                for (int a = 0; a < 4; a++)
+#pragma unroll
+                    for (int b = 0; b < 4; b++) {
+                        const double d = va[a] - vb[b]; // NaN or Inf-Inf when a member is unusable
+                        if (isfinite(d)) {
+                            acc[a][b] = __dadd_rn(acc[a][b], __dmul_rn(d, d));
+                            cnt[a][b] += 1.0;
+                        }
+                    }
+            }
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            const int64_t i = i0 + ty + 16 * a, j = j0 + tx + 16 * b;
+            if (i < N && j < N) {
+                const double c = cnt[a][b] + nfast;
+                double v = 0.0;
+                if (c > 0) {
+                    v = c != (double)G ? acc[a][b] / (c / (double)G) : acc[a][b];
+                    const double r = sqrt(v);
+                    v = __dmul_rn(r, r);
+                }
+                const double w = (i == j) ? 0.0 : v;
+                D[i * N + j] = w;
+                D[j * N + i] = w;
+            }
+        }
+}
+
+// ---------------------------------------------------------------------------------------------
 // hclust(d, "ward.D2"): nearest-neighbour chain with the Lance-Williams update on SQUARED distances,
 // one persistent block (the merges are sequential; every step is a row-wide argmin or update that
 // 1024 threads do cooperatively; no host round trips).  Merge m joins the clusters that contain

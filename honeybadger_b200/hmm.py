@@ -536,6 +536,11 @@ def set_ward_mode(mode: int):
     _lib.check(_lib.load().hb_set_ward_mode(int(mode)))
 
 
+def set_dist_mode(mode: int):
+    """dist kernel: 0 pipelined (default), 1 plain."""
+    _lib.check(_lib.load().hb_set_dist_mode(int(mode)))
+
+
 def status_dev():
     """Wait for the current stream and raise UnderflowError if the last launch hit nu == -Inf."""
     _lib.check(_lib.load().hb_status_dev(_stream()))

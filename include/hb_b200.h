@@ -400,6 +400,10 @@ int hb_set_longchain_mode(int32_t mode);
  * through distributed shared memory), one block below that; 1: always one block; 2: always the cluster.
  * Merges, their order and heights are bit-identical in every mode.  Per calling thread. */
 int hb_set_ward_mode(int32_t mode);
+/* Which kernel computes the distances.  0 (default): slabs of positions staged with cp.async three deep and a
+ * pre-pass that marks the slabs holding non-finite values; 1: the plain staged kernel.  Bit-identical
+ * results.  Per calling thread. */
+int hb_set_dist_mode(int32_t mode);
 
 /* One recursion round of the split-and-retest driver on DEVICE-RESIDENT matrices (gene-major,
  * uploaded once): `member` [K][N] (0/1, host) names the K candidate cell sets of the round, the

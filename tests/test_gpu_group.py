@@ -83,3 +83,53 @@ def test_default_mode_uses_the_cluster_from_1024_cells(monkeypatch):
         a0, b0, h0 = _linkage(D, 0)
         a1, b1, h1 = _linkage(D, 1)
         assert np.array_equal(a0, a1) and np.array_equal(b0, b1) and np.array_equal(h0, h1)
+
+
+def _dist(S, mode):
+    import torch
+    from honeybadger_b200 import _lib, hmm
+    lib = _lib.load()
+    G, N = S.shape
+    s = hmm.alloc_rows(G, N, torch.float64, "cuda")
+    s.copy_(torch.from_numpy(S).cuda())
+    D = torch.empty((N, N), dtype=torch.float64, device="cuda")
+    hmm.set_dist_mode(mode)
+    try:
+        _lib.check(lib.hb_dist_sq_dev(s.data_ptr(), s.stride(0), G, N, D.data_ptr(), None))
+        torch.cuda.synchronize()
+    finally:
+        hmm.set_dist_mode(0)
+    return D.cpu().numpy()
+
+
+@pytest.mark.parametrize("G,N", [(1, 2), (15, 3), (16, 64), (17, 65), (100, 127), (333, 130), (1000, 257), (48, 1)])
+def test_pipelined_dist_is_bit_identical_to_the_plain_kernel(G, N):
+    rng = np.random.default_rng(G * 1000 + N)
+    S = rng.normal(size=(G, N))
+    a, b = _dist(S, 0), _dist(S, 1)
+    assert np.array_equal(a.view(np.int64), b.view(np.int64))
+    ref = ((S[:, :, None] - S[:, None, :]) ** 2).sum(axis=0)
+    np.testing.assert_allclose(a, ref, rtol=1e-12, atol=1e-12)
+
+
+def test_pipelined_dist_with_missing_values():
+    """R's NA rule (pairs with a non-finite member dropped, sum scaled by G / pairs used, no pair -> 0): NaN
+    scattered, whole NaN columns, NaN confined to some slabs and tiles, +-Inf."""
+    rng = np.random.default_rng(3)
+    G, N = 200, 150
+    S = rng.normal(size=(G, N))
+    S[rng.random((G, N)) < 0.02] = np.nan
+    S[:, 7] = np.nan
+    S[32:48, 64:128] = np.nan
+    S[5, 3] = np.inf
+    S[6, 4] = -np.inf
+    a, b = _dist(S, 0), _dist(S, 1)
+    assert np.array_equal(a.view(np.int64), b.view(np.int64))
+    d = S[:, :, None] - S[:, None, :]
+    ok = np.isfinite(d)
+    cnt = ok.sum(axis=0)
+    ss = np.where(ok, d * d, 0.0).sum(axis=0)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        ref = np.where(cnt > 0, ss / (cnt / G), 0.0)
+    np.fill_diagonal(ref, 0.0)
+    np.testing.assert_allclose(a, ref, rtol=1e-12, atol=1e-12)
