@@ -79,6 +79,7 @@ SIGNATURES = {
     "hb_runmean_ratio_dev": (_i32, [_p, _p, _i64, _i64, _i64, _i32, _p, _i64, _p]),
     "hb_dist_sq_dev": (_i32, [_p, _i64, _i64, _i64, _p, _p]),
     "hb_ward_linkage_dev": (_i32, [_p, _i64, _p, _p, _p, _p]),
+    "hb_cutree_host": (_i32, [_p, _p, _p, _i64, _p, _i32, _p]),
     "hb_group_gexp_host": (_i32, [_p, _i64, _i64, _i32, _p, _i32, _p]),
     "hb_group_allele_host": (_i32, [_p, _p, _i64, _i64, _i32, _p, _i32, _p]),
     "hb_set_gexp_mats_dev": (_i32, [_p, _i64, _i64, _i64, _p, _i64, _i64, _i32, _d, _p, _p, _i32, _p, _i64,

@@ -2048,6 +2048,21 @@ static void cut_merges_host(const int32_t *ma, const int32_t *mb, const double *
     }
 }
 
+int hb_cutree_host(const int32_t *merge_a, const int32_t *merge_b, const double *height, int64_t N,
+                   const int32_t *ks, int32_t nk, int32_t *labels)
+{
+    if (!merge_a || !merge_b || !height || !ks || !labels || N < 1 || nk < 1) return fail(HB_ERR_ARG, "bad arguments");
+    for (int64_t m = 0; m + 1 < N; m++)
+        if (merge_a[m] < 0 || merge_a[m] >= N || merge_b[m] < 0 || merge_b[m] >= N)
+            return fail(HB_ERR_ARG, "merge list names a leaf outside [0, N)");
+    if (N == 1) {
+        for (int32_t q = 0; q < nk; q++) labels[q] = 1;
+        return HB_OK;
+    }
+    cut_merges_host(merge_a, merge_b, height, N, ks, nk, labels);
+    return HB_OK;
+}
+
 // Grouping core on device-resident gene-major data (caller holds g_mu and a WsUse): runmean -> dist ->
 // Ward.D2 -> cutree for each k.  Either xg (fp64) or rg / ng (int32 counts) is given.
 static int group_core(Workspace *ws, const double *xg, const int32_t *rg, const int32_t *ng, int64_t ld, int64_t G,

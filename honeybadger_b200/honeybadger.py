@@ -95,31 +95,15 @@ def _as_frame(m, prefix_r="g", prefix_c="cell") -> pd.DataFrame:
 def cut_merges(merge_a, merge_b, height, N, ks):
     """cutree(hc, k) for each k in `ks` from a merge list (leaf representatives, any order in which
     children precede parents): the N - k lowest merges are applied with union-find; clusters are
-    numbered by first appearance in cell order, as cutree does."""
-    order = np.argsort(np.asarray(height), kind="stable")
-    a, b = np.asarray(merge_a)[order].tolist(), np.asarray(merge_b)[order].tolist()
-    parent = list(range(N))
-
-    def find(i):
-        while parent[i] != i:
-            parent[i] = parent[parent[i]]
-            i = parent[i]
-        return i
-
-    # one pass over the merges: the cuts with more clusters are prefixes of those with fewer
-    res, done = {}, 0
-    for k in sorted({int(k) for k in ks}, reverse=True):
-        upto = max(0, N - k)
-        for m in range(done, upto):
-            ra, rb = find(a[m]), find(b[m])
-            if ra != rb:
-                parent[ra] = rb
-        done = max(done, upto)
-        remap, lab = {}, np.zeros(N, dtype=np.int32)
-        for i in range(N):
-            lab[i] = remap.setdefault(find(i), len(remap) + 1)
-        res[k] = lab
-    return [res[int(k)].copy() for k in ks]
+    numbered by first appearance in cell order, as cutree does (libhb_b200: hb_cutree_host)."""
+    ma = np.ascontiguousarray(merge_a, dtype=np.int32)
+    mb = np.ascontiguousarray(merge_b, dtype=np.int32)
+    hh = np.ascontiguousarray(height, dtype=np.float64)
+    kk = np.ascontiguousarray([int(k) for k in ks], dtype=np.int32)
+    lab = np.empty((kk.size, int(N)), dtype=np.int32)
+    _lib.check(_lib.load().hb_cutree_host(ma.ctypes.data, mb.ctypes.data, hh.ctypes.data, int(N), kk.ctypes.data,
+                                          int(kk.size), lab.ctypes.data))
+    return [lab[i].copy() for i in range(kk.size)]
 
 
 def ward_groups_dev(x_dev, heights, k=101, counts=None):
@@ -326,7 +310,7 @@ def _membership(labels_per_height, N):
 
 # --------------------------------------------------------------------------- device rounds
 def _vp(a):
-    return None if a is None else a.ctypes.data_as(C.c_void_p)
+    return None if a is None else C.c_void_p(a.ctypes.data)
 
 
 def _stream():

@@ -248,6 +248,12 @@ int hb_runmean_ratio_dev(const int32_t *r, const int32_t *n, int64_t ld, int64_t
 int hb_dist_sq_dev(const double *s, int64_t ld, int64_t G, int64_t N, double *D, void *stream);
 int hb_ward_linkage_dev(double *D, int64_t N, int32_t *merge_a, int32_t *merge_b, double *height,
                         void *stream);
+/* cutree(hc, k) for each of the nk values in ks, from the merge list hb_ward_linkage_dev wrote (host copies):
+ * the N - k lowest merges (stable by height, so children stay before their parents) are applied with
+ * union-find and the clusters are numbered by first appearance in cell order, as stats::cutree numbers
+ * them (R/HoneyBADGER.R:1136, :1397).  labels is [nk][N], 1-based.  Host only, no device work. */
+int hb_cutree_host(const int32_t *merge_a, const int32_t *merge_b, const double *height, int64_t N,
+                   const int32_t *ks, int32_t nk, int32_t *labels);
 
 /* Host-buffer forms for the R side (matrices column-major [G x N] as R holds them): the whole
  * `runmean -> dist -> hclust(ward.D2) -> cutree(k)` block of R/HoneyBADGER.R:1122-1136 (window 101) and
