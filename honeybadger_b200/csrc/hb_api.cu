@@ -1995,7 +1995,7 @@ int hb_dist_sq_dev(const double *s, int64_t ld, int64_t G, int64_t N, double *D,
     if (!s || !D || G < 1 || N < 1 || ld < N) return fail(HB_ERR_ARG, "bad arguments");
     void *flags = nullptr;
     if (g_dist_mode != 1) {
-        HBTRY(ws->st_part.ensure(hb::dist_flag_bytes(G, N)));
+        HBTRY(ws->st_part.ensure(hb::dist_scratch_bytes(G, N)));
         flags = ws->st_part.p;
     }
     CU(hb::launch_dist_sq(s, ld, G, N, D, flags, (cudaStream_t)stream));
@@ -2078,7 +2078,7 @@ static int group_core(Workspace *ws, const double *xg, const int32_t *rg, const 
     CU(hb::launch_runmean(xg, rg, ng, ld, G, N, window, S, lds, st));
     HBTRY(ws->st_pool.ensure((size_t)N * N * sizeof(double)));
     HBTRY(ws->st_pool2.ensure((size_t)N * 16 + 64));
-    HBTRY(ws->st_part.ensure(std::max(hb::ward_scratch_bytes(N), hb::dist_flag_bytes(G, N))));
+    HBTRY(ws->st_part.ensure(std::max(hb::ward_scratch_bytes(N), hb::dist_scratch_bytes(G, N))));
     double *D = ws->st_pool.as<double>();
     CU(hb::launch_dist_sq(S, lds, G, N, D, g_dist_mode != 1 ? ws->st_part.p : nullptr, st));
     int32_t *d_ma = ws->st_pool2.as<int32_t>(), *d_mb = d_ma + N;

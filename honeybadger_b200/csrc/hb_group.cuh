@@ -143,33 +143,50 @@ __global__ void __launch_bounds__(256)
 }
 
 // ---------------------------------------------------------------------------------------------
-// The same distances with the loads taken off the critical path.  dist_sq_kernel stages a slab of 16
-// positions through shared memory with ordinary loads between two block barriers: while a block
-// waits for its slab nothing of it computes, and the test for non-finite values re-reads every
-// staged element.  Here
-//   * a pre-pass (dist_flag_kernel) marks every (slab of 16 positions, tile of 64 cells) that holds a
-//     non-finite value, once per matrix — the main kernel reads two bytes per slab instead;
+// The same distances with the loads and the missing-value bookkeeping taken off the critical path.
+// dist_sq_kernel stages a slab of 16 positions through shared memory with ordinary loads between two
+// block barriers: while a block waits for its slab nothing of it computes; the test for non-finite
+// values re-reads every staged element; and in a slab that holds one, every (pair, position) pays
+// an isfinite test and a second fp64 addition for the pair count — 2.3x the cost of a clean slab,
+// which is the normal case of the allele matrices (r / n is NaN wherever a cell has no coverage).
+// Here
+//   * a pre-pass (dist_mask_kernel) writes, once per matrix, a 16-bit mask of the finite positions of
+//     every (slab of 16 positions, cell) and a byte per (slab, tile of 64 cells) that says whether
+//     anything is missing at all;
+//   * the pair count of a slab is popc(mask_i & mask_j) — 16 integer instructions per thread and slab
+//     instead of 256 fp64 additions — and the sum takes a position iff its bit is set in that AND (a
+//     select after the add: NaN differences are computed and dropped), so a slab with missing values
+//     costs the same three fp64 instructions per (pair, position) as a clean one plus a bit test and a
+//     select;
 //   * slabs move with 16-byte cp.async into a three-stage ring, two slabs ahead of the arithmetic,
 //     one block barrier per slab;
 //   * columns past N are clamped (their pairs are never stored), so edge tiles stay on the fast path.
 // Per pair the same operations in the same order as dist_sq_kernel — results are bit-identical
 // (tests/test_gpu_group.py).  Needs ld even and S 16-byte aligned (the launcher checks).
 #define GP_STAGES 3
-__global__ void __launch_bounds__(256)
-    dist_flag_kernel(const double *S, int64_t ld, int64_t G, int64_t N, uint8_t *flags, int ntile)
+__global__ void __launch_bounds__(GD_T)
+    dist_mask_kernel(const double *S, int64_t ld, int64_t G, int64_t N, uint16_t *masks, uint8_t *flags, int ntile)
 {
-    const int64_t g0 = (int64_t)blockIdx.x * GD_K, c0 = (int64_t)blockIdx.y * GD_T;
-    int bad = 0;
-    for (int e = threadIdx.x; e < GD_K * GD_T; e += 256) {
-        const int64_t g = g0 + e / GD_T, c = c0 + e % GD_T;
-        if (g < G && c < N) bad |= !isfinite(S[g * ld + c]);
+    const int64_t g0 = (int64_t)blockIdx.x * GD_K, c = (int64_t)blockIdx.y * GD_T + threadIdx.x;
+    uint32_t m = 0;
+    int bad = g0 + GD_K > G; // a partial last slab takes the masked path: its rows past G have no bit
+    if (c < N) {
+#pragma unroll
+        for (int k = 0; k < GD_K; k++)
+            if (g0 + k < G) {
+                const bool ok = isfinite(S[(g0 + k) * ld + c]);
+                m |= ok ? 1u << k : 0u;
+                bad |= !ok;
+            }
     }
+    masks[((int64_t)blockIdx.x * ntile + blockIdx.y) * GD_T + threadIdx.x] = (uint16_t)m;
     bad = __syncthreads_or(bad);
     if (threadIdx.x == 0) flags[(int64_t)blockIdx.x * ntile + blockIdx.y] = bad ? 1 : 0;
 }
 
 __global__ void __launch_bounds__(256)
-    dist_sq_pipe_kernel(const double *S, int64_t ld, int64_t G, int64_t N, const uint8_t *flags, int ntile, double *D)
+    dist_sq_pipe_kernel(const double *S, int64_t ld, int64_t G, int64_t N, const uint16_t *masks, const uint8_t *flags,
+                        int ntile, double *D)
 {
     extern __shared__ __align__(16) double gp_sm[]; // [GP_STAGES][2][GD_K][GD_T]
     const int64_t i0 = (int64_t)blockIdx.y * GD_T, j0 = (int64_t)blockIdx.x * GD_T;
@@ -191,22 +208,37 @@ __global__ void __launch_bounds__(256)
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    double acc[4][4], cnt[4][4];
+    double acc[4][4];
+    int32_t cnt[4][4];
 #pragma unroll
     for (int a = 0; a < 4; a++)
 #pragma unroll
-        for (int b = 0; b < 4; b++) acc[a][b] = cnt[a][b] = 0.0;
-    double nfast = 0.0;
+        for (int b = 0; b < 4; b++) {
+            acc[a][b] = 0.0;
+            cnt[a][b] = 0;
+        }
+    int32_t nfull = 0; // positions of slabs without a missing value: counted once, not per pair
+    const uint16_t *mrow = masks + (int64_t)blockIdx.y * GD_T + ty, *mcol = masks + (int64_t)blockIdx.x * GD_T + tx;
+    const int64_t mstride = (int64_t)ntile * GD_T;
     issue(0);
     issue(1);
     for (int64_t s = 0; s < nslab; s++) {
+        const bool bad = flags[s * ntile + blockIdx.y] | flags[s * ntile + blockIdx.x];
+        uint32_t mi[4], mj[4];
+        if (bad) {
+#pragma unroll
+            for (int a = 0; a < 4; a++) {
+                mi[a] = mrow[s * mstride + 16 * a];
+                mj[a] = mcol[s * mstride + 16 * a];
+            }
+        }
         asm volatile("cp.async.wait_group 1;" ::: "memory");
         __syncthreads(); // slab s has landed for everybody, and everybody is done with slab s - 1
         issue(s + 2);    // into the stage slab s - 1 used
         const double *sa = gp_sm + (s % GP_STAGES) * (2 * GD_K * GD_T), *sb = sa + GD_K * GD_T;
-        const int kmax = (int)(G - s * GD_K < GD_K ? G - s * GD_K : GD_K);
-        const bool bad = flags[s * ntile + blockIdx.y] | flags[s * ntile + blockIdx.x];
-        if (!bad && kmax == GD_K) {
+        if (!bad) {
+            // R_euclidean (distance.c): dev = x_i - x_j; dist += dev * dev — a product and an addition, each
+            // rounded (no FMA), positions in order
 #pragma unroll 4
             for (int k = 0; k < GD_K; k++) {
                 double va[4], vb[4];
@@ -223,9 +255,18 @@ __global__ void __launch_bounds__(256)
                         acc[a][b] = __dadd_rn(acc[a][b], __dmul_rn(d, d));
                     }
             }
-            nfast += (double)GD_K;
+            nfull += GD_K;
         } else {
-            for (int k = 0; k < kmax; k++) {
+            uint32_t m[4][4];
+#pragma unroll
+            for (int a = 0; a < 4; a++)
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    m[a][b] = mi[a] & mj[b];
+                    cnt[a][b] += __popc(m[a][b]);
+                }
+#pragma unroll
+            for (int k = 0; k < GD_K; k++) {
                 double va[4], vb[4];
 #pragma unroll
                 for (int a = 0; a < 4; a++) {
@@ -236,11 +277,9 @@ __global__ void __launch_bounds__(256)
                 for (int a = 0; a < 4; a++)
 #pragma unroll
                     for (int b = 0; b < 4; b++) {
-                        const double d = va[a] - vb[b]; // NaN or Inf-Inf when a member is unusable
-                        if (isfinite(d)) {
-                            acc[a][b] = __dadd_rn(acc[a][b], __dmul_rn(d, d));
-                            cnt[a][b] += 1.0;
-                        }
+                        const double d = va[a] - vb[b]; // NaN when a member is missing: computed, not added
+                        const double t = __dadd_rn(acc[a][b], __dmul_rn(d, d));
+                        if ((m[a][b] >> k) & 1u) acc[a][b] = t; // ptxas turns any form of this into add + select
                     }
             }
         }
@@ -251,7 +290,8 @@ __global__ void __launch_bounds__(256)
         for (int b = 0; b < 4; b++) {
             const int64_t i = i0 + ty + 16 * a, j = j0 + tx + 16 * b;
             if (i < N && j < N) {
-                const double c = cnt[a][b] + nfast;
+                // if (count != nc) dist /= ((double)count / nc); return sqrt(dist); hclust squares it again
+                const double c = (double)(cnt[a][b] + nfull);
                 double v = 0.0;
                 if (c > 0) {
                     v = c != (double)G ? acc[a][b] / (c / (double)G) : acc[a][b];

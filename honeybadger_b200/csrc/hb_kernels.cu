@@ -971,13 +971,18 @@ cudaError_t launch_runmean(const double *x, const int32_t *r, const int32_t *n, 
         runmean_kernel<true><<<grid, 256, 0, st>>>(nullptr, r, n, ld, G, N, k / 2, out, ldo);
     return cudaGetLastError();
 }
-// flags: dist_flag_bytes(G, N) of scratch for the pipelined form (NULL, odd ld or a misaligned S: the plain kernel)
-size_t dist_flag_bytes(int64_t G, int64_t N) { return (size_t)((G + GD_K - 1) / GD_K) * ((N + GD_T - 1) / GD_T) + 64; }
-cudaError_t launch_dist_sq(const double *S, int64_t ld, int64_t G, int64_t N, double *D, void *flags, cudaStream_t st)
+// scratch: dist_scratch_bytes(G, N) for the pipelined form (NULL, odd ld or a misaligned S: the plain kernel) —
+// a byte per (slab, tile) and a 16-bit mask per (slab, cell)
+size_t dist_scratch_bytes(int64_t G, int64_t N)
+{
+    const size_t nslab = (size_t)((G + GD_K - 1) / GD_K), nt = (size_t)((N + GD_T - 1) / GD_T);
+    return ((nslab * nt + 255) & ~(size_t)255) + nslab * nt * GD_T * sizeof(uint16_t) + 256;
+}
+cudaError_t launch_dist_sq(const double *S, int64_t ld, int64_t G, int64_t N, double *D, void *scratch, cudaStream_t st)
 {
     const unsigned nt = (unsigned)((N + GD_T - 1) / GD_T);
     const int64_t nslab = (G + GD_K - 1) / GD_K;
-    if (flags && N >= 2 && (ld & 1) == 0 && ((uintptr_t)S & 15) == 0 && nslab <= 0x7fffffff && nt <= 65535) {
+    if (scratch && N >= 2 && (ld & 1) == 0 && ((uintptr_t)S & 15) == 0 && nslab <= 0x7fffffff && nt <= 65535) {
         constexpr int smem = GP_STAGES * 2 * GD_K * GD_T * (int)sizeof(double);
         static bool once = false;
         if (!once) {
@@ -985,8 +990,10 @@ cudaError_t launch_dist_sq(const double *S, int64_t ld, int64_t G, int64_t N, do
             if (e != cudaSuccess) return e;
             once = true;
         }
-        dist_flag_kernel<<<dim3((unsigned)nslab, nt), 256, 0, st>>>(S, ld, G, N, (uint8_t *)flags, (int)nt);
-        dist_sq_pipe_kernel<<<dim3(nt, nt), 256, smem, st>>>(S, ld, G, N, (const uint8_t *)flags, (int)nt, D);
+        uint8_t *flags = (uint8_t *)scratch;
+        uint16_t *masks = (uint16_t *)((char *)scratch + (((size_t)nslab * nt + 255) & ~(size_t)255));
+        dist_mask_kernel<<<dim3((unsigned)nslab, nt), GD_T, 0, st>>>(S, ld, G, N, masks, flags, (int)nt);
+        dist_sq_pipe_kernel<<<dim3(nt, nt), 256, smem, st>>>(S, ld, G, N, masks, flags, (int)nt, D);
         return cudaGetLastError();
     }
     dist_sq_kernel<<<dim3(nt, nt), 256, 0, st>>>(S, ld, G, N, D);

@@ -66,7 +66,7 @@ cudaError_t launch_retest_gexp_b(int64_t N, const double *partial, const double 
                                  double *p_del, cudaStream_t st);
 cudaError_t launch_runmean(const double *x, const int32_t *r, const int32_t *n, int64_t ld, int64_t G,
                            int64_t N, int32_t k, double *out, int64_t ldo, cudaStream_t st);
-size_t dist_flag_bytes(int64_t G, int64_t N);
+size_t dist_scratch_bytes(int64_t G, int64_t N);
 cudaError_t launch_dist_sq(const double *S, int64_t ld, int64_t G, int64_t N, double *D, void *flags, cudaStream_t st);
 size_t ward_scratch_bytes(int64_t N);
 cudaError_t launch_ward(double *D, int64_t N, void *work, int32_t *ma, int32_t *mb, double *height, int mode,
