@@ -84,13 +84,45 @@ def kernel_source_hash():
     return h.hexdigest()[:16]
 
 
+_SASS_TXT = None
+DOMINANT_KERNEL = {"expr": "norm3_fast_kernel", "allele": "binom2_fast_kernel"}
+
+
+def kernel_sass_hash(workload):
+    """sha256 (16 hex) over the MACHINE CODE of the workload's dominant kernel in the built library (every
+    instantiation of it; `cuobjdump -sass`, the listing of a function starts at its own offset 0, so other
+    kernels in the library do not move it).  The identity that matters for a traffic figure: same SASS, same
+    DRAM traffic on the same workload.  None when cuobjdump is not there."""
+    import hashlib
+    global _SASS_TXT
+    so = os.path.join(ROOT, "honeybadger_b200", "libhb_b200.so")
+    if _SASS_TXT is None:
+        try:
+            _SASS_TXT = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True, timeout=180).stdout
+        except Exception:
+            _SASS_TXT = ""
+    txt = _SASS_TXT
+    name, h, keep, n = DOMINANT_KERNEL[workload], hashlib.sha256(), False, 0
+    for ln in txt.splitlines():
+        if "Function :" in ln:
+            keep = name in ln
+            n += keep
+        if keep:
+            h.update(ln.strip().encode())
+    return h.hexdigest()[:16] if n else None
+
+
 def ncu_traffic(workload):
-    """dram bytes per launch from the committed ncu capture — only if it was taken on THIS kernel source
-    (profiles/traffic.json: {workload: {"bytes": .., "src": hash}}); otherwise null (stale capture)."""
+    """dram bytes per launch from the committed ncu capture — only if it was taken on THIS kernel: the SASS of
+    the dominant kernel hashes to what profiles/traffic.json recorded ("sass"), or, without cuobjdump, the device
+    sources do ("src").  Otherwise null (stale capture)."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     try:
         e = json.load(open(p)).get(workload)
-        if isinstance(e, dict) and e.get("src") == kernel_source_hash():
+        if not isinstance(e, dict):
+            return None
+        sass = kernel_sass_hash(workload)
+        if (sass is not None and e.get("sass") == sass) or e.get("src") == kernel_source_hash():
             return e.get("bytes")
     except Exception:
         pass
@@ -552,7 +584,7 @@ def main():
                 "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
                 "gpu_launches": launches_per_step * args.steps, "parity": parity, "modes": modes,
                 "sharded_level": sharded, "resident_flow": flow,
-                "kernel_source_hash": kernel_source_hash()}
+                "kernel_source_hash": kernel_source_hash(), "kernel_sass_hash": kernel_sass_hash(kind)}
         if allele is not None:
             line["allele"] = allele
         print(json.dumps(line), flush=True)
