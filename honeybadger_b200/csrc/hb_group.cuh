@@ -155,9 +155,9 @@ __global__ void __launch_bounds__(256)
 //     anything is missing at all;
 //   * the pair count of a slab is popc(mask_i & mask_j) — 16 integer instructions per thread and slab
 //     instead of 256 fp64 additions — and the sum takes a position iff its bit is set in that AND (a
-//     select after the add: NaN differences are computed and dropped), so a slab with missing values
-//     costs the same three fp64 instructions per (pair, position) as a clean one plus a bit test and a
-//     select;
+//     difference whose bit is clear is turned into a denormal, whose square is +0), so a slab with
+//     missing values costs the same three fp64 instructions per (pair, position) as a clean one plus a
+//     bit test and one 32-bit select;
 //   * slabs move with 16-byte cp.async into a three-stage ring, two slabs ahead of the arithmetic,
 //     one block barrier per slab;
 //   * columns past N are clamped (their pairs are never stored), so edge tiles stay on the fast path.
@@ -277,9 +277,18 @@ __global__ void __launch_bounds__(256)
                 for (int a = 0; a < 4; a++)
 #pragma unroll
                     for (int b = 0; b < 4; b++) {
-                        const double d = va[a] - vb[b]; // NaN when a member is missing: computed, not added
-                        const double t = __dadd_rn(acc[a][b], __dmul_rn(d, d));
-                        if ((m[a][b] >> k) & 1u) acc[a][b] = t; // ptxas turns any form of this into add + select
+                        // A missing member makes the difference NaN (or +-Inf).  Clearing the HIGH word of an
+                        // unwanted difference leaves a denormal whose square rounds to +0, and acc + 0 == acc
+                        // bit for bit (acc is a sum of squares, never -0): one integer select per (pair,
+                        // position) instead of a 64-bit select after the add.
+                        const double d = va[a] - vb[b];
+                        int hi; // and-with-immediate into a predicate, one select (the C form becomes shift, shift, and)
+                        asm("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\tand.b32 t, %1, %2;\n\tsetp.ne.u32 p, t, 0;\n\t"
+                            "selp.b32 %0, %3, 0, p;\n\t}"
+                            : "=r"(hi)
+                            : "r"(m[a][b]), "r"(1u << k), "r"(__double2hiint(d)));
+                        const double dm = __hiloint2double(hi, __double2loint(d));
+                        acc[a][b] = __dadd_rn(acc[a][b], __dmul_rn(dm, dm));
                     }
             }
         }
