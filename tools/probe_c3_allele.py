@@ -10,6 +10,7 @@ N = int(sys.argv[1]) if len(sys.argv) > 1 else 10000
 G = int(sys.argv[2]) if len(sys.argv) > 2 else 200000
 dev = torch.device("cuda:0")
 g = torch.Generator(device=dev); g.manual_seed(3)
+torch.manual_seed(3)  # torch._standard_gamma below draws from the DEFAULT generator: without this the data differ run to run
 seg = synth.segments(G)
 # tumour-like mix: clone A 60 %, clone B 20 %, normal cells 20 %.  A truncal deletion (chr14, clones A and B)
 # is visible in the all-cell pooled chain (pooled lesser-allele rate 0.17); the sub-clonal one (chr10, clone A)
