@@ -654,7 +654,55 @@ def run_sharded_level(x, cells, rank, world, dev, dist, check_cells=1024, check_
         dist.broadcast(flag, src=0)
         res["equals_single_gpu"] = bool(flag.item())
         res["checked_on"] = f"{cc * world} cells x {gg} genes (first {cc} cells of every rank)"
+        res["grouping"] = run_sharded_grouping(x, cells, rank, world, dev, dist, hd)
     return res
+
+
+def run_sharded_grouping(x, cells, rank, world, dev, dist, hd, total=20000):
+    """The grouping step of a level on sharded cells (`dist.sharded_ward_groups`): runmean local, smoothed cells
+    all-gathered, `dist` split by blocks of the symmetric matrix over the ranks, Ward + cutree on rank 0, labels
+    broadcast.  STRONG scaling by construction (a fixed population of `total` cells, the first total / world of
+    every rank): the pair count is quadratic in the cells and the linkage is sequential, so this is the part of a
+    level that does not scale with the box — timed with its sequential remainder named."""
+    import torch
+    from honeybadger_b200 import _lib, hmm
+    per = min(cells, total // world)
+    xs = hmm.to_rows(x[:, :per].contiguous())
+    sizes = [per] * world
+    hd.sharded_ward_groups(xs, sizes, [1, 2, 3, 4, 5])   # warm-up
+    torch.cuda.synchronize()
+    dist.barrier()
+    t0 = time.perf_counter()
+    labs = hd.sharded_ward_groups(xs, sizes, [1, 2, 3, 4, 5])
+    torch.cuda.synchronize()
+    t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    # this rank's share of the pair work alone (its blocks of the matrix), for the split of the total
+    lib = _lib.load()
+    G = xs.shape[0]
+    S = hmm.alloc_rows(G, per, torch.float64, dev)
+    _lib.check(lib.hb_runmean_dev(xs.data_ptr(), xs.stride(0), G, per, 101, S.data_ptr(), S.stride(0), None))
+    nblk = sum(1 for q in range(world) if hd._pair_owner(rank, q, world) == rank)
+    blk = torch.empty((per, per), dtype=torch.float64, device=dev)
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    for q in range(world):
+        if hd._pair_owner(rank, q, world) != rank:
+            continue
+        if q == rank:
+            _lib.check(lib.hb_dist_sq_dev(S.data_ptr(), S.stride(0), G, per, blk.data_ptr(), None))
+        else:
+            _lib.check(lib.hb_dist_sq_rect_dev(S.data_ptr(), S.stride(0), per, S.data_ptr(), S.stride(0), per, G,
+                                               blk.data_ptr(), blk.stride(0), None))
+    torch.cuda.synchronize()
+    td = torch.tensor([time.perf_counter() - t1], dtype=torch.float64, device=dev)
+    dist.all_reduce(td, op=dist.ReduceOp.MAX)
+    return {"ms": float(t.item()) * 1e3, "cells_total": per * world, "genes": int(G), "scaling": "strong",
+            "ms_dist_blocks_max_over_ranks": float(td.item()) * 1e3, "blocks_this_rank": nblk,
+            "groups_at_k5": int(len(np.unique(labs[-1]))),
+            "exchanges": ["all_gather(smoothed cells)", "send/recv(row panels of the distance matrix -> rank 0)",
+                          "broadcast(labels)"],
+            "sequential_on_rank0": "Ward.D2 linkage + cutree"}
 
 
 def _single_rank_level(hd, x_full, labels_full, n_cells):

@@ -78,6 +78,7 @@ SIGNATURES = {
     "hb_runmean_dev": (_i32, [_p, _i64, _i64, _i64, _i32, _p, _i64, _p]),
     "hb_runmean_ratio_dev": (_i32, [_p, _p, _i64, _i64, _i64, _i32, _p, _i64, _p]),
     "hb_dist_sq_dev": (_i32, [_p, _i64, _i64, _i64, _p, _p]),
+    "hb_dist_sq_rect_dev": (_i32, [_p, _i64, _i64, _p, _i64, _i64, _i64, _p, _i64, _p]),
     "hb_ward_linkage_dev": (_i32, [_p, _i64, _p, _p, _p, _p]),
     "hb_cutree_host": (_i32, [_p, _p, _p, _i64, _p, _i32, _p]),
     "hb_group_gexp_host": (_i32, [_p, _i64, _i64, _i32, _p, _i32, _p]),

@@ -2002,6 +2002,22 @@ int hb_dist_sq_dev(const double *s, int64_t ld, int64_t G, int64_t N, double *D,
     return HB_OK;
 }
 
+int hb_dist_sq_rect_dev(const double *sa, int64_t lda, int64_t na, const double *sb, int64_t ldb, int64_t nb,
+                        int64_t G, double *D, int64_t ldd, void *stream)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    Workspace *ws;
+    HBTRY(cur_ws(&ws));
+    WS_USE(stream);
+    if (!sa || !sb || !D || G < 1 || na < 2 || nb < 2 || lda < na || ldb < nb || ldd < nb)
+        return fail(HB_ERR_ARG, "bad arguments");
+    if ((lda & 1) || (ldb & 1) || ((uintptr_t)sa & 15) || ((uintptr_t)sb & 15))
+        return fail(HB_ERR_ARG, "hb_dist_sq_rect_dev needs even row strides and 16-byte aligned matrices");
+    HBTRY(ws->st_part.ensure(hb::dist_scratch_bytes(G, na) + hb::dist_scratch_bytes(G, nb) + 512));
+    CU(hb::launch_dist_sq_rect(sa, lda, na, sb, ldb, nb, G, D, ldd, ws->st_part.p, (cudaStream_t)stream));
+    return HB_OK;
+}
+
 int hb_ward_linkage_dev(double *D, int64_t N, int32_t *merge_a, int32_t *merge_b, double *height,
                         void *stream)
 {

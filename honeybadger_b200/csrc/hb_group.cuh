@@ -184,26 +184,33 @@ __global__ void __launch_bounds__(GD_T)
     if (threadIdx.x == 0) flags[(int64_t)blockIdx.x * ntile + blockIdx.y] = bad ? 1 : 0;
 }
 
+// SYM: one matrix, D is [N][N], only the upper-triangle tiles are computed and mirrored.  !SYM: the rows of D are
+// the cells of A, its columns the cells of B (a row block of the full matrix when the cells are sharded over
+// ranks: A = this rank's cells, B = another rank's), every tile computed, D[i * ldd + j].
+template <bool SYM>
 __global__ void __launch_bounds__(256)
-    dist_sq_pipe_kernel(const double *S, int64_t ld, int64_t G, int64_t N, const uint16_t *masks, const uint8_t *flags,
-                        int ntile, double *D)
+    dist_sq_pipe_kernel(const double *Sa, int64_t lda, int64_t Na, const uint16_t *maska, const uint8_t *flagsa,
+                        int ntile_a, const double *Sb, int64_t ldb, int64_t Nb, const uint16_t *maskb,
+                        const uint8_t *flagsb, int ntile_b, int64_t G, double *D, int64_t ldd)
 {
     extern __shared__ __align__(16) double gp_sm[]; // [GP_STAGES][2][GD_K][GD_T]
     const int64_t i0 = (int64_t)blockIdx.y * GD_T, j0 = (int64_t)blockIdx.x * GD_T;
-    if (j0 + GD_T <= i0) return; // lower triangle: mirrored from the upper one
+    if (SYM && j0 + GD_T <= i0) return; // lower triangle: mirrored from the upper one
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     const int64_t nslab = (G + GD_K - 1) / GD_K;
-    const int64_t cclamp = (N - 1) & ~(int64_t)1;
+    const int64_t clamp_a = (Na - 1) & ~(int64_t)1, clamp_b = (Nb - 1) & ~(int64_t)1;
     auto issue = [&](int64_t s) {
         if (s < nslab) {
             double *base = gp_sm + (s % GP_STAGES) * (2 * GD_K * GD_T);
             for (int e = threadIdx.x; e < 2 * GD_K * GD_T / 2; e += 256) {
                 const int which = e >> 9, k = (e >> 5) & (GD_K - 1), ch = e & 31;
                 int64_t g = s * GD_K + k, c = (which ? j0 : i0) + 2 * ch;
+                const int64_t cl = which ? clamp_b : clamp_a;
                 g = g < G ? g : G - 1;
-                c = c < cclamp ? c : cclamp;
+                c = c < cl ? c : cl;
+                const double *src = which ? Sb + g * ldb + c : Sa + g * lda + c;
                 const unsigned dst = (unsigned)__cvta_generic_to_shared(base + which * (GD_K * GD_T) + k * GD_T + 2 * ch);
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(S + g * ld + c) : "memory");
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
             }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
@@ -218,18 +225,18 @@ __global__ void __launch_bounds__(256)
             cnt[a][b] = 0;
         }
     int32_t nfull = 0; // positions of slabs without a missing value: counted once, not per pair
-    const uint16_t *mrow = masks + (int64_t)blockIdx.y * GD_T + ty, *mcol = masks + (int64_t)blockIdx.x * GD_T + tx;
-    const int64_t mstride = (int64_t)ntile * GD_T;
+    const uint16_t *mrow = maska + (int64_t)blockIdx.y * GD_T + ty, *mcol = maskb + (int64_t)blockIdx.x * GD_T + tx;
+    const int64_t mstride_a = (int64_t)ntile_a * GD_T, mstride_b = (int64_t)ntile_b * GD_T;
     issue(0);
     issue(1);
     for (int64_t s = 0; s < nslab; s++) {
-        const bool bad = flags[s * ntile + blockIdx.y] | flags[s * ntile + blockIdx.x];
+        const bool bad = flagsa[s * ntile_a + blockIdx.y] | flagsb[s * ntile_b + blockIdx.x];
         uint32_t mi[4], mj[4];
         if (bad) {
 #pragma unroll
             for (int a = 0; a < 4; a++) {
-                mi[a] = mrow[s * mstride + 16 * a];
-                mj[a] = mcol[s * mstride + 16 * a];
+                mi[a] = mrow[s * mstride_a + 16 * a];
+                mj[a] = mcol[s * mstride_b + 16 * a];
             }
         }
         asm volatile("cp.async.wait_group 1;" ::: "memory");
@@ -298,7 +305,7 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
         for (int b = 0; b < 4; b++) {
             const int64_t i = i0 + ty + 16 * a, j = j0 + tx + 16 * b;
-            if (i < N && j < N) {
+            if (i < Na && j < Nb) {
                 // if (count != nc) dist /= ((double)count / nc); return sqrt(dist); hclust squares it again
                 const double c = (double)(cnt[a][b] + nfull);
                 double v = 0.0;
@@ -307,9 +314,13 @@ __global__ void __launch_bounds__(256)
                     const double r = sqrt(v);
                     v = __dmul_rn(r, r);
                 }
-                const double w = (i == j) ? 0.0 : v;
-                D[i * N + j] = w;
-                D[j * N + i] = w;
+                if (SYM) {
+                    const double w = (i == j) ? 0.0 : v;
+                    D[i * ldd + j] = w;
+                    D[j * ldd + i] = w;
+                } else {
+                    D[i * ldd + j] = v; // a cell against itself comes out as 0 by the arithmetic
+                }
             }
         }
 }

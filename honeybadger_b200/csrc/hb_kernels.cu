@@ -978,25 +978,62 @@ size_t dist_scratch_bytes(int64_t G, int64_t N)
     const size_t nslab = (size_t)((G + GD_K - 1) / GD_K), nt = (size_t)((N + GD_T - 1) / GD_T);
     return ((nslab * nt + 255) & ~(size_t)255) + nslab * nt * GD_T * sizeof(uint16_t) + 256;
 }
+static cudaError_t dist_pipe_attr()
+{
+    constexpr int smem = GP_STAGES * 2 * GD_K * GD_T * (int)sizeof(double);
+    static bool once = false;
+    if (!once) {
+        cudaError_t e = cudaFuncSetAttribute(dist_sq_pipe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(dist_sq_pipe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        once = true;
+    }
+    return cudaSuccess;
+}
+static bool dist_pipe_ok(const double *S, int64_t ld, int64_t G, int64_t N)
+{
+    return N >= 2 && (ld & 1) == 0 && ((uintptr_t)S & 15) == 0 && (G + GD_K - 1) / GD_K <= 0x7fffffff &&
+           (N + GD_T - 1) / GD_T <= 65535;
+}
 cudaError_t launch_dist_sq(const double *S, int64_t ld, int64_t G, int64_t N, double *D, void *scratch, cudaStream_t st)
 {
     const unsigned nt = (unsigned)((N + GD_T - 1) / GD_T);
     const int64_t nslab = (G + GD_K - 1) / GD_K;
-    if (scratch && N >= 2 && (ld & 1) == 0 && ((uintptr_t)S & 15) == 0 && nslab <= 0x7fffffff && nt <= 65535) {
+    if (scratch && dist_pipe_ok(S, ld, G, N)) {
         constexpr int smem = GP_STAGES * 2 * GD_K * GD_T * (int)sizeof(double);
-        static bool once = false;
-        if (!once) {
-            cudaError_t e = cudaFuncSetAttribute(dist_sq_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-            if (e != cudaSuccess) return e;
-            once = true;
-        }
+        cudaError_t e = dist_pipe_attr();
+        if (e != cudaSuccess) return e;
         uint8_t *flags = (uint8_t *)scratch;
         uint16_t *masks = (uint16_t *)((char *)scratch + (((size_t)nslab * nt + 255) & ~(size_t)255));
         dist_mask_kernel<<<dim3((unsigned)nslab, nt), GD_T, 0, st>>>(S, ld, G, N, masks, flags, (int)nt);
-        dist_sq_pipe_kernel<<<dim3(nt, nt), 256, smem, st>>>(S, ld, G, N, masks, flags, (int)nt, D);
+        dist_sq_pipe_kernel<true><<<dim3(nt, nt), 256, smem, st>>>(S, ld, N, masks, flags, (int)nt, S, ld, N, masks, flags,
+                                                                   (int)nt, G, D, N);
         return cudaGetLastError();
     }
     dist_sq_kernel<<<dim3(nt, nt), 256, 0, st>>>(S, ld, G, N, D);
+    return cudaGetLastError();
+}
+// Rectangular block: rows = the Na cells of A, columns = the Nb cells of B, D[i * ldd + j].  scratch:
+// dist_scratch_bytes(G, Na) + dist_scratch_bytes(G, Nb).  Both matrices need an even stride and 16-byte alignment.
+cudaError_t launch_dist_sq_rect(const double *Sa, int64_t lda, int64_t Na, const double *Sb, int64_t ldb, int64_t Nb,
+                                int64_t G, double *D, int64_t ldd, void *scratch, cudaStream_t st)
+{
+    if (!scratch || !dist_pipe_ok(Sa, lda, G, Na) || !dist_pipe_ok(Sb, ldb, G, Nb)) return cudaErrorInvalidValue;
+    constexpr int smem = GP_STAGES * 2 * GD_K * GD_T * (int)sizeof(double);
+    cudaError_t e = dist_pipe_attr();
+    if (e != cudaSuccess) return e;
+    const unsigned nta = (unsigned)((Na + GD_T - 1) / GD_T), ntb = (unsigned)((Nb + GD_T - 1) / GD_T);
+    const int64_t nslab = (G + GD_K - 1) / GD_K;
+    uint8_t *fa = (uint8_t *)scratch;
+    uint16_t *ma = (uint16_t *)((char *)scratch + (((size_t)nslab * nta + 255) & ~(size_t)255));
+    char *sb = (char *)scratch + ((dist_scratch_bytes(G, Na) + 255) & ~(size_t)255);
+    uint8_t *fb = (uint8_t *)sb;
+    uint16_t *mb = (uint16_t *)(sb + (((size_t)nslab * ntb + 255) & ~(size_t)255));
+    dist_mask_kernel<<<dim3((unsigned)nslab, nta), GD_T, 0, st>>>(Sa, lda, G, Na, ma, fa, (int)nta);
+    dist_mask_kernel<<<dim3((unsigned)nslab, ntb), GD_T, 0, st>>>(Sb, ldb, G, Nb, mb, fb, (int)ntb);
+    dist_sq_pipe_kernel<false><<<dim3(ntb, nta), 256, smem, st>>>(Sa, lda, Na, ma, fa, (int)nta, Sb, ldb, Nb, mb, fb, (int)ntb,
+                                                                  G, D, ldd);
     return cudaGetLastError();
 }
 // Scratch of the linkage: the cluster form keeps one copy of the chain and the cluster sizes per CTA.

@@ -475,19 +475,143 @@ def sharded_allele_level(r_local, n_local, labels_local, n_cells, l_maf=None, n_
     return out
 
 
+def _pair_owner(r, q, world):
+    """Which rank computes the block (cells of r) x (cells of q) of the distance matrix: the symmetric pair
+    {r, q} is computed once, by the rank from which the other is at most half a ring ahead."""
+    if r == q:
+        return r
+    d = (q - r) % world
+    if 2 * d < world:
+        return r
+    if 2 * d > world:
+        return q
+    return min(r, q)   # even world, exactly opposite: the lower rank
+
+
+def sharded_ward_groups(x_local, sizes, heights, k=101, return_matrix=False):
+    """cutree(hclust(dist(t(runmean(x, k))), "ward.D2"), h) for each h (R/HoneyBADGER.R:1122-1136) with the CELLS
+    sharded over the ranks — the grouping step of a recursion level without any rank holding every cell's
+    expression.  x_local: gene-major fp64 CUDA tensor [G, N_local] (this rank's cells of the level, rank-major
+    order = the level's cell order); sizes: cells of every rank.  Steps:
+      runmean                 local (windows run along the genes of one cell)
+      smoothed matrix         all-gather (G x N doubles in total; padded to the largest shard)
+      dist                    split by BLOCKS of the symmetric matrix: rank r computes (r, q) for the q at most half
+                              a ring ahead (hb_dist_sq_rect_dev; its own diagonal block with hb_dist_sq_dev) —
+                              N^2 / (2 * world) pairs per rank, every entry bit-identical to the single-GPU kernel's
+      blocks -> rank 0        send / recv of each rank's row panel; rank 0 fills the other triangle by transposition
+      Ward.D2 + cutree        rank 0 (the nearest-neighbour chain is sequential), labels broadcast
+    Returns one int32 label array over ALL the level's cells per height (identical on every rank) — and the
+    assembled matrix on rank 0 when return_matrix (tests).  world = 1 is honeybadger.ward_groups_dev."""
+    import torch
+    import torch.distributed as dist
+    from . import _lib, hmm
+    from .honeybadger import _stream, cut_merges
+    lib = _lib.load()
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    sizes = [int(v) for v in sizes]
+    N = int(sum(sizes))
+    G, n_loc = x_local.shape
+    assert len(sizes) == world and n_loc == sizes[rank]
+    dev = x_local.device
+    heights = [int(h) for h in heights]
+    if N == 1:
+        return [np.ones(1, dtype=np.int32) for _ in heights]
+    offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    mx = max(sizes)
+    # ---- runmean of this rank's cells, then everybody's smoothed cells (padded blocks, gene-major)
+    S = torch.zeros((G, mx), dtype=torch.float64, device=dev)
+    if n_loc:
+        xr = x_local if x_local.stride(1) == 1 else x_local.contiguous()
+        tmp = hmm.alloc_rows(G, n_loc, torch.float64, dev)
+        _lib.check(lib.hb_runmean_dev(xr.data_ptr(), xr.stride(0), G, n_loc, int(k), tmp.data_ptr(), tmp.stride(0),
+                                      _stream()))
+        S[:, :n_loc] = tmp
+        del tmp
+    if world > 1:
+        src = S.cpu() if _staged(S) else S
+        parts = [torch.empty_like(src) for _ in range(world)]
+        dist.all_gather(parts, src)
+    else:
+        parts = [S]
+
+    def smoothed(q):   # rank q's cells as an aligned gene-major matrix on this device
+        t = hmm.alloc_rows(G, max(sizes[q], 2), torch.float64, dev)
+        t[:, :sizes[q]] = parts[q][:, :sizes[q]].to(dev)
+        return t
+
+    # ---- this rank's row panel of the distance matrix: the blocks it owns, zeros elsewhere
+    panel = torch.zeros((max(n_loc, 1), N), dtype=torch.float64, device=dev)
+    mine = smoothed(rank) if n_loc else None
+    for q in range(world):
+        if _pair_owner(rank, q, world) != rank or not n_loc or not sizes[q]:
+            continue
+        if q == rank:
+            if n_loc == 1:
+                continue   # a single cell: its distance to itself is 0
+            blk = torch.empty((n_loc, n_loc), dtype=torch.float64, device=dev)
+            _lib.check(lib.hb_dist_sq_dev(mine.data_ptr(), mine.stride(0), G, n_loc, blk.data_ptr(), _stream()))
+        else:
+            other = smoothed(q)
+            # the rectangular kernel wants two cells on either side; a one-cell shard is padded with a copy of itself
+            na, nb = max(n_loc, 2), max(sizes[q], 2)
+            a = mine
+            if n_loc == 1:
+                a = mine.clone()
+                a[:, 1] = a[:, 0]
+            if sizes[q] == 1:
+                other[:, 1] = other[:, 0]
+            blk = torch.empty((na, nb), dtype=torch.float64, device=dev)
+            _lib.check(lib.hb_dist_sq_rect_dev(a.data_ptr(), a.stride(0), na, other.data_ptr(), other.stride(0), nb,
+                                               G, blk.data_ptr(), blk.stride(0), _stream()))
+            blk = blk[:n_loc, :sizes[q]]
+        panel[:n_loc, offs[q]:offs[q + 1]] = blk
+    # ---- row panels to rank 0, which completes the other triangle
+    labels = torch.zeros((len(heights), N), dtype=torch.int32, device=dev)
+    D = None
+    if rank == 0:
+        D = torch.empty((N, N), dtype=torch.float64, device=dev)
+        D[offs[0]:offs[1]] = panel[:sizes[0]]
+        for r in range(1, world):
+            if sizes[r]:
+                buf = torch.empty((sizes[r], N), dtype=torch.float64, device=dev)
+                _recv(buf, r)
+                D[offs[r]:offs[r + 1]] = buf
+        for r in range(world):
+            for q in range(world):
+                if r != q and _pair_owner(r, q, world) != r:
+                    D[offs[r]:offs[r + 1], offs[q]:offs[q + 1]] = D[offs[q]:offs[q + 1], offs[r]:offs[r + 1]].t()
+        keep = D.clone() if return_matrix else None
+        ma = torch.empty(N - 1, dtype=torch.int32, device=dev)
+        mb = torch.empty(N - 1, dtype=torch.int32, device=dev)
+        hh = torch.empty(N - 1, dtype=torch.float64, device=dev)
+        _lib.check(lib.hb_ward_linkage_dev(D.data_ptr(), N, ma.data_ptr(), mb.data_ptr(), hh.data_ptr(), _stream()))
+        labs = cut_merges(ma.cpu().numpy(), mb.cpu().numpy(), hh.cpu().numpy(), N, heights)
+        labels.copy_(torch.as_tensor(np.stack(labs).astype(np.int32), device=dev))
+        D = keep
+    elif n_loc:
+        _send(panel[:n_loc].contiguous(), 0)
+    if world > 1:
+        _broadcast(labels, 0)
+    out = [a for a in labels.cpu().numpy()]
+    return (out, D) if return_matrix else out
+
+
 class ShardedGexpDriver:
     """HoneyBADGER$calcGexpCnvBoundaries(init = TRUE) with its recursion (R/HoneyBADGER.R:1091-1316) on cells SHARDED
     over the ranks: every level is `sharded_gexp_level` on the level's cells (each rank gathers ITS members of the
     sub-population on the device, ranks may hold none), the split sets g1 / g2 come back as global cell ids and the
     recursion continues on them with the found genes removed (`vi <- !(rownames %in% bound.genes.old)`, :1110).
-    Group labels come from `labels_fn(cell_ids, heights)` -> one int array per height over those cells (GLOBAL ids;
-    dist + hclust over the cells of all ranks is an input at these sizes).  Results — identical on
+    Group labels: `labels_fn=None` (default) computes them on the sharded cells (`sharded_ward_groups`: runmean local,
+    `dist` split by blocks over the ranks, Ward + cutree on rank 0); a callable `labels_fn(cell_ids, heights)` -> one
+    int array per height over those cells supplies them from outside.  Results — identical on
     every rank and to a single rank holding every cell (tests/test_gpu_sharded.py): `bound_genes_final` (list of gene
     index arrays, the reference's bound.genes.final), `regions` (genes, g1 cells), `bound_genes_old`."""
 
-    def __init__(self, x_local, n_cells, dev_mag, labels_fn, t=1e-6, min_traverse=5, min_num_genes=10, max_depth=32):
+    def __init__(self, x_local, n_cells, dev_mag, labels_fn=None, t=1e-6, min_traverse=5, min_num_genes=10, max_depth=32,
+                 window=101):
         import torch.distributed as dist
-        self.x, self.n_cells, self.dev = x_local, int(n_cells), float(dev_mag)
+        self.x, self.n_cells, self.dev, self.window = x_local, int(n_cells), float(dev_mag), int(window)
         self.labels_fn, self.t, self.H, self.min_genes, self.max_depth = labels_fn, t, min_traverse, min_num_genes, max_depth
         world = dist.get_world_size() if dist.is_initialized() else 1
         rank = dist.get_rank() if dist.is_initialized() else 0
@@ -514,7 +638,6 @@ class ShardedGexpDriver:
         xs = to_rows(xs.index_select(1, torch.as_tensor(mine - self.lo, device=dev)).contiguous()) if mine.size else \
             torch.zeros((genes.size, 0), dtype=torch.float64, device=dev)
         heights = list(range(1, min(self.H, cells.size) + 1))
-        labels = self.labels_fn(cells, heights)
         sel = (cells >= self.lo) & (cells < self.hi)
         sizes = None
         if self.world > 1:
@@ -522,6 +645,10 @@ class ShardedGexpDriver:
             cnt[dist.get_rank()] = int(mine.size)
             _all_reduce(cnt)
             sizes = cnt.cpu().numpy().tolist()
+        if self.labels_fn is None:   # grouping of the level's cells across the ranks (dist split by blocks)
+            labels = sharded_ward_groups(xs, sizes if sizes is not None else [int(mine.size)], heights, k=self.window)
+        else:
+            labels = self.labels_fn(cells, heights)
         lvl = sharded_gexp_level(xs, [np.asarray(l)[sel] for l in labels], cells.size, self.dev, t=self.t,
                                  min_num_genes=self.min_genes, local_sizes=sizes)
         if not lvl.get("runs"):

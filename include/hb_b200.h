@@ -246,6 +246,13 @@ int hb_runmean_dev(const double *x, int64_t ld, int64_t G, int64_t N, int32_t k,
 int hb_runmean_ratio_dev(const int32_t *r, const int32_t *n, int64_t ld, int64_t G, int64_t N, int32_t k,
                          double *out, int64_t ldo, void *stream);
 int hb_dist_sq_dev(const double *s, int64_t ld, int64_t G, int64_t N, double *D, void *stream);
+/* A rectangular block of the same distances: rows = the na cells (columns) of sa, columns = the nb cells of sb,
+ * D[i * ldd + j], both matrices gene-major with G rows.  Each entry is computed exactly as hb_dist_sq_dev computes
+ * it (same operations, same order), so blocks computed on different GPUs assemble into the single-GPU matrix bit
+ * for bit — the row-block split of `dist` for cells sharded over ranks (honeybadger_b200/dist.py).  Needs even
+ * lda / ldb and 16-byte aligned sa / sb; na, nb >= 2. */
+int hb_dist_sq_rect_dev(const double *sa, int64_t lda, int64_t na, const double *sb, int64_t ldb, int64_t nb,
+                        int64_t G, double *D, int64_t ldd, void *stream);
 int hb_ward_linkage_dev(double *D, int64_t N, int32_t *merge_a, int32_t *merge_b, double *height,
                         void *stream);
 /* cutree(hc, k) for each of the nk values in ks, from the merge list hb_ward_linkage_dev wrote (host copies):

@@ -98,6 +98,13 @@ def _worker(rank, world, port, q, backend="gloo"):
         ra, na, labs_a = allele_case()
         ref_a = hd.sharded_allele_level(hmm.to_rows(torch.from_numpy(ra).cuda()), hmm.to_rows(torch.from_numpy(na).cuda()),
                                         labs_a, ra.shape[1])
+        # grouping on one rank: labels, the distance matrix, and the recursion that computes its own groups
+        from honeybadger_b200 import honeybadger as hbm
+        xfull = hmm.to_rows(torch.from_numpy(x).cuda())
+        ref_labs, ref_D = hd.sharded_ward_groups(xfull, [N], [1, 2, 3, 4, 5], return_matrix=True)
+        dev_labs = hbm.ward_groups_dev(xfull, [1, 2, 3, 4, 5], 101)
+        assert all(np.array_equal(a, b) for a, b in zip(ref_labs, dev_labs))
+        ref_auto = hd.ShardedGexpDriver(xfull, N, synth.DEV).run()
         os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
         if backend == "nccl":
             dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", devno))
@@ -111,6 +118,14 @@ def _worker(rank, world, port, q, backend="gloo"):
         # the whole recursion on sharded cells (sub-populations unevenly spread over the ranks) == one rank
         drv = hd.ShardedGexpDriver(xl, N, synth.DEV, labels_fn_for(labels)).run()
         ok = ok and compare_drivers(drv, ref_drv)
+        # the grouping itself on sharded cells: dist split by blocks over the ranks, every entry of the assembled
+        # matrix bit-identical to the single-GPU one, hence the same tree and the same labels
+        labs, Dm = hd.sharded_ward_groups(xl, hd.shard_sizes(N, world), [1, 2, 3, 4, 5], return_matrix=True)
+        ok = ok and all(np.array_equal(a, b) for a, b in zip(labs, ref_labs))
+        if rank == 0:
+            ok = ok and bool(torch.equal(Dm.view(torch.int64), ref_D.view(torch.int64)))
+        auto = hd.ShardedGexpDriver(xl, N, synth.DEV).run()
+        ok = ok and compare_drivers(auto, ref_auto)
         # the allele level: integer exchanges only, so EVERYTHING is exact at any rank count
         r, n, labs = allele_case()
         lo, hi = hd.shard_range(r.shape[1], rank, world)
@@ -177,3 +192,52 @@ def test_single_rank_level_matches_the_resident_round(oracle):
         yo = oracle.viterbi_norm(lvl["pooled"][k], [-synth.DEV, 0.0, synth.DEV], [lvl["sd"][k]] * 3,
                                  oracle.sym_Pi(3, 1e-6), [0.0, 1.0, 0.0])
         assert np.array_equal(yo, lvl["y"][k])
+
+
+def _worker_groups(rank, world, port, q, sizes):
+    try:
+        import torch
+        import torch.distributed as dist
+        sys.path.insert(0, ROOT)
+        from honeybadger_b200 import _lib, dist as hd, hmm
+        torch.cuda.set_device(0)
+        _lib.check(_lib.load().hb_set_device(0))
+        N = int(sum(sizes))
+        x, _ = make_case(G=1500, N=N, seed=21)
+        ref_labs, ref_D = hd.sharded_ward_groups(hmm.to_rows(torch.from_numpy(x).cuda()), [N], [1, 2, 3, 4], k=31,
+                                                 return_matrix=True)
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        offs = np.concatenate([[0], np.cumsum(sizes)])
+        lo, hi = int(offs[rank]), int(offs[rank + 1])
+        xl = hmm.to_rows(torch.from_numpy(np.ascontiguousarray(x[:, lo:hi])).cuda()) if hi > lo else \
+            torch.zeros((x.shape[0], 0), dtype=torch.float64, device="cuda")
+        labs, Dm = hd.sharded_ward_groups(xl, sizes, [1, 2, 3, 4], k=31, return_matrix=True)
+        ok = all(np.array_equal(a, b) for a, b in zip(labs, ref_labs))
+        if rank == 0:
+            ok = ok and bool(torch.equal(Dm.view(torch.int64), ref_D.view(torch.int64)))
+        dist.barrier()
+        dist.destroy_process_group()
+        q.put((rank, bool(ok), ""))
+    except Exception:  # noqa: BLE001
+        import traceback
+        q.put((rank, False, traceback.format_exc()[-1500:]))
+
+
+@pytest.mark.parametrize("sizes", [[40, 41, 39], [5, 0, 60], [1, 70, 2, 33], [64, 1]])
+def test_sharded_grouping_with_uneven_shards(sizes):
+    """`dist` split by blocks over 2-4 ranks (odd and even rings, empty and one-cell shards): the assembled matrix is
+    bit-identical to one rank's, the labels are the same."""
+    import torch.multiprocessing as mp
+    world = len(sizes)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_worker_groups, args=(r, world, port, q, sizes)) for r in range(world)]
+    for p in ps:
+        p.start()
+    res = [q.get(timeout=300) for _ in ps]
+    for p in ps:
+        p.join(60)
+    for rank, ok, msg in res:
+        assert ok, f"rank {rank}: {msg}"
