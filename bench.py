@@ -682,18 +682,24 @@ def run_sharded_grouping(x, cells, rank, world, dev, dist, hd, total=20000):
     G = xs.shape[0]
     S = hmm.alloc_rows(G, per, torch.float64, dev)
     _lib.check(lib.hb_runmean_dev(xs.data_ptr(), xs.stride(0), G, per, 101, S.data_ptr(), S.stride(0), None))
-    nblk = sum(1 for q in range(world) if hd._pair_owner(rank, q, world) == rank)
-    blk = torch.empty((per, per), dtype=torch.float64, device=dev)
+    plans = [(q, hd._block_rows(rank, q, world, sizes)) for q in range(world)]
+    nblk = sum(1 for _, p in plans if p is not None)
     torch.cuda.synchronize()
     t1 = time.perf_counter()
-    for q in range(world):
-        if hd._pair_owner(rank, q, world) != rank:
+    for q, plan in plans:
+        if plan is None:
             continue
         if q == rank:
+            blk = torch.empty((per, per), dtype=torch.float64, device=dev)
             _lib.check(lib.hb_dist_sq_dev(S.data_ptr(), S.stride(0), G, per, blk.data_ptr(), None))
         else:
-            _lib.check(lib.hb_dist_sq_rect_dev(S.data_ptr(), S.stride(0), per, S.data_ptr(), S.stride(0), per, G,
-                                               blk.data_ptr(), blk.stride(0), None))
+            kind, a, b = plan
+            na, nb = (b - a, per) if kind == "rows" else (per, b - a)
+            blk = torch.empty((na, nb), dtype=torch.float64, device=dev)
+            pa = S.data_ptr() + (a * 8 if kind == "rows" else 0)
+            pb = S.data_ptr() + (a * 8 if kind == "cols" else 0)
+            _lib.check(lib.hb_dist_sq_rect_dev(pa, S.stride(0), na, pb, S.stride(0), nb, G, blk.data_ptr(), blk.stride(0),
+                                               None))
     torch.cuda.synchronize()
     td = torch.tensor([time.perf_counter() - t1], dtype=torch.float64, device=dev)
     dist.all_reduce(td, op=dist.ReduceOp.MAX)

@@ -477,7 +477,8 @@ def sharded_allele_level(r_local, n_local, labels_local, n_cells, l_maf=None, n_
 
 def _pair_owner(r, q, world):
     """Which rank computes the block (cells of r) x (cells of q) of the distance matrix: the symmetric pair
-    {r, q} is computed once, by the rank from which the other is at most half a ring ahead."""
+    {r, q} is computed once, by the rank from which the other is at most half a ring ahead.  (Exactly opposite
+    ranks of an even ring share their block, see _block_rows.)"""
     if r == q:
         return r
     d = (q - r) % world
@@ -488,6 +489,23 @@ def _pair_owner(r, q, world):
     return min(r, q)   # even world, exactly opposite: the lower rank
 
 
+def _block_rows(r, q, world, sizes):
+    """What rank r computes of the pair {r, q}: ("rows", a, b) = rows [a, b) of the block (r, q), every column;
+    ("cols", a, b) = the block (r, q) restricted to columns [a, b) of q's cells; None = nothing (q computes it).
+    Opposite ranks of an even ring split their block in two so that every rank carries the same number of pairs:
+    the lower rank takes the first h rows of (lo, hi), the higher rank the columns [h, n_lo) of (hi, lo)."""
+    if r == q:
+        return ("rows", 0, sizes[r])
+    d = (q - r) % world
+    if 2 * d != world:
+        return ("rows", 0, sizes[r]) if 2 * d < world else None
+    lo, hi = min(r, q), max(r, q)
+    h = (sizes[lo] // 2) & ~1                      # even: the sub-matrix stays 16-byte aligned
+    if h < 2 or sizes[lo] - h < 2 or sizes[hi] < 2:   # too small to split: the lower rank computes it all
+        return ("rows", 0, sizes[r]) if r == lo else None
+    return ("rows", 0, h) if r == lo else ("cols", h, sizes[lo])
+
+
 def sharded_ward_groups(x_local, sizes, heights, k=101, return_matrix=False):
     """cutree(hclust(dist(t(runmean(x, k))), "ward.D2"), h) for each h (R/HoneyBADGER.R:1122-1136) with the CELLS
     sharded over the ranks — the grouping step of a recursion level without any rank holding every cell's
@@ -496,8 +514,9 @@ def sharded_ward_groups(x_local, sizes, heights, k=101, return_matrix=False):
       runmean                 local (windows run along the genes of one cell)
       smoothed matrix         all-gather (G x N doubles in total; padded to the largest shard)
       dist                    split by BLOCKS of the symmetric matrix: rank r computes (r, q) for the q at most half
-                              a ring ahead (hb_dist_sq_rect_dev; its own diagonal block with hb_dist_sq_dev) —
-                              N^2 / (2 * world) pairs per rank, every entry bit-identical to the single-GPU kernel's
+                              a ring ahead (hb_dist_sq_rect_dev; its own diagonal block with hb_dist_sq_dev; the
+                              block of two exactly opposite ranks is halved between them) — N^2 / (2 * world) pairs
+                              per rank, every entry bit-identical to the single-GPU kernel's
       blocks -> rank 0        send / recv of each rank's row panel; rank 0 fills the other triangle by transposition
       Ward.D2 + cutree        rank 0 (the nearest-neighbour chain is sequential), labels broadcast
     Returns one int32 label array over ALL the level's cells per height (identical on every rank) — and the
@@ -543,29 +562,38 @@ def sharded_ward_groups(x_local, sizes, heights, k=101, return_matrix=False):
     # ---- this rank's row panel of the distance matrix: the blocks it owns, zeros elsewhere
     panel = torch.zeros((max(n_loc, 1), N), dtype=torch.float64, device=dev)
     mine = smoothed(rank) if n_loc else None
+    def rect(a, na, b, nb):   # distances of the na cells of `a` (rows) against the nb cells of `b`, [na, nb]
+        blk = torch.empty((na, nb), dtype=torch.float64, device=dev)
+        _lib.check(lib.hb_dist_sq_rect_dev(a.data_ptr(), a.stride(0), na, b.data_ptr(), b.stride(0), nb, G,
+                                           blk.data_ptr(), blk.stride(0), _stream()))
+        return blk
+
     for q in range(world):
-        if _pair_owner(rank, q, world) != rank or not n_loc or not sizes[q]:
+        plan = _block_rows(rank, q, world, sizes)
+        if plan is None or not n_loc or not sizes[q]:
             continue
+        kind, lo_, hi_ = plan
         if q == rank:
             if n_loc == 1:
                 continue   # a single cell: its distance to itself is 0
             blk = torch.empty((n_loc, n_loc), dtype=torch.float64, device=dev)
             _lib.check(lib.hb_dist_sq_dev(mine.data_ptr(), mine.stride(0), G, n_loc, blk.data_ptr(), _stream()))
+            panel[:n_loc, offs[q]:offs[q + 1]] = blk
+            continue
+        other = smoothed(q)
+        if kind == "cols":     # every cell of this rank against cells [lo_, hi_) of rank q
+            panel[:n_loc, offs[q] + lo_:offs[q] + hi_] = rect(mine, n_loc, other[:, lo_:], hi_ - lo_)
+        elif hi_ - lo_ >= 2 and sizes[q] >= 2:
+            panel[lo_:hi_, offs[q]:offs[q + 1]] = rect(mine[:, lo_:], hi_ - lo_, other, sizes[q])
         else:
-            other = smoothed(q)
             # the rectangular kernel wants two cells on either side; a one-cell shard is padded with a copy of itself
-            na, nb = max(n_loc, 2), max(sizes[q], 2)
             a = mine
             if n_loc == 1:
                 a = mine.clone()
                 a[:, 1] = a[:, 0]
             if sizes[q] == 1:
                 other[:, 1] = other[:, 0]
-            blk = torch.empty((na, nb), dtype=torch.float64, device=dev)
-            _lib.check(lib.hb_dist_sq_rect_dev(a.data_ptr(), a.stride(0), na, other.data_ptr(), other.stride(0), nb,
-                                               G, blk.data_ptr(), blk.stride(0), _stream()))
-            blk = blk[:n_loc, :sizes[q]]
-        panel[:n_loc, offs[q]:offs[q + 1]] = blk
+            panel[:n_loc, offs[q]:offs[q + 1]] = rect(a, max(n_loc, 2), other, max(sizes[q], 2))[:n_loc, :sizes[q]]
     # ---- row panels to rank 0, which completes the other triangle
     labels = torch.zeros((len(heights), N), dtype=torch.int32, device=dev)
     D = None
@@ -579,8 +607,22 @@ def sharded_ward_groups(x_local, sizes, heights, k=101, return_matrix=False):
                 D[offs[r]:offs[r + 1]] = buf
         for r in range(world):
             for q in range(world):
-                if r != q and _pair_owner(r, q, world) != r:
-                    D[offs[r]:offs[r + 1], offs[q]:offs[q + 1]] = D[offs[q]:offs[q + 1], offs[r]:offs[r + 1]].t()
+                if r == q:
+                    continue
+                plan = _block_rows(r, q, world, sizes)
+                rows_r, cols_q = slice(offs[r], offs[r + 1]), slice(offs[q], offs[q + 1])
+                if plan is None:               # all of (r, q) is the transpose of what q computed
+                    other = _block_rows(q, r, world, sizes)
+                    if other[0] == "rows" and (other[1], other[2]) == (0, sizes[q]):
+                        D[rows_r, cols_q] = D[cols_q, rows_r].t()
+                elif plan[0] == "rows" and (plan[1], plan[2]) != (0, sizes[r]):
+                    # r computed its first h rows; the rest is the transpose of q's columns [h, n_r) of (q, r)
+                    h = plan[2]
+                    D[offs[r] + h:offs[r + 1], cols_q] = D[cols_q, offs[r] + h:offs[r + 1]].t()
+                elif plan[0] == "cols":
+                    # r computed columns [h, n_q) of (r, q); the first h columns are the transpose of q's rows [0, h)
+                    h = plan[1]
+                    D[rows_r, offs[q]:offs[q] + h] = D[offs[q]:offs[q] + h, rows_r].t()
         keep = D.clone() if return_matrix else None
         ma = torch.empty(N - 1, dtype=torch.int32, device=dev)
         mb = torch.empty(N - 1, dtype=torch.int32, device=dev)
