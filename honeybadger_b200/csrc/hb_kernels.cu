@@ -1045,8 +1045,7 @@ cudaError_t launch_ward(double *D, int64_t N, void *work, int32_t *ma, int32_t *
                         cudaStream_t st)
 {
     int32_t *size = (int32_t *)work, *chain = size + (int64_t)N * WC_MAXR;
-    const bool fits = N <= (int64_t)WC_MAXR * WC_THREADS * WC_OWN / 2 - 64; // also at cluster size 8
-    if (mode != 1 && fits && (mode == 2 || N >= WARD_CLUSTER_MIN)) {
+    if (mode != 1 && (mode == 2 || N >= WARD_CLUSTER_MIN)) {
         static int cluster_max = -1; // 16 (non-portable size, opt-in), else 8, else none
         if (cluster_max < 0) {
             cluster_max = 0;
@@ -1069,7 +1068,9 @@ cudaError_t launch_ward(double *D, int64_t N, void *work, int32_t *ma, int32_t *
                 cudaGetLastError();
             }
         }
-        if (cluster_max) {
+        // a CTA's slice must fit its threads' register masks: N / r + 32 <= WC_THREADS * WC_OWN (65 k cells at 16 CTAs)
+        const bool fits = cluster_max && (N + cluster_max - 1) / cluster_max + 32 <= (int64_t)WC_THREADS * WC_OWN;
+        if (fits) {
             // measured (tools/probe_ward.py): 8 CTAs are best up to ~8 k cells, 16 beyond; a step costs ~2 us at
             // any size (L2 latency + cluster barrier), so small problems stay on one block
             int r = std::min(cluster_max, N >= 8192 ? 16 : 8);

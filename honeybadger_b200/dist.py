@@ -506,11 +506,12 @@ def _block_rows(r, q, world, sizes):
     return ("rows", 0, h) if r == lo else ("cols", h, sizes[lo])
 
 
-def sharded_ward_groups(x_local, sizes, heights, k=101, return_matrix=False):
+def sharded_ward_groups(x_local, sizes, heights, k=101, return_matrix=False, counts=None):
     """cutree(hclust(dist(t(runmean(x, k))), "ward.D2"), h) for each h (R/HoneyBADGER.R:1122-1136) with the CELLS
     sharded over the ranks — the grouping step of a recursion level without any rank holding every cell's
     expression.  x_local: gene-major fp64 CUDA tensor [G, N_local] (this rank's cells of the level, rank-major
-    order = the level's cell order); sizes: cells of every rank.  Steps:
+    order = the level's cell order); sizes: cells of every rank.  counts=(r_local, n_local) (int32, gene-major)
+    instead of x_local: the allele form, r / n smoothed with k = 31 (R/HoneyBADGER.R:1378-1397).  Steps:
       runmean                 local (windows run along the genes of one cell)
       smoothed matrix         all-gather (G x N doubles in total; padded to the largest shard)
       dist                    split by BLOCKS of the symmetric matrix: rank r computes (r, q) for the q at most half
@@ -530,9 +531,9 @@ def sharded_ward_groups(x_local, sizes, heights, k=101, return_matrix=False):
     rank = dist.get_rank() if dist.is_initialized() else 0
     sizes = [int(v) for v in sizes]
     N = int(sum(sizes))
-    G, n_loc = x_local.shape
+    G, n_loc = (counts[0] if counts is not None else x_local).shape
     assert len(sizes) == world and n_loc == sizes[rank]
-    dev = x_local.device
+    dev = (counts[0] if counts is not None else x_local).device
     heights = [int(h) for h in heights]
     if N == 1:
         return [np.ones(1, dtype=np.int32) for _ in heights]
@@ -541,10 +542,17 @@ def sharded_ward_groups(x_local, sizes, heights, k=101, return_matrix=False):
     # ---- runmean of this rank's cells, then everybody's smoothed cells (padded blocks, gene-major)
     S = torch.zeros((G, mx), dtype=torch.float64, device=dev)
     if n_loc:
-        xr = x_local if x_local.stride(1) == 1 else x_local.contiguous()
         tmp = hmm.alloc_rows(G, n_loc, torch.float64, dev)
-        _lib.check(lib.hb_runmean_dev(xr.data_ptr(), xr.stride(0), G, n_loc, int(k), tmp.data_ptr(), tmp.stride(0),
-                                      _stream()))
+        if counts is not None:
+            rr, nn = counts
+            if rr.stride(0) != nn.stride(0) or rr.stride(1) != 1 or nn.stride(1) != 1:
+                rr, nn = rr.contiguous(), nn.contiguous()
+            _lib.check(lib.hb_runmean_ratio_dev(rr.data_ptr(), nn.data_ptr(), rr.stride(0), G, n_loc, int(k),
+                                                tmp.data_ptr(), tmp.stride(0), _stream()))
+        else:
+            xr = x_local if x_local.stride(1) == 1 else x_local.contiguous()
+            _lib.check(lib.hb_runmean_dev(xr.data_ptr(), xr.stride(0), G, n_loc, int(k), tmp.data_ptr(), tmp.stride(0),
+                                          _stream()))
         S[:, :n_loc] = tmp
         del tmp
     if world > 1:

@@ -206,6 +206,11 @@ def _worker_groups(rank, world, port, q, sizes):
         x, _ = make_case(G=1500, N=N, seed=21)
         ref_labs, ref_D = hd.sharded_ward_groups(hmm.to_rows(torch.from_numpy(x).cuda()), [N], [1, 2, 3, 4], k=31,
                                                  return_matrix=True)
+        ra, na, _ = allele_case(G=6000, N=N, seed=23)
+        ref_labs_a, ref_Da = hd.sharded_ward_groups(
+            None, [N], [1, 2, 3], k=31, return_matrix=True,
+            counts=(hmm.to_rows(torch.from_numpy(ra).cuda()), hmm.to_rows(torch.from_numpy(na).cuda())))
+        assert bool(torch.isfinite(ref_Da).all())
         os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
         dist.init_process_group("gloo", rank=rank, world_size=world)
         offs = np.concatenate([[0], np.cumsum(sizes)])
@@ -216,6 +221,14 @@ def _worker_groups(rank, world, port, q, sizes):
         ok = all(np.array_equal(a, b) for a, b in zip(labs, ref_labs))
         if rank == 0:
             ok = ok and bool(torch.equal(Dm.view(torch.int64), ref_D.view(torch.int64)))
+        # the allele form: r / n with NaN wherever a cell has no coverage (the masked path of the distance kernel)
+        cl = (hmm.to_rows(torch.from_numpy(np.ascontiguousarray(ra[:, lo:hi])).cuda()),
+              hmm.to_rows(torch.from_numpy(np.ascontiguousarray(na[:, lo:hi])).cuda())) if hi > lo else \
+            (torch.zeros((ra.shape[0], 0), dtype=torch.int32, device="cuda"),) * 2
+        labs_a, Da = hd.sharded_ward_groups(None, sizes, [1, 2, 3], k=31, return_matrix=True, counts=cl)
+        ok = ok and all(np.array_equal(a, b) for a, b in zip(labs_a, ref_labs_a))
+        if rank == 0:
+            ok = ok and bool(torch.equal(Da.view(torch.int64), ref_Da.view(torch.int64)))
         dist.barrier()
         dist.destroy_process_group()
         q.put((rank, bool(ok), ""))
