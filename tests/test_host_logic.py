@@ -166,3 +166,39 @@ def test_r_shim_is_well_formed_against_the_c_abi():
                 depth -= ch in ")]"
                 nargs += ch == "," and depth == 0
             assert nargs == table[name], (name, nargs, table[name])
+
+
+def test_sharded_dist_block_plan_covers_every_pair_exactly_once():
+    """dist._block_rows: over any ring size and shard sizes (empty, one-cell, odd) every unordered pair of cells is
+    computed by exactly one rank, and the ranks' pair counts differ by little (opposite ranks halve their block)."""
+    from honeybadger_b200 import dist as hd
+    rng = np.random.default_rng(0)
+    cases = [[7], [5, 4], [64, 1], [1, 1], [40, 41, 39], [5, 0, 60], [1, 70, 2, 33], [10] * 8, [9, 0, 3, 12, 1, 8]]
+    cases += [rng.integers(0, 30, size=w).tolist() for w in (2, 3, 4, 5, 6, 7, 8) for _ in range(5)]
+    for sizes in cases:
+        W, N = len(sizes), int(sum(sizes))
+        offs = np.concatenate([[0], np.cumsum(sizes)])
+        cover = np.zeros((N, N), dtype=np.int32)
+        work = np.zeros(W)
+        for r in range(W):
+            for q in range(W):
+                plan = hd._block_rows(r, q, W, sizes)
+                if plan is None or not sizes[r] or not sizes[q]:
+                    continue
+                kind, a, b = plan
+                if r == q:
+                    assert (kind, a, b) == ("rows", 0, sizes[r])
+                    blk = np.triu(np.ones((sizes[r], sizes[r]), dtype=np.int32))      # the symmetric kernel: each pair once
+                    cover[offs[r]:offs[r + 1], offs[r]:offs[r + 1]] += blk
+                    work[r] += sizes[r] * (sizes[r] + 1) / 2
+                elif kind == "rows":
+                    cover[offs[r] + a:offs[r] + b, offs[q]:offs[q + 1]] += 1
+                    work[r] += (b - a) * sizes[q]
+                else:
+                    assert (a % 2 == 0) and a >= 2   # the column sub-matrix stays 16-byte aligned
+                    cover[offs[r]:offs[r + 1], offs[q] + a:offs[q] + b] += 1
+                    work[r] += sizes[r] * (b - a)
+        both = cover + cover.T - np.diag(np.diag(cover))
+        assert (both == 1).all(), sizes
+        if W > 1 and len(set(sizes)) == 1 and sizes[0] >= 8:
+            assert work.max() <= 1.3 * work.min(), (sizes, work)
