@@ -1973,16 +1973,21 @@ int hb_runmean_dev(const double *x, int64_t ld, int64_t G, int64_t N, int32_t k,
 {
     if (!x || !out || G < 1 || N < 1 || ld < N || ldo < N || k < 1 || (k & 1) == 0)
         return fail(HB_ERR_ARG, "bad arguments (k must be odd)");
-    CU(hb::launch_runmean(x, nullptr, nullptr, ld, G, N, k, out, ldo, (cudaStream_t)stream));
+    CU(hb::launch_runmean(x, nullptr, nullptr, ld, G, N, k, out, ldo, nullptr, (cudaStream_t)stream));
     return HB_OK;
 }
 
 int hb_runmean_ratio_dev(const int32_t *r, const int32_t *n, int64_t ld, int64_t G, int64_t N, int32_t k,
                          double *out, int64_t ldo, void *stream)
 {
+    std::lock_guard<std::mutex> lk(g_mu);
+    Workspace *ws;
+    HBTRY(cur_ws(&ws));
+    WS_USE(stream);
     if (!r || !n || !out || G < 1 || N < 1 || ld < N || ldo < N || k < 1 || (k & 1) == 0)
         return fail(HB_ERR_ARG, "bad arguments (k must be odd)");
-    CU(hb::launch_runmean(nullptr, r, n, ld, G, N, k, out, ldo, (cudaStream_t)stream));
+    HBTRY(ws->st_out.ensure((size_t)G * ldo * sizeof(double))); // the ratios, formed once
+    CU(hb::launch_runmean(nullptr, r, n, ld, G, N, k, out, ldo, ws->st_out.as<double>(), (cudaStream_t)stream));
     return HB_OK;
 }
 
@@ -2091,7 +2096,12 @@ static int group_core(Workspace *ws, const double *xg, const int32_t *rg, const 
     const int64_t lds = (N + 127) / 128 * 128;
     HBTRY(ws->st_g.ensure((size_t)G * lds * sizeof(double))); // smoothed matrix
     double *S = ws->st_g.as<double>();
-    CU(hb::launch_runmean(xg, rg, ng, ld, G, N, window, S, lds, st));
+    double *ratio = nullptr;
+    if (!xg) {
+        HBTRY(ws->st_out.ensure((size_t)G * lds * sizeof(double))); // r / n formed once, not once per window position
+        ratio = ws->st_out.as<double>();
+    }
+    CU(hb::launch_runmean(xg, rg, ng, ld, G, N, window, S, lds, ratio, st));
     HBTRY(ws->st_pool.ensure((size_t)N * N * sizeof(double)));
     HBTRY(ws->st_pool2.ensure((size_t)N * 16 + 64));
     HBTRY(ws->st_part.ensure(std::max(hb::ward_scratch_bytes(N), hb::dist_scratch_bytes(G, N))));

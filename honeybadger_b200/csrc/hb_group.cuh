@@ -46,6 +46,19 @@ __global__ void __launch_bounds__(256)
     out[g * ldo + c] = cnt ? s / (double)cnt : NAN;
 }
 
+// r / n of two int32 count planes as doubles (NaN where n == 0), once per element: runmean_kernel<true> forms the
+// ratio again for each of the k positions of every window — k fp64 divisions per output; with the ratios in a
+// scratch matrix the windows are plain sums (same divisions, same order of additions: identical results).
+__global__ void __launch_bounds__(256)
+    ratio_kernel(const int32_t *r, const int32_t *n, int64_t ld, int64_t G, int64_t N, double *out, int64_t ldo)
+{
+    const int64_t c = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
+    const int64_t g = blockIdx.x;
+    if (c >= N) return;
+    const int32_t nn = n[g * ld + c];
+    out[g * ldo + c] = nn > 0 ? (double)r[g * ld + c] / (double)nn : NAN;
+}
+
 // ---------------------------------------------------------------------------------------------
 // stats::dist(t(S)) squared, Euclidean, with R's NA rule: pairs with a non-finite member are left
 // out and the sum is scaled up by G / (pairs used); no usable pair -> NA, which the reference then

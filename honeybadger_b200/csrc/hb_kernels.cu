@@ -961,13 +961,17 @@ cudaError_t launch_retest_gexp_b(int64_t N, const double *partial, const double 
 
 // =====================================================================================
 // Grouping of cells (hb_group.cuh)
+// tmp (ratio form only): G * ldo doubles of scratch for the ratios, or NULL (the ratio is then re-formed per window position)
 cudaError_t launch_runmean(const double *x, const int32_t *r, const int32_t *n, int64_t ld, int64_t G,
-                           int64_t N, int32_t k, double *out, int64_t ldo, cudaStream_t st)
+                           int64_t N, int32_t k, double *out, int64_t ldo, double *tmp, cudaStream_t st)
 {
     dim3 grid((unsigned)G, (unsigned)((N + 255) / 256));
     if (x)
         runmean_kernel<false><<<grid, 256, 0, st>>>(x, nullptr, nullptr, ld, G, N, k / 2, out, ldo);
-    else
+    else if (tmp) {
+        ratio_kernel<<<grid, 256, 0, st>>>(r, n, ld, G, N, tmp, ldo);
+        runmean_kernel<false><<<grid, 256, 0, st>>>(tmp, nullptr, nullptr, ldo, G, N, k / 2, out, ldo);
+    } else
         runmean_kernel<true><<<grid, 256, 0, st>>>(nullptr, r, n, ld, G, N, k / 2, out, ldo);
     return cudaGetLastError();
 }

@@ -65,7 +65,7 @@ cudaError_t launch_retest_gexp_a(const double *x, int64_t ld, int64_t N, const i
 cudaError_t launch_retest_gexp_b(int64_t N, const double *partial, const double *D_total, double *p_amp,
                                  double *p_del, cudaStream_t st);
 cudaError_t launch_runmean(const double *x, const int32_t *r, const int32_t *n, int64_t ld, int64_t G,
-                           int64_t N, int32_t k, double *out, int64_t ldo, cudaStream_t st);
+                           int64_t N, int32_t k, double *out, int64_t ldo, double *tmp, cudaStream_t st);
 size_t dist_scratch_bytes(int64_t G, int64_t N);
 cudaError_t launch_dist_sq(const double *S, int64_t ld, int64_t G, int64_t N, double *D, void *scratch, cudaStream_t st);
 cudaError_t launch_dist_sq_rect(const double *Sa, int64_t lda, int64_t Na, const double *Sb, int64_t ldb, int64_t Nb,
