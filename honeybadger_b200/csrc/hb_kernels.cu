@@ -985,13 +985,15 @@ size_t dist_scratch_bytes(int64_t G, int64_t N)
 static cudaError_t dist_pipe_attr()
 {
     constexpr int smem = GP_STAGES * 2 * GD_K * GD_T * (int)sizeof(double);
-    static bool once = false;
-    if (!once) {
+    static uint64_t done = 0; // function attributes are per device: one bit per device id (callers hold the API lock)
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!((done >> (dev & 63)) & 1)) {
         cudaError_t e = cudaFuncSetAttribute(dist_sq_pipe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e == cudaSuccess)
             e = cudaFuncSetAttribute(dist_sq_pipe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
-        once = true;
+        done |= 1ull << (dev & 63);
     }
     return cudaSuccess;
 }
@@ -1050,7 +1052,11 @@ cudaError_t launch_ward(double *D, int64_t N, void *work, int32_t *ma, int32_t *
 {
     int32_t *size = (int32_t *)work, *chain = size + (int64_t)N * WC_MAXR;
     if (mode != 1 && (mode == 2 || N >= WARD_CLUSTER_MIN)) {
-        static int cluster_max = -1; // 16 (non-portable size, opt-in), else 8, else none
+        static int cluster_max_dev[64]; // per device: 0 not probed yet, else 1 + (16 non-portable size, 8, or 0 = none)
+        int devno = 0;
+        cudaGetDevice(&devno);
+        int &slot = cluster_max_dev[devno & 63];
+        int cluster_max = slot - 1;
         if (cluster_max < 0) {
             cluster_max = 0;
             for (int r : {16, 8}) {
@@ -1071,6 +1077,7 @@ cudaError_t launch_ward(double *D, int64_t N, void *work, int32_t *ma, int32_t *
                 }
                 cudaGetLastError();
             }
+            slot = cluster_max + 1;
         }
         // a CTA's slice must fit its threads' register masks: N / r + 32 <= WC_THREADS * WC_OWN (65 k cells at 16 CTAs)
         const bool fits = cluster_max && (N + cluster_max - 1) / cluster_max + 32 <= (int64_t)WC_THREADS * WC_OWN;
