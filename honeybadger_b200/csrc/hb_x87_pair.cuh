@@ -36,6 +36,11 @@ HB_HD void two_sum(double a, double b, double &s, double &e)
 HB_HD x80p x80p_from_x80(x80 a)
 {
     x80p r;
+    if (a.m == 0) { // zero keeps its sign in h; l is +0 (the subtraction below would hand back a zero of the other sign)
+        r.h = a.neg ? -0.0 : 0.0;
+        r.l = 0.0;
+        return r;
+    }
     r.h = x80_to_double(a);
     r.l = x80_to_double(x80_sub(a, x80_from_double(r.h))); // exact: at most 11 bits are left
     return r;
@@ -43,6 +48,7 @@ HB_HD x80p x80p_from_x80(x80 a)
 
 HB_HD x80 x80_from_x80p(x80p a)
 {
+    if (a.l == 0.0) return x80_from_double(a.h);
     return x80_add(x80_from_double(a.h), x80_from_double(a.l)); // exact: the sum has 64 bits
 }
 
@@ -115,6 +121,14 @@ HB_HD x80p x80p_add_double(x80p s, double v)
     two_sum(a, s1, a2, s2);
     x80p r;
     if (x80p_round(a2, s2, t1, 0.0, r)) return r;
+    // Declined.  A zero operand first: the other one comes back as it is, exactly what x80_add does (0 + 0 has no
+    // exponent to round at, and rows that start with zeros would otherwise call the integer routine at every step).
+    if (s.h == 0.0) {
+        r.h = v;
+        r.l = 0.0;
+        return r;
+    }
+    if (v == 0.0) return s;
     return x80p_add_double_slow(s, v);
 }
 
@@ -132,6 +146,8 @@ HB_HD x80p x80p_add(x80p s, x80p d)
     two_sum(e3, s2, a2, s3);
     x80p r;
     if (x80p_round(a2, s3, t2, t1, r)) return r;
+    if (s.h == 0.0) return d; // as above
+    if (d.h == 0.0) return s;
     return x80p_add_slow(s, d);
 }
 

@@ -106,6 +106,33 @@ def test_pool_mean_random_groups_bit_exact(oracle):
         assert gsd[k] == oracle.r_sd(ref)
 
 
+def test_pool_mean_zero_inflated_rows_bit_exact(oracle):
+    """Rows of zeros, rows that start with zeros, zero-inflated rows, integer counts, a constant row: the
+    double-pair accumulation (zero operands return the other operand, as the integer routine does) must give R's
+    mean down to the sign of a zero."""
+    import torch
+    from honeybadger_b200 import _lib, honeybadger as hb
+    rng = np.random.default_rng(13)
+    G, N = 300, 157
+    x = rng.gamma(2.0, 1.5, size=(G, N)) * (rng.random((G, N)) < 0.3)
+    x[:20] = 0.0
+    x[20:40, :70] = 0.0
+    x[40:60] = rng.integers(0, 4, size=(20, N))
+    x[60:70] = 1.25
+    x[70:80] = -x[70:80]
+    labels = rng.integers(1, 4, N)
+    member, _ = hb._membership([np.ones(N, int), labels], N)
+    xd = hb._to_dev_f64(x)
+    md = torch.as_tensor(member).cuda()
+    out = torch.empty((member.shape[0], G), dtype=torch.float64, device="cuda")
+    _lib.check(_lib.load().hb_pool_mean_dev(xd.data_ptr(), xd.stride(0), G, N, md.data_ptr(), member.shape[0],
+                                            out.data_ptr(), None))
+    got = out.cpu().numpy()
+    for k in range(member.shape[0]):
+        ref = np.asarray(oracle.pool_mean(x, np.nonzero(member[k])[0]), dtype=np.float64)
+        assert np.array_equal(got[k].view(np.int64), ref.view(np.int64))
+
+
 def test_function_variants_match_reference_restatement(golden_gexp, golden_allele):
     """calcGexpCnvBoundaries / calcAlleleCnvBoundaries (stateless) == the literal R restatement."""
     from honeybadger_b200 import honeybadger as hb

@@ -164,7 +164,10 @@ def test_x87_pair_fast_path_covers_expression_like_data(emul):
     """On data shaped like the pooled-mean inputs no step leaves the branch-free path (a fall-back is
     correct but serialises a warp, so this is the performance contract of the kernel)."""
     rng = np.random.default_rng(31)
-    for x in (rng.normal(size=200000) * 2.6, rng.gamma(2.0, 1.5, 200000), np.log2(rng.gamma(2, 2, 200000) + 1) - 2):
+    zi = rng.gamma(2.0, 1.5, 200000) * (rng.random(200000) < 0.3)   # zero-inflated, as un-normalised expression is
+    zi[:5000] = 0.0                                                # and starting with a long run of zeros
+    for x in (rng.normal(size=200000) * 2.6, rng.gamma(2.0, 1.5, 200000), np.log2(rng.gamma(2, 2, 200000) + 1) - 2, zi,
+              np.zeros(1000)):
         x = np.ascontiguousarray(x)
         m = float(np.mean(x))
         for mode in (0, 1):
