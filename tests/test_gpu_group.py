@@ -133,3 +133,24 @@ def test_pipelined_dist_with_missing_values():
         ref = np.where(cnt > 0, ss / (cnt / G), 0.0)
     np.fill_diagonal(ref, 0.0)
     np.testing.assert_allclose(a, ref, rtol=1e-12, atol=1e-12)
+
+
+def test_cluster_linkage_and_dist_are_reproducible_run_to_run():
+    """Same input, repeated: the cluster kernel's exchange through distributed shared memory and the cp.async ring of
+    the distance kernel must not depend on timing (a race would show up as run-to-run differences)."""
+    rng = np.random.default_rng(17)
+    N, G = 2500, 600
+    S = rng.normal(size=(G, N))
+    S[:, : N // 2] += 0.7
+    S[rng.random((G, N)) < 0.05] = np.nan
+    d0 = _dist(S, 0)
+    first = _linkage(d0, 2)
+    for _ in range(4):
+        d = _dist(S, 0)
+        assert np.array_equal(d.view(np.int64), d0.view(np.int64))
+        again = _linkage(d, 2)
+        assert all(np.array_equal(a.view(np.int64) if a.dtype == np.float64 else a,
+                                  b.view(np.int64) if b.dtype == np.float64 else b) for a, b in zip(first, again))
+    plain = _linkage(d0, 1)
+    assert np.array_equal(first[0], plain[0]) and np.array_equal(first[1], plain[1])
+    assert np.array_equal(first[2].view(np.int64), plain[2].view(np.int64))
