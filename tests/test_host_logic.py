@@ -140,6 +140,22 @@ def test_cut_merges_matches_scipy_cut_tree():
         assert first == sorted(first)          # clusters numbered in order of first appearance
 
 
+def test_cutree_entry_point_edges_and_errors():
+    """hb_cutree_host: k above the number of cells (every cell its own cluster), k = 1, two cells, equal heights
+    kept in list order (children before parents), and a merge list naming a leaf outside [0, N) is refused."""
+    from honeybadger_b200 import _lib
+    ma, mb, hh = [0, 2, 0], [1, 3, 2], [1.0, 1.0, 2.0]      # ((0,1),(2,3)) then the two pairs
+    labs = hb.cut_merges(ma, mb, hh, 4, [1, 2, 3, 4, 9])
+    assert labs[0].tolist() == [1, 1, 1, 1]
+    assert labs[1].tolist() == [1, 1, 2, 2]
+    assert labs[2].tolist() == [1, 1, 2, 3]                  # equal heights: the first merge in the list is cut last
+    assert labs[3].tolist() == [1, 2, 3, 4] and labs[4].tolist() == [1, 2, 3, 4]
+    assert hb.cut_merges([0], [1], [0.5], 2, [1, 2])[1].tolist() == [1, 2]
+    with pytest.raises(Exception):
+        hb.cut_merges([0, 7], [1, 2], [1.0, 2.0], 3, [1])
+    assert "leaf" in _lib.load().hb_last_error().decode()
+
+
 def test_r_shim_is_well_formed_against_the_c_abi():
     """R is not in this image, so nobody links r/hb_shim.c here; at least it must be valid C against
     include/hb_b200.h (argument counts and pointer types of every hb_* call) with a stand-in for the R API
