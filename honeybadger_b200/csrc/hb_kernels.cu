@@ -1316,14 +1316,54 @@ cudaError_t launch_pool_mean(const double *x, int64_t ld, int64_t G, int64_t N,
     return launch_pool_finish(mean80, state, gsize, G, K, out, st);
 }
 
-// sd(x) of each pooled vector (cov.c cov_complete1 replayed): one warp per chain; the lanes form
-// the independent per-element terms in parallel, lane 0 does the order-dependent accumulation.
+// acc + the terms of lanes [0, lim) in lane order; every lane holds the same acc and gets the same result.
+// The warp form of x80_block_add (hb_x87.cuh): each round aligns the unprocessed terms to the sum's grid, takes
+// their integer prefix sums with shuffles, applies the longest legitimate prefix in one addition, and adds the
+// term that stopped it (a tie, a term too large for the grid, the sum leaving its binade) literally.
+__device__ __forceinline__ x80 x80_block_add_warp(x80 acc, x80 term, int lane, int lim)
+{
+    const unsigned full = 0xffffffffu;
+    int start = 0;
+    while (start < lim) {
+        const bool mine = lane >= start && lane < lim && term.m != 0; // exact zeros never change the sum
+        int64_t sj = 0;
+        const bool okj = !mine || (acc.m != 0 && x80_align_term(term, acc.e, acc.neg, sj));
+        const unsigned bad = __ballot_sync(full, !okj);
+        const int f = bad ? __ffs((int)bad) - 1 : lim; // first term that cannot go on the grid
+        if (!mine || lane >= f) sj = 0;
+        uint64_t p = (uint64_t)sj; // wrapping prefix sum, and a coarse one that says whether it wrapped
+        int64_t c = sj >> 8;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint64_t up = __shfl_up_sync(full, p, o);
+            const int64_t uc = __shfl_up_sync(full, c, o);
+            if (lane >= o) {
+                p += up;
+                c += uc;
+            }
+        }
+        const bool v = !mine || lane >= f || (x80_coarse_ok(c) && x80_prefix_ok(acc.m, (int64_t)p));
+        const unsigned inv = __ballot_sync(full, !v);
+        const int g = inv ? __ffs((int)inv) - 1 : f; // first term whose prefix is not a legitimate state
+        const uint64_t pg = __shfl_sync(full, p, g > 0 ? g - 1 : 0);
+        if (g > start) acc.m += pg;
+        if (g < lim) {
+            x80 tg;
+            tg.m = __shfl_sync(full, term.m, g);
+            tg.e = __shfl_sync(full, term.e, g);
+            tg.neg = __shfl_sync(full, term.neg, g);
+            acc = x80_add(acc, tg);
+        }
+        start = g + 1;
+    }
+    return acc;
+}
+
+// sd(x) of each pooled vector (cov.c cov_complete1 replayed): one warp per vector; the lanes form the
+// per-element terms in parallel and add each block of 32 to the running 80-bit sum in order
+// (x80_block_add_warp).
 __global__ void __launch_bounds__(32) pooled_sd_kernel(const double *pooled, int64_t G, double *sd)
 {
-    __shared__ uint64_t sm_m[32];
-    __shared__ int32_t sm_e[32];
-    __shared__ uint32_t sm_s[32];
-    __shared__ double sm_mean;
     const double *xv = pooled + (int64_t)blockIdx.x * G;
     const int lane = threadIdx.x;
     x80 acc = x80_zero(), mean80 = x80_zero(), xm = x80_zero();
@@ -1343,33 +1383,13 @@ __global__ void __launch_bounds__(32) pooled_sd_kernel(const double *pooled, int
                     term = x80_mul(d, d);
                 }
             }
-            sm_m[lane] = term.m;
-            sm_e[lane] = term.e;
-            sm_s[lane] = term.neg;
-            __syncwarp();
-            if (lane == 0) {
-                const int lim = (int)((G - i0) < 32 ? (G - i0) : 32);
-                for (int j = 0; j < lim; j++) {
-                    x80 t;
-                    t.m = sm_m[j];
-                    t.e = sm_e[j];
-                    t.neg = sm_s[j];
-                    acc = x80_add(acc, t);
-                }
-            }
-            __syncwarp();
+            acc = x80_block_add_warp(acc, term, lane, (int)((G - i0) < 32 ? (G - i0) : 32));
         }
-        // broadcast lane 0's running value
-        acc.m = __shfl_sync(0xffffffffu, acc.m, 0);
-        acc.e = __shfl_sync(0xffffffffu, acc.e, 0);
-        acc.neg = __shfl_sync(0xffffffffu, acc.neg, 0);
         if (pass == 0) {
             mean80 = x80_div_u32(acc, (uint32_t)G);
         } else if (pass == 1) {
             mean80 = x80_add(mean80, x80_div_u32(acc, (uint32_t)G));
-            if (lane == 0) sm_mean = x80_to_double(mean80); // xm[i] = (double)tmp
-            __syncwarp();
-            xm = x80_from_double(sm_mean);
+            xm = x80_from_double(x80_to_double(mean80)); // xm[i] = (double)tmp
         } else if (lane == 0) {
             double var = x80_to_double(x80_div_u32(acc, (uint32_t)(G - 1)));
             sd[blockIdx.x] = sqrt(var);

@@ -277,6 +277,86 @@ HB_HD x80 x80_div_u32(x80 a, uint32_t n)
 }
 
 // (double) of an extended value: one RNE rounding 64 -> 53 bits.
+// ---- a block of terms added to a running sum as an integer prefix sum ---------------------------------
+// While the running sum stays inside one binade [2^e, 2^(e+1)) it is an integer multiple m of q = 2^(e-63),
+// and sum <- RN64(sum + term) is m <- m +- RN(term / q) — provided the term is not exactly half-way
+// between two multiples of q (then the parity of the sum decides) and the exact sum stays inside the
+// binade (otherwise the result is rounded on another grid).  So a block of terms can be rounded to the
+// grid independently (x80_align_term: any lane can do that for its own term, knowing only the sum's
+// exponent and sign) and added with an integer PREFIX SUM; the prefix sums say at which term, if any, the
+// sum leaves the binade, and that term (or a tie, or a term too large for the grid) is added literally
+// with x80_add, after which the rest of the block is aligned again.  Same results as x80_add term by term
+// (tests/test_numerics.py).  pooled_sd_kernel runs the prefix sum across the lanes of a warp
+// (x80_block_add_warp in hb_kernels.cu); x80_block_add below is the same procedure written as loops, for
+// the host tests.
+HB_HD bool x80_align_term(x80 t, int32_t acc_e, uint32_t acc_neg, int64_t &s)
+{
+    s = 0;
+    if (t.m == 0) return true;
+    const int32_t d = acc_e - t.e; // term / q = t.m / 2^d
+    if (d < 1) return false;
+    if (d >= 65) return true; // below q / 2: rounds to nothing, cannot be a tie
+    uint64_t ip, rem, half;
+    if (d == 64) {
+        ip = 0;
+        rem = t.m;
+        half = 1ull << 63;
+    } else {
+        ip = t.m >> d;
+        rem = t.m & ((1ull << d) - 1);
+        half = 1ull << (d - 1);
+    }
+    if (rem == half) return false; // a tie on the term alone
+    if (rem > half) ip += 1;
+    if (ip >> 62) return false; // fits the signed prefix sum (whose magnitude is guarded separately)
+    s = (t.neg == acc_neg) ? (int64_t)ip : -(int64_t)ip;
+    return true;
+}
+
+// Is the prefix `p` (sum of the aligned terms so far) a legitimate state of a sum that started at m?  The exact
+// sum is within half a unit of (m + p) * q: strictly above 2^63 units it is inside the binade, at 2^63 itself it
+// may lie below it (finer grid); a carry out of 64 bits has left the binade upwards.
+HB_HD bool x80_prefix_ok(uint64_t m, int64_t p)
+{
+    const uint64_t nm = m + (uint64_t)p;
+    return !(p >= 0 && nm < m) && nm > (1ull << 63);
+}
+
+// The prefix sums are taken in wrapping 64-bit arithmetic; a coarse sum of the terms >> 8 beside them (which
+// cannot wrap) says whether the true prefix is below 2^63 in magnitude, i.e. whether the wrapped value is the
+// true one.
+HB_HD bool x80_coarse_ok(int64_t c) { return c > -(1ll << 54) && c < (1ll << 54); }
+
+// acc + terms[0..n), n <= 32, in order (loop form of the warp procedure, same decisions).  *nfast: terms added
+// as integers.  An exact-zero term never changes the sum (x80_add returns the other operand) and is skipped.
+HB_HD x80 x80_block_add(x80 acc, const x80 *t, int n, int *nfast)
+{
+    int start = 0, nf = 0;
+    while (start < n) {
+        uint64_t p = 0; // wrapping
+        int64_t c = 0;
+        int g = start;
+        uint64_t m_ok = acc.m;
+        for (; g < n; g++) { // the prefix sum, up to the first term that breaks a condition
+            if (t[g].m == 0) continue;
+            int64_t sj;
+            if (acc.m == 0 || !x80_align_term(t[g], acc.e, acc.neg, sj)) break;
+            const uint64_t pn = p + (uint64_t)sj;
+            const int64_t cn = c + (sj >> 8);
+            if (!x80_coarse_ok(cn) || !x80_prefix_ok(acc.m, (int64_t)pn)) break;
+            p = pn;
+            c = cn;
+            m_ok = acc.m + p;
+        }
+        nf += g - start;
+        acc.m = m_ok;
+        if (g < n) acc = x80_add(acc, t[g]);
+        start = g + 1;
+    }
+    if (nfast) *nfast = nf;
+    return acc;
+}
+
 HB_HD double x80_to_double(x80 a)
 {
     if (a.m == 0) return a.neg ? -0.0 : 0.0;

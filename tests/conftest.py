@@ -67,6 +67,10 @@ def emul():
     L.emul_x87_sd.argtypes = [C.c_void_p, C.c_int64]
     L.emul_x87_addcheck.restype = C.c_int64
     L.emul_x87_addcheck.argtypes = [C.c_void_p, C.c_int64, C.c_double, C.c_int]
+    L.emul_x87_sd_blocked.restype = C.c_double
+    L.emul_x87_sd_blocked.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
+    L.emul_x87_blockcheck.restype = C.c_int64
+    L.emul_x87_blockcheck.argtypes = [C.c_void_p, C.c_int64, C.c_double, C.c_int, C.c_void_p]
     L.emul_x87_paircheck.restype = C.c_int64
     L.emul_x87_paircheck.argtypes = [C.c_void_p, C.c_int64, C.c_double, C.c_double, C.c_int, C.c_void_p]
     L.emul_x87_pair_add80.restype = C.c_int64

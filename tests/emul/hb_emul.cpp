@@ -456,6 +456,76 @@ double emul_x87_sd(const double *x, int64_t n)
     return sqrt(x80_to_double(x80_div_u32(SS, (uint32_t)(n - 1))));
 }
 
+// R sd() with the running sums taken block by block (x80_align_term / x80_block_add, what pooled_sd_kernel does):
+// must equal emul_x87_sd bit for bit.  *fast receives the number of terms added on the integer path, of 3 n.
+double emul_x87_sd_blocked(const double *x, int64_t n, int64_t *fast)
+{
+    x80 mean80 = x80_zero(), xm = x80_zero(), acc = x80_zero();
+    int64_t nf = 0;
+    for (int pass = 0; pass < 3; pass++) {
+        acc = x80_zero();
+        for (int64_t i0 = 0; i0 < n; i0 += 32) {
+            const int lim = (int)((n - i0) < 32 ? (n - i0) : 32);
+            x80 tt[32];
+            for (int j = 0; j < lim; j++) {
+                x80 v = x80_from_double(x[i0 + j]), term;
+                if (pass == 0)
+                    term = v;
+                else if (pass == 1)
+                    term = x80_sub(v, mean80);
+                else {
+                    x80 d = x80_sub(v, xm);
+                    term = x80_mul(d, d);
+                }
+                tt[j] = term;
+            }
+            int f = 0;
+            acc = x80_block_add(acc, tt, lim, &f);
+            nf += f;
+        }
+        if (pass == 0)
+            mean80 = x80_div_u32(acc, (uint32_t)n);
+        else if (pass == 1) {
+            mean80 = x80_add(mean80, x80_div_u32(acc, (uint32_t)n));
+            xm = x80_from_double(x80_to_double(mean80));
+        }
+    }
+    if (fast) *fast = nf;
+    return sqrt(x80_to_double(x80_div_u32(acc, (uint32_t)(n - 1))));
+}
+
+// A running sum taken block by block against the host's x87 unit after every block (mode 0: s += x[i];
+// mode 1: s += x[i] - c); returns the number of blocks whose 80-bit result differs.
+int64_t emul_x87_blockcheck(const double *x, int64_t n, double c, int mode, int64_t *fast)
+{
+    x80 acc = x80_zero();
+    const x80 C80 = x80_from_double(c);
+    volatile long double sl = 0.0L;
+    const long double cl = c;
+    int64_t bad = 0, nf = 0;
+    for (int64_t i0 = 0; i0 < n; i0 += 32) {
+        const int lim = (int)((n - i0) < 32 ? (n - i0) : 32);
+        x80 tt[32];
+        for (int j = 0; j < lim; j++) {
+            tt[j] = mode == 0 ? x80_from_double(x[i0 + j]) : x80_sub(x80_from_double(x[i0 + j]), C80);
+            if (mode == 0)
+                sl = sl + (long double)x[i0 + j];
+            else {
+                volatile long double t = (long double)x[i0 + j] - cl;
+                sl = sl + t;
+            }
+        }
+        int f = 0;
+        acc = x80_block_add(acc, tt, lim, &f);
+        nf += f;
+        long double mine = acc.m ? ldexpl((long double)acc.m, acc.e - 63) : 0.0L;
+        if (acc.neg) mine = -mine;
+        if (mine != sl) bad++;
+    }
+    if (fast) *fast = nf;
+    return bad;
+}
+
 double emul_div_by_const(double d, double b) { return div_by_const(d, b, 1.0 / b); }
 
 void emul_exp_pair(double u, double *ep, double *em)

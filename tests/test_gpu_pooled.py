@@ -133,6 +133,52 @@ def test_pool_mean_zero_inflated_rows_bit_exact(oracle):
         assert np.array_equal(got[k].view(np.int64), ref.view(np.int64))
 
 
+def test_pooled_sd_adversarial_rows_bit_exact(oracle):
+    """hb_pooled_sd_dev (running 80-bit sums added block-wise as integer prefix sums across the warp, literal
+    x80_add for ties / oversized terms / binade changes) == R's sd() on rows built to hit every branch: wide
+    exponent ranges, integers, tie-heavy increments at four accumulator scales, powers of two pulled just below
+    themselves, runs of zeros, a constant row, sums that cancel — and on very short vectors."""
+    import torch
+    from honeybadger_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(43)
+    G = 6000
+    rows = [rng.normal(size=G) * 0.3, rng.normal(size=G) * 10.0 ** rng.integers(-12, 12, G),
+            rng.integers(0, 50, G).astype(float),
+            np.ldexp(rng.integers(1, 1 << 20, G).astype(float), rng.integers(-70, 70, G)), rng.gamma(2.0, 1.5, G),
+            np.concatenate([np.zeros(1000), rng.normal(size=G - 1500), np.zeros(500)]), np.zeros(G) + 0.1,
+            np.concatenate([[float(1 << 23)], np.ldexp(rng.integers(1, 1 << 30, G - 1).astype(float), -40)])]
+    for k in (0, 5, 11, 30):
+        rows.append(np.concatenate([[2.0 ** k], np.ldexp(rng.integers(-(1 << 14), 1 << 14, G - 1).astype(float),
+                                                         k - 64 - rng.integers(0, 4, G - 1))]))
+    pw = []
+    for _ in range(G // 3):
+        k = int(rng.integers(-20, 20))
+        pw += [2.0 ** k, -2.0 ** (k - int(rng.integers(50, 70))), -2.0 ** k * (1 - 2.0 ** -int(rng.integers(1, 53)))]
+    rows.append(np.array(pw))
+    y = rng.normal(size=G // 2)
+    z = np.empty(G)
+    z[0::2] = y
+    z[1::2] = -y + np.ldexp(rng.integers(-8, 8, G // 2).astype(float), -70)
+    rows.append(z)
+    X = np.ascontiguousarray(np.stack(rows))
+
+    def run(M):
+        d = torch.from_numpy(np.ascontiguousarray(M)).cuda()
+        out = torch.empty(M.shape[0], dtype=torch.float64, device="cuda")
+        _lib.check(lib.hb_pooled_sd_dev(d.data_ptr(), M.shape[1], M.shape[0], out.data_ptr(), None))
+        return out.cpu().numpy()
+
+    got = run(X)
+    for k in range(X.shape[0]):
+        ref = oracle.r_sd(X[k])
+        assert got[k] == ref or (got[k] != got[k] and ref != ref), k
+    for g in (2, 3, 31, 32, 33, 65):
+        M = rng.normal(size=(4, g)) * 2.6 + 7.5
+        got = run(M)
+        assert all(got[k] == oracle.r_sd(M[k]) for k in range(4))
+
+
 def test_function_variants_match_reference_restatement(golden_gexp, golden_allele):
     """calcGexpCnvBoundaries / calcAlleleCnvBoundaries (stateless) == the literal R restatement."""
     from honeybadger_b200 import honeybadger as hb

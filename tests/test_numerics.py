@@ -177,6 +177,41 @@ def test_x87_pair_fast_path_covers_expression_like_data(emul):
             assert cov[6] == 0 and cov[7] == 0, cov
 
 
+def test_x87_block_accumulation_matches_the_literal_one(emul, oracle):
+    """x80_align_term / x80_block_add (pooled_sd_kernel's running sums: one integer addition per term while the sum
+    stays in its binade, x80_add for the terms that fail a condition) against the host's x87 unit block by block,
+    against the term-by-term emulation, and against R's sd() — and most terms must take the integer path."""
+    rng = np.random.default_rng(41)
+    cases = [rng.normal(size=20000) * 0.3, rng.normal(size=20000) * 0.3 + 0.05, rng.gamma(2.0, 1.5, 20000),
+             rng.normal(size=6082) * 2.6, rng.normal(size=30000) * 10.0 ** rng.integers(-12, 12, 30000),
+             rng.integers(0, 50, 20000).astype(float),
+             np.ldexp(rng.integers(1, 1 << 20, 20000).astype(float), rng.integers(-70, 70, 20000)),
+             np.concatenate([np.zeros(100), rng.normal(size=1000), np.zeros(50), rng.normal(size=1000)])]
+    t = np.ldexp(rng.integers(1, 1 << 30, 10000).astype(float), -40)
+    cases.append(np.concatenate([[float(1 << 23)], t, -t]))
+    for k in (0, 11, 30):
+        adds = np.ldexp(rng.integers(-(1 << 14), 1 << 14, 20000).astype(float), k - 64 - rng.integers(0, 4, 20000))
+        cases.append(np.concatenate([[2.0 ** k], adds]))
+    pw = []
+    for _ in range(5000):
+        k = int(rng.integers(-20, 20))
+        pw += [2.0 ** k, -2.0 ** (k - int(rng.integers(50, 70))), -2.0 ** k * (1 - 2.0 ** -int(rng.integers(1, 53)))]
+    cases.append(np.array(pw))
+    cases += [rng.normal(size=n) * 2.6 + 7.5 for n in (2, 3, 5, 31, 32, 33, 64, 65, 1001)]
+    for x in cases:
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        p = x.ctypes.data_as(C.c_void_p)
+        f = C.c_int64(0)
+        got = emul.emul_x87_sd_blocked(p, x.size, C.byref(f))
+        assert got == emul.emul_x87_sd(p, x.size) == oracle.r_sd(x)
+        assert emul.emul_x87_blockcheck(p, x.size, 0.0, 0, None) == 0
+        assert emul.emul_x87_blockcheck(p, x.size, float(x.mean()), 1, None) == 0
+    x = np.ascontiguousarray(rng.normal(size=20000) * 0.3)     # a pooled expression vector: the case the kernel serves
+    f = C.c_int64(0)
+    emul.emul_x87_sd_blocked(x.ctypes.data_as(C.c_void_p), x.size, C.byref(f))
+    assert f.value > 0.85 * 3 * x.size
+
+
 def test_binom_logpmf_host_and_device_restatements_match_oracle(emul, oracle):
     for n in list(range(0, 70)) + [100, 255, 256, 511, 512, 1245, 5000]:
         for x in sorted({0, 1, n // 3, n // 2, n - 1, n}):
