@@ -177,35 +177,42 @@ __global__ void __launch_bounds__(256)
 }
 
 // R's real_mean over the non-zero entries in column-major (cell, then gene) order; `n` is their count.
+// One warp: 32 consecutive genes of a cell are one block of terms (zeros are exact zeros and change nothing),
+// added to the 80-bit running sum in order as integer prefix sums while the sum stays in its binade
+// (x80_block_add_warp, hb_x87.cuh); the next block's values are loaded before the current one is added.
 __global__ void __launch_bounds__(32)
     nz_mean_seq_kernel(const double *__restrict__ x, int64_t ld, int64_t G, int64_t N,
                        unsigned long long n, double *out)
 {
     const int lane = threadIdx.x;
     x80 S = x80_zero(), M = x80_zero();
+    const int64_t nblk = (G + 31) / 32;
     for (int pass = 0; pass < 2; pass++) {
+        double vnext = lane < G ? x[(int64_t)lane * ld] : 0.0;
         for (int64_t c = 0; c < N; c++)
-            for (int64_t g0 = 0; g0 < G; g0 += 32) {
-                const int64_t g = g0 + lane;
-                const double v = g < G ? x[g * ld + c] : 0.0;
-                const unsigned nzmask = __ballot_sync(0xffffffffu, v != 0.0);
-                for (unsigned mrem = nzmask; mrem; mrem &= mrem - 1) {
-                    const int src = __ffs(mrem) - 1;
-                    const double w = __shfl_sync(0xffffffffu, v, src);
-                    if (lane == 0) {
-                        x80 t = x80_from_double(w);
-                        S = x80_add(S, pass ? x80_sub(t, M) : t);
-                    }
+            for (int64_t b = 0; b < nblk; b++) {
+                const double v = vnext;
+                // the block after this one (next genes of the cell, or the first genes of the next cell)
+                int64_t nb = b + 1, nc = c;
+                if (nb == nblk) {
+                    nb = 0;
+                    nc = c + 1;
                 }
+                const int64_t ng = nb * 32 + lane;
+                vnext = (nc < N && ng < G) ? x[ng * ld + nc] : 0.0;
+                x80 term = x80_zero();
+                if (v != 0.0) {
+                    term = x80_from_double(v);
+                    if (pass) term = x80_sub(term, M);
+                }
+                S = x80_block_add_warp(S, term, lane, 32);
             }
-        if (lane == 0) {
-            // n < 2^32 is checked by the caller
-            if (pass == 0) {
-                M = x80_div_u32(S, (uint32_t)n);
-                S = x80_zero();
-            } else {
-                *out = x80_to_double(x80_add(M, x80_div_u32(S, (uint32_t)n)));
-            }
+        // n < 2^32 is checked by the caller
+        if (pass == 0) {
+            M = x80_div_u32(S, (uint32_t)n);
+            S = x80_zero();
+        } else if (lane == 0) {
+            *out = x80_to_double(x80_add(M, x80_div_u32(S, (uint32_t)n)));
         }
     }
 }

@@ -1316,49 +1316,6 @@ cudaError_t launch_pool_mean(const double *x, int64_t ld, int64_t G, int64_t N,
     return launch_pool_finish(mean80, state, gsize, G, K, out, st);
 }
 
-// acc + the terms of lanes [0, lim) in lane order; every lane holds the same acc and gets the same result.
-// The warp form of x80_block_add (hb_x87.cuh): each round aligns the unprocessed terms to the sum's grid, takes
-// their integer prefix sums with shuffles, applies the longest legitimate prefix in one addition, and adds the
-// term that stopped it (a tie, a term too large for the grid, the sum leaving its binade) literally.
-__device__ __forceinline__ x80 x80_block_add_warp(x80 acc, x80 term, int lane, int lim)
-{
-    const unsigned full = 0xffffffffu;
-    int start = 0;
-    while (start < lim) {
-        const bool mine = lane >= start && lane < lim && term.m != 0; // exact zeros never change the sum
-        int64_t sj = 0;
-        const bool okj = !mine || (acc.m != 0 && x80_align_term(term, acc.e, acc.neg, sj));
-        const unsigned bad = __ballot_sync(full, !okj);
-        const int f = bad ? __ffs((int)bad) - 1 : lim; // first term that cannot go on the grid
-        if (!mine || lane >= f) sj = 0;
-        uint64_t p = (uint64_t)sj; // wrapping prefix sum, and a coarse one that says whether it wrapped
-        int64_t c = sj >> 8;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint64_t up = __shfl_up_sync(full, p, o);
-            const int64_t uc = __shfl_up_sync(full, c, o);
-            if (lane >= o) {
-                p += up;
-                c += uc;
-            }
-        }
-        const bool v = !mine || lane >= f || (x80_coarse_ok(c) && x80_prefix_ok(acc.m, (int64_t)p));
-        const unsigned inv = __ballot_sync(full, !v);
-        const int g = inv ? __ffs((int)inv) - 1 : f; // first term whose prefix is not a legitimate state
-        const uint64_t pg = __shfl_sync(full, p, g > 0 ? g - 1 : 0);
-        if (g > start) acc.m += pg;
-        if (g < lim) {
-            x80 tg;
-            tg.m = __shfl_sync(full, term.m, g);
-            tg.e = __shfl_sync(full, term.e, g);
-            tg.neg = __shfl_sync(full, term.neg, g);
-            acc = x80_add(acc, tg);
-        }
-        start = g + 1;
-    }
-    return acc;
-}
-
 // sd(x) of each pooled vector (cov.c cov_complete1 replayed): one warp per vector; the lanes form the
 // per-element terms in parallel and add each block of 32 to the running 80-bit sum in order
 // (x80_block_add_warp).
