@@ -13,6 +13,7 @@
 #pragma once
 #include "hb_device.cuh"
 #include "hb_x87.cuh"
+#include "hb_x87_pair.cuh"
 
 namespace hb {
 
@@ -66,7 +67,10 @@ __global__ void __launch_bounds__(128)
 // Column statistics of scale(): per cell, over the kept genes in order,
 //   center = (double)(sum80(x) / n)                     colMeans(x, na.rm=TRUE)
 //   scl    = sqrt((double)sum80((x - center)^2) / max(1, n-1))
-// One thread per cell; x[g * ld + c] is coalesced across the warp's cells; loads run CS_U genes ahead.
+// One thread per cell; x[g * ld + c] is coalesced across the warp's cells; loads run CS_U genes ahead.  10^4 cells
+// are only 313 warps, so the kernel runs at the LATENCY of one 80-bit addition: the running sums are carried as
+// pairs of doubles (hb_x87_pair.cuh; both passes add doubles), whose dependent chain is ~20 fp64 operations
+// instead of the ~50 integer instructions and branches of x80_add.
 #define CS_U 16
 __global__ void __launch_bounds__(32)
     col_stats_kernel(const double *__restrict__ x, int64_t ld, int64_t G, int64_t N,
@@ -76,7 +80,7 @@ __global__ void __launch_bounds__(32)
     const int64_t c = (int64_t)blockIdx.x * 32 + threadIdx.x;
     if (c >= N) return;
     const double *col = x + c;
-    x80 S = x80_zero();
+    x80p S = {0.0, 0.0};
     uint32_t n = 0;
     for (int64_t g0 = 0; g0 < G; g0 += CS_U) {
         double v[CS_U];
@@ -85,14 +89,14 @@ __global__ void __launch_bounds__(32)
 #pragma unroll
         for (int u = 0; u < CS_U; u++)
             if (g0 + u < G && (!keep || keep[g0 + u])) {
-                S = x80_add(S, x80_from_double(v[u]));
+                S = x80p_add_double(S, v[u]);
                 n++;
             }
     }
-    const double m = n ? x80_to_double(x80_div_u32(S, n)) : 0.0;
+    const double m = n ? x80_to_double(x80_div_u32(x80_from_x80p(S), n)) : 0.0;
     center[c] = m;
     if (!scl) return;
-    S = x80_zero();
+    S.h = S.l = 0.0;
     for (int64_t g0 = 0; g0 < G; g0 += CS_U) {
         double v[CS_U];
 #pragma unroll
@@ -101,11 +105,11 @@ __global__ void __launch_bounds__(32)
         for (int u = 0; u < CS_U; u++)
             if (g0 + u < G && (!keep || keep[g0 + u])) {
                 const double d = __dsub_rn(v[u], m);
-                S = x80_add(S, x80_from_double(__dmul_rn(d, d)));
+                S = x80p_add_double(S, __dmul_rn(d, d));
             }
     }
     const double den = (double)(n > 1 ? n - 1 : 1);
-    scl[c] = sqrt(__ddiv_rn(x80_to_double(S), den));
+    scl[c] = sqrt(__ddiv_rn(S.h, den)); // S.h is the running sum rounded to double
 }
 
 // out[k][c] = ((x[rows[k]][c] - center[c]) / scl[c]) - refmean[k]; each stage optional (null pointer).
@@ -133,7 +137,7 @@ __global__ void __launch_bounds__(256)
 // Stage 1 (nz_sum_kernel): the exact-to-~2^-100 sum in double-double, in parallel, plus the count.
 // The caller forms the mean from it and checks that no row mean lies within a safety margin of the
 // threshold it is compared with; only then can the serial rounding pattern matter, and stage 2
-// (nz_mean_seq_kernel: one warp, lane 0 replays R's loop in x87 arithmetic) is run instead.
+// (nz_mean_seq_kernel: one warp replays R's loop in x87 arithmetic, a block of 32 terms at a time) is run instead.
 __device__ __forceinline__ void dd_add(double &hi, double &lo, double v)
 {
     const double s = __dadd_rn(hi, v);
