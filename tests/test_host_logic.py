@@ -218,3 +218,14 @@ def test_sharded_dist_block_plan_covers_every_pair_exactly_once():
         assert (both == 1).all(), sizes
         if W > 1 and len(set(sizes)) == 1 and sizes[0] >= 8:
             assert work.max() <= 1.3 * work.min(), (sizes, work)
+
+
+def test_integration_md_names_every_exported_symbol():
+    """INTEGRATION.md's index must name each entry point include/hb_b200.h declares (the header is the contract, the
+    document says what each symbol replaces in the reference)."""
+    import re
+    hdr = open(os.path.join(ROOT, "include", "hb_b200.h")).read()
+    names = sorted(set(re.findall(r"\b(hb_[a-z0-9_]+)\s*\(", hdr)))
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    missing = [n for n in names if n not in doc]
+    assert not missing, missing
