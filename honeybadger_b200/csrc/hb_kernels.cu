@@ -1326,8 +1326,9 @@ __global__ void __launch_bounds__(32) pooled_sd_kernel(const double *pooled, int
     x80 acc = x80_zero(), mean80 = x80_zero(), xm = x80_zero();
     for (int pass = 0; pass < 3; pass++) {
         acc = x80_zero();
-        for (int64_t i0 = 0; i0 < G; i0 += 32) {
-            const int64_t i = i0 + lane;
+        // the term of element i in this pass (does not depend on the running sum: the terms of block i + 1 are formed
+        // while block i is being added, which hides their latency behind the scan's dependent chain)
+        auto make = [&](int64_t i) {
             x80 term = x80_zero();
             if (i < G) {
                 x80 v = x80_from_double(xv[i]);
@@ -1340,6 +1341,12 @@ __global__ void __launch_bounds__(32) pooled_sd_kernel(const double *pooled, int
                     term = x80_mul(d, d);
                 }
             }
+            return term;
+        };
+        x80 next = make(lane);
+        for (int64_t i0 = 0; i0 < G; i0 += 32) {
+            const x80 term = next;
+            next = make(i0 + 32 + lane);
             acc = x80_block_add_warp(acc, term, lane, (int)((G - i0) < 32 ? (G - i0) : 32));
         }
         if (pass == 0) {
