@@ -193,7 +193,7 @@ int g_host_threads = 0; // copy-out threads of the host pipeline; 0 = all but tw
 // settings do not interfere).
 thread_local int g_binom2_mode = 0; // 0 auto (lean kernel, general kernel behind its gate), 1 general kernel only
 thread_local int g_dist_mode = 0;      // 0 pipelined dist kernel (cp.async ring, flag pre-pass), 1 the plain one
-thread_local int g_ward_mode = 0;      // 0 auto (cluster kernel from 1 024 cells up), 1 single block, 2 cluster
+thread_local int g_ward_mode = 0;      // 0 auto (cluster kernel from 256 cells up), 1 single block, 2 cluster
 thread_local int g_longchain_mode = 0; // 0 auto (pooled allele rounds), 1 never, 2 also the pooled expression rounds
 thread_local int g_norm3_mode = 0; // 0 auto, 1 literal kernel only, 2 speculative kernel with every chain re-run exactly, 3 speculative kernel whenever eligible
 

@@ -496,6 +496,10 @@ __device__ __forceinline__ void wc_warp_min(uint64_t &key, uint32_t &ik)
     key = ((uint64_t)mh << 32) | ml;
     ik = mi;
 }
+// OWN: columns per thread the instantiation is unrolled for (>= what the launch needs; a tight bound keeps the
+// per-step instruction count — and with it the step's latency — down: 362 warp-instructions per step at OWN = 16
+// for a launch that needs 3)
+template <int OWN>
 __global__ void __launch_bounds__(WC_THREADS)
     ward_cluster_kernel(double *D, int64_t N, int32_t *size_rep, int32_t *chain_rep, int32_t *ma, int32_t *mb,
                         double *height)
@@ -512,7 +516,7 @@ __global__ void __launch_bounds__(WC_THREADS)
     const int64_t lo = (int64_t)rk * chunk, hi = lo + chunk < N ? lo + chunk : N;
     uint32_t alive = 0;
 #pragma unroll
-    for (int i = 0; i < WC_OWN; i++)
+    for (int i = 0; i < OWN; i++)
         if (lo + tid + (int64_t)i * WC_THREADS < hi) alive |= 1u << i;
     for (int64_t k = tid; k < N; k += WC_THREADS) size[k] = 1;
     __syncthreads();
@@ -528,14 +532,14 @@ __global__ void __launch_bounds__(WC_THREADS)
     // rounds of 64-bit shuffles and fp64 compares.
     auto argmin = [&](int32_t a, int32_t prefer) -> int32_t {
         const double *row = D + (int64_t)a * N + lo + tid;
-        double v[WC_OWN];
+        double v[OWN];
 #pragma unroll
-        for (int i = 0; i < WC_OWN; i++)
+        for (int i = 0; i < OWN; i++)
             if (i < nown && ((alive >> i) & 1u)) v[i] = __ldcg(row + (int64_t)i * WC_THREADS);
         uint64_t bk = ~0ull;
         uint32_t bi = 0xffffffffu;
 #pragma unroll
-        for (int i = 0; i < WC_OWN; i++) {
+        for (int i = 0; i < OWN; i++) {
             if (i < nown) {
                 const int32_t k = (int32_t)(lo + tid + (int64_t)i * WC_THREADS);
                 if (((alive >> i) & 1u) && k != a) {
@@ -593,15 +597,15 @@ __global__ void __launch_bounds__(WC_THREADS)
         // the union lives in slot b; slot a dies
         {
             const double *ra = D + (int64_t)a * N + lo + tid, *rb = D + (int64_t)b * N + lo + tid;
-            double va[WC_OWN], vb[WC_OWN];
+            double va[OWN], vb[OWN];
 #pragma unroll
-            for (int i = 0; i < WC_OWN; i++)
+            for (int i = 0; i < OWN; i++)
                 if (i < nown && ((alive >> i) & 1u)) {
                     va[i] = __ldcg(ra + (int64_t)i * WC_THREADS);
                     vb[i] = __ldcg(rb + (int64_t)i * WC_THREADS);
                 }
 #pragma unroll
-            for (int i = 0; i < WC_OWN; i++) {
+            for (int i = 0; i < OWN; i++) {
                 const int64_t k = lo + tid + (int64_t)i * WC_THREADS;
                 if (i < nown && ((alive >> i) & 1u) && k != a && k != b) {
                     const double nk = (double)size[k];

@@ -1045,8 +1045,19 @@ cudaError_t launch_dist_sq_rect(const double *Sa, int64_t lda, int64_t Na, const
 // Scratch of the linkage: the cluster form keeps one copy of the chain and the cluster sizes per CTA.
 size_t ward_scratch_bytes(int64_t N) { return (size_t)N * sizeof(int32_t) * 2 * WC_MAXR + (size_t)N + 256; }
 
+static cudaError_t ward_cluster_allow16()
+{
+    cudaError_t e = cudaSuccess;
+    auto set = [&](auto k) {
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    };
+    set(ward_cluster_kernel<1>), set(ward_cluster_kernel<2>), set(ward_cluster_kernel<3>), set(ward_cluster_kernel<4>);
+    set(ward_cluster_kernel<6>), set(ward_cluster_kernel<8>), set(ward_cluster_kernel<WC_OWN>);
+    return e;
+}
+
 // mode 0: cluster kernel from WARD_CLUSTER_MIN clusters up, single block below; 1: single block; 2: cluster
-#define WARD_CLUSTER_MIN 1024
+#define WARD_CLUSTER_MIN 256
 cudaError_t launch_ward(double *D, int64_t N, void *work, int32_t *ma, int32_t *mb, double *height, int mode,
                         cudaStream_t st)
 {
@@ -1060,8 +1071,7 @@ cudaError_t launch_ward(double *D, int64_t N, void *work, int32_t *ma, int32_t *
         if (cluster_max < 0) {
             cluster_max = 0;
             for (int r : {16, 8}) {
-                if (r > 8 && cudaFuncSetAttribute(ward_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed,
-                                                  1) != cudaSuccess) {
+                if (r > 8 && ward_cluster_allow16() != cudaSuccess) {
                     cudaGetLastError();
                     continue;
                 }
@@ -1071,7 +1081,7 @@ cudaError_t launch_ward(double *D, int64_t N, void *work, int32_t *ma, int32_t *
                 at[0].val.clusterDim.x = r, at[0].val.clusterDim.y = 1, at[0].val.clusterDim.z = 1;
                 cfg.gridDim = dim3(r), cfg.blockDim = dim3(WC_THREADS), cfg.attrs = at, cfg.numAttrs = 1;
                 int ncl = 0;
-                if (cudaOccupancyMaxActiveClusters(&ncl, ward_cluster_kernel, &cfg) == cudaSuccess && ncl >= 1) {
+                if (cudaOccupancyMaxActiveClusters(&ncl, ward_cluster_kernel<WC_OWN>, &cfg) == cudaSuccess && ncl >= 1) {
                     cluster_max = r;
                     break;
                 }
@@ -1082,8 +1092,9 @@ cudaError_t launch_ward(double *D, int64_t N, void *work, int32_t *ma, int32_t *
         // a CTA's slice must fit its threads' register masks: N / r + 32 <= WC_THREADS * WC_OWN (65 k cells at 16 CTAs)
         const bool fits = cluster_max && (N + cluster_max - 1) / cluster_max + 32 <= (int64_t)WC_THREADS * WC_OWN;
         if (fits) {
-            // measured (tools/probe_ward.py): 8 CTAs are best up to ~8 k cells, 16 beyond; a step costs ~2 us at
-            // any size (L2 latency + cluster barrier), so small problems stay on one block
+            // measured (tools/probe_ward.py): 8 CTAs are best up to ~8 k cells, 16 beyond; a step costs ~1.1 (1 k cells)
+            // to ~2 us (10 k) — L2 latency + cluster barrier — against 1.3 to 6.5 us on one block, which wins only
+            // below ~256 cells
             int r = std::min(cluster_max, N >= 8192 ? 16 : 8);
             if (const char *e = getenv("HB_WARD_R")) r = std::max(1, std::min(cluster_max, atoi(e))); // experiments
             if ((N + r - 1) / r + 32 > (int64_t)WC_THREADS * WC_OWN) r = cluster_max;
@@ -1092,7 +1103,15 @@ cudaError_t launch_ward(double *D, int64_t N, void *work, int32_t *ma, int32_t *
             at[0].id = cudaLaunchAttributeClusterDimension;
             at[0].val.clusterDim.x = r, at[0].val.clusterDim.y = 1, at[0].val.clusterDim.z = 1;
             cfg.gridDim = dim3(r), cfg.blockDim = dim3(WC_THREADS), cfg.stream = st, cfg.attrs = at, cfg.numAttrs = 1;
-            return cudaLaunchKernelEx(&cfg, ward_cluster_kernel, D, N, size, chain, ma, mb, height);
+            const int64_t chunk = (((N + r - 1) / r) + 31) & ~(int64_t)31;
+            const int own = (int)((chunk + WC_THREADS - 1) / WC_THREADS);
+            if (own <= 1) return cudaLaunchKernelEx(&cfg, ward_cluster_kernel<1>, D, N, size, chain, ma, mb, height);
+            if (own <= 2) return cudaLaunchKernelEx(&cfg, ward_cluster_kernel<2>, D, N, size, chain, ma, mb, height);
+            if (own <= 3) return cudaLaunchKernelEx(&cfg, ward_cluster_kernel<3>, D, N, size, chain, ma, mb, height);
+            if (own <= 4) return cudaLaunchKernelEx(&cfg, ward_cluster_kernel<4>, D, N, size, chain, ma, mb, height);
+            if (own <= 6) return cudaLaunchKernelEx(&cfg, ward_cluster_kernel<6>, D, N, size, chain, ma, mb, height);
+            if (own <= 8) return cudaLaunchKernelEx(&cfg, ward_cluster_kernel<8>, D, N, size, chain, ma, mb, height);
+            return cudaLaunchKernelEx(&cfg, ward_cluster_kernel<WC_OWN>, D, N, size, chain, ma, mb, height);
         }
     }
     uint8_t *active = (uint8_t *)(chain + (int64_t)N * WC_MAXR);

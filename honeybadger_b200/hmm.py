@@ -532,7 +532,7 @@ def set_longchain_mode(mode: int):
 
 
 def set_ward_mode(mode: int):
-    """Ward linkage kernel: 0 cluster of CTAs from 1 024 cells up (default), 1 one block, 2 always the cluster."""
+    """Ward linkage kernel: 0 cluster of CTAs from 256 cells up (default), 1 one block, 2 always the cluster."""
     _lib.check(_lib.load().hb_set_ward_mode(int(mode)))
 
 

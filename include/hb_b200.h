@@ -409,7 +409,7 @@ int hb_longchain_stats_dev(void *stream, int64_t *out /* [5] */);
  * 2: as 0 plus the pooled expression round.  Same states in every mode, posteriors within 1e-9. */
 int hb_set_longchain_mode(int32_t mode);
 /* Which kernel builds the Ward linkage (hb_ward_linkage_dev and the hb_group_* entry points).  0 (default):
- * from 1 024 cells up a thread-block cluster of up to 16 SMs (column slices per CTA, winners exchanged
+ * from 256 cells up a thread-block cluster of up to 16 SMs (column slices per CTA, winners exchanged
  * through distributed shared memory), one block below that; 1: always one block; 2: always the cluster.
  * Merges, their order and heights are bit-identical in every mode.  Per calling thread. */
 int hb_set_ward_mode(int32_t mode);

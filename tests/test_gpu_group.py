@@ -75,10 +75,10 @@ def test_cluster_linkage_matches_scipy_ward_heights():
     np.testing.assert_allclose(np.sort(h), Z[:, 2], rtol=1e-9, atol=1e-9)
 
 
-def test_default_mode_uses_the_cluster_from_1024_cells(monkeypatch):
-    """mode 0 must give the same answer on both sides of the switch-over (and run at all)."""
+def test_default_mode_on_both_sides_of_the_switch_over(monkeypatch):
+    """mode 0 (one block below 256 cells, the cluster from there) must give the single block's answer."""
     rng = np.random.default_rng(11)
-    for N in (1023, 1024):
+    for N in (255, 256, 1023, 1024):
         D = _sqdist(rng.normal(size=(N, 8)))
         a0, b0, h0 = _linkage(D, 0)
         a1, b1, h1 = _linkage(D, 1)
