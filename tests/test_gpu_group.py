@@ -154,3 +154,20 @@ def test_cluster_linkage_and_dist_are_reproducible_run_to_run():
     plain = _linkage(d0, 1)
     assert np.array_equal(first[0], plain[0]) and np.array_equal(first[1], plain[1])
     assert np.array_equal(first[2].view(np.int64), plain[2].view(np.int64))
+
+
+@pytest.mark.parametrize("N,r", [(1100, 1), (1100, 2), (4000, 4), (6000, 4), (8000, 4), (9000, 4)])
+def test_every_instantiation_of_the_cluster_kernel(N, r, monkeypatch):
+    """The cluster kernel is compiled for 1, 2, 3, 4, 6, 8 and 16 columns per thread; HB_WARD_R forces small
+    clusters so that each instantiation runs (5, 3, 4, 6, 8, 9 -> 16 columns here) and must reproduce the single
+    block merge for merge."""
+    rng = np.random.default_rng(N + r)
+    x = rng.normal(size=(N, 6))
+    x[: N // 3] += 1.5
+    D = _sqdist(x)
+    monkeypatch.setenv("HB_WARD_R", str(r))
+    a2, b2, h2 = _linkage(D, 2)
+    monkeypatch.delenv("HB_WARD_R")
+    a1, b1, h1 = _linkage(D, 1)
+    assert np.array_equal(a1, a2) and np.array_equal(b1, b2)
+    assert np.array_equal(h1.view(np.int64), h2.view(np.int64))
